@@ -1,0 +1,171 @@
+/*
+ * smarties_b200.h — C-ABI of the B200-native V-RACER / RACER learner hot path.
+ *
+ * This is the drop-in boundary for ONE path of cselab/smarties: the off-policy learner step
+ *   sample -> gather -> network forward -> ReF-ER/Retrace loss -> backward -> Adam -> replay stats
+ * i.e. what `smarties::Learner_approximator::spawnTrainTasks`, `Learner::processMemoryBuffer`,
+ * `Learner_approximator::applyGradient` and the `MemoryBuffer`/`MemoryProcessing` functions they
+ * call compute on host cores in the reference.  A `smarties::Learner` subclass (see
+ * INTEGRATION.md, "RACER_B200") forwards to these entry points; everything above it
+ * (Engine, Communicator, Worker, Master, sockets/MPI) stays the reference's.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a
+ * negative smb200_status and never throws; the caller owns host buffers, the library owns
+ * device memory behind the opaque handle; calls on one handle must be serialised by the
+ * caller.  Reference file:line citations are relative to /root/reference/source/smarties/.
+ */
+#ifndef SMARTIES_B200_H
+#define SMARTIES_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMB200_MAX_HIDDEN 8
+#define SMB200_MAX_ACTION 64
+
+typedef struct smb200_learner smb200_learner; /* opaque */
+
+enum smb200_status {
+  SMB200_OK = 0,
+  SMB200_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
+  SMB200_ERR_CUDA = -2,      /* CUDA runtime error (message via smb200_last_error) */
+  SMB200_ERR_CAPACITY = -3,  /* replay ring / episode table full */
+  SMB200_ERR_STATE = -4      /* call not valid in the current state */
+};
+
+enum smb200_algo { SMB200_VRACER = 0, SMB200_RACER = 1 };
+enum smb200_field {          /* per-transition replay arrays, Episode.h:66-75 */
+  SMB200_F_V = 0, SMB200_F_ADV = 1, SMB200_F_QRET = 2, SMB200_F_DELTA = 3, SMB200_F_RHO = 4, SMB200_F_KL = 5,
+  SMB200_F_REWARD = 6
+};
+
+/* Everything the reference reads from settings.json (Settings/HyperParameters.h:37-73), from
+ * the MDP descriptor (Core/StateAction.h:46-125) and from Bund.h that shapes the arithmetic.
+ * Zero-initialise, then call smb200_default_config() and override. */
+typedef struct smb200_config {
+  int32_t device;                       /* CUDA device ordinal */
+  int32_t algo;                         /* smb200_algo: "learner": "VRACER" | "RACER" */
+  int32_t dim_state;                    /* MDP.dimStateObserved */
+  int32_t dim_action;                   /* MDP.dimAction (continuous) */
+  uint8_t action_bounded[SMB200_MAX_ACTION]; /* MDP.bActionSpaceBounded -> SquashedNormalPolicy */
+  int32_t n_hidden;                     /* nnLayerSizes.size() */
+  int32_t hidden[SMB200_MAX_HIDDEN];    /* nnLayerSizes */
+  int32_t batch_size;                   /* batchSize_local */
+  int32_t batch_size_global;            /* batchSize (== local for one learner rank) */
+  int64_t max_tot_obs;                  /* maxTotObsNum_local */
+  int64_t max_tot_obs_global;           /* maxTotObsNum */
+  int64_t capacity_rows;                /* rows of HBM ring to allocate; 0 = derive from max_tot_obs */
+  int32_t max_episodes;                 /* episode-table slots; 0 = derive */
+  double gamma, lambda, clip_imp_weight, penal_tol, eps_anneal;
+  double learnrate, nn_lambda, expl_noise, out_weights_prefac;
+  int32_t refer_reduce_threads;         /* how many OpenMP threads' reduction order the far-policy
+                                           count emulates (MemoryProcessing.cpp:202-227); 0 = 32 */
+  int32_t world_rank, world_size;       /* learner ranks sharing the gradient (nMasters) */
+  uint64_t seed;                        /* ExecutionInfo::randSeed (sampler + weight init) */
+} smb200_config;
+
+/* Per-step scalars the reference prints / feeds back (MemoryBuffer::getMetrics,
+ * MemoryBuffer.cpp:522-575; MemoryProcessing.cpp:46-92,187-259), valid after the step. */
+typedef struct smb200_step_stats {
+  double beta, cmax, cinv;
+  int64_t n_far_policy;       /* reference-formula far-policy count (drives beta) */
+  int64_t n_far_exact;        /* exact integer count of per-transition far flags */
+  double avg_kl, avg_sq_err, max_abs_err, avg_return, stdev_q, avg_q, max_q, min_q;
+  double sum_ret_err; int64_t cnt_ret;
+  int64_t grad_step;          /* nGradSteps after the step */
+} smb200_step_stats;
+
+/* HyperParameters defaults for (dim_state, dim_action) — Settings/HyperParameters.h:37-73. */
+int smb200_default_config(smb200_config* cfg, int32_t dim_state, int32_t dim_action);
+
+/* Learner construction: RACER ctor + setupNet (Learners/RACER_common.cpp:70-115,
+ * Network/Builder.cpp:119-170) incl. weight initialisation from mt19937(seed). */
+int smb200_create(const smb200_config* cfg, smb200_learner** out);
+void smb200_destroy(smb200_learner* h);
+const char* smb200_last_error(void);
+
+int64_t smb200_n_params(const smb200_learner* h);   /* padded blob size, Parameters.h:159-176 */
+int32_t smb200_n_outputs(const smb200_learner* h);  /* 1 + 2*dA (V-RACER) */
+
+/* Weights / Adam moments as the reference's padded parameter blob (Parameters.h:28-177). */
+int smb200_set_weights(smb200_learner* h, const float* blob, int64_t n);
+int smb200_get_weights(smb200_learner* h, float* blob, int64_t n);
+int smb200_set_adam(smb200_learner* h, const float* m1, const float* m2, int64_t n, int64_t n_step);
+int smb200_get_adam(smb200_learner* h, float* m1, float* m2, int64_t n);
+/* Last summed parameter gradient (AdamOptimizer::gradSum before apply_update, Optimizer.cpp:110-120). */
+int smb200_get_grad(smb200_learner* h, float* blob, int64_t n);
+
+/* State / reward normalisers (MDPdescriptor, Core/StateAction.h:56-58;
+ * agent_XX_scaling.raw order of MemoryBuffer.cpp:277-287). rewards = {mean, scale, stdev}. */
+int smb200_set_scaling(smb200_learner* h, const float* mean, const float* scale, const float* stdev, const float rewards[3]);
+int smb200_get_scaling(smb200_learner* h, float* mean, float* scale, float* stdev, float rewards[3]);
+
+/* MemoryBuffer::pushBackEpisode + Episode::finalize + computeReturnEstimator
+ * (MemoryBuffer.cpp:133-170,479-520; Episode.cpp:244-273).  n_rows = nsteps() including the
+ * terminal/truncated row.  value/advantage may be NULL (zeros).  Thread-compatible with
+ * training only through the caller's serialisation. */
+int smb200_push_episode(smb200_learner* h, int64_t id, int32_t n_rows, int32_t terminated,
+                        const float* states, const float* actions, const float* policies,
+                        const float* rewards, const float* value, const float* advantage);
+int64_t smb200_n_transitions(const smb200_learner* h);  /* MemoryBuffer::nStoredSteps */
+int64_t smb200_n_episodes(const smb200_learner* h);     /* MemoryBuffer::nStoredEps */
+
+/* Learner::initializeLearner (Learners/Learner.cpp:47-72). */
+int smb200_initialize_learner(smb200_learner* h);
+/* counters.nGradSteps / AdamOptimizer::nStep after a restart (Approximator.h:64). */
+int smb200_set_grad_step(smb200_learner* h, int64_t n_grad_steps);
+int smb200_seed_sampler(smb200_learner* h, uint64_t seed);
+
+/* Sample_uniform::sample + Sampling::IDtoSeqStep (ReplayMemory/Sampling.cpp:26-47,82-96):
+ * B unique ascending transition ids from the handle's std::mt19937 -> (episode position in the
+ * buffer's current order, time step).  Advances the generator exactly like the reference. */
+int smb200_sample(smb200_learner* h, int64_t* episode_pos, int64_t* tstep);
+
+/* n learner steps: {spawnTrainTasks; processMemoryBuffer; applyGradient; globalGradCounterUpdate}
+ * (Learners/RACER.cpp:81-109) with the internal sampler.  stats (may be NULL) receives n entries. */
+int smb200_train_steps(smb200_learner* h, int32_t n, smb200_step_stats* stats);
+/* One step on caller-supplied samples (episode position, time step), e.g. the output of
+ * smb200_sample or of the reference's own sampler. */
+int smb200_train_step_on(smb200_learner* h, const int64_t* episode_pos, const int64_t* tstep,
+                         int32_t batch, smb200_step_stats* stats);
+
+/* Diagnostics of the last step, batch-major: net outputs O[B][nOut] (f32), output gradient
+ * g[B][nOut] (f32), standardized inputs X[B][dS].  NULL pointers are skipped. */
+int smb200_get_last_batch(smb200_learner* h, float* outputs, float* out_grad, float* inputs);
+
+/* Stand-alone sweeps (also run internally every 1000 steps):
+ * updateReturnEstimator over all episodes (MemoryProcessing.cpp:23-44,452-481) ... */
+int smb200_retrace_sweep(smb200_learner* h, double* sum_err2);
+/* ... and the reward/state moments of updateRewardsStats (MemoryProcessing.cpp:94-185):
+ * out[2*dS+3] = {sum(s-mean)[dS], sum((s-mean)^2)[dS], count, sum(r-mean), sum((r-mean)^2)}. */
+int smb200_reward_state_moments(smb200_learner* h, double* out);
+
+/* Read one per-transition array for every stored episode, concatenated in the buffer's current
+ * episode order (rows incl. the terminal row), and the episode table in the same order:
+ * ids[nEp], n_rows[nEp], aggregates[nEp][9] = {avgKL, fracFar, avgSqErr, maxAbsErr, sumQ2,
+ * sumQ, maxQ, minQ, totR} (Episode.h:77-81). */
+int smb200_read_field(smb200_learner* h, int32_t field, float* out, int64_t n);
+int smb200_read_episodes(smb200_learner* h, int64_t* ids, int64_t* n_rows, float* aggregates, int64_t n_ep);
+int64_t smb200_n_rows(const smb200_learner* h);
+int smb200_get_stats(smb200_learner* h, smb200_step_stats* out);
+
+/* Actor-side policy evaluation (RACER::selectAction, Learners/RACER.cpp:30-47): raw states in,
+ * net outputs out[n][nOut]. */
+int smb200_forward(smb200_learner* h, const float* states, int32_t n, float* outputs);
+
+/* Device-side timing of the last smb200_train_steps call (CUDA events on the library's
+ * stream), and the number of kernels it launched. */
+int smb200_last_timing(smb200_learner* h, double* ms_device, int64_t* kernel_launches);
+/* Raw access for benchmarks: run n steps on ids already resident in HBM (uploaded by
+ * smb200_presample) without any host<->device copy. */
+int smb200_presample(smb200_learner* h, int32_t n_steps);
+int smb200_train_presampled(smb200_learner* h, int32_t first, int32_t n);
+int smb200_sync(smb200_learner* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMARTIES_B200_H */

@@ -1,0 +1,672 @@
+"""CPU restatement (numpy) of the reference's V-RACER / RACER learner hot path.
+
+TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
+import this module; the product (smarties_b200/) never does.
+
+Parity status: PINNED against outputs of the reference itself — golden vectors produced by
+oracle/_ref/ref_harness (the unmodified reference compiled from /root/reference by
+oracle/Makefile) and committed under tests/golden/ (generator: tests/golden/make_golden.py).
+The reference ships no golden vectors of its own for this path.
+
+The reference is compiled with -O3 -ffast-math (CMakeLists.txt:86-89), its per-sample weight
+gradient accumulation is thread-partitioned, and libm/libmvec exp differ from numpy's, so
+float results agree with the reference to f32 round-off (tests state the tolerances), while
+sampled indices and — for identical network outputs — far-policy flags/counts are bit-exact.
+
+Every function cites the reference file:line it follows (paths relative to
+/root/reference/source/smarties/).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+f32 = np.float32
+f64 = np.float64
+FLT_EPS = float(np.finfo(np.float32).eps)
+FLT_MIN = float(np.finfo(np.float32).tiny)
+SQUASH_MAX = 8.31776613503286  # Math/Continuous_policy.h:218
+
+
+def round_up8(n: int) -> int:
+    """Utils/FunctionUtilities.h:74-83 (VEC_WIDTH 32 B / 4 B floats = 8)."""
+    return int(-(-n // 8) * 8)
+
+
+# ------------------------------------------------------------------------------------------
+# libstdc++ std::mt19937 + std::uniform_int_distribution<size_t>  (ReplayMemory/Sampling.cpp:82-96)
+# ------------------------------------------------------------------------------------------
+class Mt19937:
+    """std::mt19937(seed): numpy's MT19937 with legacy (init_genrand) seeding is the same
+    generator; raw 32-bit draws are consumed one at a time like libstdc++ does."""
+
+    def __init__(self, seed: int):
+        self.bg = np.random.MT19937()
+        self.bg._legacy_seeding(int(seed))
+        self._buf = np.empty(0, dtype=np.uint64)
+        self._pos = 0
+
+    def __call__(self) -> int:
+        if self._pos >= len(self._buf):
+            self._buf = self.bg.random_raw(4096)
+            self._pos = 0
+        v = int(self._buf[self._pos])
+        self._pos += 1
+        return v
+
+
+def uniform_int(gen: Mt19937, n: int) -> int:
+    """uniform_int_distribution<size_t>(0, n-1)(gen) as implemented by libstdc++ 13
+    (bits/uniform_int_dist.h: 32-bit URNG, range < 2^32 -> Lemire's method _S_nd<uint64>)."""
+    assert 0 < n <= 0xFFFFFFFF
+    product = gen() * n
+    low = product & 0xFFFFFFFF
+    if low < n:
+        threshold = ((1 << 32) - n) % n
+        while low < threshold:
+            product = gen() * n
+            low = product & 0xFFFFFFFF
+    return product >> 32
+
+
+def sample_uniform(gen: Mt19937, n_transitions: int, batch: int) -> np.ndarray:
+    """Sample_uniform::sample, non-episodic branch (ReplayMemory/Sampling.cpp:82-93):
+    draw, sort, unique, redraw the tail until `batch` unique ascending ids remain."""
+    ret: list[int] = []
+    while len(ret) < batch:
+        ret += [uniform_int(gen, n_transitions) for _ in range(batch - len(ret))]
+        ret = sorted(set(ret))
+    return np.asarray(ret, dtype=np.int64)
+
+
+def id_to_seq_step(ids: np.ndarray, ndata: np.ndarray):
+    """Sampling::IDtoSeqStep (ReplayMemory/Sampling.cpp:26-47): prefix walk over episodes in
+    the buffer's CURRENT vector order; returns (episode position, time step)."""
+    prefix = np.concatenate([[0], np.cumsum(ndata)])
+    seq = np.searchsorted(prefix, ids, side="right") - 1
+    obs = ids - prefix[seq]
+    return seq.astype(np.int64), obs.astype(np.int64)
+
+
+# ------------------------------------------------------------------------------------------
+# scalar helpers
+# ------------------------------------------------------------------------------------------
+def scale_net2v(x):
+    """Learners/RACER_common.cpp:23-27 (f64)."""
+    x = np.asarray(x, f64)
+    pos = 100 * (x + 51) - 100 * np.sqrt(2601 + 100 * np.maximum(x, 0))
+    neg = 100 * (x - 51) + 100 * np.sqrt(2601 - 100 * np.minimum(x, 0))
+    return np.where(x > 0, pos, neg)
+
+
+def scale_vdiff(x):
+    """Learners/RACER_common.cpp:28-32 (f64)."""
+    x = np.asarray(x, f64)
+    return np.where(x > 0, 100 - 5000 / np.sqrt(2601 + 100 * np.maximum(x, 0)),
+                    100 - 5000 / np.sqrt(2601 - 100 * np.minimum(x, 0)))
+
+
+def softplus(x):
+    """Network/Layers/Functions.h:552-555 (SMARTIES_CHEAP_SOFTPLUS)."""
+    return (x + np.sqrt(1 + x * x)) / 2
+
+
+def softplus_diff(x):
+    """Network/Layers/Functions.h:556-563."""
+    return (1 + x / np.sqrt(1 + x * x)) / 2
+
+
+def tanh_f32(x):
+    """Tanh::_eval, Network/Layers/Functions.h:103-112, evaluated in f32."""
+    x = np.asarray(x, f32)
+    e = np.exp((f32(-2) * np.abs(x)).astype(f32)).astype(f32)
+    y = ((f32(1) - e) / (f32(1) + e)).astype(f32)
+    return np.where(x > 0, y, -y).astype(f32)
+
+
+def anneal_rate(eta, t, eps):
+    """Utils/FunctionUtilities.h:69-72."""
+    return eta / (1 + t * eps)
+
+
+# ------------------------------------------------------------------------------------------
+# network description (MLP as built by RACER::setupNet, Learners/RACER_common.cpp:70-115,
+# Network/Approximator.cpp:179-229, Network/Builder.cpp:48-99)
+# ------------------------------------------------------------------------------------------
+class MlpLayout:
+    """Parameter blob layout (Network/Layers/Parameters.h:159-176): per layer W then b, each
+    rounded up to 8 floats.  Dense W is [nIn][roundUp8(nOut)] (Layer_Base.h:46,64-95)."""
+
+    def __init__(self, dS: int, hidden, n_dense_out: int, n_param_out: int):
+        self.dS, self.hidden = int(dS), [int(h) for h in hidden if h > 0]
+        self.n_dense_out, self.n_param_out = int(n_dense_out), int(n_param_out)
+        self.layers = []  # dicts: kind, nIn, nOut, ldw, w, b
+        off = 0
+        n_in = self.dS
+        lid = 1
+        for li, h in enumerate(self.hidden):
+            ld = round_up8(h)
+            L = dict(kind="dense_tanh", nIn=n_in, nOut=h, ldw=ld, w=off, id=lid)
+            off += round_up8(ld * n_in)
+            L["b"] = off
+            off += round_up8(h)
+            self.layers.append(L)
+            lid += 1
+            if li > 0:  # ParametricResidual after every hidden layer except the first (Builder.cpp:92-95)
+                R = dict(kind="residual", n=h, w=off, id=lid)
+                off += round_up8(h)
+                R["b"] = off
+                off += round_up8(h)
+                self.layers.append(R)
+                lid += 1
+            n_in = h
+        ld = round_up8(n_dense_out)
+        L = dict(kind="dense_linear", nIn=n_in, nOut=n_dense_out, ldw=ld, w=off, id=lid)
+        off += round_up8(ld * n_in)
+        L["b"] = off
+        off += round_up8(n_dense_out)
+        self.layers.append(L)
+        if n_param_out > 0:
+            P = dict(kind="param", n=n_param_out, b=off, id=lid + 1)
+            off += round_up8(n_param_out)
+            self.layers.append(P)
+        self.n_params = off
+        self.n_out = n_dense_out + n_param_out
+
+    def strip_padding(self, blob):
+        """Order of Network::save (Layer_Base.h:143-153, Layers.h:401-410,554-560)."""
+        out = []
+        for L in self.layers:
+            if L["kind"].startswith("dense"):
+                W = blob[L["w"]:L["w"] + L["nIn"] * L["ldw"]].reshape(L["nIn"], L["ldw"])[:, :L["nOut"]]
+                out += [W.ravel(), blob[L["b"]:L["b"] + L["nOut"]]]
+            elif L["kind"] == "residual":
+                out += [blob[L["w"]:L["w"] + L["n"]], blob[L["b"]:L["b"] + L["n"]]]
+            else:
+                out += [blob[L["b"]:L["b"] + L["n"]]]
+        return np.concatenate(out).astype(f32)
+
+
+def _dense_fwd(x, W, b):
+    """BaseLayer::forward (Layer_Base.h:64-80): X = b; for i: X += x_i * W[i][:] — f32,
+    sequential in i, separate multiply and add (reference build has no FMA)."""
+    acc = np.broadcast_to(b, (x.shape[0], b.shape[0])).astype(f32).copy()
+    for i in range(W.shape[0]):
+        acc += (x[:, i:i + 1] * W[i][None, :]).astype(f32)
+    return acc
+
+
+class MlpNet:
+    def __init__(self, layout: MlpLayout):
+        self.L = layout
+
+    def views(self, blob):
+        v = []
+        for L in self.L.layers:
+            if L["kind"].startswith("dense"):
+                W = blob[L["w"]:L["w"] + L["nIn"] * L["ldw"]].reshape(L["nIn"], L["ldw"])[:, :L["nOut"]]
+                v.append((W, blob[L["b"]:L["b"] + L["nOut"]]))
+            elif L["kind"] == "residual":
+                v.append((blob[L["w"]:L["w"] + L["n"]], blob[L["b"]:L["b"] + L["n"]]))
+            else:
+                v.append((None, blob[L["b"]:L["b"] + L["n"]]))
+        return v
+
+    def forward(self, blob, x):
+        """Network::forward (Network.h:101-113).  x: [B, dS] f32.  Returns (O f32 [B, nOut], cache)."""
+        x = np.asarray(x, f32)
+        Bn = x.shape[0]
+        Y = [x]  # Y[k] = output of layer k (Y[0] = input layer)
+        views = self.views(blob)
+        outs = []
+        for L, (W, b) in zip(self.L.layers, views):
+            k = L["kind"]
+            if k == "dense_tanh":
+                Y.append(tanh_f32(_dense_fwd(Y[-1], W, b)))
+            elif k == "residual":  # ParametricResidualLayer::forward (Layers.h:347-361)
+                Y.append((Y[-1] + (Y[-2] * W[None, :] + b[None, :]).astype(f32)).astype(f32))
+            elif k == "dense_linear":
+                Y.append(_dense_fwd(Y[-1], W, b))
+                outs.append(Y[-1])
+            else:  # ParamLayer::forward (Layers.h:510-521), Linear
+                Y.append(np.broadcast_to(b, (Bn, b.shape[0])).astype(f32))
+                outs.append(Y[-1])
+        return np.concatenate(outs, axis=1).astype(f32), Y
+
+    def backward(self, blob, Y, gout, sequential=True):
+        """Network::backProp for one time step (Network.h:216-226) over a batch; returns the
+        summed parameter gradient (thread-private `partialGradient` + reduceThreadsGrad,
+        Parameters.h:66-103, for ONE thread: samples accumulate in batch order, in f32).
+        gout: [B, nOut] f32 output deltas (Activation::addOutputDelta, Activation.h:112-120)."""
+        G = np.zeros(self.L.n_params, f32)
+        views = self.views(blob)
+        Bn = gout.shape[0]
+        E = [np.zeros_like(y) for y in Y]  # errvals per layer (Y index = layer id)
+        # place output deltas
+        k0 = 0
+        for li, L in enumerate(self.L.layers):
+            if L["kind"] == "dense_linear":
+                E[li + 1] = gout[:, k0:k0 + L["nOut"]].astype(f32).copy(); k0 += L["nOut"]
+            elif L["kind"] == "param":
+                E[li + 1] = gout[:, k0:k0 + L["n"]].astype(f32).copy(); k0 += L["n"]
+
+        def acc_rows(dst, contrib):  # dst[...] += sum over batch, sequential in b, f32
+            if sequential:
+                for bb in range(Bn):
+                    dst += contrib[bb]
+            else:
+                dst += contrib.sum(axis=0, dtype=f32)
+
+        for li in range(len(self.L.layers) - 1, -1, -1):
+            L = self.L.layers[li]
+            W, b = views[li]
+            yi = li + 1
+            kind = L["kind"]
+            if kind == "param":  # ParamLayer::backward (Layers.h:523-546)
+                acc_rows(G[L["b"]:L["b"] + L["n"]], E[yi])
+            elif kind.startswith("dense"):  # BaseLayer::backward (Layer_Base.h:97-113) + Layer::backward (Layers.h:123-188)
+                if kind == "dense_tanh":
+                    E[yi] = (E[yi] * (f32(1) - Y[yi] * Y[yi]).astype(f32)).astype(f32)
+                d = E[yi]
+                first = (li == 0)  # input gradient skipped for layer 1 (Approximator.cpp:145-169)
+                if not first:
+                    E[yi - 1] = (E[yi - 1] + (d @ W.T).astype(f32)).astype(f32)
+                acc_rows(G[L["b"]:L["b"] + L["nOut"]], d)
+                Gw = G[L["w"]:L["w"] + L["nIn"] * L["ldw"]].reshape(L["nIn"], L["ldw"])[:, :L["nOut"]]
+                xin = Y[yi - 1]
+                if sequential:
+                    for bb in range(Bn):
+                        Gw += (xin[bb][:, None] * d[bb][None, :]).astype(f32)
+                else:
+                    Gw += (xin.T @ d).astype(f32)
+            else:  # ParametricResidualLayer::backward (Layers.h:363-393)
+                d = E[yi]
+                E[yi - 1] = d.copy()  # memcpy into E(ID-1)
+                E[yi - 2] = (E[yi - 2] + (d * W[None, :]).astype(f32)).astype(f32)
+                acc_rows(G[L["w"]:L["w"] + L["n"]], (d * Y[yi - 2]).astype(f32))
+                acc_rows(G[L["b"]:L["b"] + L["n"]], d)
+        return G
+
+
+# ------------------------------------------------------------------------------------------
+# per-sample V-RACER loss / gradient   (Learners/RACER_train.cpp:12-67)
+# ------------------------------------------------------------------------------------------
+def vracer_sample_math(O, act, mu, qret, beta, cmax, cinv, bounded=None):
+    """O: [B, 1+2dA] network outputs (f32 values widened to f64, Approximator.h:117-173),
+    act [B,dA], mu [B,2dA] (stored f32 -> f64 Rvec, Episode.h:66), qret [B] f32.
+    Returns dict with rho, dkl, isFar, V, deltaQ (f64) and g [B, nOut] (f64 output gradient)."""
+    O = np.asarray(O, f64)
+    act = np.asarray(act, f64)
+    mu = np.asarray(mu, f64)
+    Bn, dA = act.shape
+    if bounded is None:
+        bounded = np.zeros(dA, bool)
+    bounded = np.asarray(bounded, bool)
+    mean = O[:, 1:1 + dA]
+    sraw = O[:, 1 + dA:1 + 2 * dA]
+    stdev = softplus(sraw)                      # Continuous_policy.h:78-81
+    inv = 1 / stdev
+    mu_m, mu_s = mu[:, :dA], mu[:, dA:]
+    cmean = np.where(bounded[None, :], np.clip(mean, -SQUASH_MAX, SQUASH_MAX), mean)  # :217-222
+
+    def logp(a, m, invs):                       # Continuous_policy.h:91-97 (Jacobian term of :240-249 cancels in rho)
+        return -((a - m) * invs) ** 2 / 2 + np.log(invs) - 9.1893853320467266954096885456237942e-01
+
+    if bounded.any():
+        squash = np.tanh(act)
+        J = np.maximum(1 - squash * squash, FLT_MIN)
+        lp_pi = -((act - cmean) * inv) ** 2 / 2 + np.log(inv / np.where(bounded, J, 1.0)) - 9.1893853320467266954096885456237942e-01
+        lp_mu = -((act - mu_m) * (1 / mu_s)) ** 2 / 2 + np.log((1 / mu_s) / np.where(bounded, J, 1.0)) - 9.1893853320467266954096885456237942e-01
+    else:
+        lp_pi = logp(act, mean, inv)
+        lp_mu = logp(act, mu_m, 1 / mu_s)
+    logw = np.zeros(Bn, f64)
+    for i in range(dA):                         # importanceWeight, Continuous_policy.h:648-653
+        logw = logw + (lp_pi[:, i] - lp_mu[:, i])
+    rho = np.exp(np.clip(logw, -7, 7))
+    c = (stdev / mu_s) ** 2                     # KLdivergence, OPPOSITE_KL branch :138-142
+    dm = ((mean - mu_m) / mu_s) ** 2
+    klc = (c - 1 + dm - np.log(c)) / 2
+    dkl = np.zeros(Bn, f64)
+    for i in range(dA):
+        dkl = dkl + klc[:, i]
+    # isFarPolicy takes Fval arguments (ReplayMemory/Episode.h:28-33): compare in f32
+    W32, C32, I32 = rho.astype(f32), f32(cmax), f32(cinv)
+    is_far = (C32 > f32(1)) & ((W32 > C32) | (W32 < I32))
+    V = scale_net2v(O[:, 0])
+    a_ret = np.asarray(qret, f64) - V           # A = 0 for Zero_advantage
+    dq = a_ret
+    ver = np.minimum(1.0, rho) * dq
+    g = np.zeros_like(O)
+    g[:, 0] = np.where(is_far, 0.0, ver * beta * scale_vdiff(O[:, 0]))
+    # penalG = KLDivGradient(MU, -1)  (Continuous_policy.h:709-716 -> gradKLdiv :154-170)
+    dpos = softplus_diff(sraw)
+    inv_var_mu = 1 / mu_s ** 2
+    kg_mean = -1.0 * ((mean - mu_m) * inv_var_mu)
+    kg_std = dpos * -1.0 * ((inv_var_mu - inv ** 2) * stdev)
+    # polG = policyGradient(ACT, A_RET*min(Cmax,rho))  (:694-701 -> gradLogP :145-152 / :300-316)
+    fac = (a_ret * np.minimum(cmax, rho))[:, None]
+    u = (act - cmean) * inv
+    dlp_mean = np.where(bounded[None, :], (act - mean) * inv * inv, u * inv)
+    dlp_std = (u * u - 1) * inv
+    pg_mean = fac * dlp_mean
+    blocked = bounded[None, :] & (((mean >= SQUASH_MAX) & (pg_mean > 0)) | ((mean <= -SQUASH_MAX) & (pg_mean < 0)))
+    pg_mean = np.where(blocked, 0.0, pg_mean)
+    pg_std = dpos * fac * dlp_std
+    far = is_far[:, None]
+    pg_mean = np.where(far, 0.0, pg_mean)
+    pg_std = np.where(far, 0.0, pg_std)
+    g[:, 1:1 + dA] = beta * pg_mean + (1 - beta) * kg_mean        # penalizeReFER, FunctionUtilities.h:221-228
+    g[:, 1 + dA:1 + 2 * dA] = beta * pg_std + (1 - beta) * kg_std
+    return dict(rho=rho, dkl=dkl, is_far=is_far, V=V, dq=dq, g=g)
+
+
+# ------------------------------------------------------------------------------------------
+# replay memory + learner
+# ------------------------------------------------------------------------------------------
+class Episode:
+    """ReplayMemory/Episode.h:40-231 (fields needed by the path)."""
+
+    def __init__(self, eid, S, A, MU, R, terminated):
+        N = S.shape[0]
+        self.ID = int(eid)
+        self.S = S.astype(f32)
+        self.A = A.astype(f64)         # actions / policies are Rvec = f64 in the reference
+        self.MU = MU.astype(f64)
+        self.R = R.astype(f64)
+        self.R[0] = 0.0
+        self.terminated = bool(terminated)
+        # Episode::finalize (Episode.cpp:244-266)
+        self.V = np.zeros(N, f32); self.ADV = np.zeros(N, f32); self.Q = np.zeros(N, f32)
+        self.delta = np.zeros(N, f32); self.KL = np.zeros(N, f32)
+        self.rho = np.ones(N, f32); self.rho[-1] = 0
+        self.avgKL = f32(0); self.fracFar = f32(0); self.avgSqErr = f32(0); self.maxAbsErr = f32(0)
+        self.sumQ2 = f32(0); self.sumQ = f32(0); self.maxQ = f32(-1e9); self.minQ = f32(1e9)
+        self.totR = f32(np.sum(self.R[1:].astype(f32), dtype=f32))
+        self.just_sampled = -1
+
+    @property
+    def nsteps(self):
+        return self.S.shape[0]
+
+    @property
+    def ndata(self):
+        return self.S.shape[0] - 1
+
+    def update_cumulative(self, C, invC):
+        """Episode::updateCumulative (Episode.cpp:213-242), f32."""
+        N = self.ndata
+        invN = f32(1) / f32(N)
+        C, invC = f32(C), f32(invC)
+        far = (self.rho[:N] > C) | (self.rho[:N] < invC)
+        nfar = int(far.sum())
+        sumE2 = f32(0); sumQ2 = f32(0); sumQ1 = f32(0)
+        Qv = (self.ADV[:N] + self.V[:N]).astype(f32)
+        d2 = (self.delta[:N] * self.delta[:N]).astype(f32)
+        q2 = (Qv * Qv).astype(f32)
+        for t in range(N):
+            sumE2 = f32(sumE2 + d2[t]); sumQ2 = f32(sumQ2 + q2[t]); sumQ1 = f32(sumQ1 + Qv[t])
+        self.fracFar = f32(invN * f32(nfar))
+        self.avgSqErr = f32(invN * sumE2)
+        self.maxAbsErr = f32(max(-1e9, float(np.max(np.abs(self.delta[:N])))))
+        self.sumQ2, self.sumQ = sumQ2, sumQ1
+        self.maxQ = f32(max(-1e9, float(Qv.max()))); self.minQ = f32(min(1e9, float(Qv.min())))
+        self.totR = f32(np.sum(self.R, dtype=f64))          # Utilities::sum over Real rewards
+        klsum = f32(0)
+        for t in range(self.nsteps):                          # Utilities::sum(KullbLeibDiv) over all rows
+            klsum = f32(klsum + self.KL[t])
+        self.avgKL = f32(invN * klsum)
+
+
+class VracerOracle:
+    """Learner-only V-RACER: initializeLearner + {spawnTrainTasks, processMemoryBuffer,
+    applyGradient, globalGradCounterUpdate} (Learners/RACER.cpp:61-110)."""
+
+    def __init__(self, dS, dA, hidden=(128, 128), gamma=0.995, lam=1.0, clip_imp_weight=None,
+                 penal_tol=0.1, eps_anneal=5e-7, learnrate=1e-4, nn_lambda=FLT_EPS,
+                 batch=256, max_tot_obs=None, bounded=False, sample_seed=42):
+        self.dS, self.dA = dS, dA
+        self.layout = MlpLayout(dS, hidden, 1 + dA, dA)
+        self.net = MlpNet(self.layout)
+        self.gamma, self.lam = gamma, lam
+        self.C = float(np.sqrt(dA / 2.0)) if clip_imp_weight is None else float(clip_imp_weight)  # HyperParameters.h:46
+        self.penal_tol, self.eps_anneal, self.eta, self.nn_lambda = penal_tol, eps_anneal, learnrate, nn_lambda
+        self.B = batch
+        self.max_tot_obs = int(2 ** 14 * np.sqrt(dA + dS)) if max_tot_obs is None else int(max_tot_obs)
+        self.max_tot_obs_local = self.max_tot_obs
+        self.bounded = np.full(dA, bool(bounded))
+        # MemoryBuffer.h:41-44
+        self.beta = 1.0 if self.C <= 0 else 1e-4
+        self.cmax = 1 + self.C
+        self.cinv = 1 / self.C if self.C > 0 else np.inf
+        self.state_mean = np.zeros(dS, f32); self.state_std = np.ones(dS, f32); self.state_scale = np.ones(dS, f32)
+        self.rew_mean = f32(0); self.rew_std = f32(1); self.rew_scale = f32(1)
+        self.episodes: list[Episode] = []
+        self.n_grad_steps = 0
+        self.adam_step = 0
+        self.beta_t_1, self.beta_t_2 = 0.9, 0.999            # Optimizer.h:93-94 (Real)
+        self.W = np.zeros(self.layout.n_params, f32)
+        self.M1 = np.zeros_like(self.W); self.M2 = np.zeros_like(self.W)
+        self.gen = Mt19937(sample_seed)
+        self.n_far_policy = 0
+        self.stats = dict(avgKL=0.0, avgSqErr=0.0, maxAbsErr=0.0, avgReturn=0.0, stdevQ=0.0, avgQ=0.0, maxQ=0.0, minQ=0.0,
+                          cntRet=0, sumRetErr=0.0)
+        self.last = {}
+
+    # ---- data ----
+    def load_replay(self, d):
+        for e in range(len(d["N"])):
+            o, N = int(d["start"][e]), int(d["N"][e])
+            ep = Episode(e, d["S"][o:o + N], d["A"][o:o + N], d["MU"][o:o + N], d["R"][o:o + N], d["term"][e])
+            self.retrace_episode(ep)                          # MemoryBuffer.cpp:143 computeReturnEstimator at insertion
+            self.push_back_episode(ep)
+
+    def push_back_episode(self, ep: Episode):
+        """MemoryBuffer::pushBackEpisode (MemoryBuffer.cpp:479-520): pre-training TD-error
+        placeholder sqrt(max(FLT_EPS, stats.avgSquaredErr)) (Episode.cpp:268-273)."""
+        err = f32(np.sqrt(max(FLT_EPS, self.stats["avgSqErr"])))
+        ep.delta[:] = err
+        ep.avgSqErr = f32(err * err)
+        ep.maxAbsErr = err
+        self.episodes.append(ep)
+
+    @property
+    def n_transitions(self):
+        return int(sum(ep.ndata for ep in self.episodes))
+
+    # ---- Retrace (ReplayMemory/MemoryProcessing.cpp:23-44, 391-400) ----
+    def retrace_episode(self, ep: Episode) -> float:
+        N = ep.nsteps
+        if not ep.terminated:
+            ep.Q[N - 1] = ep.V[N - 1]
+        g, l = f32(self.gamma), f32(self.lam)
+        rs = ((ep.R - f64(self.rew_mean)) * f64(self.rew_scale)).astype(f32)   # scaledReward<Fval>, Episode.h:184-189
+        w = np.where(ep.rho < 1, ep.rho, f32(1)).astype(f32)                   # clippedOffPolW, Episode.h:190-194
+        err2 = f32(0)
+        for t in range(N - 2, -1, -1):
+            old = ep.Q[t]
+            Qn, Vn, An = ep.Q[t + 1], ep.V[t + 1], ep.ADV[t + 1]
+            new = f32(rs[t + 1] + g * f32(Vn + f32(f32(l * w[t + 1]) * f32(f32(Qn - An) - Vn))))
+            ep.Q[t] = new
+            err2 = f32(err2 + f32(old - new) ** 2)
+        return float(err2)
+
+    # ---- reward / state moments (MemoryProcessing.cpp:94-185) ----
+    def update_rewards_stats(self, b_init: bool, rate_fac: float = 1.0):
+        learn_r = anneal_rate(self.eta, self.n_grad_steps, self.eps_anneal)
+        w = 1.0 if b_init else min(1.0, rate_fac * learn_r)
+        ld = np.longdouble
+        cnt = ld(0); rs = ld(0); rs2 = ld(0)
+        ss = np.zeros(self.dS, ld); ss2 = np.zeros(self.dS, ld)
+        for ep in self.episodes:
+            N = ep.ndata
+            cnt += N
+            dr = ep.R[1:N + 1].astype(ld) - ld(self.rew_mean)
+            rs += dr.sum(dtype=ld); rs2 += (dr * dr).sum(dtype=ld)
+            ds = ep.S[:N].astype(ld) - self.state_mean.astype(ld)[None, :]
+            ss += ds.sum(axis=0, dtype=ld); ss2 += (ds * ds).sum(axis=0, dtype=ld)
+
+        def upd(mean, std, lr, ev, ev2):
+            mean = f32(ld(mean) + ld(lr) * ev)
+            var = ev2 - ev * ev * ld(2 * lr - lr * lr)
+            var = max(var, ld(FLT_EPS))
+            std = f32(ld(std) + ld(lr) * (np.sqrt(var) - ld(std)))
+            return mean, std, f32(f32(1) / std)
+
+        self.rew_mean, self.rew_std, self.rew_scale = upd(self.rew_mean, self.rew_std, w, rs / cnt, rs2 / cnt)
+        for k in range(self.dS):
+            self.state_mean[k], self.state_std[k], self.state_scale[k] = upd(
+                self.state_mean[k], self.state_std[k], w, ss[k] / cnt, ss2[k] / cnt)
+
+    # ---- beta (MemoryProcessing.cpp:46-92) ----
+    def update_counters(self):
+        n_stored = self.n_transitions
+        frac = self.n_far_policy / float(max(n_stored, 1))
+        lr = 0.1 * self.B / max(float(self.max_tot_obs), float(n_stored))
+        b = self.beta
+        if frac > self.penal_tol:
+            self.beta = (1 - min(lr, b)) * b
+        else:
+            self.beta = (1 - min(lr, b)) * b + min(lr, 1 - b)
+
+    def initialize_learner(self):
+        """Learner::initializeLearner (Learners/Learner.cpp:47-72)."""
+        self.update_counters()
+        self.update_rewards_stats(True)
+        for ep in self.episodes:                              # rescaleAllReturnEstimator :460-481
+            self.retrace_episode(ep)
+
+    # ---- one gradient step ----
+    def sample(self):
+        ids = sample_uniform(self.gen, self.n_transitions, self.B)
+        nd = np.array([ep.ndata for ep in self.episodes], np.int64)
+        return id_to_seq_step(ids, nd)
+
+    def standardized(self, ep: Episode, t: int):
+        return ((ep.S[t] - self.state_mean) * self.state_scale).astype(f32)   # Episode.h:171-183
+
+    def train_step(self, seq=None, obs=None, inject_O=None):
+        """spawnTrainTasks + processMemoryBuffer + applyGradient + globalGradCounterUpdate."""
+        if seq is None:
+            seq, obs = self.sample()
+        B = len(seq)
+        eps = [self.episodes[int(s)] for s in seq]
+        X = np.stack([self.standardized(ep, int(t)) for ep, t in zip(eps, obs)])
+        O32, Y = self.net.forward(self.W, X)
+        # V(s_{t+1}) for truncated episodes (RACER_train.cpp:23-27)
+        trunc = [b for b in range(B) if (int(obs[b]) + 2 == eps[b].nsteps and not eps[b].terminated)]
+        Vnext = {}
+        if trunc:
+            Xn = np.stack([self.standardized(eps[b], int(obs[b]) + 1) for b in trunc])
+            On, _ = self.net.forward(self.W, Xn)
+            for j, b in enumerate(trunc):
+                Vnext[b] = f32(scale_net2v(f64(On[j, 0])))
+        Ouse = O32 if inject_O is None else np.asarray(inject_O)
+        act = np.stack([ep.A[int(t)] for ep, t in zip(eps, obs)])
+        mu = np.stack([ep.MU[int(t)] for ep, t in zip(eps, obs)])
+        qret = np.array([ep.Q[int(t)] for ep, t in zip(eps, obs)], f32)
+        r = vracer_sample_math(Ouse, act, mu, qret, self.beta, self.cmax, self.cinv, self.bounded)
+        g32 = r["g"].astype(f32)
+        # write-back + per-episode aggregates, in batch order (Episode.h:112-145)
+        C32, I32 = f32(self.cmax), f32(self.cinv)
+        for b in range(B):
+            ep, t = eps[b], int(obs[b])
+            invN = f32(1) / f32(ep.nsteps)
+            if b in Vnext:
+                self._update_values(ep, t + 1, Vnext[b], Vnext[b])
+            E, D, Wt = f32(r["dq"][b]), f32(r["dkl"][b]), f32(r["rho"][b])
+            was = f32((ep.rho[t] > C32) or (ep.rho[t] < I32))
+            isf = f32((Wt > C32) or (Wt < I32))
+            ep.avgKL = f32(ep.avgKL + f32(invN * f32(D - ep.KL[t])))
+            ep.fracFar = f32(ep.fracFar + f32(invN * f32(isf - was)))
+            ep.avgSqErr = f32(ep.avgSqErr + f32(invN * f32(f32(E * E) - f32(ep.delta[t] * ep.delta[t]))))
+            ep.maxAbsErr = f32(max(ep.maxAbsErr, abs(E)))
+            ep.delta[t], ep.KL[t], ep.rho[t] = E, D, Wt
+            Vv = f32(r["V"][b])
+            self._update_values(ep, t, Vv, Vv)                # Qval = Aval + Vval, Aval = 0
+        G = self.net.backward(self.W, Y, g32)
+        self.adam_step += 1                                    # prepare_update: nStep++ (Optimizer.cpp:119)
+        self.last = dict(r, seq=np.asarray(seq), obs=np.asarray(obs), X=X, O=O32, g=g32, g64=r['g'], gradSum=G.copy())
+        self.process_memory_buffer()
+        self.apply_adam(G)
+        self.n_grad_steps += 1
+        return self.last
+
+    @staticmethod
+    def _update_values(ep: Episode, t: int, V, Q):
+        """Episode::updateValues_atomic (Episode.h:131-145)."""
+        V, Q = f32(V), f32(Q)
+        oldQ = f32(ep.ADV[t] + ep.V[t])
+        ep.sumQ2 = f32(ep.sumQ2 + f32(f32(Q * Q) - f32(oldQ * oldQ)))
+        ep.sumQ = f32(ep.sumQ + f32(Q - oldQ))
+        ep.maxQ = f32(max(ep.maxQ, Q)); ep.minQ = f32(min(ep.minQ, Q))
+        ep.V[t] = V; ep.ADV[t] = f32(Q - V)
+
+    def process_memory_buffer(self):
+        """Learner::processMemoryBuffer (Learners/Learner.cpp:74-100)."""
+        step = self.n_grad_steps + 1
+        recompute = step % 1000 == 0
+        # updateTrainingStatistics (MemoryProcessing.cpp:187-259)
+        self.cmax = 1 + anneal_rate(self.C, step, self.eps_anneal)
+        self.cinv = 1 / self.cmax
+        n_off = 0
+        sumDKL = sumE2 = sumQ2 = sumQ1 = sumR = sumERet = 0.0
+        maxAbsE, maxQ, minQ = f32(-1e9), f32(-1e9), f32(1e9)
+        n_ret = 0
+        for ep in self.episodes:
+            if recompute:
+                ep.update_cumulative(self.cmax, self.cinv)
+                sumERet += self.retrace_episode(ep)
+                n_ret += ep.nsteps - 1
+            Ns = f32(ep.nsteps)
+            maxAbsE = max(maxAbsE, ep.maxAbsErr); maxQ = max(maxQ, ep.maxQ); minQ = min(minQ, ep.minQ)
+            sumDKL += float(f32(Ns * ep.avgKL))
+            n_off = int(f32(f32(n_off) + f32(Ns * ep.fracFar)))   # `Uint += float` (SURVEY §7 hard part 2)
+            sumE2 += float(f32(Ns * ep.avgSqErr))
+            sumQ2 += float(ep.sumQ2); sumQ1 += float(ep.sumQ); sumR += float(ep.totR)
+            ep.just_sampled = -1
+        if self.cmax <= 1:
+            n_off = 0
+        n_data = self.n_transitions
+        self.n_far_policy = n_off
+        lr = 0.1 * self.B / max(float(self.max_tot_obs), float(n_data))
+        st = self.stats
+        st["maxAbsErr"] += lr * (float(maxAbsE) - st["maxAbsErr"])
+        st["avgKL"] = sumDKL / n_data; st["avgSqErr"] = sumE2 / n_data
+        st["avgReturn"] = sumR / len(self.episodes); st["avgQ"] = sumQ1 / n_data
+        st["maxQ"], st["minQ"] = float(maxQ), float(minQ)
+        st["stdevQ"] = float(np.sqrt(max(sumQ2 / n_data - st["avgQ"] ** 2, 1e-16)))
+        st["cntRet"] = max(st["cntRet"], 0) + n_ret; st["sumRetErr"] += sumERet
+        if recompute:
+            self.update_rewards_stats(False, 10)
+        # applyEpisodesRemovalAlgo (MemoryProcessing.cpp:327-351): "oldest" = sort by ID descending
+        self.episodes.sort(key=lambda e: -e.ID)
+        while self.n_transitions - self.episodes[-1].nsteps > self.max_tot_obs_local:
+            self.episodes.pop()                               # removeBackEpisode (MemoryBuffer.cpp:469-477)
+        self.update_counters()
+
+    def apply_adam(self, G):
+        """AdamOptimizer::apply_update + struct Adam (Network/Optimizer.cpp:61-108,122-161), f32."""
+        # `Saru gen(nStep, thrID, generators[thrID]())` (Optimizer.cpp:139): thread 0 draws one
+        # 32-bit value from generators[0] — the sampler's generator — every update.
+        self.gen()
+        eta0 = f32(f64(f32(self.eta)) / (1 + f64(f32(self.adam_step)) * self.eps_anneal))  # annealRate<nnReal>
+        bt1, bt2 = f32(self.beta_t_1), f32(self.beta_t_2)
+        eta = f32(f32(eta0 * f32(np.sqrt(f32(f32(1) - bt2)))) / f32(f32(1) - bt1))
+        B1, B2, lam, fac = f32(0.9), f32(0.999), f32(self.nn_lambda), f32(1.0 / self.B)
+        W, M1, M2 = self.W, self.M1, self.M2
+        penal = (-W * lam).astype(f32)
+        DW = (fac * G).astype(f32)
+        M1[:] = (B1 * M1 + (f32(1) - B1) * DW).astype(f32)
+        M2[:] = (B2 * M2 + ((f32(1) - B2) * DW).astype(f32) * DW).astype(f32)
+        numer = (B1 * M1 + (f32(1) - B1) * DW).astype(f32)
+        M2[:] = np.where(M2 < M1 * M1, (M1 * M1).astype(f32), M2)
+        ret = (numer / (f32(FLT_EPS) + np.sqrt(M2).astype(f32)).astype(f32)).astype(f32)
+        W += (eta * (ret + penal).astype(f32)).astype(f32)
+        self.beta_t_1 *= 0.9
+        if self.beta_t_1 < FLT_EPS: self.beta_t_1 = 0
+        self.beta_t_2 *= 0.999
+        if self.beta_t_2 < FLT_EPS: self.beta_t_2 = 0
+
+    # ---- flat views used by tests ----
+    def concat(self, field):
+        return np.concatenate([getattr(ep, field) for ep in self.episodes])

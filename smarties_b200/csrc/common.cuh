@@ -1,0 +1,106 @@
+// common.cuh — device-visible descriptors shared by the step and sweep kernels.
+//
+// Vocabulary follows the reference (cselab/smarties): episodes, transitions (rows), the
+// replay MemoryBuffer, ReF-ER coefficients (beta, Cmax), Retrace return estimates.
+// Reference citations are relative to /root/reference/source/smarties/.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace smb200 {
+
+constexpr int kMaxLayers = 2 * 8 + 4;   // input + (dense, residual)*hidden + out + param
+constexpr int kThreads   = 256;         // every kernel here uses 256-thread CTAs
+constexpr int kTileK     = 16;          // weight-gradient tile: 16 input rows x 16 output cols
+constexpr int kTileN     = 16;
+
+enum LayerKind : int { kInput = 0, kDenseTanh = 1, kResidual = 2, kDenseLinear = 3, kParam = 4 };
+
+// One layer of the network built by RACER::setupNet (Learners/RACER_common.cpp:70-115,
+// Network/Builder.cpp:48-99).  Layer ids equal the reference's (0 = input).
+struct LayerDesc {
+  int kind;
+  int size;        // number of neurons = size of this layer's activation
+  int nIn;         // dense: fan-in
+  int ld;          // dense: row stride of W[nIn][ld] (roundUp8(size), Layer_Base.h:46)
+  int ldt;         // dense: row stride of the transposed copy WT[size][ldt]
+  int wOff, bOff;  // offsets into the padded parameter blob (Parameters.h:159-176)
+  int wtOff;       // offset into the transposed-weights blob, -1 if no input gradient needed
+  int in;          // id of the input layer (ID - link); residual: ID-1 and ID-2 implied
+  int actOff;      // offset (in floats per sample) of this layer's activation in act buffers
+};
+
+struct NetDesc {
+  int nLayers;
+  int nParams;       // padded blob size
+  int nParamsT;      // transposed blob size
+  int nOut;          // network outputs (dense-out + param layer)
+  int nOutDense;     // outputs of the linear output layer
+  int dS, dA;
+  int actPerSample;  // floats per sample over all layers
+  int maxWidth;      // widest layer
+  LayerDesc L[kMaxLayers];
+};
+
+// Work item of the weight-gradient + Adam phase.
+struct GradTile {
+  int kind;    // 0: dense 16x16 tile (row nIn = bias row), 1: residual vector, 2: param-layer bias
+  int layer;
+  int k0, n0;
+};
+
+// Scalars a step needs; double-buffered by step parity: step k reads ctrl[k&1], its
+// statistics phase writes ctrl[(k+1)&1].
+struct StepCtrl {
+  double beta, cmax, cinv;            // ReF-ER (MemoryBuffer.h:41-44)
+  double adam_bt1, adam_bt2;          // running beta powers (Optimizer.h:93, Optimizer.cpp:155-158)
+  long long adam_step;                // AdamOptimizer::nStep BEFORE this step's prepare_update
+  long long grad_step;                // counters.nGradSteps before this step
+  long long n_far_ref, n_far_exact;   // stats.nFarPolicySteps (reference formula) / exact flags
+  double avg_kl, avg_sq_err, max_abs_err, avg_return, stdev_q, avg_q, max_q, min_q;
+  double sum_ret_err; long long cnt_ret;
+};
+
+// Replay MemoryBuffer in HBM: structure-of-arrays over ring rows (one row = one time step of
+// one episode, terminal/truncated row included), plus the episode table indexed by slot.
+struct ReplayView {
+  // per row
+  float* S;  float* A;  float* MU;  float* R;           // states [rows][dS], actions [rows][dA], mu [rows][2dA], reward
+  float* V;  float* ADV; float* Q;  float* DELTA; float* RHO; float* KL;  // Episode.h:66-75
+  uint8_t* rowFlag;                                       // bit0 first row, bit1 last row, bit2 live
+  // per episode slot
+  int* epStart; int* epLen; int* epTerm; long long* epId;
+  float* epAgg;       // [9][maxEpisodes]: avgKL, fracFar, avgSqErr, maxAbsErr, sumQ2, sumQ, maxQ, minQ, totR
+  int* epOrder;       // [nEpisodes] slot at each position of the reference's `episodes` vector
+  int maxEpisodes;
+  long long capRows;
+  int dS, dA;
+  float* stateMean; float* stateScale; float* stateStd;   // MDPdescriptor (Core/StateAction.h:56-58)
+  float* rew;         // {rewardsMean, rewardsScale, rewardsStdDev}
+};
+
+enum { AGG_KL = 0, AGG_FAR = 1, AGG_E2 = 2, AGG_MAXE = 3, AGG_Q2 = 4, AGG_Q1 = 5, AGG_MAXQ = 6, AGG_MINQ = 7, AGG_TOTR = 8, AGG_N = 9 };
+
+// Per-sample record written by the loss phase and consumed by the statistics phase
+// (Episode::updateCumulative_atomic / updateValues_atomic, Episode.h:112-145).
+struct SampleRec {
+  int slot; int hasNext;
+  float dKL, dFar, dE2, absE;
+  float qOld, qNew, qNextOld, qNextNew;
+  int farDelta; int pad;
+};
+
+struct Hyper {
+  double gamma, lambda, clipImpWeight, penalTol, epsAnneal, learnrate, nnLambda;
+  long long maxTotObsGlobal; int batchGlobal; int batchLocal;
+  int referThreads; int algo;
+  unsigned char bounded[64];
+};
+
+#define SMB200_CUDA_CHECK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { \
+  smb200::set_error(#expr, e__, __FILE__, __LINE__); return -2; } } while (0)
+
+void set_error(const char* what, cudaError_t e, const char* file, int line);
+void set_error_msg(const char* msg);
+
+}  // namespace smb200

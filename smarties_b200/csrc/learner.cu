@@ -1,0 +1,867 @@
+// learner.cu — host side of the C-ABI (include/smarties_b200.h): the replay MemoryBuffer's
+// episode table and ring allocator, the bit-exact host sampler, FIFO pruning, weight
+// initialisation, and the orchestration of the step / sweep kernels on one CUDA stream.
+//
+// Mirrors (file:line relative to /root/reference/source/smarties/):
+//   Learner::initializeLearner / processMemoryBuffer     Learners/Learner.cpp:47-100
+//   Learner_approximator::spawnTrainTasks / applyGradient Learners/Learner_approximator.cpp:36-105
+//   MemoryBuffer::pushBackEpisode / removeBackEpisode     ReplayMemory/MemoryBuffer.cpp:469-520
+//   Sample_uniform::sample, Sampling::IDtoSeqStep         ReplayMemory/Sampling.cpp:26-47,82-96
+//   MemoryProcessing::applyEpisodesRemovalAlgo            ReplayMemory/MemoryProcessing.cpp:327-351
+//   Builder::build weight init, BaseLayer::initialize     Network/Builder.cpp:119-170, Layers/Layer_Base.h:115-141
+#include "step_kernels.cuh"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <random>
+#include <string>
+#include <vector>
+
+namespace smb200 {
+
+static thread_local std::string g_err;
+void set_error(const char* what, cudaError_t e, const char* file, int line) {
+  char buf[1024];
+  snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  g_err = buf;
+}
+void set_error_msg(const char* msg) { g_err = msg; }
+
+static inline int round_up(int n, int m) { return (n + m - 1) / m * m; }
+
+struct EpisodeMeta {
+  long long id;
+  int nRows;       // nsteps(): data steps + terminal row
+  int slot;
+  long long start; // first ring row
+  int terminated;
+};
+
+template <typename T>
+static int dev_alloc(T** p, size_t n) {
+  SMB200_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  SMB200_CUDA_CHECK(cudaMemset(*p, 0, n * sizeof(T)));
+  return 0;
+}
+
+}  // namespace smb200
+
+using namespace smb200;
+
+struct smb200_learner {
+  smb200_config cfg;
+  DevDescs descs;                 // host copy
+  DevDescs* dDescs = nullptr;
+  int numSMs = 148;
+  int mode = 1;                   // 1 = persistent cooperative kernel, 0 = two kernels per step
+  int persistGrid = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  // replay
+  ReplayView rp{};
+  std::vector<EpisodeMeta> episodes;      // the reference's `episodes` vector order
+  std::vector<int> freeSlots;
+  std::map<long long, long long> liveRanges;   // start -> end (exclusive) of live ring ranges
+  long long head = 0, highWater = 0;
+  long long nTransitions = 0;
+  bool orderDirty = true;
+
+  // network / optimiser
+  float *W = nullptr, *WT = nullptr, *M1 = nullptr, *M2 = nullptr, *G = nullptr;
+  float *actG = nullptr, *errG = nullptr;
+  GradTile* dTiles = nullptr; int nTiles = 0;
+  int Bpad = 0;
+
+  // step state
+  StepCtrl* dCtrl = nullptr;       // [2]
+  StepCtrl hCtrl{};                // host mirror, valid when ctrlSynced
+  long long gradStep = 0;          // host mirror of counters.nGradSteps
+  bool initialized = false;
+  SampleRec* dRec = nullptr;
+  float *lastO = nullptr, *lastG = nullptr, *lastX = nullptr;
+  SweepSums* dSums = nullptr;
+  unsigned* dBarrier = nullptr;
+  int* dSampSlot = nullptr; int* dSampT = nullptr;
+  int* hSampSlot = nullptr; int* hSampT = nullptr;    // pinned
+  smb200_step_stats* dStats = nullptr; smb200_step_stats* hStats = nullptr;   // pinned host
+  int maxSeg = 1024;
+  int presampled = 0;              // steps resident in dSampSlot/dSampT (benchmark path)
+
+  std::vector<std::pair<long long, int>> pendingEvict;   // ring ranges whose live flags are cleared after the segment
+  std::mt19937 gen;
+  double lastMs = 0; long long lastLaunches = 0;
+  long long launches = 0;
+
+  StepArgs args() const {
+    StepArgs a{};
+    a.descs = dDescs; a.rp = rp; a.W = W; a.WT = WT; a.M1 = M1; a.M2 = M2; a.G = G;
+    a.actG = actG; a.errG = errG; a.sampSlot = dSampSlot; a.sampT = dSampT; a.rec = dRec;
+    a.lastO = lastO; a.lastG = lastG; a.lastX = lastX; a.ctrl = dCtrl; a.statsOut = dStats;
+    a.tiles = dTiles; a.nTiles = nTiles; a.B = cfg.batch_size; a.Bpad = Bpad;
+    a.nEpisodes = (int)episodes.size(); a.nTransitions = nTransitions; a.nTransitionsPost = nTransitions;
+    a.barrier = dBarrier; a.stepBase = 0; a.lastStep = -1;
+    return a;
+  }
+};
+
+namespace smb200 {
+
+// ---- network description: RACER::setupNet + Approximator::buildFromSettings + Builder::addLayer ----
+static int build_net(const smb200_config& c, NetDesc& net, std::vector<GradTile>& tiles) {
+  memset(&net, 0, sizeof(net));
+  const int dS = c.dim_state, dA = c.dim_action;
+  if (c.algo != SMB200_VRACER) { set_error_msg("only learner VRACER is implemented on the device path"); return -1; }
+  if (dS < 1 || dA < 1 || dA > SMB200_MAX_ACTION || c.n_hidden < 1 || c.n_hidden > SMB200_MAX_HIDDEN) {
+    set_error_msg("unsupported dimensions"); return -1; }
+  int off = 0, offT = 0, act = 0, id = 0, width = dS;
+  auto add = [&](int kind, int size) -> LayerDesc& {
+    LayerDesc& L = net.L[id]; L.kind = kind; L.size = size; L.actOff = act; L.wtOff = -1; L.in = id - 1;
+    act += round_up(size, 4); width = std::max(width, size); ++id; return L; };
+  add(kInput, dS);
+  int nIn = dS;
+  for (int i = 0; i < c.n_hidden; ++i) {
+    const int h = c.hidden[i];
+    if (h < 1) { set_error_msg("hidden layer size must be positive"); return -1; }
+    LayerDesc& L = add(kDenseTanh, h);
+    L.nIn = nIn; L.ld = round_up(h, 8);
+    L.wOff = off; off += round_up(L.ld * nIn, 8); L.bOff = off; off += round_up(h, 8);
+    if (i > 0) { L.ldt = round_up(nIn, 4); L.wtOff = offT; offT += h * L.ldt; }
+    if (i > 0) {   // ParametricResidualLayer after every hidden layer but the first (Builder.cpp:92-95)
+      LayerDesc& R = add(kResidual, h);
+      R.wOff = off; off += round_up(h, 8); R.bOff = off; off += round_up(h, 8);
+      if (net.L[id - 3].size < h) { set_error_msg("residual over a narrower layer is not supported"); return -1; }
+    }
+    nIn = h;
+  }
+  const int nOutDense = 1 + dA;   // V-RACER: [V | mean(dA)], stdev is the ParamLayer (RACER_simpleSigma)
+  {
+    LayerDesc& L = add(kDenseLinear, nOutDense);
+    L.nIn = nIn; L.ld = round_up(nOutDense, 8);
+    L.wOff = off; off += round_up(L.ld * nIn, 8); L.bOff = off; off += round_up(nOutDense, 8);
+    L.ldt = round_up(nIn, 4); L.wtOff = offT; offT += nOutDense * L.ldt;
+    LayerDesc& P = add(kParam, dA);
+    P.bOff = off; off += round_up(dA, 8); P.wOff = off;
+  }
+  net.nLayers = id; net.nParams = off; net.nParamsT = std::max(offT, 4); net.nOut = nOutDense + dA; net.nOutDense = nOutDense;
+  net.dS = dS; net.dA = dA; net.actPerSample = act; net.maxWidth = width;
+  tiles.clear();
+  for (int l = 1; l < net.nLayers; ++l) {
+    const LayerDesc& L = net.L[l];
+    if (L.kind == kDenseTanh || L.kind == kDenseLinear) {
+      for (int k0 = 0; k0 < L.nIn + 1; k0 += kTileK)
+        for (int n0 = 0; n0 < L.size; n0 += kTileN) tiles.push_back(GradTile{0, l, k0, n0});
+    } else if (L.kind == kResidual) {
+      for (int n0 = 0; n0 < L.size; n0 += 16) tiles.push_back(GradTile{1, l, 0, n0});
+    } else if (L.kind == kParam) {
+      for (int n0 = 0; n0 < L.size; n0 += 16) tiles.push_back(GradTile{2, l, 0, n0});
+    }
+  }
+  return 0;
+}
+
+// Builder::build: layers initialise in order from generators[0] (Builder.cpp:133-137);
+// BaseLayer::initialize draws weight[o + ld*i] for i then o (Layer_Base.h:115-141).
+static void init_weights(const smb200_config& c, const NetDesc& net, std::mt19937& gen, std::vector<float>& blob) {
+  blob.assign(net.nParams, 0.f);
+  for (int l = 1; l < net.nLayers; ++l) {
+    const LayerDesc& L = net.L[l];
+    if (L.kind == kDenseTanh || L.kind == kDenseLinear) {
+      const bool out = L.kind == kDenseLinear;
+      const double prefac = out ? c.out_weights_prefac : 1.0;
+      const float fac = prefac > 0 ? (float)prefac : 1.f;
+      const double initFactor = out ? std::sqrt(1. / L.nIn) : std::sqrt(6. / (L.nIn + L.size));
+      const float init = (float)(fac * initFactor);
+      std::uniform_real_distribution<float> dis(-init, init);
+      for (int i = 0; i < L.nIn; ++i)
+        for (int o = 0; o < L.size; ++o) blob[L.wOff + o + L.ld * i] = dis(gen);
+    } else if (L.kind == kResidual) {
+      for (int o = 0; o < L.size; ++o) { blob[L.wOff + o] = 1.f; blob[L.bOff + o] = 0.f; }
+    } else if (L.kind == kParam) {   // SoftPlus::_inv(explNoise) (Functions.h:564-568, Continuous_policy.h:195-197)
+      double S = c.expl_noise;
+      if (S < (double)FLT_EPSILON) S = (double)FLT_EPSILON;
+      const double inv = (S * S - 0.25) / S;
+      for (int o = 0; o < L.size; ++o) blob[L.bOff + o] = (float)inv;
+    }
+  }
+}
+
+static int upload_weights(smb200_learner* h, const float* blob) {
+  const NetDesc& net = h->descs.net;
+  std::vector<float> wt(net.nParamsT, 0.f);
+  for (int l = 1; l < net.nLayers; ++l) {
+    const LayerDesc& L = net.L[l];
+    if (L.wtOff < 0) continue;
+    for (int k = 0; k < L.nIn; ++k)
+      for (int n = 0; n < L.size; ++n) wt[L.wtOff + n * L.ldt + k] = blob[L.wOff + k * L.ld + n];
+  }
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(h->W, blob, sizeof(float) * net.nParams, cudaMemcpyHostToDevice, h->stream));
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(h->WT, wt.data(), sizeof(float) * net.nParamsT, cudaMemcpyHostToDevice, h->stream));
+  SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+static int upload_order(smb200_learner* h) {
+  if (!h->orderDirty) return 0;
+  std::vector<int> ord(h->episodes.size());
+  for (size_t i = 0; i < ord.size(); ++i) ord[i] = h->episodes[i].slot;
+  if (!ord.empty())
+    SMB200_CUDA_CHECK(cudaMemcpyAsync(h->rp.epOrder, ord.data(), sizeof(int) * ord.size(), cudaMemcpyHostToDevice, h->stream));
+  SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));   // `ord` is pageable and dies here
+  h->orderDirty = false;
+  return 0;
+}
+
+static int push_ctrl(smb200_learner* h) {
+  StepCtrl two[2] = {h->hCtrl, h->hCtrl};
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(h->dCtrl, two, sizeof(two), cudaMemcpyHostToDevice, h->stream));
+  SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+static int pull_ctrl(smb200_learner* h) {
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(&h->hCtrl, h->dCtrl + (h->gradStep & 1), sizeof(StepCtrl), cudaMemcpyDeviceToHost, h->stream));
+  SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// ring allocation of `n` contiguous rows
+static long long ring_alloc(smb200_learner* h, long long n) {
+  const long long cap = h->rp.capRows;
+  if (n > cap) return -1;
+  long long cand = h->head;
+  for (int pass = 0; pass < 2; ++pass) {
+    while (cand + n <= cap) {
+      auto it = h->liveRanges.upper_bound(cand);            // first range starting after cand
+      if (it != h->liveRanges.begin()) {
+        auto pv = std::prev(it);
+        if (pv->second > cand) { cand = pv->second; continue; }   // cand inside a live range
+      }
+      if (it == h->liveRanges.end() || it->first >= cand + n) return cand;
+      cand = it->second;
+    }
+    cand = 0;
+  }
+  return -1;
+}
+
+static void fill_stats(const StepCtrl& c, smb200_step_stats* o) {
+  o->beta = c.beta; o->cmax = c.cmax; o->cinv = c.cinv; o->n_far_policy = c.n_far_ref; o->n_far_exact = c.n_far_exact;
+  o->avg_kl = c.avg_kl; o->avg_sq_err = c.avg_sq_err; o->max_abs_err = c.max_abs_err; o->avg_return = c.avg_return;
+  o->stdev_q = c.stdev_q; o->avg_q = c.avg_q; o->max_q = c.max_q; o->min_q = c.min_q;
+  o->sum_ret_err = c.sum_ret_err; o->cnt_ret = c.cnt_ret; o->grad_step = c.grad_step;
+}
+
+// host mirror of the per-step bookkeeping that follows the device work of one step:
+// applyEpisodesRemovalAlgo (sort by ID descending, FIFO prune) and the Adam RNG draw.
+// Returns true if the episode table changed.
+static bool host_post_step(smb200_learner* h) {
+  bool changed = false;
+  auto cmp = [](const EpisodeMeta& a, const EpisodeMeta& b) { return a.id > b.id; };
+  if (!std::is_sorted(h->episodes.begin(), h->episodes.end(), cmp)) {
+    std::sort(h->episodes.begin(), h->episodes.end(), cmp);
+    changed = true;
+  }
+  while (!h->episodes.empty() && h->nTransitions - (long long)h->episodes.back().nRows > h->cfg.max_tot_obs) {
+    const EpisodeMeta e = h->episodes.back();
+    h->episodes.pop_back();
+    h->nTransitions -= e.nRows - 1;
+    h->liveRanges.erase(e.start);
+    h->freeSlots.push_back(e.slot);
+    h->pendingEvict.emplace_back(e.start, e.nRows);
+    changed = true;
+  }
+  // `Saru gen(nStep, thrID, generators[thrID]())` (Optimizer.cpp:139): thread 0 consumes one
+  // 32-bit draw of generators[0] — the sampler's generator — every update.
+  (void)h->gen();
+  h->gradStep++;
+  if (changed) h->orderDirty = true;
+  return changed;
+}
+
+static void host_sample(smb200_learner* h, int* slotOut, int* tOut, int64_t* posOut, int64_t* tOut64) {
+  const int B = h->cfg.batch_size;
+  const long nData = (long)h->nTransitions;
+  std::uniform_int_distribution<size_t> distObs(0, nData - 1);
+  std::vector<size_t> ret(B);
+  auto it = ret.begin();
+  while (it != ret.end()) {
+    std::generate(it, ret.end(), [&]() { return distObs(h->gen); });
+    std::sort(ret.begin(), ret.end());
+    it = std::unique(ret.begin(), ret.end());
+  }
+  // IDtoSeqStep: prefix walk in vector order
+  size_t i = 0, prefix = 0;
+  for (size_t k = 0; k < h->episodes.size() && i < (size_t)B; ++k) {
+    const size_t nd = h->episodes[k].nRows - 1;
+    while (i < (size_t)B && ret[i] < prefix + nd) {
+      if (slotOut) { slotOut[i] = h->episodes[k].slot; tOut[i] = (int)(ret[i] - prefix); }
+      if (posOut) { posOut[i] = (int64_t)k; tOut64[i] = (int64_t)(ret[i] - prefix); }
+      ++i;
+    }
+    prefix += nd;
+  }
+}
+
+// cmax the device will hold after the statistics phase of step `gstep` (1-based)
+static double cmax_at(const smb200_learner* h, long long gstep) {
+  return 1.0 + h->cfg.clip_imp_weight / (1.0 + (double)gstep * h->cfg.eps_anneal);
+}
+
+// device work of `n` consecutive steps whose samples sit at [first, first+n) of dSampSlot/dSampT.
+// The caller guarantees the episode table is constant over them and that only the LAST one may
+// be an every-1000-steps sweep step.
+static int run_segment(smb200_learner* h, int first, int n, long long gstep0, int nEpPre, long long nTrPre, long long nTrPost) {
+  StepArgs a = h->args();
+  a.sampSlot = h->dSampSlot + (size_t)first * a.B;
+  a.sampT = h->dSampT + (size_t)first * a.B;
+  a.statsOut = h->dStats + first;
+  a.nEpisodes = nEpPre; a.nTransitions = nTrPre; a.nTransitionsPost = nTrPost;
+  // device-side step index == absolute grad step (its parity selects the ctrl buffer)
+  a.stepBase = (int)gstep0; a.lastStep = (int)(gstep0 + n - 1);
+  const NetDesc& net = h->descs.net;
+  const long long lastStep = gstep0 + n;              // nGradSteps()+1 of the last step
+  const int sweepLast = (lastStep % 1000) == 0;
+  if (h->mode == 1 && h->persistGrid > 0) {
+    if (launch_steps_persistent(a, net, h->persistGrid, (int)gstep0, n, sweepLast, h->stream)) return -2;
+    h->launches += 1;
+  } else {
+    for (int s = 0; s < n; ++s) {
+      if (launch_step_two_kernels(a, net, (int)gstep0 + s, sweepLast && s == n - 1, h->stream)) return -2;
+      h->launches += 2;
+    }
+  }
+  if (sweepLast) {
+    const int step = (int)(gstep0 + n - 1);
+    const double cm = cmax_at(h, lastStep);
+    if (launch_clear_sums(h->dSums, h->stream)) return -2;
+    if (launch_sweep(h->rp, (int)h->episodes.size(), 0, (float)h->cfg.gamma, (float)h->cfg.lambda, 1, (float)cm, (float)(1.0 / cm),
+                     h->dSums, h->stream)) return -2;
+    if (launch_moments(h->rp, h->highWater, h->dSums, h->numSMs, h->stream)) return -2;
+    if (launch_finalize_sweep(a, step, h->dSums, h->stream)) return -2;
+    if (launch_update_scaling(h->rp, h->dCtrl + (step & 1), h->dDescs, h->dSums, 0, h->stream)) return -2;
+    h->launches += 5;
+  }
+  for (const auto& ev : h->pendingEvict) cudaMemsetAsync(h->rp.rowFlag + ev.first, 0, ev.second, h->stream);
+  h->pendingEvict.clear();
+  return 0;
+}
+
+}  // namespace smb200
+
+// =============================================================================================
+extern "C" {
+
+const char* smb200_last_error(void) { return g_err.c_str(); }
+
+int smb200_default_config(smb200_config* c, int32_t dS, int32_t dA) {
+  if (!c || dS < 1 || dA < 1) return SMB200_ERR_INVALID;
+  memset(c, 0, sizeof(*c));
+  c->algo = SMB200_VRACER; c->dim_state = dS; c->dim_action = dA;
+  c->n_hidden = 2; c->hidden[0] = 128; c->hidden[1] = 128;
+  c->batch_size = 256; c->batch_size_global = 256;
+  c->max_tot_obs = (int64_t)(std::pow(2, 14) * std::sqrt((double)(dA + dS)));   // HyperParameters.h:53
+  c->max_tot_obs_global = c->max_tot_obs;
+  c->gamma = 0.995; c->lambda = 1; c->clip_imp_weight = std::sqrt(dA / 2.0); c->penal_tol = 0.1; c->eps_anneal = 5e-7;
+  c->learnrate = 1e-4; c->nn_lambda = (double)FLT_EPSILON; c->expl_noise = std::sqrt(0.2); c->out_weights_prefac = 1e-3;
+  c->refer_reduce_threads = 32; c->world_rank = 0; c->world_size = 1; c->seed = 42;
+  return 0;
+}
+
+int smb200_create(const smb200_config* cfg, smb200_learner** out) {
+  if (!cfg || !out) return SMB200_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    set_error_msg("smarties_b200: no CUDA device — this library has no CPU fallback"); return SMB200_ERR_CUDA; }
+  smb200_learner* h = new smb200_learner();
+  h->cfg = *cfg;
+  smb200_config& c = h->cfg;
+  if (c.batch_size_global <= 0) c.batch_size_global = c.batch_size;
+  if (c.max_tot_obs_global <= 0) c.max_tot_obs_global = c.max_tot_obs;
+  if (c.refer_reduce_threads <= 0) c.refer_reduce_threads = 32;
+  if (c.refer_reduce_threads > kThreads) c.refer_reduce_threads = kThreads;
+  if (c.batch_size < 1 || c.max_tot_obs < c.batch_size) { set_error_msg("bad batch_size / max_tot_obs"); delete h; return SMB200_ERR_INVALID; }
+  std::vector<GradTile> tiles;
+  if (build_net(c, h->descs.net, tiles)) { delete h; return SMB200_ERR_INVALID; }
+  Hyper& hp = h->descs.hp; memset(&hp, 0, sizeof(hp));
+  hp.gamma = c.gamma; hp.lambda = c.lambda; hp.clipImpWeight = c.clip_imp_weight; hp.penalTol = c.penal_tol;
+  hp.epsAnneal = c.eps_anneal; hp.learnrate = c.learnrate; hp.nnLambda = c.nn_lambda;
+  hp.maxTotObsGlobal = c.max_tot_obs_global; hp.batchGlobal = c.batch_size_global; hp.batchLocal = c.batch_size;
+  hp.referThreads = c.refer_reduce_threads; hp.algo = c.algo;
+  for (int i = 0; i < c.dim_action; ++i) hp.bounded[i] = c.action_bounded[i];
+
+#define CK(x) do { if ((x) != 0) { smb200_destroy(h); return SMB200_ERR_CUDA; } } while (0)
+#define CKC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_error(#x, e_, __FILE__, __LINE__); smb200_destroy(h); return SMB200_ERR_CUDA; } } while (0)
+  CKC(cudaSetDevice(c.device));
+  cudaDeviceProp prop; CKC(cudaGetDeviceProperties(&prop, c.device));
+  h->numSMs = prop.multiProcessorCount;
+  CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CKC(cudaEventCreate(&h->ev0)); CKC(cudaEventCreate(&h->ev1));
+  const NetDesc& net = h->descs.net;
+  const int dS = c.dim_state, dA = c.dim_action, B = c.batch_size;
+  long long cap = c.capacity_rows > 0 ? c.capacity_rows : c.max_tot_obs + c.max_tot_obs / 8 + 65536;
+  cap = (cap + 63) / 64 * 64;
+  if (cap > 0x7fffffffLL) { set_error_msg("capacity_rows must fit in 31 bits"); delete h; return SMB200_ERR_INVALID; }
+  int maxEp = c.max_episodes > 0 ? c.max_episodes : (int)std::min<long long>(cap / 2, 1 << 20);
+  ReplayView& rp = h->rp;
+  rp.capRows = cap; rp.maxEpisodes = maxEp; rp.dS = dS; rp.dA = dA;
+  CK(dev_alloc(&rp.S, (size_t)cap * dS)); CK(dev_alloc(&rp.A, (size_t)cap * dA)); CK(dev_alloc(&rp.MU, (size_t)cap * 2 * dA));
+  CK(dev_alloc(&rp.R, (size_t)cap)); CK(dev_alloc(&rp.V, (size_t)cap)); CK(dev_alloc(&rp.ADV, (size_t)cap));
+  CK(dev_alloc(&rp.Q, (size_t)cap)); CK(dev_alloc(&rp.DELTA, (size_t)cap)); CK(dev_alloc(&rp.RHO, (size_t)cap));
+  CK(dev_alloc(&rp.KL, (size_t)cap)); CK(dev_alloc(&rp.rowFlag, (size_t)cap));
+  CK(dev_alloc(&rp.epStart, (size_t)maxEp)); CK(dev_alloc(&rp.epLen, (size_t)maxEp)); CK(dev_alloc(&rp.epTerm, (size_t)maxEp));
+  CK(dev_alloc(&rp.epId, (size_t)maxEp)); CK(dev_alloc(&rp.epAgg, (size_t)maxEp * AGG_N)); CK(dev_alloc(&rp.epOrder, (size_t)maxEp));
+  CK(dev_alloc(&rp.stateMean, (size_t)dS)); CK(dev_alloc(&rp.stateScale, (size_t)dS)); CK(dev_alloc(&rp.stateStd, (size_t)dS));
+  CK(dev_alloc(&rp.rew, (size_t)4));
+  {
+    std::vector<float> ones(dS, 1.f); const float rw[4] = {0.f, 1.f, 1.f, 0.f};
+    CKC(cudaMemcpy(rp.stateScale, ones.data(), sizeof(float) * dS, cudaMemcpyHostToDevice));
+    CKC(cudaMemcpy(rp.stateStd, ones.data(), sizeof(float) * dS, cudaMemcpyHostToDevice));
+    CKC(cudaMemcpy(rp.rew, rw, sizeof(rw), cudaMemcpyHostToDevice));
+  }
+  h->freeSlots.reserve(maxEp);
+  for (int s = maxEp - 1; s >= 0; --s) h->freeSlots.push_back(s);
+
+  CK(dev_alloc(&h->W, (size_t)net.nParams)); CK(dev_alloc(&h->WT, (size_t)net.nParamsT));
+  CK(dev_alloc(&h->M1, (size_t)net.nParams)); CK(dev_alloc(&h->M2, (size_t)net.nParams)); CK(dev_alloc(&h->G, (size_t)net.nParams));
+  h->Bpad = round_up(B, 256);
+  CK(dev_alloc(&h->actG, (size_t)net.actPerSample * h->Bpad)); CK(dev_alloc(&h->errG, (size_t)net.actPerSample * h->Bpad));
+  h->nTiles = (int)tiles.size();
+  CK(dev_alloc(&h->dTiles, tiles.size()));
+  CKC(cudaMemcpy(h->dTiles, tiles.data(), sizeof(GradTile) * tiles.size(), cudaMemcpyHostToDevice));
+  CK(dev_alloc(&h->dDescs, 1));
+  CKC(cudaMemcpy(h->dDescs, &h->descs, sizeof(DevDescs), cudaMemcpyHostToDevice));
+  CK(dev_alloc(&h->dCtrl, 2)); CK(dev_alloc(&h->dRec, (size_t)B));
+  CK(dev_alloc(&h->lastO, (size_t)B * net.nOut)); CK(dev_alloc(&h->lastG, (size_t)B * net.nOut)); CK(dev_alloc(&h->lastX, (size_t)B * dS));
+  CK(dev_alloc(&h->dSums, 1)); CK(dev_alloc(&h->dBarrier, 4));
+  CK(dev_alloc(&h->dSampSlot, (size_t)h->maxSeg * B)); CK(dev_alloc(&h->dSampT, (size_t)h->maxSeg * B));
+  CK(dev_alloc(&h->dStats, (size_t)h->maxSeg));
+  CKC(cudaMallocHost(&h->hSampSlot, sizeof(int) * (size_t)h->maxSeg * B));
+  CKC(cudaMallocHost(&h->hSampT, sizeof(int) * (size_t)h->maxSeg * B));
+  CKC(cudaMallocHost(&h->hStats, sizeof(smb200_step_stats) * (size_t)h->maxSeg));
+
+  // MemoryBuffer.h:41-44 initial ReF-ER state; AdamOptimizer beta powers (Optimizer.h:93)
+  StepCtrl& k = h->hCtrl; memset(&k, 0, sizeof(k));
+  k.beta = c.clip_imp_weight <= 0 ? 1.0 : 1e-4;
+  k.cmax = 1.0 + c.clip_imp_weight; k.cinv = 1.0 / c.clip_imp_weight;
+  k.adam_bt1 = 0.9; k.adam_bt2 = 0.999;
+  CK(push_ctrl(h));
+
+  h->gen.seed((unsigned long)c.seed);
+  std::vector<float> blob;
+  init_weights(c, net, h->gen, blob);
+  CK(upload_weights(h, blob.data()));
+  CK(step_kernels_prepare(net));
+  const char* m = getenv("SMB200_MODE");
+  h->mode = (m && strcmp(m, "two") == 0) ? 0 : 1;
+  int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c.device);
+  if (!coop) h->mode = 0;
+  { StepArgs a = h->args(); h->persistGrid = persistent_grid(a, net, h->numSMs); }
+  if (h->persistGrid < 1) h->mode = 0;
+#undef CK
+#undef CKC
+  *out = h;
+  return 0;
+}
+
+void smb200_destroy(smb200_learner* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  ReplayView& rp = h->rp;
+  void* ptrs[] = {rp.S, rp.A, rp.MU, rp.R, rp.V, rp.ADV, rp.Q, rp.DELTA, rp.RHO, rp.KL, rp.rowFlag, rp.epStart, rp.epLen, rp.epTerm,
+                  rp.epId, rp.epAgg, rp.epOrder, rp.stateMean, rp.stateScale, rp.stateStd, rp.rew, h->W, h->WT, h->M1, h->M2, h->G,
+                  h->actG, h->errG, h->dTiles, h->dDescs, h->dCtrl, h->dRec, h->lastO, h->lastG, h->lastX, h->dSums, h->dBarrier,
+                  h->dSampSlot, h->dSampT, h->dStats};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (h->hSampSlot) cudaFreeHost(h->hSampSlot);
+  if (h->hSampT) cudaFreeHost(h->hSampT);
+  if (h->hStats) cudaFreeHost(h->hStats);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int64_t smb200_n_params(const smb200_learner* h) { return h ? h->descs.net.nParams : -1; }
+int32_t smb200_n_outputs(const smb200_learner* h) { return h ? h->descs.net.nOut : -1; }
+int64_t smb200_n_transitions(const smb200_learner* h) { return h ? h->nTransitions : -1; }
+int64_t smb200_n_episodes(const smb200_learner* h) { return h ? (int64_t)h->episodes.size() : -1; }
+int64_t smb200_n_rows(const smb200_learner* h) {
+  if (!h) return -1;
+  int64_t n = 0; for (const auto& e : h->episodes) n += e.nRows; return n;
+}
+
+int smb200_set_weights(smb200_learner* h, const float* blob, int64_t n) {
+  if (!h || !blob || n != h->descs.net.nParams) return SMB200_ERR_INVALID;
+  cudaSetDevice(h->cfg.device);
+  return upload_weights(h, blob);
+}
+static int d2h(smb200_learner* h, void* dst, const void* src, size_t bytes) {
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int smb200_get_weights(smb200_learner* h, float* blob, int64_t n) {
+  if (!h || !blob || n != h->descs.net.nParams) return SMB200_ERR_INVALID;
+  return d2h(h, blob, h->W, sizeof(float) * n);
+}
+int smb200_get_grad(smb200_learner* h, float* blob, int64_t n) {
+  if (!h || !blob || n != h->descs.net.nParams) return SMB200_ERR_INVALID;
+  return d2h(h, blob, h->G, sizeof(float) * n);
+}
+int smb200_get_adam(smb200_learner* h, float* m1, float* m2, int64_t n) {
+  if (!h || n != h->descs.net.nParams) return SMB200_ERR_INVALID;
+  if (m1 && d2h(h, m1, h->M1, sizeof(float) * n)) return SMB200_ERR_CUDA;
+  if (m2 && d2h(h, m2, h->M2, sizeof(float) * n)) return SMB200_ERR_CUDA;
+  return 0;
+}
+int smb200_set_adam(smb200_learner* h, const float* m1, const float* m2, int64_t n, int64_t n_step) {
+  if (!h || n != h->descs.net.nParams) return SMB200_ERR_INVALID;
+  if (m1) SMB200_CUDA_CHECK(cudaMemcpyAsync(h->M1, m1, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+  if (m2) SMB200_CUDA_CHECK(cudaMemcpyAsync(h->M2, m2, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+  SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  if (pull_ctrl(h)) return SMB200_ERR_CUDA;
+  h->hCtrl.adam_step = n_step;
+  return push_ctrl(h);
+}
+
+int smb200_set_scaling(smb200_learner* h, const float* mean, const float* scale, const float* stdev, const float rewards[3]) {
+  if (!h) return SMB200_ERR_INVALID;
+  const size_t b = sizeof(float) * h->cfg.dim_state;
+  if (mean) SMB200_CUDA_CHECK(cudaMemcpyAsync(h->rp.stateMean, mean, b, cudaMemcpyHostToDevice, h->stream));
+  if (scale) SMB200_CUDA_CHECK(cudaMemcpyAsync(h->rp.stateScale, scale, b, cudaMemcpyHostToDevice, h->stream));
+  if (stdev) SMB200_CUDA_CHECK(cudaMemcpyAsync(h->rp.stateStd, stdev, b, cudaMemcpyHostToDevice, h->stream));
+  if (rewards) SMB200_CUDA_CHECK(cudaMemcpyAsync(h->rp.rew, rewards, sizeof(float) * 3, cudaMemcpyHostToDevice, h->stream));
+  SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int smb200_get_scaling(smb200_learner* h, float* mean, float* scale, float* stdev, float rewards[3]) {
+  if (!h) return SMB200_ERR_INVALID;
+  const size_t b = sizeof(float) * h->cfg.dim_state;
+  if (mean && d2h(h, mean, h->rp.stateMean, b)) return SMB200_ERR_CUDA;
+  if (scale && d2h(h, scale, h->rp.stateScale, b)) return SMB200_ERR_CUDA;
+  if (stdev && d2h(h, stdev, h->rp.stateStd, b)) return SMB200_ERR_CUDA;
+  if (rewards && d2h(h, rewards, h->rp.rew, sizeof(float) * 3)) return SMB200_ERR_CUDA;
+  return 0;
+}
+
+int smb200_push_episode(smb200_learner* h, int64_t id, int32_t N, int32_t terminated, const float* S, const float* A,
+                        const float* MU, const float* R, const float* V, const float* ADV) {
+  if (!h || N < 2 || !S || !A || !MU || !R) { set_error_msg("push_episode: an episode needs at least s0 and sT"); return SMB200_ERR_INVALID; }
+  cudaSetDevice(h->cfg.device);
+  if (h->freeSlots.empty()) { set_error_msg("episode table full"); return SMB200_ERR_CAPACITY; }
+  const long long start = ring_alloc(h, N);
+  if (start < 0) { set_error_msg("replay ring full"); return SMB200_ERR_CAPACITY; }
+  const int slot = h->freeSlots.back(); h->freeSlots.pop_back();
+  const int dS = h->cfg.dim_state, dA = h->cfg.dim_action;
+  ReplayView& rp = h->rp;
+  cudaStream_t st = h->stream;
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(rp.S + (size_t)start * dS, S, sizeof(float) * (size_t)N * dS, cudaMemcpyHostToDevice, st));
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(rp.A + (size_t)start * dA, A, sizeof(float) * (size_t)N * dA, cudaMemcpyHostToDevice, st));
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(rp.MU + (size_t)start * 2 * dA, MU, sizeof(float) * (size_t)N * 2 * dA, cudaMemcpyHostToDevice, st));
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(rp.R + start, R, sizeof(float) * (size_t)N, cudaMemcpyHostToDevice, st));
+  if (V) SMB200_CUDA_CHECK(cudaMemcpyAsync(rp.V + start, V, sizeof(float) * (size_t)N, cudaMemcpyHostToDevice, st));
+  if (ADV) SMB200_CUDA_CHECK(cudaMemcpyAsync(rp.ADV + start, ADV, sizeof(float) * (size_t)N, cudaMemcpyHostToDevice, st));
+  else if (V) SMB200_CUDA_CHECK(cudaMemsetAsync(rp.ADV + start, 0, sizeof(float) * (size_t)N, st));
+  // last row: no action / policy (MemoryBuffer.cpp:124-130); first reward is 0 (Episode.cpp:239)
+  SMB200_CUDA_CHECK(cudaMemsetAsync(rp.A + (size_t)(start + N - 1) * dA, 0, sizeof(float) * dA, st));
+  SMB200_CUDA_CHECK(cudaMemsetAsync(rp.MU + (size_t)(start + N - 1) * 2 * dA, 0, sizeof(float) * 2 * dA, st));
+  SMB200_CUDA_CHECK(cudaMemsetAsync(rp.R + start, 0, sizeof(float), st));
+  const int meta[3] = {(int)start, N, terminated ? 1 : 0};
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(rp.epStart + slot, &meta[0], sizeof(int), cudaMemcpyHostToDevice, st));
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(rp.epLen + slot, &meta[1], sizeof(int), cudaMemcpyHostToDevice, st));
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(rp.epTerm + slot, &meta[2], sizeof(int), cudaMemcpyHostToDevice, st));
+  const long long id64 = id;
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(rp.epId + slot, &id64, sizeof(long long), cudaMemcpyHostToDevice, st));
+  // pre-training TD-error placeholder sqrt(max(EPS, stats.avgSquaredErr)) (MemoryBuffer.cpp:487)
+  if (h->initialized && pull_ctrl(h)) return SMB200_ERR_CUDA;
+  const float deltaInit = (float)std::sqrt(std::max((double)FLT_EPSILON, h->hCtrl.avg_sq_err));
+  if (launch_init_episode(rp, slot, deltaInit, V != nullptr, st)) return SMB200_ERR_CUDA;
+  // computeReturnEstimator at insertion (MemoryBuffer.cpp:143)
+  if (launch_sweep(rp, 0, slot, (float)h->cfg.gamma, (float)h->cfg.lambda, 0, 0.f, 0.f, nullptr, st)) return SMB200_ERR_CUDA;
+  SMB200_CUDA_CHECK(cudaStreamSynchronize(st));   // host buffers are the caller's: finish the copies
+  h->episodes.push_back(EpisodeMeta{id, N, slot, start, terminated ? 1 : 0});
+  h->liveRanges[start] = start + N;
+  h->head = start + N; h->highWater = std::max(h->highWater, start + N);
+  h->nTransitions += N - 1;
+  h->orderDirty = true; h->presampled = 0;
+  return 0;
+}
+
+int smb200_initialize_learner(smb200_learner* h) {
+  if (!h || h->episodes.empty()) return SMB200_ERR_STATE;
+  cudaSetDevice(h->cfg.device);
+  if (h->gradStep > 0) return 0;   // "Skipping initialization for restarted learner" (Learner.cpp:51-54)
+  // updateCounters(bInit=true): beta fixed-point step with the initial far-policy fraction
+  StepCtrl& k = h->hCtrl;
+  const double nData = (double)h->nTransitions;
+  const double lr = 0.1 * (double)h->cfg.batch_size_global / std::max((double)h->cfg.max_tot_obs_global, nData);
+  const double frac = (double)k.n_far_ref / std::max(nData, 1.0);
+  const double mn = std::min(lr, k.beta);
+  k.beta = frac > h->cfg.penal_tol ? (1 - mn) * k.beta : (1 - mn) * k.beta + std::min(lr, 1 - k.beta);
+  if (push_ctrl(h)) return SMB200_ERR_CUDA;
+  if (upload_order(h)) return SMB200_ERR_CUDA;
+  // updateRewardsStats(bInit=true), then rescaleAllReturnEstimator
+  if (launch_clear_sums(h->dSums, h->stream)) return SMB200_ERR_CUDA;
+  if (launch_moments(h->rp, h->highWater, h->dSums, h->numSMs, h->stream)) return SMB200_ERR_CUDA;
+  if (launch_update_scaling(h->rp, h->dCtrl, h->dDescs, h->dSums, 1, h->stream)) return SMB200_ERR_CUDA;
+  if (launch_sweep(h->rp, (int)h->episodes.size(), 0, (float)h->cfg.gamma, (float)h->cfg.lambda, 0, 0.f, 0.f, nullptr, h->stream))
+    return SMB200_ERR_CUDA;
+  SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  h->initialized = true;
+  return 0;
+}
+
+int smb200_set_grad_step(smb200_learner* h, int64_t n) {
+  if (!h || n < 0) return SMB200_ERR_INVALID;
+  if (pull_ctrl(h)) return SMB200_ERR_CUDA;
+  h->gradStep = n; h->hCtrl.grad_step = n; h->hCtrl.adam_step = n;
+  return push_ctrl(h);
+}
+int smb200_seed_sampler(smb200_learner* h, uint64_t seed) {
+  if (!h) return SMB200_ERR_INVALID;
+  h->gen.seed((unsigned long)seed); h->presampled = 0;
+  return 0;
+}
+
+int smb200_sample(smb200_learner* h, int64_t* pos, int64_t* t) {
+  if (!h || !pos || !t || h->nTransitions < h->cfg.batch_size) return SMB200_ERR_STATE;
+  host_sample(h, nullptr, nullptr, pos, t);
+  return 0;
+}
+
+// samples + host bookkeeping for up to `n` steps; fills pinned arrays from index 0 and returns
+// how many steps can run as one device segment (constant episode table, sweep only at the end)
+static int plan_segment(smb200_learner* h, int n) {
+  const int B = h->cfg.batch_size;
+  int cnt = 0;
+  while (cnt < n && cnt < h->maxSeg) {
+    host_sample(h, h->hSampSlot + (size_t)cnt * B, h->hSampT + (size_t)cnt * B, nullptr, nullptr);
+    const long long stepNo = h->gradStep + 1;
+    const bool changed = host_post_step(h);
+    ++cnt;
+    if (changed || stepNo % 1000 == 0) break;
+  }
+  return cnt;
+}
+
+static int upload_samples(smb200_learner* h, int cnt) {
+  const size_t bytes = sizeof(int) * (size_t)cnt * h->cfg.batch_size;
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(h->dSampSlot, h->hSampSlot, bytes, cudaMemcpyHostToDevice, h->stream));
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(h->dSampT, h->hSampT, bytes, cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+int smb200_train_steps(smb200_learner* h, int32_t n, smb200_step_stats* stats) {
+  if (!h || n < 0) return SMB200_ERR_INVALID;
+  if (h->nTransitions < h->cfg.batch_size) { set_error_msg("not enough transitions for one mini-batch"); return SMB200_ERR_STATE; }
+  cudaSetDevice(h->cfg.device);
+  h->presampled = 0;
+  const long long l0 = h->launches;
+  SMB200_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
+  int done = 0;
+  while (done < n) {
+    const long long g0 = h->gradStep;
+    // the order in effect for these steps must reach the device before host_post_step re-sorts
+    if (upload_order(h)) return SMB200_ERR_CUDA;
+    const int nEpPre = (int)h->episodes.size(); const long long nTrPre = h->nTransitions;
+    const int cnt = plan_segment(h, n - done);
+    const bool dirtyAfter = h->orderDirty;
+    if (upload_samples(h, cnt)) return SMB200_ERR_CUDA;
+    if (run_segment(h, 0, cnt, g0, nEpPre, nTrPre, h->nTransitions)) return SMB200_ERR_CUDA;
+    if (stats) {
+      SMB200_CUDA_CHECK(cudaMemcpyAsync(h->hStats, h->dStats, sizeof(smb200_step_stats) * cnt, cudaMemcpyDeviceToHost, h->stream));
+      SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+      memcpy(stats + done, h->hStats, sizeof(smb200_step_stats) * cnt);
+    } else if (done + cnt < n) {
+      SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));   // pinned sample arrays are reused
+    }
+    h->orderDirty = dirtyAfter;
+    done += cnt;
+  }
+  SMB200_CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
+  SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  h->lastMs = ms; h->lastLaunches = h->launches - l0;
+  return 0;
+}
+
+int smb200_train_step_on(smb200_learner* h, const int64_t* pos, const int64_t* t, int32_t batch, smb200_step_stats* stats) {
+  if (!h || !pos || !t || batch != h->cfg.batch_size) return SMB200_ERR_INVALID;
+  cudaSetDevice(h->cfg.device);
+  h->presampled = 0;
+  for (int b = 0; b < batch; ++b) {
+    if (pos[b] < 0 || pos[b] >= (int64_t)h->episodes.size()) return SMB200_ERR_INVALID;
+    const EpisodeMeta& e = h->episodes[pos[b]];
+    if (t[b] < 0 || t[b] >= e.nRows - 1) return SMB200_ERR_INVALID;
+    h->hSampSlot[b] = e.slot; h->hSampT[b] = (int)t[b];
+  }
+  if (upload_order(h)) return SMB200_ERR_CUDA;
+  const long long g0 = h->gradStep;
+  const int nEpPre = (int)h->episodes.size(); const long long nTrPre = h->nTransitions;
+  host_post_step(h);
+  const bool dirtyAfter = h->orderDirty;
+  if (upload_samples(h, 1)) return SMB200_ERR_CUDA;
+  if (run_segment(h, 0, 1, g0, nEpPre, nTrPre, h->nTransitions)) return SMB200_ERR_CUDA;
+  h->orderDirty = dirtyAfter;
+  if (stats) {
+    SMB200_CUDA_CHECK(cudaMemcpyAsync(h->hStats, h->dStats, sizeof(smb200_step_stats), cudaMemcpyDeviceToHost, h->stream));
+    SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    *stats = h->hStats[0];
+  } else SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int smb200_presample(smb200_learner* h, int32_t n) {
+  if (!h || n < 1 || n > h->maxSeg) return SMB200_ERR_INVALID;
+  cudaSetDevice(h->cfg.device);
+  // benchmark path: the episode table must be in its steady (sorted, un-pruned) state
+  const int B = h->cfg.batch_size;
+  for (int i = 0; i < n; ++i) {
+    host_sample(h, h->hSampSlot + (size_t)i * B, h->hSampT + (size_t)i * B, nullptr, nullptr);
+    (void)h->gen();   // the Adam update's draw (host_post_step)
+  }
+  if (upload_samples(h, n)) return SMB200_ERR_CUDA;
+  SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  h->presampled = n;
+  return 0;
+}
+
+int smb200_train_presampled(smb200_learner* h, int32_t first, int32_t n) {
+  if (!h || first < 0 || n < 1 || first + n > h->presampled) return SMB200_ERR_INVALID;
+  cudaSetDevice(h->cfg.device);
+  auto cmp = [](const EpisodeMeta& a, const EpisodeMeta& b) { return a.id > b.id; };
+  if (!std::is_sorted(h->episodes.begin(), h->episodes.end(), cmp)) { set_error_msg("presampled path needs a sorted episode table"); return SMB200_ERR_STATE; }
+  if (upload_order(h)) return SMB200_ERR_CUDA;
+  const long long l0 = h->launches;
+  SMB200_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
+  int done = 0;
+  while (done < n) {
+    const long long g0 = h->gradStep;
+    int cnt = n - done;
+    const long long toSweep = 1000 - (g0 % 1000);     // steps until (and including) the next sweep step
+    if (cnt > toSweep) cnt = (int)toSweep;
+    if (run_segment(h, first + done, cnt, g0, (int)h->episodes.size(), h->nTransitions, h->nTransitions)) return SMB200_ERR_CUDA;
+    h->gradStep += cnt;
+    done += cnt;
+  }
+  SMB200_CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
+  h->lastLaunches = h->launches - l0;
+  return 0;
+}
+
+int smb200_sync(smb200_learner* h) {
+  if (!h) return SMB200_ERR_INVALID;
+  SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->lastMs = ms;
+  return 0;
+}
+
+int smb200_last_timing(smb200_learner* h, double* ms, int64_t* launches) {
+  if (!h) return SMB200_ERR_INVALID;
+  if (ms) *ms = h->lastMs;
+  if (launches) *launches = h->lastLaunches;
+  return 0;
+}
+
+int smb200_get_last_batch(smb200_learner* h, float* O, float* g, float* X) {
+  if (!h) return SMB200_ERR_INVALID;
+  const int B = h->cfg.batch_size, nOut = h->descs.net.nOut, dS = h->cfg.dim_state;
+  if (O && d2h(h, O, h->lastO, sizeof(float) * B * nOut)) return SMB200_ERR_CUDA;
+  if (g && d2h(h, g, h->lastG, sizeof(float) * B * nOut)) return SMB200_ERR_CUDA;
+  if (X && d2h(h, X, h->lastX, sizeof(float) * B * dS)) return SMB200_ERR_CUDA;
+  return 0;
+}
+
+int smb200_retrace_sweep(smb200_learner* h, double* sumErr2) {
+  if (!h || h->episodes.empty()) return SMB200_ERR_STATE;
+  cudaSetDevice(h->cfg.device);
+  if (upload_order(h)) return SMB200_ERR_CUDA;
+  if (launch_clear_sums(h->dSums, h->stream)) return SMB200_ERR_CUDA;
+  SMB200_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
+  if (launch_sweep(h->rp, (int)h->episodes.size(), 0, (float)h->cfg.gamma, (float)h->cfg.lambda, 0, 0.f, 0.f, h->dSums, h->stream))
+    return SMB200_ERR_CUDA;
+  SMB200_CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
+  double e = 0;
+  if (d2h(h, &e, &h->dSums->sumErr2, sizeof(double))) return SMB200_ERR_CUDA;
+  float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->lastMs = ms; h->lastLaunches = 1;
+  if (sumErr2) *sumErr2 = e;
+  return 0;
+}
+
+int smb200_reward_state_moments(smb200_learner* h, double* out) {
+  if (!h || h->episodes.empty()) return SMB200_ERR_STATE;
+  cudaSetDevice(h->cfg.device);
+  const int dS = h->cfg.dim_state;
+  if (launch_clear_sums(h->dSums, h->stream)) return SMB200_ERR_CUDA;
+  SMB200_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
+  if (launch_moments(h->rp, h->highWater, h->dSums, h->numSMs, h->stream)) return SMB200_ERR_CUDA;
+  SMB200_CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
+  std::vector<double> m(2 * dS + 3);
+  if (d2h(h, m.data(), h->dSums->moments, sizeof(double) * m.size())) return SMB200_ERR_CUDA;
+  float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->lastMs = ms; h->lastLaunches = 1;
+  if (out) memcpy(out, m.data(), sizeof(double) * m.size());
+  return 0;
+}
+
+int smb200_read_field(smb200_learner* h, int32_t field, float* out, int64_t n) {
+  if (!h || !out || n != smb200_n_rows(h)) return SMB200_ERR_INVALID;
+  const float* src = nullptr;
+  switch (field) {
+    case SMB200_F_V: src = h->rp.V; break;       case SMB200_F_ADV: src = h->rp.ADV; break;
+    case SMB200_F_QRET: src = h->rp.Q; break;    case SMB200_F_DELTA: src = h->rp.DELTA; break;
+    case SMB200_F_RHO: src = h->rp.RHO; break;   case SMB200_F_KL: src = h->rp.KL; break;
+    case SMB200_F_REWARD: src = h->rp.R; break;  default: return SMB200_ERR_INVALID;
+  }
+  std::vector<float> all(h->highWater);
+  if (d2h(h, all.data(), src, sizeof(float) * h->highWater)) return SMB200_ERR_CUDA;
+  int64_t o = 0;
+  for (const auto& e : h->episodes) { memcpy(out + o, all.data() + e.start, sizeof(float) * e.nRows); o += e.nRows; }
+  return 0;
+}
+
+int smb200_read_episodes(smb200_learner* h, int64_t* ids, int64_t* nRows, float* agg, int64_t nEp) {
+  if (!h || nEp != (int64_t)h->episodes.size()) return SMB200_ERR_INVALID;
+  const int ME = h->rp.maxEpisodes;
+  std::vector<float> all;
+  if (agg) { all.resize((size_t)ME * AGG_N); if (d2h(h, all.data(), h->rp.epAgg, sizeof(float) * all.size())) return SMB200_ERR_CUDA; }
+  for (int64_t i = 0; i < nEp; ++i) {
+    const EpisodeMeta& e = h->episodes[i];
+    if (ids) ids[i] = e.id;
+    if (nRows) nRows[i] = e.nRows;
+    if (agg) for (int k = 0; k < AGG_N; ++k) agg[i * AGG_N + k] = all[(size_t)k * ME + e.slot];
+  }
+  return 0;
+}
+
+int smb200_get_stats(smb200_learner* h, smb200_step_stats* out) {
+  if (!h || !out) return SMB200_ERR_INVALID;
+  if (pull_ctrl(h)) return SMB200_ERR_CUDA;
+  fill_stats(h->hCtrl, out);
+  return 0;
+}
+
+int smb200_forward(smb200_learner* h, const float* states, int32_t n, float* outputs) {
+  if (!h || !states || !outputs || n < 1) return SMB200_ERR_INVALID;
+  cudaSetDevice(h->cfg.device);
+  const int dS = h->cfg.dim_state, nOut = h->descs.net.nOut;
+  float *dIn = nullptr, *dOut = nullptr;
+  SMB200_CUDA_CHECK(cudaMalloc(&dIn, sizeof(float) * (size_t)n * dS));
+  SMB200_CUDA_CHECK(cudaMalloc(&dOut, sizeof(float) * (size_t)n * nOut));
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(dIn, states, sizeof(float) * (size_t)n * dS, cudaMemcpyHostToDevice, h->stream));
+  StepArgs a = h->args();
+  int rc = launch_forward(a, h->descs.net, dIn, n, dOut, h->stream);
+  if (!rc) rc = d2h(h, outputs, dOut, sizeof(float) * (size_t)n * nOut);
+  cudaFree(dIn); cudaFree(dOut);
+  return rc ? SMB200_ERR_CUDA : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,55 @@
+// step_kernels.cuh — kernel argument block and host launchers of the learner step.
+#pragma once
+#include "common.cuh"
+#include "../../include/smarties_b200.h"
+
+namespace smb200 {
+
+struct DevDescs { NetDesc net; Hyper hp; };
+
+// accumulators of the every-1000-steps sweep (sweep_kernels.cu)
+struct SweepSums {
+  double sumErr2;           // sum of squared Retrace changes (updateReturnEstimator)
+  long long nRet;           // number of refreshed estimates
+  long long nFarExact;      // exact far-policy flags over all data rows
+  double moments[2 * 512 + 3];   // reward/state moments: sum(s-m)[dS], sum((s-m)^2)[dS], count, sum(r-m), sum((r-m)^2)
+};
+
+struct StepArgs {
+  const DevDescs* descs;
+  ReplayView rp;
+  float* W; float* WT; float* M1; float* M2; float* G;
+  float* actG; float* errG;          // feature-major scratch [actPerSample][Bpad]
+  const int* sampSlot; const int* sampT;   // [nSteps][B]
+  SampleRec* rec;                    // [B]
+  float* lastO; float* lastG; float* lastX;
+  StepCtrl* ctrl;                    // [2]
+  smb200_step_stats* statsOut;       // [nSteps] or nullptr
+  const GradTile* tiles; int nTiles;
+  int B, Bpad;
+  int nEpisodes; long long nTransitions;   // table during the segment (before this step's pruning)
+  long long nTransitionsPost;              // nStoredSteps() after the LAST step's pruning (beta update)
+  int stepBase;                            // samples / statsOut are indexed by (step - stepBase)
+  int lastStep;                            // absolute index of the segment's last step
+  unsigned* barrier;
+};
+
+size_t step_smem_bytes(const NetDesc& net, int TB);
+int step_kernels_prepare(const NetDesc& net);
+int launch_step_two_kernels(const StepArgs& a, const NetDesc& net, int step, int skipStats, cudaStream_t st);
+int persistent_grid(const StepArgs& a, const NetDesc& net, int numSMs);
+int launch_steps_persistent(const StepArgs& a, const NetDesc& net, int grid, int step0, int nSteps, int skipStatsLast, cudaStream_t st);
+int launch_finalize_sweep(const StepArgs& a, int step, const SweepSums* sweep, cudaStream_t st);
+int launch_forward(const StepArgs& a, const NetDesc& net, const float* states, int n, float* out, cudaStream_t st);
+
+// sweep_kernels.cu
+int launch_init_episode(const ReplayView& rp, int slot, float deltaInit, int haveValues, cudaStream_t st);
+// Retrace (+ optional exact aggregate recompute) over `nEpisodes` episodes listed in rp.epOrder,
+// or over the single episode `oneSlot` when nEpisodes == 0.
+int launch_sweep(const ReplayView& rp, int nEpisodes, int oneSlot, float gamma, float lambda,
+                 int recomputeAggregates, float cmax, float cinv, SweepSums* sums, cudaStream_t st);
+int launch_moments(const ReplayView& rp, long long rowEnd, SweepSums* sums, int numSMs, cudaStream_t st);
+int launch_update_scaling(const ReplayView& rp, const StepCtrl* ctrlCur, const DevDescs* descs, const SweepSums* sums, int bInit, cudaStream_t st);
+int launch_clear_sums(SweepSums* sums, cudaStream_t st);
+
+}  // namespace smb200

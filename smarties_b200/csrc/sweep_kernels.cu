@@ -1,0 +1,320 @@
+// sweep_kernels.cu — whole-buffer passes over the HBM replay MemoryBuffer (sm_100a).
+//
+//   k_sweep    per episode (one warp each): exact recompute of the per-episode aggregates
+//              (Episode::updateCumulative, ReplayMemory/Episode.cpp:213-242) fused with the
+//              Retrace backward recursion  Q[t] = r~[t+1] + g*(V[t+1] + l*min(1,rho[t+1])*
+//              (Q[t+1]-A[t+1]-V[t+1]))  (MemoryProcessing.cpp:23-44,391-400), evaluated as a
+//              segmented affine scan: 32 time steps per warp iteration, warp-shuffle prefix
+//              composition, coalesced 128-byte loads of r, V, A, rho.  24-32 B per transition.
+//   k_moments  streaming sum / sum-of-squares of rewards and of every state component around the
+//              current means (updateRewardsStats, MemoryProcessing.cpp:94-185), f64 accumulation,
+//              (dS+1)*4 B per transition.
+//   k_update_scaling / k_init_episode: the scalar tails of those functions and
+//              Episode::finalize + initPreTrainErrorPlaceholder (Episode.cpp:244-273).
+// Compiled with -fmad=false (see step_kernels.cu).
+#include "step_kernels.cuh"
+
+#include <cfloat>
+
+namespace smb200 {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_init_episode(ReplayView rp, int slot, float deltaInit, int haveValues) {
+  const int N = rp.epLen[slot];
+  const size_t r0 = (size_t)rp.epStart[slot];
+  const int ME = rp.maxEpisodes;
+  float tot = 0.f;
+  for (int t = threadIdx.x; t < N; t += kThreads) {
+    const size_t r = r0 + t;
+    if (!haveValues) { rp.V[r] = 0.f; rp.ADV[r] = 0.f; }
+    rp.Q[r] = 0.f; rp.DELTA[r] = deltaInit; rp.KL[r] = 0.f;
+    rp.RHO[r] = t + 1 == N ? 0.f : 1.f;
+    rp.rowFlag[r] = (uint8_t)(4 | (t == 0 ? 1 : 0) | (t + 1 == N ? 2 : 0));
+    if (t > 0) tot += rp.R[r];
+  }
+  __shared__ float sh[kThreads / 32];
+  tot = warp_sum(tot);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = tot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < kThreads / 32; ++w) s += sh[w];
+    rp.epAgg[AGG_KL * ME + slot] = 0.f; rp.epAgg[AGG_FAR * ME + slot] = 0.f;
+    rp.epAgg[AGG_E2 * ME + slot] = deltaInit * deltaInit; rp.epAgg[AGG_MAXE * ME + slot] = deltaInit;
+    rp.epAgg[AGG_Q2 * ME + slot] = 0.f; rp.epAgg[AGG_Q1 * ME + slot] = 0.f;
+    rp.epAgg[AGG_MAXQ * ME + slot] = -1e9f; rp.epAgg[AGG_MINQ * ME + slot] = 1e9f;
+    rp.epAgg[AGG_TOTR * ME + slot] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_sweep(ReplayView rp, int nEpisodes, int oneSlot, float gamma, float lambda,
+                                                    int recompute, float C, float invC, SweepSums* sums) {
+  const int lane = threadIdx.x & 31;
+  const int warpsPerBlock = kThreads / 32;
+  const int gw = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5), nw = gridDim.x * warpsPerBlock;
+  const int ME = rp.maxEpisodes;
+  const double rmean = (double)rp.rew[0], rscale = (double)rp.rew[1];
+  const int count = nEpisodes > 0 ? nEpisodes : 1;
+  float errAcc = 0.f; long long nRet = 0, nFar = 0;
+  for (int pos = gw; pos < count; pos += nw) {
+    const int slot = nEpisodes > 0 ? rp.epOrder[pos] : oneSlot;
+    const int N = rp.epLen[slot];
+    const size_t r0 = (size_t)rp.epStart[slot];
+    if (recompute) {   // Episode::updateCumulative
+      const int nd = N - 1;
+      int far = 0; float sE2 = 0.f, mAE = -1e9f, mxQ = -1e9f, mnQ = 1e9f, sQ2 = 0.f, sQ1 = 0.f, sKL = 0.f, sR = 0.f;
+      for (int t = lane; t < N; t += 32) {
+        const size_t r = r0 + t;
+        sKL += rp.KL[r]; sR += rp.R[r];
+        if (t < nd) {
+          const float w = rp.RHO[r], d = rp.DELTA[r];
+          far += (w > C || w < invC) ? 1 : 0;
+          sE2 += d * d; mAE = fmaxf(mAE, fabsf(d));
+          const float q = rp.ADV[r] + rp.V[r];
+          mxQ = fmaxf(mxQ, q); mnQ = fminf(mnQ, q); sQ2 += q * q; sQ1 += q;
+        }
+      }
+      far = __reduce_add_sync(0xffffffffu, far);
+      sE2 = warp_sum(sE2); sQ2 = warp_sum(sQ2); sQ1 = warp_sum(sQ1); sKL = warp_sum(sKL); sR = warp_sum(sR);
+      mAE = warp_max(mAE); mxQ = warp_max(mxQ); mnQ = -warp_max(-mnQ);
+      if (lane == 0) {
+        const float invN = 1.0f / (float)nd;
+        rp.epAgg[AGG_FAR * ME + slot] = invN * (float)far;
+        rp.epAgg[AGG_E2 * ME + slot] = invN * sE2; rp.epAgg[AGG_MAXE * ME + slot] = mAE;
+        rp.epAgg[AGG_Q2 * ME + slot] = sQ2; rp.epAgg[AGG_Q1 * ME + slot] = sQ1;
+        rp.epAgg[AGG_MAXQ * ME + slot] = mxQ; rp.epAgg[AGG_MINQ * ME + slot] = mnQ;
+        rp.epAgg[AGG_TOTR * ME + slot] = sR; rp.epAgg[AGG_KL * ME + slot] = invN * sKL;
+        if (C > 1.0f) nFar += far;
+      }
+    }
+    // ---- Retrace: updateReturnEstimator(EP, N-2) ----
+    float carry;   // Q[t+1] entering the current chunk
+    if (rp.epTerm[slot]) carry = rp.Q[r0 + N - 1];
+    else { carry = rp.V[r0 + N - 1]; if (lane == 0) rp.Q[r0 + N - 1] = carry; }
+    for (int tc = N - 2; tc >= 0; tc -= 32) {
+      const int t = tc - lane;
+      const bool ok = t >= 0;
+      float a = 0.f, b = 1.f, R = 0.f, Vn = 0.f, An = 0.f, cw = 0.f, oldQ = 0.f;
+      if (ok) {
+        const size_t r = r0 + t + 1;
+        R = (float)(((double)rp.R[r] - rmean) * rscale);           // scaledReward<Fval> (Episode.h:184-189)
+        Vn = rp.V[r]; An = rp.ADV[r];
+        const float w = rp.RHO[r];
+        cw = lambda * (w < 1.f ? w : 1.f);                          // clippedOffPolW (Episode.h:190-194)
+        oldQ = rp.Q[r - 1];
+        // Q[t] = a + b*Q[t+1]
+        b = gamma * cw;
+        a = R + gamma * (Vn - cw * (An + Vn));
+      }
+      // inclusive prefix composition over lanes (lane 0 = latest time step)
+      float A = a, Bc = b;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const float Ap = __shfl_up_sync(0xffffffffu, A, d), Bp = __shfl_up_sync(0xffffffffu, Bc, d);
+        if (lane >= d) { A = fmaf(Bc, Ap, A); Bc = Bc * Bp; }
+      }
+      const float Qscan = fmaf(Bc, carry, A);
+      // re-evaluate with the reference's operation order on the scanned Q[t+1]
+      float Qn = __shfl_up_sync(0xffffffffu, Qscan, 1);
+      if (lane == 0) Qn = carry;
+      const float Qt = R + gamma * (Vn + cw * (Qn - An - Vn));
+      if (ok) {
+        rp.Q[r0 + t] = Qt;
+        const float dq = oldQ - Qt;
+        errAcc += dq * dq;
+      }
+      const int lastLane = min(31, tc);
+      carry = __shfl_sync(0xffffffffu, Qt, lastLane);
+    }
+    nRet += N - 1;
+  }
+  if (sums) {
+    const float e = warp_sum(errAcc);
+    if (lane == 0) {
+      atomicAdd(&sums->sumErr2, (double)e);
+      atomicAdd(reinterpret_cast<unsigned long long*>(&sums->nRet), (unsigned long long)nRet);
+      if (recompute) atomicAdd(reinterpret_cast<unsigned long long*>(&sums->nFarExact), (unsigned long long)nFar);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+constexpr int kMomRows = 64;   // rows per tile
+
+__global__ void __launch_bounds__(kThreads) k_moments(ReplayView rp, long long rowEnd, SweepSums* sums) {
+  extern __shared__ __align__(16) float tile[];   // [kMomRows][dS]
+  __shared__ uint8_t flags[kMomRows];
+  __shared__ double shd[kThreads / 32];
+  const int dS = rp.dS, tid = threadIdx.x;
+  const int CW = dS < kThreads ? dS : kThreads;       // column threads per group
+  const int G = kThreads / CW;                          // row groups
+  const int g = tid / CW, c0 = tid - g * CW;
+  const int nColPer = (dS + CW - 1) / CW;               // columns per thread when dS > 256
+  double s1[2] = {0.0, 0.0}, s2[2] = {0.0, 0.0};        // supports dS <= 512
+  double rs1 = 0.0, rs2 = 0.0, cnt = 0.0;
+  const double rmean = (double)rp.rew[0];
+  const long long nTiles = (rowEnd + kMomRows - 1) / kMomRows;
+  for (long long tIdx = blockIdx.x; tIdx < nTiles; tIdx += gridDim.x) {
+    const long long row0 = tIdx * kMomRows;
+    const int nr = (int)min((long long)kMomRows, rowEnd - row0);
+    __syncthreads();
+    const float* src = rp.S + (size_t)row0 * dS;
+    const int nf = nr * dS;
+    if ((dS & 3) == 0) {
+      for (int i = tid * 4; i < nf; i += kThreads * 4)
+        *reinterpret_cast<float4*>(tile + i) = __ldcs(reinterpret_cast<const float4*>(src + i));
+    } else {
+      for (int i = tid; i < nf; i += kThreads) tile[i] = __ldcs(src + i);
+    }
+    if (tid < nr) {
+      const uint8_t f = rp.rowFlag[row0 + tid];
+      flags[tid] = f;
+      if ((f & 4) && !(f & 1)) {            // rewards of rows 1..N-1
+        const double dr = (double)__ldcs(rp.R + row0 + tid) - rmean;
+        rs1 += dr; rs2 += dr * dr;
+      }
+      if ((f & 4) && !(f & 2)) cnt += 1.0;  // data rows 0..N-2
+    }
+    __syncthreads();
+    if (g < G) {
+      for (int r = g; r < nr; r += G) {
+        const uint8_t f = flags[r];
+        if (!(f & 4) || (f & 2)) continue;  // states of rows 0..N-2
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int c = c0 + j * CW;
+          if (j < nColPer && c < dS) {
+            const double x = (double)tile[r * dS + c] - (double)rp.stateMean[c];
+            s1[j] += x; s2[j] += x * x;
+          }
+        }
+      }
+    }
+  }
+  // block reduction of column sums over the row groups, then one atomic per column
+  __syncthreads();
+  double* red = reinterpret_cast<double*>(tile);    // reuse: needs 2*kThreads doubles (checked by the launcher)
+  for (int j = 0; j < nColPer && j < 2; ++j) {
+    __syncthreads();
+    red[tid] = s1[j]; red[kThreads + tid] = s2[j];
+    __syncthreads();
+    if (g == 0) {
+      const int c = c0 + j * CW;
+      if (c < dS) {
+        double a = 0.0, b = 0.0;
+        for (int gg = 0; gg < G; ++gg) { a += red[gg * CW + c0]; b += red[kThreads + gg * CW + c0]; }
+        atomicAdd(&sums->moments[c], a); atomicAdd(&sums->moments[dS + c], b);
+      }
+    }
+  }
+  // rewards / count
+  const int lane = tid & 31, warp = tid >> 5;
+  double v[3] = {cnt, rs1, rs2};
+  for (int q = 0; q < 3; ++q) {
+    const double w = warp_sum_d(v[q]);
+    __syncthreads();
+    if (lane == 0) shd[warp] = w;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int k = 0; k < kThreads / 32; ++k) t += shd[k];
+      atomicAdd(&sums->moments[2 * dS + q], t);
+    }
+  }
+}
+
+// updateStats lambda of updateRewardsStats (MemoryProcessing.cpp:153-184); the reference
+// accumulates in long double, here f64.
+__device__ __forceinline__ void update_stats(float& mean, float& stdev, float& invstd, double lr, double Evar, double Evar2) {
+  mean = (float)((double)mean + lr * Evar);
+  double variance = Evar2 - Evar * Evar * (2.0 * lr - lr * lr);
+  variance = fmax(variance, (double)FLT_EPSILON);
+  stdev = (float)((double)stdev + lr * (sqrt(variance) - (double)stdev));
+  invstd = 1.0f / stdev;
+}
+
+__global__ void k_update_scaling(ReplayView rp, const StepCtrl* ctrlCur, const DevDescs* descs, const SweepSums* sums, int bInit) {
+  const int dS = rp.dS;
+  const double eta = descs->hp.learnrate, eps = descs->hp.epsAnneal;
+  const double learnR = eta / (1.0 + (double)ctrlCur->grad_step * eps);       // annealRate(eta, nGradSteps, eps)
+  const double w = bInit ? 1.0 : fmin(1.0, 10.0 * learnR);                     // Learner.cpp:83
+  const double count = sums->moments[2 * dS];
+  for (int k = threadIdx.x; k <= dS; k += blockDim.x) {
+    if (k < dS) {
+      float m = rp.stateMean[k], s = rp.stateStd[k], is = rp.stateScale[k];
+      update_stats(m, s, is, w, sums->moments[k] / count, sums->moments[dS + k] / count);
+      rp.stateMean[k] = m; rp.stateStd[k] = s; rp.stateScale[k] = is;
+    } else {
+      float m = rp.rew[0], is = rp.rew[1], s = rp.rew[2];
+      update_stats(m, s, is, w, sums->moments[2 * dS + 1] / count, sums->moments[2 * dS + 2] / count);
+      rp.rew[0] = m; rp.rew[1] = is; rp.rew[2] = s;
+    }
+  }
+}
+
+__global__ void k_clear_sums(SweepSums* s) {
+  const int n = (int)(sizeof(SweepSums) / 8);
+  long long* p = reinterpret_cast<long long*>(s);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------
+int launch_init_episode(const ReplayView& rp, int slot, float deltaInit, int haveValues, cudaStream_t st) {
+  k_init_episode<<<1, kThreads, 0, st>>>(rp, slot, deltaInit, haveValues);
+  SMB200_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_sweep(const ReplayView& rp, int nEpisodes, int oneSlot, float gamma, float lambda, int recompute, float cmax,
+                 float cinv, SweepSums* sums, cudaStream_t st) {
+  const int count = nEpisodes > 0 ? nEpisodes : 1;
+  const int wpb = kThreads / 32;
+  int blocks = (count + wpb - 1) / wpb;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_sweep<<<blocks, kThreads, 0, st>>>(rp, nEpisodes, oneSlot, gamma, lambda, recompute, cmax, cinv, sums);
+  SMB200_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_moments(const ReplayView& rp, long long rowEnd, SweepSums* sums, int numSMs, cudaStream_t st) {
+  if (rp.dS > 512) { set_error_msg("moments kernel supports dim_state <= 512"); return -1; }
+  size_t sm = sizeof(float) * kMomRows * rp.dS;
+  if (sm < sizeof(double) * 2 * kThreads) sm = sizeof(double) * 2 * kThreads;
+  const long long nTiles = (rowEnd + kMomRows - 1) / kMomRows;
+  long long blocks = nTiles < (long long)numSMs * 8 ? nTiles : (long long)numSMs * 8;
+  if (blocks < 1) blocks = 1;
+  k_moments<<<(int)blocks, kThreads, sm, st>>>(rp, rowEnd, sums);
+  SMB200_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_update_scaling(const ReplayView& rp, const StepCtrl* ctrlCur, const DevDescs* descs, const SweepSums* sums, int bInit, cudaStream_t st) {
+  k_update_scaling<<<1, 128, 0, st>>>(rp, ctrlCur, descs, sums, bInit);
+  SMB200_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_clear_sums(SweepSums* sums, cudaStream_t st) {
+  k_clear_sums<<<1, 256, 0, st>>>(sums);
+  SMB200_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace smb200

@@ -1,0 +1,89 @@
+"""Generate the golden vectors under tests/golden/ from the reference itself.
+
+Runs oracle/_ref/ref_harness (the UNMODIFIED reference compiled from /root/reference by
+oracle/Makefile, single OpenMP thread so the result is deterministic) on small seeded
+synthetic replay buffers and stores inputs + reference outputs as compressed .npz files.
+Only runs where /root/reference exists (this container); the .npz fixtures are committed.
+
+    python tests/golden/make_golden.py
+"""
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
+sys.path.insert(0, ROOT)
+from smarties_b200 import synth  # noqa: E402
+
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+
+CASES = {
+    # name: (replay kwargs, settings.json, harness args, keys filter)
+    "vracer_small": dict(
+        replay=dict(seed=123, n_ep=24, ep_len=(20, 60), dS=6, dA=3),
+        settings={"learner": "VRACER", "returnsEstimator": "retrace", "nnLayerSizes": [32, 32], "batchSize": 16,
+                  "maxTotObsNum": 2048, "minTotObsNum": 500},
+        steps=12, start_step=994, sample_seed=7, bounded=0, full_steps=list(range(12))),
+    "vracer_cfg2mini": dict(
+        replay=dict(seed=321, n_ep=40, ep_len=(50, 80), dS=32, dA=8),
+        settings={"learner": "VRACER", "dataSamplingAlgo": "uniform", "returnsEstimator": "retrace",
+                  "ERoldSeqFilter": "oldest", "nnLayerSizes": [128, 128], "maxTotObsNum": 4096, "minTotObsNum": 2000},
+        steps=4, start_step=998, sample_seed=11, bounded=0, full_steps=[0, 1, 3]),
+    "vracer_bounded": dict(
+        replay=dict(seed=99, n_ep=12, ep_len=(30, 50), dS=17, dA=6),
+        settings={"learner": "VRACER", "nnLayerSizes": [64, 64], "batchSize": 32, "maxTotObsNum": 1024,
+                  "minTotObsNum": 300},
+        steps=6, start_step=0, sample_seed=5, bounded=1, full_steps=list(range(6))),
+    # FIFO pruning: capacity below the stored data, so applyEpisodesRemovalAlgo evicts on step 1
+    "vracer_prune": dict(
+        replay=dict(seed=17, n_ep=16, ep_len=(20, 30), dS=4, dA=2),
+        settings={"learner": "VRACER", "nnLayerSizes": [16], "batchSize": 8, "maxTotObsNum": 256, "minTotObsNum": 100},
+        steps=5, start_step=0, sample_seed=3, bounded=0, full_steps=list(range(5))),
+}
+
+BIG = ("/weights", "/m1", "/m2", "/gradSum")
+
+
+def run_case(name, spec, outdir):
+    d = synth.make_replay(**spec["replay"])
+    with tempfile.TemporaryDirectory() as tmp:
+        synth.write_replay_file(os.path.join(tmp, "data.bin"), d)
+        with open(os.path.join(tmp, "settings.json"), "w") as f:
+            json.dump(spec["settings"], f)
+        cmd = [HARNESS, "--data", "data.bin", "--settings", "settings.json", "--steps", str(spec["steps"]),
+               "--threads", "1", "--startStep", str(spec["start_step"]), "--sampleSeed", str(spec["sample_seed"]),
+               "--bounded", str(spec["bounded"]), "--dump", "out.bin", "--dumpAll", "--quiet"]
+        env = dict(os.environ, OMP_NUM_THREADS="1")
+        subprocess.run(cmd, cwd=tmp, check=True, stdout=subprocess.DEVNULL, env=env)
+        D = synth.read_dump(os.path.join(tmp, "out.bin"))
+    keep = {}
+    for k, v in D.items():
+        if k.startswith("s") and k[1].isdigit():
+            s = int(k[1:k.index("/")])
+            if any(k.endswith(b) for b in BIG) and s not in spec["full_steps"]:
+                continue
+            if k.endswith("/m1") or k.endswith("/m2"):
+                if s != spec["steps"] - 1:
+                    continue
+        keep["ref:" + k] = v
+    for k in ("N", "term", "start", "S", "A", "MU", "R"):
+        keep["replay:" + k] = d[k]
+    keep["spec"] = np.frombuffer(json.dumps(dict(spec, name=name)).encode(), dtype=np.uint8)
+    path = os.path.join(outdir, name + ".npz")
+    np.savez_compressed(path, **keep)
+    print(name, os.path.getsize(path) // 1024, "KiB", len(keep), "arrays")
+
+
+if __name__ == "__main__":
+    if not os.path.exists(HARNESS):
+        sys.exit("build oracle/_ref first: make -C oracle")
+    only = sys.argv[1:]
+    for n, s in CASES.items():
+        if not only or n in only:
+            run_case(n, s, os.path.dirname(os.path.abspath(__file__)))

@@ -1,0 +1,59 @@
+"""Shared helpers of the parity tests: golden fixtures (reference outputs), the numpy oracle and
+the GPU learner are all constructed from the same spec."""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = ["vracer_small", "vracer_cfg2mini", "vracer_bounded", "vracer_prune"]
+
+
+class Golden:
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        self.spec = json.loads(bytes(z["spec"]).decode())
+        self.ref = {k[4:]: z[k] for k in z.files if k.startswith("ref:")}
+        self.replay = {k[7:]: z[k] for k in z.files if k.startswith("replay:")}
+        r = self.spec["replay"]
+        self.replay["dS"], self.replay["dA"] = r["dS"], r["dA"]
+        self.dS, self.dA = r["dS"], r["dA"]
+        self.settings = self.spec["settings"]
+        self.steps, self.start_step = self.spec["steps"], self.spec["start_step"]
+        self.sample_seed, self.bounded = self.spec["sample_seed"], bool(self.spec["bounded"])
+        self.B = int(self.ref["meta/dims"][3])
+
+    def refer(self, key):
+        """{beta, cmax, cinv, nFar, avgKL, avgSqErr, maxAbsErr, avgReturn, stdevQ, avgQ, maxQ, minQ, cntRet, sumRetErr}"""
+        return self.ref[key + "/refer"]
+
+
+def make_oracle(g: Golden):
+    import vracer_oracle as vo
+    s = g.settings
+    o = vo.VracerOracle(g.dS, g.dA, hidden=s.get("nnLayerSizes", [128, 128]), batch=s.get("batchSize", 256),
+                        max_tot_obs=s.get("maxTotObsNum"), bounded=g.bounded, sample_seed=g.sample_seed)
+    o.W[:] = g.ref["init/weights"]
+    o.load_replay(g.replay)
+    o.initialize_learner()
+    o.n_grad_steps = g.start_step
+    o.adam_step = g.start_step
+    return o
+
+
+def make_learner(g: Golden, refer_reduce_threads=1):
+    from smarties_b200 import Learner
+    L = Learner(g.dS, g.dA, dict(g.settings), bounded=g.bounded, refer_reduce_threads=refer_reduce_threads)
+    L.set_weights(g.ref["init/weights"])
+    L.load_replay(g.replay)
+    L.initialize_learner()
+    L.set_grad_step(g.start_step)
+    L.seed_sampler(g.sample_seed)
+    return L
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))

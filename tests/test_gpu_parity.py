@@ -1,0 +1,163 @@
+"""GPU: the CUDA learner (through the C-ABI) against the reference's golden vectors and the
+numpy oracle on identical replay buffers, weights and sampler seed.
+
+Bars: sampled indices, far-policy counts, Cmax bit-exact; beta to 1e-12 (same f64 formula
+driven by the integer count); floats within the stated f32 tolerances (the GPU sums the
+mini-batch gradient in batch order with FMAs, the reference without)."""
+import os
+
+import numpy as np
+import pytest
+
+from parity_utils import CASES, Golden, make_learner, make_oracle, relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL_O = 5e-6       # network outputs, absolute (values are O(1e-3..1))
+TOL_G = 5e-5       # output gradient, relative to max |g|
+TOL_GRAD = 1e-4    # summed parameter gradient, relative to max |G|
+TOL_W = 5e-6       # weights after Adam, absolute
+
+
+def _check_step(L, g, R, pre, stats):
+    O, gg, X = L.get_last_batch()
+    # identical standardized inputs <=> identical sampled rows and identical scaling
+    assert np.array_equal(X, R[pre + "/S"]), "sampled transitions differ from the reference's"
+    assert np.abs(O - R[pre + "/O"]).max() < TOL_O
+    assert relerr(gg, R[pre + "/g"]) < TOL_G
+    if pre + "/gradSum" in R:
+        assert relerr(L.get_grad(), R[pre + "/gradSum"]) < TOL_GRAD
+        assert np.abs(L.get_weights() - R[pre + "/weights"]).max() < TOL_W
+    ref = g.refer(pre + "/post")
+    assert stats["cmax"] == ref[1] and stats["cinv"] == ref[2]
+    assert stats["n_far_policy"] == int(ref[3])
+    assert stats["beta"] == pytest.approx(ref[0], rel=1e-12)
+    assert stats["avg_kl"] == pytest.approx(ref[4], rel=2e-4, abs=1e-9)
+    assert stats["avg_sq_err"] == pytest.approx(ref[5], rel=2e-4)
+    ids, rows, _ = L.read_episodes()
+    assert list(ids) == list(R[pre + "/post/epID"]) and list(rows) == list(R[pre + "/post/epLen"])
+
+
+def _check_final(L, R):
+    assert np.allclose(L.read_field("QRET"), R["final/Qret"], rtol=2e-5, atol=2e-5)
+    assert np.allclose(L.read_field("V"), R["final/V"], rtol=2e-5, atol=2e-6)
+    assert np.allclose(L.read_field("RHO"), R["final/rho"], rtol=2e-5)
+    assert np.allclose(L.read_field("KL"), R["final/KL"], rtol=2e-4, atol=1e-7)
+    assert np.allclose(L.read_field("DELTA"), R["final/delta"], rtol=2e-5, atol=2e-5)
+    mean, scale, std, rew = L.get_scaling()
+    assert np.allclose(mean, R["final/stateMean"], atol=1e-7)
+    assert np.allclose(scale, R["final/stateScale"], rtol=1e-6)
+    assert np.allclose(rew[:2], R["final/rewards"][:2], rtol=1e-6, atol=1e-8)
+    _, _, agg = L.read_episodes()
+    assert np.allclose(agg[:, :8], R["final/epAgg"][:, :8], rtol=2e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_initialize_learner_matches_reference(case):
+    g = Golden(case)
+    L = make_learner(g)
+    R = g.ref
+    mean, scale, std, rew = L.get_scaling()
+    assert np.allclose(mean, R["init/stateMean"], atol=1e-7)
+    assert np.allclose(scale, R["init/stateScale"], rtol=1e-6)
+    assert np.allclose(rew, R["init/rewards"], rtol=1e-6, atol=1e-8)
+    assert np.allclose(L.read_field("QRET"), R["init/Qret"], rtol=2e-6, atol=2e-6)
+    assert np.array_equal(L.read_field("DELTA"), R["init/delta"])
+    assert np.array_equal(L.read_field("RHO"), R["init/rho"])
+    st = L.get_stats()
+    assert st["beta"] == R["init/refer"][0] and st["cmax"] == R["init/refer"][1]
+    L.close()
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_learner_steps_match_reference(case):
+    g = Golden(case)
+    L = make_learner(g)
+    for s in range(g.steps):
+        st = L.train_steps(1)[0]
+        _check_step(L, g, g.ref, f"s{s}", st)
+    _check_final(L, g.ref)
+    L.close()
+
+
+@pytest.mark.parametrize("case", ["vracer_small", "vracer_prune"])
+def test_sampler_indices_bit_exact(case):
+    """smb200_sample == Sample_uniform::sample + IDtoSeqStep of the reference."""
+    g = Golden(case)
+    L = make_learner(g)
+    ids, _, _ = L.read_episodes()
+    pos, t = L.sample_minibatch()
+    assert np.array_equal(ids[pos], g.ref["s0/sampledEpID"])
+    assert np.array_equal(t, g.ref["s0/sampledT"])
+    L.close()
+
+
+@pytest.mark.parametrize("case", ["vracer_small", "vracer_bounded"])
+def test_multi_step_call_equals_single_steps(case):
+    """One C-ABI call for the whole run (persistent kernel over many steps) gives bit-identical
+    results to step-by-step calls."""
+    g = Golden(case)
+    A, Bm = make_learner(g), make_learner(g)
+    sa = [A.train_steps(1)[0] for _ in range(g.steps)]
+    sb = Bm.train_steps(g.steps)
+    assert sa == sb
+    assert np.array_equal(A.get_weights(), Bm.get_weights())
+    assert np.array_equal(A.read_field("QRET"), Bm.read_field("QRET"))
+    assert np.array_equal(A.read_field("RHO"), Bm.read_field("RHO"))
+    _check_final(Bm, g.ref)
+    A.close(); Bm.close()
+
+
+def test_two_kernel_mode_equals_persistent(monkeypatch):
+    g = Golden("vracer_small")
+    A = make_learner(g)
+    monkeypatch.setenv("SMB200_MODE", "two")
+    Bm = make_learner(g)
+    monkeypatch.delenv("SMB200_MODE")
+    sa, sb = A.train_steps(g.steps), Bm.train_steps(g.steps)
+    assert sa == sb
+    assert np.array_equal(A.get_weights(), Bm.get_weights())
+    A.close(); Bm.close()
+
+
+@pytest.mark.parametrize("case", ["vracer_small", "vracer_bounded"])
+def test_injected_samples_and_oracle_flags(case):
+    """Feed the oracle's samples to the GPU step by step; with the SAME network outputs the
+    far-policy flags and rho must agree: compare the oracle evaluated on the GPU's own outputs."""
+    import vracer_oracle as vo
+    g = Golden(case)
+    L, o = make_learner(g), make_oracle(g)
+    for s in range(g.steps):
+        seq, obs = o.sample()
+        beta, cmax, cinv = o.beta, o.cmax, o.cinv
+        eps = [o.episodes[int(k)] for k in seq]
+        act = np.stack([e.A[int(t)] for e, t in zip(eps, obs)])
+        mu = np.stack([e.MU[int(t)] for e, t in zip(eps, obs)])
+        qret = np.array([e.Q[int(t)] for e, t in zip(eps, obs)], np.float32)
+        rows_before = L.read_field("RHO")
+        st = L.train_step_on(seq, obs)
+        O, gg, _ = L.get_last_batch()
+        r = vo.vracer_sample_math(O, act, mu, qret, beta, cmax, cinv, o.bounded)
+        # output gradient of the GPU == oracle math on the GPU's outputs (f64 -> f32)
+        assert relerr(gg, r["g"].astype(np.float32)) < 1e-6
+        # importance weights written to the replay rows: bit-exact f32 of the f64 result
+        prefix = np.concatenate([[0], np.cumsum([e.nsteps for e in o.episodes])])
+        idx = prefix[seq] + obs
+        rho_gpu = L.read_field("RHO")[idx]
+        assert np.array_equal(rho_gpu, r["rho"].astype(np.float32))
+        o.train_step(seq, obs)
+        assert st["n_far_policy"] == o.n_far_policy
+        assert st["beta"] == pytest.approx(o.beta, rel=1e-12)
+    L.close()
+
+
+def test_forward_matches_oracle():
+    import vracer_oracle as vo
+    g = Golden("vracer_cfg2mini")
+    L, o = make_learner(g), make_oracle(g)
+    rng = np.random.default_rng(0)
+    S = rng.standard_normal((37, g.dS)).astype(np.float32)
+    X = ((S - o.state_mean) * o.state_scale).astype(np.float32)
+    O_ref, _ = o.net.forward(o.W, X)
+    assert np.abs(L.forward(S) - O_ref).max() < TOL_O
+    L.close()

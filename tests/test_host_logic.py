@@ -1,0 +1,71 @@
+"""CPU: settings surface, C-ABI library loads and exports every declared symbol (no compute
+calls without a GPU), struct layout agreement between ctypes and the C header."""
+import ctypes as C
+import math
+import os
+import re
+
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_hyperparameters_defaults_match_reference_code_defaults():
+    from smarties_b200 import HyperParameters
+    hp = HyperParameters(32, 8, {})
+    assert hp.learner == "VRACER" and hp.batchSize == 256 and hp.nnLayerSizes == [128, 128]
+    assert hp.gamma == 0.995 and hp.lambda_ == 1 and hp.penalTol == 0.1 and hp.epsAnneal == 5e-7
+    assert hp.clipImpWeight == math.sqrt(8 / 2.0)                      # HyperParameters.h:46
+    assert hp.maxTotObsNum == int(2 ** 14 * math.sqrt(40))             # HyperParameters.h:53
+    assert hp.minTotObsNum == hp.maxTotObsNum                           # HyperParameters.cpp:191
+    assert hp.outWeightsPrefac == 1e-3 and hp.nnFunc == "Tanh"
+    assert hp.returnsEstimator == "retrace"                             # AlgoFactory.cpp:134-136
+
+
+def test_hyperparameters_distributed_split():
+    from smarties_b200 import HyperParameters
+    hp = HyperParameters(32, 8, {"maxTotObsNum": 8388608})
+    hp.define_distributed_learning(8)
+    assert hp.batchSize_local == 32 and hp.maxTotObsNum_local == 1048576
+
+
+def test_settings_file_of_reference_parses():
+    from smarties_b200 import HyperParameters
+    hp = HyperParameters(4, 1, {"learner": "VRACER", "dataSamplingAlgo": "uniform", "returnsEstimator": "retrace",
+                                "ERoldSeqFilter": "oldest", "nnLayerSizes": [128, 128]})   # settings/VRACER.json
+    assert hp.nnLayerSizes == [128, 128]
+    with pytest.raises(NotImplementedError):
+        HyperParameters(4, 1, {"learner": "PPO"})
+    with pytest.raises(KeyError):
+        HyperParameters(4, 1, {"notAKey": 1})
+
+
+def test_library_exports_every_declared_symbol(built_library):
+    from smarties_b200 import EXPORTS, load_library
+    header = open(os.path.join(ROOT, "include", "smarties_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(smb200_[a-z_0-9]+)\s*\(", header)))
+    assert declared == sorted(EXPORTS)
+    lib = load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_config_struct_layout_and_defaults(built_library):
+    from smarties_b200 import load_library
+    from smarties_b200.learner import Config
+    lib = load_library()
+    cfg = Config()
+    assert lib.smb200_default_config(C.byref(cfg), 32, 8) == 0
+    assert (cfg.dim_state, cfg.dim_action, cfg.n_hidden, cfg.hidden[0], cfg.hidden[1]) == (32, 8, 2, 128, 128)
+    assert cfg.batch_size == 256 and cfg.max_tot_obs == int(2 ** 14 * math.sqrt(40))
+    assert cfg.gamma == 0.995 and cfg.clip_imp_weight == 2.0 and cfg.seed == 42 and cfg.world_size == 1
+    assert abs(cfg.nn_lambda - 1.1920928955078125e-07) < 1e-20
+
+
+def test_no_gpu_fails_loudly(built_library):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from smarties_b200 import Learner, SmartiesB200Error
+    with pytest.raises(SmartiesB200Error, match="no CPU fallback"):
+        Learner(6, 3, {"nnLayerSizes": [32, 32], "batchSize": 16, "maxTotObsNum": 2048})

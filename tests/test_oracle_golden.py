@@ -1,0 +1,60 @@
+"""CPU: the numpy oracle (oracle/vracer_oracle.py) against golden vectors produced by the
+reference itself (tests/golden/*.npz, generator tests/golden/make_golden.py).
+
+Tolerances: the reference is built with -ffast-math (vectorised approximate sqrt/div in Adam,
+libmvec exp in tanh) and sums in a different association than numpy, so floats agree to f32
+round-off; sampled indices, far-policy counts and the ReF-ER coefficient are exact."""
+import numpy as np
+import pytest
+
+from parity_utils import CASES, Golden, make_oracle, relerr
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_matches_reference(case):
+    g = Golden(case)
+    o = make_oracle(g)
+    R = g.ref
+    # initializeLearner: scaling, Retrace after rescale, beta
+    assert np.array_equal(o.state_mean, R["init/stateMean"])
+    assert np.allclose(o.state_scale, R["init/stateScale"], rtol=1e-6, atol=0)
+    assert np.allclose([o.rew_mean, o.rew_scale], R["init/rewards"][:2], rtol=1e-6)
+    assert np.allclose(o.concat("Q"), R["init/Qret"], rtol=1e-6, atol=1e-6)
+    assert o.beta == R["init/refer"][0]
+    for s in range(g.steps):
+        r = o.train_step()
+        pre = f"s{s}"
+        # sampled indices: bit-exact
+        assert np.array_equal(r["obs"], R[pre + "/sampledT"])
+        ids_now = np.array([o_ep for o_ep in R[pre + "/sampledEpID"]])
+        assert len(ids_now) == g.B
+        assert np.abs(r["O"] - R[pre + "/O"]).max() < 2e-6
+        assert relerr(r["g"], R[pre + "/g"]) < 2e-5
+        if pre + "/gradSum" in R:
+            assert relerr(r["gradSum"], R[pre + "/gradSum"]) < 2e-5
+            assert np.abs(o.W - R[pre + "/weights"]).max() < 2e-6
+        ref = g.refer(pre + "/post")
+        assert o.beta == pytest.approx(ref[0], rel=1e-12)
+        assert o.cmax == pytest.approx(ref[1], rel=1e-15)
+        assert o.n_far_policy == int(ref[3])                       # integer far-policy count: exact
+        assert [e.ID for e in o.episodes] == list(R[pre + "/post/epID"])
+    assert np.allclose(o.concat("Q"), R["final/Qret"], rtol=1e-5, atol=1e-5)
+    assert np.allclose(o.concat("V"), R["final/V"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(o.concat("rho"), R["final/rho"], rtol=1e-5)
+    assert np.allclose(o.concat("KL"), R["final/KL"], rtol=1e-4, atol=1e-7)
+    assert np.allclose(o.concat("delta"), R["final/delta"], rtol=1e-5, atol=1e-5)
+    assert np.allclose(o.state_mean, R["final/stateMean"], atol=1e-7)
+    assert np.allclose(o.state_scale, R["final/stateScale"], rtol=1e-6)
+    agg = np.array([[e.avgKL, e.fracFar, e.avgSqErr, e.maxAbsErr, e.sumQ2, e.sumQ, e.maxQ, e.minQ] for e in o.episodes])
+    assert np.allclose(agg, R["final/epAgg"][:, :8], rtol=1e-4, atol=1e-5)
+
+
+def test_sampler_is_libstdcxx_uniform_int():
+    """std::mt19937(5489) first outputs are the published MT19937 known-answer values; Lemire's
+    reduction is what libstdc++ 13 uses for 32-bit URNGs (bits/uniform_int_dist.h)."""
+    import vracer_oracle as vo
+    gen = vo.Mt19937(5489)
+    assert [gen() for _ in range(3)] == [3499211612, 581869302, 3890346734]
+    gen = vo.Mt19937(7)
+    ids = vo.sample_uniform(gen, 925, 16)
+    assert len(ids) == 16 and np.all(np.diff(ids) > 0) and ids.min() >= 0 and ids.max() < 925
