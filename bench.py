@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py — V-RACER learner throughput (transitions/s updated) on the BASELINE.json workload.
+
+    python bench.py --gpus N --steps K --warmup W          # our arm (CUDA, through the C-ABI)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path
+
+Workload (BASELINE.json configs[1], SURVEY.md §8d "cfg2"): synthetic MemoryBuffer of 1 000 000
+transitions (1000 episodes x 1000 steps, every 10th terminal), state_dim 32, act_dim 8,
+MLP(128,128), settings/VRACER.json defaults (batchSize 256, ...).  One "step" = one learner
+step {sample -> gather -> forward -> ReF-ER/Retrace loss -> backward -> Adam -> replay
+statistics}, INCLUDING the every-1000-steps full-buffer Retrace + reward/state-moment sweeps.
+
+value  = batch x K / device time (CUDA events on the library's stream, sampled transition ids
+         already resident in HBM, max over ranks);
+e2e    = the same through smb200_train_steps with HOST buffers: the sampled ids are produced on
+         host cores by the bit-exact std::mt19937 sampler and copied H2D, per-step statistics are
+         copied D2H, all inside the timed region (wall clock, barrier on both sides).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(name="cfg2: 1M-transition synthetic replay, state_dim=32 act_dim=8, MLP(128,128), VRACER.json, batch 256",
+                n_ep=1000, ep_len=1000, dS=32, dA=8, seed=123)
+SETTINGS = {"learner": "VRACER", "dataSamplingAlgo": "uniform", "returnsEstimator": "retrace", "ERoldSeqFilter": "oldest",
+            "nnLayerSizes": [128, 128], "maxTotObsNum": 1048576, "minTotObsNum": 1000000}
+BATCH = 256
+N_PARAMS = 23064
+# algorithmic bytes
+BYTES_PER_TRANSITION = 268                      # replay read 248 B + write-back 20 B
+BYTES_ADAM_PER_STEP = 7 * 4 * N_PARAMS          # w,m,v,g read + w,m,v written
+BYTES_RETRACE_PER_TRANSITION = 24               # r,V,A,rho,Q read + Q written
+BYTES_MOMENTS_PER_TRANSITION = (32 + 1) * 4
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.idx, self.lines, self.p = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.p.stdout], daemon=True).start()
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(rank=0):
+    from smarties_b200 import synth
+    w = WORKLOAD
+    return synth.make_replay(w["seed"] + rank, w["n_ep"], w["ep_len"], w["dS"], w["dA"])
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own CPU implementation (oracle/_ref)
+# ------------------------------------------------------------------------------------------
+def run_reference(steps, threads, data=None, reps=1):
+    """Times `steps` learner steps of the UNMODIFIED reference (oracle/_ref/ref_harness, built from
+    /root/reference by oracle/Makefile) on this box's host cores.  Falls back to the numpy oracle
+    port if the harness binary is absent."""
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    from smarties_b200 import synth
+    if data is None:
+        data = make_workload()
+    if os.path.exists(harness):
+        with tempfile.TemporaryDirectory() as tmp:
+            synth.write_replay_file(os.path.join(tmp, "data.bin"), data)
+            with open(os.path.join(tmp, "settings.json"), "w") as f:
+                json.dump(SETTINGS, f)
+            env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="close")
+            out = subprocess.run([harness, "--data", "data.bin", "--settings", "settings.json", "--steps", str(steps),
+                                  "--threads", str(threads), "--sampleSeed", "7", "--quiet", "--reps", str(reps)],
+                                 cwd=tmp, env=env, check=True, capture_output=True, text=True).stdout
+        line = [l for l in out.splitlines() if l.startswith('{"harness"')][-1]
+        r = json.loads(line)
+        return dict(value=r["transitions_per_s"], seconds=r["seconds_mean"], steps=steps, kind="reference", cores=threads,
+                    sample=f"{steps} learner steps of the same workload (1M-transition buffer, batch 256, sweeps every 1000 steps) "
+                           f"by the unmodified reference built -O3 -ffast-math -DSINGLE_PREC, {threads} OpenMP threads")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import vracer_oracle as vo
+    o = vo.VracerOracle(32, 8, batch=BATCH, max_tot_obs=1048576)
+    rng = np.random.default_rng(0)
+    o.W[:] = (0.05 * rng.standard_normal(o.layout.n_params)).astype(np.float32)
+    small = {k: (v[:50] if k in ("N", "term", "start") else v) for k, v in data.items()}
+    o.load_replay(small)
+    o.initialize_learner()
+    n = max(1, min(steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        o.train_step()
+    dt = time.perf_counter() - t0
+    return dict(value=BATCH * n / dt, seconds=dt, steps=n, kind="port", cores=1,
+                sample=f"{n} learner steps of the numpy oracle port on a 50-episode slice (reference harness binary absent)")
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps = min(args.steps, 20000)
+    if args.warmup:
+        pass  # the harness warms up during initializeLearner; warm-up steps are folded into the timed run's first steps
+    r = run_reference(steps, threads)
+    out = {"impl": "reference", "metric": "V-RACER learner transitions/sec updated", "value": r["value"], "unit": "transitions/s",
+           "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / r["steps"],
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": WORKLOAD["name"], "batch": BATCH, "host_threads": threads},
+           "cpu_baseline": {"value": r["value"], "unit": "transitions/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+           "e2e": {"value": r["value"], "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def flush_l2(torch, dev):
+    buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    buf.fill_(1.0)
+    torch.cuda.synchronize(dev)
+    del buf
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10000)
+    ap.add_argument("--warmup", type=int, default=1000)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=6000)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    from smarties_b200 import Learner
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        sys.exit("bench.py: no CUDA device — smarties_b200 has no CPU fallback")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    data = make_workload(rank)
+    settings = dict(SETTINGS)
+    if world > 1:  # weak scaling: every rank keeps a 1M-transition shard and a 256-sample local batch
+        settings["maxTotObsNum"] = SETTINGS["maxTotObsNum"] * world
+        settings["minTotObsNum"] = SETTINGS["minTotObsNum"] * world
+        settings["batchSize"] = BATCH * world
+    L = Learner(32, 8, settings, device=local, seed=42 + rank, world_rank=rank, world_size=world)
+    if world > 1:
+        L.attach_process_group(dist)
+    L.load_replay(data)
+    L.initialize_learner()
+    L.seed_sampler(7 + rank)
+    K, W = args.steps, args.warmup
+    # the first learner step also applies the FIFO ordering of the episode table
+    # (applyEpisodesRemovalAlgo sorts by ID); the resident-ids path needs that steady state
+    L.train_steps(1, want_stats=False)
+
+    # ---- value: device time, sampled ids resident in HBM ----
+    L.presample(W + K)
+    L.train_presampled(0, W)
+    L.sync()
+    barrier()
+    clocks = ClockSampler(local); clocks.start()
+    barrier()
+    L.train_presampled(W, K)
+    L.sync()
+    barrier()
+    ms, launches = L.last_timing()
+    ck = clocks.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = BATCH * world * K / (ms_max * 1e-3)
+
+    # ---- e2e: host sampler + H2D ids + D2H stats inside the timed region ----
+    L.train_steps(W, want_stats=True)
+    barrier()
+    t0 = time.perf_counter()
+    stats = L.train_steps(K, want_stats=True)
+    barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e = BATCH * world * K / float(t.item())
+
+    # ---- roofline of the dominant kernel (the persistent step kernel): one launch, no sweep inside ----
+    gs = stats[-1]["grad_step"]
+    n_roof = int(min(512, 999 - (gs % 1000))) if (gs % 1000) < 900 else 64
+    n_roof = max(n_roof, 8)
+    L.presample(n_roof)
+    flush_l2(torch, dev)
+    L.train_presampled(0, n_roof)
+    L.sync()
+    ms_k, _ = L.last_timing()
+    peaks, which = measured_peaks()
+    step_bytes = BYTES_PER_TRANSITION * BATCH + BYTES_ADAM_PER_STEP
+    achieved = step_bytes * n_roof / (ms_k * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "k_steps_persistent", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": which,
+            "algorithmic_bytes_per_launch": step_bytes * n_roof, "launch_ms": ms_k, "steps_per_launch": n_roof,
+            "note": "B=256 step is dependency/latency bound (2 grid barriers per step), not bandwidth bound"}
+    # the HBM-streaming sweeps, timed alone with a flushed L2
+    sweeps = {}
+    n_tr = L.n_transitions
+    for name, fn, bpt in (("k_sweep(retrace)", L.retrace_sweep, BYTES_RETRACE_PER_TRANSITION),
+                          ("k_moments", L.reward_state_moments, BYTES_MOMENTS_PER_TRANSITION)):
+        best = None
+        for _ in range(5):
+            flush_l2(torch, dev)
+            fn()
+            m, _ = L.last_timing()
+            best = m if best is None else min(best, m)
+        a = bpt * n_tr / (best * 1e-3) / 1e9
+        sweeps[name] = {"bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": a / peaks["hbm_gbs"],
+                        "ms": best, "algorithmic_bytes": bpt * n_tr}
+
+    if rank == 0:
+        out = {"metric": "V-RACER learner transitions/sec updated", "value": value, "unit": "transitions/s", "n_gpus": world,
+               "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": WORKLOAD["name"], "batch_per_gpu": BATCH, "global_batch": BATCH * world,
+                          "l2_policy": "replay buffer (252 MB/GPU) larger than L2; sampled rows are random",
+                          "mode": os.environ.get("SMB200_MODE", "persistent"), "parallelism": f"dp{world}"},
+               "clocks": ck,
+               "e2e": {"value": e2e, "unit": "transitions/s", "h2d_bytes_per_step": 2 * 4 * BATCH, "d2h_bytes_per_step": 128},
+               "gpu_launches": int(launches),
+               "roofline": roof, "roofline_sweeps": sweeps,
+               "final_stats": {k: stats[-1][k] for k in ("beta", "cmax", "n_far_policy", "grad_step")}}
+        if world == 1 and not args.no_cpu_baseline:
+            r = run_reference(args.cpu_steps, os.cpu_count() or 1, data=data)
+            out["cpu_baseline"] = {"value": r["value"], "unit": "transitions/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+        print(json.dumps(out))
+    L.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

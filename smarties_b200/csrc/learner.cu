@@ -357,6 +357,8 @@ static int run_segment(smb200_learner* h, int first, int n, long long gstep0, in
 // =============================================================================================
 extern "C" {
 
+static int ensure_seg_capacity(smb200_learner* h, int n);
+
 const char* smb200_last_error(void) { return g_err.c_str(); }
 
 int smb200_default_config(smb200_config* c, int32_t dS, int32_t dA) {
@@ -440,11 +442,8 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
   CK(dev_alloc(&h->dCtrl, 2)); CK(dev_alloc(&h->dRec, (size_t)B));
   CK(dev_alloc(&h->lastO, (size_t)B * net.nOut)); CK(dev_alloc(&h->lastG, (size_t)B * net.nOut)); CK(dev_alloc(&h->lastX, (size_t)B * dS));
   CK(dev_alloc(&h->dSums, 1)); CK(dev_alloc(&h->dBarrier, 4));
-  CK(dev_alloc(&h->dSampSlot, (size_t)h->maxSeg * B)); CK(dev_alloc(&h->dSampT, (size_t)h->maxSeg * B));
-  CK(dev_alloc(&h->dStats, (size_t)h->maxSeg));
-  CKC(cudaMallocHost(&h->hSampSlot, sizeof(int) * (size_t)h->maxSeg * B));
-  CKC(cudaMallocHost(&h->hSampT, sizeof(int) * (size_t)h->maxSeg * B));
-  CKC(cudaMallocHost(&h->hStats, sizeof(smb200_step_stats) * (size_t)h->maxSeg));
+  h->maxSeg = 0;
+  CK(ensure_seg_capacity(h, 1024));
 
   // MemoryBuffer.h:41-44 initial ReF-ER state; AdamOptimizer beta powers (Optimizer.h:93)
   StepCtrl& k = h->hCtrl; memset(&k, 0, sizeof(k));
@@ -637,6 +636,28 @@ int smb200_sample(smb200_learner* h, int64_t* pos, int64_t* t) {
   return 0;
 }
 
+// (re)allocate the per-step sample / statistics buffers for segments of up to `n` steps
+static int ensure_seg_capacity(smb200_learner* h, int n) {
+  if (n <= h->maxSeg && h->dSampSlot) return 0;
+  const int B = h->cfg.batch_size;
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->dSampSlot) cudaFree(h->dSampSlot);
+  if (h->dSampT) cudaFree(h->dSampT);
+  if (h->dStats) cudaFree(h->dStats);
+  if (h->hSampSlot) cudaFreeHost(h->hSampSlot);
+  if (h->hSampT) cudaFreeHost(h->hSampT);
+  if (h->hStats) cudaFreeHost(h->hStats);
+  h->dSampSlot = h->dSampT = nullptr; h->dStats = nullptr; h->hSampSlot = h->hSampT = nullptr; h->hStats = nullptr;
+  h->maxSeg = std::max(n, 1024);
+  if (dev_alloc(&h->dSampSlot, (size_t)h->maxSeg * B) || dev_alloc(&h->dSampT, (size_t)h->maxSeg * B) ||
+      dev_alloc(&h->dStats, (size_t)h->maxSeg)) return -2;
+  SMB200_CUDA_CHECK(cudaMallocHost(&h->hSampSlot, sizeof(int) * (size_t)h->maxSeg * B));
+  SMB200_CUDA_CHECK(cudaMallocHost(&h->hSampT, sizeof(int) * (size_t)h->maxSeg * B));
+  SMB200_CUDA_CHECK(cudaMallocHost(&h->hStats, sizeof(smb200_step_stats) * (size_t)h->maxSeg));
+  h->presampled = 0;
+  return 0;
+}
+
 // samples + host bookkeeping for up to `n` steps; fills pinned arrays from index 0 and returns
 // how many steps can run as one device segment (constant episode table, sweep only at the end)
 static int plan_segment(smb200_learner* h, int n) {
@@ -720,8 +741,9 @@ int smb200_train_step_on(smb200_learner* h, const int64_t* pos, const int64_t* t
 }
 
 int smb200_presample(smb200_learner* h, int32_t n) {
-  if (!h || n < 1 || n > h->maxSeg) return SMB200_ERR_INVALID;
+  if (!h || n < 1) return SMB200_ERR_INVALID;
   cudaSetDevice(h->cfg.device);
+  if (ensure_seg_capacity(h, n)) return SMB200_ERR_CUDA;
   // benchmark path: the episode table must be in its steady (sorted, un-pruned) state
   const int B = h->cfg.batch_size;
   for (int i = 0; i < n; ++i) {

@@ -300,6 +300,7 @@ int launch_moments(const ReplayView& rp, long long rowEnd, SweepSums* sums, int 
   const long long nTiles = (rowEnd + kMomRows - 1) / kMomRows;
   long long blocks = nTiles < (long long)numSMs * 8 ? nTiles : (long long)numSMs * 8;
   if (blocks < 1) blocks = 1;
+  if (sm > 48 * 1024) SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_moments, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   k_moments<<<(int)blocks, kThreads, sm, st>>>(rp, rowEnd, sums);
   SMB200_CUDA_CHECK(cudaGetLastError());
   return 0;

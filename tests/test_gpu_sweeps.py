@@ -39,7 +39,8 @@ def test_retrace_sweep_ragged_episodes(shape):
     mean, scale, std, rew = L.get_scaling()
     V, ADV, RHO = L.read_field("V"), L.read_field("ADV"), L.read_field("RHO")
     q_ref = _retrace_numpy(d, V, ADV, RHO, rew[0], rew[1])
-    assert np.allclose(L.read_field("QRET"), q_ref, rtol=1e-5, atol=1e-5)
+    # the warp-scan composes 32 steps at a time: a few ulp(|Q|max) per chunk, geometric decay
+    assert np.allclose(L.read_field("QRET"), q_ref, rtol=1e-5, atol=5e-5)
     # idempotence: a second sweep over unchanged V/rho changes nothing
     q1 = L.read_field("QRET")
     err2 = L.retrace_sweep()
@@ -97,7 +98,7 @@ def test_full_size_buffer_properties():
     q = np.zeros(N, np.float32)
     for t in range(N - 2, -1, -1):
         q[t] = rs[t + 1] + np.float32(0.995) * q[t + 1]
-    assert np.allclose(q1[o:o + N], q, rtol=2e-5, atol=2e-5)
+    assert np.allclose(q1[o:o + N], q, rtol=2e-5, atol=5e-5)
     # a few learner steps on the full buffer run and keep the integer counters consistent
     st = L.train_steps(3)
     assert st[-1]["grad_step"] == 3 and 0 <= st[-1]["n_far_exact"] <= 3 * 256
