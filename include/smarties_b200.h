@@ -164,6 +164,9 @@ int smb200_last_timing(smb200_learner* h, double* ms_device, int64_t* kernel_lau
 int smb200_presample(smb200_learner* h, int32_t n_steps);
 int smb200_train_presampled(smb200_learner* h, int32_t first, int32_t n);
 int smb200_sync(smb200_learner* h);
+/* Diagnostics: n presampled steps in one persistent launch with per-CTA phase timestamps
+ * (SM clock cycles), out[n][grid][8]; *grid_out = CTAs of the persistent grid. */
+int smb200_profile_phases(smb200_learner* h, int32_t n, int64_t* out, int64_t capacity, int32_t* grid_out);
 
 #ifdef __cplusplus
 }

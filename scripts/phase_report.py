@@ -1,0 +1,52 @@
+"""Phase timing of the persistent step kernel on the cfg2 workload (SM clock cycles -> us at the
+reported SM clock).  Markers: 0 step start, 1 gather done, 2 forward done, 3 loss done,
+4 backward done, 5 P1 done (scratch written), 6 after barrier 1, 7 P2/P3 done."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+from smarties_b200 import Learner, synth  # noqa: E402
+
+n_ep = int(os.environ.get("PROF_NEP", "1000"))
+n = int(os.environ.get("PROF_STEPS", "200"))
+mhz = float(os.environ.get("SM_MHZ", "1965"))
+d = synth.make_replay(123, n_ep, 1000, 32, 8)
+L = Learner(32, 8, {"maxTotObsNum": 1048576, "minTotObsNum": 1000 * n_ep})
+L.load_replay(d)
+L.initialize_learner()
+L.seed_sampler(7)
+L.train_steps(1, want_stats=False)
+L.presample(n)
+L.train_presampled(0, 50); L.sync()
+T, ms = L.profile_phases(n)
+print(f"{n} steps in {ms:.3f} ms -> {1e3 * ms / n:.2f} us/step, grid {T.shape[1]}")
+T = T[20:]                       # skip the first steps
+nP1 = 64
+p1 = T[:, :nP1, :]
+us = lambda c: c / mhz
+seg = [("start->gather", 0, 1), ("forward", 1, 2), ("loss", 2, 3), ("backward", 3, 4), ("scratch write", 4, 5),
+       ("barrier1 wait", 5, 6), ("P2 (tile+adam)", 6, 7)]
+for name, a, b in seg:
+    dlt = p1[:, :, b] - p1[:, :, a]
+    print(f"  P1 CTAs {name:16s} mean {us(dlt.mean()):6.2f} us  max-over-CTAs mean {us(dlt.max(axis=1).mean()):6.2f}")
+fine = [("fwd L1 wait W", 9, 27), ("fwd L1 compute", 27, 10), ("fwd L2 wait W", 10, 28), ("fwd L2+res", 28, 12), ("fwd L4 wait W", 12, 30), ("fwd L4 out", 30, 13), ("fwd L5 param", 13, 2),
+        ("loss stage1", 2, 8), ("loss stage2", 8, 16), ("loss stage3", 16, 3),
+        ("bwd L4 out", 20, 18), ("bwd L2+res", 18, 17), ("bwd L1", 17, 4),
+        ("P2 desc+issue", 6, 24), ("P2 tile load", 24, 25), ("P2 contraction", 25, 26), ("P2 adam+store", 26, 7)]
+for name, a, b in fine:
+    dlt = p1[:, :, b] - p1[:, :, a]
+    print(f"     {name:14s} {us(dlt.mean()):6.2f} us")
+oth = T[:, nP1:-1, :]
+if oth.shape[1]:
+    dlt = oth[:, :, 7] - oth[:, :, 6]
+    print(f"  tile-only workers P2: mean {us(dlt.mean()):.2f} us")
+st = T[:, -1, :]
+print(f"  statistics CTA (async P3): {us((st[:, 7] - st[:, 6]).mean()):.2f} us per step")
+nxt = T[1:, :-1, 0] - T[:-1, :-1, 7]
+print(f"  barrier2 wait (P2 end -> next step start): mean {us(nxt.mean()):.2f} us")
+per = T[1:, 0, 0] - T[:-1, 0, 0]
+print(f"  step period (CTA 0): {us(per.mean()):.2f} us")
+L.close()

@@ -23,9 +23,12 @@ struct LayerDesc {
   int size;        // number of neurons = size of this layer's activation
   int nIn;         // dense: fan-in
   int ld;          // dense: row stride of W[nIn][ld] (roundUp8(size), Layer_Base.h:46)
-  int ldt;         // dense: row stride of the transposed copy WT[size][ldt]
   int wOff, bOff;  // offsets into the padded parameter blob (Parameters.h:159-176)
-  int wtOff;       // offset into the transposed-weights blob, -1 if no input gradient needed
+  int needDx;      // 1 if the backward pass propagates into this layer's input (not the first layer)
+  int imgW, imgB;  // offsets into the weight IMAGE (the shared-memory layout, see NetDesc::imgFloats)
+  int ldp;         // dense: row stride of W in the image = roundUp4(size) + 4 (bank-conflict-free both ways)
+  int fwdShift;    // dense: log2 of the thread-group width of the forward pass  (power of two >= min(size, threads))
+  int bwdShift;    // dense: log2 of the thread-group width of the input-gradient pass (>= min(nIn, threads))
   int in;          // id of the input layer (ID - link); residual: ID-1 and ID-2 implied
   int actOff;      // offset (in floats per sample) of this layer's activation in act buffers
 };
@@ -33,7 +36,7 @@ struct LayerDesc {
 struct NetDesc {
   int nLayers;
   int nParams;       // padded blob size
-  int nParamsT;      // transposed blob size
+  int imgFloats;     // size of the weight image (multiple of 4 floats)
   int nOut;          // network outputs (dense-out + param layer)
   int nOutDense;     // outputs of the linear output layer
   int dS, dA;
@@ -57,6 +60,7 @@ struct StepCtrl {
   long long adam_step;                // AdamOptimizer::nStep BEFORE this step's prepare_update
   long long grad_step;                // counters.nGradSteps before this step
   long long n_far_ref, n_far_exact;   // stats.nFarPolicySteps (reference formula) / exact flags
+  float adam_eta; float pad_;         // learning rate of THIS step incl. bias correction (struct Adam ctor, Optimizer.cpp:64-67)
   double avg_kl, avg_sq_err, max_abs_err, avg_return, stdev_q, avg_q, max_q, min_q;
   double sum_ret_err; long long cnt_ret;
 };
@@ -83,11 +87,10 @@ enum { AGG_KL = 0, AGG_FAR = 1, AGG_E2 = 2, AGG_MAXE = 3, AGG_Q2 = 4, AGG_Q1 = 5
 
 // Per-sample record written by the loss phase and consumed by the statistics phase
 // (Episode::updateCumulative_atomic / updateValues_atomic, Episode.h:112-145).
-struct SampleRec {
-  int slot; int hasNext;
+struct __align__(16) SampleRec {
+  int slot; int hasNext; int farDelta; int pad;
   float dKL, dFar, dE2, absE;
   float qOld, qNew, qNextOld, qNextNew;
-  int farDelta; int pad;
 };
 
 struct Hyper {

@@ -63,6 +63,7 @@ struct smb200_learner {
   int persistGrid = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t evDone[2] = {nullptr, nullptr};   // pipeline: segment buffers free again
 
   // replay
   ReplayView rp{};
@@ -74,7 +75,8 @@ struct smb200_learner {
   bool orderDirty = true;
 
   // network / optimiser
-  float *W = nullptr, *WT = nullptr, *M1 = nullptr, *M2 = nullptr, *G = nullptr;
+  float *W = nullptr, *Wimg = nullptr, *M1 = nullptr, *M2 = nullptr, *G = nullptr;
+  long long* dDbg = nullptr; int useTma = 1;
   float *actG = nullptr, *errG = nullptr;
   GradTile* dTiles = nullptr; int nTiles = 0;
   int Bpad = 0;
@@ -101,8 +103,8 @@ struct smb200_learner {
 
   StepArgs args() const {
     StepArgs a{};
-    a.descs = dDescs; a.rp = rp; a.W = W; a.WT = WT; a.M1 = M1; a.M2 = M2; a.G = G;
-    a.actG = actG; a.errG = errG; a.sampSlot = dSampSlot; a.sampT = dSampT; a.rec = dRec;
+    a.descs = dDescs; a.rp = rp; a.W = W; a.Wimg = Wimg; a.M1 = M1; a.M2 = M2; a.G = G; a.dbgT = nullptr; a.useTma = useTma;
+    a.actG = actG; a.errG = errG; a.sampRow = dSampT; a.sampSlot = dSampSlot; a.rec = dRec;
     a.lastO = lastO; a.lastG = lastG; a.lastX = lastX; a.ctrl = dCtrl; a.statsOut = dStats;
     a.tiles = dTiles; a.nTiles = nTiles; a.B = cfg.batch_size; a.Bpad = Bpad;
     a.nEpisodes = (int)episodes.size(); a.nTransitions = nTransitions; a.nTransitionsPost = nTransitions;
@@ -120,10 +122,17 @@ static int build_net(const smb200_config& c, NetDesc& net, std::vector<GradTile>
   if (c.algo != SMB200_VRACER) { set_error_msg("only learner VRACER is implemented on the device path"); return -1; }
   if (dS < 1 || dA < 1 || dA > SMB200_MAX_ACTION || c.n_hidden < 1 || c.n_hidden > SMB200_MAX_HIDDEN) {
     set_error_msg("unsupported dimensions"); return -1; }
-  int off = 0, offT = 0, act = 0, id = 0, width = dS;
+  int off = 0, img = 0, act = 0, id = 0, width = dS;
   auto add = [&](int kind, int size) -> LayerDesc& {
-    LayerDesc& L = net.L[id]; L.kind = kind; L.size = size; L.actOff = act; L.wtOff = -1; L.in = id - 1;
+    LayerDesc& L = net.L[id]; L.kind = kind; L.size = size; L.actOff = act; L.needDx = 0; L.in = id - 1;
     act += round_up(size, 4); width = std::max(width, size); ++id; return L; };
+  // weight image (shared-memory layout): dense rows padded to roundUp4(size)+4 floats
+  const int NT = step_threads();
+  auto log2_group = [&](int n) { int sh = 3; while ((1 << sh) < std::min(n, NT)) ++sh; return sh; };
+  auto img_dense = [&](LayerDesc& L) {
+    L.fwdShift = log2_group(L.size); L.bwdShift = log2_group(L.nIn);
+    L.ldp = round_up(L.size, 4) + 4;
+    L.imgW = img; img += L.ldp * L.nIn; L.imgB = img; img += round_up(L.size, 4); };
   add(kInput, dS);
   int nIn = dS;
   for (int i = 0; i < c.n_hidden; ++i) {
@@ -132,10 +141,11 @@ static int build_net(const smb200_config& c, NetDesc& net, std::vector<GradTile>
     LayerDesc& L = add(kDenseTanh, h);
     L.nIn = nIn; L.ld = round_up(h, 8);
     L.wOff = off; off += round_up(L.ld * nIn, 8); L.bOff = off; off += round_up(h, 8);
-    if (i > 0) { L.ldt = round_up(nIn, 4); L.wtOff = offT; offT += h * L.ldt; }
+    L.needDx = i > 0; img_dense(L);
     if (i > 0) {   // ParametricResidualLayer after every hidden layer but the first (Builder.cpp:92-95)
       LayerDesc& R = add(kResidual, h);
       R.wOff = off; off += round_up(h, 8); R.bOff = off; off += round_up(h, 8);
+      R.imgW = img; img += round_up(h, 4); R.imgB = img; img += round_up(h, 4);
       if (net.L[id - 3].size < h) { set_error_msg("residual over a narrower layer is not supported"); return -1; }
     }
     nIn = h;
@@ -145,11 +155,12 @@ static int build_net(const smb200_config& c, NetDesc& net, std::vector<GradTile>
     LayerDesc& L = add(kDenseLinear, nOutDense);
     L.nIn = nIn; L.ld = round_up(nOutDense, 8);
     L.wOff = off; off += round_up(L.ld * nIn, 8); L.bOff = off; off += round_up(nOutDense, 8);
-    L.ldt = round_up(nIn, 4); L.wtOff = offT; offT += nOutDense * L.ldt;
+    L.needDx = 1; img_dense(L);
     LayerDesc& P = add(kParam, dA);
     P.bOff = off; off += round_up(dA, 8); P.wOff = off;
+    P.imgB = img; P.imgW = img; img += round_up(dA, 4);
   }
-  net.nLayers = id; net.nParams = off; net.nParamsT = std::max(offT, 4); net.nOut = nOutDense + dA; net.nOutDense = nOutDense;
+  net.nLayers = id; net.nParams = off; net.imgFloats = img; net.nOut = nOutDense + dA; net.nOutDense = nOutDense;
   net.dS = dS; net.dA = dA; net.actPerSample = act; net.maxWidth = width;
   tiles.clear();
   for (int l = 1; l < net.nLayers; ++l) {
@@ -194,15 +205,21 @@ static void init_weights(const smb200_config& c, const NetDesc& net, std::mt1993
 
 static int upload_weights(smb200_learner* h, const float* blob) {
   const NetDesc& net = h->descs.net;
-  std::vector<float> wt(net.nParamsT, 0.f);
+  std::vector<float> im(net.imgFloats, 0.f);
   for (int l = 1; l < net.nLayers; ++l) {
     const LayerDesc& L = net.L[l];
-    if (L.wtOff < 0) continue;
-    for (int k = 0; k < L.nIn; ++k)
-      for (int n = 0; n < L.size; ++n) wt[L.wtOff + n * L.ldt + k] = blob[L.wOff + k * L.ld + n];
+    if (L.kind == kDenseTanh || L.kind == kDenseLinear) {
+      for (int k = 0; k < L.nIn; ++k)
+        for (int n = 0; n < L.size; ++n) im[L.imgW + k * L.ldp + n] = blob[L.wOff + k * L.ld + n];
+      for (int n = 0; n < L.size; ++n) im[L.imgB + n] = blob[L.bOff + n];
+    } else if (L.kind == kResidual) {
+      for (int n = 0; n < L.size; ++n) { im[L.imgW + n] = blob[L.wOff + n]; im[L.imgB + n] = blob[L.bOff + n]; }
+    } else if (L.kind == kParam) {
+      for (int n = 0; n < L.size; ++n) im[L.imgB + n] = blob[L.bOff + n];
+    }
   }
   SMB200_CUDA_CHECK(cudaMemcpyAsync(h->W, blob, sizeof(float) * net.nParams, cudaMemcpyHostToDevice, h->stream));
-  SMB200_CUDA_CHECK(cudaMemcpyAsync(h->WT, wt.data(), sizeof(float) * net.nParamsT, cudaMemcpyHostToDevice, h->stream));
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(h->Wimg, im.data(), sizeof(float) * net.imgFloats, cudaMemcpyHostToDevice, h->stream));
   SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -219,6 +236,7 @@ static int upload_order(smb200_learner* h) {
 }
 
 static int push_ctrl(smb200_learner* h) {
+  h->hCtrl.adam_eta = adam_eta_for(h->cfg.learnrate, h->cfg.eps_anneal, h->hCtrl.adam_step, h->hCtrl.adam_bt1, h->hCtrl.adam_bt2);
   StepCtrl two[2] = {h->hCtrl, h->hCtrl};
   SMB200_CUDA_CHECK(cudaMemcpyAsync(h->dCtrl, two, sizeof(two), cudaMemcpyHostToDevice, h->stream));
   SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
@@ -300,7 +318,12 @@ static void host_sample(smb200_learner* h, int* slotOut, int* tOut, int64_t* pos
   for (size_t k = 0; k < h->episodes.size() && i < (size_t)B; ++k) {
     const size_t nd = h->episodes[k].nRows - 1;
     while (i < (size_t)B && ret[i] < prefix + nd) {
-      if (slotOut) { slotOut[i] = h->episodes[k].slot; tOut[i] = (int)(ret[i] - prefix); }
+      if (slotOut) {   // device form: ring row of (episode, t); slot with Episode::isTruncated(t+1) in bit 31
+        const EpisodeMeta& e = h->episodes[k];
+        const int t = (int)(ret[i] - prefix);
+        const unsigned hn = (t + 2 == e.nRows && !e.terminated) ? 0x80000000u : 0u;
+        slotOut[i] = (int)((unsigned)e.slot | hn); tOut[i] = (int)(e.start + t);
+      }
       if (posOut) { posOut[i] = (int64_t)k; tOut64[i] = (int64_t)(ret[i] - prefix); }
       ++i;
     }
@@ -319,7 +342,7 @@ static double cmax_at(const smb200_learner* h, long long gstep) {
 static int run_segment(smb200_learner* h, int first, int n, long long gstep0, int nEpPre, long long nTrPre, long long nTrPost) {
   StepArgs a = h->args();
   a.sampSlot = h->dSampSlot + (size_t)first * a.B;
-  a.sampT = h->dSampT + (size_t)first * a.B;
+  a.sampRow = h->dSampT + (size_t)first * a.B;
   a.statsOut = h->dStats + first;
   a.nEpisodes = nEpPre; a.nTransitions = nTrPre; a.nTransitionsPost = nTrPost;
   // device-side step index == absolute grad step (its parity selects the ctrl buffer)
@@ -405,6 +428,7 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
   h->numSMs = prop.multiProcessorCount;
   CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CKC(cudaEventCreate(&h->ev0)); CKC(cudaEventCreate(&h->ev1));
+  CKC(cudaEventCreateWithFlags(&h->evDone[0], cudaEventDisableTiming)); CKC(cudaEventCreateWithFlags(&h->evDone[1], cudaEventDisableTiming));
   const NetDesc& net = h->descs.net;
   const int dS = c.dim_state, dA = c.dim_action, B = c.batch_size;
   long long cap = c.capacity_rows > 0 ? c.capacity_rows : c.max_tot_obs + c.max_tot_obs / 8 + 65536;
@@ -430,7 +454,7 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
   h->freeSlots.reserve(maxEp);
   for (int s = maxEp - 1; s >= 0; --s) h->freeSlots.push_back(s);
 
-  CK(dev_alloc(&h->W, (size_t)net.nParams)); CK(dev_alloc(&h->WT, (size_t)net.nParamsT));
+  CK(dev_alloc(&h->W, (size_t)net.nParams)); CK(dev_alloc(&h->Wimg, (size_t)net.imgFloats));
   CK(dev_alloc(&h->M1, (size_t)net.nParams)); CK(dev_alloc(&h->M2, (size_t)net.nParams)); CK(dev_alloc(&h->G, (size_t)net.nParams));
   h->Bpad = round_up(B, 256);
   CK(dev_alloc(&h->actG, (size_t)net.actPerSample * h->Bpad)); CK(dev_alloc(&h->errG, (size_t)net.actPerSample * h->Bpad));
@@ -457,6 +481,7 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
   init_weights(c, net, h->gen, blob);
   CK(upload_weights(h, blob.data()));
   CK(step_kernels_prepare(net));
+  { const char* t = getenv("SMB200_TMA"); h->useTma = (t && strcmp(t, "0") == 0) ? 0 : 1; }
   const char* m = getenv("SMB200_MODE");
   h->mode = (m && strcmp(m, "two") == 0) ? 0 : 1;
   int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c.device);
@@ -475,7 +500,7 @@ void smb200_destroy(smb200_learner* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   ReplayView& rp = h->rp;
   void* ptrs[] = {rp.S, rp.A, rp.MU, rp.R, rp.V, rp.ADV, rp.Q, rp.DELTA, rp.RHO, rp.KL, rp.rowFlag, rp.epStart, rp.epLen, rp.epTerm,
-                  rp.epId, rp.epAgg, rp.epOrder, rp.stateMean, rp.stateScale, rp.stateStd, rp.rew, h->W, h->WT, h->M1, h->M2, h->G,
+                  rp.epId, rp.epAgg, rp.epOrder, rp.stateMean, rp.stateScale, rp.stateStd, rp.rew, h->W, h->Wimg, h->dDbg, h->M1, h->M2, h->G,
                   h->actG, h->errG, h->dTiles, h->dDescs, h->dCtrl, h->dRec, h->lastO, h->lastG, h->lastX, h->dSums, h->dBarrier,
                   h->dSampSlot, h->dSampT, h->dStats};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -484,6 +509,7 @@ void smb200_destroy(smb200_learner* h) {
   if (h->hStats) cudaFreeHost(h->hStats);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  for (int i = 0; i < 2; ++i) if (h->evDone[i]) cudaEventDestroy(h->evDone[i]);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -660,11 +686,11 @@ static int ensure_seg_capacity(smb200_learner* h, int n) {
 
 // samples + host bookkeeping for up to `n` steps; fills pinned arrays from index 0 and returns
 // how many steps can run as one device segment (constant episode table, sweep only at the end)
-static int plan_segment(smb200_learner* h, int n) {
+static int plan_segment(smb200_learner* h, int n, int off) {
   const int B = h->cfg.batch_size;
   int cnt = 0;
-  while (cnt < n && cnt < h->maxSeg) {
-    host_sample(h, h->hSampSlot + (size_t)cnt * B, h->hSampT + (size_t)cnt * B, nullptr, nullptr);
+  while (cnt < n && off + cnt < h->maxSeg) {
+    host_sample(h, h->hSampSlot + (size_t)(off + cnt) * B, h->hSampT + (size_t)(off + cnt) * B, nullptr, nullptr);
     const long long stepNo = h->gradStep + 1;
     const bool changed = host_post_step(h);
     ++cnt;
@@ -673,10 +699,10 @@ static int plan_segment(smb200_learner* h, int n) {
   return cnt;
 }
 
-static int upload_samples(smb200_learner* h, int cnt) {
-  const size_t bytes = sizeof(int) * (size_t)cnt * h->cfg.batch_size;
-  SMB200_CUDA_CHECK(cudaMemcpyAsync(h->dSampSlot, h->hSampSlot, bytes, cudaMemcpyHostToDevice, h->stream));
-  SMB200_CUDA_CHECK(cudaMemcpyAsync(h->dSampT, h->hSampT, bytes, cudaMemcpyHostToDevice, h->stream));
+static int upload_samples(smb200_learner* h, int off, int cnt) {
+  const size_t bytes = sizeof(int) * (size_t)cnt * h->cfg.batch_size, o = (size_t)off * h->cfg.batch_size;
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(h->dSampSlot + o, h->hSampSlot + o, bytes, cudaMemcpyHostToDevice, h->stream));
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(h->dSampT + o, h->hSampT + o, bytes, cudaMemcpyHostToDevice, h->stream));
   return 0;
 }
 
@@ -687,26 +713,37 @@ int smb200_train_steps(smb200_learner* h, int32_t n, smb200_step_stats* stats) {
   h->presampled = 0;
   const long long l0 = h->launches;
   SMB200_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
+  // Two-deep pipeline: while the GPU runs one segment, the host samples the next one (the sampler
+  // is a sequential std::mt19937 stream and must stay on the host to be bit-exact).
+  const int P = std::min(256, h->maxSeg / 2);
+  int pendCnt[2] = {0, 0}, pendDst[2] = {0, 0};
+  auto reclaim = [&](int b) -> int {
+    if (!pendCnt[b]) return 0;
+    SMB200_CUDA_CHECK(cudaEventSynchronize(h->evDone[b]));
+    if (stats) memcpy(stats + pendDst[b], h->hStats + (size_t)b * P, sizeof(smb200_step_stats) * pendCnt[b]);
+    pendCnt[b] = 0;
+    return 0;
+  };
   int done = 0;
-  while (done < n) {
+  for (int i = 0; done < n; ++i) {
+    const int b = i & 1, off = b * P;
+    if (reclaim(b)) return SMB200_ERR_CUDA;
     const long long g0 = h->gradStep;
     // the order in effect for these steps must reach the device before host_post_step re-sorts
     if (upload_order(h)) return SMB200_ERR_CUDA;
     const int nEpPre = (int)h->episodes.size(); const long long nTrPre = h->nTransitions;
-    const int cnt = plan_segment(h, n - done);
+    const int cnt = plan_segment(h, std::min(n - done, P), off);
     const bool dirtyAfter = h->orderDirty;
-    if (upload_samples(h, cnt)) return SMB200_ERR_CUDA;
-    if (run_segment(h, 0, cnt, g0, nEpPre, nTrPre, h->nTransitions)) return SMB200_ERR_CUDA;
-    if (stats) {
-      SMB200_CUDA_CHECK(cudaMemcpyAsync(h->hStats, h->dStats, sizeof(smb200_step_stats) * cnt, cudaMemcpyDeviceToHost, h->stream));
-      SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
-      memcpy(stats + done, h->hStats, sizeof(smb200_step_stats) * cnt);
-    } else if (done + cnt < n) {
-      SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));   // pinned sample arrays are reused
-    }
+    if (upload_samples(h, off, cnt)) return SMB200_ERR_CUDA;
+    if (run_segment(h, off, cnt, g0, nEpPre, nTrPre, h->nTransitions)) return SMB200_ERR_CUDA;
+    if (stats)
+      SMB200_CUDA_CHECK(cudaMemcpyAsync(h->hStats + off, h->dStats + off, sizeof(smb200_step_stats) * cnt, cudaMemcpyDeviceToHost, h->stream));
+    SMB200_CUDA_CHECK(cudaEventRecord(h->evDone[b], h->stream));
+    pendCnt[b] = cnt; pendDst[b] = done;
     h->orderDirty = dirtyAfter;
     done += cnt;
   }
+  if (reclaim(0) || reclaim(1)) return SMB200_ERR_CUDA;
   SMB200_CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
   SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
@@ -722,14 +759,15 @@ int smb200_train_step_on(smb200_learner* h, const int64_t* pos, const int64_t* t
     if (pos[b] < 0 || pos[b] >= (int64_t)h->episodes.size()) return SMB200_ERR_INVALID;
     const EpisodeMeta& e = h->episodes[pos[b]];
     if (t[b] < 0 || t[b] >= e.nRows - 1) return SMB200_ERR_INVALID;
-    h->hSampSlot[b] = e.slot; h->hSampT[b] = (int)t[b];
+    const unsigned hn = ((int)t[b] + 2 == e.nRows && !e.terminated) ? 0x80000000u : 0u;
+    h->hSampSlot[b] = (int)((unsigned)e.slot | hn); h->hSampT[b] = (int)(e.start + t[b]);
   }
   if (upload_order(h)) return SMB200_ERR_CUDA;
   const long long g0 = h->gradStep;
   const int nEpPre = (int)h->episodes.size(); const long long nTrPre = h->nTransitions;
   host_post_step(h);
   const bool dirtyAfter = h->orderDirty;
-  if (upload_samples(h, 1)) return SMB200_ERR_CUDA;
+  if (upload_samples(h, 0, 1)) return SMB200_ERR_CUDA;
   if (run_segment(h, 0, 1, g0, nEpPre, nTrPre, h->nTransitions)) return SMB200_ERR_CUDA;
   h->orderDirty = dirtyAfter;
   if (stats) {
@@ -750,7 +788,7 @@ int smb200_presample(smb200_learner* h, int32_t n) {
     host_sample(h, h->hSampSlot + (size_t)i * B, h->hSampT + (size_t)i * B, nullptr, nullptr);
     (void)h->gen();   // the Adam update's draw (host_post_step)
   }
-  if (upload_samples(h, n)) return SMB200_ERR_CUDA;
+  if (upload_samples(h, 0, n)) return SMB200_ERR_CUDA;
   SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   h->presampled = n;
   return 0;
@@ -776,6 +814,32 @@ int smb200_train_presampled(smb200_learner* h, int32_t first, int32_t n) {
   }
   SMB200_CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
   h->lastLaunches = h->launches - l0;
+  return 0;
+}
+
+// Diagnostics: run `n` presampled steps in ONE persistent launch with phase timestamps
+// (clock64 of thread 0 of every CTA at 8 markers per step).  out[n][grid][24].
+int smb200_profile_phases(smb200_learner* h, int32_t n, int64_t* out, int64_t capacity, int32_t* grid_out) {
+  if (!h || n < 1 || n > h->presampled || !out || h->mode != 1) return SMB200_ERR_INVALID;
+  const long long g0 = h->gradStep;
+  if ((g0 % 1000) + n >= 1000) return SMB200_ERR_STATE;   // keep the profiled launch free of sweeps
+  const size_t cnt = (size_t)n * h->persistGrid * 48;
+  if ((int64_t)cnt > capacity) return SMB200_ERR_INVALID;
+  cudaSetDevice(h->cfg.device);
+  if (h->dDbg) { cudaFree(h->dDbg); h->dDbg = nullptr; }
+  if (dev_alloc(&h->dDbg, cnt)) return SMB200_ERR_CUDA;
+  if (upload_order(h)) return SMB200_ERR_CUDA;
+  StepArgs a = h->args();
+  a.statsOut = h->dStats;
+  a.stepBase = (int)g0; a.lastStep = (int)(g0 + n - 1);
+  a.dbgT = h->dDbg;
+  SMB200_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
+  if (launch_steps_persistent(a, h->descs.net, h->persistGrid, (int)g0, n, 0, h->stream)) return SMB200_ERR_CUDA;
+  SMB200_CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
+  h->gradStep += n;
+  if (d2h(h, out, h->dDbg, sizeof(long long) * cnt)) return SMB200_ERR_CUDA;
+  float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->lastMs = ms; h->lastLaunches = 1;
+  if (grid_out) *grid_out = h->persistGrid;
   return 0;
 }
 

@@ -3,10 +3,12 @@
 // One learner step of the reference,
 //     spawnTrainTasks(); processMemoryBuffer(); applyGradient();      (Learners/RACER.cpp:81-109)
 // is three device phases separated by grid-wide dependencies:
-//   P1  per tile of TB sampled transitions: gather + standardise states from the HBM replay
-//       buffer, MLP forward, ReF-ER / Retrace loss and output gradient in f64, write-back of
-//       V/Q/delta/KL/rho to the replay rows, input-gradient backward; activations and deltas
-//       are left feature-major in a scratch that P2 reads.             (RACER_train.cpp:12-67)
+//   P1  per tile of TB sampled transitions: the whole network (weight IMAGE, ~100 KB) is pulled
+//       into shared memory with cp.async.bulk (TMA) right after the grid barrier; gather +
+//       standardise states from the HBM replay rows, MLP forward, ReF-ER / Retrace loss and
+//       output gradient in f64, write-back of V/Q/delta/KL/rho to the replay rows, input-
+//       gradient backward; activations and deltas are left feature-major in a scratch for P2.
+//                                                                      (RACER_train.cpp:12-67)
 //   P2  per 16x16 tile of every weight matrix: dW = A^T * Delta contracted over the whole
 //       mini-batch in batch order, fused with the reference's Adam variant in the epilogue
 //       (the per-thread gradient buffers and their reduction, Parameters.h:66-103, vanish).
@@ -25,11 +27,22 @@
 
 namespace smb200 {
 
+// threads per CTA of the step kernels.  The per-tile work is a chain of short dependent phases, so
+// it is bound by instruction latency: more resident warps per scheduler hide it.
+#ifndef SMB200_STEP_THREADS
+#define SMB200_STEP_THREADS 512
+#endif
+constexpr int kST = SMB200_STEP_THREADS;
+constexpr int kSTlog2 = kST == 256 ? 8 : (kST == 512 ? 9 : 10);
+static_assert(kST == 256 || kST == 512 || kST == 1024, "step kernels need 256, 512 or 1024 threads");
+int step_threads() { return kST; }
+
 // ------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
@@ -37,24 +50,47 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   return v;
 }
 
-// Grid-wide barrier for the persistent kernel (all CTAs co-resident: cooperative launch).
-// `counter` only grows; it is zeroed by the host before each launch.
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned nblocks) {
+// Grid-wide barrier of the persistent kernel (all CTAs co-resident: cooperative launch).
+// `counter` only grows and is zeroed by the host before each launch; every CTA keeps the
+// running target locally so the arrival is a fire-and-forget reduction.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target, unsigned nblocks) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned old = atomicAdd(counter, 1u);
-    const unsigned target = (old / nblocks + 1u) * nblocks;
+    target += nblocks;
+    // release: orders the CTA's earlier writes (made visible to this thread by bar.sync) before the
+    // arrival; acquire: orders the other CTAs' writes before everything after the second bar.sync
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
     while (ld_acquire(counter) < target) { }
-    __threadfence();
   }
   __syncthreads();
 }
 
+// ---- mbarrier + bulk async copy (TMA, cp.async.bulk -> SASS UBLKCP) ----
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  while (!mbar_try_wait(bar, parity)) { }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 // Tanh::_eval (Network/Layers/Functions.h:103-112), f32
+// (hardware exp2 / reciprocal: 2-ulp error on e and on the quotient, far inside the f32 tolerance)
 __device__ __forceinline__ float tanh_ref(float x) {
-  const float e = expf(-2.0f * fabsf(x));
-  const float y = (1.0f - e) / (1.0f + e);
+  const float e = __expf(-2.0f * fabsf(x));
+  const float y = __fdividef(1.0f - e, 1.0f + e);
   return x > 0.0f ? y : -y;
 }
 
@@ -67,35 +103,66 @@ __device__ __forceinline__ double vdiff(double x) {
   return x > 0 ? 100.0 - 5000.0 / sqrt(2601.0 + 100.0 * x) : 100.0 - 5000.0 / sqrt(2601.0 - 100.0 * x);
 }
 
+// StepCtrl is rewritten by other CTAs between steps: read it through L2
+__device__ __forceinline__ void load_ctrl(StepCtrl& dst, const StepCtrl* src) {
+  static_assert(sizeof(StepCtrl) % 8 == 0, "StepCtrl must be a multiple of 8 bytes");
+  const long long* s = reinterpret_cast<const long long*>(src);
+  long long* d = reinterpret_cast<long long*>(&dst);
+  for (int i = 0; i < (int)(sizeof(StepCtrl) / 8); ++i) d[i] = __ldcg(s + i);
+}
+
+#define DBG_T(a, step, m) do { if ((a).dbgT && threadIdx.x == 0) \
+  (a).dbgT[((size_t)((step) - (a).stepBase) * gridDim.x + blockIdx.x) * 48 + (m)] = clock64(); } while (0)
+
 // ------------------------------------------------------------------------------------------
-// batched GEMV for a tile of TB samples.  x, y live in shared memory feature-major:
-// x[k*TB + s].  Weights stream from L2 with coalesced loads over the output index; the K
-// range is split over thread groups when the layer is narrower than the CTA.
-//   mode 0: y = b + W^T x         mode 1: y = tanh(b + W^T x)        mode 2: y += W^T x
+// Batched GEMV over a tile of TB samples.  Activations live in shared memory feature-major,
+// x[k*TB + s].  The weight image `Wp` (shared memory; global memory only for networks that do
+// not fit) stores W[k][n] with row stride ldp = roundUp4(N)+4, which makes both the forward
+// access (lanes over n, one k) and the backward access (lanes over k, float4 along n) free of
+// bank conflicts.
 // ------------------------------------------------------------------------------------------
-template <int TB>
-__device__ __forceinline__ void dense_apply(const float* __restrict__ W, int ldw, int K, int N,
-                                            const float* __restrict__ bias, const float* x, float* y,
-                                            float* red, int mode) {
+template <bool SM> __device__ __forceinline__ float ldw(const float* p) { return SM ? *p : __ldcg(p); }
+template <bool SM> __device__ __forceinline__ float4 ldw4(const float* p) {
+  return SM ? *reinterpret_cast<const float4*>(p) : __ldcg(reinterpret_cast<const float4*>(p));
+}
+
+//   mode 0: y = b + x W        mode 1: y = tanh(b + x W)       (BaseLayer::forward, Layer_Base.h:64-95)
+// If yres != nullptr the ParametricResidualLayer that follows this layer is evaluated in the same
+// epilogue: yres = y + (x * resW + resB)   (Layers.h:347-361; x = output of layer ID-2 = this layer's input).
+template <int TB, bool SM>
+__device__ __forceinline__ void dense_fwd(const float* Wp, int ldp, int K, int N, const float* bias, const float* x, float* y,
+                                          float* red, int mode, int shift, const float* resW = nullptr, const float* resB = nullptr,
+                                          float* yres = nullptr) {
+  static_assert(TB == 4, "activations are read as float4 over the 4 samples of the tile");
   const int tid = threadIdx.x;
-  for (int n0 = 0; n0 < N; n0 += kThreads) {
-    const int nc = min(kThreads, N - n0);
-    int NR = 8;
-    while (NR < nc) NR <<= 1;
-    const int G = kThreads / NR;
-    const int g = tid / NR, nl = tid - g * NR;
-    const int Kc = (K + G - 1) / G;
+  for (int n0 = 0; n0 < N; n0 += kST) {
+    const int nc = min(kST, N - n0);
+    const int NR = 1 << shift;                       // thread-group width (host: power of two >= min(N, threads), >= 8)
+    const int G = kST >> shift;
+    const int g = tid >> shift, nl = tid & (NR - 1);
+    const int Kc = (K + G - 1) >> (kSTlog2 - shift);
     const int kb = g * Kc, ke = min(K, kb + Kc);
     float acc[TB];
 #pragma unroll
     for (int s = 0; s < TB; ++s) acc[s] = 0.f;
     if (nl < nc) {
-      const float* w = W + (size_t)kb * ldw + n0 + nl;
-#pragma unroll 8
-      for (int k = kb; k < ke; ++k, w += ldw) {
-        const float wv = ld_cg(w);
+      const float* w = Wp + (size_t)kb * ldp + n0 + nl;
+      const float4* x4 = reinterpret_cast<const float4*>(x) + kb;   // TB == 4: one float4 per input feature
+      int k = kb;
+      for (; k + 8 <= ke; k += 8, w += 8 * ldp, x4 += 8) {
+        float wv[8]; float4 xv[8];
 #pragma unroll
-        for (int s = 0; s < TB; ++s) acc[s] = fmaf(x[k * TB + s], wv, acc[s]);
+        for (int j = 0; j < 8; ++j) { wv[j] = ldw<SM>(w + j * ldp); xv[j] = x4[j]; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[0] = fmaf(xv[j].x, wv[j], acc[0]); acc[1] = fmaf(xv[j].y, wv[j], acc[1]);
+          acc[2] = fmaf(xv[j].z, wv[j], acc[2]); acc[3] = fmaf(xv[j].w, wv[j], acc[3]);
+        }
+      }
+      for (; k < ke; ++k, w += ldp, ++x4) {
+        const float wv = ldw<SM>(w); const float4 xv = *x4;
+        acc[0] = fmaf(xv.x, wv, acc[0]); acc[1] = fmaf(xv.y, wv, acc[1]);
+        acc[2] = fmaf(xv.z, wv, acc[2]); acc[3] = fmaf(xv.w, wv, acc[3]);
       }
     }
     if (G > 1) {
@@ -103,267 +170,483 @@ __device__ __forceinline__ void dense_apply(const float* __restrict__ W, int ldw
 #pragma unroll
       for (int s = 0; s < TB; ++s) red[(g * NR + nl) * TB + s] = acc[s];
       __syncthreads();
-      for (int idx = tid; idx < nc * TB; idx += kThreads) {
+      for (int idx = tid; idx < nc * TB; idx += kST) {
         const int n2 = idx / TB, s = idx - n2 * TB;
         float v = 0.f;
         for (int gg = 0; gg < G; ++gg) v += red[(gg * NR + n2) * TB + s];
         const int n = n0 + n2;
-        if (mode == 2) { y[n * TB + s] += v; }
-        else { v += ld_cg(bias + n); y[n * TB + s] = mode == 1 ? tanh_ref(v) : v; }
+        v += ldw<SM>(bias + n);
+        v = mode == 1 ? tanh_ref(v) : v;
+        y[n * TB + s] = v;
+        if (yres) yres[n * TB + s] = n < K ? v + (x[n * TB + s] * ldw<SM>(resW + n) + ldw<SM>(resB + n)) : v;
       }
     } else if (nl < nc) {
       const int n = n0 + nl;
-      const float bv = mode == 2 ? 0.f : ld_cg(bias + n);
+      const float bv = ldw<SM>(bias + n);
+      float rw = 0.f, rb = 0.f;
+      if (yres && n < K) { rw = ldw<SM>(resW + n); rb = ldw<SM>(resB + n); }
 #pragma unroll
       for (int s = 0; s < TB; ++s) {
-        if (mode == 2) y[n * TB + s] += acc[s];
-        else { const float v = acc[s] + bv; y[n * TB + s] = mode == 1 ? tanh_ref(v) : v; }
+        float v = acc[s] + bv;
+        v = mode == 1 ? tanh_ref(v) : v;
+        y[n * TB + s] = v;
+        if (yres) yres[n * TB + s] = n < K ? v + (x[n * TB + s] * rw + rb) : v;
       }
+    }
+  }
+  __syncthreads();
+}
+
+// E_in[k] += sum_n W[k][n] * delta[n]   (Layer::backward input gradient, Layers.h:131-145)
+template <int TB, bool SM>
+__device__ __forceinline__ void dense_bwd_dx(const float* Wp, int ldp, int K, int N, const float* e, float* ein, float* red, int shift) {
+  static_assert(TB == 4, "delta rows are read as float4 over the 4 samples of the tile");
+  const int tid = threadIdx.x;
+  const int N4 = (N + 3) >> 2;   // image rows and delta buffers are zero-padded to a multiple of 4
+  for (int k0 = 0; k0 < K; k0 += kST) {
+    const int kc = min(kST, K - k0);
+    const int KR = 1 << shift;
+    const int G = kST >> shift;
+    const int g = tid >> shift, kl = tid & (KR - 1);
+    const int Nc = (N4 + G - 1) >> (kSTlog2 - shift);
+    const int nb = g * Nc, ne = min(N4, nb + Nc);
+    float acc[TB];
+#pragma unroll
+    for (int s = 0; s < TB; ++s) acc[s] = 0.f;
+    if (kl < kc) {
+      const float* w = Wp + (size_t)(k0 + kl) * ldp;
+      const float4* e4 = reinterpret_cast<const float4*>(e);
+      int n4 = nb;
+      for (; n4 + 2 <= ne; n4 += 2) {
+        const float4 wa = ldw4<SM>(w + n4 * 4), wb = ldw4<SM>(w + n4 * 4 + 4);
+        float4 d[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = e4[n4 * 4 + j];
+        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[0] = fmaf(wv[j], d[j].x, acc[0]); acc[1] = fmaf(wv[j], d[j].y, acc[1]);
+          acc[2] = fmaf(wv[j], d[j].z, acc[2]); acc[3] = fmaf(wv[j], d[j].w, acc[3]);
+        }
+      }
+      for (; n4 < ne; ++n4) {
+        const float4 wa = ldw4<SM>(w + n4 * 4);
+        const float4 d0 = e4[n4 * 4 + 0], d1 = e4[n4 * 4 + 1], d2 = e4[n4 * 4 + 2], d3 = e4[n4 * 4 + 3];
+        acc[0] = fmaf(wa.x, d0.x, acc[0]); acc[1] = fmaf(wa.x, d0.y, acc[1]); acc[2] = fmaf(wa.x, d0.z, acc[2]); acc[3] = fmaf(wa.x, d0.w, acc[3]);
+        acc[0] = fmaf(wa.y, d1.x, acc[0]); acc[1] = fmaf(wa.y, d1.y, acc[1]); acc[2] = fmaf(wa.y, d1.z, acc[2]); acc[3] = fmaf(wa.y, d1.w, acc[3]);
+        acc[0] = fmaf(wa.z, d2.x, acc[0]); acc[1] = fmaf(wa.z, d2.y, acc[1]); acc[2] = fmaf(wa.z, d2.z, acc[2]); acc[3] = fmaf(wa.z, d2.w, acc[3]);
+        acc[0] = fmaf(wa.w, d3.x, acc[0]); acc[1] = fmaf(wa.w, d3.y, acc[1]); acc[2] = fmaf(wa.w, d3.z, acc[2]); acc[3] = fmaf(wa.w, d3.w, acc[3]);
+      }
+    }
+    if (G > 1) {
+      __syncthreads();
+#pragma unroll
+      for (int s = 0; s < TB; ++s) red[(g * KR + kl) * TB + s] = acc[s];
+      __syncthreads();
+      for (int idx = tid; idx < kc * TB; idx += kST) {
+        const int k2 = idx / TB, s = idx - k2 * TB;
+        float v = 0.f;
+        for (int gg = 0; gg < G; ++gg) v += red[(gg * KR + k2) * TB + s];
+        ein[(k0 + k2) * TB + s] += v;
+      }
+    } else if (kl < kc) {
+#pragma unroll
+      for (int s = 0; s < TB; ++s) ein[(k0 + kl) * TB + s] += acc[s];
     }
   }
   __syncthreads();
 }
 
 // Network::forward (Network/Network.h:101-113) for the tile; act[L.actOff*TB ...] per layer.
-template <int TB>
-__device__ void net_forward(const StepArgs& a, const NetDesc& net, float* act, float* red) {
+// A ParametricResidualLayer is evaluated in the epilogue of the dense layer below it; the
+// ParamLayer (state-independent stdev parameters, Layers.h:510-521) is read straight from the
+// weight image by its consumers.
+template <int TB, bool SM>
+__device__ void net_forward(const NetDesc& net, const float* Wp, float* act, float* red, uint64_t* bars, unsigned parity,
+                            const StepArgs* dbg = nullptr, int step = 0) {
   for (int l = 1; l < net.nLayers; ++l) {
+    if (dbg && l < 8) DBG_T(*dbg, step, 8 + l);
     const LayerDesc& L = net.L[l];
     float* y = act + L.actOff * TB;
     if (L.kind == kDenseTanh || L.kind == kDenseLinear) {
-      dense_apply<TB>(a.W + L.wOff, L.ld, L.nIn, L.size, a.W + L.bOff, act + net.L[L.in].actOff * TB, y, red,
-                      L.kind == kDenseTanh ? 1 : 0);
-    } else if (L.kind == kResidual) {   // ParametricResidualLayer::forward (Layers.h:347-361)
+      const bool fuse = l + 1 < net.nLayers && net.L[l + 1].kind == kResidual;
+      if (bars) { mbar_wait(&bars[l], parity); if (fuse) mbar_wait(&bars[l + 1], parity); }
+      if (dbg && l < 5) DBG_T(*dbg, step, 26 + l);
+      const LayerDesc& R = net.L[fuse ? l + 1 : l];
+      dense_fwd<TB, SM>(Wp + L.imgW, L.ldp, L.nIn, L.size, Wp + L.imgB, act + net.L[L.in].actOff * TB, y, red,
+                        L.kind == kDenseTanh ? 1 : 0, L.fwdShift, fuse ? Wp + R.imgW : nullptr, fuse ? Wp + R.imgB : nullptr,
+                        fuse ? act + R.actOff * TB : nullptr);
+      if (fuse) ++l;
+    } else if (L.kind == kResidual) {   // not preceded by a dense layer: cannot happen with Builder::addLayer
+      if (bars) mbar_wait(&bars[l], parity);
       const float* y1 = act + net.L[l - 1].actOff * TB;
       const float* y2 = act + net.L[l - 2].actOff * TB;
-      for (int idx = threadIdx.x; idx < L.size * TB; idx += kThreads) {
+      for (int idx = threadIdx.x; idx < L.size * TB; idx += kST) {
         const int n = idx / TB;
-        y[idx] = y1[idx] + (y2[idx] * ld_cg(a.W + L.wOff + n) + ld_cg(a.W + L.bOff + n));
+        y[idx] = y1[idx] + (y2[idx] * ldw<SM>(Wp + L.imgW + n) + ldw<SM>(Wp + L.imgB + n));
       }
       __syncthreads();
-    } else {                            // ParamLayer::forward (Layers.h:510-521), Linear
-      for (int idx = threadIdx.x; idx < L.size * TB; idx += kThreads) y[idx] = ld_cg(a.W + L.bOff + idx / TB);
-      __syncthreads();
+    } else if (bars) {
+      mbar_wait(&bars[l], parity);      // ParamLayer: just make sure its slice has landed
     }
   }
 }
 
-__device__ __forceinline__ float net_out(const NetDesc& net, const float* act, int TB, int j, int s) {
+// network output j of sample s: dense outputs from the activations, stdev parameters from the image
+template <bool SM>
+__device__ __forceinline__ float net_out(const NetDesc& net, const float* Wp, const float* act, int TB, int j, int s) {
   const LayerDesc& Lo = net.L[net.nLayers - 2];   // linear output layer
   const LayerDesc& Lp = net.L[net.nLayers - 1];   // param layer (stdev)
-  return j < net.nOutDense ? act[(Lo.actOff + j) * TB + s] : act[(Lp.actOff + j - net.nOutDense) * TB + s];
+  return j < net.nOutDense ? act[(Lo.actOff + j) * TB + s] : ldw<SM>(Wp + Lp.imgB + j - net.nOutDense);
+}
+
+// ------------------------------------------------------------------------------------------
+// shared-memory carve-up of the step kernels
+// ------------------------------------------------------------------------------------------
+struct SmemPlan {
+  size_t img, act, err, red, info, old, pair, samp, tiles, bars, stage, total;
+};
+__host__ __device__ inline SmemPlan smem_plan(const NetDesc& net, int TB, bool imgInSmem) {
+  SmemPlan p;
+  size_t o = ((sizeof(DevDescs) + 15) / 16) * 16;
+  p.img = o;   o += imgInSmem ? sizeof(float) * (size_t)net.imgFloats : 0;
+  p.act = o;   o += sizeof(float) * (size_t)net.actPerSample * TB;
+  p.err = o;   o += sizeof(float) * (size_t)net.actPerSample * TB;
+  p.red = o;   o += sizeof(float) * (size_t)kST * TB;
+  p.info = o;  o += sizeof(int) * 4 * TB;
+  p.old = o;   o += sizeof(float) * 8 * TB;                          // old V/ADV/rho/KL/delta (+ next row) per sample
+  o = (o + 15) / 16 * 16;
+  p.pair = o;  o += sizeof(double) * 7 * (size_t)TB * net.dA;        // per (sample, action component) terms
+  p.samp = o;  o += sizeof(double) * 8 * TB;                         // per sample scalars
+  p.tiles = o; o += sizeof(float) * 2 * kTileK * (256 + 4);          // P2 operand tiles
+  p.bars = o;  o += sizeof(uint64_t) * kMaxLayers;
+  // inputs of the NEXT step, prefetched while the weight-gradient phase runs:
+  // raw states [TB][dS], old values [8][TB], (a, mu_mean, mu_std) [3][TB*dA], info [4][TB]; then mean/scale [2][dS]
+  p.stage = o; o += sizeof(float) * ((size_t)TB * net.dS + 8 * TB + 3 * (size_t)TB * net.dA + 4 * TB + 2 * (size_t)net.dS);
+  o = (o + 15) / 16 * 16;
+  p.total = o;
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------
+// weight image -> shared memory
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int layer_img_begin(const NetDesc& net, int l) {
+  const LayerDesc& L = net.L[l];
+  return (L.kind == kParam) ? L.imgB : L.imgW;
+}
+__device__ __forceinline__ int layer_img_end(const NetDesc& net, int l) {
+  return l + 1 < net.nLayers ? layer_img_begin(net, l + 1) : net.imgFloats;
+}
+
+// Called by all threads after the data dependency (grid barrier / kernel start) is satisfied.
+__device__ __forceinline__ void load_weight_image(const StepArgs& a, const NetDesc& net, float* img, uint64_t* bars) {
+  if (a.useTma) {
+    if (threadIdx.x == 0) {
+      // order this thread's earlier generic-proxy accesses (shared reads of the old image, the
+      // acquire of the grid barrier) before the async-proxy copies
+      asm volatile("fence.proxy.async;" ::: "memory");
+      for (int l = 1; l < net.nLayers; ++l) {
+        const int b = layer_img_begin(net, l), e = layer_img_end(net, l);
+        const unsigned bytes = (unsigned)(e - b) * 4u;
+        mbar_expect_tx(&bars[l], bytes);
+        bulk_g2s(img + b, a.Wimg + b, bytes, &bars[l]);
+      }
+    }
+  } else {
+    const int n4 = net.imgFloats >> 2;
+    for (int i = threadIdx.x; i < n4; i += kST)
+      reinterpret_cast<float4*>(img)[i] = __ldcg(reinterpret_cast<const float4*>(a.Wimg) + i);
+    __syncthreads();
+  }
 }
 
 // ------------------------------------------------------------------------------------------
 // P1
 // ------------------------------------------------------------------------------------------
+// `c` is this CTA's shared-memory copy of ctrl[step&1].  If `fetchCtrl` is set it is (re)loaded here,
+// as late as possible (just before the loss needs beta/Cmax), after waiting for the statistics CTA
+// to have published the previous step's result (`readyFlag`, `readyTarget`; nullptr = already valid).
+// `staged`: this tile's inputs (sample info, raw states, action / behaviour policy, old replay
+// values) were prefetched into the shared-memory staging area during the previous step's P2.
+struct Staging {
+  float* S; float* old; float* pair; int* info; float* mean; float* scale;
+};
 template <int TB>
-__device__ void p1_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, const StepCtrl& c, int step, int tile,
-                        float* smem) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* act = smem;                             // [actPerSample][TB]
-  float* err = act + net.actPerSample * TB;      // [actPerSample][TB]
-  float* red = err + net.actPerSample * TB;      // [kThreads*TB]
-  int* info = reinterpret_cast<int*>(red + kThreads * TB);   // row[TB], slot[TB], hasNext[TB], valid[TB]
-  float* vnext = reinterpret_cast<float*>(info + 4 * TB);
+__device__ __forceinline__ Staging staging_view(const NetDesc& net, unsigned char* smraw, const SmemPlan& sp) {
+  Staging g;
+  float* f = reinterpret_cast<float*>(smraw + sp.stage);
+  g.S = f; f += TB * net.dS;
+  g.old = f; f += 8 * TB;
+  g.pair = f; f += 3 * TB * net.dA;
+  g.info = reinterpret_cast<int*>(f); f += 4 * TB;
+  g.mean = f; f += net.dS;
+  g.scale = f;
+  return g;
+}
+
+template <int TB, bool SM>
+__device__ void p1_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, StepCtrl& c, int step, int tile,
+                        unsigned char* smraw, const SmemPlan& sp, unsigned parity, bool fetchCtrl,
+                        const unsigned* readyFlag, unsigned readyTarget, bool staged) {
+  const int tid = threadIdx.x;
+  float* img = reinterpret_cast<float*>(smraw + sp.img);
+  const float* Wp = SM ? img : a.Wimg;
+  float* act = reinterpret_cast<float*>(smraw + sp.act);     // [actPerSample][TB]
+  float* err = reinterpret_cast<float*>(smraw + sp.err);     // [actPerSample][TB]
+  float* red = reinterpret_cast<float*>(smraw + sp.red);
+  const Staging stg = staging_view<TB>(net, smraw, sp);
+  int* info = staged ? stg.info : reinterpret_cast<int*>(smraw + sp.info);   // row[TB], slot[TB], hasNext[TB], valid[TB]
+  float* old = staged ? stg.old : reinterpret_cast<float*>(smraw + sp.old);  // [8][TB]: V, ADV, RHO, KL, DELTA, Vnext, ADVnext, Qret
+  double* pair = reinterpret_cast<double*>(smraw + sp.pair); // [7][TB*dA]
+  double* samp = reinterpret_cast<double*>(smraw + sp.samp); // [8][TB]
+  uint64_t* bars = (SM && a.useTma) ? reinterpret_cast<uint64_t*>(smraw + sp.bars) : nullptr;
   const int b0 = tile * TB;
   const ReplayView& rp = a.rp;
   const int dS = net.dS, dA = net.dA;
+  const int nPair = TB * dA;
 
-  if (tid < TB) {
-    const int b = b0 + tid;
-    int row = 0, slot = 0, hn = 0, valid = 0;
-    if (b < a.B) {
-      slot = a.sampSlot[(size_t)(step - a.stepBase) * a.B + b];
-      const int t = a.sampT[(size_t)(step - a.stepBase) * a.B + b];
-      row = __ldcg(rp.epStart + slot) + t;
-      hn = (t + 2 == __ldcg(rp.epLen + slot)) && !__ldcg(rp.epTerm + slot);   // Episode::isTruncated(t+1)
-      valid = 1;
+  if (!staged) {
+    if (tid < TB) {
+      const int b = b0 + tid;
+      int row = 0, slot = 0, hn = 0, valid = 0;
+      if (b < a.B) {
+        const size_t j = (size_t)(step - a.stepBase) * a.B + b;
+        row = a.sampRow[j];
+        const int sf = a.sampSlot[j];
+        slot = sf & 0x7fffffff; hn = (sf >> 31) & 1;          // Episode::isTruncated(t+1), resolved on the host
+        valid = 1;
+        // old per-transition values needed by the write-back, fetched early
+        old[0 * TB + tid] = ld_cg(rp.V + row); old[1 * TB + tid] = ld_cg(rp.ADV + row);
+        old[2 * TB + tid] = ld_cg(rp.RHO + row); old[3 * TB + tid] = ld_cg(rp.KL + row);
+        old[4 * TB + tid] = ld_cg(rp.DELTA + row); old[7 * TB + tid] = ld_cg(rp.Q + row);
+        if (hn) { old[5 * TB + tid] = ld_cg(rp.V + row + 1); old[6 * TB + tid] = ld_cg(rp.ADV + row + 1); }
+      }
+      info[tid] = row; info[TB + tid] = slot; info[2 * TB + tid] = hn; info[3 * TB + tid] = valid;
     }
-    info[tid] = row; info[TB + tid] = slot; info[2 * TB + tid] = hn; info[3 * TB + tid] = valid;
+    __syncthreads();
   }
-  __syncthreads();
   int anyNext = 0;
 #pragma unroll
   for (int s = 0; s < TB; ++s) anyNext |= info[2 * TB + s];
 
   // V(s_{t+1}) of truncated episodes (RACER_train.cpp:23-27): rare, extra forward pass
+  float* vnext = reinterpret_cast<float*>(samp + 7 * TB);   // samp[7][*] is not used by the loss stages
   if (anyNext) {
-    for (int idx = tid; idx < dS * TB; idx += kThreads) {
+    for (int idx = tid; idx < dS * TB; idx += kST) {
       const int k = idx / TB, s = idx - k * TB;
-      const int row = info[s] + 1;
-      act[idx] = info[2 * TB + s] ? (ld_cg(rp.S + (size_t)row * dS + k) - ld_cg(rp.stateMean + k)) * ld_cg(rp.stateScale + k) : 0.f;
+      const size_t row = (size_t)info[s] + 1;
+      act[idx] = info[2 * TB + s] ? (ld_cg(rp.S + row * dS + k) - ld_cg(rp.stateMean + k)) * ld_cg(rp.stateScale + k) : 0.f;
     }
     __syncthreads();
-    net_forward<TB>(a, net, act, red);
-    if (tid < TB) vnext[tid] = (float)net2v((double)net_out(net, act, TB, 0, tid));
+    net_forward<TB, SM>(net, Wp, act, red, bars, parity);
+    if (tid < TB) vnext[tid] = (float)net2v((double)net_out<SM>(net, Wp, act, TB, 0, tid));
     __syncthreads();
   }
 
   // gather + standardise: (s - mean) * scale   (Episode.h:171-183)
-  for (int idx = tid; idx < dS * TB; idx += kThreads) {
+  for (int idx = tid; idx < dS * TB; idx += kST) {
     const int k = idx / TB, s = idx - k * TB;
-    const float x = info[3 * TB + s] ? (ld_cg(rp.S + (size_t)info[s] * dS + k) - ld_cg(rp.stateMean + k)) * ld_cg(rp.stateScale + k) : 0.f;
+    float x = 0.f;
+    if (info[3 * TB + s])
+      x = staged ? (stg.S[s * dS + k] - stg.mean[k]) * stg.scale[k]
+                 : (ld_cg(rp.S + (size_t)info[s] * dS + k) - ld_cg(rp.stateMean + k)) * ld_cg(rp.stateScale + k);
     act[idx] = x;
     if (info[3 * TB + s]) a.lastX[(size_t)(b0 + s) * dS + k] = x;
   }
-  for (int idx = tid; idx < net.actPerSample * TB; idx += kThreads) err[idx] = 0.f;   // clearErrors
-  __syncthreads();
-  net_forward<TB>(a, net, act, red);
-
-  // ---- loss: one warp per sample, lanes over action components, f64 (RACER_train.cpp:31-60) ----
-  if (warp < TB && info[3 * TB + warp]) {
-    const int s = warp, b = b0 + s;
-    const size_t row = info[s];
-    const double beta = c.beta, cmax = c.cmax, cinv = c.cinv;
-    const LayerDesc& Lo = net.L[net.nLayers - 2];
-    const LayerDesc& Lp = net.L[net.nLayers - 1];
-    double logw = 0.0, dkl = 0.0;
-    // importanceWeight / KLDivergence: sums run sequentially over components like the reference
-    for (int i0 = 0; i0 < dA; i0 += 32) {
-      const int i = i0 + lane;
-      double lw_i = 0.0, kl_i = 0.0;
-      if (i < dA) {
-        const double m = (double)net_out(net, act, TB, 1 + i, s);
-        const double sraw = (double)net_out(net, act, TB, 1 + dA + i, s);
-        const double av = (double)ld_cg(rp.A + row * dA + i);
-        const double mm = (double)ld_cg(rp.MU + row * 2 * dA + i);
-        const double ms = (double)ld_cg(rp.MU + row * 2 * dA + dA + i);
-        const double stdev = (sraw + sqrt(1.0 + sraw * sraw)) / 2.0;      // SoftPlus::_eval, Functions.h:552-555
-        const double inv = 1.0 / stdev, invmu = 1.0 / ms;
-        const bool bnd = hp.bounded[i] != 0;
-        const double MAXM = 8.31776613503286;
-        const double cm = bnd ? (m > MAXM ? MAXM : (m < -MAXM ? -MAXM : m)) : m;   // Continuous_policy.h:217-222
-        const double fac0 = 9.1893853320467266954096885456237942e-01;
-        double J = 1.0;
-        if (bnd) { const double sq = tanh(av); J = fmax(1.0 - sq * sq, (double)FLT_MIN); }
-        const double z1 = (av - cm) * inv, z2 = (av - mm) * invmu;
-        const double lp_pi = -(z1 * z1) / 2.0 + log(bnd ? inv / J : inv) - fac0;     // :91-97 / :240-249
-        const double lp_mu = -(z2 * z2) / 2.0 + log(bnd ? invmu / J : invmu) - fac0;
-        lw_i = lp_pi - lp_mu;
-        const double r1 = stdev / ms, r2 = (m - mm) / ms;
-        const double cc = r1 * r1, dd = r2 * r2;                                        // OPPOSITE_KL, :138-142
-        kl_i = (cc - 1.0 + dd - log(cc)) / 2.0;
-      }
-      const int cnt = min(32, dA - i0);
-      for (int j = 0; j < cnt; ++j) {
-        logw += __shfl_sync(0xffffffffu, lw_i, j);
-        dkl += __shfl_sync(0xffffffffu, kl_i, j);
+  for (int idx = tid; idx < net.actPerSample * TB; idx += kST) err[idx] = 0.f;   // clearErrors
+  // behaviour policy and action of this thread's first (sample, component) pair
+  double pa = 0, pmm = 0, pms = 1;
+  const int p0 = tid;
+  const int p0s = p0 < nPair ? p0 / dA : 0, p0i = p0 - p0s * dA;   // one integer division per tile, reused below
+  if (p0 < nPair) {
+    const int s = p0s, i = p0i;
+    if (info[3 * TB + s]) {
+      if (staged) { pa = (double)stg.pair[p0]; pmm = (double)stg.pair[nPair + p0]; pms = (double)stg.pair[2 * nPair + p0]; }
+      else {
+        const size_t row = info[s];
+        pa = (double)ld_cg(rp.A + row * dA + i);
+        pmm = (double)ld_cg(rp.MU + row * 2 * dA + i);
+        pms = (double)ld_cg(rp.MU + row * 2 * dA + dA + i);
       }
     }
-    const double rho = exp(logw > 7.0 ? 7.0 : (logw < -7.0 ? -7.0 : logw));             // :648-653
+  }
+  __syncthreads();
+  DBG_T(a, step, 1);
+  net_forward<TB, SM>(net, Wp, act, red, bars, parity, &a, step);
+  DBG_T(a, step, 2);
+
+  // ---- loss (RACER_train.cpp:31-60), f64.  Stage 1: one thread per (sample, action component);
+  //      meanwhile warp 7 evaluates the value terms and fetches this step's ReF-ER scalars ----
+  const LayerDesc& Lo = net.L[net.nLayers - 2];
+  const LayerDesc& Lp = net.L[net.nLayers - 1];
+  for (int p = tid; p < nPair; p += kST) {
+    const int s = p == p0 ? p0s : p / dA, i = p == p0 ? p0i : p - s * dA;
+    if (!info[3 * TB + s]) continue;
+    double av = pa, mm = pmm, ms = pms;
+    if (p != p0) {
+      const size_t row = info[s];
+      av = (double)ld_cg(rp.A + row * dA + i); mm = (double)ld_cg(rp.MU + row * 2 * dA + i); ms = (double)ld_cg(rp.MU + row * 2 * dA + dA + i);
+    }
+    const double m = (double)act[(Lo.actOff + 1 + i) * TB + s];
+    const double sraw = (double)ldw<SM>(Wp + Lp.imgB + i);
+    const double root = sqrt(1.0 + sraw * sraw);
+    const double stdev = (sraw + root) / 2.0;                          // SoftPlus::_eval, Functions.h:552-555
+    const double dpos = (1.0 + sraw / root) / 2.0;                     // SoftPlus::_evalDiff
+    const double inv = 1.0 / stdev, invmu = 1.0 / ms;
+    const bool bnd = hp.bounded[i] != 0;
+    const double MAXM = 8.31776613503286;
+    const double cm = bnd ? (m > MAXM ? MAXM : (m < -MAXM ? -MAXM : m)) : m;   // Continuous_policy.h:217-222
+    const double fac0 = 9.1893853320467266954096885456237942e-01;
+    double J = 1.0;
+    if (bnd) { const double sq = tanh(av); J = fmax(1.0 - sq * sq, (double)FLT_MIN); }
+    const double z1 = (av - cm) * inv, z2 = (av - mm) * invmu;
+    const double lp_pi = -(z1 * z1) / 2.0 + log(bnd ? inv / J : inv) - fac0;       // :91-97 / :240-249
+    const double lp_mu = -(z2 * z2) / 2.0 + log(bnd ? invmu / J : invmu) - fac0;
+    const double r1 = stdev / ms, r2 = (m - mm) / ms;
+    const double cc = r1 * r1, dd = r2 * r2;                                          // OPPOSITE_KL, :138-142
+    // penalG = KLDivGradient(MU, -1): gradKLdiv, OPPOSITE_KL branch (:154-170)
+    const double invVarMu = 1.0 / (ms * ms);
+    // polG = policyGradient(ACT, f): gradLogP (:145-152 / :300-316), f applied in stage 3
+    const double u = z1;
+    pair[0 * nPair + p] = lp_pi - lp_mu;
+    pair[1 * nPair + p] = (cc - 1.0 + dd - log(cc)) / 2.0;
+    pair[2 * nPair + p] = -1.0 * ((m - mm) * invVarMu);                               // kg_mean
+    pair[3 * nPair + p] = (dpos * -1.0) * ((invVarMu - inv * inv) * stdev);           // kg_std
+    pair[4 * nPair + p] = bnd ? (av - m) * inv * inv : u * inv;                       // dLogPdMean
+    pair[5 * nPair + p] = (u * u - 1.0) * inv;                                        // dLogPdStdv
+    pair[6 * nPair + p] = dpos;
+  }
+  if (tid >= kST - 32 && tid < kST - 32 + TB) {     // value head: V = scaleNet2V(O[0]), dV/dO (RACER_common.cpp:23-32)
+    const int s = tid - (kST - 32);
+    const double O0 = (double)act[(Lo.actOff + 0) * TB + s];
+    samp[2 * TB + s] = net2v(O0);
+    samp[3 * TB + s] = vdiff(O0);
+  }
+  if (fetchCtrl && tid == kST - 1) {
+    if (readyFlag) { while (ld_acquire(readyFlag) < readyTarget) { } }
+    load_ctrl(c, &a.ctrl[step & 1]);
+  }
+  __syncthreads();
+  DBG_T(a, step, 8);
+  // Stage 2: one thread per sample — sums in component order like the reference, flags, value terms,
+  // replay write-back (RACER_train.cpp:59-60) and the record for the aggregate updates.
+  if (tid < TB && info[3 * TB + tid]) {
+    const int s = tid, b = b0 + s;
+    const size_t row = info[s];
+    const double beta = c.beta, cmax = c.cmax, cinv = c.cinv;
+    double logw = 0.0, dkl = 0.0;
+    for (int i = 0; i < dA; ++i) { logw += pair[0 * nPair + s * dA + i]; dkl += pair[1 * nPair + s * dA + i]; }
+    const double rho = exp(logw > 7.0 ? 7.0 : (logw < -7.0 ? -7.0 : logw));           // :648-653
     // isFarPolicy takes Fval arguments (Episode.h:28-33)
     const float W32 = (float)rho, C32 = (float)cmax, I32 = (float)cinv;
     const bool offW = (W32 > C32) || (W32 < I32);
     const bool isFar = (C32 > 1.0f) && offW;
-    const double O0 = (double)net_out(net, act, TB, 0, s);
-    const double Vval = net2v(O0);
-    const double Aval = 0.0;                                                           // Zero_advantage.h:39-42
-    const float qret = ld_cg(rp.Q + row);
-    const double A_RET = (double)qret - Vval, deltaQ = A_RET - Aval;
+    const float O0f = act[(Lo.actOff + 0) * TB + s];
+    const double Vval = samp[2 * TB + s];
+    const double Aval = 0.0;                                                          // Zero_advantage.h:39-42
+    const double A_RET = (double)old[7 * TB + s] - Vval, deltaQ = A_RET - Aval;
     const double Ver = fmin(1.0, rho) * deltaQ;
-    const double pgfac = A_RET * fmin(cmax, rho);
-    if (lane == 0) {
-      const double g0 = isFar ? 0.0 : Ver * beta * vdiff(O0);
-      err[(Lo.actOff + 0) * TB + s] = (float)g0;
-      a.lastG[(size_t)b * net.nOut + 0] = (float)g0;
-      a.lastO[(size_t)b * net.nOut + 0] = (float)O0;
+    const double g0 = isFar ? 0.0 : Ver * beta * samp[3 * TB + s];
+    samp[0 * TB + s] = A_RET * fmin(cmax, rho);     // pgfac
+    samp[1 * TB + s] = isFar ? 1.0 : 0.0;
+    err[(Lo.actOff + 0) * TB + s] = (float)g0;
+    a.lastG[(size_t)b * net.nOut + 0] = (float)g0;
+    a.lastO[(size_t)b * net.nOut + 0] = O0f;
+    SampleRec r;
+    r.slot = info[TB + s]; r.hasNext = info[2 * TB + s];
+    r.qNextOld = 0.f; r.qNextNew = 0.f;
+    if (r.hasNext) {
+      const float vn = vnext[s];
+      r.qNextOld = old[6 * TB + s] + old[5 * TB + s];
+      r.qNextNew = vn;
+      rp.V[row + 1] = vn; rp.ADV[row + 1] = vn - vn;
     }
-    for (int i = lane; i < dA; i += 32) {
-      const double m = (double)net_out(net, act, TB, 1 + i, s);
-      const double sraw = (double)net_out(net, act, TB, 1 + dA + i, s);
-      const double av = (double)ld_cg(rp.A + row * dA + i);
-      const double mm = (double)ld_cg(rp.MU + row * 2 * dA + i);
-      const double ms = (double)ld_cg(rp.MU + row * 2 * dA + dA + i);
-      const double root = sqrt(1.0 + sraw * sraw);
-      const double stdev = (sraw + root) / 2.0, inv = 1.0 / stdev;
-      const double dpos = (1.0 + sraw / root) / 2.0;                                    // SoftPlus::_evalDiff
-      const bool bnd = hp.bounded[i] != 0;
-      const double MAXM = 8.31776613503286;
-      const double cm = bnd ? (m > MAXM ? MAXM : (m < -MAXM ? -MAXM : m)) : m;
-      // penalG = KLDivGradient(MU, -1): gradKLdiv, OPPOSITE_KL branch (Continuous_policy.h:154-170)
-      const double invVarMu = 1.0 / (ms * ms);
-      const double kg_mean = -1.0 * ((m - mm) * invVarMu);
-      const double kg_std = (dpos * -1.0) * ((invVarMu - inv * inv) * stdev);
-      // polG = policyGradient(ACT, A_RET*min(Cmax,rho)): gradLogP (:145-152 / :300-316)
-      const double u = (av - cm) * inv;
-      const double dLogPdMean = bnd ? (av - m) * inv * inv : u * inv;
-      const double dLogPdStdv = (u * u - 1.0) * inv;
-      double pg_mean = pgfac * dLogPdMean;
-      if (bnd && ((m >= MAXM && pg_mean > 0.0) || (m <= -MAXM && pg_mean < 0.0))) pg_mean = 0.0;
-      double pg_std = (dpos * pgfac) * dLogPdStdv;
+    const float E = (float)deltaQ, D = (float)dkl;
+    const float oldRho = old[2 * TB + s], oldKL = old[3 * TB + s], oldE = old[4 * TB + s];
+    const bool wasOff = (oldRho > C32) || (oldRho < I32);
+    r.dKL = D - oldKL;
+    r.dFar = (float)offW - (float)wasOff;
+    r.farDelta = (C32 > 1.0f) ? ((int)offW - (int)wasOff) : 0;
+    r.dE2 = E * E - oldE * oldE;
+    r.absE = fabsf(E);
+    const float Vf = (float)Vval, Qf = (float)(Aval + Vval);
+    r.qOld = old[1 * TB + s] + old[0 * TB + s];
+    r.qNew = Qf;
+    r.pad = 0;
+    rp.DELTA[row] = E; rp.KL[row] = D; rp.RHO[row] = W32;
+    rp.V[row] = Vf; rp.ADV[row] = Qf - Vf;
+    a.rec[b] = r;
+  }
+  __syncthreads();
+  DBG_T(a, step, 16);
+  // Stage 3: policy / penalty gradient of every pair (penalizeReFER, FunctionUtilities.h:221-228)
+  {
+    const double beta = c.beta;
+    const double MAXM = 8.31776613503286;
+    for (int p = tid; p < nPair; p += kST) {
+      const int s = p == p0 ? p0s : p / dA, i = p == p0 ? p0i : p - s * dA;
+      if (!info[3 * TB + s]) continue;
+      const int b = b0 + s;
+      const double pgfac = samp[0 * TB + s];
+      const bool isFar = samp[1 * TB + s] != 0.0;
+      const float mf = act[(Lo.actOff + 1 + i) * TB + s];
+      const double m = (double)mf;
+      double pg_mean = pgfac * pair[4 * nPair + p];
+      if (hp.bounded[i] && ((m >= MAXM && pg_mean > 0.0) || (m <= -MAXM && pg_mean < 0.0))) pg_mean = 0.0;
+      double pg_std = (pair[6 * nPair + p] * pgfac) * pair[5 * nPair + p];
       if (isFar) { pg_mean = 0.0; pg_std = 0.0; }
-      const double g_mean = beta * pg_mean + (1.0 - beta) * kg_mean;                     // penalizeReFER
-      const double g_std = beta * pg_std + (1.0 - beta) * kg_std;
+      const double g_mean = beta * pg_mean + (1.0 - beta) * pair[2 * nPair + p];
+      const double g_std = beta * pg_std + (1.0 - beta) * pair[3 * nPair + p];
       err[(Lo.actOff + 1 + i) * TB + s] = (float)g_mean;
       err[(Lp.actOff + i) * TB + s] = (float)g_std;
       a.lastG[(size_t)b * net.nOut + 1 + i] = (float)g_mean;
       a.lastG[(size_t)b * net.nOut + 1 + dA + i] = (float)g_std;
-      a.lastO[(size_t)b * net.nOut + 1 + i] = (float)m;
-      a.lastO[(size_t)b * net.nOut + 1 + dA + i] = (float)sraw;
-    }
-    if (lane == 0) {
-      // write-back (RACER_train.cpp:59-60) + record for the aggregate updates (Episode.h:112-145)
-      SampleRec r;
-      r.slot = info[TB + s]; r.hasNext = info[2 * TB + s];
-      r.qNextOld = 0.f; r.qNextNew = 0.f;
-      if (r.hasNext) {
-        const float vn = vnext[s];
-        r.qNextOld = ld_cg(rp.ADV + row + 1) + ld_cg(rp.V + row + 1);
-        r.qNextNew = vn;
-        rp.V[row + 1] = vn; rp.ADV[row + 1] = vn - vn;
-      }
-      const float E = (float)deltaQ, D = (float)dkl;
-      const float oldRho = ld_cg(rp.RHO + row), oldKL = ld_cg(rp.KL + row), oldE = ld_cg(rp.DELTA + row);
-      const bool wasOff = (oldRho > C32) || (oldRho < I32);
-      r.dKL = D - oldKL;
-      r.dFar = (float)offW - (float)wasOff;
-      r.farDelta = (C32 > 1.0f) ? ((int)offW - (int)wasOff) : 0;
-      r.dE2 = E * E - oldE * oldE;
-      r.absE = fabsf(E);
-      const float Vf = (float)Vval, Qf = (float)(Aval + Vval);
-      r.qOld = ld_cg(rp.ADV + row) + ld_cg(rp.V + row);
-      r.qNew = Qf;
-      r.pad = 0;
-      rp.DELTA[row] = E; rp.KL[row] = D; rp.RHO[row] = W32;
-      rp.V[row] = Vf; rp.ADV[row] = Qf - Vf;
-      a.rec[b] = r;
+      a.lastO[(size_t)b * net.nOut + 1 + i] = mf;
+      a.lastO[(size_t)b * net.nOut + 1 + dA + i] = ldw<SM>(Wp + Lp.imgB + i);
     }
   }
   __syncthreads();
+  DBG_T(a, step, 3);
 
-  // ---- backward: Network::backProp, layers last to first (Network.h:216-226) ----
+  // ---- backward: Network::backProp, layers last to first (Network.h:216-226).  A residual layer
+  //      is folded into the dense layer below it: E(l) = E(res) * f'(Y_l), E(l-1) += E(res) * w_res ----
   for (int l = net.nLayers - 1; l >= 1; --l) {
     const LayerDesc& L = net.L[l];
+    if (L.kind != kDenseTanh && L.kind != kDenseLinear) continue;
+    if (l < 8) DBG_T(a, step, 16 + l);
     float* e = err + L.actOff * TB;
-    if (L.kind == kDenseTanh || L.kind == kDenseLinear) {
-      if (L.kind == kDenseTanh) {   // deltas *= 1 - Y^2 (Layer_Base.h:103-109)
-        const float* y = act + L.actOff * TB;
-        for (int idx = tid; idx < L.size * TB; idx += kThreads) e[idx] = e[idx] * (1.0f - y[idx] * y[idx]);
-        __syncthreads();
-      }
-      if (L.wtOff >= 0)             // E_in += W * delta (Layers.h:131-145); skipped for the first layer
-        dense_apply<TB>(a.WT + L.wtOff, L.ldt, L.size, L.nIn, nullptr, e, err + net.L[L.in].actOff * TB, red, 2);
-    } else if (L.kind == kResidual) {   // ParametricResidualLayer::backward (Layers.h:363-393)
-      float* e1 = err + net.L[l - 1].actOff * TB;
-      float* e2 = err + net.L[l - 2].actOff * TB;
-      for (int idx = tid; idx < L.size * TB; idx += kThreads) {
-        e1[idx] = e[idx];
-        e2[idx] += e[idx] * ld_cg(a.W + L.wOff + idx / TB);
+    float* ein = err + net.L[L.in].actOff * TB;
+    const bool fuse = l + 1 < net.nLayers && net.L[l + 1].kind == kResidual;
+    if (fuse) {                       // ParametricResidualLayer::backward (Layers.h:363-393) + deltas *= f' (Layer_Base.h:103-109)
+      const LayerDesc& R = net.L[l + 1];
+      const float* e3 = err + R.actOff * TB;
+      const float* y = act + L.actOff * TB;
+      for (int idx = tid; idx < L.size * TB; idx += kST) {
+        const float d3 = e3[idx];
+        e[idx] = L.kind == kDenseTanh ? d3 * (1.0f - y[idx] * y[idx]) : d3;
+        if (idx < L.nIn * TB) ein[idx] += d3 * ldw<SM>(Wp + R.imgW + idx / TB);
       }
       __syncthreads();
+    } else if (L.kind == kDenseTanh) {
+      const float* y = act + L.actOff * TB;
+      for (int idx = tid; idx < L.size * TB; idx += kST) e[idx] = e[idx] * (1.0f - y[idx] * y[idx]);
+      __syncthreads();
     }
+    if (L.needDx)                   // E_in += W * delta; skipped for the first layer (Approximator.cpp:145-169)
+      dense_bwd_dx<TB, SM>(Wp + L.imgW, L.ldp, L.nIn, L.size, e, ein, red, L.bwdShift);
   }
+  DBG_T(a, step, 4);
 
   // ---- activations and deltas to the feature-major scratch read by P2 ----
   const int per = net.actPerSample;
   if (TB == 4 && b0 + TB <= a.B) {
-    for (int f = tid; f < per; f += kThreads) {
+    for (int f = tid; f < per; f += kST) {
       *reinterpret_cast<float4*>(a.actG + (size_t)f * a.Bpad + b0) = *reinterpret_cast<const float4*>(act + f * 4);
       *reinterpret_cast<float4*>(a.errG + (size_t)f * a.Bpad + b0) = *reinterpret_cast<const float4*>(err + f * 4);
     }
   } else {
-    for (int idx = tid; idx < per * TB; idx += kThreads) {
+    for (int idx = tid; idx < per * TB; idx += kST) {
       const int f = idx / TB, s = idx - f * TB;
       if (b0 + s < a.B) { a.actG[(size_t)f * a.Bpad + b0 + s] = act[idx]; a.errG[(size_t)f * a.Bpad + b0 + s] = err[idx]; }
     }
@@ -380,50 +663,66 @@ struct AdamCoef { float eta, B1, B2, lambda, fac; };
 
 __device__ __forceinline__ AdamCoef adam_coef(const Hyper& hp, const StepCtrl& c) {
   AdamCoef k;
-  const long long nStep = c.adam_step + 1;                                  // prepare_update: nStep++ (Optimizer.cpp:119)
-  const float etaf = (float)hp.learnrate;
-  const float eta0 = (float)((double)etaf / (1.0 + (double)(float)(double)nStep * hp.epsAnneal));   // annealRate<nnReal>
-  const float bt1 = (float)c.adam_bt1, bt2 = (float)c.adam_bt2;
-  k.eta = eta0 * sqrtf(1.0f - bt2) / (1.0f - bt1);                          // struct Adam ctor (Optimizer.cpp:64-67)
+  k.eta = c.adam_eta;   // precomputed with the rest of ctrl (adam_eta_for)
   k.B1 = 0.9f; k.B2 = 0.999f;
   k.lambda = (float)hp.nnLambda;
   k.fac = (float)(1.0 / (double)hp.batchGlobal);
   return k;
 }
 
-__device__ __forceinline__ float adam_step(const AdamCoef& k, float G, float* w, float* m1, float* m2) {
-  const float W = *w;
+__device__ __forceinline__ float adam_step(const AdamCoef& k, float G, float W, float m1, float m2, float* w, float* pm1, float* pm2) {
   const float penal = -W * k.lambda;                       // SMARTIES_ADAMW
   const float DW = k.fac * G;
-  float M1 = k.B1 * (*m1) + (1.0f - k.B1) * DW;
-  float M2 = k.B2 * (*m2) + (1.0f - k.B2) * DW * DW;
+  float M1 = k.B1 * m1 + (1.0f - k.B1) * DW;
+  float M2 = k.B2 * m2 + (1.0f - k.B2) * DW * DW;
   const float numer = k.B1 * M1 + (1.0f - k.B1) * DW;      // SMARTIES_NESTEROV_ADAM
   M2 = M2 < M1 * M1 ? M1 * M1 : M2;                        // SMARTIES_SAFE_ADAM
   const float ret = numer / (FLT_EPSILON + sqrtf(M2));
   const float Wn = W + k.eta * (ret + penal);
-  *m1 = M1; *m2 = M2; *w = Wn;
+  *pm1 = M1; *pm2 = M2; *w = Wn;
   return Wn;
 }
 
 __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, const StepCtrl& c, const GradTile& t,
-                        float* smem) {
+                        float* tiles, int step) {
   const int tid = threadIdx.x;
-  float* As = smem;                 // [16][kBCP]
-  float* Ds = smem + kTileK * kBCP; // [16][kBCP]
+  float* As = tiles;                 // [16][kBCP]
+  float* Ds = tiles + kTileK * kBCP; // [16][kBCP]
   const LayerDesc& L = net.L[t.layer];
   // operand rows: A = activation of the input layer (dense) / of layer ID-2 (residual); D = this layer's deltas
   const int K = t.kind == 0 ? L.nIn : L.size;
   const int aOff = t.kind == 0 ? net.L[L.in].actOff : (t.kind == 1 ? net.L[t.layer - 2].actOff : 0);
   const int dOff = L.actOff;
   const int N = L.size;
-  float acc = 0.f, acc2 = 0.f;
   const int kk = tid >> 4, nn = tid & 15;
   const int warp = tid >> 5, lane = tid & 31;
+  // parameters this thread owns: fetch W, M1, M2 now, use them after the contraction
+  int p0 = -1, p1 = -1, pimg0 = -1, pimg1 = -1;
+  if (tid >= 256) {
+    // only the first 256 threads own parameters; the rest help with loads and the contraction
+  } else if (t.kind == 0) {
+    const int k = t.k0 + kk, n = t.n0 + nn;
+    if (n < N && k <= K) { p0 = k < K ? L.wOff + k * L.ld + n : L.bOff + n; pimg0 = k < K ? L.imgW + k * L.ldp + n : L.imgB + n; }
+  } else if (lane < 2) {
+    const int n = t.n0 + warp * 2 + lane;
+    if (n < N) {
+      p0 = L.bOff + n; pimg0 = L.imgB + n;
+      if (t.kind == 1) { p1 = L.wOff + n; pimg1 = L.imgW + n; }
+    }
+  }
+  float w0 = 0.f, m10 = 0.f, m20 = 0.f, w1 = 0.f, m11 = 0.f, m21 = 0.f;
+  if (p0 >= 0) { w0 = ld_cg(a.W + p0); m10 = ld_cg(a.M1 + p0); m20 = ld_cg(a.M2 + p0); }
+  if (p1 >= 0) { w1 = ld_cg(a.W + p1); m11 = ld_cg(a.M1 + p1); m21 = ld_cg(a.M2 + p1); }
+  float acc = 0.f, acc2 = 0.f;
+  float q4[4] = {0.f, 0.f, 0.f, 0.f};
+  DBG_T(a, step, 24);
   for (int bc = 0; bc < a.Bpad; bc += kBC) {
     if (bc) __syncthreads();
+    constexpr int kLD = 1024 / kST;   // float4 per thread and operand (16 rows x 64 float4)
+    float4 avs[kLD], dvs[kLD];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int q = tid + i * kThreads;
+    for (int i = 0; i < kLD; ++i) {
+      const int q = tid + i * kST;
       const int r = q >> 6, c4 = (q & 63) * 4;
       float4 av = make_float4(0.f, 0.f, 0.f, 0.f), dv = av;
       if (t.kind == 0) {
@@ -439,21 +738,37 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
           if (t.kind == 1) av = ld_cg4(a.actG + (size_t)(aOff + n) * a.Bpad + bc + c4);
         }
       }
-      *reinterpret_cast<float4*>(As + r * kBCP + c4) = av;
-      *reinterpret_cast<float4*>(Ds + r * kBCP + c4) = dv;
+      avs[i] = av; dvs[i] = dv;
+    }
+#pragma unroll
+    for (int i = 0; i < kLD; ++i) {
+      const int q = tid + i * kST;
+      const int r = q >> 6, c4 = (q & 63) * 4;
+      *reinterpret_cast<float4*>(As + r * kBCP + c4) = avs[i];
+      *reinterpret_cast<float4*>(Ds + r * kBCP + c4) = dvs[i];
     }
     __syncthreads();
+    DBG_T(a, step, 25);
     if (t.kind == 0) {
-      const float* ap = As + kk * kBCP;
-      const float* dp = Ds + nn * kBCP;
-#pragma unroll 8
-      for (int b4 = 0; b4 < kBC; b4 += 4) {
-        const float4 x = *reinterpret_cast<const float4*>(ap + b4);
-        const float4 d = *reinterpret_cast<const float4*>(dp + b4);
-        acc = fmaf(x.x, d.x, acc); acc = fmaf(x.y, d.y, acc); acc = fmaf(x.z, d.z, acc); acc = fmaf(x.w, d.w, acc);
+      // 2x2 register blocking: thread (g, k2, n2) accumulates outputs (k2|k2+8, n2|n2+8) over the
+      // slice g of the batch chunk; partials are combined through shared memory below
+      constexpr int kG = kST / 64, kBL = kBC / kG;
+      const int g = tid >> 6, k2 = (tid >> 3) & 7, n2 = tid & 7;
+      const float* a0 = As + k2 * kBCP + g * kBL;
+      const float* a1 = a0 + 8 * kBCP;
+      const float* d0 = Ds + n2 * kBCP + g * kBL;
+      const float* d1 = d0 + 8 * kBCP;
+#pragma unroll 4
+      for (int b4 = 0; b4 < kBL; b4 += 4) {
+        const float4 xa = *reinterpret_cast<const float4*>(a0 + b4), xb = *reinterpret_cast<const float4*>(a1 + b4);
+        const float4 da = *reinterpret_cast<const float4*>(d0 + b4), db = *reinterpret_cast<const float4*>(d1 + b4);
+        q4[0] = fmaf(xa.x, da.x, q4[0]); q4[0] = fmaf(xa.y, da.y, q4[0]); q4[0] = fmaf(xa.z, da.z, q4[0]); q4[0] = fmaf(xa.w, da.w, q4[0]);
+        q4[1] = fmaf(xa.x, db.x, q4[1]); q4[1] = fmaf(xa.y, db.y, q4[1]); q4[1] = fmaf(xa.z, db.z, q4[1]); q4[1] = fmaf(xa.w, db.w, q4[1]);
+        q4[2] = fmaf(xb.x, da.x, q4[2]); q4[2] = fmaf(xb.y, da.y, q4[2]); q4[2] = fmaf(xb.z, da.z, q4[2]); q4[2] = fmaf(xb.w, da.w, q4[2]);
+        q4[3] = fmaf(xb.x, db.x, q4[3]); q4[3] = fmaf(xb.y, db.y, q4[3]); q4[3] = fmaf(xb.z, db.z, q4[3]); q4[3] = fmaf(xb.w, db.w, q4[3]);
       }
-    } else {
-      // vector tiles: warp w reduces rows 2w, 2w+1 over the batch chunk
+    } else if (tid < 256) {
+      // vector tiles: warp w (of the first 8) reduces rows 2w, 2w+1 over the batch chunk
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
         const int r = warp * 2 + rr;
@@ -472,132 +787,163 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
       }
     }
   }
+  if (t.kind == 0) {   // combine the batch slices: thread (kk, nn) of the first 256 owns output (kk, nn)
+    __syncthreads();
+    float* part = As;  // [kST/64][64][4]
+    *reinterpret_cast<float4*>(part + tid * 4) = make_float4(q4[0], q4[1], q4[2], q4[3]);
+    __syncthreads();
+    if (tid < 256) {
+      const int q = (kk & 7) * 8 + (nn & 7), j = (kk >> 3) * 2 + (nn >> 3);
+      float v = 0.f;
+#pragma unroll
+      for (int g = 0; g < kST / 64; ++g) v += part[(g * 64 + q) * 4 + j];
+      acc = v;
+    }
+  }
+  DBG_T(a, step, 26);
   const AdamCoef ac = adam_coef(hp, c);
-  if (t.kind == 0) {
-    const int k = t.k0 + kk, n = t.n0 + nn;
-    if (n < N && k <= K) {
-      const int p = k < K ? L.wOff + k * L.ld + n : L.bOff + n;
-      a.G[p] = acc;
-      const float wn = adam_step(ac, acc, a.W + p, a.M1 + p, a.M2 + p);
-      if (k < K && L.wtOff >= 0) a.WT[L.wtOff + n * L.ldt + k] = wn;
-    }
-  } else if (lane < 2) {
-    const int n = t.n0 + warp * 2 + lane;
-    if (n < N) {
-      if (t.kind == 1) {
-        const int pw = L.wOff + n, pb = L.bOff + n;
-        a.G[pw] = acc2; a.G[pb] = acc;
-        adam_step(ac, acc2, a.W + pw, a.M1 + pw, a.M2 + pw);
-        adam_step(ac, acc, a.W + pb, a.M1 + pb, a.M2 + pb);
-      } else {
-        const int pb = L.bOff + n;
-        a.G[pb] = acc;
-        adam_step(ac, acc, a.W + pb, a.M1 + pb, a.M2 + pb);
-      }
-    }
+  if (p0 >= 0) {
+    a.G[p0] = acc;
+    a.Wimg[pimg0] = adam_step(ac, acc, w0, m10, m20, a.W + p0, a.M1 + p0, a.M2 + p0);
+  }
+  if (p1 >= 0) {
+    a.G[p1] = acc2;
+    a.Wimg[pimg1] = adam_step(ac, acc2, w1, m11, m21, a.W + p1, a.M1 + p1, a.M2 + p1);
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // P3: replay statistics, Cmax annealing, ReF-ER beta update; writes ctrl[(step+1)&1]
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double block_sum(double v, double* sh) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();
-  if (lane == 0) sh[warp] = v;
-  __syncthreads();
-  double r = 0.0;
-  for (int w = 0; w < kThreads / 32; ++w) r += sh[w];
-  return r;
-}
-__device__ __forceinline__ float block_max(float v, float* sh) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  __syncthreads();
-  if (lane == 0) sh[warp] = v;
-  __syncthreads();
-  float r = sh[0];
-  for (int w = 1; w < kThreads / 32; ++w) r = fmaxf(r, sh[w]);
-  return r;
-}
-
 // Episode::updateCumulative_atomic / updateValues_atomic applied in sample order, one thread
 // per run of samples that share an episode (samples are sorted, so runs are contiguous).
-__device__ void apply_sample_records(const StepArgs& a) {
+// Records are staged through shared memory 256 at a time.  Returns this thread's share of the
+// exact far-policy flag changes.
+__device__ int apply_sample_records(const StepArgs& a, float* stage /* >= 256*12 floats */) {
   const ReplayView& rp = a.rp;
   const int ME = rp.maxEpisodes;
-  for (int b = threadIdx.x; b < a.B; b += kThreads) {
-    const int slot = a.rec[b].slot;
-    if (b > 0 && a.rec[b - 1].slot == slot) continue;
-    float avgKL = rp.epAgg[AGG_KL * ME + slot], frac = rp.epAgg[AGG_FAR * ME + slot];
-    float avgE2 = rp.epAgg[AGG_E2 * ME + slot], maxE = rp.epAgg[AGG_MAXE * ME + slot];
-    float sQ2 = rp.epAgg[AGG_Q2 * ME + slot], sQ = rp.epAgg[AGG_Q1 * ME + slot];
-    float maxQ = rp.epAgg[AGG_MAXQ * ME + slot], minQ = rp.epAgg[AGG_MINQ * ME + slot];
-    const float invN = 1.0f / (float)rp.epLen[slot];
-    for (int j = b; j < a.B; ++j) {
-      const SampleRec r = a.rec[j];
-      if (r.slot != slot) break;
-      if (r.hasNext) {
-        sQ2 += r.qNextNew * r.qNextNew - r.qNextOld * r.qNextOld; sQ += r.qNextNew - r.qNextOld;
-        maxQ = fmaxf(maxQ, r.qNextNew); minQ = fminf(minQ, r.qNextNew);
-      }
-      avgKL += invN * r.dKL; frac += invN * r.dFar; avgE2 += invN * r.dE2; maxE = fmaxf(maxE, r.absE);
-      sQ2 += r.qNew * r.qNew - r.qOld * r.qOld; sQ += r.qNew - r.qOld;
-      maxQ = fmaxf(maxQ, r.qNew); minQ = fminf(minQ, r.qNew);
+  int farDelta = 0;
+  constexpr int CH = 256;
+  for (int c0 = 0; c0 < a.B; c0 += CH) {
+    const int b = c0 + threadIdx.x;
+    const int cend = min(a.B, c0 + CH);
+    const bool mine = threadIdx.x < CH && b < a.B;
+    int slot = -1, prevSlot = -2;
+    if (mine) {
+      const int4 h = __ldcg(reinterpret_cast<const int4*>(&a.rec[b]));
+      const float4 d = __ldcg(reinterpret_cast<const float4*>(&a.rec[b].dKL));
+      const float4 q = __ldcg(reinterpret_cast<const float4*>(&a.rec[b].qOld));
+      if (b > 0) prevSlot = __ldcg(&a.rec[b - 1].slot);
+      slot = h.x; farDelta += h.z;
+      float4* st = reinterpret_cast<float4*>(stage + threadIdx.x * 12);
+      st[0] = make_float4(__int_as_float(h.x), __int_as_float(h.y), 0.f, 0.f); st[1] = d; st[2] = q;
     }
-    rp.epAgg[AGG_KL * ME + slot] = avgKL; rp.epAgg[AGG_FAR * ME + slot] = frac;
-    rp.epAgg[AGG_E2 * ME + slot] = avgE2; rp.epAgg[AGG_MAXE * ME + slot] = maxE;
-    rp.epAgg[AGG_Q2 * ME + slot] = sQ2; rp.epAgg[AGG_Q1 * ME + slot] = sQ;
-    rp.epAgg[AGG_MAXQ * ME + slot] = maxQ; rp.epAgg[AGG_MINQ * ME + slot] = minQ;
+    __syncthreads();
+    if (mine && prevSlot != slot) {
+      float avgKL = rp.epAgg[AGG_KL * ME + slot], frac = rp.epAgg[AGG_FAR * ME + slot];
+      float avgE2 = rp.epAgg[AGG_E2 * ME + slot], maxE = rp.epAgg[AGG_MAXE * ME + slot];
+      float sQ2 = rp.epAgg[AGG_Q2 * ME + slot], sQ = rp.epAgg[AGG_Q1 * ME + slot];
+      float maxQ = rp.epAgg[AGG_MAXQ * ME + slot], minQ = rp.epAgg[AGG_MINQ * ME + slot];
+      const float invN = 1.0f / (float)rp.epLen[slot];
+      for (int j = b; j < a.B; ++j) {
+        int sj, hn; float4 d, q;
+        if (j < cend) {
+          const float4* st = reinterpret_cast<const float4*>(stage + (j - c0) * 12);
+          const float4 h = st[0]; sj = __float_as_int(h.x); hn = __float_as_int(h.y); d = st[1]; q = st[2];
+        } else {   // run continues past the staged chunk
+          const int4 h = __ldcg(reinterpret_cast<const int4*>(&a.rec[j])); sj = h.x; hn = h.y;
+          d = __ldcg(reinterpret_cast<const float4*>(&a.rec[j].dKL)); q = __ldcg(reinterpret_cast<const float4*>(&a.rec[j].qOld));
+        }
+        if (sj != slot) break;
+        if (hn) {
+          sQ2 += q.w * q.w - q.z * q.z; sQ += q.w - q.z;
+          maxQ = fmaxf(maxQ, q.w); minQ = fminf(minQ, q.w);
+        }
+        avgKL += invN * d.x; frac += invN * d.y; avgE2 += invN * d.z; maxE = fmaxf(maxE, d.w);
+        sQ2 += q.y * q.y - q.x * q.x; sQ += q.y - q.x;
+        maxQ = fmaxf(maxQ, q.y); minQ = fminf(minQ, q.y);
+      }
+      rp.epAgg[AGG_KL * ME + slot] = avgKL; rp.epAgg[AGG_FAR * ME + slot] = frac;
+      rp.epAgg[AGG_E2 * ME + slot] = avgE2; rp.epAgg[AGG_MAXE * ME + slot] = maxE;
+      rp.epAgg[AGG_Q2 * ME + slot] = sQ2; rp.epAgg[AGG_Q1 * ME + slot] = sQ;
+      rp.epAgg[AGG_MAXQ * ME + slot] = maxQ; rp.epAgg[AGG_MINQ * ME + slot] = minQ;
+    }
+    __syncthreads();
   }
+  return farDelta;
 }
 
 // updateTrainingStatistics reductions + updateCounters (MemoryProcessing.cpp:46-92,187-259).
 // `sweep` != nullptr on the every-1000-steps recompute: Retrace error sums come from the sweep.
+constexpr int kStatChunk = 4096;   // episode positions staged per pass (floats of shared memory)
+
 __device__ void stats_and_refer(const StepArgs& a, const Hyper& hp, const StepCtrl& c, StepCtrl& nx, int step,
-                                const SweepSums* sweep, long long farExactOverride) {
-  __shared__ double shd[kThreads / 32];
-  __shared__ float shf[kThreads / 32];
-  __shared__ unsigned long long shn[kThreads];
+                                const SweepSums* sweep, long long farExactOverride, int farDeltaMine, float* xs) {
+  __shared__ double shd[kST / 32][6];
+  __shared__ float shf[kST / 32][3];
+  __shared__ unsigned long long shn[kST];
   const ReplayView& rp = a.rp;
   const int ME = rp.maxEpisodes, nEp = a.nEpisodes, tid = threadIdx.x;
-  double sumDKL = 0, sumE2 = 0, sumQ2 = 0, sumQ1 = 0, sumR = 0;
+  const int lane = tid & 31, warp = tid >> 5;
+  double sumDKL = 0, sumE2 = 0, sumQ2 = 0, sumQ1 = 0, sumR = 0, farD = (double)farDeltaMine;
   float maxAbsE = -1e9f, maxQ = -1e9f, negMinQ = -1e9f;
-  for (int pos = tid; pos < nEp; pos += kThreads) {
-    const int slot = rp.epOrder[pos];
-    const float Ns = (float)rp.epLen[slot];
-    sumDKL += (double)(Ns * rp.epAgg[AGG_KL * ME + slot]);
-    sumE2 += (double)(Ns * rp.epAgg[AGG_E2 * ME + slot]);
-    sumQ2 += (double)rp.epAgg[AGG_Q2 * ME + slot];
-    sumQ1 += (double)rp.epAgg[AGG_Q1 * ME + slot];
-    sumR += (double)rp.epAgg[AGG_TOTR * ME + slot];
-    maxAbsE = fmaxf(maxAbsE, rp.epAgg[AGG_MAXE * ME + slot]);
-    maxQ = fmaxf(maxQ, rp.epAgg[AGG_MAXQ * ME + slot]);
-    negMinQ = fmaxf(negMinQ, -rp.epAgg[AGG_MINQ * ME + slot]);
-  }
   // `Uint nOffPol += float` inside an OpenMP reduction with schedule(static,1): thread j of T
   // accumulates episodes j, j+T, ... with a float round trip per addition, partial counts are
   // then added as integers (MemoryProcessing.cpp:202-227).
   const int T = hp.referThreads;
   unsigned long long nOff = 0;
-  if (tid < T) {
-    for (int pos = tid; pos < nEp; pos += T) {
-      const int slot = rp.epOrder[pos];
-      const float x = (float)rp.epLen[slot] * rp.epAgg[AGG_FAR * ME + slot];
-      nOff = (unsigned long long)(__ull2float_rn(nOff) + x);
+  for (int base = 0; base < nEp; base += kStatChunk) {
+    const int n = min(kStatChunk, nEp - base);
+    for (int p0 = tid; p0 < n; p0 += 4 * kST) {
+      int sl[4]; float Ns[4], far[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int p = p0 + u * kST; sl[u] = p < n ? rp.epOrder[base + p] : -1; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (sl[u] < 0) continue;
+        const int slot = sl[u];
+        Ns[u] = (float)rp.epLen[slot]; far[u] = rp.epAgg[AGG_FAR * ME + slot];
+        sumDKL += (double)(Ns[u] * rp.epAgg[AGG_KL * ME + slot]);
+        sumE2 += (double)(Ns[u] * rp.epAgg[AGG_E2 * ME + slot]);
+        sumQ2 += (double)rp.epAgg[AGG_Q2 * ME + slot];
+        sumQ1 += (double)rp.epAgg[AGG_Q1 * ME + slot];
+        sumR += (double)rp.epAgg[AGG_TOTR * ME + slot];
+        maxAbsE = fmaxf(maxAbsE, rp.epAgg[AGG_MAXE * ME + slot]);
+        maxQ = fmaxf(maxQ, rp.epAgg[AGG_MAXQ * ME + slot]);
+        negMinQ = fmaxf(negMinQ, -rp.epAgg[AGG_MINQ * ME + slot]);
+        xs[p0 + u * kST] = Ns[u] * far[u];
+      }
     }
+    __syncthreads();
+    if (tid < T) {
+      int p = (tid - base % T + T) % T;     // first position of this chunk owned by virtual thread `tid`
+      for (; p < n; p += T) nOff = (unsigned long long)(__ull2float_rn(nOff) + xs[p]);
+    }
+    __syncthreads();
   }
   shn[tid] = nOff;
-  sumDKL = block_sum(sumDKL, shd); sumE2 = block_sum(sumE2, shd); sumQ2 = block_sum(sumQ2, shd);
-  sumQ1 = block_sum(sumQ1, shd); sumR = block_sum(sumR, shd);
-  maxAbsE = block_max(maxAbsE, shf); maxQ = block_max(maxQ, shf); negMinQ = block_max(negMinQ, shf);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sumDKL += __shfl_xor_sync(0xffffffffu, sumDKL, o); sumE2 += __shfl_xor_sync(0xffffffffu, sumE2, o);
+    sumQ2 += __shfl_xor_sync(0xffffffffu, sumQ2, o); sumQ1 += __shfl_xor_sync(0xffffffffu, sumQ1, o);
+    sumR += __shfl_xor_sync(0xffffffffu, sumR, o); farD += __shfl_xor_sync(0xffffffffu, farD, o);
+    maxAbsE = fmaxf(maxAbsE, __shfl_xor_sync(0xffffffffu, maxAbsE, o));
+    maxQ = fmaxf(maxQ, __shfl_xor_sync(0xffffffffu, maxQ, o));
+    negMinQ = fmaxf(negMinQ, __shfl_xor_sync(0xffffffffu, negMinQ, o));
+  }
+  if (lane == 0) {
+    shd[warp][0] = sumDKL; shd[warp][1] = sumE2; shd[warp][2] = sumQ2; shd[warp][3] = sumQ1; shd[warp][4] = sumR; shd[warp][5] = farD;
+    shf[warp][0] = maxAbsE; shf[warp][1] = maxQ; shf[warp][2] = negMinQ;
+  }
   __syncthreads();
   if (tid == 0) {
+    sumDKL = sumE2 = sumQ2 = sumQ1 = sumR = farD = 0.0;
+    for (int w = 0; w < kST / 32; ++w) {
+      sumDKL += shd[w][0]; sumE2 += shd[w][1]; sumQ2 += shd[w][2]; sumQ1 += shd[w][3]; sumR += shd[w][4]; farD += shd[w][5];
+      maxAbsE = fmaxf(maxAbsE, shf[w][0]); maxQ = fmaxf(maxQ, shf[w][1]); negMinQ = fmaxf(negMinQ, shf[w][2]);
+    }
     unsigned long long tot = 0;
-    for (int j = 0; j < min(T, kThreads); ++j) tot += shn[j];
+    for (int j = 0; j < min(T, kST); ++j) tot += shn[j];
     const long long gstep = c.grad_step + 1;                                   // nGradSteps()+1
     const double C = hp.clipImpWeight, E = hp.epsAnneal;
     const double cmax = 1.0 + C / (1.0 + (double)gstep * E);                  // annealRate
@@ -616,10 +962,7 @@ __device__ void stats_and_refer(const StepArgs& a, const Hyper& hp, const StepCt
     const double var = sumQ2 / nData - nx.avg_q * nx.avg_q;
     nx.stdev_q = sqrt(fmax(var, 1e-16));
     if (sweep) { nx.cnt_ret = (c.cnt_ret < 0 ? 0 : c.cnt_ret) + sweep->nRet; nx.sum_ret_err = c.sum_ret_err + sweep->sumErr2; }
-    long long exact = c.n_far_exact;
-    if (farExactOverride >= 0) exact = farExactOverride;
-    else for (int b = 0; b < a.B; ++b) exact += a.rec[b].farDelta;
-    nx.n_far_exact = exact;
+    nx.n_far_exact = farExactOverride >= 0 ? farExactOverride : c.n_far_exact + (long long)farD;
     // updateCounters: beta fixed-point iteration (MemoryProcessing.cpp:73-85); it runs after
     // applyEpisodesRemovalAlgo, so nStoredSteps() is the post-pruning count
     const double nPost = (double)(step == a.lastStep ? a.nTransitionsPost : a.nTransitions);
@@ -633,6 +976,7 @@ __device__ void stats_and_refer(const StepArgs& a, const Hyper& hp, const StepCt
     double t1 = c.adam_bt1 * 0.9; if (t1 < (double)FLT_EPSILON) t1 = 0; nx.adam_bt1 = t1;
     double t2 = c.adam_bt2 * 0.999; if (t2 < (double)FLT_EPSILON) t2 = 0; nx.adam_bt2 = t2;
     nx.grad_step = c.grad_step + 1;
+    nx.adam_eta = adam_eta_for(hp.learnrate, hp.epsAnneal, nx.adam_step, nx.adam_bt1, nx.adam_bt2);
     if (a.statsOut) {
       smb200_step_stats& o = a.statsOut[step - a.stepBase];
       o.beta = nx.beta; o.cmax = nx.cmax; o.cinv = nx.cinv; o.n_far_policy = nx.n_far_ref; o.n_far_exact = nx.n_far_exact;
@@ -643,170 +987,294 @@ __device__ void stats_and_refer(const StepArgs& a, const Hyper& hp, const StepCt
   }
 }
 
-__device__ void p3_stats(const StepArgs& a, const Hyper& hp, const StepCtrl& c, StepCtrl& nx, int step) {
-  apply_sample_records(a);
+__device__ void p3_stats(const StepArgs& a, const Hyper& hp, const StepCtrl& c, StepCtrl& nx, int step, float* stage) {
+  const int fd = apply_sample_records(a, stage);
   __threadfence_block();
   __syncthreads();
-  stats_and_refer(a, hp, c, nx, step, nullptr, -1);
+  stats_and_refer(a, hp, c, nx, step, nullptr, -1, fd, stage);
 }
-
-// On a sweep step the statistics phase is replaced by the sweep kernels + k_finalize_sweep; Adam
-// bookkeeping must still advance, which stats_and_refer does there.
 
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
-using SmemHdr = DevDescs;
-
-__device__ __forceinline__ float* load_descs(const StepArgs& a, unsigned char* raw, const NetDesc*& net, const Hyper*& hp) {
-  SmemHdr* h = reinterpret_cast<SmemHdr*>(raw);
-  const int nw = (int)(sizeof(SmemHdr) / 4);
+__device__ __forceinline__ void load_descs(const StepArgs& a, unsigned char* raw, const NetDesc*& net, const Hyper*& hp) {
+  DevDescs* h = reinterpret_cast<DevDescs*>(raw);
+  const int nw = (int)(sizeof(DevDescs) / 4);
   const int* src = reinterpret_cast<const int*>(a.descs);
   int* dst = reinterpret_cast<int*>(h);
-  for (int i = threadIdx.x; i < nw; i += kThreads) dst[i] = src[i];
+  for (int i = threadIdx.x; i < nw; i += kST) dst[i] = src[i];
   __syncthreads();
   net = &h->net; hp = &h->hp;
-  return reinterpret_cast<float*>(raw + ((sizeof(SmemHdr) + 15) / 16) * 16);
 }
 
-// StepCtrl is rewritten by other CTAs between steps: read it through L2
-__device__ __forceinline__ void load_ctrl(StepCtrl& dst, const StepCtrl* src) {
-  static_assert(sizeof(StepCtrl) % 8 == 0, "StepCtrl must be a multiple of 8 bytes");
-  const long long* s = reinterpret_cast<const long long*>(src);
-  long long* d = reinterpret_cast<long long*>(&dst);
-  for (int i = 0; i < (int)(sizeof(StepCtrl) / 8); ++i) d[i] = __ldcg(s + i);
+__device__ __forceinline__ void init_bars(const StepArgs& a, const NetDesc& net, unsigned char* smraw, const SmemPlan& sp) {
+  if (a.useTma && threadIdx.x == 0) {
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + sp.bars);
+    for (int l = 0; l < net.nLayers; ++l) mbar_init(&bars[l], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
 }
 
-template <int TB>
-__global__ void __launch_bounds__(kThreads) k_p1(StepArgs a, int step) {
-  extern __shared__ __align__(16) unsigned char smraw[];
+template <int TB, bool SM>
+__global__ void __launch_bounds__(kST) k_p1(StepArgs a, int step) {
+  extern __shared__ __align__(128) unsigned char smraw[];
   const NetDesc* net; const Hyper* hp;
-  float* smem = load_descs(a, smraw, net, hp);
+  load_descs(a, smraw, net, hp);
+  const SmemPlan sp = smem_plan(*net, TB, SM);
+  __shared__ StepCtrl c;
+  if (SM) {
+    init_bars(a, *net, smraw, sp);
+    load_weight_image(a, *net, reinterpret_cast<float*>(smraw + sp.img), reinterpret_cast<uint64_t*>(smraw + sp.bars));
+  }
+  __syncthreads();
+  p1_tile<TB, SM>(a, *net, *hp, c, step, blockIdx.x, smraw, sp, 0, true, nullptr, 0, false);
+}
+
+__global__ void __launch_bounds__(kST) k_p2p3(StepArgs a, int step, int skipStats) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const NetDesc* net; const Hyper* hp;
+  load_descs(a, smraw, net, hp);
   __shared__ StepCtrl c;
   if (threadIdx.x == 0) load_ctrl(c, &a.ctrl[step & 1]);
   __syncthreads();
-  p1_tile<TB>(a, *net, *hp, c, step, blockIdx.x, smem);
+  float* tiles = reinterpret_cast<float*>(smraw + ((sizeof(DevDescs) + 15) / 16) * 16);
+  if ((int)blockIdx.x < a.nTiles) p2_tile(a, *net, *hp, c, a.tiles[blockIdx.x], tiles, step);
+  else if (!skipStats) p3_stats(a, *hp, c, a.ctrl[(step + 1) & 1], step, tiles);
 }
 
-__global__ void __launch_bounds__(kThreads) k_p2p3(StepArgs a, int step, int skipStats) {
-  extern __shared__ __align__(16) unsigned char smraw[];
+// Persistent cooperative kernel: the last CTA is the statistics CTA (P3), all others are workers
+// (P1 tiles, then P2 tiles, two grid barriers per step).  The statistics CTA never joins the
+// barriers: it watches the barrier counter to learn that every worker finished P1 of a step and
+// publishes ctrl[(step+1)&1] through `ready`, which the workers only need at their next loss stage
+// — so the replay statistics are off the critical path.
+template <int TB, bool SM>
+__global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int step0, int nSteps, int skipStatsLast) {
+  extern __shared__ __align__(128) unsigned char smraw[];
   const NetDesc* net; const Hyper* hp;
-  float* smem = load_descs(a, smraw, net, hp);
+  load_descs(a, smraw, net, hp);
+  const SmemPlan sp = smem_plan(*net, TB, SM);
   __shared__ StepCtrl c;
-  if (threadIdx.x == 0) load_ctrl(c, &a.ctrl[step & 1]);
-  __syncthreads();
-  if ((int)blockIdx.x < a.nTiles) p2_tile(a, *net, *hp, c, a.tiles[blockIdx.x], smem);
-  else if (!skipStats) p3_stats(a, *hp, c, a.ctrl[(step + 1) & 1], step);
-}
-
-template <int TB>
-__global__ void __launch_bounds__(kThreads, 1) k_steps_persistent(StepArgs a, int step0, int nSteps, int skipStatsLast) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  const NetDesc* net; const Hyper* hp;
-  float* smem = load_descs(a, smraw, net, hp);
-  __shared__ StepCtrl c;
-  const int nb = gridDim.x;
+  const int nw = gridDim.x - 1;                 // worker CTAs
+  unsigned* ready = a.barrier + 1;              // local steps whose statistics are published
+  float* tiles = reinterpret_cast<float*>(smraw + sp.tiles);
+  if ((int)blockIdx.x == nw) {                  // ---- statistics CTA ----
+    for (int s = 0; s < nSteps; ++s) {
+      if (skipStatsLast && s == nSteps - 1) break;
+      const int step = step0 + s;
+      if (threadIdx.x == 0) {
+        const unsigned target = (unsigned)(2 * s + 1) * (unsigned)nw;      // every worker passed barrier 1 of step s
+        while (ld_acquire(a.barrier) < target) { }
+        __threadfence();
+        load_ctrl(c, &a.ctrl[step & 1]);
+      }
+      __syncthreads();
+      DBG_T(a, step, 6);
+      p3_stats(a, *hp, c, a.ctrl[(step + 1) & 1], step, tiles);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ready), "r"((unsigned)(s + 1)) : "memory");
+      }
+      DBG_T(a, step, 7);
+    }
+    return;
+  }
   const int nP1 = (a.B + TB - 1) / TB;
+  unsigned barTarget = 0;
+  float* img = reinterpret_cast<float*>(smraw + sp.img);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + sp.bars);
+  const bool doP1 = (int)blockIdx.x < nP1;
+  const int tid = threadIdx.x;
+  const int dS = net->dS, dA = net->dA, nPair = TB * dA;
+  const int nS4 = dS * TB / 4;                      // float4 chunks of this tile's raw states
+  // inputs of step s+1 are prefetched into registers while P2 of step s runs, then parked in the
+  // shared-memory staging area: possible when every worker owns at most one P1 tile
+  const bool pf = doP1 && nP1 <= nw && (dS & 3) == 0 && nS4 <= 2 * kST && nPair <= kST;
+  const Staging stg = staging_view<TB>(*net, smraw, sp);
+  const int b0 = blockIdx.x * TB;
+  const ReplayView& rp = a.rp;
+  if (pf) {   // state normalisers are constant during a launch (they change only at sweeps)
+    for (int k = tid; k < dS; k += kST) { stg.mean[k] = ld_cg(rp.stateMean + k); stg.scale[k] = ld_cg(rp.stateScale + k); }
+  }
+  if (SM) init_bars(a, *net, smraw, sp);
+  // the first GradTile of this CTA never changes: keep it in registers
+  GradTile myTile = {0, 0, 0, 0};
+  if ((int)blockIdx.x < a.nTiles) myTile = a.tiles[blockIdx.x];
+  bool staged = false;
   for (int s = 0; s < nSteps; ++s) {
     const int step = step0 + s;
-    if (threadIdx.x == 0) load_ctrl(c, &a.ctrl[step & 1]);
-    __syncthreads();
-    for (int t = blockIdx.x; t < nP1; t += nb) { p1_tile<TB>(a, *net, *hp, c, step, t, smem); __syncthreads(); }
-    grid_barrier(a.barrier, nb);
-    const bool skip = skipStatsLast && s == nSteps - 1;
-    for (int t = blockIdx.x; t < a.nTiles + 1; t += nb) {
-      if (t < a.nTiles) { p2_tile(a, *net, *hp, c, a.tiles[t], smem); __syncthreads(); }
-      else if (!skip) p3_stats(a, *hp, c, a.ctrl[(step + 1) & 1], step);
+    DBG_T(a, step, 0);
+    if (SM && doP1) load_weight_image(a, *net, img, bars);
+    // ring rows of the NEXT step's samples this thread will prefetch (known long before they are needed)
+    const bool pfNow = pf && s + 1 < nSteps;
+    int nxRowS[2] = {-1, -1}, nxRowT = -1, nxSf = 0, nxRowP = -1;
+    if (pfNow) {
+      const size_t jb = (size_t)(step + 1 - a.stepBase) * a.B + b0;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int q = tid + u * kST;
+        if (q < nS4) { const int si = q / (dS >> 2); if (b0 + si < a.B) nxRowS[u] = a.sampRow[jb + si]; }
+      }
+      if (tid < TB && b0 + tid < a.B) { nxRowT = a.sampRow[jb + tid]; nxSf = a.sampSlot[jb + tid]; }
+      if (tid < nPair) { const int si = tid / dA; if (b0 + si < a.B) nxRowP = a.sampRow[jb + si]; }
     }
-    grid_barrier(a.barrier, nb);
+    bool first = true;
+    for (int t = blockIdx.x; t < nP1; t += nw) {
+      p1_tile<TB, SM>(a, *net, *hp, c, step, t, smraw, sp, (unsigned)(s & 1), first, ready, (unsigned)s, staged);
+      first = false;
+      __syncthreads();
+    }
+    DBG_T(a, step, 5);
+    grid_barrier(a.barrier, barTarget, nw);
+    DBG_T(a, step, 6);
+    // ---- issue the loads of the next step's inputs (consumed after P2) ----
+    float4 pfS[2]; float pfOld[8]; float pfPair[3]; int pfInfo[4] = {0, 0, 0, 0};
+    if (pfNow) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int q = tid + u * kST;
+        pfS[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nxRowS[u] >= 0) { const int c4 = (q % (dS >> 2)) * 4; pfS[u] = ld_cg4(rp.S + (size_t)nxRowS[u] * dS + c4); }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pfOld[j] = 0.f;
+      if (nxRowT >= 0) {
+        const int row = nxRowT, hn = (nxSf >> 31) & 1;
+        pfInfo[0] = row; pfInfo[1] = nxSf & 0x7fffffff; pfInfo[2] = hn; pfInfo[3] = 1;
+        pfOld[0] = ld_cg(rp.V + row); pfOld[1] = ld_cg(rp.ADV + row); pfOld[2] = ld_cg(rp.RHO + row); pfOld[3] = ld_cg(rp.KL + row);
+        pfOld[4] = ld_cg(rp.DELTA + row); pfOld[7] = ld_cg(rp.Q + row);
+        if (hn) { pfOld[5] = ld_cg(rp.V + row + 1); pfOld[6] = ld_cg(rp.ADV + row + 1); }
+      }
+      pfPair[0] = 0.f; pfPair[1] = 0.f; pfPair[2] = 1.f;
+      if (nxRowP >= 0) {
+        const int i = tid % dA;
+        const size_t row = nxRowP;
+        pfPair[0] = ld_cg(rp.A + row * dA + i); pfPair[1] = ld_cg(rp.MU + row * 2 * dA + i); pfPair[2] = ld_cg(rp.MU + row * 2 * dA + dA + i);
+      }
+    }
+    if (!doP1) {          // tile-only workers still need this step's Adam scalars
+      if (tid == 0) load_ctrl(c, &a.ctrl[step & 1]);
+      __syncthreads();
+    }
+    for (int t = blockIdx.x; t < a.nTiles; t += nw) {
+      p2_tile(a, *net, *hp, c, t == (int)blockIdx.x ? myTile : a.tiles[t], tiles, step);
+      __syncthreads();
+    }
+    // ---- park the prefetched inputs in shared memory (read by P1 of the next step) ----
+    if (pfNow) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int q = tid + u * kST;
+        if (q < nS4) reinterpret_cast<float4*>(stg.S)[q] = pfS[u];
+      }
+      if (tid < TB) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) stg.old[j * TB + tid] = pfOld[j];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) stg.info[j * TB + tid] = pfInfo[j];
+      }
+      if (tid < nPair) { stg.pair[tid] = pfPair[0]; stg.pair[nPair + tid] = pfPair[1]; stg.pair[2 * nPair + tid] = pfPair[2]; }
+    }
+    staged = pfNow;
+    DBG_T(a, step, 7);
+    grid_barrier(a.barrier, barTarget, nw);
   }
 }
 
 // statistics after the every-1000-steps sweep (replaces P3 on that step)
-__global__ void __launch_bounds__(kThreads) k_finalize_sweep(StepArgs a, int step, const SweepSums* sweep) {
+__global__ void __launch_bounds__(kST) k_finalize_sweep(StepArgs a, int step, const SweepSums* sweep) {
   __shared__ Hyper hp; __shared__ StepCtrl c;
+  __shared__ float xs[kStatChunk];
   if (threadIdx.x == 0) { hp = a.descs->hp; load_ctrl(c, &a.ctrl[step & 1]); }
   __syncthreads();
-  stats_and_refer(a, hp, c, a.ctrl[(step + 1) & 1], step, sweep, sweep->nFarExact);
+  stats_and_refer(a, hp, c, a.ctrl[(step + 1) & 1], step, sweep, sweep->nFarExact, 0, xs);
 }
 
 // actor-side / diagnostic forward on caller-provided raw states [n][dS] -> out[n][nOut]
 template <int TB>
-__global__ void __launch_bounds__(kThreads) k_forward(StepArgs a, const float* states, int n, float* out) {
-  extern __shared__ __align__(16) unsigned char smraw[];
+__global__ void __launch_bounds__(kST) k_forward(StepArgs a, const float* states, int n, float* out) {
+  extern __shared__ __align__(128) unsigned char smraw[];
   const NetDesc* net; const Hyper* hp;
-  float* smem = load_descs(a, smraw, net, hp);
-  float* act = smem;
-  float* red = act + 2 * net->actPerSample * TB;
+  load_descs(a, smraw, net, hp);
+  const SmemPlan sp = smem_plan(*net, TB, false);
+  float* act = reinterpret_cast<float*>(smraw + sp.act);
+  float* red = reinterpret_cast<float*>(smraw + sp.red);
   const int b0 = blockIdx.x * TB, dS = net->dS;
-  for (int idx = threadIdx.x; idx < dS * TB; idx += kThreads) {
+  for (int idx = threadIdx.x; idx < dS * TB; idx += kST) {
     const int k = idx / TB, s = idx - k * TB;
     act[idx] = b0 + s < n ? (states[(size_t)(b0 + s) * dS + k] - a.rp.stateMean[k]) * a.rp.stateScale[k] : 0.f;
   }
   __syncthreads();
-  net_forward<TB>(a, *net, act, red);
-  for (int idx = threadIdx.x; idx < net->nOut * TB; idx += kThreads) {
+  net_forward<TB, false>(*net, a.Wimg, act, red, nullptr, 0);
+  for (int idx = threadIdx.x; idx < net->nOut * TB; idx += kST) {
     const int j = idx / TB, s = idx - j * TB;
-    if (b0 + s < n) out[(size_t)(b0 + s) * net->nOut + j] = net_out(*net, act, TB, j, s);
+    if (b0 + s < n) out[(size_t)(b0 + s) * net->nOut + j] = net_out<false>(*net, a.Wimg, act, TB, j, s);
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------
-static size_t p1_smem_bytes(const NetDesc& net, int TB) {
-  size_t hdr = ((sizeof(SmemHdr) + 15) / 16) * 16;
-  return hdr + sizeof(float) * (2 * (size_t)net.actPerSample * TB + (size_t)kThreads * TB) + sizeof(int) * 4 * TB + sizeof(float) * TB + 64;
-}
-static size_t p2_smem_bytes() {
-  size_t hdr = ((sizeof(SmemHdr) + 15) / 16) * 16;
-  return hdr + sizeof(float) * 2 * kTileK * kBCP;
-}
-size_t step_smem_bytes(const NetDesc& net, int TB) { return p1_smem_bytes(net, TB) > p2_smem_bytes() ? p1_smem_bytes(net, TB) : p2_smem_bytes(); }
+static size_t p2_smem_bytes() { return ((sizeof(DevDescs) + 15) / 16) * 16 + sizeof(float) * 2 * kTileK * kBCP; }
 
-static bool g_attr_set = false;
+bool step_image_in_smem(const NetDesc& net) { return smem_plan(net, 4, true).total <= 200 * 1024; }
+size_t step_smem_bytes(const NetDesc& net, int TB) { return smem_plan(net, TB, step_image_in_smem(net)).total; }
+
 int step_kernels_prepare(const NetDesc& net) {
-  const size_t s4 = step_smem_bytes(net, 4);
-  if (s4 > 227 * 1024) { set_error_msg("network too wide for the shared-memory tile of the step kernel"); return -1; }
-  SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_p1<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s4));
+  const bool sm = step_image_in_smem(net);
+  const int sOn = (int)smem_plan(net, 4, true).total, sOff = (int)smem_plan(net, 4, false).total;
+  if (sOff > 200 * 1024) { set_error_msg("network too wide for the shared-memory tile of the step kernel"); return -1; }
+  if (sm) {
+    SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_p1<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOn));
+    SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_steps_persistent<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOn));
+  }
+  SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_p1<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOff));
+  SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_steps_persistent<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOff));
   SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_p2p3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2_smem_bytes()));
-  SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_steps_persistent<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s4));
-  SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_forward<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s4));
-  g_attr_set = true;
+  SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_forward<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOff));
   return 0;
 }
 
 int launch_step_two_kernels(const StepArgs& a, const NetDesc& net, int step, int skipStats, cudaStream_t st) {
   const int nP1 = (a.B + 3) / 4;
-  k_p1<4><<<nP1, kThreads, p1_smem_bytes(net, 4), st>>>(a, step);
-  k_p2p3<<<a.nTiles + 1, kThreads, p2_smem_bytes(), st>>>(a, step, skipStats);
+  const bool sm = step_image_in_smem(net);
+  if (sm) k_p1<4, true><<<nP1, kST, smem_plan(net, 4, true).total, st>>>(a, step);
+  else k_p1<4, false><<<nP1, kST, smem_plan(net, 4, false).total, st>>>(a, step);
+  k_p2p3<<<a.nTiles + 1, kST, p2_smem_bytes(), st>>>(a, step, skipStats);
   SMB200_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
 int persistent_grid(const StepArgs& a, const NetDesc& net, int numSMs) {
   int perSM = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_steps_persistent<4>, kThreads, step_smem_bytes(net, 4)) != cudaSuccess || perSM < 1) return 0;
-  const int want = max((a.B + 3) / 4, a.nTiles + 1);
-  return min(want, numSMs * perSM);
+  const bool sm = step_image_in_smem(net);
+  const cudaError_t e = sm ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_steps_persistent<4, true>, kST, step_smem_bytes(net, 4))
+                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_steps_persistent<4, false>, kST, step_smem_bytes(net, 4));
+  if (e != cudaSuccess || perSM < 1) return 0;
+  const int want = max((a.B + 3) / 4, a.nTiles) + 1;   // workers + the statistics CTA
+  const int g = min(want, numSMs * perSM);
+  return g >= 2 ? g : 0;
 }
 
 int launch_steps_persistent(const StepArgs& a, const NetDesc& net, int grid, int step0, int nSteps, int skipStatsLast, cudaStream_t st) {
-  SMB200_CUDA_CHECK(cudaMemsetAsync(a.barrier, 0, sizeof(unsigned), st));
+  SMB200_CUDA_CHECK(cudaMemsetAsync(a.barrier, 0, 2 * sizeof(unsigned), st));
   StepArgs aa = a;
   void* args[] = {&aa, &step0, &nSteps, &skipStatsLast};
-  SMB200_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_steps_persistent<4>, dim3(grid), dim3(kThreads), args, step_smem_bytes(net, 4), st));
+  const bool sm = step_image_in_smem(net);
+  const void* fn = sm ? (const void*)k_steps_persistent<4, true> : (const void*)k_steps_persistent<4, false>;
+  SMB200_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kST), args, step_smem_bytes(net, 4), st));
   return 0;
 }
 
 int launch_finalize_sweep(const StepArgs& a, int step, const SweepSums* sweep, cudaStream_t st) {
-  k_finalize_sweep<<<1, kThreads, 0, st>>>(a, step, sweep);
+  k_finalize_sweep<<<1, kST, 0, st>>>(a, step, sweep);
   SMB200_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
 int launch_forward(const StepArgs& a, const NetDesc& net, const float* states, int n, float* out, cudaStream_t st) {
-  k_forward<4><<<(n + 3) / 4, kThreads, p1_smem_bytes(net, 4), st>>>(a, states, n, out);
+  k_forward<4><<<(n + 3) / 4, kST, smem_plan(net, 4, false).total, st>>>(a, states, n, out);
   SMB200_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -18,9 +18,9 @@ struct SweepSums {
 struct StepArgs {
   const DevDescs* descs;
   ReplayView rp;
-  float* W; float* WT; float* M1; float* M2; float* G;
+  float* W; float* Wimg; float* M1; float* M2; float* G;   // Wimg: weights in the shared-memory image layout
   float* actG; float* errG;          // feature-major scratch [actPerSample][Bpad]
-  const int* sampSlot; const int* sampT;   // [nSteps][B]
+  const int* sampRow; const int* sampSlot;  // [nSteps][B]: ring row of (episode,t); slot | hasNext<<31
   SampleRec* rec;                    // [B]
   float* lastO; float* lastG; float* lastX;
   StepCtrl* ctrl;                    // [2]
@@ -32,8 +32,19 @@ struct StepArgs {
   int stepBase;                            // samples / statsOut are indexed by (step - stepBase)
   int lastStep;                            // absolute index of the segment's last step
   unsigned* barrier;
+  long long* dbgT;                         // optional phase timestamps [step][cta][8] (clock64)
+  int useTma;                              // weight image to shared memory by cp.async.bulk (1) or ld.global.cg (0)
 };
 
+int step_threads();
+// eta of the Adam update that follows `adam_step` completed updates (host and device use the same IEEE ops)
+__host__ __device__ inline float adam_eta_for(double learnrate, double epsAnneal, long long adam_step, double bt1d, double bt2d) {
+  const long long nStep = adam_step + 1;                                      // prepare_update: nStep++ (Optimizer.cpp:119)
+  const float etaf = (float)learnrate;
+  const float eta0 = (float)((double)etaf / (1.0 + (double)(float)(double)nStep * epsAnneal));   // annealRate<nnReal>
+  const float bt1 = (float)bt1d, bt2 = (float)bt2d;
+  return eta0 * sqrtf(1.0f - bt2) / (1.0f - bt1);                            // struct Adam ctor (Optimizer.cpp:64-67)
+}
 size_t step_smem_bytes(const NetDesc& net, int TB);
 int step_kernels_prepare(const NetDesc& net);
 int launch_step_two_kernels(const StepArgs& a, const NetDesc& net, int step, int skipStats, cudaStream_t st);

@@ -30,7 +30,7 @@ EXPORTS = [
     "smb200_n_episodes", "smb200_initialize_learner", "smb200_set_grad_step", "smb200_seed_sampler", "smb200_sample",
     "smb200_train_steps", "smb200_train_step_on", "smb200_get_last_batch", "smb200_retrace_sweep",
     "smb200_reward_state_moments", "smb200_read_field", "smb200_read_episodes", "smb200_n_rows", "smb200_get_stats",
-    "smb200_forward", "smb200_last_timing", "smb200_presample", "smb200_train_presampled", "smb200_sync",
+    "smb200_forward", "smb200_last_timing", "smb200_presample", "smb200_train_presampled", "smb200_sync", "smb200_profile_phases",
 ]
 
 FIELDS = dict(V=0, ADV=1, QRET=2, DELTA=3, RHO=4, KL=5, REWARD=6)
@@ -101,6 +101,7 @@ def load_library(path: str = LIB_PATH):
         "smb200_last_timing": (C.c_int, [H, dp, ip]),
         "smb200_presample": (C.c_int, [H, C.c_int32]), "smb200_train_presampled": (C.c_int, [H, C.c_int32, C.c_int32]),
         "smb200_sync": (C.c_int, [H]),
+        "smb200_profile_phases": (C.c_int, [H, C.c_int32, ip, C.c_int64, P(C.c_int32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -247,6 +248,15 @@ class Learner:
 
     def train_presampled(self, first, n):
         self._check(self.lib.smb200_train_presampled(self.h, int(first), int(n)))
+
+    def profile_phases(self, n):
+        """(cycles[n][grid][8], device ms) of one persistent launch over n presampled steps."""
+        cap = n * 148 * 48
+        out = np.zeros(cap, np.int64)
+        grid = C.c_int32()
+        self._check(self.lib.smb200_profile_phases(self.h, int(n), _ip(out), cap, C.byref(grid)))
+        g = grid.value
+        return out[:n * g * 48].reshape(n, g, 48), self.last_timing()[0]
 
     def sync(self):
         self._check(self.lib.smb200_sync(self.h))
