@@ -164,6 +164,16 @@ int smb200_last_timing(smb200_learner* h, double* ms_device, int64_t* kernel_lau
 int smb200_presample(smb200_learner* h, int32_t n_steps);
 int smb200_train_presampled(smb200_learner* h, int32_t first, int32_t n);
 int smb200_sync(smb200_learner* h);
+
+/* Several learner ranks (one process per GPU of one node) sharing the gradient: replaces the
+ * MPI_Iallreduce over learners_train_comm (Network/Optimizer.cpp:114-118) and the delayed
+ * reductions of counters / moments (Utils/DelayedReductor.cpp:73-82) by exchanges through
+ * peer memory inside the kernels.  comm_init allocates this rank's exchange block and returns
+ * its CUDA IPC handle (handle_bytes >= 64); the caller all-gathers the handles of all ranks
+ * (rank order) and passes them to comm_attach.  comm_error reports a timed-out peer. */
+int smb200_comm_init(smb200_learner* h, int32_t world, int32_t rank, uint8_t* handle_out, int32_t handle_bytes);
+int smb200_comm_attach(smb200_learner* h, const uint8_t* handles, int32_t handle_bytes);
+int smb200_comm_error(smb200_learner* h);
 /* Diagnostics: n presampled steps in one persistent launch with per-CTA phase timestamps
  * (SM clock cycles), out[n][grid][8]; *grid_out = CTAs of the persistent grid. */
 int smb200_profile_phases(smb200_learner* h, int32_t n, int64_t* out, int64_t capacity, int32_t* grid_out);

@@ -61,6 +61,8 @@ struct StepCtrl {
   long long grad_step;                // counters.nGradSteps before this step
   long long n_far_ref, n_far_exact;   // stats.nFarPolicySteps (reference formula) / exact flags
   float adam_eta; float pad_;         // learning rate of THIS step incl. bias correction (struct Adam ctor, Optimizer.cpp:64-67)
+  // multi-rank: global far-policy / stored counts of the previous step (DelayedReductor, MemoryProcessing.cpp:48-58)
+  double gl_far_prev, gl_stored_prev; long long cnt_seed_step;
   double avg_kl, avg_sq_err, max_abs_err, avg_return, stdev_q, avg_q, max_q, min_q;
   double sum_ret_err; long long cnt_ret;
 };

@@ -77,6 +77,9 @@ struct smb200_learner {
   // network / optimiser
   float *W = nullptr, *Wimg = nullptr, *M1 = nullptr, *M2 = nullptr, *G = nullptr;
   long long* dDbg = nullptr; int useTma = 1;
+  // multi-rank gradient exchange over peer memory (CUDA IPC)
+  CommView comm{}; unsigned char* commBuf = nullptr; int* dCommErr = nullptr; unsigned vecStamp = 0;
+  void* peerMapped[kMaxWorld] = {nullptr};
   float *actG = nullptr, *errG = nullptr;
   GradTile* dTiles = nullptr; int nTiles = 0;
   int Bpad = 0;
@@ -103,6 +106,7 @@ struct smb200_learner {
 
   StepArgs args() const {
     StepArgs a{};
+    a.comm = comm;
     a.descs = dDescs; a.rp = rp; a.W = W; a.Wimg = Wimg; a.M1 = M1; a.M2 = M2; a.G = G; a.dbgT = nullptr; a.useTma = useTma;
     a.actG = actG; a.errG = errG; a.sampRow = dSampT; a.sampSlot = dSampSlot; a.rec = dRec;
     a.lastO = lastO; a.lastG = lastG; a.lastX = lastX; a.ctrl = dCtrl; a.statsOut = dStats;
@@ -366,6 +370,7 @@ static int run_segment(smb200_learner* h, int first, int n, long long gstep0, in
     if (launch_sweep(h->rp, (int)h->episodes.size(), 0, (float)h->cfg.gamma, (float)h->cfg.lambda, 1, (float)cm, (float)(1.0 / cm),
                      h->dSums, h->stream)) return -2;
     if (launch_moments(h->rp, h->highWater, h->dSums, h->numSMs, h->stream)) return -2;
+    if (launch_peer_allreduce(h->comm, h->dSums->moments, 2 * h->cfg.dim_state + 3, ++h->vecStamp, h->stream)) return -2;
     if (launch_finalize_sweep(a, step, h->dSums, h->stream)) return -2;
     if (launch_update_scaling(h->rp, h->dCtrl + (step & 1), h->dDescs, h->dSums, 0, h->stream)) return -2;
     h->launches += 5;
@@ -476,6 +481,7 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
   k.adam_bt1 = 0.9; k.adam_bt2 = 0.999;
   CK(push_ctrl(h));
 
+  h->comm.world = 1; h->comm.rank = 0;
   h->gen.seed((unsigned long)c.seed);
   std::vector<float> blob;
   init_weights(c, net, h->gen, blob);
@@ -504,6 +510,9 @@ void smb200_destroy(smb200_learner* h) {
                   h->actG, h->errG, h->dTiles, h->dDescs, h->dCtrl, h->dRec, h->lastO, h->lastG, h->lastX, h->dSums, h->dBarrier,
                   h->dSampSlot, h->dSampT, h->dStats};
   for (void* p : ptrs) if (p) cudaFree(p);
+  for (int q = 0; q < kMaxWorld; ++q) if (h->peerMapped[q]) cudaIpcCloseMemHandle(h->peerMapped[q]);
+  if (h->commBuf) cudaFree(h->commBuf);
+  if (h->dCommErr) cudaFree(h->dCommErr);
   if (h->hSampSlot) cudaFreeHost(h->hSampSlot);
   if (h->hSampT) cudaFreeHost(h->hSampT);
   if (h->hStats) cudaFreeHost(h->hStats);
@@ -624,18 +633,28 @@ int smb200_initialize_learner(smb200_learner* h) {
   if (!h || h->episodes.empty()) return SMB200_ERR_STATE;
   cudaSetDevice(h->cfg.device);
   if (h->gradStep > 0) return 0;   // "Skipping initialization for restarted learner" (Learner.cpp:51-54)
-  // updateCounters(bInit=true): beta fixed-point step with the initial far-policy fraction
+  // updateCounters(bInit=true): beta fixed-point step with the initial far-policy fraction; with
+  // several learner ranks the counters are the sums over ranks (globalCounterRdx.get(bInit=true))
   StepCtrl& k = h->hCtrl;
-  const double nData = (double)h->nTransitions;
+  double cnts[2] = {(double)k.n_far_ref, (double)h->nTransitions};
+  if (h->comm.world > 1) {
+    double* dv = h->dSums->moments;
+    SMB200_CUDA_CHECK(cudaMemcpyAsync(dv, cnts, sizeof(cnts), cudaMemcpyHostToDevice, h->stream));
+    if (launch_peer_allreduce(h->comm, dv, 2, ++h->vecStamp, h->stream)) return SMB200_ERR_CUDA;
+    if (d2h(h, cnts, dv, sizeof(cnts))) return SMB200_ERR_CUDA;
+  }
+  const double nData = cnts[1];
   const double lr = 0.1 * (double)h->cfg.batch_size_global / std::max((double)h->cfg.max_tot_obs_global, nData);
-  const double frac = (double)k.n_far_ref / std::max(nData, 1.0);
+  const double frac = cnts[0] / std::max(nData, 1.0);
   const double mn = std::min(lr, k.beta);
   k.beta = frac > h->cfg.penal_tol ? (1 - mn) * k.beta : (1 - mn) * k.beta + std::min(lr, 1 - k.beta);
+  k.gl_far_prev = cnts[0]; k.gl_stored_prev = cnts[1]; k.cnt_seed_step = h->gradStep;
   if (push_ctrl(h)) return SMB200_ERR_CUDA;
   if (upload_order(h)) return SMB200_ERR_CUDA;
-  // updateRewardsStats(bInit=true), then rescaleAllReturnEstimator
+  // updateRewardsStats(bInit=true) (moments summed over ranks: StateRewRdx), then rescaleAllReturnEstimator
   if (launch_clear_sums(h->dSums, h->stream)) return SMB200_ERR_CUDA;
   if (launch_moments(h->rp, h->highWater, h->dSums, h->numSMs, h->stream)) return SMB200_ERR_CUDA;
+  if (launch_peer_allreduce(h->comm, h->dSums->moments, 2 * h->cfg.dim_state + 3, ++h->vecStamp, h->stream)) return SMB200_ERR_CUDA;
   if (launch_update_scaling(h->rp, h->dCtrl, h->dDescs, h->dSums, 1, h->stream)) return SMB200_ERR_CUDA;
   if (launch_sweep(h->rp, (int)h->episodes.size(), 0, (float)h->cfg.gamma, (float)h->cfg.lambda, 0, 0.f, 0.f, nullptr, h->stream))
     return SMB200_ERR_CUDA;
@@ -648,6 +667,7 @@ int smb200_set_grad_step(smb200_learner* h, int64_t n) {
   if (!h || n < 0) return SMB200_ERR_INVALID;
   if (pull_ctrl(h)) return SMB200_ERR_CUDA;
   h->gradStep = n; h->hCtrl.grad_step = n; h->hCtrl.adam_step = n;
+  h->hCtrl.gl_far_prev = (double)h->hCtrl.n_far_ref; h->hCtrl.gl_stored_prev = (double)h->nTransitions; h->hCtrl.cnt_seed_step = n;
   return push_ctrl(h);
 }
 int smb200_seed_sampler(smb200_learner* h, uint64_t seed) {
@@ -840,6 +860,66 @@ int smb200_profile_phases(smb200_learner* h, int32_t n, int64_t* out, int64_t ca
   if (d2h(h, out, h->dDbg, sizeof(long long) * cnt)) return SMB200_ERR_CUDA;
   float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->lastMs = ms; h->lastLaunches = 1;
   if (grid_out) *grid_out = h->persistGrid;
+  return 0;
+}
+
+// ---- learner ranks sharing the gradient: peer-memory buffers exchanged through CUDA IPC ----
+static void comm_layout(CommView& cm, int world, int rank, int nParams, int nTiles) {
+  cm.world = world; cm.rank = rank;
+  cm.nParamsPad = (nParams + 31) / 32 * 32; cm.nTilesPad = (nTiles + 1 + 31) / 32 * 32;
+  size_t o = 0;
+  cm.offGrad = o; o += sizeof(float) * 2 * (size_t)world * cm.nParamsPad;
+  cm.offFlag = o; o += sizeof(unsigned) * (size_t)world * cm.nTilesPad;
+  o = (o + 255) / 256 * 256;
+  cm.offCnt = o; o += sizeof(double) * 2 * (size_t)world * 4;
+  cm.offCntFlag = o; o += 256;
+  cm.offVec = o; o += sizeof(double) * 2 * (size_t)world * kCommVec;
+  cm.offVecFlag = o; o += 256;
+  cm.bytes = o;
+  cm.timeoutCycles = 6000000000LL;   // ~3 s at 2 GHz
+}
+
+int smb200_comm_init(smb200_learner* h, int32_t world, int32_t rank, uint8_t* handle_out, int32_t handle_bytes) {
+  if (!h || world < 1 || world > kMaxWorld || rank < 0 || rank >= world || !handle_out || handle_bytes < (int)sizeof(cudaIpcMemHandle_t))
+    return SMB200_ERR_INVALID;
+  if (world != h->cfg.world_size || rank != h->cfg.world_rank) { set_error_msg("comm_init: world/rank differ from the config"); return SMB200_ERR_INVALID; }
+  cudaSetDevice(h->cfg.device);
+  comm_layout(h->comm, world, rank, h->descs.net.nParams, h->nTiles);
+  h->comm.world = 1;   // stays single-rank until smb200_comm_attach
+  if (!h->commBuf) {
+    SMB200_CUDA_CHECK(cudaMalloc(&h->commBuf, h->comm.bytes));
+    SMB200_CUDA_CHECK(cudaMemset(h->commBuf, 0, h->comm.bytes));
+    if (dev_alloc(&h->dCommErr, 1)) return SMB200_ERR_CUDA;
+  }
+  cudaIpcMemHandle_t hd;
+  SMB200_CUDA_CHECK(cudaIpcGetMemHandle(&hd, h->commBuf));
+  memset(handle_out, 0, handle_bytes);
+  memcpy(handle_out, &hd, sizeof(hd));
+  return 0;
+}
+
+int smb200_comm_attach(smb200_learner* h, const uint8_t* handles, int32_t handle_bytes) {
+  if (!h || !h->commBuf || !handles || handle_bytes < (int)sizeof(cudaIpcMemHandle_t)) return SMB200_ERR_INVALID;
+  cudaSetDevice(h->cfg.device);
+  const int world = h->cfg.world_size, rank = h->cfg.world_rank;
+  for (int q = 0; q < world; ++q) {
+    if (q == rank) { h->comm.base[q] = h->commBuf; continue; }
+    cudaIpcMemHandle_t hd; memcpy(&hd, handles + (size_t)q * handle_bytes, sizeof(hd));
+    void* ptr = nullptr;
+    SMB200_CUDA_CHECK(cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->peerMapped[q] = ptr; h->comm.base[q] = reinterpret_cast<unsigned char*>(ptr);
+  }
+  h->comm.error = h->dCommErr;
+  h->comm.world = world;
+  return 0;
+}
+
+int smb200_comm_error(smb200_learner* h) {
+  if (!h) return SMB200_ERR_INVALID;
+  if (!h->dCommErr) return 0;
+  int e = 0;
+  if (d2h(h, &e, h->dCommErr, sizeof(int))) return SMB200_ERR_CUDA;
+  if (e) { set_error_msg("a peer rank did not answer within the time-out of the fused gradient exchange"); return SMB200_ERR_STATE; }
   return 0;
 }
 

@@ -65,6 +65,23 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target
   __syncthreads();
 }
 
+// ---- system-scope flags in peer memory (NVLink): release store / acquire load ----
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// bounded spin: a lost peer must not hang the GPU; the error flag is reported by the host
+__device__ __forceinline__ void wait_stamp_sys(const unsigned* p, unsigned stamp, const CommView& cm) {
+  const long long t0 = clock64();
+  while ((int)(ld_acquire_sys(p) - stamp) < 0) {
+    if (clock64() - t0 > cm.timeoutCycles) { *cm.error = 1; break; }
+  }
+}
+
 // ---- mbarrier + bulk async copy (TMA, cp.async.bulk -> SASS UBLKCP) ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -684,7 +701,7 @@ __device__ __forceinline__ float adam_step(const AdamCoef& k, float G, float W, 
 }
 
 __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, const StepCtrl& c, const GradTile& t,
-                        float* tiles, int step) {
+                        float* tiles, int step, int tileIdx) {
   const int tid = threadIdx.x;
   float* As = tiles;                 // [16][kBCP]
   float* Ds = tiles + kTileK * kBCP; // [16][kBCP]
@@ -799,6 +816,28 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
       for (int g = 0; g < kST / 64; ++g) v += part[(g * 64 + q) * 4 + j];
       acc = v;
     }
+  }
+  // ---- gradient sum over learner ranks, fused into the tile (replaces the MPI_Iallreduce of
+  //      AdamOptimizer::prepare_update, Optimizer.cpp:114-118): every rank pushes its partial tile
+  //      into every peer's slot over NVLink, publishes a stamp, waits for the peers' stamps on LOCAL
+  //      memory and adds the slots in rank order, so all ranks apply the identical update ----
+  if (a.comm.world > 1) {
+    const CommView& cm = a.comm;
+    const int N = cm.world, me = cm.rank, par = step & 1;
+    const unsigned stamp = (unsigned)(step + 1);
+    const size_t slotMe = ((size_t)par * N + me) * cm.nParamsPad;
+    if (p0 >= 0) for (int q = 0; q < N; ++q) cm.grad(q)[slotMe + p0] = acc;
+    if (p1 >= 0) for (int q = 0; q < N; ++q) cm.grad(q)[slotMe + p1] = acc2;
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence_system();
+      for (int q = 0; q < N; ++q) st_release_sys(cm.flag(q) + me * cm.nTilesPad + tileIdx, stamp);
+    }
+    if (tid < N) wait_stamp_sys(cm.flag(me) + tid * cm.nTilesPad + tileIdx, stamp, cm);
+    __syncthreads();
+    const float* mine = cm.grad(me) + (size_t)par * N * cm.nParamsPad;
+    if (p0 >= 0) { float v = 0.f; for (int q = 0; q < N; ++q) v += ld_cg(mine + (size_t)q * cm.nParamsPad + p0); acc = v; }
+    if (p1 >= 0) { float v = 0.f; for (int q = 0; q < N; ++q) v += ld_cg(mine + (size_t)q * cm.nParamsPad + p1); acc2 = v; }
   }
   DBG_T(a, step, 26);
   const AdamCoef ac = adam_coef(hp, c);
@@ -965,8 +1004,33 @@ __device__ void stats_and_refer(const StepArgs& a, const Hyper& hp, const StepCt
     nx.n_far_exact = farExactOverride >= 0 ? farExactOverride : c.n_far_exact + (long long)farD;
     // updateCounters: beta fixed-point iteration (MemoryProcessing.cpp:73-85); it runs after
     // applyEpisodesRemovalAlgo, so nStoredSteps() is the post-pruning count
-    const double nPost = (double)(step == a.lastStep ? a.nTransitionsPost : a.nTransitions);
-    const double fracOff = (double)(long long)tot / fmax(nPost, 1.0);
+    double nPost = (double)(step == a.lastStep ? a.nTransitionsPost : a.nTransitions);
+    double farGlobal = (double)(long long)tot;
+    nx.gl_far_prev = farGlobal; nx.gl_stored_prev = nPost; nx.cnt_seed_step = c.cnt_seed_step;
+    if (a.comm.world > 1) {
+      // DelayedReductor<long> (MemoryProcessing.cpp:48-58): the sums over learner ranks that reach
+      // updateCounters are those of the PREVIOUS step.  Push this step's local counts, consume the
+      // peers' counts of the previous step.
+      const CommView& cm = a.comm;
+      const int N = cm.world, me = cm.rank, par = step & 1;
+      const unsigned stamp = (unsigned)(step + 1);
+      for (int q = 0; q < N; ++q) {
+        double* d = cm.cnt(q) + ((size_t)par * N + me) * 4;
+        d[0] = farGlobal; d[1] = nPost;
+      }
+      __threadfence_system();
+      for (int q = 0; q < N; ++q) st_release_sys(cm.cntFlag(q) + me, stamp);
+      if ((long long)step == c.cnt_seed_step) { farGlobal = c.gl_far_prev; nPost = c.gl_stored_prev; }   // seeded by the host at (re)start
+      else {
+        farGlobal = 0.0; nPost = 0.0;
+        for (int q = 0; q < N; ++q) {
+          wait_stamp_sys(cm.cntFlag(me) + q, (unsigned)step, cm);     // stamp of the previous step
+          const double* d = cm.cnt(me) + ((size_t)(par ^ 1) * N + q) * 4;
+          farGlobal += __ldcg(d); nPost += __ldcg(d + 1);
+        }
+      }
+    }
+    const double fracOff = farGlobal / fmax(nPost, 1.0);
     const double lrB = 0.1 * BS / fmax(maxN, nPost);
     const double b0 = c.beta;
     const double mn = fmin(lrB, b0);
@@ -1039,7 +1103,7 @@ __global__ void __launch_bounds__(kST) k_p2p3(StepArgs a, int step, int skipStat
   if (threadIdx.x == 0) load_ctrl(c, &a.ctrl[step & 1]);
   __syncthreads();
   float* tiles = reinterpret_cast<float*>(smraw + ((sizeof(DevDescs) + 15) / 16) * 16);
-  if ((int)blockIdx.x < a.nTiles) p2_tile(a, *net, *hp, c, a.tiles[blockIdx.x], tiles, step);
+  if ((int)blockIdx.x < a.nTiles) p2_tile(a, *net, *hp, c, a.tiles[blockIdx.x], tiles, step, blockIdx.x);
   else if (!skipStats) p3_stats(a, *hp, c, a.ctrl[(step + 1) & 1], step, tiles);
 }
 
@@ -1158,7 +1222,7 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
       __syncthreads();
     }
     for (int t = blockIdx.x; t < a.nTiles; t += nw) {
-      p2_tile(a, *net, *hp, c, t == (int)blockIdx.x ? myTile : a.tiles[t], tiles, step);
+      p2_tile(a, *net, *hp, c, t == (int)blockIdx.x ? myTile : a.tiles[t], tiles, step, t);
       __syncthreads();
     }
     // ---- park the prefetched inputs in shared memory (read by P1 of the next step) ----

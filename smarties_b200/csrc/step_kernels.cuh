@@ -15,7 +15,31 @@ struct SweepSums {
   double moments[2 * 512 + 3];   // reward/state moments: sum(s-m)[dS], sum((s-m)^2)[dS], count, sum(r-m), sum((r-m)^2)
 };
 
+// Peer-memory view for the fused gradient exchange (one process per GPU, buffers shared through
+// CUDA IPC).  Every rank owns one identically laid out block:
+//   grad  [2 parity][world][nParamsPad] f32   partial gradients, slot q written by rank q
+//   flag  [world][nTilesPad] u32              stamp (step+1) of rank q's tile t
+//   cnt   [2 parity][world][4] f64            replay counters of the statistics CTA, cntFlag [world] u32
+//   vec   [2 parity][world][kCommVec] f64     small host-driven all-reduces (moments), vecFlag [world] u32
+constexpr int kMaxWorld = 8;
+constexpr int kCommVec = 2 * 512 + 8;
+struct CommView {
+  int world, rank;
+  int nParamsPad, nTilesPad;
+  unsigned char* base[kMaxWorld];      // base[q]: rank q's block as mapped into THIS process
+  size_t offGrad, offFlag, offCnt, offCntFlag, offVec, offVecFlag, bytes;
+  long long timeoutCycles;
+  int* error;                          // set to 1 if a peer wait timed out
+  __host__ __device__ float* grad(int q) const { return reinterpret_cast<float*>(base[q] + offGrad); }
+  __host__ __device__ unsigned* flag(int q) const { return reinterpret_cast<unsigned*>(base[q] + offFlag); }
+  __host__ __device__ double* cnt(int q) const { return reinterpret_cast<double*>(base[q] + offCnt); }
+  __host__ __device__ unsigned* cntFlag(int q) const { return reinterpret_cast<unsigned*>(base[q] + offCntFlag); }
+  __host__ __device__ double* vec(int q) const { return reinterpret_cast<double*>(base[q] + offVec); }
+  __host__ __device__ unsigned* vecFlag(int q) const { return reinterpret_cast<unsigned*>(base[q] + offVecFlag); }
+};
+
 struct StepArgs {
+  CommView comm;
   const DevDescs* descs;
   ReplayView rp;
   float* W; float* Wimg; float* M1; float* M2; float* G;   // Wimg: weights in the shared-memory image layout
@@ -62,5 +86,7 @@ int launch_sweep(const ReplayView& rp, int nEpisodes, int oneSlot, float gamma, 
 int launch_moments(const ReplayView& rp, long long rowEnd, SweepSums* sums, int numSMs, cudaStream_t st);
 int launch_update_scaling(const ReplayView& rp, const StepCtrl* ctrlCur, const DevDescs* descs, const SweepSums* sums, int bInit, cudaStream_t st);
 int launch_clear_sums(SweepSums* sums, cudaStream_t st);
+// sum a small f64 vector over all ranks through peer memory (in place, identical result on every rank)
+int launch_peer_allreduce(const CommView& comm, double* vec, int n, unsigned stamp, cudaStream_t st);
 
 }  // namespace smb200

@@ -275,6 +275,44 @@ __global__ void k_clear_sums(SweepSums* s) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = 0;
 }
 
+// Sum of a small f64 vector over the learner ranks through peer memory (push + stamp + local wait,
+// slots added in rank order: bit-identical on every rank).  Used for the reward/state moments and
+// the replay counters at initialisation and on sweep steps (DelayedReductor, StateRewRdx).
+__global__ void __launch_bounds__(kThreads) k_peer_allreduce(CommView cm, double* vec, int n, unsigned stamp) {
+  const int N = cm.world, me = cm.rank, par = stamp & 1;
+  for (int i = threadIdx.x; i < n; i += kThreads) {
+    const double v = vec[i];
+    for (int q = 0; q < N; ++q) cm.vec(q)[((size_t)par * N + me) * kCommVec + i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    for (int q = 0; q < N; ++q) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(cm.vecFlag(q) + me), "r"(stamp) : "memory");
+  }
+  if (threadIdx.x < N) {
+    const long long t0 = clock64();
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(cm.vecFlag(me) + threadIdx.x) : "memory");
+      if (clock64() - t0 > cm.timeoutCycles) { *cm.error = 1; break; }
+    } while ((int)(v - stamp) < 0);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += kThreads) {
+    double s = 0.0;
+    for (int q = 0; q < N; ++q) s += __ldcg(cm.vec(me) + ((size_t)par * N + q) * kCommVec + i);
+    vec[i] = s;
+  }
+}
+
+int launch_peer_allreduce(const CommView& comm, double* vec, int n, unsigned stamp, cudaStream_t st) {
+  if (comm.world <= 1) return 0;
+  if (n > kCommVec) { set_error_msg("peer all-reduce vector too long"); return -1; }
+  k_peer_allreduce<<<1, kThreads, 0, st>>>(comm, vec, n, stamp);
+  SMB200_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 int launch_init_episode(const ReplayView& rp, int slot, float deltaInit, int haveValues, cudaStream_t st) {
   k_init_episode<<<1, kThreads, 0, st>>>(rp, slot, deltaInit, haveValues);

@@ -31,6 +31,7 @@ EXPORTS = [
     "smb200_train_steps", "smb200_train_step_on", "smb200_get_last_batch", "smb200_retrace_sweep",
     "smb200_reward_state_moments", "smb200_read_field", "smb200_read_episodes", "smb200_n_rows", "smb200_get_stats",
     "smb200_forward", "smb200_last_timing", "smb200_presample", "smb200_train_presampled", "smb200_sync", "smb200_profile_phases",
+    "smb200_comm_init", "smb200_comm_attach", "smb200_comm_error",
 ]
 
 FIELDS = dict(V=0, ADV=1, QRET=2, DELTA=3, RHO=4, KL=5, REWARD=6)
@@ -102,6 +103,9 @@ def load_library(path: str = LIB_PATH):
         "smb200_presample": (C.c_int, [H, C.c_int32]), "smb200_train_presampled": (C.c_int, [H, C.c_int32, C.c_int32]),
         "smb200_sync": (C.c_int, [H]),
         "smb200_profile_phases": (C.c_int, [H, C.c_int32, ip, C.c_int64, P(C.c_int32)]),
+        "smb200_comm_init": (C.c_int, [H, C.c_int32, C.c_int32, P(C.c_uint8), C.c_int32]),
+        "smb200_comm_attach": (C.c_int, [H, P(C.c_uint8), C.c_int32]),
+        "smb200_comm_error": (C.c_int, [H]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -181,6 +185,26 @@ class Learner:
             self.close()
         except Exception:
             pass
+
+    # -- learner ranks (one process per GPU) --
+    def attach_process_group(self, dist, broadcast_weights=True):
+        """Join the learner ranks of `dist` (torch.distributed, already initialised): exchange the CUDA
+        IPC handles of the peer-memory blocks, and copy rank 0's initial weights to every rank
+        (Parameters::broadcast, Network/Layers/Parameters.h:43-46)."""
+        from .distributed import exchange_bytes, broadcast_array
+        world, rank = dist.get_world_size(), dist.get_rank()
+        HB = 64
+        mine = (C.c_uint8 * HB)()
+        self._check(self.lib.smb200_comm_init(self.h, world, rank, mine, HB))
+        handles = exchange_bytes(dist, bytes(mine))
+        blob = (C.c_uint8 * (HB * world)).from_buffer_copy(b"".join(handles))
+        self._check(self.lib.smb200_comm_attach(self.h, blob, HB))
+        if broadcast_weights:
+            self.set_weights(broadcast_array(dist, self.get_weights(), src=0))
+        dist.barrier()
+
+    def comm_check(self):
+        self._check(self.lib.smb200_comm_error(self.h))
 
     # -- replay memory --
     def push_episode(self, eid, states, actions, policies, rewards, terminated, value=None, advantage=None):
