@@ -181,6 +181,9 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
 
+    # keep stdout clean for the single JSON line (NCCL prints its version banner to stdout)
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from smarties_b200 import Learner
@@ -293,7 +296,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             r = run_reference(args.cpu_steps, os.cpu_count() or 1, data=data)
             out["cpu_baseline"] = {"value": r["value"], "unit": "transitions/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
-        print(json.dumps(out))
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
     L.close()
     if world > 1:
         dist.destroy_process_group()

@@ -868,7 +868,7 @@ static void comm_layout(CommView& cm, int world, int rank, int nParams, int nTil
   cm.world = world; cm.rank = rank;
   cm.nParamsPad = (nParams + 31) / 32 * 32; cm.nTilesPad = (nTiles + 1 + 31) / 32 * 32;
   size_t o = 0;
-  cm.offGrad = o; o += sizeof(float) * 2 * (size_t)world * cm.nParamsPad;
+  cm.offGrad = o; o += sizeof(unsigned long long) * 2 * (size_t)world * cm.nParamsPad;
   cm.offFlag = o; o += sizeof(unsigned) * (size_t)world * cm.nTilesPad;
   o = (o + 255) / 256 * 256;
   cm.offCnt = o; o += sizeof(double) * 2 * (size_t)world * 4;

@@ -82,6 +82,21 @@ __device__ __forceinline__ void wait_stamp_sys(const unsigned* p, unsigned stamp
   }
 }
 
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// poll one stamped element in LOCAL memory until the peer's store of this step has landed
+__device__ __forceinline__ float wait_value_ll(const unsigned long long* p, unsigned stamp, const CommView& cm) {
+  unsigned long long v;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    if ((unsigned)(v >> 32) == stamp) break;
+    if (clock64() - t0 > cm.timeoutCycles) { *cm.error = 1; break; }
+  }
+  return __uint_as_float((unsigned)(v & 0xffffffffull));
+}
+
 // ---- mbarrier + bulk async copy (TMA, cp.async.bulk -> SASS UBLKCP) ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -826,18 +841,25 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
     const int N = cm.world, me = cm.rank, par = step & 1;
     const unsigned stamp = (unsigned)(step + 1);
     const size_t slotMe = ((size_t)par * N + me) * cm.nParamsPad;
-    if (p0 >= 0) for (int q = 0; q < N; ++q) cm.grad(q)[slotMe + p0] = acc;
-    if (p1 >= 0) for (int q = 0; q < N; ++q) cm.grad(q)[slotMe + p1] = acc2;
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence_system();
-      for (int q = 0; q < N; ++q) st_release_sys(cm.flag(q) + me * cm.nTilesPad + tileIdx, stamp);
+    if (p0 >= 0) {
+      const unsigned long long pk = ((unsigned long long)stamp << 32) | (unsigned long long)__float_as_uint(acc);
+      for (int q = 0; q < N; ++q) if (q != me) st_volatile_u64(cm.grad(q) + slotMe + p0, pk);
     }
-    if (tid < N) wait_stamp_sys(cm.flag(me) + tid * cm.nTilesPad + tileIdx, stamp, cm);
-    __syncthreads();
-    const float* mine = cm.grad(me) + (size_t)par * N * cm.nParamsPad;
-    if (p0 >= 0) { float v = 0.f; for (int q = 0; q < N; ++q) v += ld_cg(mine + (size_t)q * cm.nParamsPad + p0); acc = v; }
-    if (p1 >= 0) { float v = 0.f; for (int q = 0; q < N; ++q) v += ld_cg(mine + (size_t)q * cm.nParamsPad + p1); acc2 = v; }
+    if (p1 >= 0) {
+      const unsigned long long pk = ((unsigned long long)stamp << 32) | (unsigned long long)__float_as_uint(acc2);
+      for (int q = 0; q < N; ++q) if (q != me) st_volatile_u64(cm.grad(q) + slotMe + p1, pk);
+    }
+    const unsigned long long* mine = cm.grad(me) + (size_t)par * N * cm.nParamsPad;
+    if (p0 >= 0) {
+      float v = 0.f;
+      for (int q = 0; q < N; ++q) v += q == me ? acc : wait_value_ll(mine + (size_t)q * cm.nParamsPad + p0, stamp, cm);
+      acc = v;
+    }
+    if (p1 >= 0) {
+      float v = 0.f;
+      for (int q = 0; q < N; ++q) v += q == me ? acc2 : wait_value_ll(mine + (size_t)q * cm.nParamsPad + p1, stamp, cm);
+      acc2 = v;
+    }
   }
   DBG_T(a, step, 26);
   const AdamCoef ac = adam_coef(hp, c);

@@ -17,8 +17,10 @@ struct SweepSums {
 
 // Peer-memory view for the fused gradient exchange (one process per GPU, buffers shared through
 // CUDA IPC).  Every rank owns one identically laid out block:
-//   grad  [2 parity][world][nParamsPad] f32   partial gradients, slot q written by rank q
-//   flag  [world][nTilesPad] u32              stamp (step+1) of rank q's tile t
+//   grad  [2 parity][world][nParamsPad] u64   partial gradients, slot q written by rank q: every
+//                                             element carries its own stamp (value | (step+1) << 32), so a
+//                                             single 8-byte store is data and flag at once (no fence,
+//                                             no second round trip — NCCL's LL idea)
 //   cnt   [2 parity][world][4] f64            replay counters of the statistics CTA, cntFlag [world] u32
 //   vec   [2 parity][world][kCommVec] f64     small host-driven all-reduces (moments), vecFlag [world] u32
 constexpr int kMaxWorld = 8;
@@ -30,7 +32,7 @@ struct CommView {
   size_t offGrad, offFlag, offCnt, offCntFlag, offVec, offVecFlag, bytes;
   long long timeoutCycles;
   int* error;                          // set to 1 if a peer wait timed out
-  __host__ __device__ float* grad(int q) const { return reinterpret_cast<float*>(base[q] + offGrad); }
+  __host__ __device__ unsigned long long* grad(int q) const { return reinterpret_cast<unsigned long long*>(base[q] + offGrad); }
   __host__ __device__ unsigned* flag(int q) const { return reinterpret_cast<unsigned*>(base[q] + offFlag); }
   __host__ __device__ double* cnt(int q) const { return reinterpret_cast<double*>(base[q] + offCnt); }
   __host__ __device__ unsigned* cntFlag(int q) const { return reinterpret_cast<unsigned*>(base[q] + offCntFlag); }

@@ -34,7 +34,7 @@ def main():
     S.retrace_sweep()
     pos, t = L.sample_minibatch()
     L.seed_sampler(11 + rank)
-    beta0 = L.get_stats()["beta"]
+    beta0, beta0_alone = L.get_stats()["beta"], S.get_stats()["beta"]
     st = L.train_steps(1)[0]
     S.train_step_on(pos, t)
     g_alone = torch.from_numpy(S.get_grad()).cuda()
@@ -45,7 +45,7 @@ def main():
         g_sum = g_sum + gs[q]
     g_fused = L.get_grad()
     res = dict(rank=rank, grad_equal=bool(np.array_equal(g_fused, g_sum.cpu().numpy())),
-               grad_maxabs=float(np.abs(g_fused).max()), beta0=beta0, beta0_alone=S.get_stats()["beta"])
+               grad_maxabs=float(np.abs(g_fused).max()), beta0=beta0, beta0_alone=beta0_alone)
     stats = L.train_steps(40)
     L.comm_check()
     w = torch.from_numpy(L.get_weights()).cuda()
