@@ -290,10 +290,11 @@ class MlpNet:
 # ------------------------------------------------------------------------------------------
 # per-sample V-RACER loss / gradient   (Learners/RACER_train.cpp:12-67)
 # ------------------------------------------------------------------------------------------
-def vracer_sample_math(O, act, mu, qret, beta, cmax, cinv, bounded=None):
-    """O: [B, 1+2dA] network outputs (f32 values widened to f64, Approximator.h:117-173),
-    act [B,dA], mu [B,2dA] (stored f32 -> f64 Rvec, Episode.h:66), qret [B] f32.
-    Returns dict with rho, dkl, isFar, V, deltaQ (f64) and g [B, nOut] (f64 output gradient)."""
+def vracer_sample_math(O, act, mu, qret, beta, cmax, cinv, bounded=None, racer=False):
+    """O: [B, nOut] network outputs (f32 values widened to f64, Approximator.h:117-173);
+    V-RACER: [V | mean(dA) | stdev-param(dA)], RACER: [V | adv coef, p1(dA), p2(dA) | mean(dA) | stdev-param(dA)]
+    (RACER_common.cpp:174-193,232-247).  act [B,dA], mu [B,2dA] (stored f32 -> f64 Rvec, Episode.h:66),
+    qret [B] f32.  Returns rho, dkl, is_far, V, A (advantage), dq (f64) and g [B, nOut] (f64 output gradient)."""
     O = np.asarray(O, f64)
     act = np.asarray(act, f64)
     mu = np.asarray(mu, f64)
@@ -301,8 +302,9 @@ def vracer_sample_math(O, act, mu, qret, beta, cmax, cinv, bounded=None):
     if bounded is None:
         bounded = np.zeros(dA, bool)
     bounded = np.asarray(bounded, bool)
-    mean = O[:, 1:1 + dA]
-    sraw = O[:, 1 + dA:1 + 2 * dA]
+    m0 = 2 + 2 * dA if racer else 1          # start of the policy means
+    mean = O[:, m0:m0 + dA]
+    sraw = O[:, m0 + dA:m0 + 2 * dA]
     stdev = softplus(sraw)                      # Continuous_policy.h:78-81
     inv = 1 / stdev
     mu_m, mu_s = mu[:, :dA], mu[:, dA:]
@@ -333,8 +335,26 @@ def vracer_sample_math(O, act, mu, qret, beta, cmax, cinv, bounded=None):
     W32, C32, I32 = rho.astype(f32), f32(cmax), f32(cinv)
     is_far = (C32 > f32(1)) & ((W32 > C32) | (W32 < I32))
     V = scale_net2v(O[:, 0])
-    a_ret = np.asarray(qret, f64) - V           # A = 0 for Zero_advantage
-    dq = a_ret
+    Aval = np.zeros(Bn, f64)                    # Zero_advantage.h:39-42
+    if racer:                                   # Gaussian_advantage::computeAdvantage (Gaus_advantage.h:73-86,116-126)
+        coef_raw = O[:, 1]
+        p1r, p2r = O[:, 2:2 + dA], O[:, 2 + dA:2 + 2 * dA]
+        coef, p1, p2 = softplus(coef_raw), softplus(p1r), softplus(p2r)
+        S = stdev * stdev                       # policy->getVariance (Continuous_policy.h:775-777)
+        dm_adv = act - cmean                    # policy->getMean() is the clamped mean for bounded dims
+        upper = act > cmean
+        terms = dm_adv ** 2 / np.where(upper, p1, p2)
+        shape_sum = np.zeros(Bn, f64)
+        for i in range(dA):
+            shape_sum = shape_sum + terms[:, i]
+        orig = np.exp(-shape_sum / 2)
+        rfac = np.sqrt(p1 / (p1 + S)) / 2 + np.sqrt(p2 / (p2 + S)) / 2
+        ratio = np.ones(Bn, f64)
+        for i in range(dA):
+            ratio = ratio * rfac[:, i]
+        Aval = coef * (orig - ratio)
+    a_ret = np.asarray(qret, f64) - V
+    dq = a_ret - Aval
     ver = np.minimum(1.0, rho) * dq
     g = np.zeros_like(O)
     g[:, 0] = np.where(is_far, 0.0, ver * beta * scale_vdiff(O[:, 0]))
@@ -355,9 +375,25 @@ def vracer_sample_math(O, act, mu, qret, beta, cmax, cinv, bounded=None):
     far = is_far[:, None]
     pg_mean = np.where(far, 0.0, pg_mean)
     pg_std = np.where(far, 0.0, pg_std)
-    g[:, 1:1 + dA] = beta * pg_mean + (1 - beta) * kg_mean        # penalizeReFER, FunctionUtilities.h:221-228
-    g[:, 1 + dA:1 + 2 * dA] = beta * pg_std + (1 - beta) * kg_std
-    return dict(rho=rho, dkl=dkl, is_far=is_far, V=V, dq=dq, g=g)
+    g[:, m0:m0 + dA] = beta * pg_mean + (1 - beta) * kg_mean        # penalizeReFER, FunctionUtilities.h:221-228
+    g[:, m0 + dA:m0 + 2 * dA] = beta * pg_std + (1 - beta) * kg_std
+    if racer:                                   # ADV.grad(act, isFar ? 0 : beta*Aer, gradient)  (Gaus_advantage.h:88-114,64-69)
+        aer = np.minimum(cmax, rho) * dq
+        err = np.where(is_far, 0.0, beta * aer)
+        expect = -ratio
+        g[:, 1] = (orig + expect) * (err * softplus_diff(coef_raw))
+        oc = (orig * coef)[:, None]
+        x1 = np.where(upper, oc * (dm_adv / p1) ** 2 / 2, 0.0)
+        x2 = np.where(act < cmean, oc * (dm_adv / p2) ** 2 / 2, 0.0)
+        F = 2 / (np.sqrt(p1 / (p1 + S)) + np.sqrt(p2 / (p2 + S)))
+        diff1 = S / np.sqrt(p1 * (p1 + S) ** 3) / 4
+        diff2 = S / np.sqrt(p2 * (p2 + S) ** 3) / 4
+        ec = (expect[:, None] * 1.0)
+        x1 = x1 + F * ec * coef[:, None] * diff1
+        x2 = x2 + F * ec * coef[:, None] * diff2
+        g[:, 2:2 + dA] = x1 * (err[:, None] * softplus_diff(p1r))
+        g[:, 2 + dA:2 + 2 * dA] = x2 * (err[:, None] * softplus_diff(p2r))
+    return dict(rho=rho, dkl=dkl, is_far=is_far, V=V, A=Aval, dq=dq, g=g)
 
 
 # ------------------------------------------------------------------------------------------
@@ -423,9 +459,10 @@ class VracerOracle:
 
     def __init__(self, dS, dA, hidden=(128, 128), gamma=0.995, lam=1.0, clip_imp_weight=None,
                  penal_tol=0.1, eps_anneal=5e-7, learnrate=1e-4, nn_lambda=FLT_EPS,
-                 batch=256, max_tot_obs=None, bounded=False, sample_seed=42):
+                 batch=256, max_tot_obs=None, bounded=False, sample_seed=42, learner="VRACER"):
         self.dS, self.dA = dS, dA
-        self.layout = MlpLayout(dS, hidden, 1 + dA, dA)
+        self.racer = learner == "RACER"
+        self.layout = MlpLayout(dS, hidden, (2 + 3 * dA) if self.racer else (1 + dA), dA)
         self.net = MlpNet(self.layout)
         self.gamma, self.lam = gamma, lam
         self.C = float(np.sqrt(dA / 2.0)) if clip_imp_weight is None else float(clip_imp_weight)  # HyperParameters.h:46
@@ -564,7 +601,7 @@ class VracerOracle:
         act = np.stack([ep.A[int(t)] for ep, t in zip(eps, obs)])
         mu = np.stack([ep.MU[int(t)] for ep, t in zip(eps, obs)])
         qret = np.array([ep.Q[int(t)] for ep, t in zip(eps, obs)], f32)
-        r = vracer_sample_math(Ouse, act, mu, qret, self.beta, self.cmax, self.cinv, self.bounded)
+        r = vracer_sample_math(Ouse, act, mu, qret, self.beta, self.cmax, self.cinv, self.bounded, self.racer)
         g32 = r["g"].astype(f32)
         # write-back + per-episode aggregates, in batch order (Episode.h:112-145)
         C32, I32 = f32(self.cmax), f32(self.cinv)
@@ -582,7 +619,7 @@ class VracerOracle:
             ep.maxAbsErr = f32(max(ep.maxAbsErr, abs(E)))
             ep.delta[t], ep.KL[t], ep.rho[t] = E, D, Wt
             Vv = f32(r["V"][b])
-            self._update_values(ep, t, Vv, Vv)                # Qval = Aval + Vval, Aval = 0
+            self._update_values(ep, t, Vv, f32(r["A"][b] + r["V"][b]))   # Qval = Aval + Vval
         G = self.net.backward(self.W, Y, g32)
         self.adam_step += 1                                    # prepare_update: nStep++ (Optimizer.cpp:119)
         self.last = dict(r, seq=np.asarray(seq), obs=np.asarray(obs), X=X, O=O32, g=g32, g64=r['g'], gradSum=G.copy())

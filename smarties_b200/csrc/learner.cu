@@ -123,7 +123,7 @@ namespace smb200 {
 static int build_net(const smb200_config& c, NetDesc& net, std::vector<GradTile>& tiles) {
   memset(&net, 0, sizeof(net));
   const int dS = c.dim_state, dA = c.dim_action;
-  if (c.algo != SMB200_VRACER) { set_error_msg("only learner VRACER is implemented on the device path"); return -1; }
+  if (c.algo != SMB200_VRACER && c.algo != SMB200_RACER) { set_error_msg("learner must be VRACER or RACER"); return -1; }
   if (dS < 1 || dA < 1 || dA > SMB200_MAX_ACTION || c.n_hidden < 1 || c.n_hidden > SMB200_MAX_HIDDEN) {
     set_error_msg("unsupported dimensions"); return -1; }
   int off = 0, img = 0, act = 0, id = 0, width = dS;
@@ -154,7 +154,8 @@ static int build_net(const smb200_config& c, NetDesc& net, std::vector<GradTile>
     }
     nIn = h;
   }
-  const int nOutDense = 1 + dA;   // V-RACER: [V | mean(dA)], stdev is the ParamLayer (RACER_simpleSigma)
+  // V-RACER: [V | mean(dA)], RACER: [V | adv coef, p1(dA), p2(dA) | mean(dA)]; stdev is the ParamLayer (RACER_simpleSigma)
+  const int nOutDense = c.algo == SMB200_RACER ? 2 + 3 * dA : 1 + dA;
   {
     LayerDesc& L = add(kDenseLinear, nOutDense);
     L.nIn = nIn; L.ld = round_up(nOutDense, 8);
@@ -196,6 +197,10 @@ static void init_weights(const smb200_config& c, const NetDesc& net, std::mt1993
       std::uniform_real_distribution<float> dis(-init, init);
       for (int i = 0; i < L.nIn; ++i)
         for (int o = 0; o < L.size; ++o) blob[L.wOff + o + L.ld * i] = dis(gen);
+      if (out && c.algo == SMB200_RACER) {   // Gaussian_advantage::setInitial (Gaus_advantage.h:31-34): bias -1 for the coefficient, 1 for the widths
+        blob[L.bOff + 1] = -1.f;
+        for (int o = 2; o < 2 + 2 * c.dim_action; ++o) blob[L.bOff + o] = 1.f;
+      }
     } else if (L.kind == kResidual) {
       for (int o = 0; o < L.size; ++o) { blob[L.wOff + o] = 1.f; blob[L.bOff + o] = 0.f; }
     } else if (L.kind == kParam) {   // SoftPlus::_inv(explNoise) (Functions.h:564-568, Continuous_policy.h:195-197)

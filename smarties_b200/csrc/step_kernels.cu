@@ -348,8 +348,8 @@ __host__ __device__ inline SmemPlan smem_plan(const NetDesc& net, int TB, bool i
   p.info = o;  o += sizeof(int) * 4 * TB;
   p.old = o;   o += sizeof(float) * 8 * TB;                          // old V/ADV/rho/KL/delta (+ next row) per sample
   o = (o + 15) / 16 * 16;
-  p.pair = o;  o += sizeof(double) * 7 * (size_t)TB * net.dA;        // per (sample, action component) terms
-  p.samp = o;  o += sizeof(double) * 8 * TB;                         // per sample scalars
+  p.pair = o;  o += sizeof(double) * 16 * (size_t)TB * net.dA;       // per (sample, action component) terms
+  p.samp = o;  o += sizeof(double) * 12 * TB;                        // per sample scalars
   p.tiles = o; o += sizeof(float) * 2 * kTileK * (256 + 4);          // P2 operand tiles
   p.bars = o;  o += sizeof(uint64_t) * kMaxLayers;
   // inputs of the NEXT step, prefetched while the weight-gradient phase runs:
@@ -430,8 +430,10 @@ __device__ void p1_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
   const Staging stg = staging_view<TB>(net, smraw, sp);
   int* info = staged ? stg.info : reinterpret_cast<int*>(smraw + sp.info);   // row[TB], slot[TB], hasNext[TB], valid[TB]
   float* old = staged ? stg.old : reinterpret_cast<float*>(smraw + sp.old);  // [8][TB]: V, ADV, RHO, KL, DELTA, Vnext, ADVnext, Qret
-  double* pair = reinterpret_cast<double*>(smraw + sp.pair); // [7][TB*dA]
-  double* samp = reinterpret_cast<double*>(smraw + sp.samp); // [8][TB]
+  double* pair = reinterpret_cast<double*>(smraw + sp.pair); // [16][TB*dA]
+  double* samp = reinterpret_cast<double*>(smraw + sp.samp); // [12][TB]
+  const bool racer = hp.algo == 1;                           // RACER: Gaussian advantage head (Math/Gaus_advantage.h)
+  const int m0 = racer ? 2 + 2 * net.dA : 1;                 // first policy-mean output (RACER_common.cpp:174-193,232-247)
   uint64_t* bars = (SM && a.useTma) ? reinterpret_cast<uint64_t*>(smraw + sp.bars) : nullptr;
   const int b0 = tile * TB;
   const ReplayView& rp = a.rp;
@@ -463,7 +465,7 @@ __device__ void p1_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
   for (int s = 0; s < TB; ++s) anyNext |= info[2 * TB + s];
 
   // V(s_{t+1}) of truncated episodes (RACER_train.cpp:23-27): rare, extra forward pass
-  float* vnext = reinterpret_cast<float*>(samp + 7 * TB);   // samp[7][*] is not used by the loss stages
+  float* vnext = reinterpret_cast<float*>(samp + 11 * TB);  // samp[11][*] is not used by the loss stages
   if (anyNext) {
     for (int idx = tid; idx < dS * TB; idx += kST) {
       const int k = idx / TB, s = idx - k * TB;
@@ -520,7 +522,7 @@ __device__ void p1_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
       const size_t row = info[s];
       av = (double)ld_cg(rp.A + row * dA + i); mm = (double)ld_cg(rp.MU + row * 2 * dA + i); ms = (double)ld_cg(rp.MU + row * 2 * dA + dA + i);
     }
-    const double m = (double)act[(Lo.actOff + 1 + i) * TB + s];
+    const double m = (double)act[(Lo.actOff + m0 + i) * TB + s];
     const double sraw = (double)ldw<SM>(Wp + Lp.imgB + i);
     const double root = sqrt(1.0 + sraw * sraw);
     const double stdev = (sraw + root) / 2.0;                          // SoftPlus::_eval, Functions.h:552-555
@@ -548,6 +550,24 @@ __device__ void p1_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
     pair[4 * nPair + p] = bnd ? (av - m) * inv * inv : u * inv;                       // dLogPdMean
     pair[5 * nPair + p] = (u * u - 1.0) * inv;                                        // dLogPdStdv
     pair[6 * nPair + p] = dpos;
+    if (racer) {   // Gaussian_advantage terms of this component (Gaus_advantage.h:73-126)
+      const double p1r = (double)act[(Lo.actOff + 2 + i) * TB + s], p2r = (double)act[(Lo.actOff + 2 + dA + i) * TB + s];
+      const double rt1 = sqrt(1.0 + p1r * p1r), rt2 = sqrt(1.0 + p2r * p2r);
+      const double p1 = (p1r + rt1) / 2.0, p2 = (p2r + rt2) / 2.0;                 // PosDefFunction::_eval
+      const double S = stdev * stdev;                                             // policy->getVariance(i)
+      const double dmA = av - cm;                                                 // policy->getMean(i): clamped for bounded dims
+      const double sq1 = sqrt(p1 / (p1 + S)), sq2 = sqrt(p2 / (p2 + S));
+      const double x1 = dmA / p1, x2 = dmA / p2;
+      pair[7 * nPair + p] = (dmA * dmA) / (av > cm ? p1 : p2);                    // diagInvMul term
+      pair[8 * nPair + p] = sq1 / 2.0 + sq2 / 2.0;                                // coefMixRatio factor
+      pair[9 * nPair + p] = av > cm ? x1 * x1 : -1.0;                             // ((a-m)/p1)^2 or "not on this side"
+      pair[10 * nPair + p] = av < cm ? x2 * x2 : -1.0;
+      pair[11 * nPair + p] = 2.0 / (sq1 + sq2);                                   // F
+      pair[12 * nPair + p] = S / sqrt(p1 * ((p1 + S) * (p1 + S) * (p1 + S))) / 4.0;   // diff1
+      pair[13 * nPair + p] = S / sqrt(p2 * ((p2 + S) * (p2 + S) * (p2 + S))) / 4.0;   // diff2
+      pair[14 * nPair + p] = (1.0 + p1r / rt1) / 2.0;                             // PosDefFunction::_evalDiff
+      pair[15 * nPair + p] = (1.0 + p2r / rt2) / 2.0;
+    }
   }
   if (tid >= kST - 32 && tid < kST - 32 + TB) {     // value head: V = scaleNet2V(O[0]), dV/dO (RACER_common.cpp:23-32)
     const int s = tid - (kST - 32);
@@ -576,12 +596,32 @@ __device__ void p1_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
     const bool isFar = (C32 > 1.0f) && offW;
     const float O0f = act[(Lo.actOff + 0) * TB + s];
     const double Vval = samp[2 * TB + s];
-    const double Aval = 0.0;                                                          // Zero_advantage.h:39-42
+    double Aval = 0.0;                                                                // Zero_advantage.h:39-42
+    double orig = 0.0, ratio = 1.0, coef = 0.0, coefRaw = 0.0, rtc = 1.0;
+    if (racer) {                                                                      // computeAdvantage, Gaus_advantage.h:73-78
+      double shape = 0.0;
+      for (int i = 0; i < dA; ++i) { shape += pair[7 * nPair + s * dA + i]; ratio *= pair[8 * nPair + s * dA + i]; }
+      orig = exp(-shape / 2.0);
+      coefRaw = (double)act[(Lo.actOff + 1) * TB + s];
+      rtc = sqrt(1.0 + coefRaw * coefRaw);
+      coef = (coefRaw + rtc) / 2.0;
+      Aval = coef * (orig - ratio);
+    }
     const double A_RET = (double)old[7 * TB + s] - Vval, deltaQ = A_RET - Aval;
     const double Ver = fmin(1.0, rho) * deltaQ;
     const double g0 = isFar ? 0.0 : Ver * beta * samp[3 * TB + s];
     samp[0 * TB + s] = A_RET * fmin(cmax, rho);     // pgfac
     samp[1 * TB + s] = isFar ? 1.0 : 0.0;
+    if (racer) {                                    // ADV.grad(act, isFar ? 0 : beta*Aer, gradient), Gaus_advantage.h:88-114
+      const double Aer = fmin(cmax, rho) * deltaQ;
+      const double errA = isFar ? 0.0 : beta * Aer;
+      const double expect = -ratio;
+      const double gc = (orig + expect) * (errA * ((1.0 + coefRaw / rtc) / 2.0));
+      samp[4 * TB + s] = orig * coef; samp[5 * TB + s] = expect; samp[6 * TB + s] = coef; samp[7 * TB + s] = errA;
+      err[(Lo.actOff + 1) * TB + s] = (float)gc;
+      a.lastG[(size_t)b * net.nOut + 1] = (float)gc;
+      a.lastO[(size_t)b * net.nOut + 1] = (float)coefRaw;
+    }
     err[(Lo.actOff + 0) * TB + s] = (float)g0;
     a.lastG[(size_t)b * net.nOut + 0] = (float)g0;
     a.lastO[(size_t)b * net.nOut + 0] = O0f;
@@ -622,7 +662,7 @@ __device__ void p1_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
       const int b = b0 + s;
       const double pgfac = samp[0 * TB + s];
       const bool isFar = samp[1 * TB + s] != 0.0;
-      const float mf = act[(Lo.actOff + 1 + i) * TB + s];
+      const float mf = act[(Lo.actOff + m0 + i) * TB + s];
       const double m = (double)mf;
       double pg_mean = pgfac * pair[4 * nPair + p];
       if (hp.bounded[i] && ((m >= MAXM && pg_mean > 0.0) || (m <= -MAXM && pg_mean < 0.0))) pg_mean = 0.0;
@@ -630,12 +670,28 @@ __device__ void p1_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
       if (isFar) { pg_mean = 0.0; pg_std = 0.0; }
       const double g_mean = beta * pg_mean + (1.0 - beta) * pair[2 * nPair + p];
       const double g_std = beta * pg_std + (1.0 - beta) * pair[3 * nPair + p];
-      err[(Lo.actOff + 1 + i) * TB + s] = (float)g_mean;
+      err[(Lo.actOff + m0 + i) * TB + s] = (float)g_mean;
       err[(Lp.actOff + i) * TB + s] = (float)g_std;
-      a.lastG[(size_t)b * net.nOut + 1 + i] = (float)g_mean;
-      a.lastG[(size_t)b * net.nOut + 1 + dA + i] = (float)g_std;
-      a.lastO[(size_t)b * net.nOut + 1 + i] = mf;
-      a.lastO[(size_t)b * net.nOut + 1 + dA + i] = ldw<SM>(Wp + Lp.imgB + i);
+      a.lastG[(size_t)b * net.nOut + m0 + i] = (float)g_mean;
+      a.lastG[(size_t)b * net.nOut + m0 + dA + i] = (float)g_std;
+      a.lastO[(size_t)b * net.nOut + m0 + i] = mf;
+      a.lastO[(size_t)b * net.nOut + m0 + dA + i] = ldw<SM>(Wp + Lp.imgB + i);
+      if (racer) {
+        const double oc = samp[4 * TB + s], expect = samp[5 * TB + s], coef = samp[6 * TB + s], errA = samp[7 * TB + s];
+        const double F = pair[11 * nPair + p];
+        double g1 = pair[9 * nPair + p] >= 0.0 ? oc * pair[9 * nPair + p] / 2.0 : 0.0;
+        double g2 = pair[10 * nPair + p] >= 0.0 ? oc * pair[10 * nPair + p] / 2.0 : 0.0;
+        g1 += F * expect * coef * pair[12 * nPair + p];
+        g2 += F * expect * coef * pair[13 * nPair + p];
+        g1 *= errA * pair[14 * nPair + p];
+        g2 *= errA * pair[15 * nPair + p];
+        err[(Lo.actOff + 2 + i) * TB + s] = (float)g1;
+        err[(Lo.actOff + 2 + dA + i) * TB + s] = (float)g2;
+        a.lastG[(size_t)b * net.nOut + 2 + i] = (float)g1;
+        a.lastG[(size_t)b * net.nOut + 2 + dA + i] = (float)g2;
+        a.lastO[(size_t)b * net.nOut + 2 + i] = act[(Lo.actOff + 2 + i) * TB + s];
+        a.lastO[(size_t)b * net.nOut + 2 + dA + i] = act[(Lo.actOff + 2 + dA + i) * TB + s];
+      }
     }
   }
   __syncthreads();

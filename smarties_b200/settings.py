@@ -92,7 +92,7 @@ class HyperParameters:
         if self.epsAnneal > 0.0001:
             self.epsAnneal = 5e-7   # "epsAnneal should be tiny. It will be set to 5e-7 for this run."
         unsupported = []
-        if self.learner not in ("VRACER",):
+        if self.learner not in ("VRACER", "RACER"):
             unsupported.append(f"learner={self.learner}")
         if self.dataSamplingAlgo != "uniform":
             unsupported.append(f"dataSamplingAlgo={self.dataSamplingAlgo}")

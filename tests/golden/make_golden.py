@@ -45,6 +45,15 @@ CASES = {
         replay=dict(seed=17, n_ep=16, ep_len=(20, 30), dS=4, dA=2),
         settings={"learner": "VRACER", "nnLayerSizes": [16], "batchSize": 8, "maxTotObsNum": 256, "minTotObsNum": 100},
         steps=5, start_step=0, sample_seed=3, bounded=0, full_steps=list(range(5))),
+    # RACER: Gaussian-shaped advantage head (Math/Gaus_advantage.h), unbounded and bounded actions
+    "racer_small": dict(
+        replay=dict(seed=41, n_ep=20, ep_len=(25, 55), dS=7, dA=3),
+        settings={"learner": "RACER", "nnLayerSizes": [32, 32], "batchSize": 16, "maxTotObsNum": 2048, "minTotObsNum": 400},
+        steps=10, start_step=995, sample_seed=9, bounded=0, full_steps=list(range(10))),
+    "racer_bounded": dict(
+        replay=dict(seed=43, n_ep=10, ep_len=(30, 40), dS=5, dA=2),
+        settings={"learner": "RACER", "nnLayerSizes": [24], "batchSize": 8, "maxTotObsNum": 1024, "minTotObsNum": 200},
+        steps=5, start_step=0, sample_seed=13, bounded=1, full_steps=list(range(5))),
 }
 
 BIG = ("/weights", "/m1", "/m2", "/gradSum")

@@ -34,6 +34,7 @@ def test_settings_file_of_reference_parses():
     hp = HyperParameters(4, 1, {"learner": "VRACER", "dataSamplingAlgo": "uniform", "returnsEstimator": "retrace",
                                 "ERoldSeqFilter": "oldest", "nnLayerSizes": [128, 128]})   # settings/VRACER.json
     assert hp.nnLayerSizes == [128, 128]
+    assert HyperParameters(4, 1, {"learner": "RACER"}).learner == "RACER"
     with pytest.raises(NotImplementedError):
         HyperParameters(4, 1, {"learner": "PPO"})
     with pytest.raises(KeyError):
