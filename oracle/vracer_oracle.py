@@ -707,3 +707,222 @@ class VracerOracle:
     # ---- flat views used by tests ----
     def concat(self, field):
         return np.concatenate([getattr(ep, field) for ep in self.episodes])
+
+
+# ------------------------------------------------------------------------------------------
+# recurrent networks (nnType "LSTM"): LSTMLayer (Network/Layers/Layer_LSTM.h:77-166) + BPTT in the
+# order of Network::backProp (Network/Network.h:155-193: layer-major, time-minor)
+# ------------------------------------------------------------------------------------------
+def sigm_f32(x):
+    """Sigm::_eval with safeExp clipped at +-SMARTIES_EXP_CUT = 8 (Functions.h:158-165, Definitions.h:43)."""
+    x = np.asarray(x, f32)
+    e = np.exp(np.clip(-np.abs(x), -8, 8).astype(f32)).astype(f32)     # exp(-|x|), |x| clipped at 8
+    pos = (f32(1) / (f32(1) + e)).astype(f32)
+    neg = (e / (f32(1) + e)).astype(f32)
+    return np.where(x > 0, pos, neg).astype(f32)
+
+
+class SeqLayout:
+    """Parameter blob for Input -> LSTM x H (ParametricResidual after every hidden layer but the first)
+    -> Linear out -> ParamLayer; same padding rules as MlpLayout (Parameters.h:159-176)."""
+
+    def __init__(self, dS, cells, n_dense_out, n_param_out):
+        self.dS, self.cells = int(dS), [int(c) for c in cells if c > 0]
+        self.layers = []
+        off, n_in = 0, self.dS
+        for li, c in enumerate(self.cells):
+            L = dict(kind="lstm", nIn=n_in, nC=c, ld=4 * c, w=off)
+            off += round_up8(4 * c * (n_in + c)); L["b"] = off; off += round_up8(4 * c)
+            self.layers.append(L)
+            if li > 0:
+                R = dict(kind="residual", n=c, w=off); off += round_up8(c); R["b"] = off; off += round_up8(c)
+                self.layers.append(R)
+            n_in = c
+        ld = round_up8(n_dense_out)
+        L = dict(kind="dense_linear", nIn=n_in, nOut=n_dense_out, ldw=ld, w=off)
+        off += round_up8(ld * n_in); L["b"] = off; off += round_up8(n_dense_out)
+        self.layers.append(L)
+        P = dict(kind="param", n=n_param_out, b=off); off += round_up8(n_param_out)
+        self.layers.append(P)
+        self.n_params, self.n_out = off, n_dense_out + n_param_out
+
+
+class SeqNet:
+    def __init__(self, layout: SeqLayout):
+        self.L = layout
+
+    def forward_seq(self, blob, X):
+        """X: [T+1, dS] standardized states of the window; the recurrent state starts at zero at the first
+        window step (Approximator.h:129-139: no `prev` activation).  Returns (O of every step [T+1, nOut], cache)."""
+        T1 = X.shape[0]
+        cache = []          # per step: list over layers of dicts
+        outs = []
+        prev = None
+        for k in range(T1):
+            acts = [dict(y=X[k].astype(f32))]
+            o_parts = []
+            for li, L in enumerate(self.L.layers):
+                kind = L["kind"]
+                if kind == "lstm":
+                    nI, nC = L["nIn"], L["nC"]
+                    W = blob[L["w"]:L["w"] + 4 * nC * (nI + nC)].reshape(nI + nC, 4 * nC)
+                    s = blob[L["b"]:L["b"] + 4 * nC].astype(f32).copy()
+                    xin = acts[-1]["y"][:nI]
+                    for i in range(nI):
+                        s += (xin[i] * W[i]).astype(f32)
+                    hp = prev[li + 1]["y"] if prev is not None else None
+                    if hp is not None:
+                        for i in range(nC):
+                            s += (hp[i] * W[nI + i]).astype(f32)
+                    cin = s[:nC].copy()
+                    g = sigm_f32(s[nC:])
+                    ig, fg, og = g[:nC], g[nC:2 * nC], g[2 * nC:]
+                    stp = prev[li + 1]["st"] if prev is not None else None
+                    old = (stp * fg).astype(f32) if stp is not None else np.zeros(nC, f32)
+                    st = ((cin * ig).astype(f32) + old).astype(f32)
+                    cop = tanh_f32(st)
+                    y = (og * cop).astype(f32)
+                    acts.append(dict(y=y, st=st, cop=cop, cin=cin, ig=ig, fg=fg, og=og, xin=xin, hp=hp, stp=stp))
+                elif kind == "residual":
+                    n = L["n"]
+                    w, b = blob[L["w"]:L["w"] + n], blob[L["b"]:L["b"] + n]
+                    y = (acts[-1]["y"][:n] + (acts[-2]["y"][:n] * w + b).astype(f32)).astype(f32)
+                    acts.append(dict(y=y))
+                elif kind == "dense_linear":
+                    W = blob[L["w"]:L["w"] + L["nIn"] * L["ldw"]].reshape(L["nIn"], L["ldw"])[:, :L["nOut"]]
+                    y = _dense_fwd(acts[-1]["y"][None, :L["nIn"]], W, blob[L["b"]:L["b"] + L["nOut"]])[0]
+                    acts.append(dict(y=y)); o_parts.append(y)
+                else:
+                    y = blob[L["b"]:L["b"] + L["n"]].astype(f32)
+                    acts.append(dict(y=y)); o_parts.append(y)
+            cache.append(acts)
+            outs.append(np.concatenate(o_parts))
+            prev = acts
+        return np.stack(outs).astype(f32), cache
+
+    def backward_seq(self, blob, cache, gout, G):
+        """BPTT with the output delta `gout` placed at the LAST cached step only; accumulates into G
+        in the reference's order (layers top to bottom, for each layer time T..0)."""
+        T = len(cache) - 1
+        nl = len(self.L.layers)
+        E = [[np.zeros_like(cache[k][li + 1]["y"]) if self.L.layers[li]["kind"] != "lstm"
+              else np.zeros(4 * self.L.layers[li]["nC"], f32) for li in range(nl)] for k in range(T + 1)]
+        Ein = [np.zeros(self.L.dS, f32) for _ in range(T + 1)]
+        k0 = 0
+        for li, L in enumerate(self.L.layers):
+            if L["kind"] == "dense_linear":
+                E[T][li] = gout[k0:k0 + L["nOut"]].astype(f32).copy(); k0 += L["nOut"]
+            elif L["kind"] == "param":
+                E[T][li] = gout[k0:k0 + L["n"]].astype(f32).copy(); k0 += L["n"]
+        sdelta = {}
+        for li in range(nl - 1, -1, -1):
+            L = self.L.layers[li]
+            kind = L["kind"]
+            for k in range(T, -1, -1):
+                a = cache[k][li + 1]
+                below = E[k][li - 1] if li > 0 else Ein[k]
+                if kind == "param":
+                    G[L["b"]:L["b"] + L["n"]] += E[k][li]
+                elif kind == "dense_linear":
+                    d = E[k][li]
+                    W = blob[L["w"]:L["w"] + L["nIn"] * L["ldw"]].reshape(L["nIn"], L["ldw"])[:, :L["nOut"]]
+                    below[:L["nIn"]] = (below[:L["nIn"]] + (W @ d).astype(f32)).astype(f32)
+                    G[L["b"]:L["b"] + L["nOut"]] += d
+                    Gw = G[L["w"]:L["w"] + L["nIn"] * L["ldw"]].reshape(L["nIn"], L["ldw"])[:, :L["nOut"]]
+                    Gw += (cache[k][li]["y"][:L["nIn"], None] * d[None, :]).astype(f32)
+                elif kind == "residual":
+                    n = L["n"]
+                    d = E[k][li]
+                    w = blob[L["w"]:L["w"] + n]
+                    E[k][li - 1][:n] = d                      # memcpy into E(ID-1) (first n entries)
+                    E[k][li - 2][:n] = (E[k][li - 2][:n] + (d * w).astype(f32)).astype(f32)
+                    G[L["w"]:L["w"] + n] += (d * cache[k][li - 1]["y"][:n]).astype(f32)
+                    G[L["b"]:L["b"] + n] += d
+                else:  # LSTMLayer::backward (Layer_LSTM.h:127-166)
+                    nI, nC = L["nIn"], L["nC"]
+                    W = blob[L["w"]:L["w"] + 4 * nC * (nI + nC)].reshape(nI + nC, 4 * nC)
+                    D = E[k][li][:nC].copy()
+                    diff = ((f32(1) - a["cop"] * a["cop"]).astype(f32) * D).astype(f32)
+                    sd = (diff * a["og"]).astype(f32)
+                    if k < T:
+                        nxt = cache[k + 1][li + 1]
+                        sd = (sd + (sdelta[(li, k + 1)] * nxt["fg"]).astype(f32)).astype(f32)
+                    sdelta[(li, k)] = sd
+                    dl = np.zeros(4 * nC, f32)
+                    dl[:nC] = a["ig"] * sd
+                    dl[nC:2 * nC] = ((a["ig"] * (f32(1) - a["ig"])).astype(f32) * a["cin"]).astype(f32) * sd
+                    if a["stp"] is not None:
+                        dl[2 * nC:3 * nC] = ((a["fg"] * (f32(1) - a["fg"])).astype(f32) * a["stp"]).astype(f32) * sd
+                    dl[3 * nC:] = ((a["og"] * (f32(1) - a["og"])).astype(f32) * D).astype(f32) * a["cop"]
+                    E[k][li] = dl
+                    if li > 0:                               # input gradient (skipped for the first layer)
+                        below[:nI] = (below[:nI] + (W[:nI] @ dl).astype(f32)).astype(f32)
+                    if a["hp"] is not None:                  # recurrent error into the previous step's E(ID)[0:nC]
+                        E[k - 1][li][:nC] = (E[k - 1][li][:nC] + (W[nI:] @ dl).astype(f32)).astype(f32)
+                    G[L["b"]:L["b"] + 4 * nC] += dl
+                    Gw = G[L["w"]:L["w"] + 4 * nC * (nI + nC)].reshape(nI + nC, 4 * nC)
+                    Gw[:nI] += (a["xin"][:, None] * dl[None, :]).astype(f32)
+                    if a["hp"] is not None:
+                        Gw[nI:] += (a["hp"][:, None] * dl[None, :]).astype(f32)
+        return G
+
+
+class RecurrentOracle(VracerOracle):
+    """RACER / V-RACER with nnType LSTM: sampled transition t is evaluated on the window
+    [t - min(nnBPTTseq, t), t] (MemoryBuffer.cpp:393-402), loss at t only, BPTT over the window."""
+
+    def __init__(self, dS, dA, cells=(64,), bptt=16, **kw):
+        learner = kw.get("learner", "VRACER")
+        super().__init__(dS, dA, hidden=(8,), **kw)
+        racer = learner == "RACER"
+        self.layout = SeqLayout(dS, cells, (2 + 3 * dA) if racer else (1 + dA), dA)
+        self.net = SeqNet(self.layout)
+        self.bptt = int(bptt)
+        self.W = np.zeros(self.layout.n_params, f32)
+        self.M1 = np.zeros_like(self.W); self.M2 = np.zeros_like(self.W)
+
+    def train_step(self, seq=None, obs=None):
+        if seq is None:
+            seq, obs = self.sample()
+        B = len(seq)
+        eps = [self.episodes[int(s)] for s in seq]
+        G = np.zeros(self.layout.n_params, f32)
+        Os, caches, Vnext = [], [], {}
+        for b in range(B):
+            ep, t = eps[b], int(obs[b])
+            n_rec = min(self.bptt, t)
+            X = np.stack([self.standardized(ep, k) for k in range(t - n_rec, t + 1)])
+            O, cache = self.net.forward_seq(self.W, X)
+            if t + 2 == ep.nsteps and not ep.terminated:     # V(s_{t+1}) with the recurrent state of step t
+                X2 = np.concatenate([X, self.standardized(ep, t + 1)[None]])
+                O2, _ = self.net.forward_seq(self.W, X2)
+                Vnext[b] = f32(scale_net2v(f64(O2[-1, 0])))
+            Os.append(O[-1]); caches.append(cache)
+        O32 = np.stack(Os)
+        act = np.stack([ep.A[int(t)] for ep, t in zip(eps, obs)])
+        mu = np.stack([ep.MU[int(t)] for ep, t in zip(eps, obs)])
+        qret = np.array([ep.Q[int(t)] for ep, t in zip(eps, obs)], f32)
+        r = vracer_sample_math(O32, act, mu, qret, self.beta, self.cmax, self.cinv, self.bounded, self.racer)
+        g32 = r["g"].astype(f32)
+        C32, I32 = f32(self.cmax), f32(self.cinv)
+        for b in range(B):
+            ep, t = eps[b], int(obs[b])
+            invN = f32(1) / f32(ep.nsteps)
+            if b in Vnext:
+                self._update_values(ep, t + 1, Vnext[b], Vnext[b])
+            E, D, Wt = f32(r["dq"][b]), f32(r["dkl"][b]), f32(r["rho"][b])
+            was = f32((ep.rho[t] > C32) or (ep.rho[t] < I32)); isf = f32((Wt > C32) or (Wt < I32))
+            ep.avgKL = f32(ep.avgKL + f32(invN * f32(D - ep.KL[t])))
+            ep.fracFar = f32(ep.fracFar + f32(invN * f32(isf - was)))
+            ep.avgSqErr = f32(ep.avgSqErr + f32(invN * f32(f32(E * E) - f32(ep.delta[t] * ep.delta[t]))))
+            ep.maxAbsErr = f32(max(ep.maxAbsErr, abs(E)))
+            ep.delta[t], ep.KL[t], ep.rho[t] = E, D, Wt
+            self._update_values(ep, t, f32(r["V"][b]), f32(r["A"][b] + r["V"][b]))
+            self.net.backward_seq(self.W, caches[b], g32[b], G)
+        self.adam_step += 1
+        X_last = np.stack([c[-1][0]["y"] for c in caches])
+        self.last = dict(r, seq=np.asarray(seq), obs=np.asarray(obs), X=X_last, O=O32, g=g32, g64=r["g"], gradSum=G.copy())
+        self.process_memory_buffer()
+        self.apply_adam(G)
+        self.n_grad_steps += 1
+        return self.last

@@ -54,6 +54,17 @@ CASES = {
         replay=dict(seed=43, n_ep=10, ep_len=(30, 40), dS=5, dA=2),
         settings={"learner": "RACER", "nnLayerSizes": [24], "batchSize": 8, "maxTotObsNum": 1024, "minTotObsNum": 200},
         steps=5, start_step=0, sample_seed=13, bounded=1, full_steps=list(range(5))),
+    # recurrent: LSTM layer, BPTT window nnBPTTseq (Layer_LSTM.h, Network.h:155-193)
+    "racer_lstm": dict(
+        replay=dict(seed=51, n_ep=14, ep_len=(12, 40), dS=6, dA=2),
+        settings={"learner": "RACER", "nnType": "LSTM", "nnLayerSizes": [16], "nnBPTTseq": 8, "batchSize": 8,
+                  "maxTotObsNum": 1024, "minTotObsNum": 200},
+        steps=6, start_step=997, sample_seed=21, bounded=0, full_steps=list(range(6))),
+    "vracer_lstm2": dict(
+        replay=dict(seed=53, n_ep=10, ep_len=(6, 30), dS=5, dA=2),
+        settings={"learner": "VRACER", "nnType": "LSTM", "nnLayerSizes": [12, 12], "nnBPTTseq": 5, "batchSize": 8,
+                  "maxTotObsNum": 1024, "minTotObsNum": 100},
+        steps=4, start_step=0, sample_seed=23, bounded=0, full_steps=list(range(4))),
 }
 
 BIG = ("/weights", "/m1", "/m2", "/gradSum")

@@ -9,6 +9,7 @@ import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["vracer_small", "vracer_cfg2mini", "vracer_bounded", "vracer_prune", "racer_small", "racer_bounded"]
+RECURRENT_CASES = ["racer_lstm", "vracer_lstm2"]     # nnType LSTM + BPTT window (configs[2] family)
 
 
 class Golden:
@@ -33,9 +34,14 @@ class Golden:
 def make_oracle(g: Golden):
     import vracer_oracle as vo
     s = g.settings
-    o = vo.VracerOracle(g.dS, g.dA, hidden=s.get("nnLayerSizes", [128, 128]), batch=s.get("batchSize", 256),
-                        max_tot_obs=s.get("maxTotObsNum"), bounded=g.bounded, sample_seed=g.sample_seed,
-                        learner=s.get("learner", "VRACER"))
+    if s.get("nnType", "FFNN") == "LSTM":
+        o = vo.RecurrentOracle(g.dS, g.dA, cells=s["nnLayerSizes"], bptt=s.get("nnBPTTseq", 16), batch=s.get("batchSize", 256),
+                               max_tot_obs=s.get("maxTotObsNum"), bounded=g.bounded, sample_seed=g.sample_seed,
+                               learner=s.get("learner", "VRACER"))
+    else:
+        o = vo.VracerOracle(g.dS, g.dA, hidden=s.get("nnLayerSizes", [128, 128]), batch=s.get("batchSize", 256),
+                            max_tot_obs=s.get("maxTotObsNum"), bounded=g.bounded, sample_seed=g.sample_seed,
+                            learner=s.get("learner", "VRACER"))
     o.W[:] = g.ref["init/weights"]
     o.load_replay(g.replay)
     o.initialize_learner()
