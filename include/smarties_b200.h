@@ -37,6 +37,7 @@ enum smb200_status {
 };
 
 enum smb200_algo { SMB200_VRACER = 0, SMB200_RACER = 1 };
+enum smb200_nn_type { SMB200_FFNN = 0, SMB200_LSTM = 1 };   /* "nnType" (Network/Builder.cpp:48-99) */
 enum smb200_field {          /* per-transition replay arrays, Episode.h:66-75 */
   SMB200_F_V = 0, SMB200_F_ADV = 1, SMB200_F_QRET = 2, SMB200_F_DELTA = 3, SMB200_F_RHO = 4, SMB200_F_KL = 5,
   SMB200_F_REWARD = 6
@@ -65,6 +66,9 @@ typedef struct smb200_config {
                                            count emulates (MemoryProcessing.cpp:202-227); 0 = 32 */
   int32_t world_rank, world_size;       /* learner ranks sharing the gradient (nMasters) */
   uint64_t seed;                        /* ExecutionInfo::randSeed (sampler + weight init) */
+  int32_t nn_type;                      /* smb200_nn_type: "nnType": "FFNN" | "LSTM" (Layers/Layer_LSTM.h) */
+  int32_t nn_bptt_seq;                  /* "nnBPTTseq": recurrent window = min(nnBPTTseq, t) past steps
+                                           (ReplayMemory/MemoryBuffer.cpp:393-402) */
 } smb200_config;
 
 /* Per-step scalars the reference prints / feeds back (MemoryBuffer::getMetrics,

@@ -14,15 +14,15 @@ constexpr int kThreads   = 256;         // every kernel here uses 256-thread CTA
 constexpr int kTileK     = 16;          // weight-gradient tile: 16 input rows x 16 output cols
 constexpr int kTileN     = 16;
 
-enum LayerKind : int { kInput = 0, kDenseTanh = 1, kResidual = 2, kDenseLinear = 3, kParam = 4 };
+enum LayerKind : int { kInput = 0, kDenseTanh = 1, kResidual = 2, kDenseLinear = 3, kParam = 4, kLSTM = 5 };
 
 // One layer of the network built by RACER::setupNet (Learners/RACER_common.cpp:70-115,
 // Network/Builder.cpp:48-99).  Layer ids equal the reference's (0 = input).
 struct LayerDesc {
   int kind;
-  int size;        // number of neurons = size of this layer's activation
-  int nIn;         // dense: fan-in
-  int ld;          // dense: row stride of W[nIn][ld] (roundUp8(size), Layer_Base.h:46)
+  int size;        // number of neurons = size of this layer's activation (LSTM: nCells)
+  int nIn;         // dense / LSTM: fan-in from the layer below
+  int ld;          // dense: row stride of W[nIn][ld] (roundUp8(size), Layer_Base.h:46); LSTM: 4*nCells, rows nIn+nCells (Layer_LSTM.h:24-29)
   int wOff, bOff;  // offsets into the padded parameter blob (Parameters.h:159-176)
   int needDx;      // 1 if the backward pass propagates into this layer's input (not the first layer)
   int imgW, imgB;  // offsets into the weight IMAGE (the shared-memory layout, see NetDesc::imgFloats)
@@ -42,14 +42,23 @@ struct NetDesc {
   int dS, dA;
   int actPerSample;  // floats per sample over all layers
   int maxWidth;      // widest layer
+  // recurrent networks (nnType LSTM): sampled transition t is evaluated on the window
+  // [t - min(bptt, t), t] (MemoryBuffer.cpp:393-402) with BPTT over the window (Network.h:155-193)
+  int recurrent;     // 1 if the hidden layers are LSTM layers
+  int bptt;          // nnBPTTseq
+  int Tc;            // bptt + 1 = longest window; P2 column of (sample b, window step k) = b*Tc + k
+  int topInOff;      // row of the compact copy (column = b) of the top hidden layer's output at the sampled step
+  int seqFloats;     // shared-memory floats of the per-sample sequence workspace (step_kernels.cu: SeqPlan)
   LayerDesc L[kMaxLayers];
 };
 
 // Work item of the weight-gradient + Adam phase.
 struct GradTile {
-  int kind;    // 0: dense 16x16 tile (row nIn = bias row), 1: residual vector, 2: param-layer bias
+  int kind;    // 0: dense / LSTM 16x16 tile (row K = bias row), 1: residual vector, 2: param-layer bias
   int layer;
   int k0, n0;
+  int cols;    // contraction length (columns of the feature-major scratch, multiple of 256)
+  int pad_[3];
 };
 
 // Scalars a step needs; double-buffered by step parity: step k reads ctrl[k&1], its

@@ -139,13 +139,28 @@ static int build_net(const smb200_config& c, NetDesc& net, std::vector<GradTile>
     L.imgW = img; img += L.ldp * L.nIn; L.imgB = img; img += round_up(L.size, 4); };
   add(kInput, dS);
   int nIn = dS;
+  const bool lstm = c.nn_type == SMB200_LSTM;
+  if (c.nn_type != SMB200_FFNN && c.nn_type != SMB200_LSTM) { set_error_msg("nnType must be FFNN or LSTM"); return -1; }
+  if (lstm && (c.nn_bptt_seq < 0 || c.nn_bptt_seq > 255)) { set_error_msg("nnBPTTseq out of range"); return -1; }
+  if (lstm) for (int i = 0; i < c.n_hidden; ++i) if (c.hidden[i] > NT) { set_error_msg("LSTM layers wider than the CTA are not supported"); return -1; }
   for (int i = 0; i < c.n_hidden; ++i) {
     const int h = c.hidden[i];
     if (h < 1) { set_error_msg("hidden layer size must be positive"); return -1; }
-    LayerDesc& L = add(kDenseTanh, h);
-    L.nIn = nIn; L.ld = round_up(h, 8);
-    L.wOff = off; off += round_up(L.ld * nIn, 8); L.bOff = off; off += round_up(h, 8);
-    L.needDx = i > 0; img_dense(L);
+    if (lstm) {   // LSTMLayer (Layers/Layer_LSTM.h): W[(nIn + nCells)][4 nCells] then 4 nCells biases
+      LayerDesc& L = add(kLSTM, h);
+      act += round_up(4 * h, 4) - round_up(h, 4);          // activation rows: [y | h_prev | -- | --], delta rows: 4 gates
+      L.nIn = nIn; L.ld = 4 * h;
+      L.wOff = off; off += round_up(4 * h * (nIn + h), 8); L.bOff = off; off += round_up(4 * h, 8);
+      L.needDx = i > 0;
+      L.fwdShift = log2_group(4 * h); L.bwdShift = log2_group(h);
+      L.ldp = round_up(4 * h, 4) + 4;
+      L.imgW = img; img += L.ldp * (nIn + h); L.imgB = img; img += round_up(4 * h, 4);
+    } else {
+      LayerDesc& L = add(kDenseTanh, h);
+      L.nIn = nIn; L.ld = round_up(h, 8);
+      L.wOff = off; off += round_up(L.ld * nIn, 8); L.bOff = off; off += round_up(h, 8);
+      L.needDx = i > 0; img_dense(L);
+    }
     if (i > 0) {   // ParametricResidualLayer after every hidden layer but the first (Builder.cpp:92-95)
       LayerDesc& R = add(kResidual, h);
       R.wOff = off; off += round_up(h, 8); R.bOff = off; off += round_up(h, 8);
@@ -166,7 +181,12 @@ static int build_net(const smb200_config& c, NetDesc& net, std::vector<GradTile>
     P.imgB = img; P.imgW = img; img += round_up(dA, 4);
   }
   net.nLayers = id; net.nParams = off; net.imgFloats = img; net.nOut = nOutDense + dA; net.nOutDense = nOutDense;
-  net.dS = dS; net.dA = dA; net.actPerSample = act; net.maxWidth = width;
+  net.dS = dS; net.dA = dA; net.maxWidth = width;
+  net.recurrent = lstm ? 1 : 0; net.bptt = lstm ? c.nn_bptt_seq : 0; net.Tc = net.bptt + 1;
+  net.topInOff = act;
+  if (lstm) act += round_up(nIn, 4);      // compact copy of the top hidden layer's output at the sampled step
+  net.actPerSample = act;
+  net.seqFloats = lstm ? seq_workspace_floats(net) : 0;
   tiles.clear();
   for (int l = 1; l < net.nLayers; ++l) {
     const LayerDesc& L = net.L[l];
@@ -177,8 +197,16 @@ static int build_net(const smb200_config& c, NetDesc& net, std::vector<GradTile>
       for (int n0 = 0; n0 < L.size; n0 += 16) tiles.push_back(GradTile{1, l, 0, n0});
     } else if (L.kind == kParam) {
       for (int n0 = 0; n0 < L.size; n0 += 16) tiles.push_back(GradTile{2, l, 0, n0});
+    } else if (L.kind == kLSTM) {
+      for (int k0 = 0; k0 < L.nIn + L.size + 1; k0 += kTileK)
+        for (int n0 = 0; n0 < 4 * L.size; n0 += kTileN) tiles.push_back(GradTile{0, l, k0, n0});
     }
   }
+  // contraction length of every tile: the mini-batch, or for recurrent networks all (sample, window step)
+  // columns; the output and stdev layers only receive a gradient at the sampled step (compact columns)
+  const int colsB = round_up(c.batch_size, 256);
+  const int colsAll = lstm ? round_up(c.batch_size * net.Tc, 256) : colsB;
+  for (auto& t : tiles) t.cols = (net.L[t.layer].kind == kDenseLinear || net.L[t.layer].kind == kParam) ? colsB : colsAll;
   return 0;
 }
 
@@ -201,6 +229,12 @@ static void init_weights(const smb200_config& c, const NetDesc& net, std::mt1993
         blob[L.bOff + 1] = -1.f;
         for (int o = 2; o < 2 + 2 * c.dim_action; ++o) blob[L.bOff + o] = 1.f;
       }
+    } else if (L.kind == kLSTM) {   // LSTMLayer::initialize (Layer_LSTM.h:168-188): gates primed with LSTM_PRIME_FAC = 1 (Bund.h:63)
+      const int nC = L.size;
+      const float init = (float)std::sqrt(6. / (L.nIn + nC));           // Tanh::_initFactor
+      std::uniform_real_distribution<float> dis(-init, init);
+      for (int o = 0; o < nC; ++o) { blob[L.bOff + o] = 0.f; blob[L.bOff + nC + o] = -1.f; blob[L.bOff + 2 * nC + o] = 1.f; blob[L.bOff + 3 * nC + o] = -1.f; }
+      for (int w = 0; w < 4 * nC * (L.nIn + nC); ++w) blob[L.wOff + w] = dis(gen);
     } else if (L.kind == kResidual) {
       for (int o = 0; o < L.size; ++o) { blob[L.wOff + o] = 1.f; blob[L.bOff + o] = 0.f; }
     } else if (L.kind == kParam) {   // SoftPlus::_inv(explNoise) (Functions.h:564-568, Continuous_policy.h:195-197)
@@ -221,6 +255,10 @@ static int upload_weights(smb200_learner* h, const float* blob) {
       for (int k = 0; k < L.nIn; ++k)
         for (int n = 0; n < L.size; ++n) im[L.imgW + k * L.ldp + n] = blob[L.wOff + k * L.ld + n];
       for (int n = 0; n < L.size; ++n) im[L.imgB + n] = blob[L.bOff + n];
+    } else if (L.kind == kLSTM) {
+      for (int k = 0; k < L.nIn + L.size; ++k)
+        for (int n = 0; n < 4 * L.size; ++n) im[L.imgW + k * L.ldp + n] = blob[L.wOff + k * L.ld + n];
+      for (int n = 0; n < 4 * L.size; ++n) im[L.imgB + n] = blob[L.bOff + n];
     } else if (L.kind == kResidual) {
       for (int n = 0; n < L.size; ++n) { im[L.imgW + n] = blob[L.wOff + n]; im[L.imgB + n] = blob[L.bOff + n]; }
     } else if (L.kind == kParam) {
@@ -405,6 +443,7 @@ int smb200_default_config(smb200_config* c, int32_t dS, int32_t dA) {
   c->gamma = 0.995; c->lambda = 1; c->clip_imp_weight = std::sqrt(dA / 2.0); c->penal_tol = 0.1; c->eps_anneal = 5e-7;
   c->learnrate = 1e-4; c->nn_lambda = (double)FLT_EPSILON; c->expl_noise = std::sqrt(0.2); c->out_weights_prefac = 1e-3;
   c->refer_reduce_threads = 32; c->world_rank = 0; c->world_size = 1; c->seed = 42;
+  c->nn_type = SMB200_FFNN; c->nn_bptt_seq = 16;
   return 0;
 }
 
@@ -424,6 +463,8 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
   if (c.batch_size < 1 || c.max_tot_obs < c.batch_size) { set_error_msg("bad batch_size / max_tot_obs"); delete h; return SMB200_ERR_INVALID; }
   std::vector<GradTile> tiles;
   if (build_net(c, h->descs.net, tiles)) { delete h; return SMB200_ERR_INVALID; }
+  memset(&h->descs.seq, 0, sizeof(h->descs.seq));
+  if (h->descs.net.recurrent) seq_plan(h->descs.net, h->descs.seq);
   Hyper& hp = h->descs.hp; memset(&hp, 0, sizeof(hp));
   hp.gamma = c.gamma; hp.lambda = c.lambda; hp.clipImpWeight = c.clip_imp_weight; hp.penalTol = c.penal_tol;
   hp.epsAnneal = c.eps_anneal; hp.learnrate = c.learnrate; hp.nnLambda = c.nn_lambda;
@@ -466,7 +507,7 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
 
   CK(dev_alloc(&h->W, (size_t)net.nParams)); CK(dev_alloc(&h->Wimg, (size_t)net.imgFloats));
   CK(dev_alloc(&h->M1, (size_t)net.nParams)); CK(dev_alloc(&h->M2, (size_t)net.nParams)); CK(dev_alloc(&h->G, (size_t)net.nParams));
-  h->Bpad = round_up(B, 256);
+  h->Bpad = net.recurrent ? round_up(B * net.Tc, 256) : round_up(B, 256);
   CK(dev_alloc(&h->actG, (size_t)net.actPerSample * h->Bpad)); CK(dev_alloc(&h->errG, (size_t)net.actPerSample * h->Bpad));
   h->nTiles = (int)tiles.size();
   CK(dev_alloc(&h->dTiles, tiles.size()));
@@ -1022,6 +1063,7 @@ int smb200_get_stats(smb200_learner* h, smb200_step_stats* out) {
 
 int smb200_forward(smb200_learner* h, const float* states, int32_t n, float* outputs) {
   if (!h || !states || !outputs || n < 1) return SMB200_ERR_INVALID;
+  if (h->descs.net.recurrent) { set_error_msg("smb200_forward: stateless evaluation is undefined for a recurrent network"); return SMB200_ERR_STATE; }
   cudaSetDevice(h->cfg.device);
   const int dS = h->cfg.dim_state, nOut = h->descs.net.nOut;
   float *dIn = nullptr, *dOut = nullptr;

@@ -24,6 +24,7 @@
 
 #include <cfloat>
 #include <cmath>
+#include <cstring>
 
 namespace smb200 {
 
@@ -333,183 +334,27 @@ __device__ __forceinline__ float net_out(const NetDesc& net, const float* Wp, co
 }
 
 // ------------------------------------------------------------------------------------------
-// shared-memory carve-up of the step kernels
+// ReF-ER / Retrace loss and output gradient of a tile of TB samples (RACER::Train,
+// Learners/RACER_train.cpp:31-60), f64.  `act` / `err` hold the network outputs / receive the
+// output gradient at [(layer.actOff + j) * TB + s].
 // ------------------------------------------------------------------------------------------
-struct SmemPlan {
-  size_t img, act, err, red, info, old, pair, samp, tiles, bars, stage, total;
+struct LossIO {
+  float* act; float* err; const int* info; const float* old; double* pair; double* samp; const float* vnext;
+  int b0; double pa, pmm, pms; int p0s, p0i;   // behaviour policy / action of the thread's first (sample, component) pair
 };
-__host__ __device__ inline SmemPlan smem_plan(const NetDesc& net, int TB, bool imgInSmem) {
-  SmemPlan p;
-  size_t o = ((sizeof(DevDescs) + 15) / 16) * 16;
-  p.img = o;   o += imgInSmem ? sizeof(float) * (size_t)net.imgFloats : 0;
-  p.act = o;   o += sizeof(float) * (size_t)net.actPerSample * TB;
-  p.err = o;   o += sizeof(float) * (size_t)net.actPerSample * TB;
-  p.red = o;   o += sizeof(float) * (size_t)kST * TB;
-  p.info = o;  o += sizeof(int) * 4 * TB;
-  p.old = o;   o += sizeof(float) * 8 * TB;                          // old V/ADV/rho/KL/delta (+ next row) per sample
-  o = (o + 15) / 16 * 16;
-  p.pair = o;  o += sizeof(double) * 16 * (size_t)TB * net.dA;       // per (sample, action component) terms
-  p.samp = o;  o += sizeof(double) * 12 * TB;                        // per sample scalars
-  p.tiles = o; o += sizeof(float) * 2 * kTileK * (256 + 4);          // P2 operand tiles
-  p.bars = o;  o += sizeof(uint64_t) * kMaxLayers;
-  // inputs of the NEXT step, prefetched while the weight-gradient phase runs:
-  // raw states [TB][dS], old values [8][TB], (a, mu_mean, mu_std) [3][TB*dA], info [4][TB]; then mean/scale [2][dS]
-  p.stage = o; o += sizeof(float) * ((size_t)TB * net.dS + 8 * TB + 3 * (size_t)TB * net.dA + 4 * TB + 2 * (size_t)net.dS);
-  o = (o + 15) / 16 * 16;
-  p.total = o;
-  return p;
-}
-
-// ------------------------------------------------------------------------------------------
-// weight image -> shared memory
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int layer_img_begin(const NetDesc& net, int l) {
-  const LayerDesc& L = net.L[l];
-  return (L.kind == kParam) ? L.imgB : L.imgW;
-}
-__device__ __forceinline__ int layer_img_end(const NetDesc& net, int l) {
-  return l + 1 < net.nLayers ? layer_img_begin(net, l + 1) : net.imgFloats;
-}
-
-// Called by all threads after the data dependency (grid barrier / kernel start) is satisfied.
-__device__ __forceinline__ void load_weight_image(const StepArgs& a, const NetDesc& net, float* img, uint64_t* bars) {
-  if (a.useTma) {
-    if (threadIdx.x == 0) {
-      // order this thread's earlier generic-proxy accesses (shared reads of the old image, the
-      // acquire of the grid barrier) before the async-proxy copies
-      asm volatile("fence.proxy.async;" ::: "memory");
-      for (int l = 1; l < net.nLayers; ++l) {
-        const int b = layer_img_begin(net, l), e = layer_img_end(net, l);
-        const unsigned bytes = (unsigned)(e - b) * 4u;
-        mbar_expect_tx(&bars[l], bytes);
-        bulk_g2s(img + b, a.Wimg + b, bytes, &bars[l]);
-      }
-    }
-  } else {
-    const int n4 = net.imgFloats >> 2;
-    for (int i = threadIdx.x; i < n4; i += kST)
-      reinterpret_cast<float4*>(img)[i] = __ldcg(reinterpret_cast<const float4*>(a.Wimg) + i);
-    __syncthreads();
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// P1
-// ------------------------------------------------------------------------------------------
-// `c` is this CTA's shared-memory copy of ctrl[step&1].  If `fetchCtrl` is set it is (re)loaded here,
-// as late as possible (just before the loss needs beta/Cmax), after waiting for the statistics CTA
-// to have published the previous step's result (`readyFlag`, `readyTarget`; nullptr = already valid).
-// `staged`: this tile's inputs (sample info, raw states, action / behaviour policy, old replay
-// values) were prefetched into the shared-memory staging area during the previous step's P2.
-struct Staging {
-  float* S; float* old; float* pair; int* info; float* mean; float* scale;
-};
-template <int TB>
-__device__ __forceinline__ Staging staging_view(const NetDesc& net, unsigned char* smraw, const SmemPlan& sp) {
-  Staging g;
-  float* f = reinterpret_cast<float*>(smraw + sp.stage);
-  g.S = f; f += TB * net.dS;
-  g.old = f; f += 8 * TB;
-  g.pair = f; f += 3 * TB * net.dA;
-  g.info = reinterpret_cast<int*>(f); f += 4 * TB;
-  g.mean = f; f += net.dS;
-  g.scale = f;
-  return g;
-}
 
 template <int TB, bool SM>
-__device__ void p1_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, StepCtrl& c, int step, int tile,
-                        unsigned char* smraw, const SmemPlan& sp, unsigned parity, bool fetchCtrl,
-                        const unsigned* readyFlag, unsigned readyTarget, bool staged) {
+__device__ __forceinline__ void loss_stages(const StepArgs& a, const NetDesc& net, const Hyper& hp, StepCtrl& c, int step, const float* Wp,
+                                            const LossIO& io, bool fetchCtrl, const unsigned* readyFlag, unsigned readyTarget) {
   const int tid = threadIdx.x;
-  float* img = reinterpret_cast<float*>(smraw + sp.img);
-  const float* Wp = SM ? img : a.Wimg;
-  float* act = reinterpret_cast<float*>(smraw + sp.act);     // [actPerSample][TB]
-  float* err = reinterpret_cast<float*>(smraw + sp.err);     // [actPerSample][TB]
-  float* red = reinterpret_cast<float*>(smraw + sp.red);
-  const Staging stg = staging_view<TB>(net, smraw, sp);
-  int* info = staged ? stg.info : reinterpret_cast<int*>(smraw + sp.info);   // row[TB], slot[TB], hasNext[TB], valid[TB]
-  float* old = staged ? stg.old : reinterpret_cast<float*>(smraw + sp.old);  // [8][TB]: V, ADV, RHO, KL, DELTA, Vnext, ADVnext, Qret
-  double* pair = reinterpret_cast<double*>(smraw + sp.pair); // [16][TB*dA]
-  double* samp = reinterpret_cast<double*>(smraw + sp.samp); // [12][TB]
-  const bool racer = hp.algo == 1;                           // RACER: Gaussian advantage head (Math/Gaus_advantage.h)
-  const int m0 = racer ? 2 + 2 * net.dA : 1;                 // first policy-mean output (RACER_common.cpp:174-193,232-247)
-  uint64_t* bars = (SM && a.useTma) ? reinterpret_cast<uint64_t*>(smraw + sp.bars) : nullptr;
-  const int b0 = tile * TB;
+  float* act = io.act; float* err = io.err; const int* info = io.info; const float* old = io.old;
+  double* pair = io.pair; double* samp = io.samp; const float* vnext = io.vnext;
+  const int b0 = io.b0, p0 = tid, p0s = io.p0s, p0i = io.p0i;
+  const double pa = io.pa, pmm = io.pmm, pms = io.pms;
   const ReplayView& rp = a.rp;
-  const int dS = net.dS, dA = net.dA;
-  const int nPair = TB * dA;
-
-  if (!staged) {
-    if (tid < TB) {
-      const int b = b0 + tid;
-      int row = 0, slot = 0, hn = 0, valid = 0;
-      if (b < a.B) {
-        const size_t j = (size_t)(step - a.stepBase) * a.B + b;
-        row = a.sampRow[j];
-        const int sf = a.sampSlot[j];
-        slot = sf & 0x7fffffff; hn = (sf >> 31) & 1;          // Episode::isTruncated(t+1), resolved on the host
-        valid = 1;
-        // old per-transition values needed by the write-back, fetched early
-        old[0 * TB + tid] = ld_cg(rp.V + row); old[1 * TB + tid] = ld_cg(rp.ADV + row);
-        old[2 * TB + tid] = ld_cg(rp.RHO + row); old[3 * TB + tid] = ld_cg(rp.KL + row);
-        old[4 * TB + tid] = ld_cg(rp.DELTA + row); old[7 * TB + tid] = ld_cg(rp.Q + row);
-        if (hn) { old[5 * TB + tid] = ld_cg(rp.V + row + 1); old[6 * TB + tid] = ld_cg(rp.ADV + row + 1); }
-      }
-      info[tid] = row; info[TB + tid] = slot; info[2 * TB + tid] = hn; info[3 * TB + tid] = valid;
-    }
-    __syncthreads();
-  }
-  int anyNext = 0;
-#pragma unroll
-  for (int s = 0; s < TB; ++s) anyNext |= info[2 * TB + s];
-
-  // V(s_{t+1}) of truncated episodes (RACER_train.cpp:23-27): rare, extra forward pass
-  float* vnext = reinterpret_cast<float*>(samp + 11 * TB);  // samp[11][*] is not used by the loss stages
-  if (anyNext) {
-    for (int idx = tid; idx < dS * TB; idx += kST) {
-      const int k = idx / TB, s = idx - k * TB;
-      const size_t row = (size_t)info[s] + 1;
-      act[idx] = info[2 * TB + s] ? (ld_cg(rp.S + row * dS + k) - ld_cg(rp.stateMean + k)) * ld_cg(rp.stateScale + k) : 0.f;
-    }
-    __syncthreads();
-    net_forward<TB, SM>(net, Wp, act, red, bars, parity);
-    if (tid < TB) vnext[tid] = (float)net2v((double)net_out<SM>(net, Wp, act, TB, 0, tid));
-    __syncthreads();
-  }
-
-  // gather + standardise: (s - mean) * scale   (Episode.h:171-183)
-  for (int idx = tid; idx < dS * TB; idx += kST) {
-    const int k = idx / TB, s = idx - k * TB;
-    float x = 0.f;
-    if (info[3 * TB + s])
-      x = staged ? (stg.S[s * dS + k] - stg.mean[k]) * stg.scale[k]
-                 : (ld_cg(rp.S + (size_t)info[s] * dS + k) - ld_cg(rp.stateMean + k)) * ld_cg(rp.stateScale + k);
-    act[idx] = x;
-    if (info[3 * TB + s]) a.lastX[(size_t)(b0 + s) * dS + k] = x;
-  }
-  for (int idx = tid; idx < net.actPerSample * TB; idx += kST) err[idx] = 0.f;   // clearErrors
-  // behaviour policy and action of this thread's first (sample, component) pair
-  double pa = 0, pmm = 0, pms = 1;
-  const int p0 = tid;
-  const int p0s = p0 < nPair ? p0 / dA : 0, p0i = p0 - p0s * dA;   // one integer division per tile, reused below
-  if (p0 < nPair) {
-    const int s = p0s, i = p0i;
-    if (info[3 * TB + s]) {
-      if (staged) { pa = (double)stg.pair[p0]; pmm = (double)stg.pair[nPair + p0]; pms = (double)stg.pair[2 * nPair + p0]; }
-      else {
-        const size_t row = info[s];
-        pa = (double)ld_cg(rp.A + row * dA + i);
-        pmm = (double)ld_cg(rp.MU + row * 2 * dA + i);
-        pms = (double)ld_cg(rp.MU + row * 2 * dA + dA + i);
-      }
-    }
-  }
-  __syncthreads();
-  DBG_T(a, step, 1);
-  net_forward<TB, SM>(net, Wp, act, red, bars, parity, &a, step);
-  DBG_T(a, step, 2);
-
+  const int dA = net.dA, nPair = TB * dA;
+  const bool racer = hp.algo == 1;
+  const int m0 = racer ? 2 + 2 * net.dA : 1;
   // ---- loss (RACER_train.cpp:31-60), f64.  Stage 1: one thread per (sample, action component);
   //      meanwhile warp 7 evaluates the value terms and fetches this step's ReF-ER scalars ----
   const LayerDesc& Lo = net.L[net.nLayers - 2];
@@ -696,6 +541,190 @@ __device__ void p1_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
   }
   __syncthreads();
   DBG_T(a, step, 3);
+}
+
+// ------------------------------------------------------------------------------------------
+// shared-memory carve-up of the step kernels
+// ------------------------------------------------------------------------------------------
+struct SmemPlan {
+  size_t img, act, err, red, info, old, pair, samp, tiles, bars, stage, total;
+};
+__host__ __device__ inline SmemPlan smem_plan(const NetDesc& net, int TB, bool imgInSmem) {
+  SmemPlan p;
+  size_t o = ((sizeof(DevDescs) + 15) / 16) * 16;
+  p.img = o;   o += imgInSmem ? sizeof(float) * (size_t)net.imgFloats : 0;
+  p.act = o;   o += sizeof(float) * (size_t)net.actPerSample * TB;
+  p.err = o;   o += sizeof(float) * (size_t)net.actPerSample * TB;
+  p.red = o;   o += sizeof(float) * (size_t)kST * TB;
+  p.info = o;  o += sizeof(int) * 4 * TB;
+  p.old = o;   o += sizeof(float) * 8 * TB;                          // old V/ADV/rho/KL/delta (+ next row) per sample
+  o = (o + 15) / 16 * 16;
+  p.pair = o;  o += sizeof(double) * 16 * (size_t)TB * net.dA;       // per (sample, action component) terms
+  p.samp = o;  o += sizeof(double) * 12 * TB;                        // per sample scalars
+  p.tiles = o; o += sizeof(float) * 2 * kTileK * (256 + 4);          // P2 operand tiles
+  p.bars = o;  o += sizeof(uint64_t) * kMaxLayers;
+  // inputs of the NEXT step, prefetched while the weight-gradient phase runs:
+  // raw states [TB][dS], old values [8][TB], (a, mu_mean, mu_std) [3][TB*dA], info [4][TB]; then mean/scale [2][dS]
+  p.stage = o; o += sizeof(float) * ((size_t)TB * net.dS + 8 * TB + 3 * (size_t)TB * net.dA + 4 * TB + 2 * (size_t)net.dS);
+  o = (o + 15) / 16 * 16;
+  p.total = o;
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------
+// weight image -> shared memory
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int layer_img_begin(const NetDesc& net, int l) {
+  const LayerDesc& L = net.L[l];
+  return (L.kind == kParam) ? L.imgB : L.imgW;
+}
+__device__ __forceinline__ int layer_img_end(const NetDesc& net, int l) {
+  return l + 1 < net.nLayers ? layer_img_begin(net, l + 1) : net.imgFloats;
+}
+
+// Called by all threads after the data dependency (grid barrier / kernel start) is satisfied.
+__device__ __forceinline__ void load_weight_image(const StepArgs& a, const NetDesc& net, float* img, uint64_t* bars) {
+  if (a.useTma) {
+    if (threadIdx.x == 0) {
+      // order this thread's earlier generic-proxy accesses (shared reads of the old image, the
+      // acquire of the grid barrier) before the async-proxy copies
+      asm volatile("fence.proxy.async;" ::: "memory");
+      for (int l = 1; l < net.nLayers; ++l) {
+        const int b = layer_img_begin(net, l), e = layer_img_end(net, l);
+        const unsigned bytes = (unsigned)(e - b) * 4u;
+        mbar_expect_tx(&bars[l], bytes);
+        bulk_g2s(img + b, a.Wimg + b, bytes, &bars[l]);
+      }
+    }
+  } else {
+    const int n4 = net.imgFloats >> 2;
+    for (int i = threadIdx.x; i < n4; i += kST)
+      reinterpret_cast<float4*>(img)[i] = __ldcg(reinterpret_cast<const float4*>(a.Wimg) + i);
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// P1
+// ------------------------------------------------------------------------------------------
+// `c` is this CTA's shared-memory copy of ctrl[step&1].  If `fetchCtrl` is set it is (re)loaded here,
+// as late as possible (just before the loss needs beta/Cmax), after waiting for the statistics CTA
+// to have published the previous step's result (`readyFlag`, `readyTarget`; nullptr = already valid).
+// `staged`: this tile's inputs (sample info, raw states, action / behaviour policy, old replay
+// values) were prefetched into the shared-memory staging area during the previous step's P2.
+struct Staging {
+  float* S; float* old; float* pair; int* info; float* mean; float* scale;
+};
+template <int TB>
+__device__ __forceinline__ Staging staging_view(const NetDesc& net, unsigned char* smraw, const SmemPlan& sp) {
+  Staging g;
+  float* f = reinterpret_cast<float*>(smraw + sp.stage);
+  g.S = f; f += TB * net.dS;
+  g.old = f; f += 8 * TB;
+  g.pair = f; f += 3 * TB * net.dA;
+  g.info = reinterpret_cast<int*>(f); f += 4 * TB;
+  g.mean = f; f += net.dS;
+  g.scale = f;
+  return g;
+}
+
+template <int TB, bool SM>
+__device__ void p1_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, StepCtrl& c, int step, int tile,
+                        unsigned char* smraw, const SmemPlan& sp, unsigned parity, bool fetchCtrl,
+                        const unsigned* readyFlag, unsigned readyTarget, bool staged) {
+  const int tid = threadIdx.x;
+  float* img = reinterpret_cast<float*>(smraw + sp.img);
+  const float* Wp = SM ? img : a.Wimg;
+  float* act = reinterpret_cast<float*>(smraw + sp.act);     // [actPerSample][TB]
+  float* err = reinterpret_cast<float*>(smraw + sp.err);     // [actPerSample][TB]
+  float* red = reinterpret_cast<float*>(smraw + sp.red);
+  const Staging stg = staging_view<TB>(net, smraw, sp);
+  int* info = staged ? stg.info : reinterpret_cast<int*>(smraw + sp.info);   // row[TB], slot[TB], hasNext[TB], valid[TB]
+  float* old = staged ? stg.old : reinterpret_cast<float*>(smraw + sp.old);  // [8][TB]: V, ADV, RHO, KL, DELTA, Vnext, ADVnext, Qret
+  double* pair = reinterpret_cast<double*>(smraw + sp.pair); // [16][TB*dA]
+  double* samp = reinterpret_cast<double*>(smraw + sp.samp); // [12][TB]
+  const bool racer = hp.algo == 1;                           // RACER: Gaussian advantage head (Math/Gaus_advantage.h)
+  const int m0 = racer ? 2 + 2 * net.dA : 1;                 // first policy-mean output (RACER_common.cpp:174-193,232-247)
+  uint64_t* bars = (SM && a.useTma) ? reinterpret_cast<uint64_t*>(smraw + sp.bars) : nullptr;
+  const int b0 = tile * TB;
+  const ReplayView& rp = a.rp;
+  const int dS = net.dS, dA = net.dA;
+  const int nPair = TB * dA;
+
+  if (!staged) {
+    if (tid < TB) {
+      const int b = b0 + tid;
+      int row = 0, slot = 0, hn = 0, valid = 0;
+      if (b < a.B) {
+        const size_t j = (size_t)(step - a.stepBase) * a.B + b;
+        row = a.sampRow[j];
+        const int sf = a.sampSlot[j];
+        slot = sf & 0x7fffffff; hn = (sf >> 31) & 1;          // Episode::isTruncated(t+1), resolved on the host
+        valid = 1;
+        // old per-transition values needed by the write-back, fetched early
+        old[0 * TB + tid] = ld_cg(rp.V + row); old[1 * TB + tid] = ld_cg(rp.ADV + row);
+        old[2 * TB + tid] = ld_cg(rp.RHO + row); old[3 * TB + tid] = ld_cg(rp.KL + row);
+        old[4 * TB + tid] = ld_cg(rp.DELTA + row); old[7 * TB + tid] = ld_cg(rp.Q + row);
+        if (hn) { old[5 * TB + tid] = ld_cg(rp.V + row + 1); old[6 * TB + tid] = ld_cg(rp.ADV + row + 1); }
+      }
+      info[tid] = row; info[TB + tid] = slot; info[2 * TB + tid] = hn; info[3 * TB + tid] = valid;
+    }
+    __syncthreads();
+  }
+  int anyNext = 0;
+#pragma unroll
+  for (int s = 0; s < TB; ++s) anyNext |= info[2 * TB + s];
+
+  // V(s_{t+1}) of truncated episodes (RACER_train.cpp:23-27): rare, extra forward pass
+  float* vnext = reinterpret_cast<float*>(samp + 11 * TB);  // samp[11][*] is not used by the loss stages
+  if (anyNext) {
+    for (int idx = tid; idx < dS * TB; idx += kST) {
+      const int k = idx / TB, s = idx - k * TB;
+      const size_t row = (size_t)info[s] + 1;
+      act[idx] = info[2 * TB + s] ? (ld_cg(rp.S + row * dS + k) - ld_cg(rp.stateMean + k)) * ld_cg(rp.stateScale + k) : 0.f;
+    }
+    __syncthreads();
+    net_forward<TB, SM>(net, Wp, act, red, bars, parity);
+    if (tid < TB) vnext[tid] = (float)net2v((double)net_out<SM>(net, Wp, act, TB, 0, tid));
+    __syncthreads();
+  }
+
+  // gather + standardise: (s - mean) * scale   (Episode.h:171-183)
+  for (int idx = tid; idx < dS * TB; idx += kST) {
+    const int k = idx / TB, s = idx - k * TB;
+    float x = 0.f;
+    if (info[3 * TB + s])
+      x = staged ? (stg.S[s * dS + k] - stg.mean[k]) * stg.scale[k]
+                 : (ld_cg(rp.S + (size_t)info[s] * dS + k) - ld_cg(rp.stateMean + k)) * ld_cg(rp.stateScale + k);
+    act[idx] = x;
+    if (info[3 * TB + s]) a.lastX[(size_t)(b0 + s) * dS + k] = x;
+  }
+  for (int idx = tid; idx < net.actPerSample * TB; idx += kST) err[idx] = 0.f;   // clearErrors
+  // behaviour policy and action of this thread's first (sample, component) pair
+  double pa = 0, pmm = 0, pms = 1;
+  const int p0 = tid;
+  const int p0s = p0 < nPair ? p0 / dA : 0, p0i = p0 - p0s * dA;   // one integer division per tile, reused below
+  if (p0 < nPair) {
+    const int s = p0s, i = p0i;
+    if (info[3 * TB + s]) {
+      if (staged) { pa = (double)stg.pair[p0]; pmm = (double)stg.pair[nPair + p0]; pms = (double)stg.pair[2 * nPair + p0]; }
+      else {
+        const size_t row = info[s];
+        pa = (double)ld_cg(rp.A + row * dA + i);
+        pmm = (double)ld_cg(rp.MU + row * 2 * dA + i);
+        pms = (double)ld_cg(rp.MU + row * 2 * dA + dA + i);
+      }
+    }
+  }
+  __syncthreads();
+  DBG_T(a, step, 1);
+  net_forward<TB, SM>(net, Wp, act, red, bars, parity, &a, step);
+  DBG_T(a, step, 2);
+
+  {
+    LossIO io{act, err, info, old, pair, samp, vnext, b0, pa, pmm, pms, p0s, p0i};
+    loss_stages<TB, SM>(a, net, hp, c, step, Wp, io, fetchCtrl, readyFlag, readyTarget);
+  }
 
   // ---- backward: Network::backProp, layers last to first (Network.h:216-226).  A residual layer
   //      is folded into the dense layer below it: E(l) = E(res) * f'(Y_l), E(l-1) += E(res) * w_res ----
@@ -742,6 +771,392 @@ __device__ void p1_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
 }
 
 // ------------------------------------------------------------------------------------------
+// Recurrent networks (nnType LSTM): P1 of ONE sampled transition per CTA.
+//
+// The reference evaluates the sampled step t on the window [t - min(nnBPTTseq, t), t] starting
+// from a zero recurrent state (MemoryBuffer.cpp:393-402, Approximator.h:129-139), places the
+// output gradient at step t only and back-propagates through time layer by layer
+// (Network::backProp, Network.h:155-193).  Here the forward pass is layer-major as well: the
+// input contribution b + x_k Wx of every window step is one batched product, only h_{k-1} Wh and
+// the gates run sequentially; the backward recurrence carries the state delta and the forget
+// gate of step k+1 in registers and overwrites the stored gates by the gate deltas, which then
+// leave for the P2 scratch as [feature][sample*Tc + k] rows.
+// ------------------------------------------------------------------------------------------
+static inline int seq_stride(int n) {            // >= n, == 4 (mod 32): float4-aligned and conflict-free for seq_store
+  int s = (n + 3) / 4 * 4;
+  while ((s & 31) != 4) s += 4;
+  return s;
+}
+
+void seq_plan(const NetDesc& net, SeqPlan& p) {
+  memset(&p, 0, sizeof(p));
+  const int T = net.Tc + 1;
+  p.T = T;
+  int o = 0;
+  for (int l = 0; l < net.nLayers; ++l) {
+    const LayerDesc& L = net.L[l];
+    if (L.kind == kInput || L.kind == kResidual || L.kind == kLSTM) {
+      const int n4 = (L.size + 3) / 4 * 4;
+      p.yStride[l] = seq_stride(L.kind == kLSTM ? 3 * n4 : n4); p.yOff[l] = o; o += T * p.yStride[l];
+      if (L.kind == kLSTM) { p.gStride[l] = seq_stride(4 * L.size); p.gOff[l] = o; o += T * p.gStride[l]; }
+      if (L.kind != kInput) { p.eStride[l] = seq_stride(L.size); p.eOff[l] = o; o += T * p.eStride[l]; }
+    }
+  }
+  const int aps = (net.actPerSample + 3) / 4 * 4;
+  p.actTop = o; o += aps;
+  p.errTop = o; o += aps;
+  p.red = o; o += 2 * kST;
+  p.total = o;
+}
+int seq_workspace_floats(const NetDesc& net) { SeqPlan p; seq_plan(net, p); return p.total; }
+
+struct SeqSmem { size_t img, ws, info, old, pair, samp, bars, total; };
+__host__ __device__ inline SeqSmem smem_plan_seq(const NetDesc& net, bool imgInSmem) {
+  SeqSmem p;
+  size_t o = ((sizeof(DevDescs) + 15) / 16) * 16;
+  p.img = o;  o += imgInSmem ? sizeof(float) * (size_t)net.imgFloats : 0;
+  const size_t wsB = sizeof(float) * (size_t)net.seqFloats, tilesB = sizeof(float) * 2 * kTileK * (256 + 4);
+  p.ws = o;   o += wsB > tilesB ? wsB : tilesB;          // the P2 operand tiles alias the sequence workspace
+  p.info = o; o += sizeof(int) * 8;
+  p.old = o;  o += sizeof(float) * 8;
+  o = (o + 15) / 16 * 16;
+  p.pair = o; o += sizeof(double) * 16 * (size_t)net.dA;
+  p.samp = o; o += sizeof(double) * 12;
+  p.bars = o; o += sizeof(uint64_t) * kMaxLayers;
+  o = (o + 15) / 16 * 16;
+  p.total = o;
+  return p;
+}
+
+// Sigm::_eval with safeExp clipped at +-SMARTIES_EXP_CUT = 8 (Functions.h:158-165, FunctionUtilities.h:51-54)
+__device__ __forceinline__ float sigm_ref(float x) {
+  const float e = __expf(-fminf(fabsf(x), 8.0f));
+  return x > 0.0f ? __fdividef(1.0f, 1.0f + e) : __fdividef(e, 1.0f + e);
+}
+
+// rows [rowOff, rowOff+nFeat) x columns [col0, col0+Tc) of a feature-major P2 scratch
+//   <- src[(k - kShift)*stride + f] for window steps k < T1 (zero outside the window).
+// A warp covers 4 features x 8 steps: conflict-free shared reads (stride == 4 mod 32), 32-byte global runs.
+__device__ __forceinline__ void seq_store(float* dst, int Bpad, int rowOff, int nFeat, int col0, int Tc, int T1,
+                                          const float* src, int stride, int kShift) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fB = (nFeat + 3) >> 2, kB = (Tc + 7) >> 3;
+  for (int blk = warp; blk < fB * kB; blk += kST / 32) {
+    const int fb = blk / kB;
+    const int f = fb * 4 + (lane & 3), k = (blk - fb * kB) * 8 + (lane >> 2);
+    if (f < nFeat && k < Tc) {
+      const int ks = k - kShift;
+      dst[(size_t)(rowOff + f) * Bpad + col0 + k] = (k < T1 && ks >= 0) ? src[ks * stride + f] : 0.0f;
+    }
+  }
+}
+
+// LSTMLayer::forward for window steps [0, Tn) (Layers/Layer_LSTM.h:77-125)
+template <bool SM>
+__device__ void lstm_forward(const LayerDesc& L, const float* Wp, const float* in, int is, float* Gt, int gs, float* Y, int ys,
+                             float* red, int Tn) {
+  const int tid = threadIdx.x;
+  const int nC = L.size, nI = L.nIn, N4 = 4 * nC, ldp = L.ldp, nC4 = (nC + 3) / 4 * 4;
+  const float* Wx = Wp + L.imgW;
+  const float* Wh = Wx + (size_t)nI * ldp;
+  const float* bias = Wp + L.imgB;
+  // (a) suminp = b + x_k Wx for every window step, four steps per thread
+  const int nq = (Tn + 3) >> 2;
+  for (int idx = tid; idx < N4 * nq; idx += kST) {
+    const int kq = idx / N4, n = idx - kq * N4, k0 = kq * 4;
+    const float bv = ldw<SM>(bias + n);
+    float acc[4] = {bv, bv, bv, bv};
+    const float* x[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = in + (size_t)min(k0 + j, Tn - 1) * is;
+    const float* w = Wx + n;
+    int i = 0;
+    for (; i + 4 <= nI; i += 4) {
+      const float w0 = ldw<SM>(w + (size_t)(i + 0) * ldp), w1 = ldw<SM>(w + (size_t)(i + 1) * ldp);
+      const float w2 = ldw<SM>(w + (size_t)(i + 2) * ldp), w3 = ldw<SM>(w + (size_t)(i + 3) * ldp);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 xv = *reinterpret_cast<const float4*>(x[j] + i);
+        acc[j] = fmaf(xv.x, w0, acc[j]); acc[j] = fmaf(xv.y, w1, acc[j]); acc[j] = fmaf(xv.z, w2, acc[j]); acc[j] = fmaf(xv.w, w3, acc[j]);
+      }
+    }
+    for (; i < nI; ++i) {
+      const float wv = ldw<SM>(w + (size_t)i * ldp);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(x[j][i], wv, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (k0 + j < Tn) Gt[(size_t)(k0 + j) * gs + n] = acc[j];
+  }
+  __syncthreads();
+  // (b) the recurrence: suminp += h_{k-1} Wh, gates, cell state, output
+  const int sh = L.fwdShift, NR = 1 << sh, G = kST >> sh;
+  const int g = tid >> sh, nl = tid & (NR - 1);
+  const int Kc = (((nC + G - 1) / G) + 3) / 4 * 4;
+  const int kb = min(nC, g * Kc), ke = min(nC, kb + Kc);
+  for (int k = 0; k < Tn; ++k) {
+    if (k > 0) {
+      const float* hprev = Y + (size_t)(k - 1) * ys;
+      for (int n0 = 0; n0 < N4; n0 += NR) {
+        const int n = n0 + nl;
+        float acc = 0.0f;
+        if (n < N4) {
+          const float* w = Wh + n;
+          int i = kb;
+          for (; i + 4 <= ke; i += 4) {
+            const float4 hv = *reinterpret_cast<const float4*>(hprev + i);
+            acc = fmaf(hv.x, ldw<SM>(w + (size_t)(i + 0) * ldp), acc); acc = fmaf(hv.y, ldw<SM>(w + (size_t)(i + 1) * ldp), acc);
+            acc = fmaf(hv.z, ldw<SM>(w + (size_t)(i + 2) * ldp), acc); acc = fmaf(hv.w, ldw<SM>(w + (size_t)(i + 3) * ldp), acc);
+          }
+          for (; i < ke; ++i) acc = fmaf(hprev[i], ldw<SM>(w + (size_t)i * ldp), acc);
+          if (G == 1) Gt[(size_t)k * gs + n] += acc;
+        }
+        if (G > 1) red[g * NR + nl] = acc;
+      }
+      __syncthreads();
+    }
+    if (tid < nC) {
+      const int o = tid;
+      float* gk = Gt + (size_t)k * gs;
+      float s0 = gk[o], s1 = gk[nC + o], s2 = gk[2 * nC + o], s3 = gk[3 * nC + o];
+      if (k > 0 && G > 1) {
+        for (int gg = 0; gg < G; ++gg) {
+          s0 += red[gg * NR + o]; s1 += red[gg * NR + nC + o]; s2 += red[gg * NR + 2 * nC + o]; s3 += red[gg * NR + 3 * nC + o];
+        }
+      }
+      const float ig = sigm_ref(s1), fg = sigm_ref(s2), og = sigm_ref(s3);
+      const float oldPass = k > 0 ? Y[(size_t)(k - 1) * ys + nC4 + o] * fg : 0.0f;
+      const float st = s0 * ig + oldPass;
+      const float cop = tanh_ref(st);
+      gk[o] = s0; gk[nC + o] = ig; gk[2 * nC + o] = fg; gk[3 * nC + o] = og;
+      float* yk = Y + (size_t)k * ys;
+      yk[o] = og * cop; yk[nC4 + o] = st; yk[2 * nC4 + o] = cop;
+    }
+    __syncthreads();
+  }
+}
+
+// LSTMLayer::backward + Layer::backward for window steps T1-1 .. 0 (Layer_LSTM.h:127-166, Layers.h:123-188).
+// E: error on y per step (from the layers above); on return Gt holds the four gate deltas of every step
+// and, if the layer is not the first one, Ein has received Wx * delta.
+template <bool SM>
+__device__ void lstm_backward(const LayerDesc& L, const float* Wp, float* Gt, int gs, const float* Y, int ys, const float* E, int es,
+                              float* Ein, int eis, float* red, int T1) {
+  const int tid = threadIdx.x;
+  const int nC = L.size, nI = L.nIn, N4 = 4 * nC, ldp = L.ldp, nC4 = (nC + 3) / 4 * 4;
+  const float* Wx = Wp + L.imgW;
+  const float* Wh = Wx + (size_t)nI * ldp;
+  const int sh = L.bwdShift, KR = 1 << sh, G = kST >> sh;
+  const int g = tid >> sh, il = tid & (KR - 1);
+  const int N4q = (N4 + 3) >> 2;
+  const int Nc = (N4q + G - 1) / G;
+  const int nb = min(N4q, g * Nc), ne = min(N4q, nb + Nc);
+  float sdNext = 0.0f, fgNext = 0.0f;
+  for (int k = T1 - 1; k >= 0; --k) {
+    if (tid < nC) {
+      const int o = tid;
+      float D = E[(size_t)k * es + o];
+      if (k < T1 - 1) for (int gg = 0; gg < G; ++gg) D += red[gg * KR + o];      // Wh * delta of step k+1
+      float* gk = Gt + (size_t)k * gs;
+      const float cin = gk[o], ig = gk[nC + o], fg = gk[2 * nC + o], og = gk[3 * nC + o];
+      const float cop = Y[(size_t)k * ys + 2 * nC4 + o];
+      const float diff = (1.0f - cop * cop) * D;
+      const float sd = diff * og + (k < T1 - 1 ? sdNext * fgNext : 0.0f);
+      gk[o] = ig * sd;
+      gk[nC + o] = ig * (1.0f - ig) * cin * sd;
+      gk[2 * nC + o] = k > 0 ? fg * (1.0f - fg) * Y[(size_t)(k - 1) * ys + nC4 + o] * sd : 0.0f;
+      gk[3 * nC + o] = og * (1.0f - og) * D * cop;
+      sdNext = sd; fgNext = fg;
+    }
+    __syncthreads();
+    if (k > 0) {
+      float acc = 0.0f;
+      if (il < nC) {
+        const float* w = Wh + (size_t)il * ldp;
+        const float* dl = Gt + (size_t)k * gs;
+        for (int n4 = nb; n4 < ne; ++n4) {
+          const float4 wv = ldw4<SM>(w + n4 * 4), dv = *reinterpret_cast<const float4*>(dl + n4 * 4);
+          acc = fmaf(wv.x, dv.x, acc); acc = fmaf(wv.y, dv.y, acc); acc = fmaf(wv.z, dv.z, acc); acc = fmaf(wv.w, dv.w, acc);
+        }
+      }
+      red[g * KR + il] = acc;
+      __syncthreads();
+    }
+  }
+  if (L.needDx) {   // error on the layer below, all window steps at once
+    for (int idx = tid; idx < nI * T1; idx += kST) {
+      const int k = idx / nI, i = idx - k * nI;
+      const float* w = Wx + (size_t)i * ldp;
+      const float* dl = Gt + (size_t)k * gs;
+      float acc = 0.0f;
+      for (int n4 = 0; n4 < N4q; ++n4) {
+        const float4 wv = ldw4<SM>(w + n4 * 4), dv = *reinterpret_cast<const float4*>(dl + n4 * 4);
+        acc = fmaf(wv.x, dv.x, acc); acc = fmaf(wv.y, dv.y, acc); acc = fmaf(wv.z, dv.z, acc); acc = fmaf(wv.w, dv.w, acc);
+      }
+      Ein[(size_t)k * eis + i] += acc;
+    }
+    __syncthreads();
+  }
+}
+
+template <bool SM>
+__device__ void p1_seq(const StepArgs& a, const DevDescs& dd, StepCtrl& c, int step, int b, unsigned char* smraw, const SeqSmem& sp,
+                       unsigned parity, bool fetchCtrl, const unsigned* readyFlag, unsigned readyTarget) {
+  const NetDesc& net = dd.net; const SeqPlan& sq = dd.seq; const Hyper& hp = dd.hp;
+  const int tid = threadIdx.x;
+  float* img = reinterpret_cast<float*>(smraw + sp.img);
+  const float* Wp = SM ? img : a.Wimg;
+  float* ws = reinterpret_cast<float*>(smraw + sp.ws);
+  int* info = reinterpret_cast<int*>(smraw + sp.info);        // row, slot, hasNext, valid, nRecurr
+  float* old = reinterpret_cast<float*>(smraw + sp.old);      // V, ADV, RHO, KL, DELTA, Vnext, ADVnext, Qret
+  double* pair = reinterpret_cast<double*>(smraw + sp.pair);
+  double* samp = reinterpret_cast<double*>(smraw + sp.samp);
+  uint64_t* bars = (SM && a.useTma) ? reinterpret_cast<uint64_t*>(smraw + sp.bars) : nullptr;
+  float* red = ws + sq.red;
+  float* actTop = ws + sq.actTop;
+  float* errTop = ws + sq.errTop;
+  const ReplayView& rp = a.rp;
+  const int dS = net.dS, dA = net.dA, Tc = net.Tc;
+
+  if (tid == 0) {
+    const size_t j = (size_t)(step - a.stepBase) * a.B + b;
+    const int row = a.sampRow[j];
+    const int sf = a.sampSlot[j];
+    const int slot = sf & 0x7fffffff, hn = (sf >> 31) & 1;
+    const int t = row - __ldcg(rp.epStart + slot);
+    info[0] = row; info[1] = slot; info[2] = hn; info[3] = 1; info[4] = min(net.bptt, t);
+    old[0] = ld_cg(rp.V + row); old[1] = ld_cg(rp.ADV + row); old[2] = ld_cg(rp.RHO + row); old[3] = ld_cg(rp.KL + row);
+    old[4] = ld_cg(rp.DELTA + row); old[7] = ld_cg(rp.Q + row);
+    old[5] = 0.f; old[6] = 0.f;
+    if (hn) { old[5] = ld_cg(rp.V + row + 1); old[6] = ld_cg(rp.ADV + row + 1); }
+  }
+  for (int idx = tid; idx < sq.red; idx += kST) ws[idx] = 0.0f;     // pads, error buffers, top vectors
+  __syncthreads();
+  const int row = info[0], hn = info[2], nRec = info[4];
+  const int T1 = nRec + 1, Tn = T1 + hn;            // window steps; + the state after the sampled step (RACER_train.cpp:23-27)
+  // gather + standardise the window's states (Episode.h:171-183)
+  float* X = ws + sq.yOff[0];
+  const int xs = sq.yStride[0];
+  for (int idx = tid; idx < Tn * dS; idx += kST) {
+    const int k = idx / dS, i = idx - k * dS;
+    X[k * xs + i] = (ld_cg(rp.S + (size_t)(row - nRec + k) * dS + i) - ld_cg(rp.stateMean + i)) * ld_cg(rp.stateScale + i);
+  }
+  double pa = 0, pmm = 0, pms = 1;
+  if (tid < dA) {
+    pa = (double)ld_cg(rp.A + (size_t)row * dA + tid);
+    pmm = (double)ld_cg(rp.MU + (size_t)row * 2 * dA + tid);
+    pms = (double)ld_cg(rp.MU + (size_t)row * 2 * dA + dA + tid);
+  }
+  __syncthreads();
+  if (tid < dS) a.lastX[(size_t)b * dS + tid] = X[nRec * xs + tid];
+  DBG_T(a, step, 1);
+
+  // ---- forward, layer-major ----
+  const LayerDesc& Lo = net.L[net.nLayers - 2];
+  const LayerDesc& Lp = net.L[net.nLayers - 1];
+  float* vnext = reinterpret_cast<float*>(samp + 11);
+  for (int l = 1; l < net.nLayers; ++l) {
+    const LayerDesc& L = net.L[l];
+    if (bars) mbar_wait(&bars[l], parity);
+    if (L.kind == kLSTM) {
+      lstm_forward<SM>(L, Wp, ws + sq.yOff[L.in], sq.yStride[L.in], ws + sq.gOff[l], sq.gStride[l], ws + sq.yOff[l], sq.yStride[l], red, Tn);
+    } else if (L.kind == kResidual) {       // ParametricResidualLayer::forward (Layers.h:347-361)
+      const float* y1 = ws + sq.yOff[l - 1]; const float* y2 = ws + sq.yOff[l - 2];
+      const int s1 = sq.yStride[l - 1], s2 = sq.yStride[l - 2], ys = sq.yStride[l];
+      float* y = ws + sq.yOff[l];
+      for (int idx = tid; idx < Tn * L.size; idx += kST) {
+        const int k = idx / L.size, j = idx - k * L.size;
+        y[k * ys + j] = y1[k * s1 + j] + (y2[k * s2 + j] * ldw<SM>(Wp + L.imgW + j) + ldw<SM>(Wp + L.imgB + j));
+      }
+      __syncthreads();
+    } else if (L.kind == kDenseLinear) {    // outputs at the sampled step and, if needed, at the step after it
+      const float* in = ws + sq.yOff[L.in]; const int is = sq.yStride[L.in];
+      const float* x0 = in + (size_t)(T1 - 1) * is;
+      const float* x1 = in + (size_t)(Tn - 1) * is;
+      const int sh = L.fwdShift, NR = 1 << sh, G = kST >> sh;
+      const int g = tid >> sh, nl = tid & (NR - 1);
+      const int K = L.nIn, N = L.size, Kc = (K + G - 1) / G;
+      const int kb = min(K, g * Kc), ke = min(K, kb + Kc);
+      float a0 = 0.0f, a1 = 0.0f;
+      if (nl < N) {
+        const float* w = Wp + L.imgW + nl;
+        for (int i = kb; i < ke; ++i) { const float wv = ldw<SM>(w + (size_t)i * L.ldp); a0 = fmaf(x0[i], wv, a0); a1 = fmaf(x1[i], wv, a1); }
+      }
+      red[g * NR + nl] = a0; red[kST + g * NR + nl] = a1;
+      __syncthreads();
+      if (tid < N) {
+        float v0 = 0.0f, v1 = 0.0f;
+        for (int gg = 0; gg < G; ++gg) { v0 += red[gg * NR + tid]; v1 += red[kST + gg * NR + tid]; }
+        const float bv = ldw<SM>(Wp + L.imgB + tid);
+        actTop[L.actOff + tid] = v0 + bv;
+        if (tid == 0 && hn) vnext[0] = (float)net2v((double)(v1 + bv));
+      }
+      __syncthreads();
+    }
+  }
+  DBG_T(a, step, 2);
+
+  {
+    LossIO io{actTop, errTop, info, old, pair, samp, vnext, b, pa, pmm, pms, 0, tid < dA ? tid : 0};
+    loss_stages<1, SM>(a, net, hp, c, step, Wp, io, fetchCtrl, readyFlag, readyTarget);
+  }
+
+  // ---- backward through time, layers last to first ----
+  const int col0 = b * Tc;
+  {   // output layer: error on the top hidden layer at the sampled step (Layers.h:131-145)
+    const int lt = Lo.in;
+    float* e = ws + sq.eOff[lt] + (size_t)(T1 - 1) * sq.eStride[lt];
+    const int sh = Lo.bwdShift, KR = 1 << sh, G = kST >> sh;
+    const int g = tid >> sh, il = tid & (KR - 1);
+    const int K = Lo.nIn, N = Lo.size, Nc = (N + G - 1) / G;
+    const int nb = min(N, g * Nc), ne = min(N, nb + Nc);
+    float acc = 0.0f;
+    if (il < K) {
+      const float* w = Wp + Lo.imgW + (size_t)il * Lo.ldp;
+      for (int n = nb; n < ne; ++n) acc = fmaf(ldw<SM>(w + n), errTop[Lo.actOff + n], acc);
+    }
+    red[g * KR + il] = acc;
+    __syncthreads();
+    if (tid < K) { float v = 0.0f; for (int gg = 0; gg < G; ++gg) v += red[gg * KR + tid]; e[tid] += v; }
+    __syncthreads();
+  }
+  for (int l = net.nLayers - 3; l >= 1; --l) {
+    const LayerDesc& L = net.L[l];
+    if (L.kind == kResidual) {               // ParametricResidualLayer::backward (Layers.h:363-393)
+      const float* e = ws + sq.eOff[l]; const int es = sq.eStride[l];
+      float* e1 = ws + sq.eOff[l - 1]; float* e2 = ws + sq.eOff[l - 2];
+      const int es1 = sq.eStride[l - 1], es2 = sq.eStride[l - 2];
+      for (int idx = tid; idx < T1 * L.size; idx += kST) {
+        const int k = idx / L.size, j = idx - k * L.size;
+        const float d = e[k * es + j];
+        e1[k * es1 + j] = d;
+        e2[k * es2 + j] += d * ldw<SM>(Wp + L.imgW + j);
+      }
+      __syncthreads();
+      seq_store(a.errG, a.Bpad, L.actOff, L.size, col0, Tc, T1, e, es, 0);
+      seq_store(a.actG, a.Bpad, L.actOff, L.size, col0, Tc, T1, ws + sq.yOff[l], sq.yStride[l], 0);
+    } else if (L.kind == kLSTM) {
+      float* Gt = ws + sq.gOff[l];
+      const float* Y = ws + sq.yOff[l];
+      lstm_backward<SM>(L, Wp, Gt, sq.gStride[l], Y, sq.yStride[l], ws + sq.eOff[l], sq.eStride[l],
+                        L.in > 0 ? ws + sq.eOff[L.in] : nullptr, L.in > 0 ? sq.eStride[L.in] : 0, red, T1);
+      seq_store(a.errG, a.Bpad, L.actOff, 4 * L.size, col0, Tc, T1, Gt, sq.gStride[l], 0);            // gate deltas
+      seq_store(a.actG, a.Bpad, L.actOff, L.size, col0, Tc, T1, Y, sq.yStride[l], 0);                 // y_k
+      seq_store(a.actG, a.Bpad, L.actOff + L.size, L.size, col0, Tc, T1, Y, sq.yStride[l], 1);        // h_{k-1}
+    }
+  }
+  seq_store(a.actG, a.Bpad, net.L[0].actOff, dS, col0, Tc, T1, X, xs, 0);
+  // compact columns (one per sample): output / stdev gradients and the top hidden output at the sampled step
+  {
+    const float* ytop = ws + sq.yOff[Lo.in] + (size_t)(T1 - 1) * sq.yStride[Lo.in];
+    for (int i = tid; i < Lo.nIn; i += kST) a.actG[(size_t)(net.topInOff + i) * a.Bpad + b] = ytop[i];
+    for (int n = tid; n < Lo.size; n += kST) a.errG[(size_t)(Lo.actOff + n) * a.Bpad + b] = errTop[Lo.actOff + n];
+    for (int i = tid; i < Lp.size; i += kST) a.errG[(size_t)(Lp.actOff + i) * a.Bpad + b] = errTop[Lp.actOff + i];
+  }
+  DBG_T(a, step, 4);
+}
+
+// ------------------------------------------------------------------------------------------
 // P2: weight gradient tile + Adam  (Layers.h:160-187, Optimizer.cpp:61-108,122-161)
 // ------------------------------------------------------------------------------------------
 constexpr int kBC = 256;          // batch chunk staged in shared memory
@@ -778,10 +1193,15 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
   float* Ds = tiles + kTileK * kBCP; // [16][kBCP]
   const LayerDesc& L = net.L[t.layer];
   // operand rows: A = activation of the input layer (dense) / of layer ID-2 (residual); D = this layer's deltas
-  const int K = t.kind == 0 ? L.nIn : L.size;
-  const int aOff = t.kind == 0 ? net.L[L.in].actOff : (t.kind == 1 ? net.L[t.layer - 2].actOff : 0);
+  // LSTM layers: rows [0, nIn) of W multiply the layer input, rows [nIn, nIn + nCells) the previous step's
+  // output (stored next to y in the layer's activation rows), N = 4 nCells gate deltas (Layer_LSTM.h:24-29)
+  const bool lstm = L.kind == kLSTM;
+  const int K = t.kind == 0 ? (lstm ? L.nIn + L.size : L.nIn) : L.size;
+  const int aOff = t.kind == 0 ? ((net.recurrent && L.kind == kDenseLinear) ? net.topInOff : net.L[L.in].actOff)
+                               : (t.kind == 1 ? net.L[t.layer - 2].actOff : 0);
+  const int hOff = L.actOff + L.size - L.nIn;
   const int dOff = L.actOff;
-  const int N = L.size;
+  const int N = lstm ? 4 * L.size : L.size;
   const int kk = tid >> 4, nn = tid & 15;
   const int warp = tid >> 5, lane = tid & 31;
   // parameters this thread owns: fetch W, M1, M2 now, use them after the contraction
@@ -804,7 +1224,7 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
   float acc = 0.f, acc2 = 0.f;
   float q4[4] = {0.f, 0.f, 0.f, 0.f};
   DBG_T(a, step, 24);
-  for (int bc = 0; bc < a.Bpad; bc += kBC) {
+  for (int bc = 0; bc < t.cols; bc += kBC) {
     if (bc) __syncthreads();
     constexpr int kLD = 1024 / kST;   // float4 per thread and operand (16 rows x 64 float4)
     float4 avs[kLD], dvs[kLD];
@@ -815,7 +1235,7 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
       float4 av = make_float4(0.f, 0.f, 0.f, 0.f), dv = av;
       if (t.kind == 0) {
         const int k = t.k0 + r;
-        if (k < K) av = ld_cg4(a.actG + (size_t)(aOff + k) * a.Bpad + bc + c4);
+        if (k < K) av = ld_cg4(a.actG + (size_t)((lstm && k >= L.nIn ? hOff : aOff) + k) * a.Bpad + bc + c4);
         else if (k == K) av = make_float4(1.f, 1.f, 1.f, 1.f);            // bias row: db += delta
         const int n = t.n0 + r;
         if (n < N) dv = ld_cg4(a.errG + (size_t)(dOff + n) * a.Bpad + bc + c4);
@@ -1149,9 +1569,9 @@ __device__ __forceinline__ void load_descs(const StepArgs& a, unsigned char* raw
   net = &h->net; hp = &h->hp;
 }
 
-__device__ __forceinline__ void init_bars(const StepArgs& a, const NetDesc& net, unsigned char* smraw, const SmemPlan& sp) {
+__device__ __forceinline__ void init_bars(const StepArgs& a, const NetDesc& net, unsigned char* smraw, size_t barsOff) {
   if (a.useTma && threadIdx.x == 0) {
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + sp.bars);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + barsOff);
     for (int l = 0; l < net.nLayers; ++l) mbar_init(&bars[l], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1166,11 +1586,27 @@ __global__ void __launch_bounds__(kST) k_p1(StepArgs a, int step) {
   const SmemPlan sp = smem_plan(*net, TB, SM);
   __shared__ StepCtrl c;
   if (SM) {
-    init_bars(a, *net, smraw, sp);
+    init_bars(a, *net, smraw, sp.bars);
     load_weight_image(a, *net, reinterpret_cast<float*>(smraw + sp.img), reinterpret_cast<uint64_t*>(smraw + sp.bars));
   }
   __syncthreads();
   p1_tile<TB, SM>(a, *net, *hp, c, step, blockIdx.x, smraw, sp, 0, true, nullptr, 0, false);
+}
+
+// recurrent networks: one sampled transition (its whole BPTT window) per CTA
+template <bool SM>
+__global__ void __launch_bounds__(kST) k_p1_seq(StepArgs a, int step) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const NetDesc* net; const Hyper* hp;
+  load_descs(a, smraw, net, hp);
+  const SeqSmem sp = smem_plan_seq(*net, SM);
+  __shared__ StepCtrl c;
+  if (SM) {
+    init_bars(a, *net, smraw, sp.bars);
+    load_weight_image(a, *net, reinterpret_cast<float*>(smraw + sp.img), reinterpret_cast<uint64_t*>(smraw + sp.bars));
+  }
+  __syncthreads();
+  p1_seq<SM>(a, *reinterpret_cast<const DevDescs*>(smraw), c, step, blockIdx.x, smraw, sp, 0, true, nullptr, 0);
 }
 
 __global__ void __launch_bounds__(kST) k_p2p3(StepArgs a, int step, int skipStats) {
@@ -1190,12 +1626,15 @@ __global__ void __launch_bounds__(kST) k_p2p3(StepArgs a, int step, int skipStat
 // barriers: it watches the barrier counter to learn that every worker finished P1 of a step and
 // publishes ctrl[(step+1)&1] through `ready`, which the workers only need at their next loss stage
 // — so the replay statistics are off the critical path.
-template <int TB, bool SM>
+template <int TB, bool SM, bool REC>
 __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int step0, int nSteps, int skipStatsLast) {
   extern __shared__ __align__(128) unsigned char smraw[];
   const NetDesc* net; const Hyper* hp;
   load_descs(a, smraw, net, hp);
-  const SmemPlan sp = smem_plan(*net, TB, SM);
+  SmemPlan sp;
+  SeqSmem sps;
+  if (REC) { sps = smem_plan_seq(*net, SM); sp.img = sps.img; sp.tiles = sps.ws; sp.bars = sps.bars; sp.stage = sps.ws; }
+  else sp = smem_plan(*net, TB, SM);
   __shared__ StepCtrl c;
   const int nw = gridDim.x - 1;                 // worker CTAs
   unsigned* ready = a.barrier + 1;              // local steps whose statistics are published
@@ -1222,7 +1661,7 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
     }
     return;
   }
-  const int nP1 = (a.B + TB - 1) / TB;
+  const int nP1 = REC ? a.B : (a.B + TB - 1) / TB;
   unsigned barTarget = 0;
   float* img = reinterpret_cast<float*>(smraw + sp.img);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + sp.bars);
@@ -1232,16 +1671,16 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
   const int nS4 = dS * TB / 4;                      // float4 chunks of this tile's raw states
   // inputs of step s+1 are prefetched into registers while P2 of step s runs, then parked in the
   // shared-memory staging area: possible when every worker owns at most one P1 tile
-  const bool pf = doP1 && nP1 <= nw && (dS & 3) == 0 && nS4 <= 2 * kST && nPair <= kST;
+  const bool pf = !REC && doP1 && nP1 <= nw && (dS & 3) == 0 && nS4 <= 2 * kST && nPair <= kST;
   const Staging stg = staging_view<TB>(*net, smraw, sp);
   const int b0 = blockIdx.x * TB;
   const ReplayView& rp = a.rp;
   if (pf) {   // state normalisers are constant during a launch (they change only at sweeps)
     for (int k = tid; k < dS; k += kST) { stg.mean[k] = ld_cg(rp.stateMean + k); stg.scale[k] = ld_cg(rp.stateScale + k); }
   }
-  if (SM) init_bars(a, *net, smraw, sp);
+  if (SM) init_bars(a, *net, smraw, sp.bars);
   // the first GradTile of this CTA never changes: keep it in registers
-  GradTile myTile = {0, 0, 0, 0};
+  GradTile myTile = {0, 0, 0, 0, 0, {0, 0, 0}};
   if ((int)blockIdx.x < a.nTiles) myTile = a.tiles[blockIdx.x];
   bool staged = false;
   for (int s = 0; s < nSteps; ++s) {
@@ -1263,7 +1702,8 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
     }
     bool first = true;
     for (int t = blockIdx.x; t < nP1; t += nw) {
-      p1_tile<TB, SM>(a, *net, *hp, c, step, t, smraw, sp, (unsigned)(s & 1), first, ready, (unsigned)s, staged);
+      if (REC) p1_seq<SM>(a, *reinterpret_cast<const DevDescs*>(smraw), c, step, t, smraw, sps, (unsigned)(s & 1), first, ready, (unsigned)s);
+      else p1_tile<TB, SM>(a, *net, *hp, c, step, t, smraw, sp, (unsigned)(s & 1), first, ready, (unsigned)s, staged);
       first = false;
       __syncthreads();
     }
@@ -1360,41 +1800,63 @@ __global__ void __launch_bounds__(kST) k_forward(StepArgs a, const float* states
 // ------------------------------------------------------------------------------------------
 static size_t p2_smem_bytes() { return ((sizeof(DevDescs) + 15) / 16) * 16 + sizeof(float) * 2 * kTileK * kBCP; }
 
-bool step_image_in_smem(const NetDesc& net) { return smem_plan(net, 4, true).total <= 200 * 1024; }
-size_t step_smem_bytes(const NetDesc& net, int TB) { return smem_plan(net, TB, step_image_in_smem(net)).total; }
+constexpr size_t kSmemBudget = 200 * 1024;
+static size_t plan_total(const NetDesc& net, bool img) { return net.recurrent ? smem_plan_seq(net, img).total : smem_plan(net, 4, img).total; }
+bool step_image_in_smem(const NetDesc& net) { return plan_total(net, true) <= kSmemBudget; }
+size_t step_smem_bytes(const NetDesc& net, int TB) { (void)TB; return plan_total(net, step_image_in_smem(net)); }
 
 int step_kernels_prepare(const NetDesc& net) {
   const bool sm = step_image_in_smem(net);
-  const int sOn = (int)smem_plan(net, 4, true).total, sOff = (int)smem_plan(net, 4, false).total;
-  if (sOff > 200 * 1024) { set_error_msg("network too wide for the shared-memory tile of the step kernel"); return -1; }
-  if (sm) {
-    SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_p1<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOn));
-    SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_steps_persistent<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOn));
+  const int sOn = (int)plan_total(net, true), sOff = (int)plan_total(net, false);
+  if (sOff > (int)kSmemBudget) { set_error_msg("network too wide for the shared-memory tile of the step kernel"); return -1; }
+  if (net.recurrent) {
+    if (sm) {
+      SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_p1_seq<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOn));
+      SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_steps_persistent<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOn));
+    }
+    SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_p1_seq<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOff));
+    SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_steps_persistent<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOff));
+  } else {
+    if (sm) {
+      SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_p1<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOn));
+      SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_steps_persistent<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOn));
+    }
+    SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_p1<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOff));
+    SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_steps_persistent<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOff));
+    SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_forward<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan(net, 4, false).total));
   }
-  SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_p1<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOff));
-  SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_steps_persistent<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOff));
   SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_p2p3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2_smem_bytes()));
-  SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_forward<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOff));
   return 0;
 }
 
 int launch_step_two_kernels(const StepArgs& a, const NetDesc& net, int step, int skipStats, cudaStream_t st) {
-  const int nP1 = (a.B + 3) / 4;
   const bool sm = step_image_in_smem(net);
-  if (sm) k_p1<4, true><<<nP1, kST, smem_plan(net, 4, true).total, st>>>(a, step);
-  else k_p1<4, false><<<nP1, kST, smem_plan(net, 4, false).total, st>>>(a, step);
+  const size_t smem = step_smem_bytes(net, 4);
+  if (net.recurrent) {
+    if (sm) k_p1_seq<true><<<a.B, kST, smem, st>>>(a, step);
+    else k_p1_seq<false><<<a.B, kST, smem, st>>>(a, step);
+  } else {
+    const int nP1 = (a.B + 3) / 4;
+    if (sm) k_p1<4, true><<<nP1, kST, smem, st>>>(a, step);
+    else k_p1<4, false><<<nP1, kST, smem, st>>>(a, step);
+  }
   k_p2p3<<<a.nTiles + 1, kST, p2_smem_bytes(), st>>>(a, step, skipStats);
   SMB200_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
+static const void* persistent_fn(const NetDesc& net) {
+  const bool sm = step_image_in_smem(net);
+  if (net.recurrent) return sm ? (const void*)k_steps_persistent<4, true, true> : (const void*)k_steps_persistent<4, false, true>;
+  return sm ? (const void*)k_steps_persistent<4, true, false> : (const void*)k_steps_persistent<4, false, false>;
+}
+
 int persistent_grid(const StepArgs& a, const NetDesc& net, int numSMs) {
   int perSM = 0;
-  const bool sm = step_image_in_smem(net);
-  const cudaError_t e = sm ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_steps_persistent<4, true>, kST, step_smem_bytes(net, 4))
-                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_steps_persistent<4, false>, kST, step_smem_bytes(net, 4));
+  const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, persistent_fn(net), kST, step_smem_bytes(net, 4));
   if (e != cudaSuccess || perSM < 1) return 0;
-  const int want = max((a.B + 3) / 4, a.nTiles) + 1;   // workers + the statistics CTA
+  const int nP1 = net.recurrent ? a.B : (a.B + 3) / 4;
+  const int want = max(nP1, a.nTiles) + 1;   // workers + the statistics CTA
   const int g = min(want, numSMs * perSM);
   return g >= 2 ? g : 0;
 }
@@ -1403,9 +1865,7 @@ int launch_steps_persistent(const StepArgs& a, const NetDesc& net, int grid, int
   SMB200_CUDA_CHECK(cudaMemsetAsync(a.barrier, 0, 2 * sizeof(unsigned), st));
   StepArgs aa = a;
   void* args[] = {&aa, &step0, &nSteps, &skipStatsLast};
-  const bool sm = step_image_in_smem(net);
-  const void* fn = sm ? (const void*)k_steps_persistent<4, true> : (const void*)k_steps_persistent<4, false>;
-  SMB200_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kST), args, step_smem_bytes(net, 4), st));
+  SMB200_CUDA_CHECK(cudaLaunchCooperativeKernel(persistent_fn(net), dim3(grid), dim3(kST), args, step_smem_bytes(net, 4), st));
   return 0;
 }
 

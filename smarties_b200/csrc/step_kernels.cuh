@@ -5,7 +5,22 @@
 
 namespace smb200 {
 
-struct DevDescs { NetDesc net; Hyper hp; };
+// Shared-memory workspace of ONE sampled transition of a recurrent network: every layer's values
+// for all steps of the BPTT window (+ the state after the sampled step), offsets in floats.
+struct SeqPlan {
+  int T;                                          // time slots = Tc + 1
+  int yOff[kMaxLayers], yStride[kMaxLayers];      // layer output y at window step k: ws[yOff + k*yStride ...]
+                                                  //   (LSTM: [y | cell state | tanh(state)], each roundUp4(nCells))
+  int gOff[kMaxLayers], gStride[kMaxLayers];      // LSTM: [cell input | input gate | forget gate | output gate], later the 4 gate deltas
+  int eOff[kMaxLayers], eStride[kMaxLayers];      // hidden layers: error on y at every window step
+  int actTop, errTop;                             // activations / output gradient at the sampled step, indexed by LayerDesc::actOff
+  int red;                                        // 2*threads floats of reduction scratch
+  int total;
+};
+void seq_plan(const NetDesc& net, SeqPlan& p);
+int seq_workspace_floats(const NetDesc& net);
+
+struct DevDescs { NetDesc net; Hyper hp; SeqPlan seq; };
 
 // accumulators of the every-1000-steps sweep (sweep_kernels.cu)
 struct SweepSums {

@@ -46,7 +46,7 @@ class Config(C.Structure):
         ("gamma", C.c_double), ("lambda_", C.c_double), ("clip_imp_weight", C.c_double), ("penal_tol", C.c_double),
         ("eps_anneal", C.c_double), ("learnrate", C.c_double), ("nn_lambda", C.c_double), ("expl_noise", C.c_double),
         ("out_weights_prefac", C.c_double), ("refer_reduce_threads", C.c_int32), ("world_rank", C.c_int32),
-        ("world_size", C.c_int32), ("seed", C.c_uint64),
+        ("world_size", C.c_int32), ("seed", C.c_uint64), ("nn_type", C.c_int32), ("nn_bptt_seq", C.c_int32),
     ]
 
 
@@ -158,6 +158,7 @@ class Learner:
         cfg.expl_noise, cfg.out_weights_prefac = hp.explNoise, hp.outWeightsPrefac
         cfg.refer_reduce_threads = refer_reduce_threads
         cfg.world_rank, cfg.world_size, cfg.seed = world_rank, world_size, seed
+        cfg.nn_type, cfg.nn_bptt_seq = {"FFNN": 0, "LSTM": 1}[hp.nnType], int(hp.nnBPTTseq)
         if bounded is not None:
             b = np.broadcast_to(np.asarray(bounded, dtype=bool), (dim_action,))
             for i in range(dim_action):

@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from parity_utils import CASES, Golden, make_learner, make_oracle, relerr
+from parity_utils import CASES, RECURRENT_CASES, Golden, make_learner, make_oracle, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -52,7 +52,7 @@ def _check_final(L, R):
     assert np.allclose(agg[:, :8], R["final/epAgg"][:, :8], rtol=2e-4, atol=2e-5)
 
 
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", CASES + RECURRENT_CASES)
 def test_initialize_learner_matches_reference(case):
     g = Golden(case)
     L = make_learner(g)
@@ -69,7 +69,7 @@ def test_initialize_learner_matches_reference(case):
     L.close()
 
 
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", CASES + RECURRENT_CASES)
 def test_learner_steps_match_reference(case):
     g = Golden(case)
     L = make_learner(g)
@@ -92,7 +92,7 @@ def test_sampler_indices_bit_exact(case):
     L.close()
 
 
-@pytest.mark.parametrize("case", ["vracer_small", "vracer_bounded"])
+@pytest.mark.parametrize("case", ["vracer_small", "vracer_bounded", "racer_lstm"])
 def test_multi_step_call_equals_single_steps(case):
     """One C-ABI call for the whole run (persistent kernel over many steps) gives bit-identical
     results to step-by-step calls."""
@@ -108,8 +108,9 @@ def test_multi_step_call_equals_single_steps(case):
     A.close(); Bm.close()
 
 
-def test_two_kernel_mode_equals_persistent(monkeypatch):
-    g = Golden("vracer_small")
+@pytest.mark.parametrize("case", ["vracer_small", "vracer_lstm2"])
+def test_two_kernel_mode_equals_persistent(monkeypatch, case):
+    g = Golden(case)
     A = make_learner(g)
     monkeypatch.setenv("SMB200_MODE", "two")
     Bm = make_learner(g)
