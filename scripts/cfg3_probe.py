@@ -4,6 +4,9 @@ import os
 import sys
 import time
 
+if os.environ.get("PROF_PHASES"):
+    os.environ.setdefault("SMB200_PROFILE", "1")
+
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
 from smarties_b200 import Learner, synth  # noqa: E402

@@ -4,6 +4,8 @@ reported SM clock).  Markers: 0 step start, 1 gather done, 2 forward done, 3 los
 import os
 import sys
 
+os.environ.setdefault("SMB200_PROFILE", "1")   # the library flavour with phase timestamps
+
 import numpy as np
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
@@ -32,7 +34,7 @@ seg = [("start->gather", 0, 1), ("forward", 1, 2), ("loss", 2, 3), ("backward", 
 for name, a, b in seg:
     dlt = p1[:, :, b] - p1[:, :, a]
     print(f"  P1 CTAs {name:16s} mean {us(dlt.mean()):6.2f} us  max-over-CTAs mean {us(dlt.max(axis=1).mean()):6.2f}")
-fine = [("fwd L1 wait W", 9, 27), ("fwd L1 compute", 27, 10), ("fwd L2 wait W", 10, 28), ("fwd L2+res", 28, 12), ("fwd L4 wait W", 12, 30), ("fwd L4 out", 30, 13), ("fwd L5 param", 13, 2),
+fine = [("fwd L1 wait W", 9, 27), ("fwd L1 compute", 27, 10), ("fwd L2 wait W", 10, 28), ("fwd L2+res", 28, 12), ("fwd L4 wait W", 12, 30), ("fwd L4 out", 30, 31 if os.environ.get("ICACHE_PROBE") else 13), ("fwd L4 again", 31, 32 if os.environ.get("ICACHE_PROBE") else 31), ("fwd L5 param", 13, 2),
         ("loss stage1", 2, 8), ("loss stage2", 8, 16), ("loss stage3", 16, 3),
         ("bwd L4 out", 20, 18), ("bwd L2+res", 18, 17), ("bwd L1", 17, 4),
         ("P2 desc+issue", 6, 24), ("P2 tile load", 24, 25), ("P2 contraction", 25, 26), ("P2 adam+store", 26, 7)]

@@ -13,6 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsmarties_b200.so")
+OUT_PROF = os.path.join(HERE, "libsmarties_b200_prof.so")     # same sources + phase timestamps (scripts/phase_report.py)
 SOURCES = ["step_kernels.cu", "sweep_kernels.cu", "learner.cu"]
 HEADERS = ["common.cuh", "step_kernels.cuh", os.path.join("..", "..", "include", "smarties_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -21,36 +22,41 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
 
 
 def _stale() -> bool:
-    if not os.path.exists(OUT):
+    if not os.path.exists(OUT) or not os.path.exists(OUT_PROF):
         return True
     t = os.path.getmtime(OUT)
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
-        return OUT
+def _compile(out: str, suffix: str, defines, logname: str, verbose: bool) -> None:
     objs = []
     procs = []
     for s in SOURCES:
-        o = os.path.join(CSRC, s.replace(".cu", ".o"))
-        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+        o = os.path.join(CSRC, s.replace(".cu", suffix + ".o"))
+        cmd = [NVCC, *FLAGS, *defines, "-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     log = []
     for s, p in procs:
-        out, _ = p.communicate()
-        log.append(out)
+        o, _ = p.communicate()
+        log.append(o)
         if p.returncode != 0:
-            sys.stderr.write(out)
+            sys.stderr.write(o)
             raise RuntimeError(f"nvcc failed on {s}")
-    cmd = [NVCC, "-shared", "-o", OUT, *objs, "-cudart", "static"]
-    subprocess.run(cmd, check=True)
-    with open(os.path.join(CSRC, "ptxas.log"), "w") as f:
+    subprocess.run([NVCC, "-shared", "-o", out, *objs, "-cudart", "static"], check=True)
+    with open(os.path.join(CSRC, logname), "w") as f:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale():
+        return OUT
+    extra = os.environ.get("SMB200_PROF_DEFINES", "").split()
+    _compile(OUT_PROF, "_prof", ["-DSMB200_MARKERS", *extra], "ptxas_prof.log", False)
+    _compile(OUT, "", [], "ptxas.log", verbose)
     return OUT
 
 

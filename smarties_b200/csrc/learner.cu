@@ -101,6 +101,9 @@ struct smb200_learner {
 
   std::vector<std::pair<long long, int>> pendingEvict;   // ring ranges whose live flags are cleared after the segment
   std::mt19937 gen;
+  // host sampler scratch + id -> (episode position, t) lookup, rebuilt when the episode table changes
+  std::vector<size_t> sampIds, sampTmp;
+  std::vector<long long> epPrefix; std::vector<int> bucketFirst; int bucketShift = 0; bool lookupDirty = true;
   double lastMs = 0; long long lastLaunches = 0;
   long long launches = 0;
 
@@ -345,36 +348,75 @@ static bool host_post_step(smb200_learner* h) {
   // 32-bit draw of generators[0] — the sampler's generator — every update.
   (void)h->gen();
   h->gradStep++;
-  if (changed) h->orderDirty = true;
+  if (changed) { h->orderDirty = true; h->lookupDirty = true; }
   return changed;
+}
+
+// ascending LSD radix sort of n ids < 2^bits (8-bit digits).  Any correct sort reproduces the
+// reference's std::sort output: the keys are plain integers.
+static void radix_sort_ids(size_t* a, size_t* tmp, int n, int bits) {
+  size_t* src = a; size_t* dst = tmp;
+  for (int sh = 0; sh < bits; sh += 8) {
+    unsigned cnt[256]; memset(cnt, 0, sizeof(cnt));
+    for (int i = 0; i < n; ++i) cnt[(src[i] >> sh) & 255]++;
+    unsigned sum = 0;
+    for (int d = 0; d < 256; ++d) { const unsigned c = cnt[d]; cnt[d] = sum; sum += c; }
+    for (int i = 0; i < n; ++i) dst[cnt[(src[i] >> sh) & 255]++] = src[i];
+    std::swap(src, dst);
+  }
+  if (src != a) memcpy(a, src, sizeof(size_t) * n);
+}
+
+// Sampling::IDtoSeqStep walks the episodes accumulating ndata() (Sampling.cpp:26-47).  The same
+// map, id -> (position, t), through prefix sums and a coarse bucket table rebuilt only when the
+// episode table changes.
+static void rebuild_lookup(smb200_learner* h) {
+  const size_t nEp = h->episodes.size();
+  h->epPrefix.resize(nEp + 1);
+  long long p = 0;
+  for (size_t k = 0; k < nEp; ++k) { h->epPrefix[k] = p; p += h->episodes[k].nRows - 1; }
+  h->epPrefix[nEp] = p;
+  int sh = 0;
+  while (((p >> sh) + 1) > (1 << 16)) ++sh;            // at most 64 Ki buckets
+  h->bucketShift = sh;
+  const size_t nb = (size_t)(p >> sh) + 1;
+  h->bucketFirst.assign(nb, 0);
+  size_t k = 0;
+  for (size_t b = 0; b < nb; ++b) {
+    const long long first = (long long)b << sh;
+    while (k + 1 < nEp && h->epPrefix[k + 1] <= first) ++k;
+    h->bucketFirst[b] = (int)k;
+  }
+  h->lookupDirty = false;
 }
 
 static void host_sample(smb200_learner* h, int* slotOut, int* tOut, int64_t* posOut, int64_t* tOut64) {
   const int B = h->cfg.batch_size;
   const long nData = (long)h->nTransitions;
   std::uniform_int_distribution<size_t> distObs(0, nData - 1);
-  std::vector<size_t> ret(B);
+  if ((int)h->sampIds.size() != B) { h->sampIds.resize(B); h->sampTmp.resize(B); }
+  std::vector<size_t>& ret = h->sampIds;
+  int bits = 1; while ((1ull << bits) < (unsigned long long)nData) ++bits;
   auto it = ret.begin();
-  while (it != ret.end()) {
+  while (it != ret.end()) {     // Sample_uniform::sample (Sampling.cpp:82-93): draw, sort, drop duplicates, redraw the tail
     std::generate(it, ret.end(), [&]() { return distObs(h->gen); });
-    std::sort(ret.begin(), ret.end());
+    radix_sort_ids(ret.data(), h->sampTmp.data(), B, bits);
     it = std::unique(ret.begin(), ret.end());
   }
-  // IDtoSeqStep: prefix walk in vector order
-  size_t i = 0, prefix = 0;
-  for (size_t k = 0; k < h->episodes.size() && i < (size_t)B; ++k) {
-    const size_t nd = h->episodes[k].nRows - 1;
-    while (i < (size_t)B && ret[i] < prefix + nd) {
-      if (slotOut) {   // device form: ring row of (episode, t); slot with Episode::isTruncated(t+1) in bit 31
-        const EpisodeMeta& e = h->episodes[k];
-        const int t = (int)(ret[i] - prefix);
-        const unsigned hn = (t + 2 == e.nRows && !e.terminated) ? 0x80000000u : 0u;
-        slotOut[i] = (int)((unsigned)e.slot | hn); tOut[i] = (int)(e.start + t);
-      }
-      if (posOut) { posOut[i] = (int64_t)k; tOut64[i] = (int64_t)(ret[i] - prefix); }
-      ++i;
+  if (h->lookupDirty) rebuild_lookup(h);
+  const long long* prefix = h->epPrefix.data();
+  const int sh = h->bucketShift;
+  for (int i = 0; i < B; ++i) {
+    const long long id = (long long)ret[i];
+    size_t k = (size_t)h->bucketFirst[(size_t)(id >> sh)];
+    while (prefix[k + 1] <= id) ++k;
+    const long long t = id - prefix[k];
+    if (slotOut) {   // device form: ring row of (episode, t); slot with Episode::isTruncated(t+1) in bit 31
+      const EpisodeMeta& e = h->episodes[k];
+      const unsigned hn = ((int)t + 2 == e.nRows && !e.terminated) ? 0x80000000u : 0u;
+      slotOut[i] = (int)((unsigned)e.slot | hn); tOut[i] = (int)(e.start + t);
     }
-    prefix += nd;
+    if (posOut) { posOut[i] = (int64_t)k; tOut64[i] = (int64_t)t; }
   }
 }
 
@@ -671,7 +713,7 @@ int smb200_push_episode(smb200_learner* h, int64_t id, int32_t N, int32_t termin
   h->liveRanges[start] = start + N;
   h->head = start + N; h->highWater = std::max(h->highWater, start + N);
   h->nTransitions += N - 1;
-  h->orderDirty = true; h->presampled = 0;
+  h->orderDirty = true; h->lookupDirty = true; h->presampled = 0;
   return 0;
 }
 

@@ -144,8 +144,16 @@ __device__ __forceinline__ void load_ctrl(StepCtrl& dst, const StepCtrl* src) {
   for (int i = 0; i < (int)(sizeof(StepCtrl) / 8); ++i) d[i] = __ldcg(s + i);
 }
 
+// phase timestamps exist only in the profiling flavour of the library (-DSMB200_MARKERS, libsmarties_b200_prof.so)
+#ifdef SMB200_MARKERS
 #define DBG_T(a, step, m) do { if ((a).dbgT && threadIdx.x == 0) \
   (a).dbgT[((size_t)((step) - (a).stepBase) * gridDim.x + blockIdx.x) * 48 + (m)] = clock64(); } while (0)
+#define DBG_TW(a, step, m, w) do { if ((a) && (a)->dbgT && threadIdx.x == (w) * 32) \
+  (a)->dbgT[((size_t)((step) - (a)->stepBase) * gridDim.x + blockIdx.x) * 48 + (m)] = clock64(); } while (0)
+#else
+#define DBG_T(a, step, m) do { } while (0)
+#define DBG_TW(a, step, m, w) do { } while (0)
+#endif
 
 // ------------------------------------------------------------------------------------------
 // Batched GEMV over a tile of TB samples.  Activations live in shared memory feature-major,
@@ -206,6 +214,7 @@ __device__ __forceinline__ void dense_fwd(const float* Wp, int ldp, int K, int N
       for (int idx = tid; idx < nc * TB; idx += kST) {
         const int n2 = idx / TB, s = idx - n2 * TB;
         float v = 0.f;
+#pragma unroll 4
         for (int gg = 0; gg < G; ++gg) v += red[(gg * NR + n2) * TB + s];
         const int n = n0 + n2;
         v += ldw<SM>(bias + n);
@@ -279,6 +288,7 @@ __device__ __forceinline__ void dense_bwd_dx(const float* Wp, int ldp, int K, in
       for (int idx = tid; idx < kc * TB; idx += kST) {
         const int k2 = idx / TB, s = idx - k2 * TB;
         float v = 0.f;
+#pragma unroll 4
         for (int gg = 0; gg < G; ++gg) v += red[(gg * KR + k2) * TB + s];
         ein[(k0 + k2) * TB + s] += v;
       }
@@ -309,6 +319,13 @@ __device__ void net_forward(const NetDesc& net, const float* Wp, float* act, flo
       dense_fwd<TB, SM>(Wp + L.imgW, L.ldp, L.nIn, L.size, Wp + L.imgB, act + net.L[L.in].actOff * TB, y, red,
                         L.kind == kDenseTanh ? 1 : 0, L.fwdShift, fuse ? Wp + R.imgW : nullptr, fuse ? Wp + R.imgB : nullptr,
                         fuse ? act + R.actOff * TB : nullptr);
+#ifdef SMB200_ICACHE_PROBE   // does a warm instruction cache change the cost of a layer?  (idempotent repeat of the output layer)
+      if (dbg && L.kind == kDenseLinear) {
+        DBG_T(*dbg, step, 31);
+        dense_fwd<TB, SM>(Wp + L.imgW, L.ldp, L.nIn, L.size, Wp + L.imgB, act + net.L[L.in].actOff * TB, y, red, 0, L.fwdShift);
+        DBG_T(*dbg, step, 32);
+      }
+#endif
       if (fuse) ++l;
     } else if (L.kind == kResidual) {   // not preceded by a dense layer: cannot happen with Builder::addLayer
       if (bars) mbar_wait(&bars[l], parity);
@@ -1186,7 +1203,7 @@ __device__ __forceinline__ float adam_step(const AdamCoef& k, float G, float W, 
   return Wn;
 }
 
-__device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, const StepCtrl& c, const GradTile& t,
+__device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, const StepCtrl& c, const GradTile t,
                         float* tiles, int step, int tileIdx) {
   const int tid = threadIdx.x;
   float* As = tiles;                 // [16][kBCP]
@@ -1223,6 +1240,7 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
   if (p1 >= 0) { w1 = ld_cg(a.W + p1); m11 = ld_cg(a.M1 + p1); m21 = ld_cg(a.M2 + p1); }
   float acc = 0.f, acc2 = 0.f;
   float q4[4] = {0.f, 0.f, 0.f, 0.f};
+  const AdamCoef ac = adam_coef(hp, c);
   DBG_T(a, step, 24);
   for (int bc = 0; bc < t.cols; bc += kBC) {
     if (bc) __syncthreads();
@@ -1338,7 +1356,9 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
     }
   }
   DBG_T(a, step, 26);
-  const AdamCoef ac = adam_coef(hp, c);
+  // the parameter / moment loads issued before the contraction are consumed only here: keep the
+  // compiler from hoisting the first Adam multiplications (and with them the wait) above the tile loop
+  asm volatile("" : "+f"(w0), "+f"(m10), "+f"(m20), "+f"(w1), "+f"(m11), "+f"(m21));
   if (p0 >= 0) {
     a.G[p0] = acc;
     a.Wimg[pimg0] = adam_step(ac, acc, w0, m10, m20, a.W + p0, a.M1 + p0, a.M2 + p0);
@@ -1683,6 +1703,12 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
   GradTile myTile = {0, 0, 0, 0, 0, {0, 0, 0}};
   if ((int)blockIdx.x < a.nTiles) myTile = a.tiles[blockIdx.x];
   bool staged = false;
+  // loop-invariant index arithmetic of the input prefetch (integer divisions)
+  const int q4s = max(dS >> 2, 1);
+  int pfSi[2], pfC4[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) { const int q = tid + u * kST; pfSi[u] = q / q4s; pfC4[u] = (q - pfSi[u] * q4s) * 4; }
+  const int pfPs = tid / dA, pfPi = tid - pfPs * dA;
   for (int s = 0; s < nSteps; ++s) {
     const int step = step0 + s;
     DBG_T(a, step, 0);
@@ -1695,10 +1721,10 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int q = tid + u * kST;
-        if (q < nS4) { const int si = q / (dS >> 2); if (b0 + si < a.B) nxRowS[u] = a.sampRow[jb + si]; }
+        if (q < nS4) { const int si = pfSi[u]; if (b0 + si < a.B) nxRowS[u] = a.sampRow[jb + si]; }
       }
       if (tid < TB && b0 + tid < a.B) { nxRowT = a.sampRow[jb + tid]; nxSf = a.sampSlot[jb + tid]; }
-      if (tid < nPair) { const int si = tid / dA; if (b0 + si < a.B) nxRowP = a.sampRow[jb + si]; }
+      if (tid < nPair) { const int si = pfPs; if (b0 + si < a.B) nxRowP = a.sampRow[jb + si]; }
     }
     bool first = true;
     for (int t = blockIdx.x; t < nP1; t += nw) {
@@ -1717,7 +1743,7 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
       for (int u = 0; u < 2; ++u) {
         const int q = tid + u * kST;
         pfS[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (nxRowS[u] >= 0) { const int c4 = (q % (dS >> 2)) * 4; pfS[u] = ld_cg4(rp.S + (size_t)nxRowS[u] * dS + c4); }
+        if (nxRowS[u] >= 0) pfS[u] = ld_cg4(rp.S + (size_t)nxRowS[u] * dS + pfC4[u]);
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) pfOld[j] = 0.f;
@@ -1730,7 +1756,7 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
       }
       pfPair[0] = 0.f; pfPair[1] = 0.f; pfPair[2] = 1.f;
       if (nxRowP >= 0) {
-        const int i = tid % dA;
+        const int i = pfPi;
         const size_t row = nxRowP;
         pfPair[0] = ld_cg(rp.A + row * dA + i); pfPair[1] = ld_cg(rp.MU + row * 2 * dA + i); pfPair[2] = ld_cg(rp.MU + row * 2 * dA + dA + i);
       }
@@ -1740,7 +1766,9 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
       __syncthreads();
     }
     for (int t = blockIdx.x; t < a.nTiles; t += nw) {
-      p2_tile(a, *net, *hp, c, t == (int)blockIdx.x ? myTile : a.tiles[t], tiles, step, t);
+      GradTile gt = myTile;
+      if (t != (int)blockIdx.x) gt = a.tiles[t];
+      p2_tile(a, *net, *hp, c, gt, tiles, step, t);
       __syncthreads();
     }
     // ---- park the prefetched inputs in shared memory (read by P1 of the next step) ----

@@ -64,23 +64,34 @@ __global__ void __launch_bounds__(kThreads) k_init_episode(ReplayView rp, int sl
 }
 
 // ------------------------------------------------------------------------------------------
+// One CTA (8 warps) per episode.  The episode is walked from its end in super-chunks of 1024 time
+// steps: every thread holds 4 steps (coalesced: position p = j*256 + tid, p = 0 the latest step), so
+// a 1000-step episode is ONE pass with all of its loads in flight at once.  The recursion
+// Q[t] = a_t + b_t Q[t+1] is composed by a warp-shuffle scan inside each run of 32 steps, the 32 run
+// composites are scanned by warp 0 through shared memory, and every element is then re-evaluated with
+// the reference's operation order on the scanned Q[t+1].
+constexpr int kSweepPer = 4;                         // time steps per thread and super-chunk
+constexpr int kSweepChunk = kSweepPer * kThreads;    // 1024
+
 __global__ void __launch_bounds__(kThreads) k_sweep(ReplayView rp, int nEpisodes, int oneSlot, float gamma, float lambda,
                                                     int recompute, float C, float invC, SweepSums* sums) {
-  const int lane = threadIdx.x & 31;
-  const int warpsPerBlock = kThreads / 32;
-  const int gw = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5), nw = gridDim.x * warpsPerBlock;
+  __shared__ float segA[32], segB[32], segQin[32];
+  __shared__ float shCarry;
+  __shared__ float shRed[kThreads / 32][8];
+  __shared__ int shFar[kThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ME = rp.maxEpisodes;
   const double rmean = (double)rp.rew[0], rscale = (double)rp.rew[1];
   const int count = nEpisodes > 0 ? nEpisodes : 1;
   float errAcc = 0.f; long long nRet = 0, nFar = 0;
-  for (int pos = gw; pos < count; pos += nw) {
+  for (int pos = blockIdx.x; pos < count; pos += gridDim.x) {
     const int slot = nEpisodes > 0 ? rp.epOrder[pos] : oneSlot;
     const int N = rp.epLen[slot];
     const size_t r0 = (size_t)rp.epStart[slot];
-    if (recompute) {   // Episode::updateCumulative
+    if (recompute) {   // Episode::updateCumulative (Episode.cpp:213-242)
       const int nd = N - 1;
       int far = 0; float sE2 = 0.f, mAE = -1e9f, mxQ = -1e9f, mnQ = 1e9f, sQ2 = 0.f, sQ1 = 0.f, sKL = 0.f, sR = 0.f;
-      for (int t = lane; t < N; t += 32) {
+      for (int t = tid; t < N; t += kThreads) {
         const size_t r = r0 + t;
         sKL += rp.KL[r]; sR += rp.R[r];
         if (t < nd) {
@@ -94,7 +105,19 @@ __global__ void __launch_bounds__(kThreads) k_sweep(ReplayView rp, int nEpisodes
       far = __reduce_add_sync(0xffffffffu, far);
       sE2 = warp_sum(sE2); sQ2 = warp_sum(sQ2); sQ1 = warp_sum(sQ1); sKL = warp_sum(sKL); sR = warp_sum(sR);
       mAE = warp_max(mAE); mxQ = warp_max(mxQ); mnQ = -warp_max(-mnQ);
+      __syncthreads();
       if (lane == 0) {
+        shFar[warp] = far;
+        shRed[warp][0] = sE2; shRed[warp][1] = sQ2; shRed[warp][2] = sQ1; shRed[warp][3] = sKL; shRed[warp][4] = sR;
+        shRed[warp][5] = mAE; shRed[warp][6] = mxQ; shRed[warp][7] = mnQ;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        far = 0; sE2 = sQ2 = sQ1 = sKL = sR = 0.f; mAE = -1e9f; mxQ = -1e9f; mnQ = 1e9f;
+        for (int w = 0; w < kThreads / 32; ++w) {
+          far += shFar[w]; sE2 += shRed[w][0]; sQ2 += shRed[w][1]; sQ1 += shRed[w][2]; sKL += shRed[w][3]; sR += shRed[w][4];
+          mAE = fmaxf(mAE, shRed[w][5]); mxQ = fmaxf(mxQ, shRed[w][6]); mnQ = fminf(mnQ, shRed[w][7]);
+        }
         const float invN = 1.0f / (float)nd;
         rp.epAgg[AGG_FAR * ME + slot] = invN * (float)far;
         rp.epAgg[AGG_E2 * ME + slot] = invN * sE2; rp.epAgg[AGG_MAXE * ME + slot] = mAE;
@@ -104,51 +127,85 @@ __global__ void __launch_bounds__(kThreads) k_sweep(ReplayView rp, int nEpisodes
         if (C > 1.0f) nFar += far;
       }
     }
-    // ---- Retrace: updateReturnEstimator(EP, N-2) ----
-    float carry;   // Q[t+1] entering the current chunk
-    if (rp.epTerm[slot]) carry = rp.Q[r0 + N - 1];
-    else { carry = rp.V[r0 + N - 1]; if (lane == 0) rp.Q[r0 + N - 1] = carry; }
-    for (int tc = N - 2; tc >= 0; tc -= 32) {
-      const int t = tc - lane;
-      const bool ok = t >= 0;
-      float a = 0.f, b = 1.f, R = 0.f, Vn = 0.f, An = 0.f, cw = 0.f, oldQ = 0.f;
-      if (ok) {
-        const size_t r = r0 + t + 1;
-        R = (float)(((double)rp.R[r] - rmean) * rscale);           // scaledReward<Fval> (Episode.h:184-189)
-        Vn = rp.V[r]; An = rp.ADV[r];
-        const float w = rp.RHO[r];
-        cw = lambda * (w < 1.f ? w : 1.f);                          // clippedOffPolW (Episode.h:190-194)
-        oldQ = rp.Q[r - 1];
-        // Q[t] = a + b*Q[t+1]
-        b = gamma * cw;
-        a = R + gamma * (Vn - cw * (An + Vn));
+    // ---- Retrace: updateReturnEstimator(EP, N-2) (MemoryProcessing.cpp:23-44) ----
+    __syncthreads();
+    if (tid == 0) {
+      float c0;   // Q of the last row
+      if (rp.epTerm[slot]) c0 = rp.Q[r0 + N - 1];
+      else { c0 = rp.V[r0 + N - 1]; rp.Q[r0 + N - 1] = c0; }
+      shCarry = c0;
+    }
+    for (int top = N - 2; top >= 0; top -= kSweepChunk) {     // `top` = latest time step of this super-chunk
+      float R[kSweepPer], Vn[kSweepPer], An[kSweepPer], cw[kSweepPer], oldQ[kSweepPer], A[kSweepPer], Bc[kSweepPer];
+#pragma unroll
+      for (int j = 0; j < kSweepPer; ++j) {
+        const int t = top - (j * kThreads + tid);
+        float rr = 0.f, w = 0.f;
+        Vn[j] = 0.f; An[j] = 0.f; oldQ[j] = 0.f;
+        if (t >= 0) {
+          const size_t r = r0 + t + 1;
+          rr = rp.R[r]; Vn[j] = rp.V[r]; An[j] = rp.ADV[r]; w = rp.RHO[r]; oldQ[j] = rp.Q[r - 1];
+        }
+        R[j] = t >= 0 ? (float)(((double)rr - rmean) * rscale) : 0.f;      // scaledReward<Fval> (Episode.h:184-189)
+        cw[j] = t >= 0 ? lambda * (w < 1.f ? w : 1.f) : 0.f;               // clippedOffPolW (Episode.h:190-194)
+        // Q[t] = a + b*Q[t+1]; identity map outside the episode
+        Bc[j] = t >= 0 ? gamma * cw[j] : 1.f;
+        A[j] = t >= 0 ? R[j] + gamma * (Vn[j] - cw[j] * (An[j] + Vn[j])) : 0.f;
       }
-      // inclusive prefix composition over lanes (lane 0 = latest time step)
-      float A = a, Bc = b;
+      // inclusive composition inside each run of 32 steps (lane 0 = latest time step)
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        const float Ap = __shfl_up_sync(0xffffffffu, A, d), Bp = __shfl_up_sync(0xffffffffu, Bc, d);
-        if (lane >= d) { A = fmaf(Bc, Ap, A); Bc = Bc * Bp; }
+#pragma unroll
+        for (int j = 0; j < kSweepPer; ++j) {
+          const float Ap = __shfl_up_sync(0xffffffffu, A[j], d), Bp = __shfl_up_sync(0xffffffffu, Bc[j], d);
+          if (lane >= d) { A[j] = fmaf(Bc[j], Ap, A[j]); Bc[j] = Bc[j] * Bp; }
+        }
       }
-      const float Qscan = fmaf(Bc, carry, A);
-      // re-evaluate with the reference's operation order on the scanned Q[t+1]
-      float Qn = __shfl_up_sync(0xffffffffu, Qscan, 1);
-      if (lane == 0) Qn = carry;
-      const float Qt = R + gamma * (Vn + cw * (Qn - An - Vn));
-      if (ok) {
-        rp.Q[r0 + t] = Qt;
-        const float dq = oldQ - Qt;
-        errAcc += dq * dq;
+      if (lane == 31) {
+#pragma unroll
+        for (int j = 0; j < kSweepPer; ++j) { segA[j * (kThreads / 32) + warp] = A[j]; segB[j * (kThreads / 32) + warp] = Bc[j]; }
       }
-      const int lastLane = min(31, tc);
-      carry = __shfl_sync(0xffffffffu, Qt, lastLane);
+      __syncthreads();
+      if (warp == 0) {      // the 32 run composites, in time order: exclusive scan seeded with the incoming carry
+        float sa = segA[lane], sb = segB[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const float Ap = __shfl_up_sync(0xffffffffu, sa, d), Bp = __shfl_up_sync(0xffffffffu, sb, d);
+          if (lane >= d) { sa = fmaf(sb, Ap, sa); sb = sb * Bp; }
+        }
+        const float qEnd = fmaf(sb, shCarry, sa);          // Q after run `lane`
+        float qin = __shfl_up_sync(0xffffffffu, qEnd, 1);
+        if (lane == 0) qin = shCarry;
+        segQin[lane] = qin;
+      }
+      __syncthreads();
+      float lastQ = 0.f; int lastT = -1;
+#pragma unroll
+      for (int j = 0; j < kSweepPer; ++j) {
+        const int t = top - (j * kThreads + tid);
+        const float qin = segQin[j * (kThreads / 32) + warp];
+        const float Qscan = fmaf(Bc[j], qin, A[j]);
+        // re-evaluate with the reference's operation order on the scanned Q[t+1]
+        float Qn = __shfl_up_sync(0xffffffffu, Qscan, 1);
+        if (lane == 0) Qn = qin;
+        const float Qt = R[j] + gamma * (Vn[j] + cw[j] * (Qn - An[j] - Vn[j]));
+        if (t >= 0) {
+          rp.Q[r0 + t] = Qt;
+          const float dq = oldQ[j] - Qt;
+          errAcc += dq * dq;
+          if (t == top - (kSweepChunk - 1) || t == 0) { lastQ = Qt; lastT = t; }
+        }
+      }
+      __syncthreads();
+      if (lastT >= 0 && lastT == max(0, top - (kSweepChunk - 1))) shCarry = lastQ;     // earliest step of the super-chunk
+      __syncthreads();
     }
     nRet += N - 1;
   }
   if (sums) {
     const float e = warp_sum(errAcc);
-    if (lane == 0) {
-      atomicAdd(&sums->sumErr2, (double)e);
+    if (lane == 0) atomicAdd(&sums->sumErr2, (double)e);
+    if (tid == 0) {
       atomicAdd(reinterpret_cast<unsigned long long*>(&sums->nRet), (unsigned long long)nRet);
       if (recompute) atomicAdd(reinterpret_cast<unsigned long long*>(&sums->nFarExact), (unsigned long long)nFar);
     }
@@ -229,6 +286,71 @@ __global__ void __launch_bounds__(kThreads) k_moments(ReplayView rp, long long r
   double v[3] = {cnt, rs1, rs2};
   for (int q = 0; q < 3; ++q) {
     const double w = warp_sum_d(v[q]);
+    __syncthreads();
+    if (lane == 0) shd[warp] = w;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int k = 0; k < kThreads / 32; ++k) t += shd[k];
+      atomicAdd(&sums->moments[2 * dS + q], t);
+    }
+  }
+}
+
+// Streaming variant for state widths with dS/4 a power of two (4, 8, 16, 32, 64, ...): no shared-memory
+// staging.  Thread (rl, cq) owns the column quad cq of rows rl, rl+RP, ...; a warp reads whole 128-byte
+// row segments; U float4 loads per thread are in flight before the first is consumed; f64 accumulation.
+constexpr int kMomU = 8;
+
+__global__ void __launch_bounds__(kThreads, 2) k_moments_v4(ReplayView rp, long long rowEnd, SweepSums* sums) {
+  __shared__ double red[kThreads][8];
+  __shared__ double shd[kThreads / 32];
+  const int dS = rp.dS, CQ = dS >> 2, RP = kThreads / CQ;
+  const int tid = threadIdx.x, cq = tid % CQ, rl = tid / CQ;
+  double m[4], s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) m[c] = (double)rp.stateMean[cq * 4 + c];
+  double rs1 = 0.0, rs2 = 0.0, cnt = 0.0;
+  const double rmean = (double)rp.rew[0];
+  const long long tileRows = (long long)RP * kMomU;
+  const float4* S4 = reinterpret_cast<const float4*>(rp.S);
+  for (long long row0 = (long long)blockIdx.x * tileRows; row0 < rowEnd; row0 += (long long)gridDim.x * tileRows) {
+    float4 x[kMomU]; unsigned f[kMomU]; float rw[kMomU];
+#pragma unroll
+    for (int u = 0; u < kMomU; ++u) {
+      const long long row = row0 + (long long)u * RP + rl;
+      const bool ok = row < rowEnd;
+      f[u] = ok ? (unsigned)rp.rowFlag[row] : 0u;
+      x[u] = ok ? __ldcs(S4 + row * CQ + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+      rw[u] = (ok && cq == 0) ? __ldcs(rp.R + row) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kMomU; ++u) {
+      if ((f[u] & 4u) && !(f[u] & 2u)) {            // states of rows 0..N-2
+        const double d0 = (double)x[u].x - m[0], d1 = (double)x[u].y - m[1], d2 = (double)x[u].z - m[2], d3 = (double)x[u].w - m[3];
+        s1[0] += d0; s1[1] += d1; s1[2] += d2; s1[3] += d3;
+        s2[0] = fma(d0, d0, s2[0]); s2[1] = fma(d1, d1, s2[1]); s2[2] = fma(d2, d2, s2[2]); s2[3] = fma(d3, d3, s2[3]);
+        if (cq == 0) cnt += 1.0;
+      }
+      if (cq == 0 && (f[u] & 4u) && !(f[u] & 1u)) {  // rewards of rows 1..N-1
+        const double dr = (double)rw[u] - rmean;
+        rs1 += dr; rs2 = fma(dr, dr, rs2);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { red[tid][c] = s1[c]; red[tid][4 + c] = s2[c]; }
+  __syncthreads();
+  for (int idx = tid; idx < CQ * 8; idx += kThreads) {
+    const int q = idx >> 3, v = idx & 7;
+    double a = 0.0;
+    for (int r = 0; r < RP; ++r) a += red[r * CQ + q][v];
+    atomicAdd(&sums->moments[(v < 4 ? 0 : dS) + q * 4 + (v & 3)], a);
+  }
+  const int lane = tid & 31, warp = tid >> 5;
+  double v3[3] = {cnt, rs1, rs2};
+  for (int q = 0; q < 3; ++q) {
+    const double w = warp_sum_d(v3[q]);
     __syncthreads();
     if (lane == 0) shd[warp] = w;
     __syncthreads();
@@ -323,8 +445,7 @@ int launch_init_episode(const ReplayView& rp, int slot, float deltaInit, int hav
 int launch_sweep(const ReplayView& rp, int nEpisodes, int oneSlot, float gamma, float lambda, int recompute, float cmax,
                  float cinv, SweepSums* sums, cudaStream_t st) {
   const int count = nEpisodes > 0 ? nEpisodes : 1;
-  const int wpb = kThreads / 32;
-  int blocks = (count + wpb - 1) / wpb;
+  int blocks = count;                           // one CTA per episode, at most one full wave of 8 CTAs per SM
   if (blocks > 148 * 8) blocks = 148 * 8;
   k_sweep<<<blocks, kThreads, 0, st>>>(rp, nEpisodes, oneSlot, gamma, lambda, recompute, cmax, cinv, sums);
   SMB200_CUDA_CHECK(cudaGetLastError());
@@ -333,6 +454,16 @@ int launch_sweep(const ReplayView& rp, int nEpisodes, int oneSlot, float gamma, 
 
 int launch_moments(const ReplayView& rp, long long rowEnd, SweepSums* sums, int numSMs, cudaStream_t st) {
   if (rp.dS > 512) { set_error_msg("moments kernel supports dim_state <= 512"); return -1; }
+  const int CQ = rp.dS >> 2;
+  if ((rp.dS & 3) == 0 && (CQ & (CQ - 1)) == 0 && CQ <= kThreads) {     // streaming variant
+    const long long tileRows = (long long)(kThreads / CQ) * kMomU;
+    const long long nT = (rowEnd + tileRows - 1) / tileRows;
+    long long blocks = nT < (long long)numSMs * 2 ? nT : (long long)numSMs * 2;
+    if (blocks < 1) blocks = 1;
+    k_moments_v4<<<(int)blocks, kThreads, 0, st>>>(rp, rowEnd, sums);
+    SMB200_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
   size_t sm = sizeof(float) * kMomRows * rp.dS;
   if (sm < sizeof(double) * 2 * kThreads) sm = sizeof(double) * 2 * kThreads;
   const long long nTiles = (rowEnd + kMomRows - 1) / kMomRows;

@@ -17,7 +17,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsmarties_b200.so")
+# SMB200_PROFILE=1 selects the flavour with phase timestamps compiled in (scripts/phase_report.py)
+LIB_PATH = os.path.join(_HERE, "libsmarties_b200_prof.so" if os.environ.get("SMB200_PROFILE") else "libsmarties_b200.so")
 
 MAX_HIDDEN = 8
 MAX_ACTION = 64
