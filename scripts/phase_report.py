@@ -15,15 +15,32 @@ from smarties_b200 import Learner, synth  # noqa: E402
 n_ep = int(os.environ.get("PROF_NEP", "1000"))
 n = int(os.environ.get("PROF_STEPS", "200"))
 mhz = float(os.environ.get("SM_MHZ", "1965"))
-d = synth.make_replay(123, n_ep, 1000, 32, 8)
-L = Learner(32, 8, {"maxTotObsNum": 1048576, "minTotObsNum": 1000 * n_ep})
+world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+d = synth.make_replay(123 + rank, n_ep, 1000, 32, 8)
+if world > 1:      # launched by torch.distributed.run: the fused gradient exchange is part of P2
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = Learner(32, 8, {"maxTotObsNum": 1048576 * world, "minTotObsNum": 1000 * n_ep * world, "batchSize": 256 * world},
+                device=local, seed=42 + rank, world_rank=rank, world_size=world)
+    L.attach_process_group(dist)
+else:
+    L = Learner(32, 8, {"maxTotObsNum": 1048576, "minTotObsNum": 1000 * n_ep})
 L.load_replay(d)
 L.initialize_learner()
-L.seed_sampler(7)
+L.seed_sampler(7 + rank)
 L.train_steps(1, want_stats=False)
 L.presample(n)
 L.train_presampled(0, 50); L.sync()
+if world > 1:
+    dist.barrier()
 T, ms = L.profile_phases(n)
+if world > 1:
+    dist.barrier()
+    import time
+    time.sleep(0.3 * rank)     # keep the ranks' reports apart
+    print(f"--- rank {rank} of {world}")
 print(f"{n} steps in {ms:.3f} ms -> {1e3 * ms / n:.2f} us/step, grid {T.shape[1]}")
 T = T[20:]                       # skip the first steps
 nP1 = 64
@@ -37,7 +54,8 @@ for name, a, b in seg:
 fine = [("fwd L1 wait W", 9, 27), ("fwd L1 compute", 27, 10), ("fwd L2 wait W", 10, 28), ("fwd L2+res", 28, 12), ("fwd L4 wait W", 12, 30), ("fwd L4 out", 30, 31 if os.environ.get("ICACHE_PROBE") else 13), ("fwd L4 again", 31, 32 if os.environ.get("ICACHE_PROBE") else 31), ("fwd L5 param", 13, 2),
         ("loss stage1", 2, 8), ("loss stage2", 8, 16), ("loss stage3", 16, 3),
         ("bwd L4 out", 20, 18), ("bwd L2+res", 18, 17), ("bwd L1", 17, 4),
-        ("P2 desc+issue", 6, 24), ("P2 tile load", 24, 25), ("P2 contraction", 25, 26), ("P2 adam+store", 26, 7)]
+        ("P2 desc+issue", 6, 24), ("P2 tile load", 24, 25), ("P2 contraction", 25, 33 if world > 1 else 26), ("P2 peer stores", 33, 34 if world > 1 else 33),
+        ("P2 peer wait", 34, 26 if world > 1 else 34), ("P2 adam+store", 26, 7)]
 for name, a, b in fine:
     dlt = p1[:, :, b] - p1[:, :, a]
     print(f"     {name:14s} {us(dlt.mean()):6.2f} us")
@@ -51,4 +69,9 @@ nxt = T[1:, :-1, 0] - T[:-1, :-1, 7]
 print(f"  barrier2 wait (P2 end -> next step start): mean {us(nxt.mean()):.2f} us")
 per = T[1:, 0, 0] - T[:-1, 0, 0]
 print(f"  step period (CTA 0): {us(per.mean()):.2f} us")
+sys.stdout.flush()
+if world > 1:
+    dist.barrier()
 L.close()
+if world > 1:
+    dist.destroy_process_group()

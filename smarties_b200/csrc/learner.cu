@@ -959,7 +959,7 @@ static void comm_layout(CommView& cm, int world, int rank, int nParams, int nTil
   cm.offGrad = o; o += sizeof(unsigned long long) * 2 * (size_t)world * cm.nParamsPad;
   cm.offFlag = o; o += sizeof(unsigned) * (size_t)world * cm.nTilesPad;
   o = (o + 255) / 256 * 256;
-  cm.offCnt = o; o += sizeof(double) * 2 * (size_t)world * 4;
+  cm.offCnt = o; o += sizeof(unsigned long long) * 4 * (size_t)world * 4;   // [step & 3][rank][4] stamped words
   cm.offCntFlag = o; o += 256;
   cm.offVec = o; o += sizeof(double) * 2 * (size_t)world * kCommVec;
   cm.offVecFlag = o; o += 256;

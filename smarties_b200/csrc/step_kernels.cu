@@ -86,16 +86,29 @@ __device__ __forceinline__ void wait_stamp_sys(const unsigned* p, unsigned stamp
 __device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// poll one stamped element in LOCAL memory until the peer's store of this step has landed
-__device__ __forceinline__ float wait_value_ll(const unsigned long long* p, unsigned stamp, const CommView& cm) {
-  unsigned long long v;
+// Poll the stamped elements `p[q * stride]` (q = 0..N-1, q != me) in LOCAL memory until every
+// peer's store of this step has landed.  All N-1 loads of a round are issued back to back, so a
+// round costs one L2 latency, not N-1.  out[q] = low word of slot q.
+__device__ __forceinline__ void wait_values_ll(const unsigned long long* p, size_t stride, int N, int me, unsigned stamp,
+                                               const CommView& cm, unsigned (&out)[kMaxWorld]) {
+  unsigned long long v[kMaxWorld];
   const long long t0 = clock64();
   while (true) {
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    if ((unsigned)(v >> 32) == stamp) break;
+#pragma unroll
+    for (int q = 0; q < kMaxWorld; ++q)
+      if (q < N && q != me) asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v[q]) : "l"(p + (size_t)q * stride) : "memory");
+    bool ok = true;
+#pragma unroll
+    for (int q = 0; q < kMaxWorld; ++q)
+      if (q < N && q != me) ok = ok && ((unsigned)(v[q] >> 32) == stamp);
+    if (ok) break;
     if (clock64() - t0 > cm.timeoutCycles) { *cm.error = 1; break; }
   }
-  return __uint_as_float((unsigned)(v & 0xffffffffull));
+#pragma unroll
+  for (int q = 0; q < kMaxWorld; ++q) out[q] = (q < N && q != me) ? (unsigned)(v[q] & 0xffffffffull) : 0u;
+}
+__device__ __forceinline__ unsigned long long ll_pack(unsigned v, unsigned stamp) {
+  return ((unsigned long long)stamp << 32) | (unsigned long long)v;
 }
 
 // ---- mbarrier + bulk async copy (TMA, cp.async.bulk -> SASS UBLKCP) ----
@@ -1331,6 +1344,7 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
   //      into every peer's slot over NVLink, publishes a stamp, waits for the peers' stamps on LOCAL
   //      memory and adds the slots in rank order, so all ranks apply the identical update ----
   if (a.comm.world > 1) {
+    DBG_T(a, step, 33);
     const CommView& cm = a.comm;
     const int N = cm.world, me = cm.rank, par = step & 1;
     const unsigned stamp = (unsigned)(step + 1);
@@ -1343,15 +1357,21 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
       const unsigned long long pk = ((unsigned long long)stamp << 32) | (unsigned long long)__float_as_uint(acc2);
       for (int q = 0; q < N; ++q) if (q != me) st_volatile_u64(cm.grad(q) + slotMe + p1, pk);
     }
+    DBG_T(a, step, 34);
     const unsigned long long* mine = cm.grad(me) + (size_t)par * N * cm.nParamsPad;
+    unsigned got[kMaxWorld];
     if (p0 >= 0) {
+      wait_values_ll(mine + p0, cm.nParamsPad, N, me, stamp, cm, got);
       float v = 0.f;
-      for (int q = 0; q < N; ++q) v += q == me ? acc : wait_value_ll(mine + (size_t)q * cm.nParamsPad + p0, stamp, cm);
+#pragma unroll
+      for (int q = 0; q < kMaxWorld; ++q) if (q < N) v += q == me ? acc : __uint_as_float(got[q]);
       acc = v;
     }
     if (p1 >= 0) {
+      wait_values_ll(mine + p1, cm.nParamsPad, N, me, stamp, cm, got);
       float v = 0.f;
-      for (int q = 0; q < N; ++q) v += q == me ? acc2 : wait_value_ll(mine + (size_t)q * cm.nParamsPad + p1, stamp, cm);
+#pragma unroll
+      for (int q = 0; q < kMaxWorld; ++q) if (q < N) v += q == me ? acc2 : __uint_as_float(got[q]);
       acc2 = v;
     }
   }
@@ -1530,21 +1550,31 @@ __device__ void stats_and_refer(const StepArgs& a, const Hyper& hp, const StepCt
       // updateCounters are those of the PREVIOUS step.  Push this step's local counts, consume the
       // peers' counts of the previous step.
       const CommView& cm = a.comm;
-      const int N = cm.world, me = cm.rank, par = step & 1;
+      const int N = cm.world, me = cm.rank;
       const unsigned stamp = (unsigned)(step + 1);
+      // stamped 64-bit words (32 value bits + the step stamp, one NVLink store each: no fence, no
+      // separate flag): [far lo, far hi, stored lo, stored hi] per (step & 3, rank).  Four slots:
+      // the statistics CTAs run asynchronously, a peer may be up to two steps ahead of this reader.
+      const unsigned long long fw = (unsigned long long)(long long)farGlobal, sw = (unsigned long long)(long long)nPost;
       for (int q = 0; q < N; ++q) {
-        double* d = cm.cnt(q) + ((size_t)par * N + me) * 4;
-        d[0] = farGlobal; d[1] = nPost;
+        if (q == me) continue;
+        unsigned long long* d = reinterpret_cast<unsigned long long*>(cm.cnt(q)) + ((size_t)(step & 3) * N + me) * 4;
+        st_volatile_u64(d + 0, ll_pack((unsigned)fw, stamp)); st_volatile_u64(d + 1, ll_pack((unsigned)(fw >> 32), stamp));
+        st_volatile_u64(d + 2, ll_pack((unsigned)sw, stamp)); st_volatile_u64(d + 3, ll_pack((unsigned)(sw >> 32), stamp));
       }
-      __threadfence_system();
-      for (int q = 0; q < N; ++q) st_release_sys(cm.cntFlag(q) + me, stamp);
       if ((long long)step == c.cnt_seed_step) { farGlobal = c.gl_far_prev; nPost = c.gl_stored_prev; }   // seeded by the host at (re)start
       else {
+        // this rank's own counts of the previous step travel in ctrl (gl_*_prev); the peers' arrived
+        // a whole step ago (stamp of the previous step == step)
+        const unsigned long long* d = reinterpret_cast<const unsigned long long*>(cm.cnt(me)) + (size_t)((step + 3) & 3) * N * 4;
+        unsigned w0[kMaxWorld], w1[kMaxWorld], w2[kMaxWorld], w3[kMaxWorld];
+        wait_values_ll(d + 0, 4, N, me, (unsigned)step, cm, w0); wait_values_ll(d + 1, 4, N, me, (unsigned)step, cm, w1);
+        wait_values_ll(d + 2, 4, N, me, (unsigned)step, cm, w2); wait_values_ll(d + 3, 4, N, me, (unsigned)step, cm, w3);
         farGlobal = 0.0; nPost = 0.0;
         for (int q = 0; q < N; ++q) {
-          wait_stamp_sys(cm.cntFlag(me) + q, (unsigned)step, cm);     // stamp of the previous step
-          const double* d = cm.cnt(me) + ((size_t)(par ^ 1) * N + q) * 4;
-          farGlobal += __ldcg(d); nPost += __ldcg(d + 1);
+          if (q == me) { farGlobal += c.gl_far_prev; nPost += c.gl_stored_prev; continue; }
+          farGlobal += (double)(long long)(((unsigned long long)w1[q] << 32) | w0[q]);
+          nPost += (double)(long long)(((unsigned long long)w3[q] << 32) | w2[q]);
         }
       }
     }
