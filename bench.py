@@ -53,6 +53,20 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
+def ncu_traffic(kernel, steps=None):
+    """DRAM bytes per launch from the committed ncu --set full capture (scripts/ncu_capture.sh), or None."""
+    p = os.path.join(ROOT, "profiles", "r1", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f)
+    for k, v in t.items():
+        if isinstance(v, dict) and kernel in k:
+            b = v["dram_bytes"]
+            return b * steps / t["_steps_per_persistent_launch"] if steps else b
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -263,7 +277,10 @@ def main():
     step_bytes = BYTES_PER_TRANSITION * BATCH + BYTES_ADAM_PER_STEP
     achieved = step_bytes * n_roof / (ms_k * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": "k_steps_persistent", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": which,
+            "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic("k_steps_persistent", n_roof), "peak_source": which,
+            "traffic_source": "profiles/r1/ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of a "
+                              "256-step launch, scaled to this launch's step count; below the algorithmic bytes because the "
+                              "Adam state stays L2-resident)",
             "algorithmic_bytes_per_launch": step_bytes * n_roof, "launch_ms": ms_k, "steps_per_launch": n_roof,
             "note": "B=256 step is dependency/latency bound (2 grid barriers per step), not bandwidth bound"}
     # the HBM-streaming sweeps, timed alone with a flushed L2
@@ -279,7 +296,7 @@ def main():
             best = m if best is None else min(best, m)
         a = bpt * n_tr / (best * 1e-3) / 1e9
         sweeps[name] = {"bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": a / peaks["hbm_gbs"],
-                        "ms": best, "algorithmic_bytes": bpt * n_tr}
+                        "ms": best, "algorithmic_bytes": bpt * n_tr, "traffic": ncu_traffic(name.split("(")[0])}
 
     if rank == 0:
         out = {"metric": "V-RACER learner transitions/sec updated", "value": value, "unit": "transitions/s", "n_gpus": world,

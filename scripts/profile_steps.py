@@ -19,6 +19,11 @@ start = int(os.environ.get("PROF_START", "0"))
 if start:
     L.set_grad_step(start)
 L.presample(steps)
+L.train_presampled(0, min(steps, 8)); L.sync()      # warm-up launch (not captured)
+L.presample(steps)
+if os.environ.get("PROF_RANGE"):                    # ncu --profile-from-start off: capture only what follows
+    import torch
+    torch.cuda.profiler.start()
 t0 = time.perf_counter()
 L.train_presampled(0, steps)
 L.sync()
@@ -26,4 +31,6 @@ print("steps", steps, "device ms", L.last_timing(), "wall", time.perf_counter() 
 if os.environ.get("PROF_SWEEPS"):
     L.retrace_sweep(); print("retrace ms", L.last_timing())
     L.reward_state_moments(); print("moments ms", L.last_timing())
+if os.environ.get("PROF_RANGE"):
+    torch.cuda.profiler.stop()
 L.close()
