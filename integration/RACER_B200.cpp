@@ -1,0 +1,276 @@
+// integration/RACER_B200.cpp — the reference-side binding of libsmarties_b200.so.
+//
+// This is the ONE translation unit a maintainer of the reference adds to libsmarties (see
+// INTEGRATION.md).  It is written against the reference's own headers and is compiled here by
+// integration/Makefile from the sources under /root/reference (nothing of the reference is
+// copied into this repository).  What it does:
+//
+//   * RACER_B200<Advantage> derives from the reference's RACER<Advantage, Continuous_policy, Rvec>
+//     (Learners/RACER.h:44-98).  Everything actor-side stays the reference's: Learner::select
+//     (Learners/Learner.cpp:31-45), RACER::selectAction / processTerminal (RACER.cpp:30-59) on the
+//     host Approximator, MemoryBuffer::storeState/storeAction/terminateCurrentEpisode, the
+//     DataCoordinator, the Communicator / Worker / Master plumbing and every app.
+//   * setupTasks (RACER.cpp:61-110) is overridden: the three reference tasks
+//     {initializeLearner} / {spawnTrainTasks, processMemoryBuffer} / {applyGradient,
+//     globalGradCounterUpdate} become {smb200_initialize_learner} / {mirror finished episodes into
+//     the HBM replay, smb200_train_steps(1), copy the new weights into the host network used by the
+//     actors}.  The host MemoryBuffer keeps receiving episodes and is pruned first-in-first-out
+//     exactly like MemoryProcessing::applyEpisodesRemovalAlgo (MemoryProcessing.cpp:327-351).
+//   * smarties::createLearner (Learners/AlgoFactory.cpp:60-340) is wrapped: AlgoFactory.cpp is
+//     compiled with -DcreateLearner=createLearner_reference and this file provides
+//     createLearner, which returns a RACER_B200 when the environment variable SMARTIES_B200 is set
+//     and the settings are ones the device path covers, and the reference learner otherwise.
+//
+// Errors of the C-ABI become die() (Utils/Warnings.h:36-44), like every other fatal error of the
+// reference.
+#include "smarties/Learners/AlgoFactory.h"
+#include "smarties/Learners/RACER.h"
+#include "smarties/Math/Continuous_policy.h"
+#include "smarties/Math/Zero_advantage.h"
+#include "smarties/Math/Gaus_advantage.h"
+#include "smarties/Network/Approximator.h"
+#include "smarties/Network/Optimizer.h"
+#include "smarties/ReplayMemory/MemoryProcessing.h"
+#include "smarties/Utils/Warnings.h"
+#include "smarties/Utils/SstreamUtilities.h"
+
+#include <smarties_b200.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <fstream>
+#include <unistd.h>
+#include <unordered_set>
+
+namespace smarties
+{
+
+// the reference's own factory (AlgoFactory.cpp built with -DcreateLearner=createLearner_reference)
+std::unique_ptr<Learner> createLearner_reference(const Uint learnerID, MDPdescriptor& MDP, ExecutionInfo& distrib);
+
+template<typename Advantage_t>
+class RACER_B200 : public RACER<Advantage_t, Continuous_policy, Rvec>
+{
+  using Base = RACER<Advantage_t, Continuous_policy, Rvec>;
+  using Base::data; using Base::settings; using Base::distrib; using Base::MDP; using Base::networks;
+  using Base::algoSubStepID; using Base::nObsB4StartTraining; using Base::bTrain; using Base::aInfo;
+  using Base::profiler; using Base::learn_rank; using Base::learn_size;
+
+  smb200_learner* gpu = nullptr;
+  const bool isRacer;
+  std::unordered_set<const Episode*> mirrored;      // episodes already resident in the HBM replay
+  std::vector<float> bufS, bufA, bufMU, bufR, bufV, bufADV, wblob;
+  smb200_step_stats last{};
+  double secPush = 0, secStep = 0, secSync = 0;
+  long nPushed = 0;
+
+  void check(const int rc, const char* what) const {
+    if (rc) _die("smarties_b200 %s: %s", what, smb200_last_error());
+  }
+
+  Parameters* hostWeights() const { return networks[0]->opt->weights.get(); }
+
+  void createDeviceLearner()
+  {
+    smb200_config c;
+    check(smb200_default_config(&c, (int32_t) MDP.dimStateObserved, (int32_t) MDP.dimAction), "default_config");
+    const char* dev = std::getenv("SMARTIES_B200_DEVICE");
+    c.device = dev ? std::atoi(dev) : 0;
+    c.algo = isRacer ? SMB200_RACER : SMB200_VRACER;
+    if (MDP.dimAction > SMB200_MAX_ACTION || settings.nnLayerSizes.size() > SMB200_MAX_HIDDEN) die("network too large for smarties_b200");
+    for (Uint i = 0; i < MDP.dimAction; ++i) c.action_bounded[i] = MDP.bActionSpaceBounded[i] ? 1 : 0;
+    c.n_hidden = (int32_t) settings.nnLayerSizes.size();
+    for (int i = 0; i < c.n_hidden; ++i) c.hidden[i] = (int32_t) settings.nnLayerSizes[i];
+    c.batch_size = (int32_t) settings.batchSize_local;  c.batch_size_global = (int32_t) settings.batchSize;
+    c.max_tot_obs = settings.maxTotObsNum_local;         c.max_tot_obs_global = settings.maxTotObsNum;
+    c.gamma = settings.gamma; c.lambda = settings.lambda; c.clip_imp_weight = settings.clipImpWeight;
+    c.penal_tol = settings.penalTol; c.eps_anneal = settings.epsAnneal; c.learnrate = settings.learnrate;
+    c.nn_lambda = settings.nnLambda; c.expl_noise = settings.explNoise; c.out_weights_prefac = settings.outWeightsPrefac;
+    c.refer_reduce_threads = (int32_t) distrib.nThreads;
+    c.world_rank = (int32_t) learn_rank; c.world_size = (int32_t) learn_size;
+    c.seed = distrib.randSeed;
+    c.nn_type = settings.nnType == "LSTM" ? SMB200_LSTM : SMB200_FFNN;
+    c.nn_bptt_seq = (int32_t) settings.nnBPTTseq;
+    // an episode occupies nsteps() = ndata()+1 rows and is at least two rows long: room for the worst case,
+    // plus the episodes that arrive between two pruning passes
+    c.capacity_rows = 2 * (int64_t) settings.maxTotObsNum_local + 65536;
+    c.max_episodes = (int32_t) std::min<long>(1 << 20, (long) settings.maxTotObsNum_local + 4096);
+    check(smb200_create(&c, &gpu), "create");
+    Parameters* W = hostWeights();
+    if ((int64_t) W->nParams != smb200_n_params(gpu))
+      _die("parameter blob mismatch: reference %lu vs device %ld floats", (unsigned long) W->nParams, (long) smb200_n_params(gpu));
+    // same initial policy on both sides: the device learner starts from the host network's weights
+    check(smb200_set_weights(gpu, W->params, W->nParams), "set_weights");
+    wblob.resize(W->nParams);
+  }
+
+  // Episode (ReplayMemory/Episode.h:40-110) -> the row-major f32 arrays of smb200_push_episode
+  void pushToDevice(const Episode& EP)
+  {
+    const Uint N = EP.nsteps(), dS = MDP.dimStateObserved, dA = MDP.dimAction, dP = MDP.policyVecDim;
+    bufS.assign((size_t) N * dS, 0.f); bufA.assign((size_t) N * dA, 0.f); bufMU.assign((size_t) N * dP, 0.f);
+    bufR.assign(N, 0.f); bufV.assign(N, 0.f); bufADV.assign(N, 0.f);
+    for (Uint t = 0; t < N; ++t) {
+      for (Uint k = 0; k < dS && k < EP.states[t].size(); ++k) bufS[(size_t) t * dS + k] = EP.states[t][k];
+      if (t < EP.actions.size())  for (Uint k = 0; k < dA && k < EP.actions[t].size(); ++k)  bufA[(size_t) t * dA + k]  = (float) EP.actions[t][k];
+      if (t < EP.policies.size()) for (Uint k = 0; k < dP && k < EP.policies[t].size(); ++k) bufMU[(size_t) t * dP + k] = (float) EP.policies[t][k];
+      bufR[t] = (float) EP.rewards[t];
+      if (t < EP.stateValue.size())      bufV[t]   = EP.stateValue[t];
+      if (t < EP.actionAdvantage.size()) bufADV[t] = EP.actionAdvantage[t];
+    }
+    check(smb200_push_episode(gpu, (int64_t) EP.ID, (int32_t) N, EP.bReachedTermState ? 1 : 0, bufS.data(), bufA.data(),
+                              bufMU.data(), bufR.data(), bufV.data(), bufADV.data()), "push_episode");
+    ++nPushed;
+  }
+
+  // new episodes -> HBM; then the first-in-first-out pruning of the host copy
+  // (MemoryProcessing::applyEpisodesRemovalAlgo with ERoldSeqFilter "oldest")
+  void mirrorEpisodes()
+  {
+    std::lock_guard<std::mutex> lock(data->dataset_mutex);
+    for (const auto& e : data->episodes)
+      if (mirrored.insert(e.get()).second) pushToDevice(*e);
+    std::sort(data->episodes.begin(), data->episodes.end(),
+              [](const std::unique_ptr<Episode>& a, const std::unique_ptr<Episode>& b) { return a->ID > b->ID; });
+    const long maxTotObs = settings.maxTotObsNum_local;
+    while (data->episodes.size() > 1 && data->nStoredSteps() - (long) data->episodes.back()->nsteps() > maxTotObs) {
+      mirrored.erase(data->episodes.back().get());
+      data->removeBackEpisode();
+      data->stats.nPrunedEps++;
+    }
+  }
+
+  void pullScaling()
+  {
+    const Uint dS = MDP.dimStateObserved;
+    std::vector<float> mean(dS), scale(dS), stdev(dS); float rew[3];
+    check(smb200_get_scaling(gpu, mean.data(), scale.data(), stdev.data(), rew), "get_scaling");
+    for (Uint k = 0; k < dS; ++k) { MDP.stateMean[k] = mean[k]; MDP.stateScale[k] = scale[k]; MDP.stateStdDev[k] = stdev[k]; }
+    MDP.rewardsMean = rew[0]; MDP.rewardsScale = rew[1]; MDP.rewardsStdDev = rew[2];
+  }
+
+  void pullWeights()
+  {
+    check(smb200_get_weights(gpu, wblob.data(), (int64_t) wblob.size()), "get_weights");
+    std::copy(wblob.begin(), wblob.end(), hostWeights()->params);   // read by the actors' forward passes
+  }
+
+  void publishStats()
+  {
+    data->beta = last.beta; data->CmaxRet = last.cmax; data->CinvRet = last.cinv;
+    ReplayStats& s = data->stats;
+    s.nFarPolicySteps = (Uint) last.n_far_policy; s.avgKLdivergence = last.avg_kl; s.avgSquaredErr = last.avg_sq_err;
+    s.maxAbsError = last.max_abs_err; s.avgReturn = last.avg_return; s.stdevQ = last.stdev_q; s.avgQ = last.avg_q;
+    s.maxQ = last.max_q; s.minQ = last.min_q;
+    s.countReturnsEstimateUpdates = (Sint) last.cnt_ret; s.sumReturnsEstimateErrors = last.sum_ret_err;
+  }
+
+  static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+ public:
+  RACER_B200(MDPdescriptor& M, HyperParameters& S, ExecutionInfo& D, const bool racer) : Base(M, S, D), isRacer(racer)
+  {
+    if (D.world_rank == 0) printf("smarties_b200: learner steps of this agent run on the GPU (libsmarties_b200.so)\n");
+    createDeviceLearner();
+  }
+  ~RACER_B200() override
+  {
+    if (gpu && distrib.world_rank == 0)
+      printf("smarties_b200: %ld gradient steps, %ld episodes mirrored; seconds in push %.3f, device steps %.3f, weight sync %.3f\n",
+             (long) data->nGradSteps(), nPushed, secPush, secStep, secSync);
+    smb200_destroy(gpu);
+  }
+
+  void setupTasks(TaskQueue& tasks) override
+  {
+    if (not bTrain) return;
+    algoSubStepID = -1;
+
+    auto stepInit = [&]()      // Learner::initializeLearner (Learner.cpp:47-72)
+    {
+      if (algoSubStepID >= 0) return;
+      if (data->nStoredSteps() < nObsB4StartTraining) return;
+      mirrorEpisodes();
+      check(smb200_initialize_learner(gpu), "initialize_learner");
+      pullScaling();
+      data->counters.nGatheredB4Startup = nObsB4StartTraining;
+      algoSubStepID = 0;
+    };
+    tasks.add(stepInit);
+
+    auto stepMain = [&]()      // spawnTrainTasks + processMemoryBuffer + applyGradient (RACER.cpp:81-109)
+    {
+      if (algoSubStepID not_eq 0) return;
+      if (this->blockGradientUpdates()) return;
+      const double t0 = now();
+      mirrorEpisodes();
+      const double t1 = now();
+      check(smb200_train_steps(gpu, 1, &last), "train_steps");
+      const double t2 = now();
+      pullWeights();
+      if ((data->nGradSteps() + 1) % 1000 == 0) pullScaling();   // the every-1000-steps moment sweep moved the normalisers
+      publishStats();
+      const double t3 = now();
+      secPush += t1 - t0; secStep += t2 - t1; secSync += t3 - t2;
+      this->logStats();
+      this->globalGradCounterUpdate();
+    };
+    tasks.add(stepMain);
+  }
+};
+
+static std::ifstream openSettings(ExecutionInfo& D, const Uint ID)   // same lookup order as the reference factory
+{
+  char cwd[512];
+  if (!getcwd(cwd, 512)) cwd[0] = 0;
+  if (chdir(D.initial_runDir)) {}
+  char name[256];
+  snprintf(name, 256, "settings_%02u.json", (unsigned) ID);
+  std::ifstream ret(name, std::ifstream::in);
+  if (!ret.is_open()) ret.open("settings.json", std::ifstream::in);
+  if (chdir(cwd)) {}
+  return ret;
+}
+
+std::unique_ptr<Learner> createLearner(const Uint learnerID, MDPdescriptor& MDP, ExecutionInfo& distrib)
+{
+  if (!std::getenv("SMARTIES_B200")) return createLearner_reference(learnerID, MDP, distrib);
+
+  HyperParameters settings(MDP.dimObs(), MDP.dimAct());
+  std::ifstream ifs = openSettings(distrib, learnerID);
+  settings.initializeOpts(ifs, distrib);
+  const bool covered =
+      (settings.learner == "VRACER" || settings.learner == "RACER") && !MDP.bDiscreteActions() &&
+      settings.dataSamplingAlgo == "uniform" && (settings.returnsEstimator == "default" || settings.returnsEstimator == "retrace") &&
+      (settings.ERoldSeqFilter == "oldest" || settings.ERoldSeqFilter == "default") &&
+      (settings.nnType == "FFNN" || settings.nnType == "LSTM") && settings.nnFunc == "Tanh" && settings.nnOutputFunc == "Linear" &&
+      settings.ESpopSize == 1 && settings.targetDelay == 0 && MDP.nAppendedObs == 0 &&
+      std::all_of(settings.encoderLayerSizes.begin(), settings.encoderLayerSizes.end(), [](Uint n) { return n == 0; });
+  if (!covered) {
+    warn("SMARTIES_B200 is set but these settings are outside the device path: using the reference CPU learner.");
+    return createLearner_reference(learnerID, MDP, distrib);
+  }
+  if (settings.returnsEstimator == "default") settings.returnsEstimator = "retrace";   // AlgoFactory.cpp:134-136
+  const ActionInfo aInfo = ActionInfo(MDP);
+  std::unique_ptr<Learner> ret;
+  std::ostringstream o;
+  o << MDP.dimState << " ";
+  if (settings.learner == "RACER") {
+    using R = RACER<Param_advantage, Continuous_policy, Rvec>;
+    MDP.policyVecDim = R::getnDimPolicy(aInfo);
+    ret = std::make_unique<RACER_B200<Param_advantage>>(MDP, settings, distrib, true);
+  } else {
+    using R = RACER<Zero_advantage, Continuous_policy, Rvec>;
+    MDP.policyVecDim = R::getnDimPolicy(aInfo);
+    ret = std::make_unique<RACER_B200<Zero_advantage>>(MDP, settings, distrib, false);
+  }
+  o << MDP.dimAction << " " << MDP.policyVecDim;
+  if (distrib.world_rank == 0) { std::ofstream fout("problem_size.log", std::ios::app); fout << o.str() << std::endl; }
+  char lName[256];
+  snprintf(lName, 256, "agent_%02u", (unsigned) learnerID);
+  ret->setLearnerName(std::string(lName), learnerID);
+  return ret;
+}
+
+}  // namespace smarties
