@@ -113,7 +113,7 @@ def make_workload(rank=0):
 # ------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the reference's own CPU implementation (oracle/_ref)
 # ------------------------------------------------------------------------------------------
-def run_reference(steps, threads, data=None, reps=1):
+def run_reference(steps, threads, data=None, reps=1, settings=None, learner_flag=None):
     """Times `steps` learner steps of the UNMODIFIED reference (oracle/_ref/ref_harness, built from
     /root/reference by oracle/Makefile) on this box's host cores.  Falls back to the numpy oracle
     port if the harness binary is absent."""
@@ -125,7 +125,7 @@ def run_reference(steps, threads, data=None, reps=1):
         with tempfile.TemporaryDirectory() as tmp:
             synth.write_replay_file(os.path.join(tmp, "data.bin"), data)
             with open(os.path.join(tmp, "settings.json"), "w") as f:
-                json.dump(SETTINGS, f)
+                json.dump(settings or SETTINGS, f)
             env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="close")
             out = subprocess.run([harness, "--data", "data.bin", "--settings", "settings.json", "--steps", str(steps),
                                   "--threads", str(threads), "--sampleSeed", "7", "--quiet", "--reps", str(reps)],

@@ -38,6 +38,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <fstream>
 #include <unistd.h>
@@ -62,7 +63,9 @@ class RACER_B200 : public RACER<Advantage_t, Continuous_policy, Rvec>
   std::unordered_set<const Episode*> mirrored;      // episodes already resident in the HBM replay
   std::vector<float> bufS, bufA, bufMU, bufR, bufV, bufADV, wblob;
   smb200_step_stats last{};
-  double secPush = 0, secStep = 0, secSync = 0;
+  int maxStepsPerCall = 16;
+  std::vector<smb200_step_stats> stepStats;
+  double secPush = 0, secStep = 0, secSync = 0, tTrainStart = 0;
   long nPushed = 0;
 
   void check(const int rc, const char* what) const {
@@ -172,13 +175,16 @@ class RACER_B200 : public RACER<Advantage_t, Continuous_policy, Rvec>
   RACER_B200(MDPdescriptor& M, HyperParameters& S, ExecutionInfo& D, const bool racer) : Base(M, S, D), isRacer(racer)
   {
     if (D.world_rank == 0) printf("smarties_b200: learner steps of this agent run on the GPU (libsmarties_b200.so)\n");
+    if (const char* m = std::getenv("SMARTIES_B200_MAXSTEPS")) maxStepsPerCall = std::max(1, std::min(256, std::atoi(m)));
+    stepStats.resize(maxStepsPerCall);
     createDeviceLearner();
   }
   ~RACER_B200() override
   {
     if (gpu && distrib.world_rank == 0)
-      printf("smarties_b200: %ld gradient steps, %ld episodes mirrored; seconds in push %.3f, device steps %.3f, weight sync %.3f\n",
-             (long) data->nGradSteps(), nPushed, secPush, secStep, secSync);
+      printf("smarties_b200: %ld gradient steps, %ld episodes mirrored; seconds in push %.3f, device steps %.3f, weight sync %.3f; "
+             "%.3f s of wall clock since training started\n",
+             (long) data->nGradSteps(), nPushed, secPush, secStep, secSync, tTrainStart > 0 ? now() - tTrainStart : 0.0);
     smb200_destroy(gpu);
   }
 
@@ -195,6 +201,7 @@ class RACER_B200 : public RACER<Advantage_t, Continuous_policy, Rvec>
       check(smb200_initialize_learner(gpu), "initialize_learner");
       pullScaling();
       data->counters.nGatheredB4Startup = nObsB4StartTraining;
+      tTrainStart = now();
       algoSubStepID = 0;
     };
     tasks.add(stepInit);
@@ -203,18 +210,28 @@ class RACER_B200 : public RACER<Advantage_t, Continuous_policy, Rvec>
     {
       if (algoSubStepID not_eq 0) return;
       if (this->blockGradientUpdates()) return;
+      // The reference runs one step per pass of the task loop; when the actors are ahead by k
+      // observations it runs k passes back to back (Learner::blockGradientUpdates, Learner.cpp:119-126).
+      // Those k steps go to the device as ONE call (one persistent launch); SMARTIES_B200_MAXSTEPS=1
+      // restores the strict per-step hand-off.
+      const long ahead = (long) std::floor(this->nLocTimeStepsTrain() / std::max((Real) 1e-9, this->obsPerStep_loc)) - this->nGradSteps();
+      const long toSweep = 1000 - (this->nGradSteps() + 1) % 1000;          // stop at the every-1000-steps boundary
+      const int k = (int) std::max<long>(1, std::min<long>({(long) maxStepsPerCall, ahead, toSweep + 1}));
       const double t0 = now();
       mirrorEpisodes();
       const double t1 = now();
-      check(smb200_train_steps(gpu, 1, &last), "train_steps");
+      check(smb200_train_steps(gpu, k, stepStats.data()), "train_steps");
       const double t2 = now();
       pullWeights();
-      if ((data->nGradSteps() + 1) % 1000 == 0) pullScaling();   // the every-1000-steps moment sweep moved the normalisers
-      publishStats();
       const double t3 = now();
       secPush += t1 - t0; secStep += t2 - t1; secSync += t3 - t2;
-      this->logStats();
-      this->globalGradCounterUpdate();
+      for (int i = 0; i < k; ++i) {
+        last = stepStats[i];
+        if ((this->nGradSteps() + 1) % 1000 == 0) pullScaling();   // the every-1000-steps moment sweep moved the normalisers
+        publishStats();
+        this->logStats();
+        this->globalGradCounterUpdate();
+      }
     };
     tasks.add(stepMain);
   }

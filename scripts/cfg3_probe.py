@@ -43,3 +43,8 @@ if os.environ.get("PROF_PHASES"):
     per = (T[1:, 0, 0] - T[:-1, 0, 0]) / mhz
     print(f"  step period {per.mean():.2f} us")
 L.close()
+if os.environ.get("CFG3_REF_STEPS"):     # the reference's CPU learner on the same workload, all host cores
+    import bench
+    n = int(os.environ["CFG3_REF_STEPS"])
+    r = bench.run_reference(n, os.cpu_count() or 1, data=d, settings={k: v for k, v in S.items()})
+    print(f"cfg3 reference CPU: {r['value']:.3e} transitions/s ({r['cores']} threads, {n} steps, {1e3 * r['seconds'] / n:.2f} ms/step)")

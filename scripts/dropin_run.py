@@ -1,0 +1,75 @@
+"""Drop-in runs of whole smarties applications, once with the reference CPU learner and once with the
+learner steps on the GPU through libsmarties_b200.so (integration/RACER_B200.cpp, selected by
+SMARTIES_B200=1).  Same binary interface, same settings file, same command line.
+
+  --app cart_pole   BASELINE.json configs[0]: the reference's apps/cart_pole_cpp + settings/VRACER.json
+  --app synth_env   configs[3] shape: integration/synth_env.cpp (17 states, 6 bounded actions, 1000-step
+                    truncated episodes) with --envs 64 forked environment processes feeding one learner
+
+Needs the prebuilt files under oracle/_ref/ (integration/Makefile).  Reports wall-clock of the whole run and
+the environment time steps / gradient steps per second after the initial data collection.
+
+usage: python scripts/dropin_run.py [--app cart_pole] [--envs 1] [--steps 20000] [--threads 8] [--arms ref,b200]"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import tempfile
+import time
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+SETTINGS = {"learner": "VRACER", "dataSamplingAlgo": "uniform", "returnsEstimator": "retrace", "ERoldSeqFilter": "oldest",
+            "nnLayerSizes": [128, 128]}     # == settings/VRACER.json of the reference
+
+
+def run_arm(arm, steps, threads, seed, settings=None, timeout=1500, app="cart_pole", envs=1, extra_env=None):
+    exe = os.path.join(ROOT, "oracle", "_ref", "b200" if arm == "b200" else "", app)
+    if not os.path.exists(exe):
+        return {"arm": arm, "error": f"{exe} missing (make -C integration)"}
+    tmp = tempfile.mkdtemp(prefix=f"cartpole_{arm}_")
+    with open(os.path.join(tmp, "settings.json"), "w") as f:
+        json.dump(settings or SETTINGS, f)
+    env = dict(os.environ)
+    env.pop("SMARTIES_B200", None)
+    if arm == "b200":
+        env["SMARTIES_B200"] = "1"
+    env.update(extra_env or {})
+    t0 = time.perf_counter()
+    p = subprocess.run([exe, "--nTrainSteps", str(steps), "--nThreads", str(threads), "--randSeed", str(seed),
+                        "--nEnvironments", str(envs)], cwd=tmp, env=env, capture_output=True, text=True, timeout=timeout)
+    wall = time.perf_counter() - t0
+    out = {"arm": arm, "app": app, "envs": envs, "host_threads": threads, "rc": p.returncode, "wall_s": round(wall, 2), "steps": steps}
+    rows = []
+    sp = os.path.join(tmp, "agent_00_stats.txt")
+    if os.path.exists(sp):
+        for l in open(sp):
+            f = l.split()
+            if len(f) > 3 and f[0].isdigit():
+                rows.append(f)
+    if rows:   # columns: ID #/T avgR avgr stdr DKL RMSE ... nFarP beta net
+        out["stat_rows"] = len(rows)
+        out["grad_steps_logged"] = 1000 * int(rows[-1][1])      # one row per 1000 gradient steps
+        out["avgR_first"], out["avgR_last"] = float(rows[0][2]), float(rows[-1][2])
+        out["avgR_max"] = max(float(r[2]) for r in rows)
+        out["beta_last"] = float(rows[-1][-2])
+    out["b200_lines"] = [l for l in p.stdout.splitlines() if l.startswith("smarties_b200")]
+    if p.returncode != 0:
+        out["tail"] = (p.stdout[-1500:] + p.stderr[-1500:])
+    shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=20000)
+    ap.add_argument("--threads", type=int, default=min(8, os.cpu_count() or 1))
+    ap.add_argument("--seed", type=int, default=7)
+    ap.add_argument("--arms", default="ref,b200")
+    ap.add_argument("--app", default="cart_pole", choices=["cart_pole", "synth_env"])
+    ap.add_argument("--envs", type=int, default=1)
+    ap.add_argument("--max-steps-per-call", type=int, default=0, help="SMARTIES_B200_MAXSTEPS (0 = binding default)")
+    a = ap.parse_args()
+    xe = {"SMARTIES_B200_MAXSTEPS": str(a.max_steps_per_call)} if a.max_steps_per_call else None
+    for arm in a.arms.split(","):
+        print(json.dumps(run_arm(arm, a.steps, a.threads, a.seed, app=a.app, envs=a.envs, extra_env=xe)), flush=True)
