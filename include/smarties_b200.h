@@ -69,6 +69,8 @@ typedef struct smb200_config {
   int32_t nn_type;                      /* smb200_nn_type: "nnType": "FFNN" | "LSTM" (Layers/Layer_LSTM.h) */
   int32_t nn_bptt_seq;                  /* "nnBPTTseq": recurrent window = min(nnBPTTseq, t) past steps
                                            (ReplayMemory/MemoryBuffer.cpp:393-402) */
+  int64_t min_tot_obs;                  /* minTotObsNum_local = nObsB4StartTraining: only recorded in checkpoints
+                                           ("nInitialData", MemoryBuffer.cpp:300); 0 = max_tot_obs */
 } smb200_config;
 
 /* Per-step scalars the reference prints / feeds back (MemoryBuffer::getMetrics,
@@ -152,9 +154,31 @@ int smb200_reward_state_moments(smb200_learner* h, double* out);
  * ids[nEp], n_rows[nEp], aggregates[nEp][9] = {avgKL, fracFar, avgSqErr, maxAbsErr, sumQ2,
  * sumQ, maxQ, minQ, totR} (Episode.h:77-81). */
 int smb200_read_field(smb200_learner* h, int32_t field, float* out, int64_t n);
+/* Inverse of smb200_read_field (restores per-transition arrays, e.g. from a reference checkpoint). */
+int smb200_write_field(smb200_learner* h, int32_t field, const float* in, int64_t n);
 int smb200_read_episodes(smb200_learner* h, int64_t* ids, int64_t* n_rows, float* aggregates, int64_t n_ep);
 int64_t smb200_n_rows(const smb200_learner* h);
 int smb200_get_stats(smb200_learner* h, smb200_step_stats* out);
+
+/* Checkpoints in the reference's own file formats (byte-compatible both ways; fully observed states):
+ * Learner_approximator::save / restart (Learners/Learner_approximator.cpp:118-142) =
+ *   <base>_net_{weights,tgt_weights,1stMom,2ndMom}.raw   Network::save, padding stripped (Network/Network.cpp:22-67)
+ *   <base>_scaling.raw                                   3*dS + 3 doubles (ReplayMemory/MemoryBuffer.cpp:277-287)
+ *   <base>_rank_XXX_learner_status.raw / _data.raw       counters + packed episodes (MemoryBuffer.cpp:289-324,
+ *                                                        Episode::packEpisode, ReplayMemory/Episode.cpp:24-93)
+ * base = "<dir>/agent_00".  smb200_save also writes the *_backup.raw twins the reference writes.  smb200_restart
+ * needs a freshly created learner; like the reference it accepts a directory that only holds some of the files. */
+int smb200_save(smb200_learner* h, const char* base);
+/* The two pieces of MemoryBuffer::restart a binding needs when the reference itself has read the files
+ * (integration/RACER_B200.cpp): an episode with its stored per-transition values (Episode::unpackEpisode,
+ * Episode.cpp:95-128; aggregates recomputed with cmax like Episode::updateCumulative, return estimates kept),
+ * and the ReF-ER scalars of the status file ("CmaxReFER", "beta", MemoryBuffer.cpp:252-254). */
+int smb200_push_episode_restored(smb200_learner* h, int64_t id, int32_t n_rows, int32_t terminated,
+                                 const float* states, const float* actions, const float* policies, const float* rewards,
+                                 const float* value, const float* advantage, const float* q_ret, const float* delta,
+                                 const float* rho, const float* kl, double cmax);
+int smb200_set_refer(smb200_learner* h, double beta, double cmax);
+int smb200_restart(smb200_learner* h, const char* base);
 
 /* Actor-side policy evaluation (RACER::selectAction, Learners/RACER.cpp:30-47): raw states in,
  * net outputs out[n][nOut]. */

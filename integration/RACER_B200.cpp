@@ -42,6 +42,7 @@
 #include <cstdlib>
 #include <fstream>
 #include <unistd.h>
+#include <unordered_map>
 #include <unordered_set>
 
 namespace smarties
@@ -61,6 +62,11 @@ class RACER_B200 : public RACER<Advantage_t, Continuous_policy, Rvec>
   smb200_learner* gpu = nullptr;
   const bool isRacer;
   std::unordered_set<const Episode*> mirrored;      // episodes already resident in the HBM replay
+  // Episode::ID (a time stamp) is not unique; the device gets ID * 2^20 + sequence number, which keeps the
+  // first-in-first-out order of the reference (ID descending) and identifies the episode for save()
+  std::unordered_map<int64_t, Episode*> byTag;
+  std::unordered_map<const Episode*, int64_t> tagOf;
+  int64_t nextSeq = 0;
   std::vector<float> bufS, bufA, bufMU, bufR, bufV, bufADV, wblob;
   smb200_step_stats last{};
   int maxStepsPerCall = 16;
@@ -109,7 +115,7 @@ class RACER_B200 : public RACER<Advantage_t, Continuous_policy, Rvec>
   }
 
   // Episode (ReplayMemory/Episode.h:40-110) -> the row-major f32 arrays of smb200_push_episode
-  void pushToDevice(const Episode& EP)
+  void pushToDevice(const Episode& EP, const bool restoredValues = false)
   {
     const Uint N = EP.nsteps(), dS = MDP.dimStateObserved, dA = MDP.dimAction, dP = MDP.policyVecDim;
     bufS.assign((size_t) N * dS, 0.f); bufA.assign((size_t) N * dA, 0.f); bufMU.assign((size_t) N * dP, 0.f);
@@ -122,7 +128,17 @@ class RACER_B200 : public RACER<Advantage_t, Continuous_policy, Rvec>
       if (t < EP.stateValue.size())      bufV[t]   = EP.stateValue[t];
       if (t < EP.actionAdvantage.size()) bufADV[t] = EP.actionAdvantage[t];
     }
-    check(smb200_push_episode(gpu, (int64_t) EP.ID, (int32_t) N, EP.bReachedTermState ? 1 : 0, bufS.data(), bufA.data(),
+    const int64_t tag = (int64_t) std::max<Sint>(EP.ID, 0) * (1 << 20) + (nextSeq++ & ((1 << 20) - 1));
+    byTag[tag] = const_cast<Episode*>(&EP); tagOf[&EP] = tag;
+    if (restoredValues) {   // an episode read from a checkpoint: keep its return estimates, TD errors, importance weights
+      std::vector<float> q(EP.returnEstimator.begin(), EP.returnEstimator.end()), d(EP.deltaValue.begin(), EP.deltaValue.end()),
+                         w(EP.offPolicImpW.begin(), EP.offPolicImpW.end()), kl(EP.KullbLeibDiv.begin(), EP.KullbLeibDiv.end());
+      q.resize(N, 0.f); d.resize(N, 0.f); w.resize(N, 0.f); kl.resize(N, 0.f);
+      check(smb200_push_episode_restored(gpu, tag, (int32_t) N, EP.bReachedTermState ? 1 : 0, bufS.data(), bufA.data(), bufMU.data(),
+                                         bufR.data(), bufV.data(), bufADV.data(), q.data(), d.data(), w.data(), kl.data(),
+                                         (double) data->CmaxRet), "push_episode_restored");
+    } else
+    check(smb200_push_episode(gpu, tag, (int32_t) N, EP.bReachedTermState ? 1 : 0, bufS.data(), bufA.data(),
                               bufMU.data(), bufR.data(), bufV.data(), bufADV.data()), "push_episode");
     ++nPushed;
   }
@@ -138,7 +154,10 @@ class RACER_B200 : public RACER<Advantage_t, Continuous_policy, Rvec>
               [](const std::unique_ptr<Episode>& a, const std::unique_ptr<Episode>& b) { return a->ID > b->ID; });
     const long maxTotObs = settings.maxTotObsNum_local;
     while (data->episodes.size() > 1 && data->nStoredSteps() - (long) data->episodes.back()->nsteps() > maxTotObs) {
-      mirrored.erase(data->episodes.back().get());
+      const Episode* gone = data->episodes.back().get();
+      mirrored.erase(gone);
+      const auto it = tagOf.find(gone);
+      if (it != tagOf.end()) { byTag.erase(it->second); tagOf.erase(it); }
       data->removeBackEpisode();
       data->stats.nPrunedEps++;
     }
@@ -186,6 +205,69 @@ class RACER_B200 : public RACER<Advantage_t, Continuous_policy, Rvec>
              "%.3f s of wall clock since training started\n",
              (long) data->nGradSteps(), nPushed, secPush, secStep, secSync, tTrainStart > 0 ? now() - tTrainStart : 0.0);
     smb200_destroy(gpu);
+  }
+
+  // Learner_approximator::save (Learner_approximator.cpp:133-142): the reference's own writers produce the files;
+  // what lives on the device (Adam moments, per-transition values of the replay) is copied into the host objects first.
+  void save() override
+  {
+    AdamOptimizer* const adam = dynamic_cast<AdamOptimizer*>(networks[0]->opt.get());
+    Parameters* M1 = adam ? adam->_1stMom.get() : nullptr, * M2 = adam ? adam->_2ndMom.get() : nullptr;
+    if (M1 && M2) check(smb200_get_adam(gpu, M1->params, M2->params, (int64_t) M1->nParams), "get_adam");
+    {
+      std::lock_guard<std::mutex> lock(data->dataset_mutex);
+      const int64_t nEp = smb200_n_episodes(gpu), nRows = smb200_n_rows(gpu);
+      std::vector<int64_t> ids(nEp), rows(nEp);
+      check(smb200_read_episodes(gpu, ids.data(), rows.data(), nullptr, nEp), "read_episodes");
+      std::vector<float> F[6];
+      const int fid[6] = {SMB200_F_V, SMB200_F_ADV, SMB200_F_QRET, SMB200_F_DELTA, SMB200_F_RHO, SMB200_F_KL};
+      for (int k = 0; k < 6; ++k) { F[k].resize(nRows); check(smb200_read_field(gpu, fid[k], F[k].data(), nRows), "read_field"); }
+      int64_t o = 0;
+      for (int64_t e = 0; e < nEp; ++e) {
+        const auto it = byTag.find(ids[e]);
+        const int64_t N = rows[e];
+        if (it != byTag.end() && (int64_t) it->second->nsteps() == N) {
+          Episode& EP = * it->second;
+          EP.stateValue.assign(F[0].begin() + o, F[0].begin() + o + N);
+          EP.actionAdvantage.assign(F[1].begin() + o, F[1].begin() + o + N);
+          EP.returnEstimator.assign(F[2].begin() + o, F[2].begin() + o + N);
+          EP.deltaValue.assign(F[3].begin() + o, F[3].begin() + o + N);
+          EP.offPolicImpW.assign(F[4].begin() + o, F[4].begin() + o + N);
+          EP.KullbLeibDiv.assign(F[5].begin() + o, F[5].begin() + o + N);
+        }
+        o += N;
+      }
+    }
+    Base::save();
+  }
+
+  // Learner_approximator::restart (Learner_approximator.cpp:118-131): the reference's own readers fill the host network,
+  // optimiser, MDP scaling, counters and episodes; the device learner is then loaded from those objects.
+  void restart() override
+  {
+    Base::restart();
+    Parameters* W = hostWeights();
+    check(smb200_set_weights(gpu, W->params, W->nParams), "set_weights");
+    if (data->nGradSteps() <= 0 && data->nStoredEps() == 0) return;      // nothing but (maybe) a policy was found
+    AdamOptimizer* const adam = dynamic_cast<AdamOptimizer*>(networks[0]->opt.get());
+    Parameters* M1 = adam ? adam->_1stMom.get() : nullptr, * M2 = adam ? adam->_2ndMom.get() : nullptr;
+    if (M1 && M2) check(smb200_set_adam(gpu, M1->params, M2->params, (int64_t) M1->nParams, data->nGradSteps()), "set_adam");
+    const Uint dS = MDP.dimStateObserved;
+    std::vector<float> mean(MDP.stateMean.begin(), MDP.stateMean.end()), scale(MDP.stateScale.begin(), MDP.stateScale.end()),
+                       stdev(MDP.stateStdDev.begin(), MDP.stateStdDev.end());
+    mean.resize(dS, 0.f); scale.resize(dS, 1.f); stdev.resize(dS, 1.f);
+    const float rew[3] = {(float) MDP.rewardsMean, (float) MDP.rewardsScale, (float) MDP.rewardsStdDev};
+    check(smb200_set_scaling(gpu, mean.data(), scale.data(), stdev.data(), rew), "set_scaling");
+    {
+      std::lock_guard<std::mutex> lock(data->dataset_mutex);
+      for (const auto& e : data->episodes)
+        if (mirrored.insert(e.get()).second) pushToDevice(*e, true);
+    }
+    check(smb200_set_grad_step(gpu, data->nGradSteps()), "set_grad_step");
+    check(smb200_set_refer(gpu, data->beta, data->CmaxRet), "set_refer");
+    if (distrib.world_rank == 0)
+      printf("smarties_b200: restarted the device learner at gradient step %ld with %ld episodes (%ld transitions)\n",
+             (long) data->nGradSteps(), (long) smb200_n_episodes(gpu), (long) smb200_n_transitions(gpu));
   }
 
   void setupTasks(TaskQueue& tasks) override

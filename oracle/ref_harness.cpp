@@ -81,8 +81,8 @@ struct SynthData {
 };
 
 struct Args {
-  std::string data, settings, dump, weights;
-  int steps = 10, threads = 1, bounded = 0, dumpAll = 0, quiet = 0, reps = 1;
+  std::string data, settings, dump, weights, restart;
+  int steps = 10, threads = 1, bounded = 0, dumpAll = 0, quiet = 0, reps = 1, save = 0;
   long startStep = 0;
   unsigned long seed = 42, sampleSeed = 0;
   std::set<long> dumpSteps;
@@ -105,6 +105,8 @@ static Args parse(int argc, char** argv) {
     else if(k=="--sampleSeed") a.sampleSeed = std::stoul(next());
     else if(k=="--dumpAll") a.dumpAll = 1;
     else if(k=="--quiet") a.quiet = 1;
+    else if(k=="--save") a.save = 1;                 // Learner_approximator::save() after the last step (files agent_00_* in the cwd)
+    else if(k=="--restart") a.restart = next();      // Learner_approximator::restart() from that directory instead of filling the buffer
     else if(k=="--reps") a.reps = std::stoi(next());
     else if(k=="--dumpSteps") { std::stringstream ss(next()); std::string tok; while(std::getline(ss, tok, ',')) a.dumpSteps.insert(std::stol(tok)); }
     else { fprintf(stderr, "unknown arg %s\n", k.c_str()); exit(1); }
@@ -185,7 +187,9 @@ struct Probe : public Base
     MDPdescriptor& MDP = data->MDP;
     const Uint dA = MDP.dimAction, dP = MDP.policyVecDim;
     // ---- fill the replay memory (recipe: SURVEY.md §8c) ----
-    for(int64_t e=0; e<SD.nEp; ++e) {
+    const bool restarted = args.restart.size() > 0;
+    if(restarted) { distrib.restart = args.restart; this->restart(); }    // Learner_approximator.cpp:118-131
+    for(int64_t e=0; e<SD.nEp && !restarted; ++e) {
       std::unique_ptr<Episode> EP = std::make_unique<Episode>(MDP);
       const int64_t N = SD.N[e], o = SD.start[e];
       for(int64_t t=0; t<N; ++t) {
@@ -241,8 +245,10 @@ struct Probe : public Base
 
     // start the gradient-step counter where asked (so that short runs cover the every-1000-steps
     // sweeps); Adam's own step counter follows as in a restart (Approximator.h:64)
-    data->counters.nGradSteps = args.startStep;
-    networks[0]->setNgradSteps(args.startStep);
+    if(!restarted) {
+      data->counters.nGradSteps = args.startStep;
+      networks[0]->setNgradSteps(args.startStep);
+    }
     if(args.sampleSeed) distrib.generators[0].seed(args.sampleSeed);
 
     recO.assign(B*nOut, 0); recG.assign(B*nOut, 0); recS.assign(B*dS, 0); recT.assign(B, 0); recEp.assign(B, 0);
@@ -290,6 +296,7 @@ struct Probe : public Base
       dumpTransitions(D, "final"); dumpScaling(D, "final"); dumpRefer(D, "final");
       D.close();
     }
+    if(args.save) this->save();     // Learner_approximator::save (Learner_approximator.cpp:133-142)
     if(!args.quiet) printf("%s\n", profiler->printStatAndReset().c_str());
     const double medSec = totSec / args.reps;
     printf("{\"harness\": \"reference\", \"steps\": %d, \"reps\": %d, \"threads\": %d, \"batch\": %lu, "

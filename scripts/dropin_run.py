@@ -23,11 +23,14 @@ SETTINGS = {"learner": "VRACER", "dataSamplingAlgo": "uniform", "returnsEstimato
             "nnLayerSizes": [128, 128]}     # == settings/VRACER.json of the reference
 
 
-def run_arm(arm, steps, threads, seed, settings=None, timeout=1500, app="cart_pole", envs=1, extra_env=None):
+def run_arm(arm, steps, threads, seed, settings=None, timeout=1500, app="cart_pole", envs=1, extra_env=None,
+            keep_dir=None, restart=None):
+    """keep_dir: run there and keep the files (checkpoints); restart: directory of an earlier run (--restart)."""
     exe = os.path.join(ROOT, "oracle", "_ref", "b200" if arm == "b200" else "", app)
     if not os.path.exists(exe):
         return {"arm": arm, "error": f"{exe} missing (make -C integration)"}
-    tmp = tempfile.mkdtemp(prefix=f"cartpole_{arm}_")
+    tmp = keep_dir or tempfile.mkdtemp(prefix=f"cartpole_{arm}_")
+    os.makedirs(tmp, exist_ok=True)
     with open(os.path.join(tmp, "settings.json"), "w") as f:
         json.dump(settings or SETTINGS, f)
     env = dict(os.environ)
@@ -37,7 +40,8 @@ def run_arm(arm, steps, threads, seed, settings=None, timeout=1500, app="cart_po
     env.update(extra_env or {})
     t0 = time.perf_counter()
     p = subprocess.run([exe, "--nTrainSteps", str(steps), "--nThreads", str(threads), "--randSeed", str(seed),
-                        "--nEnvironments", str(envs)], cwd=tmp, env=env, capture_output=True, text=True, timeout=timeout)
+                        "--nEnvironments", str(envs)] + (["--restart", restart] if restart else []),
+                       cwd=tmp, env=env, capture_output=True, text=True, timeout=timeout)
     wall = time.perf_counter() - t0
     out = {"arm": arm, "app": app, "envs": envs, "host_threads": threads, "rc": p.returncode, "wall_s": round(wall, 2), "steps": steps}
     rows = []
@@ -54,9 +58,11 @@ def run_arm(arm, steps, threads, seed, settings=None, timeout=1500, app="cart_po
         out["avgR_max"] = max(float(r[2]) for r in rows)
         out["beta_last"] = float(rows[-1][-2])
     out["b200_lines"] = [l for l in p.stdout.splitlines() if l.startswith("smarties_b200")]
+    out["restart_lines"] = sorted(set(l for l in p.stdout.splitlines() if l.startswith("Restarting from file")))
     if p.returncode != 0:
         out["tail"] = (p.stdout[-1500:] + p.stderr[-1500:])
-    shutil.rmtree(tmp, ignore_errors=True)
+    if not keep_dir:
+        shutil.rmtree(tmp, ignore_errors=True)
     return out
 
 

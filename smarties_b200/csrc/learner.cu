@@ -41,6 +41,7 @@ struct EpisodeMeta {
   int slot;
   long long start; // first ring row
   int terminated;
+  int agentId;     // Episode::agentID (only carried through checkpoints)
 };
 
 template <typename T>
@@ -72,6 +73,9 @@ struct smb200_learner {
   std::map<long long, long long> liveRanges;   // start -> end (exclusive) of live ring ranges
   long long head = 0, highWater = 0;
   long long nTransitions = 0;
+  long long nGatheredB4Startup = 0;       // counters.nGatheredB4Startup, set by initializeLearner (Learner.cpp:60)
+  long long nSeenEps = 0, nSeenObs = 0;   // counters.nSeenEpisodes_loc / nSeenTransitions_loc (ReplayStatsCounters.h:43-50)
+  std::vector<float> tgtBlob;             // AdamOptimizer::target_weights: with targetDelay 0 the weights at construction / restart
   bool orderDirty = true;
 
   // network / optimiser
@@ -574,6 +578,7 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
   std::vector<float> blob;
   init_weights(c, net, h->gen, blob);
   CK(upload_weights(h, blob.data()));
+  h->tgtBlob = blob;
   CK(step_kernels_prepare(net));
   { const char* t = getenv("SMB200_TMA"); h->useTma = (t && strcmp(t, "0") == 0) ? 0 : 1; }
   const char* m = getenv("SMB200_MODE");
@@ -623,6 +628,9 @@ int64_t smb200_n_rows(const smb200_learner* h) {
 int smb200_set_weights(smb200_learner* h, const float* blob, int64_t n) {
   if (!h || !blob || n != h->descs.net.nParams) return SMB200_ERR_INVALID;
   cudaSetDevice(h->cfg.device);
+  // target weights (unused by RACER with targetDelay 0, but part of the checkpoint): they follow the weights
+  // until training starts, like `target_weights->copy(weights)` of a restart without a tgt file (Optimizer.cpp:207-210)
+  if (h->gradStep == 0) h->tgtBlob.assign(blob, blob + n);
   return upload_weights(h, blob);
 }
 static int d2h(smb200_learner* h, void* dst, const void* src, size_t bytes) {
@@ -674,8 +682,12 @@ int smb200_get_scaling(smb200_learner* h, float* mean, float* scale, float* stde
   return 0;
 }
 
-int smb200_push_episode(smb200_learner* h, int64_t id, int32_t N, int32_t terminated, const float* S, const float* A,
-                        const float* MU, const float* R, const float* V, const float* ADV) {
+// `restored` (may be null): {Q, DELTA, RHO, KL} of a checkpointed episode (Episode::unpackEpisode, Episode.cpp:95-128):
+// copied as they are; the aggregates are recomputed with (cmax, cinv) like MemoryBuffer::restart does
+// (Episode::updateCumulative, MemoryBuffer.cpp:257) and the return estimate is NOT re-evaluated.
+static int push_episode_impl(smb200_learner* h, int64_t id, int32_t N, int32_t terminated, const float* S, const float* A,
+                             const float* MU, const float* R, const float* V, const float* ADV, const float* const* restored,
+                             float cmax, float cinv) {
   if (!h || N < 2 || !S || !A || !MU || !R) { set_error_msg("push_episode: an episode needs at least s0 and sT"); return SMB200_ERR_INVALID; }
   cudaSetDevice(h->cfg.device);
   if (h->freeSlots.empty()) { set_error_msg("episode table full"); return SMB200_ERR_CAPACITY; }
@@ -706,15 +718,28 @@ int smb200_push_episode(smb200_learner* h, int64_t id, int32_t N, int32_t termin
   if (h->initialized && pull_ctrl(h)) return SMB200_ERR_CUDA;
   const float deltaInit = (float)std::sqrt(std::max((double)FLT_EPSILON, h->hCtrl.avg_sq_err));
   if (launch_init_episode(rp, slot, deltaInit, V != nullptr, st)) return SMB200_ERR_CUDA;
-  // computeReturnEstimator at insertion (MemoryBuffer.cpp:143)
-  if (launch_sweep(rp, 0, slot, (float)h->cfg.gamma, (float)h->cfg.lambda, 0, 0.f, 0.f, nullptr, st)) return SMB200_ERR_CUDA;
+  if (restored) {
+    float* dst[4] = {rp.Q, rp.DELTA, rp.RHO, rp.KL};
+    for (int k = 0; k < 4; ++k)
+      SMB200_CUDA_CHECK(cudaMemcpyAsync(dst[k] + start, restored[k], sizeof(float) * (size_t)N, cudaMemcpyHostToDevice, st));
+    if (launch_sweep(rp, 0, slot, (float)h->cfg.gamma, (float)h->cfg.lambda, 2, cmax, cinv, nullptr, st)) return SMB200_ERR_CUDA;
+  } else {
+    // computeReturnEstimator at insertion (MemoryBuffer.cpp:143)
+    if (launch_sweep(rp, 0, slot, (float)h->cfg.gamma, (float)h->cfg.lambda, 0, 0.f, 0.f, nullptr, st)) return SMB200_ERR_CUDA;
+  }
   SMB200_CUDA_CHECK(cudaStreamSynchronize(st));   // host buffers are the caller's: finish the copies
   h->episodes.push_back(EpisodeMeta{id, N, slot, start, terminated ? 1 : 0});
   h->liveRanges[start] = start + N;
   h->head = start + N; h->highWater = std::max(h->highWater, start + N);
   h->nTransitions += N - 1;
+  h->nSeenEps += 1; h->nSeenObs += N - 1;
   h->orderDirty = true; h->lookupDirty = true; h->presampled = 0;
   return 0;
+}
+
+int smb200_push_episode(smb200_learner* h, int64_t id, int32_t N, int32_t terminated, const float* S, const float* A,
+                        const float* MU, const float* R, const float* V, const float* ADV) {
+  return push_episode_impl(h, id, N, terminated, S, A, MU, R, V, ADV, nullptr, 0.f, 0.f);
 }
 
 int smb200_initialize_learner(smb200_learner* h) {
@@ -748,6 +773,7 @@ int smb200_initialize_learner(smb200_learner* h) {
     return SMB200_ERR_CUDA;
   SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   h->initialized = true;
+  h->nGatheredB4Startup = h->cfg.min_tot_obs > 0 ? h->cfg.min_tot_obs : h->cfg.max_tot_obs;
   return 0;
 }
 
@@ -1117,6 +1143,281 @@ int smb200_forward(smb200_learner* h, const float* states, int32_t n, float* out
   if (!rc) rc = d2h(h, outputs, dOut, sizeof(float) * (size_t)n * nOut);
   cudaFree(dIn); cudaFree(dOut);
   return rc ? SMB200_ERR_CUDA : 0;
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// Checkpoint files of the reference (row f2): Learner_approximator::save / restart
+// (Learners/Learner_approximator.cpp:118-142) = Network::save/restart of weights, target weights and
+// the two Adam moments (Network/Network.cpp:22-67, Optimizer.cpp:180-215; per layer, padding
+// stripped: Layer_Base.h:143-169, Layers.h:401-418,554-566, Layer_LSTM.h:189-211) +
+// MemoryBuffer::save/restart (ReplayMemory/MemoryBuffer.cpp:172-324: scaling, counters, episodes
+// packed by Episode::packEpisode, Episode.cpp:24-93).  Byte-compatible both ways for MDPs whose
+// state is fully observed (the device replay does not store latent state components).
+// =============================================================================================
+namespace smb200 {
+
+static size_t stripped_size(const NetDesc& net) {
+  size_t n = 0;
+  for (int l = 1; l < net.nLayers; ++l) {
+    const LayerDesc& L = net.L[l];
+    if (L.kind == kDenseTanh || L.kind == kDenseLinear) n += (size_t)L.size * (L.nIn + 1);
+    else if (L.kind == kLSTM) n += (size_t)4 * L.size * (L.nIn + L.size + 1);
+    else if (L.kind == kResidual) n += 2 * (size_t)L.size;
+    else if (L.kind == kParam) n += L.size;
+  }
+  return n;
+}
+// dir = +1: padded blob -> file order; dir = -1: file order -> padded blob
+static void strip_copy(const NetDesc& net, float* blob, float* flat, int dir) {
+  size_t o = 0;
+  auto mv = [&](int blobIdx) { if (dir > 0) flat[o] = blob[blobIdx]; else blob[blobIdx] = flat[o]; ++o; };
+  for (int l = 1; l < net.nLayers; ++l) {
+    const LayerDesc& L = net.L[l];
+    if (L.kind == kDenseTanh || L.kind == kDenseLinear) {
+      for (int i = 0; i < L.nIn; ++i) for (int n = 0; n < L.size; ++n) mv(L.wOff + n + L.ld * i);
+      for (int n = 0; n < L.size; ++n) mv(L.bOff + n);
+    } else if (L.kind == kLSTM) {
+      for (int w = 0; w < 4 * L.size * (L.nIn + L.size); ++w) mv(L.wOff + w);
+      for (int n = 0; n < 4 * L.size; ++n) mv(L.bOff + n);
+    } else if (L.kind == kResidual) {
+      for (int n = 0; n < L.size; ++n) mv(L.wOff + n);
+      for (int n = 0; n < L.size; ++n) mv(L.bOff + n);
+    } else if (L.kind == kParam) {
+      for (int n = 0; n < L.size; ++n) mv(L.bOff + n);
+    }
+  }
+}
+// the reference writes <name>_backup.raw first and then copies it to <name>.raw (Network.cpp:27-39)
+static int write_both(const std::string& stem, const void* data, size_t bytes, bool text = false) {
+  for (const char* suffix : {"_backup.raw", ".raw"}) {
+    FILE* f = fopen((stem + suffix).c_str(), text ? "w" : "wb");
+    if (!f) { set_error_msg(("cannot write " + stem + suffix).c_str()); return -1; }
+    const size_t w = fwrite(data, 1, bytes, f);
+    fclose(f);
+    if (w != bytes) { set_error_msg(("short write on " + stem + suffix).c_str()); return -1; }
+  }
+  return 0;
+}
+static int read_all(const std::string& path, std::vector<unsigned char>& out) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return 1;
+  fseek(f, 0, SEEK_END); const long n = ftell(f); fseek(f, 0, SEEK_SET);
+  out.resize(n > 0 ? (size_t)n : 0);
+  const size_t r = out.empty() ? 0 : fread(out.data(), 1, out.size(), f);
+  fclose(f);
+  return r == out.size() ? 0 : -1;
+}
+static const float* field_ptr(const ReplayView& rp, int field) {
+  switch (field) {
+    case SMB200_F_V: return rp.V;         case SMB200_F_ADV: return rp.ADV;   case SMB200_F_QRET: return rp.Q;
+    case SMB200_F_DELTA: return rp.DELTA; case SMB200_F_RHO: return rp.RHO;   case SMB200_F_KL: return rp.KL;
+    case SMB200_F_REWARD: return rp.R;    default: return nullptr;
+  }
+}
+
+}  // namespace smb200
+
+extern "C" {
+
+int smb200_write_field(smb200_learner* h, int32_t field, const float* in, int64_t n) {
+  if (!h || !in || n != smb200_n_rows(h)) return SMB200_ERR_INVALID;
+  float* dst = const_cast<float*>(field_ptr(h->rp, field));
+  if (!dst) return SMB200_ERR_INVALID;
+  cudaSetDevice(h->cfg.device);
+  int64_t o = 0;
+  for (const auto& e : h->episodes) {
+    SMB200_CUDA_CHECK(cudaMemcpyAsync(dst + e.start, in + o, sizeof(float) * e.nRows, cudaMemcpyHostToDevice, h->stream));
+    o += e.nRows;
+  }
+  SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int smb200_push_episode_restored(smb200_learner* h, int64_t id, int32_t N, int32_t terminated, const float* S, const float* A,
+                                 const float* MU, const float* R, const float* V, const float* ADV, const float* Q,
+                                 const float* DELTA, const float* RHO, const float* KL, double cmax) {
+  if (!V || !ADV || !Q || !DELTA || !RHO || !KL || !(cmax > 0)) return SMB200_ERR_INVALID;
+  const float* rest[4] = {Q, DELTA, RHO, KL};
+  return push_episode_impl(h, id, N, terminated, S, A, MU, R, V, ADV, rest, (float)cmax, (float)(1.0 / cmax));
+}
+
+int smb200_set_refer(smb200_learner* h, double beta, double cmax) {
+  if (!h || !(cmax > 0) || beta < 0 || beta > 1) return SMB200_ERR_INVALID;
+  cudaSetDevice(h->cfg.device);
+  if (pull_ctrl(h)) return SMB200_ERR_CUDA;
+  h->hCtrl.beta = beta; h->hCtrl.cmax = cmax; h->hCtrl.cinv = 1.0 / cmax;
+  h->initialized = true;
+  return push_ctrl(h);
+}
+
+int smb200_save(smb200_learner* h, const char* base_c) {
+  if (!h || !base_c) return SMB200_ERR_INVALID;
+  cudaSetDevice(h->cfg.device);
+  const std::string base(base_c);
+  const NetDesc& net = h->descs.net;
+  const size_t nP = net.nParams, nF = stripped_size(net);
+  // ---- Approximator::save -> AdamOptimizer::save (Optimizer.cpp:180-197) ----
+  std::vector<float> blob(nP), flat(nF);
+  const float* src[4] = {h->W, nullptr, h->M1, h->M2};
+  const char* name[4] = {"_net_weights", "_net_tgt_weights", "_net_1stMom", "_net_2ndMom"};
+  for (int k = 0; k < 4; ++k) {
+    if (src[k]) { if (d2h(h, blob.data(), src[k], sizeof(float) * nP)) return SMB200_ERR_CUDA; }
+    else blob = h->tgtBlob;
+    strip_copy(net, blob.data(), flat.data(), +1);
+    if (write_both(base + name[k], flat.data(), sizeof(float) * nF)) return SMB200_ERR_STATE;
+  }
+  // ---- MemoryBuffer::save (MemoryBuffer.cpp:267-324) ----
+  const int dS = h->cfg.dim_state, dA = h->cfg.dim_action, dP = 2 * dA;
+  {
+    std::vector<float> mean(dS), scale(dS), stdev(dS); float rew[4];
+    if (smb200_get_scaling(h, mean.data(), scale.data(), stdev.data(), rew)) return SMB200_ERR_CUDA;
+    std::vector<double> V;
+    V.insert(V.end(), mean.begin(), mean.end()); V.insert(V.end(), scale.begin(), scale.end()); V.insert(V.end(), stdev.begin(), stdev.end());
+    V.push_back((double)rew[2]); V.push_back((double)rew[1]); V.push_back((double)rew[0]);    // rewardsStdDev, rewardsScale, rewardsMean
+    if (write_both(base + "_scaling", V.data(), sizeof(double) * V.size())) return SMB200_ERR_STATE;
+  }
+  if (pull_ctrl(h)) return SMB200_ERR_CUDA;
+  char rk[16]; snprintf(rk, sizeof(rk), "%03d", h->cfg.world_rank);
+  const std::string stem = base + "_rank_" + rk + "_learner_";
+  {
+    char txt[512];
+    // `doneGradSteps = counters.nGradSteps + 1`: Learner::save runs inside logStats, before the step counter moves
+    const int len = snprintf(txt, sizeof(txt), "nStoredEps: %lu\nnStoredObs: %lu\nnLocalSeenEps: %lu\nnLocalSeenObs: %lu\n"
+                             "nInitialData: %ld\nnGradSteps: %ld\nCmaxReFER: %le\nbeta: %le\n",
+                             (unsigned long)h->episodes.size(), (unsigned long)h->nTransitions, (unsigned long)h->nSeenEps,
+                             (unsigned long)h->nSeenObs, (long)h->nGatheredB4Startup, (long)(h->gradStep + 1), h->hCtrl.cmax, h->hCtrl.beta);
+    if (write_both(stem + "status", txt, (size_t)len, true)) return SMB200_ERR_STATE;
+  }
+  {
+    const long long hw = h->highWater;
+    std::vector<float> S((size_t)hw * dS), A((size_t)hw * dA), MU((size_t)hw * dP), F[7];
+    if (d2h(h, S.data(), h->rp.S, sizeof(float) * S.size()) || d2h(h, A.data(), h->rp.A, sizeof(float) * A.size()) ||
+        d2h(h, MU.data(), h->rp.MU, sizeof(float) * MU.size())) return SMB200_ERR_CUDA;
+    const int fid[7] = {SMB200_F_REWARD, SMB200_F_QRET, SMB200_F_ADV, SMB200_F_V, SMB200_F_DELTA, SMB200_F_RHO, SMB200_F_KL};
+    for (int k = 0; k < 7; ++k) { F[k].resize(hw); if (d2h(h, F[k].data(), field_ptr(h->rp, fid[k]), sizeof(float) * hw)) return SMB200_ERR_CUDA; }
+    std::vector<unsigned char> out;
+    for (const auto& e : h->episodes) {
+      const size_t N = e.nRows, tot = (size_t)(dS + dA + dP + 1 + 6) * N + 10;    // Episode::computeTotalEpisodeSize (Episode.h:211-219)
+      std::vector<float> buf(tot, 0.f);
+      float* b = buf.data();
+      for (size_t t = 0; t < N; ++t) {
+        const size_t r = (size_t)e.start + t;
+        memcpy(b, S.data() + r * dS, sizeof(float) * dS); b[dS] = F[0][r]; b += dS + 1;
+        memcpy(b, A.data() + r * dA, sizeof(float) * dA); b += dA;
+        memcpy(b, MU.data() + r * dP, sizeof(float) * dP); b += dP;
+      }
+      for (int k = 1; k < 7; ++k) { memcpy(b, F[k].data() + e.start, sizeof(float) * N); b += N; }
+      char* c = reinterpret_cast<char*>(b);
+      const bool term = e.terminated != 0; const ptrdiff_t id = (ptrdiff_t)e.id, js = -1, ag = (ptrdiff_t)e.agentId;
+      memcpy(c, &term, sizeof(bool)); c += sizeof(bool);
+      memcpy(c, &id, sizeof(ptrdiff_t)); c += sizeof(ptrdiff_t);
+      memcpy(c, &js, sizeof(ptrdiff_t)); c += sizeof(ptrdiff_t);      // just_sampled: reset by updateTrainingStatistics every step
+      memcpy(c, &ag, sizeof(ptrdiff_t));
+      const size_t seqLen = N;
+      const unsigned char* p0 = reinterpret_cast<const unsigned char*>(&seqLen);
+      out.insert(out.end(), p0, p0 + sizeof(size_t));
+      const unsigned char* p1 = reinterpret_cast<const unsigned char*>(buf.data());
+      out.insert(out.end(), p1, p1 + sizeof(float) * tot);
+    }
+    if (write_both(stem + "data", out.data(), out.size())) return SMB200_ERR_STATE;
+  }
+  return 0;
+}
+
+int smb200_restart(smb200_learner* h, const char* base_c) {
+  if (!h || !base_c) return SMB200_ERR_INVALID;
+  if (!h->episodes.empty() || h->gradStep != 0) { set_error_msg("restart needs a freshly created learner"); return SMB200_ERR_STATE; }
+  cudaSetDevice(h->cfg.device);
+  const std::string base(base_c);
+  const NetDesc& net = h->descs.net;
+  const size_t nP = net.nParams, nF = stripped_size(net);
+  std::vector<unsigned char> raw;
+  // ---- AdamOptimizer::restart (Optimizer.cpp:199-215): weights are mandatory, the rest optional ----
+  std::vector<float> blob(nP, 0.f), m1(nP, 0.f), m2(nP, 0.f);
+  auto load_net = [&](const char* name, std::vector<float>& dst) -> int {
+    const int rc = read_all(base + name + ".raw", raw);
+    if (rc) return rc;
+    if (raw.size() != sizeof(float) * nF) { set_error_msg((std::string("Mismatch in restarted file ") + base + name).c_str()); return -1; }
+    strip_copy(net, dst.data(), reinterpret_cast<float*>(raw.data()), -1);
+    return 0;
+  };
+  if (d2h(h, blob.data(), h->W, sizeof(float) * nP)) return SMB200_ERR_CUDA;     // padding keeps its current (zero) content
+  int rc = load_net("_net_weights", blob);
+  if (rc > 0) { set_error_msg(("Parameters restart file " + base + "_net_weights.raw not found").c_str()); return SMB200_ERR_STATE; }
+  if (rc < 0) return SMB200_ERR_STATE;
+  if (upload_weights(h, blob.data())) return SMB200_ERR_CUDA;
+  h->tgtBlob = blob;
+  { std::vector<float> t = blob; const int r2 = load_net("_net_tgt_weights", t); if (r2 < 0) return SMB200_ERR_STATE; if (r2 == 0) h->tgtBlob = t; }
+  if (load_net("_net_1stMom", m1) < 0 || load_net("_net_2ndMom", m2) < 0) return SMB200_ERR_STATE;
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(h->M1, m1.data(), sizeof(float) * nP, cudaMemcpyHostToDevice, h->stream));
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(h->M2, m2.data(), sizeof(float) * nP, cudaMemcpyHostToDevice, h->stream));
+  SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  // ---- MemoryBuffer::restart (MemoryBuffer.cpp:172-265) ----
+  const int dS = h->cfg.dim_state, dA = h->cfg.dim_action, dP = 2 * dA;
+  if (read_all(base + "_scaling.raw", raw)) return 0;                  // "Parameters restart file ... not found": nothing else is read
+  if (raw.size() != sizeof(double) * (3 * (size_t)dS + 3)) { set_error_msg("Mismatch in restarted file _scaling.raw"); return SMB200_ERR_STATE; }
+  {
+    const double* V = reinterpret_cast<const double*>(raw.data());
+    std::vector<float> mean(V, V + dS), scale(V + dS, V + 2 * dS), stdev(V + 2 * dS, V + 3 * dS);
+    const float rew[3] = {(float)V[3 * dS + 2], (float)V[3 * dS + 1], (float)V[3 * dS + 0]};
+    if (smb200_set_scaling(h, mean.data(), scale.data(), stdev.data(), rew)) return SMB200_ERR_CUDA;
+  }
+  char rk[16]; snprintf(rk, sizeof(rk), "%03d", h->cfg.world_rank);
+  const std::string stem = base + "_rank_" + rk + "_learner_";
+  FILE* fs = fopen((stem + "status.raw").c_str(), "r");
+  std::vector<unsigned char> dat;
+  if (!fs || read_all(stem + "data.raw", dat)) { if (fs) fclose(fs); return 0; }   // scaling only (evaluation runs)
+  unsigned long nEps = 0, nObs = 0, seenEps = 0, seenObs = 0; long nInit = 0, grad = 0; double cmax = 0, beta = 0;
+  int pass = 1;
+  pass = pass && 1 == fscanf(fs, "nStoredEps: %lu\n", &nEps);     pass = pass && 1 == fscanf(fs, "nStoredObs: %lu\n", &nObs);
+  pass = pass && 1 == fscanf(fs, "nLocalSeenEps: %lu\n", &seenEps); pass = pass && 1 == fscanf(fs, "nLocalSeenObs: %lu\n", &seenObs);
+  pass = pass && 1 == fscanf(fs, "nInitialData: %ld\n", &nInit);    pass = pass && 1 == fscanf(fs, "nGradSteps: %ld\n", &grad);
+  pass = pass && 1 == fscanf(fs, "CmaxReFER: %le\n", &cmax);        pass = pass && 1 == fscanf(fs, "beta: %le\n", &beta);
+  fclose(fs);
+  if (!pass || grad < 0) { set_error_msg("malformed learner_status.raw"); return SMB200_ERR_STATE; }
+  const float C = (float)cmax, invC = (float)(1.0 / cmax);
+  size_t pos = 0;
+  std::vector<float> S, A, MU, R;
+  for (unsigned long e = 0; e < nEps; ++e) {
+    if (pos + sizeof(size_t) > dat.size()) { set_error_msg("Unable to find sequence in learner_data.raw"); return SMB200_ERR_STATE; }
+    size_t N; memcpy(&N, dat.data() + pos, sizeof(size_t)); pos += sizeof(size_t);
+    const size_t tot = (size_t)(dS + dA + dP + 1 + 6) * N + 10;
+    if (N < 2 || pos + sizeof(float) * tot > dat.size()) { set_error_msg("mismatch in learner_data.raw"); return SMB200_ERR_STATE; }
+    const float* b = reinterpret_cast<const float*>(dat.data() + pos); pos += sizeof(float) * tot;
+    S.resize(N * dS); A.resize(N * dA); MU.resize(N * dP); R.resize(N);
+    for (size_t t = 0; t < N; ++t) {
+      memcpy(S.data() + t * dS, b, sizeof(float) * dS); R[t] = b[dS]; b += dS + 1;
+      memcpy(A.data() + t * dA, b, sizeof(float) * dA); b += dA;
+      memcpy(MU.data() + t * dP, b, sizeof(float) * dP); b += dP;
+    }
+    const float* Q = b; const float* ADV = b + N; const float* V = b + 2 * N;
+    const float* rest[4] = {Q, b + 3 * N, b + 4 * N, b + 5 * N};    // Q, delta, rho, KL
+    const char* c = reinterpret_cast<const char*>(b + 6 * N);
+    bool term; ptrdiff_t id, js, ag;
+    memcpy(&term, c, sizeof(bool)); c += sizeof(bool);
+    memcpy(&id, c, sizeof(ptrdiff_t)); c += sizeof(ptrdiff_t);
+    memcpy(&js, c, sizeof(ptrdiff_t)); c += sizeof(ptrdiff_t);
+    memcpy(&ag, c, sizeof(ptrdiff_t));
+    const int r2 = push_episode_impl(h, (int64_t)id, (int32_t)N, term ? 1 : 0, S.data(), A.data(), MU.data(), R.data(), V, ADV, rest, C, invC);
+    if (r2) return r2;
+    h->episodes.back().agentId = (int)ag;
+  }
+  if ((unsigned long)h->nTransitions != nObs) { set_error_msg("learner_status.raw and learner_data.raw disagree on nStoredObs"); return SMB200_ERR_STATE; }
+  h->nSeenEps = (long long)seenEps; h->nSeenObs = (long long)seenObs; h->nGatheredB4Startup = nInit;
+  // counters.nGradSteps = doneGradSteps; Approximator::setNgradSteps(nGradSteps()) (Learner_approximator.cpp:130);
+  // the running beta powers of Adam are NOT part of a checkpoint: they restart from beta_1, beta_2 (Optimizer.h:94)
+  if (pull_ctrl(h)) return SMB200_ERR_CUDA;
+  StepCtrl& k = h->hCtrl;
+  k.beta = beta; k.cmax = cmax; k.cinv = 1.0 / cmax;
+  h->gradStep = grad; k.grad_step = grad; k.adam_step = grad;
+  k.n_far_ref = 0; k.avg_sq_err = 0;                              // ReplayStats are not restored (zero until the next statistics pass)
+  k.gl_far_prev = 0; k.gl_stored_prev = (double)h->nTransitions; k.cnt_seed_step = grad;
+  if (push_ctrl(h)) return SMB200_ERR_CUDA;
+  h->initialized = true;
+  h->orderDirty = true; h->lookupDirty = true;
+  return 0;
 }
 
 }  // extern "C"

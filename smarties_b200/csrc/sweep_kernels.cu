@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(kThreads) k_sweep(ReplayView rp, int nEpisodes
         if (C > 1.0f) nFar += far;
       }
     }
+    if (recompute == 2) { __syncthreads(); continue; }     // aggregates only (restart: the stored return estimates are kept)
     // ---- Retrace: updateReturnEstimator(EP, N-2) (MemoryProcessing.cpp:23-44) ----
     __syncthreads();
     if (tid == 0) {

@@ -32,7 +32,8 @@ EXPORTS = [
     "smb200_train_steps", "smb200_train_step_on", "smb200_get_last_batch", "smb200_retrace_sweep",
     "smb200_reward_state_moments", "smb200_read_field", "smb200_read_episodes", "smb200_n_rows", "smb200_get_stats",
     "smb200_forward", "smb200_last_timing", "smb200_presample", "smb200_train_presampled", "smb200_sync", "smb200_profile_phases",
-    "smb200_comm_init", "smb200_comm_attach", "smb200_comm_error",
+    "smb200_comm_init", "smb200_comm_attach", "smb200_comm_error", "smb200_write_field", "smb200_save", "smb200_restart",
+    "smb200_push_episode_restored", "smb200_set_refer",
 ]
 
 FIELDS = dict(V=0, ADV=1, QRET=2, DELTA=3, RHO=4, KL=5, REWARD=6)
@@ -48,6 +49,7 @@ class Config(C.Structure):
         ("eps_anneal", C.c_double), ("learnrate", C.c_double), ("nn_lambda", C.c_double), ("expl_noise", C.c_double),
         ("out_weights_prefac", C.c_double), ("refer_reduce_threads", C.c_int32), ("world_rank", C.c_int32),
         ("world_size", C.c_int32), ("seed", C.c_uint64), ("nn_type", C.c_int32), ("nn_bptt_seq", C.c_int32),
+        ("min_tot_obs", C.c_int64),
     ]
 
 
@@ -98,6 +100,10 @@ def load_library(path: str = LIB_PATH):
         "smb200_retrace_sweep": (C.c_int, [H, dp]), "smb200_reward_state_moments": (C.c_int, [H, dp]),
         "smb200_read_field": (C.c_int, [H, C.c_int32, fp, C.c_int64]),
         "smb200_read_episodes": (C.c_int, [H, ip, ip, fp, C.c_int64]),
+        "smb200_write_field": (C.c_int, [H, C.c_int32, fp, C.c_int64]),
+        "smb200_save": (C.c_int, [H, C.c_char_p]), "smb200_restart": (C.c_int, [H, C.c_char_p]),
+        "smb200_push_episode_restored": (C.c_int, [H, C.c_int64, C.c_int32, C.c_int32] + [fp] * 10 + [C.c_double]),
+        "smb200_set_refer": (C.c_int, [H, C.c_double, C.c_double]),
         "smb200_get_stats": (C.c_int, [H, P(StepStats)]),
         "smb200_forward": (C.c_int, [H, fp, C.c_int32, fp]),
         "smb200_last_timing": (C.c_int, [H, dp, ip]),
@@ -160,6 +166,7 @@ class Learner:
         cfg.refer_reduce_threads = refer_reduce_threads
         cfg.world_rank, cfg.world_size, cfg.seed = world_rank, world_size, seed
         cfg.nn_type, cfg.nn_bptt_seq = {"FFNN": 0, "LSTM": 1}[hp.nnType], int(hp.nnBPTTseq)
+        cfg.min_tot_obs = hp.minTotObsNum_local
         if bounded is not None:
             b = np.broadcast_to(np.asarray(bounded, dtype=bool), (dim_action,))
             for i in range(dim_action):
@@ -236,6 +243,18 @@ class Learner:
         out = np.empty(n, np.float32)
         self._check(self.lib.smb200_read_field(self.h, FIELDS[name], _fp(out), n))
         return out
+
+    def write_field(self, name, values):
+        v = _f32(values)
+        self._check(self.lib.smb200_write_field(self.h, FIELDS[name], _fp(v), v.size))
+
+    def save(self, base):
+        """Learner_approximator::save(): the reference's checkpoint files `<base>_net_weights.raw`, ... (base = dir/agent_00)."""
+        self._check(self.lib.smb200_save(self.h, os.fsencode(base)))
+
+    def restart(self, base):
+        """Learner_approximator::restart() from files written by the reference or by save()."""
+        self._check(self.lib.smb200_restart(self.h, os.fsencode(base)))
 
     def read_episodes(self):
         n = self.n_episodes

@@ -67,11 +67,30 @@ CASES = {
         steps=4, start_step=0, sample_seed=23, bounded=0, full_steps=list(range(4))),
 }
 
+# checkpoint cases: phase A runs `steps` steps and calls Learner_approximator::save(); phase B is a fresh process
+# that calls restart() on those files and runs `steps_after` more steps.  Stored: the checkpoint files byte for
+# byte ("ckpt:<file>") and the dumps of phase B ("ref2:<key>").
+CKPT_CASES = {
+    "vracer_ckpt": dict(
+        replay=dict(seed=123, n_ep=24, ep_len=(20, 60), dS=6, dA=3),
+        settings={"learner": "VRACER", "returnsEstimator": "retrace", "nnLayerSizes": [32, 32], "batchSize": 16,
+                  "maxTotObsNum": 2048, "minTotObsNum": 500},
+        steps=8, start_step=995, sample_seed=7, bounded=0, full_steps=[7], steps_after=4, sample_seed_after=19),
+    "racer_lstm_ckpt": dict(
+        replay=dict(seed=51, n_ep=14, ep_len=(12, 40), dS=6, dA=2),
+        settings={"learner": "RACER", "nnType": "LSTM", "nnLayerSizes": [16], "nnBPTTseq": 8, "batchSize": 8,
+                  "maxTotObsNum": 1024, "minTotObsNum": 200},
+        steps=5, start_step=0, sample_seed=21, bounded=1, full_steps=[4], steps_after=3, sample_seed_after=29),
+}
+CKPT_FILES = ["agent_00_net_weights.raw", "agent_00_net_tgt_weights.raw", "agent_00_net_1stMom.raw", "agent_00_net_2ndMom.raw",
+              "agent_00_scaling.raw", "agent_00_rank_000_learner_status.raw", "agent_00_rank_000_learner_data.raw"]
+
 BIG = ("/weights", "/m1", "/m2", "/gradSum")
 
 
 def run_case(name, spec, outdir):
     d = synth.make_replay(**spec["replay"])
+    ckpt, D2 = {}, {}
     with tempfile.TemporaryDirectory() as tmp:
         synth.write_replay_file(os.path.join(tmp, "data.bin"), d)
         with open(os.path.join(tmp, "settings.json"), "w") as f:
@@ -80,9 +99,25 @@ def run_case(name, spec, outdir):
                "--threads", "1", "--startStep", str(spec["start_step"]), "--sampleSeed", str(spec["sample_seed"]),
                "--bounded", str(spec["bounded"]), "--dump", "out.bin", "--dumpAll", "--quiet"]
         env = dict(os.environ, OMP_NUM_THREADS="1")
+        if "steps_after" in spec:
+            cmd.append("--save")
         subprocess.run(cmd, cwd=tmp, check=True, stdout=subprocess.DEVNULL, env=env)
         D = synth.read_dump(os.path.join(tmp, "out.bin"))
+        if "steps_after" in spec:
+            for fn in CKPT_FILES:
+                ckpt[fn] = np.fromfile(os.path.join(tmp, fn), dtype=np.uint8)
+            tmp2 = os.path.join(tmp, "phaseB")
+            os.makedirs(tmp2)
+            cmd = [HARNESS, "--data", "../data.bin", "--settings", "../settings.json", "--steps", str(spec["steps_after"]),
+                   "--threads", "1", "--sampleSeed", str(spec["sample_seed_after"]), "--bounded", str(spec["bounded"]),
+                   "--restart", tmp, "--dump", "out2.bin", "--dumpAll", "--quiet"]
+            subprocess.run(cmd, cwd=tmp2, check=True, stdout=subprocess.DEVNULL, env=env)
+            D2 = synth.read_dump(os.path.join(tmp2, "out2.bin"))
     keep = {}
+    for fn, b in ckpt.items():
+        keep["ckpt:" + fn] = b
+    for k, v in D2.items():
+        keep["ref2:" + k] = v
     for k, v in D.items():
         if k.startswith("s") and k[1].isdigit():
             s = int(k[1:k.index("/")])
@@ -104,6 +139,6 @@ if __name__ == "__main__":
     if not os.path.exists(HARNESS):
         sys.exit("build oracle/_ref first: make -C oracle")
     only = sys.argv[1:]
-    for n, s in CASES.items():
-        if not only or n in only:
+    for n, s in {**CASES, **CKPT_CASES}.items():
+        if (not only and n in CASES) or n in only:
             run_case(n, s, os.path.dirname(os.path.abspath(__file__)))

@@ -8,6 +8,7 @@ import os
 import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CKPT_CASES = ["vracer_ckpt", "racer_lstm_ckpt"]
 CASES = ["vracer_small", "vracer_cfg2mini", "vracer_bounded", "vracer_prune", "racer_small", "racer_bounded"]
 RECURRENT_CASES = ["racer_lstm", "vracer_lstm2"]     # nnType LSTM + BPTT window (configs[2] family)
 
@@ -18,6 +19,10 @@ class Golden:
         self.spec = json.loads(bytes(z["spec"]).decode())
         self.ref = {k[4:]: z[k] for k in z.files if k.startswith("ref:")}
         self.replay = {k[7:]: z[k] for k in z.files if k.startswith("replay:")}
+        # checkpoint cases (tests/golden/make_golden.py CKPT_CASES): the files Learner_approximator::save() wrote after
+        # `steps` steps, and the dumps of a fresh reference process that restarted from them ("phase B")
+        self.ckpt = {k[5:]: z[k] for k in z.files if k.startswith("ckpt:")}
+        self.ref2 = {k[5:]: z[k] for k in z.files if k.startswith("ref2:")}
         r = self.spec["replay"]
         self.replay["dS"], self.replay["dA"] = r["dS"], r["dA"]
         self.dS, self.dA = r["dS"], r["dA"]
@@ -29,6 +34,23 @@ class Golden:
     def refer(self, key):
         """{beta, cmax, cinv, nFar, avgKL, avgSqErr, maxAbsErr, avgReturn, stdevQ, avgQ, maxQ, minQ, cntRet, sumRetErr}"""
         return self.ref[key + "/refer"]
+
+
+class PhaseB:
+    """View of a checkpoint golden that looks like a Golden of the restarted run."""
+    def __init__(self, g: Golden):
+        self.ref = g.ref2
+        self.steps = g.spec["steps_after"]
+
+    def refer(self, key):
+        return self.ref[key + "/refer"]
+
+
+def write_checkpoint(g: Golden, directory):
+    for fn, b in g.ckpt.items():
+        with open(os.path.join(directory, fn), "wb") as f:
+            f.write(bytes(b))
+    return os.path.join(directory, "agent_00")
 
 
 def make_oracle(g: Golden):

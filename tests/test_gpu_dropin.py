@@ -5,6 +5,8 @@ the development container (integration/Makefile, outputs under oracle/_ref/, whi
 import os
 import sys
 
+import numpy as np
+
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -36,3 +38,35 @@ def test_synthetic_env_many_actors_on_the_device_learner():
     done = [l for l in r["b200_lines"] if "gradient steps" in l]
     assert done and int(done[0].split()[1]) >= 1000, r
     assert r["stat_rows"] >= 1 and 0.0 < r["beta_last"] <= 1.0, r
+
+
+def test_checkpoints_cross_between_reference_and_device_learner(tmp_path):
+    """saveFreq checkpoints written through the binding (the reference's own writers, fed from the device) are
+    restarted by the plain reference binary and by the device learner; a checkpoint of the reference restarts
+    the device learner."""
+    for exe in ("b200/cart_pole", "cart_pole"):
+        if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", exe)):
+            pytest.skip("oracle/_ref binaries not built")
+    from dropin_run import SETTINGS, run_arm
+    S = dict(SETTINGS, saveFreq=1000)
+    a, b, c, d = (str(tmp_path / n) for n in "abcd")
+    r = run_arm("b200", steps=2500, threads=4, seed=7, settings=S, keep_dir=a)
+    assert r["rc"] == 0, r
+    files = ["agent_00_net_weights.raw", "agent_00_net_1stMom.raw", "agent_00_net_2ndMom.raw", "agent_00_scaling.raw",
+             "agent_00_rank_000_learner_status.raw", "agent_00_rank_000_learner_data.raw"]
+    for fn in files:
+        assert os.path.getsize(os.path.join(a, fn)) > 0, fn
+    m1 = np.fromfile(os.path.join(a, "agent_00_net_1stMom.raw"), np.float32)
+    assert np.abs(m1).max() > 0, "Adam moments of the device learner did not reach the checkpoint"
+    status = open(os.path.join(a, "agent_00_rank_000_learner_status.raw")).read()
+    assert "nGradSteps: 2000" in status, status
+    # the reference restarts from the device learner's checkpoint ...
+    r2 = run_arm("ref", steps=3600, threads=4, seed=8, settings=S, keep_dir=b, restart=a)
+    assert r2["rc"] == 0 and any("agent_00_net_weights" in l for l in r2["restart_lines"]), r2
+    assert r2["grad_steps_logged"] >= 3000, r2                 # continued from step 2000, not from 0
+    # ... and so does the device learner, from its own and from the reference's checkpoint
+    for src, dst in ((a, c), (b, d)):
+        r3 = run_arm("b200", steps=3600 if src == a else 4700, threads=4, seed=9, settings=S, keep_dir=dst, restart=src)
+        assert r3["rc"] == 0, r3
+        assert any("restarted the device learner at gradient step" in l for l in r3["b200_lines"]), r3
+        assert r3["grad_steps_logged"] >= (3000 if src == a else 4000) and 0.0 < r3["beta_last"] <= 1.0, r3

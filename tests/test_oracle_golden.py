@@ -58,3 +58,38 @@ def test_sampler_is_libstdcxx_uniform_int():
     gen = vo.Mt19937(7)
     ids = vo.sample_uniform(gen, 925, 16)
     assert len(ids) == 16 and np.all(np.diff(ids) > 0) and ids.min() >= 0 and ids.max() < 925
+
+
+@pytest.mark.parametrize("case", ["vracer_ckpt", "racer_lstm_ckpt"])
+def test_checkpoint_golden_layout(case):
+    """The reference's checkpoint files (written by Learner_approximator::save in the golden run) parse with the
+    layout the device library implements (include/smarties_b200.h, smb200_save): per episode `size_t N`, then
+    N x [state | reward | action | policy], six length-N arrays (Qret, A, V, delta, rho, KL) and a 10-float tail
+    {bool terminated; ssize_t ID, just_sampled, agentID}; they hold exactly the reference's final in-memory state."""
+    from parity_utils import Golden
+    g = Golden(case)
+    R, dS, dA = g.ref, g.dS, g.dA
+    dP = 2 * dA
+    raw = bytes(g.ckpt["agent_00_rank_000_learner_data.raw"])
+    pos, out = 0, {k: [] for k in ("Qret", "A", "V", "delta", "rho", "KL", "id", "len", "S0")}
+    while pos < len(raw):
+        N = int(np.frombuffer(raw, np.uint64, 1, pos)[0]); pos += 8
+        tot = (dS + dA + dP + 7) * N + 10
+        buf = np.frombuffer(raw, np.float32, tot, pos); pos += 4 * tot
+        tup = buf[:(dS + 1 + dA + dP) * N].reshape(N, dS + 1 + dA + dP)
+        out["S0"].append(tup[0, :dS])
+        rest = buf[(dS + 1 + dA + dP) * N:]
+        for i, k in enumerate(("Qret", "A", "V", "delta", "rho", "KL")):
+            out[k].append(rest[i * N:(i + 1) * N])
+        tail = rest[6 * N:].tobytes()
+        out["id"].append(int(np.frombuffer(tail, np.int64, 1, 1)[0])); out["len"].append(N)
+        assert int(np.frombuffer(tail, np.int64, 1, 9)[0]) == -1 and int(np.frombuffer(tail, np.int64, 1, 17)[0]) == 0
+    assert out["id"] == list(R["final/epID"]) and out["len"] == list(R["final/epLen"])
+    for k in ("Qret", "A", "V", "delta", "rho", "KL"):
+        assert np.array_equal(np.concatenate(out[k]), R["final/" + k]), k
+    sc = np.frombuffer(bytes(g.ckpt["agent_00_scaling.raw"]), np.float64)
+    assert np.array_equal(sc[:dS].astype(np.float32), R["final/stateMean"])
+    assert np.array_equal(sc[dS:2 * dS].astype(np.float32), R["final/stateScale"])
+    assert np.array_equal(sc[3 * dS:].astype(np.float32), R["final/rewards"][[2, 1, 0]])     # file: stdev, scale, mean
+    status = bytes(g.ckpt["agent_00_rank_000_learner_status.raw"]).decode()
+    assert f"nGradSteps: {g.start_step + g.steps + 1}\n" in status and f"nStoredEps: {len(out['id'])}\n" in status
