@@ -51,14 +51,14 @@ seg = [("start->gather", 0, 1), ("forward", 1, 2), ("loss", 2, 3), ("backward", 
 for name, a, b in seg:
     dlt = p1[:, :, b] - p1[:, :, a]
     print(f"  P1 CTAs {name:16s} mean {us(dlt.mean()):6.2f} us  max-over-CTAs mean {us(dlt.max(axis=1).mean()):6.2f}")
-fine = [("fwd L1 wait W", 9, 27), ("fwd L1 compute", 27, 10), ("fwd L2 wait W", 10, 28), ("fwd L2+res", 28, 12), ("fwd L4 wait W", 12, 30), ("fwd L4 out", 30, 31 if os.environ.get("ICACHE_PROBE") else 13), ("fwd L4 again", 31, 32 if os.environ.get("ICACHE_PROBE") else 31), ("fwd L5 param", 13, 2),
+fine = [("start: fence.proxy", 0, 41), ("start: TMA issue", 41, 37), ("start: next idx", 37, 38), ("start: gather", 38, 1), ("fwd L1 wait W", 9, 27), ("fwd L1 compute", 27, 10), ("fwd L2 wait W", 10, 28), ("fwd L2+res", 28, 12), ("fwd L4 wait W", 12, 30), ("fwd L4 out", 30, 31 if os.environ.get("ICACHE_PROBE") else 13), ("fwd L4 again", 31, 32 if os.environ.get("ICACHE_PROBE") else 31), ("fwd L5 param", 13, 2),
         ("loss stage1", 2, 8), ("loss stage2", 8, 16), ("loss stage3", 16, 3),
         ("bwd L4 out", 20, 18), ("bwd L2+res", 18, 17), ("bwd L1", 17, 4),
-        ("P2 desc+issue", 6, 24), ("P2 tile load", 24, 25), ("P2 contraction", 25, 33 if world > 1 else 26), ("P2 peer stores", 33, 34 if world > 1 else 33),
+        ("P2 pf states", 6, 39), ("P2 pf old vals", 39, 40), ("P2 pf pairs", 40, 35), ("P2 ctrl+tile", 35, 36), ("P2 param loads", 36, 24), ("P2 tile load", 24, 25), ("P2 contraction", 25, 33 if world > 1 else 26), ("P2 peer stores", 33, 34 if world > 1 else 33),
         ("P2 peer wait", 34, 26 if world > 1 else 34), ("P2 adam+store", 26, 7)]
 for name, a, b in fine:
     dlt = p1[:, :, b] - p1[:, :, a]
-    print(f"     {name:14s} {us(dlt.mean()):6.2f} us")
+    print(f"     {name:18s} {us(np.median(dlt)):6.2f} us")      # median: some markers are skipped on a launch's last step
 oth = T[:, nP1:-1, :]
 if oth.shape[1]:
     dlt = oth[:, :, 7] - oth[:, :, 6]

@@ -132,6 +132,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// ---- cp.async (LDGSTS): global -> shared without a register round trip ----
+__device__ __forceinline__ void cp_async16_cg(void* dst, const void* src) {     // bypasses L1: safe for data other CTAs rewrite
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_ca(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4_ca(void* dst, const void* src) {      // only for replay data that is immutable during a launch
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // Tanh::_eval (Network/Layers/Functions.h:103-112), f32
 // (hardware exp2 / reciprocal: 2-ulp error on e and on the quotient, far inside the f32 tolerance)
 __device__ __forceinline__ float tanh_ref(float x) {
@@ -577,7 +589,7 @@ __device__ __forceinline__ void loss_stages(const StepArgs& a, const NetDesc& ne
 // shared-memory carve-up of the step kernels
 // ------------------------------------------------------------------------------------------
 struct SmemPlan {
-  size_t img, act, err, red, info, old, pair, samp, tiles, bars, stage, total;
+  size_t img, act, err, red, info, old, pair, samp, tiles, bars, stage, chunks, total;
 };
 __host__ __device__ inline SmemPlan smem_plan(const NetDesc& net, int TB, bool imgInSmem) {
   SmemPlan p;
@@ -595,7 +607,11 @@ __host__ __device__ inline SmemPlan smem_plan(const NetDesc& net, int TB, bool i
   p.bars = o;  o += sizeof(uint64_t) * kMaxLayers;
   // inputs of the NEXT step, prefetched while the weight-gradient phase runs:
   // raw states [TB][dS], old values [8][TB], (a, mu_mean, mu_std) [3][TB*dA], info [4][TB]; then mean/scale [2][dS]
+  // then the 16-byte chunks [8][TB][4] the old values arrive in (cp.async.cg moves 16 bytes)
+  o = (o + 15) / 16 * 16;
   p.stage = o; o += sizeof(float) * ((size_t)TB * net.dS + 8 * TB + 3 * (size_t)TB * net.dA + 4 * TB + 2 * (size_t)net.dS);
+  o = (o + 15) / 16 * 16;
+  p.chunks = o; o += sizeof(float) * 8 * TB * 4;
   o = (o + 15) / 16 * 16;
   p.total = o;
   return p;
@@ -613,17 +629,27 @@ __device__ __forceinline__ int layer_img_end(const NetDesc& net, int l) {
 }
 
 // Called by all threads after the data dependency (grid barrier / kernel start) is satisfied.
-__device__ __forceinline__ void load_weight_image(const StepArgs& a, const NetDesc& net, float* img, uint64_t* bars) {
+__device__ __forceinline__ void load_weight_image(const StepArgs& a, const NetDesc& net, float* img, uint64_t* bars, int step = 0) {
   if (a.useTma) {
-    if (threadIdx.x == 0) {
-      // order this thread's earlier generic-proxy accesses (shared reads of the old image, the
-      // acquire of the grid barrier) before the async-proxy copies
-      asm volatile("fence.proxy.async;" ::: "memory");
-      for (int l = 1; l < net.nLayers; ++l) {
-        const int b = layer_img_begin(net, l), e = layer_img_end(net, l);
-        const unsigned bytes = (unsigned)(e - b) * 4u;
-        mbar_expect_tx(&bars[l], bytes);
-        bulk_g2s(img + b, a.Wimg + b, bytes, &bars[l]);
+    // One issuing thread per layer, in different warps: a fence.proxy.async costs ~0.4 us and every bulk copy
+    // ~0.17 us of issue time (measured, profiles/r1/phase_report_mlp_v4.txt) — serialised in one thread the last
+    // layer's copy left 1.3 us after the barrier.  The fence orders the CTA's earlier generic-proxy accesses (shared
+    // reads of the old image, made visible to this thread by bar.sync; the acquire of the grid barrier) before
+    // this thread's async-proxy copies.
+    if ((threadIdx.x & 31) == 0) {
+      const int w = threadIdx.x >> 5;
+      if (w + 1 < net.nLayers) {
+        // state-space specific proxy fences (SASS FENCE.VIEW.ASYNC.G + MEMBAR.ALL.CTA, FENCE.VIEW.ASYNC.S); the
+        // unqualified fence.proxy.async adds a MEMBAR.ALL.GPU (0.4-0.7 us measured) that the acquire of the grid
+        // barrier has already paid for
+        asm volatile("fence.proxy.async.global;\n\tfence.proxy.async.shared::cta;" ::: "memory");
+        if (w == 0) DBG_T(a, step, 41);
+        for (int l = 1 + w; l < net.nLayers; l += kST / 32) {
+          const int b = layer_img_begin(net, l), e = layer_img_end(net, l);
+          const unsigned bytes = (unsigned)(e - b) * 4u;
+          mbar_expect_tx(&bars[l], bytes);
+          bulk_g2s(img + b, a.Wimg + b, bytes, &bars[l]);
+        }
       }
     }
   } else {
@@ -1571,7 +1597,9 @@ __device__ void stats_and_refer(const StepArgs& a, const Hyper& hp, const StepCt
         wait_values_ll(d + 0, 4, N, me, (unsigned)step, cm, w0); wait_values_ll(d + 1, 4, N, me, (unsigned)step, cm, w1);
         wait_values_ll(d + 2, 4, N, me, (unsigned)step, cm, w2); wait_values_ll(d + 3, 4, N, me, (unsigned)step, cm, w3);
         farGlobal = 0.0; nPost = 0.0;
-        for (int q = 0; q < N; ++q) {
+#pragma unroll
+        for (int q = 0; q < kMaxWorld; ++q) {
+          if (q >= N) continue;
           if (q == me) { farGlobal += c.gl_far_prev; nPost += c.gl_stored_prev; continue; }
           farGlobal += (double)(long long)(((unsigned long long)w1[q] << 32) | w0[q]);
           nPost += (double)(long long)(((unsigned long long)w3[q] << 32) | w2[q]);
@@ -1683,7 +1711,7 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
   load_descs(a, smraw, net, hp);
   SmemPlan sp;
   SeqSmem sps;
-  if (REC) { sps = smem_plan_seq(*net, SM); sp.img = sps.img; sp.tiles = sps.ws; sp.bars = sps.bars; sp.stage = sps.ws; }
+  if (REC) { sps = smem_plan_seq(*net, SM); sp.img = sps.img; sp.tiles = sps.ws; sp.bars = sps.bars; sp.stage = sps.ws; sp.chunks = sps.ws; }
   else sp = smem_plan(*net, TB, SM);
   __shared__ StepCtrl c;
   const int nw = gridDim.x - 1;                 // worker CTAs
@@ -1742,12 +1770,19 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
   for (int s = 0; s < nSteps; ++s) {
     const int step = step0 + s;
     DBG_T(a, step, 0);
-    if (SM && doP1) load_weight_image(a, *net, img, bars);
+    if (SM && doP1) load_weight_image(a, *net, img, bars, step);
+    DBG_T(a, step, 37);
     // ring rows of the NEXT step's samples this thread will prefetch (known long before they are needed)
     const bool pfNow = pf && s + 1 < nSteps;
     int nxRowS[2] = {-1, -1}, nxRowT = -1, nxSf = 0, nxRowP = -1;
     if (pfNow) {
       const size_t jb = (size_t)(step + 1 - a.stepBase) * a.B + b0;
+      // the index loads below are only consumed after barrier 1 and the compiler is free to issue them there: pull
+      // their lines into L2 now so that they cost an L2 hit, not a DRAM round trip, on the path to P2
+      if (tid == 64) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.sampRow + jb));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.sampSlot + jb));
+      }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int q = tid + u * kST;
@@ -1757,6 +1792,7 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
       if (tid < nPair) { const int si = pfPs; if (b0 + si < a.B) nxRowP = a.sampRow[jb + si]; }
     }
     bool first = true;
+    DBG_T(a, step, 38);
     for (int t = blockIdx.x; t < nP1; t += nw) {
       if (REC) p1_seq<SM>(a, *reinterpret_cast<const DevDescs*>(smraw), c, step, t, smraw, sps, (unsigned)(s & 1), first, ready, (unsigned)s);
       else p1_tile<TB, SM>(a, *net, *hp, c, step, t, smraw, sp, (unsigned)(s & 1), first, ready, (unsigned)s, staged);
@@ -1766,31 +1802,46 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
     DBG_T(a, step, 5);
     grid_barrier(a.barrier, barTarget, nw);
     DBG_T(a, step, 6);
-    // ---- issue the loads of the next step's inputs (consumed after P2) ----
-    float4 pfS[2]; float pfOld[8]; float pfPair[3]; int pfInfo[4] = {0, 0, 0, 0};
+    // ---- copy the next step's inputs straight into the shared-memory staging area (cp.async: no registers are
+    //      held across P2; the staging area was last read by this step's P1).  Raw states, actions and behaviour
+    //      policies are immutable during a launch (.ca); the per-transition values other CTAs rewrite every step
+    //      (V, A, rho, KL, delta, Q) bypass L1 (.cg moves 16 bytes: the aligned chunk around the element) ----
+    float* chunks = reinterpret_cast<float*>(smraw + sp.chunks);
     if (pfNow) {
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int q = tid + u * kST;
-        pfS[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (nxRowS[u] >= 0) pfS[u] = ld_cg4(rp.S + (size_t)nxRowS[u] * dS + pfC4[u]);
+        if (q < nS4) {
+          float4* dst = reinterpret_cast<float4*>(stg.S) + q;
+          if (nxRowS[u] >= 0) cp_async16_ca(dst, rp.S + (size_t)nxRowS[u] * dS + pfC4[u]);
+          else *dst = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) pfOld[j] = 0.f;
-      if (nxRowT >= 0) {
+      DBG_T(a, step, 39);
+      if (tid < TB) {
         const int row = nxRowT, hn = (nxSf >> 31) & 1;
-        pfInfo[0] = row; pfInfo[1] = nxSf & 0x7fffffff; pfInfo[2] = hn; pfInfo[3] = 1;
-        pfOld[0] = ld_cg(rp.V + row); pfOld[1] = ld_cg(rp.ADV + row); pfOld[2] = ld_cg(rp.RHO + row); pfOld[3] = ld_cg(rp.KL + row);
-        pfOld[4] = ld_cg(rp.DELTA + row); pfOld[7] = ld_cg(rp.Q + row);
-        if (hn) { pfOld[5] = ld_cg(rp.V + row + 1); pfOld[6] = ld_cg(rp.ADV + row + 1); }
+        stg.info[0 * TB + tid] = row < 0 ? 0 : row; stg.info[1 * TB + tid] = nxSf & 0x7fffffff;
+        stg.info[2 * TB + tid] = row < 0 ? 0 : hn;  stg.info[3 * TB + tid] = row < 0 ? 0 : 1;
+        if (row >= 0) {
+          const int c0 = row & ~3, c1 = (row + 1) & ~3;
+          float* ch = chunks + tid * 4;
+          cp_async16_cg(ch + 0 * TB * 4, rp.V + c0);     cp_async16_cg(ch + 1 * TB * 4, rp.ADV + c0);
+          cp_async16_cg(ch + 2 * TB * 4, rp.RHO + c0);   cp_async16_cg(ch + 3 * TB * 4, rp.KL + c0);
+          cp_async16_cg(ch + 4 * TB * 4, rp.DELTA + c0); cp_async16_cg(ch + 7 * TB * 4, rp.Q + c0);
+          if (hn) { cp_async16_cg(ch + 5 * TB * 4, rp.V + c1); cp_async16_cg(ch + 6 * TB * 4, rp.ADV + c1); }
+        }
       }
-      pfPair[0] = 0.f; pfPair[1] = 0.f; pfPair[2] = 1.f;
-      if (nxRowP >= 0) {
-        const int i = pfPi;
-        const size_t row = nxRowP;
-        pfPair[0] = ld_cg(rp.A + row * dA + i); pfPair[1] = ld_cg(rp.MU + row * 2 * dA + i); pfPair[2] = ld_cg(rp.MU + row * 2 * dA + dA + i);
+      DBG_T(a, step, 40);
+      if (tid < nPair) {
+        if (nxRowP >= 0) {
+          const size_t row = nxRowP;
+          cp_async4_ca(stg.pair + tid, rp.A + row * dA + pfPi);
+          cp_async4_ca(stg.pair + nPair + tid, rp.MU + row * 2 * dA + pfPi);
+          cp_async4_ca(stg.pair + 2 * nPair + tid, rp.MU + row * 2 * dA + dA + pfPi);
+        } else { stg.pair[tid] = 0.f; stg.pair[nPair + tid] = 0.f; stg.pair[2 * nPair + tid] = 1.f; }
       }
     }
+    DBG_T(a, step, 35);
     if (!doP1) {          // tile-only workers still need this step's Adam scalars
       if (tid == 0) load_ctrl(c, &a.ctrl[step & 1]);
       __syncthreads();
@@ -1798,23 +1849,24 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
     for (int t = blockIdx.x; t < a.nTiles; t += nw) {
       GradTile gt = myTile;
       if (t != (int)blockIdx.x) gt = a.tiles[t];
+      DBG_T(a, step, 36);
       p2_tile(a, *net, *hp, c, gt, tiles, step, t);
       __syncthreads();
     }
-    // ---- park the prefetched inputs in shared memory (read by P1 of the next step) ----
+    // ---- the copies have had the whole weight-gradient phase to land; pick each old value out of its chunk ----
     if (pfNow) {
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int q = tid + u * kST;
-        if (q < nS4) reinterpret_cast<float4*>(stg.S)[q] = pfS[u];
-      }
+      cp_async_wait_all();
       if (tid < TB) {
+        const int row = nxRowT < 0 ? 0 : nxRowT, e0 = row & 3, e1 = (row + 1) & 3, hn = nxRowT < 0 ? 0 : (nxSf >> 31) & 1;
+        const float* ch = chunks + tid * 4;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) stg.old[j * TB + tid] = pfOld[j];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) stg.info[j * TB + tid] = pfInfo[j];
+        for (int j = 0; j < 8; ++j) {
+          const bool nextRow = j == 5 || j == 6;
+          float v = 0.f;
+          if (nxRowT >= 0 && (!nextRow || hn)) v = ch[j * TB * 4 + (nextRow ? e1 : e0)];
+          stg.old[j * TB + tid] = v;
+        }
       }
-      if (tid < nPair) { stg.pair[tid] = pfPair[0]; stg.pair[nPair + tid] = pfPair[1]; stg.pair[2 * nPair + tid] = pfPair[2]; }
     }
     staged = pfNow;
     DBG_T(a, step, 7);
