@@ -515,7 +515,7 @@ __device__ __forceinline__ void loss_stages(const StepArgs& a, const NetDesc& ne
     SampleRec r;
     r.slot = info[TB + s]; r.hasNext = info[2 * TB + s];
     r.qNextOld = 0.f; r.qNextNew = 0.f;
-    if (r.hasNext) {
+    if (r.hasNext && vnext) {
       const float vn = vnext[s];
       r.qNextOld = old[6 * TB + s] + old[5 * TB + s];
       r.qNextNew = vn;
@@ -535,7 +535,12 @@ __device__ __forceinline__ void loss_stages(const StepArgs& a, const NetDesc& ne
     r.pad = 0;
     rp.DELTA[row] = E; rp.KL[row] = D; rp.RHO[row] = W32;
     rp.V[row] = Vf; rp.ADV[row] = Qf - Vf;
-    a.rec[b] = r;
+    if (vnext) a.rec[b] = r;
+    else {      // qNextOld / qNextNew of this record belong to the helper CTA
+      *reinterpret_cast<int4*>(&a.rec[b].slot) = make_int4(r.slot, r.hasNext, r.farDelta, 0);
+      *reinterpret_cast<float4*>(&a.rec[b].dKL) = make_float4(r.dKL, r.dFar, r.dE2, r.absE);
+      *reinterpret_cast<float2*>(&a.rec[b].qOld) = make_float2(r.qOld, r.qNew);
+    }
   }
   __syncthreads();
   DBG_T(a, step, 16);
@@ -687,7 +692,7 @@ __device__ __forceinline__ Staging staging_view(const NetDesc& net, unsigned cha
 template <int TB, bool SM>
 __device__ void p1_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, StepCtrl& c, int step, int tile,
                         unsigned char* smraw, const SmemPlan& sp, unsigned parity, bool fetchCtrl,
-                        const unsigned* readyFlag, unsigned readyTarget, bool staged) {
+                        const unsigned* readyFlag, unsigned readyTarget, bool staged, bool helped = false) {
   const int tid = threadIdx.x;
   float* img = reinterpret_cast<float*>(smraw + sp.img);
   const float* Wp = SM ? img : a.Wimg;
@@ -727,9 +732,12 @@ __device__ void p1_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
     }
     __syncthreads();
   }
+  // `helped`: V(s_{t+1}) of truncated episodes is evaluated by an otherwise idle CTA (next_state_helper), which
+  // also writes it back; this CTA then only flags the sample in its record
   int anyNext = 0;
 #pragma unroll
   for (int s = 0; s < TB; ++s) anyNext |= info[2 * TB + s];
+  if (helped) anyNext = 0;
 
   // V(s_{t+1}) of truncated episodes (RACER_train.cpp:23-27): rare, extra forward pass
   float* vnext = reinterpret_cast<float*>(samp + 11 * TB);  // samp[11][*] is not used by the loss stages
@@ -778,7 +786,7 @@ __device__ void p1_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
   DBG_T(a, step, 2);
 
   {
-    LossIO io{act, err, info, old, pair, samp, vnext, b0, pa, pmm, pms, p0s, p0i};
+    LossIO io{act, err, info, old, pair, samp, helped ? nullptr : vnext, b0, pa, pmm, pms, p0s, p0i};
     loss_stages<TB, SM>(a, net, hp, c, step, Wp, io, fetchCtrl, readyFlag, readyTarget);
   }
 
@@ -1634,6 +1642,78 @@ __device__ void p3_stats(const StepArgs& a, const Hyper& hp, const StepCtrl& c, 
   stats_and_refer(a, hp, c, nx, step, nullptr, -1, fd, stage);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// V(s_{t+1}) of sampled transitions whose successor is the last row of a TRUNCATED episode
+// (RACER_train.cpp:22-27: `NET.forward(bID, t+1); MB.setValues(bID, t+1, V)`).  About one sample in
+// 1100 at cfg2, i.e. one in four steps has one — and the extra forward pass (4.7 us) used to delay
+// the grid barrier for every CTA.  The worker CTAs that own no P1 tile are idle during P1: helper j
+// scans this step's samples (bit 31 of sampSlot), takes the flagged samples [TB*j, TB*j + TB), ...,
+// pulls the weight image, evaluates the value head and performs the write-back of the reference
+// (Episode::updateValues_atomic inputs: old and new Q of row t+1 go to the sample's record).
+// Returns true if the image was loaded (the caller tracks the mbarrier parity).
+// ------------------------------------------------------------------------------------------
+template <int TB, bool SM>
+__device__ bool next_state_helper(const StepArgs& a, const NetDesc& net, int step, int helper, int nHelpers, unsigned char* smraw,
+                                  const SmemPlan& sp, unsigned parity) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int shCount[kST / 32];
+  __shared__ int shList[TB];
+  float* img = reinterpret_cast<float*>(smraw + sp.img);
+  const float* Wp = SM ? img : a.Wimg;
+  float* act = reinterpret_cast<float*>(smraw + sp.act);
+  float* red = reinterpret_cast<float*>(smraw + sp.red);
+  uint64_t* bars = (SM && a.useTma) ? reinterpret_cast<uint64_t*>(smraw + sp.bars) : nullptr;
+  const ReplayView& rp = a.rp;
+  const int dS = net.dS;
+  const size_t j0 = (size_t)(step - a.stepBase) * a.B;
+  bool loaded = false;
+  for (int first = helper * TB; ; first += nHelpers * TB) {       // flagged samples [first, first + TB)
+    // ---- ranks of the flagged samples: ballot + prefix over the batch ----
+    int total = 0;
+    if (tid < TB) shList[tid] = -1;
+    for (int c0 = 0; c0 < a.B; c0 += kST) {
+      const int b = c0 + tid;
+      const int flagged = (b < a.B) ? (int)((unsigned)__ldcg(a.sampSlot + j0 + b) >> 31) : 0;
+      const unsigned m = __ballot_sync(0xffffffffu, flagged);
+      __syncthreads();
+      if (lane == 0) shCount[warp] = __popc(m);
+      __syncthreads();
+      int before = total;
+      for (int w = 0; w < warp; ++w) before += shCount[w];
+      const int rank = before + __popc(m & ((1u << lane) - 1u));
+      if (flagged && rank >= first && rank < first + TB) shList[rank - first] = b;
+      for (int w = 0; w < kST / 32; ++w) total += shCount[w];
+    }
+    __syncthreads();
+    if (total <= first) break;
+    if (!loaded) { if (SM) load_weight_image(a, net, img, bars, step); loaded = true; }
+    // ---- gather + standardise the successor states, forward, value head ----
+    for (int idx = tid; idx < dS * TB; idx += kST) {
+      const int k = idx / TB, s = idx - k * TB;
+      const int b = shList[s];
+      float x = 0.f;
+      if (b >= 0) {
+        const size_t row = (size_t)__ldcg(a.sampRow + j0 + b) + 1;
+        x = (ld_cg(rp.S + row * dS + k) - ld_cg(rp.stateMean + k)) * ld_cg(rp.stateScale + k);
+      }
+      act[idx] = x;
+    }
+    __syncthreads();
+    net_forward<TB, SM>(net, Wp, act, red, first == helper * TB ? bars : nullptr, parity);
+    if (tid < TB && shList[tid] >= 0) {
+      const int b = shList[tid];
+      const size_t row = (size_t)__ldcg(a.sampRow + j0 + b) + 1;
+      const float vn = (float)net2v((double)net_out<SM>(net, Wp, act, TB, 0, tid));
+      const float qOld = ld_cg(rp.ADV + row) + ld_cg(rp.V + row);
+      rp.V[row] = vn; rp.ADV[row] = vn - vn;
+      *reinterpret_cast<float2*>(&a.rec[b].qNextOld) = make_float2(qOld, vn);
+    }
+    __syncthreads();
+  }
+  return loaded;
+}
+
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
@@ -1750,6 +1830,9 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
   // inputs of step s+1 are prefetched into registers while P2 of step s runs, then parked in the
   // shared-memory staging area: possible when every worker owns at most one P1 tile
   const bool pf = !REC && doP1 && nP1 <= nw && (dS & 3) == 0 && nS4 <= 2 * kST && nPair <= kST;
+  // idle worker CTAs evaluate V(s_{t+1}) of truncated episodes for the P1 CTAs (next_state_helper)
+  const int nHelpers = (!REC && nP1 < nw) ? nw - nP1 : 0;
+  unsigned helpParity = 0;
   const Staging stg = staging_view<TB>(*net, smraw, sp);
   const int b0 = blockIdx.x * TB;
   const ReplayView& rp = a.rp;
@@ -1795,9 +1878,12 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
     DBG_T(a, step, 38);
     for (int t = blockIdx.x; t < nP1; t += nw) {
       if (REC) p1_seq<SM>(a, *reinterpret_cast<const DevDescs*>(smraw), c, step, t, smraw, sps, (unsigned)(s & 1), first, ready, (unsigned)s);
-      else p1_tile<TB, SM>(a, *net, *hp, c, step, t, smraw, sp, (unsigned)(s & 1), first, ready, (unsigned)s, staged);
+      else p1_tile<TB, SM>(a, *net, *hp, c, step, t, smraw, sp, (unsigned)(s & 1), first, ready, (unsigned)s, staged, nHelpers > 0);
       first = false;
       __syncthreads();
+    }
+    if (!REC && nHelpers > 0 && !doP1) {
+      if (next_state_helper<TB, SM>(a, *net, step, (int)blockIdx.x - nP1, nHelpers, smraw, sp, helpParity)) helpParity ^= 1u;
     }
     DBG_T(a, step, 5);
     grid_barrier(a.barrier, barTarget, nw);
