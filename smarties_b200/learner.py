@@ -18,7 +18,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # SMB200_PROFILE=1 selects the flavour with phase timestamps compiled in (scripts/phase_report.py)
-LIB_PATH = os.path.join(_HERE, "libsmarties_b200_prof.so" if os.environ.get("SMB200_PROFILE") else "libsmarties_b200.so")
+LIB_PATH = os.environ.get("SMB200_LIB") or os.path.join(   # SMB200_LIB: another build of the same library (A/B experiments)
+    _HERE, "libsmarties_b200_prof.so" if os.environ.get("SMB200_PROFILE") else "libsmarties_b200.so")
 
 MAX_HIDDEN = 8
 MAX_ACTION = 64
