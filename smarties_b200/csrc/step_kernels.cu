@@ -820,16 +820,22 @@ __device__ void p1_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
   DBG_T(a, step, 4);
 
   // ---- activations and deltas to the feature-major scratch read by P2 ----
+  //      TILE-major for feed-forward nets: scratch[(tile * per + feature) * 4 + sample] — the tile's block is one
+  //      contiguous, fully coalesced 16-byte-per-thread store (the feature-major layout cost 32 sectors per warp
+  //      store); P2 reads it back as 256-byte runs of 16 features (p2_tile) ----
   const int per = net.actPerSample;
-  if (TB == 4 && b0 + TB <= a.B) {
+  static_assert(TB == 4, "tile-major scratch layout assumes 4 samples per tile");
+  float* actT = a.actG + (size_t)tile * per * 4;
+  float* errT = a.errG + (size_t)tile * per * 4;
+  if (b0 + TB <= a.B) {
     for (int f = tid; f < per; f += kST) {
-      *reinterpret_cast<float4*>(a.actG + (size_t)f * a.Bpad + b0) = *reinterpret_cast<const float4*>(act + f * 4);
-      *reinterpret_cast<float4*>(a.errG + (size_t)f * a.Bpad + b0) = *reinterpret_cast<const float4*>(err + f * 4);
+      *reinterpret_cast<float4*>(actT + f * 4) = *reinterpret_cast<const float4*>(act + f * 4);
+      *reinterpret_cast<float4*>(errT + f * 4) = *reinterpret_cast<const float4*>(err + f * 4);
     }
   } else {
     for (int idx = tid; idx < per * TB; idx += kST) {
-      const int f = idx / TB, s = idx - f * TB;
-      if (b0 + s < a.B) { a.actG[(size_t)f * a.Bpad + b0 + s] = act[idx]; a.errG[(size_t)f * a.Bpad + b0 + s] = err[idx]; }
+      const int s = idx & 3;
+      if (b0 + s < a.B) { actT[idx] = act[idx]; errT[idx] = err[idx]; }
     }
   }
 }
@@ -1296,19 +1302,24 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
 #pragma unroll
     for (int i = 0; i < kLD; ++i) {
       const int q = tid + i * kST;
-      const int r = q >> 6, c4 = (q & 63) * 4;
+      // feed-forward nets: tile-major scratch, 16 consecutive lanes read 16 consecutive features of one P1 tile (256 B);
+      // recurrent nets: feature-major scratch [feature][column], 64 consecutive lanes read one 1 KB row
+      const bool tm = !net.recurrent;
+      const int r = tm ? (q & 15) : (q >> 6), c4 = tm ? (q >> 4) * 4 : (q & 63) * 4;
+      const size_t tb = (size_t)((bc + c4) >> 2) * net.actPerSample;       // first feature of that P1 tile (tile-major)
       float4 av = make_float4(0.f, 0.f, 0.f, 0.f), dv = av;
       if (t.kind == 0) {
         const int k = t.k0 + r;
-        if (k < K) av = ld_cg4(a.actG + (size_t)((lstm && k >= L.nIn ? hOff : aOff) + k) * a.Bpad + bc + c4);
+        if (k < K) av = tm ? ld_cg4(a.actG + (tb + aOff + k) * 4)
+                           : ld_cg4(a.actG + (size_t)((lstm && k >= L.nIn ? hOff : aOff) + k) * a.Bpad + bc + c4);
         else if (k == K) av = make_float4(1.f, 1.f, 1.f, 1.f);            // bias row: db += delta
         const int n = t.n0 + r;
-        if (n < N) dv = ld_cg4(a.errG + (size_t)(dOff + n) * a.Bpad + bc + c4);
+        if (n < N) dv = tm ? ld_cg4(a.errG + (tb + dOff + n) * 4) : ld_cg4(a.errG + (size_t)(dOff + n) * a.Bpad + bc + c4);
       } else {
         const int n = t.n0 + r;
         if (n < N) {
-          dv = ld_cg4(a.errG + (size_t)(dOff + n) * a.Bpad + bc + c4);
-          if (t.kind == 1) av = ld_cg4(a.actG + (size_t)(aOff + n) * a.Bpad + bc + c4);
+          dv = tm ? ld_cg4(a.errG + (tb + dOff + n) * 4) : ld_cg4(a.errG + (size_t)(dOff + n) * a.Bpad + bc + c4);
+          if (t.kind == 1) av = tm ? ld_cg4(a.actG + (tb + aOff + n) * 4) : ld_cg4(a.actG + (size_t)(aOff + n) * a.Bpad + bc + c4);
         }
       }
       avs[i] = av; dvs[i] = dv;
@@ -1316,7 +1327,8 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
 #pragma unroll
     for (int i = 0; i < kLD; ++i) {
       const int q = tid + i * kST;
-      const int r = q >> 6, c4 = (q & 63) * 4;
+      const bool tm = !net.recurrent;
+      const int r = tm ? (q & 15) : (q >> 6), c4 = tm ? (q >> 4) * 4 : (q & 63) * 4;
       *reinterpret_cast<float4*>(As + r * kBCP + c4) = avs[i];
       *reinterpret_cast<float4*>(Ds + r * kBCP + c4) = dvs[i];
     }
