@@ -982,7 +982,8 @@ static void comm_layout(CommView& cm, int world, int rank, int nParams, int nTil
   cm.world = world; cm.rank = rank;
   cm.nParamsPad = (nParams + 31) / 32 * 32; cm.nTilesPad = (nTiles + 1 + 31) / 32 * 32;
   size_t o = 0;
-  cm.offGrad = o; o += sizeof(unsigned long long) * 2 * (size_t)world * cm.nParamsPad;
+  cm.offGrad = o; o += sizeof(unsigned) * 4 * (size_t)world * cm.nParamsPad;        // 4-byte elements, four rotating slots
+  cm.gradBytes = o - cm.offGrad;
   cm.offFlag = o; o += sizeof(unsigned) * (size_t)world * cm.nTilesPad;
   o = (o + 255) / 256 * 256;
   cm.offCnt = o; o += sizeof(unsigned long long) * 4 * (size_t)world * 4;   // [step & 3][rank][4] stamped words
@@ -1003,6 +1004,7 @@ int smb200_comm_init(smb200_learner* h, int32_t world, int32_t rank, uint8_t* ha
   if (!h->commBuf) {
     SMB200_CUDA_CHECK(cudaMalloc(&h->commBuf, h->comm.bytes));
     SMB200_CUDA_CHECK(cudaMemset(h->commBuf, 0, h->comm.bytes));
+    SMB200_CUDA_CHECK(cudaMemset(h->commBuf + h->comm.offGrad, 0xFF, h->comm.gradBytes));     // "not arrived yet" (kPoison)
     if (dev_alloc(&h->dCommErr, 1)) return SMB200_ERR_CUDA;
   }
   cudaIpcMemHandle_t hd;

@@ -107,6 +107,36 @@ __device__ __forceinline__ void wait_values_ll(const unsigned long long* p, size
 #pragma unroll
   for (int q = 0; q < kMaxWorld; ++q) out[q] = (q < N && q != me) ? (unsigned)(v[q] & 0xffffffffull) : 0u;
 }
+// ---- gradient exchange elements: plain 4-byte values, "not arrived yet" = the poison pattern ----
+// Every slot is written once per use by exactly one peer and reset to the poison by its reader right after it was
+// read; slots rotate over four steps, so the next writer of a slot is causally three exchanges behind the reset.
+// 0xFFFFFFFF is a NaN no arithmetic produces (the default NaN is 0x7FFFFFFF); a gradient that really carried it would
+// end in the bounded wait's error flag, not in a wrong sum.
+constexpr unsigned kPoison = 0xFFFFFFFFu;
+__device__ __forceinline__ void st_volatile_u32(unsigned* p, unsigned v) {
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void wait_values_poison(unsigned* p, size_t stride, int N, int me, const CommView& cm, unsigned (&out)[kMaxWorld]) {
+  unsigned v[kMaxWorld];
+  const long long t0 = clock64();
+  while (true) {
+#pragma unroll
+    for (int q = 0; q < kMaxWorld; ++q)
+      if (q < N && q != me) asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v[q]) : "l"(p + (size_t)q * stride) : "memory");
+    bool ok = true;
+#pragma unroll
+    for (int q = 0; q < kMaxWorld; ++q)
+      if (q < N && q != me) ok = ok && (v[q] != kPoison);
+    if (ok) break;
+    if (clock64() - t0 > cm.timeoutCycles) { *cm.error = 1; break; }
+  }
+#pragma unroll
+  for (int q = 0; q < kMaxWorld; ++q) {
+    out[q] = (q < N && q != me) ? v[q] : 0u;
+    if (q < N && q != me) st_volatile_u32(p + (size_t)q * stride, kPoison);      // free the slot for its next use
+  }
+}
+
 __device__ __forceinline__ unsigned long long ll_pack(unsigned v, unsigned stamp) {
   return ((unsigned long long)stamp << 32) | (unsigned long long)v;
 }
@@ -392,6 +422,7 @@ __device__ __forceinline__ void loss_stages(const StepArgs& a, const NetDesc& ne
   float* act = io.act; float* err = io.err; const int* info = io.info; const float* old = io.old;
   double* pair = io.pair; double* samp = io.samp; const float* vnext = io.vnext;
   const int b0 = io.b0, p0 = tid, p0s = io.p0s, p0i = io.p0i;
+  const bool keep = step == a.lastStep || a.lastStep < 0;      // smb200_get_last_batch only ever sees a launch's last step
   const double pa = io.pa, pmm = io.pmm, pms = io.pms;
   const ReplayView& rp = a.rp;
   const int dA = net.dA, nPair = TB * dA;
@@ -506,12 +537,12 @@ __device__ __forceinline__ void loss_stages(const StepArgs& a, const NetDesc& ne
       const double gc = (orig + expect) * (errA * ((1.0 + coefRaw / rtc) / 2.0));
       samp[4 * TB + s] = orig * coef; samp[5 * TB + s] = expect; samp[6 * TB + s] = coef; samp[7 * TB + s] = errA;
       err[(Lo.actOff + 1) * TB + s] = (float)gc;
-      a.lastG[(size_t)b * net.nOut + 1] = (float)gc;
-      a.lastO[(size_t)b * net.nOut + 1] = (float)coefRaw;
+      if (keep) a.lastG[(size_t)b * net.nOut + 1] = (float)gc;
+      if (keep) a.lastO[(size_t)b * net.nOut + 1] = (float)coefRaw;
     }
     err[(Lo.actOff + 0) * TB + s] = (float)g0;
-    a.lastG[(size_t)b * net.nOut + 0] = (float)g0;
-    a.lastO[(size_t)b * net.nOut + 0] = O0f;
+    if (keep) a.lastG[(size_t)b * net.nOut + 0] = (float)g0;
+    if (keep) a.lastO[(size_t)b * net.nOut + 0] = O0f;
     SampleRec r;
     r.slot = info[TB + s]; r.hasNext = info[2 * TB + s];
     r.qNextOld = 0.f; r.qNextNew = 0.f;
@@ -564,10 +595,10 @@ __device__ __forceinline__ void loss_stages(const StepArgs& a, const NetDesc& ne
       const double g_std = beta * pg_std + (1.0 - beta) * pair[3 * nPair + p];
       err[(Lo.actOff + m0 + i) * TB + s] = (float)g_mean;
       err[(Lp.actOff + i) * TB + s] = (float)g_std;
-      a.lastG[(size_t)b * net.nOut + m0 + i] = (float)g_mean;
-      a.lastG[(size_t)b * net.nOut + m0 + dA + i] = (float)g_std;
-      a.lastO[(size_t)b * net.nOut + m0 + i] = mf;
-      a.lastO[(size_t)b * net.nOut + m0 + dA + i] = ldw<SM>(Wp + Lp.imgB + i);
+      if (keep) a.lastG[(size_t)b * net.nOut + m0 + i] = (float)g_mean;
+      if (keep) a.lastG[(size_t)b * net.nOut + m0 + dA + i] = (float)g_std;
+      if (keep) a.lastO[(size_t)b * net.nOut + m0 + i] = mf;
+      if (keep) a.lastO[(size_t)b * net.nOut + m0 + dA + i] = ldw<SM>(Wp + Lp.imgB + i);
       if (racer) {
         const double oc = samp[4 * TB + s], expect = samp[5 * TB + s], coef = samp[6 * TB + s], errA = samp[7 * TB + s];
         const double F = pair[11 * nPair + p];
@@ -579,10 +610,10 @@ __device__ __forceinline__ void loss_stages(const StepArgs& a, const NetDesc& ne
         g2 *= errA * pair[15 * nPair + p];
         err[(Lo.actOff + 2 + i) * TB + s] = (float)g1;
         err[(Lo.actOff + 2 + dA + i) * TB + s] = (float)g2;
-        a.lastG[(size_t)b * net.nOut + 2 + i] = (float)g1;
-        a.lastG[(size_t)b * net.nOut + 2 + dA + i] = (float)g2;
-        a.lastO[(size_t)b * net.nOut + 2 + i] = act[(Lo.actOff + 2 + i) * TB + s];
-        a.lastO[(size_t)b * net.nOut + 2 + dA + i] = act[(Lo.actOff + 2 + dA + i) * TB + s];
+        if (keep) a.lastG[(size_t)b * net.nOut + 2 + i] = (float)g1;
+        if (keep) a.lastG[(size_t)b * net.nOut + 2 + dA + i] = (float)g2;
+        if (keep) a.lastO[(size_t)b * net.nOut + 2 + i] = act[(Lo.actOff + 2 + i) * TB + s];
+        if (keep) a.lastO[(size_t)b * net.nOut + 2 + dA + i] = act[(Lo.actOff + 2 + dA + i) * TB + s];
       }
     }
   }
@@ -761,7 +792,7 @@ __device__ void p1_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
       x = staged ? (stg.S[s * dS + k] - stg.mean[k]) * stg.scale[k]
                  : (ld_cg(rp.S + (size_t)info[s] * dS + k) - ld_cg(rp.stateMean + k)) * ld_cg(rp.stateScale + k);
     act[idx] = x;
-    if (info[3 * TB + s]) a.lastX[(size_t)(b0 + s) * dS + k] = x;
+    if (info[3 * TB + s] && (step == a.lastStep || a.lastStep < 0)) a.lastX[(size_t)(b0 + s) * dS + k] = x;
   }
   for (int idx = tid; idx < net.actPerSample * TB; idx += kST) err[idx] = 0.f;   // clearErrors
   // behaviour policy and action of this thread's first (sample, component) pair
@@ -1118,7 +1149,7 @@ __device__ void p1_seq(const StepArgs& a, const DevDescs& dd, StepCtrl& c, int s
     pms = (double)ld_cg(rp.MU + (size_t)row * 2 * dA + dA + tid);
   }
   __syncthreads();
-  if (tid < dS) a.lastX[(size_t)b * dS + tid] = X[nRec * xs + tid];
+  if (tid < dS && (step == a.lastStep || a.lastStep < 0)) a.lastX[(size_t)b * dS + tid] = X[nRec * xs + tid];
   DBG_T(a, step, 1);
 
   // ---- forward, layer-major ----
@@ -1392,29 +1423,28 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
   if (a.comm.world > 1) {
     DBG_T(a, step, 33);
     const CommView& cm = a.comm;
-    const int N = cm.world, me = cm.rank, par = step & 1;
-    const unsigned stamp = (unsigned)(step + 1);
-    const size_t slotMe = ((size_t)par * N + me) * cm.nParamsPad;
+    const int N = cm.world, me = cm.rank, rot = step & 3;
+    const size_t slotMe = ((size_t)rot * N + me) * cm.nParamsPad;
     if (p0 >= 0) {
-      const unsigned long long pk = ((unsigned long long)stamp << 32) | (unsigned long long)__float_as_uint(acc);
-      for (int q = 0; q < N; ++q) if (q != me) st_volatile_u64(cm.grad(q) + slotMe + p0, pk);
+      const unsigned pk = __float_as_uint(acc);
+      for (int q = 0; q < N; ++q) if (q != me) st_volatile_u32(cm.grad(q) + slotMe + p0, pk);
     }
     if (p1 >= 0) {
-      const unsigned long long pk = ((unsigned long long)stamp << 32) | (unsigned long long)__float_as_uint(acc2);
-      for (int q = 0; q < N; ++q) if (q != me) st_volatile_u64(cm.grad(q) + slotMe + p1, pk);
+      const unsigned pk = __float_as_uint(acc2);
+      for (int q = 0; q < N; ++q) if (q != me) st_volatile_u32(cm.grad(q) + slotMe + p1, pk);
     }
     DBG_T(a, step, 34);
-    const unsigned long long* mine = cm.grad(me) + (size_t)par * N * cm.nParamsPad;
+    unsigned* mine = cm.grad(me) + (size_t)rot * N * cm.nParamsPad;
     unsigned got[kMaxWorld];
     if (p0 >= 0) {
-      wait_values_ll(mine + p0, cm.nParamsPad, N, me, stamp, cm, got);
+      wait_values_poison(mine + p0, cm.nParamsPad, N, me, cm, got);
       float v = 0.f;
 #pragma unroll
       for (int q = 0; q < kMaxWorld; ++q) if (q < N) v += q == me ? acc : __uint_as_float(got[q]);
       acc = v;
     }
     if (p1 >= 0) {
-      wait_values_ll(mine + p1, cm.nParamsPad, N, me, stamp, cm, got);
+      wait_values_poison(mine + p1, cm.nParamsPad, N, me, cm, got);
       float v = 0.f;
 #pragma unroll
       for (int q = 0; q < kMaxWorld; ++q) if (q < N) v += q == me ? acc2 : __uint_as_float(got[q]);

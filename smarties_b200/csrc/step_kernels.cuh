@@ -44,10 +44,10 @@ struct CommView {
   int world, rank;
   int nParamsPad, nTilesPad;
   unsigned char* base[kMaxWorld];      // base[q]: rank q's block as mapped into THIS process
-  size_t offGrad, offFlag, offCnt, offCntFlag, offVec, offVecFlag, bytes;
+  size_t offGrad, gradBytes, offFlag, offCnt, offCntFlag, offVec, offVecFlag, bytes;
   long long timeoutCycles;
   int* error;                          // set to 1 if a peer wait timed out
-  __host__ __device__ unsigned long long* grad(int q) const { return reinterpret_cast<unsigned long long*>(base[q] + offGrad); }
+  __host__ __device__ unsigned* grad(int q) const { return reinterpret_cast<unsigned*>(base[q] + offGrad); }   // [step & 3][rank][nParamsPad]
   __host__ __device__ unsigned* flag(int q) const { return reinterpret_cast<unsigned*>(base[q] + offFlag); }
   __host__ __device__ double* cnt(int q) const { return reinterpret_cast<double*>(base[q] + offCnt); }
   __host__ __device__ unsigned* cntFlag(int q) const { return reinterpret_cast<unsigned*>(base[q] + offCntFlag); }
