@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <random>
@@ -808,7 +809,7 @@ static int ensure_seg_capacity(smb200_learner* h, int n) {
   if (h->hSampT) cudaFreeHost(h->hSampT);
   if (h->hStats) cudaFreeHost(h->hStats);
   h->dSampSlot = h->dSampT = nullptr; h->dStats = nullptr; h->hSampSlot = h->hSampT = nullptr; h->hStats = nullptr;
-  h->maxSeg = std::max(n, 1024);
+  h->maxSeg = std::max(n, 2048);
   if (dev_alloc(&h->dSampSlot, (size_t)h->maxSeg * B) || dev_alloc(&h->dSampT, (size_t)h->maxSeg * B) ||
       dev_alloc(&h->dStats, (size_t)h->maxSeg)) return -2;
   SMB200_CUDA_CHECK(cudaMallocHost(&h->hSampSlot, sizeof(int) * (size_t)h->maxSeg * B));
@@ -849,7 +850,10 @@ int smb200_train_steps(smb200_learner* h, int32_t n, smb200_step_stats* stats) {
   SMB200_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
   // Two-deep pipeline: while the GPU runs one segment, the host samples the next one (the sampler
   // is a sequential std::mt19937 stream and must stay on the host to be bit-exact).
-  const int P = std::min(256, h->maxSeg / 2);
+  // Each half of the pinned buffers holds one segment.  Segments grow 64 -> 256 -> 1000 steps: a short first one so
+  // that the device starts early, long ones afterwards (every launch of the persistent kernel costs ~0.1 ms of
+  // start-up and drain; a segment always ends at an every-1000-steps sweep or when the episode table changes).
+  const int P = h->maxSeg / 2;
   int pendCnt[2] = {0, 0}, pendDst[2] = {0, 0};
   auto reclaim = [&](int b) -> int {
     if (!pendCnt[b]) return 0;
@@ -859,14 +863,20 @@ int smb200_train_steps(smb200_learner* h, int32_t n, smb200_step_stats* stats) {
     return 0;
   };
   int done = 0;
+  double hostPlan = 0, hostWait = 0;      // SMB200_HOST_TIMING=1: where the host side of the pipeline spends its time
   for (int i = 0; done < n; ++i) {
     const int b = i & 1, off = b * P;
+    const auto tw0 = std::chrono::steady_clock::now();
     if (reclaim(b)) return SMB200_ERR_CUDA;
+    hostWait += std::chrono::duration<double>(std::chrono::steady_clock::now() - tw0).count();
     const long long g0 = h->gradStep;
     // the order in effect for these steps must reach the device before host_post_step re-sorts
     if (upload_order(h)) return SMB200_ERR_CUDA;
     const int nEpPre = (int)h->episodes.size(); const long long nTrPre = h->nTransitions;
-    const int cnt = plan_segment(h, std::min(n - done, P), off);
+    const auto tp0 = std::chrono::steady_clock::now();
+    const int segLen = i == 0 ? 64 : (i == 1 ? 256 : 1000);
+    const int cnt = plan_segment(h, std::min(std::min(n - done, P), segLen), off);
+    hostPlan += std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count();
     const bool dirtyAfter = h->orderDirty;
     if (upload_samples(h, off, cnt)) return SMB200_ERR_CUDA;
     if (run_segment(h, off, cnt, g0, nEpPre, nTrPre, h->nTransitions)) return SMB200_ERR_CUDA;
@@ -882,6 +892,9 @@ int smb200_train_steps(smb200_learner* h, int32_t n, smb200_step_stats* stats) {
   SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
   h->lastMs = ms; h->lastLaunches = h->launches - l0;
+  if (getenv("SMB200_HOST_TIMING"))
+    fprintf(stderr, "smb200_train_steps(%d): device span %.3f ms, host sampling %.3f ms, host waiting for the device %.3f ms, %lld launches\n",
+            n, ms, 1e3 * hostPlan, 1e3 * hostWait, (long long)h->lastLaunches);
   return 0;
 }
 

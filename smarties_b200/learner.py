@@ -66,6 +66,28 @@ class StepStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class StepStatsList:
+    """Per-step statistics of one smb200_train_steps call: behaves like a list of dicts, converted on access (the C array
+    is what the call filled; building 10^4 Python dicts is not part of a learner step)."""
+
+    def __init__(self, arr):
+        self._a = arr
+
+    def __len__(self):
+        return len(self._a)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._a[j].as_dict() for j in range(*i.indices(len(self._a)))]
+        return self._a[i].as_dict()
+
+    def __iter__(self):
+        return (s.as_dict() for s in self._a)
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+
 _lib = None
 
 
@@ -281,7 +303,7 @@ class Learner:
     def train_steps(self, n, want_stats=True):
         st = (StepStats * n)() if want_stats else None
         self._check(self.lib.smb200_train_steps(self.h, int(n), st))
-        return [s.as_dict() for s in st] if want_stats else None
+        return StepStatsList(st) if want_stats else None
 
     def train_step_on(self, pos, t):
         pos, t = np.ascontiguousarray(pos, np.int64), np.ascontiguousarray(t, np.int64)
