@@ -3,6 +3,7 @@ learner steps on the GPU through libsmarties_b200.so (integration/RACER_B200.cpp
 SMARTIES_B200=1).  Same binary interface, same settings file, same command line.
 
   --app cart_pole   BASELINE.json configs[0]: the reference's apps/cart_pole_cpp + settings/VRACER.json
+  --app py_env      a Python environment (integration/py_env.py) through the reference's pybind11 module
   --app synth_env   configs[3] shape: integration/synth_env.cpp (17 states, 6 bounded actions, 1000-step
                     truncated episodes) with --envs 64 forked environment processes feeding one learner
 
@@ -15,6 +16,7 @@ import json
 import os
 import shutil
 import subprocess
+import sys
 import tempfile
 import time
 
@@ -27,6 +29,13 @@ def run_arm(arm, steps, threads, seed, settings=None, timeout=1500, app="cart_po
             keep_dir=None, restart=None):
     """keep_dir: run there and keep the files (checkpoints); restart: directory of an earlier run (--restart)."""
     exe = os.path.join(ROOT, "oracle", "_ref", "b200" if arm == "b200" else "", app)
+    cmd0 = [exe]
+    pyenv = {}
+    if app == "py_env":      # a Python app through the reference's pybind11 module
+        pydir = os.path.join(ROOT, "oracle", "_ref", "b200" if arm == "b200" else "", "py")
+        exe = pydir
+        cmd0 = [sys.executable, os.path.join(ROOT, "integration", "py_env.py")]
+        pyenv = {"PYTHONPATH": pydir}
     if not os.path.exists(exe):
         return {"arm": arm, "error": f"{exe} missing (make -C integration)"}
     tmp = keep_dir or tempfile.mkdtemp(prefix=f"cartpole_{arm}_")
@@ -37,9 +46,10 @@ def run_arm(arm, steps, threads, seed, settings=None, timeout=1500, app="cart_po
     env.pop("SMARTIES_B200", None)
     if arm == "b200":
         env["SMARTIES_B200"] = "1"
+    env.update(pyenv)
     env.update(extra_env or {})
     t0 = time.perf_counter()
-    p = subprocess.run([exe, "--nTrainSteps", str(steps), "--nThreads", str(threads), "--randSeed", str(seed),
+    p = subprocess.run(cmd0 + ["--nTrainSteps", str(steps), "--nThreads", str(threads), "--randSeed", str(seed),
                         "--nEnvironments", str(envs)] + (["--restart", restart] if restart else []),
                        cwd=tmp, env=env, capture_output=True, text=True, timeout=timeout)
     wall = time.perf_counter() - t0
@@ -72,7 +82,7 @@ if __name__ == "__main__":
     ap.add_argument("--threads", type=int, default=min(8, os.cpu_count() or 1))
     ap.add_argument("--seed", type=int, default=7)
     ap.add_argument("--arms", default="ref,b200")
-    ap.add_argument("--app", default="cart_pole", choices=["cart_pole", "synth_env"])
+    ap.add_argument("--app", default="cart_pole", choices=["cart_pole", "synth_env", "py_env"])
     ap.add_argument("--envs", type=int, default=1)
     ap.add_argument("--max-steps-per-call", type=int, default=0, help="SMARTIES_B200_MAXSTEPS (0 = binding default)")
     a = ap.parse_args()

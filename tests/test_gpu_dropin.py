@@ -70,3 +70,16 @@ def test_checkpoints_cross_between_reference_and_device_learner(tmp_path):
         assert r3["rc"] == 0, r3
         assert any("restarted the device learner at gradient step" in l for l in r3["b200_lines"]), r3
         assert r3["grad_steps_logged"] >= (3000 if src == a else 4000) and 0.0 < r3["beta_last"] <= 1.0, r3
+
+
+def test_python_app_through_pybind11_module_on_the_device_learner():
+    """A Python environment (`import smarties`, the reference's pybind11 module linked against the library with the
+    binding) trains on the device learner: same script, same settings file as with the reference learner."""
+    if not os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "b200", "py")):
+        pytest.skip("oracle/_ref/b200/py not built (make -C integration needs /root/reference)")
+    from dropin_run import run_arm
+    r = run_arm("b200", steps=3000, threads=4, seed=5, timeout=600, app="py_env")
+    assert any("run on the GPU" in l for l in r["b200_lines"]), r
+    done = [l for l in r["b200_lines"] if "gradient steps" in l]
+    assert done and int(done[0].split()[1]) >= 2999, r
+    assert r["stat_rows"] >= 2 and 0.0 < r["beta_last"] <= 1.0, r
