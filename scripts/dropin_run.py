@@ -4,6 +4,7 @@ SMARTIES_B200=1).  Same binary interface, same settings file, same command line.
 
   --app cart_pole   BASELINE.json configs[0]: the reference's apps/cart_pole_cpp + settings/VRACER.json
   --app py_env      a Python environment (integration/py_env.py) through the reference's pybind11 module
+  --app c_env       a C environment on the C interface Fortran apps bind (integration/c_env.c, smarties_extern.h)
   --app synth_env   configs[3] shape: integration/synth_env.cpp (17 states, 6 bounded actions, 1000-step
                     truncated episodes) with --envs 64 forked environment processes feeding one learner
 
@@ -82,7 +83,7 @@ if __name__ == "__main__":
     ap.add_argument("--threads", type=int, default=min(8, os.cpu_count() or 1))
     ap.add_argument("--seed", type=int, default=7)
     ap.add_argument("--arms", default="ref,b200")
-    ap.add_argument("--app", default="cart_pole", choices=["cart_pole", "synth_env", "py_env"])
+    ap.add_argument("--app", default="cart_pole", choices=["cart_pole", "synth_env", "py_env", "c_env"])
     ap.add_argument("--envs", type=int, default=1)
     ap.add_argument("--max-steps-per-call", type=int, default=0, help="SMARTIES_B200_MAXSTEPS (0 = binding default)")
     a = ap.parse_args()

@@ -83,3 +83,15 @@ def test_python_app_through_pybind11_module_on_the_device_learner():
     done = [l for l in r["b200_lines"] if "gradient steps" in l]
     assert done and int(done[0].split()[1]) >= 2999, r
     assert r["stat_rows"] >= 2 and 0.0 < r["beta_last"] <= 1.0, r
+
+
+def test_c_app_through_the_fortran_interface_on_the_device_learner():
+    """An environment written in C against include/smarties_extern.h (the ABI Fortran apps bind) on the device learner."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "b200", "c_env")):
+        pytest.skip("oracle/_ref/b200/c_env not built (make -C integration needs /root/reference)")
+    from dropin_run import run_arm
+    r = run_arm("b200", steps=3000, threads=4, seed=5, timeout=600, app="c_env")
+    assert r.get("rc") == 0, r
+    done = [l for l in r["b200_lines"] if "gradient steps" in l]
+    assert done and int(done[0].split()[1]) >= 2999, r
+    assert r["stat_rows"] >= 2 and 0.0 < r["beta_last"] <= 1.0, r
