@@ -1326,10 +1326,12 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
   float q4[4] = {0.f, 0.f, 0.f, 0.f};
   const AdamCoef ac = adam_coef(hp, c);
   DBG_T(a, step, 24);
-  for (int bc = 0; bc < t.cols; bc += kBC) {
-    if (bc) __syncthreads();
-    constexpr int kLD = 1024 / kST;   // float4 per thread and operand (16 rows x 64 float4)
-    float4 avs[kLD], dvs[kLD];
+  // Operand tiles of one batch chunk: global -> registers -> shared memory.  The loads of chunk c+1 are issued
+  // before the contraction of chunk c (software pipelining: recurrent nets contract over B * (Tc+1) columns, 17 chunks
+  // at cfg3, and paid one L2 round trip per chunk).
+  constexpr int kLD = 1024 / kST;   // float4 per thread and operand (16 rows x 64 float4)
+  float4 avs[kLD], dvs[kLD];
+  auto load_chunk = [&](int bc) {
 #pragma unroll
     for (int i = 0; i < kLD; ++i) {
       const int q = tid + i * kST;
@@ -1355,6 +1357,10 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
       }
       avs[i] = av; dvs[i] = dv;
     }
+  };
+  load_chunk(0);
+  for (int bc = 0; bc < t.cols; bc += kBC) {
+    if (bc) __syncthreads();
 #pragma unroll
     for (int i = 0; i < kLD; ++i) {
       const int q = tid + i * kST;
@@ -1363,6 +1369,7 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
       *reinterpret_cast<float4*>(As + r * kBCP + c4) = avs[i];
       *reinterpret_cast<float4*>(Ds + r * kBCP + c4) = dvs[i];
     }
+    if (bc + kBC < t.cols) load_chunk(bc + kBC);
     __syncthreads();
     DBG_T(a, step, 25);
     if (t.kind == 0) {
