@@ -88,11 +88,51 @@ __device__ void v3(const float* W, const float* b, const float* x, float* y, flo
   __syncthreads();
 }
 
+// V5: tensor cores, mma.sync.m16n8k8 TF32 with the 3xTF32 split (a = hi + lo, hi*hi + hi*lo + lo*hi accumulated in f32):
+// m = output neuron (8 m-tiles of 16), n = sample (8 columns, 4 used), k = input; warp = (m-tile, K half); the weight
+// image needs row stride == 8 (mod 32) floats (136) for conflict-free fragment loads.
+constexpr int LDM = 136;
+__device__ __forceinline__ unsigned tf32_of(float f) { unsigned u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(f)); return u; }
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ void v5(const float* W, const float* b, const float* x, float* y, float* red) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+  const int mt = warp & 7, kh = warp >> 3;
+  float c[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
+  float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* w = W + (kh * 64 + tig) * LDM + mt * 16 + gid;
+  const float* xx = x + (kh * 64 + tig) * 4 + gid;
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const float af[4] = {w[ks * 8 * LDM], w[ks * 8 * LDM + 8], w[(ks * 8 + 4) * LDM], w[(ks * 8 + 4) * LDM + 8]};
+    const float b0f = gid < 4 ? xx[ks * 32] : 0.f, b1f = gid < 4 ? xx[ks * 32 + 16] : 0.f;
+    unsigned ah[4], al[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ah[i] = tf32_of(af[i]); al[i] = tf32_of(af[i] - __uint_as_float(ah[i])); }
+    const unsigned bh0 = tf32_of(b0f), bh1 = tf32_of(b1f);
+    const unsigned bl0 = tf32_of(b0f - __uint_as_float(bh0)), bl1 = tf32_of(b1f - __uint_as_float(bh1));
+    if (ks & 1) { mma_tf32(d1, al, bh0, bh1); mma_tf32(d2, ah, bl0, bl1); mma_tf32(d0, ah, bh0, bh1); }
+    else        { mma_tf32(c1, al, bh0, bh1); mma_tf32(c2, ah, bl0, bl1); mma_tf32(c, ah, bh0, bh1); }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (c[i] + d0[i]) + ((c1[i] + d1[i]) + (c2[i] + d2[i]));
+  if (tig < 2) {      // columns 2*tig, 2*tig+1 are real samples
+    float* r0 = red + ((kh * 128) + mt * 16 + gid) * 4 + 2 * tig;
+    r0[0] = c[0]; r0[1] = c[1]; r0[8 * 4] = c[2]; r0[8 * 4 + 1] = c[3];
+  }
+  __syncthreads();
+  { const int n2 = tid >> 2, s = tid & 3; y[n2 * 4 + s] = tanh_ref(b[n2] + red[n2 * 4 + s] + red[(128 + n2) * 4 + s]); }
+  __syncthreads();
+}
+
 template <int V>
 __global__ void bench(const float* Wg, const float* bg, const float* xg, float* yg, long long* cyc) {
   extern __shared__ __align__(16) float sm[];
-  float* W = sm; float* b = W + K * LDP; float* x = b + N; float* y = x + K * 4; float* red = y + N * 4;
+  float* W = sm; float* b = W + K * LDP; float* x = b + N; float* y = x + K * 4; float* red = y + N * 4; float* Wm = red + T * 16;
   for (int i = threadIdx.x; i < K * LDP; i += T) W[i] = Wg[i];
+  for (int i = threadIdx.x; i < K * LDM; i += T) { const int k = i / LDM, n = i - k * LDM; Wm[i] = n < N ? Wg[k * LDP + n] : 0.f; }
   for (int i = threadIdx.x; i < N; i += T) b[i] = bg[i];
   for (int i = threadIdx.x; i < K * 4; i += T) x[i] = xg[i];
   __syncthreads();
@@ -103,6 +143,7 @@ __global__ void bench(const float* Wg, const float* bg, const float* xg, float* 
     if (V == 2) v1<16>(W, b, x, y, red);
     if (V == 3) v3(W, b, x, y, red);
     if (V == 4) v1<4>(W, b, x, y, red);
+    if (V == 5) v5(Wm, b, x, y, red);
   }
   long long t1 = clock64();
   for (int i = threadIdx.x; i < N * 4; i += T) yg[i] = y[i];
@@ -116,10 +157,10 @@ int main() {
   for (int i = 0; i < K * 4; ++i) x[i] = cosf(0.3f * i);
   static float ref[N * 4];
   for (int n = 0; n < N; ++n) for (int s = 0; s < 4; ++s) { double a = b[n]; for (int k = 0; k < K; ++k) a += (double)x[k * 4 + s] * W[k * LDP + n]; ref[n * 4 + s] = (float)tanh(a); }
-  const size_t smem = (K * LDP + N + K * 4 + N * 4 + T * 16) * 4;
-  const char* names[] = {"V0 lanes-over-n, 4 K-groups", "V1 quads, 8 K-groups", "V1 quads, 16 K-groups", "V3 warp-owned columns + shuffle reduce-scatter", "V1 quads, 4 K-groups"};
+  const size_t smem = (K * LDP + N + K * 4 + N * 4 + T * 16 + K * LDM) * 4;
+  const char* names[] = {"V0 lanes-over-n, 4 K-groups", "V1 quads, 8 K-groups", "V1 quads, 16 K-groups", "V3 warp-owned columns + shuffle reduce-scatter", "V1 quads, 4 K-groups", "V5 mma.sync m16n8k8 3xTF32, 8 m-tiles x 2 K-halves"};
 #define RUN(V) { cudaFuncSetAttribute(bench<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); bench<V><<<1, T, smem>>>(W, b, x, y, cyc); cudaDeviceSynchronize(); \
     double e = 0; for (int i = 0; i < N * 4; ++i) e = fmax(e, fabs((double)y[i] - ref[i])); printf("%-48s %6lld cycles/layer  max err %.2e  (%s)\n", names[V], *cyc, e, cudaGetErrorString(cudaGetLastError())); }
-  RUN(0) RUN(1) RUN(2) RUN(3) RUN(4)
+  RUN(0) RUN(1) RUN(2) RUN(3) RUN(4) RUN(5)
   return 0;
 }
