@@ -86,6 +86,7 @@ struct smb200_learner {
   CommView comm{}; unsigned char* commBuf = nullptr; int* dCommErr = nullptr; unsigned vecStamp = 0;
   void* peerMapped[kMaxWorld] = {nullptr};
   float *actG = nullptr, *errG = nullptr;
+  float* tcPartial = nullptr; int useTc = 0;     // tensor-core weight gradient of LSTM layers (recurrent nets)
   GradTile* dTiles = nullptr; int nTiles = 0;
   int Bpad = 0;
 
@@ -116,6 +117,7 @@ struct smb200_learner {
     StepArgs a{};
     a.comm = comm;
     a.descs = dDescs; a.rp = rp; a.W = W; a.Wimg = Wimg; a.M1 = M1; a.M2 = M2; a.G = G; a.dbgT = nullptr; a.useTma = useTma;
+    a.useTc = useTc; a.tcPartial = tcPartial;
     a.actG = actG; a.errG = errG; a.sampRow = dSampT; a.sampSlot = dSampSlot; a.rec = dRec;
     a.lastO = lastO; a.lastG = lastG; a.lastX = lastX; a.ctrl = dCtrl; a.statsOut = dStats;
     a.tiles = dTiles; a.nTiles = nTiles; a.B = cfg.batch_size; a.Bpad = Bpad;
@@ -556,6 +558,16 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
   CK(dev_alloc(&h->M1, (size_t)net.nParams)); CK(dev_alloc(&h->M2, (size_t)net.nParams)); CK(dev_alloc(&h->G, (size_t)net.nParams));
   h->Bpad = net.recurrent ? round_up(B * net.Tc, 256) : round_up(B, 256);
   CK(dev_alloc(&h->actG, (size_t)net.actPerSample * h->Bpad)); CK(dev_alloc(&h->errG, (size_t)net.actPerSample * h->Bpad));
+  if (net.recurrent) {      // LSTM weight gradients on the tensor cores unless SMB200_TC=0
+    const char* e = getenv("SMB200_TC");
+    const TcPlan tp = tc_plan(net, h->Bpad, tc_staging_bytes(net));
+    if (!(e && strcmp(e, "0") == 0) && tp.nItems > 0) {
+      CK(dev_alloc(&h->tcPartial, (size_t)tp.nItems * 128 * 64));
+      h->useTc = 1;
+    }
+  }
+  CK(dev_alloc(&h->dCommErr, 1));
+  h->comm.error = h->dCommErr;
   h->nTiles = (int)tiles.size();
   CK(dev_alloc(&h->dTiles, tiles.size()));
   CKC(cudaMemcpy(h->dTiles, tiles.data(), sizeof(GradTile) * tiles.size(), cudaMemcpyHostToDevice));
@@ -607,6 +619,7 @@ void smb200_destroy(smb200_learner* h) {
   for (int q = 0; q < kMaxWorld; ++q) if (h->peerMapped[q]) cudaIpcCloseMemHandle(h->peerMapped[q]);
   if (h->commBuf) cudaFree(h->commBuf);
   if (h->dCommErr) cudaFree(h->dCommErr);
+  if (h->tcPartial) cudaFree(h->tcPartial);
   if (h->hSampSlot) cudaFreeHost(h->hSampSlot);
   if (h->hSampT) cudaFreeHost(h->hSampT);
   if (h->hStats) cudaFreeHost(h->hStats);
@@ -1018,7 +1031,6 @@ int smb200_comm_init(smb200_learner* h, int32_t world, int32_t rank, uint8_t* ha
     SMB200_CUDA_CHECK(cudaMalloc(&h->commBuf, h->comm.bytes));
     SMB200_CUDA_CHECK(cudaMemset(h->commBuf, 0, h->comm.bytes));
     SMB200_CUDA_CHECK(cudaMemset(h->commBuf + h->comm.offGrad, 0xFF, h->comm.gradBytes));     // "not arrived yet" (kPoison)
-    if (dev_alloc(&h->dCommErr, 1)) return SMB200_ERR_CUDA;
   }
   cudaIpcMemHandle_t hd;
   SMB200_CUDA_CHECK(cudaIpcGetMemHandle(&hd, h->commBuf));
@@ -1048,6 +1060,7 @@ int smb200_comm_error(smb200_learner* h) {
   if (!h->dCommErr) return 0;
   int e = 0;
   if (d2h(h, &e, h->dCommErr, sizeof(int))) return SMB200_ERR_CUDA;
+  if (e == 2) { set_error_msg("a tensor-core weight-gradient item did not complete (tcgen05 commit never arrived)"); return SMB200_ERR_STATE; }
   if (e) { set_error_msg("a peer rank did not answer within the time-out of the fused gradient exchange"); return SMB200_ERR_STATE; }
   return 0;
 }

@@ -1288,7 +1288,7 @@ __device__ __forceinline__ float adam_step(const AdamCoef& k, float G, float W, 
 }
 
 __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, const StepCtrl& c, const GradTile t,
-                        float* tiles, int step, int tileIdx) {
+                        float* tiles, int step, int tileIdx, const TcPlan* tc = nullptr) {
   const int tid = threadIdx.x;
   float* As = tiles;                 // [16][kBCP]
   float* Ds = tiles + kTileK * kBCP; // [16][kBCP]
@@ -1358,6 +1358,21 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
       avs[i] = av; dvs[i] = dv;
     }
   };
+  // LSTM layers whose contraction ran on the tensor cores (tc_wgrad_item): add the K-slices of this tile's outputs in
+  // slice order and skip the SIMT contraction
+  const bool fromTc = tc && lstm && t.kind == 0 && tc->slices[t.layer] > 0;
+  if (fromTc) {
+    if (tid < 256) {
+      const int k = t.k0 + kk, n = t.n0 + nn;
+      if (n < N && k <= K) {
+        const int nS = tc->slices[t.layer];
+        const float* src = a.tcPartial + ((size_t)(tc->item0[t.layer] + (n >> 6) * nS) * 128 + k) * 64 + (n & 63);
+        float v = 0.f;
+        for (int sl = 0; sl < nS; ++sl) v += ld_cg(src + (size_t)sl * 128 * 64);
+        acc = v;
+      }
+    }
+  } else {
   load_chunk(0);
   for (int bc = 0; bc < t.cols; bc += kBC) {
     if (bc) __syncthreads();
@@ -1410,7 +1425,8 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
       }
     }
   }
-  if (t.kind == 0) {   // combine the batch slices: thread (kk, nn) of the first 256 owns output (kk, nn)
+  }
+  if (t.kind == 0 && !fromTc) {   // combine the batch slices: thread (kk, nn) of the first 256 owns output (kk, nn)
     __syncthreads();
     float* part = As;  // [kST/64][64][4]
     *reinterpret_cast<float4*>(part + tid * 4) = make_float4(q4[0], q4[1], q4[2], q4[3]);
@@ -1470,6 +1486,128 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
     a.G[p1] = acc2;
     a.Wimg[pimg1] = adam_step(ac, acc2, w1, m11, m21, a.W + p1, a.M1 + p1, a.M2 + p1);
   }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Tensor-core weight gradient of LSTM layers (recurrent nets, persistent kernel only).
+//
+// dW[k][n] = sum over the B*(Tc+1) (sample, window step) columns of  A[k][col] * Delta[n][col],  A = [x | h_prev | 1]
+// (K = nIn + nCells + 1 <= 128 rows), Delta = the 4*nCells gate deltas — the one large contraction of this path
+// (97 x 256 outputs over 4224 columns at cfg3).  Work item = (layer, n-tile of 64 gate columns, K-slice of Wc columns):
+//   1. all threads stage the slice of both operands from the feature-major scratch into shared memory, split into a
+//      TF32 "hi" part and the f32 remainder "lo" (3xTF32: hi*hi + hi*lo + lo*hi keeps f32 accuracy — plain TF32 misses the
+//      parity tolerances, profiles/r1/microbench_tcgen05_tf32.txt), in the UMMA no-swizzle K-major layout
+//      smem[k-chunk][row] (one float4 = 4 columns; leading byte offset = (rows+1)*16 B so that the staging stores are
+//      conflict-free, stride byte offset 128 B);
+//   2. one thread issues Wc/8 x 3 tcgen05.mma.cta_group::1.kind::tf32 (M 128, N 64, accumulator in tensor memory) and
+//      commits them to an mbarrier;
+//   3. warps 0-3 read the accumulator with tcgen05.ld.32x32b and store the partial tile to global memory.
+// After a grid barrier the 16x16 tile owners of p2_tile add the K-slices in slice order (deterministic) and continue with the
+// exchange and Adam.  The staging area is the whole dynamic shared memory between the descriptors and the sample scalars
+// (weight image + sequence workspace: both dead during P2, the image is reloaded after barrier 2).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t umma_desc(const void* base, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;                                               // cute/arch/mma_sm100_desc.hpp:98-123
+  d |= (uint64_t)((smem_u32(base) >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                                       // version 1 (Blackwell); no swizzle, base offset 0
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ float tf32_hi(float x) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u); }
+__device__ __forceinline__ void split4(const float4 v, float4& h, float4& l) {
+  h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+  l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+}
+constexpr int kTcLdA = 129, kTcLdB = 65;          // rows + 1 float4 per k-chunk
+
+__device__ void tc_wgrad_item(const StepArgs& a, const NetDesc& net, const TcPlan& plan, int item, unsigned char* staging,
+                              uint32_t tmem_d, uint64_t* bar, unsigned& phase) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int l = 1;
+  for (; l < net.nLayers; ++l) if (plan.slices[l] && item >= plan.item0[l] && item < plan.item0[l] + plan.slices[l] * plan.nT[l]) break;
+  const LayerDesc& L = net.L[l];
+  const int li = item - plan.item0[l], nt = li / plan.slices[l], sl = li - nt * plan.slices[l];
+  const int Wc = plan.Wc, KC = Wc >> 2, col0 = sl * Wc;
+  const int K = L.nIn + L.size, N = 4 * L.size, n0 = nt * 64;
+  const int aOff = net.L[L.in].actOff, hOff = L.actOff + L.size - L.nIn, dOff = L.actOff;
+  const int cols = a.Bpad;
+  float4* Ah = reinterpret_cast<float4*>(staging);
+  float4* Al = Ah + (size_t)KC * kTcLdA;
+  float4* Bh = Al + (size_t)KC * kTcLdA;
+  float4* Bl = Bh + (size_t)KC * kTcLdB;
+  // ---- 1. stage + split: 8 consecutive lanes read 8 consecutive k-chunks (128 B) of one scratch row ----
+  for (int q = tid; q < 128 * KC; q += kST) {
+    const int r = q / KC, cc = q - r * KC, col = col0 + 4 * cc;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < cols) {
+      if (r < K) v = ld_cg4(a.actG + (size_t)((r >= L.nIn ? hOff : aOff) + r) * a.Bpad + col);
+      else if (r == K) v = make_float4(1.f, 1.f, 1.f, 1.f);       // bias row: db += delta
+    }
+    float4 h, lo; split4(v, h, lo);
+    Ah[cc * kTcLdA + r] = h; Al[cc * kTcLdA + r] = lo;
+  }
+  for (int q = tid; q < 64 * KC; q += kST) {
+    const int r = q / KC, cc = q - r * KC, col = col0 + 4 * cc, n = n0 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < cols && n < N) v = ld_cg4(a.errG + (size_t)(dOff + n) * a.Bpad + col);
+    float4 h, lo; split4(v, h, lo);
+    Bh[cc * kTcLdB + r] = h; Bl[cc * kTcLdB + r] = lo;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic stores -> tensor-core (async proxy) reads
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // ---- 2. MMA issue by one thread ----
+  if (tid == 0) {
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);   // f32 <- tf32 x tf32, K-major, N 64, M 128
+    for (int kk = 0; kk < Wc / 8; ++kk) {
+      const uint64_t dah = umma_desc(Ah + (size_t)(2 * kk) * kTcLdA, kTcLdA * 16, 128), dal = umma_desc(Al + (size_t)(2 * kk) * kTcLdA, kTcLdA * 16, 128);
+      const uint64_t dbh = umma_desc(Bh + (size_t)(2 * kk) * kTcLdB, kTcLdB * 16, 128), dbl = umma_desc(Bl + (size_t)(2 * kk) * kTcLdB, kTcLdB * 16, 128);
+      umma_tf32(tmem_d, dal, dbh, idesc, kk > 0);
+      umma_tf32(tmem_d, dah, dbl, idesc, 1);
+      umma_tf32(tmem_d, dah, dbh, idesc, 1);
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  }
+  // ---- 3. accumulator -> registers -> partial tile ----
+  if (warp < 4) {
+    uint32_t ok = 0;
+    for (int spin = 0; spin < (1 << 24) && !ok; ++spin)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp * 32 <= K) {                     // rows beyond the bias row are padding
+      uint32_t v[64];
+      const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
+#define SMB200_TMEM_LD32(off) asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 " \
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" \
+        : "=r"(v[off+0]),"=r"(v[off+1]),"=r"(v[off+2]),"=r"(v[off+3]),"=r"(v[off+4]),"=r"(v[off+5]),"=r"(v[off+6]),"=r"(v[off+7]), \
+          "=r"(v[off+8]),"=r"(v[off+9]),"=r"(v[off+10]),"=r"(v[off+11]),"=r"(v[off+12]),"=r"(v[off+13]),"=r"(v[off+14]),"=r"(v[off+15]), \
+          "=r"(v[off+16]),"=r"(v[off+17]),"=r"(v[off+18]),"=r"(v[off+19]),"=r"(v[off+20]),"=r"(v[off+21]),"=r"(v[off+22]),"=r"(v[off+23]), \
+          "=r"(v[off+24]),"=r"(v[off+25]),"=r"(v[off+26]),"=r"(v[off+27]),"=r"(v[off+28]),"=r"(v[off+29]),"=r"(v[off+30]),"=r"(v[off+31]) \
+        : "r"(taddr + off))
+      SMB200_TMEM_LD32(0); SMB200_TMEM_LD32(32);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int row = warp * 32 + lane;
+      if (ok && row <= K) {
+        float4* dst = reinterpret_cast<float4*>(a.tcPartial + ((size_t)item * 128 + row) * 64);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+      }
+    }
+    if (!ok && lane == 0 && a.comm.error) *a.comm.error = 2;       // reported by the host like a peer time-out
+  }
+  phase ^= 1u;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();                            // the next item overwrites the staging area and the accumulator
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1846,12 +1984,22 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
   const int nw = gridDim.x - 1;                 // worker CTAs
   unsigned* ready = a.barrier + 1;              // local steps whose statistics are published
   float* tiles = reinterpret_cast<float*>(smraw + sp.tiles);
+  // recurrent nets: LSTM weight gradients on the tensor cores (one more grid barrier per step, between the K-slice
+  // items and the tiles that add them up)
+  TcPlan tcp; tcp.nItems = 0;
+  const size_t descBytes = ((sizeof(DevDescs) + 15) / 16) * 16;
+  if (REC && a.useTc) tcp = tc_plan(*net, a.Bpad, sps.info - descBytes);
+  const bool tcOn = REC && a.useTc && tcp.nItems > 0;
+  const int barsPerStep = tcOn ? 3 : 2;
+  __shared__ __align__(8) uint64_t tcBar;
+  __shared__ uint32_t tcTmem;
+  unsigned tcPhase = 0;
   if ((int)blockIdx.x == nw) {                  // ---- statistics CTA ----
     for (int s = 0; s < nSteps; ++s) {
       if (skipStatsLast && s == nSteps - 1) break;
       const int step = step0 + s;
       if (threadIdx.x == 0) {
-        const unsigned target = (unsigned)(2 * s + 1) * (unsigned)nw;      // every worker passed barrier 1 of step s
+        const unsigned target = (unsigned)(barsPerStep * s + 1) * (unsigned)nw;      // every worker passed barrier 1 of step s
         while (ld_acquire(a.barrier) < target) { }
         __threadfence();
         load_ctrl(c, &a.ctrl[step & 1]);
@@ -1867,6 +2015,19 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
       DBG_T(a, step, 7);
     }
     return;
+  }
+  if (tcOn) {       // worker CTAs: 64 columns of tensor memory (the 128 x 64 f32 accumulator) for the whole launch
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&tcBar)) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 32) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tcTmem)), "r"(64u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
   const int nP1 = REC ? a.B : (a.B + TB - 1) / TB;
   unsigned barTarget = 0;
@@ -1981,11 +2142,16 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
       if (tid == 0) load_ctrl(c, &a.ctrl[step & 1]);
       __syncthreads();
     }
+    if (tcOn) {
+      for (int it = blockIdx.x; it < tcp.nItems; it += nw)
+        tc_wgrad_item(a, *net, tcp, it, smraw + descBytes, tcTmem, &tcBar, tcPhase);
+      grid_barrier(a.barrier, barTarget, nw);
+    }
     for (int t = blockIdx.x; t < a.nTiles; t += nw) {
       GradTile gt = myTile;
       if (t != (int)blockIdx.x) gt = a.tiles[t];
       DBG_T(a, step, 36);
-      p2_tile(a, *net, *hp, c, gt, tiles, step, t);
+      p2_tile(a, *net, *hp, c, gt, tiles, step, t, tcOn ? &tcp : nullptr);
       __syncthreads();
     }
     // ---- the copies have had the whole weight-gradient phase to land; pick each old value out of its chunk ----
@@ -2006,6 +2172,11 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
     staged = pfNow;
     DBG_T(a, step, 7);
     grid_barrier(a.barrier, barTarget, nw);
+  }
+  if (tcOn) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tcTmem), "r"(64u) : "memory");
   }
 }
 
@@ -2048,6 +2219,11 @@ static size_t p2_smem_bytes() { return ((sizeof(DevDescs) + 15) / 16) * 16 + siz
 constexpr size_t kSmemBudget = 200 * 1024;
 static size_t plan_total(const NetDesc& net, bool img) { return net.recurrent ? smem_plan_seq(net, img).total : smem_plan(net, 4, img).total; }
 bool step_image_in_smem(const NetDesc& net) { return plan_total(net, true) <= kSmemBudget; }
+size_t tc_staging_bytes(const NetDesc& net) {
+  if (!net.recurrent) return 0;
+  return smem_plan_seq(net, step_image_in_smem(net)).info - ((sizeof(DevDescs) + 15) / 16) * 16;
+}
+
 size_t step_smem_bytes(const NetDesc& net, int TB) { (void)TB; return plan_total(net, step_image_in_smem(net)); }
 
 int step_kernels_prepare(const NetDesc& net) {

@@ -75,9 +75,30 @@ struct StepArgs {
   unsigned* barrier;
   long long* dbgT;                         // optional phase timestamps [step][cta][8] (clock64)
   int useTma;                              // weight image to shared memory by cp.async.bulk (1) or ld.global.cg (0)
+  // recurrent nets: weight gradient of the LSTM layers on the tensor cores (tcgen05, see tc_wgrad_item)
+  int useTc; float* tcPartial;             // [item][128][64] f32 partial tiles of the K-slices
 };
 
 int step_threads();
+// Work decomposition of the tensor-core weight gradient: per LSTM layer, n-tiles of 64 gate columns x K-slices of Wc
+// scratch columns; shared by the host (allocation of the partial tiles) and the kernel.
+struct TcPlan { int Wc; int nItems; int item0[kMaxLayers]; int slices[kMaxLayers]; int nT[kMaxLayers]; };
+__host__ __device__ inline TcPlan tc_plan(const NetDesc& net, int cols, size_t stagingBytes) {
+  TcPlan p; p.nItems = 0;
+  int Wc = (int)(stagingBytes / 1552) / 8 * 8;          // (Wc/4) * (129 + 65) float4, hi and lo images
+  if (Wc > 96) Wc = 96;
+  p.Wc = Wc;
+  for (int l = 0; l < kMaxLayers; ++l) { p.item0[l] = 0; p.slices[l] = 0; p.nT[l] = 0; }
+  if (Wc < 8) return p;
+  for (int l = 1; l < net.nLayers; ++l) {
+    const LayerDesc& L = net.L[l];
+    if (L.kind != kLSTM || L.nIn + L.size + 1 > 128) continue;   // the 128 MMA rows hold [x | h_prev | 1]
+    p.item0[l] = p.nItems; p.slices[l] = (cols + Wc - 1) / Wc; p.nT[l] = (4 * L.size + 63) / 64;
+    p.nItems += p.slices[l] * p.nT[l];
+  }
+  return p;
+}
+size_t tc_staging_bytes(const NetDesc& net);
 // eta of the Adam update that follows `adam_step` completed updates (host and device use the same IEEE ops)
 __host__ __device__ inline float adam_eta_for(double learnrate, double epsAnneal, long long adam_step, double bt1d, double bt2d) {
   const long long nStep = adam_step + 1;                                      // prepare_update: nStep++ (Optimizer.cpp:119)
