@@ -562,7 +562,7 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
     const char* e = getenv("SMB200_TC");
     const TcPlan tp = tc_plan(net, h->Bpad, tc_staging_bytes(net));
     if (!(e && strcmp(e, "0") == 0) && tp.nItems > 0) {
-      CK(dev_alloc(&h->tcPartial, (size_t)tp.nItems * 128 * 64));
+      CK(dev_alloc(&h->tcPartial, (size_t)tp.nItems * 128 * 128));
       h->useTc = 1;
     }
   }

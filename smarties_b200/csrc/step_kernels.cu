@@ -1366,9 +1366,17 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
       const int k = t.k0 + kk, n = t.n0 + nn;
       if (n < N && k <= K) {
         const int nS = tc->slices[t.layer];
-        const float* src = a.tcPartial + ((size_t)(tc->item0[t.layer] + (n >> 6) * nS) * 128 + k) * 64 + (n & 63);
+        const float* src = a.tcPartial + ((size_t)(tc->item0[t.layer] + (n >> 7) * nS) * 128 + k) * 128 + (n & 127);
         float v = 0.f;
-        for (int sl = 0; sl < nS; ++sl) v += ld_cg(src + (size_t)sl * 128 * 64);
+        int sl = 0;
+        for (; sl + 8 <= nS; sl += 8) {       // eight loads in flight, added in slice order
+          float x[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) x[u] = ld_cg(src + (size_t)(sl + u) * 128 * 128);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v += x[u];
+        }
+        for (; sl < nS; ++sl) v += ld_cg(src + (size_t)sl * 128 * 128);
         acc = v;
       }
     }
@@ -1525,7 +1533,8 @@ __device__ __forceinline__ void split4(const float4 v, float4& h, float4& l) {
   h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
   l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
 }
-constexpr int kTcLdA = 129, kTcLdB = 65;          // rows + 1 float4 per k-chunk
+constexpr int kTcLdA = 129, kTcLdB = 129;         // rows + 1 float4 per k-chunk
+constexpr int kTcN = 128;                         // gate columns per item = N of the MMA = TMEM columns
 
 __device__ void tc_wgrad_item(const StepArgs& a, const NetDesc& net, const TcPlan& plan, int item, unsigned char* staging,
                               uint32_t tmem_d, uint64_t* bar, unsigned& phase) {
@@ -1535,30 +1544,47 @@ __device__ void tc_wgrad_item(const StepArgs& a, const NetDesc& net, const TcPla
   const LayerDesc& L = net.L[l];
   const int li = item - plan.item0[l], nt = li / plan.slices[l], sl = li - nt * plan.slices[l];
   const int Wc = plan.Wc, KC = Wc >> 2, col0 = sl * Wc;
-  const int K = L.nIn + L.size, N = 4 * L.size, n0 = nt * 64;
+  const int K = L.nIn + L.size, N = 4 * L.size, n0 = nt * kTcN;
   const int aOff = net.L[L.in].actOff, hOff = L.actOff + L.size - L.nIn, dOff = L.actOff;
   const int cols = a.Bpad;
   float4* Ah = reinterpret_cast<float4*>(staging);
   float4* Al = Ah + (size_t)KC * kTcLdA;
   float4* Bh = Al + (size_t)KC * kTcLdA;
   float4* Bl = Bh + (size_t)KC * kTcLdB;
-  // ---- 1. stage + split: 8 consecutive lanes read 8 consecutive k-chunks (128 B) of one scratch row ----
-  for (int q = tid; q < 128 * KC; q += kST) {
-    const int r = q / KC, cc = q - r * KC, col = col0 + 4 * cc;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (col < cols) {
-      if (r < K) v = ld_cg4(a.actG + (size_t)((r >= L.nIn ? hOff : aOff) + r) * a.Bpad + col);
-      else if (r == K) v = make_float4(1.f, 1.f, 1.f, 1.f);       // bias row: db += delta
+  // ---- 1. stage + split: 8 consecutive lanes read 8 consecutive k-chunks (128 B) of one scratch row; four loads per
+  //         thread are in flight before the first is split ----
+  for (int q0 = tid; q0 < 128 * KC; q0 += 4 * kST) {
+    float4 v[4]; int dst[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int q = q0 + u * kST;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f); dst[u] = -1;
+      if (q < 128 * KC) {
+        const int r = q / KC, cc = q - r * KC, col = col0 + 4 * cc;
+        dst[u] = cc * kTcLdA + r;
+        if (col < cols) {
+          if (r < K) v[u] = ld_cg4(a.actG + (size_t)((r >= L.nIn ? hOff : aOff) + r) * a.Bpad + col);
+          else if (r == K) v[u] = make_float4(1.f, 1.f, 1.f, 1.f);       // bias row: db += delta
+        }
+      }
     }
-    float4 h, lo; split4(v, h, lo);
-    Ah[cc * kTcLdA + r] = h; Al[cc * kTcLdA + r] = lo;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (dst[u] >= 0) { float4 h, lo; split4(v[u], h, lo); Ah[dst[u]] = h; Al[dst[u]] = lo; }
   }
-  for (int q = tid; q < 64 * KC; q += kST) {
-    const int r = q / KC, cc = q - r * KC, col = col0 + 4 * cc, n = n0 + r;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (col < cols && n < N) v = ld_cg4(a.errG + (size_t)(dOff + n) * a.Bpad + col);
-    float4 h, lo; split4(v, h, lo);
-    Bh[cc * kTcLdB + r] = h; Bl[cc * kTcLdB + r] = lo;
+  for (int q0 = tid; q0 < kTcN * KC; q0 += 4 * kST) {
+    float4 v[4]; int dst[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int q = q0 + u * kST;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f); dst[u] = -1;
+      if (q < kTcN * KC) {
+        const int r = q / KC, cc = q - r * KC, col = col0 + 4 * cc, n = n0 + r;
+        dst[u] = cc * kTcLdB + r;
+        if (col < cols && n < N) v[u] = ld_cg4(a.errG + (size_t)(dOff + n) * a.Bpad + col);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (dst[u] >= 0) { float4 h, lo; split4(v[u], h, lo); Bh[dst[u]] = h; Bl[dst[u]] = lo; }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic stores -> tensor-core (async proxy) reads
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1566,7 +1592,7 @@ __device__ void tc_wgrad_item(const StepArgs& a, const NetDesc& net, const TcPla
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   // ---- 2. MMA issue by one thread ----
   if (tid == 0) {
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);   // f32 <- tf32 x tf32, K-major, N 64, M 128
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (((uint32_t)kTcN >> 3) << 17) | ((128u >> 4) << 24);   // f32 <- tf32 x tf32, K-major, N 128, M 128
     for (int kk = 0; kk < Wc / 8; ++kk) {
       const uint64_t dah = umma_desc(Ah + (size_t)(2 * kk) * kTcLdA, kTcLdA * 16, 128), dal = umma_desc(Al + (size_t)(2 * kk) * kTcLdA, kTcLdA * 16, 128);
       const uint64_t dbh = umma_desc(Bh + (size_t)(2 * kk) * kTcLdB, kTcLdB * 16, 128), dbl = umma_desc(Bl + (size_t)(2 * kk) * kTcLdB, kTcLdB * 16, 128);
@@ -1585,7 +1611,6 @@ __device__ void tc_wgrad_item(const StepArgs& a, const NetDesc& net, const TcPla
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (warp * 32 <= K) {                     // rows beyond the bias row are padding
       uint32_t v[64];
-      const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
 #define SMB200_TMEM_LD32(off) asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 " \
         "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" \
         : "=r"(v[off+0]),"=r"(v[off+1]),"=r"(v[off+2]),"=r"(v[off+3]),"=r"(v[off+4]),"=r"(v[off+5]),"=r"(v[off+6]),"=r"(v[off+7]), \
@@ -1593,14 +1618,18 @@ __device__ void tc_wgrad_item(const StepArgs& a, const NetDesc& net, const TcPla
           "=r"(v[off+16]),"=r"(v[off+17]),"=r"(v[off+18]),"=r"(v[off+19]),"=r"(v[off+20]),"=r"(v[off+21]),"=r"(v[off+22]),"=r"(v[off+23]), \
           "=r"(v[off+24]),"=r"(v[off+25]),"=r"(v[off+26]),"=r"(v[off+27]),"=r"(v[off+28]),"=r"(v[off+29]),"=r"(v[off+30]),"=r"(v[off+31]) \
         : "r"(taddr + off))
-      SMB200_TMEM_LD32(0); SMB200_TMEM_LD32(32);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       const int row = warp * 32 + lane;
-      if (ok && row <= K) {
-        float4* dst = reinterpret_cast<float4*>(a.tcPartial + ((size_t)item * 128 + row) * 64);
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+      for (int half = 0; half < kTcN / 64; ++half) {
+        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + half * 64;
+        SMB200_TMEM_LD32(0); SMB200_TMEM_LD32(32);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (ok && row <= K) {
+          float4* dst = reinterpret_cast<float4*>(a.tcPartial + ((size_t)item * 128 + row) * kTcN + half * 64);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
       }
     }
     if (!ok && lane == 0 && a.comm.error) *a.comm.error = 2;       // reported by the host like a peer time-out
@@ -2016,13 +2045,13 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
     }
     return;
   }
-  if (tcOn) {       // worker CTAs: 64 columns of tensor memory (the 128 x 64 f32 accumulator) for the whole launch
+  if (tcOn) {       // worker CTAs: 128 columns of tensor memory (the 128 x 128 f32 accumulator) for the whole launch
     if (threadIdx.x == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&tcBar)) : "memory");
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 32) {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tcTmem)), "r"(64u) : "memory");
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tcTmem)), "r"(128u) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -2176,7 +2205,7 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
   if (tcOn) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tcTmem), "r"(64u) : "memory");
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tcTmem), "r"(128u) : "memory");
   }
 }
 

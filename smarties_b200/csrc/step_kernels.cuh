@@ -76,16 +76,16 @@ struct StepArgs {
   long long* dbgT;                         // optional phase timestamps [step][cta][8] (clock64)
   int useTma;                              // weight image to shared memory by cp.async.bulk (1) or ld.global.cg (0)
   // recurrent nets: weight gradient of the LSTM layers on the tensor cores (tcgen05, see tc_wgrad_item)
-  int useTc; float* tcPartial;             // [item][128][64] f32 partial tiles of the K-slices
+  int useTc; float* tcPartial;             // [item][128][128] f32 partial tiles of the K-slices
 };
 
 int step_threads();
-// Work decomposition of the tensor-core weight gradient: per LSTM layer, n-tiles of 64 gate columns x K-slices of Wc
+// Work decomposition of the tensor-core weight gradient: per LSTM layer, n-tiles of 128 gate columns x K-slices of Wc
 // scratch columns; shared by the host (allocation of the partial tiles) and the kernel.
 struct TcPlan { int Wc; int nItems; int item0[kMaxLayers]; int slices[kMaxLayers]; int nT[kMaxLayers]; };
 __host__ __device__ inline TcPlan tc_plan(const NetDesc& net, int cols, size_t stagingBytes) {
   TcPlan p; p.nItems = 0;
-  int Wc = (int)(stagingBytes / 1552) / 8 * 8;          // (Wc/4) * (129 + 65) float4, hi and lo images
+  int Wc = (int)(stagingBytes / 2064) / 8 * 8;          // (Wc/4) * (129 + 129) float4, hi and lo images
   if (Wc > 96) Wc = 96;
   p.Wc = Wc;
   for (int l = 0; l < kMaxLayers; ++l) { p.item0[l] = 0; p.slices[l] = 0; p.nT[l] = 0; }
@@ -93,7 +93,7 @@ __host__ __device__ inline TcPlan tc_plan(const NetDesc& net, int cols, size_t s
   for (int l = 1; l < net.nLayers; ++l) {
     const LayerDesc& L = net.L[l];
     if (L.kind != kLSTM || L.nIn + L.size + 1 > 128) continue;   // the 128 MMA rows hold [x | h_prev | 1]
-    p.item0[l] = p.nItems; p.slices[l] = (cols + Wc - 1) / Wc; p.nT[l] = (4 * L.size + 63) / 64;
+    p.item0[l] = p.nItems; p.slices[l] = (cols + Wc - 1) / Wc; p.nT[l] = (4 * L.size + 127) / 128;
     p.nItems += p.slices[l] * p.nT[l];
   }
   return p;
