@@ -23,9 +23,14 @@ L.seed_sampler(7)
 L.train_steps(1, want_stats=False)
 L.presample(steps + 20)
 L.train_presampled(0, 20); L.sync()
+if os.environ.get("PROF_RANGE"):                    # ncu --profile-from-start off: capture only the timed launch
+    import torch
+    torch.cuda.profiler.start()
 t0 = time.perf_counter()
 L.train_presampled(20, steps)
 L.sync()
+if os.environ.get("PROF_RANGE"):
+    torch.cuda.profiler.stop()
 ms, nl = L.last_timing()
 print(f"cfg3: {steps} steps, device {ms:.3f} ms -> {1e3 * ms / steps:.1f} us/step, {128 * steps / (ms * 1e-3):.3e} transitions/s, launches {nl}, wall {time.perf_counter() - t0:.3f}s")
 print("stats", L.get_stats())

@@ -13,3 +13,7 @@ PROF_RANGE=1 PROF_STEPS=256 PROF_SWEEPS=1 ncu --set full --clock-control none --
 tail -5 gpurun_out/ncu_full.log
 ncu -i gpurun_out/full_steps.ncu-rep --page raw --csv > gpurun_out/full_steps_raw.csv 2>/dev/null
 ls -la gpurun_out/*.ncu-rep gpurun_out/*.csv
+# cfg3 (RACER + LSTM): the persistent kernel with the tcgen05 weight-gradient contraction — tensor-pipe evidence
+PROF_RANGE=1 PROF_STEPS=64 ncu --set full --clock-control none --import-source on --profile-from-start off \
+    -k regex:'k_steps_persistent' -o gpurun_out/full_cfg3 -f python scripts/cfg3_probe.py > gpurun_out/ncu_cfg3.log 2>&1 || true
+ncu -i gpurun_out/full_cfg3.ncu-rep --page raw --csv > gpurun_out/full_cfg3_raw.csv 2>/dev/null
