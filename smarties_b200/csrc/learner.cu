@@ -478,6 +478,7 @@ static int run_segment(smb200_learner* h, int first, int n, long long gstep0, in
 extern "C" {
 
 static int ensure_seg_capacity(smb200_learner* h, int n);
+int smb200_comm_error(smb200_learner* h);
 
 const char* smb200_last_error(void) { return g_err.c_str(); }
 
@@ -905,6 +906,7 @@ int smb200_train_steps(smb200_learner* h, int32_t n, smb200_step_stats* stats) {
   SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
   h->lastMs = ms; h->lastLaunches = h->launches - l0;
+  if (h->useTc && smb200_comm_error(h)) return SMB200_ERR_STATE;     // a tensor-core item that never completed must not pass silently
   if (getenv("SMB200_HOST_TIMING"))
     fprintf(stderr, "smb200_train_steps(%d): device span %.3f ms, host sampling %.3f ms, host waiting for the device %.3f ms, %lld launches\n",
             n, ms, 1e3 * hostPlan, 1e3 * hostWait, (long long)h->lastLaunches);

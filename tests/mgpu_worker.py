@@ -17,7 +17,9 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dS, dA, Bl = 12, 4, 32
-    settings = {"nnLayerSizes": [64, 64], "batchSize": Bl * world, "maxTotObsNum": 4096 * world, "minTotObsNum": 1000 * world}
+    net = ({"learner": "RACER", "nnType": "LSTM", "nnLayerSizes": [24], "nnBPTTseq": 6} if os.environ.get("MGPU_NET") == "lstm"
+           else {"nnLayerSizes": [64, 64]})       # lstm: the tensor-core weight gradient feeds the exchange
+    settings = dict(net, batchSize=Bl * world, maxTotObsNum=4096 * world, minTotObsNum=1000 * world)
     d = synth.make_replay(100 + rank, 30, (40, 70), dS, dA)
     L = Learner(dS, dA, settings, device=local, seed=5 + rank, world_rank=rank, world_size=world)
     L.attach_process_group(dist)
@@ -26,7 +28,7 @@ def main():
     L.initialize_learner()
     L.seed_sampler(11 + rank)
     # a single-rank clone of this shard: same weights, same samples, same global scaling
-    S = Learner(dS, dA, {"nnLayerSizes": [64, 64], "batchSize": Bl, "maxTotObsNum": 4096, "minTotObsNum": 1000}, device=local, seed=5)
+    S = Learner(dS, dA, dict(net, batchSize=Bl, maxTotObsNum=4096, minTotObsNum=1000), device=local, seed=5)
     S.set_weights(w0)
     S.load_replay(d)
     S.initialize_learner()
