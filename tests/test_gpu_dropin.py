@@ -95,3 +95,19 @@ def test_c_app_through_the_fortran_interface_on_the_device_learner():
     done = [l for l in r["b200_lines"] if "gradient steps" in l]
     assert done and int(done[0].split()[1]) >= 2999, r
     assert r["stat_rows"] >= 2 and 0.0 < r["beta_last"] <= 1.0, r
+
+
+def test_cart_pole_recurrent_racer_on_the_device_learner():
+    """settings/RACER_RNN.json of the reference (RACER, LSTM layers, BPTT window): the actors run the reference's recurrent
+    `Approximator` on the host, the learner steps — including the tcgen05 weight-gradient contraction — run on the GPU."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "b200", "cart_pole")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/b200/cart_pole not built (make -C integration needs /root/reference)")
+    from dropin_run import run_arm
+    S = {"learner": "RACER", "nnType": "LSTM", "nnLayerSizes": [32, 32], "clipImpWeight": 4, "explNoise": 0.1, "gamma": 0.99,
+         "epsAnneal": 0, "nnLambda": 1e-6, "maxTotObsNum": 16384, "minTotObsNum": 4096}
+    r = run_arm("b200", steps=2000, threads=4, seed=7, settings=S, timeout=600)
+    assert r.get("rc") == 0, r
+    done = [l for l in r["b200_lines"] if "gradient steps" in l]
+    assert done and int(done[0].split()[1]) >= 1999, r
+    assert r["stat_rows"] >= 1 and 0.0 < r["beta_last"] <= 1.0 and np.isfinite(r["avgR_last"]), r
