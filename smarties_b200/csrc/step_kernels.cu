@@ -7,11 +7,16 @@
 //       into shared memory with cp.async.bulk (TMA) right after the grid barrier; gather +
 //       standardise states from the HBM replay rows, MLP forward, ReF-ER / Retrace loss and
 //       output gradient in f64, write-back of V/Q/delta/KL/rho to the replay rows, input-
-//       gradient backward; activations and deltas are left feature-major in a scratch for P2.
-//                                                                      (RACER_train.cpp:12-67)
+//       gradient backward; activations and deltas are left in a scratch for P2 (tile-major for
+//       feed-forward nets, feature-major [feature][sample*Tc+k] for recurrent ones).  The next
+//       step's inputs arrive by cp.async during P2; V(s_t+1) of truncated episodes is evaluated by
+//       otherwise idle worker CTAs (next_state_helper).                 (RACER_train.cpp:12-67)
 //   P2  per 16x16 tile of every weight matrix: dW = A^T * Delta contracted over the whole
-//       mini-batch in batch order, fused with the reference's Adam variant in the epilogue
-//       (the per-thread gradient buffers and their reduction, Parameters.h:66-103, vanish).
+//       mini-batch in batch order, fused with the gradient exchange between learner ranks (peer
+//       memory over NVLink) and the reference's Adam variant in the epilogue (the per-thread
+//       gradient buffers and their reduction, Parameters.h:66-103, vanish).  LSTM layers contract
+//       on the tensor cores first (tcgen05.mma kind::tf32, 3xTF32, accumulator in TMEM:
+//       tc_wgrad_item), the tiles then add the K-slices.
 //   P3  one CTA, concurrent with P2: per-episode aggregate updates in sample order
 //       (Episode.h:112-145), the per-step replay statistics, Cmax annealing and the ReF-ER
 //       beta fixed-point update (MemoryProcessing.cpp:46-92,187-259).
@@ -1449,8 +1454,8 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
   }
   // ---- gradient sum over learner ranks, fused into the tile (replaces the MPI_Iallreduce of
   //      AdamOptimizer::prepare_update, Optimizer.cpp:114-118): every rank pushes its partial tile
-  //      into every peer's slot over NVLink, publishes a stamp, waits for the peers' stamps on LOCAL
-  //      memory and adds the slots in rank order, so all ranks apply the identical update ----
+  //      into every peer's slot over NVLink as 4-byte elements (poison = not arrived yet), polls its own
+  //      slots in LOCAL memory and adds them in rank order, so all ranks apply the identical update ----
   if (a.comm.world > 1) {
     DBG_T(a, step, 33);
     const CommView& cm = a.comm;
@@ -2066,8 +2071,8 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
   const int tid = threadIdx.x;
   const int dS = net->dS, dA = net->dA, nPair = TB * dA;
   const int nS4 = dS * TB / 4;                      // float4 chunks of this tile's raw states
-  // inputs of step s+1 are prefetched into registers while P2 of step s runs, then parked in the
-  // shared-memory staging area: possible when every worker owns at most one P1 tile
+  // inputs of step s+1 are copied into the shared-memory staging area (cp.async) while P2 of step s runs:
+  // possible when every worker owns at most one P1 tile
   const bool pf = !REC && doP1 && nP1 <= nw && (dS & 3) == 0 && nS4 <= 2 * kST && nPair <= kST;
   // idle worker CTAs evaluate V(s_{t+1}) of truncated episodes for the P1 CTAs (next_state_helper)
   const int nHelpers = (!REC && nP1 < nw) ? nw - nP1 : 0;
