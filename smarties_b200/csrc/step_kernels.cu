@@ -1542,7 +1542,8 @@ constexpr int kTcLdA = 129, kTcLdB = 129;         // rows + 1 float4 per k-chunk
 constexpr int kTcN = 128;                         // gate columns per item = N of the MMA = TMEM columns
 
 __device__ void tc_wgrad_item(const StepArgs& a, const NetDesc& net, const TcPlan& plan, int item, unsigned char* staging,
-                              uint32_t tmem_d, uint64_t* bar, unsigned& phase) {
+                              uint32_t tmem_d, uint64_t* bar, unsigned& phase, int step) {
+  DBG_T(a, step, 42);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int l = 1;
   for (; l < net.nLayers; ++l) if (plan.slices[l] && item >= plan.item0[l] && item < plan.item0[l] + plan.slices[l] * plan.nT[l]) break;
@@ -1556,45 +1557,43 @@ __device__ void tc_wgrad_item(const StepArgs& a, const NetDesc& net, const TcPla
   float4* Al = Ah + (size_t)KC * kTcLdA;
   float4* Bh = Al + (size_t)KC * kTcLdA;
   float4* Bl = Bh + (size_t)KC * kTcLdB;
-  // ---- 1. stage + split: 8 consecutive lanes read 8 consecutive k-chunks (128 B) of one scratch row; four loads per
-  //         thread are in flight before the first is split ----
-  for (int q0 = tid; q0 < 128 * KC; q0 += 4 * kST) {
-    float4 v[4]; int dst[4];
+  // ---- 1. stage + split: 8 consecutive lanes read 8 consecutive k-chunks (128 B) of one scratch row.  Wc <= 96 means at
+  //         most 6 float4 per thread and operand: ALL loads of both operands are issued before the first is split
+  //         (the staging is a latency chain of L2 round trips otherwise: 4.8 us with four loads in flight) ----
+  constexpr int kU = 6;
+  float4 va[kU], vb[kU]; int da[kU], db[kU];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int q = q0 + u * kST;
-      v[u] = make_float4(0.f, 0.f, 0.f, 0.f); dst[u] = -1;
-      if (q < 128 * KC) {
-        const int r = q / KC, cc = q - r * KC, col = col0 + 4 * cc;
-        dst[u] = cc * kTcLdA + r;
-        if (col < cols) {
-          if (r < K) v[u] = ld_cg4(a.actG + (size_t)((r >= L.nIn ? hOff : aOff) + r) * a.Bpad + col);
-          else if (r == K) v[u] = make_float4(1.f, 1.f, 1.f, 1.f);       // bias row: db += delta
-        }
+  for (int u = 0; u < kU; ++u) {
+    const int q = tid + u * kST;
+    va[u] = make_float4(0.f, 0.f, 0.f, 0.f); da[u] = -1;
+    if (q < 128 * KC) {
+      const int r = q / KC, cc = q - r * KC, col = col0 + 4 * cc;
+      da[u] = cc * kTcLdA + r;
+      if (col < cols) {
+        if (r < K) va[u] = ld_cg4(a.actG + (size_t)((r >= L.nIn ? hOff : aOff) + r) * a.Bpad + col);
+        else if (r == K) va[u] = make_float4(1.f, 1.f, 1.f, 1.f);       // bias row: db += delta
       }
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) if (dst[u] >= 0) { float4 h, lo; split4(v[u], h, lo); Ah[dst[u]] = h; Al[dst[u]] = lo; }
   }
-  for (int q0 = tid; q0 < kTcN * KC; q0 += 4 * kST) {
-    float4 v[4]; int dst[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int q = q0 + u * kST;
-      v[u] = make_float4(0.f, 0.f, 0.f, 0.f); dst[u] = -1;
-      if (q < kTcN * KC) {
-        const int r = q / KC, cc = q - r * KC, col = col0 + 4 * cc, n = n0 + r;
-        dst[u] = cc * kTcLdB + r;
-        if (col < cols && n < N) v[u] = ld_cg4(a.errG + (size_t)(dOff + n) * a.Bpad + col);
-      }
+  for (int u = 0; u < kU; ++u) {
+    const int q = tid + u * kST;
+    vb[u] = make_float4(0.f, 0.f, 0.f, 0.f); db[u] = -1;
+    if (q < kTcN * KC) {
+      const int r = q / KC, cc = q - r * KC, col = col0 + 4 * cc, n = n0 + r;
+      db[u] = cc * kTcLdB + r;
+      if (col < cols && n < N) vb[u] = ld_cg4(a.errG + (size_t)(dOff + n) * a.Bpad + col);
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) if (dst[u] >= 0) { float4 h, lo; split4(v[u], h, lo); Bh[dst[u]] = h; Bl[dst[u]] = lo; }
   }
+#pragma unroll
+  for (int u = 0; u < kU; ++u) if (da[u] >= 0) { float4 h, lo; split4(va[u], h, lo); Ah[da[u]] = h; Al[da[u]] = lo; }
+#pragma unroll
+  for (int u = 0; u < kU; ++u) if (db[u] >= 0) { float4 h, lo; split4(vb[u], h, lo); Bh[db[u]] = h; Bl[db[u]] = lo; }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic stores -> tensor-core (async proxy) reads
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  DBG_T(a, step, 43);
   // ---- 2. MMA issue by one thread ----
   if (tid == 0) {
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (((uint32_t)kTcN >> 3) << 17) | ((128u >> 4) << 24);   // f32 <- tf32 x tf32, K-major, N 128, M 128
@@ -1614,6 +1613,7 @@ __device__ void tc_wgrad_item(const StepArgs& a, const NetDesc& net, const TcPla
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                    : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    DBG_T(a, step, 44);
     if (warp * 32 <= K) {                     // rows beyond the bias row are padding
       uint32_t v[64];
 #define SMB200_TMEM_LD32(off) asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 " \
@@ -1642,6 +1642,7 @@ __device__ void tc_wgrad_item(const StepArgs& a, const NetDesc& net, const TcPla
   phase ^= 1u;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();                            // the next item overwrites the staging area and the accumulator
+  DBG_T(a, step, 45);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -2178,8 +2179,9 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
     }
     if (tcOn) {
       for (int it = blockIdx.x; it < tcp.nItems; it += nw)
-        tc_wgrad_item(a, *net, tcp, it, smraw + descBytes, tcTmem, &tcBar, tcPhase);
+        tc_wgrad_item(a, *net, tcp, it, smraw + descBytes, tcTmem, &tcBar, tcPhase, step);
       grid_barrier(a.barrier, barTarget, nw);
+      DBG_T(a, step, 46);
     }
     for (int t = blockIdx.x; t < a.nTiles; t += nw) {
       GradTile gt = myTile;
