@@ -1000,7 +1000,28 @@ __device__ void lstm_forward(const LayerDesc& L, const float* Wp, const float* i
   const int g = tid >> sh, nl = tid & (NR - 1);
   const int Kc = (((nC + G - 1) / G) + 3) / 4 * 4;
   const int kb = min(nC, g * Kc), ke = min(nC, kb + Kc);
+  // Register-resident recurrent weights: when one pass covers all 4*nCells gate columns and this thread's K-slice is
+  // exactly 32 rows (cfg3: 64 cells, 512 threads), its 32 weights stay in registers for the whole window instead of
+  // 32 scalar shared-memory loads per step (the recurrence is bound by the shared-memory pipe).  Same FMA order.
+  const bool regW = SM && N4 <= NR && (ke - kb) == 32 && nl < N4;
+  float wreg[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) wreg[i] = regW ? ldw<SM>(Wh + nl + (size_t)(kb + i) * ldp) : 0.0f;
   for (int k = 0; k < Tn; ++k) {
+    if (k > 0 && regW) {
+      const float* hprev = Y + (size_t)(k - 1) * ys + kb;
+      float acc = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 hv = *reinterpret_cast<const float4*>(hprev + i);
+        acc = fmaf(hv.x, wreg[i + 0], acc); acc = fmaf(hv.y, wreg[i + 1], acc);
+        acc = fmaf(hv.z, wreg[i + 2], acc); acc = fmaf(hv.w, wreg[i + 3], acc);
+      }
+      if (G == 1) Gt[(size_t)k * gs + nl] += acc; else red[g * NR + nl] = acc;
+      __syncthreads();
+    } else if (k > 0 && N4 <= NR && (ke - kb) == 32 && SM) {      // idle lanes of the register path still join the barrier
+      __syncthreads();
+    } else
     if (k > 0) {
       const float* hprev = Y + (size_t)(k - 1) * ys;
       for (int n0 = 0; n0 < N4; n0 += NR) {
