@@ -1079,6 +1079,11 @@ __device__ void lstm_backward(const LayerDesc& L, const float* Wp, float* Gt, in
   const int Nc = (N4q + G - 1) / G;
   const int nb = min(N4q, g * Nc), ne = min(N4q, nb + Nc);
   float sdNext = 0.0f, fgNext = 0.0f;
+  // register-resident recurrent weights (see lstm_forward): this thread's 8 float4 of row `il` of Wh
+  const bool regW = SM && il < nC && (ne - nb) == 8;
+  float4 wreg[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) wreg[j] = regW ? ldw4<SM>(Wh + (size_t)il * ldp + (nb + j) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   for (int k = T1 - 1; k >= 0; --k) {
     if (tid < nC) {
       const int o = tid;
@@ -1098,6 +1103,14 @@ __device__ void lstm_backward(const LayerDesc& L, const float* Wp, float* Gt, in
     __syncthreads();
     if (k > 0) {
       float acc = 0.0f;
+      if (regW) {
+        const float* dl = Gt + (size_t)k * gs + nb * 4;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 wv = wreg[j], dv = *reinterpret_cast<const float4*>(dl + j * 4);
+          acc = fmaf(wv.x, dv.x, acc); acc = fmaf(wv.y, dv.y, acc); acc = fmaf(wv.z, dv.z, acc); acc = fmaf(wv.w, dv.w, acc);
+        }
+      } else
       if (il < nC) {
         const float* w = Wh + (size_t)il * ldp;
         const float* dl = Gt + (size_t)k * gs;
