@@ -142,6 +142,16 @@ int smb200_train_step_on(smb200_learner* h, const int64_t* episode_pos, const in
  * g[B][nOut] (f32), standardized inputs X[B][dS].  NULL pointers are skipped. */
 int smb200_get_last_batch(smb200_learner* h, float* outputs, float* out_grad, float* inputs);
 
+/* Output-gradient statistics file of the reference: StatsTracker::track_vector / reduce_stats / printToFile
+ * (Utils/StatsTracker.cpp:28-107, called from Approximator::setGradient, Network/Approximator.h:197, and
+ * Learner_approximator::spawnTrainTasks, Learners/Learner_approximator.cpp:89).  Once `base` is set, every learner step
+ * that starts with nGradSteps % 1000 == 0 appends the mean and root-mean-square over the mini-batch of each network
+ * output's gradient (2*nOut floats) to "<base>_outGrad_stats.raw" (base = "<learner_name>_<net name>", e.g.
+ * "agent_00_net"); the file begins with the float nOut + 0.1 when that step is the learner's first.  Rank 0 writes,
+ * from its own samples, like the reference.  NULL or "" switches it off (the default).  Not written by the
+ * benchmark-only smb200_train_presampled path. */
+int smb200_set_grad_stats(smb200_learner* h, const char* base);
+
 /* Stand-alone sweeps (also run internally every 1000 steps):
  * updateReturnEstimator over all episodes (MemoryProcessing.cpp:23-44,452-481) ... */
 int smb200_retrace_sweep(smb200_learner* h, double* sum_err2);

@@ -396,6 +396,59 @@ def vracer_sample_math(O, act, mu, qret, beta, cmax, cinv, bounded=None, racer=F
     return dict(rho=rho, dkl=dkl, is_far=is_far, V=V, A=Aval, dq=dq, g=g)
 
 
+
+# ------------------------------------------------------------------------------------------
+# Output-gradient statistics (Utils/StatsTracker.cpp:28-107)
+# ------------------------------------------------------------------------------------------
+CLIP_LEARNR = 1e-3   # Settings/Bund.h:97
+
+
+class StatsTracker:
+    """Per net output: sum and sum of squares of the gradient handed to Approximator::setGradient
+    (Network/Approximator.h:197 -> track_vector, StatsTracker.cpp:28-36), reduced once per learner step by
+    reduce_stats (:99-106, called from Learner_approximator.cpp:89 with iter = nGradSteps()).  `words` is what
+    printToFile (:66-86) has written to `<base>_outGrad_stats.raw` so far, as float32 words: the header n_stats + 0.1
+    if the very first reduce_stats call printed, then per printed step the means followed by the root mean squares.
+    np.longdouble is the x86-64 80-bit long double of the reference's accumulators."""
+
+    def __init__(self, n_stats: int):
+        self.n = n_stats
+        self.cnt = 0
+        self.sum = np.zeros(n_stats, np.longdouble)
+        self.sq = np.zeros(n_stats, np.longdouble)
+        self.avg = np.zeros(n_stats, np.longdouble)     # exponential averages kept after finalize (:88-97)
+        self.std = np.zeros(n_stats, np.longdouble)
+        self.inst_mean = np.zeros(n_stats, np.longdouble)
+        self.inst_stdv = np.zeros(n_stats, np.longdouble)
+        self.n_step = 0
+        self.words: list = []
+
+    def track_vector(self, grad):
+        g = np.asarray(grad, f64).astype(np.longdouble)
+        assert g.shape == (self.n,)
+        self.cnt += 1
+        self.sum += g
+        self.sq += g * g
+
+    def reduce_stats(self, it: int):
+        old_m, old_s = self.avg.copy(), self.std.copy()
+        cnt = max(np.longdouble(2.2e-16), np.longdouble(self.cnt))          # advance + update (:38-64)
+        mean = (self.sum / cnt).astype(f64)                                  # `const Real mean`
+        rms = np.sqrt((self.sq / cnt).astype(f64))
+        self.cnt = 0; self.sum[:] = 0; self.sq[:] = 0
+        if it % 1000 == 0:                                                   # printToFile
+            if self.n_step == 0:
+                self.words.append(f32(self.n + .1))
+            self.words.extend(mean.astype(f32)); self.words.extend(rms.astype(f32))
+        self.inst_mean, self.inst_stdv = mean.astype(np.longdouble), rms.astype(np.longdouble)   # finalize
+        self.n_step += 1
+        self.avg = (1 - CLIP_LEARNR) * old_m + CLIP_LEARNR * self.inst_mean
+        self.std = (1 - CLIP_LEARNR) * old_s + CLIP_LEARNR * self.inst_stdv
+
+    def file_words(self):
+        return np.asarray(self.words, f32)
+
+
 # ------------------------------------------------------------------------------------------
 # replay memory + learner
 # ------------------------------------------------------------------------------------------
@@ -603,6 +656,7 @@ class VracerOracle:
         qret = np.array([ep.Q[int(t)] for ep, t in zip(eps, obs)], f32)
         r = vracer_sample_math(Ouse, act, mu, qret, self.beta, self.cmax, self.cinv, self.bounded, self.racer)
         g32 = r["g"].astype(f32)
+        self._track_grad_stats(r["g"])
         # write-back + per-episode aggregates, in batch order (Episode.h:112-145)
         C32, I32 = f32(self.cmax), f32(self.cinv)
         for b in range(B):
@@ -627,6 +681,16 @@ class VracerOracle:
         self.apply_adam(G)
         self.n_grad_steps += 1
         return self.last
+
+    def _track_grad_stats(self, g64):
+        """Approximator::setGradient -> track_vector per sample, then updateGradStats once per step
+        (Network/Approximator.h:65-68,197; Learner_approximator.cpp:89).  Active once `self.grad_stats` is set."""
+        tr = getattr(self, "grad_stats", None)
+        if tr is None:
+            return
+        for row in g64:
+            tr.track_vector(row)
+        tr.reduce_stats(self.n_grad_steps)
 
     @staticmethod
     def _update_values(ep: Episode, t: int, V, Q):
@@ -904,6 +968,7 @@ class RecurrentOracle(VracerOracle):
         qret = np.array([ep.Q[int(t)] for ep, t in zip(eps, obs)], f32)
         r = vracer_sample_math(O32, act, mu, qret, self.beta, self.cmax, self.cinv, self.bounded, self.racer)
         g32 = r["g"].astype(f32)
+        self._track_grad_stats(r["g"])
         C32, I32 = f32(self.cmax), f32(self.cinv)
         for b in range(B):
             ep, t = eps[b], int(obs[b])

@@ -113,6 +113,12 @@ struct smb200_learner {
   double lastMs = 0; long long lastLaunches = 0;
   long long launches = 0;
 
+  // output-gradient statistics file of the reference (StatsTracker, Utils/StatsTracker.cpp:28-107); off until
+  // smb200_set_grad_stats names the file.  trackerSteps = StatsTracker::nStep (reduce_stats calls since construction).
+  std::string gradStatsBase; long long trackerSteps = 0;
+  float* hGradStat[2] = {nullptr, nullptr};      // pinned [B][nOut], one per pipeline half
+  bool grad_stats_step(long long nGradSteps) const { return !gradStatsBase.empty() && nGradSteps % 1000 == 0; }
+
   StepArgs args() const {
     StepArgs a{};
     a.comm = comm;
@@ -354,7 +360,7 @@ static bool host_post_step(smb200_learner* h) {
   // `Saru gen(nStep, thrID, generators[thrID]())` (Optimizer.cpp:139): thread 0 consumes one
   // 32-bit draw of generators[0] — the sampler's generator — every update.
   (void)h->gen();
-  h->gradStep++;
+  h->gradStep++; h->trackerSteps++;
   if (changed) { h->orderDirty = true; h->lookupDirty = true; }
   return changed;
 }
@@ -430,6 +436,36 @@ static void host_sample(smb200_learner* h, int* slotOut, int* tOut, int64_t* pos
 // cmax the device will hold after the statistics phase of step `gstep` (1-based)
 static double cmax_at(const smb200_learner* h, long long gstep) {
   return 1.0 + h->cfg.clip_imp_weight / (1.0 + (double)gstep * h->cfg.eps_anneal);
+}
+
+// StatsTracker::advance + update + printToFile (Utils/StatsTracker.cpp:40-89) for the step whose output gradients
+// g[B][nOut] were just read back: per net output the mean and the root mean square over the mini-batch (long double
+// sums like the reference), appended as 2*nOut floats to <base>_outGrad_stats.raw; the file starts with the float
+// nOut + 0.1 when this is the tracker's very first step.  Only learner rank 0 writes (StatsTracker.cpp:70).
+static int write_grad_stats(const smb200_learner* h, const float* g, bool firstTrackerStep) {
+  if (h->cfg.world_rank != 0) return 0;
+  const int B = h->cfg.batch_size, nOut = h->descs.net.nOut;
+  std::vector<float> row(2 * (size_t)nOut);
+  const long double cnt = std::max((long double)2.2e-16, (long double)B);
+  for (int o = 0; o < nOut; ++o) {
+    long double sum = 0, sq = 0;
+    for (int b = 0; b < B; ++b) { const long double v = g[(size_t)b * nOut + o]; sum += v; sq += v * v; }
+    row[o] = (float)(double)(sum / cnt);
+    row[nOut + o] = (float)std::sqrt((double)(sq / cnt));
+  }
+  const std::string fn = h->gradStatsBase + "_outGrad_stats.raw";
+  FILE* f = fopen(fn.c_str(), firstTrackerStep ? "wb" : "ab");
+  if (!f) { set_error_msg(("cannot open " + fn).c_str()); return -1; }
+  if (firstTrackerStep) { const float hdr = (float)(nOut + .1); fwrite(&hdr, sizeof(float), 1, f); }
+  fwrite(row.data(), sizeof(float), row.size(), f);
+  fclose(f);
+  return 0;
+}
+// queue the read-back of the output gradients of the segment that just went onto the stream (its last step)
+static int fetch_grad_stats(smb200_learner* h, int half) {
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(h->hGradStat[half], h->lastG, sizeof(float) * (size_t)h->cfg.batch_size * h->descs.net.nOut,
+                                    cudaMemcpyDeviceToHost, h->stream));
+  return 0;
 }
 
 // device work of `n` consecutive steps whose samples sit at [first, first+n) of dSampSlot/dSampT.
@@ -624,6 +660,7 @@ void smb200_destroy(smb200_learner* h) {
   if (h->hSampSlot) cudaFreeHost(h->hSampSlot);
   if (h->hSampT) cudaFreeHost(h->hSampT);
   if (h->hStats) cudaFreeHost(h->hStats);
+  for (float* p : h->hGradStat) if (p) cudaFreeHost(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (int i = 0; i < 2; ++i) if (h->evDone[i]) cudaEventDestroy(h->evDone[i]);
@@ -805,6 +842,17 @@ int smb200_seed_sampler(smb200_learner* h, uint64_t seed) {
   return 0;
 }
 
+int smb200_set_grad_stats(smb200_learner* h, const char* base) {
+  if (!h) return SMB200_ERR_INVALID;
+  h->gradStatsBase = base ? base : "";
+  if (!h->gradStatsBase.empty() && !h->hGradStat[0]) {
+    cudaSetDevice(h->cfg.device);
+    const size_t bytes = sizeof(float) * (size_t)h->cfg.batch_size * h->descs.net.nOut;
+    for (float*& p : h->hGradStat) SMB200_CUDA_CHECK(cudaMallocHost(&p, bytes));
+  }
+  return 0;
+}
+
 int smb200_sample(smb200_learner* h, int64_t* pos, int64_t* t) {
   if (!h || !pos || !t || h->nTransitions < h->cfg.batch_size) return SMB200_ERR_STATE;
   host_sample(h, nullptr, nullptr, pos, t);
@@ -843,7 +891,9 @@ static int plan_segment(smb200_learner* h, int n, int off) {
     const long long stepNo = h->gradStep + 1;
     const bool changed = host_post_step(h);
     ++cnt;
-    if (changed || stepNo % 1000 == 0) break;
+    // a step whose output gradients go to the statistics file ends its segment: smb200's diagnostics
+    // buffer (lastG) holds the last step of a launch
+    if (changed || stepNo % 1000 == 0 || h->grad_stats_step(stepNo - 1)) break;
   }
   return cnt;
 }
@@ -868,12 +918,13 @@ int smb200_train_steps(smb200_learner* h, int32_t n, smb200_step_stats* stats) {
   // that the device starts early, long ones afterwards (every launch of the persistent kernel costs ~0.1 ms of
   // start-up and drain; a segment always ends at an every-1000-steps sweep or when the episode table changes).
   const int P = h->maxSeg / 2;
-  int pendCnt[2] = {0, 0}, pendDst[2] = {0, 0};
+  int pendCnt[2] = {0, 0}, pendDst[2] = {0, 0}, pendGradStat[2] = {0, 0};   // pendGradStat: 1 = append, 2 = new file
   auto reclaim = [&](int b) -> int {
     if (!pendCnt[b]) return 0;
     SMB200_CUDA_CHECK(cudaEventSynchronize(h->evDone[b]));
     if (stats) memcpy(stats + pendDst[b], h->hStats + (size_t)b * P, sizeof(smb200_step_stats) * pendCnt[b]);
-    pendCnt[b] = 0;
+    if (pendGradStat[b] && write_grad_stats(h, h->hGradStat[b], pendGradStat[b] == 2)) return -1;
+    pendCnt[b] = 0; pendGradStat[b] = 0;
     return 0;
   };
   int done = 0;
@@ -883,7 +934,7 @@ int smb200_train_steps(smb200_learner* h, int32_t n, smb200_step_stats* stats) {
     const auto tw0 = std::chrono::steady_clock::now();
     if (reclaim(b)) return SMB200_ERR_CUDA;
     hostWait += std::chrono::duration<double>(std::chrono::steady_clock::now() - tw0).count();
-    const long long g0 = h->gradStep;
+    const long long g0 = h->gradStep, tr0 = h->trackerSteps;
     // the order in effect for these steps must reach the device before host_post_step re-sorts
     if (upload_order(h)) return SMB200_ERR_CUDA;
     const int nEpPre = (int)h->episodes.size(); const long long nTrPre = h->nTransitions;
@@ -896,6 +947,10 @@ int smb200_train_steps(smb200_learner* h, int32_t n, smb200_step_stats* stats) {
     if (run_segment(h, off, cnt, g0, nEpPre, nTrPre, h->nTransitions)) return SMB200_ERR_CUDA;
     if (stats)
       SMB200_CUDA_CHECK(cudaMemcpyAsync(h->hStats + off, h->dStats + off, sizeof(smb200_step_stats) * cnt, cudaMemcpyDeviceToHost, h->stream));
+    if (h->grad_stats_step(g0 + cnt - 1)) {         // plan_segment ended the segment on that step
+      if (fetch_grad_stats(h, b)) return SMB200_ERR_CUDA;
+      pendGradStat[b] = tr0 + cnt - 1 == 0 ? 2 : 1;
+    }
     SMB200_CUDA_CHECK(cudaEventRecord(h->evDone[b], h->stream));
     pendCnt[b] = cnt; pendDst[b] = done;
     h->orderDirty = dirtyAfter;
@@ -925,18 +980,21 @@ int smb200_train_step_on(smb200_learner* h, const int64_t* pos, const int64_t* t
     h->hSampSlot[b] = (int)((unsigned)e.slot | hn); h->hSampT[b] = (int)(e.start + t[b]);
   }
   if (upload_order(h)) return SMB200_ERR_CUDA;
-  const long long g0 = h->gradStep;
+  const long long g0 = h->gradStep, tr0 = h->trackerSteps;
   const int nEpPre = (int)h->episodes.size(); const long long nTrPre = h->nTransitions;
   host_post_step(h);
   const bool dirtyAfter = h->orderDirty;
   if (upload_samples(h, 0, 1)) return SMB200_ERR_CUDA;
   if (run_segment(h, 0, 1, g0, nEpPre, nTrPre, h->nTransitions)) return SMB200_ERR_CUDA;
   h->orderDirty = dirtyAfter;
+  const bool gradStat = h->grad_stats_step(g0);
+  if (gradStat && fetch_grad_stats(h, 0)) return SMB200_ERR_CUDA;
   if (stats) {
     SMB200_CUDA_CHECK(cudaMemcpyAsync(h->hStats, h->dStats, sizeof(smb200_step_stats), cudaMemcpyDeviceToHost, h->stream));
     SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
     *stats = h->hStats[0];
   } else SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  if (gradStat && write_grad_stats(h, h->hGradStat[0], tr0 == 0)) return SMB200_ERR_STATE;
   return 0;
 }
 
@@ -971,7 +1029,7 @@ int smb200_train_presampled(smb200_learner* h, int32_t first, int32_t n) {
     const long long toSweep = 1000 - (g0 % 1000);     // steps until (and including) the next sweep step
     if (cnt > toSweep) cnt = (int)toSweep;
     if (run_segment(h, first + done, cnt, g0, (int)h->episodes.size(), h->nTransitions, h->nTransitions)) return SMB200_ERR_CUDA;
-    h->gradStep += cnt;
+    h->gradStep += cnt; h->trackerSteps += cnt;
     done += cnt;
   }
   SMB200_CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
@@ -998,7 +1056,7 @@ int smb200_profile_phases(smb200_learner* h, int32_t n, int64_t* out, int64_t ca
   SMB200_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
   if (launch_steps_persistent(a, h->descs.net, h->persistGrid, (int)g0, n, 0, h->stream)) return SMB200_ERR_CUDA;
   SMB200_CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
-  h->gradStep += n;
+  h->gradStep += n; h->trackerSteps += n;
   if (d2h(h, out, h->dDbg, sizeof(long long) * cnt)) return SMB200_ERR_CUDA;
   float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->lastMs = ms; h->lastLaunches = 1;
   if (grid_out) *grid_out = h->persistGrid;

@@ -34,7 +34,7 @@ EXPORTS = [
     "smb200_reward_state_moments", "smb200_read_field", "smb200_read_episodes", "smb200_n_rows", "smb200_get_stats",
     "smb200_forward", "smb200_last_timing", "smb200_presample", "smb200_train_presampled", "smb200_sync", "smb200_profile_phases",
     "smb200_comm_init", "smb200_comm_attach", "smb200_comm_error", "smb200_write_field", "smb200_save", "smb200_restart",
-    "smb200_push_episode_restored", "smb200_set_refer",
+    "smb200_push_episode_restored", "smb200_set_refer", "smb200_set_grad_stats",
 ]
 
 FIELDS = dict(V=0, ADV=1, QRET=2, DELTA=3, RHO=4, KL=5, REWARD=6)
@@ -127,6 +127,7 @@ def load_library(path: str = LIB_PATH):
         "smb200_save": (C.c_int, [H, C.c_char_p]), "smb200_restart": (C.c_int, [H, C.c_char_p]),
         "smb200_push_episode_restored": (C.c_int, [H, C.c_int64, C.c_int32, C.c_int32] + [fp] * 10 + [C.c_double]),
         "smb200_set_refer": (C.c_int, [H, C.c_double, C.c_double]),
+        "smb200_set_grad_stats": (C.c_int, [H, C.c_char_p]),
         "smb200_get_stats": (C.c_int, [H, P(StepStats)]),
         "smb200_forward": (C.c_int, [H, fp, C.c_int32, fp]),
         "smb200_last_timing": (C.c_int, [H, dp, ip]),
@@ -294,6 +295,11 @@ class Learner:
 
     def seed_sampler(self, seed):
         self._check(self.lib.smb200_seed_sampler(self.h, int(seed)))
+
+    def set_grad_stats(self, base):
+        """StatsTracker file of the reference (Utils/StatsTracker.cpp:66-89): `<base>_outGrad_stats.raw`, one row of
+        per-output gradient mean / rms for every step that starts at nGradSteps % 1000 == 0.  None switches it off."""
+        self._check(self.lib.smb200_set_grad_stats(self.h, os.fsencode(base) if base else None))
 
     def sample_minibatch(self):
         pos, t = np.empty(self.B, np.int64), np.empty(self.B, np.int64)

@@ -135,9 +135,33 @@ def run_case(name, spec, outdir):
     print(name, os.path.getsize(path) // 1024, "KiB", len(keep), "arrays")
 
 
+def run_grad_stats(outdir):
+    """outgrad_stats.npz: for every case the file `agent_00_net_outGrad_stats.raw` the reference's StatsTracker
+    (Utils/StatsTracker.cpp:66-89) wrote during the same run as the case's .npz (as float32 words; empty when the run
+    crossed no step with nGradSteps % 1000 == 0)."""
+    keep = {}
+    for name, spec in CASES.items():
+        d = synth.make_replay(**spec["replay"])
+        with tempfile.TemporaryDirectory() as tmp:
+            synth.write_replay_file(os.path.join(tmp, "data.bin"), d)
+            with open(os.path.join(tmp, "settings.json"), "w") as f:
+                json.dump(spec["settings"], f)
+            cmd = [HARNESS, "--data", "data.bin", "--settings", "settings.json", "--steps", str(spec["steps"]),
+                   "--threads", "1", "--startStep", str(spec["start_step"]), "--sampleSeed", str(spec["sample_seed"]),
+                   "--bounded", str(spec["bounded"]), "--quiet"]
+            subprocess.run(cmd, cwd=tmp, check=True, stdout=subprocess.DEVNULL, env=dict(os.environ, OMP_NUM_THREADS="1"))
+            fn = os.path.join(tmp, "agent_00_net_outGrad_stats.raw")
+            keep[name] = np.fromfile(fn, dtype=np.float32) if os.path.exists(fn) else np.zeros(0, np.float32)
+        print(name, "outGrad_stats:", keep[name].size, "floats")
+    np.savez_compressed(os.path.join(outdir, "outgrad_stats.npz"), **keep)
+
+
 if __name__ == "__main__":
     if not os.path.exists(HARNESS):
         sys.exit("build oracle/_ref first: make -C oracle")
+    if sys.argv[1:] == ["outgrad_stats"]:
+        run_grad_stats(os.path.dirname(os.path.abspath(__file__)))
+        sys.exit(0)
     only = sys.argv[1:]
     for n, s in {**CASES, **CKPT_CASES}.items():
         if (not only and n in CASES) or n in only:

@@ -31,6 +31,10 @@ class Golden:
         self.sample_seed, self.bounded = self.spec["sample_seed"], bool(self.spec["bounded"])
         self.B = int(self.ref["meta/dims"][3])
 
+    @staticmethod
+    def path(name):
+        return os.path.join(GOLDEN_DIR, name)
+
     def refer(self, key):
         """{beta, cmax, cinv, nFar, avgKL, avgSqErr, maxAbsErr, avgReturn, stdevQ, avgQ, maxQ, minQ, cntRet, sumRetErr}"""
         return self.ref[key + "/refer"]

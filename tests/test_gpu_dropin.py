@@ -60,6 +60,10 @@ def test_checkpoints_cross_between_reference_and_device_learner(tmp_path):
     assert np.abs(m1).max() > 0, "Adam moments of the device learner did not reach the checkpoint"
     status = open(os.path.join(a, "agent_00_rank_000_learner_status.raw")).read()
     assert "nGradSteps: 2000" in status, status
+    # the reference's output-gradient statistics file (StatsTracker) is written by the device learner as well:
+    # header nOutputs + 0.1 (V, mean, stdev of one action), then mean | rms rows of steps 0, 1000, 2000
+    gs = np.fromfile(os.path.join(a, "agent_00_net_outGrad_stats.raw"), np.float32)
+    assert gs.size >= 1 + 2 * 6 and (gs.size - 1) % 6 == 0 and gs[0] == np.float32(3.1) and np.isfinite(gs).all(), gs
     # the reference restarts from the device learner's checkpoint ...
     r2 = run_arm("ref", steps=3600, threads=4, seed=8, settings=S, keep_dir=b, restart=a)
     assert r2["rc"] == 0 and any("agent_00_net_weights" in l for l in r2["restart_lines"]), r2

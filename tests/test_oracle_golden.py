@@ -93,3 +93,35 @@ def test_checkpoint_golden_layout(case):
     assert np.array_equal(sc[3 * dS:].astype(np.float32), R["final/rewards"][[2, 1, 0]])     # file: stdev, scale, mean
     status = bytes(g.ckpt["agent_00_rank_000_learner_status.raw"]).decode()
     assert f"nGradSteps: {g.start_step + g.steps + 1}\n" in status and f"nStoredEps: {len(out['id'])}\n" in status
+
+
+@pytest.mark.parametrize("case", CASES + RECURRENT_CASES)
+def test_grad_stats_file_matches_reference(case):
+    """StatsTracker (Utils/StatsTracker.cpp): the `<learner>_<net>_outGrad_stats.raw` file the reference wrote during the
+    golden run (tests/golden/outgrad_stats.npz, generator `make_golden.py outgrad_stats`) against (a) the tracker
+    restatement fed with the reference's own per-sample output gradients — header and layout exact, values to f32
+    round-off of the dumped gradients — and (b) the oracle's run of the same steps."""
+    import vracer_oracle as vo
+    g = Golden(case)
+    want = np.load(g.path("outgrad_stats.npz"))[case]
+    n_out = g.ref["s0/g"].shape[1]
+    tr = vo.StatsTracker(n_out)
+    for s in range(g.steps):
+        for row in g.ref[f"s{s}/g"]:
+            tr.track_vector(row)
+        tr.reduce_stats(g.start_step + s)
+    got = tr.file_words()
+    printed = [s for s in range(g.steps) if (g.start_step + s) % 1000 == 0]
+    header = 1 if printed and printed[0] == 0 else 0
+    assert want.size == header + 2 * n_out * len(printed) and got.size == want.size
+    if header:
+        assert got[0] == want[0] == np.float32(n_out + .1)
+    # means cancel over the mini-batch: absolute bar at f32 round-off of the largest entry
+    assert np.allclose(got, want, rtol=2e-6, atol=1e-6 * np.abs(want[header:]).max())
+    o = make_oracle(g)
+    o.grad_stats = vo.StatsTracker(n_out)
+    for s in range(g.steps):
+        o.train_step()
+    mine = o.grad_stats.file_words()
+    assert mine.size == want.size and np.abs(mine - want).max() < 2e-5 * max(np.abs(want[header:]).max(), 1e-30)
+    assert o.grad_stats.n_step == g.steps
