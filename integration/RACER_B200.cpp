@@ -112,11 +112,19 @@ class RACER_B200 : public RACER<Advantage_t, Continuous_policy, Rvec>
     // same initial policy on both sides: the device learner starts from the host network's weights
     check(smb200_set_weights(gpu, W->params, W->nParams), "set_weights");
     wblob.resize(W->nParams);
-    // the reference's output-gradient statistics file <learner>_<net>_outGrad_stats.raw (Approximator::updateGradStats,
-    // Network/Approximator.h:65-68; written every 1000 steps by StatsTracker::printToFile); SMARTIES_B200_GRADSTATS=0: off
+  }
+
+  // the reference's output-gradient statistics file <learner>_<net>_outGrad_stats.raw (Approximator::updateGradStats,
+  // Network/Approximator.h:65-68; written every 1000 steps by StatsTracker::printToFile); SMARTIES_B200_GRADSTATS=0: off.
+  // Named on the first learner step: the factory sets learner_name after the constructor (Learner::setLearnerName).
+  bool gradStatsNamed = false;
+  void nameGradStats()
+  {
+    if (gradStatsNamed) return;
+    gradStatsNamed = true;
     const char* gs = std::getenv("SMARTIES_B200_GRADSTATS");
-    if (bTrain && !(gs && std::atoi(gs) == 0))
-      check(smb200_set_grad_stats(gpu, (this->learner_name + "_" + networks[0]->name).c_str()), "set_grad_stats");
+    if (gs && std::atoi(gs) == 0) return;
+    check(smb200_set_grad_stats(gpu, (this->learner_name + "_" + networks[0]->name).c_str()), "set_grad_stats");
   }
 
   // Episode (ReplayMemory/Episode.h:40-110) -> the row-major f32 arrays of smb200_push_episode
@@ -305,6 +313,7 @@ class RACER_B200 : public RACER<Advantage_t, Continuous_policy, Rvec>
       const long toSweep = 1000 - (this->nGradSteps() + 1) % 1000;          // stop at the every-1000-steps boundary
       const int k = (int) std::max<long>(1, std::min<long>({(long) maxStepsPerCall, ahead, toSweep + 1}));
       const double t0 = now();
+      nameGradStats();
       mirrorEpisodes();
       const double t1 = now();
       check(smb200_train_steps(gpu, k, stepStats.data()), "train_steps");
