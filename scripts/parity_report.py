@@ -8,9 +8,9 @@ import numpy as np
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
-from parity_utils import CASES, Golden, make_learner, relerr  # noqa: E402
+from parity_utils import CASES, RECURRENT_CASES, Golden, make_learner, relerr  # noqa: E402
 
-for case in CASES:
+for case in (sys.argv[1:] or CASES + RECURRENT_CASES):
     g = Golden(case)
     L = make_learner(g)
     R = g.ref

@@ -65,6 +65,20 @@ CASES = {
         settings={"learner": "VRACER", "nnType": "LSTM", "nnLayerSizes": [12, 12], "nnBPTTseq": 5, "batchSize": 8,
                   "maxTotObsNum": 1024, "minTotObsNum": 100},
         steps=4, start_step=0, sample_seed=23, bounded=0, full_steps=list(range(4))),
+    # 64 LSTM cells: the shape at which the device recurrence keeps the recurrent weights in registers
+    # (lstm_forward / lstm_backward, smarties_b200/csrc/step_kernels.cu) and P2 contracts 128 gate columns per tensor-core item
+    "racer_lstm64": dict(
+        replay=dict(seed=61, n_ep=12, ep_len=(20, 45), dS=6, dA=2),
+        settings={"learner": "RACER", "nnType": "LSTM", "nnLayerSizes": [64], "nnBPTTseq": 12, "batchSize": 8,
+                  "maxTotObsNum": 1024, "minTotObsNum": 200},
+        steps=4, start_step=998, sample_seed=31, bounded=0, full_steps=[0, 3]),
+    # BASELINE.json configs[2] itself on a small buffer: RACER + LSTM(64), nnBPTTseq 32, batch 128, state 32, action 8
+    "racer_cfg3mini": dict(
+        replay=dict(seed=77, n_ep=40, ep_len=(50, 80), dS=32, dA=8),
+        settings={"learner": "RACER", "nnType": "LSTM", "nnLayerSizes": [64], "nnBPTTseq": 32, "batchSize": 128,
+                  "clipImpWeight": 4, "explNoise": 0.1, "gamma": 0.99, "epsAnneal": 0, "nnLambda": 1e-6,
+                  "maxTotObsNum": 4096, "minTotObsNum": 2000},
+        steps=3, start_step=998, sample_seed=33, bounded=0, full_steps=[0, 2]),
 }
 
 # checkpoint cases: phase A runs `steps` steps and calls Learner_approximator::save(); phase B is a fresh process

@@ -10,7 +10,7 @@ import numpy as np
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CKPT_CASES = ["vracer_ckpt", "racer_lstm_ckpt"]
 CASES = ["vracer_small", "vracer_cfg2mini", "vracer_bounded", "vracer_prune", "racer_small", "racer_bounded"]
-RECURRENT_CASES = ["racer_lstm", "vracer_lstm2"]     # nnType LSTM + BPTT window (configs[2] family)
+RECURRENT_CASES = ["racer_lstm", "vracer_lstm2", "racer_lstm64", "racer_cfg3mini"]     # nnType LSTM + BPTT window (configs[2] family)
 
 
 class Golden:
@@ -60,14 +60,17 @@ def write_checkpoint(g: Golden, directory):
 def make_oracle(g: Golden):
     import vracer_oracle as vo
     s = g.settings
+    # every hyper-parameter of settings.json the path reads (Settings/HyperParameters.h:37-73); absent keys = reference defaults
+    kw = dict(batch=s.get("batchSize", 256), max_tot_obs=s.get("maxTotObsNum"), bounded=g.bounded, sample_seed=g.sample_seed,
+              learner=s.get("learner", "VRACER"))
+    for key, arg in (("gamma", "gamma"), ("lambda", "lam"), ("clipImpWeight", "clip_imp_weight"), ("penalTol", "penal_tol"),
+                     ("epsAnneal", "eps_anneal"), ("learnrate", "learnrate"), ("nnLambda", "nn_lambda")):
+        if key in s:
+            kw[arg] = s[key]
     if s.get("nnType", "FFNN") == "LSTM":
-        o = vo.RecurrentOracle(g.dS, g.dA, cells=s["nnLayerSizes"], bptt=s.get("nnBPTTseq", 16), batch=s.get("batchSize", 256),
-                               max_tot_obs=s.get("maxTotObsNum"), bounded=g.bounded, sample_seed=g.sample_seed,
-                               learner=s.get("learner", "VRACER"))
+        o = vo.RecurrentOracle(g.dS, g.dA, cells=s["nnLayerSizes"], bptt=s.get("nnBPTTseq", 16), **kw)
     else:
-        o = vo.VracerOracle(g.dS, g.dA, hidden=s.get("nnLayerSizes", [128, 128]), batch=s.get("batchSize", 256),
-                            max_tot_obs=s.get("maxTotObsNum"), bounded=g.bounded, sample_seed=g.sample_seed,
-                            learner=s.get("learner", "VRACER"))
+        o = vo.VracerOracle(g.dS, g.dA, hidden=s.get("nnLayerSizes", [128, 128]), **kw)
     o.W[:] = g.ref["init/weights"]
     o.load_replay(g.replay)
     o.initialize_learner()
