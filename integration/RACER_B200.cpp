@@ -101,6 +101,7 @@ class RACER_B200 : public RACER<Advantage_t, Continuous_policy, Rvec>
     c.seed = distrib.randSeed;
     c.nn_type = settings.nnType == "LSTM" ? SMB200_LSTM : SMB200_FFNN;
     c.nn_bptt_seq = (int32_t) settings.nnBPTTseq;
+    c.returns_estimator = settings.returnsEstimator == "GAE" ? SMB200_GAE : SMB200_RETRACE;
     // an episode occupies nsteps() = ndata()+1 rows and is at least two rows long: room for the worst case,
     // plus the episodes that arrive between two pruning passes
     c.capacity_rows = 2 * (int64_t) settings.maxTotObsNum_local + 65536;
@@ -355,7 +356,7 @@ std::unique_ptr<Learner> createLearner(const Uint learnerID, MDPdescriptor& MDP,
   settings.initializeOpts(ifs, distrib);
   const bool covered =
       (settings.learner == "VRACER" || settings.learner == "RACER") && !MDP.bDiscreteActions() &&
-      settings.dataSamplingAlgo == "uniform" && (settings.returnsEstimator == "default" || settings.returnsEstimator == "retrace") &&
+      settings.dataSamplingAlgo == "uniform" && (settings.returnsEstimator == "default" || settings.returnsEstimator == "retrace" || settings.returnsEstimator == "GAE") &&
       (settings.ERoldSeqFilter == "oldest" || settings.ERoldSeqFilter == "default") &&
       (settings.nnType == "FFNN" || settings.nnType == "LSTM") && settings.nnFunc == "Tanh" && settings.nnOutputFunc == "Linear" &&
       settings.ESpopSize == 1 && settings.targetDelay == 0 && MDP.nAppendedObs == 0 &&

@@ -512,8 +512,12 @@ class VracerOracle:
 
     def __init__(self, dS, dA, hidden=(128, 128), gamma=0.995, lam=1.0, clip_imp_weight=None,
                  penal_tol=0.1, eps_anneal=5e-7, learnrate=1e-4, nn_lambda=FLT_EPS,
-                 batch=256, max_tot_obs=None, bounded=False, sample_seed=42, learner="VRACER"):
+                 batch=256, max_tot_obs=None, bounded=False, sample_seed=42, learner="VRACER",
+                 returns_estimator="retrace"):
         self.dS, self.dA = dS, dA
+        if returns_estimator not in ("retrace", "GAE"):   # createReturnEstimator (MemoryProcessing.cpp:419-450)
+            raise NotImplementedError(returns_estimator)
+        self.gae = returns_estimator == "GAE"
         self.racer = learner == "RACER"
         self.layout = MlpLayout(dS, hidden, (2 + 3 * dA) if self.racer else (1 + dA), dA)
         self.net = MlpNet(self.layout)
@@ -575,7 +579,10 @@ class VracerOracle:
         for t in range(N - 2, -1, -1):
             old = ep.Q[t]
             Qn, Vn, An = ep.Q[t + 1], ep.V[t + 1], ep.ADV[t + 1]
-            new = f32(rs[t + 1] + g * f32(Vn + f32(f32(l * w[t + 1]) * f32(f32(Qn - An) - Vn))))
+            if self.gae:     # computeGAE (MemoryProcessing.cpp:411-417)
+                new = f32(rs[t + 1] + g * f32(Vn + f32(l * f32(Qn - Vn))))
+            else:            # computeRetrace (:391-400)
+                new = f32(rs[t + 1] + g * f32(Vn + f32(f32(l * w[t + 1]) * f32(f32(Qn - An) - Vn))))
             ep.Q[t] = new
             err2 = f32(err2 + f32(old - new) ** 2)
         return float(err2)

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kThreads) k_init_episode(ReplayView rp, int sl
 constexpr int kSweepPer = 4;                         // time steps per thread and super-chunk
 constexpr int kSweepChunk = kSweepPer * kThreads;    // 1024
 
-__global__ void __launch_bounds__(kThreads) k_sweep(ReplayView rp, int nEpisodes, int oneSlot, float gamma, float lambda,
+__global__ void __launch_bounds__(kThreads) k_sweep(ReplayView rp, int nEpisodes, int oneSlot, float gamma, float lambda, int gae,
                                                     int recompute, float C, float invC, SweepSums* sums) {
   __shared__ float segA[32], segB[32], segQin[32];
   __shared__ float shCarry;
@@ -146,6 +146,9 @@ __global__ void __launch_bounds__(kThreads) k_sweep(ReplayView rp, int nEpisodes
         if (t >= 0) {
           const size_t r = r0 + t + 1;
           rr = rp.R[r]; Vn[j] = rp.V[r]; An[j] = rp.ADV[r]; w = rp.RHO[r]; oldQ[j] = rp.Q[r - 1];
+          // computeGAE (MemoryProcessing.cpp:411-417): R + gamma*(V + lambda*(Q' - V)) is the Retrace expression below
+          // with the clipped importance weight 1 and no advantage term (Q' - 0 - V rounds like Q' - V)
+          if (gae) { An[j] = 0.f; w = 1.f; }
         }
         R[j] = t >= 0 ? (float)(((double)rr - rmean) * rscale) : 0.f;      // scaledReward<Fval> (Episode.h:184-189)
         cw[j] = t >= 0 ? lambda * (w < 1.f ? w : 1.f) : 0.f;               // clippedOffPolW (Episode.h:190-194)
@@ -443,12 +446,12 @@ int launch_init_episode(const ReplayView& rp, int slot, float deltaInit, int hav
   return 0;
 }
 
-int launch_sweep(const ReplayView& rp, int nEpisodes, int oneSlot, float gamma, float lambda, int recompute, float cmax,
+int launch_sweep(const ReplayView& rp, int nEpisodes, int oneSlot, float gamma, float lambda, int gae, int recompute, float cmax,
                  float cinv, SweepSums* sums, cudaStream_t st) {
   const int count = nEpisodes > 0 ? nEpisodes : 1;
   int blocks = count;                           // one CTA per episode, at most one full wave of 8 CTAs per SM
   if (blocks > 148 * 8) blocks = 148 * 8;
-  k_sweep<<<blocks, kThreads, 0, st>>>(rp, nEpisodes, oneSlot, gamma, lambda, recompute, cmax, cinv, sums);
+  k_sweep<<<blocks, kThreads, 0, st>>>(rp, nEpisodes, oneSlot, gamma, lambda, gae, recompute, cmax, cinv, sums);
   SMB200_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

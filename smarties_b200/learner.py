@@ -50,7 +50,7 @@ class Config(C.Structure):
         ("eps_anneal", C.c_double), ("learnrate", C.c_double), ("nn_lambda", C.c_double), ("expl_noise", C.c_double),
         ("out_weights_prefac", C.c_double), ("refer_reduce_threads", C.c_int32), ("world_rank", C.c_int32),
         ("world_size", C.c_int32), ("seed", C.c_uint64), ("nn_type", C.c_int32), ("nn_bptt_seq", C.c_int32),
-        ("min_tot_obs", C.c_int64),
+        ("min_tot_obs", C.c_int64), ("returns_estimator", C.c_int32),
     ]
 
 
@@ -191,6 +191,7 @@ class Learner:
         cfg.world_rank, cfg.world_size, cfg.seed = world_rank, world_size, seed
         cfg.nn_type, cfg.nn_bptt_seq = {"FFNN": 0, "LSTM": 1}[hp.nnType], int(hp.nnBPTTseq)
         cfg.min_tot_obs = hp.minTotObsNum_local
+        cfg.returns_estimator = {"retrace": 0, "GAE": 1}[hp.returnsEstimator]
         if bounded is not None:
             b = np.broadcast_to(np.asarray(bounded, dtype=bool), (dim_action,))
             for i in range(dim_action):

@@ -96,7 +96,7 @@ class HyperParameters:
             unsupported.append(f"learner={self.learner}")
         if self.dataSamplingAlgo != "uniform":
             unsupported.append(f"dataSamplingAlgo={self.dataSamplingAlgo}")
-        if self.returnsEstimator != "retrace":
+        if self.returnsEstimator not in ("retrace", "GAE"):      # "retraceExplore" is not an affine recursion: not covered
             unsupported.append(f"returnsEstimator={self.returnsEstimator}")
         if self.ERoldSeqFilter not in ("oldest", "default"):
             unsupported.append(f"ERoldSeqFilter={self.ERoldSeqFilter}")

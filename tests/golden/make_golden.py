@@ -65,6 +65,12 @@ CASES = {
         settings={"learner": "VRACER", "nnType": "LSTM", "nnLayerSizes": [12, 12], "nnBPTTseq": 5, "batchSize": 8,
                   "maxTotObsNum": 1024, "minTotObsNum": 100},
         steps=4, start_step=0, sample_seed=23, bounded=0, full_steps=list(range(4))),
+    # returnsEstimator GAE (MemoryProcessing.cpp:411-417): Q[t] = r + gamma (V + lambda (Q[t+1] - V)), no importance weights
+    "vracer_gae": dict(
+        replay=dict(seed=29, n_ep=20, ep_len=(20, 60), dS=6, dA=3),
+        settings={"learner": "VRACER", "returnsEstimator": "GAE", "lambda": 0.9, "nnLayerSizes": [32, 32], "batchSize": 16,
+                  "maxTotObsNum": 2048, "minTotObsNum": 500},
+        steps=10, start_step=995, sample_seed=17, bounded=0, full_steps=[0, 9]),
     # 64 LSTM cells: the shape at which the device recurrence keeps the recurrent weights in registers
     # (lstm_forward / lstm_backward, smarties_b200/csrc/step_kernels.cu) and P2 contracts 128 gate columns per tensor-core item
     "racer_lstm64": dict(

@@ -9,7 +9,7 @@ import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CKPT_CASES = ["vracer_ckpt", "racer_lstm_ckpt"]
-CASES = ["vracer_small", "vracer_cfg2mini", "vracer_bounded", "vracer_prune", "racer_small", "racer_bounded"]
+CASES = ["vracer_small", "vracer_cfg2mini", "vracer_bounded", "vracer_prune", "racer_small", "racer_bounded", "vracer_gae"]
 RECURRENT_CASES = ["racer_lstm", "vracer_lstm2", "racer_lstm64", "racer_cfg3mini"]     # nnType LSTM + BPTT window (configs[2] family)
 
 
@@ -64,7 +64,8 @@ def make_oracle(g: Golden):
     kw = dict(batch=s.get("batchSize", 256), max_tot_obs=s.get("maxTotObsNum"), bounded=g.bounded, sample_seed=g.sample_seed,
               learner=s.get("learner", "VRACER"))
     for key, arg in (("gamma", "gamma"), ("lambda", "lam"), ("clipImpWeight", "clip_imp_weight"), ("penalTol", "penal_tol"),
-                     ("epsAnneal", "eps_anneal"), ("learnrate", "learnrate"), ("nnLambda", "nn_lambda")):
+                     ("epsAnneal", "eps_anneal"), ("learnrate", "learnrate"), ("nnLambda", "nn_lambda"),
+                     ("returnsEstimator", "returns_estimator")):
         if key in s:
             kw[arg] = s[key]
     if s.get("nnType", "FFNN") == "LSTM":
