@@ -359,6 +359,8 @@ std::unique_ptr<Learner> createLearner(const Uint learnerID, MDPdescriptor& MDP,
       settings.dataSamplingAlgo == "uniform" && (settings.returnsEstimator == "default" || settings.returnsEstimator == "retrace" || settings.returnsEstimator == "GAE") &&
       (settings.ERoldSeqFilter == "oldest" || settings.ERoldSeqFilter == "default") &&
       (settings.nnType == "FFNN" || settings.nnType == "LSTM") && settings.nnFunc == "Tanh" && settings.nnOutputFunc == "Linear" &&
+      // a partially observable MDP turns a feed-forward request into MGU layers (Network/Approximator.cpp:219-223)
+      !(MDP.isPartiallyObservable && !settings.bRecurrent) &&
       settings.ESpopSize == 1 && settings.targetDelay == 0 && MDP.nAppendedObs == 0 &&
       std::all_of(settings.encoderLayerSizes.begin(), settings.encoderLayerSizes.end(), [](Uint n) { return n == 0; });
   if (!covered) {

@@ -797,13 +797,18 @@ class SeqLayout:
     """Parameter blob for Input -> LSTM x H (ParametricResidual after every hidden layer but the first)
     -> Linear out -> ParamLayer; same padding rules as MlpLayout (Parameters.h:159-176)."""
 
-    def __init__(self, dS, cells, n_dense_out, n_param_out):
+    def __init__(self, dS, cells, n_dense_out, n_param_out, cell_type="LSTM"):
         self.dS, self.cells = int(dS), [int(c) for c in cells if c > 0]
         self.layers = []
         off, n_in = 0, self.dS
+        # gates per cell: LSTMLayer 4 (Layer_LSTM.h:30-37), MGULayer 2 — "MGU" and "GRU" both build it (Builder.cpp:67-72,
+        # Layer_GRU.h:27-33)
+        kind, ng = ("lstm", 4) if cell_type == "LSTM" else ("mgu", 2)
+        if cell_type not in ("LSTM", "MGU", "GRU"):
+            raise NotImplementedError(cell_type)
         for li, c in enumerate(self.cells):
-            L = dict(kind="lstm", nIn=n_in, nC=c, ld=4 * c, w=off)
-            off += round_up8(4 * c * (n_in + c)); L["b"] = off; off += round_up8(4 * c)
+            L = dict(kind=kind, nIn=n_in, nC=c, ld=ng * c, w=off)
+            off += round_up8(ng * c * (n_in + c)); L["b"] = off; off += round_up8(ng * c)
             self.layers.append(L)
             if li > 0:
                 R = dict(kind="residual", n=c, w=off); off += round_up8(c); R["b"] = off; off += round_up8(c)
@@ -854,6 +859,27 @@ class SeqNet:
                     cop = tanh_f32(st)
                     y = (og * cop).astype(f32)
                     acts.append(dict(y=y, st=st, cop=cop, cin=cin, ig=ig, fg=fg, og=og, xin=xin, hp=hp, stp=stp))
+                elif kind == "mgu":     # MGULayer::forward (Layer_GRU.h:65-120): W rows [input | recurrent], columns [forget | state]
+                    nI, nC = L["nIn"], L["nC"]
+                    W = blob[L["w"]:L["w"] + 2 * nC * (nI + nC)].reshape(nI + nC, 2 * nC)
+                    s = blob[L["b"]:L["b"] + 2 * nC].astype(f32).copy()
+                    xin = acts[-1]["y"][:nI]
+                    for i in range(nI):
+                        s += (xin[i] * W[i]).astype(f32)
+                    hp = prev[li + 1]["y"] if prev is not None else None
+                    fpre, spre = s[:nC].copy(), s[nC:].copy()
+                    if hp is not None:
+                        for i in range(nC):
+                            fpre += (W[nI + i, :nC] * hp[i]).astype(f32)
+                        fg = sigm_f32(fpre)
+                        for i in range(nC):
+                            spre += ((W[nI + i, nC:] * hp[i]).astype(f32) * fg[i]).astype(f32)
+                        st = tanh_f32(spre)
+                        y = ((fg * st).astype(f32) + ((f32(1) - fg).astype(f32) * hp).astype(f32)).astype(f32)
+                    else:
+                        fg, st = sigm_f32(fpre), tanh_f32(spre)
+                        y = (fg * st).astype(f32)
+                    acts.append(dict(y=y, fg=fg, st=st, xin=xin, hp=hp))
                 elif kind == "residual":
                     n = L["n"]
                     w, b = blob[L["w"]:L["w"] + n], blob[L["b"]:L["b"] + n]
@@ -876,8 +902,8 @@ class SeqNet:
         in the reference's order (layers top to bottom, for each layer time T..0)."""
         T = len(cache) - 1
         nl = len(self.L.layers)
-        E = [[np.zeros_like(cache[k][li + 1]["y"]) if self.L.layers[li]["kind"] != "lstm"
-              else np.zeros(4 * self.L.layers[li]["nC"], f32) for li in range(nl)] for k in range(T + 1)]
+        E = [[np.zeros_like(cache[k][li + 1]["y"]) if self.L.layers[li]["kind"] not in ("lstm", "mgu")
+              else np.zeros(self.L.layers[li]["ld"], f32) for li in range(nl)] for k in range(T + 1)]
         Ein = [np.zeros(self.L.dS, f32) for _ in range(T + 1)]
         k0 = 0
         for li, L in enumerate(self.L.layers):
@@ -909,6 +935,32 @@ class SeqNet:
                     E[k][li - 2][:n] = (E[k][li - 2][:n] + (d * w).astype(f32)).astype(f32)
                     G[L["w"]:L["w"] + n] += (d * cache[k][li - 1]["y"][:n]).astype(f32)
                     G[L["b"]:L["b"] + n] += d
+                elif kind == "mgu":  # MGULayer::backward (Layer_GRU.h:122-214)
+                    nI, nC = L["nIn"], L["nC"]
+                    W = blob[L["w"]:L["w"] + 2 * nC * (nI + nC)].reshape(nI + nC, 2 * nC)
+                    fg, st, hp = a["fg"], a["st"], a["hp"]
+                    dO = E[k][li][:nC].copy()
+                    pO = hp if hp is not None else np.zeros(nC, f32)
+                    dS_ = ((dO * fg).astype(f32) * (f32(1) - (st * st).astype(f32)).astype(f32)).astype(f32)             # 1)
+                    dFp = (W[nI:, nC:] @ dS_).astype(f32) if hp is not None else np.zeros(nC, f32)                        # 2)
+                    dF = ((((st - pO).astype(f32) * dO).astype(f32) + (dFp * pO).astype(f32)).astype(f32)
+                          * fg).astype(f32) * (f32(1) - fg).astype(f32)                                                  # 3)
+                    dF = dF.astype(f32)
+                    if hp is not None:                                                                                   # 4)
+                        Ep = E[k - 1][li]
+                        Ep[:nC] = (Ep[:nC] + (((f32(1) - fg).astype(f32) * dO).astype(f32) + (fg * dFp).astype(f32)).astype(f32)).astype(f32)
+                        Ep[:nC] = (Ep[:nC] + (W[nI:, :nC] @ dF).astype(f32)).astype(f32)
+                    E[k][li][nC:] = dF
+                    # input gradient: spanCompInpGrads = nInputs for every MGU layer (Layer_GRU.h:47), the first one included
+                    below[:nI] = (below[:nI] + (W[:nI, :nC] @ dF).astype(f32)).astype(f32)
+                    below[:nI] = (below[:nI] + (W[:nI, nC:] @ dS_).astype(f32)).astype(f32)
+                    dl = np.concatenate([dF, dS_]).astype(f32)
+                    G[L["b"]:L["b"] + 2 * nC] += dl
+                    Gw = G[L["w"]:L["w"] + 2 * nC * (nI + nC)].reshape(nI + nC, 2 * nC)
+                    Gw[:nI] += (a["xin"][:, None] * dl[None, :]).astype(f32)
+                    if hp is not None:
+                        Gw[nI:, :nC] += (hp[:, None] * dF[None, :]).astype(f32)
+                        Gw[nI:, nC:] += ((hp[:, None] * dS_[None, :]).astype(f32) * fg[:, None]).astype(f32)
                 else:  # LSTMLayer::backward (Layer_LSTM.h:127-166)
                     nI, nC = L["nIn"], L["nC"]
                     W = blob[L["w"]:L["w"] + 4 * nC * (nI + nC)].reshape(nI + nC, 4 * nC)
@@ -942,11 +994,11 @@ class RecurrentOracle(VracerOracle):
     """RACER / V-RACER with nnType LSTM: sampled transition t is evaluated on the window
     [t - min(nnBPTTseq, t), t] (MemoryBuffer.cpp:393-402), loss at t only, BPTT over the window."""
 
-    def __init__(self, dS, dA, cells=(64,), bptt=16, **kw):
+    def __init__(self, dS, dA, cells=(64,), bptt=16, cell_type="LSTM", **kw):
         learner = kw.get("learner", "VRACER")
         super().__init__(dS, dA, hidden=(8,), **kw)
         racer = learner == "RACER"
-        self.layout = SeqLayout(dS, cells, (2 + 3 * dA) if racer else (1 + dA), dA)
+        self.layout = SeqLayout(dS, cells, (2 + 3 * dA) if racer else (1 + dA), dA, cell_type)
         self.net = SeqNet(self.layout)
         self.bptt = int(bptt)
         self.W = np.zeros(self.layout.n_params, f32)

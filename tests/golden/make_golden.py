@@ -71,6 +71,18 @@ CASES = {
         settings={"learner": "VRACER", "returnsEstimator": "GAE", "lambda": 0.9, "nnLayerSizes": [32, 32], "batchSize": 16,
                   "maxTotObsNum": 2048, "minTotObsNum": 500},
         steps=10, start_step=995, sample_seed=17, bounded=0, full_steps=[0, 9]),
+    # MGU cells (Layer_GRU.h; "MGU" and "GRU" build the same layer, and it is what partially observable MDPs get by
+    # default, Approximator.cpp:219-223): oracle-only so far — the device path does not cover them yet
+    "racer_mgu": dict(
+        replay=dict(seed=71, n_ep=14, ep_len=(12, 40), dS=6, dA=2),
+        settings={"learner": "RACER", "nnType": "MGU", "nnLayerSizes": [16], "nnBPTTseq": 8, "batchSize": 8,
+                  "maxTotObsNum": 1024, "minTotObsNum": 200},
+        steps=6, start_step=997, sample_seed=41, bounded=0, full_steps=list(range(6))),
+    "vracer_gru2": dict(
+        replay=dict(seed=73, n_ep=10, ep_len=(6, 30), dS=5, dA=2),
+        settings={"learner": "VRACER", "nnType": "GRU", "nnLayerSizes": [16, 16], "nnBPTTseq": 5, "batchSize": 8,
+                  "maxTotObsNum": 1024, "minTotObsNum": 100},
+        steps=4, start_step=0, sample_seed=43, bounded=1, full_steps=list(range(4))),
     # 64 LSTM cells: the shape at which the device recurrence keeps the recurrent weights in registers
     # (lstm_forward / lstm_backward, smarties_b200/csrc/step_kernels.cu) and P2 contracts 128 gate columns per tensor-core item
     "racer_lstm64": dict(

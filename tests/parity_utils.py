@@ -10,6 +10,7 @@ import numpy as np
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CKPT_CASES = ["vracer_ckpt", "racer_lstm_ckpt"]
 CASES = ["vracer_small", "vracer_cfg2mini", "vracer_bounded", "vracer_prune", "racer_small", "racer_bounded", "vracer_gae"]
+ORACLE_ONLY_CASES = ["racer_mgu", "vracer_gru2"]     # MGU cells: oracle pinned, device path not built
 RECURRENT_CASES = ["racer_lstm", "vracer_lstm2", "racer_lstm64", "racer_cfg3mini"]     # nnType LSTM + BPTT window (configs[2] family)
 
 
@@ -68,8 +69,8 @@ def make_oracle(g: Golden):
                      ("returnsEstimator", "returns_estimator")):
         if key in s:
             kw[arg] = s[key]
-    if s.get("nnType", "FFNN") == "LSTM":
-        o = vo.RecurrentOracle(g.dS, g.dA, cells=s["nnLayerSizes"], bptt=s.get("nnBPTTseq", 16), **kw)
+    if s.get("nnType", "FFNN") in ("LSTM", "MGU", "GRU"):
+        o = vo.RecurrentOracle(g.dS, g.dA, cells=s["nnLayerSizes"], bptt=s.get("nnBPTTseq", 16), cell_type=s["nnType"], **kw)
     else:
         o = vo.VracerOracle(g.dS, g.dA, hidden=s.get("nnLayerSizes", [128, 128]), **kw)
     o.W[:] = g.ref["init/weights"]

@@ -114,9 +114,11 @@ def test_mlp_backprop_matches_finite_differences():
     assert np.all(G[np.setdiff1d(np.arange(lay.n_params), used)] == 0)               # padding never receives a gradient
 
 
-def test_lstm_bptt_matches_finite_differences():
+@pytest.mark.parametrize("cell,cells", [("LSTM", [6]), ("MGU", [8]), ("MGU", [8, 8])])
+def test_recurrent_bptt_matches_finite_differences(cell, cells):
+    """units/Network/Network.cpp of the reference checks every layer type this way (LSTM and MGU/GRU among them)."""
     rng = np.random.default_rng(9)
-    lay = vo.SeqLayout(4, [6], 3, 2)
+    lay = vo.SeqLayout(4, cells, 3, 2, cell)
     net = vo.SeqNet(lay)
     blob = rng.normal(0, 0.4, lay.n_params).astype(f32)
     X = rng.normal(0, 1, (5, 4)).astype(f32)          # seq_len 5 like units/Network/Network.cpp
