@@ -87,6 +87,38 @@ def id_to_seq_step(ids: np.ndarray, ndata: np.ndarray):
     return seq.astype(np.int64), obs.astype(np.int64)
 
 
+class DiscreteDistribution:
+    """libstdc++ std::discrete_distribution<Uint> built from float weights (bits/random.tcc, param_type::_M_initialize and
+    operator()): weights widened to double, divided by their sequential sum, cumulated sequentially, last entry forced to
+    1; a draw is generate_canonical<double, 53> — two 32-bit outputs of the generator, low word first — located by
+    std::lower_bound.  Used by the prioritized samplers (ReplayMemory/Sampling.cpp:145,206,231)."""
+
+    def __init__(self, weights):
+        p = np.asarray(weights, f32).astype(f64)
+        if p.size < 2:
+            self.cp = np.zeros(0, f64)
+            return
+        total = np.add.accumulate(p)[-1]                      # std::accumulate(..., 0.0): left to right
+        self.cp = np.add.accumulate(p / total)                # std::partial_sum
+        self.cp[-1] = 1.0
+
+    def __call__(self, gen: Mt19937) -> int:
+        if self.cp.size == 0:
+            return 0
+        lo, hi = gen(), gen()
+        u = (float(lo) + float(hi) * 4294967296.0) / 18446744073709551616.0
+        if u >= 1.0:
+            u = float(np.nextafter(1.0, 0.0))
+        return int(np.searchsorted(self.cp, u, side="left"))
+
+
+def canonical_float(gen: Mt19937) -> np.float32:
+    """std::uniform_real_distribution<float>(0, 1): generate_canonical<float, 24> = one 32-bit draw / 2^32 in float,
+    clamped below 1 (bits/random.tcc)."""
+    u = f32(f32(gen()) / f32(4294967296.0))
+    return f32(np.nextafter(f32(1), f32(0))) if u >= f32(1) else u
+
+
 # ------------------------------------------------------------------------------------------
 # scalar helpers
 # ------------------------------------------------------------------------------------------
@@ -513,8 +545,11 @@ class VracerOracle:
     def __init__(self, dS, dA, hidden=(128, 128), gamma=0.995, lam=1.0, clip_imp_weight=None,
                  penal_tol=0.1, eps_anneal=5e-7, learnrate=1e-4, nn_lambda=FLT_EPS,
                  batch=256, max_tot_obs=None, bounded=False, sample_seed=42, learner="VRACER",
-                 returns_estimator="retrace"):
+                 returns_estimator="retrace", sampling="uniform"):
         self.dS, self.dA = dS, dA
+        if sampling not in ("uniform", "PERerr", "PERseq"):    # Sampling::prepareSampler (Sampling.cpp:298-335); PERrank ranks
+            raise NotImplementedError(sampling)               # tied errors by the unstable std::sort: not restated
+        self.sampling, self.dist = sampling, None
         if returns_estimator not in ("retrace", "GAE"):   # createReturnEstimator (MemoryProcessing.cpp:419-450)
             raise NotImplementedError(returns_estimator)
         self.gae = returns_estimator == "GAE"
@@ -629,13 +664,43 @@ class VracerOracle:
         """Learner::initializeLearner (Learners/Learner.cpp:47-72)."""
         self.update_counters()
         self.update_rewards_stats(True)
+        self.update_sampler()                                 # Learner.cpp:63
         for ep in self.episodes:                              # rescaleAllReturnEstimator :460-481
             self.retrace_episode(ep)
 
+    # ---- samplers ----
+    def update_sampler(self):
+        """MemoryBuffer::updateSampler -> Sampling::prepare: TSample_impErr (Sampling.cpp:173-206) weighs every transition
+        by sqrt(sqrt(delta^2 + eps)), Sample_impSeq (:230-255) every episode by sqrt(sqrt(avgSquaredErr + eps)) * ndata;
+        float arithmetic, the distribution itself in double.  Sample_uniform::prepare does nothing."""
+        eps32 = f32(FLT_EPS)
+        if self.sampling == "PERerr":
+            w = np.concatenate([np.sqrt(np.sqrt((ep.delta[:ep.ndata] * ep.delta[:ep.ndata]).astype(f32) + eps32)).astype(f32)
+                                for ep in self.episodes])
+            self.dist = DiscreteDistribution(w)
+        elif self.sampling == "PERseq":
+            w = np.array([f32(np.sqrt(np.sqrt(f32(ep.avgSqErr + eps32)))) * f32(ep.ndata) for ep in self.episodes], f32)
+            self.dist = DiscreteDistribution(w)
+
     # ---- one gradient step ----
     def sample(self):
-        ids = sample_uniform(self.gen, self.n_transitions, self.B)
         nd = np.array([ep.ndata for ep in self.episodes], np.int64)
+        if self.sampling == "PERseq":      # Sample_impSeq::sample, transition branch (Sampling.cpp:276-294)
+            S: list = []
+            while len(S) < self.B:
+                for _ in range(self.B - len(S)):
+                    k = self.dist(self.gen)
+                    S.append((k, int(canonical_float(self.gen) * f32(nd[k]))))     # float * Uint -> float -> Uint
+                S = sorted(set(S))
+            return np.array([a for a, _ in S], np.int64), np.array([b for _, b in S], np.int64)
+        if self.sampling == "PERerr":      # TSample_impErr::sample (:208-225): same draw / sort / unique loop as uniform
+            ret: list = []
+            while len(ret) < self.B:
+                ret += [self.dist(self.gen) for _ in range(self.B - len(ret))]
+                ret = sorted(set(ret))
+            ids = np.asarray(ret, np.int64)
+        else:
+            ids = sample_uniform(self.gen, self.n_transitions, self.B)
         return id_to_seq_step(ids, nd)
 
     def standardized(self, ep: Episode, t: int):
@@ -750,6 +815,7 @@ class VracerOracle:
         self.episodes.sort(key=lambda e: -e.ID)
         while self.n_transitions - self.episodes[-1].nsteps > self.max_tot_obs_local:
             self.episodes.pop()                               # removeBackEpisode (MemoryBuffer.cpp:469-477)
+        self.update_sampler()                                 # RM.updateSampler() (MemoryProcessing.cpp:350)
         self.update_counters()
 
     def apply_adam(self, G):

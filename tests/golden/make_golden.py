@@ -71,6 +71,18 @@ CASES = {
         settings={"learner": "VRACER", "returnsEstimator": "GAE", "lambda": 0.9, "nnLayerSizes": [32, 32], "batchSize": 16,
                   "maxTotObsNum": 2048, "minTotObsNum": 500},
         steps=10, start_step=995, sample_seed=17, bounded=0, full_steps=[0, 9]),
+    # prioritized samplers (Sampling.cpp:173-296): which transitions are drawn depends on the stored TD errors; the PER
+    # weights themselves are unused by RACER (Approximator.h:196).  Oracle-only so far.
+    "vracer_pererr": dict(
+        replay=dict(seed=81, n_ep=18, ep_len=(20, 50), dS=5, dA=2),
+        settings={"learner": "VRACER", "dataSamplingAlgo": "PERerr", "nnLayerSizes": [24, 24], "batchSize": 16,
+                  "maxTotObsNum": 2048, "minTotObsNum": 300},
+        steps=8, start_step=0, sample_seed=51, bounded=0, full_steps=[0, 7]),
+    "vracer_perseq": dict(
+        replay=dict(seed=83, n_ep=18, ep_len=(20, 50), dS=5, dA=2),
+        settings={"learner": "VRACER", "dataSamplingAlgo": "PERseq", "nnLayerSizes": [24, 24], "batchSize": 16,
+                  "maxTotObsNum": 2048, "minTotObsNum": 300},
+        steps=8, start_step=0, sample_seed=53, bounded=0, full_steps=[0, 7]),
     # MGU cells (Layer_GRU.h; "MGU" and "GRU" build the same layer, and it is what partially observable MDPs get by
     # default, Approximator.cpp:219-223): oracle-only so far — the device path does not cover them yet
     "racer_mgu": dict(

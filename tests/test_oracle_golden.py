@@ -22,12 +22,12 @@ def test_oracle_matches_reference(case):
     assert np.allclose(o.concat("Q"), R["init/Qret"], rtol=1e-6, atol=1e-6)
     assert o.beta == R["init/refer"][0]
     for s in range(g.steps):
+        order = np.array([e.ID for e in o.episodes])          # the episode vector the sampler walks (before this step's re-sort)
         r = o.train_step()
         pre = f"s{s}"
-        # sampled indices: bit-exact
+        # sampled (episode, time step): bit-exact
         assert np.array_equal(r["obs"], R[pre + "/sampledT"])
-        ids_now = np.array([o_ep for o_ep in R[pre + "/sampledEpID"]])
-        assert len(ids_now) == g.B
+        assert np.array_equal(order[r["seq"]], R[pre + "/sampledEpID"]) and len(r["seq"]) == g.B
         assert np.abs(r["O"] - R[pre + "/O"]).max() < 2e-6
         assert relerr(r["g"], R[pre + "/g"]) < 2e-5
         if pre + "/gradSum" in R:
