@@ -87,6 +87,92 @@ def id_to_seq_step(ids: np.ndarray, ndata: np.ndarray):
     return seq.astype(np.int64), obs.astype(np.int64)
 
 
+def std_sort(v: list, comp, depth_limit=None) -> None:
+    """libstdc++ std::sort (bits/stl_algo.h: __introsort_loop with median-of-three pivots down to runs of 16, heap sort
+    past depth 2*floor(log2 n), then __final_insertion_sort), in place.  It is not a stable sort: where the comparator
+    ties (episodes with equal far-policy fraction, say) the resulting order is a property of this exact algorithm, and the
+    order of the episode vector decides which episode a sampled transition id belongs to (Sampling.cpp:26-47) and which
+    episode is pruned (MemoryProcessing.cpp:327-351).  `depth_limit` is for the tests only (0 = heap-sort branch at once)."""
+    def unguarded_linear_insert(last):
+        val = v[last]; nxt = last - 1
+        while comp(val, v[nxt]):
+            v[last] = v[nxt]; last = nxt; nxt -= 1
+        v[last] = val
+
+    def insertion_sort(first, last):
+        for i in range(first + 1, last):
+            if comp(v[i], v[first]):
+                val = v[i]; v[first + 1:i + 1] = v[first:i]; v[first] = val
+            else:
+                unguarded_linear_insert(i)
+
+    def heap_sort(first, last):                      # std::__partial_sort(first, last, last): make_heap + sort_heap
+        def adjust(hole, length, val):               # std::__adjust_heap + __push_heap
+            top = hole; child = hole
+            while child < (length - 1) // 2:
+                child = 2 * (child + 1)
+                if comp(v[first + child], v[first + child - 1]):
+                    child -= 1
+                v[first + hole] = v[first + child]; hole = child
+            if (length & 1) == 0 and child == (length - 2) // 2:
+                child = 2 * (child + 1)
+                v[first + hole] = v[first + child - 1]; hole = child - 1
+            parent = (hole - 1) // 2
+            while hole > top and comp(v[first + parent], val):
+                v[first + hole] = v[first + parent]; hole = parent; parent = (hole - 1) // 2
+            v[first + hole] = val
+        n = last - first
+        if n >= 2:
+            parent = (n - 2) // 2
+            while True:
+                adjust(parent, n, v[first + parent])
+                if parent == 0:
+                    break
+                parent -= 1
+        while last - first > 1:
+            last -= 1
+            val = v[last]; v[last] = v[first]
+            adjust(0, last - first, val)
+
+    def introsort_loop(first, last, depth):
+        while last - first > 16:
+            if depth == 0:
+                heap_sort(first, last)
+                return
+            depth -= 1
+            mid = first + (last - first) // 2
+            a, b, c = first + 1, mid, last - 1       # __move_median_to_first(first, first + 1, mid, last - 1)
+            if comp(v[a], v[b]):
+                m = b if comp(v[b], v[c]) else (c if comp(v[a], v[c]) else a)
+            else:
+                m = a if comp(v[a], v[c]) else (c if comp(v[b], v[c]) else b)
+            v[first], v[m] = v[m], v[first]
+            lo, hi = first + 1, last                  # __unguarded_partition(first + 1, last, first)
+            while True:
+                while comp(v[lo], v[first]):
+                    lo += 1
+                hi -= 1
+                while comp(v[first], v[hi]):
+                    hi -= 1
+                if not lo < hi:
+                    break
+                v[lo], v[hi] = v[hi], v[lo]
+                lo += 1
+            introsort_loop(lo, last, depth)
+            last = lo
+
+    n = len(v)
+    if n < 2:
+        return
+    introsort_loop(0, n, 2 * (n.bit_length() - 1) if depth_limit is None else depth_limit)   # std::__lg(n) * 2
+    if n > 16:                                        # __final_insertion_sort
+        insertion_sort(0, 16)
+        for i in range(16, n):
+            unguarded_linear_insert(i)
+    else:
+        insertion_sort(0, n)
+
+
 class DiscreteDistribution:
     """libstdc++ std::discrete_distribution<Uint> built from float weights (bits/random.tcc, param_type::_M_initialize and
     operator()): weights widened to double, divided by their sequential sum, cumulated sequentially, last entry forced to
@@ -545,8 +631,12 @@ class VracerOracle:
     def __init__(self, dS, dA, hidden=(128, 128), gamma=0.995, lam=1.0, clip_imp_weight=None,
                  penal_tol=0.1, eps_anneal=5e-7, learnrate=1e-4, nn_lambda=FLT_EPS,
                  batch=256, max_tot_obs=None, bounded=False, sample_seed=42, learner="VRACER",
-                 returns_estimator="retrace", sampling="uniform"):
+                 returns_estimator="retrace", sampling="uniform", er_filter="oldest"):
         self.dS, self.dA = dS, dA
+        # getERfilterAlgo (MemoryProcessing.cpp:261-298): "a goes before b"; the episodes to delete end up at the back
+        self.er_before = {"oldest": lambda a, b: a.ID > b.ID, "default": lambda a, b: a.ID > b.ID,
+                          "farpolfrac": lambda a, b: a.fracFar < b.fracFar, "maxkldiv": lambda a, b: a.avgKL < b.avgKL,
+                          "minerror": lambda a, b: a.avgSqErr > b.avgSqErr}[er_filter]
         if sampling not in ("uniform", "PERerr", "PERseq"):    # Sampling::prepareSampler (Sampling.cpp:298-335); PERrank ranks
             raise NotImplementedError(sampling)               # tied errors by the unstable std::sort: not restated
         self.sampling, self.dist = sampling, None
@@ -812,7 +902,7 @@ class VracerOracle:
         if recompute:
             self.update_rewards_stats(False, 10)
         # applyEpisodesRemovalAlgo (MemoryProcessing.cpp:327-351): "oldest" = sort by ID descending
-        self.episodes.sort(key=lambda e: -e.ID)
+        std_sort(self.episodes, self.er_before)               # std::sort: ties fall as libstdc++'s introsort leaves them
         while self.n_transitions - self.episodes[-1].nsteps > self.max_tot_obs_local:
             self.episodes.pop()                               # removeBackEpisode (MemoryBuffer.cpp:469-477)
         self.update_sampler()                                 # RM.updateSampler() (MemoryProcessing.cpp:350)

@@ -83,6 +83,24 @@ CASES = {
         settings={"learner": "VRACER", "dataSamplingAlgo": "PERseq", "nnLayerSizes": [24, 24], "batchSize": 16,
                   "maxTotObsNum": 2048, "minTotObsNum": 300},
         steps=8, start_step=0, sample_seed=53, bounded=0, full_steps=[0, 7]),
+    # episode filters other than FIFO (getERfilterAlgo, MemoryProcessing.cpp:261-298): the whole episode vector is re-sorted
+    # by a per-episode aggregate every step (unstable std::sort, many ties), more than 16 episodes so that the introsort
+    # partitions, capacity below the stored data so that episodes are pruned.  Oracle-only so far.
+    "vracer_farpolfrac": dict(
+        replay=dict(seed=91, n_ep=40, ep_len=(10, 30), dS=4, dA=2),
+        settings={"learner": "VRACER", "ERoldSeqFilter": "farpolfrac", "nnLayerSizes": [16], "batchSize": 16,
+                  "maxTotObsNum": 700, "minTotObsNum": 300},
+        steps=8, start_step=0, sample_seed=61, bounded=0, full_steps=[0, 7]),
+    "vracer_maxkldiv": dict(
+        replay=dict(seed=93, n_ep=40, ep_len=(10, 30), dS=4, dA=2),
+        settings={"learner": "VRACER", "ERoldSeqFilter": "maxkldiv", "nnLayerSizes": [16], "batchSize": 16,
+                  "maxTotObsNum": 700, "minTotObsNum": 300},
+        steps=8, start_step=0, sample_seed=63, bounded=0, full_steps=[0, 7]),
+    "vracer_minerror": dict(
+        replay=dict(seed=95, n_ep=40, ep_len=(10, 30), dS=4, dA=2),
+        settings={"learner": "VRACER", "ERoldSeqFilter": "minerror", "nnLayerSizes": [16], "batchSize": 16,
+                  "maxTotObsNum": 700, "minTotObsNum": 300},
+        steps=8, start_step=0, sample_seed=65, bounded=0, full_steps=[0, 7]),
     # MGU cells (Layer_GRU.h; "MGU" and "GRU" build the same layer, and it is what partially observable MDPs get by
     # default, Approximator.cpp:219-223): oracle-only so far — the device path does not cover them yet
     "racer_mgu": dict(

@@ -11,7 +11,8 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CKPT_CASES = ["vracer_ckpt", "racer_lstm_ckpt"]
 CASES = ["vracer_small", "vracer_cfg2mini", "vracer_bounded", "vracer_prune", "racer_small", "racer_bounded", "vracer_gae"]
 # oracle pinned, device path not built: MGU cells, prioritized samplers (f3)
-ORACLE_ONLY_CASES = ["racer_mgu", "vracer_gru2", "vracer_pererr", "vracer_perseq"]
+ORACLE_ONLY_CASES = ["racer_mgu", "vracer_gru2", "vracer_pererr", "vracer_perseq", "vracer_farpolfrac", "vracer_maxkldiv",
+                     "vracer_minerror"]
 RECURRENT_CASES = ["racer_lstm", "vracer_lstm2", "racer_lstm64", "racer_cfg3mini"]     # nnType LSTM + BPTT window (configs[2] family)
 
 
@@ -67,7 +68,7 @@ def make_oracle(g: Golden):
               learner=s.get("learner", "VRACER"))
     for key, arg in (("gamma", "gamma"), ("lambda", "lam"), ("clipImpWeight", "clip_imp_weight"), ("penalTol", "penal_tol"),
                      ("epsAnneal", "eps_anneal"), ("learnrate", "learnrate"), ("nnLambda", "nn_lambda"),
-                     ("returnsEstimator", "returns_estimator"), ("dataSamplingAlgo", "sampling")):
+                     ("returnsEstimator", "returns_estimator"), ("dataSamplingAlgo", "sampling"), ("ERoldSeqFilter", "er_filter")):
         if key in s:
             kw[arg] = s[key]
     if s.get("nnType", "FFNN") in ("LSTM", "MGU", "GRU"):

@@ -125,3 +125,20 @@ def test_grad_stats_file_matches_reference(case):
     mine = o.grad_stats.file_words()
     assert mine.size == want.size and np.abs(mine - want).max() < 2e-5 * max(np.abs(want[header:]).max(), 1e-30)
     assert o.grad_stats.n_step == g.steps
+
+
+def test_std_sort_restatement_matches_libstdcxx():
+    """oracle std_sort against permutations produced by g++'s std::sort / std::partial_sort on keys full of ties
+    (tests/golden/std_sort_vectors.npz, generator make_std_sort_vectors.py): the unstable order is reproduced exactly."""
+    import vracer_oracle as vo
+    z = np.load(Golden.path("std_sort_vectors.npz"))
+    names = sorted({k.split("/")[0] for k in z.files})
+    assert len(names) == 96
+    for name in names:
+        keys, perm = z[name + "/keys"], z[name + "/perm"]
+        heap = name.startswith("heap")
+        if heap and len(keys) <= 16:
+            continue                                   # runs of <= 16 never reach the heap-sort branch inside std::sort
+        v = [(float(k), i) for i, k in enumerate(keys)]
+        vo.std_sort(v, lambda a, b: a[0] < b[0], depth_limit=0 if heap else None)
+        assert [i for _, i in v] == list(perm), name
