@@ -637,12 +637,13 @@ class VracerOracle:
         self.er_before = {"oldest": lambda a, b: a.ID > b.ID, "default": lambda a, b: a.ID > b.ID,
                           "farpolfrac": lambda a, b: a.fracFar < b.fracFar, "maxkldiv": lambda a, b: a.avgKL < b.avgKL,
                           "minerror": lambda a, b: a.avgSqErr > b.avgSqErr}[er_filter]
-        if sampling not in ("uniform", "PERerr", "PERseq"):    # Sampling::prepareSampler (Sampling.cpp:298-335); PERrank ranks
-            raise NotImplementedError(sampling)               # tied errors by the unstable std::sort: not restated
+        if sampling not in ("uniform", "PERerr", "PERseq", "PERrank"):    # Sampling::prepareSampler (Sampling.cpp:298-335)
+            raise NotImplementedError(sampling)
         self.sampling, self.dist = sampling, None
-        if returns_estimator not in ("retrace", "GAE"):   # createReturnEstimator (MemoryProcessing.cpp:419-450)
+        if returns_estimator not in ("retrace", "GAE", "retraceExplore"):   # createReturnEstimator (MemoryProcessing.cpp:419-450)
             raise NotImplementedError(returns_estimator)
         self.gae = returns_estimator == "GAE"
+        self.explore = returns_estimator == "retraceExplore"
         self.racer = learner == "RACER"
         self.layout = MlpLayout(dS, hidden, (2 + 3 * dA) if self.racer else (1 + dA), dA)
         self.net = MlpNet(self.layout)
@@ -708,6 +709,9 @@ class VracerOracle:
                 new = f32(rs[t + 1] + g * f32(Vn + f32(l * f32(Qn - Vn))))
             else:            # computeRetrace (:391-400)
                 new = f32(rs[t + 1] + g * f32(Vn + f32(f32(l * w[t + 1]) * f32(f32(Qn - An) - Vn))))
+                if self.explore:   # computeRetraceExplBonus (:402-409): (1 - gamma) * (|Q' - A - V| - stats.maxAbsError) on top
+                    E = f32(abs(f32(f32(Qn - An) - Vn)) - f32(self.stats["maxAbsErr"]))
+                    new = f32(f32(f32(f32(1) - g) * E) + new)
             ep.Q[t] = new
             err2 = f32(err2 + f32(old - new) ** 2)
         return float(err2)
@@ -771,6 +775,20 @@ class VracerOracle:
         elif self.sampling == "PERseq":
             w = np.array([f32(np.sqrt(np.sqrt(f32(ep.avgSqErr + eps32)))) * f32(ep.ndata) for ep in self.episodes], f32)
             self.dist = DiscreteDistribution(w)
+        elif self.sampling == "PERrank":
+            # TSample_impRank::prepare (Sampling.cpp:102-146): all squared errors ranked by std::sort (descending, unstable:
+            # never-sampled transitions of an episode share one placeholder error), weight (rank+1)^-1/4 computed in double
+            # (std::sqrt of an unsigned) and stored as float; zero errors weigh 1
+            errs, prefix = [], []
+            for i, ep in enumerate(self.episodes):
+                prefix.append(len(errs))
+                d2 = (ep.delta[:ep.ndata] * ep.delta[:ep.ndata]).astype(f32)
+                errs += [(float(d2[j]), i, j) for j in range(ep.ndata)]
+            std_sort(errs, lambda a, b: a[0] > b[0])
+            w = np.ones(len(errs), f32)
+            for r, (e, i, j) in enumerate(errs):
+                w[prefix[i] + j] = f32(1.0 / np.sqrt(np.sqrt(float(r + 1)))) if e > 0 else f32(1)
+            self.dist = DiscreteDistribution(w)
 
     # ---- one gradient step ----
     def sample(self):
@@ -783,7 +801,8 @@ class VracerOracle:
                     S.append((k, int(canonical_float(self.gen) * f32(nd[k]))))     # float * Uint -> float -> Uint
                 S = sorted(set(S))
             return np.array([a for a, _ in S], np.int64), np.array([b for _, b in S], np.int64)
-        if self.sampling == "PERerr":      # TSample_impErr::sample (:208-225): same draw / sort / unique loop as uniform
+        if self.sampling in ("PERerr", "PERrank"):   # TSample_impErr / TSample_impRank::sample (:148-166, :208-225): the
+            # same draw / sort / unique loop as the uniform sampler
             ret: list = []
             while len(ret) < self.B:
                 ret += [self.dist(self.gen) for _ in range(self.B - len(ret))]

@@ -83,6 +83,17 @@ CASES = {
         settings={"learner": "VRACER", "dataSamplingAlgo": "PERseq", "nnLayerSizes": [24, 24], "batchSize": 16,
                   "maxTotObsNum": 2048, "minTotObsNum": 300},
         steps=8, start_step=0, sample_seed=53, bounded=0, full_steps=[0, 7]),
+    "vracer_perrank": dict(
+        replay=dict(seed=85, n_ep=18, ep_len=(20, 50), dS=5, dA=2),
+        settings={"learner": "VRACER", "dataSamplingAlgo": "PERrank", "nnLayerSizes": [24, 24], "batchSize": 16,
+                  "maxTotObsNum": 2048, "minTotObsNum": 300},
+        steps=8, start_step=0, sample_seed=55, bounded=0, full_steps=[0, 7]),
+    # retraceExplore (MemoryProcessing.cpp:402-409): Retrace plus an exploration bonus on |Q - A - V|
+    "vracer_explore": dict(
+        replay=dict(seed=87, n_ep=20, ep_len=(20, 60), dS=6, dA=3),
+        settings={"learner": "VRACER", "returnsEstimator": "retraceExplore", "lambda": 0.9, "nnLayerSizes": [32, 32],
+                  "batchSize": 16, "maxTotObsNum": 2048, "minTotObsNum": 500},
+        steps=10, start_step=995, sample_seed=57, bounded=0, full_steps=[0, 9]),
     # episode filters other than FIFO (getERfilterAlgo, MemoryProcessing.cpp:261-298): the whole episode vector is re-sorted
     # by a per-episode aggregate every step (unstable std::sort, many ties), more than 16 episodes so that the introsort
     # partitions, capacity below the stored data so that episodes are pruned.  Oracle-only so far.
