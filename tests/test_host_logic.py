@@ -41,6 +41,19 @@ def test_settings_file_of_reference_parses():
         HyperParameters(4, 1, {"notAKey": 1})
 
 
+def test_settings_outside_the_device_path_are_rejected_loudly():
+    """What the device library covers of createReturnEstimator / prepareSampler / getERfilterAlgo / Builder::addLayer
+    (the oracle covers more: tests/parity_utils.ORACLE_ONLY_CASES); everything else raises instead of running something else."""
+    from smarties_b200 import HyperParameters
+    assert HyperParameters(4, 1, {"returnsEstimator": "GAE"}).returnsEstimator == "GAE"
+    assert HyperParameters(4, 1, {"nnType": "LSTM", "nnLayerSizes": [32]}).nnType == "LSTM"
+    for bad in ({"returnsEstimator": "retraceExplore"}, {"dataSamplingAlgo": "PERrank"}, {"dataSamplingAlgo": "PERerr"},
+                {"dataSamplingAlgo": "PERseq"}, {"ERoldSeqFilter": "farpolfrac"}, {"ERoldSeqFilter": "maxkldiv"},
+                {"ERoldSeqFilter": "minerror"}, {"nnType": "MGU"}, {"nnType": "GRU"}, {"nnFunc": "Relu"}):
+        with pytest.raises(NotImplementedError):
+            HyperParameters(4, 1, bad)
+
+
 def test_library_exports_every_declared_symbol(built_library):
     from smarties_b200 import EXPORTS, load_library
     header = open(os.path.join(ROOT, "include", "smarties_b200.h")).read()
@@ -61,6 +74,19 @@ def test_config_struct_layout_and_defaults(built_library):
     assert cfg.batch_size == 256 and cfg.max_tot_obs == int(2 ** 14 * math.sqrt(40))
     assert cfg.gamma == 0.995 and cfg.clip_imp_weight == 2.0 and cfg.seed == 42 and cfg.world_size == 1
     assert abs(cfg.nn_lambda - 1.1920928955078125e-07) < 1e-20
+    assert cfg.returns_estimator == 0 and cfg.nn_type == 0 and cfg.min_tot_obs == 0
+    # sizeof(smb200_config) as the C compiler sees it: a drifted ctypes mirror would shift every later field
+    import subprocess
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        src = os.path.join(tmp, "s.c")
+        with open(src, "w") as f:
+            f.write('#include <stdio.h>\n#include "smarties_b200.h"\nint main(void) { printf("%zu %zu", sizeof(smb200_config), '
+                    'sizeof(smb200_step_stats)); return 0; }\n')
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", os.path.join(tmp, "s")], check=True)
+        sizes = subprocess.run([os.path.join(tmp, "s")], capture_output=True, text=True, check=True).stdout.split()
+    from smarties_b200.learner import StepStats
+    assert [int(x) for x in sizes] == [C.sizeof(Config), C.sizeof(StepStats)]
 
 
 def test_no_gpu_fails_loudly(built_library):
