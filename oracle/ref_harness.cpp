@@ -18,6 +18,8 @@
 #include "smarties/Math/Continuous_policy.h"
 #include "smarties/Math/Zero_advantage.h"
 #include "smarties/Math/Gaus_advantage.h"
+#include "smarties/Math/Discrete_policy.h"
+#include "smarties/Math/Discrete_advantage.h"
 #include "smarties/ReplayMemory/MemoryProcessing.h"
 #include "smarties/Utils/Profiler.h"
 
@@ -59,7 +61,7 @@ struct SynthData {
   int64_t dS = 0, dA = 0, nEp = 0;
   std::vector<int64_t> N, term, start;
   std::vector<float> S, A, MU, R;
-  void load(const std::string& path) {
+  void load(const std::string& path, int64_t dPolicy = 0) {   // dPolicy: columns of MU (0 = 2*dA, Gaussian mean | stdev)
     FILE* f = fopen(path.c_str(), "rb");
     if(!f) { perror(path.c_str()); exit(1); }
     int64_t hdr[4];
@@ -71,7 +73,7 @@ struct SynthData {
       int64_t v[2]; if(fread(v, 8, 2, f) != 2) exit(1);
       N[i] = v[0]; term[i] = v[1]; start[i] = tot; tot += v[0];
     }
-    S.resize(tot*dS); A.resize(tot*dA); MU.resize(tot*2*dA); R.resize(tot);
+    S.resize(tot*dS); A.resize(tot*dA); MU.resize(tot*(dPolicy > 0 ? dPolicy : 2*dA)); R.resize(tot);
     if(fread(S.data(), 4, S.size(), f) != S.size()) exit(1);
     if(fread(A.data(), 4, A.size(), f) != A.size()) exit(1);
     if(fread(MU.data(), 4, MU.size(), f) != MU.size()) exit(1);
@@ -83,6 +85,7 @@ struct SynthData {
 struct Args {
   std::string data, settings, dump, weights, restart;
   int steps = 10, threads = 1, bounded = 0, dumpAll = 0, quiet = 0, reps = 1, save = 0;
+  int discrete = 0;   // > 0: one discrete action component with that many options (RACER<Discrete_advantage, Discrete_policy, Uint>)
   long startStep = 0;
   unsigned long seed = 42, sampleSeed = 0;
   std::set<long> dumpSteps;
@@ -100,6 +103,7 @@ static Args parse(int argc, char** argv) {
     else if(k=="--steps") a.steps = std::stoi(next());
     else if(k=="--threads") a.threads = std::stoi(next());
     else if(k=="--bounded") a.bounded = std::stoi(next());
+    else if(k=="--discrete") a.discrete = std::stoi(next());
     else if(k=="--startStep") a.startStep = std::stol(next());
     else if(k=="--seed") a.seed = std::stoul(next());
     else if(k=="--sampleSeed") a.sampleSeed = std::stoul(next());
@@ -313,7 +317,7 @@ int main(int argc, char** argv)
   Args args = parse(argc, argv);
   if(args.data.empty()) { fprintf(stderr, "usage: ref_harness --data FILE [--settings JSON] [--steps K] [--threads T] ...\n"); return 1; }
   omp_set_num_threads(args.threads);
-  SynthData SD; SD.load(args.data);
+  SynthData SD; SD.load(args.data, args.discrete);
 
   std::vector<std::string> av = {"ref_harness"};
   ExecutionInfo distrib(av);
@@ -328,6 +332,10 @@ int main(int argc, char** argv)
   MDPdescriptor MDP;
   MDP.dimState = SD.dS; MDP.dimAction = SD.dA;
   MDP.bActionSpaceBounded = std::vector<bool>(SD.dA, args.bounded != 0);
+  if(args.discrete > 0) {      // what Communicator::setNumberOfOptions sets up for an app (Communicator.cpp: discreteActionValues)
+    if(SD.dA != 1) { fprintf(stderr, "--discrete needs a one-component action\n"); return 1; }
+    MDP.discreteActionValues = std::vector<Uint>(1, (Uint) args.discrete);
+  }
   MDP.synchronize([](void*, size_t){});
 
   HyperParameters settings(MDP.dimObs(), MDP.dimAct());
@@ -337,7 +345,13 @@ int main(int argc, char** argv)
   const ActionInfo aInfo(MDP);
 
   int ret = 1;
-  if(settings.learner == "VRACER") {
+  if(args.discrete > 0 && settings.learner == "RACER") {
+    using L = RACER<Discrete_advantage, Discrete_policy, Uint>;
+    MDP.policyVecDim = L::getnDimPolicy(aInfo);
+    Probe<L> learner(MDP, settings, distrib);
+    learner.setLearnerName("agent_00", 0);
+    ret = learner.run(args, SD, distrib);
+  } else if(settings.learner == "VRACER") {
     using L = RACER<Zero_advantage, Continuous_policy, Rvec>;
     MDP.policyVecDim = L::getnDimPolicy(aInfo);
     Probe<L> learner(MDP, settings, distrib);

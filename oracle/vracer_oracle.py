@@ -173,6 +173,24 @@ def std_sort(v: list, comp, depth_limit=None) -> None:
         insertion_sort(0, n)
 
 
+def uint_plus_float(n: int, x) -> int:
+    """`Uint n; n += x;` with float x as gcc compiles it for x86-64 (MemoryProcessing.cpp:202-227, nOffPol): n is rounded to
+    float, added, and converted back with cvttss2si — directly below 2^63, so a negative sum wraps to 2^64 - |sum|, and as
+    cvttss2si(f - 2^63) ^ 2^63 from there on, so anything >= 2^64 (such as the float nearest to a wrapped value) becomes 0.
+    A negative sum does occur in the reference: with clipImpWeight < 1 (one action component) the initial CinvRet = 1/C
+    exceeds 1 (MemoryBuffer.h:41-44), every stored importance weight 1 counts as "was far", and the per-episode far-policy
+    fractions go negative until the first every-1000-steps recompute."""
+    two63 = f32(9223372036854775808.0)
+    f = f32(f32(n) + f32(x))
+    indefinite = 1 << 63
+    if f < two63:
+        t = int(np.trunc(f)) if f > -two63 else -indefinite
+        return t & 0xFFFFFFFFFFFFFFFF
+    gq = f32(f - two63)
+    t = int(np.trunc(gq)) if gq < two63 else indefinite
+    return (t ^ indefinite) & 0xFFFFFFFFFFFFFFFF
+
+
 class DiscreteDistribution:
     """libstdc++ std::discrete_distribution<Uint> built from float weights (bits/random.tcc, param_type::_M_initialize and
     operator()): weights widened to double, divided by their sequential sum, cumulated sequentially, last entry forced to
@@ -408,6 +426,58 @@ class MlpNet:
 # ------------------------------------------------------------------------------------------
 # per-sample V-RACER loss / gradient   (Learners/RACER_train.cpp:12-67)
 # ------------------------------------------------------------------------------------------
+def discrete_sample_math(O, act, mu, qret, beta, cmax, cinv):
+    """RACER<Discrete_advantage, Discrete_policy, Uint>::Train (Learners/RACER_train.cpp:12-67) for K action options:
+    O [B, 1 + 2K] = [V | advantages(K) | policy pre-activations(K)] (RACER_common.cpp:109-135), act [B, 1] the stored
+    action message (label + 0.1, Core/StateAction.h:320-341), mu [B, K] the behaviour probabilities.  Policy: SoftPlus of
+    the pre-activations, normalised (Math/Discrete_policy.h:64-85); advantage centred with the policy's expectation
+    (Math/Discrete_advantage.h:44-75).  Same return dict as vracer_sample_math."""
+    O = np.asarray(O, f64)
+    mu = np.asarray(mu, f64)
+    Bn = O.shape[0]
+    K = (O.shape[1] - 1) // 2
+    opt = np.floor(np.asarray(act, f64)[:, 0]).astype(np.int64)           # actionMessage2label (StateAction.h:304-319)
+    adv, raw = O[:, 1:1 + K], O[:, 1 + K:1 + 2 * K]
+    unnorm = softplus(raw)
+    norm = np.zeros(Bn, f64)
+    for j in range(K):
+        norm = norm + unnorm[:, j]
+    norm = np.maximum(norm, np.finfo(f64).eps)
+    probs = unnorm / norm[:, None]
+    rows = np.arange(Bn)
+    rho = probs[rows, opt] / mu[rows, opt]                                # importanceWeight (:87-94): no clipping here
+    dkl = np.zeros(Bn, f64)
+    for j in range(K):                                                    # KLDivergence (:129-133)
+        dkl = dkl + probs[:, j] * np.log(probs[:, j] / mu[:, j])
+    W32, C32, I32 = rho.astype(f32), f32(cmax), f32(cinv)
+    is_far = (C32 > f32(1)) & ((W32 > C32) | (W32 < I32))
+    expA = np.zeros(Bn, f64)
+    for j in range(K):
+        expA = expA + probs[:, j] * adv[:, j]
+    Aval = adv[rows, opt] - expA
+    V = scale_net2v(O[:, 0])
+    a_ret = np.asarray(qret, f64) - V
+    dq = a_ret - Aval
+    g = np.zeros_like(O)
+    g[:, 0] = np.where(is_far, 0.0, np.minimum(1.0, rho) * dq * beta * scale_vdiff(O[:, 0]))
+    dpos = softplus_diff(raw)
+    onehot = np.zeros((Bn, K), f64); onehot[rows, opt] = 1.0
+    penal = np.zeros((Bn, K), f64)                                        # KLDivGradient(MU, -1) (:158-167)
+    for j in range(K):
+        tmp = -1.0 * (1 + np.log(probs[:, j] / mu[:, j])) / norm
+        ej = np.zeros((Bn, K), f64); ej[:, j] = 1.0
+        penal = penal + tmp[:, None] * (ej - probs[:, j:j + 1])
+    penal = penal * dpos
+    fac = a_ret * np.minimum(cmax, rho)                                   # policyGradient(ACT, fac) (:139-147)
+    pol = onehot * (fac / unnorm[rows, opt])[:, None]
+    pol = (pol - (fac / norm)[:, None]) * dpos
+    pol = np.where(is_far[:, None], 0.0, pol)
+    g[:, 1 + K:1 + 2 * K] = beta * pol + (1 - beta) * penal               # penalizeReFER
+    err = np.where(is_far, 0.0, beta * np.minimum(cmax, rho) * dq)        # ADV.grad(act, isFar ? 0 : beta*Aer) (:53-61)
+    g[:, 1:1 + K] = err[:, None] * (onehot - probs)
+    return dict(rho=rho, dkl=dkl, is_far=is_far, V=V, A=Aval, dq=dq, g=g)
+
+
 def vracer_sample_math(O, act, mu, qret, beta, cmax, cinv, bounded=None, racer=False):
     """O: [B, nOut] network outputs (f32 values widened to f64, Approximator.h:117-173);
     V-RACER: [V | mean(dA) | stdev-param(dA)], RACER: [V | adv coef, p1(dA), p2(dA) | mean(dA) | stdev-param(dA)]
@@ -631,8 +701,9 @@ class VracerOracle:
     def __init__(self, dS, dA, hidden=(128, 128), gamma=0.995, lam=1.0, clip_imp_weight=None,
                  penal_tol=0.1, eps_anneal=5e-7, learnrate=1e-4, nn_lambda=FLT_EPS,
                  batch=256, max_tot_obs=None, bounded=False, sample_seed=42, learner="VRACER",
-                 returns_estimator="retrace", sampling="uniform", er_filter="oldest"):
+                 returns_estimator="retrace", sampling="uniform", er_filter="oldest", discrete=0):
         self.dS, self.dA = dS, dA
+        self.discrete = int(discrete)        # K options of a discrete action space (then dA == 1 and learner == "RACER")
         # getERfilterAlgo (MemoryProcessing.cpp:261-298): "a goes before b"; the episodes to delete end up at the back
         self.er_before = {"oldest": lambda a, b: a.ID > b.ID, "default": lambda a, b: a.ID > b.ID,
                           "farpolfrac": lambda a, b: a.fracFar < b.fracFar, "maxkldiv": lambda a, b: a.avgKL < b.avgKL,
@@ -645,7 +716,10 @@ class VracerOracle:
         self.gae = returns_estimator == "GAE"
         self.explore = returns_estimator == "retraceExplore"
         self.racer = learner == "RACER"
-        self.layout = MlpLayout(dS, hidden, (2 + 3 * dA) if self.racer else (1 + dA), dA)
+        if self.discrete:                    # [V | adv(K) | policy(K)] from one linear layer, no ParamLayer (RACER_common.cpp:71-107)
+            self.layout = MlpLayout(dS, hidden, 1 + 2 * self.discrete, 0)
+        else:
+            self.layout = MlpLayout(dS, hidden, (2 + 3 * dA) if self.racer else (1 + dA), dA)
         self.net = MlpNet(self.layout)
         self.gamma, self.lam = gamma, lam
         self.C = float(np.sqrt(dA / 2.0)) if clip_imp_weight is None else float(clip_imp_weight)  # HyperParameters.h:46
@@ -835,7 +909,10 @@ class VracerOracle:
         act = np.stack([ep.A[int(t)] for ep, t in zip(eps, obs)])
         mu = np.stack([ep.MU[int(t)] for ep, t in zip(eps, obs)])
         qret = np.array([ep.Q[int(t)] for ep, t in zip(eps, obs)], f32)
-        r = vracer_sample_math(Ouse, act, mu, qret, self.beta, self.cmax, self.cinv, self.bounded, self.racer)
+        if self.discrete:
+            r = discrete_sample_math(Ouse, act, mu, qret, self.beta, self.cmax, self.cinv)
+        else:
+            r = vracer_sample_math(Ouse, act, mu, qret, self.beta, self.cmax, self.cinv, self.bounded, self.racer)
         g32 = r["g"].astype(f32)
         self._track_grad_stats(r["g"])
         # write-back + per-episode aggregates, in batch order (Episode.h:112-145)
@@ -902,7 +979,7 @@ class VracerOracle:
             Ns = f32(ep.nsteps)
             maxAbsE = max(maxAbsE, ep.maxAbsErr); maxQ = max(maxQ, ep.maxQ); minQ = min(minQ, ep.minQ)
             sumDKL += float(f32(Ns * ep.avgKL))
-            n_off = int(f32(f32(n_off) + f32(Ns * ep.fracFar)))   # `Uint += float` (SURVEY §7 hard part 2)
+            n_off = uint_plus_float(n_off, f32(Ns * ep.fracFar))  # `Uint += float` (SURVEY §7 hard part 2)
             sumE2 += float(f32(Ns * ep.avgSqErr))
             sumQ2 += float(ep.sumQ2); sumQ1 += float(ep.sumQ); sumR += float(ep.totR)
             ep.just_sampled = -1

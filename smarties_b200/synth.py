@@ -41,6 +41,27 @@ def make_replay(seed: int, n_ep: int, ep_len, dS: int, dA: int, term_every: int 
     return dict(dS=dS, dA=dA, N=N, term=term, start=start, S=S, A=A, MU=MU, R=R)
 
 
+def make_replay_discrete(seed: int, n_ep: int, ep_len, dS: int, n_options: int, term_every: int = 10):
+    """Discrete action space with `n_options` labels (one action component): the stored action is the reference's
+    action message `label + 0.1` (Core/StateAction.h:320-341), the behaviour policy the vector of option probabilities
+    (Math/Discrete_policy.h:198) the label was drawn from.  Same container as make_replay (dA = 1, MU has n_options
+    columns)."""
+    d = make_replay(seed, n_ep, ep_len, dS, 1, term_every)
+    rng = np.random.default_rng(seed + 1000003)
+    tot = d["S"].shape[0]
+    logits = rng.standard_normal((tot, n_options)).astype(np.float32)
+    p = np.exp(logits - logits.max(axis=1, keepdims=True))
+    MU = (p / p.sum(axis=1, keepdims=True)).astype(np.float32)
+    u = rng.random(tot)
+    label = np.minimum((np.cumsum(MU.astype(np.float64), axis=1) < u[:, None]).sum(axis=1), n_options - 1)
+    A = (label.astype(np.float32) + np.float32(0.1)).reshape(tot, 1).astype(np.float32)
+    last = d["start"] + d["N"] - 1
+    A[last] = 0
+    MU[last] = 0
+    d.update(A=A, MU=MU, n_options=n_options)
+    return d
+
+
 def write_replay_file(path: str, d) -> None:
     """Binary file read by oracle/ref_harness.cpp (SynthData::load)."""
     with open(path, "wb") as f:

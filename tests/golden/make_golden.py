@@ -112,6 +112,19 @@ CASES = {
         settings={"learner": "VRACER", "ERoldSeqFilter": "minerror", "nnLayerSizes": [16], "batchSize": 16,
                   "maxTotObsNum": 700, "minTotObsNum": 300},
         steps=8, start_step=0, sample_seed=65, bounded=0, full_steps=[0, 7]),
+    # one action component: clipImpWeight = sqrt(1/2) < 1, so the initial CinvRet = 1/C > 1 and every stored importance weight
+    # counts as "was far" until the first recompute -> negative per-episode far-policy fractions and the wrap-around of
+    # `Uint += float` in updateTrainingStatistics (oracle: uint_plus_float).  Oracle-only: the device count saturates instead.
+    "vracer_da1": dict(
+        replay=dict(seed=99, n_ep=16, ep_len=(20, 40), dS=4, dA=1),
+        settings={"learner": "VRACER", "nnLayerSizes": [16, 16], "batchSize": 8, "maxTotObsNum": 1024, "minTotObsNum": 200},
+        steps=8, start_step=0, sample_seed=69, bounded=0, full_steps=[0, 7]),
+    # discrete action space (RACER<Discrete_advantage, Discrete_policy, Uint>: Math/Discrete_policy.h, Discrete_advantage.h):
+    # 5 options, network outputs [V | advantages | policy].  Oracle-only so far.
+    "racer_discrete": dict(
+        replay=dict(seed=97, n_ep=20, ep_len=(20, 50), dS=6, dA=1, n_options=5),
+        settings={"learner": "RACER", "nnLayerSizes": [32, 32], "batchSize": 16, "maxTotObsNum": 2048, "minTotObsNum": 300},
+        steps=10, start_step=995, sample_seed=67, bounded=0, full_steps=[0, 9]),
     # MGU cells (Layer_GRU.h; "MGU" and "GRU" build the same layer, and it is what partially observable MDPs get by
     # default, Approximator.cpp:219-223): oracle-only so far — the device path does not cover them yet
     "racer_mgu": dict(
@@ -161,8 +174,20 @@ CKPT_FILES = ["agent_00_net_weights.raw", "agent_00_net_tgt_weights.raw", "agent
 BIG = ("/weights", "/m1", "/m2", "/gradSum")
 
 
+def make_replay(spec):
+    r = dict(spec["replay"])
+    if "n_options" in r:       # discrete action space: dA = 1, the behaviour policy is a probability vector
+        r.pop("dA")
+        return synth.make_replay_discrete(**r)
+    return synth.make_replay(**r)
+
+
+def harness_flags(spec):
+    return ["--discrete", str(spec["replay"]["n_options"])] if "n_options" in spec["replay"] else []
+
+
 def run_case(name, spec, outdir):
-    d = synth.make_replay(**spec["replay"])
+    d = make_replay(spec)
     ckpt, D2 = {}, {}
     with tempfile.TemporaryDirectory() as tmp:
         synth.write_replay_file(os.path.join(tmp, "data.bin"), d)
@@ -170,7 +195,7 @@ def run_case(name, spec, outdir):
             json.dump(spec["settings"], f)
         cmd = [HARNESS, "--data", "data.bin", "--settings", "settings.json", "--steps", str(spec["steps"]),
                "--threads", "1", "--startStep", str(spec["start_step"]), "--sampleSeed", str(spec["sample_seed"]),
-               "--bounded", str(spec["bounded"]), "--dump", "out.bin", "--dumpAll", "--quiet"]
+               "--bounded", str(spec["bounded"]), "--dump", "out.bin", "--dumpAll", "--quiet"] + harness_flags(spec)
         env = dict(os.environ, OMP_NUM_THREADS="1")
         if "steps_after" in spec:
             cmd.append("--save")
@@ -214,14 +239,14 @@ def run_grad_stats(outdir):
     crossed no step with nGradSteps % 1000 == 0)."""
     keep = {}
     for name, spec in CASES.items():
-        d = synth.make_replay(**spec["replay"])
+        d = make_replay(spec)
         with tempfile.TemporaryDirectory() as tmp:
             synth.write_replay_file(os.path.join(tmp, "data.bin"), d)
             with open(os.path.join(tmp, "settings.json"), "w") as f:
                 json.dump(spec["settings"], f)
             cmd = [HARNESS, "--data", "data.bin", "--settings", "settings.json", "--steps", str(spec["steps"]),
                    "--threads", "1", "--startStep", str(spec["start_step"]), "--sampleSeed", str(spec["sample_seed"]),
-                   "--bounded", str(spec["bounded"]), "--quiet"]
+                   "--bounded", str(spec["bounded"]), "--quiet"] + harness_flags(spec)
             subprocess.run(cmd, cwd=tmp, check=True, stdout=subprocess.DEVNULL, env=dict(os.environ, OMP_NUM_THREADS="1"))
             fn = os.path.join(tmp, "agent_00_net_outGrad_stats.raw")
             keep[name] = np.fromfile(fn, dtype=np.float32) if os.path.exists(fn) else np.zeros(0, np.float32)

@@ -12,7 +12,7 @@ CKPT_CASES = ["vracer_ckpt", "racer_lstm_ckpt"]
 CASES = ["vracer_small", "vracer_cfg2mini", "vracer_bounded", "vracer_prune", "racer_small", "racer_bounded", "vracer_gae"]
 # oracle pinned, device path not built: MGU cells, prioritized samplers (f3)
 ORACLE_ONLY_CASES = ["racer_mgu", "vracer_gru2", "vracer_pererr", "vracer_perseq", "vracer_farpolfrac", "vracer_maxkldiv",
-                     "vracer_minerror", "vracer_perrank", "vracer_explore"]
+                     "vracer_minerror", "vracer_perrank", "vracer_explore", "racer_discrete", "vracer_da1"]
 RECURRENT_CASES = ["racer_lstm", "vracer_lstm2", "racer_lstm64", "racer_cfg3mini"]     # nnType LSTM + BPTT window (configs[2] family)
 
 
@@ -71,6 +71,8 @@ def make_oracle(g: Golden):
                      ("returnsEstimator", "returns_estimator"), ("dataSamplingAlgo", "sampling"), ("ERoldSeqFilter", "er_filter")):
         if key in s:
             kw[arg] = s[key]
+    if "n_options" in g.spec["replay"]:
+        kw["discrete"] = g.spec["replay"]["n_options"]
     if s.get("nnType", "FFNN") in ("LSTM", "MGU", "GRU"):
         o = vo.RecurrentOracle(g.dS, g.dA, cells=s["nnLayerSizes"], bptt=s.get("nnBPTTseq", 16), cell_type=s["nnType"], **kw)
     else:
