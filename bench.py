@@ -152,6 +152,28 @@ def run_reference(steps, threads, data=None, reps=1, settings=None, learner_flag
                 sample=f"{n} learner steps of the numpy oracle port on a 50-episode slice (reference harness binary absent)")
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_baseline_block(r, data=None, single_thread_steps=400):
+    """The `cpu_baseline` object: the all-cores run `r` plus the CPU model and the same harness on ONE thread
+    over a shorter sample."""
+    blk = {"value": r["value"], "unit": "transitions/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+           "cpu_model": cpu_model()}
+    if r["kind"] == "reference" and r["cores"] > 1 and single_thread_steps > 0:
+        r1 = run_reference(single_thread_steps, 1, data=data)
+        blk["single_thread"] = {"value": r1["value"], "unit": "transitions/s", "sample": r1["sample"]}
+    return blk
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -165,7 +187,7 @@ def reference_arm(args):
            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / r["steps"],
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": WORKLOAD["name"], "batch": BATCH, "host_threads": threads},
-           "cpu_baseline": {"value": r["value"], "unit": "transitions/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+           "cpu_baseline": cpu_baseline_block(r, single_thread_steps=0),
            "e2e": {"value": r["value"], "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
@@ -312,7 +334,7 @@ def main():
                "final_stats": {k: stats[-1][k] for k in ("beta", "cmax", "n_far_policy", "grad_step")}}
         if world == 1 and not args.no_cpu_baseline:
             r = run_reference(args.cpu_steps, os.cpu_count() or 1, data=data)
-            out["cpu_baseline"] = {"value": r["value"], "unit": "transitions/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+            out["cpu_baseline"] = cpu_baseline_block(r, data=data)
         os.write(real_stdout, (json.dumps(out) + "\n").encode())
     L.close()
     if world > 1:
