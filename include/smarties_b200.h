@@ -219,6 +219,10 @@ int smb200_comm_error(smb200_learner* h);
 /* Diagnostics: n presampled steps in one persistent launch with per-CTA phase timestamps
  * (SM clock cycles), out[n][grid][8]; *grid_out = CTAs of the persistent grid. */
 int smb200_profile_phases(smb200_learner* h, int32_t n, int64_t* out, int64_t capacity, int32_t* grid_out);
+/* Diagnostics, host only (no GPU needed): the statistics phase's emulation of the reference's
+ * `Uint nOffPol += float` (ReplayMemory/MemoryProcessing.cpp:202-227) with x86-64 conversion semantics —
+ * the same inline function the device code calls, compiled for the host.  Returns the new count. */
+uint64_t smb200_uint_plus_float(uint64_t n, float x);
 
 #ifdef __cplusplus
 }

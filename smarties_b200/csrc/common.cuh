@@ -111,6 +111,32 @@ struct Hyper {
   unsigned char bounded[64];
 };
 
+// `Uint n; n += x;` with float x exactly as gcc compiles it for x86-64 in the reference's far-policy
+// count (MemoryProcessing.cpp:202-227, `nOffPol += Nsteps * EP.fracFarPolSteps`): n is rounded to float,
+// added, and converted back with cvttss2si — directly below 2^63 (a negative sum wraps to 2^64 - |sum|,
+// out of range gives the "integer indefinite" 2^63), as cvttss2si(f - 2^63) ^ 2^63 from there on (anything
+// >= 2^64, such as the float nearest to a wrapped value, becomes 0).  CUDA's own float -> unsigned
+// conversion saturates instead.  Host and device: tests/test_host_logic.py pins this against the oracle's
+// `uint_plus_float` through smb200_uint_plus_float.
+__host__ __device__ inline unsigned long long uint_plus_float_x86(unsigned long long n, float x) {
+  const float two63 = 9223372036854775808.0f;
+  const unsigned long long indefinite = 0x8000000000000000ull;
+#ifdef __CUDA_ARCH__
+  const float f = __ull2float_rn(n) + x;
+#else
+  const volatile float nf = (float)n;          // volatile: no double-precision contraction of the float sum
+  const volatile float fv = nf + x;
+  const float f = fv;
+#endif
+  if (!(f >= two63)) {                         // gcc: `comiss; jae` — an unordered compare (NaN) takes this branch too
+    if (!(f > -two63)) return indefinite;      // below the signed range, or NaN
+    return (unsigned long long)(long long)f;   // truncation; negative values wrap
+  }
+  const float g = f - two63;
+  const unsigned long long t = g < two63 ? (unsigned long long)(long long)g : indefinite;
+  return t ^ indefinite;
+}
+
 #define SMB200_CUDA_CHECK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { \
   smb200::set_error(#expr, e__, __FILE__, __LINE__); return -2; } } while (0)
 

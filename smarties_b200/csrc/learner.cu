@@ -1065,6 +1065,9 @@ int smb200_profile_phases(smb200_learner* h, int32_t n, int64_t* out, int64_t ca
   return 0;
 }
 
+// Host build of the inline function the statistics phase uses for the reference's `Uint += float`.
+uint64_t smb200_uint_plus_float(uint64_t n, float x) { return (uint64_t)uint_plus_float_x86((unsigned long long)n, x); }
+
 // ---- learner ranks sharing the gradient: peer-memory buffers exchanged through CUDA IPC ----
 static void comm_layout(CommView& cm, int world, int rank, int nParams, int nTiles) {
   cm.world = world; cm.rank = rank;

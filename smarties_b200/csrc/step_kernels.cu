@@ -1784,7 +1784,7 @@ __device__ void stats_and_refer(const StepArgs& a, const Hyper& hp, const StepCt
     __syncthreads();
     if (tid < T) {
       int p = (tid - base % T + T) % T;     // first position of this chunk owned by virtual thread `tid`
-      for (; p < n; p += T) nOff = (unsigned long long)(__ull2float_rn(nOff) + xs[p]);
+      for (; p < n; p += T) nOff = uint_plus_float_x86(nOff, xs[p]);   // the reference's `Uint += float`, x86 semantics
     }
     __syncthreads();
   }

@@ -1,0 +1,48 @@
+"""GPU: device cases written AFTER the round's GPU budget was spent — compiled for sm_100a and pinned on the CPU side, but
+never run on a B200 yet.  Each case runs in a child process (a CUDA fault cannot poison the context of other tests; the
+file sorts last) and is a non-strict xfail until its first green run on the box, when it moves to test_gpu_parity.py.
+
+vracer_da1 — one action component (cart-pole's shape): clipImpWeight = sqrt(1/2) < 1, so the reference starts with
+CinvRet = 1/C > 1 (MemoryBuffer.h:41-44), every stored importance weight 1 counts as "was far", per-episode far-policy
+fractions go negative and `Uint nOffPol += float` (MemoryProcessing.cpp:202-227) wraps through x86's cvttss2si.  The
+statistics phase now converts with the same semantics (`uint_plus_float_x86`, csrc/common.cuh; host build pinned to the
+oracle by tests/test_host_logic.py::test_uint_plus_float_x86_matches_oracle)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+CHILD = r"""
+import sys
+sys.path[:0] = [{root!r}, {oracle!r}, {tests!r}]
+import numpy as np
+from parity_utils import Golden, make_learner
+from test_gpu_parity import _check_step, _check_final
+g = Golden({case!r})
+L = make_learner(g)
+R = g.ref
+st = L.get_stats()
+assert st["beta"] == R["init/refer"][0] and st["cmax"] == R["init/refer"][1] and st["cinv"] == R["init/refer"][2]
+assert np.allclose(L.read_field("QRET"), R["init/Qret"], rtol=2e-5, atol=2e-5)
+for s in range(g.steps):
+    _check_step(L, g, R, f"s{{s}}", L.train_steps(1)[0])
+_check_final(L, R)
+L.close()
+print("ok")
+"""
+
+
+def _run_child(case):
+    code = CHILD.format(root=os.path.dirname(HERE), oracle=os.path.join(os.path.dirname(HERE), "oracle"), tests=HERE, case=case)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (r.stdout[-3000:] + "\n" + r.stderr[-3000:])
+
+
+@pytest.mark.xfail(strict=False, reason="first run on a B200 pending (written after the round's GPU budget was spent)")
+def test_one_action_component_far_policy_count_wraps_like_the_reference():
+    _run_child("vracer_da1")

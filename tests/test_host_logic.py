@@ -96,3 +96,36 @@ def test_no_gpu_fails_loudly(built_library):
     from smarties_b200 import Learner, SmartiesB200Error
     with pytest.raises(SmartiesB200Error, match="no CPU fallback"):
         Learner(6, 3, {"nnLayerSizes": [32, 32], "batchSize": 16, "maxTotObsNum": 2048})
+
+
+def test_uint_plus_float_x86_matches_oracle(built_library):
+    """The statistics phase counts far-policy steps with the reference's `Uint nOffPol += float`
+    (MemoryProcessing.cpp:202-227).  The inline function the device code calls, compiled for the host, against the
+    oracle's restatement (pinned to the reference goldens vracer_da1 / racer_discrete, where the sum goes negative):
+    wrap-around of negative sums, the 2^63 'integer indefinite', zero from 2^64 on, float rounding of large counts."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import vracer_oracle as vo
+    from smarties_b200 import load_library
+    lib = load_library()
+    lib.smb200_uint_plus_float.restype = C.c_uint64
+    lib.smb200_uint_plus_float.argtypes = [C.c_uint64, C.c_float]
+    M = (1 << 64) - 1
+    ns = [0, 1, 2, 7, 255, (1 << 24) - 1, 1 << 24, (1 << 24) + 1, (1 << 31) + 5, (1 << 53) + 1, (1 << 62) + 12345,
+          (1 << 63) - 1, 1 << 63, (1 << 63) + (1 << 40), M - 1000, M - 1, M]
+    xs = [0.0, 0.4, 0.5, 0.99, 1.0, 1.5, 3.75, 199.0, -0.25, -1.0, -1.5, -7.0, -200.5, 1e10, -1e10, 9.3e18, -9.3e18, 1.9e19,
+          -1.9e19, 3e19, float(2 ** 63), float(-2 ** 63), float(2 ** 64)]
+    rng = np.random.default_rng(5)
+    ns += [int(v) for v in rng.integers(0, 1 << 40, 200)]
+    xs += [float(np.float32(v)) for v in rng.standard_normal(50) * 300.0]
+    bad = []
+    for n in ns:
+        for x in xs:
+            got, want = lib.smb200_uint_plus_float(n, x), vo.uint_plus_float(n, np.float32(x))
+            if got != want:
+                bad.append((n, x, got, want))
+    assert not bad, bad[:5]
+    # the sequence of the goldens: a negative sum wraps, the next addition gives 0
+    n = lib.smb200_uint_plus_float(0, -40.0)
+    assert n == (1 << 64) - 40 and lib.smb200_uint_plus_float(n, 3.0) == 0
