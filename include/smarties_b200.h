@@ -40,7 +40,9 @@ enum smb200_algo { SMB200_VRACER = 0, SMB200_RACER = 1 };
 enum smb200_nn_type { SMB200_FFNN = 0, SMB200_LSTM = 1 };   /* "nnType" (Network/Builder.cpp:48-99) */
 /* "returnsEstimator" (createReturnEstimator, ReplayMemory/MemoryProcessing.cpp:419-450): Retrace (:391-400; also what
  * "default" means for RACER / V-RACER, Learners/AlgoFactory.cpp:134-136) or GAE (:411-417). */
-enum smb200_returns_estimator { SMB200_RETRACE = 0, SMB200_GAE = 1 };
+enum smb200_returns_estimator { SMB200_RETRACE = 0, SMB200_GAE = 1,
+                                SMB200_RETRACE_EXPLORE = 2 /* computeRetraceExplBonus, MemoryProcessing.cpp:402-409; accepted only
+                                                              with SMB200_UNVERIFIED=1 in the environment until its first GPU run */ };
 enum smb200_field {          /* per-transition replay arrays, Episode.h:66-75 */
   SMB200_F_V = 0, SMB200_F_ADV = 1, SMB200_F_QRET = 2, SMB200_F_DELTA = 3, SMB200_F_RHO = 4, SMB200_F_KL = 5,
   SMB200_F_REWARD = 6
@@ -74,7 +76,7 @@ typedef struct smb200_config {
                                            (ReplayMemory/MemoryBuffer.cpp:393-402) */
   int64_t min_tot_obs;                  /* minTotObsNum_local = nObsB4StartTraining: only recorded in checkpoints
                                            ("nInitialData", MemoryBuffer.cpp:300); 0 = max_tot_obs */
-  int32_t returns_estimator;            /* smb200_returns_estimator: "returnsEstimator": "retrace" | "GAE" */
+  int32_t returns_estimator;            /* smb200_returns_estimator: "returnsEstimator": "retrace" | "GAE" | ("retraceExplore") */
 } smb200_config;
 
 /* Per-step scalars the reference prints / feeds back (MemoryBuffer::getMetrics,

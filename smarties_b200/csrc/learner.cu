@@ -495,8 +495,11 @@ static int run_segment(smb200_learner* h, int first, int n, long long gstep0, in
     const int step = (int)(gstep0 + n - 1);
     const double cm = cmax_at(h, lastStep);
     if (launch_clear_sums(h->dSums, h->stream)) return -2;
-    if (launch_sweep(h->rp, (int)h->episodes.size(), 0, (float)h->cfg.gamma, (float)h->cfg.lambda, h->cfg.returns_estimator == SMB200_GAE, 1, (float)cm, (float)(1.0 / cm),
-                     h->dSums, h->stream)) return -2;
+    // retraceExplore: baseline = stats.maxAbsError BEFORE this step's update (createReturnEstimator at the top of
+    // updateTrainingStatistics, MemoryProcessing.cpp:196) = ctrl[step & 1], still device-resident here
+    if (launch_sweep(h->rp, (int)h->episodes.size(), 0, (float)h->cfg.gamma, (float)h->cfg.lambda, h->cfg.returns_estimator, 1, (float)cm, (float)(1.0 / cm),
+                     h->dSums, h->stream, 0.f, h->dCtrl + (step & 1))) return -2;
+    if (h->cfg.returns_estimator == SMB200_RETRACE_EXPLORE) h->launches += 1;
     if (launch_moments(h->rp, h->highWater, h->dSums, h->numSMs, h->stream)) return -2;
     if (launch_peer_allreduce(h->comm, h->dSums->moments, 2 * h->cfg.dim_state + 3, ++h->vecStamp, h->stream)) return -2;
     if (launch_finalize_sweep(a, step, h->dSums, h->stream)) return -2;
@@ -547,8 +550,11 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
   if (c.refer_reduce_threads <= 0) c.refer_reduce_threads = 32;
   if (c.refer_reduce_threads > kThreads) c.refer_reduce_threads = kThreads;
   if (c.batch_size < 1 || c.max_tot_obs < c.batch_size) { set_error_msg("bad batch_size / max_tot_obs"); delete h; return SMB200_ERR_INVALID; }
-  if (c.returns_estimator != SMB200_RETRACE && c.returns_estimator != SMB200_GAE) {
-    set_error_msg("returnsEstimator must be retrace or GAE"); delete h; return SMB200_ERR_INVALID; }
+  // retraceExplore: the sequential sweep kernel exists but has not run on a GPU yet — opt-in until it has
+  const char* unv = getenv("SMB200_UNVERIFIED");
+  const bool exploreOk = c.returns_estimator == SMB200_RETRACE_EXPLORE && unv && unv[0] == '1';
+  if (c.returns_estimator != SMB200_RETRACE && c.returns_estimator != SMB200_GAE && !exploreOk) {
+    set_error_msg("returnsEstimator must be retrace or GAE (retraceExplore: only with SMB200_UNVERIFIED=1)"); delete h; return SMB200_ERR_INVALID; }
   std::vector<GradTile> tiles;
   if (build_net(c, h->descs.net, tiles)) { delete h; return SMB200_ERR_INVALID; }
   memset(&h->descs.seq, 0, sizeof(h->descs.seq));
@@ -776,10 +782,11 @@ static int push_episode_impl(smb200_learner* h, int64_t id, int32_t N, int32_t t
     float* dst[4] = {rp.Q, rp.DELTA, rp.RHO, rp.KL};
     for (int k = 0; k < 4; ++k)
       SMB200_CUDA_CHECK(cudaMemcpyAsync(dst[k] + start, restored[k], sizeof(float) * (size_t)N, cudaMemcpyHostToDevice, st));
-    if (launch_sweep(rp, 0, slot, (float)h->cfg.gamma, (float)h->cfg.lambda, h->cfg.returns_estimator == SMB200_GAE, 2, cmax, cinv, nullptr, st)) return SMB200_ERR_CUDA;
+    if (launch_sweep(rp, 0, slot, (float)h->cfg.gamma, (float)h->cfg.lambda, h->cfg.returns_estimator, 2, cmax, cinv, nullptr, st)) return SMB200_ERR_CUDA;
   } else {
     // computeReturnEstimator at insertion (MemoryBuffer.cpp:143)
-    if (launch_sweep(rp, 0, slot, (float)h->cfg.gamma, (float)h->cfg.lambda, h->cfg.returns_estimator == SMB200_GAE, 0, 0.f, 0.f, nullptr, st)) return SMB200_ERR_CUDA;
+    if (launch_sweep(rp, 0, slot, (float)h->cfg.gamma, (float)h->cfg.lambda, h->cfg.returns_estimator, 0, 0.f, 0.f, nullptr, st,
+                     (float)h->hCtrl.max_abs_err)) return SMB200_ERR_CUDA;
   }
   SMB200_CUDA_CHECK(cudaStreamSynchronize(st));   // host buffers are the caller's: finish the copies
   h->episodes.push_back(EpisodeMeta{id, N, slot, start, terminated ? 1 : 0});
@@ -823,7 +830,8 @@ int smb200_initialize_learner(smb200_learner* h) {
   if (launch_moments(h->rp, h->highWater, h->dSums, h->numSMs, h->stream)) return SMB200_ERR_CUDA;
   if (launch_peer_allreduce(h->comm, h->dSums->moments, 2 * h->cfg.dim_state + 3, ++h->vecStamp, h->stream)) return SMB200_ERR_CUDA;
   if (launch_update_scaling(h->rp, h->dCtrl, h->dDescs, h->dSums, 1, h->stream)) return SMB200_ERR_CUDA;
-  if (launch_sweep(h->rp, (int)h->episodes.size(), 0, (float)h->cfg.gamma, (float)h->cfg.lambda, h->cfg.returns_estimator == SMB200_GAE, 0, 0.f, 0.f, nullptr, h->stream))
+  if (launch_sweep(h->rp, (int)h->episodes.size(), 0, (float)h->cfg.gamma, (float)h->cfg.lambda, h->cfg.returns_estimator, 0, 0.f, 0.f, nullptr, h->stream,
+                   (float)h->hCtrl.max_abs_err))
     return SMB200_ERR_CUDA;
   SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   h->initialized = true;
@@ -1160,7 +1168,8 @@ int smb200_retrace_sweep(smb200_learner* h, double* sumErr2) {
   if (upload_order(h)) return SMB200_ERR_CUDA;
   if (launch_clear_sums(h->dSums, h->stream)) return SMB200_ERR_CUDA;
   SMB200_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
-  if (launch_sweep(h->rp, (int)h->episodes.size(), 0, (float)h->cfg.gamma, (float)h->cfg.lambda, h->cfg.returns_estimator == SMB200_GAE, 0, 0.f, 0.f, h->dSums, h->stream))
+  if (launch_sweep(h->rp, (int)h->episodes.size(), 0, (float)h->cfg.gamma, (float)h->cfg.lambda, h->cfg.returns_estimator, 0, 0.f, 0.f, h->dSums, h->stream,
+                   0.f, h->dCtrl + (h->gradStep & 1)))
     return SMB200_ERR_CUDA;
   SMB200_CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
   double e = 0;

@@ -119,9 +119,11 @@ int launch_forward(const StepArgs& a, const NetDesc& net, const float* states, i
 int launch_init_episode(const ReplayView& rp, int slot, float deltaInit, int haveValues, cudaStream_t st);
 // Retrace (+ optional exact aggregate recompute) over `nEpisodes` episodes listed in rp.epOrder,
 // or over the single episode `oneSlot` when nEpisodes == 0.  gae != 0: the GAE recursion instead (no importance weight,
-// no advantage term; MemoryProcessing.cpp:411-417).
-int launch_sweep(const ReplayView& rp, int nEpisodes, int oneSlot, float gamma, float lambda, int gae,
-                 int recomputeAggregates, float cmax, float cinv, SweepSums* sums, cudaStream_t st);
+// no advantage term; MemoryProcessing.cpp:411-417).  estimator = smb200_returns_estimator; 2 (retraceExplore, :402-409) runs
+// k_sweep_explore with the baseline `stats.maxAbsError` taken from exploreCtrl (device) or, if null, exploreBaseline.
+int launch_sweep(const ReplayView& rp, int nEpisodes, int oneSlot, float gamma, float lambda, int estimator,
+                 int recomputeAggregates, float cmax, float cinv, SweepSums* sums, cudaStream_t st,
+                 float exploreBaseline = 0.f, const StepCtrl* exploreCtrl = nullptr);
 int launch_moments(const ReplayView& rp, long long rowEnd, SweepSums* sums, int numSMs, cudaStream_t st);
 int launch_update_scaling(const ReplayView& rp, const StepCtrl* ctrlCur, const DevDescs* descs, const SweepSums* sums, int bInit, cudaStream_t st);
 int launch_clear_sums(SweepSums* sums, cudaStream_t st);

@@ -217,6 +217,88 @@ __global__ void __launch_bounds__(kThreads) k_sweep(ReplayView rp, int nEpisodes
 }
 
 // ------------------------------------------------------------------------------------------
+// "returnsEstimator": "retraceExplore" (computeRetraceExplBonus, MemoryProcessing.cpp:402-409):
+//   Q[t] = (1 - g) * (|Q[t+1] - A[t+1] - V[t+1]| - baseline) + Retrace(t),  baseline = stats.maxAbsError when the estimator
+// is created (createReturnEstimator, :427-435).  The absolute value makes the recursion non-affine, so there is no scan:
+// one CTA per episode stages 1024 time steps (coalesced, all loads in flight at once) in shared memory, ONE thread runs the
+// recursion over the staged chunk in the reference's operation order (~8 dependent f32 operations per step), all threads
+// write Q back and accumulate the squared change.  Aggregates are recomputed by k_sweep(recompute = 2) beforehand.
+// `ctrl` != nullptr: the baseline is read from the device-resident statistics of the step (the every-1000-steps recompute
+// is enqueued behind a running launch, the host does not hold the value).
+// NOT YET RUN ON A GPU (written after the round's GPU budget was spent): reachable only with SMB200_UNVERIFIED=1.
+__global__ void __launch_bounds__(kThreads) k_sweep_explore(ReplayView rp, int nEpisodes, int oneSlot, float gamma, float lambda,
+                                                            float baselineHost, const StepCtrl* ctrl, SweepSums* sums) {
+  __shared__ float sR[kSweepChunk], sV[kSweepChunk], sA[kSweepChunk], sW[kSweepChunk], sQ[kSweepChunk];
+  __shared__ float shCarry;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const double rmean = (double)rp.rew[0], rscale = (double)rp.rew[1];
+  const float baseline = ctrl ? (float)ctrl->max_abs_err : baselineHost;      // `const Fval baseline = RM.stats.maxAbsError`
+  const float coef = 1.0f - gamma;                                            // `const Fval coef = (1-gamma)`
+  const int count = nEpisodes > 0 ? nEpisodes : 1;
+  float errAcc = 0.f; long long nRet = 0;
+  for (int pos = blockIdx.x; pos < count; pos += gridDim.x) {
+    const int slot = nEpisodes > 0 ? rp.epOrder[pos] : oneSlot;
+    const int N = rp.epLen[slot];
+    const size_t r0 = (size_t)rp.epStart[slot];
+    __syncthreads();
+    if (tid == 0) {      // updateReturnEstimator (MemoryProcessing.cpp:23-33): Q of the last row
+      float c0;
+      if (rp.epTerm[slot]) c0 = rp.Q[r0 + N - 1];
+      else { c0 = rp.V[r0 + N - 1]; rp.Q[r0 + N - 1] = c0; }
+      shCarry = c0;
+    }
+    for (int top = N - 2; top >= 0; top -= kSweepChunk) {     // `top` = latest time step of this chunk, position p = top - t
+      const int n = min(kSweepChunk, top + 1);
+      float oldQ[kSweepPer];
+#pragma unroll
+      for (int j = 0; j < kSweepPer; ++j) {
+        const int p = j * kThreads + tid;
+        oldQ[j] = 0.f;
+        if (p < n) {
+          const size_t r = r0 + (top - p) + 1;
+          const float w = rp.RHO[r];
+          sR[p] = (float)(((double)rp.R[r] - rmean) * rscale);                // scaledReward<Fval> (Episode.h:184-189)
+          sV[p] = rp.V[r]; sA[p] = rp.ADV[r];
+          sW[p] = lambda * (w < 1.f ? w : 1.f);                               // lambda * clippedOffPolW (Episode.h:190-194)
+          oldQ[j] = rp.Q[r - 1];
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        float Qn = shCarry;
+        for (int p = 0; p < n; ++p) {
+          const float Vn = sV[p];
+          const float d = Qn - sA[p] - Vn;
+          float Qt = sR[p] + gamma * (Vn + sW[p] * d);                        // computeRetrace (:391-400)
+          const float E = fabsf(d) - baseline;
+          Qt = coef * E + Qt;                                                 // computeRetraceExplBonus (:402-409)
+          sQ[p] = Qt; Qn = Qt;
+        }
+        shCarry = Qn;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < kSweepPer; ++j) {
+        const int p = j * kThreads + tid;
+        if (p < n) {
+          const float Qt = sQ[p];
+          rp.Q[r0 + (top - p)] = Qt;
+          const float dq = oldQ[j] - Qt;
+          errAcc += dq * dq;
+        }
+      }
+      __syncthreads();
+    }
+    nRet += N - 1;
+  }
+  if (sums) {
+    const float e = warp_sum(errAcc);
+    if (lane == 0) atomicAdd(&sums->sumErr2, (double)e);
+    if (tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&sums->nRet), (unsigned long long)nRet);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 constexpr int kMomRows = 64;   // rows per tile
 
 __global__ void __launch_bounds__(kThreads) k_moments(ReplayView rp, long long rowEnd, SweepSums* sums) {
@@ -446,11 +528,24 @@ int launch_init_episode(const ReplayView& rp, int slot, float deltaInit, int hav
   return 0;
 }
 
-int launch_sweep(const ReplayView& rp, int nEpisodes, int oneSlot, float gamma, float lambda, int gae, int recompute, float cmax,
-                 float cinv, SweepSums* sums, cudaStream_t st) {
+int launch_sweep(const ReplayView& rp, int nEpisodes, int oneSlot, float gamma, float lambda, int estimator, int recompute, float cmax,
+                 float cinv, SweepSums* sums, cudaStream_t st, float exploreBaseline, const StepCtrl* exploreCtrl) {
   const int count = nEpisodes > 0 ? nEpisodes : 1;
   int blocks = count;                           // one CTA per episode, at most one full wave of 8 CTAs per SM
   if (blocks > 148 * 8) blocks = 148 * 8;
+  const int gae = estimator == 1;
+  if (estimator == 2) {                         // retraceExplore: aggregates by k_sweep, the sequential recursion on its own
+    if (recompute) {
+      k_sweep<<<blocks, kThreads, 0, st>>>(rp, nEpisodes, oneSlot, gamma, lambda, 0, 2, cmax, cinv, sums);
+      SMB200_CUDA_CHECK(cudaGetLastError());
+    }
+    if (recompute != 2) {
+      if (blocks > 148 * 4) blocks = 148 * 4;   // 20 KB of static shared memory per CTA
+      k_sweep_explore<<<blocks, kThreads, 0, st>>>(rp, nEpisodes, oneSlot, gamma, lambda, exploreBaseline, exploreCtrl, sums);
+      SMB200_CUDA_CHECK(cudaGetLastError());
+    }
+    return 0;
+  }
   k_sweep<<<blocks, kThreads, 0, st>>>(rp, nEpisodes, oneSlot, gamma, lambda, gae, recompute, cmax, cinv, sums);
   SMB200_CUDA_CHECK(cudaGetLastError());
   return 0;

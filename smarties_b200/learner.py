@@ -191,7 +191,7 @@ class Learner:
         cfg.world_rank, cfg.world_size, cfg.seed = world_rank, world_size, seed
         cfg.nn_type, cfg.nn_bptt_seq = {"FFNN": 0, "LSTM": 1}[hp.nnType], int(hp.nnBPTTseq)
         cfg.min_tot_obs = hp.minTotObsNum_local
-        cfg.returns_estimator = {"retrace": 0, "GAE": 1}[hp.returnsEstimator]
+        cfg.returns_estimator = {"retrace": 0, "GAE": 1, "retraceExplore": 2}[hp.returnsEstimator]
         if bounded is not None:
             b = np.broadcast_to(np.asarray(bounded, dtype=bool), (dim_action,))
             for i in range(dim_action):

@@ -6,7 +6,13 @@ vracer_da1 — one action component (cart-pole's shape): clipImpWeight = sqrt(1/
 CinvRet = 1/C > 1 (MemoryBuffer.h:41-44), every stored importance weight 1 counts as "was far", per-episode far-policy
 fractions go negative and `Uint nOffPol += float` (MemoryProcessing.cpp:202-227) wraps through x86's cvttss2si.  The
 statistics phase now converts with the same semantics (`uint_plus_float_x86`, csrc/common.cuh; host build pinned to the
-oracle by tests/test_host_logic.py::test_uint_plus_float_x86_matches_oracle)."""
+oracle by tests/test_host_logic.py::test_uint_plus_float_x86_matches_oracle).
+
+vracer_explore — "returnsEstimator": "retraceExplore" (computeRetraceExplBonus, MemoryProcessing.cpp:402-409): the bonus
+(1 - gamma) * (|Q' - A - V| - stats.maxAbsError) makes the recursion non-affine; `k_sweep_explore` (csrc/sweep_kernels.cu) stages
+an episode in shared memory and runs the recursion sequentially in the reference's operation order.  The golden covers the
+initial sweep (baseline 0), insertion and the step-1000 recompute (baseline = the device-resident statistic).  The setting is
+accepted only with SMB200_UNVERIFIED=1 until this test has been green."""
 import os
 import subprocess
 import sys
@@ -39,10 +45,16 @@ print("ok")
 
 def _run_child(case):
     code = CHILD.format(root=os.path.dirname(HERE), oracle=os.path.join(os.path.dirname(HERE), "oracle"), tests=HERE, case=case)
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, SMB200_UNVERIFIED="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (r.stdout[-3000:] + "\n" + r.stderr[-3000:])
 
 
 @pytest.mark.xfail(strict=False, reason="first run on a B200 pending (written after the round's GPU budget was spent)")
 def test_one_action_component_far_policy_count_wraps_like_the_reference():
     _run_child("vracer_da1")
+
+
+@pytest.mark.xfail(strict=False, reason="first run on a B200 pending (written after the round's GPU budget was spent)")
+def test_retrace_explore_estimator_matches_reference():
+    _run_child("vracer_explore")
