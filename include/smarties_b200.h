@@ -225,6 +225,15 @@ int smb200_profile_phases(smb200_learner* h, int32_t n, int64_t* out, int64_t ca
  * `Uint nOffPol += float` (ReplayMemory/MemoryProcessing.cpp:202-227) with x86-64 conversion semantics —
  * the same inline function the device code calls, compiled for the host.  Returns the new count. */
 uint64_t smb200_uint_plus_float(uint64_t n, float x);
+/* Diagnostics, host only (no GPU needed): the host half of n_steps learner steps with no device work — the library's own
+ * Sample_uniform::sample + Sampling::IDtoSeqStep (ReplayMemory/Sampling.cpp:26-47,82-93), FIFO applyEpisodesRemovalAlgo
+ * (ReplayMemory/MemoryProcessing.cpp:327-351), ring allocator and the Adam update's draw from the sampler's generator
+ * (Network/Optimizer.cpp:139) — on n_ep episodes given as (id, rows incl. the terminal row, terminated) in push order.
+ * ep_id_out / t_out [n_steps][batch_size]: sampled episode id and time step; n_ep_after [n_steps] and order_out
+ * [n_steps][n_ep] (padded with -1): the episode vector after each step (both optional). */
+int smb200_host_replay_trace(int32_t batch_size, int64_t max_tot_obs, int64_t capacity_rows, int32_t n_ep, const int64_t* ids,
+                             const int32_t* n_rows, const int32_t* terminated, uint64_t seed, int32_t n_steps,
+                             int64_t* ep_id_out, int64_t* t_out, int32_t* n_ep_after, int64_t* order_out);
 
 #ifdef __cplusplus
 }

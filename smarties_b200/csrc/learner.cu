@@ -743,6 +743,17 @@ int smb200_get_scaling(smb200_learner* h, float* mean, float* scale, float* stde
 }
 
 // `restored` (may be null): {Q, DELTA, RHO, KL} of a checkpointed episode (Episode::unpackEpisode, Episode.cpp:95-128):
+// host bookkeeping of MemoryBuffer::pushBackEpisode (MemoryBuffer.cpp:479-520): the episode goes to the back of the
+// reference's `episodes` vector, its ring range becomes live, counters advance
+static void host_add_episode(smb200_learner* h, int64_t id, int32_t N, int32_t terminated, int slot, long long start) {
+  h->episodes.push_back(EpisodeMeta{id, N, slot, start, terminated ? 1 : 0});
+  h->liveRanges[start] = start + N;
+  h->head = start + N; h->highWater = std::max(h->highWater, start + N);
+  h->nTransitions += N - 1;
+  h->nSeenEps += 1; h->nSeenObs += N - 1;
+  h->orderDirty = true; h->lookupDirty = true; h->presampled = 0;
+}
+
 // copied as they are; the aggregates are recomputed with (cmax, cinv) like MemoryBuffer::restart does
 // (Episode::updateCumulative, MemoryBuffer.cpp:257) and the return estimate is NOT re-evaluated.
 static int push_episode_impl(smb200_learner* h, int64_t id, int32_t N, int32_t terminated, const float* S, const float* A,
@@ -789,12 +800,7 @@ static int push_episode_impl(smb200_learner* h, int64_t id, int32_t N, int32_t t
                      (float)h->hCtrl.max_abs_err)) return SMB200_ERR_CUDA;
   }
   SMB200_CUDA_CHECK(cudaStreamSynchronize(st));   // host buffers are the caller's: finish the copies
-  h->episodes.push_back(EpisodeMeta{id, N, slot, start, terminated ? 1 : 0});
-  h->liveRanges[start] = start + N;
-  h->head = start + N; h->highWater = std::max(h->highWater, start + N);
-  h->nTransitions += N - 1;
-  h->nSeenEps += 1; h->nSeenObs += N - 1;
-  h->orderDirty = true; h->lookupDirty = true; h->presampled = 0;
+  host_add_episode(h, id, N, terminated, slot, start);
   return 0;
 }
 
@@ -1071,6 +1077,45 @@ int smb200_profile_phases(smb200_learner* h, int32_t n, int64_t* out, int64_t ca
   float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->lastMs = ms; h->lastLaunches = 1;
   if (grid_out) *grid_out = h->persistGrid;
   return 0;
+}
+
+// Host half of the learner step without any device work (diagnostics for the CPU test suite): the SAME host functions the
+// learner runs — ring allocator, host_add_episode, host_sample, host_post_step — on an episode table given as
+// (id, rows, terminated) in push order.  Per step: sampled (episode id, t) in sample order; after the step's FIFO
+// sort / pruning: the number of episodes and their ids in the reference's vector order (padded with -1).
+int smb200_host_replay_trace(int32_t batch_size, int64_t max_tot_obs, int64_t capacity_rows, int32_t n_ep, const int64_t* ids,
+                             const int32_t* n_rows, const int32_t* terminated, uint64_t seed, int32_t n_steps,
+                             int64_t* ep_id_out, int64_t* t_out, int32_t* n_ep_after, int64_t* order_out) {
+  if (batch_size < 1 || n_ep < 1 || n_steps < 0 || !ids || !n_rows || !terminated || !ep_id_out || !t_out) return SMB200_ERR_INVALID;
+  smb200_learner* h = new smb200_learner();
+  memset(&h->cfg, 0, sizeof(h->cfg));
+  h->cfg.batch_size = batch_size; h->cfg.max_tot_obs = max_tot_obs;
+  long long cap = capacity_rows > 0 ? capacity_rows : max_tot_obs + max_tot_obs / 8 + 65536;   // smb200_create's default
+  h->rp.capRows = (cap + 63) / 64 * 64;
+  for (int s = n_ep - 1; s >= 0; --s) h->freeSlots.push_back(s);
+  int rc = 0;
+  for (int e = 0; e < n_ep && !rc; ++e) {
+    if (n_rows[e] < 2) { set_error_msg("push_episode: an episode needs at least s0 and sT"); rc = SMB200_ERR_INVALID; break; }
+    const long long start = ring_alloc(h, n_rows[e]);
+    if (start < 0) { set_error_msg("replay ring full"); rc = SMB200_ERR_CAPACITY; break; }
+    const int slot = h->freeSlots.back(); h->freeSlots.pop_back();
+    host_add_episode(h, ids[e], n_rows[e], terminated[e], slot, start);
+  }
+  if (!rc && h->nTransitions < batch_size) { set_error_msg("not enough transitions for one mini-batch"); rc = SMB200_ERR_STATE; }
+  if (!rc) {
+    h->gen.seed((unsigned long)seed);
+    std::vector<int64_t> pos(batch_size);
+    for (int s = 0; s < n_steps; ++s) {
+      host_sample(h, nullptr, nullptr, pos.data(), t_out + (size_t)s * batch_size);
+      for (int i = 0; i < batch_size; ++i) ep_id_out[(size_t)s * batch_size + i] = h->episodes[(size_t)pos[i]].id;
+      host_post_step(h);
+      if (n_ep_after) n_ep_after[s] = (int32_t)h->episodes.size();
+      if (order_out)
+        for (int k = 0; k < n_ep; ++k) order_out[(size_t)s * n_ep + k] = k < (int)h->episodes.size() ? h->episodes[k].id : -1;
+    }
+  }
+  delete h;
+  return rc;
 }
 
 // Host build of the inline function the statistics phase uses for the reference's `Uint += float`.

@@ -1,0 +1,86 @@
+"""CPU: the host half of the learner step — the library's own sampler (Sample_uniform::sample + Sampling::IDtoSeqStep,
+ReplayMemory/Sampling.cpp:26-47,82-93), FIFO episode removal (MemoryProcessing.cpp:327-351), ring allocator and the Adam
+update's draw from the sampler's generator (Optimizer.cpp:139) — bit-exact against what the reference binary sampled and
+kept in every golden run, through the host-only C-ABI diagnostic smb200_host_replay_trace (no device work, no GPU)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from parity_utils import CASES, ORACLE_ONLY_CASES, RECURRENT_CASES, Golden
+
+UNIFORM_FIFO = [c for c in CASES + RECURRENT_CASES + ORACLE_ONLY_CASES
+                if c not in ("vracer_pererr", "vracer_perseq", "vracer_perrank", "vracer_farpolfrac", "vracer_maxkldiv", "vracer_minerror")]
+
+
+def _trace(lib, batch, max_tot_obs, ids, rows, term, seed, steps, capacity=0):
+    P = C.POINTER
+    lib.smb200_host_replay_trace.restype = C.c_int
+    lib.smb200_host_replay_trace.argtypes = [C.c_int32, C.c_int64, C.c_int64, C.c_int32, P(C.c_int64), P(C.c_int32), P(C.c_int32),
+                                             C.c_uint64, C.c_int32, P(C.c_int64), P(C.c_int64), P(C.c_int32), P(C.c_int64)]
+    ids, rows, term = (np.ascontiguousarray(ids, np.int64), np.ascontiguousarray(rows, np.int32), np.ascontiguousarray(term, np.int32))
+    n = len(ids)
+    ep = np.zeros((steps, batch), np.int64); t = np.zeros((steps, batch), np.int64)
+    n_after = np.zeros(steps, np.int32); order = np.zeros((steps, n), np.int64)
+    rc = lib.smb200_host_replay_trace(batch, max_tot_obs, capacity, n, ids.ctypes.data_as(P(C.c_int64)), rows.ctypes.data_as(P(C.c_int32)),
+                                      term.ctypes.data_as(P(C.c_int32)), seed, steps, ep.ctypes.data_as(P(C.c_int64)),
+                                      t.ctypes.data_as(P(C.c_int64)), n_after.ctypes.data_as(P(C.c_int32)), order.ctypes.data_as(P(C.c_int64)))
+    return rc, ep, t, n_after, order
+
+
+@pytest.mark.parametrize("case", UNIFORM_FIFO)
+def test_host_sampler_and_fifo_match_the_reference_run(built_library, case):
+    from smarties_b200 import HyperParameters, load_library
+    g = Golden(case)
+    s = g.settings
+    assert s.get("dataSamplingAlgo", "uniform") == "uniform" and s.get("ERoldSeqFilter", "oldest") in ("oldest", "default")
+    max_obs = s.get("maxTotObsNum", HyperParameters(g.dS, g.dA, {}).maxTotObsNum)
+    rows = np.asarray(g.replay["N"], np.int32)
+    rc, ep, t, n_after, order = _trace(load_library(), g.B, max_obs, np.arange(len(rows)), rows, g.replay["term"], g.sample_seed, g.steps)
+    assert rc == 0
+    for k in range(g.steps):
+        assert np.array_equal(ep[k], g.ref[f"s{k}/sampledEpID"]), f"step {k}: sampled episodes"
+        assert np.array_equal(t[k], g.ref[f"s{k}/sampledT"]), f"step {k}: sampled time steps"
+        if f"s{k}/post/epID" in g.ref:       # full dumps only at the steps make_golden.py lists
+            kept = g.ref[f"s{k}/post/epID"]
+            assert n_after[k] == len(kept) and np.array_equal(order[k, :len(kept)], kept), f"step {k}: episode vector"
+            assert np.all(order[k, len(kept):] == -1)
+
+
+def test_host_sampler_is_unique_ascending_and_full_range(built_library):
+    """Sample_uniform::sample (Sampling.cpp:82-93): B unique ascending ids; here at the extremes — a batch as large as the
+    buffer must return every transition exactly once, ragged episodes map to (episode, t) with t < ndata."""
+    from smarties_b200 import load_library
+    rows = np.array([2, 5, 3, 2, 9, 4], np.int32)                   # ndata = rows - 1 -> 19 transitions
+    nd = int((rows - 1).sum())
+    rc, ep, t, n_after, _ = _trace(load_library(), nd, 1 << 20, np.arange(6) + 10, rows, np.zeros(6, np.int32), 11, 4)
+    assert rc == 0 and np.all(n_after == 6)
+    want = sorted((10 + e, k) for e in range(6) for k in range(rows[e] - 1))
+    for k in range(4):
+        # step 0 samples in push order (ascending ids); from step 1 on the vector is sorted by id descending
+        got = sorted(zip(ep[k].tolist(), t[k].tolist()))
+        assert got == want
+    assert ep[0].tolist() == sorted(ep[0].tolist()) and ep[1].tolist() == sorted(ep[1].tolist(), reverse=True)
+
+
+def test_host_trace_rejects_bad_input(built_library):
+    from smarties_b200 import load_library
+    lib = load_library()
+    rc, *_ = _trace(lib, 64, 1 << 20, [0, 1], [5, 5], [0, 0], 1, 1)         # 8 transitions < batch 64
+    assert rc != 0 and b"not enough transitions" in lib.smb200_last_error()
+    rc, *_ = _trace(lib, 2, 1 << 20, [0, 1], [5, 1], [0, 0], 1, 1)          # an episode needs s0 and sT
+    assert rc != 0
+    rc, *_ = _trace(lib, 2, 1 << 20, [0, 1, 2], [40, 40, 40], [0, 0, 0], 1, 1, capacity=64)   # ring of 64 rows
+    assert rc != 0 and b"ring full" in lib.smb200_last_error()
+
+
+def test_fifo_pruning_frees_ring_rows_for_reuse(built_library):
+    """maxTotObsNum below the stored transitions: the oldest episodes leave from the back of the id-descending vector
+    while `nTransitions - back.nsteps > maxTotObsNum` (MemoryBuffer.cpp:469-477 / MemoryProcessing.cpp:340-349)."""
+    from smarties_b200 import load_library
+    rows = np.full(10, 11, np.int32)                                  # 10 episodes x 10 transitions
+    rc, ep, t, n_after, order = _trace(load_library(), 4, 55, np.arange(10), rows, np.ones(10, np.int32), 5, 3)
+    assert rc == 0
+    # pops while nTransitions - 11 > 55: 100 -> 90 -> 80 -> 70 -> 60 (60 - 11 = 49: stop), 6 episodes stay
+    assert n_after.tolist() == [6, 6, 6] and order[0, :6].tolist() == [9, 8, 7, 6, 5, 4]
+    assert set(ep[1].tolist()) <= {4, 5, 6, 7, 8, 9} and set(ep[2].tolist()) <= {4, 5, 6, 7, 8, 9}
