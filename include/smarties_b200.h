@@ -225,6 +225,11 @@ int smb200_profile_phases(smb200_learner* h, int32_t n, int64_t* out, int64_t ca
  * `Uint nOffPol += float` (ReplayMemory/MemoryProcessing.cpp:202-227) with x86-64 conversion semantics —
  * the same inline function the device code calls, compiled for the host.  Returns the new count. */
 uint64_t smb200_uint_plus_float(uint64_t n, float x);
+/* Diagnostics, host only (no GPU needed): the padded parameter blob smb200_create starts from — the layout of
+ * Network/Layers/Parameters.h:159-176 initialised like Builder::build does from generators[0] of a run with randSeed =
+ * cfg->seed (Network/Builder.cpp:133-137, Layer_Base.h:115-141, Layer_LSTM.h:168-188, ExecutionInfo.cpp:391).
+ * Returns the blob size in floats (blob may be NULL to query it), negative on error. */
+int64_t smb200_host_init_weights(const smb200_config* cfg, float* blob, int64_t n);
 /* Diagnostics, host only (no GPU needed): the host half of n_steps learner steps with no device work — the library's own
  * Sample_uniform::sample + Sampling::IDtoSeqStep (ReplayMemory/Sampling.cpp:26-47,82-93), FIFO applyEpisodesRemovalAlgo
  * (ReplayMemory/MemoryProcessing.cpp:327-351), ring allocator and the Adam update's draw from the sampler's generator

@@ -1118,6 +1118,27 @@ int smb200_host_replay_trace(int32_t batch_size, int64_t max_tot_obs, int64_t ca
   return rc;
 }
 
+// Network construction without a device (diagnostics for the CPU test suite): the padded parameter blob that smb200_create
+// would upload — build_net's layout (Parameters.h:159-176) filled by init_weights from mt19937(cfg->seed), i.e.
+// Builder::build on generators[0] of a run with randSeed = seed (Builder.cpp:133-137, ExecutionInfo.cpp:391).
+// blob == nullptr: only returns the blob size.
+int64_t smb200_host_init_weights(const smb200_config* cfg, float* blob, int64_t n) {
+  if (!cfg) return SMB200_ERR_INVALID;
+  NetDesc* net = new NetDesc();
+  std::vector<GradTile> tiles;
+  if (build_net(*cfg, *net, tiles)) { delete net; return SMB200_ERR_INVALID; }
+  const int64_t np = net->nParams;
+  if (blob) {
+    if (n != np) { delete net; set_error_msg("init_weights: blob size mismatch"); return SMB200_ERR_INVALID; }
+    std::mt19937 gen((unsigned long)cfg->seed);
+    std::vector<float> w;
+    init_weights(*cfg, *net, gen, w);
+    memcpy(blob, w.data(), sizeof(float) * (size_t)np);
+  }
+  delete net;
+  return np;
+}
+
 // Host build of the inline function the statistics phase uses for the reference's `Uint += float`.
 uint64_t smb200_uint_plus_float(uint64_t n, float x) { return (uint64_t)uint_plus_float_x86((unsigned long long)n, x); }
 

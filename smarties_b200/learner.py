@@ -34,7 +34,7 @@ EXPORTS = [
     "smb200_reward_state_moments", "smb200_read_field", "smb200_read_episodes", "smb200_n_rows", "smb200_get_stats",
     "smb200_forward", "smb200_last_timing", "smb200_presample", "smb200_train_presampled", "smb200_sync", "smb200_profile_phases",
     "smb200_comm_init", "smb200_comm_attach", "smb200_comm_error", "smb200_write_field", "smb200_save", "smb200_restart",
-    "smb200_push_episode_restored", "smb200_set_refer", "smb200_set_grad_stats", "smb200_uint_plus_float", "smb200_host_replay_trace",
+    "smb200_push_episode_restored", "smb200_set_refer", "smb200_set_grad_stats", "smb200_uint_plus_float", "smb200_host_replay_trace", "smb200_host_init_weights",
 ]
 
 FIELDS = dict(V=0, ADV=1, QRET=2, DELTA=3, RHO=4, KL=5, REWARD=6)
@@ -161,41 +161,54 @@ class SmartiesB200Error(RuntimeError):
     pass
 
 
+def make_config(dim_state: int, dim_action: int, settings=None, *, device: int = 0, bounded=None, seed: int = 42,
+                capacity_rows: int = 0, max_episodes: int = 0, refer_reduce_threads: int = 32, world_rank: int = 0,
+                world_size: int = 1):
+    """settings.json surface -> smb200_config (what integration/RACER_B200.cpp fills from the reference's HyperParameters).
+    Returns (Config, HyperParameters).  Host only: usable without a GPU."""
+    from .settings import HyperParameters
+
+    lib = load_library()
+    hp = settings if isinstance(settings, HyperParameters) else HyperParameters(dim_state, dim_action, settings or {})
+    hp.define_distributed_learning(world_size)
+    cfg = Config()
+    if lib.smb200_default_config(C.byref(cfg), dim_state, dim_action) != 0:
+        raise SmartiesB200Error("smb200_default_config: " + lib.smb200_last_error().decode())
+    cfg.device = device
+    cfg.algo = {"VRACER": 0, "RACER": 1}[hp.learner]
+    hidden = [int(h) for h in hp.nnLayerSizes if int(h) > 0]
+    cfg.n_hidden = len(hidden)
+    for i, h in enumerate(hidden):
+        cfg.hidden[i] = h
+    cfg.batch_size, cfg.batch_size_global = hp.batchSize_local, hp.batchSize
+    cfg.max_tot_obs, cfg.max_tot_obs_global = hp.maxTotObsNum_local, hp.maxTotObsNum
+    cfg.capacity_rows, cfg.max_episodes = capacity_rows, max_episodes
+    cfg.gamma, cfg.lambda_, cfg.clip_imp_weight, cfg.penal_tol = hp.gamma, hp.lambda_, hp.clipImpWeight, hp.penalTol
+    cfg.eps_anneal, cfg.learnrate, cfg.nn_lambda = hp.epsAnneal, hp.learnrate, hp.nnLambda
+    cfg.expl_noise, cfg.out_weights_prefac = hp.explNoise, hp.outWeightsPrefac
+    cfg.refer_reduce_threads = refer_reduce_threads
+    cfg.world_rank, cfg.world_size, cfg.seed = world_rank, world_size, seed
+    cfg.nn_type, cfg.nn_bptt_seq = {"FFNN": 0, "LSTM": 1}[hp.nnType], int(hp.nnBPTTseq)
+    cfg.min_tot_obs = hp.minTotObsNum_local
+    cfg.returns_estimator = {"retrace": 0, "GAE": 1, "retraceExplore": 2}[hp.returnsEstimator]
+    if bounded is not None:
+        b = np.broadcast_to(np.asarray(bounded, dtype=bool), (dim_action,))
+        for i in range(dim_action):
+            cfg.action_bounded[i] = int(b[i])
+    return cfg, hp
+
+
 class Learner:
     """V-RACER learner on one B200 (the hot path of smarties::RACER<Zero_advantage,...>)."""
 
     def __init__(self, dim_state: int, dim_action: int, settings: dict | None = None, *, device: int = 0,
                  bounded=None, seed: int = 42, capacity_rows: int = 0, max_episodes: int = 0,
                  refer_reduce_threads: int = 32, world_rank: int = 0, world_size: int = 1):
-        from .settings import HyperParameters
-
         self.lib = load_library()
-        hp = settings if isinstance(settings, HyperParameters) else HyperParameters(dim_state, dim_action, settings or {})
-        hp.define_distributed_learning(world_size)
+        cfg, hp = make_config(dim_state, dim_action, settings, device=device, bounded=bounded, seed=seed,
+                              capacity_rows=capacity_rows, max_episodes=max_episodes,
+                              refer_reduce_threads=refer_reduce_threads, world_rank=world_rank, world_size=world_size)
         self.hp = hp
-        cfg = Config()
-        self._check(self.lib.smb200_default_config(C.byref(cfg), dim_state, dim_action))
-        cfg.device = device
-        cfg.algo = {"VRACER": 0, "RACER": 1}[hp.learner]
-        hidden = [int(h) for h in hp.nnLayerSizes if int(h) > 0]
-        cfg.n_hidden = len(hidden)
-        for i, h in enumerate(hidden):
-            cfg.hidden[i] = h
-        cfg.batch_size, cfg.batch_size_global = hp.batchSize_local, hp.batchSize
-        cfg.max_tot_obs, cfg.max_tot_obs_global = hp.maxTotObsNum_local, hp.maxTotObsNum
-        cfg.capacity_rows, cfg.max_episodes = capacity_rows, max_episodes
-        cfg.gamma, cfg.lambda_, cfg.clip_imp_weight, cfg.penal_tol = hp.gamma, hp.lambda_, hp.clipImpWeight, hp.penalTol
-        cfg.eps_anneal, cfg.learnrate, cfg.nn_lambda = hp.epsAnneal, hp.learnrate, hp.nnLambda
-        cfg.expl_noise, cfg.out_weights_prefac = hp.explNoise, hp.outWeightsPrefac
-        cfg.refer_reduce_threads = refer_reduce_threads
-        cfg.world_rank, cfg.world_size, cfg.seed = world_rank, world_size, seed
-        cfg.nn_type, cfg.nn_bptt_seq = {"FFNN": 0, "LSTM": 1}[hp.nnType], int(hp.nnBPTTseq)
-        cfg.min_tot_obs = hp.minTotObsNum_local
-        cfg.returns_estimator = {"retrace": 0, "GAE": 1, "retraceExplore": 2}[hp.returnsEstimator]
-        if bounded is not None:
-            b = np.broadcast_to(np.asarray(bounded, dtype=bool), (dim_action,))
-            for i in range(dim_action):
-                cfg.action_bounded[i] = int(b[i])
         self.cfg = cfg
         self.dS, self.dA, self.B = dim_state, dim_action, hp.batchSize_local
         h = C.c_void_p()

@@ -84,3 +84,42 @@ def test_fifo_pruning_frees_ring_rows_for_reuse(built_library):
     # pops while nTransitions - 11 > 55: 100 -> 90 -> 80 -> 70 -> 60 (60 - 11 = 49: stop), 6 episodes stay
     assert n_after.tolist() == [6, 6, 6] and order[0, :6].tolist() == [9, 8, 7, 6, 5, 4]
     assert set(ep[1].tolist()) <= {4, 5, 6, 7, 8, 9} and set(ep[2].tolist()) <= {4, 5, 6, 7, 8, 9}
+
+
+DEVICE_NET_CASES = CASES + RECURRENT_CASES + ["vracer_da1", "vracer_explore"]
+
+
+@pytest.mark.parametrize("case", DEVICE_NET_CASES)
+def test_network_construction_is_bit_exact_with_the_reference_builder(built_library, monkeypatch, case):
+    """RACER::setupNet + Builder::build (Learners/RACER_common.cpp:70-115, Network/Builder.cpp:48-99,133-137): the padded
+    parameter blob of Parameters.h:159-176 (Appendix B of SURVEY.md) with every layer initialised from generators[0] =
+    mt19937(randSeed) — dense Xavier draws in (i, o) order, LSTM gate biases, residual ones, the ParamLayer's inverse SoftPlus
+    of explNoise, RACER's advantage biases.  The library's own build_net + init_weights (what smb200_create uploads), run on
+    the host, against the weights the reference binary started from in every golden run (randSeed 42): identical bits."""
+    from smarties_b200 import load_library
+    from smarties_b200.learner import make_config
+    monkeypatch.setenv("SMB200_UNVERIFIED", "1")        # vracer_explore's setting is opt-in; the network is the same
+    g = Golden(case)
+    lib = load_library()
+    lib.smb200_host_init_weights.restype = C.c_int64
+    cfg, _ = make_config(g.dS, g.dA, dict(g.settings), bounded=g.bounded, seed=42)
+    n = lib.smb200_host_init_weights(C.byref(cfg), None, 0)
+    ref = g.ref["init/weights"]
+    assert n == ref.size
+    w = np.zeros(n, np.float32)
+    assert lib.smb200_host_init_weights(C.byref(cfg), w.ctypes.data_as(C.POINTER(C.c_float)), n) == n
+    assert np.array_equal(w.view(np.uint32), ref.view(np.uint32))
+
+
+def test_network_construction_rejects_what_the_device_path_does_not_build(built_library):
+    from smarties_b200 import load_library
+    from smarties_b200.learner import make_config
+    lib = load_library()
+    lib.smb200_host_init_weights.restype = C.c_int64
+    cfg, _ = make_config(6, 3, {"nnLayerSizes": [32, 32]})
+    assert lib.smb200_host_init_weights(C.byref(cfg), None, 0) == 1616
+    w = np.zeros(10, np.float32)
+    assert lib.smb200_host_init_weights(C.byref(cfg), w.ctypes.data_as(C.POINTER(C.c_float)), 10) < 0   # wrong blob size
+    cfg.n_hidden = 0
+    assert lib.smb200_host_init_weights(C.byref(cfg), None, 0) < 0
+    assert lib.smb200_host_init_weights(None, None, 0) < 0
