@@ -230,6 +230,11 @@ uint64_t smb200_uint_plus_float(uint64_t n, float x);
  * cfg->seed (Network/Builder.cpp:133-137, Layer_Base.h:115-141, Layer_LSTM.h:168-188, ExecutionInfo.cpp:391).
  * Returns the blob size in floats (blob may be NULL to query it), negative on error. */
 int64_t smb200_host_init_weights(const smb200_config* cfg, float* blob, int64_t n);
+/* Diagnostics, host only (no GPU needed): the library's conversion between the padded parameter blob and the order
+ * Network::save writes to <name>_net_{weights,tgt_weights,1stMom,2ndMom}.raw (Network/Network.cpp:22-67; padding stripped per
+ * layer: Layer_Base.h:143-169, Layers.h:401-418,554-566, Layer_LSTM.h:189-211) — what smb200_save / smb200_restart use.
+ * dir = +1: blob -> flat, -1: flat -> blob.  Returns the stripped size in floats (flat may be NULL to query it). */
+int64_t smb200_host_strip_weights(const smb200_config* cfg, float* blob, int64_t n_blob, float* flat, int64_t n_flat, int32_t dir);
 /* Diagnostics, host only (no GPU needed): the host half of n_steps learner steps with no device work — the library's own
  * Sample_uniform::sample + Sampling::IDtoSeqStep (ReplayMemory/Sampling.cpp:26-47,82-93), FIFO applyEpisodesRemovalAlgo
  * (ReplayMemory/MemoryProcessing.cpp:327-351), ring allocator and the Adam update's draw from the sampler's generator

@@ -1389,6 +1389,26 @@ static const float* field_ptr(const ReplayView& rp, int field) {
 
 extern "C" {
 
+// Checkpoint weight order without a device (diagnostics for the CPU test suite): the library's own strip_copy between the
+// padded parameter blob (Parameters.h:159-176) and the order Network::save writes (Network.cpp:22-67; per layer, padding
+// stripped: Layer_Base.h:143-169, Layers.h:401-418,554-566, Layer_LSTM.h:189-211).  dir = +1: blob -> flat, -1: flat -> blob
+// (padding left untouched).  flat == nullptr: returns the stripped size.
+int64_t smb200_host_strip_weights(const smb200_config* cfg, float* blob, int64_t n_blob, float* flat, int64_t n_flat, int32_t dir) {
+  if (!cfg) return SMB200_ERR_INVALID;
+  NetDesc* net = new NetDesc();
+  std::vector<GradTile> tiles;
+  if (build_net(*cfg, *net, tiles)) { delete net; return SMB200_ERR_INVALID; }
+  const int64_t ns = (int64_t)stripped_size(*net);
+  if (flat) {
+    if (!blob || n_blob != net->nParams || n_flat != ns || (dir != 1 && dir != -1)) {
+      delete net; set_error_msg("strip_weights: size mismatch"); return SMB200_ERR_INVALID; }
+    strip_copy(*net, blob, flat, dir);
+  }
+  delete net;
+  return ns;
+}
+
+
 int smb200_write_field(smb200_learner* h, int32_t field, const float* in, int64_t n) {
   if (!h || !in || n != smb200_n_rows(h)) return SMB200_ERR_INVALID;
   float* dst = const_cast<float*>(field_ptr(h->rp, field));

@@ -123,3 +123,31 @@ def test_network_construction_rejects_what_the_device_path_does_not_build(built_
     cfg.n_hidden = 0
     assert lib.smb200_host_init_weights(C.byref(cfg), None, 0) < 0
     assert lib.smb200_host_init_weights(None, None, 0) < 0
+
+
+@pytest.mark.parametrize("case", ["vracer_ckpt", "racer_lstm_ckpt"])
+def test_checkpoint_weight_order_matches_the_reference_files(built_library, case):
+    """Network::save (Network.cpp:22-67) strips the padding of the parameter blob layer by layer.  The library's strip_copy
+    (used by smb200_save / smb200_restart), run on the host: the reference's final weights in blob form -> exactly the bytes of
+    the <name>_net_weights.raw the reference wrote; the initial weights -> its _tgt_weights.raw (targetDelay 0: the target
+    network keeps the weights of construction); and back into a blob."""
+    from smarties_b200 import load_library
+    from smarties_b200.learner import make_config
+    g = Golden(case)
+    lib = load_library()
+    lib.smb200_host_strip_weights.restype = C.c_int64
+    fp = C.POINTER(C.c_float)
+    cfg, _ = make_config(g.dS, g.dA, dict(g.settings), bounded=g.bounded)
+    ns = lib.smb200_host_strip_weights(C.byref(cfg), None, 0, None, 0, 1)
+    for blob_key, fname in (("final/weights", "agent_00_net_weights.raw"), ("init/weights", "agent_00_net_tgt_weights.raw")):
+        file_bytes = bytes(g.ckpt[fname])
+        assert 4 * ns == len(file_bytes)
+        blob = np.ascontiguousarray(g.ref[blob_key], np.float32).copy()
+        flat = np.zeros(ns, np.float32)
+        assert lib.smb200_host_strip_weights(C.byref(cfg), blob.ctypes.data_as(fp), blob.size, flat.ctypes.data_as(fp), ns, 1) == ns
+        assert flat.tobytes() == file_bytes, fname
+        back = np.zeros_like(blob)
+        assert lib.smb200_host_strip_weights(C.byref(cfg), back.ctypes.data_as(fp), back.size, flat.ctypes.data_as(fp), ns, -1) == ns
+        assert np.array_equal(back.view(np.uint32), blob.view(np.uint32))       # the reference keeps its padding at zero
+    bad = np.zeros(3, np.float32)
+    assert lib.smb200_host_strip_weights(C.byref(cfg), bad.ctypes.data_as(fp), 3, bad.ctypes.data_as(fp), 3, 1) < 0
