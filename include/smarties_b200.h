@@ -235,6 +235,10 @@ int64_t smb200_host_init_weights(const smb200_config* cfg, float* blob, int64_t 
  * layer: Layer_Base.h:143-169, Layers.h:401-418,554-566, Layer_LSTM.h:189-211) — what smb200_save / smb200_restart use.
  * dir = +1: blob -> flat, -1: flat -> blob.  Returns the stripped size in floats (flat may be NULL to query it). */
 int64_t smb200_host_strip_weights(const smb200_config* cfg, float* blob, int64_t n_blob, float* flat, int64_t n_flat, int32_t dir);
+/* Diagnostics, host only (no GPU needed): the writer of <base>_outGrad_stats.raw (StatsTracker::reduce_stats / printToFile,
+ * Utils/StatsTracker.cpp:28-107) that smb200_set_grad_stats switches on, fed with per-sample output gradients
+ * g[batch][n_out]; first_tracker_step != 0 starts the file with the n_out + 0.1 header, otherwise the row is appended. */
+int smb200_host_write_grad_stats(const char* base, int32_t batch, int32_t n_out, const float* g, int32_t first_tracker_step);
 /* Diagnostics, host only (no GPU needed): the host half of n_steps learner steps with no device work — the library's own
  * Sample_uniform::sample + Sampling::IDtoSeqStep (ReplayMemory/Sampling.cpp:26-47,82-93), FIFO applyEpisodesRemovalAlgo
  * (ReplayMemory/MemoryProcessing.cpp:327-351), ring allocator and the Adam update's draw from the sampler's generator

@@ -442,9 +442,12 @@ static double cmax_at(const smb200_learner* h, long long gstep) {
 // g[B][nOut] were just read back: per net output the mean and the root mean square over the mini-batch (long double
 // sums like the reference), appended as 2*nOut floats to <base>_outGrad_stats.raw; the file starts with the float
 // nOut + 0.1 when this is the tracker's very first step.  Only learner rank 0 writes (StatsTracker.cpp:70).
+static int write_grad_stats_file(const std::string& base, int B, int nOut, const float* g, bool firstTrackerStep);
 static int write_grad_stats(const smb200_learner* h, const float* g, bool firstTrackerStep) {
   if (h->cfg.world_rank != 0) return 0;
-  const int B = h->cfg.batch_size, nOut = h->descs.net.nOut;
+  return write_grad_stats_file(h->gradStatsBase, h->cfg.batch_size, h->descs.net.nOut, g, firstTrackerStep);
+}
+static int write_grad_stats_file(const std::string& base, int B, int nOut, const float* g, bool firstTrackerStep) {
   std::vector<float> row(2 * (size_t)nOut);
   const long double cnt = std::max((long double)2.2e-16, (long double)B);
   for (int o = 0; o < nOut; ++o) {
@@ -453,7 +456,7 @@ static int write_grad_stats(const smb200_learner* h, const float* g, bool firstT
     row[o] = (float)(double)(sum / cnt);
     row[nOut + o] = (float)std::sqrt((double)(sq / cnt));
   }
-  const std::string fn = h->gradStatsBase + "_outGrad_stats.raw";
+  const std::string fn = base + "_outGrad_stats.raw";
   FILE* f = fopen(fn.c_str(), firstTrackerStep ? "wb" : "ab");
   if (!f) { set_error_msg(("cannot open " + fn).c_str()); return -1; }
   if (firstTrackerStep) { const float hdr = (float)(nOut + .1); fwrite(&hdr, sizeof(float), 1, f); }
@@ -1137,6 +1140,13 @@ int64_t smb200_host_init_weights(const smb200_config* cfg, float* blob, int64_t 
   }
   delete net;
   return np;
+}
+
+// The StatsTracker file writer without a device (diagnostics for the CPU test suite): g = per-sample output gradients
+// [batch][n_out] of a step that starts at nGradSteps % 1000 == 0, reduced and appended exactly as the learner does.
+int smb200_host_write_grad_stats(const char* base, int32_t batch, int32_t n_out, const float* g, int32_t first_tracker_step) {
+  if (!base || !g || batch < 1 || n_out < 1) return SMB200_ERR_INVALID;
+  return write_grad_stats_file(base, batch, n_out, g, first_tracker_step != 0) ? SMB200_ERR_STATE : 0;
 }
 
 // Host build of the inline function the statistics phase uses for the reference's `Uint += float`.

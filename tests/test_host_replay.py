@@ -1,7 +1,11 @@
-"""CPU: the host half of the learner step — the library's own sampler (Sample_uniform::sample + Sampling::IDtoSeqStep,
-ReplayMemory/Sampling.cpp:26-47,82-93), FIFO episode removal (MemoryProcessing.cpp:327-351), ring allocator and the Adam
-update's draw from the sampler's generator (Optimizer.cpp:139) — bit-exact against what the reference binary sampled and
-kept in every golden run, through the host-only C-ABI diagnostic smb200_host_replay_trace (no device work, no GPU)."""
+"""CPU: the library's own HOST code against the reference binary's golden runs, through host-only C-ABI diagnostics
+(no device work, no GPU; the same functions the learner runs):
+  smb200_host_replay_trace     sampler (Sample_uniform::sample + Sampling::IDtoSeqStep, ReplayMemory/Sampling.cpp:26-47,82-93),
+                               FIFO episode removal (MemoryProcessing.cpp:327-351), ring allocator, the Adam update's draw from
+                               the sampler's generator (Optimizer.cpp:139) — sampled (episode, t) and episode order bit-exact
+  smb200_host_init_weights     RACER::setupNet + Builder::build: parameter blob layout and initial values bit-exact
+  smb200_host_strip_weights    Network::save order: byte-identical to the reference's checkpoint weight files
+  smb200_host_write_grad_stats StatsTracker file: header, append rule, values"""
 import ctypes as C
 
 import numpy as np
@@ -151,3 +155,30 @@ def test_checkpoint_weight_order_matches_the_reference_files(built_library, case
         assert np.array_equal(back.view(np.uint32), blob.view(np.uint32))       # the reference keeps its padding at zero
     bad = np.zeros(3, np.float32)
     assert lib.smb200_host_strip_weights(C.byref(cfg), bad.ctypes.data_as(fp), 3, bad.ctypes.data_as(fp), 3, 1) < 0
+
+
+@pytest.mark.parametrize("case", CASES + RECURRENT_CASES)
+def test_grad_stats_writer_matches_the_reference_file(built_library, tmp_path, case):
+    """StatsTracker (Utils/StatsTracker.cpp:28-107): the library's own file writer (row a26), run on the host with the
+    reference's per-sample output gradients of the tracker steps, against the `<learner>_<net>_outGrad_stats.raw` the
+    reference wrote in the same golden run (tests/golden/outgrad_stats.npz): same size, same header word, same
+    overwrite-then-append rule, values to f32 round-off of the dumped gradients."""
+    from smarties_b200 import load_library
+    g = Golden(case)
+    lib = load_library()
+    want = np.load(g.path("outgrad_stats.npz"))[case]
+    n_out = g.ref["s0/g"].shape[1]
+    base = str(tmp_path / "agent_00_net")
+    printed = [s for s in range(g.steps) if (g.start_step + s) % 1000 == 0]
+    for s in printed:
+        gs = np.ascontiguousarray(g.ref[f"s{s}/g"], np.float32)
+        assert lib.smb200_host_write_grad_stats(base.encode(), gs.shape[0], n_out, gs.ctypes.data_as(C.POINTER(C.c_float)), int(s == 0)) == 0
+    if not printed:
+        assert want.size == 0
+        return
+    got = np.fromfile(base + "_outGrad_stats.raw", np.float32)
+    header = 1 if printed[0] == 0 else 0
+    assert got.size == want.size == header + 2 * n_out * len(printed)
+    if header:
+        assert got[0] == want[0] == np.float32(n_out + .1)
+    assert np.allclose(got, want, rtol=2e-6, atol=1e-6 * np.abs(want[header:]).max())
