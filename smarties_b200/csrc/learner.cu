@@ -625,7 +625,7 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
   CK(dev_alloc(&h->lastO, (size_t)B * net.nOut)); CK(dev_alloc(&h->lastG, (size_t)B * net.nOut)); CK(dev_alloc(&h->lastX, (size_t)B * dS));
   CK(dev_alloc(&h->dSums, 1)); CK(dev_alloc(&h->dBarrier, 4));
   h->maxSeg = 0;
-  CK(ensure_seg_capacity(h, 1024));
+  CK(ensure_seg_capacity(h, 1));          // the default segment capacity (2048 steps up to B = 8192)
 
   // MemoryBuffer.h:41-44 initial ReF-ER state; AdamOptimizer beta powers (Optimizer.h:93)
   StepCtrl& k = h->hCtrl; memset(&k, 0, sizeof(k));
@@ -890,7 +890,9 @@ static int ensure_seg_capacity(smb200_learner* h, int n) {
   if (h->hSampT) cudaFreeHost(h->hSampT);
   if (h->hStats) cudaFreeHost(h->hStats);
   h->dSampSlot = h->dSampT = nullptr; h->dStats = nullptr; h->hSampSlot = h->hSampT = nullptr; h->hStats = nullptr;
-  h->maxSeg = std::max(n, 2048);
+  // 2048 steps per pair of pipeline halves, fewer for very large mini-batches (the pinned sample arrays hold maxSeg * B
+  // ints each: 2 MB at B = 256; capped at 64 MB from B = 8192 on)
+  h->maxSeg = std::max(n, std::min(2048, std::max(64, (1 << 24) / B)));
   if (dev_alloc(&h->dSampSlot, (size_t)h->maxSeg * B) || dev_alloc(&h->dSampT, (size_t)h->maxSeg * B) ||
       dev_alloc(&h->dStats, (size_t)h->maxSeg)) return -2;
   SMB200_CUDA_CHECK(cudaMallocHost(&h->hSampSlot, sizeof(int) * (size_t)h->maxSeg * B));
