@@ -18,7 +18,19 @@ def _worker(rank, world, port, q):
     w = np.full(1000, float(rank + 1), np.float32)
     w = broadcast_array(dist, w, src=0)
     sh = shard_settings({"batchSize": 256, "maxTotObsNum": 2097152}, world)
-    q.put((rank, [h[0] for h in handles], [len(h) for h in handles], float(w[0]), float(w[-1]), sh))
+    # every rank samples its own shard with its own generator (randSeed += world_rank, ExecutionInfo.cpp:387): the
+    # library's host sampler (smb200_host_replay_trace, no device) on this rank's episodes, exchanged for the cross-check
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_host_replay import _trace
+    from smarties_b200 import load_library
+    rows = np.full(40, 26, np.int32)                           # 40 episodes x 25 transitions per rank
+    ids = np.arange(40) * world + rank                         # episodes dealt round-robin (DataCoordinator.cpp:91-112)
+    rc, ep, t, n_after, _ = _trace(load_library(), sh["batchSize_local"], sh["maxTotObsNum_local"], ids, rows,
+                                   np.zeros(40, np.int32), 42 + rank, 3)
+    assert rc == 0
+    picks = exchange_bytes(dist, np.stack([ep, t]).tobytes())
+    q.put((rank, [h[0] for h in handles], [len(h) for h in handles], float(w[0]), float(w[-1]), sh, picks))
     dist.destroy_process_group()
 
 
@@ -34,10 +46,20 @@ def test_two_rank_plumbing():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, firsts, lens, w0, w1, sh in res:
+    for rank, firsts, lens, w0, w1, sh, picks in res:
         assert firsts == [0, 1] and lens == [64, 64]          # handles arrive in rank order
         assert w0 == 1.0 and w1 == 1.0                          # rank 0's weights everywhere
         assert sh["batchSize_local"] == 128 and sh["maxTotObsNum_local"] == 1048576
+        # the local mini-batches of the two ranks: 128 unique (episode, t) each, from disjoint episode sets, different
+        # draws (own generator per rank) — together the global batch of 256
+        per_rank = [np.frombuffer(b, np.int64).reshape(2, 3, 128) for b in picks]
+        for r, (ep, t) in enumerate(per_rank):
+            assert np.all(ep % world == r) and np.all((t >= 0) & (t < 25))
+            for k in range(3):
+                assert len(set(zip(ep[k].tolist(), t[k].tolist()))) == 128
+        assert not np.array_equal(per_rank[0][1], per_rank[1][1])
+    # both ranks saw the same exchanged picks
+    assert res[0][6] == res[1][6]
 
 
 def test_per_rank_shards_cover_global_batch():
