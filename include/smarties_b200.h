@@ -239,6 +239,12 @@ int64_t smb200_host_strip_weights(const smb200_config* cfg, float* blob, int64_t
  * Utils/StatsTracker.cpp:28-107) that smb200_set_grad_stats switches on, fed with per-sample output gradients
  * g[batch][n_out]; first_tracker_step != 0 starts the file with the n_out + 0.1 header, otherwise the row is appended. */
 int smb200_host_write_grad_stats(const char* base, int32_t batch, int32_t n_out, const float* g, int32_t first_tracker_step);
+/* Diagnostics, host only (no GPU needed): the episode format of <name>_rank_XXX_learner_data.raw (MemoryBuffer::save /
+ * restart, ReplayMemory/MemoryBuffer.cpp:172-324; Episode::packEpisode / unpackEpisode, Episode.cpp:24-130).  Every episode of
+ * the file image `in` is read with the parser smb200_restart uses and written to `out` with the packer smb200_save uses;
+ * returns the bytes written.  ids / n_rows / terminated (optional, capacity max_eps) report the episodes read. */
+int64_t smb200_host_repack_episodes(int32_t dim_state, int32_t dim_action, const uint8_t* in, int64_t n_in, uint8_t* out, int64_t capacity,
+                                    int64_t max_eps, int64_t* n_episodes, int64_t* ids, int32_t* n_rows, int32_t* terminated);
 /* Diagnostics, host only (no GPU needed): the host half of n_steps learner steps with no device work — the library's own
  * Sample_uniform::sample + Sampling::IDtoSeqStep (ReplayMemory/Sampling.cpp:26-47,82-93), FIFO applyEpisodesRemovalAlgo
  * (ReplayMemory/MemoryProcessing.cpp:327-351), ring allocator and the Adam update's draw from the sampler's generator

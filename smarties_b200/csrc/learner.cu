@@ -1380,6 +1380,62 @@ static int write_both(const std::string& stem, const void* data, size_t bytes, b
   }
   return 0;
 }
+// One episode of <...>_learner_data.raw: `size_t N` followed by Episode::packEpisode's floats (Episode.cpp:24-85;
+// size Episode::computeTotalEpisodeSize, Episode.h:211-219): N x [state | reward | action | policy], six length-N arrays
+// (Qret, A, V, delta, rho, KL) and a 10-float tail {bool terminated; ssize_t ID, just_sampled, agentID}.
+// F = {reward, Qret, A, V, delta, rho, KL}, N values each.
+static void pack_episode(std::vector<unsigned char>& out, int dS, int dA, int dP, size_t N, const float* S, const float* A,
+                         const float* MU, const float* const F[7], bool term, ptrdiff_t id, ptrdiff_t agentId) {
+  const size_t tot = (size_t)(dS + dA + dP + 1 + 6) * N + 10;
+  std::vector<float> buf(tot, 0.f);
+  float* b = buf.data();
+  for (size_t t = 0; t < N; ++t) {
+    memcpy(b, S + t * dS, sizeof(float) * dS); b[dS] = F[0][t]; b += dS + 1;
+    memcpy(b, A + t * dA, sizeof(float) * dA); b += dA;
+    memcpy(b, MU + t * dP, sizeof(float) * dP); b += dP;
+  }
+  for (int k = 1; k < 7; ++k) { memcpy(b, F[k], sizeof(float) * N); b += N; }
+  char* c = reinterpret_cast<char*>(b);
+  const ptrdiff_t js = -1;                                           // just_sampled: reset by updateTrainingStatistics every step
+  memcpy(c, &term, sizeof(bool)); c += sizeof(bool);
+  memcpy(c, &id, sizeof(ptrdiff_t)); c += sizeof(ptrdiff_t);
+  memcpy(c, &js, sizeof(ptrdiff_t)); c += sizeof(ptrdiff_t);
+  memcpy(c, &agentId, sizeof(ptrdiff_t));
+  const size_t seqLen = N;
+  const unsigned char* p0 = reinterpret_cast<const unsigned char*>(&seqLen);
+  out.insert(out.end(), p0, p0 + sizeof(size_t));
+  const unsigned char* p1 = reinterpret_cast<const unsigned char*>(buf.data());
+  out.insert(out.end(), p1, p1 + sizeof(float) * tot);
+}
+// The inverse (Episode::unpackEpisode, Episode.cpp:87-130): reads the episode at `pos` and advances it.  S/A/MU/R are copied
+// out of the interleaved tuples; Q, ADV, V, delta, rho, KL point into `dat`.
+struct UnpackedEpisode {
+  size_t N = 0;
+  std::vector<float> S, A, MU, R;
+  const float *Q = nullptr, *ADV = nullptr, *V = nullptr, *delta = nullptr, *rho = nullptr, *KL = nullptr;
+  bool term = false; ptrdiff_t id = 0, js = 0, ag = 0;
+};
+static int unpack_episode(const std::vector<unsigned char>& dat, size_t& pos, int dS, int dA, int dP, UnpackedEpisode& u) {
+  if (pos + sizeof(size_t) > dat.size()) { set_error_msg("Unable to find sequence in learner_data.raw"); return SMB200_ERR_STATE; }
+  size_t N; memcpy(&N, dat.data() + pos, sizeof(size_t)); pos += sizeof(size_t);
+  const size_t tot = (size_t)(dS + dA + dP + 1 + 6) * N + 10;
+  if (N < 2 || pos + sizeof(float) * tot > dat.size()) { set_error_msg("mismatch in learner_data.raw"); return SMB200_ERR_STATE; }
+  const float* b = reinterpret_cast<const float*>(dat.data() + pos); pos += sizeof(float) * tot;
+  u.N = N;
+  u.S.resize(N * dS); u.A.resize(N * dA); u.MU.resize(N * dP); u.R.resize(N);
+  for (size_t t = 0; t < N; ++t) {
+    memcpy(u.S.data() + t * dS, b, sizeof(float) * dS); u.R[t] = b[dS]; b += dS + 1;
+    memcpy(u.A.data() + t * dA, b, sizeof(float) * dA); b += dA;
+    memcpy(u.MU.data() + t * dP, b, sizeof(float) * dP); b += dP;
+  }
+  u.Q = b; u.ADV = b + N; u.V = b + 2 * N; u.delta = b + 3 * N; u.rho = b + 4 * N; u.KL = b + 5 * N;
+  const char* c = reinterpret_cast<const char*>(b + 6 * N);
+  memcpy(&u.term, c, sizeof(bool)); c += sizeof(bool);
+  memcpy(&u.id, c, sizeof(ptrdiff_t)); c += sizeof(ptrdiff_t);
+  memcpy(&u.js, c, sizeof(ptrdiff_t)); c += sizeof(ptrdiff_t);
+  memcpy(&u.ag, c, sizeof(ptrdiff_t));
+  return 0;
+}
 static int read_all(const std::string& path, std::vector<unsigned char>& out) {
   FILE* f = fopen(path.c_str(), "rb");
   if (!f) return 1;
@@ -1400,6 +1456,35 @@ static const float* field_ptr(const ReplayView& rp, int field) {
 }  // namespace smb200
 
 extern "C" {
+
+// The episode file format without a device (diagnostics for the CPU test suite): every episode of a <...>_learner_data.raw
+// image is read by the parser smb200_restart uses and written again by the packer smb200_save uses.  Returns the bytes
+// written to `out` (negative on error); ids / n_rows / terminated (each optional, capacity max_eps) describe what was read.
+int64_t smb200_host_repack_episodes(int32_t dim_state, int32_t dim_action, const uint8_t* in, int64_t n_in, uint8_t* out, int64_t capacity,
+                                    int64_t max_eps, int64_t* n_episodes, int64_t* ids, int32_t* n_rows, int32_t* terminated) {
+  if (dim_state < 1 || dim_action < 1 || !in || n_in < 0 || !out) return SMB200_ERR_INVALID;
+  const int dS = dim_state, dA = dim_action, dP = 2 * dA;
+  const std::vector<unsigned char> dat(in, in + n_in);
+  std::vector<unsigned char> packed;
+  size_t pos = 0; int64_t n = 0;
+  UnpackedEpisode u;
+  while (pos < dat.size()) {
+    const int rc = unpack_episode(dat, pos, dS, dA, dP, u);
+    if (rc) return rc;
+    const float* F[7] = {u.R.data(), u.Q, u.ADV, u.V, u.delta, u.rho, u.KL};
+    pack_episode(packed, dS, dA, dP, u.N, u.S.data(), u.A.data(), u.MU.data(), F, u.term, u.id, u.ag);
+    if (n < max_eps) {
+      if (ids) ids[n] = (int64_t)u.id;
+      if (n_rows) n_rows[n] = (int32_t)u.N;
+      if (terminated) terminated[n] = u.term ? 1 : 0;
+    }
+    ++n;
+  }
+  if ((int64_t)packed.size() > capacity) { set_error_msg("repack_episodes: output buffer too small"); return SMB200_ERR_CAPACITY; }
+  memcpy(out, packed.data(), packed.size());
+  if (n_episodes) *n_episodes = n;
+  return (int64_t)packed.size();
+}
 
 // Checkpoint weight order without a device (diagnostics for the CPU test suite): the library's own strip_copy between the
 // padded parameter blob (Parameters.h:159-176) and the order Network::save writes (Network.cpp:22-67; per layer, padding
@@ -1499,27 +1584,11 @@ int smb200_save(smb200_learner* h, const char* base_c) {
     for (int k = 0; k < 7; ++k) { F[k].resize(hw); if (d2h(h, F[k].data(), field_ptr(h->rp, fid[k]), sizeof(float) * hw)) return SMB200_ERR_CUDA; }
     std::vector<unsigned char> out;
     for (const auto& e : h->episodes) {
-      const size_t N = e.nRows, tot = (size_t)(dS + dA + dP + 1 + 6) * N + 10;    // Episode::computeTotalEpisodeSize (Episode.h:211-219)
-      std::vector<float> buf(tot, 0.f);
-      float* b = buf.data();
-      for (size_t t = 0; t < N; ++t) {
-        const size_t r = (size_t)e.start + t;
-        memcpy(b, S.data() + r * dS, sizeof(float) * dS); b[dS] = F[0][r]; b += dS + 1;
-        memcpy(b, A.data() + r * dA, sizeof(float) * dA); b += dA;
-        memcpy(b, MU.data() + r * dP, sizeof(float) * dP); b += dP;
-      }
-      for (int k = 1; k < 7; ++k) { memcpy(b, F[k].data() + e.start, sizeof(float) * N); b += N; }
-      char* c = reinterpret_cast<char*>(b);
-      const bool term = e.terminated != 0; const ptrdiff_t id = (ptrdiff_t)e.id, js = -1, ag = (ptrdiff_t)e.agentId;
-      memcpy(c, &term, sizeof(bool)); c += sizeof(bool);
-      memcpy(c, &id, sizeof(ptrdiff_t)); c += sizeof(ptrdiff_t);
-      memcpy(c, &js, sizeof(ptrdiff_t)); c += sizeof(ptrdiff_t);      // just_sampled: reset by updateTrainingStatistics every step
-      memcpy(c, &ag, sizeof(ptrdiff_t));
-      const size_t seqLen = N;
-      const unsigned char* p0 = reinterpret_cast<const unsigned char*>(&seqLen);
-      out.insert(out.end(), p0, p0 + sizeof(size_t));
-      const unsigned char* p1 = reinterpret_cast<const unsigned char*>(buf.data());
-      out.insert(out.end(), p1, p1 + sizeof(float) * tot);
+      const size_t r = (size_t)e.start;
+      const float* Fe[7];
+      for (int k = 0; k < 7; ++k) Fe[k] = F[k].data() + r;
+      pack_episode(out, dS, dA, dP, (size_t)e.nRows, S.data() + r * dS, A.data() + r * dA, MU.data() + r * dP, Fe, e.terminated != 0,
+                   (ptrdiff_t)e.id, (ptrdiff_t)e.agentId);
     }
     if (write_both(stem + "data", out.data(), out.size())) return SMB200_ERR_STATE;
   }
@@ -1579,30 +1648,14 @@ int smb200_restart(smb200_learner* h, const char* base_c) {
   if (!pass || grad < 0) { set_error_msg("malformed learner_status.raw"); return SMB200_ERR_STATE; }
   const float C = (float)cmax, invC = (float)(1.0 / cmax);
   size_t pos = 0;
-  std::vector<float> S, A, MU, R;
+  UnpackedEpisode u;
   for (unsigned long e = 0; e < nEps; ++e) {
-    if (pos + sizeof(size_t) > dat.size()) { set_error_msg("Unable to find sequence in learner_data.raw"); return SMB200_ERR_STATE; }
-    size_t N; memcpy(&N, dat.data() + pos, sizeof(size_t)); pos += sizeof(size_t);
-    const size_t tot = (size_t)(dS + dA + dP + 1 + 6) * N + 10;
-    if (N < 2 || pos + sizeof(float) * tot > dat.size()) { set_error_msg("mismatch in learner_data.raw"); return SMB200_ERR_STATE; }
-    const float* b = reinterpret_cast<const float*>(dat.data() + pos); pos += sizeof(float) * tot;
-    S.resize(N * dS); A.resize(N * dA); MU.resize(N * dP); R.resize(N);
-    for (size_t t = 0; t < N; ++t) {
-      memcpy(S.data() + t * dS, b, sizeof(float) * dS); R[t] = b[dS]; b += dS + 1;
-      memcpy(A.data() + t * dA, b, sizeof(float) * dA); b += dA;
-      memcpy(MU.data() + t * dP, b, sizeof(float) * dP); b += dP;
-    }
-    const float* Q = b; const float* ADV = b + N; const float* V = b + 2 * N;
-    const float* rest[4] = {Q, b + 3 * N, b + 4 * N, b + 5 * N};    // Q, delta, rho, KL
-    const char* c = reinterpret_cast<const char*>(b + 6 * N);
-    bool term; ptrdiff_t id, js, ag;
-    memcpy(&term, c, sizeof(bool)); c += sizeof(bool);
-    memcpy(&id, c, sizeof(ptrdiff_t)); c += sizeof(ptrdiff_t);
-    memcpy(&js, c, sizeof(ptrdiff_t)); c += sizeof(ptrdiff_t);
-    memcpy(&ag, c, sizeof(ptrdiff_t));
-    const int r2 = push_episode_impl(h, (int64_t)id, (int32_t)N, term ? 1 : 0, S.data(), A.data(), MU.data(), R.data(), V, ADV, rest, C, invC);
+    const int r1 = unpack_episode(dat, pos, dS, dA, dP, u);
+    if (r1) return r1;
+    const float* rest[4] = {u.Q, u.delta, u.rho, u.KL};
+    const int r2 = push_episode_impl(h, (int64_t)u.id, (int32_t)u.N, u.term ? 1 : 0, u.S.data(), u.A.data(), u.MU.data(), u.R.data(), u.V, u.ADV, rest, C, invC);
     if (r2) return r2;
-    h->episodes.back().agentId = (int)ag;
+    h->episodes.back().agentId = (int)u.ag;
   }
   if ((unsigned long)h->nTransitions != nObs) { set_error_msg("learner_status.raw and learner_data.raw disagree on nStoredObs"); return SMB200_ERR_STATE; }
   h->nSeenEps = (long long)seenEps; h->nSeenObs = (long long)seenObs; h->nGatheredB4Startup = nInit;

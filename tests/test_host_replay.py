@@ -5,6 +5,7 @@
                                the sampler's generator (Optimizer.cpp:139) — sampled (episode, t) and episode order bit-exact
   smb200_host_init_weights     RACER::setupNet + Builder::build: parameter blob layout and initial values bit-exact
   smb200_host_strip_weights    Network::save order: byte-identical to the reference's checkpoint weight files
+  smb200_host_repack_episodes  MemoryBuffer::save/restart episode format: the reference's file parsed and re-packed, byte-identical
   smb200_host_write_grad_stats StatsTracker file: header, append rule, values"""
 import ctypes as C
 
@@ -182,3 +183,37 @@ def test_grad_stats_writer_matches_the_reference_file(built_library, tmp_path, c
     if header:
         assert got[0] == want[0] == np.float32(n_out + .1)
     assert np.allclose(got, want, rtol=2e-6, atol=1e-6 * np.abs(want[header:]).max())
+
+
+@pytest.mark.parametrize("case", ["vracer_ckpt", "racer_lstm_ckpt"])
+def test_episode_file_parser_and_packer_round_trip_the_reference_file(built_library, case):
+    """MemoryBuffer::save / restart (MemoryBuffer.cpp:172-324), Episode::packEpisode / unpackEpisode (Episode.cpp:24-130):
+    the reference's `agent_00_rank_000_learner_data.raw` read by the parser of smb200_restart and written again by the packer
+    of smb200_save, both on the host: byte-identical file, episodes and lengths as the reference held them in memory."""
+    from smarties_b200 import load_library
+    g = Golden(case)
+    lib = load_library()
+    lib.smb200_host_repack_episodes.restype = C.c_int64
+    raw = bytes(g.ckpt["agent_00_rank_000_learner_data.raw"])
+    src = np.frombuffer(raw, np.uint8).copy()
+    out = np.zeros(src.size + 64, np.uint8)
+    n_ep = C.c_int64(0)
+    cap = 1024
+    ids = np.zeros(cap, np.int64); rows = np.zeros(cap, np.int32); term = np.zeros(cap, np.int32)
+    u8, i64, i32 = C.POINTER(C.c_uint8), C.POINTER(C.c_int64), C.POINTER(C.c_int32)
+    n = lib.smb200_host_repack_episodes(C.c_int32(g.dS), C.c_int32(g.dA), src.ctypes.data_as(u8), C.c_int64(src.size), out.ctypes.data_as(u8),
+                                        C.c_int64(out.size), C.c_int64(cap), C.byref(n_ep), ids.ctypes.data_as(i64), rows.ctypes.data_as(i32),
+                                        term.ctypes.data_as(i32))
+    assert n == src.size and out[:n].tobytes() == raw
+    k = n_ep.value
+    assert ids[:k].tolist() == list(g.ref["final/epID"]) and rows[:k].tolist() == list(g.ref["final/epLen"])
+    want_term = {int(i): int(t) for i, t in enumerate(g.replay["term"])}
+    assert [want_term[int(i)] for i in ids[:k]] == term[:k].tolist()
+    # a truncated image is an error, not a partial read
+    bad = lib.smb200_host_repack_episodes(C.c_int32(g.dS), C.c_int32(g.dA), src.ctypes.data_as(u8), C.c_int64(src.size - 12), out.ctypes.data_as(u8),
+                                          C.c_int64(out.size), C.c_int64(cap), None, None, None, None)
+    assert bad < 0 and b"learner_data.raw" in lib.smb200_last_error()
+    # wrong dimensions do not parse to the end of the file either
+    bad = lib.smb200_host_repack_episodes(C.c_int32(g.dS + 1), C.c_int32(g.dA), src.ctypes.data_as(u8), C.c_int64(src.size), out.ctypes.data_as(u8),
+                                          C.c_int64(out.size), C.c_int64(cap), None, None, None, None)
+    assert bad < 0
