@@ -245,6 +245,13 @@ int smb200_host_write_grad_stats(const char* base, int32_t batch, int32_t n_out,
  * returns the bytes written.  ids / n_rows / terminated (optional, capacity max_eps) report the episodes read. */
 int64_t smb200_host_repack_episodes(int32_t dim_state, int32_t dim_action, const uint8_t* in, int64_t n_in, uint8_t* out, int64_t capacity,
                                     int64_t max_eps, int64_t* n_episodes, int64_t* ids, int32_t* n_rows, int32_t* terminated);
+/* Diagnostics, host only (no GPU needed): host builds of scalar device functions of the step kernel, same source lines.
+ * smb200_host_adam: n elements of the Adam variant of Network/Optimizer.cpp:61-108,122-161 (Nesterov + safe + AdamW) as the
+ * weight-gradient epilogue applies it, after adam_step_done completed updates with running beta powers bt1, bt2.
+ * smb200_host_value_scaling: scaleNet2V and scaleVdiff (Learners/RACER_common.cpp:23-32). */
+int smb200_host_adam(int64_t n, const float* G, float* W, float* M1, float* M2, double learnrate, double eps_anneal, int64_t adam_step_done,
+                     double bt1, double bt2, double nn_lambda, int32_t batch_global);
+int smb200_host_value_scaling(int64_t n, const double* x, double* v, double* dvdx);
 /* Diagnostics, host only (no GPU needed): the host half of n_steps learner steps with no device work — the library's own
  * Sample_uniform::sample + Sampling::IDtoSeqStep (ReplayMemory/Sampling.cpp:26-47,82-93), FIFO applyEpisodesRemovalAlgo
  * (ReplayMemory/MemoryProcessing.cpp:327-351), ring allocator and the Adam update's draw from the sampler's generator

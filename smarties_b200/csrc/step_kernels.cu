@@ -188,11 +188,11 @@ __device__ __forceinline__ float tanh_ref(float x) {
 }
 
 // scaleNet2V / scaleVdiff (Learners/RACER_common.cpp:23-32), f64
-__device__ __forceinline__ double net2v(double x) {
+__host__ __device__ __forceinline__ double net2v(double x) {
   return x > 0 ? 100.0 * (x + 51.0) - 100.0 * sqrt(2601.0 + 100.0 * x)
                : 100.0 * (x - 51.0) + 100.0 * sqrt(2601.0 - 100.0 * x);
 }
-__device__ __forceinline__ double vdiff(double x) {
+__host__ __device__ __forceinline__ double vdiff(double x) {
   return x > 0 ? 100.0 - 5000.0 / sqrt(2601.0 + 100.0 * x) : 100.0 - 5000.0 / sqrt(2601.0 - 100.0 * x);
 }
 
@@ -1313,7 +1313,7 @@ __device__ __forceinline__ AdamCoef adam_coef(const Hyper& hp, const StepCtrl& c
   return k;
 }
 
-__device__ __forceinline__ float adam_step(const AdamCoef& k, float G, float W, float m1, float m2, float* w, float* pm1, float* pm2) {
+__host__ __device__ __forceinline__ float adam_step(const AdamCoef& k, float G, float W, float m1, float m2, float* w, float* pm1, float* pm2) {
   const float penal = -W * k.lambda;                       // SMARTIES_ADAMW
   const float DW = k.fac * G;
   float M1 = k.B1 * m1 + (1.0f - k.B1) * DW;
@@ -2373,3 +2373,31 @@ int launch_forward(const StepArgs& a, const NetDesc& net, const float* states, i
 }
 
 }  // namespace smb200
+
+// ------------------------------------------------------------------------------------------
+// Host builds of scalar device functions (diagnostics for the CPU test suite, tests/test_host_replay.py): the same source
+// lines the kernels compile, evaluated by the host compiler (x86-64 has no contraction into FMAs, the device build uses
+// -fmad=false: identical IEEE operations).
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+// n elements of AdamOptimizer::apply_update (struct Adam, Network/Optimizer.cpp:61-108) exactly as the P2 epilogue applies it:
+// eta from adam_eta_for after `adam_step` completed updates with the running beta powers bt1 / bt2, then adam_step per element.
+int smb200_host_adam(int64_t n, const float* G, float* W, float* M1, float* M2, double learnrate, double eps_anneal, int64_t adam_step_done,
+                     double bt1, double bt2, double nn_lambda, int32_t batch_global) {
+  if (n < 0 || !G || !W || !M1 || !M2 || batch_global < 1) return -1;
+  smb200::AdamCoef k;
+  k.eta = smb200::adam_eta_for(learnrate, eps_anneal, adam_step_done, bt1, bt2);
+  k.B1 = 0.9f; k.B2 = 0.999f; k.lambda = (float)nn_lambda; k.fac = (float)(1.0 / (double)batch_global);     // adam_coef
+  for (int64_t i = 0; i < n; ++i) smb200::adam_step(k, G[i], W[i], M1[i], M2[i], &W[i], &M1[i], &M2[i]);
+  return 0;
+}
+
+// scaleNet2V / scaleVdiff (Learners/RACER_common.cpp:23-32) of n network outputs, f64
+int smb200_host_value_scaling(int64_t n, const double* x, double* v, double* dvdx) {
+  if (n < 0 || !x || !v || !dvdx) return -1;
+  for (int64_t i = 0; i < n; ++i) { v[i] = smb200::net2v(x[i]); dvdx[i] = smb200::vdiff(x[i]); }
+  return 0;
+}
+
+}  // extern "C"

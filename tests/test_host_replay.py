@@ -6,7 +6,8 @@
   smb200_host_init_weights     RACER::setupNet + Builder::build: parameter blob layout and initial values bit-exact
   smb200_host_strip_weights    Network::save order: byte-identical to the reference's checkpoint weight files
   smb200_host_repack_episodes  MemoryBuffer::save/restart episode format: the reference's file parsed and re-packed, byte-identical
-  smb200_host_write_grad_stats StatsTracker file: header, append rule, values"""
+  smb200_host_write_grad_stats StatsTracker file: header, append rule, values
+  smb200_host_adam / smb200_host_value_scaling   host builds of device source lines (Adam epilogue, scaleNet2V): bit-exact with the oracle"""
 import ctypes as C
 
 import numpy as np
@@ -217,3 +218,49 @@ def test_episode_file_parser_and_packer_round_trip_the_reference_file(built_libr
     bad = lib.smb200_host_repack_episodes(C.c_int32(g.dS + 1), C.c_int32(g.dA), src.ctypes.data_as(u8), C.c_int64(src.size), out.ctypes.data_as(u8),
                                           C.c_int64(out.size), C.c_int64(cap), None, None, None, None)
     assert bad < 0
+
+
+def test_adam_epilogue_source_is_bit_exact_with_the_reference_optimizer(built_library):
+    """struct Adam + AdamOptimizer::apply_update (Network/Optimizer.cpp:61-108,122-161: Nesterov, "safe", AdamW, annealed and
+    bias-corrected learning rate, running beta powers): the source lines of the weight-gradient epilogue (`adam_step`,
+    `adam_eta_for`), built for the host, against the oracle's f32 restatement (pinned to the reference's weights after every
+    golden step) over 40 consecutive updates incl. late steps where beta_1^t underflows to 0: identical bits in W, M1, M2."""
+    import vracer_oracle as vo
+    from smarties_b200 import load_library
+    lib = load_library()
+    fp = C.POINTER(C.c_float)
+    rng = np.random.default_rng(3)
+    for start, B in ((0, 256), (130, 16), (20000, 256)):
+        o = vo.VracerOracle(6, 3, hidden=[32, 32], batch=B)
+        n = o.W.size
+        o.W[:] = (rng.standard_normal(n) * 0.1).astype(np.float32)
+        o.adam_step = start
+        o.beta_t_1, o.beta_t_2 = 0.9, 0.999
+        for _ in range(start):                                   # the running powers as Optimizer.cpp:155-158 leaves them
+            o.beta_t_1 *= 0.9
+            if o.beta_t_1 < vo.FLT_EPS: o.beta_t_1 = 0
+            o.beta_t_2 *= 0.999
+            if o.beta_t_2 < vo.FLT_EPS: o.beta_t_2 = 0
+        W, M1, M2 = o.W.copy(), o.M1.copy(), o.M2.copy()
+        for k in range(40):
+            G = (rng.standard_normal(n) * (10.0 if k % 7 == 0 else 0.01)).astype(np.float32)
+            done, bt1, bt2 = o.adam_step, o.beta_t_1, o.beta_t_2
+            assert lib.smb200_host_adam(C.c_int64(n), G.ctypes.data_as(fp), W.ctypes.data_as(fp), M1.ctypes.data_as(fp), M2.ctypes.data_as(fp),
+                                        C.c_double(o.eta), C.c_double(o.eps_anneal), C.c_int64(done), C.c_double(bt1), C.c_double(bt2),
+                                        C.c_double(o.nn_lambda), C.c_int32(B)) == 0
+            o.adam_step += 1                                     # prepare_update: nStep++ (Optimizer.cpp:119)
+            o.apply_adam(G)
+            for mine, ref, name in ((W, o.W, "W"), (M1, o.M1, "M1"), (M2, o.M2, "M2")):
+                assert np.array_equal(mine.view(np.uint32), ref.view(np.uint32)), (start, k, name)
+
+
+def test_value_scaling_source_matches_the_oracle(built_library):
+    """scaleNet2V / scaleVdiff (Learners/RACER_common.cpp:23-32), the device source built for the host, f64."""
+    import vracer_oracle as vo
+    from smarties_b200 import load_library
+    lib = load_library()
+    dp = C.POINTER(C.c_double)
+    x = np.concatenate([np.linspace(-30, 30, 2001), [0.0, -0.0, 1e-300, -1e-300, 1e6, -1e6]])
+    v, d = np.zeros_like(x), np.zeros_like(x)
+    assert lib.smb200_host_value_scaling(C.c_int64(x.size), x.ctypes.data_as(dp), v.ctypes.data_as(dp), d.ctypes.data_as(dp)) == 0
+    assert np.array_equal(v, vo.scale_net2v(x)) and np.array_equal(d, vo.scale_vdiff(x))
