@@ -252,6 +252,12 @@ int64_t smb200_host_repack_episodes(int32_t dim_state, int32_t dim_action, const
 int smb200_host_adam(int64_t n, const float* G, float* W, float* M1, float* M2, double learnrate, double eps_anneal, int64_t adam_step_done,
                      double bt1, double bt2, double nn_lambda, int32_t batch_global);
 int smb200_host_value_scaling(int64_t n, const double* x, double* v, double* dvdx);
+/* updateReturnEstimator(EP, N-2) of one episode (ReplayMemory/MemoryProcessing.cpp:23-44) for estimator = retrace / GAE /
+ * retraceExplore (:391-417), sequentially on the host with the scalar functions the sweep kernels call (reward scaling,
+ * clipped importance weight, the recursion's expression order).  Q is updated in place; returns the sum of squared changes. */
+double smb200_host_return_estimator(int32_t n_rows, int32_t terminated, int32_t estimator, const float* R, const float* V,
+                                    const float* ADV, const float* RHO, float* Q, double gamma, double lambda,
+                                    float reward_mean, float reward_scale, double max_abs_err);
 /* Diagnostics, host only (no GPU needed): the host half of n_steps learner steps with no device work — the library's own
  * Sample_uniform::sample + Sampling::IDtoSeqStep (ReplayMemory/Sampling.cpp:26-47,82-93), FIFO applyEpisodesRemovalAlgo
  * (ReplayMemory/MemoryProcessing.cpp:327-351), ring allocator and the Adam update's draw from the sampler's generator

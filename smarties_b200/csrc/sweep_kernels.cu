@@ -217,6 +217,26 @@ __global__ void __launch_bounds__(kThreads) k_sweep(ReplayView rp, int nEpisodes
 }
 
 // ------------------------------------------------------------------------------------------
+// Scalar pieces of the return estimators, host + device (the host build is pinned to the oracle by
+// tests/test_host_replay.py through smb200_host_return_estimator; -fmad=false keeps the device build on the same IEEE operations).
+__host__ __device__ __forceinline__ float scaled_reward(float r, double rmean, double rscale) {      // scaledReward<Fval>, Episode.h:184-189
+  return (float)(((double)r - rmean) * rscale);
+}
+__host__ __device__ __forceinline__ float lambda_clipped_weight(float lambda, float w) {            // lambda * clippedOffPolW, Episode.h:190-194
+  return lambda * (w < 1.f ? w : 1.f);
+}
+// computeRetrace (MemoryProcessing.cpp:391-400) on the row t+1: R, V, A of that row, cw = lambda * min(1, rho), Qn = Q[t+1]
+__host__ __device__ __forceinline__ float retrace_step(float R, float Vn, float An, float cw, float Qn, float gamma) {
+  return R + gamma * (Vn + cw * (Qn - An - Vn));
+}
+// computeRetraceExplBonus (:402-409): C * (|Q' - A - V| - B) + computeRetrace, C = 1 - gamma, B = stats.maxAbsError
+__host__ __device__ __forceinline__ float retrace_explore_step(float R, float Vn, float An, float cw, float Qn, float gamma, float coef,
+                                                               float baseline) {
+  const float E = fabsf(Qn - An - Vn) - baseline;
+  return coef * E + retrace_step(R, Vn, An, cw, Qn, gamma);
+}
+
+// ------------------------------------------------------------------------------------------
 // "returnsEstimator": "retraceExplore" (computeRetraceExplBonus, MemoryProcessing.cpp:402-409):
 //   Q[t] = (1 - g) * (|Q[t+1] - A[t+1] - V[t+1]| - baseline) + Retrace(t),  baseline = stats.maxAbsError when the estimator
 // is created (createReturnEstimator, :427-435).  The absolute value makes the recursion non-affine, so there is no scan:
@@ -257,9 +277,9 @@ __global__ void __launch_bounds__(kThreads) k_sweep_explore(ReplayView rp, int n
         if (p < n) {
           const size_t r = r0 + (top - p) + 1;
           const float w = rp.RHO[r];
-          sR[p] = (float)(((double)rp.R[r] - rmean) * rscale);                // scaledReward<Fval> (Episode.h:184-189)
+          sR[p] = scaled_reward(rp.R[r], rmean, rscale);
           sV[p] = rp.V[r]; sA[p] = rp.ADV[r];
-          sW[p] = lambda * (w < 1.f ? w : 1.f);                               // lambda * clippedOffPolW (Episode.h:190-194)
+          sW[p] = lambda_clipped_weight(lambda, w);
           oldQ[j] = rp.Q[r - 1];
         }
       }
@@ -267,11 +287,7 @@ __global__ void __launch_bounds__(kThreads) k_sweep_explore(ReplayView rp, int n
       if (tid == 0) {
         float Qn = shCarry;
         for (int p = 0; p < n; ++p) {
-          const float Vn = sV[p];
-          const float d = Qn - sA[p] - Vn;
-          float Qt = sR[p] + gamma * (Vn + sW[p] * d);                        // computeRetrace (:391-400)
-          const float E = fabsf(d) - baseline;
-          Qt = coef * E + Qt;                                                 // computeRetraceExplBonus (:402-409)
+          const float Qt = retrace_explore_step(sR[p], sV[p], sA[p], sW[p], Qn, gamma, coef, baseline);
           sQ[p] = Qt; Qn = Qt;
         }
         shCarry = Qn;
@@ -587,3 +603,30 @@ int launch_clear_sums(SweepSums* sums, cudaStream_t st) {
 }
 
 }  // namespace smb200
+
+// Host build of the estimator arithmetic above (diagnostics for the CPU test suite): updateReturnEstimator(EP, N-2)
+// (MemoryProcessing.cpp:23-44) of ONE episode, sequentially, with the scalar functions the device code calls.
+// estimator = smb200_returns_estimator (0 retrace, 1 GAE, 2 retraceExplore); arrays hold the N rows of the episode;
+// Q is updated in place; returns the sum of squared changes (f32 accumulation like the reference's sumErr2 of one episode).
+extern "C" double smb200_host_return_estimator(int32_t n_rows, int32_t terminated, int32_t estimator, const float* R, const float* V,
+                                               const float* ADV, const float* RHO, float* Q, double gamma, double lambda,
+                                               float reward_mean, float reward_scale, double max_abs_err) {
+  using namespace smb200;
+  if (n_rows < 2 || !R || !V || !ADV || !RHO || !Q) return -1.0;
+  const float g = (float)gamma, l = (float)lambda, coef = 1.0f - g, baseline = (float)max_abs_err;
+  const double rmean = (double)reward_mean, rscale = (double)reward_scale;
+  const int N = n_rows;
+  if (!terminated) Q[N - 1] = V[N - 1];
+  float err2 = 0.f;
+  for (int t = N - 2; t >= 0; --t) {
+    const float r = scaled_reward(R[t + 1], rmean, rscale);
+    const float An = estimator == 1 ? 0.f : ADV[t + 1];
+    const float cw = lambda_clipped_weight(l, estimator == 1 ? 1.f : RHO[t + 1]);
+    const float Qt = estimator == 2 ? retrace_explore_step(r, V[t + 1], An, cw, Q[t + 1], g, coef, baseline)
+                                    : retrace_step(r, V[t + 1], An, cw, Q[t + 1], g);
+    const float d = Q[t] - Qt;
+    err2 += d * d;
+    Q[t] = Qt;
+  }
+  return (double)err2;
+}

@@ -7,7 +7,9 @@
   smb200_host_strip_weights    Network::save order: byte-identical to the reference's checkpoint weight files
   smb200_host_repack_episodes  MemoryBuffer::save/restart episode format: the reference's file parsed and re-packed, byte-identical
   smb200_host_write_grad_stats StatsTracker file: header, append rule, values
-  smb200_host_adam / smb200_host_value_scaling   host builds of device source lines (Adam epilogue, scaleNet2V): bit-exact with the oracle"""
+  smb200_host_adam / smb200_host_value_scaling / smb200_host_return_estimator
+                               host builds of device source lines (Adam epilogue, scaleNet2V, Retrace / GAE / retraceExplore
+                               recursion): bit-exact with the oracle"""
 import ctypes as C
 
 import numpy as np
@@ -264,3 +266,32 @@ def test_value_scaling_source_matches_the_oracle(built_library):
     v, d = np.zeros_like(x), np.zeros_like(x)
     assert lib.smb200_host_value_scaling(C.c_int64(x.size), x.ctypes.data_as(dp), v.ctypes.data_as(dp), d.ctypes.data_as(dp)) == 0
     assert np.array_equal(v, vo.scale_net2v(x)) and np.array_equal(d, vo.scale_vdiff(x))
+
+
+@pytest.mark.parametrize("case,estimator", [("vracer_small", 0), ("vracer_gae", 1), ("vracer_explore", 2)])
+def test_return_estimator_source_is_bit_exact_with_the_oracle(built_library, case, estimator):
+    """computeRetrace / computeGAE / computeRetraceExplBonus (MemoryProcessing.cpp:391-417) and updateReturnEstimator (:23-44):
+    the scalar functions the sweep kernels call (reward scaling, clipped importance weight, expression order of the recursion),
+    built for the host and run sequentially over every episode of a golden buffer after some learner steps (non-trivial V, A,
+    rho, non-zero maxAbsError), against the oracle's restatement — itself pinned to the reference's Q_ret: identical bits."""
+    from parity_utils import make_oracle
+    from smarties_b200 import load_library
+    lib = load_library()
+    lib.smb200_host_return_estimator.restype = C.c_double
+    fp = C.POINTER(C.c_float)
+    g = Golden(case)
+    o = make_oracle(g)
+    for _ in range(3):
+        o.train_step()
+    assert o.stats["maxAbsErr"] > 0
+    for ep in o.episodes:
+        N = ep.nsteps
+        R, V, A, W = (np.ascontiguousarray(x, np.float32) for x in (ep.R, ep.V, ep.ADV, ep.rho))
+        Q = np.ascontiguousarray(ep.Q, np.float32).copy()
+        err = lib.smb200_host_return_estimator(C.c_int32(N), C.c_int32(int(ep.terminated)), C.c_int32(estimator), R.ctypes.data_as(fp),
+                                               V.ctypes.data_as(fp), A.ctypes.data_as(fp), W.ctypes.data_as(fp), Q.ctypes.data_as(fp),
+                                               C.c_double(o.gamma), C.c_double(o.lam), C.c_float(o.rew_mean), C.c_float(o.rew_scale),
+                                               C.c_double(o.stats["maxAbsErr"]))
+        want_err = o.retrace_episode(ep)
+        assert np.array_equal(Q.view(np.uint32), np.asarray(ep.Q, np.float32).view(np.uint32)), ep.ID
+        assert err == pytest.approx(want_err, rel=1e-5)        # the oracle squares with numpy's scalar power (powf), not d * d
