@@ -132,9 +132,12 @@ def run_reference(steps, threads, data=None, reps=1, settings=None, learner_flag
                                  cwd=tmp, env=env, check=True, capture_output=True, text=True).stdout
         line = [l for l in out.splitlines() if l.startswith('{"harness"')][-1]
         r = json.loads(line)
-        return dict(value=r["transitions_per_s"], seconds=r["seconds_mean"], steps=steps, kind="reference", cores=threads,
-                    sample=f"{steps} learner steps of the same workload (1M-transition buffer, batch 256, sweeps every 1000 steps) "
-                           f"by the unmodified reference built -O3 -ffast-math -DSINGLE_PREC, {threads} OpenMP threads")
+        med = reps >= 3 and "transitions_per_s_median" in r          # >= 3 repetitions, median
+        return dict(value=r["transitions_per_s_median"] if med else r["transitions_per_s"],
+                    seconds=r["seconds_median"] if med else r["seconds_mean"], steps=steps, kind="reference", cores=threads,
+                    sample=(f"median of {reps} consecutive runs of " if med else "") +
+                           f"{steps} learner steps of the same workload (1M-transition buffer, batch 256, sweeps every 1000 steps) "
+                           f"by the unmodified reference built -O3 -ffast-math -DSINGLE_PREC, {threads} OpenMP threads, OMP_PROC_BIND=close")
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import vracer_oracle as vo
     o = vo.VracerOracle(32, 8, batch=BATCH, max_tot_obs=1048576)
@@ -169,7 +172,7 @@ def cpu_baseline_block(r, data=None, single_thread_steps=400):
     blk = {"value": r["value"], "unit": "transitions/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
            "cpu_model": cpu_model()}
     if r["kind"] == "reference" and r["cores"] > 1 and single_thread_steps > 0:
-        r1 = run_reference(single_thread_steps, 1, data=data)
+        r1 = run_reference(single_thread_steps, 1, data=data, reps=3)
         blk["single_thread"] = {"value": r1["value"], "unit": "transitions/s", "sample": r1["sample"]}
     return blk
 
@@ -333,7 +336,7 @@ def main():
                "roofline": roof, "roofline_sweeps": sweeps,
                "final_stats": {k: stats[-1][k] for k in ("beta", "cmax", "n_far_policy", "grad_step")}}
         if world == 1 and not args.no_cpu_baseline:
-            r = run_reference(args.cpu_steps, os.cpu_count() or 1, data=data)
+            r = run_reference(args.cpu_steps, os.cpu_count() or 1, data=data, reps=3)
             out["cpu_baseline"] = cpu_baseline_block(r, data=data)
         os.write(real_stdout, (json.dumps(out) + "\n").encode())
     L.close()

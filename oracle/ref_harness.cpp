@@ -23,6 +23,7 @@
 #include "smarties/ReplayMemory/MemoryProcessing.h"
 #include "smarties/Utils/Profiler.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -259,6 +260,7 @@ struct Probe : public Base
     std::vector<double> trBeta, trCmax, trWnorm; std::vector<int64_t> trNfar;
 
     double bestSec = 1e300, totSec = 0;
+    std::vector<double> repSec;
     for(int rep=0; rep<args.reps; ++rep)
     {
       const auto t0 = std::chrono::steady_clock::now();
@@ -291,7 +293,7 @@ struct Probe : public Base
         }
       }
       const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-      bestSec = std::min(bestSec, sec); totSec += sec;
+      bestSec = std::min(bestSec, sec); totSec += sec; repSec.push_back(sec);
     }
     if(D.on()) {
       D.f64("trace/beta", trBeta); D.f64("trace/Cmax", trCmax); D.i64("trace/nFar", trNfar);
@@ -302,12 +304,15 @@ struct Probe : public Base
     }
     if(args.save) this->save();     // Learner_approximator::save (Learner_approximator.cpp:133-142)
     if(!args.quiet) printf("%s\n", profiler->printStatAndReset().c_str());
-    const double medSec = totSec / args.reps;
+    const double medSec = totSec / args.reps;      // mean over the repetitions (name kept)
+    std::sort(repSec.begin(), repSec.end());
+    const double median = repSec.empty() ? medSec : (repSec.size() % 2 ? repSec[repSec.size()/2]
+                                                                        : 0.5 * (repSec[repSec.size()/2 - 1] + repSec[repSec.size()/2]));
     printf("{\"harness\": \"reference\", \"steps\": %d, \"reps\": %d, \"threads\": %d, \"batch\": %lu, "
-           "\"seconds_mean\": %.6f, \"seconds_best\": %.6f, \"steps_per_s\": %.3f, \"transitions_per_s\": %.3f, "
-           "\"nTransitions\": %ld, \"nEpisodes\": %ld}\n",
-           args.steps, args.reps, args.threads, (unsigned long) B, medSec, bestSec, args.steps/medSec,
-           B*args.steps/medSec, data->nStoredSteps(), data->nStoredEps());
+           "\"seconds_mean\": %.6f, \"seconds_best\": %.6f, \"seconds_median\": %.6f, \"steps_per_s\": %.3f, "
+           "\"transitions_per_s\": %.3f, \"transitions_per_s_median\": %.3f, \"nTransitions\": %ld, \"nEpisodes\": %ld}\n",
+           args.steps, args.reps, args.threads, (unsigned long) B, medSec, bestSec, median, args.steps/medSec,
+           B*args.steps/medSec, B*args.steps/median, data->nStoredSteps(), data->nStoredEps());
     return 0;
   }
 };
