@@ -77,6 +77,13 @@ typedef struct smb200_config {
   int64_t min_tot_obs;                  /* minTotObsNum_local = nObsB4StartTraining: only recorded in checkpoints
                                            ("nInitialData", MemoryBuffer.cpp:300); 0 = max_tot_obs */
   int32_t returns_estimator;            /* smb200_returns_estimator: "returnsEstimator": "retrace" | "GAE" | ("retraceExplore") */
+  int32_t discrete_options;             /* 0: continuous actions.  K > 0: one discrete action with K options
+                                           (ActionInfo::dimDiscrete, Core/StateAction.h; RACER<Discrete_advantage, Discrete_policy, Uint>,
+                                           Math/Discrete_policy.h, Discrete_advantage.h): dim_action = 1, the stored action is the
+                                           option label (+0.1, StateAction.h:320-341), the behaviour policy has K columns, the net
+                                           outputs [V | advantages(K) | policy(K)] and has no ParamLayer.  Only the network
+                                           construction is built so far (smb200_host_init_weights, pinned to the reference);
+                                           smb200_create rejects K != 0 until the loss stage exists */
 } smb200_config;
 
 /* Per-step scalars the reference prints / feeds back (MemoryBuffer::getMetrics,

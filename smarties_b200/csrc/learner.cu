@@ -89,6 +89,7 @@ struct smb200_learner {
   float* tcPartial = nullptr; int useTc = 0;     // tensor-core weight gradient of LSTM layers (recurrent nets)
   GradTile* dTiles = nullptr; int nTiles = 0;
   int Bpad = 0;
+  int dP = 0;                     // columns of the behaviour policy MU: 2 * dim_action (mean, stdev), or the K option probabilities
 
   // step state
   StepCtrl* dCtrl = nullptr;       // [2]
@@ -186,17 +187,23 @@ static int build_net(const smb200_config& c, NetDesc& net, std::vector<GradTile>
     nIn = h;
   }
   // V-RACER: [V | mean(dA)], RACER: [V | adv coef, p1(dA), p2(dA) | mean(dA)]; stdev is the ParamLayer (RACER_simpleSigma)
-  const int nOutDense = c.algo == SMB200_RACER ? 2 + 3 * dA : 1 + dA;
+  // discrete action with K options (RACER_common.cpp:109-135): [V | advantages(K) | policy(K)], no ParamLayer — kept here as
+  // an EMPTY last layer (0 parameters, 0 activations: the blob layout is the reference's) so that "last layer = ParamLayer" holds
+  const int K = c.discrete_options;
+  if (K < 0 || K > 64 || (K > 0 && (dA != 1 || c.algo != SMB200_RACER || K < 2))) {
+    set_error_msg("discrete actions: one action component, 2..64 options, learner RACER"); return -1; }
+  const int nOutDense = K > 0 ? 1 + 2 * K : (c.algo == SMB200_RACER ? 2 + 3 * dA : 1 + dA);
+  const int nParamOut = K > 0 ? 0 : dA;
   {
     LayerDesc& L = add(kDenseLinear, nOutDense);
     L.nIn = nIn; L.ld = round_up(nOutDense, 8);
     L.wOff = off; off += round_up(L.ld * nIn, 8); L.bOff = off; off += round_up(nOutDense, 8);
     L.needDx = 1; img_dense(L);
-    LayerDesc& P = add(kParam, dA);
-    P.bOff = off; off += round_up(dA, 8); P.wOff = off;
-    P.imgB = img; P.imgW = img; img += round_up(dA, 4);
+    LayerDesc& P = add(kParam, nParamOut);
+    P.bOff = off; off += round_up(nParamOut, 8); P.wOff = off;
+    P.imgB = img; P.imgW = img; img += round_up(nParamOut, 4);
   }
-  net.nLayers = id; net.nParams = off; net.imgFloats = img; net.nOut = nOutDense + dA; net.nOutDense = nOutDense;
+  net.nLayers = id; net.nParams = off; net.imgFloats = img; net.nOut = nOutDense + nParamOut; net.nOutDense = nOutDense;
   net.dS = dS; net.dA = dA; net.maxWidth = width;
   net.recurrent = lstm ? 1 : 0; net.bptt = lstm ? c.nn_bptt_seq : 0; net.Tc = net.bptt + 1;
   net.topInOff = act;
@@ -241,7 +248,7 @@ static void init_weights(const smb200_config& c, const NetDesc& net, std::mt1993
       std::uniform_real_distribution<float> dis(-init, init);
       for (int i = 0; i < L.nIn; ++i)
         for (int o = 0; o < L.size; ++o) blob[L.wOff + o + L.ld * i] = dis(gen);
-      if (out && c.algo == SMB200_RACER) {   // Gaussian_advantage::setInitial (Gaus_advantage.h:31-34): bias -1 for the coefficient, 1 for the widths
+      if (out && c.algo == SMB200_RACER && c.discrete_options == 0) {   // Gaussian_advantage::setInitial (Gaus_advantage.h:31-34): bias -1 for the coefficient, 1 for the widths
         blob[L.bOff + 1] = -1.f;
         for (int o = 2; o < 2 + 2 * c.dim_action; ++o) blob[L.bOff + o] = 1.f;
       }
@@ -558,6 +565,8 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
   const bool exploreOk = c.returns_estimator == SMB200_RETRACE_EXPLORE && unv && unv[0] == '1';
   if (c.returns_estimator != SMB200_RETRACE && c.returns_estimator != SMB200_GAE && !exploreOk) {
     set_error_msg("returnsEstimator must be retrace or GAE (retraceExplore: only with SMB200_UNVERIFIED=1)"); delete h; return SMB200_ERR_INVALID; }
+  if (c.discrete_options != 0) {   // network construction is built (build_net / init_weights, pinned on the host); the loss stage is not
+    set_error_msg("discrete actions: the device loss stage (Discrete_policy / Discrete_advantage) is not built yet"); delete h; return SMB200_ERR_INVALID; }
   std::vector<GradTile> tiles;
   if (build_net(c, h->descs.net, tiles)) { delete h; return SMB200_ERR_INVALID; }
   memset(&h->descs.seq, 0, sizeof(h->descs.seq));
@@ -585,7 +594,8 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
   int maxEp = c.max_episodes > 0 ? c.max_episodes : (int)std::min<long long>(cap / 2, 1 << 20);
   ReplayView& rp = h->rp;
   rp.capRows = cap; rp.maxEpisodes = maxEp; rp.dS = dS; rp.dA = dA;
-  CK(dev_alloc(&rp.S, (size_t)cap * dS)); CK(dev_alloc(&rp.A, (size_t)cap * dA)); CK(dev_alloc(&rp.MU, (size_t)cap * 2 * dA));
+  h->dP = c.discrete_options > 0 ? c.discrete_options : 2 * dA;
+  CK(dev_alloc(&rp.S, (size_t)cap * dS)); CK(dev_alloc(&rp.A, (size_t)cap * dA)); CK(dev_alloc(&rp.MU, (size_t)cap * h->dP));
   CK(dev_alloc(&rp.R, (size_t)cap)); CK(dev_alloc(&rp.V, (size_t)cap)); CK(dev_alloc(&rp.ADV, (size_t)cap));
   CK(dev_alloc(&rp.Q, (size_t)cap)); CK(dev_alloc(&rp.DELTA, (size_t)cap)); CK(dev_alloc(&rp.RHO, (size_t)cap));
   CK(dev_alloc(&rp.KL, (size_t)cap)); CK(dev_alloc(&rp.rowFlag, (size_t)cap));
@@ -770,17 +780,18 @@ static int push_episode_impl(smb200_learner* h, int64_t id, int32_t N, int32_t t
   const int slot = h->freeSlots.back(); h->freeSlots.pop_back();
   const int dS = h->cfg.dim_state, dA = h->cfg.dim_action;
   ReplayView& rp = h->rp;
+  const int dP = h->dP;
   cudaStream_t st = h->stream;
   SMB200_CUDA_CHECK(cudaMemcpyAsync(rp.S + (size_t)start * dS, S, sizeof(float) * (size_t)N * dS, cudaMemcpyHostToDevice, st));
   SMB200_CUDA_CHECK(cudaMemcpyAsync(rp.A + (size_t)start * dA, A, sizeof(float) * (size_t)N * dA, cudaMemcpyHostToDevice, st));
-  SMB200_CUDA_CHECK(cudaMemcpyAsync(rp.MU + (size_t)start * 2 * dA, MU, sizeof(float) * (size_t)N * 2 * dA, cudaMemcpyHostToDevice, st));
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(rp.MU + (size_t)start * dP, MU, sizeof(float) * (size_t)N * dP, cudaMemcpyHostToDevice, st));
   SMB200_CUDA_CHECK(cudaMemcpyAsync(rp.R + start, R, sizeof(float) * (size_t)N, cudaMemcpyHostToDevice, st));
   if (V) SMB200_CUDA_CHECK(cudaMemcpyAsync(rp.V + start, V, sizeof(float) * (size_t)N, cudaMemcpyHostToDevice, st));
   if (ADV) SMB200_CUDA_CHECK(cudaMemcpyAsync(rp.ADV + start, ADV, sizeof(float) * (size_t)N, cudaMemcpyHostToDevice, st));
   else if (V) SMB200_CUDA_CHECK(cudaMemsetAsync(rp.ADV + start, 0, sizeof(float) * (size_t)N, st));
   // last row: no action / policy (MemoryBuffer.cpp:124-130); first reward is 0 (Episode.cpp:239)
   SMB200_CUDA_CHECK(cudaMemsetAsync(rp.A + (size_t)(start + N - 1) * dA, 0, sizeof(float) * dA, st));
-  SMB200_CUDA_CHECK(cudaMemsetAsync(rp.MU + (size_t)(start + N - 1) * 2 * dA, 0, sizeof(float) * 2 * dA, st));
+  SMB200_CUDA_CHECK(cudaMemsetAsync(rp.MU + (size_t)(start + N - 1) * dP, 0, sizeof(float) * dP, st));
   SMB200_CUDA_CHECK(cudaMemsetAsync(rp.R + start, 0, sizeof(float), st));
   const int meta[3] = {(int)start, N, terminated ? 1 : 0};
   SMB200_CUDA_CHECK(cudaMemcpyAsync(rp.epStart + slot, &meta[0], sizeof(int), cudaMemcpyHostToDevice, st));
@@ -1554,7 +1565,7 @@ int smb200_save(smb200_learner* h, const char* base_c) {
     if (write_both(base + name[k], flat.data(), sizeof(float) * nF)) return SMB200_ERR_STATE;
   }
   // ---- MemoryBuffer::save (MemoryBuffer.cpp:267-324) ----
-  const int dS = h->cfg.dim_state, dA = h->cfg.dim_action, dP = 2 * dA;
+  const int dS = h->cfg.dim_state, dA = h->cfg.dim_action, dP = h->dP;
   {
     std::vector<float> mean(dS), scale(dS), stdev(dS); float rew[4];
     if (smb200_get_scaling(h, mean.data(), scale.data(), stdev.data(), rew)) return SMB200_ERR_CUDA;
@@ -1624,7 +1635,7 @@ int smb200_restart(smb200_learner* h, const char* base_c) {
   SMB200_CUDA_CHECK(cudaMemcpyAsync(h->M2, m2.data(), sizeof(float) * nP, cudaMemcpyHostToDevice, h->stream));
   SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   // ---- MemoryBuffer::restart (MemoryBuffer.cpp:172-265) ----
-  const int dS = h->cfg.dim_state, dA = h->cfg.dim_action, dP = 2 * dA;
+  const int dS = h->cfg.dim_state, dA = h->cfg.dim_action, dP = h->dP;
   if (read_all(base + "_scaling.raw", raw)) return 0;                  // "Parameters restart file ... not found": nothing else is read
   if (raw.size() != sizeof(double) * (3 * (size_t)dS + 3)) { set_error_msg("Mismatch in restarted file _scaling.raw"); return SMB200_ERR_STATE; }
   {

@@ -52,7 +52,7 @@ class Config(C.Structure):
         ("eps_anneal", C.c_double), ("learnrate", C.c_double), ("nn_lambda", C.c_double), ("expl_noise", C.c_double),
         ("out_weights_prefac", C.c_double), ("refer_reduce_threads", C.c_int32), ("world_rank", C.c_int32),
         ("world_size", C.c_int32), ("seed", C.c_uint64), ("nn_type", C.c_int32), ("nn_bptt_seq", C.c_int32),
-        ("min_tot_obs", C.c_int64), ("returns_estimator", C.c_int32),
+        ("min_tot_obs", C.c_int64), ("returns_estimator", C.c_int32), ("discrete_options", C.c_int32),
     ]
 
 
@@ -165,7 +165,7 @@ class SmartiesB200Error(RuntimeError):
 
 def make_config(dim_state: int, dim_action: int, settings=None, *, device: int = 0, bounded=None, seed: int = 42,
                 capacity_rows: int = 0, max_episodes: int = 0, refer_reduce_threads: int = 32, world_rank: int = 0,
-                world_size: int = 1):
+                world_size: int = 1, discrete_options: int = 0):
     """settings.json surface -> smb200_config (what integration/RACER_B200.cpp fills from the reference's HyperParameters).
     Returns (Config, HyperParameters).  Host only: usable without a GPU."""
     from .settings import HyperParameters
@@ -193,6 +193,7 @@ def make_config(dim_state: int, dim_action: int, settings=None, *, device: int =
     cfg.nn_type, cfg.nn_bptt_seq = {"FFNN": 0, "LSTM": 1}[hp.nnType], int(hp.nnBPTTseq)
     cfg.min_tot_obs = hp.minTotObsNum_local
     cfg.returns_estimator = {"retrace": 0, "GAE": 1, "retraceExplore": 2}[hp.returnsEstimator]
+    cfg.discrete_options = int(discrete_options)     # from the MDP (Communicator::setNumberOfOptions), not from settings.json
     if bounded is not None:
         b = np.broadcast_to(np.asarray(bounded, dtype=bool), (dim_action,))
         for i in range(dim_action):

@@ -295,3 +295,31 @@ def test_return_estimator_source_is_bit_exact_with_the_oracle(built_library, cas
         want_err = o.retrace_episode(ep)
         assert np.array_equal(Q.view(np.uint32), np.asarray(ep.Q, np.float32).view(np.uint32)), ep.ID
         assert err == pytest.approx(want_err, rel=1e-5)        # the oracle squares with numpy's scalar power (powf), not d * d
+
+
+def test_discrete_action_network_construction_matches_the_reference(built_library):
+    """RACER<Discrete_advantage, Discrete_policy, Uint>::setupNet (Learners/RACER_common.cpp:70-135): outputs
+    [V | advantages(K) | policy(K)] from one linear layer, no ParamLayer, no initial biases.  Only the construction of this
+    network exists on the device side so far (smb200_create rejects discrete_options != 0): layout and
+    initial weights identical to the reference's in the golden run with 5 options."""
+    from smarties_b200 import load_library
+    from smarties_b200.learner import make_config
+    g = Golden("racer_discrete")
+    K = g.spec["replay"]["n_options"]
+    lib = load_library()
+    lib.smb200_host_init_weights.restype = C.c_int64
+    cfg, _ = make_config(g.dS, g.dA, dict(g.settings), seed=42, discrete_options=K)
+    ref = g.ref["init/weights"]
+    n = lib.smb200_host_init_weights(C.byref(cfg), None, 0)
+    assert n == ref.size
+    w = np.zeros(n, np.float32)
+    assert lib.smb200_host_init_weights(C.byref(cfg), w.ctypes.data_as(C.POINTER(C.c_float)), n) == n
+    assert np.array_equal(w.view(np.uint32), ref.view(np.uint32))
+    # one action component, at least two options, learner RACER
+    for bad in (dict(discrete_options=1), dict(discrete_options=65)):
+        cfg, _ = make_config(g.dS, g.dA, dict(g.settings), **bad)
+        assert lib.smb200_host_init_weights(C.byref(cfg), None, 0) < 0
+    cfg, _ = make_config(g.dS, 2, dict(g.settings), discrete_options=K)
+    assert lib.smb200_host_init_weights(C.byref(cfg), None, 0) < 0
+    cfg, _ = make_config(g.dS, 1, {"learner": "VRACER"}, discrete_options=K)
+    assert lib.smb200_host_init_weights(C.byref(cfg), None, 0) < 0
