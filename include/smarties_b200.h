@@ -259,6 +259,12 @@ int64_t smb200_host_repack_episodes(int32_t dim_state, int32_t dim_action, const
 int smb200_host_adam(int64_t n, const float* G, float* W, float* M1, float* M2, double learnrate, double eps_anneal, int64_t adam_step_done,
                      double bt1, double bt2, double nn_lambda, int32_t batch_global);
 int smb200_host_value_scaling(int64_t n, const double* x, double* v, double* dvdx);
+/* Groundwork for discrete actions: RACER<Discrete_advantage, Discrete_policy, Uint>::Train per
+ * sample (Learners/RACER_train.cpp:12-67, Math/Discrete_policy.h:64-167, Math/Discrete_advantage.h:44-75) as the
+ * __host__ __device__ function the device loss stage will call, run on the host over a batch.  O [B][1+2K], act [B] (label + 0.1),
+ * mu [B][K], qret [B]; g [B][1+2K] output gradients, out [B][6] = {rho, D_KL, isFar, V, A, deltaQ}. */
+int smb200_host_discrete_loss(int32_t B, int32_t K, const float* O, const float* act, const float* mu, const float* qret, double beta,
+                              double cmax, double cinv, double* g, double* out);
 /* updateReturnEstimator(EP, N-2) of one episode (ReplayMemory/MemoryProcessing.cpp:23-44) for estimator = retrace / GAE /
  * retraceExplore (:391-417), sequentially on the host with the scalar functions the sweep kernels call (reward scaling,
  * clipped importance weight, the recursion's expression order).  Q is updated in place; returns the sum of squared changes. */

@@ -196,6 +196,58 @@ __host__ __device__ __forceinline__ double vdiff(double x) {
   return x > 0 ? 100.0 - 5000.0 / sqrt(2601.0 + 100.0 * x) : 100.0 - 5000.0 / sqrt(2601.0 - 100.0 * x);
 }
 
+// RACER<Discrete_advantage, Discrete_policy, Uint>::Train for ONE sample with K action options (Learners/RACER_train.cpp:12-67;
+// Math/Discrete_policy.h:64-167: SoftPlus of the pre-activations, normalised; importance weight without clipping; KL
+// divergence and its gradient; policy gradient; Math/Discrete_advantage.h:44-75: advantage centred with the policy's
+// expectation), f64.  O = [V | advantages(K) | policy pre-activations(K)], act = stored action message (label + 0.1,
+// Core/StateAction.h:304-341), mu = behaviour probabilities.  g receives the 1 + 2K output gradients; out = {rho, dkl,
+// isFar, V, A, deltaQ}.  GROUNDWORK for SURVEY.md §8 row f4: no kernel calls this yet; its host build is pinned to the
+// oracle (itself pinned to the reference golden racer_discrete) by tests/test_host_replay.py.
+constexpr int kMaxOptions = 64;
+__host__ __device__ inline void discrete_sample_loss(int K, const float* O, float act, const float* mu, float qret, double beta,
+                                                     double cmax, double cinv, double* g, double* out) {
+  double unnorm[kMaxOptions], probs[kMaxOptions], dpos[kMaxOptions];
+  const int opt = (int)floor((double)act);                                  // actionMessage2label
+  const float* adv = O + 1; const float* raw = O + 1 + K;
+  double norm = 0.0;
+  for (int j = 0; j < K; ++j) {
+    const double x = (double)raw[j], root = sqrt(1.0 + x * x);
+    unnorm[j] = (x + root) / 2.0;                                           // SoftPlus::_eval (Functions.h:552-555)
+    dpos[j] = (1.0 + x / root) / 2.0;                                       // SoftPlus::_evalDiff
+    norm = norm + unnorm[j];
+  }
+  norm = norm > 2.220446049250313e-16 ? norm : 2.220446049250313e-16;       // max(norm, eps<Real>)
+  double dkl = 0.0, expA = 0.0;
+  for (int j = 0; j < K; ++j) probs[j] = unnorm[j] / norm;
+  for (int j = 0; j < K; ++j) dkl = dkl + probs[j] * log(probs[j] / (double)mu[j]);          // KLDivergence (:129-133)
+  for (int j = 0; j < K; ++j) expA = expA + probs[j] * (double)adv[j];
+  const double rho = probs[opt] / (double)mu[opt];                          // importanceWeight (:87-94)
+  const float W32 = (float)rho, C32 = (float)cmax, I32 = (float)cinv;       // isFarPolicy takes Fval arguments (Episode.h:28-33)
+  const bool isFar = (C32 > 1.0f) && ((W32 > C32) || (W32 < I32));
+  const double Aval = (double)adv[opt] - expA;
+  const double O0 = (double)O[0];
+  const double V = net2v(O0);
+  const double a_ret = (double)qret - V, dq = a_ret - Aval;
+  const double rmin1 = rho < 1.0 ? rho : 1.0, rminC = rho < cmax ? rho : cmax;
+  g[0] = isFar ? 0.0 : rmin1 * dq * beta * vdiff(O0);
+  // penalG = KLDivGradient(MU, -1) (:158-167); polG = policyGradient(ACT, A_RET * min(Cmax, rho)) (:139-147)
+  for (int i = 0; i < K; ++i) g[1 + K + i] = 0.0;
+  for (int j = 0; j < K; ++j) {
+    const double tmp = -1.0 * (1.0 + log(probs[j] / (double)mu[j])) / norm;
+    for (int i = 0; i < K; ++i) g[1 + K + i] = g[1 + K + i] + tmp * ((i == j ? 1.0 : 0.0) - probs[j]);
+  }
+  const double fac = a_ret * rminC;
+  const double err = isFar ? 0.0 : beta * rminC * dq;                       // ADV.grad(act, isFar ? 0 : beta * Aer) (:53-61)
+  for (int i = 0; i < K; ++i) {
+    const double penal = g[1 + K + i] * dpos[i];
+    double pol = ((i == opt ? fac / unnorm[opt] : 0.0) - fac / norm) * dpos[i];
+    if (isFar) pol = 0.0;
+    g[1 + K + i] = beta * pol + (1.0 - beta) * penal;                       // penalizeReFER (FunctionUtilities.h:221-228)
+    g[1 + i] = err * ((i == opt ? 1.0 : 0.0) - probs[i]);
+  }
+  out[0] = rho; out[1] = dkl; out[2] = isFar ? 1.0 : 0.0; out[3] = V; out[4] = Aval; out[5] = dq;
+}
+
 // StepCtrl is rewritten by other CTAs between steps: read it through L2
 __device__ __forceinline__ void load_ctrl(StepCtrl& dst, const StepCtrl* src) {
   static_assert(sizeof(StepCtrl) % 8 == 0, "StepCtrl must be a multiple of 8 bytes");
@@ -2397,6 +2449,16 @@ int smb200_host_adam(int64_t n, const float* G, float* W, float* M1, float* M2, 
 int smb200_host_value_scaling(int64_t n, const double* x, double* v, double* dvdx) {
   if (n < 0 || !x || !v || !dvdx) return -1;
   for (int64_t i = 0; i < n; ++i) { v[i] = smb200::net2v(x[i]); dvdx[i] = smb200::vdiff(x[i]); }
+  return 0;
+}
+
+// discrete_sample_loss over a batch: O [B][1 + 2K] f32, act [B], mu [B][K], qret [B]; g [B][1 + 2K], out [B][6]
+int smb200_host_discrete_loss(int32_t B, int32_t K, const float* O, const float* act, const float* mu, const float* qret, double beta,
+                              double cmax, double cinv, double* g, double* out) {
+  if (B < 0 || K < 2 || K > smb200::kMaxOptions || !O || !act || !mu || !qret || !g || !out) return -1;
+  for (int b = 0; b < B; ++b)
+    smb200::discrete_sample_loss(K, O + (size_t)b * (1 + 2 * K), act[b], mu + (size_t)b * K, qret[b], beta, cmax, cinv,
+                                 g + (size_t)b * (1 + 2 * K), out + (size_t)b * 6);
   return 0;
 }
 

@@ -323,3 +323,59 @@ def test_discrete_action_network_construction_matches_the_reference(built_librar
     assert lib.smb200_host_init_weights(C.byref(cfg), None, 0) < 0
     cfg, _ = make_config(g.dS, 1, {"learner": "VRACER"}, discrete_options=K)
     assert lib.smb200_host_init_weights(C.byref(cfg), None, 0) < 0
+
+
+def _discrete_loss(lib, O, act, mu, qret, beta, cmax, cinv):
+    fp, dp = C.POINTER(C.c_float), C.POINTER(C.c_double)
+    O, act, mu, qret = (np.ascontiguousarray(x, np.float32) for x in (O, act, mu, qret))
+    B, K = mu.shape
+    g = np.zeros((B, 1 + 2 * K)); out = np.zeros((B, 6))
+    rc = lib.smb200_host_discrete_loss(C.c_int32(B), C.c_int32(K), O.ctypes.data_as(fp), act.ctypes.data_as(fp), mu.ctypes.data_as(fp),
+                                       qret.ctypes.data_as(fp), C.c_double(beta), C.c_double(cmax), C.c_double(cinv),
+                                       g.ctypes.data_as(dp), out.ctypes.data_as(dp))
+    assert rc == 0
+    return g, out
+
+
+@pytest.mark.parametrize("K", [2, 5, 17])
+def test_discrete_loss_source_matches_the_oracle(built_library, K):
+    """Groundwork for row f4: the per-sample loss of discrete-action RACER as the __host__ __device__ function the device loss
+    stage will call, built for the host, against the oracle's Discrete_policy / Discrete_advantage restatement (pinned to the
+    reference golden racer_discrete) on random samples, near- and far-policy, both signs of the value head."""
+    import vracer_oracle as vo
+    from smarties_b200 import load_library
+    rng = np.random.default_rng(K)
+    B = 96
+    O = (rng.standard_normal((B, 1 + 2 * K)) * np.r_[3.0, np.ones(2 * K)]).astype(np.float32)
+    p = np.exp(rng.standard_normal((B, K))); mu = (p / p.sum(1, keepdims=True)).astype(np.float32)
+    label = rng.integers(0, K, B)
+    act = (label + 0.1).astype(np.float32)
+    qret = rng.standard_normal(B).astype(np.float32)
+    for beta, cmax in ((0.3, 2.5), (1e-4, 1.2), (0.9, 1.0)):
+        cinv = 1.0 / cmax
+        g, out = _discrete_loss(load_library(), O, act, mu, qret, beta, cmax, cinv)
+        r = vo.discrete_sample_math(O, act.reshape(B, 1), mu, qret, beta, cmax, cinv)
+        assert np.array_equal(out[:, 2] != 0, r["is_far"])
+        if cmax > 1.1:
+            assert r["is_far"].any() and not r["is_far"].all()
+        for k, name in ((0, "rho"), (1, "dkl"), (3, "V"), (4, "A"), (5, "dq")):
+            assert np.allclose(out[:, k], r[name], rtol=1e-13, atol=1e-15), name
+        assert np.allclose(g, r["g"], rtol=1e-12, atol=1e-15)
+
+
+def test_discrete_loss_source_matches_the_reference_golden(built_library):
+    """The same function on the reference's own step: network outputs, sampled actions / behaviour policies and ReF-ER scalars
+    of step 0 of the golden racer_discrete -> the output gradient the reference back-propagated (f32 dump)."""
+    from parity_utils import make_oracle, relerr
+    from smarties_b200 import load_library
+    g = Golden("racer_discrete")
+    o = make_oracle(g)
+    seq, obs = o.sample()
+    assert np.array_equal([o.episodes[int(k)].ID for k in seq], g.ref["s0/sampledEpID"]) and np.array_equal(obs, g.ref["s0/sampledT"])
+    eps = [o.episodes[int(k)] for k in seq]
+    act = np.array([e.A[int(t)][0] for e, t in zip(eps, obs)], np.float32)
+    mu = np.stack([e.MU[int(t)] for e, t in zip(eps, obs)])
+    qret = np.array([e.Q[int(t)] for e, t in zip(eps, obs)], np.float32)
+    O = np.asarray(g.ref["s0/O"], np.float32)
+    grad, out = _discrete_loss(load_library(), O, act, mu, qret, o.beta, o.cmax, o.cinv)
+    assert relerr(grad, g.ref["s0/g"]) < 1e-6
