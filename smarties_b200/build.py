@@ -45,8 +45,10 @@ def _compile(out: str, suffix: str, defines, logname: str, verbose: bool) -> Non
             sys.stderr.write(o)
             raise RuntimeError(f"nvcc failed on {s}")
     subprocess.run([NVCC, "-shared", "-o", out, *objs, "-cudart", "static"], check=True)
+    # the tracked log keeps registers / spills / shared memory per kernel; compile times would change it on every build
+    kept = [l for l in "\n".join(log).splitlines() if "Compile time" not in l]
     with open(os.path.join(CSRC, logname), "w") as f:
-        f.write("\n".join(log))
+        f.write("\n".join(kept) + "\n")
     if verbose:
         print("\n".join(log))
 
