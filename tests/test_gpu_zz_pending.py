@@ -46,7 +46,7 @@ print("ok")
 def _run_child(case):
     code = CHILD.format(root=os.path.dirname(HERE), oracle=os.path.join(os.path.dirname(HERE), "oracle"), tests=HERE, case=case)
     env = dict(os.environ, SMB200_UNVERIFIED="1")
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=180, env=env)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (r.stdout[-3000:] + "\n" + r.stderr[-3000:])
 
 
