@@ -379,3 +379,29 @@ def test_discrete_loss_source_matches_the_reference_golden(built_library):
     O = np.asarray(g.ref["s0/O"], np.float32)
     grad, out = _discrete_loss(load_library(), O, act, mu, qret, o.beta, o.cmax, o.cinv)
     assert relerr(grad, g.ref["s0/g"]) < 1e-6
+
+
+def test_host_sampler_at_full_buffer_size_matches_the_oracle(built_library):
+    """BASELINE.json configs[1] size: 1000 ragged episodes, ~1 M transitions, batch 256 — the library's host sampler (64 Ki-bucket
+    id -> (episode, t) lookup with a non-zero bucket shift, radix sort of the ids) against the oracle's restatement of
+    libstdc++'s uniform_int_distribution + Sampling::IDtoSeqStep (pinned to the reference on the small goldens), 30 steps incl.
+    the change of the episode order after the first step's FIFO sort.  Integer results: identical."""
+    import vracer_oracle as vo
+    from smarties_b200 import load_library
+    rng = np.random.default_rng(11)
+    n_ep, B, steps, seed = 1000, 256, 30, 42
+    rows = rng.integers(900, 1101, n_ep).astype(np.int32)
+    rc, ep, t, n_after, order = _trace(load_library(), B, 1 << 21, np.arange(n_ep), rows, np.zeros(n_ep, np.int32), seed, steps)
+    assert rc == 0 and np.all(n_after == n_ep)
+    gen = vo.Mt19937(seed)
+    ids_order = np.arange(n_ep)                                   # push order at step 0
+    n_tr = int((rows - 1).sum())
+    assert n_tr > 900_000
+    for k in range(steps):
+        nd = (rows[ids_order] - 1).astype(np.int64)
+        seq, obs = vo.id_to_seq_step(vo.sample_uniform(gen, n_tr, B), nd)
+        assert np.array_equal(ep[k], ids_order[np.asarray(seq, np.int64)]), k
+        assert np.array_equal(t[k], obs), k
+        ids_order = np.arange(n_ep)[::-1]                         # applyEpisodesRemovalAlgo: ID descending from the first step on
+        gen()                                                     # the Adam update's draw (Optimizer.cpp:139)
+    assert order[0].tolist() == list(range(n_ep - 1, -1, -1))
