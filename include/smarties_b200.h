@@ -279,7 +279,9 @@ double smb200_host_return_estimator(int32_t n_rows, int32_t terminated, int32_t 
  * [n_steps][n_ep] (padded with -1): the episode vector after each step (both optional). */
 int smb200_host_replay_trace(int32_t batch_size, int64_t max_tot_obs, int64_t capacity_rows, int32_t n_ep, const int64_t* ids,
                              const int32_t* n_rows, const int32_t* terminated, uint64_t seed, int32_t n_steps,
-                             int64_t* ep_id_out, int64_t* t_out, int32_t* n_ep_after, int64_t* order_out);
+                             int64_t* ep_id_out, int64_t* t_out, int32_t* n_ep_after, int64_t* order_out,
+                             const int32_t* push_before_step /* optional, non-decreasing: episode e arrives before that learner step */,
+                             int64_t* start_out /* optional [n_steps][n_ep]: first ring row of each live episode after the step */);
 
 #ifdef __cplusplus
 }

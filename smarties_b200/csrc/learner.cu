@@ -1101,7 +1101,8 @@ int smb200_profile_phases(smb200_learner* h, int32_t n, int64_t* out, int64_t ca
 // sort / pruning: the number of episodes and their ids in the reference's vector order (padded with -1).
 int smb200_host_replay_trace(int32_t batch_size, int64_t max_tot_obs, int64_t capacity_rows, int32_t n_ep, const int64_t* ids,
                              const int32_t* n_rows, const int32_t* terminated, uint64_t seed, int32_t n_steps,
-                             int64_t* ep_id_out, int64_t* t_out, int32_t* n_ep_after, int64_t* order_out) {
+                             int64_t* ep_id_out, int64_t* t_out, int32_t* n_ep_after, int64_t* order_out,
+                             const int32_t* push_before_step, int64_t* start_out) {
   if (batch_size < 1 || n_ep < 1 || n_steps < 0 || !ids || !n_rows || !terminated || !ep_id_out || !t_out) return SMB200_ERR_INVALID;
   smb200_learner* h = new smb200_learner();
   memset(&h->cfg, 0, sizeof(h->cfg));
@@ -1109,25 +1110,38 @@ int smb200_host_replay_trace(int32_t batch_size, int64_t max_tot_obs, int64_t ca
   long long cap = capacity_rows > 0 ? capacity_rows : max_tot_obs + max_tot_obs / 8 + 65536;   // smb200_create's default
   h->rp.capRows = (cap + 63) / 64 * 64;
   for (int s = n_ep - 1; s >= 0; --s) h->freeSlots.push_back(s);
-  int rc = 0;
-  for (int e = 0; e < n_ep && !rc; ++e) {
-    if (n_rows[e] < 2) { set_error_msg("push_episode: an episode needs at least s0 and sT"); rc = SMB200_ERR_INVALID; break; }
-    const long long start = ring_alloc(h, n_rows[e]);
-    if (start < 0) { set_error_msg("replay ring full"); rc = SMB200_ERR_CAPACITY; break; }
-    const int slot = h->freeSlots.back(); h->freeSlots.pop_back();
-    host_add_episode(h, ids[e], n_rows[e], terminated[e], slot, start);
-  }
+  int rc = 0, next = 0;
+  // episodes arrive in the order given; push_before_step[e] (non-decreasing; absent = 0) is the learner step before which
+  // episode e is pushed — the actors keep feeding the buffer while the learner trains
+  auto push_until = [&](int step) {
+    for (; next < n_ep && !rc && (!push_before_step || push_before_step[next] <= step); ++next) {
+      const int e = next;
+      if (n_rows[e] < 2) { set_error_msg("push_episode: an episode needs at least s0 and sT"); rc = SMB200_ERR_INVALID; break; }
+      if (h->freeSlots.empty()) { set_error_msg("episode table full"); rc = SMB200_ERR_CAPACITY; break; }
+      const long long start = ring_alloc(h, n_rows[e]);
+      if (start < 0) { set_error_msg("replay ring full"); rc = SMB200_ERR_CAPACITY; break; }
+      const int slot = h->freeSlots.back(); h->freeSlots.pop_back();
+      host_add_episode(h, ids[e], n_rows[e], terminated[e], slot, start);
+    }
+  };
+  push_until(0);
   if (!rc && h->nTransitions < batch_size) { set_error_msg("not enough transitions for one mini-batch"); rc = SMB200_ERR_STATE; }
   if (!rc) {
     h->gen.seed((unsigned long)seed);
     std::vector<int64_t> pos(batch_size);
-    for (int s = 0; s < n_steps; ++s) {
+    for (int s = 0; s < n_steps && !rc; ++s) {
+      if (s > 0) push_until(s);
+      if (rc) break;
       host_sample(h, nullptr, nullptr, pos.data(), t_out + (size_t)s * batch_size);
       for (int i = 0; i < batch_size; ++i) ep_id_out[(size_t)s * batch_size + i] = h->episodes[(size_t)pos[i]].id;
       host_post_step(h);
+      h->pendingEvict.clear();        // the learner clears the live flags of evicted rows on the device here
       if (n_ep_after) n_ep_after[s] = (int32_t)h->episodes.size();
-      if (order_out)
-        for (int k = 0; k < n_ep; ++k) order_out[(size_t)s * n_ep + k] = k < (int)h->episodes.size() ? h->episodes[k].id : -1;
+      for (int k = 0; k < n_ep; ++k) {
+        const bool live = k < (int)h->episodes.size();
+        if (order_out) order_out[(size_t)s * n_ep + k] = live ? h->episodes[k].id : -1;
+        if (start_out) start_out[(size_t)s * n_ep + k] = live ? h->episodes[k].start : -1;
+      }
     }
   }
   delete h;

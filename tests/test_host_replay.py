@@ -21,18 +21,25 @@ UNIFORM_FIFO = [c for c in CASES + RECURRENT_CASES + ORACLE_ONLY_CASES
                 if c not in ("vracer_pererr", "vracer_perseq", "vracer_perrank", "vracer_farpolfrac", "vracer_maxkldiv", "vracer_minerror")]
 
 
-def _trace(lib, batch, max_tot_obs, ids, rows, term, seed, steps, capacity=0):
+def _trace(lib, batch, max_tot_obs, ids, rows, term, seed, steps, capacity=0, push_before_step=None, want_starts=False):
     P = C.POINTER
     lib.smb200_host_replay_trace.restype = C.c_int
     lib.smb200_host_replay_trace.argtypes = [C.c_int32, C.c_int64, C.c_int64, C.c_int32, P(C.c_int64), P(C.c_int32), P(C.c_int32),
-                                             C.c_uint64, C.c_int32, P(C.c_int64), P(C.c_int64), P(C.c_int32), P(C.c_int64)]
+                                             C.c_uint64, C.c_int32, P(C.c_int64), P(C.c_int64), P(C.c_int32), P(C.c_int64),
+                                             P(C.c_int32), P(C.c_int64)]
     ids, rows, term = (np.ascontiguousarray(ids, np.int64), np.ascontiguousarray(rows, np.int32), np.ascontiguousarray(term, np.int32))
     n = len(ids)
     ep = np.zeros((steps, batch), np.int64); t = np.zeros((steps, batch), np.int64)
     n_after = np.zeros(steps, np.int32); order = np.zeros((steps, n), np.int64)
+    sched = None if push_before_step is None else np.ascontiguousarray(push_before_step, np.int32)
+    starts = np.zeros((steps, n), np.int64) if want_starts else None
     rc = lib.smb200_host_replay_trace(batch, max_tot_obs, capacity, n, ids.ctypes.data_as(P(C.c_int64)), rows.ctypes.data_as(P(C.c_int32)),
                                       term.ctypes.data_as(P(C.c_int32)), seed, steps, ep.ctypes.data_as(P(C.c_int64)),
-                                      t.ctypes.data_as(P(C.c_int64)), n_after.ctypes.data_as(P(C.c_int32)), order.ctypes.data_as(P(C.c_int64)))
+                                      t.ctypes.data_as(P(C.c_int64)), n_after.ctypes.data_as(P(C.c_int32)), order.ctypes.data_as(P(C.c_int64)),
+                                      None if sched is None else sched.ctypes.data_as(P(C.c_int32)),
+                                      None if starts is None else starts.ctypes.data_as(P(C.c_int64)))
+    if want_starts:
+        return rc, ep, t, n_after, order, starts
     return rc, ep, t, n_after, order
 
 
@@ -405,3 +412,42 @@ def test_host_sampler_at_full_buffer_size_matches_the_oracle(built_library):
         ids_order = np.arange(n_ep)[::-1]                         # applyEpisodesRemovalAlgo: ID descending from the first step on
         gen()                                                     # the Adam update's draw (Optimizer.cpp:139)
     assert order[0].tolist() == list(range(n_ep - 1, -1, -1))
+
+
+def test_replay_under_churn_matches_the_reference_sequence_and_keeps_the_ring_consistent(built_library):
+    """configs[3]'s situation on the host: actors keep pushing episodes while the learner steps, maxTotObsNum forces FIFO
+    removal, the HBM ring (capacity barely above the live rows) wraps and reuses freed ranges.  Against a direct model of the
+    reference's sequence — pushBackEpisode appends (MemoryBuffer.cpp:479-520); every step: sample on the current vector
+    (Sampling.cpp:26-47,82-93), sort by ID descending, removeBackEpisode while nStoredSteps - back.nsteps > maxTotObsNum
+    (MemoryProcessing.cpp:327-351), one generator draw for Adam (Optimizer.cpp:139) — with the oracle's sampler:
+    sampled (episode, t) and the episode vector identical at every step; live ring ranges never overlap nor leave the ring."""
+    import vracer_oracle as vo
+    from smarties_b200 import load_library
+    rng = np.random.default_rng(23)
+    n_ep, B, steps, seed, max_obs, cap = 120, 16, 200, 9, 600, 1024
+    rows = rng.integers(8, 41, n_ep).astype(np.int32)
+    sched = np.sort(np.r_[np.zeros(20, np.int64), rng.integers(1, steps, n_ep - 20)]).astype(np.int32)   # 20 up front, the rest while training
+    rc, ep, t, n_after, order, starts = _trace(load_library(), B, max_obs, np.arange(n_ep), rows, rng.integers(0, 2, n_ep), seed, steps,
+                                               capacity=cap, push_before_step=sched, want_starts=True)
+    assert rc == 0, load_library().smb200_last_error()
+    gen = vo.Mt19937(seed)
+    vec, nxt, pruned = [], 0, 0
+    for k in range(steps):
+        while nxt < n_ep and sched[nxt] <= k:
+            vec.append(nxt); nxt += 1
+        nd = (rows[vec] - 1).astype(np.int64)
+        seq, obs = vo.id_to_seq_step(vo.sample_uniform(gen, int(nd.sum()), B), nd)
+        assert np.array_equal(ep[k], np.asarray(vec)[np.asarray(seq, np.int64)]), k
+        assert np.array_equal(t[k], obs), k
+        vec.sort(reverse=True)
+        while int((rows[vec] - 1).sum()) - int(rows[vec[-1]]) > max_obs:
+            vec.pop(); pruned += 1
+        gen()
+        assert n_after[k] == len(vec) and order[k, :len(vec)].tolist() == vec, k
+        # ring consistency: every live episode inside the ring, no two live ranges overlap
+        s0 = starts[k, :len(vec)]; s1 = s0 + rows[vec]
+        assert s0.min() >= 0 and s1.max() <= cap
+        o = np.argsort(s0)
+        assert np.all(s1[o][:-1] <= s0[o][1:]), k
+    assert pruned > 40 and nxt == n_ep                     # the ring (1024 rows) held ~2900 rows over the run: ranges were reused
+    assert int(rows.sum()) > 2 * cap
