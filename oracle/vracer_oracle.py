@@ -1,7 +1,9 @@
 """CPU restatement (numpy) of the reference's V-RACER / RACER learner hot path.
 
 TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
-import this module; the product (smarties_b200/) never does.
+import this module; the product (smarties_b200/) never does.  (scripts/parity_report.py — the
+measured-error table of DESIGN.md — and scripts/dropin_run.py — imported by tests/test_gpu_dropin.py —
+are test tools of the same kind: they use it, and the binaries under oracle/_ref/, as the checker.)
 
 Parity status: PINNED against outputs of the reference itself — golden vectors produced by
 oracle/_ref/ref_harness (the unmodified reference compiled from /root/reference by
