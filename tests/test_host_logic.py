@@ -139,3 +139,27 @@ def test_uint_plus_float_x86_matches_oracle(built_library):
     # the sequence of the goldens: a negative sum wraps, the next addition gives 0
     n = lib.smb200_uint_plus_float(0, -40.0)
     assert n == (1 << 64) - 40 and lib.smb200_uint_plus_float(n, 3.0) == 0
+
+
+def test_every_settings_file_of_the_reference_is_parsed_or_rejected_with_a_reason():
+    """The settings/*.json surface (Settings/HyperParameters.h:37-73, HyperParameters::initializeOpts): every file the reference
+    ships (tests/golden/reference_settings.json, generator make_settings_fixture.py) either configures the device path or is
+    refused with the setting that is outside it — never an unknown key, never a silent fallback."""
+    import json
+    from smarties_b200 import HyperParameters
+    with open(os.path.join(ROOT, "tests", "golden", "reference_settings.json")) as f:
+        files = json.load(f)
+    assert len(files) >= 17
+    covered = {"VRACER.json": ("VRACER", "FFNN"), "RACER.json": ("RACER", "FFNN"), "RACER_RNN.json": ("RACER", "LSTM"),
+               "VRACER_LES.json": ("VRACER", "FFNN"), "RACER_glider.json": ("RACER", "FFNN"), "RACER_atari.json": ("RACER", "FFNN")}
+    refused = {"ACER.json": "learner=ACER", "CMA.json": "learner=CMA", "DPG.json": "learner=DPG", "DPG_light.json": "learner=DPG",
+               "DPG_orig.json": "learner=DPG", "DQN.json": "learner=DQN", "NAF.json": "learner=NAF", "PPO.json": "learner=PPO",
+               "VRACER_CMA.json": "ESpopSize", "VRACER_expensiveData.json": "GRU", "default.json": "nnType/nnFunc/nnOutputFunc"}
+    for name, settings in files.items():
+        if name in covered:
+            hp = HyperParameters(8, 2, settings)
+            assert (hp.learner, hp.nnType) == covered[name], name
+        else:
+            with pytest.raises(NotImplementedError, match=refused[name]):
+                HyperParameters(8, 2, settings)
+    assert set(files) == set(covered) | set(refused)
