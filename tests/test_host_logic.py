@@ -163,3 +163,21 @@ def test_every_settings_file_of_the_reference_is_parsed_or_rejected_with_a_reaso
             with pytest.raises(NotImplementedError, match=refused[name]):
                 HyperParameters(8, 2, settings)
     assert set(files) == set(covered) | set(refused)
+
+
+def test_binding_loads_the_library_and_dies_loudly_without_a_gpu(tmp_path):
+    """integration/RACER_B200.cpp compiled into the reference (oracle/_ref/b200/, integration/Makefile): the reference's own
+    cart-pole app starts, the wrapped factory picks the device learner, fills smb200_config from the reference's settings and
+    calls smb200_create — which, on a box without a GPU, must end the run with the library's message (never a CPU path)."""
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: tests/test_gpu_dropin.py runs the real thing")
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "b200", "cart_pole")):
+        pytest.skip("oracle/_ref binaries not built (python -c 'import __graft_entry__ as g; g.build()')")
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from dropin_run import SETTINGS, run_arm
+    r = run_arm("b200", steps=500, threads=2, seed=7, settings=dict(SETTINGS), keep_dir=str(tmp_path))
+    assert r["rc"] != 0
+    assert any("learner steps of this agent run on the GPU" in l for l in r["b200_lines"]), r
+    assert "smarties_b200 create" in r["tail"] and "no CPU fallback" in r["tail"], r["tail"][-600:]
