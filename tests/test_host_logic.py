@@ -181,3 +181,17 @@ def test_binding_loads_the_library_and_dies_loudly_without_a_gpu(tmp_path):
     assert r["rc"] != 0
     assert any("learner steps of this agent run on the GPU" in l for l in r["b200_lines"]), r
     assert "smarties_b200 create" in r["tail"] and "no CPU fallback" in r["tail"], r["tail"][-600:]
+
+
+def test_binding_falls_back_to_the_reference_learner_outside_the_device_path(tmp_path):
+    """SMARTIES_B200=1 with a setting the device path does not cover (here the retraceExplore estimator): the wrapped factory
+    hands the agent to the reference's own CPU learner (createLearner_reference) — the app trains, no device learner is created.
+    Runs without a GPU: nothing of the library is called on this path."""
+    import sys
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "b200", "cart_pole")):
+        pytest.skip("oracle/_ref binaries not built (python -c 'import __graft_entry__ as g; g.build()')")
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from dropin_run import SETTINGS, run_arm
+    r = run_arm("b200", steps=1200, threads=2, seed=7, settings=dict(SETTINGS, returnsEstimator="retraceExplore"), keep_dir=str(tmp_path))
+    assert r["rc"] == 0, r
+    assert r["b200_lines"] == [] and r["grad_steps_logged"] >= 1000, r
