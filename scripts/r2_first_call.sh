@@ -26,6 +26,15 @@ EOF
   echo "$case rc=$?" >> $OUT/pending_$case.log
 done
 
+timeout 300 python - > $OUT/pending_full_size.log 2>&1 <<'EOF'
+import os, sys
+root = os.getcwd()
+sys.path[:0] = [root, os.path.join(root, "tests")]
+import test_gpu_zz_pending as t
+exec(compile(t.CHILD_FULL.format(root=root, oracle=os.path.join(root, "oracle"), tests=os.path.join(root, "tests")), "child", "exec"))
+EOF
+echo "full size rc=$?" >> $OUT/pending_full_size.log
+
 timeout 900 python -m pytest tests -m gpu -x -q > $OUT/gpu_tests.log 2>&1
 echo "gpu tests rc=$?" >> $OUT/gpu_tests.log
 
@@ -40,4 +49,4 @@ echo "cluster_layer rc=$?" >> $OUT/cluster_layer.txt
 
 timeout 600 python bench.py > $OUT/bench_1gpu.json 2> $OUT/bench_1gpu.err
 echo "bench rc=$?" >> $OUT/bench_1gpu.err
-tail -3 $OUT/pending.log $OUT/pending_vracer_da1.log $OUT/pending_vracer_explore.log $OUT/gpu_tests.log $OUT/batch_sweep.log $OUT/cluster_layer.txt
+tail -3 $OUT/pending.log $OUT/pending_vracer_da1.log $OUT/pending_vracer_explore.log $OUT/pending_full_size.log $OUT/gpu_tests.log $OUT/batch_sweep.log $OUT/cluster_layer.txt

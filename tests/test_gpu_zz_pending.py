@@ -43,6 +43,42 @@ print("ok")
 """
 
 
+CHILD_FULL = r"""
+import json, os, sys
+sys.path[:0] = [{root!r}, {oracle!r}, {tests!r}]
+import numpy as np
+import bench
+from smarties_b200 import Learner
+z = np.load(os.path.join({tests!r}, "golden", "cfg2_full_props.npz"))
+spec = json.loads(bytes(z["spec"]).decode())
+# the library's own network initialisation at randSeed 42 IS the reference's (tests/test_host_replay.py), the harness ran 1 thread
+L = Learner(32, 8, dict(bench.SETTINGS), seed=spec["seed"], refer_reduce_threads=1)
+L.load_replay(bench.make_workload())
+L.initialize_learner()
+L.seed_sampler(spec["sample_seed"])
+mean, scale, std, rew = L.get_scaling()
+assert np.allclose(mean, z["init/stateMean"], atol=1e-7) and np.allclose(scale, z["init/stateScale"], rtol=1e-6)
+assert np.allclose(rew, z["init/rewards"], rtol=1e-6, atol=1e-8)
+q = L.read_field("QRET")
+assert q.size == 1001000
+assert np.allclose(q[::spec["stride"]], z["init/Qret_sub"], rtol=2e-5, atol=5e-5)
+q64 = q.astype(np.float64)
+assert abs(q64.sum() - z["init/Qret_sum"][0]) < 1e-5 * np.abs(q64).sum()
+assert abs((q64 * q64).sum() - z["init/Qret_sum"][1]) < 1e-4 * z["init/Qret_sum"][1]
+st = L.get_stats()
+assert st["beta"] == z["init/refer"][0] and st["cmax"] == z["init/refer"][1]
+for k in range(spec["steps"]):
+    st = L.train_steps(1)[0]
+    ref = z[f"s{{k}}/post/refer"]
+    assert st["cmax"] == ref[1] and st["cinv"] == ref[2] and st["n_far_policy"] == int(ref[3]), (k, st, ref[:4])
+    assert abs(st["beta"] - ref[0]) <= 1e-12 * ref[0]
+    O, g, X = L.get_last_batch()
+    assert np.abs(O[:, 0] - z[f"s{{k}}/O_V"]).max() < 5e-6, k
+L.close()
+print("ok")
+"""
+
+
 def _run_child(case):
     code = CHILD.format(root=os.path.dirname(HERE), oracle=os.path.join(os.path.dirname(HERE), "oracle"), tests=HERE, case=case)
     env = dict(os.environ, SMB200_UNVERIFIED="1")
@@ -58,3 +94,15 @@ def test_one_action_component_far_policy_count_wraps_like_the_reference():
 @pytest.mark.xfail(strict=False, reason="first run on a B200 pending (written after the round's GPU budget was spent)")
 def test_retrace_explore_estimator_matches_reference():
     _run_child("vracer_explore")
+
+
+@pytest.mark.xfail(strict=False, reason="first run on a B200 pending (written after the round's GPU budget was spent)")
+def test_full_size_run_matches_the_reference_binary():
+    """BASELINE.json configs[1] at its full size (the bench workload) against values of the reference binary at that size
+    (tests/golden/cfg2_full_props.npz): normalisers and Retrace estimates after initializeLearner (subsample + checksums), then
+    three learner steps — ReF-ER scalars, far-policy counts, value outputs of the sampled transitions.  Every ingredient is a
+    verified path; only this combination has not run on a GPU yet."""
+    root = os.path.dirname(HERE)
+    code = CHILD_FULL.format(root=root, oracle=os.path.join(root, "oracle"), tests=HERE)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (r.stdout[-3000:] + "\n" + r.stderr[-3000:])
