@@ -15,7 +15,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.acti
 timeout 400 python -m pytest tests/test_gpu_zz_pending.py -m gpu -q -rxX --tb=long > $OUT/pending.log 2>&1
 echo "pending rc=$?" >> $OUT/pending.log
 # xfail hides the child's report: run the children once more in the open so that a failure shows its assertion
-for case in vracer_da1 vracer_explore; do
+for case in vracer_da1 vracer_explore vracer_b1024; do
   SMB200_UNVERIFIED=1 timeout 200 python - "$case" > $OUT/pending_$case.log 2>&1 <<'EOF'
 import os, sys
 root = os.getcwd()
@@ -49,4 +49,4 @@ echo "cluster_layer rc=$?" >> $OUT/cluster_layer.txt
 
 timeout 600 python bench.py > $OUT/bench_1gpu.json 2> $OUT/bench_1gpu.err
 echo "bench rc=$?" >> $OUT/bench_1gpu.err
-tail -3 $OUT/pending.log $OUT/pending_vracer_da1.log $OUT/pending_vracer_explore.log $OUT/pending_full_size.log $OUT/gpu_tests.log $OUT/batch_sweep.log $OUT/cluster_layer.txt
+tail -3 $OUT/pending.log $OUT/pending_vracer_da1.log $OUT/pending_vracer_explore.log $OUT/pending_vracer_b1024.log $OUT/pending_full_size.log $OUT/gpu_tests.log $OUT/batch_sweep.log $OUT/cluster_layer.txt

@@ -40,6 +40,13 @@ CASES = {
         settings={"learner": "VRACER", "nnLayerSizes": [64, 64], "batchSize": 32, "maxTotObsNum": 1024,
                   "minTotObsNum": 300},
         steps=6, start_step=0, sample_seed=5, bounded=1, full_steps=list(range(6))),
+    # a mini-batch beyond one wave of 4-sample tiles (1024 samples = 256 tiles > the persistent grid's worker CTAs): every CTA
+    # loops over several tiles, no next-mini-batch staging, no helper CTAs — the regime of the batch-size sweep.
+    # Oracle pinned; device case pending (tests/test_gpu_zz_pending.py): nothing above B = 256 has run on a GPU yet.
+    "vracer_b1024": dict(
+        replay=dict(seed=71, n_ep=60, ep_len=(40, 70), dS=12, dA=4),
+        settings={"learner": "VRACER", "nnLayerSizes": [64, 64], "batchSize": 1024, "maxTotObsNum": 8192, "minTotObsNum": 2500},
+        steps=3, start_step=998, sample_seed=17, bounded=0, full_steps=[0, 2]),
     # FIFO pruning: capacity below the stored data, so applyEpisodesRemovalAlgo evicts on step 1
     "vracer_prune": dict(
         replay=dict(seed=17, n_ep=16, ep_len=(20, 30), dS=4, dA=2),

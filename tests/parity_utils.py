@@ -12,7 +12,8 @@ CKPT_CASES = ["vracer_ckpt", "racer_lstm_ckpt"]
 CASES = ["vracer_small", "vracer_cfg2mini", "vracer_bounded", "vracer_prune", "racer_small", "racer_bounded", "vracer_gae"]
 # oracle pinned, device path not built: MGU cells, prioritized samplers (f3)
 ORACLE_ONLY_CASES = ["racer_mgu", "vracer_gru2", "vracer_pererr", "vracer_perseq", "vracer_farpolfrac", "vracer_maxkldiv",
-                     "vracer_minerror", "vracer_perrank", "vracer_explore", "racer_discrete", "vracer_da1"]
+                     "vracer_minerror", "vracer_perrank", "vracer_explore", "racer_discrete", "vracer_da1",
+                     "vracer_b1024"]       # vracer_b1024: inside the device path, first GPU run pending (test_gpu_zz_pending.py)
 RECURRENT_CASES = ["racer_lstm", "vracer_lstm2", "racer_lstm64", "racer_cfg3mini"]     # nnType LSTM + BPTT window (configs[2] family)
 
 

@@ -106,3 +106,12 @@ def test_full_size_run_matches_the_reference_binary():
     code = CHILD_FULL.format(root=root, oracle=os.path.join(root, "oracle"), tests=HERE)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (r.stdout[-3000:] + "\n" + r.stderr[-3000:])
+
+
+@pytest.mark.xfail(strict=False, reason="first run on a B200 pending (written after the round's GPU budget was spent)")
+def test_mini_batch_of_1024_matches_reference():
+    """batchSize 1024 = 256 four-sample tiles, more than the worker CTAs of the persistent grid: every CTA loops over several
+    tiles, the next-mini-batch staging and the helper CTAs are off, the weight gradient contracts four 256-column chunks —
+    the regime of the batch-size sweep, which has not run on a GPU yet.  Golden vracer_b1024 (three steps
+    across the every-1000-steps sweep)."""
+    _run_child("vracer_b1024")
