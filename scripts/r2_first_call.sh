@@ -1,7 +1,7 @@
 #!/bin/bash
 # First gpurun call of the next round: everything that was written after round 1's GPU budget was spent, in one call
 # (≈ 6-8 minutes of box time).  Every step is bounded by its own timeout; outputs land in gpurun_out/r2/.
-#   gpurun --timeout 900 -- bash scripts/r2_first_call.sh
+#   gpurun --timeout 1200 -- bash scripts/r2_first_call.sh
 # 1. the pending device cases (x86 `Uint += float` count with one action component; retraceExplore sweep)
 # 2. the whole GPU suite (regression check of round 1's state on a fresh box)
 # 3. batch-size sweep of the MLP step (256 ... 65 536), one process per batch size
@@ -12,9 +12,8 @@ OUT=gpurun_out/r2
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv > $OUT/gpu.txt 2>&1
 
-timeout 400 python -m pytest tests/test_gpu_zz_pending.py -m gpu -q -rxX --tb=long > $OUT/pending.log 2>&1
-echo "pending rc=$?" >> $OUT/pending.log
-# xfail hides the child's report: run the children once more in the open so that a failure shows its assertion
+# the pending cases in the open (under pytest they are non-strict xfails whose report is hidden); the full suite below
+# lists them again as XPASS / XFAIL (-rxX)
 for case in vracer_da1 vracer_explore vracer_b1024; do
   SMB200_UNVERIFIED=1 timeout 200 python - "$case" > $OUT/pending_$case.log 2>&1 <<'EOF'
 import os, sys
@@ -35,7 +34,7 @@ exec(compile(t.CHILD_FULL.format(root=root, oracle=os.path.join(root, "oracle"),
 EOF
 echo "full size rc=$?" >> $OUT/pending_full_size.log
 
-timeout 900 python -m pytest tests -m gpu -x -q > $OUT/gpu_tests.log 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q -rxX > $OUT/gpu_tests.log 2>&1
 echo "gpu tests rc=$?" >> $OUT/gpu_tests.log
 
 : > $OUT/batch_sweep.log
@@ -49,4 +48,4 @@ echo "cluster_layer rc=$?" >> $OUT/cluster_layer.txt
 
 timeout 600 python bench.py > $OUT/bench_1gpu.json 2> $OUT/bench_1gpu.err
 echo "bench rc=$?" >> $OUT/bench_1gpu.err
-tail -3 $OUT/pending.log $OUT/pending_vracer_da1.log $OUT/pending_vracer_explore.log $OUT/pending_vracer_b1024.log $OUT/pending_full_size.log $OUT/gpu_tests.log $OUT/batch_sweep.log $OUT/cluster_layer.txt
+tail -3 $OUT/pending_vracer_da1.log $OUT/pending_vracer_explore.log $OUT/pending_vracer_b1024.log $OUT/pending_full_size.log $OUT/gpu_tests.log $OUT/batch_sweep.log $OUT/cluster_layer.txt
