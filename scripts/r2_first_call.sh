@@ -25,14 +25,17 @@ EOF
   echo "$case rc=$?" >> $OUT/pending_$case.log
 done
 
-timeout 300 python - > $OUT/pending_full_size.log 2>&1 <<'EOF'
+: > $OUT/pending_full_size.log
+for fx in cfg2_full_props.npz cfg3_full_props.npz; do
+  timeout 300 python - "$fx" >> $OUT/pending_full_size.log 2>&1 <<'EOF'
 import os, sys
 root = os.getcwd()
 sys.path[:0] = [root, os.path.join(root, "tests")]
 import test_gpu_zz_pending as t
-exec(compile(t.CHILD_FULL.format(root=root, oracle=os.path.join(root, "oracle"), tests=os.path.join(root, "tests")), "child", "exec"))
+exec(compile(t.CHILD_FULL.format(root=root, oracle=os.path.join(root, "oracle"), tests=os.path.join(root, "tests"), fixture=sys.argv[1]), "child", "exec"))
 EOF
-echo "full size rc=$?" >> $OUT/pending_full_size.log
+  echo "full size $fx rc=$?" >> $OUT/pending_full_size.log
+done
 
 timeout 900 python -m pytest tests -m gpu -x -q -rxX > $OUT/gpu_tests.log 2>&1
 echo "gpu tests rc=$?" >> $OUT/gpu_tests.log

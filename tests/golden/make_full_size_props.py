@@ -2,7 +2,7 @@
 BASELINE.json configs[1] (the workload of bench.py: 1000 episodes x 1000 steps = 1 M transitions, 32 states, 8 actions,
 MLP(128,128), batch 256, randSeed 42, sampler seed 7): the sampled (episode, t) of three learner steps, the ReF-ER scalars
 around them, the reward / state normalisers and the Retrace estimates after initializeLearner as checksums and a strided
-subsample (the full arrays are 4 MB each).  Run in the build container:  python tests/golden/make_full_size_props.py"""
+subsample (the full arrays are 4 MB each).  Run in the build container:  python tests/golden/make_full_size_props.py [cfg3]"""
 import json
 import os
 import subprocess
@@ -20,16 +20,21 @@ from smarties_b200 import synth  # noqa: E402
 HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 STEPS, SAMPLE_SEED, STRIDE = 3, 7, 997
 
+# configs[1] (cfg2_full_props.npz) and configs[2] (cfg3_full_props.npz: RACER + LSTM(64), nnBPTTseq 32, batch 128, same buffer)
+CFG3 = {"learner": "RACER", "nnType": "LSTM", "nnLayerSizes": [64], "nnBPTTseq": 32, "batchSize": 128, "clipImpWeight": 4,
+        "explNoise": 0.1, "gamma": 0.99, "epsAnneal": 0, "nnLambda": 1e-6, "maxTotObsNum": 1048576, "minTotObsNum": 1000000}
+NAME, SETTINGS = ("cfg3_full_props.npz", CFG3) if sys.argv[1:] == ["cfg3"] else ("cfg2_full_props.npz", bench.SETTINGS)
+
 d = bench.make_workload()
 with tempfile.TemporaryDirectory() as tmp:
     synth.write_replay_file(os.path.join(tmp, "data.bin"), d)
     with open(os.path.join(tmp, "settings.json"), "w") as f:
-        json.dump(bench.SETTINGS, f)
+        json.dump(SETTINGS, f)
     subprocess.run([HARNESS, "--data", "data.bin", "--settings", "settings.json", "--steps", str(STEPS), "--threads", "1",
                     "--sampleSeed", str(SAMPLE_SEED), "--dump", "out.bin", "--dumpSteps", "0,1,2", "--quiet"],
                    cwd=tmp, check=True, stdout=subprocess.DEVNULL, env=dict(os.environ, OMP_NUM_THREADS="1"))
     D = synth.read_dump(os.path.join(tmp, "out.bin"))
-keep = {"spec": np.frombuffer(json.dumps(dict(workload=bench.WORKLOAD, settings=bench.SETTINGS, steps=STEPS, sample_seed=SAMPLE_SEED,
+keep = {"spec": np.frombuffer(json.dumps(dict(workload=bench.WORKLOAD, settings=SETTINGS, steps=STEPS, sample_seed=SAMPLE_SEED,
                                               stride=STRIDE, seed=42)).encode(), dtype=np.uint8)}
 for k in ("init/refer", "init/stateMean", "init/stateScale", "init/stateStdDev", "init/rewards", "init/epLen"):
     keep[k] = D[k]
@@ -40,6 +45,6 @@ for s in range(STEPS):
     for k in ("sampledEpID", "sampledT", "pre/refer", "post/refer"):
         keep[f"s{s}/{k}"] = D[f"s{s}/{k}"]
     keep[f"s{s}/O_V"] = np.asarray(D[f"s{s}/O"][:, 0], np.float64)          # value outputs of the sampled transitions
-path = os.path.join(HERE, "cfg2_full_props.npz")
+path = os.path.join(HERE, NAME)
 np.savez_compressed(path, **keep)
 print(path, os.path.getsize(path) // 1024, "KiB", sorted(keep))

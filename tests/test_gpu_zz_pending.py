@@ -49,10 +49,10 @@ sys.path[:0] = [{root!r}, {oracle!r}, {tests!r}]
 import numpy as np
 import bench
 from smarties_b200 import Learner
-z = np.load(os.path.join({tests!r}, "golden", "cfg2_full_props.npz"))
+z = np.load(os.path.join({tests!r}, "golden", {fixture!r}))
 spec = json.loads(bytes(z["spec"]).decode())
 # the library's own network initialisation at randSeed 42 IS the reference's (tests/test_host_replay.py), the harness ran 1 thread
-L = Learner(32, 8, dict(bench.SETTINGS), seed=spec["seed"], refer_reduce_threads=1)
+L = Learner(32, 8, dict(spec["settings"]), seed=spec["seed"], refer_reduce_threads=1)
 L.load_replay(bench.make_workload())
 L.initialize_learner()
 L.seed_sampler(spec["sample_seed"])
@@ -97,13 +97,15 @@ def test_retrace_explore_estimator_matches_reference():
 
 
 @pytest.mark.xfail(strict=False, reason="first run on a B200 pending (written after the round's GPU budget was spent)")
-def test_full_size_run_matches_the_reference_binary():
-    """BASELINE.json configs[1] at its full size (the bench workload) against values of the reference binary at that size
-    (tests/golden/cfg2_full_props.npz): normalisers and Retrace estimates after initializeLearner (subsample + checksums), then
-    three learner steps — ReF-ER scalars, far-policy counts, value outputs of the sampled transitions.  Every ingredient is a
-    verified path; only this combination has not run on a GPU yet."""
+@pytest.mark.parametrize("fixture", ["cfg2_full_props.npz", "cfg3_full_props.npz"])
+def test_full_size_run_matches_the_reference_binary(fixture):
+    """BASELINE.json configs[1] (the bench workload) and configs[2] (RACER + LSTM(64), BPTT 32, batch 128 on the same buffer) at
+    their full size against values of the reference binary at that size (tests/golden/cfg{2,3}_full_props.npz): normalisers and
+    Retrace estimates after initializeLearner (subsample + checksums), then three learner steps — ReF-ER scalars, far-policy
+    counts, value outputs of the sampled transitions.  Every ingredient is a verified path; only this combination has not run
+    on a GPU yet."""
     root = os.path.dirname(HERE)
-    code = CHILD_FULL.format(root=root, oracle=os.path.join(root, "oracle"), tests=HERE)
+    code = CHILD_FULL.format(root=root, oracle=os.path.join(root, "oracle"), tests=HERE, fixture=fixture)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (r.stdout[-3000:] + "\n" + r.stderr[-3000:])
 

@@ -455,17 +455,19 @@ def test_replay_under_churn_matches_the_reference_sequence_and_keeps_the_ring_co
     assert int(rows.sum()) > 2 * cap
 
 
-def test_host_sampler_at_full_buffer_size_matches_the_reference_binary(built_library):
-    """The workload of bench.py (BASELINE.json configs[1]: 1000 x 1000-step episodes = 1 M transitions, batch 256): the sampled
-    (episode, t) of the reference binary's first three learner steps (tests/golden/cfg2_full_props.npz, generator
-    make_full_size_props.py) against the library's host sampler: identical."""
+@pytest.mark.parametrize("fixture,batch", [("cfg2_full_props.npz", 256), ("cfg3_full_props.npz", 128)])
+def test_host_sampler_at_full_buffer_size_matches_the_reference_binary(built_library, fixture, batch):
+    """The workload of bench.py (BASELINE.json configs[1]: 1000 x 1000-step episodes = 1 M transitions, batch 256) and configs[2]
+    on the same buffer (RACER + LSTM(64), batch 128): the sampled (episode, t) of the reference binary's first three learner
+    steps (tests/golden/cfg{2,3}_full_props.npz, generator make_full_size_props.py) against the library's host sampler: identical."""
     import json
     from smarties_b200 import load_library
-    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cfg2_full_props.npz"))
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", fixture))
     spec = json.loads(bytes(z["spec"]).decode())
     rows = np.asarray(z["init/epLen"], np.int32)
     assert rows.size == 1000 and int((rows - 1).sum()) == 1_000_000
-    rc, ep, t, n_after, _ = _trace(load_library(), 256, spec["settings"]["maxTotObsNum"], np.arange(rows.size), rows,
+    assert spec["settings"].get("batchSize", 256) == batch
+    rc, ep, t, n_after, _ = _trace(load_library(), batch, spec["settings"]["maxTotObsNum"], np.arange(rows.size), rows,
                                    np.zeros(rows.size, np.int32), spec["sample_seed"], spec["steps"])
     assert rc == 0 and np.all(n_after == rows.size)
     for k in range(spec["steps"]):
