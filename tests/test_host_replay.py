@@ -472,3 +472,42 @@ def test_host_sampler_at_full_buffer_size_matches_the_reference_binary(built_lib
     assert rc == 0 and np.all(n_after == rows.size)
     for k in range(spec["steps"]):
         assert np.array_equal(ep[k], z[f"s{k}/sampledEpID"]) and np.array_equal(t[k], z[f"s{k}/sampledT"]), k
+
+
+def test_retrace_at_full_buffer_size_matches_the_reference_binary(built_library):
+    """rescaleAllReturnEstimator after initializeLearner on the 1 M-transition buffer of bench.py: the scalar functions of the
+    sweep kernels (reward scaling with the reference's own normalisers, clipped importance weight, recursion order), run on the
+    host over all 1000 episodes, against the reference binary's Q_ret at that size (subsample and checksums of
+    tests/golden/cfg2_full_props.npz)."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")))
+    import bench
+    from smarties_b200 import load_library
+    lib = load_library()
+    lib.smb200_host_return_estimator.restype = C.c_double
+    fp = C.POINTER(C.c_float)
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cfg2_full_props.npz"))
+    spec = json.loads(bytes(z["spec"]).decode())
+    d = bench.make_workload()
+    rmean, rscale = float(z["init/rewards"][0]), float(z["init/rewards"][1])
+    out = []
+    for e in range(len(d["N"])):
+        o, N = int(d["start"][e]), int(d["N"][e])
+        R = np.ascontiguousarray(d["R"][o:o + N], np.float32).copy(); R[0] = 0.0
+        V = np.zeros(N, np.float32); A = np.zeros(N, np.float32)
+        W = np.ones(N, np.float32); W[-1] = 0.0                      # Episode::finalize: impW 1 except the last row
+        Q = np.zeros(N, np.float32)
+        err = lib.smb200_host_return_estimator(C.c_int32(N), C.c_int32(int(d["term"][e])), C.c_int32(0), R.ctypes.data_as(fp),
+                                               V.ctypes.data_as(fp), A.ctypes.data_as(fp), W.ctypes.data_as(fp), Q.ctypes.data_as(fp),
+                                               C.c_double(0.995), C.c_double(1.0), C.c_float(rmean), C.c_float(rscale), C.c_double(0.0))
+        assert err >= 0
+        out.append(Q)
+    q = np.concatenate(out)
+    assert q.size == 1001000
+    sub = q[::spec["stride"]]
+    assert np.array_equal(sub, z["init/Qret_sub"])                 # bit-identical to the reference binary (1005 of 1005 values)
+    q64 = q.astype(np.float64)
+    assert abs(q64.sum() - z["init/Qret_sum"][0]) < 1e-6 * np.abs(q64).sum()
+    assert abs((q64 * q64).sum() - z["init/Qret_sum"][1]) < 1e-6 * z["init/Qret_sum"][1]
+    assert abs(np.abs(q64).max() - z["init/Qret_sum"][2]) < 1e-5
