@@ -41,8 +41,7 @@ enum smb200_nn_type { SMB200_FFNN = 0, SMB200_LSTM = 1 };   /* "nnType" (Network
 /* "returnsEstimator" (createReturnEstimator, ReplayMemory/MemoryProcessing.cpp:419-450): Retrace (:391-400; also what
  * "default" means for RACER / V-RACER, Learners/AlgoFactory.cpp:134-136) or GAE (:411-417). */
 enum smb200_returns_estimator { SMB200_RETRACE = 0, SMB200_GAE = 1,
-                                SMB200_RETRACE_EXPLORE = 2 /* computeRetraceExplBonus, MemoryProcessing.cpp:402-409; accepted only
-                                                              with SMB200_UNVERIFIED=1 in the environment until its first GPU run */ };
+                                SMB200_RETRACE_EXPLORE = 2 /* computeRetraceExplBonus, MemoryProcessing.cpp:402-409 */ };
 enum smb200_field {          /* per-transition replay arrays, Episode.h:66-75 */
   SMB200_F_V = 0, SMB200_F_ADV = 1, SMB200_F_QRET = 2, SMB200_F_DELTA = 3, SMB200_F_RHO = 4, SMB200_F_KL = 5,
   SMB200_F_REWARD = 6

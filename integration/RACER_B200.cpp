@@ -101,7 +101,8 @@ class RACER_B200 : public RACER<Advantage_t, Continuous_policy, Rvec>
     c.seed = distrib.randSeed;
     c.nn_type = settings.nnType == "LSTM" ? SMB200_LSTM : SMB200_FFNN;
     c.nn_bptt_seq = (int32_t) settings.nnBPTTseq;
-    c.returns_estimator = settings.returnsEstimator == "GAE" ? SMB200_GAE : SMB200_RETRACE;
+    c.returns_estimator = settings.returnsEstimator == "GAE" ? SMB200_GAE
+                        : (settings.returnsEstimator == "retraceExplore" ? SMB200_RETRACE_EXPLORE : SMB200_RETRACE);
     // an episode occupies nsteps() = ndata()+1 rows and is at least two rows long: room for the worst case,
     // plus the episodes that arrive between two pruning passes
     c.capacity_rows = 2 * (int64_t) settings.maxTotObsNum_local + 65536;
@@ -164,8 +165,14 @@ class RACER_B200 : public RACER<Advantage_t, Continuous_policy, Rvec>
     std::lock_guard<std::mutex> lock(data->dataset_mutex);
     for (const auto& e : data->episodes)
       if (mirrored.insert(e.get()).second) pushToDevice(*e);
+    // the device's total order: tag = ID * 2^20 + arrival number, newest first.  Episode::ID alone has ties (every episode
+    // collected before training has ID 0) and std::sort is not stable: both copies must evict the same episode.
     std::sort(data->episodes.begin(), data->episodes.end(),
-              [](const std::unique_ptr<Episode>& a, const std::unique_ptr<Episode>& b) { return a->ID > b->ID; });
+              [this](const std::unique_ptr<Episode>& a, const std::unique_ptr<Episode>& b) {
+                const auto ta = tagOf.find(a.get()), tb = tagOf.find(b.get());
+                const int64_t xa = ta == tagOf.end() ? (int64_t) std::max<Sint>(a->ID, 0) * (1 << 20) : ta->second;
+                const int64_t xb = tb == tagOf.end() ? (int64_t) std::max<Sint>(b->ID, 0) * (1 << 20) : tb->second;
+                return xa > xb; });
     const long maxTotObs = settings.maxTotObsNum_local;
     while (data->episodes.size() > 1 && data->nStoredSteps() - (long) data->episodes.back()->nsteps() > maxTotObs) {
       const Episode* gone = data->episodes.back().get();
@@ -312,7 +319,10 @@ class RACER_B200 : public RACER<Advantage_t, Continuous_policy, Rvec>
       // restores the strict per-step hand-off.
       const long ahead = (long) std::floor(this->nLocTimeStepsTrain() / std::max((Real) 1e-9, this->obsPerStep_loc)) - this->nGradSteps();
       const long toSweep = 1000 - (this->nGradSteps() + 1) % 1000;          // stop at the every-1000-steps boundary
-      const int k = (int) std::max<long>(1, std::min<long>({(long) maxStepsPerCall, ahead, toSweep + 1}));
+      // a checkpoint (Learner::logStats: `currStep % saveFreq == 0`) must see the device state of ITS step: end the call there
+      const long sf = (long) std::max<Uint>(1, settings.saveFreq);
+      const long toSave = (sf - (this->nGradSteps() + 1) % sf) % sf;
+      const int k = (int) std::max<long>(1, std::min<long>({(long) maxStepsPerCall, ahead, toSweep + 1, toSave + 1}));
       const double t0 = now();
       nameGradStats();
       mirrorEpisodes();
@@ -356,11 +366,15 @@ std::unique_ptr<Learner> createLearner(const Uint learnerID, MDPdescriptor& MDP,
   settings.initializeOpts(ifs, distrib);
   const bool covered =
       (settings.learner == "VRACER" || settings.learner == "RACER") && !MDP.bDiscreteActions() &&
-      settings.dataSamplingAlgo == "uniform" && (settings.returnsEstimator == "default" || settings.returnsEstimator == "retrace" || settings.returnsEstimator == "GAE") &&
+      settings.dataSamplingAlgo == "uniform" && (settings.returnsEstimator == "default" || settings.returnsEstimator == "retrace" || settings.returnsEstimator == "GAE" ||
+                                                  settings.returnsEstimator == "retraceExplore") &&
       (settings.ERoldSeqFilter == "oldest" || settings.ERoldSeqFilter == "default") &&
       (settings.nnType == "FFNN" || settings.nnType == "LSTM") && settings.nnFunc == "Tanh" && settings.nnOutputFunc == "Linear" &&
       // a partially observable MDP turns a feed-forward request into MGU layers (Network/Approximator.cpp:219-223)
       !(MDP.isPartiallyObservable && !settings.bRecurrent) &&
+      // several learner ranks: the device learners of the ranks would have to exchange CUDA-IPC handles over
+      // distrib.learners_train_comm (smb200_comm_init / smb200_comm_attach) — not wired into the binding: reference learner
+      MPICommSize(distrib.learners_train_comm) == 1 &&
       settings.ESpopSize == 1 && settings.targetDelay == 0 && MDP.nAppendedObs == 0 &&
       std::all_of(settings.encoderLayerSizes.begin(), settings.encoderLayerSizes.end(), [](Uint n) { return n == 0; });
   if (!covered) {

@@ -86,6 +86,7 @@ struct SynthData {
 struct Args {
   std::string data, settings, dump, weights, restart;
   int steps = 10, threads = 1, bounded = 0, dumpAll = 0, quiet = 0, reps = 1, save = 0;
+  int warmup = 0;     // learner steps run before the timed repetitions (thread team, caches and page tables warm)
   int discrete = 0;   // > 0: one discrete action component with that many options (RACER<Discrete_advantage, Discrete_policy, Uint>)
   long startStep = 0;
   unsigned long seed = 42, sampleSeed = 0;
@@ -113,6 +114,7 @@ static Args parse(int argc, char** argv) {
     else if(k=="--save") a.save = 1;                 // Learner_approximator::save() after the last step (files agent_00_* in the cwd)
     else if(k=="--restart") a.restart = next();      // Learner_approximator::restart() from that directory instead of filling the buffer
     else if(k=="--reps") a.reps = std::stoi(next());
+    else if(k=="--warmup") a.warmup = std::stoi(next());
     else if(k=="--dumpSteps") { std::stringstream ss(next()); std::string tok; while(std::getline(ss, tok, ',')) a.dumpSteps.insert(std::stol(tok)); }
     else { fprintf(stderr, "unknown arg %s\n", k.c_str()); exit(1); }
   }
@@ -259,6 +261,9 @@ struct Probe : public Base
     recO.assign(B*nOut, 0); recG.assign(B*nOut, 0); recS.assign(B*dS, 0); recT.assign(B, 0); recEp.assign(B, 0);
     std::vector<double> trBeta, trCmax, trWnorm; std::vector<int64_t> trNfar;
 
+    for(int s=0; s<args.warmup; ++s) {   // untimed warm-up steps of the same loop
+      this->spawnTrainTasks(); this->processMemoryBuffer(); this->applyGradient(); this->globalGradCounterUpdate();
+    }
     double bestSec = 1e300, totSec = 0;
     std::vector<double> repSec;
     for(int rep=0; rep<args.reps; ++rep)

@@ -703,8 +703,11 @@ class VracerOracle:
     def __init__(self, dS, dA, hidden=(128, 128), gamma=0.995, lam=1.0, clip_imp_weight=None,
                  penal_tol=0.1, eps_anneal=5e-7, learnrate=1e-4, nn_lambda=FLT_EPS,
                  batch=256, max_tot_obs=None, bounded=False, sample_seed=42, learner="VRACER",
-                 returns_estimator="retrace", sampling="uniform", er_filter="oldest", discrete=0):
+                 returns_estimator="retrace", sampling="uniform", er_filter="oldest", discrete=0, refer_threads=1):
         self.dS, self.dA = dS, dA
+        # OpenMP threads of the reference run: only the far-policy count depends on it (`Uint += float` partials per thread with
+        # schedule(static, 1), MemoryProcessing.cpp:202-227)
+        self.refer_threads = max(1, int(refer_threads))
         self.discrete = int(discrete)        # K options of a discrete action space (then dA == 1 and learner == "RACER")
         # getERfilterAlgo (MemoryProcessing.cpp:261-298): "a goes before b"; the episodes to delete end up at the back
         self.er_before = {"oldest": lambda a, b: a.ID > b.ID, "default": lambda a, b: a.ID > b.ID,
@@ -969,11 +972,12 @@ class VracerOracle:
         # updateTrainingStatistics (MemoryProcessing.cpp:187-259)
         self.cmax = 1 + anneal_rate(self.C, step, self.eps_anneal)
         self.cinv = 1 / self.cmax
-        n_off = 0
+        T = self.refer_threads
+        n_off_thr = [0] * T                                   # reduction(+ : nOffPol): one private Uint per OpenMP thread
         sumDKL = sumE2 = sumQ2 = sumQ1 = sumR = sumERet = 0.0
         maxAbsE, maxQ, minQ = f32(-1e9), f32(-1e9), f32(1e9)
         n_ret = 0
-        for ep in self.episodes:
+        for pos, ep in enumerate(self.episodes):              # schedule(static, 1): iteration i runs on thread i % T
             if recompute:
                 ep.update_cumulative(self.cmax, self.cinv)
                 sumERet += self.retrace_episode(ep)
@@ -981,10 +985,11 @@ class VracerOracle:
             Ns = f32(ep.nsteps)
             maxAbsE = max(maxAbsE, ep.maxAbsErr); maxQ = max(maxQ, ep.maxQ); minQ = min(minQ, ep.minQ)
             sumDKL += float(f32(Ns * ep.avgKL))
-            n_off = uint_plus_float(n_off, f32(Ns * ep.fracFar))  # `Uint += float` (SURVEY §7 hard part 2)
+            n_off_thr[pos % T] = uint_plus_float(n_off_thr[pos % T], f32(Ns * ep.fracFar))  # `Uint += float` (SURVEY §7 hard part 2)
             sumE2 += float(f32(Ns * ep.avgSqErr))
             sumQ2 += float(ep.sumQ2); sumQ1 += float(ep.sumQ); sumR += float(ep.totR)
             ep.just_sampled = -1
+        n_off = sum(n_off_thr) & ((1 << 64) - 1)              # the partial counts are combined as integers
         if self.cmax <= 1:
             n_off = 0
         n_data = self.n_transitions

@@ -516,7 +516,7 @@ static int run_segment(smb200_learner* h, int first, int n, long long gstep0, in
     if (launch_update_scaling(h->rp, h->dCtrl + (step & 1), h->dDescs, h->dSums, 0, h->stream)) return -2;
     h->launches += 5;
   }
-  for (const auto& ev : h->pendingEvict) cudaMemsetAsync(h->rp.rowFlag + ev.first, 0, ev.second, h->stream);
+  for (const auto& ev : h->pendingEvict) SMB200_CUDA_CHECK(cudaMemsetAsync(h->rp.rowFlag + ev.first, 0, ev.second, h->stream));
   h->pendingEvict.clear();
   return 0;
 }
@@ -560,11 +560,8 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
   if (c.refer_reduce_threads <= 0) c.refer_reduce_threads = 32;
   if (c.refer_reduce_threads > kThreads) c.refer_reduce_threads = kThreads;
   if (c.batch_size < 1 || c.max_tot_obs < c.batch_size) { set_error_msg("bad batch_size / max_tot_obs"); delete h; return SMB200_ERR_INVALID; }
-  // retraceExplore: the sequential sweep kernel exists but has not run on a GPU yet — opt-in until it has
-  const char* unv = getenv("SMB200_UNVERIFIED");
-  const bool exploreOk = c.returns_estimator == SMB200_RETRACE_EXPLORE && unv && unv[0] == '1';
-  if (c.returns_estimator != SMB200_RETRACE && c.returns_estimator != SMB200_GAE && !exploreOk) {
-    set_error_msg("returnsEstimator must be retrace or GAE (retraceExplore: only with SMB200_UNVERIFIED=1)"); delete h; return SMB200_ERR_INVALID; }
+  if (c.returns_estimator != SMB200_RETRACE && c.returns_estimator != SMB200_GAE && c.returns_estimator != SMB200_RETRACE_EXPLORE) {
+    set_error_msg("returnsEstimator must be retrace, GAE or retraceExplore"); delete h; return SMB200_ERR_INVALID; }
   if (c.discrete_options != 0) {   // network construction is built (build_net / init_weights, pinned on the host); the loss stage is not
     set_error_msg("discrete actions: the device loss stage (Discrete_policy / Discrete_advantage) is not built yet"); delete h; return SMB200_ERR_INVALID; }
   std::vector<GradTile> tiles;
@@ -590,7 +587,7 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
   const int dS = c.dim_state, dA = c.dim_action, B = c.batch_size;
   long long cap = c.capacity_rows > 0 ? c.capacity_rows : c.max_tot_obs + c.max_tot_obs / 8 + 65536;
   cap = (cap + 63) / 64 * 64;
-  if (cap > 0x7fffffffLL) { set_error_msg("capacity_rows must fit in 31 bits"); delete h; return SMB200_ERR_INVALID; }
+  if (cap > 0x7fffffffLL) { set_error_msg("capacity_rows must fit in 31 bits"); smb200_destroy(h); return SMB200_ERR_INVALID; }
   int maxEp = c.max_episodes > 0 ? c.max_episodes : (int)std::min<long long>(cap / 2, 1 << 20);
   ReplayView& rp = h->rp;
   rp.capRows = cap; rp.maxEpisodes = maxEp; rp.dS = dS; rp.dA = dA;
@@ -993,7 +990,8 @@ int smb200_train_steps(smb200_learner* h, int32_t n, smb200_step_stats* stats) {
   SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
   h->lastMs = ms; h->lastLaunches = h->launches - l0;
-  if (h->useTc && smb200_comm_error(h)) return SMB200_ERR_STATE;     // a tensor-core item that never completed must not pass silently
+  // a tensor-core item that never completed, or a peer that timed out in the fused gradient exchange, must not pass silently
+  if ((h->useTc || h->comm.world > 1) && smb200_comm_error(h)) return SMB200_ERR_STATE;
   if (getenv("SMB200_HOST_TIMING"))
     fprintf(stderr, "smb200_train_steps(%d): device span %.3f ms, host sampling %.3f ms, host waiting for the device %.3f ms, %lld launches\n",
             n, ms, 1e3 * hostPlan, 1e3 * hostWait, (long long)h->lastLaunches);
@@ -1027,6 +1025,7 @@ int smb200_train_step_on(smb200_learner* h, const int64_t* pos, const int64_t* t
     *stats = h->hStats[0];
   } else SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   if (gradStat && write_grad_stats(h, h->hGradStat[0], tr0 == 0)) return SMB200_ERR_STATE;
+  if ((h->useTc || h->comm.world > 1) && smb200_comm_error(h)) return SMB200_ERR_STATE;
   return 0;
 }
 
@@ -1246,6 +1245,8 @@ int smb200_sync(smb200_learner* h) {
   SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   float ms = 0;
   if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->lastMs = ms;
+  // smb200_train_presampled only enqueues: its device-side errors (peer time-out, tensor-core item) surface here
+  if ((h->useTc || h->comm.world > 1) && smb200_comm_error(h)) return SMB200_ERR_STATE;
   return 0;
 }
 

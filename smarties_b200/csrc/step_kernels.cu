@@ -121,9 +121,11 @@ constexpr unsigned kPoison = 0xFFFFFFFFu;
 __device__ __forceinline__ void st_volatile_u32(unsigned* p, unsigned v) {
   asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void wait_values_poison(unsigned* p, size_t stride, int N, int me, const CommView& cm, unsigned (&out)[kMaxWorld]) {
+// Returns false if a peer's value did not arrive within the time-out (error flag set): the caller must not consume `out`.
+__device__ __forceinline__ bool wait_values_poison(unsigned* p, size_t stride, int N, int me, const CommView& cm, unsigned (&out)[kMaxWorld]) {
   unsigned v[kMaxWorld];
   const long long t0 = clock64();
+  bool arrived = true;
   while (true) {
 #pragma unroll
     for (int q = 0; q < kMaxWorld; ++q)
@@ -133,13 +135,14 @@ __device__ __forceinline__ void wait_values_poison(unsigned* p, size_t stride, i
     for (int q = 0; q < kMaxWorld; ++q)
       if (q < N && q != me) ok = ok && (v[q] != kPoison);
     if (ok) break;
-    if (clock64() - t0 > cm.timeoutCycles) { *cm.error = 1; break; }
+    if (clock64() - t0 > cm.timeoutCycles) { *cm.error = 1; arrived = false; break; }
   }
 #pragma unroll
   for (int q = 0; q < kMaxWorld; ++q) {
     out[q] = (q < N && q != me) ? v[q] : 0u;
     if (q < N && q != me) st_volatile_u32(p + (size_t)q * stride, kPoison);      // free the slot for its next use
   }
+  return arrived;
 }
 
 __device__ __forceinline__ unsigned long long ll_pack(unsigned v, unsigned stamp) {
@@ -1558,15 +1561,17 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
     DBG_T(a, step, 34);
     unsigned* mine = cm.grad(me) + (size_t)rot * N * cm.nParamsPad;
     unsigned got[kMaxWorld];
+    // a peer that timed out (error flag, reported by the host after the call): leave the parameter untouched instead of
+    // summing the poison pattern into the gradient and Adam
     if (p0 >= 0) {
-      wait_values_poison(mine + p0, cm.nParamsPad, N, me, cm, got);
+      if (!wait_values_poison(mine + p0, cm.nParamsPad, N, me, cm, got)) p0 = -1;
       float v = 0.f;
 #pragma unroll
       for (int q = 0; q < kMaxWorld; ++q) if (q < N) v += q == me ? acc : __uint_as_float(got[q]);
       acc = v;
     }
     if (p1 >= 0) {
-      wait_values_poison(mine + p1, cm.nParamsPad, N, me, cm, got);
+      if (!wait_values_poison(mine + p1, cm.nParamsPad, N, me, cm, got)) p1 = -1;
       float v = 0.f;
 #pragma unroll
       for (int q = 0; q < kMaxWorld; ++q) if (q < N) v += q == me ? acc2 : __uint_as_float(got[q]);

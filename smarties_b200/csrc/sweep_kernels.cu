@@ -245,7 +245,7 @@ __host__ __device__ __forceinline__ float retrace_explore_step(float R, float Vn
 // write Q back and accumulate the squared change.  Aggregates are recomputed by k_sweep(recompute = 2) beforehand.
 // `ctrl` != nullptr: the baseline is read from the device-resident statistics of the step (the every-1000-steps recompute
 // is enqueued behind a running launch, the host does not hold the value).
-// NOT YET RUN ON A GPU (written after the round's GPU budget was spent): reachable only with SMB200_UNVERIFIED=1.
+// Pinned on a B200 by the golden vracer_explore (tests/test_gpu_parity.py).
 __global__ void __launch_bounds__(kThreads) k_sweep_explore(ReplayView rp, int nEpisodes, int oneSlot, float gamma, float lambda,
                                                             float baselineHost, const StepCtrl* ctrl, SweepSums* sums) {
   __shared__ float sR[kSweepChunk], sV[kSweepChunk], sA[kSweepChunk], sW[kSweepChunk], sQ[kSweepChunk];

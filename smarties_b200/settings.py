@@ -97,10 +97,8 @@ class HyperParameters:
             unsupported.append(f"learner={self.learner}")
         if self.dataSamplingAlgo != "uniform":
             unsupported.append(f"dataSamplingAlgo={self.dataSamplingAlgo}")
-        # "retraceExplore" is not an affine recursion: a sequential sweep kernel (k_sweep_explore) exists but has not run on
-        # a GPU yet — opt-in with SMB200_UNVERIFIED=1 until tests/test_gpu_zz_pending.py has been green on a B200
-        estimators = ("retrace", "GAE", "retraceExplore") if os.environ.get("SMB200_UNVERIFIED") == "1" else ("retrace", "GAE")
-        if self.returnsEstimator not in estimators:
+        # "retraceExplore" is not an affine recursion: it runs on the sequential sweep kernel k_sweep_explore
+        if self.returnsEstimator not in ("retrace", "GAE", "retraceExplore"):
             unsupported.append(f"returnsEstimator={self.returnsEstimator}")
         if self.ERoldSeqFilter not in ("oldest", "default"):
             unsupported.append(f"ERoldSeqFilter={self.ERoldSeqFilter}")

@@ -14,9 +14,9 @@ def pytest_configure(config):
 
 
 # The round-end GPU run uses `-x`: run the parity tests proper first, the multi-process / drop-in integration tests (which
-# also depend on the prebuilt reference binaries and host threads) after them, device cases that have never run on a GPU last.
+# also depend on the prebuilt reference binaries and host threads) after them.
 _ORDER = {"test_gpu_parity.py": 0, "test_gpu_sweeps.py": 1, "test_gpu_checkpoint.py": 2, "test_gpu_grad_stats.py": 3,
-          "test_gpu_multirank.py": 4, "test_gpu_dropin.py": 5, "test_gpu_zz_pending.py": 6}
+          "test_gpu_full_size.py": 4, "test_gpu_multirank.py": 5, "test_gpu_dropin.py": 6}
 
 
 def pytest_collection_modifyitems(session, config, items):

@@ -160,6 +160,14 @@ CASES = {
         steps=3, start_step=998, sample_seed=33, bounded=0, full_steps=[0, 2]),
 }
 
+# The same runs by a MULTI-THREADED reference (`threads` OpenMP threads: what bench.py's reference arm and the binding use).
+# Sampling is thread-independent (generators[0]); what changes with the thread count is the far-policy count — the
+# `Uint += float` partials of updateTrainingStatistics are per OpenMP thread with schedule(static, 1)
+# (MemoryProcessing.cpp:202-227), deterministic for a given T — and, through it, beta; floats move by summation order only.
+# (Checked when generating: four consecutive harness runs per case gave identical counts, beta and weights.)
+for _base, _T in (("vracer_small", 8), ("vracer_small", 16), ("vracer_cfg2mini", 8), ("vracer_cfg2mini", 16), ("racer_small", 8)):
+    CASES[f"{_base}_t{_T}"] = dict(CASES[_base], threads=_T)
+
 # checkpoint cases: phase A runs `steps` steps and calls Learner_approximator::save(); phase B is a fresh process
 # that calls restart() on those files and runs `steps_after` more steps.  Stored: the checkpoint files byte for
 # byte ("ckpt:<file>") and the dumps of phase B ("ref2:<key>").
@@ -200,10 +208,11 @@ def run_case(name, spec, outdir):
         synth.write_replay_file(os.path.join(tmp, "data.bin"), d)
         with open(os.path.join(tmp, "settings.json"), "w") as f:
             json.dump(spec["settings"], f)
+        T = str(spec.get("threads", 1))
         cmd = [HARNESS, "--data", "data.bin", "--settings", "settings.json", "--steps", str(spec["steps"]),
-               "--threads", "1", "--startStep", str(spec["start_step"]), "--sampleSeed", str(spec["sample_seed"]),
+               "--threads", T, "--startStep", str(spec["start_step"]), "--sampleSeed", str(spec["sample_seed"]),
                "--bounded", str(spec["bounded"]), "--dump", "out.bin", "--dumpAll", "--quiet"] + harness_flags(spec)
-        env = dict(os.environ, OMP_NUM_THREADS="1")
+        env = dict(os.environ, OMP_NUM_THREADS=T)
         if "steps_after" in spec:
             cmd.append("--save")
         subprocess.run(cmd, cwd=tmp, check=True, stdout=subprocess.DEVNULL, env=env)
@@ -251,10 +260,11 @@ def run_grad_stats(outdir):
             synth.write_replay_file(os.path.join(tmp, "data.bin"), d)
             with open(os.path.join(tmp, "settings.json"), "w") as f:
                 json.dump(spec["settings"], f)
+            T = str(spec.get("threads", 1))
             cmd = [HARNESS, "--data", "data.bin", "--settings", "settings.json", "--steps", str(spec["steps"]),
-                   "--threads", "1", "--startStep", str(spec["start_step"]), "--sampleSeed", str(spec["sample_seed"]),
+                   "--threads", T, "--startStep", str(spec["start_step"]), "--sampleSeed", str(spec["sample_seed"]),
                    "--bounded", str(spec["bounded"]), "--quiet"] + harness_flags(spec)
-            subprocess.run(cmd, cwd=tmp, check=True, stdout=subprocess.DEVNULL, env=dict(os.environ, OMP_NUM_THREADS="1"))
+            subprocess.run(cmd, cwd=tmp, check=True, stdout=subprocess.DEVNULL, env=dict(os.environ, OMP_NUM_THREADS=T))
             fn = os.path.join(tmp, "agent_00_net_outGrad_stats.raw")
             keep[name] = np.fromfile(fn, dtype=np.float32) if os.path.exists(fn) else np.zeros(0, np.float32)
         print(name, "outGrad_stats:", keep[name].size, "floats")

@@ -9,11 +9,14 @@ import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CKPT_CASES = ["vracer_ckpt", "racer_lstm_ckpt"]
-CASES = ["vracer_small", "vracer_cfg2mini", "vracer_bounded", "vracer_prune", "racer_small", "racer_bounded", "vracer_gae"]
+CASES = ["vracer_small", "vracer_cfg2mini", "vracer_bounded", "vracer_prune", "racer_small", "racer_bounded", "vracer_gae",
+         "vracer_da1", "vracer_explore", "vracer_b1024"]
+# golden runs of a reference with 8 / 16 OpenMP threads: the far-policy count (and beta) depend on the thread count
+# (MemoryProcessing.cpp:202-227); the device reproduces it with refer_reduce_threads = T
+THREADED_CASES = ["vracer_small_t8", "vracer_small_t16", "vracer_cfg2mini_t8", "vracer_cfg2mini_t16", "racer_small_t8"]
 # oracle pinned, device path not built: MGU cells, prioritized samplers (f3)
 ORACLE_ONLY_CASES = ["racer_mgu", "vracer_gru2", "vracer_pererr", "vracer_perseq", "vracer_farpolfrac", "vracer_maxkldiv",
-                     "vracer_minerror", "vracer_perrank", "vracer_explore", "racer_discrete", "vracer_da1",
-                     "vracer_b1024"]       # vracer_b1024: inside the device path, first GPU run pending (test_gpu_zz_pending.py)
+                     "vracer_minerror", "vracer_perrank", "racer_discrete"]
 RECURRENT_CASES = ["racer_lstm", "vracer_lstm2", "racer_lstm64", "racer_cfg3mini"]     # nnType LSTM + BPTT window (configs[2] family)
 
 
@@ -34,6 +37,7 @@ class Golden:
         self.steps, self.start_step = self.spec["steps"], self.spec["start_step"]
         self.sample_seed, self.bounded = self.spec["sample_seed"], bool(self.spec["bounded"])
         self.B = int(self.ref["meta/dims"][3])
+        self.threads = int(self.spec.get("threads", 1))      # OpenMP threads of the reference run that produced the golden
 
     @staticmethod
     def path(name):
@@ -66,7 +70,7 @@ def make_oracle(g: Golden):
     s = g.settings
     # every hyper-parameter of settings.json the path reads (Settings/HyperParameters.h:37-73); absent keys = reference defaults
     kw = dict(batch=s.get("batchSize", 256), max_tot_obs=s.get("maxTotObsNum"), bounded=g.bounded, sample_seed=g.sample_seed,
-              learner=s.get("learner", "VRACER"))
+              learner=s.get("learner", "VRACER"), refer_threads=g.threads)
     for key, arg in (("gamma", "gamma"), ("lambda", "lam"), ("clipImpWeight", "clip_imp_weight"), ("penalTol", "penal_tol"),
                      ("epsAnneal", "eps_anneal"), ("learnrate", "learnrate"), ("nnLambda", "nn_lambda"),
                      ("returnsEstimator", "returns_estimator"), ("dataSamplingAlgo", "sampling"), ("ERoldSeqFilter", "er_filter")):
@@ -86,9 +90,10 @@ def make_oracle(g: Golden):
     return o
 
 
-def make_learner(g: Golden, refer_reduce_threads=1):
+def make_learner(g: Golden, refer_reduce_threads=None):
     from smarties_b200 import Learner
-    L = Learner(g.dS, g.dA, dict(g.settings), bounded=g.bounded, refer_reduce_threads=refer_reduce_threads)
+    L = Learner(g.dS, g.dA, dict(g.settings), bounded=g.bounded,
+                refer_reduce_threads=g.threads if refer_reduce_threads is None else refer_reduce_threads)
     L.set_weights(g.ref["init/weights"])
     L.load_replay(g.replay)
     L.initialize_learner()

@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from parity_utils import CASES, RECURRENT_CASES, Golden, make_learner, make_oracle, relerr
+from parity_utils import CASES, RECURRENT_CASES, THREADED_CASES, Golden, make_learner, make_oracle, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -65,12 +65,17 @@ def test_initialize_learner_matches_reference(case):
     assert np.array_equal(L.read_field("DELTA"), R["init/delta"])
     assert np.array_equal(L.read_field("RHO"), R["init/rho"])
     st = L.get_stats()
-    assert st["beta"] == R["init/refer"][0] and st["cmax"] == R["init/refer"][1]
+    assert st["beta"] == R["init/refer"][0] and st["cmax"] == R["init/refer"][1] and st["cinv"] == R["init/refer"][2]
     L.close()
 
 
-@pytest.mark.parametrize("case", CASES + RECURRENT_CASES)
+@pytest.mark.parametrize("case", CASES + RECURRENT_CASES + THREADED_CASES)
 def test_learner_steps_match_reference(case):
+    """Every step of the golden run.  Among CASES: vracer_da1 — one action component, clipImpWeight < 1: the reference's
+    `Uint += float` far-policy count wraps through x86's cvttss2si (uint_plus_float_x86, csrc/common.cuh); vracer_explore —
+    "returnsEstimator": "retraceExplore" (k_sweep_explore); vracer_b1024 — several P1 tiles per CTA.  THREADED_CASES: goldens
+    of a reference that ran 8 / 16 OpenMP threads; the far-policy count is reduced over per-thread `Uint += float` partials
+    (MemoryProcessing.cpp:202-227) and the device learner is built with refer_reduce_threads = that thread count."""
     g = Golden(case)
     L = make_learner(g)
     for s in range(g.steps):

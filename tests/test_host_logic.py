@@ -47,21 +47,11 @@ def test_settings_outside_the_device_path_are_rejected_loudly():
     from smarties_b200 import HyperParameters
     assert HyperParameters(4, 1, {"returnsEstimator": "GAE"}).returnsEstimator == "GAE"
     assert HyperParameters(4, 1, {"nnType": "LSTM", "nnLayerSizes": [32]}).nnType == "LSTM"
-    for bad in ({"returnsEstimator": "retraceExplore"}, {"dataSamplingAlgo": "PERrank"}, {"dataSamplingAlgo": "PERerr"},
+    for bad in ({"returnsEstimator": "nonsense"}, {"dataSamplingAlgo": "PERrank"}, {"dataSamplingAlgo": "PERerr"},
                 {"dataSamplingAlgo": "PERseq"}, {"ERoldSeqFilter": "farpolfrac"}, {"ERoldSeqFilter": "maxkldiv"},
                 {"ERoldSeqFilter": "minerror"}, {"nnType": "MGU"}, {"nnType": "GRU"}, {"nnFunc": "Relu"}):
         with pytest.raises(NotImplementedError):
             HyperParameters(4, 1, bad)
-
-
-def test_unverified_device_paths_are_opt_in(monkeypatch):
-    """Kernels that compile but have not run on a GPU yet (tests/test_gpu_zz_pending.py) stay behind SMB200_UNVERIFIED=1."""
-    from smarties_b200 import HyperParameters
-    monkeypatch.delenv("SMB200_UNVERIFIED", raising=False)
-    with pytest.raises(NotImplementedError):
-        HyperParameters(4, 1, {"returnsEstimator": "retraceExplore"})
-    monkeypatch.setenv("SMB200_UNVERIFIED", "1")
-    assert HyperParameters(4, 1, {"returnsEstimator": "retraceExplore"}).returnsEstimator == "retraceExplore"
 
 
 def test_library_exports_every_declared_symbol(built_library):

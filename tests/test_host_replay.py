@@ -114,7 +114,6 @@ def test_network_construction_is_bit_exact_with_the_reference_builder(built_libr
     the host, against the weights the reference binary started from in every golden run (randSeed 42): identical bits."""
     from smarties_b200 import load_library
     from smarties_b200.learner import make_config
-    monkeypatch.setenv("SMB200_UNVERIFIED", "1")        # vracer_explore's setting is opt-in; the network is the same
     g = Golden(case)
     lib = load_library()
     lib.smb200_host_init_weights.restype = C.c_int64
