@@ -174,7 +174,7 @@ def test_binding_loads_the_library_and_dies_loudly_without_a_gpu(tmp_path):
 
 
 def test_binding_falls_back_to_the_reference_learner_outside_the_device_path(tmp_path):
-    """SMARTIES_B200=1 with a setting the device path does not cover (here the retraceExplore estimator): the wrapped factory
+    """SMARTIES_B200=1 with a setting the device path does not cover (here a prioritised sampler): the wrapped factory
     hands the agent to the reference's own CPU learner (createLearner_reference) — the app trains, no device learner is created.
     Runs without a GPU: nothing of the library is called on this path."""
     import sys
@@ -182,6 +182,6 @@ def test_binding_falls_back_to_the_reference_learner_outside_the_device_path(tmp
         pytest.skip("oracle/_ref binaries not built (python -c 'import __graft_entry__ as g; g.build()')")
     sys.path.insert(0, os.path.join(ROOT, "scripts"))
     from dropin_run import SETTINGS, run_arm
-    r = run_arm("b200", steps=1200, threads=2, seed=7, settings=dict(SETTINGS, returnsEstimator="retraceExplore"), keep_dir=str(tmp_path))
+    r = run_arm("b200", steps=1200, threads=2, seed=7, settings=dict(SETTINGS, dataSamplingAlgo="PERrank"), keep_dir=str(tmp_path))
     assert r["rc"] == 0, r
     assert r["b200_lines"] == [] and r["grad_steps_logged"] >= 1000, r
