@@ -50,6 +50,9 @@ for s in range(STEPS):
     for k in ("sampledEpID", "sampledT", "pre/refer", "post/refer"):
         keep[f"s{s}/{k}"] = D[f"s{s}/{k}"]
     keep[f"s{s}/O_V"] = np.asarray(D[f"s{s}/O"][:, 0], np.float64)          # value outputs of the sampled transitions
+# the network the run started from: generators[0] = mt19937(randSeed) has already seeded the other OpenMP threads' generators
+# (one draw each, Settings/ExecutionInfo.cpp:389-393), so the initial weights depend on the thread count
+keep["init/weights"] = np.asarray(D["init/weights"], np.float32)
 keep["s0/gradSum"] = np.asarray(D["s0/gradSum"], np.float32)               # summed parameter gradient of the first step
 keep["s0/weights"] = np.asarray(D["s0/weights"], np.float32)               # weights after its Adam update
 path = os.path.join(HERE, NAME)

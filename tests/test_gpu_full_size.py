@@ -25,6 +25,10 @@ def test_full_size_run_matches_the_reference_binary(fixture):
     spec = json.loads(bytes(z["spec"]).decode())
     # the library's own network initialisation at randSeed 42 IS the reference's (tests/test_host_replay.py)
     L = Learner(32, 8, dict(spec["settings"]), seed=spec["seed"], refer_reduce_threads=spec.get("threads", 1))
+    if spec.get("threads", 1) == 1:     # the library's own initialisation at randSeed 42 IS the single-thread reference's
+        assert np.array_equal(L.get_weights(), z["init/weights"])
+    # a T-thread reference draws T - 1 seeds from generators[0] before it builds the network (ExecutionInfo.cpp:389-393)
+    L.set_weights(z["init/weights"])
     L.load_replay(bench.make_workload())
     L.initialize_learner()
     L.seed_sampler(spec["sample_seed"])
