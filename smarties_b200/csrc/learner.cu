@@ -89,6 +89,9 @@ struct smb200_learner {
   float* tcPartial = nullptr; int useTc = 0;     // tensor-core weight gradient of LSTM layers (recurrent nets)
   GradTile* dTiles = nullptr; int nTiles = 0;
   int Bpad = 0;
+  // cluster step kernel (feed-forward nets, cluster_step.cuh)
+  ClusterPlan cplan{}; ClusterPlan* dCplan = nullptr; std::vector<int> cidx; int* dCidx = nullptr;
+  float* cimg = nullptr; float* cpart = nullptr; int clusterP1 = 0;      // clusterP1 > 0: the cluster kernel runs the steps
   int dP = 0;                     // columns of the behaviour policy MU: 2 * dim_action (mean, stdev), or the K option probabilities
 
   // step state
@@ -125,6 +128,7 @@ struct smb200_learner {
     a.comm = comm;
     a.descs = dDescs; a.rp = rp; a.W = W; a.Wimg = Wimg; a.M1 = M1; a.M2 = M2; a.G = G; a.dbgT = nullptr; a.useTma = useTma;
     a.useTc = useTc; a.tcPartial = tcPartial;
+    a.cplan = dCplan; a.cimg = cimg; a.cpart = cpart; a.cidx = dCidx; a.cClusters = clusterP1;
     a.actG = actG; a.errG = errG; a.sampRow = dSampT; a.sampSlot = dSampSlot; a.rec = dRec;
     a.lastO = lastO; a.lastG = lastG; a.lastX = lastX; a.ctrl = dCtrl; a.statsOut = dStats;
     a.tiles = dTiles; a.nTiles = nTiles; a.B = cfg.batch_size; a.Bpad = Bpad;
@@ -287,6 +291,16 @@ static int upload_weights(smb200_learner* h, const float* blob) {
     } else if (L.kind == kParam) {
       for (int n = 0; n < L.size; ++n) im[L.imgB + n] = blob[L.bOff + n];
     }
+  }
+  std::vector<float> cim;
+  if (h->cimg) {       // the cluster kernel's image: [common | kCL rank blocks], positions from the index maps
+    cim.assign(cluster_image_floats(h->cplan), 0.f);
+    const int* iA = h->cidx.data(); const int* iB = iA + net.nParams;
+    for (int p = 0; p < net.nParams; ++p) {
+      if (iA[p] >= 0) cim[iA[p]] = blob[p];
+      if (iB[p] >= 0) cim[iB[p]] = blob[p];
+    }
+    SMB200_CUDA_CHECK(cudaMemcpyAsync(h->cimg, cim.data(), sizeof(float) * cim.size(), cudaMemcpyHostToDevice, h->stream));
   }
   SMB200_CUDA_CHECK(cudaMemcpyAsync(h->W, blob, sizeof(float) * net.nParams, cudaMemcpyHostToDevice, h->stream));
   SMB200_CUDA_CHECK(cudaMemcpyAsync(h->Wimg, im.data(), sizeof(float) * net.imgFloats, cudaMemcpyHostToDevice, h->stream));
@@ -492,7 +506,10 @@ static int run_segment(smb200_learner* h, int first, int n, long long gstep0, in
   const NetDesc& net = h->descs.net;
   const long long lastStep = gstep0 + n;              // nGradSteps()+1 of the last step
   const int sweepLast = (lastStep % 1000) == 0;
-  if (h->mode == 1 && h->persistGrid > 0) {
+  if (h->mode == 1 && h->clusterP1 > 0) {
+    if (launch_steps_cluster(a, h->clusterP1, h->cplan.bTotal, (int)gstep0, n, sweepLast, h->stream)) return -2;
+    h->launches += 1;
+  } else if (h->mode == 1 && h->persistGrid > 0) {
     if (launch_steps_persistent(a, net, h->persistGrid, (int)gstep0, n, sweepLast, h->stream)) return -2;
     h->launches += 1;
   } else {
@@ -641,6 +658,32 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
   k.adam_bt1 = 0.9; k.adam_bt2 = 0.999;
   CK(push_ctrl(h));
 
+  // cluster step kernel: plan, co-resident clusters, image / partial-gradient buffers (before the first weight upload)
+  {
+    const char* m0 = getenv("SMB200_MODE");
+    int coop0 = 0; cudaDeviceGetAttribute(&coop0, cudaDevAttrCooperativeLaunch, c.device);
+    cluster_plan_build(net, 4 * 33 - 1, h->cplan, h->cidx);
+    if (h->cplan.ok && coop0 && !(m0 && strcmp(m0, "two") == 0)) {
+      CK(cluster_prepare(h->cplan));
+      const int maxC = std::min(33, cluster_max_active(h->cplan));
+      if (maxC >= 2) {
+        cluster_plan_build(net, kCL * maxC - 1, h->cplan, h->cidx);      // the P2 partition depends on the worker count
+        if (h->cplan.ok) h->clusterP1 = maxC - 1;
+      }
+    }
+    if (getenv("SMB200_DEBUG"))
+      fprintf(stderr, "smb200: cluster kernel %s: %d P1 clusters, %d B of dynamic shared memory, image %zu floats, P2 chunk %d x %d parts\n",
+              h->clusterP1 > 0 ? "on" : "off", h->clusterP1, h->cplan.bTotal, h->cplan.ok ? cluster_image_floats(h->cplan) : (size_t)0,
+              h->cplan.chunk, h->cplan.parts);
+    if (h->clusterP1 > 0) {
+      CK(dev_alloc(&h->dCplan, 1));
+      CKC(cudaMemcpy(h->dCplan, &h->cplan, sizeof(ClusterPlan), cudaMemcpyHostToDevice));
+      CK(dev_alloc(&h->dCidx, h->cidx.size()));
+      CKC(cudaMemcpy(h->dCidx, h->cidx.data(), sizeof(int) * h->cidx.size(), cudaMemcpyHostToDevice));
+      CK(dev_alloc(&h->cimg, cluster_image_floats(h->cplan)));
+      CK(dev_alloc(&h->cpart, (size_t)h->clusterP1 * net.nParams));
+    }
+  }
   h->comm.world = 1; h->comm.rank = 0;
   h->gen.seed((unsigned long)c.seed);
   std::vector<float> blob;
@@ -669,7 +712,7 @@ void smb200_destroy(smb200_learner* h) {
   void* ptrs[] = {rp.S, rp.A, rp.MU, rp.R, rp.V, rp.ADV, rp.Q, rp.DELTA, rp.RHO, rp.KL, rp.rowFlag, rp.epStart, rp.epLen, rp.epTerm,
                   rp.epId, rp.epAgg, rp.epOrder, rp.stateMean, rp.stateScale, rp.stateStd, rp.rew, h->W, h->Wimg, h->dDbg, h->M1, h->M2, h->G,
                   h->actG, h->errG, h->dTiles, h->dDescs, h->dCtrl, h->dRec, h->lastO, h->lastG, h->lastX, h->dSums, h->dBarrier,
-                  h->dSampSlot, h->dSampT, h->dStats};
+                  h->dSampSlot, h->dSampT, h->dStats, h->dCplan, h->dCidx, h->cimg, h->cpart};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int q = 0; q < kMaxWorld; ++q) if (h->peerMapped[q]) cudaIpcCloseMemHandle(h->peerMapped[q]);
   if (h->commBuf) cudaFree(h->commBuf);
@@ -1074,7 +1117,8 @@ int smb200_profile_phases(smb200_learner* h, int32_t n, int64_t* out, int64_t ca
   if (!h || n < 1 || n > h->presampled || !out || h->mode != 1) return SMB200_ERR_INVALID;
   const long long g0 = h->gradStep;
   if ((g0 % 1000) + n >= 1000) return SMB200_ERR_STATE;   // keep the profiled launch free of sweeps
-  const size_t cnt = (size_t)n * h->persistGrid * 48;
+  const int pgrid = h->clusterP1 > 0 ? (h->clusterP1 + 1) * kCL : h->persistGrid;
+  const size_t cnt = (size_t)n * pgrid * 48;
   if ((int64_t)cnt > capacity) return SMB200_ERR_INVALID;
   cudaSetDevice(h->cfg.device);
   if (h->dDbg) { cudaFree(h->dDbg); h->dDbg = nullptr; }
@@ -1085,12 +1129,13 @@ int smb200_profile_phases(smb200_learner* h, int32_t n, int64_t* out, int64_t ca
   a.stepBase = (int)g0; a.lastStep = (int)(g0 + n - 1);
   a.dbgT = h->dDbg;
   SMB200_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
-  if (launch_steps_persistent(a, h->descs.net, h->persistGrid, (int)g0, n, 0, h->stream)) return SMB200_ERR_CUDA;
+  if (h->clusterP1 > 0) { if (launch_steps_cluster(a, h->clusterP1, h->cplan.bTotal, (int)g0, n, 0, h->stream)) return SMB200_ERR_CUDA; }
+  else if (launch_steps_persistent(a, h->descs.net, h->persistGrid, (int)g0, n, 0, h->stream)) return SMB200_ERR_CUDA;
   SMB200_CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
   h->gradStep += n; h->trackerSteps += n;
   if (d2h(h, out, h->dDbg, sizeof(long long) * cnt)) return SMB200_ERR_CUDA;
   float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->lastMs = ms; h->lastLaunches = 1;
-  if (grid_out) *grid_out = h->persistGrid;
+  if (grid_out) *grid_out = pgrid;
   return 0;
 }
 

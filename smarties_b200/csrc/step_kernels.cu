@@ -27,9 +27,12 @@
 // explicitly; everything else rounds like the reference's x86-64 (no-FMA) build.
 #include "step_kernels.cuh"
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 namespace smb200 {
 
@@ -2428,6 +2431,8 @@ int launch_forward(const StepArgs& a, const NetDesc& net, const float* states, i
   SMB200_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
+
+#include "cluster_step.cuh"
 
 }  // namespace smb200
 

@@ -1,5 +1,6 @@
 // step_kernels.cuh — kernel argument block and host launchers of the learner step.
 #pragma once
+#include <vector>
 #include "common.cuh"
 #include "../../include/smarties_b200.h"
 
@@ -55,7 +56,45 @@ struct CommView {
   __host__ __device__ unsigned* vecFlag(int q) const { return reinterpret_cast<unsigned*>(base[q] + offVecFlag); }
 };
 
+// ------------------------------------------------------------------------------------------
+// Cluster step kernel (feed-forward nets, cluster_step.cuh): every pass of kTS sampled transitions runs on a thread-block
+// CLUSTER of kCL CTAs.  Each CTA keeps 1/kCL of the output columns of every hidden layer (its "slice") in shared memory,
+// the layer outputs are exchanged through distributed shared memory, and the weight gradient of the pass is formed inside
+// the cluster (one partial sum per cluster and parameter instead of one contraction over the whole mini-batch).
+// ------------------------------------------------------------------------------------------
+constexpr int kCL = 4;            // CTAs per cluster
+constexpr int kTS = 8;            // sampled transitions per cluster pass
+constexpr int kXS = 12;           // row stride of the activation buffers [feature][kXS]: 8 samples + 4 pad (conflict-free float4 rows)
+constexpr int kOwn = kTS / kCL;   // samples whose loss stage a CTA evaluates
+struct CDense {                   // one hidden dense layer (+ the ParametricResidual after it)
+  int layer, resLayer;            // NetDesc layer ids (resLayer = -1: no residual)
+  int K, Kp, N, NS, Np;           // fan-in (Kp: padded to 16), fan-out, slice width per CTA (multiple of 4), Np = roundUp16(kCL * NS)
+  int ldf, ldt;                   // row strides: forward slice image [Kp][ldf = NS + 2], transposed [NS][ldt = Kp + 4]
+  int needDx;
+  int iWf, iB, iWt;               // float offsets in the CTA's block of the weight image
+  int iRW, iRB;                   // residual w / b [Np] in the COMMON block (-1)
+  int sXout, sYs, sDs, sE, sEpart;   // shared-memory float offsets in the activation area
+  int gW, gB, gRW, gRB;           // offsets in the CTA's gradient accumulator: dW [K][NS + 1], db [NS], dRW [NS], dRB [NS]
+};
+struct ClusterPlan {
+  int ok;                         // the cluster kernel covers this network
+  int nDense; CDense L[SMB200_MAX_HIDDEN];
+  int oLayer, pLayer, oK, oKp, oN, oNp, ldo;   // linear output layer, replicated in every CTA: [oKp][ldo = oNp + 2]
+  int nP;                         // ParamLayer size
+  int iOW, iOB, iP;               // common block: output weights, output bias, ParamLayer values
+  int commonFloats, rankFloats, rankFwdFloats;   // weight image = [common | kCL rank blocks]; a rank block = [forward part | transposed part]
+  int sX0, sDout, sGstd, actFloats;
+  int gOW, gOB, gP, gaccFloats;   // dWout rows of the CTA's slice of the top layer [NStop][oN + 1]; bias and ParamLayer on rank 0
+  int bPlan, bCommon, bRank, bAct, bGacc, bAct2, bErr2, bInfo, bOld, bPair, bSamp, bBars, bStage, bTotal;   // byte offsets
+  int stageFloats;
+  int bHelpImg, bHelpAct, bHelpTotal;            // helper CTAs: [common | kCL forward parts] + one activation area
+  int chunk, chunkPad, parts;     // P2: parameters per worker CTA, padded to a warp multiple, partial-sum groups per parameter
+};
+
 struct StepArgs {
+  // cluster step kernel
+  const ClusterPlan* cplan; float* cimg; float* cpart; const int* cidx;   // image, per-cluster partial gradients [clusters][nParams], image positions [3][nParams]
+  int cClusters;                     // P1 clusters of the launch
   CommView comm;
   const DevDescs* descs;
   ReplayView rp;
@@ -114,6 +153,12 @@ int persistent_grid(const StepArgs& a, const NetDesc& net, int numSMs);
 int launch_steps_persistent(const StepArgs& a, const NetDesc& net, int grid, int step0, int nSteps, int skipStatsLast, cudaStream_t st);
 int launch_finalize_sweep(const StepArgs& a, int step, const SweepSums* sweep, cudaStream_t st);
 int launch_forward(const StepArgs& a, const NetDesc& net, const float* states, int n, float* out, cudaStream_t st);
+// cluster step kernel (cluster_step.cuh)
+void cluster_plan_build(const NetDesc& net, int numWorkersHint, ClusterPlan& cp, std::vector<int>& idx);
+size_t cluster_image_floats(const ClusterPlan& cp);
+int cluster_prepare(const ClusterPlan& cp);
+int cluster_max_active(const ClusterPlan& cp);
+int launch_steps_cluster(const StepArgs& a, int p1Clusters, int bytes, int step0, int nSteps, int skipStatsLast, cudaStream_t st);
 
 // sweep_kernels.cu
 int launch_init_episode(const ReplayView& rp, int slot, float deltaInit, int haveValues, cudaStream_t st);

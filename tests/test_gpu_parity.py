@@ -121,16 +121,33 @@ def test_two_kernel_mode_equals_persistent(monkeypatch, case):
     Bm = make_learner(g)
     monkeypatch.delenv("SMB200_MODE")
     sa, sb = A.train_steps(g.steps), Bm.train_steps(g.steps)
-    if g.settings.get("nnType", "FFNN") == "LSTM":
-        # the persistent kernel contracts the LSTM weight gradient on the tensor cores (tcgen05, 3xTF32 split), the
-        # two-kernel mode on the SIMT tiles: same mathematics, different rounding of the 4-byte sums
+    if True:
+        # recurrent nets: the persistent kernel contracts the LSTM weight gradient on the tensor cores (tcgen05, 3xTF32 split),
+        # the two-kernel mode on the SIMT tiles; feed-forward nets: the cluster kernel sums dot products by a lane butterfly and
+        # the gradient per cluster, the two-kernel mode in k / batch order: same mathematics, different rounding of the 4-byte sums
         for x, y in zip(sa, sb):
             assert x["n_far_policy"] == y["n_far_policy"] and x["grad_step"] == y["grad_step"]
             assert x["beta"] == pytest.approx(y["beta"], rel=1e-12) and x["avg_sq_err"] == pytest.approx(y["avg_sq_err"], rel=1e-5)
         assert np.abs(A.get_weights() - Bm.get_weights()).max() < 1e-6
-    else:
-        assert sa == sb
-        assert np.array_equal(A.get_weights(), Bm.get_weights())
+    A.close(); Bm.close()
+
+
+@pytest.mark.parametrize("case", ["vracer_small", "vracer_cfg2mini", "racer_bounded", "vracer_b1024"])
+def test_cluster_kernel_equals_tile_kernel(monkeypatch, case):
+    """Feed-forward nets run on the cluster step kernel (cluster_step.cuh); SMB200_CLUSTER=0 selects the persistent tile
+    kernel.  Same samples, same integer far-policy counts, floats equal to f32 round-off of the different summation orders."""
+    g = Golden(case)
+    A = make_learner(g)
+    monkeypatch.setenv("SMB200_CLUSTER", "0")
+    Bm = make_learner(g)
+    monkeypatch.delenv("SMB200_CLUSTER")
+    sa, sb = A.train_steps(g.steps), Bm.train_steps(g.steps)
+    for x, y in zip(sa, sb):
+        assert x["n_far_policy"] == y["n_far_policy"] and x["grad_step"] == y["grad_step"]
+        assert x["beta"] == pytest.approx(y["beta"], rel=1e-12) and x["avg_sq_err"] == pytest.approx(y["avg_sq_err"], rel=1e-5)
+    assert relerr(A.get_grad(), Bm.get_grad()) < 5e-6
+    assert np.abs(A.get_weights() - Bm.get_weights()).max() < 1e-6
+    assert np.allclose(A.read_field("QRET"), Bm.read_field("QRET"), rtol=1e-5, atol=1e-6)
     A.close(); Bm.close()
 
 
