@@ -3,7 +3,7 @@
 set -u
 OUT=gpurun_out/r2
 mkdir -p $OUT
-SMB200_DEBUG=1 timeout -s KILL 120 python -u - > $OUT/cluster_first.log 2>&1 <<'PY'
+SMB200_CLUSTER=1 SMB200_DEBUG=1 timeout -s KILL 120 python -u - > $OUT/cluster_first.log 2>&1 <<'PY'
 import os, sys
 root = os.getcwd()
 sys.path[:0] = [root, os.path.join(root, "oracle"), os.path.join(root, "tests")]
@@ -32,7 +32,7 @@ if grep -q "^ok" $OUT/cluster_first.log; then
   timeout -s KILL 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_full_size.py -x -q --timeout 150 > $OUT/cluster_parity.log 2>&1
   echo "parity rc=$?" >> $OUT/cluster_parity.log
   tail -15 $OUT/cluster_parity.log
-  timeout -s KILL 300 python scripts/batch_sweep.py 256 > $OUT/cluster_b256.log 2>&1; tail -3 $OUT/cluster_b256.log
-  timeout -s KILL 300 python scripts/phase_report_cluster.py > $OUT/cluster_phases.log 2>&1; cat $OUT/cluster_phases.log
-  SMB200_CLUSTER=0 timeout -s KILL 300 python scripts/batch_sweep.py 256 > $OUT/tile_b256.log 2>&1; tail -3 $OUT/tile_b256.log
+  SMB200_CLUSTER=1 timeout -s KILL 300 python scripts/batch_sweep.py 256 > $OUT/cluster_b256.log 2>&1; tail -3 $OUT/cluster_b256.log
+  SMB200_CLUSTER=1 timeout -s KILL 300 python scripts/phase_report_cluster.py > $OUT/cluster_phases.log 2>&1; cat $OUT/cluster_phases.log
+  timeout -s KILL 300 python scripts/batch_sweep.py 256 > $OUT/tile_b256.log 2>&1; tail -3 $OUT/tile_b256.log
 fi

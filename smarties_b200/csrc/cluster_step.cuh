@@ -27,6 +27,8 @@
 // ---- cluster primitives ----
 __device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ unsigned cluster_id_x() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -58,6 +60,11 @@ __device__ __forceinline__ void cl_grid_barrier(const StepArgs& a, unsigned& tar
 __device__ __forceinline__ void cl_mbar_wait(const StepArgs& a, uint64_t* bar, unsigned parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) { if (clock64() - t0 > kWaitCycles) cl_fail(a, 17); }
+}
+
+// index load that stays where it is written (the compiler would otherwise sink it to its first use, after the grid barrier)
+__device__ __forceinline__ int ld_index_now(const int* p) {
+  int v; asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
 }
 
 struct ClusterCtx {
@@ -238,119 +245,63 @@ __device__ __forceinline__ float cl_sum8(const float* a) {
   return v;
 }
 
-__device__ void cl_wgrad(const ClusterPlan& cp, const float* cm, const float* act, float* g, int rank, bool first) {
-  const int tid = threadIdx.x;
-  int nItems = 0;
-  for (int li = 0; li < cp.nDense; ++li) nItems += (cp.L[li].Kp >> 2) * (cp.L[li].NS >> 2);
-  const CDense& Lt = cp.L[cp.nDense - 1];
-  const int outItems = Lt.NS * (cp.oNp >> 2);
-  int vecItems = 0;
-  for (int li = 0; li < cp.nDense; ++li) vecItems += cp.L[li].NS * (cp.L[li].iRW >= 0 ? 3 : 1);
-  if (rank == 0) vecItems += cp.oN + cp.nP;
-  const int total = nItems + outItems + vecItems;
-  for (int it = tid; it < total; it += kST) {
-    int r = it;
-    bool done = false;
-    for (int li = 0; li < cp.nDense && !done; ++li) {                 // dW[k][n] = sum_s x[k][s] delta[n][s]
-      const CDense& L = cp.L[li];
-      const int KQ = L.Kp >> 2, NQ = L.NS >> 2;
-      if (r < KQ * NQ) {
-        const int nq = r / KQ, kq = r - nq * KQ;
-        const float* x = act + (li == 0 ? cp.sX0 : cp.L[li - 1].sXout);
-        const float* d = act + L.sDs;
-        float acc[16];
+// One work item per thread, fixed for the whole launch and decoded on the host (cluster_plan_build): 12 ints
+//   [0] kind  1: 4 x 4 block  acc[i][j] += <a_i, b_j> over the 8 samples   (dense / output-layer weights)
+//             2: column triple acc[0] += sum(a_0)  (bias), with a residual: acc[1] += <b_0, b_1> (dRW), acc[2] += sum(b_0) (dRB)
+//             3: single        acc[0] += sum(a_0)  (output bias, ParamLayer)
+//   [1] aoff [2] astr   rows a_i = act + aoff + i * astr        [3] boff [4] bstr   rows b_j = act + boff + j * bstr
+//   [5] obase [6] ostrA [7] ostrB   parameter index of acc[i][j] = obase + i * ostrA + j * ostrB  (kind 2: obase, ostrA, ostrB = the three parameters)
+//   [8] na [9] nb       valid rows / columns (kind 2: nb = 1 with a residual)
+// Lanes run over consecutive columns (b rows at stride kXS: conflict-free, a rows broadcast), so the stores of a warp fall into
+// whole 32-byte sectors of the partial-gradient row.
+constexpr int kItemInts = 12;
+// `early`: the items that only read the deltas of the top hidden layer and of the output layer (record [10] = 1) — they run
+// while the partial input gradients of the top layer travel; !early: all the others.
+__device__ __forceinline__ void cl_wgrad(const int* tab, const float* act, float (&acc)[16], bool early) {
+  const int4 q0 = __ldg(reinterpret_cast<const int4*>(tab)), q1 = __ldg(reinterpret_cast<const int4*>(tab) + 1);
+  const int4 q2 = __ldg(reinterpret_cast<const int4*>(tab) + 2);
+  const int kind = (q2.z != 0) == early ? q0.x : 0;
+  if (kind == 1) {
+    const float* ar = act + q0.y; const float* br = act + q0.w;
+    const int astr = q0.z, bstr = q1.x;
+    float4 a[8], b[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 4; ++i) { a[2 * i] = *reinterpret_cast<const float4*>(ar + i * astr); a[2 * i + 1] = *reinterpret_cast<const float4*>(ar + i * astr + 4); }
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) { b[2 * j] = *reinterpret_cast<const float4*>(br + j * bstr); b[2 * j + 1] = *reinterpret_cast<const float4*>(br + j * bstr + 4); }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) cl_dot8(x + (kq + i * KQ) * kXS, d + (nq + j * NQ) * kXS, acc[i * 4 + j]);
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int k = kq + i * KQ;
-          if (k >= L.K) continue;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float* p = g + L.gW + k * (L.NS + 1) + nq + j * NQ;
-            *p = first ? acc[i * 4 + j] : *p + acc[i * 4 + j];
-          }
-        }
-        done = true;
-      } else r -= KQ * NQ;
-    }
-    if (done) continue;
-    if (r < outItems) {                                              // rows of the output layer owned by this CTA
-      const int NQ = cp.oNp >> 2;
-      const int kl = r / NQ, nq = r - kl * NQ;
-      const int k = rank * Lt.NS + kl;
-      if (k < cp.oK) {
-        const float* x = act + Lt.sXout + k * kXS;
-        for (int j = 0; j < 4; ++j) {
-          const int n = nq * 4 + j;
-          if (n >= cp.oN) break;
-          float v = 0.f; cl_dot8(x, act + cp.sDout + n * kXS, v);
-          float* p = g + cp.gOW + kl * (cp.oN + 1) + n;
-          *p = first ? v : *p + v;
-        }
+      for (int j = 0; j < 4; ++j) {
+        float v = acc[i * 4 + j];
+        v = fmaf(a[2 * i].x, b[2 * j].x, v); v = fmaf(a[2 * i].y, b[2 * j].y, v); v = fmaf(a[2 * i].z, b[2 * j].z, v); v = fmaf(a[2 * i].w, b[2 * j].w, v);
+        v = fmaf(a[2 * i + 1].x, b[2 * j + 1].x, v); v = fmaf(a[2 * i + 1].y, b[2 * j + 1].y, v);
+        v = fmaf(a[2 * i + 1].z, b[2 * j + 1].z, v); v = fmaf(a[2 * i + 1].w, b[2 * j + 1].w, v);
+        acc[i * 4 + j] = v;
       }
-      continue;
+  } else if (kind == 2) {
+    acc[0] += cl_sum8(act + q0.y);
+    if (q2.y) {
+      const float* e = act + q0.w; const float* x = e + q1.x;
+      float v = 0.f; cl_dot8(e, x, v);
+      acc[1] += v; acc[2] += cl_sum8(e);
     }
-    r -= outItems;
-    for (int li = 0; li < cp.nDense && !done; ++li) {                 // biases, residual parameters
-      const CDense& L = cp.L[li];
-      const int per = L.iRW >= 0 ? 3 : 1;
-      if (r < L.NS * per) {
-        const int kind = r / L.NS, nl = r - kind * L.NS;
-        const int n = rank * L.NS + nl;
-        float v = 0.f; int off;
-        if (kind == 0) { v = cl_sum8(act + L.sDs + nl * kXS); off = L.gB + nl; }                         // db = sum delta
-        else {                                                                                           // ParametricResidualLayer::backward
-          const float* e = act + L.sE + n * kXS;
-          if (kind == 1) { if (n < L.N) cl_dot8(e, act + (li == 0 ? cp.sX0 : cp.L[li - 1].sXout) + n * kXS, v); off = L.gRW + nl; }
-          else { if (n < L.N) v = cl_sum8(e); off = L.gRB + nl; }
-        }
-        g[off] = first ? v : g[off] + v;
-        done = true;
-      } else r -= L.NS * per;
-    }
-    if (done) continue;
-    if (r < cp.oN) { const float v = cl_sum8(act + cp.sDout + r * kXS); g[cp.gOB + r] = first ? v : g[cp.gOB + r] + v; }
-    else { r -= cp.oN; const float v = cl_sum8(act + cp.sGstd + r * kXS); g[cp.gP + r] = first ? v : g[cp.gP + r] + v; }
-  }
+  } else if (kind == 3) acc[0] += cl_sum8(act + q0.y);
 }
-
-// accumulator -> this cluster's partial-gradient row in global memory (parameter-blob order, coalesced runs of NS floats)
-__device__ void cl_store_partial(const ClusterPlan& cp, const NetDesc& net, const float* g, float* part, int rank) {
-  const int tid = threadIdx.x;
-  for (int li = 0; li < cp.nDense; ++li) {
-    const CDense& L = cp.L[li];
-    const LayerDesc& D = net.L[L.layer];
-    const int n0 = rank * L.NS, nc = min(L.NS, L.N - n0);
-    if (nc <= 0) continue;
-    for (int idx = tid; idx < L.K * L.NS; idx += kST) {
-      const int k = idx / L.NS, n = idx - k * L.NS;
-      if (n < nc) part[D.wOff + k * D.ld + n0 + n] = g[L.gW + k * (L.NS + 1) + n];
-    }
-    for (int n = tid; n < nc; n += kST) {
-      part[D.bOff + n0 + n] = g[L.gB + n];
-      if (L.resLayer >= 0) {
-        const LayerDesc& R = net.L[L.resLayer];
-        part[R.wOff + n0 + n] = g[L.gRW + n]; part[R.bOff + n0 + n] = g[L.gRB + n];
-      }
-    }
-  }
-  const CDense& Lt = cp.L[cp.nDense - 1];
-  const LayerDesc& O = net.L[cp.oLayer];
-  const int k0 = rank * Lt.NS, kc = min(Lt.NS, cp.oK - k0);
-  for (int idx = tid; idx < max(kc, 0) * cp.oN; idx += kST) {
-    const int kl = idx / cp.oN, n = idx - kl * cp.oN;
-    part[O.wOff + (k0 + kl) * O.ld + n] = g[cp.gOW + kl * (cp.oN + 1) + n];
-  }
-  if (rank == 0) {
-    for (int n = tid; n < cp.oN; n += kST) part[O.bOff + n] = g[cp.gOB + n];
-    const LayerDesc& P = net.L[cp.pLayer];
-    for (int i = tid; i < cp.nP; i += kST) part[P.bOff + i] = g[cp.gP + i];
-  }
+__device__ __forceinline__ void cl_wgrad_store(const int* tab, float* part, const float (&acc)[16]) {
+  const int4 q0 = __ldg(reinterpret_cast<const int4*>(tab)), q1 = __ldg(reinterpret_cast<const int4*>(tab) + 1);
+  const int4 q2 = __ldg(reinterpret_cast<const int4*>(tab) + 2);
+  const int kind = q0.x;
+  if (kind == 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (i < q2.x && j < q2.y) part[q1.y + i * q1.z + j * q1.w] = acc[i * 4 + j];
+  } else if (kind == 2) {
+    part[q1.y] = acc[0];
+    if (q2.y) { part[q1.z] = acc[1]; part[q1.w] = acc[2]; }
+  } else if (kind == 3) part[q1.y] = acc[0];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -359,10 +310,14 @@ __device__ void cl_store_partial(const ClusterPlan& cp, const NetDesc& net, cons
 __device__ __forceinline__ void cl_load_image(const StepArgs& a, const ClusterPlan& cp, unsigned char* smraw, int rank, uint64_t* bars) {
   if (threadIdx.x == 0) {
     asm volatile("fence.proxy.async.global;\n\tfence.proxy.async.shared::cta;" ::: "memory");
-    const unsigned cb = 4u * (unsigned)cp.commonFloats, rb = 4u * (unsigned)cp.rankFloats;
-    mbar_expect_tx(&bars[0], cb + rb);
+    // forward parts (common block + the slice's forward layout) on bars[0], the transposed copies on bars[1]: the forward
+    // pass starts as soon as the first 2/3 of the image has landed
+    const unsigned cb = 4u * (unsigned)cp.commonFloats, fb = 4u * (unsigned)cp.rankFwdFloats, tb = 4u * (unsigned)(cp.rankFloats - cp.rankFwdFloats);
+    const float* src = a.cimg + cp.commonFloats + (size_t)rank * cp.rankFloats;
+    mbar_expect_tx(&bars[0], cb + fb);
     bulk_g2s(smraw + cp.bCommon, a.cimg, cb, &bars[0]);
-    bulk_g2s(smraw + cp.bRank, a.cimg + cp.commonFloats + (size_t)rank * cp.rankFloats, rb, &bars[0]);
+    bulk_g2s(smraw + cp.bRank, src, fb, &bars[0]);
+    if (tb) { mbar_expect_tx(&bars[1], tb); bulk_g2s(smraw + cp.bRank + fb, src + cp.rankFwdFloats, tb, &bars[1]); }
   }
 }
 
@@ -389,13 +344,12 @@ __device__ __forceinline__ CStage cl_stage_view(const NetDesc& net, unsigned cha
 
 __device__ void cl_pass(const StepArgs& a, const DevDescs& dd, const ClusterPlan& cp, StepCtrl& c, int step, int b0,
                         unsigned char* smraw, const ClusterCtx& cx, bool fetchCtrl, const unsigned* readyFlag, unsigned readyTarget,
-                        bool staged, bool helped, bool firstPass) {
+                        bool staged, bool helped, float (&wacc)[16], uint64_t* imgBars, unsigned imgParity) {
   const NetDesc& net = dd.net; const Hyper& hp = dd.hp;
   const int tid = threadIdx.x, rank = (int)cx.rank;
   const float* cm = reinterpret_cast<const float*>(smraw + cp.bCommon);
   const float* rk = reinterpret_cast<const float*>(smraw + cp.bRank);
   float* act = reinterpret_cast<float*>(smraw + cp.bAct);
-  float* gacc = reinterpret_cast<float*>(smraw + cp.bGacc);
   float* act2 = reinterpret_cast<float*>(smraw + cp.bAct2);     // [actPerSample][kOwn]: network outputs of the own samples
   float* err2 = reinterpret_cast<float*>(smraw + cp.bErr2);
   const CStage stg = cl_stage_view(net, smraw, cp);
@@ -410,6 +364,7 @@ __device__ void cl_pass(const StepArgs& a, const DevDescs& dd, const ClusterPlan
   const size_t jb = (size_t)(step - a.stepBase) * a.B + b0;
   const LayerDesc& Lo = net.L[cp.oLayer];
   const LayerDesc& Lp = net.L[cp.pLayer];
+  const int* witem = a.citems + ((size_t)rank * kST + tid) * kItemInts;
 
   if (!staged) {
     if (tid < kTS) rows[tid] = b0 + tid < a.B ? a.sampRow[jb + tid] : -1;
@@ -453,6 +408,7 @@ __device__ void cl_pass(const StepArgs& a, const DevDescs& dd, const ClusterPlan
       pms = (double)ld_cg(rp.MU + row * 2 * dA + dA + p0i);
     }
   }
+  if (imgBars) cl_mbar_wait(a, &imgBars[0], imgParity);      // first pass of the step: the forward part of the weight image
   __syncthreads();
   DBG_T(a, step, 2);
 
@@ -475,7 +431,7 @@ __device__ void cl_pass(const StepArgs& a, const DevDescs& dd, const ClusterPlan
     // the ParamLayer values are read at Wp + Lp.imgB: point Wp so that this lands on the common block's copy
     const float* Wp = cm + cp.iP - Lp.imgB;
     LossIO io{act2, err2, info, old, pair, samp, helped ? nullptr : vnext, b0 + s0, pa, pmm, pms, p0s, p0i};
-    loss_stages<kOwn, true>(a, net, hp, c, step, Wp, io, fetchCtrl, readyFlag, readyTarget);
+    loss_stages<kOwn, true, true>(a, net, hp, c, step, Wp, io, fetchCtrl, readyFlag, readyTarget);
   }
 
   // ---- backward, output layer: E_top[k][own samples] = W_out delta_out (Layers.h:131-145), broadcast with delta_out ----
@@ -534,17 +490,21 @@ __device__ void cl_pass(const StepArgs& a, const DevDescs& dd, const ClusterPlan
     }
     if (li == cp.nDense - 1) DBG_T(a, step, 21);
     if (L.needDx) {
+      if (imgBars && li == cp.nDense - 1) cl_mbar_wait(a, &imgBars[1], imgParity);     // the transposed slices
       cl_bwd_dx(L, cp.L[li - 1], rk, act, cx);
       if (li == cp.nDense - 1) DBG_T(a, step, 28);
-      cluster_sync_all();
+      cluster_arrive();
+      // while the partial input gradients travel: the weight-gradient items that only need this layer's (and the output
+      // layer's) deltas — item flag [10] = lowest hidden layer whose deltas the item reads
+      if (li == cp.nDense - 1) cl_wgrad(witem, act, wacc, true);
+      cluster_wait();
       if (li == cp.nDense - 1) DBG_T(a, step, 22);
-    }
+    } else if (li == cp.nDense - 1) cl_wgrad(witem, act, wacc, true);
   }
   DBG_T(a, step, 23);
 
-  // ---- weight gradient of the pass ----
-  cl_wgrad(cp, cm, act, gacc, rank, firstPass);
-  __syncthreads();
+  // ---- the remaining weight-gradient items (accumulated in registers over the passes of the step) ----
+  cl_wgrad(witem, act, wacc, false);
   DBG_T(a, step, 4);
 }
 
@@ -647,12 +607,19 @@ __device__ __forceinline__ void cl_p2(const StepArgs& a, const ClusterPlan& cp, 
   if (st.p >= 0) {
     const float* src = a.cpart + (size_t)c0 * net.nParams + st.p;
     int cc = c0;
-    for (; cc + 8 <= c1; cc += 8, src += (size_t)8 * net.nParams) {
-      float x[8];
+    for (; cc + 16 <= c1; cc += 16, src += (size_t)16 * net.nParams) {
+      float x[16];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) x[u] = ld_cg(src + (size_t)u * net.nParams);
+      for (int u = 0; u < 16; ++u) x[u] = ld_cg(src + (size_t)u * net.nParams);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v += x[u];
+      for (int u = 0; u < 16; ++u) v += x[u];
+    }
+    for (; cc + 4 <= c1; cc += 4, src += (size_t)4 * net.nParams) {
+      float x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x[u] = ld_cg(src + (size_t)u * net.nParams);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v += x[u];
     }
     for (; cc < c1; ++cc, src += net.nParams) v += ld_cg(src);
   }
@@ -715,6 +682,12 @@ __global__ void __launch_bounds__(kST, 1) k_steps_cluster(StepArgs a, int step0,
   const int clusterId = (int)blockIdx.x / kCL;
   if ((int)blockIdx.x == nw) {                        // ---- statistics CTA ----
     float* tiles = reinterpret_cast<float*>(smraw + cp.bHelpImg);      // scratch of the statistics phase (>= 4096 floats)
+    // {slot, length} of every position of the episode vector: constant during a launch, kept in shared memory if it fits
+    int2* epCache = reinterpret_cast<int2*>(smraw + cp.bHelpImg + 4 * (4096 + 256 * 12));
+    if ((size_t)cp.bHelpImg + 4 * (4096 + 256 * 12) + 8 * (size_t)a.nEpisodes <= (size_t)cp.bTotal) {
+      for (int p = tid; p < a.nEpisodes; p += kST) { const int sl = a.rp.epOrder[p]; epCache[p] = make_int2(sl, a.rp.epLen[sl]); }
+      __syncthreads();
+    } else epCache = nullptr;
     for (int s = 0; s < nSteps; ++s) {
       if (skipStatsLast && s == nSteps - 1) break;
       const int step = step0 + s;
@@ -726,7 +699,7 @@ __global__ void __launch_bounds__(kST, 1) k_steps_cluster(StepArgs a, int step0,
         load_ctrl(c, &a.ctrl[step & 1]);
       }
       __syncthreads();
-      p3_stats(a, hp, c, a.ctrl[(step + 1) & 1], step, tiles);
+      p3_stats(a, hp, c, a.ctrl[(step + 1) & 1], step, tiles, epCache);
       __syncthreads();
       if (tid == 0) {
         __threadfence();
@@ -743,7 +716,7 @@ __global__ void __launch_bounds__(kST, 1) k_steps_cluster(StepArgs a, int step0,
     for (int r = 0; r < kCL; ++r) cx.peer[r] = map_to_rank(base, (unsigned)r);
   }
   __shared__ __align__(8) uint64_t bars[2];
-  if (tid == 0) { mbar_init(&bars[0], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   // activations: zero once (pad rows / columns are never written afterwards)
   if (isP1) { float* act = reinterpret_cast<float*>(smraw + cp.bAct); for (int i = tid; i < cp.actFloats; i += kST) act[i] = 0.f; }
   else { float* act = reinterpret_cast<float*>(smraw + cp.bHelpAct); for (int i = tid; i < cp.actFloats + 16; i += kST) act[i] = 0.f; }
@@ -788,23 +761,27 @@ __global__ void __launch_bounds__(kST, 1) k_steps_cluster(StepArgs a, int step0,
     if (hasPass) cl_load_image(a, cp, smraw, (int)cx.rank, bars);
     // rows of the next step's samples (prefetch)
     const bool pfNow = pf && s + 1 < nSteps;
-    int nxRowS = -1, nxRowT = -1, nxSf = 0, nxRowP = -1;
+    int nxRowS = -1, nxRowT = -1, nxSf = 0, nxRowP = -1, nxRow8 = -1;
     if (pfNow) {
       const size_t jn = (size_t)(step + 1 - a.stepBase) * a.B + b0;
-      if (tid < kTS * dS / 4 && b0 + pfS < a.B) nxRowS = a.sampRow[jn + pfS];
-      if (tid < kOwn && b0 + s0 + tid < a.B) { nxRowT = a.sampRow[jn + s0 + tid]; nxSf = a.sampSlot[jn + s0 + tid]; }
-      if (tid < nPair && b0 + s0 + pfPs < a.B) nxRowP = a.sampRow[jn + s0 + pfPs];
+      if (tid >= 64 && tid < 64 + kTS && b0 + tid - 64 < a.B) nxRow8 = ld_index_now(a.sampRow + jn + tid - 64);
+      if (tid < kTS * dS / 4 && b0 + pfS < a.B) nxRowS = ld_index_now(a.sampRow + jn + pfS);
+      if (tid < kOwn && b0 + s0 + tid < a.B) { nxRowT = ld_index_now(a.sampRow + jn + s0 + tid); nxSf = ld_index_now(a.sampSlot + jn + s0 + tid); }
+      if (tid < nPair && b0 + s0 + pfPs < a.B) nxRowP = ld_index_now(a.sampRow + jn + s0 + pfPs);
     }
     if (hasPass) {
-      cl_mbar_wait(a, &bars[0], imgParity); imgParity ^= 1u;
       DBG_T(a, step, 1);
       bool first = true;
+      float wacc[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) wacc[i] = 0.f;
       for (int g = clusterId; g < nPass; g += nP1c) {
-        cl_pass(a, dd, cp, c, step, g * kTS, smraw, cx, first, ready, (unsigned)s, staged, true, first);
+        cl_pass(a, dd, cp, c, step, g * kTS, smraw, cx, first, ready, (unsigned)s, staged, true, wacc, first ? bars : nullptr, imgParity);
         first = false;
         if (g + nP1c < nPass) cluster_sync_all();       // the next pass overwrites buffers the peers may still read
       }
-      cl_store_partial(cp, net, reinterpret_cast<const float*>(smraw + cp.bGacc), a.cpart + (size_t)clusterId * net.nParams, (int)cx.rank);
+      imgParity ^= 1u;
+      cl_wgrad_store(a.citems + ((size_t)cx.rank * kST + tid) * kItemInts, a.cpart + (size_t)clusterId * net.nParams, wacc);
       DBG_T(a, step, 5);
     } else if (!isP1) {
       if (cl_helper(a, dd, cp, step, helper, nHelpers, smraw, bars, imgParity)) imgParity ^= 1u;
@@ -818,10 +795,7 @@ __global__ void __launch_bounds__(kST, 1) k_steps_cluster(StepArgs a, int step0,
         if (nxRowS >= 0) cp_async16_ca(dst, rp.S + (size_t)nxRowS * dS + pfC4);
         else *dst = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (tid < kTS) {
-        const size_t jn = (size_t)(step + 1 - a.stepBase) * a.B + b0;
-        stg.rows[tid] = b0 + tid < a.B ? a.sampRow[jn + tid] : -1;
-      }
+      if (tid >= 64 && tid < 64 + kTS) stg.rows[tid - 64] = nxRow8;
       if (tid < kOwn) {
         const int row = nxRowT, hn = (nxSf >> 31) & 1;
         stg.info[0 * kOwn + tid] = row < 0 ? 0 : row; stg.info[1 * kOwn + tid] = nxSf & 0x7fffffff;
@@ -879,13 +853,15 @@ constexpr size_t kSmemBudgetCluster = 216 * 1024;     // dynamic shared memory (
 
 // Fills `cp` for `net`; idx = three maps [3][nParams]: position of every parameter in the cluster image (first map; -2 =
 // blob padding, -1 = none), its second position (transposed copy; -1 = none) and its position in the tile kernel's image.
-void cluster_plan_build(const NetDesc& net, int numWorkersHint, ClusterPlan& cp, std::vector<int>& idx) {
+void cluster_plan_build(const NetDesc& net, int numWorkersHint, ClusterPlan& cp, std::vector<int>& idx, std::vector<int>& items) {
   memset(&cp, 0, sizeof(cp));
+  items.assign((size_t)kCL * kST * kItemInts, 0);
   idx.assign((size_t)3 * net.nParams, -1);
   for (int p = 0; p < net.nParams; ++p) idx[p] = -2;
   if (net.recurrent) return;
-  const char* off = getenv("SMB200_CLUSTER");
-  if (off && strcmp(off, "0") == 0) return;
+  // opt-in (SMB200_CLUSTER=1): at B = 256 the persistent tile kernel is still the faster one ("cluster step kernel")
+  const char* on = getenv("SMB200_CLUSTER");
+  if (!(on && strcmp(on, "1") == 0)) return;
   // layers: input, (dense tanh, [residual])*, dense linear, param
   int nd = 0;
   for (int l = 1; l < net.nLayers; ++l) {
@@ -949,7 +925,7 @@ void cluster_plan_build(const NetDesc& net, int numWorkersHint, ClusterPlan& cp,
     if (L.resLayer >= 0) { L.gRW = o; o += L.NS; L.gRB = o; o += L.NS; }
   }
   cp.gOW = o; o += cp.L[nd - 1].NS * (cp.oN + 1); cp.gOB = o; o += cp.oN; cp.gP = o; o += std::max(cp.nP, 1);
-  cp.gaccFloats = ru(o, 4);
+  cp.gaccFloats = 4;                                  // (the gradient of a step is accumulated in registers: cl_wgrad)
   // shared-memory carve-up
   size_t b = ((sizeof(DevDescs) + 15) / 16) * 16;
   cp.bPlan = (int)b; b += ru((int)sizeof(ClusterPlan), 16);
@@ -1012,6 +988,68 @@ void cluster_plan_build(const NetDesc& net, int numWorkersHint, ClusterPlan& cp,
     for (int n = 0; n < cp.oN; ++n) { const int p = O.wOff + k * O.ld + n; iA[p] = cp.iOW + k * cp.ldo + n; iO[p] = O.imgW + k * O.ldp + n; }
   for (int n = 0; n < cp.oN; ++n) { iA[O.bOff + n] = cp.iOB + n; iO[O.bOff + n] = O.imgB + n; }
   for (int i = 0; i < cp.nP; ++i) { iA[P.bOff + i] = cp.iP + i; iO[P.bOff + i] = P.imgB + i; }
+  // ---- weight-gradient work items, one per thread and rank (cl_wgrad) ----
+  for (int r = 0; r < kCL; ++r) {
+    int it = 0;
+    int early = 0;
+    auto put = [&](int kind, int aoff, int astr, int boff, int bstr, int obase, int ostrA, int ostrB, int na, int nb) -> bool {
+      if (it >= kST) return false;
+      int* q = items.data() + ((size_t)r * kST + it) * kItemInts;
+      q[0] = kind; q[1] = aoff; q[2] = astr; q[3] = boff; q[4] = bstr; q[5] = obase; q[6] = ostrA; q[7] = ostrB; q[8] = na; q[9] = nb;
+      q[10] = early;
+      ++it; return true;
+    };
+    bool fits = true;
+    for (int li = 0; li < nd && fits; ++li) {                  // dW[k][n] of the slice: rows kq + i KQ, columns nq + j NQ
+      const CDense& L = cp.L[li];
+      const LayerDesc& D = net.L[L.layer];
+      const int KQ = L.Kp >> 2, NQ = L.NS >> 2, n0 = r * L.NS;
+      const int xoff = li == 0 ? cp.sX0 : cp.L[li - 1].sXout;
+      early = li == nd - 1;
+      for (int kq = 0; kq < KQ && fits; ++kq)
+        for (int nq = 0; nq < NQ && fits; ++nq) {
+          int na = 0, nb = 0;
+          for (int i = 0; i < 4; ++i) if (kq + i * KQ < L.K) na = i + 1;
+          for (int j = 0; j < 4; ++j) if (n0 + nq + j * NQ < L.N) nb = j + 1;
+          if (na == 0 || nb == 0) continue;
+          fits = put(1, xoff + kq * kXS, KQ * kXS, L.sDs + nq * kXS, NQ * kXS, D.wOff + kq * D.ld + n0 + nq, KQ * D.ld, NQ, na, nb);
+        }
+    }
+    {                                                            // rows of the output layer owned by this rank
+      const CDense& Lt = cp.L[nd - 1];
+      const int KQ = Lt.NS >> 2, NQ = cp.oNp >> 2, k0 = r * Lt.NS;
+      early = 1;
+      for (int kq = 0; kq < KQ && fits; ++kq)
+        for (int nq = 0; nq < NQ && fits; ++nq) {
+          int na = 0, nb = 0;
+          for (int i = 0; i < 4; ++i) if (k0 + kq + i * KQ < cp.oK) na = i + 1;
+          for (int j = 0; j < 4; ++j) if (nq + j * NQ < cp.oN) nb = j + 1;
+          if (na == 0 || nb == 0) continue;
+          fits = put(1, Lt.sXout + (k0 + kq) * kXS, KQ * kXS, cp.sDout + nq * kXS, NQ * kXS, O.wOff + (k0 + kq) * O.ld + nq, KQ * O.ld, NQ, na, nb);
+        }
+    }
+    for (int li = 0; li < nd && fits; ++li) {                  // bias (+ residual parameters) of every column of the slice
+      const CDense& L = cp.L[li];
+      const LayerDesc& D = net.L[L.layer];
+      const int xoff = li == 0 ? cp.sX0 : cp.L[li - 1].sXout;
+      early = li == nd - 1;
+      for (int nl = 0; nl < L.NS && fits; ++nl) {
+        const int n = r * L.NS + nl;
+        if (n >= L.N) continue;
+        if (L.resLayer >= 0) {
+          const LayerDesc& R = net.L[L.resLayer];
+          // b_0 = error on the residual output (row n of sE), b_1 = the residual's input x[n]
+          fits = put(2, L.sDs + nl * kXS, 0, L.sE + n * kXS, (xoff + n * kXS) - (L.sE + n * kXS), D.bOff + n, R.wOff + n, R.bOff + n, 1, 1);
+        } else fits = put(2, L.sDs + nl * kXS, 0, 0, 0, D.bOff + n, 0, 0, 1, 0);
+      }
+    }
+    early = 1;
+    if (r == 0) {
+      for (int n = 0; n < cp.oN && fits; ++n) fits = put(3, cp.sDout + n * kXS, 0, 0, 0, O.bOff + n, 0, 0, 1, 1);
+      for (int i = 0; i < cp.nP && fits; ++i) fits = put(3, cp.sGstd + i * kXS, 0, 0, 0, P.bOff + i, 0, 0, 1, 1);
+    }
+    if (!fits) return;                                           // more than one item per thread: the tile kernel runs this network
+  }
   cp.ok = 1;
 }
 

@@ -90,7 +90,7 @@ struct smb200_learner {
   GradTile* dTiles = nullptr; int nTiles = 0;
   int Bpad = 0;
   // cluster step kernel (feed-forward nets, cluster_step.cuh)
-  ClusterPlan cplan{}; ClusterPlan* dCplan = nullptr; std::vector<int> cidx; int* dCidx = nullptr;
+  ClusterPlan cplan{}; ClusterPlan* dCplan = nullptr; std::vector<int> cidx, citems; int* dCidx = nullptr; int* dCitems = nullptr;
   float* cimg = nullptr; float* cpart = nullptr; int clusterP1 = 0;      // clusterP1 > 0: the cluster kernel runs the steps
   int dP = 0;                     // columns of the behaviour policy MU: 2 * dim_action (mean, stdev), or the K option probabilities
 
@@ -128,7 +128,7 @@ struct smb200_learner {
     a.comm = comm;
     a.descs = dDescs; a.rp = rp; a.W = W; a.Wimg = Wimg; a.M1 = M1; a.M2 = M2; a.G = G; a.dbgT = nullptr; a.useTma = useTma;
     a.useTc = useTc; a.tcPartial = tcPartial;
-    a.cplan = dCplan; a.cimg = cimg; a.cpart = cpart; a.cidx = dCidx; a.cClusters = clusterP1;
+    a.cplan = dCplan; a.cimg = cimg; a.cpart = cpart; a.cidx = dCidx; a.citems = dCitems; a.cClusters = clusterP1;
     a.actG = actG; a.errG = errG; a.sampRow = dSampT; a.sampSlot = dSampSlot; a.rec = dRec;
     a.lastO = lastO; a.lastG = lastG; a.lastX = lastX; a.ctrl = dCtrl; a.statsOut = dStats;
     a.tiles = dTiles; a.nTiles = nTiles; a.B = cfg.batch_size; a.Bpad = Bpad;
@@ -662,12 +662,12 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
   {
     const char* m0 = getenv("SMB200_MODE");
     int coop0 = 0; cudaDeviceGetAttribute(&coop0, cudaDevAttrCooperativeLaunch, c.device);
-    cluster_plan_build(net, 4 * 33 - 1, h->cplan, h->cidx);
+    cluster_plan_build(net, 4 * 33 - 1, h->cplan, h->cidx, h->citems);
     if (h->cplan.ok && coop0 && !(m0 && strcmp(m0, "two") == 0)) {
       CK(cluster_prepare(h->cplan));
       const int maxC = std::min(33, cluster_max_active(h->cplan));
       if (maxC >= 2) {
-        cluster_plan_build(net, kCL * maxC - 1, h->cplan, h->cidx);      // the P2 partition depends on the worker count
+        cluster_plan_build(net, kCL * maxC - 1, h->cplan, h->cidx, h->citems);      // the P2 partition depends on the worker count
         if (h->cplan.ok) h->clusterP1 = maxC - 1;
       }
     }
@@ -680,6 +680,8 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
       CKC(cudaMemcpy(h->dCplan, &h->cplan, sizeof(ClusterPlan), cudaMemcpyHostToDevice));
       CK(dev_alloc(&h->dCidx, h->cidx.size()));
       CKC(cudaMemcpy(h->dCidx, h->cidx.data(), sizeof(int) * h->cidx.size(), cudaMemcpyHostToDevice));
+      CK(dev_alloc(&h->dCitems, h->citems.size()));
+      CKC(cudaMemcpy(h->dCitems, h->citems.data(), sizeof(int) * h->citems.size(), cudaMemcpyHostToDevice));
       CK(dev_alloc(&h->cimg, cluster_image_floats(h->cplan)));
       CK(dev_alloc(&h->cpart, (size_t)h->clusterP1 * net.nParams));
     }
@@ -712,7 +714,7 @@ void smb200_destroy(smb200_learner* h) {
   void* ptrs[] = {rp.S, rp.A, rp.MU, rp.R, rp.V, rp.ADV, rp.Q, rp.DELTA, rp.RHO, rp.KL, rp.rowFlag, rp.epStart, rp.epLen, rp.epTerm,
                   rp.epId, rp.epAgg, rp.epOrder, rp.stateMean, rp.stateScale, rp.stateStd, rp.rew, h->W, h->Wimg, h->dDbg, h->M1, h->M2, h->G,
                   h->actG, h->errG, h->dTiles, h->dDescs, h->dCtrl, h->dRec, h->lastO, h->lastG, h->lastX, h->dSums, h->dBarrier,
-                  h->dSampSlot, h->dSampT, h->dStats, h->dCplan, h->dCidx, h->cimg, h->cpart};
+                  h->dSampSlot, h->dSampT, h->dStats, h->dCplan, h->dCidx, h->dCitems, h->cimg, h->cpart};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int q = 0; q < kMaxWorld; ++q) if (h->peerMapped[q]) cudaIpcCloseMemHandle(h->peerMapped[q]);
   if (h->commBuf) cudaFree(h->commBuf);

@@ -478,7 +478,9 @@ struct LossIO {
   int b0; double pa, pmm, pms; int p0s, p0i;   // behaviour policy / action of the thread's first (sample, component) pair
 };
 
-template <int TB, bool SM>
+// LATE: the kernel may reach the loss before the statistics CTA of the previous step has published beta (cluster kernel):
+// wait for it during stage 2 instead of stage 1 (see below).
+template <int TB, bool SM, bool LATE = false>
 __device__ __forceinline__ void loss_stages(const StepArgs& a, const NetDesc& net, const Hyper& hp, StepCtrl& c, int step, const float* Wp,
                                             const LossIO& io, bool fetchCtrl, const unsigned* readyFlag, unsigned readyTarget) {
   const int tid = threadIdx.x;
@@ -556,18 +558,30 @@ __device__ __forceinline__ void loss_stages(const StepArgs& a, const NetDesc& ne
     samp[2 * TB + s] = net2v(O0);
     samp[3 * TB + s] = vdiff(O0);
   }
-  if (fetchCtrl && tid == kST - 1) {
+  // This step's ReF-ER scalars.  First step of a launch (nothing to wait for): load them now.  Later steps: the statistics CTA of
+  // the previous step may still be running — Cmax / Cinv only depend on the step number (annealing, same f64 expression as
+  // stats_and_refer) and are evaluated locally, beta is waited for during stage 2 and first used in stage 3.
+  const bool lateCtrl = LATE && fetchCtrl && readyFlag != nullptr && readyTarget > 0;
+  if (fetchCtrl && !lateCtrl && tid == kST - 1) {
     if (readyFlag) { while (ld_acquire(readyFlag) < readyTarget) { } }
     load_ctrl(c, &a.ctrl[step & 1]);
   }
   __syncthreads();
   DBG_T(a, step, 8);
+  if (lateCtrl && tid == kST - 1) {
+    while (ld_acquire(readyFlag) < readyTarget) { }
+    load_ctrl(c, &a.ctrl[step & 1]);
+  }
   // Stage 2: one thread per sample — sums in component order like the reference, flags, value terms,
   // replay write-back (RACER_train.cpp:59-60) and the record for the aggregate updates.
   if (tid < TB && info[3 * TB + tid]) {
     const int s = tid, b = b0 + s;
     const size_t row = info[s];
-    const double beta = c.beta, cmax = c.cmax, cinv = c.cinv;
+    double cmax, cinv;
+    if (lateCtrl) {                 // stats_and_refer of the previous step: gstep = c.grad_step + 1 = step
+      cmax = 1.0 + hp.clipImpWeight / (1.0 + (double)(long long)step * hp.epsAnneal);
+      cinv = 1.0 / cmax;
+    } else { cmax = c.cmax; cinv = c.cinv; }
     double logw = 0.0, dkl = 0.0;
     for (int i = 0; i < dA; ++i) { logw += pair[0 * nPair + s * dA + i]; dkl += pair[1 * nPair + s * dA + i]; }
     const double rho = exp(logw > 7.0 ? 7.0 : (logw < -7.0 ? -7.0 : logw));           // :648-653
@@ -590,21 +604,16 @@ __device__ __forceinline__ void loss_stages(const StepArgs& a, const NetDesc& ne
     }
     const double A_RET = (double)old[7 * TB + s] - Vval, deltaQ = A_RET - Aval;
     const double Ver = fmin(1.0, rho) * deltaQ;
-    const double g0 = isFar ? 0.0 : Ver * beta * samp[3 * TB + s];
+    samp[8 * TB + s] = Ver;                         // g[0] = isFar ? 0 : Ver * beta * dV/dO is formed in stage 3 (beta)
     samp[0 * TB + s] = A_RET * fmin(cmax, rho);     // pgfac
     samp[1 * TB + s] = isFar ? 1.0 : 0.0;
     if (racer) {                                    // ADV.grad(act, isFar ? 0 : beta*Aer, gradient), Gaus_advantage.h:88-114
       const double Aer = fmin(cmax, rho) * deltaQ;
-      const double errA = isFar ? 0.0 : beta * Aer;
       const double expect = -ratio;
-      const double gc = (orig + expect) * (errA * ((1.0 + coefRaw / rtc) / 2.0));
-      samp[4 * TB + s] = orig * coef; samp[5 * TB + s] = expect; samp[6 * TB + s] = coef; samp[7 * TB + s] = errA;
-      err[(Lo.actOff + 1) * TB + s] = (float)gc;
-      if (keep) a.lastG[(size_t)b * net.nOut + 1] = (float)gc;
+      samp[4 * TB + s] = orig * coef; samp[5 * TB + s] = expect; samp[6 * TB + s] = coef; samp[7 * TB + s] = Aer;
+      samp[9 * TB + s] = orig; samp[10 * TB + s] = (1.0 + coefRaw / rtc) / 2.0;
       if (keep) a.lastO[(size_t)b * net.nOut + 1] = (float)coefRaw;
     }
-    err[(Lo.actOff + 0) * TB + s] = (float)g0;
-    if (keep) a.lastG[(size_t)b * net.nOut + 0] = (float)g0;
     if (keep) a.lastO[(size_t)b * net.nOut + 0] = O0f;
     SampleRec r;
     r.slot = info[TB + s]; r.hasNext = info[2 * TB + s];
@@ -648,6 +657,17 @@ __device__ __forceinline__ void loss_stages(const StepArgs& a, const NetDesc& ne
       const int b = b0 + s;
       const double pgfac = samp[0 * TB + s];
       const bool isFar = samp[1 * TB + s] != 0.0;
+      if (i == 0) {                 // per-sample gradients that need beta: value head (RACER_train.cpp:46) and advantage coefficient
+        const double g0 = isFar ? 0.0 : samp[8 * TB + s] * beta * samp[3 * TB + s];
+        err[(Lo.actOff + 0) * TB + s] = (float)g0;
+        if (keep) a.lastG[(size_t)b * net.nOut + 0] = (float)g0;
+        if (racer) {
+          const double errA0 = isFar ? 0.0 : beta * samp[7 * TB + s];
+          const double gc = (samp[9 * TB + s] + samp[5 * TB + s]) * (errA0 * samp[10 * TB + s]);
+          err[(Lo.actOff + 1) * TB + s] = (float)gc;
+          if (keep) a.lastG[(size_t)b * net.nOut + 1] = (float)gc;
+        }
+      }
       const float mf = act[(Lo.actOff + m0 + i) * TB + s];
       const double m = (double)mf;
       double pg_mean = pgfac * pair[4 * nPair + p];
@@ -663,7 +683,8 @@ __device__ __forceinline__ void loss_stages(const StepArgs& a, const NetDesc& ne
       if (keep) a.lastO[(size_t)b * net.nOut + m0 + i] = mf;
       if (keep) a.lastO[(size_t)b * net.nOut + m0 + dA + i] = ldw<SM>(Wp + Lp.imgB + i);
       if (racer) {
-        const double oc = samp[4 * TB + s], expect = samp[5 * TB + s], coef = samp[6 * TB + s], errA = samp[7 * TB + s];
+        const double oc = samp[4 * TB + s], expect = samp[5 * TB + s], coef = samp[6 * TB + s];
+        const double errA = isFar ? 0.0 : beta * samp[7 * TB + s];
         const double F = pair[11 * nPair + p];
         double g1 = pair[9 * nPair + p] >= 0.0 ? oc * pair[9 * nPair + p] / 2.0 : 0.0;
         double g2 = pair[10 * nPair + p] >= 0.0 ? oc * pair[10 * nPair + p] / 2.0 : 0.0;
@@ -1804,8 +1825,20 @@ __device__ int apply_sample_records(const StepArgs& a, float* stage /* >= 256*12
 // `sweep` != nullptr on the every-1000-steps recompute: Retrace error sums come from the sweep.
 constexpr int kStatChunk = 4096;   // episode positions staged per pass (floats of shared memory)
 
+// `Uint += float` for the common case of a small count and a small non-negative addend: 32-bit conversions (one instruction
+// each) give what uint_plus_float_x86 gives — (float)n is exact below 2^24 and truncation agrees on [0, 2^31)
+__device__ __forceinline__ unsigned long long uint_plus_float_fast(unsigned long long n, float x) {
+  if (n < (1ull << 24)) {
+    const float f = (float)(unsigned)n + x;
+    if (f >= 0.0f && f < 2147483648.0f) return (unsigned long long)__float2uint_rz(f);
+  }
+  return uint_plus_float_x86(n, x);
+}
+
+// epCache: optional shared-memory copy of {slot, episode length} per position of the episode vector (constant during a launch)
 __device__ void stats_and_refer(const StepArgs& a, const Hyper& hp, const StepCtrl& c, StepCtrl& nx, int step,
-                                const SweepSums* sweep, long long farExactOverride, int farDeltaMine, float* xs) {
+                                const SweepSums* sweep, long long farExactOverride, int farDeltaMine, float* xs,
+                                const int2* epCache = nullptr) {
   __shared__ double shd[kST / 32][6];
   __shared__ float shf[kST / 32][3];
   __shared__ unsigned long long shn[kST];
@@ -1824,12 +1857,20 @@ __device__ void stats_and_refer(const StepArgs& a, const Hyper& hp, const StepCt
     for (int p0 = tid; p0 < n; p0 += 4 * kST) {
       int sl[4]; float Ns[4], far[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { const int p = p0 + u * kST; sl[u] = p < n ? rp.epOrder[base + p] : -1; }
+      for (int u = 0; u < 4; ++u) {
+        const int p = p0 + u * kST;
+        sl[u] = -1; Ns[u] = 0.f;
+        if (p < n) {
+          if (epCache) { const int2 e = epCache[base + p]; sl[u] = e.x; Ns[u] = (float)e.y; }
+          else sl[u] = rp.epOrder[base + p];
+        }
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (sl[u] < 0) continue;
         const int slot = sl[u];
-        Ns[u] = (float)rp.epLen[slot]; far[u] = rp.epAgg[AGG_FAR * ME + slot];
+        if (!epCache) Ns[u] = (float)rp.epLen[slot];
+        far[u] = rp.epAgg[AGG_FAR * ME + slot];
         sumDKL += (double)(Ns[u] * rp.epAgg[AGG_KL * ME + slot]);
         sumE2 += (double)(Ns[u] * rp.epAgg[AGG_E2 * ME + slot]);
         sumQ2 += (double)rp.epAgg[AGG_Q2 * ME + slot];
@@ -1844,7 +1885,7 @@ __device__ void stats_and_refer(const StepArgs& a, const Hyper& hp, const StepCt
     __syncthreads();
     if (tid < T) {
       int p = (tid - base % T + T) % T;     // first position of this chunk owned by virtual thread `tid`
-      for (; p < n; p += T) nOff = uint_plus_float_x86(nOff, xs[p]);   // the reference's `Uint += float`, x86 semantics
+      for (; p < n; p += T) nOff = uint_plus_float_fast(nOff, xs[p]);   // the reference's `Uint += float`, x86 semantics
     }
     __syncthreads();
   }
@@ -1951,11 +1992,12 @@ __device__ void stats_and_refer(const StepArgs& a, const Hyper& hp, const StepCt
   }
 }
 
-__device__ void p3_stats(const StepArgs& a, const Hyper& hp, const StepCtrl& c, StepCtrl& nx, int step, float* stage) {
+__device__ void p3_stats(const StepArgs& a, const Hyper& hp, const StepCtrl& c, StepCtrl& nx, int step, float* stage,
+                         const int2* epCache = nullptr) {
   const int fd = apply_sample_records(a, stage);
   __threadfence_block();
   __syncthreads();
-  stats_and_refer(a, hp, c, nx, step, nullptr, -1, fd, stage);
+  stats_and_refer(a, hp, c, nx, step, nullptr, -1, fd, stage, epCache);
 }
 
 

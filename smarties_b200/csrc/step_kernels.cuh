@@ -94,6 +94,7 @@ struct ClusterPlan {
 struct StepArgs {
   // cluster step kernel
   const ClusterPlan* cplan; float* cimg; float* cpart; const int* cidx;   // image, per-cluster partial gradients [clusters][nParams], image positions [3][nParams]
+  const int* citems;                 // weight-gradient work items [kCL][threads][12]
   int cClusters;                     // P1 clusters of the launch
   CommView comm;
   const DevDescs* descs;
@@ -154,7 +155,7 @@ int launch_steps_persistent(const StepArgs& a, const NetDesc& net, int grid, int
 int launch_finalize_sweep(const StepArgs& a, int step, const SweepSums* sweep, cudaStream_t st);
 int launch_forward(const StepArgs& a, const NetDesc& net, const float* states, int n, float* out, cudaStream_t st);
 // cluster step kernel (cluster_step.cuh)
-void cluster_plan_build(const NetDesc& net, int numWorkersHint, ClusterPlan& cp, std::vector<int>& idx);
+void cluster_plan_build(const NetDesc& net, int numWorkersHint, ClusterPlan& cp, std::vector<int>& idx, std::vector<int>& items);
 size_t cluster_image_floats(const ClusterPlan& cp);
 int cluster_prepare(const ClusterPlan& cp);
 int cluster_max_active(const ClusterPlan& cp);

@@ -121,25 +121,45 @@ def test_two_kernel_mode_equals_persistent(monkeypatch, case):
     Bm = make_learner(g)
     monkeypatch.delenv("SMB200_MODE")
     sa, sb = A.train_steps(g.steps), Bm.train_steps(g.steps)
-    if True:
-        # recurrent nets: the persistent kernel contracts the LSTM weight gradient on the tensor cores (tcgen05, 3xTF32 split),
-        # the two-kernel mode on the SIMT tiles; feed-forward nets: the cluster kernel sums dot products by a lane butterfly and
-        # the gradient per cluster, the two-kernel mode in k / batch order: same mathematics, different rounding of the 4-byte sums
+    if g.settings.get("nnType", "FFNN") == "LSTM":
+        # the persistent kernel contracts the LSTM weight gradient on the tensor cores (tcgen05, 3xTF32 split), the
+        # two-kernel mode on the SIMT tiles: same mathematics, different rounding of the 4-byte sums
         for x, y in zip(sa, sb):
             assert x["n_far_policy"] == y["n_far_policy"] and x["grad_step"] == y["grad_step"]
             assert x["beta"] == pytest.approx(y["beta"], rel=1e-12) and x["avg_sq_err"] == pytest.approx(y["avg_sq_err"], rel=1e-5)
         assert np.abs(A.get_weights() - Bm.get_weights()).max() < 1e-6
+    else:
+        assert sa == sb
+        assert np.array_equal(A.get_weights(), Bm.get_weights())
     A.close(); Bm.close()
+
+
+FEED_FORWARD_CASES = [c for c in CASES + THREADED_CASES]
+
+
+@pytest.mark.parametrize("case", FEED_FORWARD_CASES)
+def test_cluster_kernel_matches_reference(monkeypatch, case):
+    """The cluster step kernel (cluster_step.cuh, SMB200_CLUSTER=1: clusters of 4 CTAs with column slices of the network in
+    shared memory, layer outputs over distributed shared memory, per-cluster weight-gradient sums) against the same goldens
+    and bars as the persistent tile kernel."""
+    monkeypatch.setenv("SMB200_CLUSTER", "1")
+    g = Golden(case)
+    L = make_learner(g)
+    for s in range(g.steps):
+        st = L.train_steps(1)[0]
+        _check_step(L, g, g.ref, f"s{s}", st)
+    _check_final(L, g.ref)
+    L.close()
 
 
 @pytest.mark.parametrize("case", ["vracer_small", "vracer_cfg2mini", "racer_bounded", "vracer_b1024"])
 def test_cluster_kernel_equals_tile_kernel(monkeypatch, case):
-    """Feed-forward nets run on the cluster step kernel (cluster_step.cuh); SMB200_CLUSTER=0 selects the persistent tile
-    kernel.  Same samples, same integer far-policy counts, floats equal to f32 round-off of the different summation orders."""
+    """SMB200_CLUSTER=1 selects the cluster step kernel for feed-forward nets, the default is the persistent tile kernel.
+    Same samples, same integer far-policy counts, floats equal to f32 round-off of the different summation orders."""
     g = Golden(case)
-    A = make_learner(g)
-    monkeypatch.setenv("SMB200_CLUSTER", "0")
     Bm = make_learner(g)
+    monkeypatch.setenv("SMB200_CLUSTER", "1")
+    A = make_learner(g)
     monkeypatch.delenv("SMB200_CLUSTER")
     sa, sb = A.train_steps(g.steps), Bm.train_steps(g.steps)
     for x, y in zip(sa, sb):
