@@ -170,6 +170,11 @@ int smb200_retrace_sweep(smb200_learner* h, double* sum_err2);
 /* ... and the reward/state moments of updateRewardsStats (MemoryProcessing.cpp:94-185):
  * out[2*dS+3] = {sum(s-mean)[dS], sum((s-mean)^2)[dS], count, sum(r-mean), sum((r-mean)^2)}. */
 int smb200_reward_state_moments(smb200_learner* h, double* out);
+/* Both of them, plus the exact recompute of the per-episode aggregates (Episode::updateCumulative, Episode.cpp:213-242), as
+ * the ONE pass over the buffer the learner runs every 1000 steps (MemoryProcessing.cpp:187-259 followed by :94-185; both read
+ * the normalisers of before the pass): k_sweep_fused, state rows streamed through shared memory by cp.async.bulk.
+ * moments[2*dS+3] as above.  Needs dim_state % 4 == 0 with dim_state / 4 a power of two, estimator retrace or GAE. */
+int smb200_fused_sweep(smb200_learner* h, double* sum_err2, double* moments);
 
 /* Read one per-transition array for every stored episode, concatenated in the buffer's current
  * episode order (rows incl. the terminal row), and the episode table in the same order:

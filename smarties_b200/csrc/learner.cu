@@ -524,10 +524,18 @@ static int run_segment(smb200_learner* h, int first, int n, long long gstep0, in
     if (launch_clear_sums(h->dSums, h->stream)) return -2;
     // retraceExplore: baseline = stats.maxAbsError BEFORE this step's update (createReturnEstimator at the top of
     // updateTrainingStatistics, MemoryProcessing.cpp:196) = ctrl[step & 1], still device-resident here
+    const char* fz = getenv("SMB200_FUSED_SWEEP");
+    if (sweep_fused_supported(h->rp, h->cfg.returns_estimator) && !(fz && fz[0] == '0')) {
+      // Retrace + aggregates + moments in one pass over the buffer (both read the normalisers of BEFORE this sweep)
+      if (launch_sweep_fused(h->rp, (int)h->episodes.size(), (float)h->cfg.gamma, (float)h->cfg.lambda, h->cfg.returns_estimator, (float)cm,
+                             (float)(1.0 / cm), h->dSums, h->numSMs, h->stream)) return -2;
+      h->launches -= 1;
+    } else {
     if (launch_sweep(h->rp, (int)h->episodes.size(), 0, (float)h->cfg.gamma, (float)h->cfg.lambda, h->cfg.returns_estimator, 1, (float)cm, (float)(1.0 / cm),
                      h->dSums, h->stream, 0.f, h->dCtrl + (step & 1))) return -2;
     if (h->cfg.returns_estimator == SMB200_RETRACE_EXPLORE) h->launches += 1;
     if (launch_moments(h->rp, h->highWater, h->dSums, h->numSMs, h->stream)) return -2;
+    }
     if (launch_peer_allreduce(h->comm, h->dSums->moments, 2 * h->cfg.dim_state + 3, ++h->vecStamp, h->stream)) return -2;
     if (launch_finalize_sweep(a, step, h->dSums, h->stream)) return -2;
     if (launch_update_scaling(h->rp, h->dCtrl + (step & 1), h->dDescs, h->dSums, 0, h->stream)) return -2;
@@ -1327,6 +1335,30 @@ int smb200_retrace_sweep(smb200_learner* h, double* sumErr2) {
   if (d2h(h, &e, &h->dSums->sumErr2, sizeof(double))) return SMB200_ERR_CUDA;
   float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->lastMs = ms; h->lastLaunches = 1;
   if (sumErr2) *sumErr2 = e;
+  return 0;
+}
+
+// The every-1000-steps pass as ONE kernel (k_sweep_fused): Retrace / GAE over all episodes, exact recompute of the episode
+// aggregates, reward and state moments; without the statistics / normaliser update that follows it inside a learner step.
+int smb200_fused_sweep(smb200_learner* h, double* sumErr2, double* moments) {
+  if (!h || h->episodes.empty()) return SMB200_ERR_STATE;
+  if (!sweep_fused_supported(h->rp, h->cfg.returns_estimator)) { set_error_msg("fused sweep: unsupported state width or estimator"); return SMB200_ERR_INVALID; }
+  cudaSetDevice(h->cfg.device);
+  const int dS = h->cfg.dim_state;
+  if (upload_order(h)) return SMB200_ERR_CUDA;
+  if (launch_clear_sums(h->dSums, h->stream)) return SMB200_ERR_CUDA;
+  const double cm = cmax_at(h, h->gradStep);
+  SMB200_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
+  if (launch_sweep_fused(h->rp, (int)h->episodes.size(), (float)h->cfg.gamma, (float)h->cfg.lambda, h->cfg.returns_estimator, (float)cm,
+                         (float)(1.0 / cm), h->dSums, h->numSMs, h->stream)) return SMB200_ERR_CUDA;
+  SMB200_CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
+  double e = 0;
+  std::vector<double> m(2 * dS + 3);
+  if (d2h(h, &e, &h->dSums->sumErr2, sizeof(double))) return SMB200_ERR_CUDA;
+  if (d2h(h, m.data(), h->dSums->moments, sizeof(double) * m.size())) return SMB200_ERR_CUDA;
+  float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->lastMs = ms; h->lastLaunches = 1;
+  if (sumErr2) *sumErr2 = e;
+  if (moments) memcpy(moments, m.data(), sizeof(double) * m.size());
   return 0;
 }
 

@@ -171,6 +171,10 @@ int launch_sweep(const ReplayView& rp, int nEpisodes, int oneSlot, float gamma, 
                  int recomputeAggregates, float cmax, float cinv, SweepSums* sums, cudaStream_t st,
                  float exploreBaseline = 0.f, const StepCtrl* exploreCtrl = nullptr);
 int launch_moments(const ReplayView& rp, long long rowEnd, SweepSums* sums, int numSMs, cudaStream_t st);
+// Retrace / GAE + exact aggregates + reward / state moments of every episode in ONE pass (k_sweep_fused)
+bool sweep_fused_supported(const ReplayView& rp, int estimator);
+int launch_sweep_fused(const ReplayView& rp, int nEpisodes, float gamma, float lambda, int estimator, float cmax, float cinv,
+                       SweepSums* sums, int numSMs, cudaStream_t st);
 int launch_update_scaling(const ReplayView& rp, const StepCtrl* ctrlCur, const DevDescs* descs, const SweepSums* sums, int bInit, cudaStream_t st);
 int launch_clear_sums(SweepSums* sums, cudaStream_t st);
 // sum a small f64 vector over all ranks through peer memory (in place, identical result on every rank)

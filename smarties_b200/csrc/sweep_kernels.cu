@@ -464,6 +464,294 @@ __global__ void __launch_bounds__(kThreads, 2) k_moments_v4(ReplayView rp, long 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// The every-1000-steps pass over the whole buffer in ONE kernel (24 B + 132 B per transition): per episode
+//   * Retrace / GAE backward recursion (same segmented affine scan and re-evaluation as k_sweep),
+//   * exact recompute of the episode aggregates (Episode::updateCumulative) from the SAME loaded rows (+ KL, delta),
+//   * reward moments from the rewards the recursion loads anyway,
+//   * state moments (updateRewardsStats) from the episode's state rows, which stream into shared memory through a ring of
+//     cp.async.bulk copies (TMA, 16 KB per stage, kFuseStages stages per CTA, mbarrier completion): the copies of the next
+//     tiles — also of the CTA's NEXT episodes — are in flight while the scan of the current episode runs, so the DRAM pipe
+//     never waits for a register-bound load loop.  Episode bounds replace the row flags (no flag reads, no dead ring rows).
+// One CTA walks the episodes pos = blockIdx.x, blockIdx.x + gridDim.x, ...; f64 moment accumulators live in registers for
+// the whole kernel, one block reduction + one atomic per column at the end.
+// Requires dS % 4 == 0 and dS / 4 a power of two <= 256 (else: k_sweep + k_moments).
+// ------------------------------------------------------------------------------------------
+constexpr int kFuseStages = 6;
+constexpr int kFuseTileBytes = 16384;
+constexpr int kFuseMaxEp = 512;                 // episodes of one CTA whose (start, length) are cached in shared memory per round
+
+__device__ __forceinline__ uint32_t sw_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sw_mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sw_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sw_mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sw_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sw_mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned ok = 0;
+  while (!ok)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(sw_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void sw_bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(sw_smem_u32(dst)), "l"(src), "r"(bytes), "r"(sw_smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 2) k_sweep_fused(ReplayView rp, int nEpisodes, float gamma, float lambda, int gae,
+                                                             float C, float invC, SweepSums* sums) {
+  extern __shared__ __align__(128) unsigned char fsm[];
+  float* ring = reinterpret_cast<float*>(fsm);                                   // [kFuseStages][kFuseTileBytes]
+  __shared__ __align__(8) uint64_t full[kFuseStages];
+  __shared__ int epR0[kFuseMaxEp], epN[kFuseMaxEp], epSlot[kFuseMaxEp], epTermS[kFuseMaxEp];
+  __shared__ float segA[32], segB[32], segQin[32];
+  __shared__ float shCarry;
+  __shared__ float shRed[kThreads / 32][8];
+  __shared__ int shFar[kThreads / 32];
+  __shared__ double redD[kThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ME = rp.maxEpisodes, dS = rp.dS, CQ = dS >> 2, RP = kThreads / CQ;
+  const int tileRows = kFuseTileBytes / (dS * 4);                                // = 4 * RP
+  const int cq = tid % CQ, rl = tid / CQ;
+  const double rmean = (double)rp.rew[0], rscale = (double)rp.rew[1];
+  double m[4], s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) m[c] = (double)rp.stateMean[cq * 4 + c];
+  double rs1 = 0.0, rs2 = 0.0, cnt = 0.0;
+  float errAcc = 0.f; long long nRet = 0, nFar = 0;
+  if (tid == 0) {
+    for (int s = 0; s < kFuseStages; ++s) sw_mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const int myCount = nEpisodes > (int)blockIdx.x ? (nEpisodes - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  unsigned long long consumed = 0;               // tiles consumed so far by this CTA (stage = consumed % stages, parity from the count)
+  for (int e0 = 0; e0 < myCount; e0 += kFuseMaxEp) {
+    const int ne = min(kFuseMaxEp, myCount - e0);
+    __syncthreads();                             // the previous round's tables and ring are drained
+    for (int i = tid; i < ne; i += kThreads) {
+      const int slot = rp.epOrder[blockIdx.x + (size_t)(e0 + i) * gridDim.x];
+      epSlot[i] = slot; epR0[i] = rp.epStart[slot]; epN[i] = rp.epLen[slot]; epTermS[i] = rp.epTerm[slot];
+    }
+    __syncthreads();
+    // producer state (thread 0): next tile to issue = (pEp, pTile); the stream of this round's tiles is issued in order
+    int pEp = 0, pTile = 0; unsigned long long issued = consumed;
+    auto produce = [&]() {                       // thread 0 only
+      while (pEp < ne && issued < consumed + kFuseStages) {
+        const int nS = epN[pEp] - 1;
+        const int nT = (nS + tileRows - 1) / tileRows;
+        if (pTile >= nT) { ++pEp; pTile = 0; continue; }
+        const int rows = min(tileRows, nS - pTile * tileRows);
+        const int st = (int)(issued % kFuseStages);
+        const unsigned bytes = (unsigned)rows * (unsigned)dS * 4u;
+        sw_mbar_expect_tx(&full[st], bytes);
+        sw_bulk_g2s(ring + (size_t)st * (kFuseTileBytes / 4), rp.S + ((size_t)epR0[pEp] + (size_t)pTile * tileRows) * dS, bytes, &full[st]);
+        ++issued; ++pTile;
+      }
+    };
+    if (tid == 0) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); produce(); }
+    for (int ei = 0; ei < ne; ++ei) {
+      const int slot = epSlot[ei], N = epN[ei];
+      const size_t r0 = (size_t)epR0[ei];
+      const int nd = N - 1;
+      // ---- Retrace + aggregates of the episode (rows in registers; see k_sweep for the scan) ----
+      int far = 0; float sE2 = 0.f, mAE = -1e9f, mxQ = -1e9f, mnQ = 1e9f, sQ2 = 0.f, sQ1 = 0.f, sKL = 0.f, sR = 0.f;
+      // lane 0 of the LAST warp: Q of the last row (the carry of the recursion) and row 0 of the aggregates (the loop below
+      // covers rows 1 .. N-1).  Its loads are in flight together with the first chunk's; shCarry is first read after the
+      // chunk's first block barrier.
+      float c0 = 0.f, kl0 = 0.f, rr0 = 0.f, w0 = 1.f, d0 = 0.f, a0 = 0.f, v0 = 0.f;
+      const bool edge = tid == kThreads - 32;
+      if (edge) {
+        c0 = epTermS[ei] ? rp.Q[r0 + N - 1] : rp.V[r0 + N - 1];
+        kl0 = rp.KL[r0]; rr0 = rp.R[r0]; w0 = rp.RHO[r0]; d0 = rp.DELTA[r0]; a0 = rp.ADV[r0]; v0 = rp.V[r0];
+      }
+      bool firstChunk = true;
+      for (int top = N - 2; top >= 0; top -= kSweepChunk) {
+        float R[kSweepPer], Vn[kSweepPer], An[kSweepPer], cw[kSweepPer], oldQ[kSweepPer], A[kSweepPer], Bc[kSweepPer];
+#pragma unroll
+        for (int j = 0; j < kSweepPer; ++j) {
+          const int t = top - (j * kThreads + tid);
+          float rr = 0.f, w = 0.f;
+          Vn[j] = 0.f; An[j] = 0.f; oldQ[j] = 0.f;
+          if (t >= 0) {
+            const size_t r = r0 + t + 1;
+            rr = rp.R[r]; Vn[j] = rp.V[r]; An[j] = rp.ADV[r]; w = rp.RHO[r]; oldQ[j] = rp.Q[r - 1];
+            const float kl = rp.KL[r];
+            // aggregates of row t + 1 (Episode::updateCumulative): KL and reward of every row, the rest of data rows only
+            sKL += kl; sR += rr;
+            const double dr = (double)rr - rmean;           // reward moments: rows 1 .. N-1
+            rs1 += dr; rs2 = fma(dr, dr, rs2);
+            if (t + 1 < nd) {
+              const float d = rp.DELTA[r];
+              far += (w > C || w < invC) ? 1 : 0;
+              sE2 += d * d; mAE = fmaxf(mAE, fabsf(d));
+              const float q = An[j] + Vn[j];
+              mxQ = fmaxf(mxQ, q); mnQ = fminf(mnQ, q); sQ2 += q * q; sQ1 += q;
+            }
+            if (gae) { An[j] = 0.f; w = 1.f; }
+          }
+          R[j] = t >= 0 ? (float)(((double)rr - rmean) * rscale) : 0.f;
+          cw[j] = t >= 0 ? lambda * (w < 1.f ? w : 1.f) : 0.f;
+          Bc[j] = t >= 0 ? gamma * cw[j] : 1.f;
+          A[j] = t >= 0 ? R[j] + gamma * (Vn[j] - cw[j] * (An[j] + Vn[j])) : 0.f;
+        }
+        if (firstChunk && edge) {
+          if (!epTermS[ei]) rp.Q[r0 + N - 1] = c0;
+          shCarry = c0;
+          sKL += kl0; sR += rr0;
+          if (nd > 0) {
+            far += (w0 > C || w0 < invC) ? 1 : 0;
+            sE2 += d0 * d0; mAE = fmaxf(mAE, fabsf(d0));
+            const float q = a0 + v0;
+            mxQ = fmaxf(mxQ, q); mnQ = fminf(mnQ, q); sQ2 += q * q; sQ1 += q;
+          }
+        }
+        firstChunk = false;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+          for (int j = 0; j < kSweepPer; ++j) {
+            const float Ap = __shfl_up_sync(0xffffffffu, A[j], d), Bp = __shfl_up_sync(0xffffffffu, Bc[j], d);
+            if (lane >= d) { A[j] = fmaf(Bc[j], Ap, A[j]); Bc[j] = Bc[j] * Bp; }
+          }
+        }
+        if (lane == 31) {
+#pragma unroll
+          for (int j = 0; j < kSweepPer; ++j) { segA[j * (kThreads / 32) + warp] = A[j]; segB[j * (kThreads / 32) + warp] = Bc[j]; }
+        }
+        __syncthreads();
+        if (warp == 0) {
+          float sa = segA[lane], sb = segB[lane];
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const float Ap = __shfl_up_sync(0xffffffffu, sa, d), Bp = __shfl_up_sync(0xffffffffu, sb, d);
+            if (lane >= d) { sa = fmaf(sb, Ap, sa); sb = sb * Bp; }
+          }
+          const float qEnd = fmaf(sb, shCarry, sa);
+          float qin = __shfl_up_sync(0xffffffffu, qEnd, 1);
+          if (lane == 0) qin = shCarry;
+          segQin[lane] = qin;
+        }
+        __syncthreads();
+        float lastQ = 0.f; int lastT = -1;
+#pragma unroll
+        for (int j = 0; j < kSweepPer; ++j) {
+          const int t = top - (j * kThreads + tid);
+          const float qin = segQin[j * (kThreads / 32) + warp];
+          const float Qscan = fmaf(Bc[j], qin, A[j]);
+          float Qn = __shfl_up_sync(0xffffffffu, Qscan, 1);
+          if (lane == 0) Qn = qin;
+          const float Qt = R[j] + gamma * (Vn[j] + cw[j] * (Qn - An[j] - Vn[j]));
+          if (t >= 0) {
+            rp.Q[r0 + t] = Qt;
+            const float dq = oldQ[j] - Qt;
+            errAcc += dq * dq;
+            if (t == top - (kSweepChunk - 1) || t == 0) { lastQ = Qt; lastT = t; }
+          }
+        }
+        __syncthreads();
+        if (lastT >= 0 && lastT == max(0, top - (kSweepChunk - 1))) shCarry = lastQ;
+        __syncthreads();
+      }
+      nRet += N - 1;
+      // ---- aggregates: block reduction, written by thread 0 ----
+      far = __reduce_add_sync(0xffffffffu, far);
+      sE2 = warp_sum(sE2); sQ2 = warp_sum(sQ2); sQ1 = warp_sum(sQ1); sKL = warp_sum(sKL); sR = warp_sum(sR);
+      mAE = warp_max(mAE); mxQ = warp_max(mxQ); mnQ = -warp_max(-mnQ);
+      if (lane == 0) {
+        shFar[warp] = far;
+        shRed[warp][0] = sE2; shRed[warp][1] = sQ2; shRed[warp][2] = sQ1; shRed[warp][3] = sKL; shRed[warp][4] = sR;
+        shRed[warp][5] = mAE; shRed[warp][6] = mxQ; shRed[warp][7] = mnQ;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        far = 0; sE2 = sQ2 = sQ1 = sKL = sR = 0.f; mAE = -1e9f; mxQ = -1e9f; mnQ = 1e9f;
+        for (int w = 0; w < kThreads / 32; ++w) {
+          far += shFar[w]; sE2 += shRed[w][0]; sQ2 += shRed[w][1]; sQ1 += shRed[w][2]; sKL += shRed[w][3]; sR += shRed[w][4];
+          mAE = fmaxf(mAE, shRed[w][5]); mxQ = fmaxf(mxQ, shRed[w][6]); mnQ = fminf(mnQ, shRed[w][7]);
+        }
+        const float invN = 1.0f / (float)nd;
+        rp.epAgg[AGG_FAR * ME + slot] = invN * (float)far;
+        rp.epAgg[AGG_E2 * ME + slot] = invN * sE2; rp.epAgg[AGG_MAXE * ME + slot] = mAE;
+        rp.epAgg[AGG_Q2 * ME + slot] = sQ2; rp.epAgg[AGG_Q1 * ME + slot] = sQ1;
+        rp.epAgg[AGG_MAXQ * ME + slot] = mxQ; rp.epAgg[AGG_MINQ * ME + slot] = mnQ;
+        rp.epAgg[AGG_TOTR * ME + slot] = sR; rp.epAgg[AGG_KL * ME + slot] = invN * sKL;
+        if (C > 1.0f) nFar += far;
+      }
+      // ---- state moments of the data rows 0 .. N-2 from the shared-memory ring ----
+      const int nS = nd, nT = (nS + tileRows - 1) / tileRows;
+      for (int ti = 0; ti < nT; ++ti) {
+        const int st = (int)(consumed % kFuseStages);
+        sw_mbar_wait(&full[st], (unsigned)((consumed / kFuseStages) & 1));
+        const int rows = min(tileRows, nS - ti * tileRows);
+        const float4* tile = reinterpret_cast<const float4*>(ring + (size_t)st * (kFuseTileBytes / 4));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int row = u * RP + rl;
+          if (row < rows) {
+            const float4 x = tile[row * CQ + cq];
+            const double d0 = (double)x.x - m[0], d1 = (double)x.y - m[1], d2 = (double)x.z - m[2], d3 = (double)x.w - m[3];
+            s1[0] += d0; s1[1] += d1; s1[2] += d2; s1[3] += d3;
+            s2[0] = fma(d0, d0, s2[0]); s2[1] = fma(d1, d1, s2[1]); s2[2] = fma(d2, d2, s2[2]); s2[3] = fma(d3, d3, s2[3]);
+          }
+        }
+        ++consumed;
+        __syncthreads();                         // every thread is done with the stage: it can be refilled
+        if (tid == 0) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); produce(); }
+      }
+      cnt += tid == 0 ? (double)nS : 0.0;
+    }
+  }
+  // ---- block reduction of the moment accumulators, one atomic per column ----
+  __syncthreads();
+  double* red = reinterpret_cast<double*>(fsm);          // [kThreads][8] doubles = 16 KB of the (drained) ring
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { red[tid * 8 + c] = s1[c]; red[tid * 8 + 4 + c] = s2[c]; }
+  __syncthreads();
+  for (int idx = tid; idx < CQ * 8; idx += kThreads) {
+    const int q = idx >> 3, v = idx & 7;
+    double acc = 0.0;
+    for (int r = 0; r < RP; ++r) acc += red[(r * CQ + q) * 8 + v];
+    atomicAdd(&sums->moments[(v < 4 ? 0 : dS) + q * 4 + (v & 3)], acc);
+  }
+  double v3[3] = {cnt, rs1, rs2};
+  for (int q = 0; q < 3; ++q) {
+    const double w = warp_sum_d(v3[q]);
+    __syncthreads();
+    if (lane == 0) redD[warp] = w;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int k = 0; k < kThreads / 32; ++k) t += redD[k];
+      atomicAdd(&sums->moments[2 * dS + q], t);
+    }
+  }
+  const float e = warp_sum(errAcc);
+  if (lane == 0) atomicAdd(&sums->sumErr2, (double)e);
+  if (tid == 0) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(&sums->nRet), (unsigned long long)nRet);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&sums->nFarExact), (unsigned long long)nFar);
+  }
+}
+
+bool sweep_fused_supported(const ReplayView& rp, int estimator) {
+  const int CQ = rp.dS >> 2;
+  return estimator != 2 && (rp.dS & 3) == 0 && CQ >= 1 && (CQ & (CQ - 1)) == 0 && CQ <= kThreads && rp.dS * 4 * 4 * (kThreads / CQ) == kFuseTileBytes;
+}
+
+int launch_sweep_fused(const ReplayView& rp, int nEpisodes, float gamma, float lambda, int estimator, float cmax, float cinv,
+                       SweepSums* sums, int numSMs, cudaStream_t st) {
+  static bool attr = false;
+  const int smem = kFuseStages * kFuseTileBytes;
+  if (!attr) { SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_sweep_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+  int blocks = nEpisodes < numSMs * 2 ? nEpisodes : numSMs * 2;
+  if (blocks < 1) blocks = 1;
+  k_sweep_fused<<<blocks, kThreads, smem, st>>>(rp, nEpisodes, gamma, lambda, estimator == 1, cmax, cinv, sums);
+  SMB200_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 // updateStats lambda of updateRewardsStats (MemoryProcessing.cpp:153-184); the reference
 // accumulates in long double, here f64.
 __device__ __forceinline__ void update_stats(float& mean, float& stdev, float& invstd, double lr, double Evar, double Evar2) {

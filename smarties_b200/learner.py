@@ -30,7 +30,7 @@ EXPORTS = [
     "smb200_n_outputs", "smb200_set_weights", "smb200_get_weights", "smb200_set_adam", "smb200_get_adam",
     "smb200_get_grad", "smb200_set_scaling", "smb200_get_scaling", "smb200_push_episode", "smb200_n_transitions",
     "smb200_n_episodes", "smb200_initialize_learner", "smb200_set_grad_step", "smb200_seed_sampler", "smb200_sample",
-    "smb200_train_steps", "smb200_train_step_on", "smb200_get_last_batch", "smb200_retrace_sweep",
+    "smb200_train_steps", "smb200_train_step_on", "smb200_get_last_batch", "smb200_retrace_sweep", "smb200_fused_sweep",
     "smb200_reward_state_moments", "smb200_read_field", "smb200_read_episodes", "smb200_n_rows", "smb200_get_stats",
     "smb200_forward", "smb200_last_timing", "smb200_presample", "smb200_train_presampled", "smb200_sync", "smb200_profile_phases",
     "smb200_comm_init", "smb200_comm_attach", "smb200_comm_error", "smb200_write_field", "smb200_save", "smb200_restart",
@@ -124,6 +124,7 @@ def load_library(path: str = LIB_PATH):
         "smb200_train_step_on": (C.c_int, [H, ip, ip, C.c_int32, P(StepStats)]),
         "smb200_get_last_batch": (C.c_int, [H, fp, fp, fp]),
         "smb200_retrace_sweep": (C.c_int, [H, dp]), "smb200_reward_state_moments": (C.c_int, [H, dp]),
+        "smb200_fused_sweep": (C.c_int, [H, dp, dp]),
         "smb200_read_field": (C.c_int, [H, C.c_int32, fp, C.c_int64]),
         "smb200_read_episodes": (C.c_int, [H, ip, ip, fp, C.c_int64]),
         "smb200_write_field": (C.c_int, [H, C.c_int32, fp, C.c_int64]),
@@ -411,6 +412,13 @@ class Learner:
         e = C.c_double()
         self._check(self.lib.smb200_retrace_sweep(self.h, C.byref(e)))
         return e.value
+
+    def fused_sweep(self):
+        """(sum of squared Retrace changes, moments[2*dS+3]) of the one-pass sweep kernel (Retrace + aggregates + moments)."""
+        e = C.c_double()
+        out = np.empty(2 * self.dS + 3, np.float64)
+        self._check(self.lib.smb200_fused_sweep(self.h, C.byref(e), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return e.value, out
 
     def reward_state_moments(self):
         out = np.empty(2 * self.dS + 3, np.float64)

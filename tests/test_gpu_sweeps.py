@@ -103,3 +103,48 @@ def test_full_size_buffer_properties():
     st = L.train_steps(3)
     assert st[-1]["grad_step"] == 3 and 0 <= st[-1]["n_far_exact"] <= 3 * 256
     L.close()
+
+
+@pytest.mark.parametrize("shape", [dict(n_ep=9, ep_len=(1, 6), dS=4), dict(n_ep=40, ep_len=(100, 300), dS=8),
+                                   dict(n_ep=12, ep_len=(900, 2300), dS=32), dict(n_ep=300, ep_len=(20, 40), dS=32)])
+def test_fused_sweep_equals_separate_kernels(shape):
+    """k_sweep_fused (Retrace + exact aggregates + reward / state moments in one pass, state rows through the cp.async.bulk
+    ring) against k_sweep(recompute) + k_moments on identical buffers: Retrace estimates bit-identical (same scan, same
+    operation order), moments equal to f64 round-off of the different summation order, aggregates to f32 round-off, the
+    integer far-policy count exact.  Shapes: one-step episodes, episodes longer than the 1024-step super-chunk and than one
+    16 KB state tile, many short episodes (several per CTA)."""
+    dS = shape.pop("dS")
+    d = synth.make_replay(21, dA=2, dS=dS, **shape)
+    A, Bm = _learner(d), _learner(d)
+    rng = np.random.default_rng(3)
+    rows = int(d["N"].sum())
+    for L in (A, Bm):        # non-trivial values in every array the sweep reads
+        L.initialize_learner()
+    for name, gen in (("V", lambda: rng.standard_normal(rows)), ("ADV", lambda: 0.1 * rng.standard_normal(rows)),
+                      ("RHO", lambda: np.exp(0.7 * rng.standard_normal(rows))), ("KL", lambda: rng.random(rows)),
+                      ("DELTA", lambda: rng.standard_normal(rows))):
+        v = gen().astype(np.float32)
+        A.write_field(name, v); Bm.write_field(name, v)
+    eA, mA = A.fused_sweep()
+    eB = Bm.retrace_sweep()
+    mB = Bm.reward_state_moments()
+    assert np.array_equal(A.read_field("QRET"), Bm.read_field("QRET"))
+    assert eA == pytest.approx(eB, rel=1e-5)
+    assert mA[2 * dS] == mB[2 * dS]
+    assert np.allclose(mA, mB, rtol=1e-11, atol=1e-9)
+    # aggregates: the fused kernel recomputed them; a learner step's every-1000-steps path is covered by the step goldens
+    _, _, aggA = A.read_episodes()
+    V, ADV, RHO, KL, DL = (A.read_field(k) for k in ("V", "ADV", "RHO", "KL", "DELTA"))
+    cm = 1 + np.sqrt(2 / 2.0)        # Cmax at gradient step 0 with dA = 2 (clipImpWeight = sqrt(dA / 2)), epsAnneal irrelevant at step 0
+    o = 0
+    for e, N in enumerate(d["N"]):
+        N = int(N); nd = N - 1
+        w, dl = RHO[o:o + nd], DL[o:o + nd]
+        far = np.count_nonzero((w > np.float32(cm)) | (w < np.float32(1 / cm)))
+        assert aggA[e, 1] == pytest.approx(far / nd, rel=1e-6)
+        assert aggA[e, 0] == pytest.approx(KL[o:o + N].astype(np.float64).sum() / nd, rel=2e-5)
+        assert aggA[e, 2] == pytest.approx((dl.astype(np.float64) ** 2).sum() / nd, rel=2e-5)
+        q = (ADV[o:o + nd] + V[o:o + nd])
+        assert aggA[e, 6] == q.max() and aggA[e, 7] == q.min()
+        o += N
+    A.close(); Bm.close()
