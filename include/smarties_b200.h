@@ -37,7 +37,9 @@ enum smb200_status {
 };
 
 enum smb200_algo { SMB200_VRACER = 0, SMB200_RACER = 1 };
-enum smb200_nn_type { SMB200_FFNN = 0, SMB200_LSTM = 1 };   /* "nnType" (Network/Builder.cpp:48-99) */
+enum smb200_nn_type { SMB200_FFNN = 0, SMB200_LSTM = 1,
+                      SMB200_MGU = 2 /* "MGU" and "GRU" build the same MGULayer (Builder.cpp:67-72, Layers/Layer_GRU.h); it is also
+                                        what a partially observable MDP gets for a feed-forward request (Approximator.cpp:219-223) */ };
 /* "returnsEstimator" (createReturnEstimator, ReplayMemory/MemoryProcessing.cpp:419-450): Retrace (:391-400; also what
  * "default" means for RACER / V-RACER, Learners/AlgoFactory.cpp:134-136) or GAE (:411-417). */
 enum smb200_returns_estimator { SMB200_RETRACE = 0, SMB200_GAE = 1,
@@ -70,7 +72,7 @@ typedef struct smb200_config {
                                            count emulates (MemoryProcessing.cpp:202-227); 0 = 32 */
   int32_t world_rank, world_size;       /* learner ranks sharing the gradient (nMasters) */
   uint64_t seed;                        /* ExecutionInfo::randSeed (sampler + weight init) */
-  int32_t nn_type;                      /* smb200_nn_type: "nnType": "FFNN" | "LSTM" (Layers/Layer_LSTM.h) */
+  int32_t nn_type;                      /* smb200_nn_type: "nnType": "FFNN" | "LSTM" (Layers/Layer_LSTM.h) | "MGU" / "GRU" (Layers/Layer_GRU.h) */
   int32_t nn_bptt_seq;                  /* "nnBPTTseq": recurrent window = min(nnBPTTseq, t) past steps
                                            (ReplayMemory/MemoryBuffer.cpp:393-402) */
   int64_t min_tot_obs;                  /* minTotObsNum_local = nObsB4StartTraining: only recorded in checkpoints

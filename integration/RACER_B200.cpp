@@ -28,6 +28,8 @@
 #include "smarties/Math/Continuous_policy.h"
 #include "smarties/Math/Zero_advantage.h"
 #include "smarties/Math/Gaus_advantage.h"
+#include "smarties/Math/Discrete_policy.h"
+#include "smarties/Math/Discrete_advantage.h"
 #include "smarties/Network/Approximator.h"
 #include "smarties/Network/Optimizer.h"
 #include "smarties/ReplayMemory/MemoryProcessing.h"
@@ -51,10 +53,10 @@ namespace smarties
 // the reference's own factory (AlgoFactory.cpp built with -DcreateLearner=createLearner_reference)
 std::unique_ptr<Learner> createLearner_reference(const Uint learnerID, MDPdescriptor& MDP, ExecutionInfo& distrib);
 
-template<typename Advantage_t>
-class RACER_B200 : public RACER<Advantage_t, Continuous_policy, Rvec>
+template<typename Advantage_t, typename Policy_t = Continuous_policy, typename Action_t = Rvec>
+class RACER_B200 : public RACER<Advantage_t, Policy_t, Action_t>
 {
-  using Base = RACER<Advantage_t, Continuous_policy, Rvec>;
+  using Base = RACER<Advantage_t, Policy_t, Action_t>;
   using Base::data; using Base::settings; using Base::distrib; using Base::MDP; using Base::networks;
   using Base::algoSubStepID; using Base::nObsB4StartTraining; using Base::bTrain; using Base::aInfo;
   using Base::profiler; using Base::learn_rank; using Base::learn_size;
@@ -87,6 +89,8 @@ class RACER_B200 : public RACER<Advantage_t, Continuous_policy, Rvec>
     const char* dev = std::getenv("SMARTIES_B200_DEVICE");
     c.device = dev ? std::atoi(dev) : 0;
     c.algo = isRacer ? SMB200_RACER : SMB200_VRACER;
+    // discrete action space (RACER<Discrete_advantage, Discrete_policy, Uint>): one component, its number of options
+    if (MDP.bDiscreteActions()) c.discrete_options = (int32_t) MDP.discreteActionValues[0];
     if (MDP.dimAction > SMB200_MAX_ACTION || settings.nnLayerSizes.size() > SMB200_MAX_HIDDEN) die("network too large for smarties_b200");
     for (Uint i = 0; i < MDP.dimAction; ++i) c.action_bounded[i] = MDP.bActionSpaceBounded[i] ? 1 : 0;
     c.n_hidden = (int32_t) settings.nnLayerSizes.size();
@@ -99,7 +103,9 @@ class RACER_B200 : public RACER<Advantage_t, Continuous_policy, Rvec>
     c.refer_reduce_threads = (int32_t) distrib.nThreads;
     c.world_rank = (int32_t) learn_rank; c.world_size = (int32_t) learn_size;
     c.seed = distrib.randSeed;
-    c.nn_type = settings.nnType == "LSTM" ? SMB200_LSTM : SMB200_FFNN;
+    // a partially observable MDP turns a feed-forward request into MGU layers (Network/Approximator.cpp:219-223)
+    const bool mgu = settings.nnType == "MGU" || settings.nnType == "GRU" || (MDP.isPartiallyObservable && !settings.bRecurrent);
+    c.nn_type = settings.nnType == "LSTM" ? SMB200_LSTM : (mgu ? SMB200_MGU : SMB200_FFNN);
     c.nn_bptt_seq = (int32_t) settings.nnBPTTseq;
     c.returns_estimator = settings.returnsEstimator == "GAE" ? SMB200_GAE
                         : (settings.returnsEstimator == "retraceExplore" ? SMB200_RETRACE_EXPLORE : SMB200_RETRACE);
@@ -364,14 +370,18 @@ std::unique_ptr<Learner> createLearner(const Uint learnerID, MDPdescriptor& MDP,
   HyperParameters settings(MDP.dimObs(), MDP.dimAct());
   std::ifstream ifs = openSettings(distrib, learnerID);
   settings.initializeOpts(ifs, distrib);
+  // "V-RACER makes little sense with discrete action-spaces": the reference's factory overrides the user (AlgoFactory.cpp:78-83)
+  if (settings.learner == "VRACER" && MDP.bDiscreteActions()) settings.learner = "RACER";
   const bool covered =
-      (settings.learner == "VRACER" || settings.learner == "RACER") && !MDP.bDiscreteActions() &&
+      (settings.learner == "VRACER" || settings.learner == "RACER") &&
+      // discrete actions: RACER<Discrete_advantage, Discrete_policy, Uint> (AlgoFactory.cpp:100-113), one component, feed-forward net
+      (!MDP.bDiscreteActions() || (settings.learner == "RACER" && MDP.dimAction == 1 && MDP.discreteActionValues[0] >= 2 &&
+                                   MDP.discreteActionValues[0] <= 64 && settings.nnType == "FFNN" && !MDP.isPartiallyObservable)) &&
       settings.dataSamplingAlgo == "uniform" && (settings.returnsEstimator == "default" || settings.returnsEstimator == "retrace" || settings.returnsEstimator == "GAE" ||
                                                   settings.returnsEstimator == "retraceExplore") &&
       (settings.ERoldSeqFilter == "oldest" || settings.ERoldSeqFilter == "default") &&
-      (settings.nnType == "FFNN" || settings.nnType == "LSTM") && settings.nnFunc == "Tanh" && settings.nnOutputFunc == "Linear" &&
-      // a partially observable MDP turns a feed-forward request into MGU layers (Network/Approximator.cpp:219-223)
-      !(MDP.isPartiallyObservable && !settings.bRecurrent) &&
+      (settings.nnType == "FFNN" || settings.nnType == "LSTM" || settings.nnType == "MGU" || settings.nnType == "GRU") &&
+      settings.nnFunc == "Tanh" && settings.nnOutputFunc == "Linear" &&
       // several learner ranks: the device learners of the ranks would have to exchange CUDA-IPC handles over
       // distrib.learners_train_comm (smb200_comm_init / smb200_comm_attach) — not wired into the binding: reference learner
       MPICommSize(distrib.learners_train_comm) == 1 &&
@@ -386,7 +396,11 @@ std::unique_ptr<Learner> createLearner(const Uint learnerID, MDPdescriptor& MDP,
   std::unique_ptr<Learner> ret;
   std::ostringstream o;
   o << MDP.dimState << " ";
-  if (settings.learner == "RACER") {
+  if (settings.learner == "RACER" && MDP.bDiscreteActions()) {
+    using R = RACER<Discrete_advantage, Discrete_policy, Uint>;
+    MDP.policyVecDim = R::getnDimPolicy(aInfo);
+    ret = std::make_unique<RACER_B200<Discrete_advantage, Discrete_policy, Uint>>(MDP, settings, distrib, true);
+  } else if (settings.learner == "RACER") {
     using R = RACER<Param_advantage, Continuous_policy, Rvec>;
     MDP.policyVecDim = R::getnDimPolicy(aInfo);
     ret = std::make_unique<RACER_B200<Param_advantage>>(MDP, settings, distrib, true);

@@ -14,7 +14,10 @@ constexpr int kThreads   = 256;         // every kernel here uses 256-thread CTA
 constexpr int kTileK     = 16;          // weight-gradient tile: 16 input rows x 16 output cols
 constexpr int kTileN     = 16;
 
-enum LayerKind : int { kInput = 0, kDenseTanh = 1, kResidual = 2, kDenseLinear = 3, kParam = 4, kLSTM = 5 };
+enum LayerKind : int { kInput = 0, kDenseTanh = 1, kResidual = 2, kDenseLinear = 3, kParam = 4, kLSTM = 5, kMGU = 6 };
+// gate columns per cell of a recurrent-cell layer: LSTMLayer 4 (Layer_LSTM.h:24-29), MGULayer 2 (forget | state, Layer_GRU.h:27-33)
+__host__ __device__ inline int cell_gates(int kind) { return kind == kLSTM ? 4 : (kind == kMGU ? 2 : 1); }
+__host__ __device__ inline bool is_cell_layer(int kind) { return kind == kLSTM || kind == kMGU; }
 
 // One layer of the network built by RACER::setupNet (Learners/RACER_common.cpp:70-115,
 // Network/Builder.cpp:48-99).  Layer ids equal the reference's (0 = input).
@@ -22,7 +25,7 @@ struct LayerDesc {
   int kind;
   int size;        // number of neurons = size of this layer's activation (LSTM: nCells)
   int nIn;         // dense / LSTM: fan-in from the layer below
-  int ld;          // dense: row stride of W[nIn][ld] (roundUp8(size), Layer_Base.h:46); LSTM: 4*nCells, rows nIn+nCells (Layer_LSTM.h:24-29)
+  int ld;          // dense: row stride of W[nIn][ld] (roundUp8(size), Layer_Base.h:46); LSTM: 4*nCells, MGU: 2*nCells, rows nIn+nCells
   int wOff, bOff;  // offsets into the padded parameter blob (Parameters.h:159-176)
   int needDx;      // 1 if the backward pass propagates into this layer's input (not the first layer)
   int imgW, imgB;  // offsets into the weight IMAGE (the shared-memory layout, see NetDesc::imgFloats)
@@ -49,6 +52,8 @@ struct NetDesc {
   int Tc;            // bptt + 1 = longest window; P2 column of (sample b, window step k) = b*Tc + k
   int topInOff;      // row of the compact copy (column = b) of the top hidden layer's output at the sampled step
   int seqFloats;     // shared-memory floats of the per-sample sequence workspace (step_kernels.cu: SeqPlan)
+  int discrete;      // K > 0: one discrete action component with K options — outputs [V | advantages(K) | policy(K)], MU rows of K
+                     // probabilities (RACER<Discrete_advantage, Discrete_policy, Uint>, Learners/RACER.cpp:114)
   LayerDesc L[kMaxLayers];
 };
 
@@ -58,7 +63,8 @@ struct GradTile {
   int layer;
   int k0, n0;
   int cols;    // contraction length (columns of the feature-major scratch, multiple of 256)
-  int pad_[3];
+  int nLimit;  // > 0: the tile's columns end here (MGU layers: tiles do not straddle the forget | state halves)
+  int pad_[2];
 };
 
 // Scalars a step needs; double-buffered by step parity: step k reads ctrl[k&1], its

@@ -160,22 +160,24 @@ static int build_net(const smb200_config& c, NetDesc& net, std::vector<GradTile>
     L.imgW = img; img += L.ldp * L.nIn; L.imgB = img; img += round_up(L.size, 4); };
   add(kInput, dS);
   int nIn = dS;
-  const bool lstm = c.nn_type == SMB200_LSTM;
-  if (c.nn_type != SMB200_FFNN && c.nn_type != SMB200_LSTM) { set_error_msg("nnType must be FFNN or LSTM"); return -1; }
+  const bool lstm = c.nn_type == SMB200_LSTM || c.nn_type == SMB200_MGU;      // recurrent-cell layers
+  const int cellKind = c.nn_type == SMB200_MGU ? kMGU : kLSTM, ng = cell_gates(cellKind);
+  if (c.nn_type != SMB200_FFNN && !lstm) { set_error_msg("nnType must be FFNN, LSTM, MGU or GRU"); return -1; }
   if (lstm && (c.nn_bptt_seq < 0 || c.nn_bptt_seq > 255)) { set_error_msg("nnBPTTseq out of range"); return -1; }
   if (lstm) for (int i = 0; i < c.n_hidden; ++i) if (c.hidden[i] > NT) { set_error_msg("LSTM layers wider than the CTA are not supported"); return -1; }
   for (int i = 0; i < c.n_hidden; ++i) {
     const int h = c.hidden[i];
     if (h < 1) { set_error_msg("hidden layer size must be positive"); return -1; }
-    if (lstm) {   // LSTMLayer (Layers/Layer_LSTM.h): W[(nIn + nCells)][4 nCells] then 4 nCells biases
-      LayerDesc& L = add(kLSTM, h);
-      act += round_up(4 * h, 4) - round_up(h, 4);          // activation rows: [y | h_prev | -- | --], delta rows: 4 gates
-      L.nIn = nIn; L.ld = 4 * h;
-      L.wOff = off; off += round_up(4 * h * (nIn + h), 8); L.bOff = off; off += round_up(4 * h, 8);
+    if (lstm) {   // LSTMLayer (Layers/Layer_LSTM.h): W[(nIn + nCells)][4 nCells] then 4 nCells biases; MGULayer (Layer_GRU.h): 2 nCells
+      LayerDesc& L = add(cellKind, h);
+      // activation rows: [y | h_prev | (MGU: h_prev * forget) | --], delta rows: the gates
+      act += round_up(4 * h, 4) - round_up(h, 4);
+      L.nIn = nIn; L.ld = ng * h;
+      L.wOff = off; off += round_up(ng * h * (nIn + h), 8); L.bOff = off; off += round_up(ng * h, 8);
       L.needDx = i > 0;
-      L.fwdShift = log2_group(4 * h); L.bwdShift = log2_group(h);
-      L.ldp = round_up(4 * h, 4) + 4;
-      L.imgW = img; img += L.ldp * (nIn + h); L.imgB = img; img += round_up(4 * h, 4);
+      L.fwdShift = log2_group(ng * h); L.bwdShift = log2_group(h);
+      L.ldp = round_up(ng * h, 4) + 4;
+      L.imgW = img; img += L.ldp * (nIn + h); L.imgB = img; img += round_up(ng * h, 4);
     } else {
       LayerDesc& L = add(kDenseTanh, h);
       L.nIn = nIn; L.ld = round_up(h, 8);
@@ -208,7 +210,7 @@ static int build_net(const smb200_config& c, NetDesc& net, std::vector<GradTile>
     P.imgB = img; P.imgW = img; img += round_up(nParamOut, 4);
   }
   net.nLayers = id; net.nParams = off; net.imgFloats = img; net.nOut = nOutDense + nParamOut; net.nOutDense = nOutDense;
-  net.dS = dS; net.dA = dA; net.maxWidth = width;
+  net.dS = dS; net.dA = dA; net.maxWidth = width; net.discrete = K;
   net.recurrent = lstm ? 1 : 0; net.bptt = lstm ? c.nn_bptt_seq : 0; net.Tc = net.bptt + 1;
   net.topInOff = act;
   if (lstm) act += round_up(nIn, 4);      // compact copy of the top hidden layer's output at the sampled step
@@ -227,6 +229,12 @@ static int build_net(const smb200_config& c, NetDesc& net, std::vector<GradTile>
     } else if (L.kind == kLSTM) {
       for (int k0 = 0; k0 < L.nIn + L.size + 1; k0 += kTileK)
         for (int n0 = 0; n0 < 4 * L.size; n0 += kTileN) tiles.push_back(GradTile{0, l, k0, n0});
+    } else if (L.kind == kMGU) {      // the recurrent rows of the two column halves multiply different inputs: h_prev | h_prev * forget
+      for (int k0 = 0; k0 < L.nIn + L.size + 1; k0 += kTileK)
+        for (int half = 0; half < 2; ++half)
+          for (int n0 = half * L.size; n0 < (half + 1) * L.size; n0 += kTileN) {
+            GradTile t{0, l, k0, n0}; t.nLimit = (half + 1) * L.size; tiles.push_back(t);
+          }
     }
   }
   // contraction length of every tile: the mini-batch, or for recurrent networks all (sample, window step)
@@ -262,6 +270,12 @@ static void init_weights(const smb200_config& c, const NetDesc& net, std::mt1993
       std::uniform_real_distribution<float> dis(-init, init);
       for (int o = 0; o < nC; ++o) { blob[L.bOff + o] = 0.f; blob[L.bOff + nC + o] = -1.f; blob[L.bOff + 2 * nC + o] = 1.f; blob[L.bOff + 3 * nC + o] = -1.f; }
       for (int w = 0; w < 4 * nC * (L.nIn + nC); ++w) blob[L.wOff + w] = dis(gen);
+    } else if (L.kind == kMGU) {    // MGULayer::initialize (Layer_GRU.h:216-231): forget gate primed with LSTM_PRIME_FAC = 1, state bias 0
+      const int nC = L.size;
+      const float init = (float)std::sqrt(6. / (L.nIn + nC));           // Tanh::_initFactor
+      std::uniform_real_distribution<float> dis(-init, init);
+      for (int o = 0; o < nC; ++o) { blob[L.bOff + o] = 1.f; blob[L.bOff + nC + o] = 0.f; }
+      for (int w = 0; w < 2 * nC * (L.nIn + nC); ++w) blob[L.wOff + w] = dis(gen);
     } else if (L.kind == kResidual) {
       for (int o = 0; o < L.size; ++o) { blob[L.wOff + o] = 1.f; blob[L.bOff + o] = 0.f; }
     } else if (L.kind == kParam) {   // SoftPlus::_inv(explNoise) (Functions.h:564-568, Continuous_policy.h:195-197)
@@ -282,10 +296,11 @@ static int upload_weights(smb200_learner* h, const float* blob) {
       for (int k = 0; k < L.nIn; ++k)
         for (int n = 0; n < L.size; ++n) im[L.imgW + k * L.ldp + n] = blob[L.wOff + k * L.ld + n];
       for (int n = 0; n < L.size; ++n) im[L.imgB + n] = blob[L.bOff + n];
-    } else if (L.kind == kLSTM) {
+    } else if (is_cell_layer(L.kind)) {
+      const int ng = cell_gates(L.kind);
       for (int k = 0; k < L.nIn + L.size; ++k)
-        for (int n = 0; n < 4 * L.size; ++n) im[L.imgW + k * L.ldp + n] = blob[L.wOff + k * L.ld + n];
-      for (int n = 0; n < 4 * L.size; ++n) im[L.imgB + n] = blob[L.bOff + n];
+        for (int n = 0; n < ng * L.size; ++n) im[L.imgW + k * L.ldp + n] = blob[L.wOff + k * L.ld + n];
+      for (int n = 0; n < ng * L.size; ++n) im[L.imgB + n] = blob[L.bOff + n];
     } else if (L.kind == kResidual) {
       for (int n = 0; n < L.size; ++n) { im[L.imgW + n] = blob[L.wOff + n]; im[L.imgB + n] = blob[L.bOff + n]; }
     } else if (L.kind == kParam) {
@@ -587,8 +602,8 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
   if (c.batch_size < 1 || c.max_tot_obs < c.batch_size) { set_error_msg("bad batch_size / max_tot_obs"); delete h; return SMB200_ERR_INVALID; }
   if (c.returns_estimator != SMB200_RETRACE && c.returns_estimator != SMB200_GAE && c.returns_estimator != SMB200_RETRACE_EXPLORE) {
     set_error_msg("returnsEstimator must be retrace, GAE or retraceExplore"); delete h; return SMB200_ERR_INVALID; }
-  if (c.discrete_options != 0) {   // network construction is built (build_net / init_weights, pinned on the host); the loss stage is not
-    set_error_msg("discrete actions: the device loss stage (Discrete_policy / Discrete_advantage) is not built yet"); delete h; return SMB200_ERR_INVALID; }
+  if (c.discrete_options != 0 && c.nn_type != SMB200_FFNN) {
+    set_error_msg("discrete actions: feed-forward networks only"); delete h; return SMB200_ERR_INVALID; }
   std::vector<GradTile> tiles;
   if (build_net(c, h->descs.net, tiles)) { delete h; return SMB200_ERR_INVALID; }
   memset(&h->descs.seq, 0, sizeof(h->descs.seq));
@@ -1448,7 +1463,7 @@ static size_t stripped_size(const NetDesc& net) {
   for (int l = 1; l < net.nLayers; ++l) {
     const LayerDesc& L = net.L[l];
     if (L.kind == kDenseTanh || L.kind == kDenseLinear) n += (size_t)L.size * (L.nIn + 1);
-    else if (L.kind == kLSTM) n += (size_t)4 * L.size * (L.nIn + L.size + 1);
+    else if (is_cell_layer(L.kind)) n += (size_t)cell_gates(L.kind) * L.size * (L.nIn + L.size + 1);
     else if (L.kind == kResidual) n += 2 * (size_t)L.size;
     else if (L.kind == kParam) n += L.size;
   }
@@ -1463,9 +1478,10 @@ static void strip_copy(const NetDesc& net, float* blob, float* flat, int dir) {
     if (L.kind == kDenseTanh || L.kind == kDenseLinear) {
       for (int i = 0; i < L.nIn; ++i) for (int n = 0; n < L.size; ++n) mv(L.wOff + n + L.ld * i);
       for (int n = 0; n < L.size; ++n) mv(L.bOff + n);
-    } else if (L.kind == kLSTM) {
-      for (int w = 0; w < 4 * L.size * (L.nIn + L.size); ++w) mv(L.wOff + w);
-      for (int n = 0; n < 4 * L.size; ++n) mv(L.bOff + n);
+    } else if (is_cell_layer(L.kind)) {
+      const int ng = cell_gates(L.kind);
+      for (int w = 0; w < ng * L.size * (L.nIn + L.size); ++w) mv(L.wOff + w);
+      for (int n = 0; n < ng * L.size; ++n) mv(L.bOff + n);
     } else if (L.kind == kResidual) {
       for (int n = 0; n < L.size; ++n) mv(L.wOff + n);
       for (int n = 0; n < L.size; ++n) mv(L.bOff + n);

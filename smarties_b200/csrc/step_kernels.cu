@@ -480,12 +480,73 @@ struct LossIO {
 
 // LATE: the kernel may reach the loss before the statistics CTA of the previous step has published beta (cluster kernel):
 // wait for it during stage 2 instead of stage 1 (see below).
-template <int TB, bool SM, bool LATE = false>
+// DISC: discrete action space (RACER<Discrete_advantage, Discrete_policy, Uint>): one thread per sample evaluates
+// discrete_sample_loss, the write-back and the record are those of the continuous case.
+template <int TB, bool SM, bool LATE = false, bool DISC = false>
 __device__ __forceinline__ void loss_stages(const StepArgs& a, const NetDesc& net, const Hyper& hp, StepCtrl& c, int step, const float* Wp,
                                             const LossIO& io, bool fetchCtrl, const unsigned* readyFlag, unsigned readyTarget) {
   const int tid = threadIdx.x;
   float* act = io.act; float* err = io.err; const int* info = io.info; const float* old = io.old;
   double* pair = io.pair; double* samp = io.samp; const float* vnext = io.vnext;
+  if (DISC) {
+    const int K = net.discrete, b0d = io.b0;
+    const LayerDesc& Lod = net.L[net.nLayers - 2];
+    const bool keepd = step == a.lastStep || a.lastStep < 0;
+    if (fetchCtrl && tid == kST - 1) {
+      if (readyFlag) { while (ld_acquire(readyFlag) < readyTarget) { } }
+      load_ctrl(c, &a.ctrl[step & 1]);
+    }
+    __syncthreads();
+    if (tid < TB && info[3 * TB + tid]) {
+      const int s = tid, b = b0d + s;
+      const size_t row = info[s];
+      const ReplayView& rpd = a.rp;
+      float O[2 * kMaxOptions + 1], mu[kMaxOptions];
+      double g[2 * kMaxOptions + 1], out[6];
+      for (int j = 0; j < 1 + 2 * K; ++j) O[j] = act[(Lod.actOff + j) * TB + s];
+      for (int j = 0; j < K; ++j) mu[j] = ld_cg(rpd.MU + row * K + j);
+      const float actMsg = ld_cg(rpd.A + row);
+      discrete_sample_loss(K, O, actMsg, mu, old[7 * TB + s], c.beta, c.cmax, c.cinv, g, out);
+      for (int j = 0; j < 1 + 2 * K; ++j) {
+        err[(Lod.actOff + j) * TB + s] = (float)g[j];
+        if (keepd) { a.lastG[(size_t)b * net.nOut + j] = (float)g[j]; a.lastO[(size_t)b * net.nOut + j] = O[j]; }
+      }
+      const double rho = out[0], dkl = out[1], Vval = out[3], Aval = out[4], deltaQ = out[5];
+      const float W32 = (float)rho, C32 = (float)c.cmax, I32 = (float)c.cinv;
+      const bool offW = (W32 > C32) || (W32 < I32);
+      SampleRec r;
+      r.slot = info[TB + s]; r.hasNext = info[2 * TB + s];
+      r.qNextOld = 0.f; r.qNextNew = 0.f;
+      if (r.hasNext && vnext) {
+        const float vn = vnext[s];
+        r.qNextOld = old[6 * TB + s] + old[5 * TB + s];
+        r.qNextNew = vn;
+        rpd.V[row + 1] = vn; rpd.ADV[row + 1] = vn - vn;
+      }
+      const float E = (float)deltaQ, D = (float)dkl;
+      const float oldRho = old[2 * TB + s], oldKL = old[3 * TB + s], oldE = old[4 * TB + s];
+      const bool wasOff = (oldRho > C32) || (oldRho < I32);
+      r.dKL = D - oldKL;
+      r.dFar = (float)offW - (float)wasOff;
+      r.farDelta = (C32 > 1.0f) ? ((int)offW - (int)wasOff) : 0;
+      r.dE2 = E * E - oldE * oldE;
+      r.absE = fabsf(E);
+      const float Vf = (float)Vval, Qf = (float)(Aval + Vval);
+      r.qOld = old[1 * TB + s] + old[0 * TB + s];
+      r.qNew = Qf;
+      r.pad = 0;
+      rpd.DELTA[row] = E; rpd.KL[row] = D; rpd.RHO[row] = W32;
+      rpd.V[row] = Vf; rpd.ADV[row] = Qf - Vf;
+      if (vnext) a.rec[b] = r;
+      else {
+        *reinterpret_cast<int4*>(&a.rec[b].slot) = make_int4(r.slot, r.hasNext, r.farDelta, 0);
+        *reinterpret_cast<float4*>(&a.rec[b].dKL) = make_float4(r.dKL, r.dFar, r.dE2, r.absE);
+        *reinterpret_cast<float2*>(&a.rec[b].qOld) = make_float2(r.qOld, r.qNew);
+      }
+    }
+    __syncthreads();
+    return;
+  }
   const int b0 = io.b0, p0 = tid, p0s = io.p0s, p0i = io.p0i;
   const bool keep = step == a.lastStep || a.lastStep < 0;      // smb200_get_last_batch only ever sees a launch's last step
   const double pa = io.pa, pmm = io.pmm, pms = io.pms;
@@ -804,7 +865,7 @@ __device__ __forceinline__ Staging staging_view(const NetDesc& net, unsigned cha
   return g;
 }
 
-template <int TB, bool SM>
+template <int TB, bool SM, bool DISC = false>
 __device__ void p1_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, StepCtrl& c, int step, int tile,
                         unsigned char* smraw, const SmemPlan& sp, unsigned parity, bool fetchCtrl,
                         const unsigned* readyFlag, unsigned readyTarget, bool staged, bool helped = false) {
@@ -883,7 +944,7 @@ __device__ void p1_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
   double pa = 0, pmm = 0, pms = 1;
   const int p0 = tid;
   const int p0s = p0 < nPair ? p0 / dA : 0, p0i = p0 - p0s * dA;   // one integer division per tile, reused below
-  if (p0 < nPair) {
+  if (!DISC && p0 < nPair) {
     const int s = p0s, i = p0i;
     if (info[3 * TB + s]) {
       if (staged) { pa = (double)stg.pair[p0]; pmm = (double)stg.pair[nPair + p0]; pms = (double)stg.pair[2 * nPair + p0]; }
@@ -902,7 +963,7 @@ __device__ void p1_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
 
   {
     LossIO io{act, err, info, old, pair, samp, helped ? nullptr : vnext, b0, pa, pmm, pms, p0s, p0i};
-    loss_stages<TB, SM>(a, net, hp, c, step, Wp, io, fetchCtrl, readyFlag, readyTarget);
+    loss_stages<TB, SM, false, DISC>(a, net, hp, c, step, Wp, io, fetchCtrl, readyFlag, readyTarget);
   }
 
   // ---- backward: Network::backProp, layers last to first (Network.h:216-226).  A residual layer
@@ -980,10 +1041,11 @@ void seq_plan(const NetDesc& net, SeqPlan& p) {
   int o = 0;
   for (int l = 0; l < net.nLayers; ++l) {
     const LayerDesc& L = net.L[l];
-    if (L.kind == kInput || L.kind == kResidual || L.kind == kLSTM) {
+    if (L.kind == kInput || L.kind == kResidual || is_cell_layer(L.kind)) {
       const int n4 = (L.size + 3) / 4 * 4;
-      p.yStride[l] = seq_stride(L.kind == kLSTM ? 3 * n4 : n4); p.yOff[l] = o; o += T * p.yStride[l];
-      if (L.kind == kLSTM) { p.gStride[l] = seq_stride(4 * L.size); p.gOff[l] = o; o += T * p.gStride[l]; }
+      // LSTM: [y | cell state | tanh(state)]; MGU: [y | h_prev * forget]
+      p.yStride[l] = seq_stride(L.kind == kLSTM ? 3 * n4 : (L.kind == kMGU ? 2 * n4 : n4)); p.yOff[l] = o; o += T * p.yStride[l];
+      if (is_cell_layer(L.kind)) { p.gStride[l] = seq_stride(cell_gates(L.kind) * L.size); p.gOff[l] = o; o += T * p.gStride[l]; }
       if (L.kind != kInput) { p.eStride[l] = seq_stride(L.size); p.eOff[l] = o; o += T * p.eStride[l]; }
     }
   }
@@ -1218,6 +1280,155 @@ __device__ void lstm_backward(const LayerDesc& L, const float* Wp, float* Gt, in
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// MGULayer (Layers/Layer_GRU.h:17-275; "MGU" and "GRU" build it, and it is what a partially observable MDP gets by default):
+//   forget(k) = sigm(b_f + x_k Wff + h_{k-1} Wfr),  state(k) = tanh(b_s + x_k Wsf + (forget(k) * h_{k-1}) Wsr),
+//   h_k = forget * state + (1 - forget) * h_{k-1};   W rows [input | recurrent], columns [forget | state].
+// Gt per step: [forget | state], overwritten by [dL/dforget-input | dL/dstate-input] in the backward pass;
+// Y per step: [h_k | h_{k-1} * forget(k)] (the second block feeds the weight gradient of the Wsr rows).
+// ------------------------------------------------------------------------------------------
+template <bool SM>
+__device__ void mgu_forward(const LayerDesc& L, const float* Wp, const float* in, int is, float* Gt, int gs, float* Y, int ys,
+                            float* red, int Tn) {
+  const int tid = threadIdx.x;
+  const int nC = L.size, nI = L.nIn, N2 = 2 * nC, ldp = L.ldp, nC4 = (nC + 3) / 4 * 4;
+  const float* Wx = Wp + L.imgW;
+  const float* Wh = Wx + (size_t)nI * ldp;
+  const float* bias = Wp + L.imgB;
+  // (a) b + x_k Wx for every window step (as lstm_forward)
+  const int nq = (Tn + 3) >> 2;
+  for (int idx = tid; idx < N2 * nq; idx += kST) {
+    const int kq = idx / N2, n = idx - kq * N2, k0 = kq * 4;
+    const float bv = ldw<SM>(bias + n);
+    float acc[4] = {bv, bv, bv, bv};
+    const float* x[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = in + (size_t)min(k0 + j, Tn - 1) * is;
+    const float* w = Wx + n;
+    for (int i = 0; i < nI; ++i) {
+      const float wv = ldw<SM>(w + (size_t)i * ldp);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(x[j][i], wv, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (k0 + j < Tn) Gt[(size_t)(k0 + j) * gs + n] = acc[j];
+  }
+  __syncthreads();
+  // (b) the recurrence: two dependent products per step.  Thread group g of G takes a K-slice of the nCells recurrent rows.
+  int sh = 3; while ((1 << sh) < min(nC, kST)) ++sh;
+  const int NR = 1 << sh, G = kST >> sh;
+  const int g = tid >> sh, nl = tid & (NR - 1);
+  const int Kc = (nC + G - 1) / G;
+  const int kb = min(nC, g * Kc), ke = min(nC, kb + Kc);
+  for (int k = 0; k < Tn; ++k) {
+    float* gk = Gt + (size_t)k * gs;
+    float* yk = Y + (size_t)k * ys;
+    const float* hprev = Y + (size_t)(k - 1) * ys;
+    if (k > 0) {                                 // forget pre-activation += h_{k-1} Wfr
+      float acc = 0.0f;
+      if (nl < nC) for (int i = kb; i < ke; ++i) acc = fmaf(hprev[i], ldw<SM>(Wh + (size_t)i * ldp + nl), acc);
+      red[g * NR + nl] = acc;
+      __syncthreads();
+    }
+    float fg = 0.0f;
+    if (tid < nC) {
+      float s0 = gk[tid];
+      if (k > 0) for (int gg = 0; gg < G; ++gg) s0 += red[gg * NR + tid];
+      fg = sigm_ref(s0);
+      gk[tid] = fg;
+      yk[nC4 + tid] = k > 0 ? hprev[tid] * fg : 0.0f;      // forget(k) * h_{k-1}
+    }
+    __syncthreads();
+    if (k > 0) {                                 // state pre-activation += (forget * h_{k-1}) Wsr
+      float acc = 0.0f;
+      if (nl < nC) for (int i = kb; i < ke; ++i) acc = fmaf(yk[nC4 + i], ldw<SM>(Wh + (size_t)i * ldp + nC + nl), acc);
+      red[g * NR + nl] = acc;
+      __syncthreads();
+    }
+    if (tid < nC) {
+      float s1 = gk[nC + tid];
+      if (k > 0) for (int gg = 0; gg < G; ++gg) s1 += red[gg * NR + tid];
+      const float st = tanh_ref(s1);
+      gk[nC + tid] = st;
+      yk[tid] = k > 0 ? fg * st + (1.0f - fg) * hprev[tid] : fg * st;
+    }
+    __syncthreads();
+  }
+}
+
+// MGULayer::backward for window steps T1-1 .. 0 (Layer_GRU.h:122-214).  E: error on h per step — the recurrent part of step k
+// is added into E of step k-1 here; on return Gt holds [dLdF | dLdS] of every step and Ein has received Wx * delta.
+template <bool SM>
+__device__ void mgu_backward(const LayerDesc& L, const float* Wp, float* Gt, int gs, const float* Y, int ys, float* E, int es,
+                             float* Ein, int eis, float* red, int T1) {
+  const int tid = threadIdx.x;
+  const int nC = L.size, nI = L.nIn, N2 = 2 * nC, ldp = L.ldp;
+  const float* Wx = Wp + L.imgW;
+  const float* Wh = Wx + (size_t)nI * ldp;
+  int sh = 3; while ((1 << sh) < min(nC, kST)) ++sh;
+  const int KR = 1 << sh, G = kST >> sh;
+  const int g = tid >> sh, il = tid & (KR - 1);
+  const int Nc = (nC + G - 1) / G;
+  const int nb = min(nC, g * Nc), ne = min(nC, nb + Nc);
+  for (int k = T1 - 1; k >= 0; --k) {
+    float* gk = Gt + (size_t)k * gs;
+    const float* hprev = Y + (size_t)(k - 1) * ys;
+    float dO = 0.f, fg = 0.f, st = 0.f;
+    if (tid < nC) {                                                   // 1) dLdS = dLdO * forget * tanh'
+      dO = E[(size_t)k * es + tid]; fg = gk[tid]; st = gk[nC + tid];
+      gk[nC + tid] = dO * fg * (1.0f - st * st);
+    }
+    __syncthreads();
+    if (k > 0) {                                                      // 2) dLdFprevOut = Wsr dLdS
+      float acc = 0.0f;
+      if (il < nC) {
+        const float* w = Wh + (size_t)il * ldp + nC;
+        for (int n = nb; n < ne; ++n) acc = fmaf(ldw<SM>(w + n), gk[nC + n], acc);
+      }
+      red[g * KR + il] = acc;
+      __syncthreads();
+    }
+    float dFp = 0.f;
+    if (tid < nC) {                                                   // 3) dLdF, and the element-wise part of 4)
+      const float pO = k > 0 ? hprev[tid] : 0.0f;
+      if (k > 0) for (int gg = 0; gg < G; ++gg) dFp += red[gg * KR + tid];
+      gk[tid] = ((st - pO) * dO + dFp * pO) * fg * (1.0f - fg);
+      if (k > 0) E[(size_t)(k - 1) * es + tid] += (1.0f - fg) * dO + fg * dFp;
+    }
+    __syncthreads();
+    if (k > 0) {                                                      // 4) dLdprevOut += Wfr dLdF
+      float acc = 0.0f;
+      if (il < nC) {
+        const float* w = Wh + (size_t)il * ldp;
+        for (int n = nb; n < ne; ++n) acc = fmaf(ldw<SM>(w + n), gk[n], acc);
+      }
+      red[g * KR + il] = acc;
+      __syncthreads();
+      if (tid < nC) {
+        float v = 0.0f;
+        for (int gg = 0; gg < G; ++gg) v += red[gg * KR + tid];
+        E[(size_t)(k - 1) * es + tid] += v;
+      }
+      __syncthreads();
+    }
+  }
+  if (L.needDx) {   // error on the layer below, all window steps at once: Wff dLdF + Wsf dLdS
+    const int N2q = (N2 + 3) >> 2;
+    for (int idx = tid; idx < nI * T1; idx += kST) {
+      const int k = idx / nI, i = idx - k * nI;
+      const float* w = Wx + (size_t)i * ldp;
+      const float* dl = Gt + (size_t)k * gs;
+      float acc = 0.0f;
+      for (int n4 = 0; n4 < N2q; ++n4) {
+        const float4 wv = ldw4<SM>(w + n4 * 4), dv = *reinterpret_cast<const float4*>(dl + n4 * 4);
+        acc = fmaf(wv.x, dv.x, acc); acc = fmaf(wv.y, dv.y, acc); acc = fmaf(wv.z, dv.z, acc); acc = fmaf(wv.w, dv.w, acc);
+      }
+      Ein[(size_t)k * eis + i] += acc;
+    }
+    __syncthreads();
+  }
+}
+
 template <bool SM>
 __device__ void p1_seq(const StepArgs& a, const DevDescs& dd, StepCtrl& c, int step, int b, unsigned char* smraw, const SeqSmem& sp,
                        unsigned parity, bool fetchCtrl, const unsigned* readyFlag, unsigned readyTarget) {
@@ -1279,6 +1490,8 @@ __device__ void p1_seq(const StepArgs& a, const DevDescs& dd, StepCtrl& c, int s
     if (bars) mbar_wait(&bars[l], parity);
     if (L.kind == kLSTM) {
       lstm_forward<SM>(L, Wp, ws + sq.yOff[L.in], sq.yStride[L.in], ws + sq.gOff[l], sq.gStride[l], ws + sq.yOff[l], sq.yStride[l], red, Tn);
+    } else if (L.kind == kMGU) {
+      mgu_forward<SM>(L, Wp, ws + sq.yOff[L.in], sq.yStride[L.in], ws + sq.gOff[l], sq.gStride[l], ws + sq.yOff[l], sq.yStride[l], red, Tn);
     } else if (L.kind == kResidual) {       // ParametricResidualLayer::forward (Layers.h:347-361)
       const float* y1 = ws + sq.yOff[l - 1]; const float* y2 = ws + sq.yOff[l - 2];
       const int s1 = sq.yStride[l - 1], s2 = sq.yStride[l - 2], ys = sq.yStride[l];
@@ -1362,6 +1575,16 @@ __device__ void p1_seq(const StepArgs& a, const DevDescs& dd, StepCtrl& c, int s
       seq_store(a.errG, a.Bpad, L.actOff, 4 * L.size, col0, Tc, T1, Gt, sq.gStride[l], 0);            // gate deltas
       seq_store(a.actG, a.Bpad, L.actOff, L.size, col0, Tc, T1, Y, sq.yStride[l], 0);                 // y_k
       seq_store(a.actG, a.Bpad, L.actOff + L.size, L.size, col0, Tc, T1, Y, sq.yStride[l], 1);        // h_{k-1}
+    } else if (L.kind == kMGU) {
+      float* Gt = ws + sq.gOff[l];
+      const float* Y = ws + sq.yOff[l];
+      const int nC4 = (L.size + 3) / 4 * 4;
+      mgu_backward<SM>(L, Wp, Gt, sq.gStride[l], Y, sq.yStride[l], ws + sq.eOff[l], sq.eStride[l],
+                       L.in > 0 ? ws + sq.eOff[L.in] : nullptr, L.in > 0 ? sq.eStride[L.in] : 0, red, T1);
+      seq_store(a.errG, a.Bpad, L.actOff, 2 * L.size, col0, Tc, T1, Gt, sq.gStride[l], 0);            // [dLdF | dLdS]
+      seq_store(a.actG, a.Bpad, L.actOff, L.size, col0, Tc, T1, Y, sq.yStride[l], 0);                 // h_k
+      seq_store(a.actG, a.Bpad, L.actOff + L.size, L.size, col0, Tc, T1, Y, sq.yStride[l], 1);        // h_{k-1}
+      seq_store(a.actG, a.Bpad, L.actOff + 2 * L.size, L.size, col0, Tc, T1, Y + nC4, sq.yStride[l], 0);   // h_{k-1} * forget(k)
     }
   }
   seq_store(a.actG, a.Bpad, net.L[0].actOff, dS, col0, Tc, T1, X, xs, 0);
@@ -1414,13 +1637,14 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
   // operand rows: A = activation of the input layer (dense) / of layer ID-2 (residual); D = this layer's deltas
   // LSTM layers: rows [0, nIn) of W multiply the layer input, rows [nIn, nIn + nCells) the previous step's
   // output (stored next to y in the layer's activation rows), N = 4 nCells gate deltas (Layer_LSTM.h:24-29)
-  const bool lstm = L.kind == kLSTM;
+  const bool lstm = is_cell_layer(L.kind);           // LSTM or MGU cells: rows [input | recurrent]
   const int K = t.kind == 0 ? (lstm ? L.nIn + L.size : L.nIn) : L.size;
   const int aOff = t.kind == 0 ? ((net.recurrent && L.kind == kDenseLinear) ? net.topInOff : net.L[L.in].actOff)
                                : (t.kind == 1 ? net.L[t.layer - 2].actOff : 0);
-  const int hOff = L.actOff + L.size - L.nIn;
+  // recurrent rows k >= nIn read h_{k-1}; the state columns of an MGU layer read h_{k-1} * forget(k) (Layer_GRU.h:205-212)
+  const int hOff = (L.kind == kMGU && t.n0 >= L.size ? L.actOff + 2 * L.size : L.actOff + L.size) - L.nIn;
   const int dOff = L.actOff;
-  const int N = lstm ? 4 * L.size : L.size;
+  const int N = t.nLimit > 0 ? t.nLimit : cell_gates(L.kind) * L.size;
   const int kk = tid >> 4, nn = tid & 15;
   const int warp = tid >> 5, lane = tid & 31;
   // parameters this thread owns: fetch W, M1, M2 now, use them after the contraction
@@ -2094,7 +2318,7 @@ __device__ __forceinline__ void init_bars(const StepArgs& a, const NetDesc& net,
   __syncthreads();
 }
 
-template <int TB, bool SM>
+template <int TB, bool SM, bool DISC = false>
 __global__ void __launch_bounds__(kST) k_p1(StepArgs a, int step) {
   extern __shared__ __align__(128) unsigned char smraw[];
   const NetDesc* net; const Hyper* hp;
@@ -2106,7 +2330,7 @@ __global__ void __launch_bounds__(kST) k_p1(StepArgs a, int step) {
     load_weight_image(a, *net, reinterpret_cast<float*>(smraw + sp.img), reinterpret_cast<uint64_t*>(smraw + sp.bars));
   }
   __syncthreads();
-  p1_tile<TB, SM>(a, *net, *hp, c, step, blockIdx.x, smraw, sp, 0, true, nullptr, 0, false);
+  p1_tile<TB, SM, DISC>(a, *net, *hp, c, step, blockIdx.x, smraw, sp, 0, true, nullptr, 0, false);
 }
 
 // recurrent networks: one sampled transition (its whole BPTT window) per CTA
@@ -2142,7 +2366,7 @@ __global__ void __launch_bounds__(kST) k_p2p3(StepArgs a, int step, int skipStat
 // barriers: it watches the barrier counter to learn that every worker finished P1 of a step and
 // publishes ctrl[(step+1)&1] through `ready`, which the workers only need at their next loss stage
 // — so the replay statistics are off the critical path.
-template <int TB, bool SM, bool REC>
+template <int TB, bool SM, bool REC, bool DISC = false>
 __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int step0, int nSteps, int skipStatsLast) {
   extern __shared__ __align__(128) unsigned char smraw[];
   const NetDesc* net; const Hyper* hp;
@@ -2210,7 +2434,7 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
   const int nS4 = dS * TB / 4;                      // float4 chunks of this tile's raw states
   // inputs of step s+1 are copied into the shared-memory staging area (cp.async) while P2 of step s runs:
   // possible when every worker owns at most one P1 tile
-  const bool pf = !REC && doP1 && nP1 <= nw && (dS & 3) == 0 && nS4 <= 2 * kST && nPair <= kST;
+  const bool pf = !REC && !DISC && doP1 && nP1 <= nw && (dS & 3) == 0 && nS4 <= 2 * kST && nPair <= kST;
   // idle worker CTAs evaluate V(s_{t+1}) of truncated episodes for the P1 CTAs (next_state_helper)
   const int nHelpers = (!REC && nP1 < nw) ? nw - nP1 : 0;
   unsigned helpParity = 0;
@@ -2222,7 +2446,7 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
   }
   if (SM) init_bars(a, *net, smraw, sp.bars);
   // the first GradTile of this CTA never changes: keep it in registers
-  GradTile myTile = {0, 0, 0, 0, 0, {0, 0, 0}};
+  GradTile myTile = {0, 0, 0, 0, 0, 0, {0, 0}};
   if ((int)blockIdx.x < a.nTiles) myTile = a.tiles[blockIdx.x];
   bool staged = false;
   // loop-invariant index arithmetic of the input prefetch (integer divisions)
@@ -2259,7 +2483,7 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
     DBG_T(a, step, 38);
     for (int t = blockIdx.x; t < nP1; t += nw) {
       if (REC) p1_seq<SM>(a, *reinterpret_cast<const DevDescs*>(smraw), c, step, t, smraw, sps, (unsigned)(s & 1), first, ready, (unsigned)s);
-      else p1_tile<TB, SM>(a, *net, *hp, c, step, t, smraw, sp, (unsigned)(s & 1), first, ready, (unsigned)s, staged, nHelpers > 0);
+      else p1_tile<TB, SM, DISC>(a, *net, *hp, c, step, t, smraw, sp, (unsigned)(s & 1), first, ready, (unsigned)s, staged, nHelpers > 0);
       first = false;
       __syncthreads();
     }
@@ -2416,6 +2640,11 @@ int step_kernels_prepare(const NetDesc& net) {
     }
     SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_p1<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOff));
     SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_steps_persistent<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOff));
+    if (net.discrete) {
+      if (!sm) { set_error_msg("discrete-action network too large for the shared-memory weight image"); return -1; }
+      SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_p1<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOn));
+      SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_steps_persistent<4, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOn));
+    }
     SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_forward<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan(net, 4, false).total));
   }
   SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_p2p3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2_smem_bytes()));
@@ -2430,7 +2659,8 @@ int launch_step_two_kernels(const StepArgs& a, const NetDesc& net, int step, int
     else k_p1_seq<false><<<a.B, kST, smem, st>>>(a, step);
   } else {
     const int nP1 = (a.B + 3) / 4;
-    if (sm) k_p1<4, true><<<nP1, kST, smem, st>>>(a, step);
+    if (net.discrete) k_p1<4, true, true><<<nP1, kST, smem, st>>>(a, step);
+    else if (sm) k_p1<4, true><<<nP1, kST, smem, st>>>(a, step);
     else k_p1<4, false><<<nP1, kST, smem, st>>>(a, step);
   }
   k_p2p3<<<a.nTiles + 1, kST, p2_smem_bytes(), st>>>(a, step, skipStats);
@@ -2441,6 +2671,7 @@ int launch_step_two_kernels(const StepArgs& a, const NetDesc& net, int step, int
 static const void* persistent_fn(const NetDesc& net) {
   const bool sm = step_image_in_smem(net);
   if (net.recurrent) return sm ? (const void*)k_steps_persistent<4, true, true> : (const void*)k_steps_persistent<4, false, true>;
+  if (net.discrete) return (const void*)k_steps_persistent<4, true, false, true>;
   return sm ? (const void*)k_steps_persistent<4, true, false> : (const void*)k_steps_persistent<4, false, false>;
 }
 

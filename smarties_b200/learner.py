@@ -192,7 +192,7 @@ def make_config(dim_state: int, dim_action: int, settings=None, *, device: int =
     cfg.expl_noise, cfg.out_weights_prefac = hp.explNoise, hp.outWeightsPrefac
     cfg.refer_reduce_threads = refer_reduce_threads
     cfg.world_rank, cfg.world_size, cfg.seed = world_rank, world_size, seed
-    cfg.nn_type, cfg.nn_bptt_seq = {"FFNN": 0, "LSTM": 1}[hp.nnType], int(hp.nnBPTTseq)
+    cfg.nn_type, cfg.nn_bptt_seq = {"FFNN": 0, "LSTM": 1, "MGU": 2, "GRU": 2}[hp.nnType], int(hp.nnBPTTseq)
     cfg.min_tot_obs = hp.minTotObsNum_local
     cfg.returns_estimator = {"retrace": 0, "GAE": 1, "retraceExplore": 2}[hp.returnsEstimator]
     cfg.discrete_options = int(discrete_options)     # from the MDP (Communicator::setNumberOfOptions), not from settings.json
@@ -208,11 +208,12 @@ class Learner:
 
     def __init__(self, dim_state: int, dim_action: int, settings: dict | None = None, *, device: int = 0,
                  bounded=None, seed: int = 42, capacity_rows: int = 0, max_episodes: int = 0,
-                 refer_reduce_threads: int = 32, world_rank: int = 0, world_size: int = 1):
+                 refer_reduce_threads: int = 32, world_rank: int = 0, world_size: int = 1, discrete_options: int = 0):
         self.lib = load_library()
         cfg, hp = make_config(dim_state, dim_action, settings, device=device, bounded=bounded, seed=seed,
                               capacity_rows=capacity_rows, max_episodes=max_episodes,
-                              refer_reduce_threads=refer_reduce_threads, world_rank=world_rank, world_size=world_size)
+                              refer_reduce_threads=refer_reduce_threads, world_rank=world_rank, world_size=world_size,
+                              discrete_options=discrete_options)
         self.hp = hp
         self.cfg = cfg
         self.dS, self.dA, self.B = dim_state, dim_action, hp.batchSize_local

@@ -102,7 +102,7 @@ class HyperParameters:
             unsupported.append(f"returnsEstimator={self.returnsEstimator}")
         if self.ERoldSeqFilter not in ("oldest", "default"):
             unsupported.append(f"ERoldSeqFilter={self.ERoldSeqFilter}")
-        if self.nnType not in ("FFNN", "LSTM") or self.nnFunc != "Tanh" or self.nnOutputFunc != "Linear":
+        if self.nnType not in ("FFNN", "LSTM", "MGU", "GRU") or self.nnFunc != "Tanh" or self.nnOutputFunc != "Linear":
             unsupported.append(f"nnType/nnFunc/nnOutputFunc={self.nnType}/{self.nnFunc}/{self.nnOutputFunc}")
         if self.ESpopSize != 1 or self.targetDelay != 0 or any(int(e) > 0 for e in self.encoderLayerSizes):
             unsupported.append("ESpopSize/targetDelay/encoderLayerSizes")

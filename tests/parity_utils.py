@@ -10,14 +10,15 @@ import numpy as np
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CKPT_CASES = ["vracer_ckpt", "racer_lstm_ckpt"]
 CASES = ["vracer_small", "vracer_cfg2mini", "vracer_bounded", "vracer_prune", "racer_small", "racer_bounded", "vracer_gae",
-         "vracer_da1", "vracer_explore", "vracer_b1024"]
+         "vracer_da1", "vracer_explore", "vracer_b1024", "racer_discrete"]
 # golden runs of a reference with 8 / 16 OpenMP threads: the far-policy count (and beta) depend on the thread count
 # (MemoryProcessing.cpp:202-227); the device reproduces it with refer_reduce_threads = T
 THREADED_CASES = ["vracer_small_t8", "vracer_small_t16", "vracer_cfg2mini_t8", "vracer_cfg2mini_t16", "racer_small_t8"]
-# oracle pinned, device path not built: MGU cells, prioritized samplers (f3)
-ORACLE_ONLY_CASES = ["racer_mgu", "vracer_gru2", "vracer_pererr", "vracer_perseq", "vracer_farpolfrac", "vracer_maxkldiv",
-                     "vracer_minerror", "vracer_perrank", "racer_discrete"]
-RECURRENT_CASES = ["racer_lstm", "vracer_lstm2", "racer_lstm64", "racer_cfg3mini"]     # nnType LSTM + BPTT window (configs[2] family)
+# oracle pinned, device path not built: prioritized samplers and non-FIFO filters
+ORACLE_ONLY_CASES = ["vracer_pererr", "vracer_perseq", "vracer_farpolfrac", "vracer_maxkldiv",
+                     "vracer_minerror", "vracer_perrank"]
+RECURRENT_CASES = ["racer_lstm", "vracer_lstm2", "racer_lstm64", "racer_cfg3mini",      # nnType LSTM + BPTT window (configs[2] family)
+                   "racer_mgu", "vracer_gru2"]     # MGU cells (Layer_GRU.h): "MGU" / "GRU", the default of partially observable MDPs
 
 
 class Golden:
@@ -93,7 +94,8 @@ def make_oracle(g: Golden):
 def make_learner(g: Golden, refer_reduce_threads=None):
     from smarties_b200 import Learner
     L = Learner(g.dS, g.dA, dict(g.settings), bounded=g.bounded,
-                refer_reduce_threads=g.threads if refer_reduce_threads is None else refer_reduce_threads)
+                refer_reduce_threads=g.threads if refer_reduce_threads is None else refer_reduce_threads,
+                discrete_options=g.spec["replay"].get("n_options", 0))
     L.set_weights(g.ref["init/weights"])
     L.load_replay(g.replay)
     L.initialize_learner()

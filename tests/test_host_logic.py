@@ -47,9 +47,10 @@ def test_settings_outside_the_device_path_are_rejected_loudly():
     from smarties_b200 import HyperParameters
     assert HyperParameters(4, 1, {"returnsEstimator": "GAE"}).returnsEstimator == "GAE"
     assert HyperParameters(4, 1, {"nnType": "LSTM", "nnLayerSizes": [32]}).nnType == "LSTM"
+    assert HyperParameters(4, 1, {"nnType": "GRU", "nnLayerSizes": [32]}).bRecurrent
     for bad in ({"returnsEstimator": "nonsense"}, {"dataSamplingAlgo": "PERrank"}, {"dataSamplingAlgo": "PERerr"},
                 {"dataSamplingAlgo": "PERseq"}, {"ERoldSeqFilter": "farpolfrac"}, {"ERoldSeqFilter": "maxkldiv"},
-                {"ERoldSeqFilter": "minerror"}, {"nnType": "MGU"}, {"nnType": "GRU"}, {"nnFunc": "Relu"}):
+                {"ERoldSeqFilter": "minerror"}, {"nnType": "RNN"}, {"nnFunc": "Relu"}):
         with pytest.raises(NotImplementedError):
             HyperParameters(4, 1, bad)
 
@@ -141,10 +142,11 @@ def test_every_settings_file_of_the_reference_is_parsed_or_rejected_with_a_reaso
         files = json.load(f)
     assert len(files) >= 17
     covered = {"VRACER.json": ("VRACER", "FFNN"), "RACER.json": ("RACER", "FFNN"), "RACER_RNN.json": ("RACER", "LSTM"),
-               "VRACER_LES.json": ("VRACER", "FFNN"), "RACER_glider.json": ("RACER", "FFNN"), "RACER_atari.json": ("RACER", "FFNN")}
+               "VRACER_LES.json": ("VRACER", "FFNN"), "RACER_glider.json": ("RACER", "FFNN"), "RACER_atari.json": ("RACER", "FFNN"),
+               "VRACER_expensiveData.json": ("VRACER", "GRU")}
     refused = {"ACER.json": "learner=ACER", "CMA.json": "learner=CMA", "DPG.json": "learner=DPG", "DPG_light.json": "learner=DPG",
                "DPG_orig.json": "learner=DPG", "DQN.json": "learner=DQN", "NAF.json": "learner=NAF", "PPO.json": "learner=PPO",
-               "VRACER_CMA.json": "ESpopSize", "VRACER_expensiveData.json": "GRU", "default.json": "nnType/nnFunc/nnOutputFunc"}
+               "VRACER_CMA.json": "ESpopSize", "default.json": "nnType/nnFunc/nnOutputFunc"}
     for name, settings in files.items():
         if name in covered:
             hp = HyperParameters(8, 2, settings)

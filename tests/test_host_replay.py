@@ -102,7 +102,7 @@ def test_fifo_pruning_frees_ring_rows_for_reuse(built_library):
     assert set(ep[1].tolist()) <= {4, 5, 6, 7, 8, 9} and set(ep[2].tolist()) <= {4, 5, 6, 7, 8, 9}
 
 
-DEVICE_NET_CASES = CASES + RECURRENT_CASES + ["vracer_da1", "vracer_explore"]
+DEVICE_NET_CASES = CASES + RECURRENT_CASES
 
 
 @pytest.mark.parametrize("case", DEVICE_NET_CASES)
@@ -117,7 +117,7 @@ def test_network_construction_is_bit_exact_with_the_reference_builder(built_libr
     g = Golden(case)
     lib = load_library()
     lib.smb200_host_init_weights.restype = C.c_int64
-    cfg, _ = make_config(g.dS, g.dA, dict(g.settings), bounded=g.bounded, seed=42)
+    cfg, _ = make_config(g.dS, g.dA, dict(g.settings), bounded=g.bounded, seed=42, discrete_options=g.spec["replay"].get("n_options", 0))
     n = lib.smb200_host_init_weights(C.byref(cfg), None, 0)
     ref = g.ref["init/weights"]
     assert n == ref.size
