@@ -44,6 +44,14 @@ enum smb200_nn_type { SMB200_FFNN = 0, SMB200_LSTM = 1,
  * "default" means for RACER / V-RACER, Learners/AlgoFactory.cpp:134-136) or GAE (:411-417). */
 enum smb200_returns_estimator { SMB200_RETRACE = 0, SMB200_GAE = 1,
                                 SMB200_RETRACE_EXPLORE = 2 /* computeRetraceExplBonus, MemoryProcessing.cpp:402-409 */ };
+/* "dataSamplingAlgo" (Sampling::prepareSampler, ReplayMemory/Sampling.cpp:298-335): uniform, or prioritized by the rank of the
+ * squared TD error (TSample_impRank, :101-166), by the TD error (TSample_impErr, :169-226), by the episode's mean squared error
+ * (Sample_impSeq, :230-296).  "ERoldSeqFilter" (getERfilterAlgo, MemoryProcessing.cpp:261-298): which episodes leave a full
+ * buffer — the oldest, or the ones with the largest far-policy fraction / the largest KL divergence / the smallest error.
+ * Everything but uniform + oldest makes every learner step a separate launch with one host round trip (the sampler and the
+ * episode order of step k+1 depend on values step k wrote), like the reference re-prepares its sampler every step. */
+enum smb200_sampling { SMB200_SAMPLE_UNIFORM = 0, SMB200_SAMPLE_PER_RANK = 1, SMB200_SAMPLE_PER_ERR = 2, SMB200_SAMPLE_PER_SEQ = 3 };
+enum smb200_er_filter { SMB200_FILTER_OLDEST = 0, SMB200_FILTER_FARPOLFRAC = 1, SMB200_FILTER_MAXKLDIV = 2, SMB200_FILTER_MINERROR = 3 };
 enum smb200_field {          /* per-transition replay arrays, Episode.h:66-75 */
   SMB200_F_V = 0, SMB200_F_ADV = 1, SMB200_F_QRET = 2, SMB200_F_DELTA = 3, SMB200_F_RHO = 4, SMB200_F_KL = 5,
   SMB200_F_REWARD = 6
@@ -82,9 +90,9 @@ typedef struct smb200_config {
                                            (ActionInfo::dimDiscrete, Core/StateAction.h; RACER<Discrete_advantage, Discrete_policy, Uint>,
                                            Math/Discrete_policy.h, Discrete_advantage.h): dim_action = 1, the stored action is the
                                            option label (+0.1, StateAction.h:320-341), the behaviour policy has K columns, the net
-                                           outputs [V | advantages(K) | policy(K)] and has no ParamLayer.  Only the network
-                                           construction is built so far (smb200_host_init_weights, pinned to the reference);
-                                           smb200_create rejects K != 0 until the loss stage exists */
+                                           outputs [V | advantages(K) | policy(K)] and has no ParamLayer.  Feed-forward nets. */
+  int32_t data_sampling;                /* smb200_sampling: "dataSamplingAlgo" */
+  int32_t er_filter;                    /* smb200_er_filter: "ERoldSeqFilter" */
 } smb200_config;
 
 /* Per-step scalars the reference prints / feeds back (MemoryBuffer::getMetrics,

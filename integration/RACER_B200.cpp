@@ -107,6 +107,10 @@ class RACER_B200 : public RACER<Advantage_t, Policy_t, Action_t>
     const bool mgu = settings.nnType == "MGU" || settings.nnType == "GRU" || (MDP.isPartiallyObservable && !settings.bRecurrent);
     c.nn_type = settings.nnType == "LSTM" ? SMB200_LSTM : (mgu ? SMB200_MGU : SMB200_FFNN);
     c.nn_bptt_seq = (int32_t) settings.nnBPTTseq;
+    c.data_sampling = settings.dataSamplingAlgo == "PERrank" ? SMB200_SAMPLE_PER_RANK : settings.dataSamplingAlgo == "PERerr" ? SMB200_SAMPLE_PER_ERR
+                    : settings.dataSamplingAlgo == "PERseq" ? SMB200_SAMPLE_PER_SEQ : SMB200_SAMPLE_UNIFORM;
+    c.er_filter = settings.ERoldSeqFilter == "farpolfrac" ? SMB200_FILTER_FARPOLFRAC : settings.ERoldSeqFilter == "maxkldiv" ? SMB200_FILTER_MAXKLDIV
+                : settings.ERoldSeqFilter == "minerror" ? SMB200_FILTER_MINERROR : SMB200_FILTER_OLDEST;
     c.returns_estimator = settings.returnsEstimator == "GAE" ? SMB200_GAE
                         : (settings.returnsEstimator == "retraceExplore" ? SMB200_RETRACE_EXPLORE : SMB200_RETRACE);
     // an episode occupies nsteps() = ndata()+1 rows and is at least two rows long: room for the worst case,
@@ -377,7 +381,10 @@ std::unique_ptr<Learner> createLearner(const Uint learnerID, MDPdescriptor& MDP,
       // discrete actions: RACER<Discrete_advantage, Discrete_policy, Uint> (AlgoFactory.cpp:100-113), one component, feed-forward net
       (!MDP.bDiscreteActions() || (settings.learner == "RACER" && MDP.dimAction == 1 && MDP.discreteActionValues[0] >= 2 &&
                                    MDP.discreteActionValues[0] <= 64 && settings.nnType == "FFNN" && !MDP.isPartiallyObservable)) &&
-      settings.dataSamplingAlgo == "uniform" && (settings.returnsEstimator == "default" || settings.returnsEstimator == "retrace" || settings.returnsEstimator == "GAE" ||
+      // prioritized samplers run on the device learner (one launch per step); the non-FIFO episode filters do too, but this binding
+      // prunes its host copy of the episodes first-in-first-out (mirrorEpisodes), so they stay with the reference learner here
+      (settings.dataSamplingAlgo == "uniform" || settings.dataSamplingAlgo == "PERrank" || settings.dataSamplingAlgo == "PERerr" ||
+       settings.dataSamplingAlgo == "PERseq") && (settings.returnsEstimator == "default" || settings.returnsEstimator == "retrace" || settings.returnsEstimator == "GAE" ||
                                                   settings.returnsEstimator == "retraceExplore") &&
       (settings.ERoldSeqFilter == "oldest" || settings.ERoldSeqFilter == "default") &&
       (settings.nnType == "FFNN" || settings.nnType == "LSTM" || settings.nnType == "MGU" || settings.nnType == "GRU") &&

@@ -9,6 +9,8 @@ import sys
 from collections import OrderedDict
 
 src, dst = sys.argv[1], sys.argv[2]
+import os
+os.makedirs(dst, exist_ok=True)
 
 # ---- launch list ----
 rows = list(csv.reader(l for l in open(f"{src}/launches_bench.csv") if not l.startswith("==")))

@@ -31,6 +31,7 @@ print("steps", steps, "device ms", L.last_timing(), "wall", time.perf_counter() 
 if os.environ.get("PROF_SWEEPS"):
     L.retrace_sweep(); print("retrace ms", L.last_timing())
     L.reward_state_moments(); print("moments ms", L.last_timing())
+    L.fused_sweep(); print("fused sweep ms", L.last_timing())
 if os.environ.get("PROF_RANGE"):
     torch.cuda.profiler.stop()
 L.close()

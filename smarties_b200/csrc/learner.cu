@@ -21,7 +21,9 @@
 #include <map>
 #include <mutex>
 #include <random>
+#include <limits>
 #include <string>
+#include <tuple>
 #include <vector>
 
 namespace smb200 {
@@ -109,6 +111,12 @@ struct smb200_learner {
   int maxSeg = 1024;
   int presampled = 0;              // steps resident in dSampSlot/dSampT (benchmark path)
 
+  // prioritized samplers / non-FIFO filters: host copies of the keys, refreshed after every step
+  std::vector<float> keyDelta;           // deltaValue of every ring row (PERrank / PERerr: Episode::SquaredError)
+  std::vector<float> keyAgg[3];          // per slot: fracFarPolSteps, avgKLDivergence, avgSquaredErr (filters, PERseq)
+  std::discrete_distribution<size_t> perDist;
+  bool samplerStale = false;             // a restart: the distribution is prepared before the first step
+  bool slow_mode() const { return cfg.data_sampling != SMB200_SAMPLE_UNIFORM || cfg.er_filter != SMB200_FILTER_OLDEST; }
   std::vector<std::pair<long long, int>> pendingEvict;   // ring ranges whose live flags are cleared after the segment
   std::mt19937 gen;
   // host sampler scratch + id -> (episode position, t) lookup, rebuilt when the episode table changes
@@ -380,6 +388,22 @@ static void fill_stats(const StepCtrl& c, smb200_step_stats* o) {
 static bool host_post_step(smb200_learner* h) {
   bool changed = false;
   auto cmp = [](const EpisodeMeta& a, const EpisodeMeta& b) { return a.id > b.id; };
+  if (h->cfg.er_filter != SMB200_FILTER_OLDEST) {
+    // getERfilterAlgo (MemoryProcessing.cpp:261-298): "a goes before b", the episodes to delete end up at the back; the keys are
+    // the per-episode aggregates AFTER this step's updates (fetch_keys).  The reference sorts every step with the unstable
+    // std::sort — same comparator, same starting order, same libstdc++: same result, ties included.
+    const float* far = h->keyAgg[0].data(); const float* kl = h->keyAgg[1].data(); const float* e2 = h->keyAgg[2].data();
+    const std::vector<EpisodeMeta> before = h->episodes;
+    switch (h->cfg.er_filter) {
+      case SMB200_FILTER_FARPOLFRAC:
+        std::sort(h->episodes.begin(), h->episodes.end(), [far](const EpisodeMeta& a, const EpisodeMeta& b) { return far[a.slot] < far[b.slot]; }); break;
+      case SMB200_FILTER_MAXKLDIV:
+        std::sort(h->episodes.begin(), h->episodes.end(), [kl](const EpisodeMeta& a, const EpisodeMeta& b) { return kl[a.slot] < kl[b.slot]; }); break;
+      default:
+        std::sort(h->episodes.begin(), h->episodes.end(), [e2](const EpisodeMeta& a, const EpisodeMeta& b) { return e2[a.slot] > e2[b.slot]; }); break;
+    }
+    for (size_t i = 0; i < before.size() && !changed; ++i) changed = before[i].slot != h->episodes[i].slot;
+  } else
   if (!std::is_sorted(h->episodes.begin(), h->episodes.end(), cmp)) {
     std::sort(h->episodes.begin(), h->episodes.end(), cmp);
     changed = true;
@@ -469,6 +493,126 @@ static void host_sample(smb200_learner* h, int* slotOut, int* tOut, int64_t* pos
   }
 }
 
+// ---- prioritized samplers (ReplayMemory/Sampling.cpp:101-296) ----
+// Host copies of what the samplers / filters read, after a step (or initializeLearner) has completed on the device.
+static int fetch_keys(smb200_learner* h) {
+  const int ds = h->cfg.data_sampling;
+  if (ds == SMB200_SAMPLE_PER_RANK || ds == SMB200_SAMPLE_PER_ERR) {
+    h->keyDelta.resize((size_t)h->highWater);
+    if (h->highWater > 0)
+      SMB200_CUDA_CHECK(cudaMemcpyAsync(h->keyDelta.data(), h->rp.DELTA, sizeof(float) * (size_t)h->highWater, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (ds == SMB200_SAMPLE_PER_SEQ || h->cfg.er_filter != SMB200_FILTER_OLDEST) {
+    int maxSlot = 0;
+    for (const auto& e : h->episodes) maxSlot = std::max(maxSlot, e.slot);
+    const int which[3] = {AGG_FAR, AGG_KL, AGG_E2};
+    for (int k = 0; k < 3; ++k) {
+      h->keyAgg[k].resize((size_t)maxSlot + 1);
+      SMB200_CUDA_CHECK(cudaMemcpyAsync(h->keyAgg[k].data(), h->rp.epAgg + (size_t)which[k] * h->rp.maxEpisodes, sizeof(float) * ((size_t)maxSlot + 1),
+                                        cudaMemcpyDeviceToHost, h->stream));
+    }
+  }
+  SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// Sampling::prepare of the three prioritized samplers: float weights, the distribution itself is libstdc++'s
+// std::discrete_distribution<Uint> (sequential double sums) — the class the reference instantiates.
+static void prepare_sampler(smb200_learner* h) {
+  const int ds = h->cfg.data_sampling;
+  if (ds == SMB200_SAMPLE_UNIFORM) return;
+  const float EPS = std::numeric_limits<float>::epsilon();
+  const size_t nEp = h->episodes.size();
+  std::vector<float> probs;
+  if (ds == SMB200_SAMPLE_PER_SEQ) {                 // Sample_impSeq::prepare (:230-255)
+    probs.assign(nEp, 1.f);
+    for (size_t i = 0; i < nEp; ++i) {
+      const EpisodeMeta& e = h->episodes[i];
+      const unsigned long ndata = (unsigned long)(e.nRows - 1);
+      const float P = std::sqrt(std::sqrt(h->keyAgg[2][e.slot] + EPS)) * ndata;
+      probs[i] = P;
+    }
+  } else {
+    const size_t nData = (size_t)h->nTransitions;
+    probs.assign(nData, 1.f);
+    std::vector<size_t> prefixes(nEp);
+    size_t prefix = 0;
+    for (size_t i = 0; i < nEp; ++i) { prefixes[i] = prefix; prefix += (size_t)(h->episodes[i].nRows - 1); }
+    if (ds == SMB200_SAMPLE_PER_ERR) {               // TSample_impErr::prepare (:169-206)
+      for (size_t i = 0; i < nEp; ++i) {
+        const EpisodeMeta& e = h->episodes[i];
+        const float* d = h->keyDelta.data() + e.start;
+        float* probs_i = probs.data() + prefixes[i];
+        for (int j = 0; j < e.nRows - 1; ++j) {
+          const float deltasq = d[j] * d[j];                           // Episode::SquaredError
+          probs_i[j] = std::sqrt(std::sqrt(deltasq + EPS));
+        }
+      }
+    } else {                                         // TSample_impRank::prepare (:101-146)
+      using TupEST = std::tuple<float, unsigned, unsigned>;
+      std::vector<TupEST> errors(nData);
+      for (size_t i = 0; i < nEp; ++i) {
+        const EpisodeMeta& e = h->episodes[i];
+        const float* d = h->keyDelta.data() + e.start;
+        TupEST* err_i = errors.data() + prefixes[i];
+        for (int j = 0; j < e.nRows - 1; ++j) err_i[j] = std::make_tuple(d[j] * d[j], (unsigned)i, (unsigned)j);
+      }
+      std::sort(errors.begin(), errors.end(), [](const TupEST& a, const TupEST& b) { return std::get<0>(a) > std::get<0>(b); });
+      for (unsigned i = 0; i < (unsigned)nData; ++i) {
+        const float P = std::get<0>(errors[i]) > 0 ? 1 / std::sqrt(std::sqrt(i + 1)) : 1;      // std::sqrt(unsigned): double
+        probs[prefixes[std::get<1>(errors[i])] + std::get<2>(errors[i])] = P;
+      }
+    }
+  }
+  h->perDist = std::discrete_distribution<size_t>(probs.begin(), probs.end());
+}
+
+// TSample_impRank / TSample_impErr::sample (:148-166, :208-225) and Sample_impSeq::sample, transition branch (:276-294):
+// fills the device form of the mini-batch like host_sample.
+static void host_sample_per(smb200_learner* h, int* slotOut, int* tOut, int64_t* posOut, int64_t* tOut64) {
+  const int B = h->cfg.batch_size;
+  std::vector<std::pair<size_t, size_t>> S((size_t)B);        // (episode position, t)
+  if (h->cfg.data_sampling == SMB200_SAMPLE_PER_SEQ) {
+    std::uniform_real_distribution<float> distT(0, 1);
+    auto it = S.begin();
+    while (it != S.end()) {
+      std::generate(it, S.end(), [&]() {
+        const size_t _s = h->perDist(h->gen);
+        const size_t _t = distT(h->gen) * (unsigned long)(h->episodes[_s].nRows - 1);
+        return std::pair<size_t, size_t>{_s, _t};
+      });
+      std::sort(S.begin(), S.end());
+      it = std::unique(S.begin(), S.end());
+    }
+  } else {
+    std::vector<size_t> ret((size_t)B);
+    auto it = ret.begin();
+    while (it != ret.end()) {
+      std::generate(it, ret.end(), [&]() { return h->perDist(h->gen); });
+      std::sort(ret.begin(), ret.end());
+      it = std::unique(ret.begin(), ret.end());
+    }
+    if (h->lookupDirty) rebuild_lookup(h);
+    const long long* prefix = h->epPrefix.data();
+    const int sh = h->bucketShift;
+    for (int i = 0; i < B; ++i) {                    // Sampling::IDtoSeqStep
+      const long long id = (long long)ret[i];
+      size_t k = (size_t)h->bucketFirst[(size_t)(id >> sh)];
+      while (prefix[k + 1] <= id) ++k;
+      S[i] = {k, (size_t)(id - prefix[k])};
+    }
+  }
+  for (int i = 0; i < B; ++i) {
+    const size_t k = S[i].first; const long long t = (long long)S[i].second;
+    if (slotOut) {
+      const EpisodeMeta& e = h->episodes[k];
+      const unsigned hn = ((int)t + 2 == e.nRows && !e.terminated) ? 0x80000000u : 0u;
+      slotOut[i] = (int)((unsigned)e.slot | hn); tOut[i] = (int)(e.start + t);
+    }
+    if (posOut) { posOut[i] = (int64_t)k; tOut64[i] = (int64_t)t; }
+  }
+}
+
 // cmax the device will hold after the statistics phase of step `gstep` (1-based)
 static double cmax_at(const smb200_learner* h, long long gstep) {
   return 1.0 + h->cfg.clip_imp_weight / (1.0 + (double)gstep * h->cfg.eps_anneal);
@@ -504,6 +648,13 @@ static int write_grad_stats_file(const std::string& base, int B, int nOut, const
 static int fetch_grad_stats(smb200_learner* h, int half) {
   SMB200_CUDA_CHECK(cudaMemcpyAsync(h->hGradStat[half], h->lastG, sizeof(float) * (size_t)h->cfg.batch_size * h->descs.net.nOut,
                                     cudaMemcpyDeviceToHost, h->stream));
+  return 0;
+}
+
+// clear the live flags of the ring rows of evicted episodes (enqueued behind the kernels that may still read them)
+static int flush_evictions(smb200_learner* h) {
+  for (const auto& ev : h->pendingEvict) SMB200_CUDA_CHECK(cudaMemsetAsync(h->rp.rowFlag + ev.first, 0, ev.second, h->stream));
+  h->pendingEvict.clear();
   return 0;
 }
 
@@ -556,9 +707,7 @@ static int run_segment(smb200_learner* h, int first, int n, long long gstep0, in
     if (launch_update_scaling(h->rp, h->dCtrl + (step & 1), h->dDescs, h->dSums, 0, h->stream)) return -2;
     h->launches += 5;
   }
-  for (const auto& ev : h->pendingEvict) SMB200_CUDA_CHECK(cudaMemsetAsync(h->rp.rowFlag + ev.first, 0, ev.second, h->stream));
-  h->pendingEvict.clear();
-  return 0;
+  return flush_evictions(h);
 }
 
 }  // namespace smb200
@@ -602,6 +751,10 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
   if (c.batch_size < 1 || c.max_tot_obs < c.batch_size) { set_error_msg("bad batch_size / max_tot_obs"); delete h; return SMB200_ERR_INVALID; }
   if (c.returns_estimator != SMB200_RETRACE && c.returns_estimator != SMB200_GAE && c.returns_estimator != SMB200_RETRACE_EXPLORE) {
     set_error_msg("returnsEstimator must be retrace, GAE or retraceExplore"); delete h; return SMB200_ERR_INVALID; }
+  if (c.data_sampling < 0 || c.data_sampling > SMB200_SAMPLE_PER_SEQ || c.er_filter < 0 || c.er_filter > SMB200_FILTER_MINERROR) {
+    set_error_msg("unknown dataSamplingAlgo / ERoldSeqFilter"); delete h; return SMB200_ERR_INVALID; }
+  if ((c.data_sampling != SMB200_SAMPLE_UNIFORM || c.er_filter != SMB200_FILTER_OLDEST) && c.world_size > 1) {
+    set_error_msg("prioritized samplers / non-FIFO filters: one learner rank only"); delete h; return SMB200_ERR_INVALID; }
   if (c.discrete_options != 0 && c.nn_type != SMB200_FFNN) {
     set_error_msg("discrete actions: feed-forward networks only"); delete h; return SMB200_ERR_INVALID; }
   std::vector<GradTile> tiles;
@@ -921,6 +1074,10 @@ int smb200_initialize_learner(smb200_learner* h) {
   SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   h->initialized = true;
   h->nGatheredB4Startup = h->cfg.min_tot_obs > 0 ? h->cfg.min_tot_obs : h->cfg.max_tot_obs;
+  if (h->slow_mode()) {                  // data->updateSampler() (Learner.cpp:63)
+    if (fetch_keys(h)) return SMB200_ERR_CUDA;
+    prepare_sampler(h);
+  }
   return 0;
 }
 
@@ -950,7 +1107,10 @@ int smb200_set_grad_stats(smb200_learner* h, const char* base) {
 
 int smb200_sample(smb200_learner* h, int64_t* pos, int64_t* t) {
   if (!h || !pos || !t || h->nTransitions < h->cfg.batch_size) return SMB200_ERR_STATE;
-  host_sample(h, nullptr, nullptr, pos, t);
+  if (h->cfg.data_sampling != SMB200_SAMPLE_UNIFORM) {
+    if (h->samplerStale) { if (fetch_keys(h)) return SMB200_ERR_CUDA; prepare_sampler(h); h->samplerStale = false; }
+    host_sample_per(h, nullptr, nullptr, pos, t);
+  } else host_sample(h, nullptr, nullptr, pos, t);
   return 0;
 }
 
@@ -1002,11 +1162,58 @@ static int upload_samples(smb200_learner* h, int off, int cnt) {
   return 0;
 }
 
+// Prioritized samplers / non-FIFO filters: the mini-batch of step k+1 and the episode order depend on the TD errors and episode
+// aggregates step k wrote, so every step is its own launch followed by one host round trip (keys D2H, std::sort /
+// std::discrete_distribution on the host like the reference, which re-prepares its sampler every step: MemoryProcessing.cpp:350).
+static int train_steps_slow(smb200_learner* h, int32_t n, smb200_step_stats* stats) {
+  const long long l0 = h->launches;
+  SMB200_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
+  if (pull_ctrl(h)) return SMB200_ERR_CUDA;
+  for (int i = 0; i < n; ++i) {
+    if (h->samplerStale) { if (fetch_keys(h)) return SMB200_ERR_CUDA; prepare_sampler(h); h->samplerStale = false; }
+    if (upload_order(h)) return SMB200_ERR_CUDA;
+    const long long g0 = h->gradStep, tr0 = h->trackerSteps;
+    const int nEpPre = (int)h->episodes.size(); const long long nTrPre = h->nTransitions;
+    const double betaPrev = h->hCtrl.beta;
+    if (h->cfg.data_sampling == SMB200_SAMPLE_UNIFORM) host_sample(h, h->hSampSlot, h->hSampT, nullptr, nullptr);
+    else host_sample_per(h, h->hSampSlot, h->hSampT, nullptr, nullptr);
+    if (upload_samples(h, 0, 1)) return SMB200_ERR_CUDA;
+    // the device's beta update assumes no pruning (the pruned episodes are only known once the post-step keys are here)
+    if (run_segment(h, 0, 1, g0, nEpPre, nTrPre, nTrPre)) return SMB200_ERR_CUDA;
+    const bool gradStat = h->grad_stats_step(g0);
+    if (gradStat && fetch_grad_stats(h, 0)) return SMB200_ERR_CUDA;
+    if (fetch_keys(h)) return SMB200_ERR_CUDA;                       // synchronises the stream
+    if (gradStat && write_grad_stats(h, h->hGradStat[0], tr0 == 0)) return SMB200_ERR_STATE;
+    host_post_step(h);                                               // filter sort, pruning, Adam's RNG draw, gradStep++
+    if (flush_evictions(h)) return SMB200_ERR_CUDA;
+    if (pull_ctrl(h)) return SMB200_ERR_CUDA;                        // ctrl[(g0 + 1) & 1]
+    if (h->nTransitions != nTrPre) {
+      // updateCounters runs after applyEpisodesRemovalAlgo: beta with the post-pruning count (MemoryProcessing.cpp:73-85)
+      const double farGlobal = (double)h->hCtrl.n_far_ref, nPost = (double)h->nTransitions;
+      const double maxN = (double)h->cfg.max_tot_obs_global, BS = (double)h->cfg.batch_size_global;
+      const double fracOff = farGlobal / std::max(nPost, 1.0);
+      const double lrB = 0.1 * BS / std::max(maxN, nPost);
+      const double mn = std::min(lrB, betaPrev);
+      h->hCtrl.beta = fracOff > h->cfg.penal_tol ? (1.0 - mn) * betaPrev : (1.0 - mn) * betaPrev + std::min(lrB, 1.0 - betaPrev);
+      h->hCtrl.gl_stored_prev = nPost;
+      if (push_ctrl(h)) return SMB200_ERR_CUDA;
+    }
+    if (stats) { fill_stats(h->hCtrl, stats + i); }
+    prepare_sampler(h);                                              // RM.updateSampler() after the removal
+  }
+  SMB200_CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
+  SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  h->lastMs = ms; h->lastLaunches = h->launches - l0;
+  return 0;
+}
+
 int smb200_train_steps(smb200_learner* h, int32_t n, smb200_step_stats* stats) {
   if (!h || n < 0) return SMB200_ERR_INVALID;
   if (h->nTransitions < h->cfg.batch_size) { set_error_msg("not enough transitions for one mini-batch"); return SMB200_ERR_STATE; }
   cudaSetDevice(h->cfg.device);
   h->presampled = 0;
+  if (h->slow_mode()) return train_steps_slow(h, n, stats);
   const long long l0 = h->launches;
   SMB200_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
   // Two-deep pipeline: while the GPU runs one segment, the host samples the next one (the sampler
@@ -1068,6 +1275,7 @@ int smb200_train_steps(smb200_learner* h, int32_t n, smb200_step_stats* stats) {
 
 int smb200_train_step_on(smb200_learner* h, const int64_t* pos, const int64_t* t, int32_t batch, smb200_step_stats* stats) {
   if (!h || !pos || !t || batch != h->cfg.batch_size) return SMB200_ERR_INVALID;
+  if (h->slow_mode()) { set_error_msg("train_step_on: uniform sampling with the FIFO filter only"); return SMB200_ERR_STATE; }
   cudaSetDevice(h->cfg.device);
   h->presampled = 0;
   for (int b = 0; b < batch; ++b) {
@@ -1099,6 +1307,7 @@ int smb200_train_step_on(smb200_learner* h, const int64_t* pos, const int64_t* t
 
 int smb200_presample(smb200_learner* h, int32_t n) {
   if (!h || n < 1) return SMB200_ERR_INVALID;
+  if (h->slow_mode()) { set_error_msg("presample: uniform sampling with the FIFO filter only"); return SMB200_ERR_STATE; }
   cudaSetDevice(h->cfg.device);
   if (ensure_seg_capacity(h, n)) return SMB200_ERR_CUDA;
   // benchmark path: the episode table must be in its steady (sorted, un-pruned) state
@@ -1791,6 +2000,7 @@ int smb200_restart(smb200_learner* h, const char* base_c) {
   if (push_ctrl(h)) return SMB200_ERR_CUDA;
   h->initialized = true;
   h->orderDirty = true; h->lookupDirty = true;
+  h->samplerStale = h->slow_mode();      // (the reference never prepares the sampler of a restarted learner before its first step)
   return 0;
 }
 

@@ -326,8 +326,7 @@ __device__ __forceinline__ void dense_fwd(const float* Wp, int ldp, int K, int N
     }
     if (G > 1) {
       __syncthreads();
-#pragma unroll
-      for (int s = 0; s < TB; ++s) red[(g * NR + nl) * TB + s] = acc[s];
+      *reinterpret_cast<float4*>(red + (g * NR + nl) * TB) = make_float4(acc[0], acc[1], acc[2], acc[3]);
       __syncthreads();
       for (int idx = tid; idx < nc * TB; idx += kST) {
         const int n2 = idx / TB, s = idx - n2 * TB;
@@ -400,8 +399,7 @@ __device__ __forceinline__ void dense_bwd_dx(const float* Wp, int ldp, int K, in
     }
     if (G > 1) {
       __syncthreads();
-#pragma unroll
-      for (int s = 0; s < TB; ++s) red[(g * KR + kl) * TB + s] = acc[s];
+      *reinterpret_cast<float4*>(red + (g * KR + kl) * TB) = make_float4(acc[0], acc[1], acc[2], acc[3]);
       __syncthreads();
       for (int idx = tid; idx < kc * TB; idx += kST) {
         const int k2 = idx / TB, s = idx - k2 * TB;

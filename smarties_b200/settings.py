@@ -95,12 +95,12 @@ class HyperParameters:
         unsupported = []
         if self.learner not in ("VRACER", "RACER"):
             unsupported.append(f"learner={self.learner}")
-        if self.dataSamplingAlgo != "uniform":
+        if self.dataSamplingAlgo not in ("uniform", "PERrank", "PERerr", "PERseq"):
             unsupported.append(f"dataSamplingAlgo={self.dataSamplingAlgo}")
         # "retraceExplore" is not an affine recursion: it runs on the sequential sweep kernel k_sweep_explore
         if self.returnsEstimator not in ("retrace", "GAE", "retraceExplore"):
             unsupported.append(f"returnsEstimator={self.returnsEstimator}")
-        if self.ERoldSeqFilter not in ("oldest", "default"):
+        if self.ERoldSeqFilter not in ("oldest", "default", "farpolfrac", "maxkldiv", "minerror"):
             unsupported.append(f"ERoldSeqFilter={self.ERoldSeqFilter}")
         if self.nnType not in ("FFNN", "LSTM", "MGU", "GRU") or self.nnFunc != "Tanh" or self.nnOutputFunc != "Linear":
             unsupported.append(f"nnType/nnFunc/nnOutputFunc={self.nnType}/{self.nnFunc}/{self.nnOutputFunc}")

@@ -14,9 +14,9 @@ CASES = ["vracer_small", "vracer_cfg2mini", "vracer_bounded", "vracer_prune", "r
 # golden runs of a reference with 8 / 16 OpenMP threads: the far-policy count (and beta) depend on the thread count
 # (MemoryProcessing.cpp:202-227); the device reproduces it with refer_reduce_threads = T
 THREADED_CASES = ["vracer_small_t8", "vracer_small_t16", "vracer_cfg2mini_t8", "vracer_cfg2mini_t16", "racer_small_t8"]
-# oracle pinned, device path not built: prioritized samplers and non-FIFO filters
-ORACLE_ONLY_CASES = ["vracer_pererr", "vracer_perseq", "vracer_farpolfrac", "vracer_maxkldiv",
-                     "vracer_minerror", "vracer_perrank"]
+# prioritized samplers and non-FIFO episode filters: one launch per step with a host round trip
+SLOW_CASES = ["vracer_pererr", "vracer_perseq", "vracer_perrank", "vracer_farpolfrac", "vracer_maxkldiv", "vracer_minerror"]
+ORACLE_ONLY_CASES = []
 RECURRENT_CASES = ["racer_lstm", "vracer_lstm2", "racer_lstm64", "racer_cfg3mini",      # nnType LSTM + BPTT window (configs[2] family)
                    "racer_mgu", "vracer_gru2"]     # MGU cells (Layer_GRU.h): "MGU" / "GRU", the default of partially observable MDPs
 

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 
-@pytest.mark.parametrize("net", ["mlp", "lstm"])
+@pytest.mark.parametrize("net", ["mlp", "lstm", "mlp_cluster"])      # mlp_cluster: the opt-in cluster step kernel (per-parameter exchange in its P2)
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_fused_allreduce(world, net):
     import torch
@@ -20,7 +20,10 @@ def test_fused_allreduce(world, net):
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", str(29610 + world), os.path.join(ROOT, "tests", "mgpu_worker.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, MGPU_NET=net))
+    env = dict(os.environ, MGPU_NET=net.split("_")[0])
+    if net.endswith("_cluster"):
+        env["SMB200_CLUSTER"] = "1"
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("MGPU_RESULT ")][-1]
     res = json.loads(line[len("MGPU_RESULT "):])

@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from parity_utils import CASES, RECURRENT_CASES, THREADED_CASES, Golden, make_learner, make_oracle, relerr
+from parity_utils import CASES, RECURRENT_CASES, SLOW_CASES, THREADED_CASES, Golden, make_learner, make_oracle, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -69,13 +69,16 @@ def test_initialize_learner_matches_reference(case):
     L.close()
 
 
-@pytest.mark.parametrize("case", CASES + RECURRENT_CASES + THREADED_CASES)
+@pytest.mark.parametrize("case", CASES + RECURRENT_CASES + THREADED_CASES + SLOW_CASES)
 def test_learner_steps_match_reference(case):
     """Every step of the golden run.  Among CASES: vracer_da1 — one action component, clipImpWeight < 1: the reference's
     `Uint += float` far-policy count wraps through x86's cvttss2si (uint_plus_float_x86, csrc/common.cuh); vracer_explore —
     "returnsEstimator": "retraceExplore" (k_sweep_explore); vracer_b1024 — several P1 tiles per CTA.  THREADED_CASES: goldens
     of a reference that ran 8 / 16 OpenMP threads; the far-policy count is reduced over per-thread `Uint += float` partials
-    (MemoryProcessing.cpp:202-227) and the device learner is built with refer_reduce_threads = that thread count."""
+    (MemoryProcessing.cpp:202-227) and the device learner is built with refer_reduce_threads = that thread count.
+    SLOW_CASES: prioritized samplers (PERrank / PERerr / PERseq: std::discrete_distribution over TD errors the device wrote the
+    step before) and the farpolfrac / maxkldiv / minerror episode filters (std::sort of the episode vector by device-resident
+    aggregates every step, pruning): sampled (episode, t) and episode order identical to the reference run."""
     g = Golden(case)
     L = make_learner(g)
     for s in range(g.steps):

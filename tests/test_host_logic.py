@@ -48,9 +48,9 @@ def test_settings_outside_the_device_path_are_rejected_loudly():
     assert HyperParameters(4, 1, {"returnsEstimator": "GAE"}).returnsEstimator == "GAE"
     assert HyperParameters(4, 1, {"nnType": "LSTM", "nnLayerSizes": [32]}).nnType == "LSTM"
     assert HyperParameters(4, 1, {"nnType": "GRU", "nnLayerSizes": [32]}).bRecurrent
-    for bad in ({"returnsEstimator": "nonsense"}, {"dataSamplingAlgo": "PERrank"}, {"dataSamplingAlgo": "PERerr"},
-                {"dataSamplingAlgo": "PERseq"}, {"ERoldSeqFilter": "farpolfrac"}, {"ERoldSeqFilter": "maxkldiv"},
-                {"ERoldSeqFilter": "minerror"}, {"nnType": "RNN"}, {"nnFunc": "Relu"}):
+    assert HyperParameters(4, 1, {"dataSamplingAlgo": "PERrank", "ERoldSeqFilter": "minerror"}).dataSamplingAlgo == "PERrank"
+    for bad in ({"returnsEstimator": "nonsense"}, {"dataSamplingAlgo": "PERx"}, {"ERoldSeqFilter": "youngest"},
+                {"nnType": "RNN"}, {"nnFunc": "Relu"}):
         with pytest.raises(NotImplementedError):
             HyperParameters(4, 1, bad)
 
@@ -176,7 +176,7 @@ def test_binding_loads_the_library_and_dies_loudly_without_a_gpu(tmp_path):
 
 
 def test_binding_falls_back_to_the_reference_learner_outside_the_device_path(tmp_path):
-    """SMARTIES_B200=1 with a setting the device path does not cover (here a prioritised sampler): the wrapped factory
+    """SMARTIES_B200=1 with a setting the device path does not cover (here a non-FIFO episode filter, which this binding leaves to the reference learner): the wrapped factory
     hands the agent to the reference's own CPU learner (createLearner_reference) — the app trains, no device learner is created.
     Runs without a GPU: nothing of the library is called on this path."""
     import sys
@@ -184,6 +184,6 @@ def test_binding_falls_back_to_the_reference_learner_outside_the_device_path(tmp
         pytest.skip("oracle/_ref binaries not built (python -c 'import __graft_entry__ as g; g.build()')")
     sys.path.insert(0, os.path.join(ROOT, "scripts"))
     from dropin_run import SETTINGS, run_arm
-    r = run_arm("b200", steps=1200, threads=2, seed=7, settings=dict(SETTINGS, dataSamplingAlgo="PERrank"), keep_dir=str(tmp_path))
+    r = run_arm("b200", steps=1200, threads=2, seed=7, settings=dict(SETTINGS, ERoldSeqFilter="farpolfrac"), keep_dir=str(tmp_path))
     assert r["rc"] == 0, r
     assert r["b200_lines"] == [] and r["grad_steps_logged"] >= 1000, r

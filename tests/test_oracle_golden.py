@@ -7,10 +7,10 @@ round-off; sampled indices, far-policy counts and the ReF-ER coefficient are exa
 import numpy as np
 import pytest
 
-from parity_utils import CASES, ORACLE_ONLY_CASES, RECURRENT_CASES, THREADED_CASES, Golden, make_oracle, relerr
+from parity_utils import CASES, ORACLE_ONLY_CASES, RECURRENT_CASES, SLOW_CASES, THREADED_CASES, Golden, make_oracle, relerr
 
 
-@pytest.mark.parametrize("case", CASES + RECURRENT_CASES + ORACLE_ONLY_CASES + THREADED_CASES)
+@pytest.mark.parametrize("case", CASES + RECURRENT_CASES + ORACLE_ONLY_CASES + THREADED_CASES + SLOW_CASES)
 def test_oracle_matches_reference(case):
     g = Golden(case)
     o = make_oracle(g)
