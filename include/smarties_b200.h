@@ -155,6 +155,12 @@ int smb200_sample(smb200_learner* h, int64_t* episode_pos, int64_t* tstep);
 /* n learner steps: {spawnTrainTasks; processMemoryBuffer; applyGradient; globalGradCounterUpdate}
  * (Learners/RACER.cpp:81-109) with the internal sampler.  stats (may be NULL) receives n entries. */
 int smb200_train_steps(smb200_learner* h, int32_t n, smb200_step_stats* stats);
+/* The same, plus the padded parameter blob after the last step (the layout of smb200_get_weights) in the same call: the copy
+ * shares the call's stream synchronisation.  This is how the binding refreshes the host network its actors evaluate
+ * (RACER::selectAction, Learners/RACER.cpp:30-47) without a second device round trip per learner call. */
+int smb200_train_steps_weights(smb200_learner* h, int32_t n, smb200_step_stats* stats, float* weights, int64_t n_weights);
+/* cudaHostRegister / cudaHostUnregister (bytes = 0) of a caller-owned buffer that the calls above copy into. */
+int smb200_pin_host_buffer(void* ptr, int64_t bytes);
 /* One step on caller-supplied samples (episode position, time step), e.g. the output of
  * smb200_sample or of the reference's own sampler. */
 int smb200_train_step_on(smb200_learner* h, const int64_t* episode_pos, const int64_t* tstep,

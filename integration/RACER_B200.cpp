@@ -124,6 +124,8 @@ class RACER_B200 : public RACER<Advantage_t, Policy_t, Action_t>
     // same initial policy on both sides: the device learner starts from the host network's weights
     check(smb200_set_weights(gpu, W->params, W->nParams), "set_weights");
     wblob.resize(W->nParams);
+    // the actors read this blob while the device writes the next policy into it: page-locked, so that the copy is one DMA
+    if (smb200_pin_host_buffer(W->params, (int64_t) (sizeof(nnReal) * W->nParams))) warn("smarties_b200: host weights stay pageable");
   }
 
   // the reference's output-gradient statistics file <learner>_<net>_outGrad_stats.raw (Approximator::updateGradStats,
@@ -235,6 +237,7 @@ class RACER_B200 : public RACER<Advantage_t, Policy_t, Action_t>
       printf("smarties_b200: %ld gradient steps, %ld episodes mirrored; seconds in push %.3f, device steps %.3f, weight sync %.3f; "
              "%.3f s of wall clock since training started\n",
              (long) data->nGradSteps(), nPushed, secPush, secStep, secSync, tTrainStart > 0 ? now() - tTrainStart : 0.0);
+    if (gpu) smb200_pin_host_buffer(hostWeights()->params, 0);
     smb200_destroy(gpu);
   }
 
@@ -337,10 +340,10 @@ class RACER_B200 : public RACER<Advantage_t, Policy_t, Action_t>
       nameGradStats();
       mirrorEpisodes();
       const double t1 = now();
-      check(smb200_train_steps(gpu, k, stepStats.data()), "train_steps");
+      // the new weights land in the host network (page-locked once, below) behind the last step of the same call
+      check(smb200_train_steps_weights(gpu, k, stepStats.data(), hostWeights()->params, (int64_t) hostWeights()->nParams), "train_steps_weights");
       const double t2 = now();
-      pullWeights();
-      const double t3 = now();
+      const double t3 = t2;
       secPush += t1 - t0; secStep += t2 - t1; secSync += t3 - t2;
       for (int i = 0; i < k; ++i) {
         last = stepStats[i];

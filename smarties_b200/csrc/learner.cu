@@ -1208,12 +1208,35 @@ static int train_steps_slow(smb200_learner* h, int32_t n, smb200_step_stats* sta
   return 0;
 }
 
-int smb200_train_steps(smb200_learner* h, int32_t n, smb200_step_stats* stats) {
+static int train_steps_impl(smb200_learner* h, int32_t n, smb200_step_stats* stats, float* weightsOut);
+int smb200_train_steps(smb200_learner* h, int32_t n, smb200_step_stats* stats) { return train_steps_impl(h, n, stats, nullptr); }
+
+// smb200_train_steps + the weights after the last step in the same call: the copy is enqueued behind the last launch and shares
+// the call's one stream synchronisation (the actors' host network gets the new policy without a second round trip).
+int smb200_train_steps_weights(smb200_learner* h, int32_t n, smb200_step_stats* stats, float* weights, int64_t n_weights) {
+  if (!h || !weights || n_weights != h->descs.net.nParams) return SMB200_ERR_INVALID;
+  return train_steps_impl(h, n, stats, weights);
+}
+
+// Page-lock a host buffer the library copies into / out of (the host network's parameter blob, episode staging buffers):
+// asynchronous copies to pageable memory are staged and serialised by the driver.  bytes = 0: unregister.
+int smb200_pin_host_buffer(void* ptr, int64_t bytes) {
+  if (!ptr || bytes < 0) return SMB200_ERR_INVALID;
+  if (bytes == 0) { SMB200_CUDA_CHECK(cudaHostUnregister(ptr)); return 0; }
+  SMB200_CUDA_CHECK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+  return 0;
+}
+
+static int train_steps_impl(smb200_learner* h, int32_t n, smb200_step_stats* stats, float* weightsOut) {
   if (!h || n < 0) return SMB200_ERR_INVALID;
   if (h->nTransitions < h->cfg.batch_size) { set_error_msg("not enough transitions for one mini-batch"); return SMB200_ERR_STATE; }
   cudaSetDevice(h->cfg.device);
   h->presampled = 0;
-  if (h->slow_mode()) return train_steps_slow(h, n, stats);
+  if (h->slow_mode()) {
+    const int rc = train_steps_slow(h, n, stats);
+    if (!rc && weightsOut) return smb200_get_weights(h, weightsOut, h->descs.net.nParams);
+    return rc;
+  }
   const long long l0 = h->launches;
   SMB200_CUDA_CHECK(cudaEventRecord(h->ev0, h->stream));
   // Two-deep pipeline: while the GPU runs one segment, the host samples the next one (the sampler
@@ -1260,6 +1283,8 @@ int smb200_train_steps(smb200_learner* h, int32_t n, smb200_step_stats* stats) {
     h->orderDirty = dirtyAfter;
     done += cnt;
   }
+  if (weightsOut)
+    SMB200_CUDA_CHECK(cudaMemcpyAsync(weightsOut, h->W, sizeof(float) * (size_t)h->descs.net.nParams, cudaMemcpyDeviceToHost, h->stream));
   if (reclaim(0) || reclaim(1)) return SMB200_ERR_CUDA;
   SMB200_CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
   SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));

@@ -30,7 +30,7 @@ EXPORTS = [
     "smb200_n_outputs", "smb200_set_weights", "smb200_get_weights", "smb200_set_adam", "smb200_get_adam",
     "smb200_get_grad", "smb200_set_scaling", "smb200_get_scaling", "smb200_push_episode", "smb200_n_transitions",
     "smb200_n_episodes", "smb200_initialize_learner", "smb200_set_grad_step", "smb200_seed_sampler", "smb200_sample",
-    "smb200_train_steps", "smb200_train_step_on", "smb200_get_last_batch", "smb200_retrace_sweep", "smb200_fused_sweep",
+    "smb200_train_steps", "smb200_train_steps_weights", "smb200_pin_host_buffer", "smb200_train_step_on", "smb200_get_last_batch", "smb200_retrace_sweep", "smb200_fused_sweep",
     "smb200_reward_state_moments", "smb200_read_field", "smb200_read_episodes", "smb200_n_rows", "smb200_get_stats",
     "smb200_forward", "smb200_last_timing", "smb200_presample", "smb200_train_presampled", "smb200_sync", "smb200_profile_phases",
     "smb200_comm_init", "smb200_comm_attach", "smb200_comm_error", "smb200_write_field", "smb200_save", "smb200_restart",
@@ -122,6 +122,8 @@ def load_library(path: str = LIB_PATH):
         "smb200_initialize_learner": (C.c_int, [H]), "smb200_set_grad_step": (C.c_int, [H, C.c_int64]),
         "smb200_seed_sampler": (C.c_int, [H, C.c_uint64]), "smb200_sample": (C.c_int, [H, ip, ip]),
         "smb200_train_steps": (C.c_int, [H, C.c_int32, P(StepStats)]),
+        "smb200_train_steps_weights": (C.c_int, [H, C.c_int32, P(StepStats), fp, C.c_int64]),
+        "smb200_pin_host_buffer": (C.c_int, [C.c_void_p, C.c_int64]),
         "smb200_train_step_on": (C.c_int, [H, ip, ip, C.c_int32, P(StepStats)]),
         "smb200_get_last_batch": (C.c_int, [H, fp, fp, fp]),
         "smb200_retrace_sweep": (C.c_int, [H, dp]), "smb200_reward_state_moments": (C.c_int, [H, dp]),
@@ -333,6 +335,13 @@ class Learner:
         st = (StepStats * n)() if want_stats else None
         self._check(self.lib.smb200_train_steps(self.h, int(n), st))
         return StepStatsList(st) if want_stats else None
+
+    def train_steps_weights(self, n):
+        """train_steps + the weights after the last step from the same call (what the binding hands to the host actors)."""
+        st = (StepStats * n)()
+        w = np.empty(self.n_params, np.float32)
+        self._check(self.lib.smb200_train_steps_weights(self.h, int(n), st, _fp(w), self.n_params))
+        return StepStatsList(st), w
 
     def train_step_on(self, pos, t):
         pos, t = np.ascontiguousarray(pos, np.int64), np.ascontiguousarray(t, np.int64)
