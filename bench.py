@@ -430,7 +430,10 @@ def main():
     peaks, which = measured_peaks()
     sweeps = {}
     n_tr = L.n_transitions
-    for name, fn, bpt in (("k_sweep(retrace)", L.retrace_sweep, BYTES_RETRACE_PER_TRANSITION),
+    # k_sweep_fused is what a learner step runs every 1000 steps (Retrace + aggregates + moments in one pass); the two separate
+    # kernels remain for state widths it does not cover and as stand-alone entry points
+    for name, fn, bpt in (("k_sweep_fused(retrace+moments)", L.fused_sweep, BYTES_FUSED_SWEEP_PER_TRANSITION),
+                          ("k_sweep(retrace)", L.retrace_sweep, BYTES_RETRACE_PER_TRANSITION),
                           ("k_moments", L.reward_state_moments, BYTES_MOMENTS_PER_TRANSITION)):
         best = None
         for _ in range(5):
