@@ -426,6 +426,14 @@ def main():
 
     gs = stats[-1]["grad_step"]
     roof = kernel_roofline(L, torch, dev, batch_local, L.n_params, w["window"], gs)
+    if args.workload == "cfg3":        # the LSTM weight gradient is the one tcgen05 contraction of the path: tensor-pipe share from ncu
+        p3 = os.path.join(ROOT, "profiles", "r2", "ncu_cfg3.json")
+        if os.path.exists(p3):
+            with open(p3) as f:
+                n3 = json.load(f)
+            roof["tensor_pipe_pct_of_peak_ncu"] = n3["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+            roof["traffic"] = n3["dram_bytes"] * roof["steps_per_launch"] / n3["steps_per_launch"]
+            roof["traffic_source"] = n3["source"]
     # the HBM-streaming sweeps, timed alone with a flushed L2
     peaks, which = measured_peaks()
     sweeps = {}
