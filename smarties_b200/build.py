@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsmarties_b200.so")
 OUT_PROF = os.path.join(HERE, "libsmarties_b200_prof.so")     # same sources + phase timestamps (scripts/phase_report.py)
 SOURCES = ["step_kernels.cu", "sweep_kernels.cu", "learner.cu"]
-HEADERS = ["common.cuh", "step_kernels.cuh", os.path.join("..", "..", "include", "smarties_b200.h")]
+HEADERS = ["common.cuh", "step_kernels.cuh", "cluster_step.cuh", "wide_step.cuh", os.path.join("..", "..", "include", "smarties_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--threads", "3"]

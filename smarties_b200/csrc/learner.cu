@@ -94,6 +94,10 @@ struct smb200_learner {
   // cluster step kernel (feed-forward nets, cluster_step.cuh)
   ClusterPlan cplan{}; ClusterPlan* dCplan = nullptr; std::vector<int> cidx, citems; int* dCidx = nullptr; int* dCitems = nullptr;
   float* cimg = nullptr; float* cpart = nullptr; int clusterP1 = 0;      // clusterP1 > 0: the cluster kernel runs the steps
+  // wide (large-batch) step on the tensor cores (wide_step.cuh)
+  WidePlan wplan{}; WidePlan* dWplan = nullptr; std::vector<int> widx; int* dWidx = nullptr;
+  float *wimgF = nullptr, *wimgB = nullptr, *wvec = nullptr, *wpart = nullptr; int* wcnt = nullptr; int* wlist = nullptr;
+  int wGridG = 0; int wideOn = 0;          // wideOn: the wide kernels run the steps
   int dP = 0;                     // columns of the behaviour policy MU: 2 * dim_action (mean, stdev), or the K option probabilities
 
   // step state
@@ -136,6 +140,8 @@ struct smb200_learner {
     a.comm = comm;
     a.descs = dDescs; a.rp = rp; a.W = W; a.Wimg = Wimg; a.M1 = M1; a.M2 = M2; a.G = G; a.dbgT = nullptr; a.useTma = useTma;
     a.useTc = useTc; a.tcPartial = tcPartial;
+    a.wplan = dWplan; a.wimgF = wimgF; a.wimgB = wimgB; a.wvec = wvec; a.wpart = wpart; a.wGridG = wGridG; a.widx = dWidx;
+    a.wcnt = wcnt; a.wlist = wlist;
     a.cplan = dCplan; a.cimg = cimg; a.cpart = cpart; a.cidx = dCidx; a.citems = dCitems; a.cClusters = clusterP1;
     a.actG = actG; a.errG = errG; a.sampRow = dSampT; a.sampSlot = dSampSlot; a.rec = dRec;
     a.lastO = lastO; a.lastG = lastG; a.lastX = lastX; a.ctrl = dCtrl; a.statsOut = dStats;
@@ -324,6 +330,13 @@ static int upload_weights(smb200_learner* h, const float* blob) {
       if (iB[p] >= 0) cim[iB[p]] = blob[p];
     }
     SMB200_CUDA_CHECK(cudaMemcpyAsync(h->cimg, cim.data(), sizeof(float) * cim.size(), cudaMemcpyHostToDevice, h->stream));
+  }
+  std::vector<float> wf, wb, wv;
+  if (h->wimgF) {      // the wide step's split operand images and vector block
+    wide_fill_images(net, h->wplan, h->widx, blob, wf, wb, wv);
+    SMB200_CUDA_CHECK(cudaMemcpyAsync(h->wimgF, wf.data(), sizeof(float) * h->wplan.fFloats, cudaMemcpyHostToDevice, h->stream));
+    SMB200_CUDA_CHECK(cudaMemcpyAsync(h->wimgB, wb.data(), sizeof(float) * h->wplan.bFloats, cudaMemcpyHostToDevice, h->stream));
+    SMB200_CUDA_CHECK(cudaMemcpyAsync(h->wvec, wv.data(), sizeof(float) * h->wplan.vFloats, cudaMemcpyHostToDevice, h->stream));
   }
   SMB200_CUDA_CHECK(cudaMemcpyAsync(h->W, blob, sizeof(float) * net.nParams, cudaMemcpyHostToDevice, h->stream));
   SMB200_CUDA_CHECK(cudaMemcpyAsync(h->Wimg, im.data(), sizeof(float) * net.imgFloats, cudaMemcpyHostToDevice, h->stream));
@@ -672,7 +685,10 @@ static int run_segment(smb200_learner* h, int first, int n, long long gstep0, in
   const NetDesc& net = h->descs.net;
   const long long lastStep = gstep0 + n;              // nGradSteps()+1 of the last step
   const int sweepLast = (lastStep % 1000) == 0;
-  if (h->mode == 1 && h->clusterP1 > 0) {
+  if (h->wideOn && h->comm.world == 1) {
+    if (launch_steps_wide(a, net, h->wplan, h->numSMs, (int)gstep0, n, sweepLast, h->stream)) return -2;
+    h->launches += 7 * n;
+  } else if (h->mode == 1 && h->clusterP1 > 0) {
     if (launch_steps_cluster(a, h->clusterP1, h->cplan.bTotal, (int)gstep0, n, sweepLast, h->stream)) return -2;
     h->launches += 1;
   } else if (h->mode == 1 && h->persistGrid > 0) {
@@ -862,6 +878,32 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
       CK(dev_alloc(&h->cpart, (size_t)h->clusterP1 * net.nParams));
     }
   }
+  // wide step (tensor cores): batches of >= 1024 sampled transitions per rank unless SMB200_WIDE says otherwise
+  // (SMB200_WIDE=0: never, =1: whenever the plan covers the network)
+  {
+    const char* w = getenv("SMB200_WIDE");
+    const bool never = w && strcmp(w, "0") == 0, always = w && strcmp(w, "1") == 0;
+    if (!never && (always || B >= 1024) && c.world_size <= 1) {
+      wide_plan_build(net, hp, h->wplan, h->widx);
+      if (h->wplan.ok) {
+        CK(wide_prepare(h->wplan, net));
+        h->wGridG = wide_grid_g(h->wplan, B, h->numSMs);
+        CK(dev_alloc(&h->dWplan, 1));
+        CKC(cudaMemcpy(h->dWplan, &h->wplan, sizeof(WidePlan), cudaMemcpyHostToDevice));
+        CK(dev_alloc(&h->dWidx, h->widx.size()));
+        CKC(cudaMemcpy(h->dWidx, h->widx.data(), sizeof(int) * h->widx.size(), cudaMemcpyHostToDevice));
+        CK(dev_alloc(&h->wimgF, (size_t)h->wplan.fFloats)); CK(dev_alloc(&h->wimgB, (size_t)h->wplan.bFloats));
+        CK(dev_alloc(&h->wvec, (size_t)h->wplan.vFloats));
+        CK(dev_alloc(&h->wpart, (size_t)h->wGridG * h->wplan.recFloats));
+        CK(dev_alloc(&h->wcnt, 4)); CK(dev_alloc(&h->wlist, (size_t)B));
+        h->wideOn = 1;
+      }
+      if (getenv("SMB200_DEBUG"))
+        fprintf(stderr, "smb200: wide step %s: %d dense layers, shared memory fwd %d / bwd %d / wgrad %d B (%d stages of %d B), record %d floats x %d CTAs\n",
+                h->wideOn ? "on" : "off", h->wplan.nD, h->wplan.sfTotal, h->wplan.sbTotal, h->wplan.sgTotal, h->wplan.sgStages, h->wplan.sgStageBytes,
+                h->wplan.recFloats, h->wGridG);
+    }
+  }
   h->comm.world = 1; h->comm.rank = 0;
   h->gen.seed((unsigned long)c.seed);
   std::vector<float> blob;
@@ -890,7 +932,8 @@ void smb200_destroy(smb200_learner* h) {
   void* ptrs[] = {rp.S, rp.A, rp.MU, rp.R, rp.V, rp.ADV, rp.Q, rp.DELTA, rp.RHO, rp.KL, rp.rowFlag, rp.epStart, rp.epLen, rp.epTerm,
                   rp.epId, rp.epAgg, rp.epOrder, rp.stateMean, rp.stateScale, rp.stateStd, rp.rew, h->W, h->Wimg, h->dDbg, h->M1, h->M2, h->G,
                   h->actG, h->errG, h->dTiles, h->dDescs, h->dCtrl, h->dRec, h->lastO, h->lastG, h->lastX, h->dSums, h->dBarrier,
-                  h->dSampSlot, h->dSampT, h->dStats, h->dCplan, h->dCidx, h->dCitems, h->cimg, h->cpart};
+                  h->dSampSlot, h->dSampT, h->dStats, h->dCplan, h->dCidx, h->dCitems, h->cimg, h->cpart,
+                  h->dWplan, h->dWidx, h->wimgF, h->wimgB, h->wvec, h->wpart, h->wcnt, h->wlist};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int q = 0; q < kMaxWorld; ++q) if (h->peerMapped[q]) cudaIpcCloseMemHandle(h->peerMapped[q]);
   if (h->commBuf) cudaFree(h->commBuf);
@@ -1552,6 +1595,13 @@ int smb200_sync(smb200_learner* h) {
   // smb200_train_presampled only enqueues: its device-side errors (peer time-out, tensor-core item) surface here
   if ((h->useTc || h->comm.world > 1) && smb200_comm_error(h)) return SMB200_ERR_STATE;
   return 0;
+}
+
+int smb200_step_kernel(const smb200_learner* h) {
+  if (!h) return -1;
+  if (h->wideOn && h->comm.world == 1) return 3;
+  if (h->mode == 1 && h->clusterP1 > 0) return 2;
+  return (h->mode == 1 && h->persistGrid > 0) ? 1 : 0;
 }
 
 int smb200_last_timing(smb200_learner* h, double* ms, int64_t* launches) {

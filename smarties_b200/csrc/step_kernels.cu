@@ -2704,6 +2704,7 @@ int launch_forward(const StepArgs& a, const NetDesc& net, const float* states, i
 }
 
 #include "cluster_step.cuh"
+#include "wide_step.cuh"
 
 }  // namespace smb200
 

@@ -91,7 +91,50 @@ struct ClusterPlan {
   int chunk, chunkPad, parts;     // P2: parameters per worker CTA, padded to a warp multiple, partial-sum groups per parameter
 };
 
+// ------------------------------------------------------------------------------------------
+// Wide (large-batch) learner step of feed-forward V-RACER nets (wide_step.cuh): tiles of 128 sampled transitions, every
+// dense product of the network as tcgen05.mma kind::tf32 contractions (3xTF32: f32 accuracy) with the weights stationary in
+// shared memory, the activations of a tile as the A operand in TENSOR MEMORY, accumulators in tensor memory.
+// ------------------------------------------------------------------------------------------
+constexpr int kWideM = 128;                      // samples per tile = M of the forward / input-gradient MMAs
+constexpr int kWideMaxD = 4;                     // dense layers (hidden layers + the linear output layer) the wide path takes
+constexpr int kWideKS = 16;                      // samples per stage of the weight-gradient contraction
+constexpr int kWideLD = 130;                     // float4 rows per k-chunk of a staged weight-gradient operand (== 2 mod 8: conflict-free stores)
+struct WDense {
+  int layer, res;          // NetDesc ids: the dense layer, the ParametricResidual evaluated after it (-1: none)
+  int K, Kp, N, Np;        // fan-in (Kp = roundUp16), fan-out (Np = 16 / 32 / 64 / 128)
+  int isTanh;
+  int inOff, yOff, zOff;   // scratch rows: the layer's input, its own output y, the block output z (= y unless a residual follows)
+  int fImg, bImg;          // float offsets of the [hi | lo] operand images: forward float4 [Kp/4][Np], transposed float4 [Np/4][Kp] (-1)
+  int vB, vRW, vRB;        // float offsets in the vector block: bias [Np], residual weight / bias [Np] (-1)
+  int gCol;                // weight-gradient kernel: first TMEM column of this layer's accumulator
+  int gN;                  // its N: hidden layers Kp (D[n][k], M = delta rows), output layer NpG (D[k][j], M = input rows)
+  int gPart;               // float offset of the accumulator in a CTA's partial record: [column][128 rows]
+  int vSum;                // float offset of this layer's vector sums in the partial record: delta row sums [Np] (hidden layers) /
+                           //   output-gradient row sums [NpG] (output layer); then residual bias / weight sums [Np] each
+};
+struct WidePlan {
+  int ok;                  // the wide path covers this network
+  int nD; WDense D[kWideMaxD];
+  int NpG;                 // rows of the output-gradient operand: roundUp16(nOut) (dense outputs, then the ParamLayer's)
+  int fFloats, bFloats, vFloats;        // sizes of the forward image, the transposed image, the vector block
+  int vP;                               // ParamLayer values in the vector block
+  int recFloats;                        // partial record of one weight-gradient CTA
+  int gCols;                            // TMEM columns of the weight-gradient kernel (power of two)
+  int sfVec, sfImg, sfActO, sfGP, sfOld, sfInfo, sfSamp, sfPair, sfBars, sfTotal;   // forward kernel: byte offsets in dynamic shared memory
+  int sbVec, sbImg, sbBars, sbTotal;                                               // input-gradient kernel
+  int sgStage, sgStageBytes, sgStages, sgBars, sgTotal;                             // weight-gradient kernel
+  int sgOpA[kWideMaxD], sgOpB[kWideMaxD];   // byte offsets of a layer's M-side / N-side operand inside a stage ([hi | lo] each)
+  int sgRowsA[kWideMaxD], sgRowsB[kWideMaxD];   // staged rows of those operands
+};
+
 struct StepArgs {
+  // wide step (wide_step.cuh)
+  const WidePlan* wplan; float* wimgF; float* wimgB; float* wvec;   // operand images and the vector block (biases, residual vectors, ParamLayer)
+  float* wpart; int wGridG;            // [wGridG][recFloats] partial records of the weight-gradient kernel
+  const int* widx;                     // [5][nParams]: record position, image positions (tile image, forward, transposed, vector block)
+  int* wcnt;                           // [0] flagged samples of the step (V(s_t+1) list), [1] exact far-policy flag changes
+  int* wlist;                          // [B] flagged samples
   // cluster step kernel
   const ClusterPlan* cplan; float* cimg; float* cpart; const int* cidx;   // image, per-cluster partial gradients [clusters][nParams], image positions [3][nParams]
   const int* citems;                 // weight-gradient work items [kCL][threads][12]
@@ -160,6 +203,15 @@ size_t cluster_image_floats(const ClusterPlan& cp);
 int cluster_prepare(const ClusterPlan& cp);
 int cluster_max_active(const ClusterPlan& cp);
 int launch_steps_cluster(const StepArgs& a, int p1Clusters, int bytes, int step0, int nSteps, int skipStatsLast, cudaStream_t st);
+
+// wide step (wide_step.cuh)
+void wide_plan_build(const NetDesc& net, const Hyper& hp, WidePlan& wp, std::vector<int>& idx);
+void wide_fill_images(const NetDesc& net, const WidePlan& wp, const std::vector<int>& idx, const float* blob,
+                      std::vector<float>& imgF, std::vector<float>& imgB, std::vector<float>& vecs);
+int wide_prepare(const WidePlan& wp, const NetDesc& net);
+int wide_grid_g(const WidePlan& wp, int B, int numSMs);
+int launch_steps_wide(const StepArgs& a, const NetDesc& net, const WidePlan& wp, int numSMs, int step0, int nSteps, int skipStatsLast,
+                      cudaStream_t st);
 
 // sweep_kernels.cu
 int launch_init_episode(const ReplayView& rp, int slot, float deltaInit, int haveValues, cudaStream_t st);

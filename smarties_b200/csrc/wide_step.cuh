@@ -1,0 +1,989 @@
+// wide_step.cuh — the LARGE-BATCH learner step of feed-forward V-RACER nets on the 5th-generation tensor cores.
+// Included by step_kernels.cu (inside namespace smb200, after the tile kernel's device functions).
+//
+// For mini-batches of >= 1024 sampled transitions the dense products of the step ARE contractions (SURVEY.md §8d batch
+// sweep): forward  Y[s][n] = sum_k X[s][k] W[k][n],  input gradient  E[s][k] = sum_n D[s][n] W[k][n],  weight gradient
+// dW[k][n] = sum_s X[s][k] D[s][n]  (Network::forward / backProp, Network/Network.h:101-226; BaseLayer, Layers/Layer_Base.h:
+// 64-113; Layers.h:123-188).  They run as tcgen05.mma.cta_group::1.kind::tf32 with M = 128 (one TILE of 128 sampled
+// transitions, or 128 feature rows) and the f32 accumulator in tensor memory.  Every operand is split into its TF32 "hi" part
+// and the f32 remainder "lo" and every product is three MMAs (lo*hi + hi*lo + hi*hi): f32 accuracy, the parity tolerances of
+// the tile kernel hold (plain TF32 misses them, profiles/r1/microbench_tcgen05_tf32.txt).
+//
+// One learner step = stream-ordered kernels (the batch is large, launches are noise):
+//   k_wide_fwd    persistent, one CTA per SM, tiles of 128 samples: the forward weights of the whole network stay in shared
+//                 memory as pre-split UMMA operand images (K-major, no swizzle; written by the Adam kernel; fetched once per
+//                 launch with cp.async.bulk); the tile's activations are the A operand IN TENSOR MEMORY (tcgen05.st by the
+//                 epilogue that produced them — they never touch shared memory), accumulator in tensor memory; gather +
+//                 standardise, all layers, then the ReF-ER / Retrace loss in f64 (the tile kernel's formulas, one thread per
+//                 (sample, action component)), replay write-back and per-sample records; activations and the output gradient
+//                 leave for the other kernels as a feature-major scratch [feature][sample] (coalesced 128-byte rows).
+//   k_wide_next   V(s_t+1) of the few samples whose successor ends a truncated episode (RACER_train.cpp:22-27).
+//   k_wide_records / k_wide_stats   Episode::updateCumulative_atomic in sample order — one thread per run of samples of an
+//                 episode, all runs in parallel — then the tile kernel's own statistics / ReF-ER beta update on one CTA.
+//   k_wide_bwd    the same structure with the TRANSPOSED weight images: deltas of a tile as the TMEM A operand,
+//                 E = D W^T per layer, tanh' and the ParametricResidual in the epilogue.
+//   k_wide_wgrad  persistent split-K contraction over the samples: per 16-sample stage the operand rows come from the scratch
+//                 (float4 = 4 samples of one feature), are split and stored as K-major operand images (double-buffered stages,
+//                 freed by tcgen05.commit -> mbarrier), one MMA set per dense layer accumulates in tensor memory for the whole
+//                 launch; bias / residual / ParamLayer gradients are summed by the staging threads from the registers they
+//                 hold anyway.  One partial record per CTA.
+//   k_wide_adam   adds the per-CTA partial records in CTA order (deterministic), the reference's Adam variant (adam_step), and
+//                 rewrites every image of the weights: blob, tile-kernel image, split forward and transposed operand images.
+#pragma once
+
+// ------------------------------------------------------------------------------------------
+// tcgen05 / tensor-memory primitives (forms checked on a B200 by scripts/micro/tc_ts_mn.cu)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+               ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tm_ld8(uint32_t addr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void tm_st8(uint32_t addr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded mbarrier wait: a lost MMA completion must not hang the box (reported like a peer time-out)
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, unsigned parity) {
+  for (int spin = 0; spin < (1 << 26); ++spin) if (mbar_try_wait(bar, parity)) return true;
+  return false;
+}
+__host__ __device__ constexpr uint32_t wide_idesc(int n) {      // f32 <- tf32 x tf32, both operands K-major, M = 128 (mma_sm100_desc.hpp:412-439)
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_free(uint32_t base, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+}
+
+// the plan (host-built, a few hundred bytes) -> shared memory
+__device__ __forceinline__ const WidePlan* load_wide_plan(const StepArgs& a, unsigned char* dst) {
+  const int nw = (int)(sizeof(WidePlan) / 4);
+  const int* src = reinterpret_cast<const int*>(a.wplan);
+  int* d = reinterpret_cast<int*>(dst);
+  for (int i = threadIdx.x; i < nw; i += kST) d[i] = src[i];
+  return reinterpret_cast<const WidePlan*>(dst);
+}
+constexpr int kWideDescBytes = (int)(((sizeof(DevDescs) + 15) / 16) * 16);
+constexpr int kWidePlanBytes = (int)(((sizeof(WidePlan) + 15) / 16) * 16);
+
+// TMEM columns of the forward / input-gradient kernels
+constexpr uint32_t kWAcc = 0, kWAh = 128, kWAl = 256;
+
+// one dense product of a 128-sample tile: D[128][Np] = A[128][Kc] (TMEM, hi at kWAh, lo at kWAl) * image (shared memory,
+// float4 [Kc/4][rows], rows = N of the MMA), three MMAs per 8 contraction columns.  Issued by ONE thread.
+__device__ __forceinline__ void wide_issue(uint32_t tmem, const float* imgHi, const float* imgLo, int Kc, int rows, uint64_t* bar) {
+  tc_fence_after();
+  const uint32_t idesc = wide_idesc(rows);
+  for (int kk = 0; kk < Kc / 8; ++kk) {
+    const uint64_t dbh = umma_desc(imgHi + (size_t)(2 * kk) * rows * 4, rows * 16, 128);
+    const uint64_t dbl = umma_desc(imgLo + (size_t)(2 * kk) * rows * 4, rows * 16, 128);
+    umma_tf32_ts(tmem + kWAcc, tmem + kWAl + 8 * kk, dbh, idesc, kk > 0);
+    umma_tf32_ts(tmem + kWAcc, tmem + kWAh + 8 * kk, dbl, idesc, 1);
+    umma_tf32_ts(tmem + kWAcc, tmem + kWAh + 8 * kk, dbh, idesc, 1);
+  }
+  tc_commit(bar);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_wide_fwd
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kST, 1) k_wide_fwd(StepArgs a, int step) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const NetDesc* netp; const Hyper* hpp;
+  load_descs(a, smraw, netp, hpp);
+  const WidePlan& wp = *load_wide_plan(a, smraw + kWideDescBytes);
+  __shared__ StepCtrl c;
+  __shared__ uint32_t tmemSlot;
+  __syncthreads();
+  const NetDesc& net = *netp; const Hyper& hp = *hpp;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, cg = warp >> 2;          // TMEM lane quarter of this warp (hardware rule: warp % 4), column group
+  float* vec = reinterpret_cast<float*>(smraw + wp.sfVec);
+  float* img = reinterpret_cast<float*>(smraw + wp.sfImg);
+  float* actO = reinterpret_cast<float*>(smraw + wp.sfActO);      // [Np_out][128]: outputs, later the output gradient
+  float* gP = reinterpret_cast<float*>(smraw + wp.sfGP);          // [dA][128]: gradient of the ParamLayer outputs (stdev)
+  float* old = reinterpret_cast<float*>(smraw + wp.sfOld);        // [8][128]
+  int* info = reinterpret_cast<int*>(smraw + wp.sfInfo);          // row, slot, hasNext, valid  [4][128]
+  double* samp = reinterpret_cast<double*>(smraw + wp.sfSamp);    // [5][128]
+  double* pairS = reinterpret_cast<double*>(smraw + wp.sfPair);   // [2][128 * dA]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + wp.sfBars);   // [0] weight image, [1] MMA completion
+  const ReplayView& rp = a.rp;
+  const int dS = net.dS, dA = net.dA, nPair = kWideM * dA;
+  constexpr int TBW = kWideM;
+  const LayerDesc& Lo = net.L[net.nLayers - 2];
+  const LayerDesc& Lp = net.L[net.nLayers - 1];
+  const WDense& Dout = wp.D[wp.nD - 1];
+  const int fHalf = wp.fFloats >> 1;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    load_ctrl(c, &a.ctrl[step & 1]);
+  }
+  if (warp == 0) tmem_alloc(&tmemSlot, 512u);
+  for (int i = tid; i < wp.vFloats; i += kST) vec[i] = ld_cg(a.wvec + i);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmemSlot;
+  if (tid == 0) {          // the whole forward image: hi halves then lo halves, <= 64 KB per bulk copy
+    asm volatile("fence.proxy.async.global;\n\tfence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&bars[0], (unsigned)wp.fFloats * 4u);
+    for (int off = 0; off < wp.fFloats; off += 16384) {
+      const unsigned n = (unsigned)min(16384, wp.fFloats - off) * 4u;
+      bulk_g2s(img + off, a.wimgF + off, n, &bars[0]);
+    }
+  }
+  const int nTiles = (a.B + TBW - 1) / TBW;
+  const size_t j0 = (size_t)(step - a.stepBase) * a.B;
+  const bool keep = step == a.lastStep || a.lastStep < 0;
+  unsigned mmaPar = 0;
+  bool imgReady = false, fault = false;
+  const uint32_t laneBase = (uint32_t)(q * 32) << 16;
+
+  for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+    const int b0 = tile * TBW, s = q * 32 + lane, b = b0 + s;
+    const bool valid = b < a.B;
+    int row = 0;
+    if (valid) row = __ldg(a.sampRow + j0 + b);
+    if (cg == 0) {       // sample info + the old per-transition values of the write-back
+      int slot = 0, hn = 0;
+      if (valid) {
+        const int sf = __ldg(a.sampSlot + j0 + b);
+        slot = sf & 0x7fffffff; hn = (sf >> 31) & 1;
+        old[0 * TBW + s] = ld_cg(rp.V + row); old[1 * TBW + s] = ld_cg(rp.ADV + row);
+        old[2 * TBW + s] = ld_cg(rp.RHO + row); old[3 * TBW + s] = ld_cg(rp.KL + row);
+        old[4 * TBW + s] = ld_cg(rp.DELTA + row); old[7 * TBW + s] = ld_cg(rp.Q + row);
+        if (hn) { const int i = atomicAdd(a.wcnt, 1); a.wlist[i] = b; }      // V(s_t+1): k_wide_next
+      }
+      info[s] = row; info[TBW + s] = slot; info[2 * TBW + s] = hn; info[3 * TBW + s] = valid ? 1 : 0;
+    }
+    // ---- gather + standardise (Episode.h:171-183): the tile's states become the A operand of the first layer ----
+    {
+      const WDense& D0 = wp.D[0];
+      for (int j8 = cg; j8 < D0.Kp / 8; j8 += 4) {
+        float x[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int k = 8 * j8 + jj;
+          x[jj] = (valid && k < dS) ? (ld_cg(rp.S + (size_t)row * dS + k) - ld_cg(rp.stateMean + k)) * ld_cg(rp.stateScale + k) : 0.f;
+        }
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int k = 8 * j8 + jj;
+          const float h = tf32_hi(x[jj]);
+          hi[jj] = __float_as_uint(h); lo[jj] = __float_as_uint(x[jj] - h);
+          if (k < dS) {
+            a.actG[(size_t)(D0.inOff + k) * a.Bpad + b] = x[jj];
+            if (keep && valid) a.lastX[(size_t)b * dS + k] = x[jj];
+          }
+        }
+        tm_st8(tmem + laneBase + kWAh + 8 * j8, hi);
+        tm_st8(tmem + laneBase + kWAl + 8 * j8, lo);
+      }
+      tm_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (!imgReady) { mbar_wait(&bars[0], 0); imgReady = true; }
+    // ---- layers ----
+    for (int d = 0; d < wp.nD; ++d) {
+      const WDense& D = wp.D[d];
+      if (tid == 0) wide_issue(tmem, img + D.fImg, img + fHalf + D.fImg, D.Kp, D.Np, &bars[1]);
+      if (!mbar_wait_bounded(&bars[1], mmaPar)) fault = true;
+      mmaPar ^= 1u;
+      tc_fence_after();
+      const float* bias = vec + D.vB;
+      if (D.isTanh) {
+        const bool res = D.res >= 0;
+        const float* rw = vec + (res ? D.vRW : 0); const float* rb = vec + (res ? D.vRB : 0);
+        for (int j8 = cg; j8 < D.Np / 8; j8 += 4) {
+          uint32_t v[8], xh[8], xl[8];
+          tm_ld8(tmem + laneBase + kWAcc + 8 * j8, v);
+          if (res) { tm_ld8(tmem + laneBase + kWAh + 8 * j8, xh); tm_ld8(tmem + laneBase + kWAl + 8 * j8, xl); }
+          tm_wait_ld();
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int n = 8 * j8 + jj;
+            float y = 0.f, z = 0.f;
+            if (n < D.N) {
+              y = tanh_ref(__uint_as_float(v[jj]) + bias[n]);          // BaseLayer::forward (Layer_Base.h:64-95)
+              z = y;
+              if (res) {                                              // ParametricResidualLayer::forward (Layers.h:347-361)
+                const float xin = __uint_as_float(xh[jj]) + __uint_as_float(xl[jj]);     // hi + lo is the f32 value, exactly
+                z = y + (xin * rw[n] + rb[n]);
+              }
+              a.actG[(size_t)(D.yOff + n) * a.Bpad + b] = y;
+              if (res) a.actG[(size_t)(D.zOff + n) * a.Bpad + b] = z;
+            }
+            const float h = tf32_hi(z);
+            hi[jj] = __float_as_uint(h); lo[jj] = __float_as_uint(z - h);
+          }
+          tm_st8(tmem + laneBase + kWAh + 8 * j8, hi);
+          tm_st8(tmem + laneBase + kWAl + 8 * j8, lo);
+        }
+        tm_wait_st();
+      } else {
+        for (int j8 = cg; j8 < D.Np / 8; j8 += 4) {
+          uint32_t v[8];
+          tm_ld8(tmem + laneBase + kWAcc + 8 * j8, v);
+          tm_wait_ld();
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int n = 8 * j8 + jj;
+            if (n < D.N) actO[n * TBW + s] = __uint_as_float(v[jj]) + bias[n];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncthreads();
+    }
+
+    // ---- ReF-ER / Retrace loss and output gradient (RACER::Train, Learners/RACER_train.cpp:31-60; the formulas and their
+    //      operation order are those of loss_stages above), f64, V-RACER: outputs [V | mean(dA)], stdev = ParamLayer ----
+    constexpr int PP = 2;                 // (sample, component) pairs per thread: 128 * dA <= 2 * kST (dA <= 8)
+    const int m0 = 1;
+    double r_kgm[PP], r_kgs[PP], r_dlm[PP], r_dls[PP], r_dpos[PP];
+#pragma unroll
+    for (int it = 0; it < PP; ++it) {
+      const int p = tid + it * kST;
+      r_kgm[it] = r_kgs[it] = r_dlm[it] = r_dls[it] = r_dpos[it] = 0.0;
+      if (p >= nPair) continue;
+      const int sp = p / dA, i = p - sp * dA;
+      if (!info[3 * TBW + sp]) continue;
+      const size_t prow = info[sp];
+      const double av = (double)ld_cg(rp.A + prow * dA + i), mm = (double)ld_cg(rp.MU + prow * 2 * dA + i),
+                   ms = (double)ld_cg(rp.MU + prow * 2 * dA + dA + i);
+      const double m = (double)actO[(m0 + i) * TBW + sp];
+      const double sraw = (double)vec[wp.vP + i];
+      const double root = sqrt(1.0 + sraw * sraw);
+      const double stdev = (sraw + root) / 2.0;                          // SoftPlus::_eval, Functions.h:552-555
+      const double dpos = (1.0 + sraw / root) / 2.0;                     // SoftPlus::_evalDiff
+      const double inv = 1.0 / stdev, invmu = 1.0 / ms;
+      const bool bnd = hp.bounded[i] != 0;
+      const double MAXM = 8.31776613503286;
+      const double cm = bnd ? (m > MAXM ? MAXM : (m < -MAXM ? -MAXM : m)) : m;   // Continuous_policy.h:217-222
+      const double fac0 = 9.1893853320467266954096885456237942e-01;
+      double J = 1.0;
+      if (bnd) { const double sq = tanh(av); J = fmax(1.0 - sq * sq, (double)FLT_MIN); }
+      const double z1 = (av - cm) * inv, z2 = (av - mm) * invmu;
+      const double lp_pi = -(z1 * z1) / 2.0 + log(bnd ? inv / J : inv) - fac0;       // :91-97 / :240-249
+      const double lp_mu = -(z2 * z2) / 2.0 + log(bnd ? invmu / J : invmu) - fac0;
+      const double r1 = stdev / ms, r2 = (m - mm) / ms;
+      const double cc = r1 * r1, dd = r2 * r2;                                          // OPPOSITE_KL, :138-142
+      const double invVarMu = 1.0 / (ms * ms);
+      const double u = z1;
+      pairS[0 * nPair + p] = lp_pi - lp_mu;
+      pairS[1 * nPair + p] = (cc - 1.0 + dd - log(cc)) / 2.0;
+      r_kgm[it] = -1.0 * ((m - mm) * invVarMu);                               // kg_mean
+      r_kgs[it] = (dpos * -1.0) * ((invVarMu - inv * inv) * stdev);           // kg_std
+      r_dlm[it] = bnd ? (av - m) * inv * inv : u * inv;                       // dLogPdMean
+      r_dls[it] = (u * u - 1.0) * inv;                                        // dLogPdStdv
+      r_dpos[it] = dpos;
+    }
+    if (tid < TBW) {     // value head: V = scaleNet2V(O[0]), dV/dO (RACER_common.cpp:23-32)
+      const double O0 = (double)actO[0 * TBW + tid];
+      samp[2 * TBW + tid] = net2v(O0);
+      samp[3 * TBW + tid] = vdiff(O0);
+    }
+    __syncthreads();
+    if (tid < TBW && info[3 * TBW + tid]) {     // one thread per sample: sums in component order, flags, write-back, record
+      const int sp = tid, bb = b0 + sp;
+      const size_t prow = info[sp];
+      const double cmax = c.cmax, cinv = c.cinv;
+      double logw = 0.0, dkl = 0.0;
+      for (int i = 0; i < dA; ++i) { logw += pairS[0 * nPair + sp * dA + i]; dkl += pairS[1 * nPair + sp * dA + i]; }
+      const double rho = exp(logw > 7.0 ? 7.0 : (logw < -7.0 ? -7.0 : logw));           // :648-653
+      const float W32 = (float)rho, C32 = (float)cmax, I32 = (float)cinv;               // isFarPolicy takes Fval arguments (Episode.h:28-33)
+      const bool offW = (W32 > C32) || (W32 < I32);
+      const bool isFar = (C32 > 1.0f) && offW;
+      const float O0f = actO[0 * TBW + sp];
+      const double Vval = samp[2 * TBW + sp];
+      const double Aval = 0.0;                                                          // Zero_advantage.h:39-42
+      const double A_RET = (double)old[7 * TBW + sp] - Vval, deltaQ = A_RET - Aval;
+      const double Ver = fmin(1.0, rho) * deltaQ;
+      samp[4 * TBW + sp] = Ver;
+      samp[0 * TBW + sp] = A_RET * fmin(cmax, rho);     // pgfac
+      samp[1 * TBW + sp] = isFar ? 1.0 : 0.0;
+      if (keep) a.lastO[(size_t)bb * net.nOut + 0] = O0f;
+      const float E = (float)deltaQ, Dk = (float)dkl;
+      const float oldRho = old[2 * TBW + sp], oldKL = old[3 * TBW + sp], oldE = old[4 * TBW + sp];
+      const bool wasOff = (oldRho > C32) || (oldRho < I32);
+      const float Vf = (float)Vval, Qf = (float)(Aval + Vval);
+      rp.DELTA[prow] = E; rp.KL[prow] = Dk; rp.RHO[prow] = W32;
+      rp.V[prow] = Vf; rp.ADV[prow] = Qf - Vf;
+      // qNextOld / qNextNew of the record belong to k_wide_next
+      *reinterpret_cast<int4*>(&a.rec[bb].slot) = make_int4(info[TBW + sp], info[2 * TBW + sp], (C32 > 1.0f) ? ((int)offW - (int)wasOff) : 0, 0);
+      *reinterpret_cast<float4*>(&a.rec[bb].dKL) = make_float4(Dk - oldKL, (float)offW - (float)wasOff, E * E - oldE * oldE, fabsf(E));
+      *reinterpret_cast<float2*>(&a.rec[bb].qOld) = make_float2(old[1 * TBW + sp] + old[0 * TBW + sp], Qf);
+    }
+    __syncthreads();
+    {
+      const double beta = c.beta;
+      const double MAXM = 8.31776613503286;
+#pragma unroll
+      for (int it = 0; it < PP; ++it) {
+        const int p = tid + it * kST;
+        if (p >= nPair) continue;
+        const int sp = p / dA, i = p - sp * dA;
+        if (!info[3 * TBW + sp]) continue;
+        const int bb = b0 + sp;
+        const double pgfac = samp[0 * TBW + sp];
+        const bool isFar = samp[1 * TBW + sp] != 0.0;
+        const float mf = actO[(m0 + i) * TBW + sp];
+        const double m = (double)mf;
+        double pg_mean = pgfac * r_dlm[it];
+        if (hp.bounded[i] && ((m >= MAXM && pg_mean > 0.0) || (m <= -MAXM && pg_mean < 0.0))) pg_mean = 0.0;
+        double pg_std = (r_dpos[it] * pgfac) * r_dls[it];
+        if (isFar) { pg_mean = 0.0; pg_std = 0.0; }
+        const double g_mean = beta * pg_mean + (1.0 - beta) * r_kgm[it];      // penalizeReFER (FunctionUtilities.h:221-228)
+        const double g_std = beta * pg_std + (1.0 - beta) * r_kgs[it];
+        actO[(m0 + i) * TBW + sp] = (float)g_mean;        // the output gradient replaces the output (read above, by this thread only)
+        gP[i * TBW + sp] = (float)g_std;
+        if (keep) {
+          a.lastG[(size_t)bb * net.nOut + m0 + i] = (float)g_mean; a.lastG[(size_t)bb * net.nOut + m0 + dA + i] = (float)g_std;
+          a.lastO[(size_t)bb * net.nOut + m0 + i] = mf; a.lastO[(size_t)bb * net.nOut + m0 + dA + i] = vec[wp.vP + i];
+        }
+        if (i == 0) {       // value head (RACER_train.cpp:46)
+          const double g0 = isFar ? 0.0 : samp[4 * TBW + sp] * beta * samp[3 * TBW + sp];
+          actO[0 * TBW + sp] = (float)g0;
+          if (keep) a.lastG[(size_t)bb * net.nOut + 0] = (float)g0;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- output gradient -> scratch rows of the output layer / the ParamLayer (zero for the padding samples of the last tile) ----
+    for (int idx = tid; idx < net.nOut * TBW; idx += kST) {
+      const int j = idx >> 7, sp = idx & (TBW - 1);
+      float g = 0.f;
+      if (info[3 * TBW + sp]) g = j < net.nOutDense ? actO[j * TBW + sp] : gP[(j - net.nOutDense) * TBW + sp];
+      const int rowG = j < net.nOutDense ? Lo.actOff + j : Lp.actOff + (j - net.nOutDense);
+      a.errG[(size_t)rowG * a.Bpad + b0 + sp] = g;
+    }
+    __syncthreads();
+  }
+  if (!imgReady) mbar_wait(&bars[0], 0);       // no tile: still consume the copy before the CTA (and its shared memory) goes away
+  if (fault && lane == 0 && a.comm.error) *a.comm.error = 2;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_free(tmem, 512u);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_wide_next: V(s_t+1) of the flagged samples (list filled by k_wide_fwd), 4 per pass, weights from the tile image in L2
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kST) k_wide_next(StepArgs a, int step) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const NetDesc* netp; const Hyper* hpp;
+  load_descs(a, smraw, netp, hpp);
+  const NetDesc& net = *netp;
+  constexpr int TB = 4;
+  const SmemPlan sp = smem_plan(net, TB, false);
+  float* act = reinterpret_cast<float*>(smraw + sp.act);
+  float* red = reinterpret_cast<float*>(smraw + sp.red);
+  const ReplayView& rp = a.rp;
+  const int tid = threadIdx.x, dS = net.dS;
+  const int count = min(__ldcg(a.wcnt), a.B);
+  const size_t j0 = (size_t)(step - a.stepBase) * a.B;
+  for (int first = blockIdx.x * TB; first < count; first += gridDim.x * TB) {
+    for (int idx = tid; idx < dS * TB; idx += kST) {
+      const int k = idx / TB, s = idx - k * TB;
+      float x = 0.f;
+      if (first + s < count) {
+        const int b = __ldcg(a.wlist + first + s);
+        const size_t row = (size_t)__ldcg(a.sampRow + j0 + b) + 1;
+        x = (ld_cg(rp.S + row * dS + k) - ld_cg(rp.stateMean + k)) * ld_cg(rp.stateScale + k);
+      }
+      act[idx] = x;
+    }
+    __syncthreads();
+    net_forward<TB, false>(net, a.Wimg, act, red, nullptr, 0);
+    if (tid < TB && first + tid < count) {
+      const int b = __ldcg(a.wlist + first + tid);
+      const size_t row = (size_t)__ldcg(a.sampRow + j0 + b) + 1;
+      const float vn = (float)net2v((double)net_out<false>(net, a.Wimg, act, TB, 0, tid));
+      const float qOld = ld_cg(rp.ADV + row) + ld_cg(rp.V + row);
+      rp.V[row] = vn; rp.ADV[row] = vn - vn;
+      *reinterpret_cast<float2*>(&a.rec[b].qNextOld) = make_float2(qOld, vn);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_wide_records: Episode::updateCumulative_atomic / updateValues_atomic (Episode.h:112-145) in sample order.  Samples are
+// sorted, so the samples of an episode are one contiguous run: the thread of a run's first sample applies the whole run
+// (the arithmetic of apply_sample_records above), all runs in parallel.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_wide_records(StepArgs a) {
+  const ReplayView& rp = a.rp;
+  const int ME = rp.maxEpisodes;
+  const int b = blockIdx.x * 256 + threadIdx.x;
+  int far = 0;
+  if (b < a.B) {
+    const int4 h = __ldcg(reinterpret_cast<const int4*>(&a.rec[b]));
+    far = h.z;
+    const int slot = h.x;
+    const int prevSlot = b > 0 ? __ldcg(&a.rec[b - 1].slot) : -2;
+    if (prevSlot != slot) {
+      float avgKL = rp.epAgg[AGG_KL * ME + slot], frac = rp.epAgg[AGG_FAR * ME + slot];
+      float avgE2 = rp.epAgg[AGG_E2 * ME + slot], maxE = rp.epAgg[AGG_MAXE * ME + slot];
+      float sQ2 = rp.epAgg[AGG_Q2 * ME + slot], sQ = rp.epAgg[AGG_Q1 * ME + slot];
+      float maxQ = rp.epAgg[AGG_MAXQ * ME + slot], minQ = rp.epAgg[AGG_MINQ * ME + slot];
+      const float invN = 1.0f / (float)rp.epLen[slot];
+      for (int j = b; j < a.B; ++j) {
+        const int4 hj = __ldcg(reinterpret_cast<const int4*>(&a.rec[j]));
+        if (hj.x != slot) break;
+        const float4 d = __ldcg(reinterpret_cast<const float4*>(&a.rec[j].dKL));
+        const float4 qv = __ldcg(reinterpret_cast<const float4*>(&a.rec[j].qOld));
+        if (hj.y) {
+          sQ2 += qv.w * qv.w - qv.z * qv.z; sQ += qv.w - qv.z;
+          maxQ = fmaxf(maxQ, qv.w); minQ = fminf(minQ, qv.w);
+        }
+        avgKL += invN * d.x; frac += invN * d.y; avgE2 += invN * d.z; maxE = fmaxf(maxE, d.w);
+        sQ2 += qv.y * qv.y - qv.x * qv.x; sQ += qv.y - qv.x;
+        maxQ = fmaxf(maxQ, qv.y); minQ = fminf(minQ, qv.y);
+      }
+      rp.epAgg[AGG_KL * ME + slot] = avgKL; rp.epAgg[AGG_FAR * ME + slot] = frac;
+      rp.epAgg[AGG_E2 * ME + slot] = avgE2; rp.epAgg[AGG_MAXE * ME + slot] = maxE;
+      rp.epAgg[AGG_Q2 * ME + slot] = sQ2; rp.epAgg[AGG_Q1 * ME + slot] = sQ;
+      rp.epAgg[AGG_MAXQ * ME + slot] = maxQ; rp.epAgg[AGG_MINQ * ME + slot] = minQ;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) far += __shfl_xor_sync(0xffffffffu, far, o);
+  if ((threadIdx.x & 31) == 0 && far != 0) atomicAdd(a.wcnt + 1, far);      // exact far-policy flag changes (integers: any order)
+}
+
+__global__ void __launch_bounds__(kST) k_wide_stats(StepArgs a, int step) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const NetDesc* netp; const Hyper* hpp;
+  load_descs(a, smraw, netp, hpp);
+  __shared__ StepCtrl c;
+  int fd = 0;
+  if (threadIdx.x == 0) { load_ctrl(c, &a.ctrl[step & 1]); fd = __ldcg(a.wcnt + 1); a.wcnt[1] = 0; }
+  __syncthreads();
+  stats_and_refer(a, *hpp, c, a.ctrl[(step + 1) & 1], step, nullptr, -1, fd, reinterpret_cast<float*>(smraw + kWideDescBytes));
+}
+
+// ------------------------------------------------------------------------------------------
+// k_wide_bwd: Network::backProp (Network.h:216-226) of a tile on the tensor cores.  For the dense layers from the output
+// layer down to the second hidden layer:  E = D W^T  (A = the layer's deltas in TMEM, B = the TRANSPOSED image), then in the
+// epilogue, for the layer below:  + the ParametricResidual path of the layer above (Layers.h:363-393), the residual layer's
+// own error to the scratch (its parameter gradients are formed by k_wide_wgrad), deltas *= tanh' (Layer_Base.h:103-109).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kST, 1) k_wide_bwd(StepArgs a, int step) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const NetDesc* netp; const Hyper* hpp;
+  load_descs(a, smraw, netp, hpp);
+  const WidePlan& wp = *load_wide_plan(a, smraw + kWideDescBytes);
+  __shared__ uint32_t tmemSlot;
+  __syncthreads();
+  const NetDesc& net = *netp;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, cg = warp >> 2;
+  float* vec = reinterpret_cast<float*>(smraw + wp.sbVec);
+  float* img = reinterpret_cast<float*>(smraw + wp.sbImg);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + wp.sbBars);
+  const int bHalf = wp.bFloats >> 1;
+  constexpr int TBW = kWideM;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(&tmemSlot, 512u);
+  for (int i = tid; i < wp.vFloats; i += kST) vec[i] = ld_cg(a.wvec + i);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmemSlot;
+  if (tid == 0) {
+    asm volatile("fence.proxy.async.global;\n\tfence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&bars[0], (unsigned)wp.bFloats * 4u);
+    for (int off = 0; off < wp.bFloats; off += 16384) {
+      const unsigned n = (unsigned)min(16384, wp.bFloats - off) * 4u;
+      bulk_g2s(img + off, a.wimgB + off, n, &bars[0]);
+    }
+  }
+  const int nTiles = (a.B + TBW - 1) / TBW;
+  unsigned mmaPar = 0;
+  bool imgReady = false, fault = false;
+  const uint32_t laneBase = (uint32_t)(q * 32) << 16;
+  const LayerDesc& Lo = net.L[net.nLayers - 2];
+
+  for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+    const int b0 = tile * TBW, s = q * 32 + lane, b = b0 + s;
+    // ---- the output gradient of the tile -> A operand ----
+    {
+      const WDense& D = wp.D[wp.nD - 1];
+      for (int j8 = cg; j8 < D.Np / 8; j8 += 4) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int n = 8 * j8 + jj;
+          const float g = n < D.N ? ld_cg(a.errG + (size_t)(Lo.actOff + n) * a.Bpad + b) : 0.f;
+          const float h = tf32_hi(g);
+          hi[jj] = __float_as_uint(h); lo[jj] = __float_as_uint(g - h);
+        }
+        tm_st8(tmem + laneBase + kWAh + 8 * j8, hi);
+        tm_st8(tmem + laneBase + kWAl + 8 * j8, lo);
+      }
+      tm_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (!imgReady) { mbar_wait(&bars[0], 0); imgReady = true; }
+    float carry[32];          // E_z(d) * w_res(d): the residual path into the layer below, columns 8 * (cg + 4 i) + jj
+#pragma unroll
+    for (int i = 0; i < 32; ++i) carry[i] = 0.f;
+    for (int d = wp.nD - 1; d >= 1; --d) {
+      const WDense& D = wp.D[d];           // product through this layer's weights
+      const WDense& H = wp.D[d - 1];       // the hidden layer that receives the error
+      // contraction over this layer's outputs (Np columns of the A operand), N = its Kp input rows
+      if (tid == 0) wide_issue(tmem, img + D.bImg, img + bHalf + D.bImg, D.Np, D.Kp, &bars[1]);
+      if (!mbar_wait_bounded(&bars[1], mmaPar)) fault = true;
+      mmaPar ^= 1u;
+      tc_fence_after();
+      const bool res = H.res >= 0;
+      const bool more = d - 1 >= 1;        // the layer below propagates further
+      const float* rw = vec + (res ? H.vRW : 0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j8 = cg + 4 * i;
+        if (j8 >= H.Np / 8) continue;
+        uint32_t v[8];
+        const bool have = 8 * j8 < D.Kp;
+        if (have) { tm_ld8(tmem + laneBase + kWAcc + 8 * j8, v); tm_wait_ld(); }
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int n = 8 * j8 + jj;
+          float delta = 0.f, cnew = 0.f;
+          if (n < H.N) {
+            const float ez = (have ? __uint_as_float(v[jj]) : 0.f) + carry[8 * i + jj];      // E_in = W * delta (+ residual path)
+            const float y = ld_cg(a.actG + (size_t)(H.yOff + n) * a.Bpad + b);
+            delta = ez * (1.0f - y * y);
+            if (res) { a.errG[(size_t)(H.zOff + n) * a.Bpad + b] = ez; cnew = ez * rw[n]; }
+            a.errG[(size_t)(H.yOff + n) * a.Bpad + b] = delta;
+          }
+          carry[8 * i + jj] = cnew;
+          const float h = tf32_hi(delta);
+          hi[jj] = __float_as_uint(h); lo[jj] = __float_as_uint(delta - h);
+        }
+        if (more) { tm_st8(tmem + laneBase + kWAh + 8 * j8, hi); tm_st8(tmem + laneBase + kWAl + 8 * j8, lo); }
+      }
+      if (more) tm_wait_st();
+      tc_fence_before();
+      __syncthreads();
+    }
+  }
+  if (!imgReady) mbar_wait(&bars[0], 0);
+  if (fault && lane == 0 && a.comm.error) *a.comm.error = 2;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_free(tmem, 512u);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_wide_wgrad: the weight gradients as split-K contractions over the samples (Layers.h:160-187).  CTA g owns the 16-sample
+// stages [g * nStages / G, (g + 1) * nStages / G).  Per stage and dense layer two operands are staged from the feature-major
+// scratch: thread (r = tid / 4, cc = tid % 4) loads the float4 of feature row r, samples 4 cc .. 4 cc + 3 (four lanes = one
+// 64-byte run), splits it and stores hi / lo into the K-major images  float4 [4 k-chunks][LD rows]  (LD = 130 or rows + 2:
+// conflict-free 16-byte stores).  Hidden layers: M side = the layer's deltas (D[n][k], N = Kp input rows), output layer: M side
+// = its input rows, N side = the output-gradient rows [dense | ParamLayer].  Vector gradients (biases, residual w / b,
+// ParamLayer) are the row sums of what the thread just loaded.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kST, 1) k_wide_wgrad(StepArgs a, int step) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const NetDesc* netp; const Hyper* hpp;
+  load_descs(a, smraw, netp, hpp);
+  const WidePlan& wp = *load_wide_plan(a, smraw + kWideDescBytes);
+  __shared__ uint32_t tmemSlot;
+  __syncthreads();
+  const NetDesc& net = *netp;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r = tid >> 2, cc = tid & 3;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + wp.sgBars);      // [stage]: the MMAs that read the stage have completed
+  if (tid == 0) {
+    for (int i = 0; i < wp.sgStages; ++i) mbar_init(&bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(&tmemSlot, (uint32_t)wp.gCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmemSlot;
+  const int Bt = (a.B + kWideM - 1) / kWideM * kWideM;       // the scratch is defined (zero deltas) up to the tile boundary
+  const int nSt = Bt / kWideKS;
+  const int G = gridDim.x, g = blockIdx.x;
+  const int st0 = (int)((long long)g * nSt / G), st1 = (int)((long long)(g + 1) * nSt / G);
+  const LayerDesc& Lo = net.L[net.nLayers - 2];
+  const LayerDesc& Lp = net.L[net.nLayers - 1];
+  float sA[kWideMaxD], sE[kWideMaxD], sEX[kWideMaxD];
+#pragma unroll
+  for (int d = 0; d < kWideMaxD; ++d) { sA[d] = 0.f; sE[d] = 0.f; sEX[d] = 0.f; }
+  bool fault = false;
+
+  for (int it = st0; it < st1; ++it) {
+    const int slot = (it - st0) % wp.sgStages, use = (it - st0) / wp.sgStages;
+    const int col = it * kWideKS + 4 * cc;
+    // ---- loads of every operand of the stage first (one L2 round trip), then split + store ----
+    float4 vA[kWideMaxD], vB[kWideMaxD], vE[kWideMaxD];
+#pragma unroll
+    for (int d = 0; d < kWideMaxD; ++d) {
+      vA[d] = make_float4(0.f, 0.f, 0.f, 0.f); vB[d] = vA[d]; vE[d] = vA[d];
+      if (d >= wp.nD) continue;
+      const WDense& D = wp.D[d];
+      const bool out = d == wp.nD - 1;
+      if (!out) {
+        if (r < D.N) vA[d] = ld_cg4(a.errG + (size_t)(D.yOff + r) * a.Bpad + col);         // deltas of the layer
+        if (r < D.K) vB[d] = ld_cg4(a.actG + (size_t)(D.inOff + r) * a.Bpad + col);        // its input
+        if (D.res >= 0 && r < D.N) vE[d] = ld_cg4(a.errG + (size_t)(D.zOff + r) * a.Bpad + col);   // error on the residual layer
+      } else {
+        if (r < D.K) vA[d] = ld_cg4(a.actG + (size_t)(D.inOff + r) * a.Bpad + col);
+        if (r < net.nOut) {
+          const int rowG = r < net.nOutDense ? Lo.actOff + r : Lp.actOff + (r - net.nOutDense);
+          vB[d] = ld_cg4(a.errG + (size_t)rowG * a.Bpad + col);
+        }
+      }
+    }
+    if (use > 0) { if (!mbar_wait_bounded(&bars[slot], (unsigned)((use - 1) & 1))) fault = true; }     // MMAs of the stage's previous use
+    unsigned char* stg = smraw + wp.sgStage + (size_t)slot * wp.sgStageBytes;
+#pragma unroll
+    for (int d = 0; d < kWideMaxD; ++d) {
+      if (d >= wp.nD) continue;
+      const WDense& D = wp.D[d];
+      const bool out = d == wp.nD - 1;
+      {
+        float4 h, l; split4(vA[d], h, l);
+        float4* Ah = reinterpret_cast<float4*>(stg + wp.sgOpA[d]);
+        float4* Al = Ah + 4 * kWideLD;
+        Ah[cc * kWideLD + r] = h; Al[cc * kWideLD + r] = l;
+      }
+      const int rowsB = wp.sgRowsB[d];
+      if (r < rowsB) {
+        float4 h, l; split4(vB[d], h, l);
+        float4* Bh = reinterpret_cast<float4*>(stg + wp.sgOpB[d]);
+        float4* Bl = Bh + 4 * (rowsB + 2);
+        Bh[cc * (rowsB + 2) + r] = h; Bl[cc * (rowsB + 2) + r] = l;
+      }
+      if (!out) {
+        sA[d] += vA[d].x; sA[d] += vA[d].y; sA[d] += vA[d].z; sA[d] += vA[d].w;                   // db += delta
+        if (D.res >= 0) {                                                                         // ParametricResidualLayer::backward
+          sE[d] += vE[d].x; sE[d] += vE[d].y; sE[d] += vE[d].z; sE[d] += vE[d].w;
+          sEX[d] = fmaf(vE[d].x, vB[d].x, sEX[d]); sEX[d] = fmaf(vE[d].y, vB[d].y, sEX[d]);
+          sEX[d] = fmaf(vE[d].z, vB[d].z, sEX[d]); sEX[d] = fmaf(vE[d].w, vB[d].w, sEX[d]);
+        }
+      } else { sA[d] += vB[d].x; sA[d] += vB[d].y; sA[d] += vB[d].z; sA[d] += vB[d].w; }         // output bias / ParamLayer
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      for (int d = 0; d < wp.nD; ++d) {
+        const WDense& D = wp.D[d];
+        const int rowsB = wp.sgRowsB[d], ldB = rowsB + 2;
+        const float4* Ah = reinterpret_cast<const float4*>(stg + wp.sgOpA[d]);
+        const float4* Al = Ah + 4 * kWideLD;
+        const float4* Bh = reinterpret_cast<const float4*>(stg + wp.sgOpB[d]);
+        const float4* Bl = Bh + 4 * ldB;
+        const uint32_t idesc = wide_idesc(D.gN);
+        const uint32_t acc = tmem + (uint32_t)D.gCol;
+#pragma unroll
+        for (int kk = 0; kk < kWideKS / 8; ++kk) {
+          const uint64_t dah = umma_desc(Ah + 2 * kk * kWideLD, kWideLD * 16, 128), dal = umma_desc(Al + 2 * kk * kWideLD, kWideLD * 16, 128);
+          const uint64_t dbh = umma_desc(Bh + 2 * kk * ldB, ldB * 16, 128), dbl = umma_desc(Bl + 2 * kk * ldB, ldB * 16, 128);
+          umma_tf32(acc, dal, dbh, idesc, (it > st0 || kk > 0) ? 1u : 0u);
+          umma_tf32(acc, dah, dbl, idesc, 1u);
+          umma_tf32(acc, dah, dbh, idesc, 1u);
+        }
+      }
+      tc_commit(&bars[slot]);
+    }
+  }
+  // ---- all MMAs done: accumulators and vector sums -> this CTA's partial record ----
+  float* rec = a.wpart + (size_t)g * wp.recFloats;
+  const int nMine = st1 - st0;
+  if (nMine > 0) {
+    const int last = nMine - 1;
+    if (!mbar_wait_bounded(&bars[last % wp.sgStages], (unsigned)((last / wp.sgStages) & 1))) fault = true;
+  }
+  tc_fence_after();
+  {
+    const int q = warp & 3, cg = warp >> 2;
+    const uint32_t laneBase = (uint32_t)(q * 32) << 16;
+    const int m = q * 32 + lane;
+    for (int d = 0; d < wp.nD; ++d) {
+      const WDense& D = wp.D[d];
+      for (int j8 = cg; j8 < D.gN / 8; j8 += 4) {
+        uint32_t v[8];
+        if (nMine > 0) { tm_ld8(tmem + laneBase + (uint32_t)D.gCol + 8 * j8, v); tm_wait_ld(); }
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) rec[D.gPart + (size_t)(8 * j8 + jj) * 128 + m] = nMine > 0 ? __uint_as_float(v[jj]) : 0.f;
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < kWideMaxD; ++d) {
+    if (d >= wp.nD) continue;
+    const WDense& D = wp.D[d];
+    float x = sA[d], y = sE[d], z = sEX[d];
+    x += __shfl_xor_sync(0xffffffffu, x, 1); x += __shfl_xor_sync(0xffffffffu, x, 2);
+    y += __shfl_xor_sync(0xffffffffu, y, 1); y += __shfl_xor_sync(0xffffffffu, y, 2);
+    z += __shfl_xor_sync(0xffffffffu, z, 1); z += __shfl_xor_sync(0xffffffffu, z, 2);
+    if (cc == 0) {
+      const bool out = d == wp.nD - 1;
+      const int rows = out ? wp.NpG : D.Np;
+      if (r < rows) {
+        rec[D.vSum + r] = x;
+        if (!out && D.res >= 0) { rec[D.vSum + D.Np + r] = y; rec[D.vSum + 2 * D.Np + r] = z; }
+      }
+    }
+  }
+  if (fault && lane == 0 && a.comm.error) *a.comm.error = 2;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_free(tmem, (uint32_t)wp.gCols);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_wide_adam: gradient = sum of the partial records in CTA order; AdamOptimizer::apply_update (adam_step); every image of
+// the weights is rewritten here: blob, tile-kernel image, split forward / transposed operand images, vector block.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_wide_adam(StepArgs a, int step, int nParams, int recFloats, int fHalf, int bHalf) {
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p == 0) a.wcnt[0] = 0;                        // the V(s_t+1) list of the next step starts empty
+  if (p >= nParams) return;
+  const int rpos = __ldg(a.widx + p);
+  if (rpos < 0) return;                             // padding of the parameter blob
+  const float* src = a.wpart + rpos;
+  const int G = a.wGridG;
+  float acc = 0.f;
+  int g = 0;
+  for (; g + 8 <= G; g += 8) {                      // eight loads in flight, added in CTA order
+    float x[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) x[u] = ld_cg(src + (size_t)(g + u) * recFloats);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += x[u];
+  }
+  for (; g < G; ++g) acc += ld_cg(src + (size_t)g * recFloats);
+  const DevDescs* dd = a.descs;
+  AdamCoef ac;
+  ac.eta = __ldcg(&a.ctrl[step & 1].adam_eta);
+  ac.B1 = 0.9f; ac.B2 = 0.999f;
+  ac.lambda = (float)dd->hp.nnLambda;
+  ac.fac = (float)(1.0 / (double)dd->hp.batchGlobal);
+  a.G[p] = acc;
+  const float Wn = adam_step(ac, acc, ld_cg(a.W + p), ld_cg(a.M1 + p), ld_cg(a.M2 + p), a.W + p, a.M1 + p, a.M2 + p);
+  const int pi = __ldg(a.widx + nParams + p), pf = __ldg(a.widx + 2 * nParams + p), pb = __ldg(a.widx + 3 * nParams + p),
+            pv = __ldg(a.widx + 4 * nParams + p);
+  if (pi >= 0) a.Wimg[pi] = Wn;
+  const float h = tf32_hi(Wn), l = Wn - h;
+  if (pf >= 0) { a.wimgF[pf] = h; a.wimgF[fHalf + pf] = l; }
+  if (pb >= 0) { a.wimgB[pb] = h; a.wimgB[bHalf + pb] = l; }
+  if (pv >= 0) a.wvec[pv] = Wn;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: plan, index maps, images, launchers
+// ------------------------------------------------------------------------------------------
+static inline int wide_np(int n) { return n <= 16 ? 16 : (n <= 32 ? 32 : (n <= 64 ? 64 : 128)); }
+static inline int wide_up(int n, int m) { return (n + m - 1) / m * m; }
+
+// idx: [5][nParams] — position of the parameter's gradient in a partial record; its positions in the tile-kernel image, the
+// forward image (hi half), the transposed image (hi half) and the vector block; -1 = none.
+void wide_plan_build(const NetDesc& net, const Hyper& hp, WidePlan& wp, std::vector<int>& idx) {
+  memset(&wp, 0, sizeof(wp));
+  const int nP = net.nParams;
+  idx.assign((size_t)5 * nP, -1);
+  if (net.recurrent || net.discrete || hp.algo != 0 || net.dA > 8 || net.dS > 128) return;     // feed-forward V-RACER, dA <= 8 (two pairs per thread)
+  int nD = 0;
+  for (int l = 1; l < net.nLayers; ++l) {
+    const LayerDesc& L = net.L[l];
+    if (L.kind != kDenseTanh && L.kind != kDenseLinear) continue;
+    if (nD == kWideMaxD || L.size > 128 || L.nIn > 128) return;
+    WDense& d = wp.D[nD];
+    d.layer = l; d.res = (l + 1 < net.nLayers && net.L[l + 1].kind == kResidual) ? l + 1 : -1;
+    d.K = L.nIn; d.Kp = wide_up(L.nIn, 16); d.N = L.size; d.Np = wide_np(L.size); d.isTanh = L.kind == kDenseTanh ? 1 : 0;
+    d.inOff = net.L[L.in].actOff; d.yOff = L.actOff; d.zOff = d.res >= 0 ? net.L[d.res].actOff : L.actOff;
+    if (d.res >= 0 && d.N > d.K) return;
+    ++nD;
+  }
+  if (nD < 2 || wp.D[nD - 1].isTanh || net.L[net.nLayers - 1].kind != kParam || wp.D[nD - 1].layer != net.nLayers - 2) return;
+  for (int d = 0; d + 1 < nD; ++d) if (!wp.D[d].isTanh || wp.D[d + 1].Kp > wp.D[d].Np) return;
+  wp.nD = nD;
+  wp.NpG = wide_up(net.nOut, 16);
+  if (wp.NpG > 128) return;
+  // images: [hi of every layer | lo of every layer]
+  int f = 0, b = 0, v = 0;
+  for (int d = 0; d < nD; ++d) {
+    WDense& D = wp.D[d];
+    D.fImg = f; f += D.Kp * D.Np;
+    D.bImg = -1;
+    if (d >= 1) { D.bImg = b; b += D.Np * D.Kp; }
+    D.vB = v; v += D.Np;
+    D.vRW = D.vRB = -1;
+    if (D.res >= 0) { D.vRW = v; v += D.Np; D.vRB = v; v += D.Np; }
+  }
+  const int dA4 = wide_up(net.dA, 4);
+  const int vP = v; v += dA4;                       // ParamLayer values
+  wp.vP = vP;
+  wp.fFloats = 2 * f; wp.bFloats = 2 * b; wp.vFloats = v;
+  // weight-gradient kernel: accumulators, partial record, stage layout
+  int col = 0, rec = 0, sg = 0;
+  for (int d = 0; d < nD; ++d) {
+    WDense& D = wp.D[d];
+    const bool out = d == nD - 1;
+    D.gN = out ? wp.NpG : D.Kp;
+    D.gCol = col; col += D.gN;
+    D.gPart = rec; rec += D.gN * 128;
+    wp.sgRowsA[d] = 128; wp.sgRowsB[d] = D.gN;
+    wp.sgOpA[d] = sg; sg += 2 * 4 * kWideLD * 16;
+    wp.sgOpB[d] = sg; sg += 2 * 4 * (D.gN + 2) * 16;
+  }
+  for (int d = 0; d < nD; ++d) {
+    WDense& D = wp.D[d];
+    const bool out = d == nD - 1;
+    D.vSum = rec; rec += out ? wp.NpG : (D.res >= 0 ? 3 * D.Np : D.Np);
+  }
+  if (col > 512) return;
+  wp.gCols = col <= 32 ? 32 : (col <= 64 ? 64 : (col <= 128 ? 128 : (col <= 256 ? 256 : 512)));
+  wp.recFloats = wide_up(rec, 32);
+  wp.sgStageBytes = sg;
+  // shared-memory layouts
+  const int kMax = 227 * 1024 - 2048;               // static shared memory of the kernels (ctrl, slots, statistics scratch) stays below 2 KB
+  int o = kWideDescBytes + kWidePlanBytes;
+  auto take = [&](int bytes) { const int at = o; o += (bytes + 127) / 128 * 128; return at; };
+  wp.sfBars = take(64);
+  wp.sfVec = take(4 * wp.vFloats);
+  wp.sfImg = take(4 * wp.fFloats);
+  wp.sfActO = take(4 * wp.D[nD - 1].Np * kWideM);
+  wp.sfGP = take(4 * net.dA * kWideM);
+  wp.sfOld = take(4 * 8 * kWideM);
+  wp.sfInfo = take(4 * 4 * kWideM);
+  wp.sfSamp = take(8 * 5 * kWideM);
+  wp.sfPair = take(8 * 2 * kWideM * net.dA);
+  wp.sfTotal = o;
+  o = kWideDescBytes + kWidePlanBytes;
+  wp.sbBars = take(64);
+  wp.sbVec = take(4 * wp.vFloats);
+  wp.sbImg = take(4 * wp.bFloats);
+  wp.sbTotal = o;
+  o = kWideDescBytes + kWidePlanBytes;
+  wp.sgBars = take(64);
+  wp.sgStage = take(0);
+  wp.sgStages = (kMax - o) / sg;
+  if (wp.sgStages > 4) wp.sgStages = 4;
+  wp.sgTotal = o + wp.sgStages * sg;
+  if (wp.sfTotal > kMax || wp.sbTotal > kMax || wp.sgStages < 2) return;
+  // index maps
+  int* iRec = idx.data(); int* iImg = iRec + nP; int* iF = iImg + nP; int* iB = iF + nP; int* iV = iB + nP;
+  for (int d = 0; d < nD; ++d) {
+    const WDense& D = wp.D[d];
+    const LayerDesc& L = net.L[D.layer];
+    const bool out = d == nD - 1;
+    for (int k = 0; k < D.K; ++k)
+      for (int n = 0; n < D.N; ++n) {
+        const int p = L.wOff + k * L.ld + n;
+        iRec[p] = out ? D.gPart + n * 128 + k : D.gPart + k * 128 + n;
+        iImg[p] = L.imgW + k * L.ldp + n;
+        iF[p] = D.fImg + ((k >> 2) * D.Np + n) * 4 + (k & 3);
+        if (D.bImg >= 0) iB[p] = D.bImg + ((n >> 2) * D.Kp + k) * 4 + (n & 3);
+      }
+    for (int n = 0; n < D.N; ++n) {
+      const int p = L.bOff + n;
+      iRec[p] = D.vSum + n; iImg[p] = L.imgB + n; iV[p] = D.vB + n;
+    }
+    if (D.res >= 0) {
+      const LayerDesc& R = net.L[D.res];
+      for (int n = 0; n < D.N; ++n) {
+        iRec[R.bOff + n] = D.vSum + D.Np + n; iImg[R.bOff + n] = R.imgB + n; iV[R.bOff + n] = D.vRB + n;
+        iRec[R.wOff + n] = D.vSum + 2 * D.Np + n; iImg[R.wOff + n] = R.imgW + n; iV[R.wOff + n] = D.vRW + n;
+      }
+    }
+  }
+  {
+    const LayerDesc& P = net.L[net.nLayers - 1];
+    const WDense& D = wp.D[nD - 1];
+    for (int i = 0; i < P.size; ++i) {
+      const int p = P.bOff + i;
+      iRec[p] = D.vSum + net.nOutDense + i; iImg[p] = P.imgB + i; iV[p] = vP + i;
+    }
+  }
+  wp.ok = 1;
+}
+
+// operand images and vector block of a parameter blob (host; the Adam kernel keeps them current afterwards)
+void wide_fill_images(const NetDesc& net, const WidePlan& wp, const std::vector<int>& idx, const float* blob,
+                      std::vector<float>& imgF, std::vector<float>& imgB, std::vector<float>& vecs) {
+  const int nP = net.nParams;
+  imgF.assign(wp.fFloats, 0.f); imgB.assign(wp.bFloats > 0 ? wp.bFloats : 1, 0.f); vecs.assign(wp.vFloats, 0.f);
+  const int* iF = idx.data() + 2 * (size_t)nP; const int* iB = iF + nP; const int* iV = iB + nP;
+  const int fHalf = wp.fFloats / 2, bHalf = wp.bFloats / 2;
+  for (int p = 0; p < nP; ++p) {
+    const float w = blob[p];
+    uint32_t u; memcpy(&u, &w, 4);
+    // cvt.rna.tf32.f32: round to nearest, ties away from zero, on the 13 dropped mantissa bits
+    uint32_t hu = u;
+    if ((u & 0x7f800000u) != 0x7f800000u) hu = (u + 0x1000u) & 0xffffe000u;
+    float h; memcpy(&h, &hu, 4);
+    const float l = w - h;
+    if (iF[p] >= 0) { imgF[iF[p]] = h; imgF[fHalf + iF[p]] = l; }
+    if (iB[p] >= 0) { imgB[iB[p]] = h; imgB[bHalf + iB[p]] = l; }
+    if (iV[p] >= 0) vecs[iV[p]] = w;
+  }
+}
+
+int wide_prepare(const WidePlan& wp, const NetDesc& net) {
+  SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_wide_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, wp.sfTotal));
+  SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_wide_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, wp.sbTotal));
+  SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_wide_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, wp.sgTotal));
+  SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_wide_next, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan(net, 4, false).total));
+  SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_wide_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, kWideDescBytes + 4 * kStatChunk));
+  return 0;
+}
+
+int wide_grid_g(const WidePlan& wp, int B, int numSMs) {
+  const int nSt = wide_up(B, kWideM) / kWideKS;
+  return nSt < numSMs ? nSt : numSMs;
+}
+
+int launch_steps_wide(const StepArgs& a, const NetDesc& net, const WidePlan& wp, int numSMs, int step0, int nSteps, int skipStatsLast,
+                      cudaStream_t st) {
+  const int nTiles = (a.B + kWideM - 1) / kWideM;
+  const int gridT = nTiles < numSMs ? nTiles : numSMs;
+  for (int s = 0; s < nSteps; ++s) {
+    const int step = step0 + s;
+    const bool skipStats = skipStatsLast && s == nSteps - 1;
+    k_wide_fwd<<<gridT, kST, wp.sfTotal, st>>>(a, step);
+    k_wide_next<<<16, kST, smem_plan(net, 4, false).total, st>>>(a, step);
+    if (!skipStats) {
+      k_wide_records<<<(a.B + 255) / 256, 256, 0, st>>>(a);
+      k_wide_stats<<<1, kST, kWideDescBytes + 4 * kStatChunk, st>>>(a, step);
+    }
+    k_wide_bwd<<<gridT, kST, wp.sbTotal, st>>>(a, step);
+    k_wide_wgrad<<<a.wGridG, kST, wp.sgTotal, st>>>(a, step);
+    k_wide_adam<<<(net.nParams + 255) / 256, 256, 0, st>>>(a, step, net.nParams, wp.recFloats, wp.fFloats / 2, wp.bFloats / 2);
+  }
+  SMB200_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

@@ -137,7 +137,7 @@ def load_library(path: str = LIB_PATH):
         "smb200_set_grad_stats": (C.c_int, [H, C.c_char_p]),
         "smb200_get_stats": (C.c_int, [H, P(StepStats)]),
         "smb200_forward": (C.c_int, [H, fp, C.c_int32, fp]),
-        "smb200_last_timing": (C.c_int, [H, dp, ip]),
+        "smb200_last_timing": (C.c_int, [H, dp, ip]), "smb200_step_kernel": (C.c_int, [H]),
         "smb200_presample": (C.c_int, [H, C.c_int32]), "smb200_train_presampled": (C.c_int, [H, C.c_int32, C.c_int32]),
         "smb200_sync": (C.c_int, [H]),
         "smb200_profile_phases": (C.c_int, [H, C.c_int32, ip, C.c_int64, P(C.c_int32)]),
@@ -363,6 +363,13 @@ class Learner:
         self._check(self.lib.smb200_profile_phases(self.h, int(n), _ip(out), cap, C.byref(grid)))
         g = grid.value
         return out[:n * g * 48].reshape(n, g, 48), self.last_timing()[0]
+
+    def step_kernel(self):
+        """0 two kernels per step, 1 persistent tile kernel, 2 cluster kernel, 3 wide step (tensor cores)"""
+        return int(self.lib.smb200_step_kernel(self.h))
+
+    def wide_step_active(self):
+        return self.step_kernel() == 3
 
     def sync(self):
         self._check(self.lib.smb200_sync(self.h))

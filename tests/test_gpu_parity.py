@@ -174,6 +174,47 @@ def test_cluster_kernel_equals_tile_kernel(monkeypatch, case):
     A.close(); Bm.close()
 
 
+WIDE_CASES = [c for c in CASES + THREADED_CASES if c.startswith("vracer")]      # feed-forward V-RACER: what the wide step takes
+
+
+@pytest.mark.parametrize("case", WIDE_CASES)
+def test_wide_step_matches_reference(monkeypatch, case):
+    """The large-batch step (wide_step.cuh: tiles of 128 sampled transitions, every dense product as 3xTF32 tcgen05.mma with the
+    activations as the A operand in tensor memory, split-K weight gradient on the tensor cores, parallel per-episode records)
+    against the same goldens and bars as the tile kernel.  SMB200_WIDE=1 forces it for every batch size (partial tiles);
+    vracer_b1024 is the batch size at which it is the default."""
+    monkeypatch.setenv("SMB200_WIDE", "1")
+    g = Golden(case)
+    L = make_learner(g)
+    assert L.wide_step_active()
+    for s in range(g.steps):
+        st = L.train_steps(1)[0]
+        _check_step(L, g, g.ref, f"s{s}", st)
+    _check_final(L, g.ref)
+    L.close()
+
+
+@pytest.mark.parametrize("case", ["vracer_small", "vracer_cfg2mini", "vracer_bounded", "vracer_b1024"])
+def test_wide_step_equals_tile_kernel(monkeypatch, case):
+    """Same samples, same integer far-policy counts, floats equal to f32 round-off (3xTF32 products, different summation order)."""
+    g = Golden(case)
+    monkeypatch.setenv("SMB200_WIDE", "0")
+    Bm = make_learner(g)
+    assert not Bm.wide_step_active()
+    monkeypatch.setenv("SMB200_WIDE", "1")
+    A = make_learner(g)
+    monkeypatch.delenv("SMB200_WIDE")
+    sa, sb = A.train_steps(g.steps), Bm.train_steps(g.steps)
+    for x, y in zip(sa, sb):
+        assert x["n_far_policy"] == y["n_far_policy"] and x["grad_step"] == y["grad_step"]
+        assert x["beta"] == pytest.approx(y["beta"], rel=1e-12) and x["avg_sq_err"] == pytest.approx(y["avg_sq_err"], rel=1e-5)
+    assert relerr(A.get_grad(), Bm.get_grad()) < 5e-6
+    assert np.abs(A.get_weights() - Bm.get_weights()).max() < 1e-6
+    assert np.allclose(A.read_field("QRET"), Bm.read_field("QRET"), rtol=1e-5, atol=1e-6)
+    assert np.array_equal(A.read_field("RHO"), Bm.read_field("RHO")) or np.allclose(A.read_field("RHO"), Bm.read_field("RHO"), rtol=1e-5)
+    A.close(); Bm.close()
+
+
 @pytest.mark.parametrize("case", ["vracer_small", "vracer_bounded"])
 def test_injected_samples_and_oracle_flags(case):
     """Feed the oracle's samples to the GPU step by step; with the SAME network outputs the
