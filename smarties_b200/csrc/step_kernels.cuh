@@ -119,6 +119,7 @@ struct WidePlan {
   int NpG;                 // rows of the output-gradient operand: roundUp16(nOut) (dense outputs, then the ParamLayer's)
   int fFloats, bFloats, vFloats;        // sizes of the forward image, the transposed image, the vector block
   int vP;                               // ParamLayer values in the vector block
+  int vMsc;                             // forward kernel's shared memory: state mean / scale [2][Kp0] behind the vector block
   int recFloats;                        // partial record of one weight-gradient CTA
   int gCols;                            // TMEM columns of the weight-gradient kernel (power of two)
   int sfVec, sfImg, sfActO, sfGP, sfOld, sfInfo, sfSamp, sfPair, sfBars, sfTotal;   // forward kernel: byte offsets in dynamic shared memory

@@ -16,7 +16,8 @@
 //                 epilogue that produced them — they never touch shared memory), accumulator in tensor memory; gather +
 //                 standardise, all layers, then the ReF-ER / Retrace loss in f64 (the tile kernel's formulas, one thread per
 //                 (sample, action component)), replay write-back and per-sample records; activations and the output gradient
-//                 leave for the other kernels as a feature-major scratch [feature][sample] (coalesced 128-byte rows).
+//                 leave for the other kernels as a scratch [tile][feature][128 samples] (coalesced 128-byte warp stores, one
+//                 contiguous block per tile).
 //   k_wide_next   V(s_t+1) of the few samples whose successor ends a truncated episode (RACER_train.cpp:22-27).
 //   k_wide_records / k_wide_stats   Episode::updateCumulative_atomic in sample order — one thread per run of samples of an
 //                 episode, all runs in parallel — then the tile kernel's own statistics / ReF-ER beta update on one CTA.
@@ -82,19 +83,29 @@ constexpr int kWideDescBytes = (int)(((sizeof(DevDescs) + 15) / 16) * 16);
 constexpr int kWidePlanBytes = (int)(((sizeof(WidePlan) + 15) / 16) * 16);
 
 // TMEM columns of the forward / input-gradient kernels
-constexpr uint32_t kWAcc = 0, kWAh = 128, kWAl = 256;
+constexpr uint32_t kWAcc = 0, kWAh = 128, kWAl = 256, kWCarry = 384;
 
 // one dense product of a 128-sample tile: D[128][Np] = A[128][Kc] (TMEM, hi at kWAh, lo at kWAl) * image (shared memory,
 // float4 [Kc/4][rows], rows = N of the MMA), three MMAs per 8 contraction columns.  Issued by ONE thread.
 __device__ __forceinline__ void wide_issue(uint32_t tmem, const float* imgHi, const float* imgLo, int Kc, int rows, uint64_t* bar) {
   tc_fence_after();
   const uint32_t idesc = wide_idesc(rows);
-  for (int kk = 0; kk < Kc / 8; ++kk) {
-    const uint64_t dbh = umma_desc(imgHi + (size_t)(2 * kk) * rows * 4, rows * 16, 128);
-    const uint64_t dbl = umma_desc(imgLo + (size_t)(2 * kk) * rows * 4, rows * 16, 128);
-    umma_tf32_ts(tmem + kWAcc, tmem + kWAl + 8 * kk, dbh, idesc, kk > 0);
-    umma_tf32_ts(tmem + kWAcc, tmem + kWAh + 8 * kk, dbl, idesc, 1);
-    umma_tf32_ts(tmem + kWAcc, tmem + kWAh + 8 * kk, dbh, idesc, 1);
+  // one descriptor per image, advanced by two k-chunks (2 * rows * 16 bytes, in 16-byte units) per MMA set: the issuing thread
+  // is the critical path of a layer, every instruction in this loop counts
+  uint64_t dbh = umma_desc(imgHi, rows * 16, 128), dbl = umma_desc(imgLo, rows * 16, 128);
+  const uint64_t inc = (uint64_t)(2 * rows);
+  uint32_t ah = tmem + kWAh, al = tmem + kWAl;
+  const uint32_t acc = tmem + kWAcc;
+  const int n = Kc / 8;
+  umma_tf32_ts(acc, al, dbh, idesc, 0u);
+  umma_tf32_ts(acc, ah, dbl, idesc, 1u);
+  umma_tf32_ts(acc, ah, dbh, idesc, 1u);
+#pragma unroll 4
+  for (int kk = 1; kk < n; ++kk) {
+    dbh += inc; dbl += inc; ah += 8; al += 8;
+    umma_tf32_ts(acc, al, dbh, idesc, 1u);
+    umma_tf32_ts(acc, ah, dbl, idesc, 1u);
+    umma_tf32_ts(acc, ah, dbh, idesc, 1u);
   }
   tc_commit(bar);
 }
@@ -137,6 +148,10 @@ __global__ void __launch_bounds__(kST, 1) k_wide_fwd(StepArgs a, int step) {
   }
   if (warp == 0) tmem_alloc(&tmemSlot, 512u);
   for (int i = tid; i < wp.vFloats; i += kST) vec[i] = ld_cg(a.wvec + i);
+  for (int i = tid; i < wp.D[0].Kp; i += kST) {
+    vec[wp.vMsc + i] = i < net.dS ? ld_cg(a.rp.stateMean + i) : 0.f;
+    vec[wp.vMsc + wp.D[0].Kp + i] = i < net.dS ? ld_cg(a.rp.stateScale + i) : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -156,49 +171,73 @@ __global__ void __launch_bounds__(kST, 1) k_wide_fwd(StepArgs a, int step) {
   bool imgReady = false, fault = false;
   const uint32_t laneBase = (uint32_t)(q * 32) << 16;
 
+  // Inputs of a tile, fetched ONE TILE AHEAD into registers (the gather is a dependent chain sample index -> ring row -> state
+  // row, ~2 DRAM round trips, that would otherwise open every tile): the thread's <= 2 chunks of 8 state components of its
+  // sample, and (column group 0) the sample's old replay values.
+  const WDense& D0 = wp.D[0];
+  const float* msc = vec + wp.vMsc;                // [2][Kp0]: state mean, state scale (Core/StateAction.h:56-58)
+  int pfRow = 0, pfSlot = 0; float pfX[2][8], pfOld[6];
+  auto prefetch = [&](int tile) {
+    const int bb = tile * TBW + q * 32 + lane;
+    const bool ok = tile < nTiles && bb < a.B;
+    pfRow = ok ? __ldg(a.sampRow + j0 + bb) : 0;
+#pragma unroll
+    for (int c2 = 0; c2 < 2; ++c2) {
+      const int j8 = cg + 4 * c2;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int k = 8 * j8 + jj;
+        pfX[c2][jj] = (ok && k < dS) ? ld_cg(rp.S + (size_t)pfRow * dS + k) : 0.f;
+      }
+    }
+    if (cg == 0) {
+      pfSlot = ok ? __ldg(a.sampSlot + j0 + bb) : 0;
+      if (ok) {
+        pfOld[0] = ld_cg(rp.V + pfRow); pfOld[1] = ld_cg(rp.ADV + pfRow); pfOld[2] = ld_cg(rp.RHO + pfRow);
+        pfOld[3] = ld_cg(rp.KL + pfRow); pfOld[4] = ld_cg(rp.DELTA + pfRow); pfOld[5] = ld_cg(rp.Q + pfRow);
+      }
+    }
+  };
+  prefetch(blockIdx.x);
   for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
     const int b0 = tile * TBW, s = q * 32 + lane, b = b0 + s;
     const bool valid = b < a.B;
-    int row = 0;
-    if (valid) row = __ldg(a.sampRow + j0 + b);
+    // scratch of the tile: [feature][128 samples], tile after tile (one contiguous block per tile: the kernels that follow
+    // stream it, and every DRAM page that is opened is used completely)
+    float* actT = a.actG + (size_t)tile * net.actPerSample * TBW;
+    float* errT = a.errG + (size_t)tile * net.actPerSample * TBW;
     if (cg == 0) {       // sample info + the old per-transition values of the write-back
       int slot = 0, hn = 0;
       if (valid) {
-        const int sf = __ldg(a.sampSlot + j0 + b);
-        slot = sf & 0x7fffffff; hn = (sf >> 31) & 1;
-        old[0 * TBW + s] = ld_cg(rp.V + row); old[1 * TBW + s] = ld_cg(rp.ADV + row);
-        old[2 * TBW + s] = ld_cg(rp.RHO + row); old[3 * TBW + s] = ld_cg(rp.KL + row);
-        old[4 * TBW + s] = ld_cg(rp.DELTA + row); old[7 * TBW + s] = ld_cg(rp.Q + row);
+        slot = pfSlot & 0x7fffffff; hn = (pfSlot >> 31) & 1;
+        old[0 * TBW + s] = pfOld[0]; old[1 * TBW + s] = pfOld[1]; old[2 * TBW + s] = pfOld[2];
+        old[3 * TBW + s] = pfOld[3]; old[4 * TBW + s] = pfOld[4]; old[7 * TBW + s] = pfOld[5];
         if (hn) { const int i = atomicAdd(a.wcnt, 1); a.wlist[i] = b; }      // V(s_t+1): k_wide_next
       }
-      info[s] = row; info[TBW + s] = slot; info[2 * TBW + s] = hn; info[3 * TBW + s] = valid ? 1 : 0;
+      info[s] = pfRow; info[TBW + s] = slot; info[2 * TBW + s] = hn; info[3 * TBW + s] = valid ? 1 : 0;
     }
-    // ---- gather + standardise (Episode.h:171-183): the tile's states become the A operand of the first layer ----
-    {
-      const WDense& D0 = wp.D[0];
-      for (int j8 = cg; j8 < D0.Kp / 8; j8 += 4) {
-        float x[8];
+    // ---- standardise (Episode.h:171-183): the tile's states become the A operand of the first layer ----
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const int k = 8 * j8 + jj;
-          x[jj] = (valid && k < dS) ? (ld_cg(rp.S + (size_t)row * dS + k) - ld_cg(rp.stateMean + k)) * ld_cg(rp.stateScale + k) : 0.f;
-        }
-        uint32_t hi[8], lo[8];
+    for (int c2 = 0; c2 < 2; ++c2) {
+      const int j8 = cg + 4 * c2;
+      if (j8 >= D0.Kp / 8) continue;
+      uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const int k = 8 * j8 + jj;
-          const float h = tf32_hi(x[jj]);
-          hi[jj] = __float_as_uint(h); lo[jj] = __float_as_uint(x[jj] - h);
-          if (k < dS) {
-            a.actG[(size_t)(D0.inOff + k) * a.Bpad + b] = x[jj];
-            if (keep && valid) a.lastX[(size_t)b * dS + k] = x[jj];
-          }
+      for (int jj = 0; jj < 8; ++jj) {
+        const int k = 8 * j8 + jj;
+        const float x = (valid && k < dS) ? (pfX[c2][jj] - msc[k]) * msc[D0.Kp + k] : 0.f;
+        const float h = tf32_hi(x);
+        hi[jj] = __float_as_uint(h); lo[jj] = __float_as_uint(x - h);
+        if (k < dS) {
+          actT[(D0.inOff + k) * TBW + s] = x;
+          if (keep && valid) a.lastX[(size_t)b * dS + k] = x;
         }
-        tm_st8(tmem + laneBase + kWAh + 8 * j8, hi);
-        tm_st8(tmem + laneBase + kWAl + 8 * j8, lo);
       }
-      tm_wait_st();
+      tm_st8(tmem + laneBase + kWAh + 8 * j8, hi);
+      tm_st8(tmem + laneBase + kWAl + 8 * j8, lo);
     }
+    tm_wait_st();
+    prefetch(tile + gridDim.x);
     tc_fence_before();
     __syncthreads();
     if (!imgReady) { mbar_wait(&bars[0], 0); imgReady = true; }
@@ -217,22 +256,33 @@ __global__ void __launch_bounds__(kST, 1) k_wide_fwd(StepArgs a, int step) {
           uint32_t v[8], xh[8], xl[8];
           tm_ld8(tmem + laneBase + kWAcc + 8 * j8, v);
           if (res) { tm_ld8(tmem + laneBase + kWAh + 8 * j8, xh); tm_ld8(tmem + laneBase + kWAl + 8 * j8, xl); }
+          const int n0 = 8 * j8;
+          float bv[8], rwv[8], rbv[8];
+          *reinterpret_cast<float4*>(bv) = *reinterpret_cast<const float4*>(bias + n0);
+          *reinterpret_cast<float4*>(bv + 4) = *reinterpret_cast<const float4*>(bias + n0 + 4);
+          if (res) {
+            *reinterpret_cast<float4*>(rwv) = *reinterpret_cast<const float4*>(rw + n0);
+            *reinterpret_cast<float4*>(rwv + 4) = *reinterpret_cast<const float4*>(rw + n0 + 4);
+            *reinterpret_cast<float4*>(rbv) = *reinterpret_cast<const float4*>(rb + n0);
+            *reinterpret_cast<float4*>(rbv + 4) = *reinterpret_cast<const float4*>(rb + n0 + 4);
+          }
+          float* yp = actT + (D.yOff + n0) * TBW + s;
+          float* zp = actT + (D.zOff + n0) * TBW + s;
           tm_wait_ld();
           uint32_t hi[8], lo[8];
+          // no branches inside: the eight columns are independent instruction streams (the padding columns have zero weights
+          // and biases: tanh(0) = 0, and are not stored)
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
-            const int n = 8 * j8 + jj;
-            float y = 0.f, z = 0.f;
-            if (n < D.N) {
-              y = tanh_ref(__uint_as_float(v[jj]) + bias[n]);          // BaseLayer::forward (Layer_Base.h:64-95)
-              z = y;
-              if (res) {                                              // ParametricResidualLayer::forward (Layers.h:347-361)
-                const float xin = __uint_as_float(xh[jj]) + __uint_as_float(xl[jj]);     // hi + lo is the f32 value, exactly
-                z = y + (xin * rw[n] + rb[n]);
-              }
-              a.actG[(size_t)(D.yOff + n) * a.Bpad + b] = y;
-              if (res) a.actG[(size_t)(D.zOff + n) * a.Bpad + b] = z;
+            const float y = tanh_ref(__uint_as_float(v[jj]) + bv[jj]);          // BaseLayer::forward (Layer_Base.h:64-95)
+            float z = y;
+            if (res) {                                                         // ParametricResidualLayer::forward (Layers.h:347-361)
+              const float xin = __uint_as_float(xh[jj]) + __uint_as_float(xl[jj]);     // hi + lo is the f32 value, exactly
+              z = y + (xin * rwv[jj] + rbv[jj]);
             }
+            const bool in = n0 + jj < D.N;
+            z = in ? z : 0.f;
+            if (in) { yp[jj * TBW] = y; if (res) zp[jj * TBW] = z; }
             const float h = tf32_hi(z);
             hi[jj] = __float_as_uint(h); lo[jj] = __float_as_uint(z - h);
           }
@@ -375,7 +425,7 @@ __global__ void __launch_bounds__(kST, 1) k_wide_fwd(StepArgs a, int step) {
       float g = 0.f;
       if (info[3 * TBW + sp]) g = j < net.nOutDense ? actO[j * TBW + sp] : gP[(j - net.nOutDense) * TBW + sp];
       const int rowG = j < net.nOutDense ? Lo.actOff + j : Lp.actOff + (j - net.nOutDense);
-      a.errG[(size_t)rowG * a.Bpad + b0 + sp] = g;
+      errT[rowG * TBW + sp] = g;
     }
     __syncthreads();
   }
@@ -389,18 +439,27 @@ __global__ void __launch_bounds__(kST, 1) k_wide_fwd(StepArgs a, int step) {
 // ------------------------------------------------------------------------------------------
 // k_wide_next: V(s_t+1) of the flagged samples (list filled by k_wide_fwd), 4 per pass, weights from the tile image in L2
 // ------------------------------------------------------------------------------------------
+template <bool SM>
 __global__ void __launch_bounds__(kST) k_wide_next(StepArgs a, int step) {
   extern __shared__ __align__(128) unsigned char smraw[];
   const NetDesc* netp; const Hyper* hpp;
   load_descs(a, smraw, netp, hpp);
   const NetDesc& net = *netp;
   constexpr int TB = 4;
-  const SmemPlan sp = smem_plan(net, TB, false);
+  const SmemPlan sp = smem_plan(net, TB, SM);
+  float* img = reinterpret_cast<float*>(smraw + sp.img);
+  const float* Wp = SM ? img : a.Wimg;
   float* act = reinterpret_cast<float*>(smraw + sp.act);
   float* red = reinterpret_cast<float*>(smraw + sp.red);
+  uint64_t* bars = (SM && a.useTma) ? reinterpret_cast<uint64_t*>(smraw + sp.bars) : nullptr;
   const ReplayView& rp = a.rp;
   const int tid = threadIdx.x, dS = net.dS;
   const int count = min(__ldcg(a.wcnt), a.B);
+  if ((int)blockIdx.x * TB >= count) return;
+  if (SM) {        // the tile kernel's weight image (one bulk copy per layer), as in its own V(s_t+1) helper
+    init_bars(a, net, smraw, sp.bars);
+    load_weight_image(a, net, img, reinterpret_cast<uint64_t*>(smraw + sp.bars), step);
+  }
   const size_t j0 = (size_t)(step - a.stepBase) * a.B;
   for (int first = blockIdx.x * TB; first < count; first += gridDim.x * TB) {
     for (int idx = tid; idx < dS * TB; idx += kST) {
@@ -414,11 +473,11 @@ __global__ void __launch_bounds__(kST) k_wide_next(StepArgs a, int step) {
       act[idx] = x;
     }
     __syncthreads();
-    net_forward<TB, false>(net, a.Wimg, act, red, nullptr, 0);
+    net_forward<TB, SM>(net, Wp, act, red, first == (int)blockIdx.x * TB ? bars : nullptr, 0);
     if (tid < TB && first + tid < count) {
       const int b = __ldcg(a.wlist + first + tid);
       const size_t row = (size_t)__ldcg(a.sampRow + j0 + b) + 1;
-      const float vn = (float)net2v((double)net_out<false>(net, a.Wimg, act, TB, 0, tid));
+      const float vn = (float)net2v((double)net_out<SM>(net, Wp, act, TB, 0, tid));
       const float qOld = ld_cg(rp.ADV + row) + ld_cg(rp.V + row);
       rp.V[row] = vn; rp.ADV[row] = vn - vn;
       *reinterpret_cast<float2*>(&a.rec[b].qNextOld) = make_float2(qOld, vn);
@@ -448,18 +507,28 @@ __global__ void __launch_bounds__(256) k_wide_records(StepArgs a) {
       float sQ2 = rp.epAgg[AGG_Q2 * ME + slot], sQ = rp.epAgg[AGG_Q1 * ME + slot];
       float maxQ = rp.epAgg[AGG_MAXQ * ME + slot], minQ = rp.epAgg[AGG_MINQ * ME + slot];
       const float invN = 1.0f / (float)rp.epLen[slot];
-      for (int j = b; j < a.B; ++j) {
-        const int4 hj = __ldcg(reinterpret_cast<const int4*>(&a.rec[j]));
-        if (hj.x != slot) break;
-        const float4 d = __ldcg(reinterpret_cast<const float4*>(&a.rec[j].dKL));
-        const float4 qv = __ldcg(reinterpret_cast<const float4*>(&a.rec[j].qOld));
-        if (hj.y) {
-          sQ2 += qv.w * qv.w - qv.z * qv.z; sQ += qv.w - qv.z;
-          maxQ = fmaxf(maxQ, qv.w); minQ = fminf(minQ, qv.w);
+      bool open = true;
+      for (int j = b; open && j < a.B; j += 4) {       // the run is applied in order; four records travel at a time
+        int4 hj[4]; float4 dj[4], qj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int jj = min(j + u, a.B - 1);
+          hj[u] = __ldcg(reinterpret_cast<const int4*>(&a.rec[jj]));
+          dj[u] = __ldcg(reinterpret_cast<const float4*>(&a.rec[jj].dKL));
+          qj[u] = __ldcg(reinterpret_cast<const float4*>(&a.rec[jj].qOld));
         }
-        avgKL += invN * d.x; frac += invN * d.y; avgE2 += invN * d.z; maxE = fmaxf(maxE, d.w);
-        sQ2 += qv.y * qv.y - qv.x * qv.x; sQ += qv.y - qv.x;
-        maxQ = fmaxf(maxQ, qv.y); minQ = fminf(minQ, qv.y);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (!open || j + u >= a.B || hj[u].x != slot) { open = false; continue; }
+          const float4 d = dj[u], qv = qj[u];
+          if (hj[u].y) {
+            sQ2 += qv.w * qv.w - qv.z * qv.z; sQ += qv.w - qv.z;
+            maxQ = fmaxf(maxQ, qv.w); minQ = fminf(minQ, qv.w);
+          }
+          avgKL += invN * d.x; frac += invN * d.y; avgE2 += invN * d.z; maxE = fmaxf(maxE, d.w);
+          sQ2 += qv.y * qv.y - qv.x * qv.x; sQ += qv.y - qv.x;
+          maxQ = fmaxf(maxQ, qv.y); minQ = fminf(minQ, qv.y);
+        }
       }
       rp.epAgg[AGG_KL * ME + slot] = avgKL; rp.epAgg[AGG_FAR * ME + slot] = frac;
       rp.epAgg[AGG_E2 * ME + slot] = avgE2; rp.epAgg[AGG_MAXE * ME + slot] = maxE;
@@ -528,66 +597,94 @@ __global__ void __launch_bounds__(kST, 1) k_wide_bwd(StepArgs a, int step) {
   const uint32_t laneBase = (uint32_t)(q * 32) << 16;
   const LayerDesc& Lo = net.L[net.nLayers - 2];
 
-  for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
-    const int b0 = tile * TBW, s = q * 32 + lane, b = b0 + s;
-    // ---- the output gradient of the tile -> A operand ----
-    {
-      const WDense& D = wp.D[wp.nD - 1];
-      for (int j8 = cg; j8 < D.Np / 8; j8 += 4) {
-        uint32_t hi[8], lo[8];
+  // the output gradient of a tile: chunk cg of the output layer's Np / 8 column chunks (Np <= 32: at most one chunk per thread),
+  // fetched one tile ahead
+  const WDense& DO = wp.D[wp.nD - 1];
+  const bool gMine = cg < DO.Np / 8;
+  float gv[8];
+  auto fetch_g = [&](int tile) {
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const int n = 8 * j8 + jj;
-          const float g = n < D.N ? ld_cg(a.errG + (size_t)(Lo.actOff + n) * a.Bpad + b) : 0.f;
-          const float h = tf32_hi(g);
-          hi[jj] = __float_as_uint(h); lo[jj] = __float_as_uint(g - h);
-        }
-        tm_st8(tmem + laneBase + kWAh + 8 * j8, hi);
-        tm_st8(tmem + laneBase + kWAl + 8 * j8, lo);
-      }
+    for (int jj = 0; jj < 8; ++jj) {
+      const int n = 8 * cg + jj;
+      gv[jj] = (gMine && tile < nTiles && n < DO.N) ? ld_cg(a.errG + ((size_t)tile * net.actPerSample + Lo.actOff + n) * TBW + q * 32 + lane) : 0.f;
+    }
+  };
+  fetch_g(blockIdx.x);
+  for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+    const int s = q * 32 + lane;
+    const float* actT = a.actG + (size_t)tile * net.actPerSample * TBW;
+    float* errT = a.errG + (size_t)tile * net.actPerSample * TBW;
+    // ---- the output gradient of the tile -> A operand ----
+    if (gMine) {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) { const float h = tf32_hi(gv[jj]); hi[jj] = __float_as_uint(h); lo[jj] = __float_as_uint(gv[jj] - h); }
+      tm_st8(tmem + laneBase + kWAh + 8 * cg, hi);
+      tm_st8(tmem + laneBase + kWAl + 8 * cg, lo);
       tm_wait_st();
     }
     tc_fence_before();
     __syncthreads();
+    fetch_g(tile + gridDim.x);
     if (!imgReady) { mbar_wait(&bars[0], 0); imgReady = true; }
-    float carry[32];          // E_z(d) * w_res(d): the residual path into the layer below, columns 8 * (cg + 4 i) + jj
-#pragma unroll
-    for (int i = 0; i < 32; ++i) carry[i] = 0.f;
     for (int d = wp.nD - 1; d >= 1; --d) {
       const WDense& D = wp.D[d];           // product through this layer's weights
       const WDense& H = wp.D[d - 1];       // the hidden layer that receives the error
       // contraction over this layer's outputs (Np columns of the A operand), N = its Kp input rows
       if (tid == 0) wide_issue(tmem, img + D.bImg, img + bHalf + D.bImg, D.Np, D.Kp, &bars[1]);
+      // the layer's outputs (tanh') do not depend on the product: fetch them while the tensor core works
+      float yv[32];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j8 = cg + 4 * i;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int n = 8 * j8 + jj;
+          yv[8 * i + jj] = (j8 < H.Np / 8 && n < H.N) ? ld_cg(actT + (H.yOff + n) * TBW + s) : 0.f;
+        }
+      }
       if (!mbar_wait_bounded(&bars[1], mmaPar)) fault = true;
       mmaPar ^= 1u;
       tc_fence_after();
       const bool res = H.res >= 0;
       const bool more = d - 1 >= 1;        // the layer below propagates further
+      const bool haveCarry = d < wp.nD - 1 && D.res >= 0;      // E_z(d) * w_res(d), left in tensor memory by the previous epilogue
       const float* rw = vec + (res ? H.vRW : 0);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int j8 = cg + 4 * i;
         if (j8 >= H.Np / 8) continue;
-        uint32_t v[8];
+        uint32_t v[8], cy[8];
         const bool have = 8 * j8 < D.Kp;
-        if (have) { tm_ld8(tmem + laneBase + kWAcc + 8 * j8, v); tm_wait_ld(); }
-        uint32_t hi[8], lo[8];
+        if (have) tm_ld8(tmem + laneBase + kWAcc + 8 * j8, v);
+        if (haveCarry) tm_ld8(tmem + laneBase + kWCarry + 8 * j8, cy);
+        if (have || haveCarry) tm_wait_ld();
+        uint32_t hi[8], lo[8], cn[8];
+        const int n0 = 8 * j8;
+        float rwv[8];
+        if (res) {
+          *reinterpret_cast<float4*>(rwv) = *reinterpret_cast<const float4*>(rw + n0);
+          *reinterpret_cast<float4*>(rwv + 4) = *reinterpret_cast<const float4*>(rw + n0 + 4);
+        }
+        float* ep = errT + (H.zOff + n0) * TBW + s;
+        float* dp = errT + (H.yOff + n0) * TBW + s;
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
-          const int n = 8 * j8 + jj;
-          float delta = 0.f, cnew = 0.f;
-          if (n < H.N) {
-            const float ez = (have ? __uint_as_float(v[jj]) : 0.f) + carry[8 * i + jj];      // E_in = W * delta (+ residual path)
-            const float y = ld_cg(a.actG + (size_t)(H.yOff + n) * a.Bpad + b);
-            delta = ez * (1.0f - y * y);
-            if (res) { a.errG[(size_t)(H.zOff + n) * a.Bpad + b] = ez; cnew = ez * rw[n]; }
-            a.errG[(size_t)(H.yOff + n) * a.Bpad + b] = delta;
-          }
-          carry[8 * i + jj] = cnew;
+          const bool in = n0 + jj < H.N;
+          const float ez = (have ? __uint_as_float(v[jj]) : 0.f) + (haveCarry ? __uint_as_float(cy[jj]) : 0.f);   // E_in = W * delta (+ residual path)
+          const float y = yv[8 * i + jj];
+          const float delta = in ? ez * (1.0f - y * y) : 0.f;
+          float cnew = 0.f;
+          if (res) { cnew = in ? ez * rwv[jj] : 0.f; if (in) ep[jj * TBW] = ez; }
+          if (in) dp[jj * TBW] = delta;
+          cn[jj] = __float_as_uint(cnew);
           const float h = tf32_hi(delta);
           hi[jj] = __float_as_uint(h); lo[jj] = __float_as_uint(delta - h);
         }
-        if (more) { tm_st8(tmem + laneBase + kWAh + 8 * j8, hi); tm_st8(tmem + laneBase + kWAl + 8 * j8, lo); }
+        if (more) {
+          tm_st8(tmem + laneBase + kWAh + 8 * j8, hi); tm_st8(tmem + laneBase + kWAl + 8 * j8, lo);
+          if (res) tm_st8(tmem + laneBase + kWCarry + 8 * j8, cn);
+        }
       }
       if (more) tm_wait_st();
       tc_fence_before();
@@ -610,6 +707,7 @@ __global__ void __launch_bounds__(kST, 1) k_wide_bwd(StepArgs a, int step) {
 // = its input rows, N side = the output-gradient rows [dense | ParamLayer].  Vector gradients (biases, residual w / b,
 // ParamLayer) are the row sums of what the thread just loaded.
 // ------------------------------------------------------------------------------------------
+template <int ND>
 __global__ void __launch_bounds__(kST, 1) k_wide_wgrad(StepArgs a, int step) {
   extern __shared__ __align__(128) unsigned char smraw[];
   const NetDesc* netp; const Hyper* hpp;
@@ -636,57 +734,79 @@ __global__ void __launch_bounds__(kST, 1) k_wide_wgrad(StepArgs a, int step) {
   const int st0 = (int)((long long)g * nSt / G), st1 = (int)((long long)(g + 1) * nSt / G);
   const LayerDesc& Lo = net.L[net.nLayers - 2];
   const LayerDesc& Lp = net.L[net.nLayers - 1];
-  float sA[kWideMaxD], sE[kWideMaxD], sEX[kWideMaxD];
+  // this thread's operand rows: scratch row pointers (nullptr = zero row) and shared-memory slots, fixed for the whole launch
+  const float* pA[ND]; const float* pB[ND]; const float* pE[ND];
+  int oA[ND], oB[ND], ldB[ND];
 #pragma unroll
-  for (int d = 0; d < kWideMaxD; ++d) { sA[d] = 0.f; sE[d] = 0.f; sEX[d] = 0.f; }
+  for (int d = 0; d < ND; ++d) {
+    const WDense& D = wp.D[d];
+    const bool out = d == ND - 1;
+    pA[d] = pB[d] = pE[d] = nullptr;
+    if (!out) {
+      if (r < D.N) pA[d] = a.errG + (D.yOff + r) * kWideM + 4 * cc;                    // deltas of the layer (tile-relative)
+      if (r < D.K) pB[d] = a.actG + (D.inOff + r) * kWideM + 4 * cc;                   // its input
+      if (D.res >= 0 && r < D.N) pE[d] = a.errG + (D.zOff + r) * kWideM + 4 * cc;      // error on the residual layer
+    } else {
+      if (r < D.K) pA[d] = a.actG + (D.inOff + r) * kWideM + 4 * cc;
+      if (r < net.nOut) pB[d] = a.errG + (r < net.nOutDense ? Lo.actOff + r : Lp.actOff + (r - net.nOutDense)) * kWideM + 4 * cc;
+    }
+    ldB[d] = wp.sgRowsB[d] + 2;
+    oA[d] = wp.sgOpA[d] + (cc * kWideLD + r) * 16;
+    oB[d] = r < wp.sgRowsB[d] ? wp.sgOpB[d] + (cc * ldB[d] + r) * 16 : -1;
+  }
+  // operand descriptors of stage 0 (the issuing thread adds the stage offset and the k-chunk offset: the issue loop is the
+  // serial part of a stage)
+  __shared__ uint64_t gd[ND][5]; __shared__ uint32_t gi[ND][2];      // read by the issuing thread only: no registers of the other 511
+  if (tid == 0) {
+    for (int d = 0; d < ND; ++d) {
+      const unsigned char* s0 = smraw + wp.sgStage;
+      const int lb = wp.sgRowsB[d] + 2;
+      gd[d][0] = umma_desc(s0 + wp.sgOpA[d], kWideLD * 16, 128); gd[d][1] = umma_desc(s0 + wp.sgOpA[d] + 4 * kWideLD * 16, kWideLD * 16, 128);
+      gd[d][2] = umma_desc(s0 + wp.sgOpB[d], lb * 16, 128); gd[d][3] = umma_desc(s0 + wp.sgOpB[d] + 4 * lb * 16, lb * 16, 128);
+      gd[d][4] = (uint64_t)lb; gi[d][0] = wide_idesc(wp.D[d].gN); gi[d][1] = tmem + (uint32_t)wp.D[d].gCol;
+    }
+  }
+  float sA[ND], sE[ND], sEX[ND];
+#pragma unroll
+  for (int d = 0; d < ND; ++d) { sA[d] = 0.f; sE[d] = 0.f; sEX[d] = 0.f; }
   bool fault = false;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 vA[ND], vB[ND], vE[ND], nA[ND], nB[ND], nE[ND];
+  auto fetch = [&](int it, float4 (&xA)[ND], float4 (&xB)[ND], float4 (&xE)[ND]) {
+    // stage `it` = samples [16 (it % 8), +16) of tile it / 8: a 64-byte run of every row of the tile's block
+    const size_t col = (size_t)(it >> 3) * net.actPerSample * kWideM + (size_t)(it & 7) * kWideKS;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      xA[d] = (pA[d] && it < st1) ? ld_cg4(pA[d] + col) : zero4;
+      xB[d] = (pB[d] && it < st1) ? ld_cg4(pB[d] + col) : zero4;
+      xE[d] = (pE[d] && it < st1) ? ld_cg4(pE[d] + col) : zero4;
+    }
+  };
+  fetch(st0, nA, nB, nE);
 
   for (int it = st0; it < st1; ++it) {
     const int slot = (it - st0) % wp.sgStages, use = (it - st0) / wp.sgStages;
-    const int col = it * kWideKS + 4 * cc;
-    // ---- loads of every operand of the stage first (one L2 round trip), then split + store ----
-    float4 vA[kWideMaxD], vB[kWideMaxD], vE[kWideMaxD];
 #pragma unroll
-    for (int d = 0; d < kWideMaxD; ++d) {
-      vA[d] = make_float4(0.f, 0.f, 0.f, 0.f); vB[d] = vA[d]; vE[d] = vA[d];
-      if (d >= wp.nD) continue;
-      const WDense& D = wp.D[d];
-      const bool out = d == wp.nD - 1;
-      if (!out) {
-        if (r < D.N) vA[d] = ld_cg4(a.errG + (size_t)(D.yOff + r) * a.Bpad + col);         // deltas of the layer
-        if (r < D.K) vB[d] = ld_cg4(a.actG + (size_t)(D.inOff + r) * a.Bpad + col);        // its input
-        if (D.res >= 0 && r < D.N) vE[d] = ld_cg4(a.errG + (size_t)(D.zOff + r) * a.Bpad + col);   // error on the residual layer
-      } else {
-        if (r < D.K) vA[d] = ld_cg4(a.actG + (size_t)(D.inOff + r) * a.Bpad + col);
-        if (r < net.nOut) {
-          const int rowG = r < net.nOutDense ? Lo.actOff + r : Lp.actOff + (r - net.nOutDense);
-          vB[d] = ld_cg4(a.errG + (size_t)rowG * a.Bpad + col);
-        }
-      }
-    }
+    for (int d = 0; d < ND; ++d) { vA[d] = nA[d]; vB[d] = nB[d]; vE[d] = nE[d]; }
+    fetch(it + 1, nA, nB, nE);          // the next stage's rows travel while this one is split, stored and multiplied
     if (use > 0) { if (!mbar_wait_bounded(&bars[slot], (unsigned)((use - 1) & 1))) fault = true; }     // MMAs of the stage's previous use
     unsigned char* stg = smraw + wp.sgStage + (size_t)slot * wp.sgStageBytes;
 #pragma unroll
-    for (int d = 0; d < kWideMaxD; ++d) {
-      if (d >= wp.nD) continue;
-      const WDense& D = wp.D[d];
-      const bool out = d == wp.nD - 1;
+    for (int d = 0; d < ND; ++d) {
+      const bool out = d == ND - 1;
       {
         float4 h, l; split4(vA[d], h, l);
-        float4* Ah = reinterpret_cast<float4*>(stg + wp.sgOpA[d]);
-        float4* Al = Ah + 4 * kWideLD;
-        Ah[cc * kWideLD + r] = h; Al[cc * kWideLD + r] = l;
+        float4* Ah = reinterpret_cast<float4*>(stg + oA[d]);
+        Ah[0] = h; Ah[4 * kWideLD] = l;
       }
-      const int rowsB = wp.sgRowsB[d];
-      if (r < rowsB) {
+      if (oB[d] >= 0) {
         float4 h, l; split4(vB[d], h, l);
-        float4* Bh = reinterpret_cast<float4*>(stg + wp.sgOpB[d]);
-        float4* Bl = Bh + 4 * (rowsB + 2);
-        Bh[cc * (rowsB + 2) + r] = h; Bl[cc * (rowsB + 2) + r] = l;
+        float4* Bh = reinterpret_cast<float4*>(stg + oB[d]);
+        Bh[0] = h; Bh[4 * ldB[d]] = l;
       }
       if (!out) {
         sA[d] += vA[d].x; sA[d] += vA[d].y; sA[d] += vA[d].z; sA[d] += vA[d].w;                   // db += delta
-        if (D.res >= 0) {                                                                         // ParametricResidualLayer::backward
+        if (pE[d]) {                                                                              // ParametricResidualLayer::backward
           sE[d] += vE[d].x; sE[d] += vE[d].y; sE[d] += vE[d].z; sE[d] += vE[d].w;
           sEX[d] = fmaf(vE[d].x, vB[d].x, sEX[d]); sEX[d] = fmaf(vE[d].y, vB[d].y, sEX[d]);
           sEX[d] = fmaf(vE[d].z, vB[d].z, sEX[d]); sEX[d] = fmaf(vE[d].w, vB[d].w, sEX[d]);
@@ -698,22 +818,17 @@ __global__ void __launch_bounds__(kST, 1) k_wide_wgrad(StepArgs a, int step) {
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      for (int d = 0; d < wp.nD; ++d) {
-        const WDense& D = wp.D[d];
-        const int rowsB = wp.sgRowsB[d], ldB = rowsB + 2;
-        const float4* Ah = reinterpret_cast<const float4*>(stg + wp.sgOpA[d]);
-        const float4* Al = Ah + 4 * kWideLD;
-        const float4* Bh = reinterpret_cast<const float4*>(stg + wp.sgOpB[d]);
-        const float4* Bl = Bh + 4 * ldB;
-        const uint32_t idesc = wide_idesc(D.gN);
-        const uint32_t acc = tmem + (uint32_t)D.gCol;
+      const uint64_t sOff = (uint64_t)((slot * wp.sgStageBytes) >> 4);
+      const uint32_t first = it > st0 ? 1u : 0u;
+#pragma unroll
+      for (int d = 0; d < ND; ++d) {
 #pragma unroll
         for (int kk = 0; kk < kWideKS / 8; ++kk) {
-          const uint64_t dah = umma_desc(Ah + 2 * kk * kWideLD, kWideLD * 16, 128), dal = umma_desc(Al + 2 * kk * kWideLD, kWideLD * 16, 128);
-          const uint64_t dbh = umma_desc(Bh + 2 * kk * ldB, ldB * 16, 128), dbl = umma_desc(Bl + 2 * kk * ldB, ldB * 16, 128);
-          umma_tf32(acc, dal, dbh, idesc, (it > st0 || kk > 0) ? 1u : 0u);
-          umma_tf32(acc, dah, dbl, idesc, 1u);
-          umma_tf32(acc, dah, dbh, idesc, 1u);
+          const uint64_t dah = gd[d][0] + sOff + (uint64_t)(2 * kk * kWideLD), dal = gd[d][1] + sOff + (uint64_t)(2 * kk * kWideLD);
+          const uint64_t dbh = gd[d][2] + sOff + (uint64_t)(2 * kk) * gd[d][4], dbl = gd[d][3] + sOff + (uint64_t)(2 * kk) * gd[d][4];
+          umma_tf32(gi[d][1], dal, dbh, gi[d][0], kk > 0 ? 1u : first);
+          umma_tf32(gi[d][1], dah, dbl, gi[d][0], 1u);
+          umma_tf32(gi[d][1], dah, dbh, gi[d][0], 1u);
         }
       }
       tc_commit(&bars[slot]);
@@ -731,7 +846,7 @@ __global__ void __launch_bounds__(kST, 1) k_wide_wgrad(StepArgs a, int step) {
     const int q = warp & 3, cg = warp >> 2;
     const uint32_t laneBase = (uint32_t)(q * 32) << 16;
     const int m = q * 32 + lane;
-    for (int d = 0; d < wp.nD; ++d) {
+    for (int d = 0; d < ND; ++d) {
       const WDense& D = wp.D[d];
       for (int j8 = cg; j8 < D.gN / 8; j8 += 4) {
         uint32_t v[8];
@@ -742,15 +857,14 @@ __global__ void __launch_bounds__(kST, 1) k_wide_wgrad(StepArgs a, int step) {
     }
   }
 #pragma unroll
-  for (int d = 0; d < kWideMaxD; ++d) {
-    if (d >= wp.nD) continue;
+  for (int d = 0; d < ND; ++d) {
     const WDense& D = wp.D[d];
     float x = sA[d], y = sE[d], z = sEX[d];
     x += __shfl_xor_sync(0xffffffffu, x, 1); x += __shfl_xor_sync(0xffffffffu, x, 2);
     y += __shfl_xor_sync(0xffffffffu, y, 1); y += __shfl_xor_sync(0xffffffffu, y, 2);
     z += __shfl_xor_sync(0xffffffffu, z, 1); z += __shfl_xor_sync(0xffffffffu, z, 2);
     if (cc == 0) {
-      const bool out = d == wp.nD - 1;
+      const bool out = d == ND - 1;
       const int rows = out ? wp.NpG : D.Np;
       if (r < rows) {
         rec[D.vSum + r] = x;
@@ -769,23 +883,32 @@ __global__ void __launch_bounds__(kST, 1) k_wide_wgrad(StepArgs a, int step) {
 // the weights is rewritten here: blob, tile-kernel image, split forward / transposed operand images, vector block.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_wide_adam(StepArgs a, int step, int nParams, int recFloats, int fHalf, int bHalf) {
-  const int p = blockIdx.x * 256 + threadIdx.x;
-  if (p == 0) a.wcnt[0] = 0;                        // the V(s_t+1) list of the next step starts empty
-  if (p >= nParams) return;
-  const int rpos = __ldg(a.widx + p);
-  if (rpos < 0) return;                             // padding of the parameter blob
-  const float* src = a.wpart + rpos;
+  __shared__ float part[8][33];
+  const int px = threadIdx.x & 31, sy = threadIdx.x >> 5;       // 32 consecutive parameters (coalesced rows of a record) x 8 slices of the records
+  const int p = blockIdx.x * 32 + px;
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.wcnt[0] = 0;       // the V(s_t+1) list of the next step starts empty
+  const int rpos = p < nParams ? __ldg(a.widx + p) : -1;        // -1: padding of the parameter blob
   const int G = a.wGridG;
   float acc = 0.f;
-  int g = 0;
-  for (; g + 8 <= G; g += 8) {                      // eight loads in flight, added in CTA order
-    float x[8];
+  if (rpos >= 0) {
+    const int g0 = sy * G / 8, g1 = (sy + 1) * G / 8;
+    const float* src = a.wpart + rpos;
+    int g = g0;
+    for (; g + 8 <= g1; g += 8) {                    // eight loads in flight, added in CTA order
+      float x[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) x[u] = ld_cg(src + (size_t)(g + u) * recFloats);
+      for (int u = 0; u < 8; ++u) x[u] = ld_cg(src + (size_t)(g + u) * recFloats);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) acc += x[u];
+      for (int u = 0; u < 8; ++u) acc += x[u];
+    }
+    for (; g < g1; ++g) acc += ld_cg(src + (size_t)g * recFloats);
   }
-  for (; g < G; ++g) acc += ld_cg(src + (size_t)g * recFloats);
+  part[sy][px] = acc;
+  __syncthreads();
+  if (sy != 0 || rpos < 0) return;
+  acc = 0.f;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) acc += part[u][px];    // slices in order: the sum is a fixed function of the grid size
   const DevDescs* dd = a.descs;
   AdamCoef ac;
   ac.eta = __ldcg(&a.ctrl[step & 1].adam_eta);
@@ -815,7 +938,7 @@ void wide_plan_build(const NetDesc& net, const Hyper& hp, WidePlan& wp, std::vec
   memset(&wp, 0, sizeof(wp));
   const int nP = net.nParams;
   idx.assign((size_t)5 * nP, -1);
-  if (net.recurrent || net.discrete || hp.algo != 0 || net.dA > 8 || net.dS > 128) return;     // feed-forward V-RACER, dA <= 8 (two pairs per thread)
+  if (net.recurrent || net.discrete || hp.algo != 0 || net.dA > 8 || net.dS > 64) return;     // feed-forward V-RACER, dA <= 8 (two pairs per thread)
   int nD = 0;
   for (int l = 1; l < net.nLayers; ++l) {
     const LayerDesc& L = net.L[l];
@@ -848,6 +971,7 @@ void wide_plan_build(const NetDesc& net, const Hyper& hp, WidePlan& wp, std::vec
   const int vP = v; v += dA4;                       // ParamLayer values
   wp.vP = vP;
   wp.fFloats = 2 * f; wp.bFloats = 2 * b; wp.vFloats = v;
+  wp.vMsc = v;                                      // forward kernel only: state mean / scale [2][Kp0] behind the vector block
   // weight-gradient kernel: accumulators, partial record, stage layout
   int col = 0, rec = 0, sg = 0;
   for (int d = 0; d < nD; ++d) {
@@ -874,7 +998,7 @@ void wide_plan_build(const NetDesc& net, const Hyper& hp, WidePlan& wp, std::vec
   int o = kWideDescBytes + kWidePlanBytes;
   auto take = [&](int bytes) { const int at = o; o += (bytes + 127) / 128 * 128; return at; };
   wp.sfBars = take(64);
-  wp.sfVec = take(4 * wp.vFloats);
+  wp.sfVec = take(4 * (wp.vFloats + 2 * wp.D[0].Kp));
   wp.sfImg = take(4 * wp.fFloats);
   wp.sfActO = take(4 * wp.D[nD - 1].Np * kWideM);
   wp.sfGP = take(4 * net.dA * kWideM);
@@ -956,8 +1080,12 @@ void wide_fill_images(const NetDesc& net, const WidePlan& wp, const std::vector<
 int wide_prepare(const WidePlan& wp, const NetDesc& net) {
   SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_wide_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, wp.sfTotal));
   SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_wide_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, wp.sbTotal));
-  SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_wide_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, wp.sgTotal));
-  SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_wide_next, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan(net, 4, false).total));
+  SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_wide_wgrad<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, wp.sgTotal));
+  SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_wide_wgrad<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, wp.sgTotal));
+  SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_wide_wgrad<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, wp.sgTotal));
+  SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_wide_next<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan(net, 4, false).total));
+  if (step_image_in_smem(net))
+    SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_wide_next<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan(net, 4, true).total));
   SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_wide_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, kWideDescBytes + 4 * kStatChunk));
   return 0;
 }
@@ -975,14 +1103,17 @@ int launch_steps_wide(const StepArgs& a, const NetDesc& net, const WidePlan& wp,
     const int step = step0 + s;
     const bool skipStats = skipStatsLast && s == nSteps - 1;
     k_wide_fwd<<<gridT, kST, wp.sfTotal, st>>>(a, step);
-    k_wide_next<<<16, kST, smem_plan(net, 4, false).total, st>>>(a, step);
+    if (step_image_in_smem(net)) k_wide_next<true><<<16, kST, smem_plan(net, 4, true).total, st>>>(a, step);
+    else k_wide_next<false><<<16, kST, smem_plan(net, 4, false).total, st>>>(a, step);
     if (!skipStats) {
       k_wide_records<<<(a.B + 255) / 256, 256, 0, st>>>(a);
       k_wide_stats<<<1, kST, kWideDescBytes + 4 * kStatChunk, st>>>(a, step);
     }
     k_wide_bwd<<<gridT, kST, wp.sbTotal, st>>>(a, step);
-    k_wide_wgrad<<<a.wGridG, kST, wp.sgTotal, st>>>(a, step);
-    k_wide_adam<<<(net.nParams + 255) / 256, 256, 0, st>>>(a, step, net.nParams, wp.recFloats, wp.fFloats / 2, wp.bFloats / 2);
+    if (wp.nD == 2) k_wide_wgrad<2><<<a.wGridG, kST, wp.sgTotal, st>>>(a, step);
+    else if (wp.nD == 3) k_wide_wgrad<3><<<a.wGridG, kST, wp.sgTotal, st>>>(a, step);
+    else k_wide_wgrad<4><<<a.wGridG, kST, wp.sgTotal, st>>>(a, step);
+    k_wide_adam<<<(net.nParams + 31) / 32, 256, 0, st>>>(a, step, net.nParams, wp.recFloats, wp.fFloats / 2, wp.bFloats / 2);
   }
   SMB200_CUDA_CHECK(cudaGetLastError());
   return 0;
