@@ -98,6 +98,7 @@ struct smb200_learner {
   WidePlan wplan{}; WidePlan* dWplan = nullptr; std::vector<int> widx; int* dWidx = nullptr;
   float *wimgF = nullptr, *wimgB = nullptr, *wvec = nullptr, *wpart = nullptr; int* wcnt = nullptr; int* wlist = nullptr;
   int wGridG = 0; int wideOn = 0;          // wideOn: the wide kernels run the steps
+  cudaStream_t wAux = nullptr; cudaEvent_t wEv[3] = {nullptr, nullptr, nullptr};   // auxiliary stream of the wide step (V(s_t+1), records, statistics)
   int dP = 0;                     // columns of the behaviour policy MU: 2 * dim_action (mean, stdev), or the K option probabilities
 
   // step state
@@ -686,7 +687,7 @@ static int run_segment(smb200_learner* h, int first, int n, long long gstep0, in
   const long long lastStep = gstep0 + n;              // nGradSteps()+1 of the last step
   const int sweepLast = (lastStep % 1000) == 0;
   if (h->wideOn && h->comm.world == 1) {
-    if (launch_steps_wide(a, net, h->wplan, h->numSMs, (int)gstep0, n, sweepLast, h->stream)) return -2;
+    if (launch_steps_wide(a, net, h->wplan, h->numSMs, (int)gstep0, n, sweepLast, h->stream, h->wAux, h->wEv[0], h->wEv[1], h->wEv[2])) return -2;
     h->launches += 7 * n;
   } else if (h->mode == 1 && h->clusterP1 > 0) {
     if (launch_steps_cluster(a, h->clusterP1, h->cplan.bTotal, (int)gstep0, n, sweepLast, h->stream)) return -2;
@@ -896,6 +897,8 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
         CK(dev_alloc(&h->wvec, (size_t)h->wplan.vFloats));
         CK(dev_alloc(&h->wpart, (size_t)h->wGridG * h->wplan.recFloats));
         CK(dev_alloc(&h->wcnt, 4)); CK(dev_alloc(&h->wlist, (size_t)B));
+        CKC(cudaStreamCreateWithFlags(&h->wAux, cudaStreamNonBlocking));
+        for (int i = 0; i < 3; ++i) CKC(cudaEventCreateWithFlags(&h->wEv[i], cudaEventDisableTiming));
         h->wideOn = 1;
       }
       if (getenv("SMB200_DEBUG"))
@@ -946,6 +949,8 @@ void smb200_destroy(smb200_learner* h) {
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (int i = 0; i < 2; ++i) if (h->evDone[i]) cudaEventDestroy(h->evDone[i]);
+  for (int i = 0; i < 3; ++i) if (h->wEv[i]) cudaEventDestroy(h->wEv[i]);
+  if (h->wAux) cudaStreamDestroy(h->wAux);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }

@@ -124,7 +124,7 @@ struct WidePlan {
   int gCols;                            // TMEM columns of the weight-gradient kernel (power of two)
   int sfVec, sfImg, sfActO, sfGP, sfOld, sfInfo, sfSamp, sfPair, sfBars, sfTotal;   // forward kernel: byte offsets in dynamic shared memory
   int sbVec, sbImg, sbBars, sbTotal;                                               // input-gradient kernel
-  int sgStage, sgStageBytes, sgStages, sgBars, sgTotal;                             // weight-gradient kernel
+  int sgStage, sgStageBytes, sgStages, sgBars, sgRaw, sgTotal;                      // weight-gradient kernel (sgRaw: ring of two raw stages)
   int sgOpA[kWideMaxD], sgOpB[kWideMaxD];   // byte offsets of a layer's M-side / N-side operand inside a stage ([hi | lo] each)
   int sgRowsA[kWideMaxD], sgRowsB[kWideMaxD];   // staged rows of those operands
 };
@@ -212,7 +212,7 @@ void wide_fill_images(const NetDesc& net, const WidePlan& wp, const std::vector<
 int wide_prepare(const WidePlan& wp, const NetDesc& net);
 int wide_grid_g(const WidePlan& wp, int B, int numSMs);
 int launch_steps_wide(const StepArgs& a, const NetDesc& net, const WidePlan& wp, int numSMs, int step0, int nSteps, int skipStatsLast,
-                      cudaStream_t st);
+                      cudaStream_t st, cudaStream_t aux, cudaEvent_t evF, cudaEvent_t evN, cudaEvent_t evS);
 
 // sweep_kernels.cu
 int launch_init_episode(const ReplayView& rp, int slot, float deltaInit, int haveValues, cudaStream_t st);

@@ -491,24 +491,50 @@ __global__ void __launch_bounds__(kST) k_wide_next(StepArgs a, int step) {
 // sorted, so the samples of an episode are one contiguous run: the thread of a run's first sample applies the whole run
 // (the arithmetic of apply_sample_records above), all runs in parallel.
 // ------------------------------------------------------------------------------------------
+constexpr int kRecWin = 512;          // records staged per CTA: its own 256 and the 256 that follow (runs that start here and end there)
 __global__ void __launch_bounds__(256) k_wide_records(StepArgs a) {
+  __shared__ __align__(16) float win[kRecWin * 12];
   const ReplayView& rp = a.rp;
   const int ME = rp.maxEpisodes;
-  const int b = blockIdx.x * 256 + threadIdx.x;
+  const int c0 = blockIdx.x * 256, b = c0 + threadIdx.x;
+  const int nWin = min(kRecWin, a.B - c0);
+  {
+    const float4* src = reinterpret_cast<const float4*>(a.rec + c0);
+    float4* dst = reinterpret_cast<float4*>(win);
+    for (int i = threadIdx.x; i < nWin * 3; i += 256) dst[i] = __ldcg(src + i);      // one coalesced pass
+  }
+  __syncthreads();
   int far = 0;
   if (b < a.B) {
-    const int4 h = __ldcg(reinterpret_cast<const int4*>(&a.rec[b]));
-    far = h.z;
-    const int slot = h.x;
-    const int prevSlot = b > 0 ? __ldcg(&a.rec[b - 1].slot) : -2;
+    const float4* mine = reinterpret_cast<const float4*>(win + threadIdx.x * 12);
+    const float4 h0 = mine[0];
+    far = __float_as_int(h0.z);
+    const int slot = __float_as_int(h0.x);
+    const int prevSlot = threadIdx.x > 0 ? __float_as_int(mine[-3].x) : (b > 0 ? __ldcg(&a.rec[b - 1].slot) : -2);
     if (prevSlot != slot) {
       float avgKL = rp.epAgg[AGG_KL * ME + slot], frac = rp.epAgg[AGG_FAR * ME + slot];
       float avgE2 = rp.epAgg[AGG_E2 * ME + slot], maxE = rp.epAgg[AGG_MAXE * ME + slot];
       float sQ2 = rp.epAgg[AGG_Q2 * ME + slot], sQ = rp.epAgg[AGG_Q1 * ME + slot];
       float maxQ = rp.epAgg[AGG_MAXQ * ME + slot], minQ = rp.epAgg[AGG_MINQ * ME + slot];
       const float invN = 1.0f / (float)rp.epLen[slot];
+      auto apply = [&](int hn, const float4 d, const float4 qv) {
+        if (hn) {
+          sQ2 += qv.w * qv.w - qv.z * qv.z; sQ += qv.w - qv.z;
+          maxQ = fmaxf(maxQ, qv.w); minQ = fminf(minQ, qv.w);
+        }
+        avgKL += invN * d.x; frac += invN * d.y; avgE2 += invN * d.z; maxE = fmaxf(maxE, d.w);
+        sQ2 += qv.y * qv.y - qv.x * qv.x; sQ += qv.y - qv.x;
+        maxQ = fmaxf(maxQ, qv.y); minQ = fminf(minQ, qv.y);
+      };
       bool open = true;
-      for (int j = b; open && j < a.B; j += 4) {       // the run is applied in order; four records travel at a time
+      int j = b;
+      for (; j < c0 + nWin; ++j) {                    // the staged part of the run, in order
+        const float4* rj = reinterpret_cast<const float4*>(win + (j - c0) * 12);
+        const float4 hj = rj[0];
+        if (__float_as_int(hj.x) != slot) { open = false; break; }
+        apply(__float_as_int(hj.y), rj[1], rj[2]);
+      }
+      for (; open && j < a.B; j += 4) {               // a run longer than the window: four records travel at a time
         int4 hj[4]; float4 dj[4], qj[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -520,14 +546,7 @@ __global__ void __launch_bounds__(256) k_wide_records(StepArgs a) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           if (!open || j + u >= a.B || hj[u].x != slot) { open = false; continue; }
-          const float4 d = dj[u], qv = qj[u];
-          if (hj[u].y) {
-            sQ2 += qv.w * qv.w - qv.z * qv.z; sQ += qv.w - qv.z;
-            maxQ = fmaxf(maxQ, qv.w); minQ = fminf(minQ, qv.w);
-          }
-          avgKL += invN * d.x; frac += invN * d.y; avgE2 += invN * d.z; maxE = fmaxf(maxE, d.w);
-          sQ2 += qv.y * qv.y - qv.x * qv.x; sQ += qv.y - qv.x;
-          maxQ = fmaxf(maxQ, qv.y); minQ = fminf(minQ, qv.y);
+          apply(hj[u].y, dj[u], qj[u]);
         }
       }
       rp.epAgg[AGG_KL * ME + slot] = avgKL; rp.epAgg[AGG_FAR * ME + slot] = frac;
@@ -718,9 +737,9 @@ __global__ void __launch_bounds__(kST, 1) k_wide_wgrad(StepArgs a, int step) {
   const NetDesc& net = *netp;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r = tid >> 2, cc = tid & 3;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + wp.sgBars);      // [stage]: the MMAs that read the stage have completed
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + wp.sgBars);      // [0]: the MMAs that read the operand images have completed
   if (tid == 0) {
-    for (int i = 0; i < wp.sgStages; ++i) mbar_init(&bars[i], 1);
+    mbar_init(&bars[0], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(&tmemSlot, (uint32_t)wp.gCols);
@@ -771,26 +790,45 @@ __global__ void __launch_bounds__(kST, 1) k_wide_wgrad(StepArgs a, int step) {
   for (int d = 0; d < ND; ++d) { sA[d] = 0.f; sE[d] = 0.f; sEX[d] = 0.f; }
   bool fault = false;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 vA[ND], vB[ND], vE[ND], nA[ND], nB[ND], nE[ND];
-  auto fetch = [&](int it, float4 (&xA)[ND], float4 (&xB)[ND], float4 (&xE)[ND]) {
-    // stage `it` = samples [16 (it % 8), +16) of tile it / 8: a 64-byte run of every row of the tile's block
-    const size_t col = (size_t)(it >> 3) * net.actPerSample * kWideM + (size_t)(it & 7) * kWideKS;
+  // Raw operand rows travel global -> shared memory by cp.async (LDGSTS, no registers), TWO stages ahead of their use: ~115 KB
+  // in flight per SM is what keeps HBM busy (one stage of register prefetch left the kernel latency bound at 2.4 us per stage).
+  // Ring of two raw stages [stage][operand][thread] float4; every thread reads back exactly the 16-byte slots it copied, so
+  // cp.async.wait_group is the only synchronisation the raw ring needs.
+  float4* raw = reinterpret_cast<float4*>(smraw + wp.sgRaw);
+  int qA[ND], qB[ND], qE[ND], nOps = 0;
 #pragma unroll
-    for (int d = 0; d < ND; ++d) {
-      xA[d] = (pA[d] && it < st1) ? ld_cg4(pA[d] + col) : zero4;
-      xB[d] = (pB[d] && it < st1) ? ld_cg4(pB[d] + col) : zero4;
-      xE[d] = (pE[d] && it < st1) ? ld_cg4(pE[d] + col) : zero4;
+  for (int d = 0; d < ND; ++d) { qA[d] = nOps++; qB[d] = nOps++; qE[d] = (d < ND - 1 && wp.D[d].res >= 0) ? nOps++ : -1; }
+  auto issue = [&](int it) {
+    if (it < st1) {
+      // stage `it` = samples [16 (it % 8), +16) of tile it / 8: a 64-byte run of every row of the tile's block
+      const size_t col = (size_t)(it >> 3) * net.actPerSample * kWideM + (size_t)(it & 7) * kWideKS;
+      float4* dst = raw + (size_t)((it - st0) & 1) * nOps * kST + tid;
+#pragma unroll
+      for (int d = 0; d < ND; ++d) {
+        if (pA[d]) cp_async16_cg(dst + qA[d] * kST, pA[d] + col);
+        if (pB[d]) cp_async16_cg(dst + qB[d] * kST, pB[d] + col);
+        if (pE[d]) cp_async16_cg(dst + qE[d] * kST, pE[d] + col);
+      }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  fetch(st0, nA, nB, nE);
+  issue(st0); issue(st0 + 1);
+  unsigned char* stg = smraw + wp.sgStage;          // ONE stage of operand images: the MMAs of a stage take ~0.3 us of its ~1 us
+  float4 vA[ND], vB[ND], vE[ND];
 
   for (int it = st0; it < st1; ++it) {
-    const int slot = (it - st0) % wp.sgStages, use = (it - st0) / wp.sgStages;
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    {
+      const float4* src = raw + (size_t)((it - st0) & 1) * nOps * kST + tid;
 #pragma unroll
-    for (int d = 0; d < ND; ++d) { vA[d] = nA[d]; vB[d] = nB[d]; vE[d] = nE[d]; }
-    fetch(it + 1, nA, nB, nE);          // the next stage's rows travel while this one is split, stored and multiplied
-    if (use > 0) { if (!mbar_wait_bounded(&bars[slot], (unsigned)((use - 1) & 1))) fault = true; }     // MMAs of the stage's previous use
-    unsigned char* stg = smraw + wp.sgStage + (size_t)slot * wp.sgStageBytes;
+      for (int d = 0; d < ND; ++d) {
+        vA[d] = pA[d] ? src[qA[d] * kST] : zero4;
+        vB[d] = pB[d] ? src[qB[d] * kST] : zero4;
+        vE[d] = pE[d] ? src[qE[d] * kST] : zero4;
+      }
+    }
+    issue(it + 2);                                   // refills the raw slots this thread has just read
+    if (it > st0) { if (!mbar_wait_bounded(&bars[0], (unsigned)((it - st0 - 1) & 1))) fault = true; }     // MMAs of the previous stage
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
       const bool out = d == ND - 1;
@@ -818,28 +856,27 @@ __global__ void __launch_bounds__(kST, 1) k_wide_wgrad(StepArgs a, int step) {
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      const uint64_t sOff = (uint64_t)((slot * wp.sgStageBytes) >> 4);
       const uint32_t first = it > st0 ? 1u : 0u;
 #pragma unroll
       for (int d = 0; d < ND; ++d) {
 #pragma unroll
         for (int kk = 0; kk < kWideKS / 8; ++kk) {
-          const uint64_t dah = gd[d][0] + sOff + (uint64_t)(2 * kk * kWideLD), dal = gd[d][1] + sOff + (uint64_t)(2 * kk * kWideLD);
-          const uint64_t dbh = gd[d][2] + sOff + (uint64_t)(2 * kk) * gd[d][4], dbl = gd[d][3] + sOff + (uint64_t)(2 * kk) * gd[d][4];
+          const uint64_t dah = gd[d][0] + (uint64_t)(2 * kk * kWideLD), dal = gd[d][1] + (uint64_t)(2 * kk * kWideLD);
+          const uint64_t dbh = gd[d][2] + (uint64_t)(2 * kk) * gd[d][4], dbl = gd[d][3] + (uint64_t)(2 * kk) * gd[d][4];
           umma_tf32(gi[d][1], dal, dbh, gi[d][0], kk > 0 ? 1u : first);
           umma_tf32(gi[d][1], dah, dbl, gi[d][0], 1u);
           umma_tf32(gi[d][1], dah, dbh, gi[d][0], 1u);
         }
       }
-      tc_commit(&bars[slot]);
+      tc_commit(&bars[0]);
     }
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   // ---- all MMAs done: accumulators and vector sums -> this CTA's partial record ----
   float* rec = a.wpart + (size_t)g * wp.recFloats;
   const int nMine = st1 - st0;
   if (nMine > 0) {
-    const int last = nMine - 1;
-    if (!mbar_wait_bounded(&bars[last % wp.sgStages], (unsigned)((last / wp.sgStages) & 1))) fault = true;
+    if (!mbar_wait_bounded(&bars[0], (unsigned)((nMine - 1) & 1))) fault = true;
   }
   tc_fence_after();
   {
@@ -1014,11 +1051,15 @@ void wide_plan_build(const NetDesc& net, const Hyper& hp, WidePlan& wp, std::vec
   wp.sbTotal = o;
   o = kWideDescBytes + kWidePlanBytes;
   wp.sgBars = take(64);
-  wp.sgStage = take(0);
-  wp.sgStages = (kMax - o) / sg;
-  if (wp.sgStages > 4) wp.sgStages = 4;
-  wp.sgTotal = o + wp.sgStages * sg;
-  if (wp.sfTotal > kMax || wp.sbTotal > kMax || wp.sgStages < 2) return;
+  wp.sgStage = take(sg);
+  wp.sgStages = 1;
+  {
+    int nOps = 0;
+    for (int d = 0; d < nD; ++d) nOps += 2 + ((d < nD - 1 && wp.D[d].res >= 0) ? 1 : 0);
+    wp.sgRaw = take(2 * nOps * kST * 16);
+  }
+  wp.sgTotal = o;
+  if (wp.sfTotal > kMax || wp.sbTotal > kMax || wp.sgTotal > kMax) return;
   // index maps
   int* iRec = idx.data(); int* iImg = iRec + nP; int* iF = iImg + nP; int* iB = iF + nP; int* iV = iB + nP;
   for (int d = 0; d < nD; ++d) {
@@ -1095,25 +1136,37 @@ int wide_grid_g(const WidePlan& wp, int B, int numSMs) {
   return nSt < numSMs ? nSt : numSMs;
 }
 
+// Stream plan of a step.  main: fwd -> bwd -> wgrad -> adam;  aux (forked after fwd): next -> records -> stats.  The tile
+// kernels run on the SMALLEST grid that keeps their makespan (512 tiles on 148 SMs are four rounds on 128 CTAs just as well), so
+// the auxiliary kernels find free SMs beside them.  adam waits for `next` (which reads the old weight image), the next
+// step's fwd waits for the statistics (ReF-ER coefficients, record buffer).
 int launch_steps_wide(const StepArgs& a, const NetDesc& net, const WidePlan& wp, int numSMs, int step0, int nSteps, int skipStatsLast,
-                      cudaStream_t st) {
+                      cudaStream_t st, cudaStream_t aux, cudaEvent_t evF, cudaEvent_t evN, cudaEvent_t evS) {
   const int nTiles = (a.B + kWideM - 1) / kWideM;
-  const int gridT = nTiles < numSMs ? nTiles : numSMs;
+  const int rounds = (nTiles + numSMs - 1) / numSMs;
+  const int gridT = (nTiles + rounds - 1) / rounds;
+  const bool sm = step_image_in_smem(net);
   for (int s = 0; s < nSteps; ++s) {
     const int step = step0 + s;
     const bool skipStats = skipStatsLast && s == nSteps - 1;
     k_wide_fwd<<<gridT, kST, wp.sfTotal, st>>>(a, step);
-    if (step_image_in_smem(net)) k_wide_next<true><<<16, kST, smem_plan(net, 4, true).total, st>>>(a, step);
-    else k_wide_next<false><<<16, kST, smem_plan(net, 4, false).total, st>>>(a, step);
+    SMB200_CUDA_CHECK(cudaEventRecord(evF, st));
+    SMB200_CUDA_CHECK(cudaStreamWaitEvent(aux, evF, 0));
+    if (sm) k_wide_next<true><<<16, kST, smem_plan(net, 4, true).total, aux>>>(a, step);
+    else k_wide_next<false><<<16, kST, smem_plan(net, 4, false).total, aux>>>(a, step);
+    SMB200_CUDA_CHECK(cudaEventRecord(evN, aux));
     if (!skipStats) {
-      k_wide_records<<<(a.B + 255) / 256, 256, 0, st>>>(a);
-      k_wide_stats<<<1, kST, kWideDescBytes + 4 * kStatChunk, st>>>(a, step);
+      k_wide_records<<<(a.B + 255) / 256, 256, 0, aux>>>(a);
+      k_wide_stats<<<1, kST, kWideDescBytes + 4 * kStatChunk, aux>>>(a, step);
     }
+    SMB200_CUDA_CHECK(cudaEventRecord(evS, aux));
     k_wide_bwd<<<gridT, kST, wp.sbTotal, st>>>(a, step);
     if (wp.nD == 2) k_wide_wgrad<2><<<a.wGridG, kST, wp.sgTotal, st>>>(a, step);
     else if (wp.nD == 3) k_wide_wgrad<3><<<a.wGridG, kST, wp.sgTotal, st>>>(a, step);
     else k_wide_wgrad<4><<<a.wGridG, kST, wp.sgTotal, st>>>(a, step);
+    SMB200_CUDA_CHECK(cudaStreamWaitEvent(st, evN, 0));
     k_wide_adam<<<(net.nParams + 31) / 32, 256, 0, st>>>(a, step, net.nParams, wp.recFloats, wp.fFloats / 2, wp.bFloats / 2);
+    SMB200_CUDA_CHECK(cudaStreamWaitEvent(st, evS, 0));
   }
   SMB200_CUDA_CHECK(cudaGetLastError());
   return 0;
