@@ -289,12 +289,31 @@ def kernel_roofline(L, torch, dev, batch, n_params, window, gs, kernel="k_steps_
                     "for the HBM-streaming kernels and roofline_batch_sweep for the approach to the bound with the batch size"}
 
 
+# algorithmic multiply-adds per updated transition of the cfg2 network (~122 kFLOP): forward 32*128 + 128*128 +
+# 128*9, input gradient 128*128 + 128*9 (none below the first layer), weight gradient = forward
+MACS_PER_TRANSITION_CFG2 = 2 * (32 * 128 + 128 * 128 + 128 * 9) + (128 * 128 + 128 * 9)
+
+
+def ncu_wide():
+    """Per-kernel ncu --set full summary of the wide step at B = 65536 (scripts/r2_wide_profiles.sh -> profiles/r2/ncu_wide.json)."""
+    p = os.path.join(ROOT, "profiles", "r2", "ncu_wide.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        return json.load(f)
+
+
 def batch_sweep(torch, dev, data, wl, batches, steps=60):
-    """the step kernel at growing mini-batches (per GPU), same buffer and network: us/step, transitions/s and the
-    fraction of the HBM roofline of the algorithmic bytes."""
+    """the learner step at growing mini-batches (per GPU), same buffer and network.  B = 256 runs the persistent tile
+    kernel (a latency chain), from B = 1024 on the wide step runs (wide_step.cuh: 128-sample tiles, every dense product as 3xTF32
+    tcgen05.mma).  Per batch size: us/step, transitions/s, the fraction of the HBM roofline of the ALGORITHMIC bytes, and the
+    tensor-side numbers: algorithmic TFLOP/s (2 x 60.8 k multiply-adds per transition), the TF32 TFLOP/s the tensor cores
+    execute for it (x3: hi*hi + hi*lo + lo*hi keeps f32 accuracy) and its fraction of the TF32 peak (= half the measured bf16 peak)."""
     from smarties_b200 import Learner
     w = WORKLOADS[wl]
     peaks, _ = measured_peaks()
+    tf32_peak = peaks["bf16_tflops"] / 2.0
+    names = {0: "two kernels per step", 1: "persistent tile kernel", 2: "cluster kernel", 3: "wide step (tcgen05, 3xTF32)"}
     out = []
     for B in batches:
         L = Learner(32, 8, dict(w["settings"], batchSize=B), seed=42)
@@ -312,9 +331,15 @@ def batch_sweep(torch, dev, data, wl, batches, steps=60):
         ms, _ = L.last_timing()
         sb = step_bytes(B, L.n_params, w["window"])
         a = sb * n / (ms * 1e-3) / 1e9
-        out.append({"batch": B, "steps": n, "us_per_step": 1e3 * ms / n, "transitions_per_s": B * n / (ms * 1e-3),
-                    "algorithmic_bytes_per_step": sb, "achieved_gbs": a, "frac": a / peaks["hbm_gbs"],
-                    "gflops": 2 * 122e3 / 2 * B * n / (ms * 1e-3) / 1e9 if wl == "cfg2" else None})
+        tps = B * n / (ms * 1e-3)
+        e = {"batch": B, "steps": n, "kernel": names.get(L.step_kernel(), "?"), "us_per_step": 1e3 * ms / n, "transitions_per_s": tps,
+             "algorithmic_bytes_per_step": sb, "achieved_gbs": a, "frac": a / peaks["hbm_gbs"]}
+        if wl == "cfg2":
+            alg = 2.0 * MACS_PER_TRANSITION_CFG2 * tps / 1e12
+            e["tensor"] = {"algorithmic_tflops": alg, "executed_tf32_tflops": 3.0 * alg if L.step_kernel() == 3 else 0.0,
+                           "peak_tf32_tflops": tf32_peak, "frac_of_tf32_peak": (3.0 * alg if L.step_kernel() == 3 else 0.0) / tf32_peak,
+                           "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2"}
+        out.append(e)
         L.close()
     return out
 
@@ -469,6 +494,9 @@ def main():
             out["ranks_identical"] = ranks_identical
         if world == 1 and args.workload == "cfg2" and not args.batch and not args.no_batch_sweep:
             out["roofline_batch_sweep"] = batch_sweep(torch, dev, data, args.workload, (256, 1024, 4096, 16384, 65536))
+            nw = ncu_wide()
+            if nw:      # per-kernel ncu evidence of the wide step (tensor-pipe share, DRAM bytes), captured at B = 65536
+                out["roofline_wide_kernels"] = nw
         if world == 1 and not args.no_cpu_baseline:
             cpu_steps = args.cpu_steps or (6000 if args.workload == "cfg2" else 150)
             rs = dict(w["settings"], batchSize=batch_local)

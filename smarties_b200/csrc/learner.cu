@@ -688,7 +688,7 @@ static int run_segment(smb200_learner* h, int first, int n, long long gstep0, in
   const int sweepLast = (lastStep % 1000) == 0;
   if (h->wideOn && h->comm.world == 1) {
     if (launch_steps_wide(a, net, h->wplan, h->numSMs, (int)gstep0, n, sweepLast, h->stream, h->wAux, h->wEv[0], h->wEv[1], h->wEv[2])) return -2;
-    h->launches += 7 * n;
+    h->launches += 8 * n;
   } else if (h->mode == 1 && h->clusterP1 > 0) {
     if (launch_steps_cluster(a, h->clusterP1, h->cplan.bTotal, (int)gstep0, n, sweepLast, h->stream)) return -2;
     h->launches += 1;

@@ -122,7 +122,7 @@ struct WidePlan {
   int vMsc;                             // forward kernel's shared memory: state mean / scale [2][Kp0] behind the vector block
   int recFloats;                        // partial record of one weight-gradient CTA
   int gCols;                            // TMEM columns of the weight-gradient kernel (power of two)
-  int sfVec, sfImg, sfActO, sfGP, sfOld, sfInfo, sfSamp, sfPair, sfBars, sfTotal;   // forward kernel: byte offsets in dynamic shared memory
+  int sfVec, sfImg, sfBars, sfTotal;                                               // forward kernel: byte offsets in dynamic shared memory
   int sbVec, sbImg, sbBars, sbTotal;                                               // input-gradient kernel
   int sgStage, sgStageBytes, sgStages, sgBars, sgRaw, sgTotal;                      // weight-gradient kernel (sgRaw: ring of two raw stages)
   int sgOpA[kWideMaxD], sgOpB[kWideMaxD];   // byte offsets of a layer's M-side / N-side operand inside a stage ([hi | lo] each)

@@ -113,39 +113,40 @@ __device__ __forceinline__ void wide_issue(uint32_t tmem, const float* imgHi, co
 // ------------------------------------------------------------------------------------------
 // k_wide_fwd
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kST, 1) k_wide_fwd(StepArgs a, int step) {
+__global__ void __launch_bounds__(kST, 1) k_wide_fwd(StepArgs a, int step, int sfBars, int sfImg, int fFloats) {
   extern __shared__ __align__(128) unsigned char smraw[];
+  // the weight image first: its copy (<= 180 KB out of L2) runs under everything else the prologue does
+  {
+    uint64_t* bars0 = reinterpret_cast<uint64_t*>(smraw + sfBars);
+    if (threadIdx.x == 0) {
+      mbar_init(&bars0[0], 1); mbar_init(&bars0[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.global;\n\tfence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&bars0[0], (unsigned)fFloats * 4u);
+      float* img0 = reinterpret_cast<float*>(smraw + sfImg);
+      for (int off = 0; off < fFloats; off += 16384) {          // hi halves then lo halves, <= 64 KB per bulk copy
+        const unsigned n = (unsigned)min(16384, fFloats - off) * 4u;
+        bulk_g2s(img0 + off, a.wimgF + off, n, &bars0[0]);
+      }
+    }
+  }
   const NetDesc* netp; const Hyper* hpp;
   load_descs(a, smraw, netp, hpp);
   const WidePlan& wp = *load_wide_plan(a, smraw + kWideDescBytes);
-  __shared__ StepCtrl c;
   __shared__ uint32_t tmemSlot;
   __syncthreads();
-  const NetDesc& net = *netp; const Hyper& hp = *hpp;
+  const NetDesc& net = *netp;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, cg = warp >> 2;          // TMEM lane quarter of this warp (hardware rule: warp % 4), column group
   float* vec = reinterpret_cast<float*>(smraw + wp.sfVec);
   float* img = reinterpret_cast<float*>(smraw + wp.sfImg);
-  float* actO = reinterpret_cast<float*>(smraw + wp.sfActO);      // [Np_out][128]: outputs, later the output gradient
-  float* gP = reinterpret_cast<float*>(smraw + wp.sfGP);          // [dA][128]: gradient of the ParamLayer outputs (stdev)
-  float* old = reinterpret_cast<float*>(smraw + wp.sfOld);        // [8][128]
-  int* info = reinterpret_cast<int*>(smraw + wp.sfInfo);          // row, slot, hasNext, valid  [4][128]
-  double* samp = reinterpret_cast<double*>(smraw + wp.sfSamp);    // [5][128]
-  double* pairS = reinterpret_cast<double*>(smraw + wp.sfPair);   // [2][128 * dA]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + wp.sfBars);   // [0] weight image, [1] MMA completion
   const ReplayView& rp = a.rp;
-  const int dS = net.dS, dA = net.dA, nPair = kWideM * dA;
+  const int dS = net.dS;
   constexpr int TBW = kWideM;
   const LayerDesc& Lo = net.L[net.nLayers - 2];
-  const LayerDesc& Lp = net.L[net.nLayers - 1];
-  const WDense& Dout = wp.D[wp.nD - 1];
   const int fHalf = wp.fFloats >> 1;
 
-  if (tid == 0) {
-    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    load_ctrl(c, &a.ctrl[step & 1]);
-  }
   if (warp == 0) tmem_alloc(&tmemSlot, 512u);
   for (int i = tid; i < wp.vFloats; i += kST) vec[i] = ld_cg(a.wvec + i);
   for (int i = tid; i < wp.D[0].Kp; i += kST) {
@@ -156,14 +157,6 @@ __global__ void __launch_bounds__(kST, 1) k_wide_fwd(StepArgs a, int step) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmemSlot;
-  if (tid == 0) {          // the whole forward image: hi halves then lo halves, <= 64 KB per bulk copy
-    asm volatile("fence.proxy.async.global;\n\tfence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx(&bars[0], (unsigned)wp.fFloats * 4u);
-    for (int off = 0; off < wp.fFloats; off += 16384) {
-      const unsigned n = (unsigned)min(16384, wp.fFloats - off) * 4u;
-      bulk_g2s(img + off, a.wimgF + off, n, &bars[0]);
-    }
-  }
   const int nTiles = (a.B + TBW - 1) / TBW;
   const size_t j0 = (size_t)(step - a.stepBase) * a.B;
   const bool keep = step == a.lastStep || a.lastStep < 0;
@@ -172,29 +165,30 @@ __global__ void __launch_bounds__(kST, 1) k_wide_fwd(StepArgs a, int step) {
   const uint32_t laneBase = (uint32_t)(q * 32) << 16;
 
   // Inputs of a tile, fetched ONE TILE AHEAD into registers (the gather is a dependent chain sample index -> ring row -> state
-  // row, ~2 DRAM round trips, that would otherwise open every tile): the thread's <= 2 chunks of 8 state components of its
-  // sample, and (column group 0) the sample's old replay values.
+  // row, ~2 DRAM round trips, that would otherwise open every tile): the thread's <= 2 chunks of 8 state components of its sample.
   const WDense& D0 = wp.D[0];
   const float* msc = vec + wp.vMsc;                // [2][Kp0]: state mean, state scale (Core/StateAction.h:56-58)
-  int pfRow = 0, pfSlot = 0; float pfX[2][8], pfOld[6];
+  float pfX[2][8];
+  const bool vec4S = (dS & 3) == 0;
   auto prefetch = [&](int tile) {
     const int bb = tile * TBW + q * 32 + lane;
     const bool ok = tile < nTiles && bb < a.B;
-    pfRow = ok ? __ldg(a.sampRow + j0 + bb) : 0;
+    const int pfRow = ok ? __ldg(a.sampRow + j0 + bb) : 0;
 #pragma unroll
     for (int c2 = 0; c2 < 2; ++c2) {
       const int j8 = cg + 4 * c2;
+      if (vec4S) {        // state rows are 16-byte aligned: two 16-byte loads per chunk instead of eight scalar ones (LSU queue)
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* src = rp.S + (size_t)pfRow * dS + 8 * j8;
+        const float4 u0 = (ok && 8 * j8 < dS) ? ld_cg4(src) : z4, u1 = (ok && 8 * j8 + 4 < dS) ? ld_cg4(src + 4) : z4;
+        pfX[c2][0] = u0.x; pfX[c2][1] = u0.y; pfX[c2][2] = u0.z; pfX[c2][3] = u0.w;
+        pfX[c2][4] = u1.x; pfX[c2][5] = u1.y; pfX[c2][6] = u1.z; pfX[c2][7] = u1.w;
+      } else {
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const int k = 8 * j8 + jj;
-        pfX[c2][jj] = (ok && k < dS) ? ld_cg(rp.S + (size_t)pfRow * dS + k) : 0.f;
-      }
-    }
-    if (cg == 0) {
-      pfSlot = ok ? __ldg(a.sampSlot + j0 + bb) : 0;
-      if (ok) {
-        pfOld[0] = ld_cg(rp.V + pfRow); pfOld[1] = ld_cg(rp.ADV + pfRow); pfOld[2] = ld_cg(rp.RHO + pfRow);
-        pfOld[3] = ld_cg(rp.KL + pfRow); pfOld[4] = ld_cg(rp.DELTA + pfRow); pfOld[5] = ld_cg(rp.Q + pfRow);
+        for (int jj = 0; jj < 8; ++jj) {
+          const int k = 8 * j8 + jj;
+          pfX[c2][jj] = (ok && k < dS) ? ld_cg(rp.S + (size_t)pfRow * dS + k) : 0.f;
+        }
       }
     }
   };
@@ -206,16 +200,6 @@ __global__ void __launch_bounds__(kST, 1) k_wide_fwd(StepArgs a, int step) {
     // stream it, and every DRAM page that is opened is used completely)
     float* actT = a.actG + (size_t)tile * net.actPerSample * TBW;
     float* errT = a.errG + (size_t)tile * net.actPerSample * TBW;
-    if (cg == 0) {       // sample info + the old per-transition values of the write-back
-      int slot = 0, hn = 0;
-      if (valid) {
-        slot = pfSlot & 0x7fffffff; hn = (pfSlot >> 31) & 1;
-        old[0 * TBW + s] = pfOld[0]; old[1 * TBW + s] = pfOld[1]; old[2 * TBW + s] = pfOld[2];
-        old[3 * TBW + s] = pfOld[3]; old[4 * TBW + s] = pfOld[4]; old[7 * TBW + s] = pfOld[5];
-        if (hn) { const int i = atomicAdd(a.wcnt, 1); a.wlist[i] = b; }      // V(s_t+1): k_wide_next
-      }
-      info[s] = pfRow; info[TBW + s] = slot; info[2 * TBW + s] = hn; info[3 * TBW + s] = valid ? 1 : 0;
-    }
     // ---- standardise (Episode.h:171-183): the tile's states become the A operand of the first layer ----
 #pragma unroll
     for (int c2 = 0; c2 < 2; ++c2) {
@@ -290,7 +274,7 @@ __global__ void __launch_bounds__(kST, 1) k_wide_fwd(StepArgs a, int step) {
           tm_st8(tmem + laneBase + kWAl + 8 * j8, lo);
         }
         tm_wait_st();
-      } else {
+      } else {      // linear output layer: the outputs leave for the loss kernel in the scratch rows its gradient will overwrite
         for (int j8 = cg; j8 < D.Np / 8; j8 += 4) {
           uint32_t v[8];
           tm_ld8(tmem + laneBase + kWAcc + 8 * j8, v);
@@ -298,142 +282,173 @@ __global__ void __launch_bounds__(kST, 1) k_wide_fwd(StepArgs a, int step) {
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
             const int n = 8 * j8 + jj;
-            if (n < D.N) actO[n * TBW + s] = __uint_as_float(v[jj]) + bias[n];
+            if (n < D.N) errT[(Lo.actOff + n) * TBW + s] = __uint_as_float(v[jj]) + bias[n];
           }
         }
       }
       tc_fence_before();
       __syncthreads();
     }
-
-    // ---- ReF-ER / Retrace loss and output gradient (RACER::Train, Learners/RACER_train.cpp:31-60; the formulas and their
-    //      operation order are those of loss_stages above), f64, V-RACER: outputs [V | mean(dA)], stdev = ParamLayer ----
-    constexpr int PP = 2;                 // (sample, component) pairs per thread: 128 * dA <= 2 * kST (dA <= 8)
-    const int m0 = 1;
-    double r_kgm[PP], r_kgs[PP], r_dlm[PP], r_dls[PP], r_dpos[PP];
-#pragma unroll
-    for (int it = 0; it < PP; ++it) {
-      const int p = tid + it * kST;
-      r_kgm[it] = r_kgs[it] = r_dlm[it] = r_dls[it] = r_dpos[it] = 0.0;
-      if (p >= nPair) continue;
-      const int sp = p / dA, i = p - sp * dA;
-      if (!info[3 * TBW + sp]) continue;
-      const size_t prow = info[sp];
-      const double av = (double)ld_cg(rp.A + prow * dA + i), mm = (double)ld_cg(rp.MU + prow * 2 * dA + i),
-                   ms = (double)ld_cg(rp.MU + prow * 2 * dA + dA + i);
-      const double m = (double)actO[(m0 + i) * TBW + sp];
-      const double sraw = (double)vec[wp.vP + i];
-      const double root = sqrt(1.0 + sraw * sraw);
-      const double stdev = (sraw + root) / 2.0;                          // SoftPlus::_eval, Functions.h:552-555
-      const double dpos = (1.0 + sraw / root) / 2.0;                     // SoftPlus::_evalDiff
-      const double inv = 1.0 / stdev, invmu = 1.0 / ms;
-      const bool bnd = hp.bounded[i] != 0;
-      const double MAXM = 8.31776613503286;
-      const double cm = bnd ? (m > MAXM ? MAXM : (m < -MAXM ? -MAXM : m)) : m;   // Continuous_policy.h:217-222
-      const double fac0 = 9.1893853320467266954096885456237942e-01;
-      double J = 1.0;
-      if (bnd) { const double sq = tanh(av); J = fmax(1.0 - sq * sq, (double)FLT_MIN); }
-      const double z1 = (av - cm) * inv, z2 = (av - mm) * invmu;
-      const double lp_pi = -(z1 * z1) / 2.0 + log(bnd ? inv / J : inv) - fac0;       // :91-97 / :240-249
-      const double lp_mu = -(z2 * z2) / 2.0 + log(bnd ? invmu / J : invmu) - fac0;
-      const double r1 = stdev / ms, r2 = (m - mm) / ms;
-      const double cc = r1 * r1, dd = r2 * r2;                                          // OPPOSITE_KL, :138-142
-      const double invVarMu = 1.0 / (ms * ms);
-      const double u = z1;
-      pairS[0 * nPair + p] = lp_pi - lp_mu;
-      pairS[1 * nPair + p] = (cc - 1.0 + dd - log(cc)) / 2.0;
-      r_kgm[it] = -1.0 * ((m - mm) * invVarMu);                               // kg_mean
-      r_kgs[it] = (dpos * -1.0) * ((invVarMu - inv * inv) * stdev);           // kg_std
-      r_dlm[it] = bnd ? (av - m) * inv * inv : u * inv;                       // dLogPdMean
-      r_dls[it] = (u * u - 1.0) * inv;                                        // dLogPdStdv
-      r_dpos[it] = dpos;
-    }
-    if (tid < TBW) {     // value head: V = scaleNet2V(O[0]), dV/dO (RACER_common.cpp:23-32)
-      const double O0 = (double)actO[0 * TBW + tid];
-      samp[2 * TBW + tid] = net2v(O0);
-      samp[3 * TBW + tid] = vdiff(O0);
-    }
-    __syncthreads();
-    if (tid < TBW && info[3 * TBW + tid]) {     // one thread per sample: sums in component order, flags, write-back, record
-      const int sp = tid, bb = b0 + sp;
-      const size_t prow = info[sp];
-      const double cmax = c.cmax, cinv = c.cinv;
-      double logw = 0.0, dkl = 0.0;
-      for (int i = 0; i < dA; ++i) { logw += pairS[0 * nPair + sp * dA + i]; dkl += pairS[1 * nPair + sp * dA + i]; }
-      const double rho = exp(logw > 7.0 ? 7.0 : (logw < -7.0 ? -7.0 : logw));           // :648-653
-      const float W32 = (float)rho, C32 = (float)cmax, I32 = (float)cinv;               // isFarPolicy takes Fval arguments (Episode.h:28-33)
-      const bool offW = (W32 > C32) || (W32 < I32);
-      const bool isFar = (C32 > 1.0f) && offW;
-      const float O0f = actO[0 * TBW + sp];
-      const double Vval = samp[2 * TBW + sp];
-      const double Aval = 0.0;                                                          // Zero_advantage.h:39-42
-      const double A_RET = (double)old[7 * TBW + sp] - Vval, deltaQ = A_RET - Aval;
-      const double Ver = fmin(1.0, rho) * deltaQ;
-      samp[4 * TBW + sp] = Ver;
-      samp[0 * TBW + sp] = A_RET * fmin(cmax, rho);     // pgfac
-      samp[1 * TBW + sp] = isFar ? 1.0 : 0.0;
-      if (keep) a.lastO[(size_t)bb * net.nOut + 0] = O0f;
-      const float E = (float)deltaQ, Dk = (float)dkl;
-      const float oldRho = old[2 * TBW + sp], oldKL = old[3 * TBW + sp], oldE = old[4 * TBW + sp];
-      const bool wasOff = (oldRho > C32) || (oldRho < I32);
-      const float Vf = (float)Vval, Qf = (float)(Aval + Vval);
-      rp.DELTA[prow] = E; rp.KL[prow] = Dk; rp.RHO[prow] = W32;
-      rp.V[prow] = Vf; rp.ADV[prow] = Qf - Vf;
-      // qNextOld / qNextNew of the record belong to k_wide_next
-      *reinterpret_cast<int4*>(&a.rec[bb].slot) = make_int4(info[TBW + sp], info[2 * TBW + sp], (C32 > 1.0f) ? ((int)offW - (int)wasOff) : 0, 0);
-      *reinterpret_cast<float4*>(&a.rec[bb].dKL) = make_float4(Dk - oldKL, (float)offW - (float)wasOff, E * E - oldE * oldE, fabsf(E));
-      *reinterpret_cast<float2*>(&a.rec[bb].qOld) = make_float2(old[1 * TBW + sp] + old[0 * TBW + sp], Qf);
-    }
-    __syncthreads();
-    {
-      const double beta = c.beta;
-      const double MAXM = 8.31776613503286;
-#pragma unroll
-      for (int it = 0; it < PP; ++it) {
-        const int p = tid + it * kST;
-        if (p >= nPair) continue;
-        const int sp = p / dA, i = p - sp * dA;
-        if (!info[3 * TBW + sp]) continue;
-        const int bb = b0 + sp;
-        const double pgfac = samp[0 * TBW + sp];
-        const bool isFar = samp[1 * TBW + sp] != 0.0;
-        const float mf = actO[(m0 + i) * TBW + sp];
-        const double m = (double)mf;
-        double pg_mean = pgfac * r_dlm[it];
-        if (hp.bounded[i] && ((m >= MAXM && pg_mean > 0.0) || (m <= -MAXM && pg_mean < 0.0))) pg_mean = 0.0;
-        double pg_std = (r_dpos[it] * pgfac) * r_dls[it];
-        if (isFar) { pg_mean = 0.0; pg_std = 0.0; }
-        const double g_mean = beta * pg_mean + (1.0 - beta) * r_kgm[it];      // penalizeReFER (FunctionUtilities.h:221-228)
-        const double g_std = beta * pg_std + (1.0 - beta) * r_kgs[it];
-        actO[(m0 + i) * TBW + sp] = (float)g_mean;        // the output gradient replaces the output (read above, by this thread only)
-        gP[i * TBW + sp] = (float)g_std;
-        if (keep) {
-          a.lastG[(size_t)bb * net.nOut + m0 + i] = (float)g_mean; a.lastG[(size_t)bb * net.nOut + m0 + dA + i] = (float)g_std;
-          a.lastO[(size_t)bb * net.nOut + m0 + i] = mf; a.lastO[(size_t)bb * net.nOut + m0 + dA + i] = vec[wp.vP + i];
-        }
-        if (i == 0) {       // value head (RACER_train.cpp:46)
-          const double g0 = isFar ? 0.0 : samp[4 * TBW + sp] * beta * samp[3 * TBW + sp];
-          actO[0 * TBW + sp] = (float)g0;
-          if (keep) a.lastG[(size_t)bb * net.nOut + 0] = (float)g0;
-        }
-      }
-    }
-    __syncthreads();
-    // ---- output gradient -> scratch rows of the output layer / the ParamLayer (zero for the padding samples of the last tile) ----
-    for (int idx = tid; idx < net.nOut * TBW; idx += kST) {
-      const int j = idx >> 7, sp = idx & (TBW - 1);
-      float g = 0.f;
-      if (info[3 * TBW + sp]) g = j < net.nOutDense ? actO[j * TBW + sp] : gP[(j - net.nOutDense) * TBW + sp];
-      const int rowG = j < net.nOutDense ? Lo.actOff + j : Lp.actOff + (j - net.nOutDense);
-      errT[rowG * TBW + sp] = g;
-    }
-    __syncthreads();
   }
   if (!imgReady) mbar_wait(&bars[0], 0);       // no tile: still consume the copy before the CTA (and its shared memory) goes away
   if (fault && lane == 0 && a.comm.error) *a.comm.error = 2;
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_free(tmem, 512u);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_wide_loss: ReF-ER / Retrace loss and output gradient (RACER::Train, Learners/RACER_train.cpp:31-60; the formulas and their
+// operation order are those of loss_stages above), f64, V-RACER: outputs [V | mean(dA)], stdev = ParamLayer.  Its own kernel:
+// 65536 x dA (sample, component) pairs of f64 transcendental work run at full occupancy on every SM instead of on the 16 warps
+// of a tile CTA (a third of k_wide_fwd's time when it lived there).  CTA = 256 / dA samples; one thread per pair, one per sample
+// for the sums in component order, the flags, the replay write-back and the record.  Reads the outputs from the scratch rows
+// of the output layer and overwrites them with the gradient.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_wide_loss(StepArgs a, int step, int vP) {
+  __shared__ double pairS[2][256];
+  __shared__ double samp[5][256];
+  __shared__ int info[4][256];          // row, slot, hasNext, valid
+  __shared__ float qret[256];
+  __shared__ StepCtrl c;
+  const DevDescs* dd = a.descs;
+  const NetDesc& net = dd->net; const Hyper& hp = dd->hp;
+  const ReplayView& rp = a.rp;
+  const int tid = threadIdx.x, dA = net.dA, SPC = 256 / dA, nPair = SPC * dA;
+  const int per = net.actPerSample;
+  const LayerDesc& Lo = net.L[net.nLayers - 2];
+  const LayerDesc& Lp = net.L[net.nLayers - 1];
+  const int Bt = (a.B + kWideM - 1) / kWideM * kWideM;
+  const size_t j0 = (size_t)(step - a.stepBase) * a.B;
+  const bool keep = step == a.lastStep || a.lastStep < 0;
+  const int m0 = 1;
+  if (tid == 0) load_ctrl(c, &a.ctrl[step & 1]);
+  // terms of the ParamLayer's stdev outputs: the same for every sample, evaluated once per CTA (same expressions, same bits)
+  __shared__ double comp[5][8];         // root, stdev, dpos, 1 / stdev, log(1 / stdev)
+  if (tid >= 256 - 8 && tid - (256 - 8) < dA) {
+    const int k = tid - (256 - 8);
+    const double sraw = (double)ld_cg(a.wvec + vP + k);
+    const double root = sqrt(1.0 + sraw * sraw);
+    const double stdev = (sraw + root) / 2.0;                          // SoftPlus::_eval, Functions.h:552-555
+    comp[0][k] = root; comp[1][k] = stdev;
+    comp[2][k] = (1.0 + sraw / root) / 2.0;                            // SoftPlus::_evalDiff
+    comp[3][k] = 1.0 / stdev; comp[4][k] = log(1.0 / stdev);
+  }
+  float oldv[5] = {0.f, 0.f, 0.f, 0.f, 0.f};      // V, ADV, RHO, KL, DELTA of the sample thread's transition
+  if (tid < SPC) {
+    const int b = blockIdx.x * SPC + tid;
+    int row = 0, slot = 0, hn = 0;
+    if (b < a.B) {
+      row = __ldg(a.sampRow + j0 + b);
+      const int sf = __ldg(a.sampSlot + j0 + b);
+      slot = sf & 0x7fffffff; hn = (sf >> 31) & 1;
+      oldv[0] = ld_cg(rp.V + row); oldv[1] = ld_cg(rp.ADV + row); oldv[2] = ld_cg(rp.RHO + row);
+      oldv[3] = ld_cg(rp.KL + row); oldv[4] = ld_cg(rp.DELTA + row); qret[tid] = ld_cg(rp.Q + row);
+      if (hn) { const int i = atomicAdd(a.wcnt, 1); a.wlist[i] = b; }      // V(s_t+1): k_wide_next
+    }
+    info[0][tid] = row; info[1][tid] = slot; info[2][tid] = hn; info[3][tid] = b < a.B ? 1 : 0;
+  }
+  __syncthreads();
+  // ---- stage 1: one thread per (sample, action component) ----
+  const int sp = tid / dA, i = tid - sp * dA;
+  const int b = blockIdx.x * SPC + sp;
+  const bool pairOn = tid < nPair && b < Bt;
+  const bool valid = pairOn && info[3][sp];
+  float* errT = a.errG + ((size_t)(b >> 7) * per) * kWideM + (b & (kWideM - 1));       // + scratch row * 128
+  double r_kgm = 0.0, r_kgs = 0.0, r_dlm = 0.0, r_dls = 0.0, r_dpos = 0.0;
+  float mf = 0.f, srawf = 0.f;
+  if (valid) {
+    const size_t prow = info[0][sp];
+    const double av = (double)ld_cg(rp.A + prow * dA + i), mm = (double)ld_cg(rp.MU + prow * 2 * dA + i),
+                 ms = (double)ld_cg(rp.MU + prow * 2 * dA + dA + i);
+    mf = ld_cg(errT + (size_t)(Lo.actOff + m0 + i) * kWideM);
+    srawf = ld_cg(a.wvec + vP + i);
+    const double m = (double)mf;
+    const double stdev = comp[1][i], dpos = comp[2][i];
+    const double inv = comp[3][i], invmu = 1.0 / ms;
+    const bool bnd = hp.bounded[i] != 0;
+    const double MAXM = 8.31776613503286;
+    const double cm = bnd ? (m > MAXM ? MAXM : (m < -MAXM ? -MAXM : m)) : m;   // Continuous_policy.h:217-222
+    const double fac0 = 9.1893853320467266954096885456237942e-01;
+    double J = 1.0;
+    if (bnd) { const double sq = tanh(av); J = fmax(1.0 - sq * sq, (double)FLT_MIN); }
+    const double z1 = (av - cm) * inv, z2 = (av - mm) * invmu;
+    const double lp_pi = -(z1 * z1) / 2.0 + (bnd ? log(inv / J) : comp[4][i]) - fac0;       // :91-97 / :240-249
+    const double lp_mu = -(z2 * z2) / 2.0 + log(bnd ? invmu / J : invmu) - fac0;
+    const double r1 = stdev / ms, r2 = (m - mm) / ms;
+    const double cc = r1 * r1, dd2 = r2 * r2;                                         // OPPOSITE_KL, :138-142
+    const double invVarMu = 1.0 / (ms * ms);
+    const double u = z1;
+    pairS[0][tid] = lp_pi - lp_mu;
+    pairS[1][tid] = (cc - 1.0 + dd2 - log(cc)) / 2.0;
+    r_kgm = -1.0 * ((m - mm) * invVarMu);                               // kg_mean
+    r_kgs = (dpos * -1.0) * ((invVarMu - inv * inv) * stdev);           // kg_std
+    r_dlm = bnd ? (av - m) * inv * inv : u * inv;                       // dLogPdMean
+    r_dls = (u * u - 1.0) * inv;                                        // dLogPdStdv
+    r_dpos = dpos;
+  }
+  __syncthreads();
+  // ---- stage 2: one thread per sample — sums in component order like the reference, flags, value terms, replay write-back
+  //      (RACER_train.cpp:59-60) and the record for the aggregate updates ----
+  if (tid < SPC && info[3][tid]) {
+    const int bb = blockIdx.x * SPC + tid;
+    const size_t prow = info[0][tid];
+    const float* eT = a.errG + ((size_t)(bb >> 7) * per) * kWideM + (bb & (kWideM - 1));
+    const float O0f = ld_cg(eT + (size_t)(Lo.actOff + 0) * kWideM);
+    const double O0 = (double)O0f;
+    const double Vval = net2v(O0);                                                     // scaleNet2V (RACER_common.cpp:23-32)
+    const double cmax = c.cmax, cinv = c.cinv;
+    double logw = 0.0, dkl = 0.0;
+    for (int k = 0; k < dA; ++k) { logw += pairS[0][tid * dA + k]; dkl += pairS[1][tid * dA + k]; }
+    const double rho = exp(logw > 7.0 ? 7.0 : (logw < -7.0 ? -7.0 : logw));           // :648-653
+    const float W32 = (float)rho, C32 = (float)cmax, I32 = (float)cinv;               // isFarPolicy takes Fval arguments (Episode.h:28-33)
+    const bool offW = (W32 > C32) || (W32 < I32);
+    const bool isFar = (C32 > 1.0f) && offW;
+    const double Aval = 0.0;                                                          // Zero_advantage.h:39-42
+    const double A_RET = (double)qret[tid] - Vval, deltaQ = A_RET - Aval;
+    samp[4][tid] = fmin(1.0, rho) * deltaQ;           // Ver
+    samp[0][tid] = A_RET * fmin(cmax, rho);           // pgfac
+    samp[1][tid] = isFar ? 1.0 : 0.0;
+    samp[3][tid] = vdiff(O0);
+    if (keep) a.lastO[(size_t)bb * net.nOut + 0] = O0f;
+    const float E = (float)deltaQ, Dk = (float)dkl;
+    const float oldRho = oldv[2], oldKL = oldv[3], oldE = oldv[4];
+    const bool wasOff = (oldRho > C32) || (oldRho < I32);
+    const float Vf = (float)Vval, Qf = (float)(Aval + Vval);
+    rp.DELTA[prow] = E; rp.KL[prow] = Dk; rp.RHO[prow] = W32;
+    rp.V[prow] = Vf; rp.ADV[prow] = Qf - Vf;
+    // qNextOld / qNextNew of the record belong to k_wide_next
+    *reinterpret_cast<int4*>(&a.rec[bb].slot) = make_int4(info[1][tid], info[2][tid], (C32 > 1.0f) ? ((int)offW - (int)wasOff) : 0, 0);
+    *reinterpret_cast<float4*>(&a.rec[bb].dKL) = make_float4(Dk - oldKL, (float)offW - (float)wasOff, E * E - oldE * oldE, fabsf(E));
+    *reinterpret_cast<float2*>(&a.rec[bb].qOld) = make_float2(oldv[1] + oldv[0], Qf);
+  }
+  __syncthreads();
+  // ---- stage 3: policy / penalty gradient of every pair (penalizeReFER, FunctionUtilities.h:221-228) ----
+  if (!pairOn) return;
+  float g_mean_f = 0.f, g_std_f = 0.f, g0_f = 0.f;
+  if (valid) {
+    const double beta = c.beta;
+    const double MAXM = 8.31776613503286;
+    const double pgfac = samp[0][sp];
+    const bool isFar = samp[1][sp] != 0.0;
+    const double m = (double)mf;
+    double pg_mean = pgfac * r_dlm;
+    if (hp.bounded[i] && ((m >= MAXM && pg_mean > 0.0) || (m <= -MAXM && pg_mean < 0.0))) pg_mean = 0.0;
+    double pg_std = (r_dpos * pgfac) * r_dls;
+    if (isFar) { pg_mean = 0.0; pg_std = 0.0; }
+    g_mean_f = (float)(beta * pg_mean + (1.0 - beta) * r_kgm);
+    g_std_f = (float)(beta * pg_std + (1.0 - beta) * r_kgs);
+    if (i == 0) g0_f = (float)(isFar ? 0.0 : samp[4][sp] * beta * samp[3][sp]);        // value head (RACER_train.cpp:46)
+    if (keep) {
+      a.lastG[(size_t)b * net.nOut + m0 + i] = g_mean_f; a.lastG[(size_t)b * net.nOut + m0 + dA + i] = g_std_f;
+      a.lastO[(size_t)b * net.nOut + m0 + i] = mf; a.lastO[(size_t)b * net.nOut + m0 + dA + i] = srawf;
+      if (i == 0) a.lastG[(size_t)b * net.nOut + 0] = g0_f;
+    }
+  }
+  // the gradient replaces the outputs in the scratch (zero for the padding samples of the last tile)
+  errT[(size_t)(Lo.actOff + m0 + i) * kWideM] = g_mean_f;
+  errT[(size_t)(Lp.actOff + i) * kWideM] = g_std_f;
+  if (i == 0) errT[(size_t)(Lo.actOff + 0) * kWideM] = g0_f;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -577,8 +592,22 @@ __global__ void __launch_bounds__(kST) k_wide_stats(StepArgs a, int step) {
 // epilogue, for the layer below:  + the ParametricResidual path of the layer above (Layers.h:363-393), the residual layer's
 // own error to the scratch (its parameter gradients are formed by k_wide_wgrad), deltas *= tanh' (Layer_Base.h:103-109).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kST, 1) k_wide_bwd(StepArgs a, int step) {
+__global__ void __launch_bounds__(kST, 1) k_wide_bwd(StepArgs a, int step, int sbBars, int sbImg, int bFloats) {
   extern __shared__ __align__(128) unsigned char smraw[];
+  {
+    uint64_t* bars0 = reinterpret_cast<uint64_t*>(smraw + sbBars);
+    if (threadIdx.x == 0) {
+      mbar_init(&bars0[0], 1); mbar_init(&bars0[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.global;\n\tfence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&bars0[0], (unsigned)bFloats * 4u);
+      float* img0 = reinterpret_cast<float*>(smraw + sbImg);
+      for (int off = 0; off < bFloats; off += 16384) {
+        const unsigned n = (unsigned)min(16384, bFloats - off) * 4u;
+        bulk_g2s(img0 + off, a.wimgB + off, n, &bars0[0]);
+      }
+    }
+  }
   const NetDesc* netp; const Hyper* hpp;
   load_descs(a, smraw, netp, hpp);
   const WidePlan& wp = *load_wide_plan(a, smraw + kWideDescBytes);
@@ -592,24 +621,12 @@ __global__ void __launch_bounds__(kST, 1) k_wide_bwd(StepArgs a, int step) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + wp.sbBars);
   const int bHalf = wp.bFloats >> 1;
   constexpr int TBW = kWideM;
-  if (tid == 0) {
-    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
   if (warp == 0) tmem_alloc(&tmemSlot, 512u);
   for (int i = tid; i < wp.vFloats; i += kST) vec[i] = ld_cg(a.wvec + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmemSlot;
-  if (tid == 0) {
-    asm volatile("fence.proxy.async.global;\n\tfence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx(&bars[0], (unsigned)wp.bFloats * 4u);
-    for (int off = 0; off < wp.bFloats; off += 16384) {
-      const unsigned n = (unsigned)min(16384, wp.bFloats - off) * 4u;
-      bulk_g2s(img + off, a.wimgB + off, n, &bars[0]);
-    }
-  }
   const int nTiles = (a.B + TBW - 1) / TBW;
   unsigned mmaPar = 0;
   bool imgReady = false, fault = false;
@@ -1037,12 +1054,6 @@ void wide_plan_build(const NetDesc& net, const Hyper& hp, WidePlan& wp, std::vec
   wp.sfBars = take(64);
   wp.sfVec = take(4 * (wp.vFloats + 2 * wp.D[0].Kp));
   wp.sfImg = take(4 * wp.fFloats);
-  wp.sfActO = take(4 * wp.D[nD - 1].Np * kWideM);
-  wp.sfGP = take(4 * net.dA * kWideM);
-  wp.sfOld = take(4 * 8 * kWideM);
-  wp.sfInfo = take(4 * 4 * kWideM);
-  wp.sfSamp = take(8 * 5 * kWideM);
-  wp.sfPair = take(8 * 2 * kWideM * net.dA);
   wp.sfTotal = o;
   o = kWideDescBytes + kWidePlanBytes;
   wp.sbBars = take(64);
@@ -1146,10 +1157,12 @@ int launch_steps_wide(const StepArgs& a, const NetDesc& net, const WidePlan& wp,
   const int rounds = (nTiles + numSMs - 1) / numSMs;
   const int gridT = (nTiles + rounds - 1) / rounds;
   const bool sm = step_image_in_smem(net);
+  const int spc = 256 / net.dA;
   for (int s = 0; s < nSteps; ++s) {
     const int step = step0 + s;
     const bool skipStats = skipStatsLast && s == nSteps - 1;
-    k_wide_fwd<<<gridT, kST, wp.sfTotal, st>>>(a, step);
+    k_wide_fwd<<<gridT, kST, wp.sfTotal, st>>>(a, step, wp.sfBars, wp.sfImg, wp.fFloats);
+    k_wide_loss<<<(nTiles * kWideM + spc - 1) / spc, 256, 0, st>>>(a, step, wp.vP);
     SMB200_CUDA_CHECK(cudaEventRecord(evF, st));
     SMB200_CUDA_CHECK(cudaStreamWaitEvent(aux, evF, 0));
     if (sm) k_wide_next<true><<<16, kST, smem_plan(net, 4, true).total, aux>>>(a, step);
@@ -1160,7 +1173,7 @@ int launch_steps_wide(const StepArgs& a, const NetDesc& net, const WidePlan& wp,
       k_wide_stats<<<1, kST, kWideDescBytes + 4 * kStatChunk, aux>>>(a, step);
     }
     SMB200_CUDA_CHECK(cudaEventRecord(evS, aux));
-    k_wide_bwd<<<gridT, kST, wp.sbTotal, st>>>(a, step);
+    k_wide_bwd<<<gridT, kST, wp.sbTotal, st>>>(a, step, wp.sbBars, wp.sbImg, wp.bFloats);
     if (wp.nD == 2) k_wide_wgrad<2><<<a.wGridG, kST, wp.sgTotal, st>>>(a, step);
     else if (wp.nD == 3) k_wide_wgrad<3><<<a.wGridG, kST, wp.sgTotal, st>>>(a, step);
     else k_wide_wgrad<4><<<a.wGridG, kST, wp.sgTotal, st>>>(a, step);
