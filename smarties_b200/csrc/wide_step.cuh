@@ -196,10 +196,12 @@ __global__ void __launch_bounds__(kST, 1) k_wide_fwd(StepArgs a, int step, int s
   for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
     const int b0 = tile * TBW, s = q * 32 + lane, b = b0 + s;
     const bool valid = b < a.B;
-    // scratch of the tile: [feature][128 samples], tile after tile (one contiguous block per tile: the kernels that follow
-    // stream it, and every DRAM page that is opened is used completely)
+    // scratch of the tile: [stage of 16 samples][feature][16], tile after tile: every 16-sample stage of the weight-gradient
+    // kernel is ONE contiguous block (all features x 64 bytes) that it streams front to back, and the 8 features a thread
+    // writes for its sample are 8 adjacent 64-byte rows
     float* actT = a.actG + (size_t)tile * net.actPerSample * TBW;
     float* errT = a.errG + (size_t)tile * net.actPerSample * TBW;
+    const int sOff = (s >> 4) * net.actPerSample * 16 + (s & 15);
     // ---- standardise (Episode.h:171-183): the tile's states become the A operand of the first layer ----
 #pragma unroll
     for (int c2 = 0; c2 < 2; ++c2) {
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(kST, 1) k_wide_fwd(StepArgs a, int step, int s
         const float h = tf32_hi(x);
         hi[jj] = __float_as_uint(h); lo[jj] = __float_as_uint(x - h);
         if (k < dS) {
-          actT[(D0.inOff + k) * TBW + s] = x;
+          actT[(D0.inOff + k) * 16 + sOff] = x;
           if (keep && valid) a.lastX[(size_t)b * dS + k] = x;
         }
       }
@@ -233,10 +235,11 @@ __global__ void __launch_bounds__(kST, 1) k_wide_fwd(StepArgs a, int step, int s
       mmaPar ^= 1u;
       tc_fence_after();
       const float* bias = vec + D.vB;
+      const int dN = D.N, dNp8 = D.Np / 8, dY = D.yOff, dZ = D.zOff;      // registers (see k_wide_bwd)
       if (D.isTanh) {
         const bool res = D.res >= 0;
         const float* rw = vec + (res ? D.vRW : 0); const float* rb = vec + (res ? D.vRB : 0);
-        for (int j8 = cg; j8 < D.Np / 8; j8 += 4) {
+        for (int j8 = cg; j8 < dNp8; j8 += 4) {
           uint32_t v[8], xh[8], xl[8];
           tm_ld8(tmem + laneBase + kWAcc + 8 * j8, v);
           if (res) { tm_ld8(tmem + laneBase + kWAh + 8 * j8, xh); tm_ld8(tmem + laneBase + kWAl + 8 * j8, xl); }
@@ -250,8 +253,8 @@ __global__ void __launch_bounds__(kST, 1) k_wide_fwd(StepArgs a, int step, int s
             *reinterpret_cast<float4*>(rbv) = *reinterpret_cast<const float4*>(rb + n0);
             *reinterpret_cast<float4*>(rbv + 4) = *reinterpret_cast<const float4*>(rb + n0 + 4);
           }
-          float* yp = actT + (D.yOff + n0) * TBW + s;
-          float* zp = actT + (D.zOff + n0) * TBW + s;
+          float* yp = actT + (dY + n0) * 16 + sOff;
+          float* zp = actT + (dZ + n0) * 16 + sOff;
           tm_wait_ld();
           uint32_t hi[8], lo[8];
           // no branches inside: the eight columns are independent instruction streams (the padding columns have zero weights
@@ -264,9 +267,9 @@ __global__ void __launch_bounds__(kST, 1) k_wide_fwd(StepArgs a, int step, int s
               const float xin = __uint_as_float(xh[jj]) + __uint_as_float(xl[jj]);     // hi + lo is the f32 value, exactly
               z = y + (xin * rwv[jj] + rbv[jj]);
             }
-            const bool in = n0 + jj < D.N;
+            const bool in = n0 + jj < dN;
             z = in ? z : 0.f;
-            if (in) { yp[jj * TBW] = y; if (res) zp[jj * TBW] = z; }
+            if (in) { yp[jj * 16] = y; if (res) zp[jj * 16] = z; }
             const float h = tf32_hi(z);
             hi[jj] = __float_as_uint(h); lo[jj] = __float_as_uint(z - h);
           }
@@ -275,14 +278,15 @@ __global__ void __launch_bounds__(kST, 1) k_wide_fwd(StepArgs a, int step, int s
         }
         tm_wait_st();
       } else {      // linear output layer: the outputs leave for the loss kernel in the scratch rows its gradient will overwrite
-        for (int j8 = cg; j8 < D.Np / 8; j8 += 4) {
+        const int oOff = Lo.actOff;
+        for (int j8 = cg; j8 < dNp8; j8 += 4) {
           uint32_t v[8];
           tm_ld8(tmem + laneBase + kWAcc + 8 * j8, v);
           tm_wait_ld();
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
             const int n = 8 * j8 + jj;
-            if (n < D.N) errT[(Lo.actOff + n) * TBW + s] = __uint_as_float(v[jj]) + bias[n];
+            if (n < dN) errT[(oOff + n) * 16 + sOff] = __uint_as_float(v[jj]) + bias[n];
           }
         }
       }
@@ -354,14 +358,14 @@ __global__ void __launch_bounds__(256) k_wide_loss(StepArgs a, int step, int vP)
   const int b = blockIdx.x * SPC + sp;
   const bool pairOn = tid < nPair && b < Bt;
   const bool valid = pairOn && info[3][sp];
-  float* errT = a.errG + ((size_t)(b >> 7) * per) * kWideM + (b & (kWideM - 1));       // + scratch row * 128
+  float* errT = a.errG + ((size_t)(b >> 7) * per) * kWideM + ((b >> 4) & 7) * per * 16 + (b & 15);       // + scratch row * 16
   double r_kgm = 0.0, r_kgs = 0.0, r_dlm = 0.0, r_dls = 0.0, r_dpos = 0.0;
   float mf = 0.f, srawf = 0.f;
   if (valid) {
     const size_t prow = info[0][sp];
     const double av = (double)ld_cg(rp.A + prow * dA + i), mm = (double)ld_cg(rp.MU + prow * 2 * dA + i),
                  ms = (double)ld_cg(rp.MU + prow * 2 * dA + dA + i);
-    mf = ld_cg(errT + (size_t)(Lo.actOff + m0 + i) * kWideM);
+    mf = ld_cg(errT + (Lo.actOff + m0 + i) * 16);
     srawf = ld_cg(a.wvec + vP + i);
     const double m = (double)mf;
     const double stdev = comp[1][i], dpos = comp[2][i];
@@ -393,8 +397,8 @@ __global__ void __launch_bounds__(256) k_wide_loss(StepArgs a, int step, int vP)
   if (tid < SPC && info[3][tid]) {
     const int bb = blockIdx.x * SPC + tid;
     const size_t prow = info[0][tid];
-    const float* eT = a.errG + ((size_t)(bb >> 7) * per) * kWideM + (bb & (kWideM - 1));
-    const float O0f = ld_cg(eT + (size_t)(Lo.actOff + 0) * kWideM);
+    const float* eT = a.errG + ((size_t)(bb >> 7) * per) * kWideM + ((bb >> 4) & 7) * per * 16 + (bb & 15);
+    const float O0f = ld_cg(eT + (Lo.actOff + 0) * 16);
     const double O0 = (double)O0f;
     const double Vval = net2v(O0);                                                     // scaleNet2V (RACER_common.cpp:23-32)
     const double cmax = c.cmax, cinv = c.cinv;
@@ -446,9 +450,9 @@ __global__ void __launch_bounds__(256) k_wide_loss(StepArgs a, int step, int vP)
     }
   }
   // the gradient replaces the outputs in the scratch (zero for the padding samples of the last tile)
-  errT[(size_t)(Lo.actOff + m0 + i) * kWideM] = g_mean_f;
-  errT[(size_t)(Lp.actOff + i) * kWideM] = g_std_f;
-  if (i == 0) errT[(size_t)(Lo.actOff + 0) * kWideM] = g0_f;
+  errT[(Lo.actOff + m0 + i) * 16] = g_mean_f;
+  errT[(Lp.actOff + i) * 16] = g_std_f;
+  if (i == 0) errT[(Lo.actOff + 0) * 16] = g0_f;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -638,11 +642,12 @@ __global__ void __launch_bounds__(kST, 1) k_wide_bwd(StepArgs a, int step, int s
   const WDense& DO = wp.D[wp.nD - 1];
   const bool gMine = cg < DO.Np / 8;
   float gv[8];
+  const int sOff = ((q * 32 + lane) >> 4) * net.actPerSample * 16 + (lane & 15);      // scratch [stage of 16 samples][feature][16] (k_wide_fwd)
   auto fetch_g = [&](int tile) {
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
       const int n = 8 * cg + jj;
-      gv[jj] = (gMine && tile < nTiles && n < DO.N) ? ld_cg(a.errG + ((size_t)tile * net.actPerSample + Lo.actOff + n) * TBW + q * 32 + lane) : 0.f;
+      gv[jj] = (gMine && tile < nTiles && n < DO.N) ? ld_cg(a.errG + (size_t)tile * net.actPerSample * TBW + (Lo.actOff + n) * 16 + sOff) : 0.f;
     }
   };
   fetch_g(blockIdx.x);
@@ -669,15 +674,16 @@ __global__ void __launch_bounds__(kST, 1) k_wide_bwd(StepArgs a, int step, int s
       // contraction over this layer's outputs (Np columns of the A operand), N = its Kp input rows
       if (tid == 0) wide_issue(tmem, img + D.bImg, img + bHalf + D.bImg, D.Np, D.Kp, &bars[1]);
       // the layer's outputs (tanh') do not depend on the product: fetch them while the tensor core works
+      // plan fields in registers: read through the shared-memory copy inside the unrolled loops they are re-read after
+      // every global store (possible aliasing)
+      const int hN = H.N, hNp8 = H.Np / 8, hY = H.yOff, hZ = H.zOff, dKp = D.Kp;
       float yv[32];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int j8 = cg + 4 * i;
+        const float* yp = actT + (hY + 8 * j8) * 16 + sOff;
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const int n = 8 * j8 + jj;
-          yv[8 * i + jj] = (j8 < H.Np / 8 && n < H.N) ? ld_cg(actT + (H.yOff + n) * TBW + s) : 0.f;
-        }
+        for (int jj = 0; jj < 8; ++jj) yv[8 * i + jj] = (j8 < hNp8 && 8 * j8 + jj < hN) ? ld_cg(yp + jj * 16) : 0.f;
       }
       if (!mbar_wait_bounded(&bars[1], mmaPar)) fault = true;
       mmaPar ^= 1u;
@@ -689,9 +695,9 @@ __global__ void __launch_bounds__(kST, 1) k_wide_bwd(StepArgs a, int step, int s
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int j8 = cg + 4 * i;
-        if (j8 >= H.Np / 8) continue;
+        if (j8 >= hNp8) continue;
         uint32_t v[8], cy[8];
-        const bool have = 8 * j8 < D.Kp;
+        const bool have = 8 * j8 < dKp;
         if (have) tm_ld8(tmem + laneBase + kWAcc + 8 * j8, v);
         if (haveCarry) tm_ld8(tmem + laneBase + kWCarry + 8 * j8, cy);
         if (have || haveCarry) tm_wait_ld();
@@ -702,17 +708,17 @@ __global__ void __launch_bounds__(kST, 1) k_wide_bwd(StepArgs a, int step, int s
           *reinterpret_cast<float4*>(rwv) = *reinterpret_cast<const float4*>(rw + n0);
           *reinterpret_cast<float4*>(rwv + 4) = *reinterpret_cast<const float4*>(rw + n0 + 4);
         }
-        float* ep = errT + (H.zOff + n0) * TBW + s;
-        float* dp = errT + (H.yOff + n0) * TBW + s;
+        float* ep = errT + (hZ + n0) * 16 + sOff;
+        float* dp = errT + (hY + n0) * 16 + sOff;
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
-          const bool in = n0 + jj < H.N;
+          const bool in = n0 + jj < hN;
           const float ez = (have ? __uint_as_float(v[jj]) : 0.f) + (haveCarry ? __uint_as_float(cy[jj]) : 0.f);   // E_in = W * delta (+ residual path)
           const float y = yv[8 * i + jj];
           const float delta = in ? ez * (1.0f - y * y) : 0.f;
           float cnew = 0.f;
-          if (res) { cnew = in ? ez * rwv[jj] : 0.f; if (in) ep[jj * TBW] = ez; }
-          if (in) dp[jj * TBW] = delta;
+          if (res) { cnew = in ? ez * rwv[jj] : 0.f; if (in) ep[jj * 16] = ez; }
+          if (in) dp[jj * 16] = delta;
           cn[jj] = __float_as_uint(cnew);
           const float h = tf32_hi(delta);
           hi[jj] = __float_as_uint(h); lo[jj] = __float_as_uint(delta - h);
@@ -754,9 +760,9 @@ __global__ void __launch_bounds__(kST, 1) k_wide_wgrad(StepArgs a, int step) {
   const NetDesc& net = *netp;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r = tid >> 2, cc = tid & 3;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + wp.sgBars);      // [0]: the MMAs that read the operand images have completed
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smraw + wp.sgBars);      // [image stage]: the MMAs that read it have completed
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(&tmemSlot, (uint32_t)wp.gCols);
@@ -779,12 +785,12 @@ __global__ void __launch_bounds__(kST, 1) k_wide_wgrad(StepArgs a, int step) {
     const bool out = d == ND - 1;
     pA[d] = pB[d] = pE[d] = nullptr;
     if (!out) {
-      if (r < D.N) pA[d] = a.errG + (D.yOff + r) * kWideM + 4 * cc;                    // deltas of the layer (tile-relative)
-      if (r < D.K) pB[d] = a.actG + (D.inOff + r) * kWideM + 4 * cc;                   // its input
-      if (D.res >= 0 && r < D.N) pE[d] = a.errG + (D.zOff + r) * kWideM + 4 * cc;      // error on the residual layer
+      if (r < D.N) pA[d] = a.errG + (D.yOff + r) * 16 + 4 * cc;                        // deltas of the layer (stage-relative)
+      if (r < D.K) pB[d] = a.actG + (D.inOff + r) * 16 + 4 * cc;                       // its input
+      if (D.res >= 0 && r < D.N) pE[d] = a.errG + (D.zOff + r) * 16 + 4 * cc;          // error on the residual layer
     } else {
-      if (r < D.K) pA[d] = a.actG + (D.inOff + r) * kWideM + 4 * cc;
-      if (r < net.nOut) pB[d] = a.errG + (r < net.nOutDense ? Lo.actOff + r : Lp.actOff + (r - net.nOutDense)) * kWideM + 4 * cc;
+      if (r < D.K) pA[d] = a.actG + (D.inOff + r) * 16 + 4 * cc;
+      if (r < net.nOut) pB[d] = a.errG + (r < net.nOutDense ? Lo.actOff + r : Lp.actOff + (r - net.nOutDense)) * 16 + 4 * cc;
     }
     ldB[d] = wp.sgRowsB[d] + 2;
     oA[d] = wp.sgOpA[d] + (cc * kWideLD + r) * 16;
@@ -807,45 +813,46 @@ __global__ void __launch_bounds__(kST, 1) k_wide_wgrad(StepArgs a, int step) {
   for (int d = 0; d < ND; ++d) { sA[d] = 0.f; sE[d] = 0.f; sEX[d] = 0.f; }
   bool fault = false;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  // Raw operand rows travel global -> shared memory by cp.async (LDGSTS, no registers), TWO stages ahead of their use: ~115 KB
-  // in flight per SM is what keeps HBM busy (one stage of register prefetch left the kernel latency bound at 2.4 us per stage).
-  // Ring of two raw stages [stage][operand][thread] float4; every thread reads back exactly the 16-byte slots it copied, so
-  // cp.async.wait_group is the only synchronisation the raw ring needs.
-  float4* raw = reinterpret_cast<float4*>(smraw + wp.sgRaw);
+  // Pipeline of a stage (16 samples): raw rows travel global -> shared memory by cp.async (LDGSTS, no registers) into ONE raw
+  // stage [operand][thread] float4 — every thread reads back exactly the 16-byte slots it copied, so cp.async.wait_group is the
+  // only synchronisation the raw stage needs —, are picked up into registers one stage ahead, split into the hi / lo operand
+  // images of one of TWO image stages, and multiplied; the MMAs of stage i (tcgen05.commit -> mbarrier of its image stage) run
+  // while stage i + 1 is split and stage i + 2 travels.
+  float4* raw = reinterpret_cast<float4*>(smraw + wp.sgRaw) + tid;
   int qA[ND], qB[ND], qE[ND], nOps = 0;
 #pragma unroll
   for (int d = 0; d < ND; ++d) { qA[d] = nOps++; qB[d] = nOps++; qE[d] = (d < ND - 1 && wp.D[d].res >= 0) ? nOps++ : -1; }
   auto issue = [&](int it) {
     if (it < st1) {
-      // stage `it` = samples [16 (it % 8), +16) of tile it / 8: a 64-byte run of every row of the tile's block
-      const size_t col = (size_t)(it >> 3) * net.actPerSample * kWideM + (size_t)(it & 7) * kWideKS;
-      float4* dst = raw + (size_t)((it - st0) & 1) * nOps * kST + tid;
+      // stage `it` (samples [16 (it % 8), +16) of tile it / 8) is one contiguous block of the scratch: [feature][16 samples]
+      const size_t col = (size_t)it * net.actPerSample * kWideKS;
 #pragma unroll
       for (int d = 0; d < ND; ++d) {
-        if (pA[d]) cp_async16_cg(dst + qA[d] * kST, pA[d] + col);
-        if (pB[d]) cp_async16_cg(dst + qB[d] * kST, pB[d] + col);
-        if (pE[d]) cp_async16_cg(dst + qE[d] * kST, pE[d] + col);
+        if (pA[d]) cp_async16_cg(raw + qA[d] * kST, pA[d] + col);
+        if (pB[d]) cp_async16_cg(raw + qB[d] * kST, pB[d] + col);
+        if (pE[d]) cp_async16_cg(raw + qE[d] * kST, pE[d] + col);
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  issue(st0); issue(st0 + 1);
-  unsigned char* stg = smraw + wp.sgStage;          // ONE stage of operand images: the MMAs of a stage take ~0.3 us of its ~1 us
   float4 vA[ND], vB[ND], vE[ND];
+  auto pickup = [&]() {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      vA[d] = pA[d] ? raw[qA[d] * kST] : zero4;
+      vB[d] = pB[d] ? raw[qB[d] * kST] : zero4;
+      vE[d] = pE[d] ? raw[qE[d] * kST] : zero4;
+    }
+  };
+  issue(st0);
+  pickup();
+  issue(st0 + 1);
 
   for (int it = st0; it < st1; ++it) {
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    {
-      const float4* src = raw + (size_t)((it - st0) & 1) * nOps * kST + tid;
-#pragma unroll
-      for (int d = 0; d < ND; ++d) {
-        vA[d] = pA[d] ? src[qA[d] * kST] : zero4;
-        vB[d] = pB[d] ? src[qB[d] * kST] : zero4;
-        vE[d] = pE[d] ? src[qE[d] * kST] : zero4;
-      }
-    }
-    issue(it + 2);                                   // refills the raw slots this thread has just read
-    if (it > st0) { if (!mbar_wait_bounded(&bars[0], (unsigned)((it - st0 - 1) & 1))) fault = true; }     // MMAs of the previous stage
+    const int slot = (it - st0) & 1, use = (it - st0) >> 1;
+    unsigned char* stg = smraw + wp.sgStage + (size_t)slot * wp.sgStageBytes;
+    if (use > 0) { if (!mbar_wait_bounded(&bars[slot], (unsigned)((use - 1) & 1))) fault = true; }     // MMAs of the image stage's previous use
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
       const bool out = d == ND - 1;
@@ -873,27 +880,31 @@ __global__ void __launch_bounds__(kST, 1) k_wide_wgrad(StepArgs a, int step) {
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
+      const uint64_t sOff = (uint64_t)((slot * wp.sgStageBytes) >> 4);
       const uint32_t first = it > st0 ? 1u : 0u;
 #pragma unroll
       for (int d = 0; d < ND; ++d) {
 #pragma unroll
         for (int kk = 0; kk < kWideKS / 8; ++kk) {
-          const uint64_t dah = gd[d][0] + (uint64_t)(2 * kk * kWideLD), dal = gd[d][1] + (uint64_t)(2 * kk * kWideLD);
-          const uint64_t dbh = gd[d][2] + (uint64_t)(2 * kk) * gd[d][4], dbl = gd[d][3] + (uint64_t)(2 * kk) * gd[d][4];
+          const uint64_t dah = gd[d][0] + sOff + (uint64_t)(2 * kk * kWideLD), dal = gd[d][1] + sOff + (uint64_t)(2 * kk * kWideLD);
+          const uint64_t dbh = gd[d][2] + sOff + (uint64_t)(2 * kk) * gd[d][4], dbl = gd[d][3] + sOff + (uint64_t)(2 * kk) * gd[d][4];
           umma_tf32(gi[d][1], dal, dbh, gi[d][0], kk > 0 ? 1u : first);
           umma_tf32(gi[d][1], dah, dbl, gi[d][0], 1u);
           umma_tf32(gi[d][1], dah, dbh, gi[d][0], 1u);
         }
       }
-      tc_commit(&bars[0]);
+      tc_commit(&bars[slot]);
     }
+    pickup();                  // stage it + 1 (landed while this one was split) -> registers
+    issue(it + 2);             // refills the raw slots this thread has just read
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   // ---- all MMAs done: accumulators and vector sums -> this CTA's partial record ----
   float* rec = a.wpart + (size_t)g * wp.recFloats;
   const int nMine = st1 - st0;
   if (nMine > 0) {
-    if (!mbar_wait_bounded(&bars[0], (unsigned)((nMine - 1) & 1))) fault = true;
+    const int last = nMine - 1;
+    if (!mbar_wait_bounded(&bars[last & 1], (unsigned)((last >> 1) & 1))) fault = true;
   }
   tc_fence_after();
   {
@@ -1062,12 +1073,12 @@ void wide_plan_build(const NetDesc& net, const Hyper& hp, WidePlan& wp, std::vec
   wp.sbTotal = o;
   o = kWideDescBytes + kWidePlanBytes;
   wp.sgBars = take(64);
-  wp.sgStage = take(sg);
-  wp.sgStages = 1;
+  wp.sgStage = take(2 * sg);
+  wp.sgStages = 2;
   {
     int nOps = 0;
     for (int d = 0; d < nD; ++d) nOps += 2 + ((d < nD - 1 && wp.D[d].res >= 0) ? 1 : 0);
-    wp.sgRaw = take(2 * nOps * kST * 16);
+    wp.sgRaw = take(nOps * kST * 16);
   }
   wp.sgTotal = o;
   if (wp.sfTotal > kMax || wp.sbTotal > kMax || wp.sgTotal > kMax) return;
