@@ -305,7 +305,7 @@ def ncu_wide():
 
 def batch_sweep(torch, dev, data, wl, batches, steps=60):
     """the learner step at growing mini-batches (per GPU), same buffer and network.  B = 256 runs the persistent tile
-    kernel (a latency chain), from B = 1024 on the wide step runs (wide_step.cuh: 128-sample tiles, every dense product as 3xTF32
+    kernel (a latency chain) and so does B = 1024, from B = 2048 on the wide step runs (wide_step.cuh: 128-sample tiles, every dense product as 3xTF32
     tcgen05.mma).  Per batch size: us/step, transitions/s, the fraction of the HBM roofline of the ALGORITHMIC bytes, and the
     tensor-side numbers: algorithmic TFLOP/s (2 x 60.8 k multiply-adds per transition), the TF32 TFLOP/s the tensor cores
     execute for it (x3: hi*hi + hi*lo + lo*hi keeps f32 accuracy) and its fraction of the TF32 peak (= half the measured bf16 peak)."""
@@ -493,7 +493,7 @@ def main():
         if ranks_identical is not None:
             out["ranks_identical"] = ranks_identical
         if world == 1 and args.workload == "cfg2" and not args.batch and not args.no_batch_sweep:
-            out["roofline_batch_sweep"] = batch_sweep(torch, dev, data, args.workload, (256, 1024, 4096, 16384, 65536))
+            out["roofline_batch_sweep"] = batch_sweep(torch, dev, data, args.workload, (256, 1024, 2048, 4096, 16384, 65536))
             nw = ncu_wide()
             if nw:      # per-kernel ncu evidence of the wide step (tensor-pipe share, DRAM bytes), captured at B = 65536
                 out["roofline_wide_kernels"] = nw

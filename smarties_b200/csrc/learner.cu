@@ -879,12 +879,13 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
       CK(dev_alloc(&h->cpart, (size_t)h->clusterP1 * net.nParams));
     }
   }
-  // wide step (tensor cores): batches of >= 1024 sampled transitions per rank unless SMB200_WIDE says otherwise
-  // (SMB200_WIDE=0: never, =1: whenever the plan covers the network)
+  // wide step (tensor cores): batches of >= 2048 sampled transitions per rank unless SMB200_WIDE says otherwise
+  // (SMB200_WIDE=0: never, =1: whenever the plan covers the network).  Measured cross-over on B200 (cfg2 network): the
+  // persistent tile kernel takes 39 us at B = 1024 and 137 us at B = 4096, the wide step 57 us and 62 us.
   {
     const char* w = getenv("SMB200_WIDE");
     const bool never = w && strcmp(w, "0") == 0, always = w && strcmp(w, "1") == 0;
-    if (!never && (always || B >= 1024) && c.world_size <= 1) {
+    if (!never && (always || B >= 2048) && c.world_size <= 1) {
       wide_plan_build(net, hp, h->wplan, h->widx);
       if (h->wplan.ok) {
         CK(wide_prepare(h->wplan, net));

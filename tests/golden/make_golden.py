@@ -47,6 +47,12 @@ CASES = {
         replay=dict(seed=71, n_ep=60, ep_len=(40, 70), dS=12, dA=4),
         settings={"learner": "VRACER", "nnLayerSizes": [64, 64], "batchSize": 1024, "maxTotObsNum": 8192, "minTotObsNum": 2500},
         steps=3, start_step=998, sample_seed=17, bounded=0, full_steps=[0, 2]),
+    # the batch size at which the device learner switches to the wide step by default (tcgen05 tiles of 128 sampled transitions,
+    # wide_step.cuh): configs[1]'s own hidden layers, 32 tiles, three steps across the step-1000 sweep
+    "vracer_b4096": dict(
+        replay=dict(seed=83, n_ep=64, ep_len=(90, 130), dS=16, dA=4),
+        settings={"learner": "VRACER", "nnLayerSizes": [128, 128], "batchSize": 4096, "maxTotObsNum": 16384, "minTotObsNum": 5000},
+        steps=3, start_step=998, sample_seed=29, bounded=0, full_steps=[0, 2]),
     # FIFO pruning: capacity below the stored data, so applyEpisodesRemovalAlgo evicts on step 1
     "vracer_prune": dict(
         replay=dict(seed=17, n_ep=16, ep_len=(20, 30), dS=4, dA=2),

@@ -182,7 +182,7 @@ def test_wide_step_matches_reference(monkeypatch, case):
     """The large-batch step (wide_step.cuh: tiles of 128 sampled transitions, every dense product as 3xTF32 tcgen05.mma with the
     activations as the A operand in tensor memory, split-K weight gradient on the tensor cores, parallel per-episode records)
     against the same goldens and bars as the tile kernel.  SMB200_WIDE=1 forces it for every batch size (partial tiles);
-    vracer_b1024 is the batch size at which it is the default."""
+    vracer_b1024: eight full tiles (the default switches to the wide step at batch 2048)."""
     monkeypatch.setenv("SMB200_WIDE", "1")
     g = Golden(case)
     L = make_learner(g)
