@@ -15,12 +15,12 @@ KEYS = {
     "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
     "dram__bytes_read.sum": "dram_read", "dram__bytes_write.sum": "dram_write",
     "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_throughput_pct",
-    "launch__grid_size": "grid", "launch__registers_per_thread": "registers", "smsp__inst_executed.sum": "warp_instructions",
+    "launch__grid_size": "grid", "launch__block_size": "block", "launch__registers_per_thread": "registers", "smsp__inst_executed.sum": "warp_instructions",
     "launch__shared_mem_per_block_dynamic": "dynamic_smem_bytes",
 }
 out = {"_batch": B, "_source": "ncu --set full --clock-control none, one launch per kernel (scripts/r2_wide_profiles.sh)"}
 lines = []
-for k in ("fwd", "bwd", "wgrad"):
+for k in ("fwd", "loss", "bwd", "wgrad"):
     rep = os.path.join(src, f"wide_{k}.ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -44,7 +44,7 @@ for k in ("fwd", "bwd", "wgrad"):
     e["stall_share"] = {a: round(b / tot, 3) for a, b in sorted(st.items(), key=lambda kv: -kv[1])[:6]}
     e["dram_bytes"] = e.get("dram_read", 0.0) + e.get("dram_write", 0.0)
     out["k_wide_" + k] = e
-    lines.append(f"k_wide_{k}: {e.get('duration_us', 0):.1f} us, grid {int(e.get('grid', 0))} x 512 threads, {int(e.get('registers', 0))} registers, "
+    lines.append(f"k_wide_{k}: {e.get('duration_us', 0):.1f} us, grid {int(e.get('grid', 0))} x {int(e.get('block', 0))} threads, {int(e.get('registers', 0))} registers, "
                  f"tensor pipe {e.get('tensor_pipe_pct_of_peak_elapsed', 0):.1f} % of peak (elapsed), issue active {e.get('issue_active_pct', 0):.1f} %, "
                  f"DRAM {e['dram_bytes'] / 1e6:.1f} MB ({e.get('dram_throughput_pct', 0):.1f} % of peak), stalls {e['stall_share']}")
 os.makedirs(dst, exist_ok=True)

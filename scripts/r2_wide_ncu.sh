@@ -1,7 +1,7 @@
 #!/bin/bash
 # per-kernel durations of the wide step (ncu launch list; serialised, cold-cache: shares, not absolutes)
 mkdir -p gpurun_out/r2w
-for B in 1024 65536; do
+for B in 2048 65536; do
   SWEEP_STEPS=3 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name regex:k_wide -c 200 --csv --log-file gpurun_out/r2w/launches_wide_B$B.csv \
     python scripts/batch_sweep.py $B > gpurun_out/r2w/ncu_B$B.log 2>&1
   python - <<PY

@@ -311,9 +311,7 @@ __global__ void __launch_bounds__(kST, 1) k_wide_fwd(StepArgs a, int step, int s
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_wide_loss(StepArgs a, int step, int vP) {
   __shared__ double pairS[2][256];
-  __shared__ double samp[5][256];
-  __shared__ int info[4][256];          // row, slot, hasNext, valid
-  __shared__ float qret[256];
+  __shared__ double comp[5][8];         // per action component: root, stdev, dpos, 1 / stdev, log(1 / stdev) of the ParamLayer's stdev
   __shared__ StepCtrl c;
   const DevDescs* dd = a.descs;
   const NetDesc& net = dd->net; const Hyper& hp = dd->hp;
@@ -328,7 +326,6 @@ __global__ void __launch_bounds__(256) k_wide_loss(StepArgs a, int step, int vP)
   const int m0 = 1;
   if (tid == 0) load_ctrl(c, &a.ctrl[step & 1]);
   // terms of the ParamLayer's stdev outputs: the same for every sample, evaluated once per CTA (same expressions, same bits)
-  __shared__ double comp[5][8];         // root, stdev, dpos, 1 / stdev, log(1 / stdev)
   if (tid >= 256 - 8 && tid - (256 - 8) < dA) {
     const int k = tid - (256 - 8);
     const double sraw = (double)ld_cg(a.wvec + vP + k);
@@ -338,35 +335,34 @@ __global__ void __launch_bounds__(256) k_wide_loss(StepArgs a, int step, int vP)
     comp[2][k] = (1.0 + sraw / root) / 2.0;                            // SoftPlus::_evalDiff
     comp[3][k] = 1.0 / stdev; comp[4][k] = log(1.0 / stdev);
   }
-  float oldv[5] = {0.f, 0.f, 0.f, 0.f, 0.f};      // V, ADV, RHO, KL, DELTA of the sample thread's transition
-  if (tid < SPC) {
-    const int b = blockIdx.x * SPC + tid;
-    int row = 0, slot = 0, hn = 0;
-    if (b < a.B) {
-      row = __ldg(a.sampRow + j0 + b);
-      const int sf = __ldg(a.sampSlot + j0 + b);
-      slot = sf & 0x7fffffff; hn = (sf >> 31) & 1;
-      oldv[0] = ld_cg(rp.V + row); oldv[1] = ld_cg(rp.ADV + row); oldv[2] = ld_cg(rp.RHO + row);
-      oldv[3] = ld_cg(rp.KL + row); oldv[4] = ld_cg(rp.DELTA + row); qret[tid] = ld_cg(rp.Q + row);
-      if (hn) { const int i = atomicAdd(a.wcnt, 1); a.wlist[i] = b; }      // V(s_t+1): k_wide_next
-    }
-    info[0][tid] = row; info[1][tid] = slot; info[2][tid] = hn; info[3][tid] = b < a.B ? 1 : 0;
-  }
-  __syncthreads();
-  // ---- stage 1: one thread per (sample, action component) ----
+  // one thread per (sample, action component); the thread of component 0 also owns the sample's scalars (old replay values,
+  // write-back, record).  The per-sample terms (rho, V, flags) are evaluated by ALL threads of the sample, redundantly: a serial
+  // per-sample stage on 1 / dA of the threads between two more block barriers left the f64 pipe 80 % idle.
   const int sp = tid / dA, i = tid - sp * dA;
   const int b = blockIdx.x * SPC + sp;
   const bool pairOn = tid < nPair && b < Bt;
-  const bool valid = pairOn && info[3][sp];
+  const bool valid = pairOn && b < a.B;
   float* errT = a.errG + ((size_t)(b >> 7) * per) * kWideM + ((b >> 4) & 7) * per * 16 + (b & 15);       // + scratch row * 16
-  double r_kgm = 0.0, r_kgs = 0.0, r_dlm = 0.0, r_dls = 0.0, r_dpos = 0.0;
-  float mf = 0.f, srawf = 0.f;
-  if (valid) {
-    const size_t prow = info[0][sp];
-    const double av = (double)ld_cg(rp.A + prow * dA + i), mm = (double)ld_cg(rp.MU + prow * 2 * dA + i),
-                 ms = (double)ld_cg(rp.MU + prow * 2 * dA + dA + i);
+  int row = 0, slotf = 0;
+  float oldv[5] = {0.f, 0.f, 0.f, 0.f, 0.f};      // V, ADV, RHO, KL, DELTA of the transition (component-0 thread)
+  float qretf = 0.f, O0f = 0.f, mf = 0.f, srawf = 0.f, avf = 0.f, mmf = 1.f, msf = 1.f;
+  if (valid) {      // every load of the thread in flight at once
+    row = __ldg(a.sampRow + j0 + b);
+    avf = ld_cg(rp.A + (size_t)row * dA + i); mmf = ld_cg(rp.MU + (size_t)row * 2 * dA + i); msf = ld_cg(rp.MU + (size_t)row * 2 * dA + dA + i);
     mf = ld_cg(errT + (Lo.actOff + m0 + i) * 16);
+    O0f = ld_cg(errT + (Lo.actOff + 0) * 16);
+    qretf = ld_cg(rp.Q + row);
     srawf = ld_cg(a.wvec + vP + i);
+    if (i == 0) {
+      slotf = __ldg(a.sampSlot + j0 + b);
+      oldv[0] = ld_cg(rp.V + row); oldv[1] = ld_cg(rp.ADV + row); oldv[2] = ld_cg(rp.RHO + row);
+      oldv[3] = ld_cg(rp.KL + row); oldv[4] = ld_cg(rp.DELTA + row);
+    }
+  }
+  __syncthreads();        // comp, c
+  double r_kgm = 0.0, r_kgs = 0.0, r_dlm = 0.0, r_dls = 0.0, r_dpos = 0.0;
+  if (valid) {
+    const double av = (double)avf, mm = (double)mmf, ms = (double)msf;
     const double m = (double)mf;
     const double stdev = comp[1][i], dpos = comp[2][i];
     const double inv = comp[3][i], invmu = 1.0 / ms;
@@ -391,50 +387,25 @@ __global__ void __launch_bounds__(256) k_wide_loss(StepArgs a, int step, int vP)
     r_dls = (u * u - 1.0) * inv;                                        // dLogPdStdv
     r_dpos = dpos;
   }
-  __syncthreads();
-  // ---- stage 2: one thread per sample — sums in component order like the reference, flags, value terms, replay write-back
-  //      (RACER_train.cpp:59-60) and the record for the aggregate updates ----
-  if (tid < SPC && info[3][tid]) {
-    const int bb = blockIdx.x * SPC + tid;
-    const size_t prow = info[0][tid];
-    const float* eT = a.errG + ((size_t)(bb >> 7) * per) * kWideM + ((bb >> 4) & 7) * per * 16 + (bb & 15);
-    const float O0f = ld_cg(eT + (Lo.actOff + 0) * 16);
+  __syncthreads();        // pairS
+  if (!pairOn) return;
+  float g_mean_f = 0.f, g_std_f = 0.f, g0_f = 0.f;
+  if (valid) {
+    // ---- per-sample terms: sums in component order like the reference, flags, value terms ----
     const double O0 = (double)O0f;
     const double Vval = net2v(O0);                                                     // scaleNet2V (RACER_common.cpp:23-32)
-    const double cmax = c.cmax, cinv = c.cinv;
+    const double cmax = c.cmax, cinv = c.cinv, beta = c.beta;
     double logw = 0.0, dkl = 0.0;
-    for (int k = 0; k < dA; ++k) { logw += pairS[0][tid * dA + k]; dkl += pairS[1][tid * dA + k]; }
+    for (int k = 0; k < dA; ++k) { logw += pairS[0][sp * dA + k]; dkl += pairS[1][sp * dA + k]; }
     const double rho = exp(logw > 7.0 ? 7.0 : (logw < -7.0 ? -7.0 : logw));           // :648-653
     const float W32 = (float)rho, C32 = (float)cmax, I32 = (float)cinv;               // isFarPolicy takes Fval arguments (Episode.h:28-33)
     const bool offW = (W32 > C32) || (W32 < I32);
     const bool isFar = (C32 > 1.0f) && offW;
     const double Aval = 0.0;                                                          // Zero_advantage.h:39-42
-    const double A_RET = (double)qret[tid] - Vval, deltaQ = A_RET - Aval;
-    samp[4][tid] = fmin(1.0, rho) * deltaQ;           // Ver
-    samp[0][tid] = A_RET * fmin(cmax, rho);           // pgfac
-    samp[1][tid] = isFar ? 1.0 : 0.0;
-    samp[3][tid] = vdiff(O0);
-    if (keep) a.lastO[(size_t)bb * net.nOut + 0] = O0f;
-    const float E = (float)deltaQ, Dk = (float)dkl;
-    const float oldRho = oldv[2], oldKL = oldv[3], oldE = oldv[4];
-    const bool wasOff = (oldRho > C32) || (oldRho < I32);
-    const float Vf = (float)Vval, Qf = (float)(Aval + Vval);
-    rp.DELTA[prow] = E; rp.KL[prow] = Dk; rp.RHO[prow] = W32;
-    rp.V[prow] = Vf; rp.ADV[prow] = Qf - Vf;
-    // qNextOld / qNextNew of the record belong to k_wide_next
-    *reinterpret_cast<int4*>(&a.rec[bb].slot) = make_int4(info[1][tid], info[2][tid], (C32 > 1.0f) ? ((int)offW - (int)wasOff) : 0, 0);
-    *reinterpret_cast<float4*>(&a.rec[bb].dKL) = make_float4(Dk - oldKL, (float)offW - (float)wasOff, E * E - oldE * oldE, fabsf(E));
-    *reinterpret_cast<float2*>(&a.rec[bb].qOld) = make_float2(oldv[1] + oldv[0], Qf);
-  }
-  __syncthreads();
-  // ---- stage 3: policy / penalty gradient of every pair (penalizeReFER, FunctionUtilities.h:221-228) ----
-  if (!pairOn) return;
-  float g_mean_f = 0.f, g_std_f = 0.f, g0_f = 0.f;
-  if (valid) {
-    const double beta = c.beta;
+    const double A_RET = (double)qretf - Vval, deltaQ = A_RET - Aval;
+    const double pgfac = A_RET * fmin(cmax, rho);
+    // ---- policy / penalty gradient of the pair (penalizeReFER, FunctionUtilities.h:221-228) ----
     const double MAXM = 8.31776613503286;
-    const double pgfac = samp[0][sp];
-    const bool isFar = samp[1][sp] != 0.0;
     const double m = (double)mf;
     double pg_mean = pgfac * r_dlm;
     if (hp.bounded[i] && ((m >= MAXM && pg_mean > 0.0) || (m <= -MAXM && pg_mean < 0.0))) pg_mean = 0.0;
@@ -442,11 +413,26 @@ __global__ void __launch_bounds__(256) k_wide_loss(StepArgs a, int step, int vP)
     if (isFar) { pg_mean = 0.0; pg_std = 0.0; }
     g_mean_f = (float)(beta * pg_mean + (1.0 - beta) * r_kgm);
     g_std_f = (float)(beta * pg_std + (1.0 - beta) * r_kgs);
-    if (i == 0) g0_f = (float)(isFar ? 0.0 : samp[4][sp] * beta * samp[3][sp]);        // value head (RACER_train.cpp:46)
     if (keep) {
       a.lastG[(size_t)b * net.nOut + m0 + i] = g_mean_f; a.lastG[(size_t)b * net.nOut + m0 + dA + i] = g_std_f;
       a.lastO[(size_t)b * net.nOut + m0 + i] = mf; a.lastO[(size_t)b * net.nOut + m0 + dA + i] = srawf;
-      if (i == 0) a.lastG[(size_t)b * net.nOut + 0] = g0_f;
+    }
+    if (i == 0) {     // the sample's thread: value-head gradient (RACER_train.cpp:46), replay write-back (:59-60), record
+      const double Ver = fmin(1.0, rho) * deltaQ;
+      g0_f = (float)(isFar ? 0.0 : Ver * beta * vdiff(O0));
+      if (keep) { a.lastG[(size_t)b * net.nOut + 0] = g0_f; a.lastO[(size_t)b * net.nOut + 0] = O0f; }
+      const int slot = slotf & 0x7fffffff, hn = (slotf >> 31) & 1;
+      if (hn) { const int k = atomicAdd(a.wcnt, 1); a.wlist[k] = b; }      // V(s_t+1): k_wide_next
+      const float E = (float)deltaQ, Dk = (float)dkl;
+      const float oldRho = oldv[2], oldKL = oldv[3], oldE = oldv[4];
+      const bool wasOff = (oldRho > C32) || (oldRho < I32);
+      const float Vf = (float)Vval, Qf = (float)(Aval + Vval);
+      rp.DELTA[row] = E; rp.KL[row] = Dk; rp.RHO[row] = W32;
+      rp.V[row] = Vf; rp.ADV[row] = Qf - Vf;
+      // qNextOld / qNextNew of the record belong to k_wide_next
+      *reinterpret_cast<int4*>(&a.rec[b].slot) = make_int4(slot, hn, (C32 > 1.0f) ? ((int)offW - (int)wasOff) : 0, 0);
+      *reinterpret_cast<float4*>(&a.rec[b].dKL) = make_float4(Dk - oldKL, (float)offW - (float)wasOff, E * E - oldE * oldE, fabsf(E));
+      *reinterpret_cast<float2*>(&a.rec[b].qOld) = make_float2(oldv[1] + oldv[0], Qf);
     }
   }
   // the gradient replaces the outputs in the scratch (zero for the padding samples of the last tile)
