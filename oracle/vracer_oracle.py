@@ -261,6 +261,25 @@ def tanh_f32(x):
     return np.where(x > 0, y, -y).astype(f32)
 
 
+def sigm_act_f32(x):
+    """Sigm::_eval, Functions.h:158-165, f32."""
+    x = np.asarray(x, f32)
+    e = np.exp(-np.abs(x)).astype(f32)
+    return np.where(x > 0, f32(1) / (f32(1) + e), e / (f32(1) + e)).astype(f32)
+
+
+# hidden-layer functions "nnFunc" (makeFunction, Functions.h:643-668) with initFactor sqrt(6 / (in + out)):
+# name -> (eval(in), evalDiff(in, out)), f32 like the reference's SINGLE_PREC build
+ACTIVATIONS = {
+    "Tanh": (tanh_f32, lambda x, y: (f32(1) - y * y).astype(f32)),                                          # :103-116
+    "SoftSign": (lambda x: (np.asarray(x, f32) / (f32(1) + np.abs(np.asarray(x, f32)))).astype(f32),          # :328-337
+                 lambda x, y: (f32(1) / ((f32(1) + np.abs(x)) * (f32(1) + np.abs(x)))).astype(f32)),
+    "HardSign": (lambda x: (np.asarray(x, f32) / np.sqrt(f32(1) + np.asarray(x, f32) ** 2)).astype(f32),       # :220-229
+                 lambda x, y: (f32(1) / (np.sqrt(f32(1) + x * x) ** 3)).astype(f32)),
+    "Sigm": (sigm_act_f32, lambda x, y: (y * (f32(1) - y)).astype(f32)),                                       # :158-182
+}
+
+
 def anneal_rate(eta, t, eps):
     """Utils/FunctionUtilities.h:69-72."""
     return eta / (1 + t * eps)
@@ -333,9 +352,17 @@ def _dense_fwd(x, W, b):
     return acc
 
 
+class _Acts(list):
+    """Layer outputs of one forward pass + the pre-activations of the hidden dense layers."""
+    def __init__(self, it=()):
+        super().__init__(it)
+        self.pre = {}
+
+
 class MlpNet:
-    def __init__(self, layout: MlpLayout):
+    def __init__(self, layout: MlpLayout, func: str = "Tanh"):
         self.L = layout
+        self.act, self.act_diff = ACTIVATIONS[func]
 
     def views(self, blob):
         v = []
@@ -353,13 +380,15 @@ class MlpNet:
         """Network::forward (Network.h:101-113).  x: [B, dS] f32.  Returns (O f32 [B, nOut], cache)."""
         x = np.asarray(x, f32)
         Bn = x.shape[0]
-        Y = [x]  # Y[k] = output of layer k (Y[0] = input layer)
+        Y = _Acts([x])  # Y[k] = output of layer k (Y[0] = input layer); Y.pre[k] = pre-activation of hidden dense layer k
         views = self.views(blob)
         outs = []
         for L, (W, b) in zip(self.L.layers, views):
             k = L["kind"]
             if k == "dense_tanh":
-                Y.append(tanh_f32(_dense_fwd(Y[-1], W, b)))
+                pre = _dense_fwd(Y[-1], W, b)
+                Y.pre[len(Y)] = pre
+                Y.append(self.act(pre))
             elif k == "residual":  # ParametricResidualLayer::forward (Layers.h:347-361)
                 Y.append((Y[-1] + (Y[-2] * W[None, :] + b[None, :]).astype(f32)).astype(f32))
             elif k == "dense_linear":
@@ -403,7 +432,7 @@ class MlpNet:
                 acc_rows(G[L["b"]:L["b"] + L["n"]], E[yi])
             elif kind.startswith("dense"):  # BaseLayer::backward (Layer_Base.h:97-113) + Layer::backward (Layers.h:123-188)
                 if kind == "dense_tanh":
-                    E[yi] = (E[yi] * (f32(1) - Y[yi] * Y[yi]).astype(f32)).astype(f32)
+                    E[yi] = (E[yi] * self.act_diff(Y.pre[yi], Y[yi])).astype(f32)      # Function::evalDiff(in, out), Layer_Base.h:103-109
                 d = E[yi]
                 first = (li == 0)  # input gradient skipped for layer 1 (Approximator.cpp:145-169)
                 if not first:
@@ -703,7 +732,7 @@ class VracerOracle:
     def __init__(self, dS, dA, hidden=(128, 128), gamma=0.995, lam=1.0, clip_imp_weight=None,
                  penal_tol=0.1, eps_anneal=5e-7, learnrate=1e-4, nn_lambda=FLT_EPS,
                  batch=256, max_tot_obs=None, bounded=False, sample_seed=42, learner="VRACER",
-                 returns_estimator="retrace", sampling="uniform", er_filter="oldest", discrete=0, refer_threads=1):
+                 returns_estimator="retrace", sampling="uniform", er_filter="oldest", discrete=0, refer_threads=1, nn_func="Tanh"):
         self.dS, self.dA = dS, dA
         # OpenMP threads of the reference run: only the far-policy count depends on it (`Uint += float` partials per thread with
         # schedule(static, 1), MemoryProcessing.cpp:202-227)
@@ -725,7 +754,7 @@ class VracerOracle:
             self.layout = MlpLayout(dS, hidden, 1 + 2 * self.discrete, 0)
         else:
             self.layout = MlpLayout(dS, hidden, (2 + 3 * dA) if self.racer else (1 + dA), dA)
-        self.net = MlpNet(self.layout)
+        self.net = MlpNet(self.layout, nn_func)
         self.gamma, self.lam = gamma, lam
         self.C = float(np.sqrt(dA / 2.0)) if clip_imp_weight is None else float(clip_imp_weight)  # HyperParameters.h:46
         self.penal_tol, self.eps_anneal, self.eta, self.nn_lambda = penal_tol, eps_anneal, learnrate, nn_lambda

@@ -858,6 +858,7 @@ void cluster_plan_build(const NetDesc& net, int numWorkersHint, ClusterPlan& cp,
   items.assign((size_t)kCL * kST * kItemInts, 0);
   idx.assign((size_t)3 * net.nParams, -1);
   for (int p = 0; p < net.nParams; ++p) idx[p] = -2;
+  if (net.func != 0) return;        // the cluster kernel hard-wires Tanh hidden layers
   if (net.recurrent || net.discrete) return;
   // opt-in (SMB200_CLUSTER=1): at B = 256 the persistent tile kernel is still the faster one ("cluster step kernel")
   const char* on = getenv("SMB200_CLUSTER");

@@ -178,6 +178,8 @@ static int build_net(const smb200_config& c, NetDesc& net, std::vector<GradTile>
   const bool lstm = c.nn_type == SMB200_LSTM || c.nn_type == SMB200_MGU;      // recurrent-cell layers
   const int cellKind = c.nn_type == SMB200_MGU ? kMGU : kLSTM, ng = cell_gates(cellKind);
   if (c.nn_type != SMB200_FFNN && !lstm) { set_error_msg("nnType must be FFNN, LSTM, MGU or GRU"); return -1; }
+  if (c.nn_func < SMB200_TANH || c.nn_func > SMB200_SIGM || (c.nn_func != SMB200_TANH && lstm)) {
+    set_error_msg("nnFunc must be Tanh, SoftSign, HardSign or Sigm (recurrent cells: Tanh)"); return -1; }
   if (lstm && (c.nn_bptt_seq < 0 || c.nn_bptt_seq > 255)) { set_error_msg("nnBPTTseq out of range"); return -1; }
   if (lstm) for (int i = 0; i < c.n_hidden; ++i) if (c.hidden[i] > NT) { set_error_msg("LSTM layers wider than the CTA are not supported"); return -1; }
   for (int i = 0; i < c.n_hidden; ++i) {
@@ -225,7 +227,7 @@ static int build_net(const smb200_config& c, NetDesc& net, std::vector<GradTile>
     P.imgB = img; P.imgW = img; img += round_up(nParamOut, 4);
   }
   net.nLayers = id; net.nParams = off; net.imgFloats = img; net.nOut = nOutDense + nParamOut; net.nOutDense = nOutDense;
-  net.dS = dS; net.dA = dA; net.maxWidth = width; net.discrete = K;
+  net.dS = dS; net.dA = dA; net.maxWidth = width; net.discrete = K; net.func = c.nn_func;
   net.recurrent = lstm ? 1 : 0; net.bptt = lstm ? c.nn_bptt_seq : 0; net.Tc = net.bptt + 1;
   net.topInOff = act;
   if (lstm) act += round_up(nIn, 4);      // compact copy of the top hidden layer's output at the sampled step

@@ -193,6 +193,23 @@ __device__ __forceinline__ float tanh_ref(float x) {
   return x > 0.0f ? y : -y;
 }
 
+__device__ __forceinline__ float sigm_ref(float x);
+// Hidden-layer function "nnFunc" (makeFunction, Network/Layers/Functions.h:643-668): value from the pre-activation, derivative
+// from the OUTPUT (the reference's evalDiff(in, out) of Tanh and Sigm only reads `out`; SoftSign and HardSign read `in`, whose
+// terms are functions of the output: 1 + |x| = 1 / (1 - |y|),  1 + x^2 = 1 / (1 - y^2)).
+__device__ __forceinline__ float act_eval(int f, float x) {
+  if (f == 0) return tanh_ref(x);                                      // Tanh::_eval (:103-112)
+  if (f == 1) return __fdividef(x, 1.0f + fabsf(x));                   // SoftSign::_eval (:328-331)
+  if (f == 2) return x * rsqrtf(1.0f + x * x);                         // HardSign::_eval (:220-223)
+  return sigm_ref(x);                                                  // Sigm::_eval (:158-165)
+}
+__device__ __forceinline__ float act_diff(int f, float y) {
+  if (f == 0) return 1.0f - y * y;                                     // Tanh::_evalDiff
+  if (f == 1) { const float t = 1.0f - fabsf(y); return t * t; }       // SoftSign: 1 / (1 + |x|)^2
+  if (f == 2) { const float t = 1.0f - y * y; return t * sqrtf(t); }   // HardSign: 1 / (1 + x^2)^(3/2)
+  return y * (1.0f - y);                                               // Sigm::_evalDiff(in, out)
+}
+
 // scaleNet2V / scaleVdiff (Learners/RACER_common.cpp:23-32), f64
 __host__ __device__ __forceinline__ double net2v(double x) {
   return x > 0 ? 100.0 * (x + 51.0) - 100.0 * sqrt(2601.0 + 100.0 * x)
@@ -285,7 +302,7 @@ template <bool SM> __device__ __forceinline__ float4 ldw4(const float* p) {
   return SM ? *reinterpret_cast<const float4*>(p) : __ldcg(reinterpret_cast<const float4*>(p));
 }
 
-//   mode 0: y = b + x W        mode 1: y = tanh(b + x W)       (BaseLayer::forward, Layer_Base.h:64-95)
+//   mode 0: y = b + x W        mode 1 + f: y = act_f(b + x W), f = NetDesc::func       (BaseLayer::forward, Layer_Base.h:64-95)
 // If yres != nullptr the ParametricResidualLayer that follows this layer is evaluated in the same
 // epilogue: yres = y + (x * resW + resB)   (Layers.h:347-361; x = output of layer ID-2 = this layer's input).
 template <int TB, bool SM>
@@ -335,7 +352,7 @@ __device__ __forceinline__ void dense_fwd(const float* Wp, int ldp, int K, int N
         for (int gg = 0; gg < G; ++gg) v += red[(gg * NR + n2) * TB + s];
         const int n = n0 + n2;
         v += ldw<SM>(bias + n);
-        v = mode == 1 ? tanh_ref(v) : v;
+        v = mode == 1 ? tanh_ref(v) : (mode > 1 ? act_eval(mode - 1, v) : v);
         y[n * TB + s] = v;
         if (yres) yres[n * TB + s] = n < K ? v + (x[n * TB + s] * ldw<SM>(resW + n) + ldw<SM>(resB + n)) : v;
       }
@@ -347,7 +364,7 @@ __device__ __forceinline__ void dense_fwd(const float* Wp, int ldp, int K, int N
 #pragma unroll
       for (int s = 0; s < TB; ++s) {
         float v = acc[s] + bv;
-        v = mode == 1 ? tanh_ref(v) : v;
+        v = mode == 1 ? tanh_ref(v) : (mode > 1 ? act_eval(mode - 1, v) : v);
         y[n * TB + s] = v;
         if (yres) yres[n * TB + s] = n < K ? v + (x[n * TB + s] * rw + rb) : v;
       }
@@ -433,7 +450,7 @@ __device__ void net_forward(const NetDesc& net, const float* Wp, float* act, flo
       if (dbg && l < 5) DBG_T(*dbg, step, 26 + l);
       const LayerDesc& R = net.L[fuse ? l + 1 : l];
       dense_fwd<TB, SM>(Wp + L.imgW, L.ldp, L.nIn, L.size, Wp + L.imgB, act + net.L[L.in].actOff * TB, y, red,
-                        L.kind == kDenseTanh ? 1 : 0, L.fwdShift, fuse ? Wp + R.imgW : nullptr, fuse ? Wp + R.imgB : nullptr,
+                        L.kind == kDenseTanh ? 1 + net.func : 0, L.fwdShift, fuse ? Wp + R.imgW : nullptr, fuse ? Wp + R.imgB : nullptr,
                         fuse ? act + R.actOff * TB : nullptr);
 #ifdef SMB200_ICACHE_PROBE   // does a warm instruction cache change the cost of a layer?  (idempotent repeat of the output layer)
       if (dbg && L.kind == kDenseLinear) {
@@ -979,13 +996,13 @@ __device__ void p1_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
       const float* y = act + L.actOff * TB;
       for (int idx = tid; idx < L.size * TB; idx += kST) {
         const float d3 = e3[idx];
-        e[idx] = L.kind == kDenseTanh ? d3 * (1.0f - y[idx] * y[idx]) : d3;
+        e[idx] = L.kind == kDenseTanh ? d3 * act_diff(net.func, y[idx]) : d3;
         if (idx < L.nIn * TB) ein[idx] += d3 * ldw<SM>(Wp + R.imgW + idx / TB);
       }
       __syncthreads();
     } else if (L.kind == kDenseTanh) {
       const float* y = act + L.actOff * TB;
-      for (int idx = tid; idx < L.size * TB; idx += kST) e[idx] = e[idx] * (1.0f - y[idx] * y[idx]);
+      for (int idx = tid; idx < L.size * TB; idx += kST) e[idx] = e[idx] * act_diff(net.func, y[idx]);
       __syncthreads();
     }
     if (L.needDx)                   // E_in += W * delta; skipped for the first layer (Approximator.cpp:145-169)

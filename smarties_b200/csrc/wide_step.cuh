@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(kST, 1) k_wide_fwd(StepArgs a, int step, int s
       mmaPar ^= 1u;
       tc_fence_after();
       const float* bias = vec + D.vB;
-      const int dN = D.N, dNp8 = D.Np / 8, dY = D.yOff, dZ = D.zOff;      // registers (see k_wide_bwd)
+      const int dN = D.N, dNp8 = D.Np / 8, dY = D.yOff, dZ = D.zOff, func = net.func;      // registers (see k_wide_bwd)
       if (D.isTanh) {
         const bool res = D.res >= 0;
         const float* rw = vec + (res ? D.vRW : 0); const float* rb = vec + (res ? D.vRB : 0);
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(kST, 1) k_wide_fwd(StepArgs a, int step, int s
           // and biases: tanh(0) = 0, and are not stored)
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
-            const float y = tanh_ref(__uint_as_float(v[jj]) + bv[jj]);          // BaseLayer::forward (Layer_Base.h:64-95)
+            const float y = act_eval(func, __uint_as_float(v[jj]) + bv[jj]);    // BaseLayer::forward (Layer_Base.h:64-95)
             float z = y;
             if (res) {                                                         // ParametricResidualLayer::forward (Layers.h:347-361)
               const float xin = __uint_as_float(xh[jj]) + __uint_as_float(xl[jj]);     // hi + lo is the f32 value, exactly
@@ -662,7 +662,7 @@ __global__ void __launch_bounds__(kST, 1) k_wide_bwd(StepArgs a, int step, int s
       // the layer's outputs (tanh') do not depend on the product: fetch them while the tensor core works
       // plan fields in registers: read through the shared-memory copy inside the unrolled loops they are re-read after
       // every global store (possible aliasing)
-      const int hN = H.N, hNp8 = H.Np / 8, hY = H.yOff, hZ = H.zOff, dKp = D.Kp;
+      const int hN = H.N, hNp8 = H.Np / 8, hY = H.yOff, hZ = H.zOff, dKp = D.Kp, func = net.func;
       float yv[32];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -701,7 +701,7 @@ __global__ void __launch_bounds__(kST, 1) k_wide_bwd(StepArgs a, int step, int s
           const bool in = n0 + jj < hN;
           const float ez = (have ? __uint_as_float(v[jj]) : 0.f) + (haveCarry ? __uint_as_float(cy[jj]) : 0.f);   // E_in = W * delta (+ residual path)
           const float y = yv[8 * i + jj];
-          const float delta = in ? ez * (1.0f - y * y) : 0.f;
+          const float delta = in ? ez * act_diff(func, y) : 0.f;
           float cnew = 0.f;
           if (res) { cnew = in ? ez * rwv[jj] : 0.f; if (in) ep[jj * 16] = ez; }
           if (in) dp[jj * 16] = delta;
@@ -805,6 +805,7 @@ __global__ void __launch_bounds__(kST, 1) k_wide_wgrad(StepArgs a, int step) {
   // images of one of TWO image stages, and multiplied; the MMAs of stage i (tcgen05.commit -> mbarrier of its image stage) run
   // while stage i + 1 is split and stage i + 2 travels.
   float4* raw = reinterpret_cast<float4*>(smraw + wp.sgRaw) + tid;
+  const int nImg = wp.sgStages;            // image stages: 2, or 1 when four dense layers leave no room for the second
   int qA[ND], qB[ND], qE[ND], nOps = 0;
 #pragma unroll
   for (int d = 0; d < ND; ++d) { qA[d] = nOps++; qB[d] = nOps++; qE[d] = (d < ND - 1 && wp.D[d].res >= 0) ? nOps++ : -1; }
@@ -836,7 +837,7 @@ __global__ void __launch_bounds__(kST, 1) k_wide_wgrad(StepArgs a, int step) {
   issue(st0 + 1);
 
   for (int it = st0; it < st1; ++it) {
-    const int slot = (it - st0) & 1, use = (it - st0) >> 1;
+    const int slot = (it - st0) % nImg, use = (it - st0) / nImg;
     unsigned char* stg = smraw + wp.sgStage + (size_t)slot * wp.sgStageBytes;
     if (use > 0) { if (!mbar_wait_bounded(&bars[slot], (unsigned)((use - 1) & 1))) fault = true; }     // MMAs of the image stage's previous use
 #pragma unroll
@@ -890,7 +891,7 @@ __global__ void __launch_bounds__(kST, 1) k_wide_wgrad(StepArgs a, int step) {
   const int nMine = st1 - st0;
   if (nMine > 0) {
     const int last = nMine - 1;
-    if (!mbar_wait_bounded(&bars[last & 1], (unsigned)((last >> 1) & 1))) fault = true;
+    if (!mbar_wait_bounded(&bars[last % nImg], (unsigned)((last / nImg) & 1))) fault = true;
   }
   tc_fence_after();
   {
@@ -1059,12 +1060,13 @@ void wide_plan_build(const NetDesc& net, const Hyper& hp, WidePlan& wp, std::vec
   wp.sbTotal = o;
   o = kWideDescBytes + kWidePlanBytes;
   wp.sgBars = take(64);
-  wp.sgStage = take(2 * sg);
-  wp.sgStages = 2;
   {
     int nOps = 0;
     for (int d = 0; d < nD; ++d) nOps += 2 + ((d < nD - 1 && wp.D[d].res >= 0) ? 1 : 0);
-    wp.sgRaw = take(nOps * kST * 16);
+    const int rawBytes = nOps * kST * 16;
+    wp.sgStages = (o + 2 * sg + rawBytes + 256 <= kMax) ? 2 : 1;
+    wp.sgStage = take(wp.sgStages * sg);
+    wp.sgRaw = take(rawBytes);
   }
   wp.sgTotal = o;
   if (wp.sfTotal > kMax || wp.sbTotal > kMax || wp.sgTotal > kMax) return;

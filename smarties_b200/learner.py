@@ -54,7 +54,7 @@ class Config(C.Structure):
         ("out_weights_prefac", C.c_double), ("refer_reduce_threads", C.c_int32), ("world_rank", C.c_int32),
         ("world_size", C.c_int32), ("seed", C.c_uint64), ("nn_type", C.c_int32), ("nn_bptt_seq", C.c_int32),
         ("min_tot_obs", C.c_int64), ("returns_estimator", C.c_int32), ("discrete_options", C.c_int32),
-        ("data_sampling", C.c_int32), ("er_filter", C.c_int32),
+        ("data_sampling", C.c_int32), ("er_filter", C.c_int32), ("nn_func", C.c_int32),
     ]
 
 
@@ -201,6 +201,7 @@ def make_config(dim_state: int, dim_action: int, settings=None, *, device: int =
     cfg.discrete_options = int(discrete_options)     # from the MDP (Communicator::setNumberOfOptions), not from settings.json
     cfg.data_sampling = {"uniform": 0, "PERrank": 1, "PERerr": 2, "PERseq": 3}[hp.dataSamplingAlgo]
     cfg.er_filter = {"oldest": 0, "default": 0, "farpolfrac": 1, "maxkldiv": 2, "minerror": 3}[hp.ERoldSeqFilter]
+    cfg.nn_func = {"Tanh": 0, "SoftSign": 1, "HardSign": 2, "Sigm": 3}[hp.nnFunc]
     if bounded is not None:
         b = np.broadcast_to(np.asarray(bounded, dtype=bool), (dim_action,))
         for i in range(dim_action):

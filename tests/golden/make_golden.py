@@ -53,6 +53,21 @@ CASES = {
         replay=dict(seed=83, n_ep=64, ep_len=(90, 130), dS=16, dA=4),
         settings={"learner": "VRACER", "nnLayerSizes": [128, 128], "batchSize": 4096, "maxTotObsNum": 16384, "minTotObsNum": 5000},
         steps=3, start_step=998, sample_seed=29, bounded=0, full_steps=[0, 2]),
+    # hidden-layer functions other than Tanh (makeFunction, Network/Layers/Functions.h:643-668): settings/default.json asks for
+    # SoftSign; HardSign and Sigm share its weight-initialisation factor
+    "vracer_softsign": dict(
+        replay=dict(seed=91, n_ep=24, ep_len=(30, 60), dS=6, dA=2),
+        settings={"learner": "VRACER", "nnFunc": "SoftSign", "nnLayerSizes": [32, 32], "batchSize": 32, "maxTotObsNum": 4096,
+                  "minTotObsNum": 600, "clipImpWeight": 4, "epsAnneal": 0, "nnLambda": 0},
+        steps=4, start_step=997, sample_seed=13, bounded=0, full_steps=[0, 3]),
+    "vracer_hardsign": dict(
+        replay=dict(seed=92, n_ep=20, ep_len=(25, 50), dS=5, dA=3),
+        settings={"learner": "VRACER", "nnFunc": "HardSign", "nnLayerSizes": [24, 24, 24], "batchSize": 16, "maxTotObsNum": 2048, "minTotObsNum": 400},
+        steps=3, start_step=0, sample_seed=5, bounded=1, full_steps=[0, 2]),
+    "racer_sigm": dict(
+        replay=dict(seed=93, n_ep=20, ep_len=(25, 50), dS=7, dA=2),
+        settings={"learner": "RACER", "nnFunc": "Sigm", "nnLayerSizes": [32, 32], "batchSize": 16, "maxTotObsNum": 2048, "minTotObsNum": 400},
+        steps=3, start_step=0, sample_seed=9, bounded=0, full_steps=[0, 2]),
     # FIFO pruning: capacity below the stored data, so applyEpisodesRemovalAlgo evicts on step 1
     "vracer_prune": dict(
         replay=dict(seed=17, n_ep=16, ep_len=(20, 30), dS=4, dA=2),

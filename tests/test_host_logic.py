@@ -143,10 +143,10 @@ def test_every_settings_file_of_the_reference_is_parsed_or_rejected_with_a_reaso
     assert len(files) >= 17
     covered = {"VRACER.json": ("VRACER", "FFNN"), "RACER.json": ("RACER", "FFNN"), "RACER_RNN.json": ("RACER", "LSTM"),
                "VRACER_LES.json": ("VRACER", "FFNN"), "RACER_glider.json": ("RACER", "FFNN"), "RACER_atari.json": ("RACER", "FFNN"),
-               "VRACER_expensiveData.json": ("VRACER", "GRU")}
+               "VRACER_expensiveData.json": ("VRACER", "GRU"), "default.json": ("VRACER", "FFNN")}      # default.json: SoftSign hidden layers
     refused = {"ACER.json": "learner=ACER", "CMA.json": "learner=CMA", "DPG.json": "learner=DPG", "DPG_light.json": "learner=DPG",
                "DPG_orig.json": "learner=DPG", "DQN.json": "learner=DQN", "NAF.json": "learner=NAF", "PPO.json": "learner=PPO",
-               "VRACER_CMA.json": "ESpopSize", "default.json": "nnType/nnFunc/nnOutputFunc"}
+               "VRACER_CMA.json": "ESpopSize"}
     for name, settings in files.items():
         if name in covered:
             hp = HyperParameters(8, 2, settings)
