@@ -264,6 +264,16 @@ uint64_t smb200_uint_plus_float(uint64_t n, float x);
  * cfg->seed (Network/Builder.cpp:133-137, Layer_Base.h:115-141, Layer_LSTM.h:168-188, ExecutionInfo.cpp:391).
  * Returns the blob size in floats (blob may be NULL to query it), negative on error. */
 int64_t smb200_host_init_weights(const smb200_config* cfg, float* blob, int64_t n);
+/* Diagnostics, host only (no GPU needed): the wide step's plan for cfg's network (csrc/wide_step.cuh: index maps and pre-split
+ * operand images of the tensor-core kernels).  Returns 1 if the wide step covers the network, 0 if not, negative on error.
+ * info[16] = {dense layers, forward image floats, transposed image floats, vector block floats, partial-record floats, TMEM
+ * columns of the weight-gradient kernel, shared memory of k_wide_fwd / k_wide_bwd / k_wide_wgrad (bytes), image stages,
+ * NpG, 0...};  per dense layer d: dense[8 d ...] = {K, Kp, N, Np, forward image offset, transposed image offset, gN, gPart}.
+ * With blob (n_blob = smb200_n_params floats): idx[5][n_blob] receives the maps (record position, tile-image, forward-image,
+ * transposed-image and vector-block position of every parameter, -1 = none) and img_f / img_b / vec the images
+ * wide_fill_images builds from blob (sizes info[1], info[2], info[3]).  NULL pointers are skipped. */
+int smb200_host_wide_plan(const smb200_config* cfg, int32_t* info, int32_t* dense, const float* blob, int64_t n_blob, int32_t* idx,
+                          float* img_f, float* img_b, float* vec);
 /* Diagnostics, host only (no GPU needed): the library's conversion between the padded parameter blob and the order
  * Network::save writes to <name>_net_{weights,tgt_weights,1stMom,2ndMom}.raw (Network/Network.cpp:22-67; padding stripped per
  * layer: Layer_Base.h:143-169, Layers.h:401-418,554-566, Layer_LSTM.h:189-211) — what smb200_save / smb200_restart use.

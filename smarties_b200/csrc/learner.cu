@@ -1523,6 +1523,46 @@ int64_t smb200_host_init_weights(const smb200_config* cfg, float* blob, int64_t 
   return np;
 }
 
+// The wide step's host-built plan, index maps and operand images (wide_plan_build / wide_fill_images, csrc/wide_step.cuh)
+// without a device: what smb200_create builds and uploads.
+int smb200_host_wide_plan(const smb200_config* cfg, int32_t* info, int32_t* dense, const float* blob, int64_t n_blob, int32_t* idx,
+                          float* img_f, float* img_b, float* vec) {
+  if (!cfg) return SMB200_ERR_INVALID;
+  NetDesc* net = new NetDesc();
+  std::vector<GradTile> tiles;
+  if (build_net(*cfg, *net, tiles)) { delete net; return SMB200_ERR_INVALID; }
+  Hyper hp; memset(&hp, 0, sizeof(hp)); hp.algo = cfg->algo;
+  WidePlan* wp = new WidePlan();
+  std::vector<int> widx;
+  wide_plan_build(*net, hp, *wp, widx);
+  const int ok = wp->ok;
+  if (info) {
+    const int v[16] = {wp->nD, wp->fFloats, wp->bFloats, wp->vFloats, wp->recFloats, wp->gCols, wp->sfTotal, wp->sbTotal, wp->sgTotal,
+                       wp->sgStages, wp->NpG, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 16; ++i) info[i] = v[i];
+  }
+  if (dense && ok)
+    for (int d = 0; d < wp->nD; ++d) {
+      const WDense& D = wp->D[d];
+      const int v[8] = {D.K, D.Kp, D.N, D.Np, D.fImg, D.bImg, D.gN, D.gPart};
+      for (int i = 0; i < 8; ++i) dense[8 * d + i] = v[i];
+    }
+  int rc = ok;
+  if (ok && blob) {
+    if (n_blob != net->nParams) { set_error_msg("wide_plan: blob size mismatch"); rc = SMB200_ERR_INVALID; }
+    else {
+      if (idx) memcpy(idx, widx.data(), sizeof(int) * widx.size());
+      std::vector<float> f, b, v;
+      wide_fill_images(*net, *wp, widx, blob, f, b, v);
+      if (img_f) memcpy(img_f, f.data(), sizeof(float) * (size_t)wp->fFloats);
+      if (img_b) memcpy(img_b, b.data(), sizeof(float) * (size_t)wp->bFloats);
+      if (vec) memcpy(vec, v.data(), sizeof(float) * (size_t)wp->vFloats);
+    }
+  }
+  delete wp; delete net;
+  return rc;
+}
+
 // The StatsTracker file writer without a device (diagnostics for the CPU test suite): g = per-sample output gradients
 // [batch][n_out] of a step that starts at nGradSteps % 1000 == 0, reduced and appended exactly as the learner does.
 int smb200_host_write_grad_stats(const char* base, int32_t batch, int32_t n_out, const float* g, int32_t first_tracker_step) {

@@ -37,7 +37,7 @@ EXPORTS = [
     "smb200_push_episode_restored", "smb200_set_refer", "smb200_set_grad_stats", "smb200_uint_plus_float", "smb200_host_replay_trace", "smb200_host_init_weights",
     "smb200_host_strip_weights", "smb200_host_write_grad_stats", "smb200_host_repack_episodes",
     "smb200_host_adam", "smb200_host_value_scaling", "smb200_host_return_estimator",
-    "smb200_host_discrete_loss",
+    "smb200_host_discrete_loss", "smb200_host_wide_plan",
 ]
 
 FIELDS = dict(V=0, ADV=1, QRET=2, DELTA=3, RHO=4, KL=5, REWARD=6)

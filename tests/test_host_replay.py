@@ -510,3 +510,94 @@ def test_retrace_at_full_buffer_size_matches_the_reference_binary(built_library)
     assert abs(q64.sum() - z["init/Qret_sum"][0]) < 1e-6 * np.abs(q64).sum()
     assert abs((q64 * q64).sum() - z["init/Qret_sum"][1]) < 1e-6 * z["init/Qret_sum"][1]
     assert abs(np.abs(q64).max() - z["init/Qret_sum"][2]) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------
+# wide step (csrc/wide_step.cuh): plan, index maps and pre-split operand images, built on the host exactly as smb200_create does
+# ------------------------------------------------------------------------------------------
+def _wide_plan(cfg, blob=None):
+    from smarties_b200 import load_library
+    lib = load_library()
+    P = C.POINTER
+    lib.smb200_host_wide_plan.restype = C.c_int
+    lib.smb200_host_wide_plan.argtypes = [C.c_void_p, P(C.c_int32), P(C.c_int32), P(C.c_float), C.c_int64, P(C.c_int32), P(C.c_float),
+                                          P(C.c_float), P(C.c_float)]
+    info = np.zeros(16, np.int32); dense = np.zeros(8 * 4, np.int32)
+    ip = lambda a: a.ctypes.data_as(P(C.c_int32))
+    fp = lambda a: a.ctypes.data_as(P(C.c_float))
+    rc = lib.smb200_host_wide_plan(C.byref(cfg), ip(info), ip(dense), None, 0, None, None, None, None)
+    out = dict(rc=rc, info=info, dense=dense.reshape(4, 8))
+    if rc == 1 and blob is not None:
+        n = blob.size
+        idx = np.zeros(5 * n, np.int32)
+        f, b, v = np.zeros(info[1], np.float32), np.zeros(info[2], np.float32), np.zeros(info[3], np.float32)
+        assert lib.smb200_host_wide_plan(C.byref(cfg), ip(info), ip(dense), fp(blob), n, ip(idx), fp(f), fp(b), fp(v)) == 1
+        out.update(idx=idx.reshape(5, n), f=f, b=b, v=v)
+    return out
+
+
+def _tf32_hi(w):
+    """cvt.rna.tf32.f32: round to nearest, ties away from zero, on the 13 dropped mantissa bits."""
+    u = w.view(np.uint32).astype(np.uint64)
+    return ((u + 0x1000) & 0xFFFFE000).astype(np.uint32).view(np.float32)
+
+
+@pytest.mark.parametrize("case", ["vracer_cfg2mini", "vracer_b4096", "vracer_hardsign", "vracer_small"])
+def test_wide_step_plan_and_operand_images(built_library, case):
+    """Every parameter of the network has exactly one position in a weight-gradient record; the forward image holds W[k][n] at
+    float4 [k / 4][n] component k % 4 (K-major UMMA operand, no swizzle) as hi = TF32(w) and lo = w - hi with hi + lo == w
+    exactly; the transposed image holds the same values at float4 [n / 4][k] component n % 4; biases, residual vectors and the
+    ParamLayer sit in the vector block; the three tensor-core kernels fit the 227 KB of shared memory."""
+    from smarties_b200.learner import make_config
+    g = Golden(case)
+    cfg, _ = make_config(g.dS, g.dA, dict(g.settings), bounded=g.bounded, seed=42)
+    blob = g.ref["init/weights"].astype(np.float32).copy()
+    p = _wide_plan(cfg, blob)
+    assert p["rc"] == 1
+    nD, fF, bF, vF, rec, cols, sf, sb, sg, stages, NpG = [int(x) for x in p["info"][:11]]
+    hidden = [h for h in g.settings.get("nnLayerSizes", [128, 128])]
+    assert nD == len(hidden) + 1 and max(sf, sb, sg) <= 227 * 1024 and cols <= 512 and stages in (1, 2)
+    idx, f, b, v = p["idx"], p["f"], p["b"], p["v"]
+    real = idx[0] >= 0
+    # the record positions of the real parameters are distinct, inside the record, and every non-zero weight is a real parameter
+    assert len(np.unique(idx[0][real])) == real.sum() and idx[0][real].max() < rec
+    assert np.all(blob[~real] == 0)
+    hi, lo = f[:fF // 2], f[fF // 2:]
+    assert np.array_equal((hi.astype(np.float64) + lo).astype(np.float32)[idx[2][idx[2] >= 0]], blob[idx[2] >= 0])
+    assert np.array_equal(hi[idx[2][idx[2] >= 0]], _tf32_hi(blob[idx[2] >= 0]))
+    bh, bl = b[:bF // 2], b[bF // 2:]
+    sel = idx[3] >= 0
+    assert np.array_equal(bh[idx[3][sel]], _tf32_hi(blob[sel])) and np.array_equal(bl[idx[3][sel]], blob[sel] - _tf32_hi(blob[sel]))
+    assert np.array_equal(v[idx[4][idx[4] >= 0]], blob[idx[4] >= 0])
+    # layout formulas of the operand images, layer by layer (parameter blob: W[k][roundUp8(N)] then bias, Parameters.h:159-176)
+    off = 0
+    n_in = g.dS
+    sizes = hidden + [1 + g.dA]
+    for d, n_out in enumerate(sizes):
+        K, Kp, N, Np, fImg, bImg, gN, gPart = [int(x) for x in p["dense"][d]]
+        assert (K, N) == (n_in, n_out) and Kp % 16 == 0 and Np in (16, 32, 64, 128) and Kp >= K and Np >= N
+        ld = (n_out + 7) // 8 * 8
+        for k, n in ((0, 0), (K - 1, N - 1), (K // 2, N // 3)):
+            w = blob[off + k * ld + n]
+            assert hi[fImg + ((k >> 2) * Np + n) * 4 + (k & 3)] == _tf32_hi(np.array([w], np.float32))[0]
+            if d >= 1:
+                assert bh[bImg + ((n >> 2) * Kp + k) * 4 + (n & 3)] == _tf32_hi(np.array([w], np.float32))[0]
+            assert idx[0][off + k * ld + n] == (gPart + n * 128 + k if d == nD - 1 else gPart + k * 128 + n)
+        off += (ld * n_in + 7) // 8 * 8 + (n_out + 7) // 8 * 8
+        if 0 < d < nD - 1:
+            off += 2 * ((n_out + 7) // 8 * 8)        # ParametricResidual w, b after every hidden layer but the first
+        n_in = n_out
+
+
+def test_wide_step_plan_refuses_what_it_does_not_cover(built_library):
+    from smarties_b200.learner import make_config
+    for dS, dA, settings in ((8, 2, {"learner": "RACER", "nnLayerSizes": [32, 32]}),               # Gaussian advantage head
+                             (8, 2, {"nnType": "LSTM", "nnLayerSizes": [32]}),                     # recurrent cells
+                             (8, 2, {"nnLayerSizes": [256, 256]}),                                 # wider than one MMA tile
+                             (8, 12, {"nnLayerSizes": [64, 64]}),                                  # more than 8 action components
+                             (8, 2, {"nnLayerSizes": [32, 32, 32, 32]})):                          # more than 4 dense layers
+        cfg, _ = make_config(dS, dA, settings)
+        assert _wide_plan(cfg)["rc"] == 0, settings
+    cfg, _ = make_config(32, 8, {"nnLayerSizes": [128, 128]})
+    p = _wide_plan(cfg)
+    assert p["rc"] == 1 and int(p["info"][0]) == 3 and int(p["info"][9]) == 2       # cfg2: three dense layers, two image stages
