@@ -52,9 +52,10 @@ enum smb200_returns_estimator { SMB200_RETRACE = 0, SMB200_GAE = 1,
  * episode order of step k+1 depend on values step k wrote), like the reference re-prepares its sampler every step. */
 enum smb200_sampling { SMB200_SAMPLE_UNIFORM = 0, SMB200_SAMPLE_PER_RANK = 1, SMB200_SAMPLE_PER_ERR = 2, SMB200_SAMPLE_PER_SEQ = 3 };
 enum smb200_er_filter { SMB200_FILTER_OLDEST = 0, SMB200_FILTER_FARPOLFRAC = 1, SMB200_FILTER_MAXKLDIV = 2, SMB200_FILTER_MINERROR = 3 };
-/* "nnFunc": function of the hidden dense layers (makeFunction, Network/Layers/Functions.h:643-668).  The four whose weight
- * initialisation factor is sqrt(6 / (inputs + outputs)) are covered; feed-forward nets (recurrent cells keep Tanh). */
-enum smb200_nn_func { SMB200_TANH = 0, SMB200_SOFTSIGN = 1 /* settings/default.json */, SMB200_HARDSIGN = 2, SMB200_SIGM = 3 };
+/* "nnFunc": function of the hidden dense layers (makeFunction, Network/Layers/Functions.h:643-668) with its own weight
+ * initialisation factor (Function::initFactor); feed-forward nets (recurrent cells keep Tanh). */
+enum smb200_nn_func { SMB200_TANH = 0, SMB200_SOFTSIGN = 1 /* settings/default.json */, SMB200_HARDSIGN = 2, SMB200_SIGM = 3,
+                      SMB200_RELU = 4, SMB200_LRELU = 5 };
 enum smb200_field {          /* per-transition replay arrays, Episode.h:66-75 */
   SMB200_F_V = 0, SMB200_F_ADV = 1, SMB200_F_QRET = 2, SMB200_F_DELTA = 3, SMB200_F_RHO = 4, SMB200_F_KL = 5,
   SMB200_F_REWARD = 6

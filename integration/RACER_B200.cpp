@@ -111,7 +111,8 @@ class RACER_B200 : public RACER<Advantage_t, Policy_t, Action_t>
                     : settings.dataSamplingAlgo == "PERseq" ? SMB200_SAMPLE_PER_SEQ : SMB200_SAMPLE_UNIFORM;
     c.er_filter = settings.ERoldSeqFilter == "farpolfrac" ? SMB200_FILTER_FARPOLFRAC : settings.ERoldSeqFilter == "maxkldiv" ? SMB200_FILTER_MAXKLDIV
                 : settings.ERoldSeqFilter == "minerror" ? SMB200_FILTER_MINERROR : SMB200_FILTER_OLDEST;
-    c.nn_func = settings.nnFunc == "SoftSign" ? SMB200_SOFTSIGN : settings.nnFunc == "HardSign" ? SMB200_HARDSIGN : settings.nnFunc == "Sigm" ? SMB200_SIGM : SMB200_TANH;
+    c.nn_func = settings.nnFunc == "SoftSign" ? SMB200_SOFTSIGN : settings.nnFunc == "HardSign" ? SMB200_HARDSIGN : settings.nnFunc == "Sigm" ? SMB200_SIGM
+              : settings.nnFunc == "Relu" ? SMB200_RELU : settings.nnFunc == "LRelu" ? SMB200_LRELU : SMB200_TANH;
     c.returns_estimator = settings.returnsEstimator == "GAE" ? SMB200_GAE
                         : (settings.returnsEstimator == "retraceExplore" ? SMB200_RETRACE_EXPLORE : SMB200_RETRACE);
     // an episode occupies nsteps() = ndata()+1 rows and is at least two rows long: room for the worst case,
@@ -392,10 +393,11 @@ std::unique_ptr<Learner> createLearner(const Uint learnerID, MDPdescriptor& MDP,
                                                   settings.returnsEstimator == "retraceExplore") &&
       (settings.ERoldSeqFilter == "oldest" || settings.ERoldSeqFilter == "default") &&
       (settings.nnType == "FFNN" || settings.nnType == "LSTM" || settings.nnType == "MGU" || settings.nnType == "GRU") &&
-      // hidden-layer functions with the sqrt(6 / (in + out)) initialisation (Functions.h); recurrent cells keep Tanh.
+      // hidden-layer functions the device evaluates (makeFunction, Functions.h:643-668); recurrent cells keep Tanh.
       // settings/default.json asks for SoftSign.
       (settings.nnFunc == "Tanh" || (settings.nnType == "FFNN" && !MDP.isPartiallyObservable &&
-                                     (settings.nnFunc == "SoftSign" || settings.nnFunc == "HardSign" || settings.nnFunc == "Sigm"))) &&
+                                     (settings.nnFunc == "SoftSign" || settings.nnFunc == "HardSign" || settings.nnFunc == "Sigm" ||
+                                      settings.nnFunc == "Relu" || settings.nnFunc == "LRelu"))) &&
       settings.nnOutputFunc == "Linear" &&
       // several learner ranks: the device learners of the ranks would have to exchange CUDA-IPC handles over
       // distrib.learners_train_comm (smb200_comm_init / smb200_comm_attach) — not wired into the binding: reference learner

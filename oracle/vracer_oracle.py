@@ -277,6 +277,10 @@ ACTIVATIONS = {
     "HardSign": (lambda x: (np.asarray(x, f32) / np.sqrt(f32(1) + np.asarray(x, f32) ** 2)).astype(f32),       # :220-229
                  lambda x, y: (f32(1) / (np.sqrt(f32(1) + x * x) ** 3)).astype(f32)),
     "Sigm": (sigm_act_f32, lambda x, y: (y * (f32(1) - y)).astype(f32)),                                       # :158-182
+    "Relu": (lambda x: np.where(np.asarray(x, f32) > 0, x, f32(0)).astype(f32),                                # :415-423
+             lambda x, y: np.where(x > 0, f32(1), f32(0)).astype(f32)),
+    "LRelu": (lambda x: np.where(np.asarray(x, f32) > 0, x, (f32(0.1) * np.asarray(x, f32)).astype(f32)).astype(f32),   # PRELU_FAC 0.1 (:16-18,461-468)
+              lambda x, y: np.where(x > 0, f32(1), f32(0.1)).astype(f32)),
 }
 
 

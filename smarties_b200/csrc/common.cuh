@@ -52,8 +52,8 @@ struct NetDesc {
   int Tc;            // bptt + 1 = longest window; P2 column of (sample b, window step k) = b*Tc + k
   int topInOff;      // row of the compact copy (column = b) of the top hidden layer's output at the sampled step
   int seqFloats;     // shared-memory floats of the per-sample sequence workspace (step_kernels.cu: SeqPlan)
-  int func;          // "nnFunc" of the hidden dense layers: 0 Tanh, 1 SoftSign, 2 HardSign, 3 Sigm (Network/Layers/Functions.h:90-400;
-                     // the four with initFactor sqrt(6 / (inputs + outputs)))
+  int func;          // "nnFunc" of the hidden dense layers: 0 Tanh, 1 SoftSign, 2 HardSign, 3 Sigm, 4 Relu, 5 LRelu
+                     // (Network/Layers/Functions.h:90-480)
   int discrete;      // K > 0: one discrete action component with K options — outputs [V | advantages(K) | policy(K)], MU rows of K
                      // probabilities (RACER<Discrete_advantage, Discrete_policy, Uint>, Learners/RACER.cpp:114)
   LayerDesc L[kMaxLayers];

@@ -201,13 +201,17 @@ __device__ __forceinline__ float act_eval(int f, float x) {
   if (f == 0) return tanh_ref(x);                                      // Tanh::_eval (:103-112)
   if (f == 1) return __fdividef(x, 1.0f + fabsf(x));                   // SoftSign::_eval (:328-331)
   if (f == 2) return x * rsqrtf(1.0f + x * x);                         // HardSign::_eval (:220-223)
-  return sigm_ref(x);                                                  // Sigm::_eval (:158-165)
+  if (f == 3) return sigm_ref(x);                                      // Sigm::_eval (:158-165)
+  if (f == 4) return x > 0.0f ? x : 0.0f;                              // Relu::_eval (:415-418)
+  return x > 0.0f ? x : 0.1f * x;                                      // LRelu::_eval, PRELU_FAC 0.1 (:16-18,461-464)
 }
 __device__ __forceinline__ float act_diff(int f, float y) {
   if (f == 0) return 1.0f - y * y;                                     // Tanh::_evalDiff
   if (f == 1) { const float t = 1.0f - fabsf(y); return t * t; }       // SoftSign: 1 / (1 + |x|)^2
   if (f == 2) { const float t = 1.0f - y * y; return t * sqrtf(t); }   // HardSign: 1 / (1 + x^2)^(3/2)
-  return y * (1.0f - y);                                               // Sigm::_evalDiff(in, out)
+  if (f == 3) return y * (1.0f - y);                                   // Sigm::_evalDiff(in, out)
+  if (f == 4) return y > 0.0f ? 1.0f : 0.0f;                           // Relu: in > 0 <=> out > 0
+  return y > 0.0f ? 1.0f : 0.1f;                                       // LRelu
 }
 
 // scaleNet2V / scaleVdiff (Learners/RACER_common.cpp:23-32), f64

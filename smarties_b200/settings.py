@@ -102,8 +102,8 @@ class HyperParameters:
             unsupported.append(f"returnsEstimator={self.returnsEstimator}")
         if self.ERoldSeqFilter not in ("oldest", "default", "farpolfrac", "maxkldiv", "minerror"):
             unsupported.append(f"ERoldSeqFilter={self.ERoldSeqFilter}")
-        # hidden-layer functions with the sqrt(6 / (in + out)) initialisation (Functions.h); recurrent cells keep Tanh
-        func_ok = self.nnFunc == "Tanh" or (self.nnType == "FFNN" and self.nnFunc in ("SoftSign", "HardSign", "Sigm"))
+        # hidden-layer functions of makeFunction (Functions.h:643-668) the device evaluates; recurrent cells keep Tanh
+        func_ok = self.nnFunc == "Tanh" or (self.nnType == "FFNN" and self.nnFunc in ("SoftSign", "HardSign", "Sigm", "Relu", "LRelu"))
         if self.nnType not in ("FFNN", "LSTM", "MGU", "GRU") or not func_ok or self.nnOutputFunc != "Linear":
             unsupported.append(f"nnType/nnFunc/nnOutputFunc={self.nnType}/{self.nnFunc}/{self.nnOutputFunc}")
         if self.ESpopSize != 1 or self.targetDelay != 0 or any(int(e) > 0 for e in self.encoderLayerSizes):

@@ -68,6 +68,14 @@ CASES = {
         replay=dict(seed=93, n_ep=20, ep_len=(25, 50), dS=7, dA=2),
         settings={"learner": "RACER", "nnFunc": "Sigm", "nnLayerSizes": [32, 32], "batchSize": 16, "maxTotObsNum": 2048, "minTotObsNum": 400},
         steps=3, start_step=0, sample_seed=9, bounded=0, full_steps=[0, 2]),
+    "vracer_relu": dict(       # Relu: initFactor sqrt(2 / inputs) (Functions.h:404-413)
+        replay=dict(seed=94, n_ep=20, ep_len=(25, 50), dS=6, dA=2),
+        settings={"learner": "VRACER", "nnFunc": "Relu", "nnLayerSizes": [32, 32], "batchSize": 16, "maxTotObsNum": 2048, "minTotObsNum": 400},
+        steps=3, start_step=0, sample_seed=21, bounded=0, full_steps=[0, 2]),
+    "vracer_lrelu": dict(      # LRelu: initFactor sqrt(1 / inputs), slope PRELU_FAC = 0.1 below zero (Functions.h:16-18,452-468)
+        replay=dict(seed=95, n_ep=20, ep_len=(25, 50), dS=6, dA=2),
+        settings={"learner": "VRACER", "nnFunc": "LRelu", "nnLayerSizes": [32, 32], "batchSize": 16, "maxTotObsNum": 2048, "minTotObsNum": 400},
+        steps=3, start_step=0, sample_seed=22, bounded=1, full_steps=[0, 2]),
     # FIFO pruning: capacity below the stored data, so applyEpisodesRemovalAlgo evicts on step 1
     "vracer_prune": dict(
         replay=dict(seed=17, n_ep=16, ep_len=(20, 30), dS=4, dA=2),
