@@ -32,6 +32,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 namespace smb200 {
@@ -197,21 +198,43 @@ __device__ __forceinline__ float sigm_ref(float x);
 // Hidden-layer function "nnFunc" (makeFunction, Network/Layers/Functions.h:643-668): value from the pre-activation, derivative
 // from the OUTPUT (the reference's evalDiff(in, out) of Tanh and Sigm only reads `out`; SoftSign and HardSign read `in`, whose
 // terms are functions of the output: 1 + |x| = 1 / (1 - |y|),  1 + x^2 = 1 / (1 - y^2)).
-__device__ __forceinline__ float act_eval(int f, float x) {
-  if (f == 0) return tanh_ref(x);                                      // Tanh::_eval (:103-112)
-  if (f == 1) return __fdividef(x, 1.0f + fabsf(x));                   // SoftSign::_eval (:328-331)
-  if (f == 2) return x * rsqrtf(1.0f + x * x);                         // HardSign::_eval (:220-223)
-  if (f == 3) return sigm_ref(x);                                      // Sigm::_eval (:158-165)
-  if (f == 4) return x > 0.0f ? x : 0.0f;                              // Relu::_eval (:415-418)
+template <int F> __device__ __forceinline__ float act_eval_t(float x) {
+  if (F == 0) return tanh_ref(x);                                      // Tanh::_eval (:103-112)
+  if (F == 1) return __fdividef(x, 1.0f + fabsf(x));                   // SoftSign::_eval (:328-331)
+  if (F == 2) return x * rsqrtf(1.0f + x * x);                         // HardSign::_eval (:220-223)
+  if (F == 3) return sigm_ref(x);                                      // Sigm::_eval (:158-165)
+  if (F == 4) return x > 0.0f ? x : 0.0f;                              // Relu::_eval (:415-418)
   return x > 0.0f ? x : 0.1f * x;                                      // LRelu::_eval, PRELU_FAC 0.1 (:16-18,461-464)
 }
-__device__ __forceinline__ float act_diff(int f, float y) {
-  if (f == 0) return 1.0f - y * y;                                     // Tanh::_evalDiff
-  if (f == 1) { const float t = 1.0f - fabsf(y); return t * t; }       // SoftSign: 1 / (1 + |x|)^2
-  if (f == 2) { const float t = 1.0f - y * y; return t * sqrtf(t); }   // HardSign: 1 / (1 + x^2)^(3/2)
-  if (f == 3) return y * (1.0f - y);                                   // Sigm::_evalDiff(in, out)
-  if (f == 4) return y > 0.0f ? 1.0f : 0.0f;                           // Relu: in > 0 <=> out > 0
+template <int F> __device__ __forceinline__ float act_diff_t(float y) {
+  if (F == 0) return 1.0f - y * y;                                     // Tanh::_evalDiff
+  if (F == 1) { const float t = 1.0f - fabsf(y); return t * t; }       // SoftSign: 1 / (1 + |x|)^2
+  if (F == 2) { const float t = 1.0f - y * y; return t * sqrtf(t); }   // HardSign: 1 / (1 + x^2)^(3/2)
+  if (F == 3) return y * (1.0f - y);                                   // Sigm::_evalDiff(in, out)
+  if (F == 4) return y > 0.0f ? 1.0f : 0.0f;                           // Relu: in > 0 <=> out > 0
   return y > 0.0f ? 1.0f : 0.1f;                                       // LRelu
+}
+// run `body(std::integral_constant<int, F>)` with F = the runtime function id: the selection happens once per call site, the
+// element loops inside `body` are branch-free
+template <class Body> __device__ __forceinline__ void act_dispatch(int f, Body&& body) {
+  switch (f) {
+    case 0: body(std::integral_constant<int, 0>{}); break;
+    case 1: body(std::integral_constant<int, 1>{}); break;
+    case 2: body(std::integral_constant<int, 2>{}); break;
+    case 3: body(std::integral_constant<int, 3>{}); break;
+    case 4: body(std::integral_constant<int, 4>{}); break;
+    default: body(std::integral_constant<int, 5>{}); break;
+  }
+}
+__device__ __forceinline__ float act_eval(int f, float x) {
+  float y = 0.f;
+  act_dispatch(f, [&](auto F) { y = act_eval_t<decltype(F)::value>(x); });
+  return y;
+}
+__device__ __forceinline__ float act_diff(int f, float y) {
+  float d = 0.f;
+  act_dispatch(f, [&](auto F) { d = act_diff_t<decltype(F)::value>(y); });
+  return d;
 }
 
 // scaleNet2V / scaleVdiff (Learners/RACER_common.cpp:23-32), f64
@@ -987,6 +1010,7 @@ __device__ void p1_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
 
   // ---- backward: Network::backProp, layers last to first (Network.h:216-226).  A residual layer
   //      is folded into the dense layer below it: E(l) = E(res) * f'(Y_l), E(l-1) += E(res) * w_res ----
+  const int func = net.func;          // "nnFunc" of the hidden layers (0 = Tanh: the expression of round 1, unchanged)
   for (int l = net.nLayers - 1; l >= 1; --l) {
     const LayerDesc& L = net.L[l];
     if (L.kind != kDenseTanh && L.kind != kDenseLinear) continue;
@@ -1000,13 +1024,13 @@ __device__ void p1_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
       const float* y = act + L.actOff * TB;
       for (int idx = tid; idx < L.size * TB; idx += kST) {
         const float d3 = e3[idx];
-        e[idx] = L.kind == kDenseTanh ? d3 * act_diff(net.func, y[idx]) : d3;
+        e[idx] = L.kind == kDenseTanh ? d3 * (func == 0 ? 1.0f - y[idx] * y[idx] : act_diff(func, y[idx])) : d3;
         if (idx < L.nIn * TB) ein[idx] += d3 * ldw<SM>(Wp + R.imgW + idx / TB);
       }
       __syncthreads();
     } else if (L.kind == kDenseTanh) {
       const float* y = act + L.actOff * TB;
-      for (int idx = tid; idx < L.size * TB; idx += kST) e[idx] = e[idx] * act_diff(net.func, y[idx]);
+      for (int idx = tid; idx < L.size * TB; idx += kST) e[idx] = e[idx] * (func == 0 ? 1.0f - y[idx] * y[idx] : act_diff(func, y[idx]));
       __syncthreads();
     }
     if (L.needDx)                   // E_in += W * delta; skipped for the first layer (Approximator.cpp:145-169)

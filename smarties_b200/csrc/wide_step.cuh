@@ -259,9 +259,14 @@ __global__ void __launch_bounds__(kST, 1) k_wide_fwd(StepArgs a, int step, int s
           uint32_t hi[8], lo[8];
           // no branches inside: the eight columns are independent instruction streams (the padding columns have zero weights
           // and biases: tanh(0) = 0, and are not stored)
+          float yv8[8];
+          act_dispatch(func, [&](auto F) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) yv8[jj] = act_eval_t<decltype(F)::value>(__uint_as_float(v[jj]) + bv[jj]);      // BaseLayer::forward (Layer_Base.h:64-95)
+          });
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
-            const float y = act_eval(func, __uint_as_float(v[jj]) + bv[jj]);    // BaseLayer::forward (Layer_Base.h:64-95)
+            const float y = yv8[jj];
             float z = y;
             if (res) {                                                         // ParametricResidualLayer::forward (Layers.h:347-361)
               const float xin = __uint_as_float(xh[jj]) + __uint_as_float(xl[jj]);     // hi + lo is the f32 value, exactly
@@ -696,12 +701,16 @@ __global__ void __launch_bounds__(kST, 1) k_wide_bwd(StepArgs a, int step, int s
         }
         float* ep = errT + (hZ + n0) * 16 + sOff;
         float* dp = errT + (hY + n0) * 16 + sOff;
+        float dv8[8];
+        act_dispatch(func, [&](auto F) {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) dv8[jj] = act_diff_t<decltype(F)::value>(yv[8 * i + jj]);      // deltas *= f' (Layer_Base.h:103-109)
+        });
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
           const bool in = n0 + jj < hN;
           const float ez = (have ? __uint_as_float(v[jj]) : 0.f) + (haveCarry ? __uint_as_float(cy[jj]) : 0.f);   // E_in = W * delta (+ residual path)
-          const float y = yv[8 * i + jj];
-          const float delta = in ? ez * act_diff(func, y) : 0.f;
+          const float delta = in ? ez * dv8[jj] : 0.f;
           float cnew = 0.f;
           if (res) { cnew = in ? ez * rwv[jj] : 0.f; if (in) ep[jj * 16] = ez; }
           if (in) dp[jj * 16] = delta;
