@@ -236,7 +236,7 @@ int smb200_forward(smb200_learner* h, const float* states, int32_t n, float* out
  * stream), and the number of kernels it launched. */
 int smb200_last_timing(smb200_learner* h, double* ms_device, int64_t* kernel_launches);
 /* Which kernels run the learner steps of this learner: 0 two kernels per step, 1 persistent tile kernel, 2 cluster kernel,
- * 3 wide step (tcgen05 tiles of 128 sampled transitions; feed-forward V-RACER, batch_size >= 2048 or SMB200_WIDE=1). */
+ * 3 wide step (tcgen05 tiles of 128 sampled transitions; feed-forward V-RACER / RACER with continuous actions, batch_size >= 2048 or SMB200_WIDE=1). */
 int smb200_step_kernel(const smb200_learner* h);
 /* Raw access for benchmarks: run n steps on ids already resident in HBM (uploaded by
  * smb200_presample) without any host<->device copy. */

@@ -92,7 +92,7 @@ struct ClusterPlan {
 };
 
 // ------------------------------------------------------------------------------------------
-// Wide (large-batch) learner step of feed-forward V-RACER nets (wide_step.cuh): tiles of 128 sampled transitions, every
+// Wide (large-batch) learner step of feed-forward V-RACER / RACER nets (wide_step.cuh): tiles of 128 sampled transitions, every
 // dense product of the network as tcgen05.mma kind::tf32 contractions (3xTF32: f32 accuracy) with the weights stationary in
 // shared memory, the activations of a tile as the A operand in TENSOR MEMORY, accumulators in tensor memory.
 // ------------------------------------------------------------------------------------------

@@ -1,4 +1,4 @@
-// wide_step.cuh — the LARGE-BATCH learner step of feed-forward V-RACER nets on the 5th-generation tensor cores.
+// wide_step.cuh — the LARGE-BATCH learner step of feed-forward V-RACER / RACER nets on the 5th-generation tensor cores.
 // Included by step_kernels.cu (inside namespace smb200, after the tile kernel's device functions).
 //
 // For mini-batches of >= 1024 sampled transitions the dense products of the step ARE contractions (SURVEY.md §8d batch
@@ -314,8 +314,9 @@ __global__ void __launch_bounds__(kST, 1) k_wide_fwd(StepArgs a, int step, int s
 // for the sums in component order, the flags, the replay write-back and the record.  Reads the outputs from the scratch rows
 // of the output layer and overwrites them with the gradient.
 // ------------------------------------------------------------------------------------------
+template <bool RACER>
 __global__ void __launch_bounds__(256) k_wide_loss(StepArgs a, int step, int vP) {
-  __shared__ double pairS[2][256];
+  __shared__ double pairS[RACER ? 4 : 2][256];
   __shared__ double comp[5][8];         // per action component: root, stdev, dpos, 1 / stdev, log(1 / stdev) of the ParamLayer's stdev
   __shared__ StepCtrl c;
   const DevDescs* dd = a.descs;
@@ -328,7 +329,8 @@ __global__ void __launch_bounds__(256) k_wide_loss(StepArgs a, int step, int vP)
   const int Bt = (a.B + kWideM - 1) / kWideM * kWideM;
   const size_t j0 = (size_t)(step - a.stepBase) * a.B;
   const bool keep = step == a.lastStep || a.lastStep < 0;
-  const int m0 = 1;
+  // outputs: V-RACER [V | mean(dA)], RACER [V | coef, p1(dA), p2(dA) | mean(dA)] (RACER_common.cpp:174-193,232-247)
+  const int m0 = RACER ? 2 + 2 * dA : 1;
   if (tid == 0) load_ctrl(c, &a.ctrl[step & 1]);
   // terms of the ParamLayer's stdev outputs: the same for every sample, evaluated once per CTA (same expressions, same bits)
   if (tid >= 256 - 8 && tid - (256 - 8) < dA) {
@@ -350,12 +352,16 @@ __global__ void __launch_bounds__(256) k_wide_loss(StepArgs a, int step, int vP)
   float* errT = a.errG + ((size_t)(b >> 7) * per) * kWideM + ((b >> 4) & 7) * per * 16 + (b & 15);       // + scratch row * 16
   int row = 0, slotf = 0;
   float oldv[5] = {0.f, 0.f, 0.f, 0.f, 0.f};      // V, ADV, RHO, KL, DELTA of the transition (component-0 thread)
-  float qretf = 0.f, O0f = 0.f, mf = 0.f, srawf = 0.f, avf = 0.f, mmf = 1.f, msf = 1.f;
+  float qretf = 0.f, O0f = 0.f, mf = 0.f, srawf = 0.f, avf = 0.f, mmf = 1.f, msf = 1.f, p1rf = 0.f, p2rf = 0.f, coefRawf = 0.f;
   if (valid) {      // every load of the thread in flight at once
     row = __ldg(a.sampRow + j0 + b);
     avf = ld_cg(rp.A + (size_t)row * dA + i); mmf = ld_cg(rp.MU + (size_t)row * 2 * dA + i); msf = ld_cg(rp.MU + (size_t)row * 2 * dA + dA + i);
     mf = ld_cg(errT + (Lo.actOff + m0 + i) * 16);
     O0f = ld_cg(errT + (Lo.actOff + 0) * 16);
+    if (RACER) {
+      coefRawf = ld_cg(errT + (Lo.actOff + 1) * 16);
+      p1rf = ld_cg(errT + (Lo.actOff + 2 + i) * 16); p2rf = ld_cg(errT + (Lo.actOff + 2 + dA + i) * 16);
+    }
     qretf = ld_cg(rp.Q + row);
     srawf = ld_cg(a.wvec + vP + i);
     if (i == 0) {
@@ -366,6 +372,7 @@ __global__ void __launch_bounds__(256) k_wide_loss(StepArgs a, int step, int vP)
   }
   __syncthreads();        // comp, c
   double r_kgm = 0.0, r_kgs = 0.0, r_dlm = 0.0, r_dls = 0.0, r_dpos = 0.0;
+  double r_p9 = -1.0, r_p10 = -1.0, r_F = 0.0, r_d1 = 0.0, r_d2 = 0.0, r_e1 = 0.0, r_e2 = 0.0;      // RACER: Gaussian advantage terms of the pair
   if (valid) {
     const double av = (double)avf, mm = (double)mmf, ms = (double)msf;
     const double m = (double)mf;
@@ -391,10 +398,28 @@ __global__ void __launch_bounds__(256) k_wide_loss(StepArgs a, int step, int vP)
     r_dlm = bnd ? (av - m) * inv * inv : u * inv;                       // dLogPdMean
     r_dls = (u * u - 1.0) * inv;                                        // dLogPdStdv
     r_dpos = dpos;
+    if (RACER) {   // Gaussian_advantage terms of this component (Gaus_advantage.h:73-126)
+      const double p1r = (double)p1rf, p2r = (double)p2rf;
+      const double rt1 = sqrt(1.0 + p1r * p1r), rt2 = sqrt(1.0 + p2r * p2r);
+      const double p1 = (p1r + rt1) / 2.0, p2 = (p2r + rt2) / 2.0;                 // PosDefFunction::_eval
+      const double S = stdev * stdev;                                             // policy->getVariance(i)
+      const double dmA = av - cm;                                                 // policy->getMean(i): clamped for bounded dims
+      const double sq1 = sqrt(p1 / (p1 + S)), sq2 = sqrt(p2 / (p2 + S));
+      const double x1 = dmA / p1, x2 = dmA / p2;
+      pairS[2][tid] = (dmA * dmA) / (av > cm ? p1 : p2);                          // diagInvMul term
+      pairS[3][tid] = sq1 / 2.0 + sq2 / 2.0;                                      // coefMixRatio factor
+      r_p9 = av > cm ? x1 * x1 : -1.0;                                            // ((a-m)/p1)^2 or "not on this side"
+      r_p10 = av < cm ? x2 * x2 : -1.0;
+      r_F = 2.0 / (sq1 + sq2);
+      r_d1 = S / sqrt(p1 * ((p1 + S) * (p1 + S) * (p1 + S))) / 4.0;               // diff1
+      r_d2 = S / sqrt(p2 * ((p2 + S) * (p2 + S) * (p2 + S))) / 4.0;               // diff2
+      r_e1 = (1.0 + p1r / rt1) / 2.0;                                             // PosDefFunction::_evalDiff
+      r_e2 = (1.0 + p2r / rt2) / 2.0;
+    }
   }
   __syncthreads();        // pairS
   if (!pairOn) return;
-  float g_mean_f = 0.f, g_std_f = 0.f, g0_f = 0.f;
+  float g_mean_f = 0.f, g_std_f = 0.f, g0_f = 0.f, g1_f = 0.f, g2_f = 0.f, gc_f = 0.f;
   if (valid) {
     // ---- per-sample terms: sums in component order like the reference, flags, value terms ----
     const double O0 = (double)O0f;
@@ -406,7 +431,17 @@ __global__ void __launch_bounds__(256) k_wide_loss(StepArgs a, int step, int vP)
     const float W32 = (float)rho, C32 = (float)cmax, I32 = (float)cinv;               // isFarPolicy takes Fval arguments (Episode.h:28-33)
     const bool offW = (W32 > C32) || (W32 < I32);
     const bool isFar = (C32 > 1.0f) && offW;
-    const double Aval = 0.0;                                                          // Zero_advantage.h:39-42
+    double Aval = 0.0;                                                                // Zero_advantage.h:39-42
+    double orig = 0.0, ratio = 1.0, coef = 0.0, dcoef = 0.0;
+    if (RACER) {                                                                      // computeAdvantage, Gaus_advantage.h:73-78
+      double shape = 0.0;
+      for (int k = 0; k < dA; ++k) { shape += pairS[2][sp * dA + k]; ratio *= pairS[3][sp * dA + k]; }
+      orig = exp(-shape / 2.0);
+      const double coefRaw = (double)coefRawf, rtc = sqrt(1.0 + coefRaw * coefRaw);
+      coef = (coefRaw + rtc) / 2.0;
+      dcoef = (1.0 + coefRaw / rtc) / 2.0;
+      Aval = coef * (orig - ratio);
+    }
     const double A_RET = (double)qretf - Vval, deltaQ = A_RET - Aval;
     const double pgfac = A_RET * fmin(cmax, rho);
     // ---- policy / penalty gradient of the pair (penalizeReFER, FunctionUtilities.h:221-228) ----
@@ -418,9 +453,27 @@ __global__ void __launch_bounds__(256) k_wide_loss(StepArgs a, int step, int vP)
     if (isFar) { pg_mean = 0.0; pg_std = 0.0; }
     g_mean_f = (float)(beta * pg_mean + (1.0 - beta) * r_kgm);
     g_std_f = (float)(beta * pg_std + (1.0 - beta) * r_kgs);
+    if (RACER) {        // ADV.grad(act, isFar ? 0 : beta * Aer, gradient), Gaus_advantage.h:88-114
+      const double Aer = fmin(cmax, rho) * deltaQ;
+      const double errA = isFar ? 0.0 : beta * Aer;
+      const double oc = orig * coef, expect = -ratio;
+      double g1 = r_p9 >= 0.0 ? oc * r_p9 / 2.0 : 0.0;
+      double g2 = r_p10 >= 0.0 ? oc * r_p10 / 2.0 : 0.0;
+      g1 += r_F * expect * coef * r_d1;
+      g2 += r_F * expect * coef * r_d2;
+      g1 *= errA * r_e1;
+      g2 *= errA * r_e2;
+      g1_f = (float)g1; g2_f = (float)g2;
+      if (i == 0) gc_f = (float)((orig + expect) * (errA * dcoef));
+    }
     if (keep) {
       a.lastG[(size_t)b * net.nOut + m0 + i] = g_mean_f; a.lastG[(size_t)b * net.nOut + m0 + dA + i] = g_std_f;
       a.lastO[(size_t)b * net.nOut + m0 + i] = mf; a.lastO[(size_t)b * net.nOut + m0 + dA + i] = srawf;
+      if (RACER) {
+        a.lastG[(size_t)b * net.nOut + 2 + i] = g1_f; a.lastG[(size_t)b * net.nOut + 2 + dA + i] = g2_f;
+        a.lastO[(size_t)b * net.nOut + 2 + i] = p1rf; a.lastO[(size_t)b * net.nOut + 2 + dA + i] = p2rf;
+        if (i == 0) { a.lastG[(size_t)b * net.nOut + 1] = gc_f; a.lastO[(size_t)b * net.nOut + 1] = coefRawf; }
+      }
     }
     if (i == 0) {     // the sample's thread: value-head gradient (RACER_train.cpp:46), replay write-back (:59-60), record
       const double Ver = fmin(1.0, rho) * deltaQ;
@@ -444,6 +497,10 @@ __global__ void __launch_bounds__(256) k_wide_loss(StepArgs a, int step, int vP)
   errT[(Lo.actOff + m0 + i) * 16] = g_mean_f;
   errT[(Lp.actOff + i) * 16] = g_std_f;
   if (i == 0) errT[(Lo.actOff + 0) * 16] = g0_f;
+  if (RACER) {
+    errT[(Lo.actOff + 2 + i) * 16] = g1_f; errT[(Lo.actOff + 2 + dA + i) * 16] = g2_f;
+    if (i == 0) errT[(Lo.actOff + 1) * 16] = gc_f;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -999,7 +1056,7 @@ void wide_plan_build(const NetDesc& net, const Hyper& hp, WidePlan& wp, std::vec
   memset(&wp, 0, sizeof(wp));
   const int nP = net.nParams;
   idx.assign((size_t)5 * nP, -1);
-  if (net.recurrent || net.discrete || hp.algo != 0 || net.dA > 8 || net.dS > 64) return;     // feed-forward V-RACER, dA <= 8 (two pairs per thread)
+  if (net.recurrent || net.discrete || (hp.algo != 0 && hp.algo != 1) || net.dA > 8 || net.dS > 64) return;     // feed-forward V-RACER / RACER, continuous actions, dA <= 8
   int nD = 0;
   for (int l = 1; l < net.nLayers; ++l) {
     const LayerDesc& L = net.L[l];
@@ -1166,11 +1223,13 @@ int launch_steps_wide(const StepArgs& a, const NetDesc& net, const WidePlan& wp,
   const int gridT = (nTiles + rounds - 1) / rounds;
   const bool sm = step_image_in_smem(net);
   const int spc = 256 / net.dA;
+  const bool racer = net.nOutDense == 2 + 3 * net.dA;      // RACER's Gaussian advantage head (the plan admits V-RACER and RACER)
   for (int s = 0; s < nSteps; ++s) {
     const int step = step0 + s;
     const bool skipStats = skipStatsLast && s == nSteps - 1;
     k_wide_fwd<<<gridT, kST, wp.sfTotal, st>>>(a, step, wp.sfBars, wp.sfImg, wp.fFloats);
-    k_wide_loss<<<(nTiles * kWideM + spc - 1) / spc, 256, 0, st>>>(a, step, wp.vP);
+    if (racer) k_wide_loss<true><<<(nTiles * kWideM + spc - 1) / spc, 256, 0, st>>>(a, step, wp.vP);
+    else k_wide_loss<false><<<(nTiles * kWideM + spc - 1) / spc, 256, 0, st>>>(a, step, wp.vP);
     SMB200_CUDA_CHECK(cudaEventRecord(evF, st));
     SMB200_CUDA_CHECK(cudaStreamWaitEvent(aux, evF, 0));
     if (sm) k_wide_next<true><<<16, kST, smem_plan(net, 4, true).total, aux>>>(a, step);

@@ -175,7 +175,7 @@ def test_cluster_kernel_equals_tile_kernel(monkeypatch, case):
     A.close(); Bm.close()
 
 
-WIDE_CASES = [c for c in CASES + THREADED_CASES if c.startswith("vracer")]      # feed-forward V-RACER: what the wide step takes
+WIDE_CASES = [c for c in CASES + THREADED_CASES if c != "racer_discrete"]      # feed-forward V-RACER / RACER with continuous actions: what the wide step takes
 
 
 @pytest.mark.parametrize("case", WIDE_CASES)
@@ -195,7 +195,7 @@ def test_wide_step_matches_reference(monkeypatch, case):
     L.close()
 
 
-@pytest.mark.parametrize("case", ["vracer_small", "vracer_cfg2mini", "vracer_bounded", "vracer_b1024"])
+@pytest.mark.parametrize("case", ["vracer_small", "vracer_cfg2mini", "vracer_bounded", "vracer_b1024", "racer_bounded"])
 def test_wide_step_equals_tile_kernel(monkeypatch, case):
     """Same samples, same integer far-policy counts, floats equal to f32 round-off (3xTF32 products, different summation order)."""
     g = Golden(case)

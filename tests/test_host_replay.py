@@ -591,8 +591,7 @@ def test_wide_step_plan_and_operand_images(built_library, case):
 
 def test_wide_step_plan_refuses_what_it_does_not_cover(built_library):
     from smarties_b200.learner import make_config
-    for dS, dA, settings in ((8, 2, {"learner": "RACER", "nnLayerSizes": [32, 32]}),               # Gaussian advantage head
-                             (8, 2, {"nnType": "LSTM", "nnLayerSizes": [32]}),                     # recurrent cells
+    for dS, dA, settings in ((8, 2, {"nnType": "LSTM", "nnLayerSizes": [32]}),                     # recurrent cells
                              (8, 2, {"nnLayerSizes": [256, 256]}),                                 # wider than one MMA tile
                              (8, 12, {"nnLayerSizes": [64, 64]}),                                  # more than 8 action components
                              (8, 2, {"nnLayerSizes": [32, 32, 32, 32]})):                          # more than 4 dense layers
@@ -601,3 +600,6 @@ def test_wide_step_plan_refuses_what_it_does_not_cover(built_library):
     cfg, _ = make_config(32, 8, {"nnLayerSizes": [128, 128]})
     p = _wide_plan(cfg)
     assert p["rc"] == 1 and int(p["info"][0]) == 3 and int(p["info"][9]) == 2       # cfg2: three dense layers, two image stages
+    cfg, _ = make_config(32, 8, {"learner": "RACER", "nnLayerSizes": [128, 128]})    # RACER: 26 dense outputs + 8 ParamLayer outputs
+    p = _wide_plan(cfg)
+    assert p["rc"] == 1 and int(p["info"][10]) == 48 and int(p["dense"][2][3]) == 32 and max(int(x) for x in p["info"][6:9]) <= 227 * 1024
