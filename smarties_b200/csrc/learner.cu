@@ -690,7 +690,7 @@ static int run_segment(smb200_learner* h, int first, int n, long long gstep0, in
   const NetDesc& net = h->descs.net;
   const long long lastStep = gstep0 + n;              // nGradSteps()+1 of the last step
   const int sweepLast = (lastStep % 1000) == 0;
-  if (h->wideOn && h->comm.world == 1) {
+  if (h->wideOn) {
     if (launch_steps_wide(a, net, h->wplan, h->numSMs, (int)gstep0, n, sweepLast, h->stream, h->wAux, h->wEv[0], h->wEv[1], h->wEv[2])) return -2;
     h->launches += 8 * n;
   } else if (h->mode == 1 && h->clusterP1 > 0) {
@@ -889,7 +889,7 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
   {
     const char* w = getenv("SMB200_WIDE");
     const bool never = w && strcmp(w, "0") == 0, always = w && strcmp(w, "1") == 0;
-    if (!never && (always || B >= 2048) && c.world_size <= 1) {
+    if (!never && (always || B >= 2048)) {
       wide_plan_build(net, hp, h->wplan, h->widx);
       if (h->wplan.ok) {
         CK(wide_prepare(h->wplan, net));
@@ -1649,7 +1649,7 @@ int smb200_sync(smb200_learner* h) {
 
 int smb200_step_kernel(const smb200_learner* h) {
   if (!h) return -1;
-  if (h->wideOn && h->comm.world == 1) return 3;
+  if (h->wideOn) return 3;
   if (h->mode == 1 && h->clusterP1 > 0) return 2;
   return (h->mode == 1 && h->persistGrid > 0) ? 1 : 0;
 }

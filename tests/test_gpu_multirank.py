@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 
-@pytest.mark.parametrize("net", ["mlp", "lstm", "mlp_cluster"])      # mlp_cluster: the opt-in cluster step kernel (per-parameter exchange in its P2)
+# mlp_cluster: the opt-in cluster step kernel (per-parameter exchange in its P2); mlp_wide: the wide step (exchange in k_wide_adam)
+@pytest.mark.parametrize("net", ["mlp", "lstm", "mlp_cluster", "mlp_wide"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_fused_allreduce(world, net):
     import torch
@@ -23,6 +24,8 @@ def test_fused_allreduce(world, net):
     env = dict(os.environ, MGPU_NET=net.split("_")[0])
     if net.endswith("_cluster"):
         env["SMB200_CLUSTER"] = "1"
+    if net.endswith("_wide"):
+        env["SMB200_WIDE"] = "1"
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("MGPU_RESULT ")][-1]
