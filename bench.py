@@ -480,6 +480,46 @@ def main():
     final_stats = {k: stats[-1][k] for k in ("beta", "cmax", "n_far_policy", "grad_step")}
     L.close()
 
+    # ---- the same learner at a LARGE mini-batch (cfg2 only, default runs): 65 536 sampled transitions per GPU and step run the
+    #      wide step (tensor cores, wide_step.cuh); device time, ids resident in HBM, max over ranks; weights compared across ranks ----
+    large = None
+    if args.workload == "cfg2" and not args.batch and args.scaling == "weak" and not args.no_batch_sweep:
+        BL, KL, WL = 65536, 30, 3
+        s2 = dict(settings, batchSize=BL * world)
+        L2 = Learner(32, 8, s2, device=local, seed=42 + rank, world_rank=rank, world_size=world)
+        if world > 1:
+            L2.attach_process_group(dist)
+        L2.load_replay(data)
+        L2.initialize_learner()
+        L2.seed_sampler(7 + rank)
+        L2.train_steps(1, want_stats=False)
+        L2.presample(WL + KL)
+        L2.train_presampled(0, WL)
+        L2.sync()
+        barrier()
+        L2.train_presampled(WL, KL)
+        L2.sync()
+        barrier()
+        ms2, _ = L2.last_timing()
+        t = torch.tensor([ms2], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms2 = float(t.item())
+        same = None
+        if world > 1:
+            L2.comm_check()
+            dg = torch.from_numpy(np.frombuffer(hashlib.sha256(L2.get_weights().tobytes()).digest()[:8], dtype=np.int64).copy()).to(dev)
+            alld = [torch.zeros_like(dg) for _ in range(world)]
+            dist.all_gather(alld, dg)
+            same = all(bool((x == alld[0]).all().item()) for x in alld)
+        names = {0: "two kernels per step", 1: "persistent tile kernel", 2: "cluster kernel", 3: "wide step (tcgen05, 3xTF32)"}
+        tps = BL * world * KL / (ms2 * 1e-3)
+        large = {"batch_per_gpu": BL, "global_batch": BL * world, "steps": KL, "warmup": WL, "kernel": names.get(L2.step_kernel(), "?"),
+                 "us_per_step": 1e3 * ms2 / KL, "transitions_per_s": tps, "ranks_identical": same,
+                 "executed_tf32_tflops": 3.0 * 2.0 * MACS_PER_TRANSITION_CFG2 * tps / 1e12,
+                 "note": "device time with sampled ids resident in HBM (the host sampler of the e2e path costs ~30 ns per index)"}
+        L2.close()
+
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": "transitions/s", "n_gpus": world,
                "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": args.scaling,
@@ -492,6 +532,8 @@ def main():
                "roofline": roof, "roofline_sweeps": sweeps, "final_stats": final_stats}
         if ranks_identical is not None:
             out["ranks_identical"] = ranks_identical
+        if large is not None:
+            out["large_batch"] = large
         if world == 1 and args.workload == "cfg2" and not args.batch and not args.no_batch_sweep:
             out["roofline_batch_sweep"] = batch_sweep(torch, dev, data, args.workload, (256, 1024, 2048, 4096, 16384, 65536))
             nw = ncu_wide()
