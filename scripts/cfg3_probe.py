@@ -45,6 +45,9 @@ if os.environ.get("PROF_PHASES"):
     for name, a, b in (("gather", 0, 1), ("forward", 1, 2), ("loss", 2, 3), ("backward+store", 3, 4), ("P1 total", 0, 5), ("barrier1 wait", 5, 6), ("P2", 6, 7)):
         dlt = (w[:, :, b] - w[:, :, a]) / mhz
         print(f"  {name:16s} mean {dlt.mean():7.2f} us  max-over-CTAs {dlt.max(axis=1).mean():7.2f}")
+    for name, a, b in (("fwd: wait for the weight image", 1, 9), ("fwd: LSTM layer 1 (input product + recurrence)", 9, 10), ("fwd: rest (output layer)", 10, 2)):
+        dlt = (w[:, :, b] - w[:, :, a]) / mhz
+        print(f"  {name:48s} median {np.median(dlt):7.2f} us")
     for name, a, b in (("TC staging", 42, 43), ("TC mma issue+wait", 43, 44), ("TC epilogue", 44, 45), ("TC barrier", 45, 46), ("tiles (reduce, exchange, Adam)", 46, 7)):
         dlt = (w[:, :100, b] - w[:, :100, a]) / mhz
         print(f"  {name:32s} median {np.median(dlt):7.2f} us")

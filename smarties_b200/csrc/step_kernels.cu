@@ -1531,8 +1531,10 @@ __device__ void p1_seq(const StepArgs& a, const DevDescs& dd, StepCtrl& c, int s
   for (int l = 1; l < net.nLayers; ++l) {
     const LayerDesc& L = net.L[l];
     if (bars) mbar_wait(&bars[l], parity);
+    if (l == 1) DBG_T(a, step, 9);
     if (L.kind == kLSTM) {
       lstm_forward<SM>(L, Wp, ws + sq.yOff[L.in], sq.yStride[L.in], ws + sq.gOff[l], sq.gStride[l], ws + sq.yOff[l], sq.yStride[l], red, Tn);
+      if (l == 1) DBG_T(a, step, 10);
     } else if (L.kind == kMGU) {
       mgu_forward<SM>(L, Wp, ws + sq.yOff[L.in], sq.yStride[L.in], ws + sq.gOff[l], sq.gStride[l], ws + sq.yOff[l], sq.yStride[l], red, Tn);
     } else if (L.kind == kResidual) {       // ParametricResidualLayer::forward (Layers.h:347-361)
