@@ -138,8 +138,9 @@ int smb200_get_scaling(smb200_learner* h, float* mean, float* scale, float* stde
 
 /* MemoryBuffer::pushBackEpisode + Episode::finalize + computeReturnEstimator
  * (MemoryBuffer.cpp:133-170,479-520; Episode.cpp:244-273).  n_rows = nsteps() including the
- * terminal/truncated row.  value/advantage may be NULL (zeros).  Thread-compatible with
- * training only through the caller's serialisation. */
+ * terminal/truncated row.  value/advantage may be NULL (zeros).  Thread-safe against the train / forward / weight
+ * calls of the same learner (one lock per learner serialises them: actor threads may push finished episodes and
+ * evaluate the policy while the learner thread trains — MemoryBuffer::dataset_mutex of the reference). */
 int smb200_push_episode(smb200_learner* h, int64_t id, int32_t n_rows, int32_t terminated,
                         const float* states, const float* actions, const float* policies,
                         const float* rewards, const float* value, const float* advantage);
@@ -228,9 +229,16 @@ int smb200_push_episode_restored(smb200_learner* h, int64_t id, int32_t n_rows, 
 int smb200_set_refer(smb200_learner* h, double beta, double cmax);
 int smb200_restart(smb200_learner* h, const char* base);
 
-/* Actor-side policy evaluation (RACER::selectAction, Learners/RACER.cpp:30-47): raw states in,
- * net outputs out[n][nOut]. */
+/* Actor-side policy evaluation (RACER::selectAction / processTerminal, Learners/RACER.cpp:30-59): raw states in,
+ * net outputs out[n][nOut].  Feed-forward networks only (a recurrent network needs the window: smb200_forward_seq).
+ * One call answers n agents (the agents of one Master::waitForStateActionCallers poll, Core/Master.cpp:88-145). */
 int smb200_forward(smb200_learner* h, const float* states, int32_t n, float* outputs);
+/* The same for any network, on the window MemoryBuffer::agentToMinibatch builds for an agent (ReplayMemory/MemoryBuffer.cpp:440-467):
+ * states[n][max_len][dS] raw, the first lengths[i] rows of agent i are the states of its episode in progress, oldest first
+ * (1 <= lengths[i] <= max_len).  Recurrent networks are evaluated from a zero recurrent state on the newest
+ * min(lengths[i], nnBPTTseq + 1) rows (Approximator.h:129-139); feed-forward networks on the newest row.  outputs[n][nOut]
+ * are the outputs at the newest row. */
+int smb200_forward_seq(smb200_learner* h, const float* states, const int32_t* lengths, int32_t n, int32_t max_len, float* outputs);
 
 /* Device-side timing of the last smb200_train_steps call (CUDA events on the library's
  * stream), and the number of kernels it launched. */

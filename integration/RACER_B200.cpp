@@ -41,6 +41,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
+#include <mutex>
 #include <cstdlib>
 #include <fstream>
 #include <unistd.h>
@@ -60,6 +62,7 @@ class RACER_B200 : public RACER<Advantage_t, Policy_t, Action_t>
   using Base::data; using Base::settings; using Base::distrib; using Base::MDP; using Base::networks;
   using Base::algoSubStepID; using Base::nObsB4StartTraining; using Base::bTrain; using Base::aInfo;
   using Base::profiler; using Base::learn_rank; using Base::learn_size;
+  using Base::pol_start; using Base::adv_start; using Base::VsID;
 
   smb200_learner* gpu = nullptr;
   const bool isRacer;
@@ -75,6 +78,56 @@ class RACER_B200 : public RACER<Advantage_t, Policy_t, Action_t>
   std::vector<smb200_step_stats> stepStats;
   double secPush = 0, secStep = 0, secSync = 0, tTrainStart = 0;
   long nPushed = 0;
+
+  // ---- actors on the device (SMARTIES_B200_ACTORS=1): RACER::selectAction / processTerminal evaluate the policy with
+  //      smb200_forward_seq instead of the host Approximator.  The worker threads of Master::waitForStateActionCallers
+  //      (Core/Master.cpp:88-145) call Learner::select concurrently, one agent each: requests that arrive while a device call
+  //      is in flight are answered together by the next call (the first waiting thread leads it), so n pending agents
+  //      cost one launch and one round trip, not n. ----
+  bool deviceActors = false;
+  struct FwdReq { const float* states; int len; float* out; bool done; };
+  std::mutex fwdMutex; std::condition_variable fwdCv; std::vector<FwdReq*> fwdPending; bool fwdLeader = false;
+  std::vector<float> fwdS, fwdO; std::vector<int32_t> fwdL;      // the leader's packing buffers (one leader at a time)
+  long nFwdCalls = 0, nFwdAgents = 0, nFwdMax = 0;
+
+  // scaleNet2V (Learners/RACER_common.cpp:23-27; a template in a .cpp of the reference, not reachable from here)
+  static Real net2V(const Real x) { return x > 0 ? 100 * (x + 51) - 100 * std::sqrt(2601 + 100 * x) : 100 * (x - 51) + 100 * std::sqrt(2601 - 100 * x); }
+
+  Rvec deviceForward(const MiniBatch& MB)
+  {
+    const Episode& EP = * MB.episodes[0];
+    const Uint dS = MDP.dimStateObserved, nOut = (Uint) smb200_n_outputs(gpu);
+    const Sint t0 = MB.begTimeStep[0], t1 = MB.endTimeStep[0];       // the window of MemoryBuffer::agentToMinibatch
+    const int len = (int) (t1 - t0);
+    std::vector<float> st((size_t) len * dS), out(nOut);
+    for (Sint t = t0; t < t1; ++t)
+      for (Uint k = 0; k < dS; ++k) st[(size_t) (t - t0) * dS + k] = (float) EP.states[t][k];     // raw: the device standardises
+    FwdReq rq{st.data(), len, out.data(), false};
+    std::unique_lock<std::mutex> lk(fwdMutex);
+    fwdPending.push_back(&rq);
+    while (!rq.done) {
+      if (fwdLeader) { fwdCv.wait(lk); continue; }
+      fwdLeader = true;                       // lead one device call for everything that is pending now (this request included)
+      std::vector<FwdReq*> batch; batch.swap(fwdPending);
+      lk.unlock();
+      const int n = (int) batch.size();
+      int maxLen = 1;
+      for (const FwdReq* r : batch) maxLen = std::max(maxLen, r->len);
+      fwdS.assign((size_t) n * maxLen * dS, 0.f); fwdL.resize(n); fwdO.resize((size_t) n * nOut);
+      for (int i = 0; i < n; ++i) {
+        std::copy(batch[i]->states, batch[i]->states + (size_t) batch[i]->len * dS, fwdS.begin() + (size_t) i * maxLen * dS);
+        fwdL[i] = batch[i]->len;
+      }
+      check(smb200_forward_seq(gpu, fwdS.data(), fwdL.data(), n, maxLen, fwdO.data()), "forward_seq");
+      for (int i = 0; i < n; ++i) std::copy(fwdO.begin() + (size_t) i * nOut, fwdO.begin() + (size_t) (i + 1) * nOut, batch[i]->out);
+      lk.lock();
+      ++nFwdCalls; nFwdAgents += n; nFwdMax = std::max<long>(nFwdMax, n);
+      for (FwdReq* r : batch) r->done = true;
+      fwdLeader = false;
+      fwdCv.notify_all();
+    }
+    return Rvec(out.begin(), out.end());
+  }
 
   void check(const int rc, const char* what) const {
     if (rc) _die("smarties_b200 %s: %s", what, smb200_last_error());
@@ -230,6 +283,8 @@ class RACER_B200 : public RACER<Advantage_t, Policy_t, Action_t>
   {
     if (D.world_rank == 0) printf("smarties_b200: learner steps of this agent run on the GPU (libsmarties_b200.so)\n");
     if (const char* m = std::getenv("SMARTIES_B200_MAXSTEPS")) maxStepsPerCall = std::max(1, std::min(256, std::atoi(m)));
+    if (const char* m = std::getenv("SMARTIES_B200_ACTORS")) deviceActors = std::atoi(m) != 0;
+    if (deviceActors && D.world_rank == 0) printf("smarties_b200: the actors' policy evaluations run on the GPU as well (smb200_forward_seq)\n");
     stepStats.resize(maxStepsPerCall);
     createDeviceLearner();
   }
@@ -239,8 +294,31 @@ class RACER_B200 : public RACER<Advantage_t, Policy_t, Action_t>
       printf("smarties_b200: %ld gradient steps, %ld episodes mirrored; seconds in push %.3f, device steps %.3f, weight sync %.3f; "
              "%.3f s of wall clock since training started\n",
              (long) data->nGradSteps(), nPushed, secPush, secStep, secSync, tTrainStart > 0 ? now() - tTrainStart : 0.0);
+    if (gpu && deviceActors && distrib.world_rank == 0)
+      printf("smarties_b200: %ld policy evaluations in %ld device calls (largest call %ld agents)\n", nFwdAgents, nFwdCalls, nFwdMax);
     if (gpu) smb200_pin_host_buffer(hostWeights()->params, 0);
     smb200_destroy(gpu);
+  }
+
+  // RACER::selectAction (Learners/RACER.cpp:30-47) with the network outputs from the device
+  void selectAction(const MiniBatch& MB, Agent& agent) override
+  {
+    if (!deviceActors) { Base::selectAction(MB, agent); return; }
+    const Rvec output = deviceForward(MB);
+    const Policy_t pol(pol_start, aInfo, output);
+    auto action = pol.selectAction(agent, distrib.bTrain);
+    const Advantage_t adv(adv_start, aInfo, output, &pol);
+    const Real V = net2V(output[VsID]);
+    MB.appendValues(V, V + adv.computeAdvantage(action));
+    agent.setAction(action, pol.getVector());
+  }
+
+  // RACER::processTerminal (Learners/RACER.cpp:49-59)
+  void processTerminal(const MiniBatch& MB, Agent& agent) override
+  {
+    if (!deviceActors) { Base::processTerminal(MB, agent); return; }
+    if (agent.agentStatus == LAST) MB.appendValues(net2V(deviceForward(MB)[VsID]));   // truncated: not a terminal state
+    else MB.appendValues(0);
   }
 
   // Learner_approximator::save (Learner_approximator.cpp:133-142): the reference's own writers produce the files;

@@ -130,6 +130,12 @@ struct smb200_learner {
   double lastMs = 0; long long lastLaunches = 0;
   long long launches = 0;
 
+  // actor-side policy evaluation (smb200_forward / smb200_forward_seq): staging buffers that grow on demand, and the lock that
+  // lets actor threads push episodes and evaluate the policy while the learner thread trains (one stream, one call at a time)
+  std::recursive_mutex apiMutex;
+  float *fwdIn = nullptr, *fwdOut = nullptr, *hFwdIn = nullptr, *hFwdOut = nullptr; int *fwdLen = nullptr, *hFwdLen = nullptr;
+  size_t fwdInCap = 0, fwdOutCap = 0, fwdLenCap = 0;
+
   // output-gradient statistics file of the reference (StatsTracker, Utils/StatsTracker.cpp:28-107); off until
   // smb200_set_grad_stats names the file.  trackerSteps = StatsTracker::nStep (reduce_stats calls since construction).
   std::string gradStatsBase; long long trackerSteps = 0;
@@ -947,6 +953,12 @@ void smb200_destroy(smb200_learner* h) {
   if (h->commBuf) cudaFree(h->commBuf);
   if (h->dCommErr) cudaFree(h->dCommErr);
   if (h->tcPartial) cudaFree(h->tcPartial);
+  if (h->fwdIn) cudaFree(h->fwdIn);
+  if (h->fwdOut) cudaFree(h->fwdOut);
+  if (h->fwdLen) cudaFree(h->fwdLen);
+  if (h->hFwdIn) cudaFreeHost(h->hFwdIn);
+  if (h->hFwdOut) cudaFreeHost(h->hFwdOut);
+  if (h->hFwdLen) cudaFreeHost(h->hFwdLen);
   if (h->hSampSlot) cudaFreeHost(h->hSampSlot);
   if (h->hSampT) cudaFreeHost(h->hSampT);
   if (h->hStats) cudaFreeHost(h->hStats);
@@ -971,6 +983,7 @@ int64_t smb200_n_rows(const smb200_learner* h) {
 
 int smb200_set_weights(smb200_learner* h, const float* blob, int64_t n) {
   if (!h || !blob || n != h->descs.net.nParams) return SMB200_ERR_INVALID;
+  std::lock_guard<std::recursive_mutex> lock(h->apiMutex);
   cudaSetDevice(h->cfg.device);
   // target weights (unused by RACER with targetDelay 0, but part of the checkpoint): they follow the weights
   // until training starts, like `target_weights->copy(weights)` of a restart without a tgt file (Optimizer.cpp:207-210)
@@ -984,6 +997,7 @@ static int d2h(smb200_learner* h, void* dst, const void* src, size_t bytes) {
 }
 int smb200_get_weights(smb200_learner* h, float* blob, int64_t n) {
   if (!h || !blob || n != h->descs.net.nParams) return SMB200_ERR_INVALID;
+  std::lock_guard<std::recursive_mutex> lock(h->apiMutex);
   return d2h(h, blob, h->W, sizeof(float) * n);
 }
 int smb200_get_grad(smb200_learner* h, float* blob, int64_t n) {
@@ -1044,6 +1058,7 @@ static int push_episode_impl(smb200_learner* h, int64_t id, int32_t N, int32_t t
                              const float* MU, const float* R, const float* V, const float* ADV, const float* const* restored,
                              float cmax, float cinv) {
   if (!h || N < 2 || !S || !A || !MU || !R) { set_error_msg("push_episode: an episode needs at least s0 and sT"); return SMB200_ERR_INVALID; }
+  std::lock_guard<std::recursive_mutex> lock(h->apiMutex);
   cudaSetDevice(h->cfg.device);
   if (h->freeSlots.empty()) { set_error_msg("episode table full"); return SMB200_ERR_CAPACITY; }
   const long long start = ring_alloc(h, N);
@@ -1096,6 +1111,7 @@ int smb200_push_episode(smb200_learner* h, int64_t id, int32_t N, int32_t termin
 
 int smb200_initialize_learner(smb200_learner* h) {
   if (!h || h->episodes.empty()) return SMB200_ERR_STATE;
+  std::lock_guard<std::recursive_mutex> lock(h->apiMutex);
   cudaSetDevice(h->cfg.device);
   if (h->gradStep > 0) return 0;   // "Skipping initialization for restarted learner" (Learner.cpp:51-54)
   // updateCounters(bInit=true): beta fixed-point step with the initial far-policy fraction; with
@@ -1282,6 +1298,7 @@ int smb200_pin_host_buffer(void* ptr, int64_t bytes) {
 
 static int train_steps_impl(smb200_learner* h, int32_t n, smb200_step_stats* stats, float* weightsOut) {
   if (!h || n < 0) return SMB200_ERR_INVALID;
+  std::lock_guard<std::recursive_mutex> lock(h->apiMutex);
   if (h->nTransitions < h->cfg.batch_size) { set_error_msg("not enough transitions for one mini-batch"); return SMB200_ERR_STATE; }
   cudaSetDevice(h->cfg.device);
   h->presampled = 0;
@@ -1353,6 +1370,7 @@ static int train_steps_impl(smb200_learner* h, int32_t n, smb200_step_stats* sta
 
 int smb200_train_step_on(smb200_learner* h, const int64_t* pos, const int64_t* t, int32_t batch, smb200_step_stats* stats) {
   if (!h || !pos || !t || batch != h->cfg.batch_size) return SMB200_ERR_INVALID;
+  std::lock_guard<std::recursive_mutex> lock(h->apiMutex);
   if (h->slow_mode()) { set_error_msg("train_step_on: uniform sampling with the FIFO filter only"); return SMB200_ERR_STATE; }
   cudaSetDevice(h->cfg.device);
   h->presampled = 0;
@@ -1402,6 +1420,7 @@ int smb200_presample(smb200_learner* h, int32_t n) {
 
 int smb200_train_presampled(smb200_learner* h, int32_t first, int32_t n) {
   if (!h || first < 0 || n < 1 || first + n > h->presampled) return SMB200_ERR_INVALID;
+  std::lock_guard<std::recursive_mutex> lock(h->apiMutex);
   cudaSetDevice(h->cfg.device);
   auto cmp = [](const EpisodeMeta& a, const EpisodeMeta& b) { return a.id > b.id; };
   if (!std::is_sorted(h->episodes.begin(), h->episodes.end(), cmp)) { set_error_msg("presampled path needs a sorted episode table"); return SMB200_ERR_STATE; }
@@ -1763,20 +1782,81 @@ int smb200_get_stats(smb200_learner* h, smb200_step_stats* out) {
   return 0;
 }
 
+// device + page-locked host staging of the actors' requests, grown geometrically and kept for the life of the learner
+static int forward_buffers(smb200_learner* h, size_t nIn, size_t nOut, size_t nLen) {
+  if (nIn > h->fwdInCap) {
+    if (h->fwdIn) cudaFree(h->fwdIn);
+    if (h->hFwdIn) cudaFreeHost(h->hFwdIn);
+    h->fwdIn = nullptr; h->hFwdIn = nullptr; h->fwdInCap = 0;
+    const size_t cap = std::max(nIn, (size_t)4096);
+    SMB200_CUDA_CHECK(cudaMalloc(&h->fwdIn, sizeof(float) * cap));
+    SMB200_CUDA_CHECK(cudaMallocHost(&h->hFwdIn, sizeof(float) * cap));
+    h->fwdInCap = cap;
+  }
+  if (nOut > h->fwdOutCap) {
+    if (h->fwdOut) cudaFree(h->fwdOut);
+    if (h->hFwdOut) cudaFreeHost(h->hFwdOut);
+    h->fwdOut = nullptr; h->hFwdOut = nullptr; h->fwdOutCap = 0;
+    const size_t cap = std::max(nOut, (size_t)4096);
+    SMB200_CUDA_CHECK(cudaMalloc(&h->fwdOut, sizeof(float) * cap));
+    SMB200_CUDA_CHECK(cudaMallocHost(&h->hFwdOut, sizeof(float) * cap));
+    h->fwdOutCap = cap;
+  }
+  if (nLen > h->fwdLenCap) {
+    if (h->fwdLen) cudaFree(h->fwdLen);
+    if (h->hFwdLen) cudaFreeHost(h->hFwdLen);
+    h->fwdLen = nullptr; h->hFwdLen = nullptr; h->fwdLenCap = 0;
+    const size_t cap = std::max(nLen, (size_t)256);
+    SMB200_CUDA_CHECK(cudaMalloc(&h->fwdLen, sizeof(int) * cap));
+    SMB200_CUDA_CHECK(cudaMallocHost(&h->hFwdLen, sizeof(int) * cap));
+    h->fwdLenCap = cap;
+  }
+  return 0;
+}
+
 int smb200_forward(smb200_learner* h, const float* states, int32_t n, float* outputs) {
   if (!h || !states || !outputs || n < 1) return SMB200_ERR_INVALID;
-  if (h->descs.net.recurrent) { set_error_msg("smb200_forward: stateless evaluation is undefined for a recurrent network"); return SMB200_ERR_STATE; }
+  if (h->descs.net.recurrent) { set_error_msg("smb200_forward: stateless evaluation is undefined for a recurrent network (smb200_forward_seq takes the window)"); return SMB200_ERR_STATE; }
+  std::lock_guard<std::recursive_mutex> lock(h->apiMutex);
   cudaSetDevice(h->cfg.device);
   const int dS = h->cfg.dim_state, nOut = h->descs.net.nOut;
-  float *dIn = nullptr, *dOut = nullptr;
-  SMB200_CUDA_CHECK(cudaMalloc(&dIn, sizeof(float) * (size_t)n * dS));
-  SMB200_CUDA_CHECK(cudaMalloc(&dOut, sizeof(float) * (size_t)n * nOut));
-  SMB200_CUDA_CHECK(cudaMemcpyAsync(dIn, states, sizeof(float) * (size_t)n * dS, cudaMemcpyHostToDevice, h->stream));
+  const size_t nIn = (size_t)n * dS, nO = (size_t)n * nOut;
+  if (forward_buffers(h, nIn, nO, 0)) return SMB200_ERR_CUDA;
+  std::memcpy(h->hFwdIn, states, sizeof(float) * nIn);
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(h->fwdIn, h->hFwdIn, sizeof(float) * nIn, cudaMemcpyHostToDevice, h->stream));
   StepArgs a = h->args();
-  int rc = launch_forward(a, h->descs.net, dIn, n, dOut, h->stream);
-  if (!rc) rc = d2h(h, outputs, dOut, sizeof(float) * (size_t)n * nOut);
-  cudaFree(dIn); cudaFree(dOut);
-  return rc ? SMB200_ERR_CUDA : 0;
+  if (launch_forward(a, h->descs.net, h->fwdIn, n, h->fwdOut, h->stream)) return SMB200_ERR_CUDA;
+  if (d2h(h, h->hFwdOut, h->fwdOut, sizeof(float) * nO)) return SMB200_ERR_CUDA;
+  std::memcpy(outputs, h->hFwdOut, sizeof(float) * nO);
+  return 0;
+}
+
+int smb200_forward_seq(smb200_learner* h, const float* states, const int32_t* lengths, int32_t n, int32_t max_len, float* outputs) {
+  if (!h || !states || !lengths || !outputs || n < 1 || max_len < 1) return SMB200_ERR_INVALID;
+  for (int32_t i = 0; i < n; ++i)
+    if (lengths[i] < 1 || lengths[i] > max_len) { set_error_msg("smb200_forward_seq: window lengths must be in [1, max_len]"); return SMB200_ERR_INVALID; }
+  std::lock_guard<std::recursive_mutex> lock(h->apiMutex);
+  cudaSetDevice(h->cfg.device);
+  const NetDesc& net = h->descs.net;
+  const int dS = h->cfg.dim_state, nOut = net.nOut;
+  // feed-forward nets see the newest state only; recurrent nets the newest min(length, nnBPTTseq + 1) states
+  const int keep = net.recurrent ? std::min<int>(max_len, net.Tc) : 1;
+  const size_t nIn = (size_t)n * keep * dS, nO = (size_t)n * nOut;
+  if (forward_buffers(h, nIn, nO, (size_t)n)) return SMB200_ERR_CUDA;
+  for (int32_t i = 0; i < n; ++i) {
+    const int len = std::min<int>(lengths[i], keep);
+    std::memcpy(h->hFwdIn + (size_t)i * keep * dS, states + ((size_t)i * max_len + (lengths[i] - len)) * dS, sizeof(float) * (size_t)len * dS);
+    h->hFwdLen[i] = len;
+  }
+  SMB200_CUDA_CHECK(cudaMemcpyAsync(h->fwdIn, h->hFwdIn, sizeof(float) * nIn, cudaMemcpyHostToDevice, h->stream));
+  StepArgs a = h->args();
+  if (net.recurrent) {
+    SMB200_CUDA_CHECK(cudaMemcpyAsync(h->fwdLen, h->hFwdLen, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    if (launch_forward_seq(a, net, h->fwdIn, h->fwdLen, n, keep, h->fwdOut, h->stream)) return SMB200_ERR_CUDA;
+  } else if (launch_forward(a, net, h->fwdIn, n, h->fwdOut, h->stream)) return SMB200_ERR_CUDA;
+  if (d2h(h, h->hFwdOut, h->fwdOut, sizeof(float) * nO)) return SMB200_ERR_CUDA;
+  std::memcpy(outputs, h->hFwdOut, sizeof(float) * nO);
+  return 0;
 }
 
 }  // extern "C"

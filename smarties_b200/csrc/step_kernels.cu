@@ -1472,6 +1472,59 @@ __device__ void mgu_backward(const LayerDesc& L, const float* Wp, float* Gt, int
   }
 }
 
+// Network::forward over a window, layer-major (Network.h:101-113 evaluated step by step from a zero recurrent state,
+// Approximator.h:129-139): window steps [0, Tn) of the standardised states already in ws + sq.yOff[0]; the linear output
+// layer is evaluated at step T1-1 (-> actTop) and, if vnext != nullptr, at step Tn-1 (-> V(s_{t+1}), RACER_train.cpp:23-27).
+// Shared by the learner's P1 (p1_seq) and by the actors' policy evaluation (k_forward_seq).
+template <bool SM>
+__device__ __forceinline__ void seq_forward(const NetDesc& net, const SeqPlan& sq, const float* Wp, float* ws, float* red, float* actTop,
+                                            uint64_t* bars, unsigned parity, int T1, int Tn, float* vnext, const StepArgs* dbg, int step) {
+  const int tid = threadIdx.x;
+  for (int l = 1; l < net.nLayers; ++l) {
+    const LayerDesc& L = net.L[l];
+    if (bars) mbar_wait(&bars[l], parity);
+    if (dbg && l == 1) DBG_T(*dbg, step, 9);
+    if (L.kind == kLSTM) {
+      lstm_forward<SM>(L, Wp, ws + sq.yOff[L.in], sq.yStride[L.in], ws + sq.gOff[l], sq.gStride[l], ws + sq.yOff[l], sq.yStride[l], red, Tn);
+      if (dbg && l == 1) DBG_T(*dbg, step, 10);
+    } else if (L.kind == kMGU) {
+      mgu_forward<SM>(L, Wp, ws + sq.yOff[L.in], sq.yStride[L.in], ws + sq.gOff[l], sq.gStride[l], ws + sq.yOff[l], sq.yStride[l], red, Tn);
+    } else if (L.kind == kResidual) {       // ParametricResidualLayer::forward (Layers.h:347-361)
+      const float* y1 = ws + sq.yOff[l - 1]; const float* y2 = ws + sq.yOff[l - 2];
+      const int s1 = sq.yStride[l - 1], s2 = sq.yStride[l - 2], ys = sq.yStride[l];
+      float* y = ws + sq.yOff[l];
+      for (int idx = tid; idx < Tn * L.size; idx += kST) {
+        const int k = idx / L.size, j = idx - k * L.size;
+        y[k * ys + j] = y1[k * s1 + j] + (y2[k * s2 + j] * ldw<SM>(Wp + L.imgW + j) + ldw<SM>(Wp + L.imgB + j));
+      }
+      __syncthreads();
+    } else if (L.kind == kDenseLinear) {    // outputs at the sampled step and, if needed, at the step after it
+      const float* in = ws + sq.yOff[L.in]; const int is = sq.yStride[L.in];
+      const float* x0 = in + (size_t)(T1 - 1) * is;
+      const float* x1 = in + (size_t)(Tn - 1) * is;
+      const int sh = L.fwdShift, NR = 1 << sh, G = kST >> sh;
+      const int g = tid >> sh, nl = tid & (NR - 1);
+      const int K = L.nIn, N = L.size, Kc = (K + G - 1) / G;
+      const int kb = min(K, g * Kc), ke = min(K, kb + Kc);
+      float a0 = 0.0f, a1 = 0.0f;
+      if (nl < N) {
+        const float* w = Wp + L.imgW + nl;
+        for (int i = kb; i < ke; ++i) { const float wv = ldw<SM>(w + (size_t)i * L.ldp); a0 = fmaf(x0[i], wv, a0); a1 = fmaf(x1[i], wv, a1); }
+      }
+      red[g * NR + nl] = a0; red[kST + g * NR + nl] = a1;
+      __syncthreads();
+      if (tid < N) {
+        float v0 = 0.0f, v1 = 0.0f;
+        for (int gg = 0; gg < G; ++gg) { v0 += red[gg * NR + tid]; v1 += red[kST + gg * NR + tid]; }
+        const float bv = ldw<SM>(Wp + L.imgB + tid);
+        actTop[L.actOff + tid] = v0 + bv;
+        if (tid == 0 && vnext) vnext[0] = (float)net2v((double)(v1 + bv));
+      }
+      __syncthreads();
+    }
+  }
+}
+
 template <bool SM>
 __device__ void p1_seq(const StepArgs& a, const DevDescs& dd, StepCtrl& c, int step, int b, unsigned char* smraw, const SeqSmem& sp,
                        unsigned parity, bool fetchCtrl, const unsigned* readyFlag, unsigned readyTarget) {
@@ -1528,49 +1581,7 @@ __device__ void p1_seq(const StepArgs& a, const DevDescs& dd, StepCtrl& c, int s
   const LayerDesc& Lo = net.L[net.nLayers - 2];
   const LayerDesc& Lp = net.L[net.nLayers - 1];
   float* vnext = reinterpret_cast<float*>(samp + 11);
-  for (int l = 1; l < net.nLayers; ++l) {
-    const LayerDesc& L = net.L[l];
-    if (bars) mbar_wait(&bars[l], parity);
-    if (l == 1) DBG_T(a, step, 9);
-    if (L.kind == kLSTM) {
-      lstm_forward<SM>(L, Wp, ws + sq.yOff[L.in], sq.yStride[L.in], ws + sq.gOff[l], sq.gStride[l], ws + sq.yOff[l], sq.yStride[l], red, Tn);
-      if (l == 1) DBG_T(a, step, 10);
-    } else if (L.kind == kMGU) {
-      mgu_forward<SM>(L, Wp, ws + sq.yOff[L.in], sq.yStride[L.in], ws + sq.gOff[l], sq.gStride[l], ws + sq.yOff[l], sq.yStride[l], red, Tn);
-    } else if (L.kind == kResidual) {       // ParametricResidualLayer::forward (Layers.h:347-361)
-      const float* y1 = ws + sq.yOff[l - 1]; const float* y2 = ws + sq.yOff[l - 2];
-      const int s1 = sq.yStride[l - 1], s2 = sq.yStride[l - 2], ys = sq.yStride[l];
-      float* y = ws + sq.yOff[l];
-      for (int idx = tid; idx < Tn * L.size; idx += kST) {
-        const int k = idx / L.size, j = idx - k * L.size;
-        y[k * ys + j] = y1[k * s1 + j] + (y2[k * s2 + j] * ldw<SM>(Wp + L.imgW + j) + ldw<SM>(Wp + L.imgB + j));
-      }
-      __syncthreads();
-    } else if (L.kind == kDenseLinear) {    // outputs at the sampled step and, if needed, at the step after it
-      const float* in = ws + sq.yOff[L.in]; const int is = sq.yStride[L.in];
-      const float* x0 = in + (size_t)(T1 - 1) * is;
-      const float* x1 = in + (size_t)(Tn - 1) * is;
-      const int sh = L.fwdShift, NR = 1 << sh, G = kST >> sh;
-      const int g = tid >> sh, nl = tid & (NR - 1);
-      const int K = L.nIn, N = L.size, Kc = (K + G - 1) / G;
-      const int kb = min(K, g * Kc), ke = min(K, kb + Kc);
-      float a0 = 0.0f, a1 = 0.0f;
-      if (nl < N) {
-        const float* w = Wp + L.imgW + nl;
-        for (int i = kb; i < ke; ++i) { const float wv = ldw<SM>(w + (size_t)i * L.ldp); a0 = fmaf(x0[i], wv, a0); a1 = fmaf(x1[i], wv, a1); }
-      }
-      red[g * NR + nl] = a0; red[kST + g * NR + nl] = a1;
-      __syncthreads();
-      if (tid < N) {
-        float v0 = 0.0f, v1 = 0.0f;
-        for (int gg = 0; gg < G; ++gg) { v0 += red[gg * NR + tid]; v1 += red[kST + gg * NR + tid]; }
-        const float bv = ldw<SM>(Wp + L.imgB + tid);
-        actTop[L.actOff + tid] = v0 + bv;
-        if (tid == 0 && hn) vnext[0] = (float)net2v((double)(v1 + bv));
-      }
-      __syncthreads();
-    }
-  }
+  seq_forward<SM>(net, sq, Wp, ws, red, actTop, bars, parity, T1, Tn, hn ? vnext : nullptr, &a, step);
   DBG_T(a, step, 2);
 
   {
@@ -2652,6 +2663,43 @@ __global__ void __launch_bounds__(kST) k_forward(StepArgs a, const float* states
   }
 }
 
+// Actor-side policy evaluation of recurrent networks (RACER::selectAction, Learners/RACER.cpp:30-47, on the window
+// MemoryBuffer::agentToMinibatch builds: the last min(nnBPTTseq, t) + 1 states of the episode in progress, zero initial
+// recurrent state, MemoryBuffer.cpp:440-467): one CTA per agent, raw states[agent][maxLen][dS] (the first lengths[agent]
+// rows are the window, oldest first), net outputs of the window's last step -> out[agent][nOut].
+template <bool SM>
+__global__ void __launch_bounds__(kST) k_forward_seq(StepArgs a, const float* states, const int* lengths, int maxLen, float* out) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const NetDesc* net; const Hyper* hp;
+  load_descs(a, smraw, net, hp);
+  const SeqSmem sp = smem_plan_seq(*net, SM);
+  if (SM) {
+    init_bars(a, *net, smraw, sp.bars);
+    load_weight_image(a, *net, reinterpret_cast<float*>(smraw + sp.img), reinterpret_cast<uint64_t*>(smraw + sp.bars));
+  }
+  __syncthreads();
+  const SeqPlan& sq = reinterpret_cast<const DevDescs*>(smraw)->seq;
+  const float* Wp = SM ? reinterpret_cast<const float*>(smraw + sp.img) : a.Wimg;
+  float* ws = reinterpret_cast<float*>(smraw + sp.ws);
+  uint64_t* bars = (SM && a.useTma) ? reinterpret_cast<uint64_t*>(smraw + sp.bars) : nullptr;
+  const int tid = threadIdx.x, b = blockIdx.x, dS = net->dS;
+  for (int idx = tid; idx < sq.red; idx += kST) ws[idx] = 0.0f;     // pads and top vectors
+  __syncthreads();
+  const int have = max(1, min(lengths[b], maxLen));
+  const int len = min(have, net->Tc);                // at most nnBPTTseq + 1 steps: the newest ones
+  const float* src = states + ((size_t)b * maxLen + (have - len)) * dS;
+  float* X = ws + sq.yOff[0];
+  const int xs = sq.yStride[0];
+  for (int idx = tid; idx < len * dS; idx += kST) {
+    const int k = idx / dS, i = idx - k * dS;
+    X[k * xs + i] = (src[(size_t)k * dS + i] - ld_cg(a.rp.stateMean + i)) * ld_cg(a.rp.stateScale + i);
+  }
+  __syncthreads();
+  float* actTop = ws + sq.actTop;
+  seq_forward<SM>(*net, sq, Wp, ws, ws + sq.red, actTop, bars, 0, len, len, nullptr, nullptr, 0);
+  for (int j = tid; j < net->nOut; j += kST) out[(size_t)b * net->nOut + j] = net_out<SM>(*net, Wp, actTop, 1, j, 0);
+}
+
 // ------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------
@@ -2674,9 +2722,11 @@ int step_kernels_prepare(const NetDesc& net) {
   if (net.recurrent) {
     if (sm) {
       SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_p1_seq<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOn));
+      SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_forward_seq<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOn));
       SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_steps_persistent<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOn));
     }
     SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_p1_seq<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOff));
+    SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_forward_seq<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOff));
     SMB200_CUDA_CHECK(cudaFuncSetAttribute(k_steps_persistent<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sOff));
   } else {
     if (sm) {
@@ -2746,6 +2796,16 @@ int launch_finalize_sweep(const StepArgs& a, int step, const SweepSums* sweep, c
 
 int launch_forward(const StepArgs& a, const NetDesc& net, const float* states, int n, float* out, cudaStream_t st) {
   k_forward<4><<<(n + 3) / 4, kST, smem_plan(net, 4, false).total, st>>>(a, states, n, out);
+  SMB200_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_forward_seq(const StepArgs& a, const NetDesc& net, const float* states, const int* lengths, int n, int maxLen, float* out,
+                       cudaStream_t st) {
+  const bool sm = step_image_in_smem(net);
+  const size_t smem = step_smem_bytes(net, 4);
+  if (sm) k_forward_seq<true><<<n, kST, smem, st>>>(a, states, lengths, maxLen, out);
+  else k_forward_seq<false><<<n, kST, smem, st>>>(a, states, lengths, maxLen, out);
   SMB200_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

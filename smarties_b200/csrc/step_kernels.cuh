@@ -198,6 +198,8 @@ int persistent_grid(const StepArgs& a, const NetDesc& net, int numSMs);
 int launch_steps_persistent(const StepArgs& a, const NetDesc& net, int grid, int step0, int nSteps, int skipStatsLast, cudaStream_t st);
 int launch_finalize_sweep(const StepArgs& a, int step, const SweepSums* sweep, cudaStream_t st);
 int launch_forward(const StepArgs& a, const NetDesc& net, const float* states, int n, float* out, cudaStream_t st);
+int launch_forward_seq(const StepArgs& a, const NetDesc& net, const float* states, const int* lengths, int n, int maxLen, float* out,
+                       cudaStream_t st);
 // cluster step kernel (cluster_step.cuh)
 void cluster_plan_build(const NetDesc& net, int numWorkersHint, ClusterPlan& cp, std::vector<int>& idx, std::vector<int>& items);
 size_t cluster_image_floats(const ClusterPlan& cp);

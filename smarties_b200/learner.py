@@ -32,7 +32,7 @@ EXPORTS = [
     "smb200_n_episodes", "smb200_initialize_learner", "smb200_set_grad_step", "smb200_seed_sampler", "smb200_sample",
     "smb200_train_steps", "smb200_train_steps_weights", "smb200_pin_host_buffer", "smb200_train_step_on", "smb200_get_last_batch", "smb200_retrace_sweep", "smb200_fused_sweep",
     "smb200_reward_state_moments", "smb200_read_field", "smb200_read_episodes", "smb200_n_rows", "smb200_get_stats",
-    "smb200_forward", "smb200_last_timing", "smb200_step_kernel", "smb200_presample", "smb200_train_presampled", "smb200_sync", "smb200_profile_phases",
+    "smb200_forward", "smb200_forward_seq", "smb200_last_timing", "smb200_step_kernel", "smb200_presample", "smb200_train_presampled", "smb200_sync", "smb200_profile_phases",
     "smb200_comm_init", "smb200_comm_attach", "smb200_comm_error", "smb200_write_field", "smb200_save", "smb200_restart",
     "smb200_push_episode_restored", "smb200_set_refer", "smb200_set_grad_stats", "smb200_uint_plus_float", "smb200_host_replay_trace", "smb200_host_init_weights",
     "smb200_host_strip_weights", "smb200_host_write_grad_stats", "smb200_host_repack_episodes",
@@ -137,6 +137,7 @@ def load_library(path: str = LIB_PATH):
         "smb200_set_grad_stats": (C.c_int, [H, C.c_char_p]),
         "smb200_get_stats": (C.c_int, [H, P(StepStats)]),
         "smb200_forward": (C.c_int, [H, fp, C.c_int32, fp]),
+        "smb200_forward_seq": (C.c_int, [H, fp, C.POINTER(C.c_int32), C.c_int32, C.c_int32, fp]),
         "smb200_last_timing": (C.c_int, [H, dp, ip]), "smb200_step_kernel": (C.c_int, [H]),
         "smb200_presample": (C.c_int, [H, C.c_int32]), "smb200_train_presampled": (C.c_int, [H, C.c_int32, C.c_int32]),
         "smb200_sync": (C.c_int, [H]),
@@ -426,6 +427,17 @@ class Learner:
         s = _f32(states).reshape(-1, self.dS)
         out = np.empty((s.shape[0], self.n_out), np.float32)
         self._check(self.lib.smb200_forward(self.h, _fp(s), s.shape[0], _fp(out)))
+        return out
+
+    def forward_seq(self, windows, lengths):
+        """Policy evaluation of n agents on their windows: windows[n][max_len][dS] raw states (oldest first), the first
+        lengths[i] rows of agent i are valid; outputs at the newest row (recurrent nets: zero initial state)."""
+        w = _f32(windows)
+        n, max_len = w.shape[0], w.shape[1]
+        w = w.reshape(n, max_len, self.dS)
+        ln = np.ascontiguousarray(np.asarray(lengths, np.int32).reshape(n))
+        out = np.empty((n, self.n_out), np.float32)
+        self._check(self.lib.smb200_forward_seq(self.h, _fp(w), ln.ctypes.data_as(C.POINTER(C.c_int32)), n, max_len, _fp(out)))
         return out
 
     # -- stand-alone sweeps --

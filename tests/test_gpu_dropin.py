@@ -115,3 +115,62 @@ def test_cart_pole_recurrent_racer_on_the_device_learner():
     done = [l for l in r["b200_lines"] if "gradient steps" in l]
     assert done and int(done[0].split()[1]) >= 1999, r
     assert r["stat_rows"] >= 1 and 0.0 < r["beta_last"] <= 1.0 and np.isfinite(r["avgR_last"]), r
+
+
+def _policy_evaluations(r):
+    l = [x for x in r["b200_lines"] if "policy evaluations in" in x]
+    assert l, r
+    f = l[0].split()
+    return int(f[1]), int(f[5]), int(f[-2])        # agents answered, device calls, largest call
+
+
+def test_cart_pole_with_the_actors_on_the_device():
+    """SMARTIES_B200_ACTORS=1: RACER::selectAction / processTerminal (RACER.cpp:30-59) read the network outputs from
+    smb200_forward_seq; everything else of the actor (policy sampling, advantage, episode storage) stays the reference's.
+    The run has to learn like the host-actor run does."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "b200", "cart_pole")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/b200/cart_pole not built (make -C integration needs /root/reference)")
+    from dropin_run import run_arm
+    r = run_arm("b200", steps=3000, threads=4, seed=7, timeout=600, extra_env={"SMARTIES_B200_ACTORS": "1"})
+    assert r.get("rc") == 0, r
+    assert any("policy evaluations run on the GPU" in l for l in r["b200_lines"]), r
+    agents, calls, _ = _policy_evaluations(r)
+    assert agents >= 3000 and calls >= 1, r
+    done = [l for l in r["b200_lines"] if "gradient steps" in l]
+    assert done and int(done[0].split()[1]) >= 2999, r
+    assert r["stat_rows"] >= 2 and r["avgR_last"] > 5.0 and 0.0 < r["beta_last"] <= 1.0, r
+
+
+def test_many_actors_on_the_device_are_answered_in_batches():
+    """16 environment processes, 4 worker threads: requests that arrive while a device call is in flight share the next
+    call (the binding's combiner), so the number of device calls is below the number of policy evaluations."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "b200", "synth_env")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/b200/synth_env not built (make -C integration needs /root/reference)")
+    from dropin_run import run_arm
+    r = run_arm("b200", steps=20000, threads=4, seed=3, timeout=600, app="synth_env", envs=16, extra_env={"SMARTIES_B200_ACTORS": "1"})
+    assert r.get("rc") == 0, r
+    agents, calls, largest = _policy_evaluations(r)
+    assert agents >= 20000 and calls <= agents and largest >= 1, r
+    done = [l for l in r["b200_lines"] if "gradient steps" in l]
+    assert done and int(done[0].split()[1]) >= 1000, r
+    assert r["stat_rows"] >= 1 and 0.0 < r["beta_last"] <= 1.0, r
+
+
+def test_recurrent_actors_on_the_device():
+    """RACER with LSTM layers: every action of the reference's host actor is a forward pass over the window of up to
+    nnBPTTseq + 1 states; here the window goes to the device (k_forward_seq, one CTA per agent)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "b200", "cart_pole")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/b200/cart_pole not built (make -C integration needs /root/reference)")
+    from dropin_run import run_arm
+    S = {"learner": "RACER", "nnType": "LSTM", "nnLayerSizes": [32, 32], "clipImpWeight": 4, "explNoise": 0.1, "gamma": 0.99,
+         "epsAnneal": 0, "nnLambda": 1e-6, "maxTotObsNum": 16384, "minTotObsNum": 4096}
+    r = run_arm("b200", steps=2000, threads=4, seed=7, settings=S, timeout=600, extra_env={"SMARTIES_B200_ACTORS": "1"})
+    assert r.get("rc") == 0, r
+    agents, calls, _ = _policy_evaluations(r)
+    assert agents >= 2000 and calls >= 1, r
+    done = [l for l in r["b200_lines"] if "gradient steps" in l]
+    assert done and int(done[0].split()[1]) >= 1999, r
+    assert r["stat_rows"] >= 1 and 0.0 < r["beta_last"] <= 1.0 and np.isfinite(r["avgR_last"]), r

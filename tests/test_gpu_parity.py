@@ -259,6 +259,40 @@ def test_forward_matches_oracle():
     L.close()
 
 
+@pytest.mark.parametrize("case", ["racer_lstm", "vracer_lstm2", "racer_mgu", "vracer_gru2", "racer_cfg3mini", "vracer_cfg2mini"])
+def test_forward_seq_matches_oracle(case):
+    """Actor-side policy evaluation (RACER::selectAction, RACER.cpp:30-47) on the window MemoryBuffer::agentToMinibatch
+    builds (MemoryBuffer.cpp:440-467): ragged windows of 1 .. nnBPTTseq + 3 raw states per agent, zero initial recurrent
+    state, outputs at the newest state; windows longer than nnBPTTseq + 1 are cut to their newest states.  Feed-forward
+    nets see the newest state only."""
+    g = Golden(case)
+    L, o = make_learner(g), make_oracle(g)
+    rng = np.random.default_rng(3)
+    recurrent = g.settings.get("nnType", "FFNN") != "FFNN"
+    bptt = g.settings.get("nnBPTTseq", 16)
+    n, max_len = 19, bptt + 3
+    W = rng.standard_normal((n, max_len, g.dS)).astype(np.float32)
+    lens = rng.integers(1, max_len + 1, n).astype(np.int32)
+    lens[0], lens[1], lens[2] = 1, max_len, bptt + 1
+    out = L.forward_seq(W, lens)
+    assert out.shape == (n, L.n_out)
+    for i in range(n):
+        keep = min(int(lens[i]), bptt + 1) if recurrent else 1
+        X = ((W[i, lens[i] - keep:lens[i]] - o.state_mean) * o.state_scale).astype(np.float32)
+        O_ref = o.net.forward_seq(o.W, X)[0][-1] if recurrent else o.net.forward(o.W, X)[0][-1]
+        assert np.abs(out[i] - O_ref).max() < TOL_O, (i, int(lens[i]))
+    if not recurrent:
+        assert np.array_equal(out, L.forward(W[np.arange(n), lens - 1]))
+    # a second call reuses the staging buffers; a larger one grows them
+    W2 = rng.standard_normal((300, max_len, g.dS)).astype(np.float32)
+    l2 = np.full(300, max_len, np.int32)
+    out2 = L.forward_seq(W2, l2)
+    assert np.array_equal(out2[:5], L.forward_seq(W2[:5], l2[:5]))
+    with pytest.raises(Exception):
+        L.forward_seq(W, np.zeros(n, np.int32))
+    L.close()
+
+
 @pytest.mark.parametrize("case", ["racer_lstm", "vracer_lstm2"])
 def test_tensor_core_weight_gradient_matches_simt_tiles(monkeypatch, case):
     """Recurrent nets: the tcgen05 contraction of the LSTM weight gradient (3xTF32, accumulator in tensor memory, K-slices
