@@ -55,7 +55,7 @@ enum smb200_er_filter { SMB200_FILTER_OLDEST = 0, SMB200_FILTER_FARPOLFRAC = 1, 
 /* "nnFunc": function of the hidden dense layers (makeFunction, Network/Layers/Functions.h:643-668) with its own weight
  * initialisation factor (Function::initFactor); feed-forward nets (recurrent cells keep Tanh). */
 enum smb200_nn_func { SMB200_TANH = 0, SMB200_SOFTSIGN = 1 /* settings/default.json */, SMB200_HARDSIGN = 2, SMB200_SIGM = 3,
-                      SMB200_RELU = 4, SMB200_LRELU = 5 };
+                      SMB200_RELU = 4, SMB200_LRELU = 5, SMB200_EXPPLUS = 6, SMB200_SOFTPLUS = 7, SMB200_EXP = 8, SMB200_LINEAR = 9 };
 enum smb200_field {          /* per-transition replay arrays, Episode.h:66-75 */
   SMB200_F_V = 0, SMB200_F_ADV = 1, SMB200_F_QRET = 2, SMB200_F_DELTA = 3, SMB200_F_RHO = 4, SMB200_F_KL = 5,
   SMB200_F_REWARD = 6

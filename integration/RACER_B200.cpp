@@ -165,7 +165,8 @@ class RACER_B200 : public RACER<Advantage_t, Policy_t, Action_t>
     c.er_filter = settings.ERoldSeqFilter == "farpolfrac" ? SMB200_FILTER_FARPOLFRAC : settings.ERoldSeqFilter == "maxkldiv" ? SMB200_FILTER_MAXKLDIV
                 : settings.ERoldSeqFilter == "minerror" ? SMB200_FILTER_MINERROR : SMB200_FILTER_OLDEST;
     c.nn_func = settings.nnFunc == "SoftSign" ? SMB200_SOFTSIGN : settings.nnFunc == "HardSign" ? SMB200_HARDSIGN : settings.nnFunc == "Sigm" ? SMB200_SIGM
-              : settings.nnFunc == "Relu" ? SMB200_RELU : settings.nnFunc == "LRelu" ? SMB200_LRELU : SMB200_TANH;
+              : settings.nnFunc == "Relu" ? SMB200_RELU : settings.nnFunc == "LRelu" ? SMB200_LRELU : settings.nnFunc == "ExpPlus" ? SMB200_EXPPLUS
+              : settings.nnFunc == "SoftPlus" ? SMB200_SOFTPLUS : settings.nnFunc == "Exp" ? SMB200_EXP : settings.nnFunc == "Linear" ? SMB200_LINEAR : SMB200_TANH;
     c.returns_estimator = settings.returnsEstimator == "GAE" ? SMB200_GAE
                         : (settings.returnsEstimator == "retraceExplore" ? SMB200_RETRACE_EXPLORE : SMB200_RETRACE);
     // an episode occupies nsteps() = ndata()+1 rows and is at least two rows long: room for the worst case,
@@ -475,7 +476,8 @@ std::unique_ptr<Learner> createLearner(const Uint learnerID, MDPdescriptor& MDP,
       // settings/default.json asks for SoftSign.
       (settings.nnFunc == "Tanh" || (settings.nnType == "FFNN" && !MDP.isPartiallyObservable &&
                                      (settings.nnFunc == "SoftSign" || settings.nnFunc == "HardSign" || settings.nnFunc == "Sigm" ||
-                                      settings.nnFunc == "Relu" || settings.nnFunc == "LRelu"))) &&
+                                      settings.nnFunc == "Relu" || settings.nnFunc == "LRelu" || settings.nnFunc == "ExpPlus" ||
+                                      settings.nnFunc == "SoftPlus" || settings.nnFunc == "Exp" || settings.nnFunc == "Linear"))) &&
       settings.nnOutputFunc == "Linear" &&
       // several learner ranks: the device learners of the ranks would have to exchange CUDA-IPC handles over
       // distrib.learners_train_comm (smb200_comm_init / smb200_comm_attach) — not wired into the binding: reference learner

@@ -281,6 +281,14 @@ ACTIVATIONS = {
              lambda x, y: np.where(x > 0, f32(1), f32(0)).astype(f32)),
     "LRelu": (lambda x: np.where(np.asarray(x, f32) > 0, x, (f32(0.1) * np.asarray(x, f32)).astype(f32)).astype(f32),   # PRELU_FAC 0.1 (:16-18,461-468)
               lambda x, y: np.where(x > 0, f32(1), f32(0.1)).astype(f32)),
+    # Utilities::safeExp clips its argument at +-SMARTIES_EXP_CUT = 8 (FunctionUtilities.h:50-54)
+    "ExpPlus": (lambda x: np.log(f32(1) + np.exp(np.clip(np.asarray(x, f32), f32(-8), f32(8))).astype(f32)).astype(f32),      # :507-518
+                lambda x, y: (f32(1) / (f32(1) + np.exp(np.clip(-x, f32(-8), f32(8))).astype(f32))).astype(f32)),
+    "SoftPlus": (lambda x: ((np.asarray(x, f32) + np.sqrt(f32(1) + np.asarray(x, f32) ** 2)) / f32(2)).astype(f32),          # :552-563
+                 lambda x, y: ((f32(1) + x / np.sqrt(f32(1) + x * x)) / f32(2)).astype(f32)),
+    "Exp": (lambda x: np.exp(np.clip(np.asarray(x, f32), f32(-8), f32(8))).astype(f32),                                       # :604-617
+            lambda x, y: np.asarray(y, f32)),
+    "Linear": (lambda x: np.asarray(x, f32), lambda x, y: np.ones_like(np.asarray(x, f32))),                                  # :66-74
 }
 
 

@@ -184,8 +184,8 @@ static int build_net(const smb200_config& c, NetDesc& net, std::vector<GradTile>
   const bool lstm = c.nn_type == SMB200_LSTM || c.nn_type == SMB200_MGU;      // recurrent-cell layers
   const int cellKind = c.nn_type == SMB200_MGU ? kMGU : kLSTM, ng = cell_gates(cellKind);
   if (c.nn_type != SMB200_FFNN && !lstm) { set_error_msg("nnType must be FFNN, LSTM, MGU or GRU"); return -1; }
-  if (c.nn_func < SMB200_TANH || c.nn_func > SMB200_LRELU || (c.nn_func != SMB200_TANH && lstm)) {
-    set_error_msg("nnFunc must be Tanh, SoftSign, HardSign, Sigm, Relu or LRelu (recurrent cells: Tanh)"); return -1; }
+  if (c.nn_func < SMB200_TANH || c.nn_func > SMB200_LINEAR || (c.nn_func != SMB200_TANH && lstm)) {
+    set_error_msg("nnFunc must be one of makeFunction's ten names (recurrent cells: Tanh)"); return -1; }
   if (lstm && (c.nn_bptt_seq < 0 || c.nn_bptt_seq > 255)) { set_error_msg("nnBPTTseq out of range"); return -1; }
   if (lstm) for (int i = 0; i < c.n_hidden; ++i) if (c.hidden[i] > NT) { set_error_msg("LSTM layers wider than the CTA are not supported"); return -1; }
   for (int i = 0; i < c.n_hidden; ++i) {
@@ -278,9 +278,11 @@ static void init_weights(const smb200_config& c, const NetDesc& net, std::mt1993
       const bool out = L.kind == kDenseLinear;
       const double prefac = out ? c.out_weights_prefac : 1.0;
       const float fac = prefac > 0 ? (float)prefac : 1.f;
-      // Function::initFactor (Functions.h): Linear sqrt(1 / in); Tanh, Sigm, HardSign, SoftSign sqrt(6 / (in + out)); Relu sqrt(2 / in); LRelu sqrt(1 / in)
-      const double initFactor = (out || c.nn_func == SMB200_LRELU) ? std::sqrt(1. / L.nIn)
-                              : (c.nn_func == SMB200_RELU ? std::sqrt(2. / L.nIn) : std::sqrt(6. / (L.nIn + L.size)));
+      // Function::initFactor (Functions.h): Linear, LRelu sqrt(1 / in); Tanh, Sigm, HardSign, SoftSign sqrt(6 / (in + out));
+      // Relu, ExpPlus, SoftPlus, Exp sqrt(2 / in)
+      const bool in1 = out || c.nn_func == SMB200_LRELU || c.nn_func == SMB200_LINEAR;
+      const bool in2 = c.nn_func == SMB200_RELU || c.nn_func == SMB200_EXPPLUS || c.nn_func == SMB200_SOFTPLUS || c.nn_func == SMB200_EXP;
+      const double initFactor = in1 ? std::sqrt(1. / L.nIn) : (in2 ? std::sqrt(2. / L.nIn) : std::sqrt(6. / (L.nIn + L.size)));
       const float init = (float)(fac * initFactor);
       std::uniform_real_distribution<float> dis(-init, init);
       for (int i = 0; i < L.nIn; ++i)

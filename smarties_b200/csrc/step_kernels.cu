@@ -197,14 +197,21 @@ __device__ __forceinline__ float tanh_ref(float x) {
 __device__ __forceinline__ float sigm_ref(float x);
 // Hidden-layer function "nnFunc" (makeFunction, Network/Layers/Functions.h:643-668): value from the pre-activation, derivative
 // from the OUTPUT (the reference's evalDiff(in, out) of Tanh and Sigm only reads `out`; SoftSign and HardSign read `in`, whose
-// terms are functions of the output: 1 + |x| = 1 / (1 - |y|),  1 + x^2 = 1 / (1 - y^2)).
+// terms are functions of the output: 1 + |x| = 1 / (1 - |y|),  1 + x^2 = 1 / (1 - y^2);  ExpPlus y = log(1 + e^x): 1 / (1 + e^-x)
+// = 1 - e^-y, also where safeExp clips at +-8;  SoftPlus y = (x + sqrt(1 + x^2)) / 2: x = y - 1 / (4y), (1 + x / sqrt(1 + x^2)) / 2
+// = 4y^2 / (4y^2 + 1);  Exp: evalDiff(in, out) = out).
+__device__ __forceinline__ float safe_exp_ref(float x) { return expf(fminf(8.0f, fmaxf(-8.0f, x))); }   // Utilities::safeExp (FunctionUtilities.h:50-54)
 template <int F> __device__ __forceinline__ float act_eval_t(float x) {
   if (F == 0) return tanh_ref(x);                                      // Tanh::_eval (:103-112)
   if (F == 1) return __fdividef(x, 1.0f + fabsf(x));                   // SoftSign::_eval (:328-331)
   if (F == 2) return x * rsqrtf(1.0f + x * x);                         // HardSign::_eval (:220-223)
   if (F == 3) return sigm_ref(x);                                      // Sigm::_eval (:158-165)
   if (F == 4) return x > 0.0f ? x : 0.0f;                              // Relu::_eval (:415-418)
-  return x > 0.0f ? x : 0.1f * x;                                      // LRelu::_eval, PRELU_FAC 0.1 (:16-18,461-464)
+  if (F == 5) return x > 0.0f ? x : 0.1f * x;                          // LRelu::_eval, PRELU_FAC 0.1 (:16-18,461-464)
+  if (F == 6) return logf(1.0f + safe_exp_ref(x));                     // ExpPlus::_eval (:507-510)
+  if (F == 7) return (x + sqrtf(1.0f + x * x)) * 0.5f;                 // SoftPlus::_eval (:552-555)
+  if (F == 8) return safe_exp_ref(x);                                  // Exp::_eval (:604-607)
+  return x;                                                            // Linear as the hidden-layer function (:66-69)
 }
 template <int F> __device__ __forceinline__ float act_diff_t(float y) {
   if (F == 0) return 1.0f - y * y;                                     // Tanh::_evalDiff
@@ -212,7 +219,11 @@ template <int F> __device__ __forceinline__ float act_diff_t(float y) {
   if (F == 2) { const float t = 1.0f - y * y; return t * sqrtf(t); }   // HardSign: 1 / (1 + x^2)^(3/2)
   if (F == 3) return y * (1.0f - y);                                   // Sigm::_evalDiff(in, out)
   if (F == 4) return y > 0.0f ? 1.0f : 0.0f;                           // Relu: in > 0 <=> out > 0
-  return y > 0.0f ? 1.0f : 0.1f;                                       // LRelu
+  if (F == 5) return y > 0.0f ? 1.0f : 0.1f;                           // LRelu
+  if (F == 6) return -expm1f(-y);                                      // ExpPlus: 1 / (1 + safeExp(-x)) (:515-518)
+  if (F == 7) { const float q = 4.0f * y * y; return __fdividef(q, q + 1.0f); }   // SoftPlus (:560-563)
+  if (F == 8) return y;                                                // Exp::_evalDiff(in, out) = out (:614-617)
+  return 1.0f;                                                         // Linear
 }
 // run `body(std::integral_constant<int, F>)` with F = the runtime function id: the selection happens once per call site, the
 // element loops inside `body` are branch-free
@@ -223,7 +234,11 @@ template <class Body> __device__ __forceinline__ void act_dispatch(int f, Body&&
     case 2: body(std::integral_constant<int, 2>{}); break;
     case 3: body(std::integral_constant<int, 3>{}); break;
     case 4: body(std::integral_constant<int, 4>{}); break;
-    default: body(std::integral_constant<int, 5>{}); break;
+    case 5: body(std::integral_constant<int, 5>{}); break;
+    case 6: body(std::integral_constant<int, 6>{}); break;
+    case 7: body(std::integral_constant<int, 7>{}); break;
+    case 8: body(std::integral_constant<int, 8>{}); break;
+    default: body(std::integral_constant<int, 9>{}); break;
   }
 }
 __device__ __forceinline__ float act_eval(int f, float x) {

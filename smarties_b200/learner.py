@@ -202,7 +202,8 @@ def make_config(dim_state: int, dim_action: int, settings=None, *, device: int =
     cfg.discrete_options = int(discrete_options)     # from the MDP (Communicator::setNumberOfOptions), not from settings.json
     cfg.data_sampling = {"uniform": 0, "PERrank": 1, "PERerr": 2, "PERseq": 3}[hp.dataSamplingAlgo]
     cfg.er_filter = {"oldest": 0, "default": 0, "farpolfrac": 1, "maxkldiv": 2, "minerror": 3}[hp.ERoldSeqFilter]
-    cfg.nn_func = {"Tanh": 0, "SoftSign": 1, "HardSign": 2, "Sigm": 3, "Relu": 4, "LRelu": 5}[hp.nnFunc]
+    cfg.nn_func = {"Tanh": 0, "SoftSign": 1, "HardSign": 2, "Sigm": 3, "Relu": 4, "LRelu": 5, "ExpPlus": 6, "SoftPlus": 7, "Exp": 8,
+                   "Linear": 9}[hp.nnFunc]
     if bounded is not None:
         b = np.broadcast_to(np.asarray(bounded, dtype=bool), (dim_action,))
         for i in range(dim_action):

@@ -103,7 +103,7 @@ class HyperParameters:
         if self.ERoldSeqFilter not in ("oldest", "default", "farpolfrac", "maxkldiv", "minerror"):
             unsupported.append(f"ERoldSeqFilter={self.ERoldSeqFilter}")
         # hidden-layer functions of makeFunction (Functions.h:643-668) the device evaluates; recurrent cells keep Tanh
-        func_ok = self.nnFunc == "Tanh" or (self.nnType == "FFNN" and self.nnFunc in ("SoftSign", "HardSign", "Sigm", "Relu", "LRelu"))
+        func_ok = self.nnFunc == "Tanh" or (self.nnType == "FFNN" and self.nnFunc in ("SoftSign", "HardSign", "Sigm", "Relu", "LRelu", "ExpPlus", "SoftPlus", "Exp", "Linear"))
         if self.nnType not in ("FFNN", "LSTM", "MGU", "GRU") or not func_ok or self.nnOutputFunc != "Linear":
             unsupported.append(f"nnType/nnFunc/nnOutputFunc={self.nnType}/{self.nnFunc}/{self.nnOutputFunc}")
         if self.ESpopSize != 1 or self.targetDelay != 0 or any(int(e) > 0 for e in self.encoderLayerSizes):

@@ -76,6 +76,24 @@ CASES = {
         replay=dict(seed=95, n_ep=20, ep_len=(25, 50), dS=6, dA=2),
         settings={"learner": "VRACER", "nnFunc": "LRelu", "nnLayerSizes": [32, 32], "batchSize": 16, "maxTotObsNum": 2048, "minTotObsNum": 400},
         steps=3, start_step=0, sample_seed=22, bounded=1, full_steps=[0, 2]),
+    # the remaining names of makeFunction (Functions.h:643-668): initFactor sqrt(2 / inputs) for ExpPlus, SoftPlus, Exp and
+    # sqrt(1 / inputs) for Linear; their evalDiff reads the pre-activation (or, Exp, the output)
+    "vracer_expplus": dict(
+        replay=dict(seed=96, n_ep=20, ep_len=(25, 50), dS=6, dA=2),
+        settings={"learner": "VRACER", "nnFunc": "ExpPlus", "nnLayerSizes": [32, 32], "batchSize": 16, "maxTotObsNum": 2048, "minTotObsNum": 400},
+        steps=3, start_step=0, sample_seed=23, bounded=0, full_steps=[0, 2]),
+    "racer_softplus": dict(
+        replay=dict(seed=97, n_ep=20, ep_len=(25, 50), dS=7, dA=2),
+        settings={"learner": "RACER", "nnFunc": "SoftPlus", "nnLayerSizes": [32, 32], "batchSize": 16, "maxTotObsNum": 2048, "minTotObsNum": 400},
+        steps=3, start_step=0, sample_seed=24, bounded=0, full_steps=[0, 2]),
+    "vracer_exp": dict(
+        replay=dict(seed=98, n_ep=20, ep_len=(25, 50), dS=6, dA=2),
+        settings={"learner": "VRACER", "nnFunc": "Exp", "nnLayerSizes": [24, 24], "batchSize": 16, "maxTotObsNum": 2048, "minTotObsNum": 400},
+        steps=3, start_step=0, sample_seed=25, bounded=1, full_steps=[0, 2]),
+    "vracer_linear": dict(
+        replay=dict(seed=99, n_ep=20, ep_len=(25, 50), dS=6, dA=2),
+        settings={"learner": "VRACER", "nnFunc": "Linear", "nnLayerSizes": [32, 32], "batchSize": 16, "maxTotObsNum": 2048, "minTotObsNum": 400},
+        steps=3, start_step=0, sample_seed=26, bounded=0, full_steps=[0, 2]),
     # FIFO pruning: capacity below the stored data, so applyEpisodesRemovalAlgo evicts on step 1
     "vracer_prune": dict(
         replay=dict(seed=17, n_ep=16, ep_len=(20, 30), dS=4, dA=2),

@@ -11,7 +11,8 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CKPT_CASES = ["vracer_ckpt", "racer_lstm_ckpt"]
 CASES = ["vracer_small", "vracer_cfg2mini", "vracer_bounded", "vracer_prune", "racer_small", "racer_bounded", "vracer_gae",
          "vracer_da1", "vracer_explore", "vracer_b1024", "vracer_b4096", "racer_discrete",
-         "vracer_softsign", "vracer_hardsign", "racer_sigm", "vracer_relu", "vracer_lrelu"]      # "nnFunc" other than Tanh (settings/default.json: SoftSign)
+         "vracer_softsign", "vracer_hardsign", "racer_sigm", "vracer_relu", "vracer_lrelu",
+         "vracer_expplus", "racer_softplus", "vracer_exp", "vracer_linear"]      # "nnFunc" other than Tanh (settings/default.json: SoftSign)
 # golden runs of a reference with 8 / 16 OpenMP threads: the far-policy count (and beta) depend on the thread count
 # (MemoryProcessing.cpp:202-227); the device reproduces it with refer_reduce_threads = T
 THREADED_CASES = ["vracer_small_t8", "vracer_small_t16", "vracer_cfg2mini_t8", "vracer_cfg2mini_t16", "racer_small_t8"]

@@ -50,7 +50,7 @@ def test_settings_outside_the_device_path_are_rejected_loudly():
     assert HyperParameters(4, 1, {"nnType": "GRU", "nnLayerSizes": [32]}).bRecurrent
     assert HyperParameters(4, 1, {"dataSamplingAlgo": "PERrank", "ERoldSeqFilter": "minerror"}).dataSamplingAlgo == "PERrank"
     for bad in ({"returnsEstimator": "nonsense"}, {"dataSamplingAlgo": "PERx"}, {"ERoldSeqFilter": "youngest"},
-                {"nnType": "RNN"}, {"nnFunc": "ExpPlus"}, {"nnFunc": "Relu", "nnType": "LSTM", "nnLayerSizes": [16]}):
+                {"nnType": "RNN"}, {"nnFunc": "HardSigmoid"}, {"nnFunc": "Relu", "nnType": "LSTM", "nnLayerSizes": [16]}):
         with pytest.raises(NotImplementedError):
             HyperParameters(4, 1, bad)
 
