@@ -129,6 +129,15 @@ struct smb200_learner {
   std::vector<long long> epPrefix; std::vector<int> bucketFirst; int bucketShift = 0; bool lookupDirty = true;
   double lastMs = 0; long long lastLaunches = 0;
   long long launches = 0;
+  // Sample-ahead queue (uniform sampler, FIFO filter): mini-batches of the NEXT learner steps, drawn from a copy of the
+  // sampler's generator while the host would otherwise wait for the device at the end of a train call.  `gen` always stays at
+  // the true position of the reference's stream: a consumed step advances it by the number of 32-bit draws the step took
+  // (discard), so dropping the queue (an episode arrives, the sampler is re-seeded, ...) needs no repair.
+  std::vector<int> aheadSlot, aheadRow; std::vector<unsigned> aheadDraws; std::vector<unsigned char> aheadEnds;
+  int aheadHead = 0, aheadCnt = 0; std::mt19937 aheadGen; long long aheadGradStep = 0, aheadVersion = -1;
+  long long tableVersion = 0;              // bumped whenever the episode table or its order changes
+  long long aheadUsed = 0, aheadDrawn = 0; // diagnostics: steps served from the queue / drawn into it
+  void ahead_clear() { aheadHead = aheadCnt = 0; aheadVersion = -1; }
 
   // actor-side policy evaluation (smb200_forward / smb200_forward_seq): staging buffers that grow on demand, and the lock that
   // lets actor threads push episodes and evaluate the policy while the learner thread trains (one stream, one call at a time)
@@ -447,7 +456,7 @@ static bool host_post_step(smb200_learner* h) {
   // 32-bit draw of generators[0] — the sampler's generator — every update.
   (void)h->gen();
   h->gradStep++; h->trackerSteps++;
-  if (changed) { h->orderDirty = true; h->lookupDirty = true; }
+  if (changed) { h->orderDirty = true; h->lookupDirty = true; h->tableVersion++; h->ahead_clear(); }
   return changed;
 }
 
@@ -489,7 +498,18 @@ static void rebuild_lookup(smb200_learner* h) {
   h->lookupDirty = false;
 }
 
-static void host_sample(smb200_learner* h, int* slotOut, int* tOut, int64_t* posOut, int64_t* tOut64) {
+// a generator that counts its 32-bit draws (same min / max / result_type: std::uniform_int_distribution behaves identically)
+struct CountingGen {
+  using result_type = std::mt19937::result_type;
+  std::mt19937& g; unsigned n = 0;
+  explicit CountingGen(std::mt19937& g_) : g(g_) {}
+  static constexpr result_type min() { return std::mt19937::min(); }
+  static constexpr result_type max() { return std::mt19937::max(); }
+  result_type operator()() { ++n; return g(); }
+};
+
+template <class Gen>
+static void host_sample_with(smb200_learner* h, Gen& gen, int* slotOut, int* tOut, int64_t* posOut, int64_t* tOut64) {
   const int B = h->cfg.batch_size;
   const long nData = (long)h->nTransitions;
   std::uniform_int_distribution<size_t> distObs(0, nData - 1);
@@ -498,7 +518,7 @@ static void host_sample(smb200_learner* h, int* slotOut, int* tOut, int64_t* pos
   int bits = 1; while ((1ull << bits) < (unsigned long long)nData) ++bits;
   auto it = ret.begin();
   while (it != ret.end()) {     // Sample_uniform::sample (Sampling.cpp:82-93): draw, sort, drop duplicates, redraw the tail
-    std::generate(it, ret.end(), [&]() { return distObs(h->gen); });
+    std::generate(it, ret.end(), [&]() { return distObs(gen); });
     radix_sort_ids(ret.data(), h->sampTmp.data(), B, bits);
     it = std::unique(ret.begin(), ret.end());
   }
@@ -517,6 +537,72 @@ static void host_sample(smb200_learner* h, int* slotOut, int* tOut, int64_t* pos
     }
     if (posOut) { posOut[i] = (int64_t)k; tOut64[i] = (int64_t)t; }
   }
+}
+static void host_sample(smb200_learner* h, int* slotOut, int* tOut, int64_t* posOut, int64_t* tOut64) {
+  host_sample_with(h, h->gen, slotOut, tOut, posOut, tOut64);
+}
+
+// ---- sample-ahead queue (see smb200_learner::aheadSlot) ----
+constexpr int kAheadMax = 128;     // steps
+// the episode table is in its steady state: the next host_post_step neither re-sorts nor evicts
+static bool table_steady(const smb200_learner* h) {
+  if (h->cfg.er_filter != SMB200_FILTER_OLDEST || h->episodes.empty()) return false;
+  auto cmp = [](const EpisodeMeta& a, const EpisodeMeta& b) { return a.id > b.id; };
+  if (!std::is_sorted(h->episodes.begin(), h->episodes.end(), cmp)) return false;
+  return !(h->nTransitions - (long long)h->episodes.back().nRows > h->cfg.max_tot_obs);
+}
+// draw one more step into the queue; false = the queue is full, closed by a segment-ending step, or not applicable
+static bool ahead_push_one(smb200_learner* h) {
+  const int B = h->cfg.batch_size;
+  if (h->slow_mode() || h->nTransitions < B) return false;
+  if (h->aheadCnt > h->aheadHead && h->aheadVersion != h->tableVersion) h->ahead_clear();
+  if (h->aheadCnt == h->aheadHead) {                       // empty: start at the true position of the stream
+    if (!table_steady(h)) return false;
+    h->aheadHead = h->aheadCnt = 0;
+    h->aheadGen = h->gen; h->aheadGradStep = h->gradStep; h->aheadVersion = h->tableVersion;
+  } else if (h->aheadEnds[h->aheadCnt - 1]) return false;  // the step after a sweep / a statistics step is drawn after it ran
+  if (h->aheadCnt == kAheadMax) {
+    if (h->aheadHead == 0) return false;
+    const int live = h->aheadCnt - h->aheadHead;           // compact
+    memmove(h->aheadSlot.data(), h->aheadSlot.data() + (size_t)h->aheadHead * B, sizeof(int) * (size_t)live * B);
+    memmove(h->aheadRow.data(), h->aheadRow.data() + (size_t)h->aheadHead * B, sizeof(int) * (size_t)live * B);
+    memmove(h->aheadDraws.data(), h->aheadDraws.data() + h->aheadHead, sizeof(unsigned) * live);
+    memmove(h->aheadEnds.data(), h->aheadEnds.data() + h->aheadHead, live);
+    h->aheadHead = 0; h->aheadCnt = live;
+  }
+  if (h->aheadSlot.size() != (size_t)kAheadMax * B) {
+    h->aheadSlot.resize((size_t)kAheadMax * B); h->aheadRow.resize((size_t)kAheadMax * B);
+    h->aheadDraws.resize(kAheadMax); h->aheadEnds.resize(kAheadMax);
+  }
+  const int i = h->aheadCnt;
+  CountingGen cg(h->aheadGen);
+  host_sample_with(h, cg, h->aheadSlot.data() + (size_t)i * B, h->aheadRow.data() + (size_t)i * B, nullptr, nullptr);
+  (void)cg();                                              // the Adam update's draw (host_post_step)
+  const long long stepNo = h->aheadGradStep + 1;
+  h->aheadDraws[i] = cg.n;
+  h->aheadEnds[i] = (stepNo % 1000 == 0 || h->grad_stats_step(stepNo - 1)) ? 1 : 0;
+  h->aheadGradStep = stepNo; h->aheadCnt = i + 1; h->aheadDrawn++;
+  return true;
+}
+// serve up to n steps of a segment from the queue: ids into the pinned half, the stream position and the step counters
+// advance exactly like plan_segment's host_sample + host_post_step would have moved them
+static int ahead_consume(smb200_learner* h, int n, int off) {
+  if (h->aheadCnt == h->aheadHead) return 0;
+  if (h->aheadVersion != h->tableVersion || h->aheadGradStep - (h->aheadCnt - h->aheadHead) != h->gradStep) { h->ahead_clear(); return 0; }
+  const int B = h->cfg.batch_size;
+  int cnt = 0;
+  unsigned long long draws = 0;
+  while (cnt < n && off + cnt < h->maxSeg && h->aheadHead < h->aheadCnt) {
+    const int i = h->aheadHead++;
+    memcpy(h->hSampSlot + (size_t)(off + cnt) * B, h->aheadSlot.data() + (size_t)i * B, sizeof(int) * B);
+    memcpy(h->hSampT + (size_t)(off + cnt) * B, h->aheadRow.data() + (size_t)i * B, sizeof(int) * B);
+    draws += h->aheadDraws[i];
+    h->gradStep++; h->trackerSteps++; h->aheadUsed++;
+    ++cnt;
+    if (h->aheadEnds[i]) break;
+  }
+  h->gen.discard(draws);
+  return cnt;
 }
 
 // ---- prioritized samplers (ReplayMemory/Sampling.cpp:101-296) ----
@@ -1052,6 +1138,7 @@ static void host_add_episode(smb200_learner* h, int64_t id, int32_t N, int32_t t
   h->nTransitions += N - 1;
   h->nSeenEps += 1; h->nSeenObs += N - 1;
   h->orderDirty = true; h->lookupDirty = true; h->presampled = 0;
+  h->tableVersion++; h->ahead_clear();
 }
 
 // copied as they are; the aggregates are recomputed with (cmax, cinv) like MemoryBuffer::restart does
@@ -1155,19 +1242,20 @@ int smb200_initialize_learner(smb200_learner* h) {
 int smb200_set_grad_step(smb200_learner* h, int64_t n) {
   if (!h || n < 0) return SMB200_ERR_INVALID;
   if (pull_ctrl(h)) return SMB200_ERR_CUDA;
-  h->gradStep = n; h->hCtrl.grad_step = n; h->hCtrl.adam_step = n;
+  h->gradStep = n; h->hCtrl.grad_step = n; h->hCtrl.adam_step = n; h->ahead_clear();
   h->hCtrl.gl_far_prev = (double)h->hCtrl.n_far_ref; h->hCtrl.gl_stored_prev = (double)h->nTransitions; h->hCtrl.cnt_seed_step = n;
   return push_ctrl(h);
 }
 int smb200_seed_sampler(smb200_learner* h, uint64_t seed) {
   if (!h) return SMB200_ERR_INVALID;
-  h->gen.seed((unsigned long)seed); h->presampled = 0;
+  h->gen.seed((unsigned long)seed); h->presampled = 0; h->ahead_clear();
   return 0;
 }
 
 int smb200_set_grad_stats(smb200_learner* h, const char* base) {
   if (!h) return SMB200_ERR_INVALID;
   h->gradStatsBase = base ? base : "";
+  h->ahead_clear();                     // which steps end a segment depends on it
   if (!h->gradStatsBase.empty() && !h->hGradStat[0]) {
     cudaSetDevice(h->cfg.device);
     const size_t bytes = sizeof(float) * (size_t)h->cfg.batch_size * h->descs.net.nOut;
@@ -1178,6 +1266,7 @@ int smb200_set_grad_stats(smb200_learner* h, const char* base) {
 
 int smb200_sample(smb200_learner* h, int64_t* pos, int64_t* t) {
   if (!h || !pos || !t || h->nTransitions < h->cfg.batch_size) return SMB200_ERR_STATE;
+  h->ahead_clear();
   if (h->cfg.data_sampling != SMB200_SAMPLE_UNIFORM) {
     if (h->samplerStale) { if (fetch_keys(h)) return SMB200_ERR_CUDA; prepare_sampler(h); h->samplerStale = false; }
     host_sample_per(h, nullptr, nullptr, pos, t);
@@ -1339,7 +1428,9 @@ static int train_steps_impl(smb200_learner* h, int32_t n, smb200_step_stats* sta
     const int nEpPre = (int)h->episodes.size(); const long long nTrPre = h->nTransitions;
     const auto tp0 = std::chrono::steady_clock::now();
     const int segLen = i == 0 ? 64 : (i == 1 ? 256 : 1000);
-    const int cnt = plan_segment(h, std::min(std::min(n - done, P), segLen), off);
+    const int want = std::min(std::min(n - done, P), segLen);
+    int cnt = ahead_consume(h, want, off);                  // steps drawn ahead during the previous call's wait for the device
+    if (cnt == 0) cnt = plan_segment(h, want, off);
     hostPlan += std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count();
     const bool dirtyAfter = h->orderDirty;
     if (upload_samples(h, off, cnt)) return SMB200_ERR_CUDA;
@@ -1357,8 +1448,12 @@ static int train_steps_impl(smb200_learner* h, int32_t n, smb200_step_stats* sta
   }
   if (weightsOut)
     SMB200_CUDA_CHECK(cudaMemcpyAsync(weightsOut, h->W, sizeof(float) * (size_t)h->descs.net.nParams, cudaMemcpyDeviceToHost, h->stream));
-  if (reclaim(0) || reclaim(1)) return SMB200_ERR_CUDA;
   SMB200_CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
+  // the device is still working on the last segment(s): draw the next call's mini-batches meanwhile (never longer than the
+  // device takes: the event is polled between steps)
+  if (n > 0 && !getenv("SMB200_NO_SAMPLE_AHEAD"))
+    while (cudaEventQuery(h->ev1) == cudaErrorNotReady && h->aheadCnt - h->aheadHead < kAheadMax / 2 && ahead_push_one(h)) { }
+  if (reclaim(0) || reclaim(1)) return SMB200_ERR_CUDA;
   SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
   h->lastMs = ms; h->lastLaunches = h->launches - l0;
@@ -1374,6 +1469,7 @@ int smb200_train_step_on(smb200_learner* h, const int64_t* pos, const int64_t* t
   if (!h || !pos || !t || batch != h->cfg.batch_size) return SMB200_ERR_INVALID;
   std::lock_guard<std::recursive_mutex> lock(h->apiMutex);
   if (h->slow_mode()) { set_error_msg("train_step_on: uniform sampling with the FIFO filter only"); return SMB200_ERR_STATE; }
+  h->ahead_clear();
   cudaSetDevice(h->cfg.device);
   h->presampled = 0;
   for (int b = 0; b < batch; ++b) {
@@ -1406,6 +1502,7 @@ int smb200_train_step_on(smb200_learner* h, const int64_t* pos, const int64_t* t
 int smb200_presample(smb200_learner* h, int32_t n) {
   if (!h || n < 1) return SMB200_ERR_INVALID;
   if (h->slow_mode()) { set_error_msg("presample: uniform sampling with the FIFO filter only"); return SMB200_ERR_STATE; }
+  h->ahead_clear();
   cudaSetDevice(h->cfg.device);
   if (ensure_seg_capacity(h, n)) return SMB200_ERR_CUDA;
   // benchmark path: the episode table must be in its steady (sorted, un-pruned) state
@@ -2206,7 +2303,7 @@ int smb200_restart(smb200_learner* h, const char* base_c) {
   k.gl_far_prev = 0; k.gl_stored_prev = (double)h->nTransitions; k.cnt_seed_step = grad;
   if (push_ctrl(h)) return SMB200_ERR_CUDA;
   h->initialized = true;
-  h->orderDirty = true; h->lookupDirty = true;
+  h->orderDirty = true; h->lookupDirty = true; h->tableVersion++; h->ahead_clear();
   h->samplerStale = h->slow_mode();      // (the reference never prepares the sampler of a restarted learner before its first step)
   return 0;
 }

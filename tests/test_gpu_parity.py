@@ -260,6 +260,46 @@ def test_forward_matches_oracle():
     L.close()
 
 
+@pytest.mark.parametrize("case", ["vracer_cfg2mini", "vracer_prune", "racer_lstm"])
+def test_sample_ahead_queue_is_invisible(monkeypatch, case):
+    """smb200_train_steps draws the next call's mini-batches while it waits for the device (sample-ahead queue).  The sampled
+    stream, the step counters and the weights must be those of a learner that never draws ahead: calls of many sizes, the
+    every-1000-steps boundary, an episode pushed between two calls (the queue is dropped), a re-seeded sampler, the
+    benchmark's presample path."""
+    g = Golden(case)
+    monkeypatch.setenv("SMB200_NO_SAMPLE_AHEAD", "1")
+    A = make_learner(g)
+    monkeypatch.delenv("SMB200_NO_SAMPLE_AHEAD")
+    Bm = make_learner(g)
+    rng = np.random.default_rng(5)
+    ep_len = 12
+    S = rng.standard_normal((ep_len, g.dS)).astype(np.float32)
+    Aa = rng.standard_normal((ep_len, g.dA)).astype(np.float32) * 0.1
+    MU = np.concatenate([Aa * 0.9, np.full((ep_len, g.dA), 0.3, np.float32)], axis=1)
+    R = rng.standard_normal(ep_len).astype(np.float32)
+
+    def both(f):
+        ra, rb = f(A), f(Bm)
+        return ra, rb
+
+    sizes = [1, 1, 3, 20, 1, 64, 5, 200, 2, 990 - 297, 30, 1, 7]      # crosses grad step 1000 inside the 30-step call
+    for i, k in enumerate(sizes):
+        sa, sb = both(lambda L: L.train_steps(k))
+        for x, y in zip(sa, sb):
+            assert x["n_far_policy"] == y["n_far_policy"] and x["beta"] == y["beta"], (i, k)
+        (Oa, ga, Xa), (Ob, gb, Xb) = both(lambda L: L.get_last_batch())
+        assert np.array_equal(Xa, Xb) and np.array_equal(Oa, Ob), (i, k)
+        if i == 4:
+            both(lambda L: L.push_episode(10_000, S, Aa, MU, R, True))
+        if i == 6:
+            both(lambda L: L.seed_sampler(99))
+        if i == 8:
+            both(lambda L: (L.presample(6), L.train_presampled(0, 6), L.sync()))
+    assert np.array_equal(A.get_weights(), Bm.get_weights())
+    assert np.array_equal(A.read_field("RHO"), Bm.read_field("RHO"))
+    A.close(); Bm.close()
+
+
 @pytest.mark.parametrize("case", ["racer_lstm", "vracer_lstm2", "racer_mgu", "vracer_gru2", "racer_cfg3mini", "vracer_cfg2mini"])
 def test_forward_seq_matches_oracle(case):
     """Actor-side policy evaluation (RACER::selectAction, RACER.cpp:30-47) on the window MemoryBuffer::agentToMinibatch
