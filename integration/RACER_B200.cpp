@@ -144,10 +144,14 @@ class RACER_B200 : public RACER<Advantage_t, Policy_t, Action_t>
     c.algo = isRacer ? SMB200_RACER : SMB200_VRACER;
     // discrete action space (RACER<Discrete_advantage, Discrete_policy, Uint>): one component, its number of options
     if (MDP.bDiscreteActions()) c.discrete_options = (int32_t) MDP.discreteActionValues[0];
-    if (MDP.dimAction > SMB200_MAX_ACTION || settings.nnLayerSizes.size() > SMB200_MAX_HIDDEN) die("network too large for smarties_b200");
+    // RACER::setupNet (RACER_common.cpp:82-91): createEncoder's layers and nnLayerSizes are stacked in ONE network ("encodr" is renamed "net")
+    std::vector<Uint> hidden;
+    for (const Uint n : settings.encoderLayerSizes) if (n > 0) hidden.push_back(n);
+    for (const Uint n : settings.nnLayerSizes) if (n > 0) hidden.push_back(n);
+    if (MDP.dimAction > SMB200_MAX_ACTION || hidden.size() > SMB200_MAX_HIDDEN) die("network too large for smarties_b200");
     for (Uint i = 0; i < MDP.dimAction; ++i) c.action_bounded[i] = MDP.bActionSpaceBounded[i] ? 1 : 0;
-    c.n_hidden = (int32_t) settings.nnLayerSizes.size();
-    for (int i = 0; i < c.n_hidden; ++i) c.hidden[i] = (int32_t) settings.nnLayerSizes[i];
+    c.n_hidden = (int32_t) hidden.size();
+    for (int i = 0; i < c.n_hidden; ++i) c.hidden[i] = (int32_t) hidden[i];
     c.batch_size = (int32_t) settings.batchSize_local;  c.batch_size_global = (int32_t) settings.batchSize;
     c.max_tot_obs = settings.maxTotObsNum_local;         c.max_tot_obs_global = settings.maxTotObsNum;
     c.gamma = settings.gamma; c.lambda = settings.lambda; c.clip_imp_weight = settings.clipImpWeight;
@@ -482,8 +486,11 @@ std::unique_ptr<Learner> createLearner(const Uint learnerID, MDPdescriptor& MDP,
       // several learner ranks: the device learners of the ranks would have to exchange CUDA-IPC handles over
       // distrib.learners_train_comm (smb200_comm_init / smb200_comm_attach) — not wired into the binding: reference learner
       MPICommSize(distrib.learners_train_comm) == 1 &&
-      settings.ESpopSize == 1 && settings.targetDelay == 0 && MDP.nAppendedObs == 0 &&
-      std::all_of(settings.encoderLayerSizes.begin(), settings.encoderLayerSizes.end(), [](Uint n) { return n == 0; });
+      settings.ESpopSize == 1 && settings.targetDelay == 0 && MDP.nAppendedObs == 0 && MDP.conv2dDescriptors.size() == 0 &&
+      // encoder layers are the first layers of the one network; in a partially observable MDP the reference gives them another
+      // cell type than the layers after them ("RNN" vs "MGU", Approximator.cpp:219-223,265-267): reference learner
+      (!MDP.isPartiallyObservable || settings.bRecurrent ||
+       std::all_of(settings.encoderLayerSizes.begin(), settings.encoderLayerSizes.end(), [](Uint n) { return n == 0; }));
   if (!covered) {
     warn("SMARTIES_B200 is set but these settings are outside the device path: using the reference CPU learner.");
     return createLearner_reference(learnerID, MDP, distrib);

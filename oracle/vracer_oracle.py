@@ -401,8 +401,11 @@ class MlpNet:
                 pre = _dense_fwd(Y[-1], W, b)
                 Y.pre[len(Y)] = pre
                 Y.append(self.act(pre))
-            elif k == "residual":  # ParametricResidualLayer::forward (Layers.h:347-361)
-                Y.append((Y[-1] + (Y[-2] * W[None, :] + b[None, :]).astype(f32)).astype(f32))
+            elif k == "residual":  # ParametricResidualLayer::forward (Layers.h:347-361): the first min(size(ID-2), size) units
+                m = min(Y[-2].shape[1], L["n"])
+                y = Y[-1][:, :L["n"]].astype(f32).copy()
+                y[:, :m] = (y[:, :m] + (Y[-2][:, :m] * W[None, :m] + b[None, :m]).astype(f32)).astype(f32)
+                Y.append(y)
             elif k == "dense_linear":
                 Y.append(_dense_fwd(Y[-1], W, b))
                 outs.append(Y[-1])
@@ -459,10 +462,11 @@ class MlpNet:
                     Gw += (xin.T @ d).astype(f32)
             else:  # ParametricResidualLayer::backward (Layers.h:363-393)
                 d = E[yi]
+                m = min(Y[yi - 2].shape[1], L["n"])
                 E[yi - 1] = d.copy()  # memcpy into E(ID-1)
-                E[yi - 2] = (E[yi - 2] + (d * W[None, :]).astype(f32)).astype(f32)
-                acc_rows(G[L["w"]:L["w"] + L["n"]], (d * Y[yi - 2]).astype(f32))
-                acc_rows(G[L["b"]:L["b"] + L["n"]], d)
+                E[yi - 2][:, :m] = (E[yi - 2][:, :m] + (d[:, :m] * W[None, :m]).astype(f32)).astype(f32)
+                acc_rows(G[L["w"]:L["w"] + m], (d[:, :m] * Y[yi - 2][:, :m]).astype(f32))
+                acc_rows(G[L["b"]:L["b"] + m], d[:, :m])
         return G
 
 

@@ -184,7 +184,9 @@ def make_config(dim_state: int, dim_action: int, settings=None, *, device: int =
         raise SmartiesB200Error("smb200_default_config: " + lib.smb200_last_error().decode())
     cfg.device = device
     cfg.algo = {"VRACER": 0, "RACER": 1}[hp.learner]
-    hidden = [int(h) for h in hp.nnLayerSizes if int(h) > 0]
+    # RACER::setupNet (Learners/RACER_common.cpp:82-91): the "encoder" Approximator IS the one network — createEncoder builds the
+    # encoderLayerSizes layers (Approximator::buildPreprocessing), buildFromSettings continues with nnLayerSizes in the same Builder
+    hidden = [int(h) for h in hp.encoderLayerSizes if int(h) > 0] + [int(h) for h in hp.nnLayerSizes if int(h) > 0]
     cfg.n_hidden = len(hidden)
     for i, h in enumerate(hidden):
         cfg.hidden[i] = h

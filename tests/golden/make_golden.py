@@ -94,6 +94,16 @@ CASES = {
         replay=dict(seed=99, n_ep=20, ep_len=(25, 50), dS=6, dA=2),
         settings={"learner": "VRACER", "nnFunc": "Linear", "nnLayerSizes": [32, 32], "batchSize": 16, "maxTotObsNum": 2048, "minTotObsNum": 400},
         steps=3, start_step=0, sample_seed=26, bounded=0, full_steps=[0, 2]),
+    # "encoderLayerSizes": Learner_approximator::createEncoder (Learner_approximator.cpp:148-166) + RACER::setupNet
+    # (RACER_common.cpp:82-91): the encoder layers and nnLayerSizes are stacked in the one network
+    "vracer_encoder": dict(
+        replay=dict(seed=101, n_ep=20, ep_len=(25, 50), dS=6, dA=2),
+        settings={"learner": "VRACER", "encoderLayerSizes": [32], "nnLayerSizes": [32, 24], "batchSize": 16, "maxTotObsNum": 2048, "minTotObsNum": 400},
+        steps=3, start_step=0, sample_seed=31, bounded=0, full_steps=[0, 2]),
+    "racer_encoder2": dict(
+        replay=dict(seed=102, n_ep=20, ep_len=(25, 50), dS=7, dA=2),
+        settings={"learner": "RACER", "nnFunc": "SoftSign", "encoderLayerSizes": [32, 24], "nnLayerSizes": [24], "batchSize": 16, "maxTotObsNum": 2048, "minTotObsNum": 400},
+        steps=3, start_step=0, sample_seed=32, bounded=1, full_steps=[0, 2]),
     # FIFO pruning: capacity below the stored data, so applyEpisodesRemovalAlgo evicts on step 1
     "vracer_prune": dict(
         replay=dict(seed=17, n_ep=16, ep_len=(20, 30), dS=4, dA=2),
@@ -114,6 +124,11 @@ CASES = {
         settings={"learner": "RACER", "nnType": "LSTM", "nnLayerSizes": [16], "nnBPTTseq": 8, "batchSize": 8,
                   "maxTotObsNum": 1024, "minTotObsNum": 200},
         steps=6, start_step=997, sample_seed=21, bounded=0, full_steps=list(range(6))),
+    "racer_lstm_encoder": dict(      # LSTM encoder layer under an LSTM layer (nnType applies to both, Approximator.cpp:265-270)
+        replay=dict(seed=55, n_ep=14, ep_len=(12, 40), dS=6, dA=2),
+        settings={"learner": "RACER", "nnType": "LSTM", "encoderLayerSizes": [16], "nnLayerSizes": [12], "nnBPTTseq": 8, "batchSize": 8,
+                  "maxTotObsNum": 1024, "minTotObsNum": 200},
+        steps=3, start_step=0, sample_seed=23, bounded=0, full_steps=list(range(3))),
     "vracer_lstm2": dict(
         replay=dict(seed=53, n_ep=10, ep_len=(6, 30), dS=5, dA=2),
         settings={"learner": "VRACER", "nnType": "LSTM", "nnLayerSizes": [12, 12], "nnBPTTseq": 5, "batchSize": 8,

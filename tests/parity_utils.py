@@ -12,14 +12,15 @@ CKPT_CASES = ["vracer_ckpt", "racer_lstm_ckpt"]
 CASES = ["vracer_small", "vracer_cfg2mini", "vracer_bounded", "vracer_prune", "racer_small", "racer_bounded", "vracer_gae",
          "vracer_da1", "vracer_explore", "vracer_b1024", "vracer_b4096", "racer_discrete",
          "vracer_softsign", "vracer_hardsign", "racer_sigm", "vracer_relu", "vracer_lrelu",
-         "vracer_expplus", "racer_softplus", "vracer_exp", "vracer_linear"]      # "nnFunc" other than Tanh (settings/default.json: SoftSign)
+         "vracer_expplus", "racer_softplus", "vracer_exp", "vracer_linear",
+         "vracer_encoder", "racer_encoder2"]      # "encoderLayerSizes": stacked under nnLayerSizes in the one network (RACER::setupNet)      # "nnFunc" other than Tanh (settings/default.json: SoftSign)
 # golden runs of a reference with 8 / 16 OpenMP threads: the far-policy count (and beta) depend on the thread count
 # (MemoryProcessing.cpp:202-227); the device reproduces it with refer_reduce_threads = T
 THREADED_CASES = ["vracer_small_t8", "vracer_small_t16", "vracer_cfg2mini_t8", "vracer_cfg2mini_t16", "racer_small_t8"]
 # prioritized samplers and non-FIFO episode filters: one launch per step with a host round trip
 SLOW_CASES = ["vracer_pererr", "vracer_perseq", "vracer_perrank", "vracer_farpolfrac", "vracer_maxkldiv", "vracer_minerror"]
 ORACLE_ONLY_CASES = []
-RECURRENT_CASES = ["racer_lstm", "vracer_lstm2", "racer_lstm64", "racer_cfg3mini",      # nnType LSTM + BPTT window (configs[2] family)
+RECURRENT_CASES = ["racer_lstm", "vracer_lstm2", "racer_lstm64", "racer_cfg3mini", "racer_lstm_encoder",      # nnType LSTM + BPTT window (configs[2] family)
                    "racer_mgu", "vracer_gru2"]     # MGU cells (Layer_GRU.h): "MGU" / "GRU", the default of partially observable MDPs
 
 
@@ -83,9 +84,10 @@ def make_oracle(g: Golden):
     if "n_options" in g.spec["replay"]:
         kw["discrete"] = g.spec["replay"]["n_options"]
     if s.get("nnType", "FFNN") in ("LSTM", "MGU", "GRU"):
-        o = vo.RecurrentOracle(g.dS, g.dA, cells=s["nnLayerSizes"], bptt=s.get("nnBPTTseq", 16), cell_type=s["nnType"], **kw)
+        o = vo.RecurrentOracle(g.dS, g.dA, cells=[h for h in s.get("encoderLayerSizes", []) if h > 0] + s["nnLayerSizes"], bptt=s.get("nnBPTTseq", 16), cell_type=s["nnType"], **kw)
     else:
-        o = vo.VracerOracle(g.dS, g.dA, hidden=s.get("nnLayerSizes", [128, 128]), **kw)
+        # encoder layers are the first layers of the one network (RACER::setupNet, RACER_common.cpp:82-91)
+        o = vo.VracerOracle(g.dS, g.dA, hidden=[h for h in s.get("encoderLayerSizes", []) if h > 0] + s.get("nnLayerSizes", [128, 128]), **kw)
     o.W[:] = g.ref["init/weights"]
     o.load_replay(g.replay)
     o.initialize_learner()

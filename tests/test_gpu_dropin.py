@@ -174,3 +174,19 @@ def test_recurrent_actors_on_the_device():
     done = [l for l in r["b200_lines"] if "gradient steps" in l]
     assert done and int(done[0].split()[1]) >= 1999, r
     assert r["stat_rows"] >= 1 and 0.0 < r["beta_last"] <= 1.0 and np.isfinite(r["avgR_last"]), r
+
+
+def test_cart_pole_with_encoder_layers_on_the_device_learner():
+    """"encoderLayerSizes" (Learner_approximator::createEncoder, Learner_approximator.cpp:148-166): for RACER the encoder layers are
+    the first layers of the one network (RACER::setupNet, RACER_common.cpp:82-91); the binding hands the stacked list to the device."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "b200", "cart_pole")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/b200/cart_pole not built (make -C integration needs /root/reference)")
+    from dropin_run import SETTINGS, run_arm
+    S = dict(SETTINGS, encoderLayerSizes=[64], nnLayerSizes=[64, 32])
+    r = run_arm("b200", steps=3000, threads=4, seed=7, settings=S, timeout=600)
+    assert r.get("rc") == 0, r
+    assert any("run on the GPU" in l for l in r["b200_lines"]), r      # not the fall-back to the reference learner
+    done = [l for l in r["b200_lines"] if "gradient steps" in l]
+    assert done and int(done[0].split()[1]) >= 2999, r
+    assert r["stat_rows"] >= 2 and r["avgR_last"] > 5.0 and 0.0 < r["beta_last"] <= 1.0, r

@@ -49,6 +49,7 @@ def test_settings_outside_the_device_path_are_rejected_loudly():
     assert HyperParameters(4, 1, {"nnType": "LSTM", "nnLayerSizes": [32]}).nnType == "LSTM"
     assert HyperParameters(4, 1, {"nnType": "GRU", "nnLayerSizes": [32]}).bRecurrent
     assert HyperParameters(4, 1, {"dataSamplingAlgo": "PERrank", "ERoldSeqFilter": "minerror"}).dataSamplingAlgo == "PERrank"
+    assert HyperParameters(4, 1, {"encoderLayerSizes": [32], "nnLayerSizes": [32, 16]}).encoderLayerSizes == [32]
     for bad in ({"returnsEstimator": "nonsense"}, {"dataSamplingAlgo": "PERx"}, {"ERoldSeqFilter": "youngest"},
                 {"nnType": "RNN"}, {"nnFunc": "HardSigmoid"}, {"nnFunc": "Relu", "nnType": "LSTM", "nnLayerSizes": [16]}):
         with pytest.raises(NotImplementedError):
