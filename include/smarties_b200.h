@@ -98,6 +98,10 @@ typedef struct smb200_config {
   int32_t data_sampling;                /* smb200_sampling: "dataSamplingAlgo" */
   int32_t er_filter;                    /* smb200_er_filter: "ERoldSeqFilter" */
   int32_t nn_func;                      /* smb200_nn_func: "nnFunc" (default Tanh, HyperParameters.h:72) */
+  double target_delay;                  /* "targetDelay" (AdamOptimizer::tgtUpdateAlpha, Network/Optimizer.cpp:162-177): 0 = the target weights
+                                           stay what they were at construction / restart; in (0, 1): exponential average target += a (w - target)
+                                           after every update; >= 1: copy of the weights every floor(targetDelay) updates.  RACER never evaluates
+                                           the target network: the weights only reach the checkpoint (<name>_net_tgt_weights.raw). */
 } smb200_config;
 
 /* Per-step scalars the reference prints / feeds back (MemoryBuffer::getMetrics,
@@ -126,6 +130,9 @@ int32_t smb200_n_outputs(const smb200_learner* h);  /* 1 + 2*dA (V-RACER) */
 /* Weights / Adam moments as the reference's padded parameter blob (Parameters.h:28-177). */
 int smb200_set_weights(smb200_learner* h, const float* blob, int64_t n);
 int smb200_get_weights(smb200_learner* h, float* blob, int64_t n);
+/* AdamOptimizer::target_weights (padded blob like the weights). */
+int smb200_get_target_weights(smb200_learner* h, float* blob, int64_t n);
+int smb200_set_target_weights(smb200_learner* h, const float* blob, int64_t n);
 int smb200_set_adam(smb200_learner* h, const float* m1, const float* m2, int64_t n, int64_t n_step);
 int smb200_get_adam(smb200_learner* h, float* m1, float* m2, int64_t n);
 /* Last summed parameter gradient (AdamOptimizer::gradSum before apply_update, Optimizer.cpp:110-120). */

@@ -171,6 +171,7 @@ class RACER_B200 : public RACER<Advantage_t, Policy_t, Action_t>
     c.nn_func = settings.nnFunc == "SoftSign" ? SMB200_SOFTSIGN : settings.nnFunc == "HardSign" ? SMB200_HARDSIGN : settings.nnFunc == "Sigm" ? SMB200_SIGM
               : settings.nnFunc == "Relu" ? SMB200_RELU : settings.nnFunc == "LRelu" ? SMB200_LRELU : settings.nnFunc == "ExpPlus" ? SMB200_EXPPLUS
               : settings.nnFunc == "SoftPlus" ? SMB200_SOFTPLUS : settings.nnFunc == "Exp" ? SMB200_EXP : settings.nnFunc == "Linear" ? SMB200_LINEAR : SMB200_TANH;
+    c.target_delay = settings.targetDelay;       // RACER never evaluates the target weights; they are kept for the checkpoint
     c.returns_estimator = settings.returnsEstimator == "GAE" ? SMB200_GAE
                         : (settings.returnsEstimator == "retraceExplore" ? SMB200_RETRACE_EXPLORE : SMB200_RETRACE);
     // an episode occupies nsteps() = ndata()+1 rows and is at least two rows long: room for the worst case,
@@ -333,6 +334,10 @@ class RACER_B200 : public RACER<Advantage_t, Policy_t, Action_t>
     AdamOptimizer* const adam = dynamic_cast<AdamOptimizer*>(networks[0]->opt.get());
     Parameters* M1 = adam ? adam->_1stMom.get() : nullptr, * M2 = adam ? adam->_2ndMom.get() : nullptr;
     if (M1 && M2) check(smb200_get_adam(gpu, M1->params, M2->params, (int64_t) M1->nParams), "get_adam");
+    if (settings.targetDelay > 0) {   // AdamOptimizer::target_weights are maintained on the device (Optimizer.cpp:162-177)
+      Parameters* T = networks[0]->opt->target_weights.get();
+      check(smb200_get_target_weights(gpu, T->params, (int64_t) T->nParams), "get_target_weights");
+    }
     {
       std::lock_guard<std::mutex> lock(data->dataset_mutex);
       const int64_t nEp = smb200_n_episodes(gpu), nRows = smb200_n_rows(gpu);
@@ -371,6 +376,10 @@ class RACER_B200 : public RACER<Advantage_t, Policy_t, Action_t>
     AdamOptimizer* const adam = dynamic_cast<AdamOptimizer*>(networks[0]->opt.get());
     Parameters* M1 = adam ? adam->_1stMom.get() : nullptr, * M2 = adam ? adam->_2ndMom.get() : nullptr;
     if (M1 && M2) check(smb200_set_adam(gpu, M1->params, M2->params, (int64_t) M1->nParams, data->nGradSteps()), "set_adam");
+    if (settings.targetDelay > 0) {
+      Parameters* T = networks[0]->opt->target_weights.get();
+      check(smb200_set_target_weights(gpu, T->params, (int64_t) T->nParams), "set_target_weights");
+    }
     const Uint dS = MDP.dimStateObserved;
     std::vector<float> mean(MDP.stateMean.begin(), MDP.stateMean.end()), scale(MDP.stateScale.begin(), MDP.stateScale.end()),
                        stdev(MDP.stateStdDev.begin(), MDP.stateStdDev.end());
@@ -486,7 +495,7 @@ std::unique_ptr<Learner> createLearner(const Uint learnerID, MDPdescriptor& MDP,
       // several learner ranks: the device learners of the ranks would have to exchange CUDA-IPC handles over
       // distrib.learners_train_comm (smb200_comm_init / smb200_comm_attach) — not wired into the binding: reference learner
       MPICommSize(distrib.learners_train_comm) == 1 &&
-      settings.ESpopSize == 1 && settings.targetDelay == 0 && MDP.nAppendedObs == 0 && MDP.conv2dDescriptors.size() == 0 &&
+      settings.ESpopSize == 1 && MDP.nAppendedObs == 0 && MDP.conv2dDescriptors.size() == 0 &&
       // encoder layers are the first layers of the one network; in a partially observable MDP the reference gives them another
       // cell type than the layers after them ("RNN" vs "MGU", Approximator.cpp:219-223,265-267): reference learner
       (!MDP.isPartiallyObservable || settings.bRecurrent ||

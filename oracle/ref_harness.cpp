@@ -284,6 +284,8 @@ struct Probe : public Base
         this->processMemoryBuffer();
         this->applyGradient();
         this->globalGradCounterUpdate();
+        // "targetDelay" > 0: AdamOptimizer::target_weights after every update (Optimizer.cpp:162-177)
+        if(settings.targetDelay > 0) D.f32(pre+"/tgt", blob(adam()->target_weights.get()));
         if(dumpThis) {
           D.f32(pre+"/weights", blob(adam()->weights.get()));
           D.f32(pre+"/m1", blob(adam()->_1stMom.get()));

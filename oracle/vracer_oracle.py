@@ -748,8 +748,12 @@ class VracerOracle:
     def __init__(self, dS, dA, hidden=(128, 128), gamma=0.995, lam=1.0, clip_imp_weight=None,
                  penal_tol=0.1, eps_anneal=5e-7, learnrate=1e-4, nn_lambda=FLT_EPS,
                  batch=256, max_tot_obs=None, bounded=False, sample_seed=42, learner="VRACER",
-                 returns_estimator="retrace", sampling="uniform", er_filter="oldest", discrete=0, refer_threads=1, nn_func="Tanh"):
+                 returns_estimator="retrace", sampling="uniform", er_filter="oldest", discrete=0, refer_threads=1, nn_func="Tanh",
+                 target_delay=0.0):
         self.dS, self.dA = dS, dA
+        # "targetDelay" (AdamOptimizer::tgtUpdateAlpha, Optimizer.cpp:162-177): W_tgt is created on the first update (a copy of
+        # the weights the learner was constructed with, Optimizer.h / Approximator::initializeNetwork)
+        self.target_delay, self.cnt_update_delay, self.W_tgt = float(target_delay), 0, None
         # OpenMP threads of the reference run: only the far-policy count depends on it (`Uint += float` partials per thread with
         # schedule(static, 1), MemoryProcessing.cpp:202-227)
         self.refer_threads = max(1, int(refer_threads))
@@ -1073,7 +1077,18 @@ class VracerOracle:
         numer = (B1 * M1 + (f32(1) - B1) * DW).astype(f32)
         M2[:] = np.where(M2 < M1 * M1, (M1 * M1).astype(f32), M2)
         ret = (numer / (f32(FLT_EPS) + np.sqrt(M2).astype(f32)).astype(f32)).astype(f32)
+        if self.target_delay > 0 and self.W_tgt is None:
+            self.W_tgt = W.copy()                                    # target_weights->copy(weights) at construction
         W += (eta * (ret + penal).astype(f32)).astype(f32)
+        if self.target_delay > 0:                                    # "update frozen weights" (Optimizer.cpp:162-177)
+            if self.cnt_update_delay == 0:
+                self.cnt_update_delay = int(self.target_delay)       # Uint cntUpdateDelay = tgtUpdateAlpha
+                if self.target_delay >= 1:
+                    self.W_tgt[:] = W
+                else:                                                # Real alpha times the f32 difference, added to the f32 target
+                    self.W_tgt[:] = (self.W_tgt.astype(f64) + self.target_delay * (W - self.W_tgt).astype(f32).astype(f64)).astype(f32)
+            if self.cnt_update_delay > 0:
+                self.cnt_update_delay -= 1
         self.beta_t_1 *= 0.9
         if self.beta_t_1 < FLT_EPS: self.beta_t_1 = 0
         self.beta_t_2 *= 0.999

@@ -83,6 +83,7 @@ struct smb200_learner {
 
   // network / optimiser
   float *W = nullptr, *Wimg = nullptr, *M1 = nullptr, *M2 = nullptr, *G = nullptr;
+  float* Wtgt = nullptr; long long tgtPhase = 0;     // "targetDelay" > 0: target weights on the device (see StepArgs)
   long long* dDbg = nullptr; int useTma = 1;
   // multi-rank gradient exchange over peer memory (CUDA IPC)
   CommView comm{}; unsigned char* commBuf = nullptr; int* dCommErr = nullptr; unsigned vecStamp = 0;
@@ -155,6 +156,7 @@ struct smb200_learner {
     StepArgs a{};
     a.comm = comm;
     a.descs = dDescs; a.rp = rp; a.W = W; a.Wimg = Wimg; a.M1 = M1; a.M2 = M2; a.G = G; a.dbgT = nullptr; a.useTma = useTma;
+    a.Wtgt = Wtgt; a.tgtAlpha = cfg.target_delay; a.tgtPhase = tgtPhase;
     a.useTc = useTc; a.tcPartial = tcPartial;
     a.wplan = dWplan; a.wimgF = wimgF; a.wimgB = wimgB; a.wvec = wvec; a.wpart = wpart; a.wGridG = wGridG; a.widx = dWidx;
     a.wcnt = wcnt; a.wlist = wlist;
@@ -954,7 +956,7 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
     const char* m0 = getenv("SMB200_MODE");
     int coop0 = 0; cudaDeviceGetAttribute(&coop0, cudaDevAttrCooperativeLaunch, c.device);
     cluster_plan_build(net, 4 * 33 - 1, h->cplan, h->cidx, h->citems);
-    if (h->cplan.ok && coop0 && !(m0 && strcmp(m0, "two") == 0)) {
+    if (h->cplan.ok && coop0 && !(m0 && strcmp(m0, "two") == 0) && !(c.target_delay > 0)) {
       CK(cluster_prepare(h->cplan));
       const int maxC = std::min(33, cluster_max_active(h->cplan));
       if (maxC >= 2) {
@@ -983,7 +985,7 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
   {
     const char* w = getenv("SMB200_WIDE");
     const bool never = w && strcmp(w, "0") == 0, always = w && strcmp(w, "1") == 0;
-    if (!never && (always || B >= 2048)) {
+    if (!never && (always || B >= 2048) && !(c.target_delay > 0)) {
       wide_plan_build(net, hp, h->wplan, h->widx);
       if (h->wplan.ok) {
         CK(wide_prepare(h->wplan, net));
@@ -1012,6 +1014,10 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
   init_weights(c, net, h->gen, blob);
   CK(upload_weights(h, blob.data()));
   h->tgtBlob = blob;
+  if (c.target_delay > 0) {      // the Adam epilogue of the tile kernel maintains them (the wide / cluster kernels are not used then)
+    CK(dev_alloc(&h->Wtgt, (size_t)net.nParams));
+    CKC(cudaMemcpy(h->Wtgt, blob.data(), sizeof(float) * (size_t)net.nParams, cudaMemcpyHostToDevice));
+  }
   CK(step_kernels_prepare(net));
   { const char* t = getenv("SMB200_TMA"); h->useTma = (t && strcmp(t, "0") == 0) ? 0 : 1; }
   const char* m = getenv("SMB200_MODE");
@@ -1041,6 +1047,7 @@ void smb200_destroy(smb200_learner* h) {
   if (h->commBuf) cudaFree(h->commBuf);
   if (h->dCommErr) cudaFree(h->dCommErr);
   if (h->tcPartial) cudaFree(h->tcPartial);
+  if (h->Wtgt) cudaFree(h->Wtgt);
   if (h->fwdIn) cudaFree(h->fwdIn);
   if (h->fwdOut) cudaFree(h->fwdOut);
   if (h->fwdLen) cudaFree(h->fwdLen);
@@ -1075,7 +1082,10 @@ int smb200_set_weights(smb200_learner* h, const float* blob, int64_t n) {
   cudaSetDevice(h->cfg.device);
   // target weights (unused by RACER with targetDelay 0, but part of the checkpoint): they follow the weights
   // until training starts, like `target_weights->copy(weights)` of a restart without a tgt file (Optimizer.cpp:207-210)
-  if (h->gradStep == 0) h->tgtBlob.assign(blob, blob + n);
+  if (h->gradStep == 0) {
+    h->tgtBlob.assign(blob, blob + n);
+    if (h->Wtgt) SMB200_CUDA_CHECK(cudaMemcpyAsync(h->Wtgt, blob, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  }
   return upload_weights(h, blob);
 }
 static int d2h(smb200_learner* h, void* dst, const void* src, size_t bytes) {
@@ -1087,6 +1097,24 @@ int smb200_get_weights(smb200_learner* h, float* blob, int64_t n) {
   if (!h || !blob || n != h->descs.net.nParams) return SMB200_ERR_INVALID;
   std::lock_guard<std::recursive_mutex> lock(h->apiMutex);
   return d2h(h, blob, h->W, sizeof(float) * n);
+}
+int smb200_get_target_weights(smb200_learner* h, float* blob, int64_t n) {
+  if (!h || !blob || n != h->descs.net.nParams) return SMB200_ERR_INVALID;
+  std::lock_guard<std::recursive_mutex> lock(h->apiMutex);
+  if (h->Wtgt) return d2h(h, blob, h->Wtgt, sizeof(float) * n);
+  std::copy(h->tgtBlob.begin(), h->tgtBlob.end(), blob);
+  return 0;
+}
+int smb200_set_target_weights(smb200_learner* h, const float* blob, int64_t n) {
+  if (!h || !blob || n != h->descs.net.nParams) return SMB200_ERR_INVALID;
+  std::lock_guard<std::recursive_mutex> lock(h->apiMutex);
+  cudaSetDevice(h->cfg.device);
+  h->tgtBlob.assign(blob, blob + n);
+  if (h->Wtgt) {
+    SMB200_CUDA_CHECK(cudaMemcpyAsync(h->Wtgt, blob, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  }
+  return 0;
 }
 int smb200_get_grad(smb200_learner* h, float* blob, int64_t n) {
   if (!h || !blob || n != h->descs.net.nParams) return SMB200_ERR_INVALID;
@@ -1104,7 +1132,7 @@ int smb200_set_adam(smb200_learner* h, const float* m1, const float* m2, int64_t
   if (m2) SMB200_CUDA_CHECK(cudaMemcpyAsync(h->M2, m2, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
   SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   if (pull_ctrl(h)) return SMB200_ERR_CUDA;
-  h->hCtrl.adam_step = n_step;
+  h->hCtrl.adam_step = n_step; h->tgtPhase = n_step;
   return push_ctrl(h);
 }
 
@@ -1242,7 +1270,7 @@ int smb200_initialize_learner(smb200_learner* h) {
 int smb200_set_grad_step(smb200_learner* h, int64_t n) {
   if (!h || n < 0) return SMB200_ERR_INVALID;
   if (pull_ctrl(h)) return SMB200_ERR_CUDA;
-  h->gradStep = n; h->hCtrl.grad_step = n; h->hCtrl.adam_step = n; h->ahead_clear();
+  h->gradStep = n; h->hCtrl.grad_step = n; h->hCtrl.adam_step = n; h->tgtPhase = n; h->ahead_clear();
   h->hCtrl.gl_far_prev = (double)h->hCtrl.n_far_ref; h->hCtrl.gl_stored_prev = (double)h->nTransitions; h->hCtrl.cnt_seed_step = n;
   return push_ctrl(h);
 }
@@ -2179,7 +2207,7 @@ int smb200_save(smb200_learner* h, const char* base_c) {
   const size_t nP = net.nParams, nF = stripped_size(net);
   // ---- Approximator::save -> AdamOptimizer::save (Optimizer.cpp:180-197) ----
   std::vector<float> blob(nP), flat(nF);
-  const float* src[4] = {h->W, nullptr, h->M1, h->M2};
+  const float* src[4] = {h->W, h->Wtgt /* null with targetDelay 0: the host copy */, h->M1, h->M2};
   const char* name[4] = {"_net_weights", "_net_tgt_weights", "_net_1stMom", "_net_2ndMom"};
   for (int k = 0; k < 4; ++k) {
     if (src[k]) { if (d2h(h, blob.data(), src[k], sizeof(float) * nP)) return SMB200_ERR_CUDA; }
@@ -2253,6 +2281,7 @@ int smb200_restart(smb200_learner* h, const char* base_c) {
   if (upload_weights(h, blob.data())) return SMB200_ERR_CUDA;
   h->tgtBlob = blob;
   { std::vector<float> t = blob; const int r2 = load_net("_net_tgt_weights", t); if (r2 < 0) return SMB200_ERR_STATE; if (r2 == 0) h->tgtBlob = t; }
+  if (h->Wtgt) SMB200_CUDA_CHECK(cudaMemcpyAsync(h->Wtgt, h->tgtBlob.data(), sizeof(float) * nP, cudaMemcpyHostToDevice, h->stream));
   if (load_net("_net_1stMom", m1) < 0 || load_net("_net_2ndMom", m2) < 0) return SMB200_ERR_STATE;
   SMB200_CUDA_CHECK(cudaMemcpyAsync(h->M1, m1.data(), sizeof(float) * nP, cudaMemcpyHostToDevice, h->stream));
   SMB200_CUDA_CHECK(cudaMemcpyAsync(h->M2, m2.data(), sizeof(float) * nP, cudaMemcpyHostToDevice, h->stream));
@@ -2299,6 +2328,7 @@ int smb200_restart(smb200_learner* h, const char* base_c) {
   StepCtrl& k = h->hCtrl;
   k.beta = beta; k.cmax = cmax; k.cinv = 1.0 / cmax;
   h->gradStep = grad; k.grad_step = grad; k.adam_step = grad;
+  h->tgtPhase = grad;                                             // cntUpdateDelay is not part of a checkpoint: 0 in the new process
   k.n_far_ref = 0; k.avg_sq_err = 0;                              // ReplayStats are not restored (zero until the next statistics pass)
   k.gl_far_prev = 0; k.gl_stored_prev = (double)h->nTransitions; k.cnt_seed_step = grad;
   if (push_ctrl(h)) return SMB200_ERR_CUDA;

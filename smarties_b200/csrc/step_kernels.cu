@@ -1699,6 +1699,20 @@ __host__ __device__ __forceinline__ float adam_step(const AdamCoef& k, float G, 
   return Wn;
 }
 
+// "update frozen weights" of AdamOptimizer::apply_update (Network/Optimizer.cpp:162-177) for one parameter, right after its Adam
+// step: targetDelay >= 1: `cntUpdateDelay` reaches 0 every floor(targetDelay) updates, counted from construction / restart, and the
+// weights are copied; targetDelay < 1: `targetAry[j] += tgtUpdateAlpha * (paramAry[j] - targetAry[j])` (Real = double times the f32
+// difference, added to the f32 target) after every update.
+__device__ __forceinline__ void target_step(const StepArgs& a, const StepCtrl& c, int p, float wNew) {
+  if (a.tgtAlpha >= 1.0) {
+    const long long D = (long long)a.tgtAlpha;
+    if ((c.adam_step - a.tgtPhase) % D == 0) a.Wtgt[p] = wNew;
+  } else {
+    const float t = a.Wtgt[p];
+    a.Wtgt[p] = (float)((double)t + a.tgtAlpha * (double)(wNew - t));
+  }
+}
+
 __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, const StepCtrl& c, const GradTile t,
                         float* tiles, int step, int tileIdx, const TcPlan* tc = nullptr) {
   const int tid = threadIdx.x;
@@ -1903,11 +1917,15 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
   asm volatile("" : "+f"(w0), "+f"(m10), "+f"(m20), "+f"(w1), "+f"(m11), "+f"(m21));
   if (p0 >= 0) {
     a.G[p0] = acc;
-    a.Wimg[pimg0] = adam_step(ac, acc, w0, m10, m20, a.W + p0, a.M1 + p0, a.M2 + p0);
+    const float wn = adam_step(ac, acc, w0, m10, m20, a.W + p0, a.M1 + p0, a.M2 + p0);
+    a.Wimg[pimg0] = wn;
+    if (a.Wtgt) target_step(a, c, p0, wn);
   }
   if (p1 >= 0) {
     a.G[p1] = acc2;
-    a.Wimg[pimg1] = adam_step(ac, acc2, w1, m11, m21, a.W + p1, a.M1 + p1, a.M2 + p1);
+    const float wn = adam_step(ac, acc2, w1, m11, m21, a.W + p1, a.M1 + p1, a.M2 + p1);
+    a.Wimg[pimg1] = wn;
+    if (a.Wtgt) target_step(a, c, p1, wn);
   }
 }
 

@@ -144,6 +144,8 @@ struct StepArgs {
   const DevDescs* descs;
   ReplayView rp;
   float* W; float* Wimg; float* M1; float* M2; float* G;   // Wimg: weights in the shared-memory image layout
+  float* Wtgt; double tgtAlpha; long long tgtPhase;        // "targetDelay" > 0: AdamOptimizer::target_weights, its rate / period, the
+                                                           //   update count at which cntUpdateDelay was (re)set to 0 (construction, restart)
   float* actG; float* errG;          // feature-major scratch [actPerSample][Bpad]
   const int* sampRow; const int* sampSlot;  // [nSteps][B]: ring row of (episode,t); slot | hasNext<<31
   SampleRec* rec;                    // [B]

@@ -27,7 +27,7 @@ MAX_ACTION = 64
 # every symbol include/smarties_b200.h declares
 EXPORTS = [
     "smb200_default_config", "smb200_create", "smb200_destroy", "smb200_last_error", "smb200_n_params",
-    "smb200_n_outputs", "smb200_set_weights", "smb200_get_weights", "smb200_set_adam", "smb200_get_adam",
+    "smb200_n_outputs", "smb200_set_weights", "smb200_get_weights", "smb200_get_target_weights", "smb200_set_target_weights", "smb200_set_adam", "smb200_get_adam",
     "smb200_get_grad", "smb200_set_scaling", "smb200_get_scaling", "smb200_push_episode", "smb200_n_transitions",
     "smb200_n_episodes", "smb200_initialize_learner", "smb200_set_grad_step", "smb200_seed_sampler", "smb200_sample",
     "smb200_train_steps", "smb200_train_steps_weights", "smb200_pin_host_buffer", "smb200_train_step_on", "smb200_get_last_batch", "smb200_retrace_sweep", "smb200_fused_sweep",
@@ -54,7 +54,7 @@ class Config(C.Structure):
         ("out_weights_prefac", C.c_double), ("refer_reduce_threads", C.c_int32), ("world_rank", C.c_int32),
         ("world_size", C.c_int32), ("seed", C.c_uint64), ("nn_type", C.c_int32), ("nn_bptt_seq", C.c_int32),
         ("min_tot_obs", C.c_int64), ("returns_estimator", C.c_int32), ("discrete_options", C.c_int32),
-        ("data_sampling", C.c_int32), ("er_filter", C.c_int32), ("nn_func", C.c_int32),
+        ("data_sampling", C.c_int32), ("er_filter", C.c_int32), ("nn_func", C.c_int32), ("target_delay", C.c_double),
     ]
 
 
@@ -116,6 +116,7 @@ def load_library(path: str = LIB_PATH):
         "smb200_set_weights": (C.c_int, [H, fp, C.c_int64]), "smb200_get_weights": (C.c_int, [H, fp, C.c_int64]),
         "smb200_set_adam": (C.c_int, [H, fp, fp, C.c_int64, C.c_int64]), "smb200_get_adam": (C.c_int, [H, fp, fp, C.c_int64]),
         "smb200_get_grad": (C.c_int, [H, fp, C.c_int64]),
+        "smb200_get_target_weights": (C.c_int, [H, fp, C.c_int64]), "smb200_set_target_weights": (C.c_int, [H, fp, C.c_int64]),
         "smb200_set_scaling": (C.c_int, [H, fp, fp, fp, fp]), "smb200_get_scaling": (C.c_int, [H, fp, fp, fp, fp]),
         "smb200_push_episode": (C.c_int, [H, C.c_int64, C.c_int32, C.c_int32, fp, fp, fp, fp, fp, fp]),
         "smb200_n_transitions": (C.c_int64, [H]), "smb200_n_episodes": (C.c_int64, [H]), "smb200_n_rows": (C.c_int64, [H]),
@@ -206,6 +207,7 @@ def make_config(dim_state: int, dim_action: int, settings=None, *, device: int =
     cfg.er_filter = {"oldest": 0, "default": 0, "farpolfrac": 1, "maxkldiv": 2, "minerror": 3}[hp.ERoldSeqFilter]
     cfg.nn_func = {"Tanh": 0, "SoftSign": 1, "HardSign": 2, "Sigm": 3, "Relu": 4, "LRelu": 5, "ExpPlus": 6, "SoftPlus": 7, "Exp": 8,
                    "Linear": 9}[hp.nnFunc]
+    cfg.target_delay = float(hp.targetDelay)
     if bounded is not None:
         b = np.broadcast_to(np.asarray(bounded, dtype=bool), (dim_action,))
         for i in range(dim_action):
@@ -397,6 +399,12 @@ class Learner:
         return O, g, X
 
     # -- network --
+    def get_target_weights(self):
+        """AdamOptimizer::target_weights ("targetDelay"; RACER never evaluates them, they only reach the checkpoint)."""
+        w = np.empty(self.n_params, np.float32)
+        self._check(self.lib.smb200_get_target_weights(self.h, _fp(w), self.n_params))
+        return w
+
     def get_weights(self):
         w = np.empty(self.n_params, np.float32)
         self._check(self.lib.smb200_get_weights(self.h, _fp(w), self.n_params))

@@ -106,7 +106,7 @@ class HyperParameters:
         func_ok = self.nnFunc == "Tanh" or (self.nnType == "FFNN" and self.nnFunc in ("SoftSign", "HardSign", "Sigm", "Relu", "LRelu", "ExpPlus", "SoftPlus", "Exp", "Linear"))
         if self.nnType not in ("FFNN", "LSTM", "MGU", "GRU") or not func_ok or self.nnOutputFunc != "Linear":
             unsupported.append(f"nnType/nnFunc/nnOutputFunc={self.nnType}/{self.nnFunc}/{self.nnOutputFunc}")
-        if self.ESpopSize != 1 or self.targetDelay != 0:
-            unsupported.append("ESpopSize/targetDelay")
+        if self.ESpopSize != 1:
+            unsupported.append("ESpopSize")
         if unsupported:
             raise NotImplementedError("smarties_b200 device path does not cover: " + ", ".join(unsupported))

@@ -244,6 +244,19 @@ CKPT_CASES = {
         settings={"learner": "RACER", "nnType": "LSTM", "nnLayerSizes": [16], "nnBPTTseq": 8, "batchSize": 8,
                   "maxTotObsNum": 1024, "minTotObsNum": 200},
         steps=5, start_step=0, sample_seed=21, bounded=1, full_steps=[4], steps_after=3, sample_seed_after=29),
+    # "targetDelay" (AdamOptimizer::tgtUpdateAlpha, Optimizer.cpp:162-177): RACER never evaluates the target weights, they only
+    # reach <name>_net_tgt_weights.raw.  0.05: exponential average after every update; 3: copy at updates 1, 4, 7 (the checkpoint
+    # after 8 updates holds the weights after update 7; a restarted process copies at its first update again)
+    "vracer_tgt_ema": dict(
+        replay=dict(seed=124, n_ep=24, ep_len=(20, 60), dS=6, dA=3),
+        settings={"learner": "VRACER", "returnsEstimator": "retrace", "nnLayerSizes": [32, 32], "batchSize": 16, "targetDelay": 0.05,
+                  "maxTotObsNum": 2048, "minTotObsNum": 500},
+        steps=8, start_step=0, sample_seed=8, bounded=0, full_steps=[7], steps_after=4, sample_seed_after=20),
+    "vracer_tgt_copy": dict(
+        replay=dict(seed=125, n_ep=24, ep_len=(20, 60), dS=6, dA=3),
+        settings={"learner": "VRACER", "returnsEstimator": "retrace", "nnLayerSizes": [32, 32], "batchSize": 16, "targetDelay": 3,
+                  "maxTotObsNum": 2048, "minTotObsNum": 500},
+        steps=8, start_step=0, sample_seed=9, bounded=0, full_steps=[7], steps_after=4, sample_seed_after=21),
 }
 CKPT_FILES = ["agent_00_net_weights.raw", "agent_00_net_tgt_weights.raw", "agent_00_net_1stMom.raw", "agent_00_net_2ndMom.raw",
               "agent_00_scaling.raw", "agent_00_rank_000_learner_status.raw", "agent_00_rank_000_learner_data.raw"]

@@ -9,6 +9,7 @@ import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CKPT_CASES = ["vracer_ckpt", "racer_lstm_ckpt"]
+TARGET_CASES = ["vracer_tgt_ema", "vracer_tgt_copy"]     # "targetDelay" 0.05 (exponential average) and 3 (copy every 3 updates): checkpoint goldens
 CASES = ["vracer_small", "vracer_cfg2mini", "vracer_bounded", "vracer_prune", "racer_small", "racer_bounded", "vracer_gae",
          "vracer_da1", "vracer_explore", "vracer_b1024", "vracer_b4096", "racer_discrete",
          "vracer_softsign", "vracer_hardsign", "racer_sigm", "vracer_relu", "vracer_lrelu",
@@ -78,7 +79,7 @@ def make_oracle(g: Golden):
     for key, arg in (("gamma", "gamma"), ("lambda", "lam"), ("clipImpWeight", "clip_imp_weight"), ("penalTol", "penal_tol"),
                      ("epsAnneal", "eps_anneal"), ("learnrate", "learnrate"), ("nnLambda", "nn_lambda"),
                      ("returnsEstimator", "returns_estimator"), ("dataSamplingAlgo", "sampling"), ("ERoldSeqFilter", "er_filter"),
-                     ("nnFunc", "nn_func")):
+                     ("nnFunc", "nn_func"), ("targetDelay", "target_delay")):
         if key in s:
             kw[arg] = s[key]
     if "n_options" in g.spec["replay"]:

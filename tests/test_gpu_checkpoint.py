@@ -10,8 +10,8 @@ import os
 import numpy as np
 import pytest
 
-from parity_utils import CKPT_CASES, Golden, PhaseB, make_learner, write_checkpoint
-from test_gpu_parity import _check_final, _check_step
+from parity_utils import CKPT_CASES, TARGET_CASES, Golden, PhaseB, make_learner, write_checkpoint
+from test_gpu_parity import TOL_W, _check_final, _check_step
 
 pytestmark = pytest.mark.gpu
 FILES = ["agent_00_net_weights.raw", "agent_00_net_tgt_weights.raw", "agent_00_net_1stMom.raw", "agent_00_net_2ndMom.raw",
@@ -23,12 +23,17 @@ def fresh_learner(g):
     return Learner(g.dS, g.dA, dict(g.settings), bounded=g.bounded, refer_reduce_threads=1)
 
 
-@pytest.mark.parametrize("case", CKPT_CASES)
+@pytest.mark.parametrize("case", CKPT_CASES + TARGET_CASES)
 def test_restart_from_reference_files_then_train(case, tmp_path):
     g = Golden(case)
     R = g.ref2
     L = fresh_learner(g)
     L.restart(write_checkpoint(g, str(tmp_path)))
+    if case in TARGET_CASES:       # the target weights of the checkpoint are on the device, bit for bit
+        import vracer_oracle as vo
+        from parity_utils import make_oracle
+        lay = make_oracle(g).layout
+        assert np.array_equal(lay.strip_padding(L.get_target_weights()), np.frombuffer(bytes(g.ckpt["agent_00_net_tgt_weights.raw"]), np.float32))
     # (1) state after restart == state of the restarted reference, bit for bit
     assert np.array_equal(L.get_weights(), R["init/weights"])
     mean, scale, std, rew = L.get_scaling()
@@ -48,11 +53,39 @@ def test_restart_from_reference_files_then_train(case, tmp_path):
     for s in range(pb.steps):
         stats = L.train_steps(1)[0]
         _check_step(L, pb, R, f"s{s}", stats)
+        if case in TARGET_CASES:   # cntUpdateDelay restarts at 0 in the new process: copy / average from its first update on
+            assert np.abs(L.get_target_weights() - R[f"s{s}/tgt"]).max() < TOL_W, s
     _check_final(L, R)
     L.close()
 
 
-@pytest.mark.parametrize("case", CKPT_CASES)
+@pytest.mark.parametrize("case", TARGET_CASES)
+@pytest.mark.parametrize("per_call", [1, 8])
+def test_target_weights_follow_the_reference(case, per_call, tmp_path):
+    """"targetDelay" 0.05 / 3 (AdamOptimizer::apply_update, Optimizer.cpp:162-177) in the Adam epilogue of the weight-gradient
+    tiles: the target weights after every update against the reference's (one step per launch and all eight in one
+    persistent launch), and the checkpoint file against the one the reference wrote."""
+    g = Golden(case)
+    R = g.ref
+    L = make_learner(g)
+    assert L.step_kernel() in (0, 1)                    # the tile kernels maintain them
+    if per_call == 1:
+        for s in range(g.steps):
+            L.train_steps(1)
+            assert np.abs(L.get_target_weights() - R[f"s{s}/tgt"]).max() < TOL_W, s
+    else:
+        L.train_steps(g.steps)
+        assert np.abs(L.get_target_weights() - R[f"s{g.steps - 1}/tgt"]).max() < TOL_W
+    assert np.abs(L.get_weights() - R[f"s{g.steps - 1}/weights"]).max() < TOL_W
+    assert np.abs(L.get_target_weights() - L.get_weights()).max() > 1e-6
+    L.save(str(tmp_path / "agent_00"))
+    own = np.fromfile(tmp_path / "agent_00_net_tgt_weights.raw", np.float32)
+    ref = np.frombuffer(bytes(g.ckpt["agent_00_net_tgt_weights.raw"]), np.float32)
+    assert own.shape == ref.shape and np.abs(own - ref).max() < TOL_W
+    L.close()
+
+
+@pytest.mark.parametrize("case", CKPT_CASES + TARGET_CASES)
 def test_restart_then_save_is_byte_identical(case, tmp_path):
     g = Golden(case)
     src, dst = tmp_path / "in", tmp_path / "out"

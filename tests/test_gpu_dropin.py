@@ -190,3 +190,23 @@ def test_cart_pole_with_encoder_layers_on_the_device_learner():
     done = [l for l in r["b200_lines"] if "gradient steps" in l]
     assert done and int(done[0].split()[1]) >= 2999, r
     assert r["stat_rows"] >= 2 and r["avgR_last"] > 5.0 and 0.0 < r["beta_last"] <= 1.0, r
+
+
+def test_target_delay_reaches_the_checkpoint_through_the_binding(tmp_path):
+    """"targetDelay": 0.01 — the device maintains AdamOptimizer::target_weights (Optimizer.cpp:162-177), the binding copies them
+    into the host optimiser before the reference's own writers save <name>_net_tgt_weights.raw; the reference restarts from it."""
+    for exe in ("b200/cart_pole", "cart_pole"):
+        if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", exe)):
+            pytest.skip("oracle/_ref binaries not built")
+    from dropin_run import SETTINGS, run_arm
+    S = dict(SETTINGS, saveFreq=1000, targetDelay=0.01)
+    a, b = str(tmp_path / "a"), str(tmp_path / "b")
+    r = run_arm("b200", steps=2500, threads=4, seed=7, settings=S, keep_dir=a)
+    assert r["rc"] == 0 and any("run on the GPU" in l for l in r["b200_lines"]), r
+    w = np.fromfile(os.path.join(a, "agent_00_net_weights.raw"), np.float32)
+    t = np.fromfile(os.path.join(a, "agent_00_net_tgt_weights.raw"), np.float32)
+    assert w.shape == t.shape and np.isfinite(t).all()
+    d = np.abs(w - t).max()
+    assert 0 < d < 0.5, d                      # an exponential average that trails the weights, not a copy and not the initial weights
+    r2 = run_arm("ref", steps=3600, threads=4, seed=8, settings=S, keep_dir=b, restart=a)
+    assert r2["rc"] == 0 and r2["grad_steps_logged"] >= 3000, r2

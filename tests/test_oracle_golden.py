@@ -7,7 +7,7 @@ round-off; sampled indices, far-policy counts and the ReF-ER coefficient are exa
 import numpy as np
 import pytest
 
-from parity_utils import CASES, ORACLE_ONLY_CASES, RECURRENT_CASES, SLOW_CASES, THREADED_CASES, Golden, make_oracle, relerr
+from parity_utils import CASES, ORACLE_ONLY_CASES, RECURRENT_CASES, SLOW_CASES, TARGET_CASES, THREADED_CASES, Golden, make_oracle, relerr
 
 
 @pytest.mark.parametrize("case", CASES + RECURRENT_CASES + ORACLE_ONLY_CASES + THREADED_CASES + SLOW_CASES)
@@ -47,6 +47,28 @@ def test_oracle_matches_reference(case):
     assert np.allclose(o.state_scale, R["final/stateScale"], rtol=1e-6)
     agg = np.array([[e.avgKL, e.fracFar, e.avgSqErr, e.maxAbsErr, e.sumQ2, e.sumQ, e.maxQ, e.minQ] for e in o.episodes])
     assert np.allclose(agg, R["final/epAgg"][:, :8], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("case", TARGET_CASES)
+def test_oracle_target_weights_match_reference(case):
+    """"targetDelay" > 0 (AdamOptimizer::apply_update, Optimizer.cpp:162-177): the target weights after every update — the
+    exponential average (0.05) and the periodic copy (3: updates 1, 4, 7) — against the reference's own."""
+    g = Golden(case)
+    o = make_oracle(g)
+    R = g.ref
+    seen = []
+    for s in range(g.steps):
+        o.train_step()
+        assert np.abs(o.W_tgt - R[f"s{s}/tgt"]).max() < 2e-6, s
+        seen.append(float(np.abs(o.W_tgt - o.W).max()))
+    assert np.abs(o.W - R[f"s{g.steps - 1}/weights"]).max() < 2e-6
+    if g.settings["targetDelay"] >= 1:
+        assert [x == 0.0 for x in seen] == [s % 3 == 0 for s in range(g.steps)]      # copies at updates 1, 4, 7
+    else:
+        assert min(seen) > 0.0
+    # the checkpoint file holds them, padding stripped (Optimizer.cpp:180-197)
+    tgt_file = np.frombuffer(bytes(g.ckpt["agent_00_net_tgt_weights.raw"]), np.float32)
+    assert np.abs(o.layout.strip_padding(o.W_tgt) - tgt_file).max() < 2e-6
 
 
 def test_sampler_is_libstdcxx_uniform_int():
