@@ -173,6 +173,14 @@ struct smb200_learner {
 namespace smb200 {
 
 // ---- network description: RACER::setupNet + Approximator::buildFromSettings + Builder::addLayer ----
+// does any ParametricResidual link a narrower layer (hidden sizes that grow)?  The cluster kernel and the wide step assume
+// equal or shrinking widths; such nets run on the tile kernels.
+static bool residual_widens(const NetDesc& net) {
+  for (int l = 2; l < net.nLayers; ++l)
+    if (net.L[l].kind == kResidual && net.L[l - 2].size < net.L[l].size) return true;
+  return false;
+}
+
 static int build_net(const smb200_config& c, NetDesc& net, std::vector<GradTile>& tiles) {
   memset(&net, 0, sizeof(net));
   const int dS = c.dim_state, dA = c.dim_action;
@@ -222,7 +230,11 @@ static int build_net(const smb200_config& c, NetDesc& net, std::vector<GradTile>
       LayerDesc& R = add(kResidual, h);
       R.wOff = off; off += round_up(h, 8); R.bOff = off; off += round_up(h, 8);
       R.imgW = img; img += round_up(h, 4); R.imgB = img; img += round_up(h, 4);
-      if (net.L[id - 3].size < h) { set_error_msg("residual over a narrower layer is not supported"); return -1; }
+      // a residual over a NARROWER dense layer (hidden sizes that grow) links the first min(size below, size) units only
+      // (ParametricResidualLayer::forward, Layers.h:347-361): handled by the tile kernels; see residual_widens().  Over a
+      // narrower recurrent-cell layer the reference's `sizes[ID-2]` is the cell layer's whole work array (4 nCells: output |
+      // cell state | ...), so its extra units link to the lower layer's CELL STATES — an accident that is not reproduced.
+      if (lstm && net.L[id - 3].size < h) { set_error_msg("residual over a narrower recurrent-cell layer is not supported"); return -1; }
     }
     nIn = h;
   }
@@ -956,7 +968,7 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
     const char* m0 = getenv("SMB200_MODE");
     int coop0 = 0; cudaDeviceGetAttribute(&coop0, cudaDevAttrCooperativeLaunch, c.device);
     cluster_plan_build(net, 4 * 33 - 1, h->cplan, h->cidx, h->citems);
-    if (h->cplan.ok && coop0 && !(m0 && strcmp(m0, "two") == 0) && !(c.target_delay > 0)) {
+    if (h->cplan.ok && coop0 && !(m0 && strcmp(m0, "two") == 0) && !(c.target_delay > 0) && !residual_widens(net)) {
       CK(cluster_prepare(h->cplan));
       const int maxC = std::min(33, cluster_max_active(h->cplan));
       if (maxC >= 2) {
@@ -985,7 +997,7 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
   {
     const char* w = getenv("SMB200_WIDE");
     const bool never = w && strcmp(w, "0") == 0, always = w && strcmp(w, "1") == 0;
-    if (!never && (always || B >= 2048) && !(c.target_delay > 0)) {
+    if (!never && (always || B >= 2048) && !(c.target_delay > 0) && !residual_widens(net)) {
       wide_plan_build(net, hp, h->wplan, h->widx);
       if (h->wplan.ok) {
         CK(wide_prepare(h->wplan, net));

@@ -1758,6 +1758,7 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
   // at cfg3, and paid one L2 round trip per chunk).
   constexpr int kLD = 1024 / kST;   // float4 per thread and operand (16 rows x 64 float4)
   float4 avs[kLD], dvs[kLD];
+  const int nLink = t.kind == 1 ? net.L[t.layer - 2].size : 0x7fffffff;    // ParametricResidual: min(size of layer ID-2, size) linked units
   auto load_chunk = [&](int bc) {
 #pragma unroll
     for (int i = 0; i < kLD; ++i) {
@@ -1777,7 +1778,7 @@ __device__ void p2_tile(const StepArgs& a, const NetDesc& net, const Hyper& hp, 
         if (n < N) dv = tm ? ld_cg4(a.errG + (tb + dOff + n) * 4) : ld_cg4(a.errG + (size_t)(dOff + n) * a.Bpad + bc + c4);
       } else {
         const int n = t.n0 + r;
-        if (n < N) {
+        if (n < N && n < nLink) {     // residual: units beyond the layer below have no skip link and no gradient (Layers.h:363-393)
           dv = tm ? ld_cg4(a.errG + (tb + dOff + n) * 4) : ld_cg4(a.errG + (size_t)(dOff + n) * a.Bpad + bc + c4);
           if (t.kind == 1) av = tm ? ld_cg4(a.actG + (tb + aOff + n) * 4) : ld_cg4(a.actG + (size_t)(aOff + n) * a.Bpad + bc + c4);
         }

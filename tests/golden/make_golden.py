@@ -104,6 +104,12 @@ CASES = {
         replay=dict(seed=102, n_ep=20, ep_len=(25, 50), dS=7, dA=2),
         settings={"learner": "RACER", "nnFunc": "SoftSign", "encoderLayerSizes": [32, 24], "nnLayerSizes": [24], "batchSize": 16, "maxTotObsNum": 2048, "minTotObsNum": 400},
         steps=3, start_step=0, sample_seed=32, bounded=1, full_steps=[0, 2]),
+    # hidden sizes that GROW: the ParametricResidual after a layer links only the first min(size below, size) units
+    # (ParametricResidualLayer::forward / backward, Layers.h:347-393); the other units' skip parameters get no gradient
+    "vracer_widen": dict(
+        replay=dict(seed=103, n_ep=20, ep_len=(25, 50), dS=6, dA=2),
+        settings={"learner": "VRACER", "nnLayerSizes": [24, 32, 40], "batchSize": 16, "maxTotObsNum": 2048, "minTotObsNum": 400},
+        steps=3, start_step=0, sample_seed=33, bounded=0, full_steps=[0, 2]),
     # FIFO pruning: capacity below the stored data, so applyEpisodesRemovalAlgo evicts on step 1
     "vracer_prune": dict(
         replay=dict(seed=17, n_ep=16, ep_len=(20, 30), dS=4, dA=2),

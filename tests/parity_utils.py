@@ -14,7 +14,7 @@ CASES = ["vracer_small", "vracer_cfg2mini", "vracer_bounded", "vracer_prune", "r
          "vracer_da1", "vracer_explore", "vracer_b1024", "vracer_b4096", "racer_discrete",
          "vracer_softsign", "vracer_hardsign", "racer_sigm", "vracer_relu", "vracer_lrelu",
          "vracer_expplus", "racer_softplus", "vracer_exp", "vracer_linear",
-         "vracer_encoder", "racer_encoder2"]      # "encoderLayerSizes": stacked under nnLayerSizes in the one network (RACER::setupNet)      # "nnFunc" other than Tanh (settings/default.json: SoftSign)
+         "vracer_encoder", "racer_encoder2", "vracer_widen"]      # "encoderLayerSizes": stacked under nnLayerSizes in the one network (RACER::setupNet)      # "nnFunc" other than Tanh (settings/default.json: SoftSign)
 # golden runs of a reference with 8 / 16 OpenMP threads: the far-policy count (and beta) depend on the thread count
 # (MemoryProcessing.cpp:202-227); the device reproduces it with refer_reduce_threads = T
 THREADED_CASES = ["vracer_small_t8", "vracer_small_t16", "vracer_cfg2mini_t8", "vracer_cfg2mini_t16", "racer_small_t8"]

@@ -139,7 +139,8 @@ def test_two_kernel_mode_equals_persistent(monkeypatch, case):
 
 # discrete actions and hidden-layer functions other than Tanh: tile kernel only
 FEED_FORWARD_CASES = [c for c in CASES + THREADED_CASES if c not in ("racer_discrete", "vracer_softsign", "vracer_hardsign", "racer_sigm", "vracer_relu", "vracer_lrelu",
-                                                                      "vracer_expplus", "racer_softplus", "vracer_exp", "vracer_linear")]
+                                                                      "vracer_expplus", "racer_softplus", "vracer_exp", "vracer_linear",
+                                                                      "vracer_widen")]      # a residual over a narrower layer: tile kernels only
 
 
 @pytest.mark.parametrize("case", FEED_FORWARD_CASES)
@@ -176,7 +177,7 @@ def test_cluster_kernel_equals_tile_kernel(monkeypatch, case):
     A.close(); Bm.close()
 
 
-WIDE_CASES = [c for c in CASES + THREADED_CASES if c != "racer_discrete"]      # feed-forward V-RACER / RACER with continuous actions: what the wide step takes
+WIDE_CASES = [c for c in CASES + THREADED_CASES if c not in ("racer_discrete", "vracer_widen")]      # feed-forward V-RACER / RACER with continuous actions: what the wide step takes
 
 
 @pytest.mark.parametrize("case", WIDE_CASES)
