@@ -568,7 +568,9 @@ static bool table_steady(const smb200_learner* h) {
 // draw one more step into the queue; false = the queue is full, closed by a segment-ending step, or not applicable
 static bool ahead_push_one(smb200_learner* h) {
   const int B = h->cfg.batch_size;
-  if (h->slow_mode() || h->nTransitions < B) return false;
+  // short calls of small mini-batches are what the queue is for; a step of a wide mini-batch takes the host longer to draw
+  // than a launch costs (and the queue would hold kAheadMax * B ids)
+  if (h->slow_mode() || h->nTransitions < B || B > 4096) return false;
   if (h->aheadCnt > h->aheadHead && h->aheadVersion != h->tableVersion) h->ahead_clear();
   if (h->aheadCnt == h->aheadHead) {                       // empty: start at the true position of the stream
     if (!table_steady(h)) return false;
