@@ -26,7 +26,8 @@ if world > 1:      # launched by torch.distributed.run: the fused gradient excha
                 device=local, seed=42 + rank, world_rank=rank, world_size=world)
     L.attach_process_group(dist)
 else:
-    L = Learner(32, 8, {"maxTotObsNum": 1048576, "minTotObsNum": 1000 * n_ep})
+    cap = 1 << (1000 * n_ep - 1).bit_length()          # PROF_NEP=8000: the 8 M-transition buffer of the strong-scaling arm
+    L = Learner(32, 8, {"maxTotObsNum": max(1048576, cap), "minTotObsNum": 1000 * n_ep})
 L.load_replay(d)
 L.initialize_learner()
 L.seed_sampler(7 + rank)

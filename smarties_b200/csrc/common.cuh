@@ -95,6 +95,7 @@ struct ReplayView {
   int* epStart; int* epLen; int* epTerm; long long* epId;
   float* epAgg;       // [9][maxEpisodes]: avgKL, fracFar, avgSqErr, maxAbsErr, sumQ2, sumQ, maxQ, minQ, totR
   int* epOrder;       // [nEpisodes] slot at each position of the reference's `episodes` vector
+  int* epPos;         // [maxEpisodes] the inverse: position of a slot
   int maxEpisodes;
   long long capRows;
   int dS, dA;

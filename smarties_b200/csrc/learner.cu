@@ -84,6 +84,7 @@ struct smb200_learner {
   // network / optimiser
   float *W = nullptr, *Wimg = nullptr, *M1 = nullptr, *M2 = nullptr, *G = nullptr;
   float* Wtgt = nullptr; long long tgtPhase = 0;     // "targetDelay" > 0: target weights on the device (see StepArgs)
+  int statsIncremental = 1;                          // SMB200_STATS_FULL=1: full scan of the episode aggregates every step
   long long* dDbg = nullptr; int useTma = 1;
   // multi-rank gradient exchange over peer memory (CUDA IPC)
   CommView comm{}; unsigned char* commBuf = nullptr; int* dCommErr = nullptr; unsigned vecStamp = 0;
@@ -157,6 +158,7 @@ struct smb200_learner {
     a.comm = comm;
     a.descs = dDescs; a.rp = rp; a.W = W; a.Wimg = Wimg; a.M1 = M1; a.M2 = M2; a.G = G; a.dbgT = nullptr; a.useTma = useTma;
     a.Wtgt = Wtgt; a.tgtAlpha = cfg.target_delay; a.tgtPhase = tgtPhase;
+    a.statsIncremental = statsIncremental;
     a.useTc = useTc; a.tcPartial = tcPartial;
     a.wplan = dWplan; a.wimgF = wimgF; a.wimgB = wimgB; a.wvec = wvec; a.wpart = wpart; a.wGridG = wGridG; a.widx = dWidx;
     a.wcnt = wcnt; a.wlist = wlist;
@@ -382,10 +384,12 @@ static int upload_weights(smb200_learner* h, const float* blob) {
 
 static int upload_order(smb200_learner* h) {
   if (!h->orderDirty) return 0;
-  std::vector<int> ord(h->episodes.size());
-  for (size_t i = 0; i < ord.size(); ++i) ord[i] = h->episodes[i].slot;
-  if (!ord.empty())
+  std::vector<int> ord(h->episodes.size()), pos((size_t)h->rp.maxEpisodes, 0);
+  for (size_t i = 0; i < ord.size(); ++i) { ord[i] = h->episodes[i].slot; pos[(size_t)ord[i]] = (int)i; }
+  if (!ord.empty()) {
     SMB200_CUDA_CHECK(cudaMemcpyAsync(h->rp.epOrder, ord.data(), sizeof(int) * ord.size(), cudaMemcpyHostToDevice, h->stream));
+    SMB200_CUDA_CHECK(cudaMemcpyAsync(h->rp.epPos, pos.data(), sizeof(int) * pos.size(), cudaMemcpyHostToDevice, h->stream));
+  }
   SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));   // `ord` is pageable and dies here
   h->orderDirty = false;
   return 0;
@@ -922,7 +926,7 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
   CK(dev_alloc(&rp.Q, (size_t)cap)); CK(dev_alloc(&rp.DELTA, (size_t)cap)); CK(dev_alloc(&rp.RHO, (size_t)cap));
   CK(dev_alloc(&rp.KL, (size_t)cap)); CK(dev_alloc(&rp.rowFlag, (size_t)cap));
   CK(dev_alloc(&rp.epStart, (size_t)maxEp)); CK(dev_alloc(&rp.epLen, (size_t)maxEp)); CK(dev_alloc(&rp.epTerm, (size_t)maxEp));
-  CK(dev_alloc(&rp.epId, (size_t)maxEp)); CK(dev_alloc(&rp.epAgg, (size_t)maxEp * AGG_N)); CK(dev_alloc(&rp.epOrder, (size_t)maxEp));
+  CK(dev_alloc(&rp.epId, (size_t)maxEp)); CK(dev_alloc(&rp.epAgg, (size_t)maxEp * AGG_N)); CK(dev_alloc(&rp.epOrder, (size_t)maxEp)); CK(dev_alloc(&rp.epPos, (size_t)maxEp));
   CK(dev_alloc(&rp.stateMean, (size_t)dS)); CK(dev_alloc(&rp.stateScale, (size_t)dS)); CK(dev_alloc(&rp.stateStd, (size_t)dS));
   CK(dev_alloc(&rp.rew, (size_t)4));
   {
@@ -1035,6 +1039,7 @@ int smb200_create(const smb200_config* cfg, smb200_learner** out) {
   }
   CK(step_kernels_prepare(net));
   { const char* t = getenv("SMB200_TMA"); h->useTma = (t && strcmp(t, "0") == 0) ? 0 : 1; }
+  { const char* t = getenv("SMB200_STATS_FULL"); h->statsIncremental = (t && strcmp(t, "1") == 0) ? 0 : 1; }
   const char* m = getenv("SMB200_MODE");
   h->mode = (m && strcmp(m, "two") == 0) ? 0 : 1;
   int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c.device);
@@ -1053,7 +1058,7 @@ void smb200_destroy(smb200_learner* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   ReplayView& rp = h->rp;
   void* ptrs[] = {rp.S, rp.A, rp.MU, rp.R, rp.V, rp.ADV, rp.Q, rp.DELTA, rp.RHO, rp.KL, rp.rowFlag, rp.epStart, rp.epLen, rp.epTerm,
-                  rp.epId, rp.epAgg, rp.epOrder, rp.stateMean, rp.stateScale, rp.stateStd, rp.rew, h->W, h->Wimg, h->dDbg, h->M1, h->M2, h->G,
+                  rp.epId, rp.epAgg, rp.epOrder, rp.epPos, rp.stateMean, rp.stateScale, rp.stateStd, rp.rew, h->W, h->Wimg, h->dDbg, h->M1, h->M2, h->G,
                   h->actG, h->errG, h->dTiles, h->dDescs, h->dCtrl, h->dRec, h->lastO, h->lastG, h->lastX, h->dSums, h->dBarrier,
                   h->dSampSlot, h->dSampT, h->dStats, h->dCplan, h->dCidx, h->dCitems, h->cimg, h->cpart,
                   h->dWplan, h->dWidx, h->wimgF, h->wimgB, h->wvec, h->wpart, h->wcnt, h->wlist};

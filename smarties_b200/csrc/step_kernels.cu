@@ -2081,7 +2081,11 @@ __device__ void tc_wgrad_item(const StepArgs& a, const NetDesc& net, const TcPla
 // per run of samples that share an episode (samples are sorted, so runs are contiguous).
 // Records are staged through shared memory 256 at a time.  Returns this thread's share of the
 // exact far-policy flag changes.
-__device__ int apply_sample_records(const StepArgs& a, float* stage /* >= 256*12 floats */) {
+// Incremental statistics (persistent kernel, see stats_incremental): what the thread that owns a run of samples of one episode
+// adds to the launch-resident sums / maxima, and the episode's new far-policy term at its position of the episode vector.
+struct StatInc { float* xsAll; const int* epPos; double d[4]; float mx[3]; };
+
+__device__ int apply_sample_records(const StepArgs& a, float* stage /* >= 256*12 floats */, StatInc* inc = nullptr) {
   const ReplayView& rp = a.rp;
   const int ME = rp.maxEpisodes;
   int farDelta = 0;
@@ -2106,7 +2110,9 @@ __device__ int apply_sample_records(const StepArgs& a, float* stage /* >= 256*12
       float avgE2 = rp.epAgg[AGG_E2 * ME + slot], maxE = rp.epAgg[AGG_MAXE * ME + slot];
       float sQ2 = rp.epAgg[AGG_Q2 * ME + slot], sQ = rp.epAgg[AGG_Q1 * ME + slot];
       float maxQ = rp.epAgg[AGG_MAXQ * ME + slot], minQ = rp.epAgg[AGG_MINQ * ME + slot];
-      const float invN = 1.0f / (float)rp.epLen[slot];
+      const float Nf = (float)rp.epLen[slot];
+      const float invN = 1.0f / Nf;
+      const float oKL = avgKL, oE2 = avgE2, oQ2 = sQ2, oQ1 = sQ;
       for (int j = b; j < a.B; ++j) {
         int sj, hn; float4 d, q;
         if (j < cend) {
@@ -2129,6 +2135,12 @@ __device__ int apply_sample_records(const StepArgs& a, float* stage /* >= 256*12
       rp.epAgg[AGG_E2 * ME + slot] = avgE2; rp.epAgg[AGG_MAXE * ME + slot] = maxE;
       rp.epAgg[AGG_Q2 * ME + slot] = sQ2; rp.epAgg[AGG_Q1 * ME + slot] = sQ;
       rp.epAgg[AGG_MAXQ * ME + slot] = maxQ; rp.epAgg[AGG_MINQ * ME + slot] = minQ;
+      if (inc) {      // the same float products the full scan of stats_and_refer forms, old term out, new term in
+        inc->d[0] += (double)(Nf * avgKL) - (double)(Nf * oKL); inc->d[1] += (double)(Nf * avgE2) - (double)(Nf * oE2);
+        inc->d[2] += (double)sQ2 - (double)oQ2; inc->d[3] += (double)sQ - (double)oQ1;
+        inc->mx[0] = fmaxf(inc->mx[0], maxE); inc->mx[1] = fmaxf(inc->mx[1], maxQ); inc->mx[2] = fmaxf(inc->mx[2], -minQ);
+        inc->xsAll[inc->epPos[slot]] = Nf * frac;
+      }
     }
     __syncthreads();
   }
@@ -2149,10 +2161,38 @@ __device__ __forceinline__ unsigned long long uint_plus_float_fast(unsigned long
   return uint_plus_float_x86(n, x);
 }
 
+// One virtual OpenMP thread's chain `n += xs[p]` over positions p, p + T, ... < n_pos (MemoryProcessing.cpp:202-227).  While the
+// count is below 2^24 and the terms are non-negative the integer round trip of every addition is a float truncation:
+// (float)n is exact, cvttss2si(s) == trunc(s), and the next (float)n' is that same truncated value — so the chain runs as
+// fadd + trunc on a float (a dozen cycles per term instead of two int<->float conversions); the count only grows, so checking
+// the FINAL value proves every intermediate one was in range.  Anything else (a negative or NaN term, 2^24 reached) is redone
+// with the exact x86 emulation from where it started.
+__device__ __forceinline__ unsigned long long far_chain(unsigned long long n, const float* xs, int p, int n_pos, int T) {
+  if (n < (1ull << 24)) {
+    float f = (float)(unsigned)n;
+    bool bad = false;
+    int q = p;
+#pragma unroll 8
+    for (; q < n_pos; q += T) { const float x = xs[q]; bad |= !(x >= 0.0f); f = truncf(f + x); }
+    if (!bad && f < 16777216.0f) return (unsigned long long)f;
+  }
+  for (; p < n_pos; p += T) n = uint_plus_float_fast(n, xs[p]);
+  return n;
+}
+
 // epCache: optional shared-memory copy of {slot, episode length} per position of the episode vector (constant during a launch)
+// Launch-resident state of the statistics CTA of the persistent kernel (the episode table is fixed during a launch, the
+// per-episode maxima only grow between two sweeps): the sums and maxima of the last full scan, kept up to date by the deltas of
+// the episodes each step touches.
+struct StatKeep { double sum[5]; float mx[3]; int valid; };
+
+__device__ void refer_tail(const StepArgs& a, const Hyper& hp, const StepCtrl& c, StepCtrl& nx, int step, const SweepSums* sweep,
+                           long long farExactOverride, double sumDKL, double sumE2, double sumQ2, double sumQ1, double sumR, double farD,
+                           float maxAbsE, float maxQ, float negMinQ, unsigned long long tot);
+
 __device__ void stats_and_refer(const StepArgs& a, const Hyper& hp, const StepCtrl& c, StepCtrl& nx, int step,
                                 const SweepSums* sweep, long long farExactOverride, int farDeltaMine, float* xs,
-                                const int2* epCache = nullptr) {
+                                const int2* epCache = nullptr, StatKeep* keep = nullptr, float* xsAll = nullptr) {
   __shared__ double shd[kST / 32][6];
   __shared__ float shf[kST / 32][3];
   __shared__ unsigned long long shn[kST];
@@ -2194,12 +2234,13 @@ __device__ void stats_and_refer(const StepArgs& a, const Hyper& hp, const StepCt
         maxQ = fmaxf(maxQ, rp.epAgg[AGG_MAXQ * ME + slot]);
         negMinQ = fmaxf(negMinQ, -rp.epAgg[AGG_MINQ * ME + slot]);
         xs[p0 + u * kST] = Ns[u] * far[u];
+        if (xsAll) xsAll[base + p0 + u * kST] = Ns[u] * far[u];
       }
     }
     __syncthreads();
     if (tid < T) {
-      int p = (tid - base % T + T) % T;     // first position of this chunk owned by virtual thread `tid`
-      for (; p < n; p += T) nOff = uint_plus_float_fast(nOff, xs[p]);   // the reference's `Uint += float`, x86 semantics
+      const int p = (tid - base % T + T) % T;     // first position of this chunk owned by virtual thread `tid`
+      nOff = far_chain(nOff, xs, p, n, T);        // the reference's `Uint += float`, x86 semantics
     }
     __syncthreads();
   }
@@ -2226,6 +2267,20 @@ __device__ void stats_and_refer(const StepArgs& a, const Hyper& hp, const StepCt
     }
     unsigned long long tot = 0;
     for (int j = 0; j < min(T, kST); ++j) tot += shn[j];
+    if (keep) {
+      keep->sum[0] = sumDKL; keep->sum[1] = sumE2; keep->sum[2] = sumQ2; keep->sum[3] = sumQ1; keep->sum[4] = sumR;
+      keep->mx[0] = maxAbsE; keep->mx[1] = maxQ; keep->mx[2] = negMinQ; keep->valid = 1;
+    }
+    refer_tail(a, hp, c, nx, step, sweep, farExactOverride, sumDKL, sumE2, sumQ2, sumQ1, sumR, farD, maxAbsE, maxQ, negMinQ, tot);
+  }
+}
+
+// the scalar end of updateTrainingStatistics + updateCounters (MemoryProcessing.cpp:46-92,229-259), one thread
+__device__ void refer_tail(const StepArgs& a, const Hyper& hp, const StepCtrl& c, StepCtrl& nx, int step, const SweepSums* sweep,
+                           long long farExactOverride, double sumDKL, double sumE2, double sumQ2, double sumQ1, double sumR, double farD,
+                           float maxAbsE, float maxQ, float negMinQ, unsigned long long tot) {
+  const int nEp = a.nEpisodes;
+  {
     const long long gstep = c.grad_step + 1;                                   // nGradSteps()+1
     const double C = hp.clipImpWeight, E = hp.epsAnneal;
     const double cmax = 1.0 + C / (1.0 + (double)gstep * E);                  // annealRate
@@ -2306,12 +2361,68 @@ __device__ void stats_and_refer(const StepArgs& a, const Hyper& hp, const StepCt
   }
 }
 
+// Statistics of a step of the persistent kernel after the first one of a launch: the sums move by what apply_sample_records
+// changed (StatInc), the maxima can only have grown, the far-policy count walks the launch-resident terms `xsAll` (shared memory)
+// with the reference's `Uint += float` chains (MemoryProcessing.cpp:202-227) — no pass over the episode aggregates in HBM.
+__device__ void stats_incremental(const StepArgs& a, const Hyper& hp, const StepCtrl& c, StepCtrl& nx, int step, int farDeltaMine,
+                                  const StatInc& inc, StatKeep& keep, const float* xsAll) {
+  __shared__ double shd[kST / 32][5];
+  __shared__ float shf[kST / 32][3];
+  __shared__ unsigned long long shn[kST];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nEp = a.nEpisodes, T = hp.referThreads;
+  double d0 = inc.d[0], d1 = inc.d[1], d2 = inc.d[2], d3 = inc.d[3], farD = (double)farDeltaMine;
+  float m0 = inc.mx[0], m1 = inc.mx[1], m2 = inc.mx[2];
+  __syncthreads();                                   // xsAll entries written by the run owners
+  unsigned long long nOff = 0;
+  if (tid < T) nOff = far_chain(0, xsAll, tid, nEp, T);
+  shn[tid] = nOff;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+    d2 += __shfl_xor_sync(0xffffffffu, d2, o); d3 += __shfl_xor_sync(0xffffffffu, d3, o);
+    farD += __shfl_xor_sync(0xffffffffu, farD, o);
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+    m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+  }
+  if (lane == 0) { shd[warp][0] = d0; shd[warp][1] = d1; shd[warp][2] = d2; shd[warp][3] = d3; shd[warp][4] = farD;
+                   shf[warp][0] = m0; shf[warp][1] = m1; shf[warp][2] = m2; }
+  __syncthreads();
+  if (tid == 0) {
+    d0 = d1 = d2 = d3 = farD = 0.0;
+    for (int w = 0; w < kST / 32; ++w) {
+      d0 += shd[w][0]; d1 += shd[w][1]; d2 += shd[w][2]; d3 += shd[w][3]; farD += shd[w][4];
+      m0 = fmaxf(m0, shf[w][0]); m1 = fmaxf(m1, shf[w][1]); m2 = fmaxf(m2, shf[w][2]);
+    }
+    keep.sum[0] += d0; keep.sum[1] += d1; keep.sum[2] += d2; keep.sum[3] += d3;
+    keep.mx[0] = fmaxf(keep.mx[0], m0); keep.mx[1] = fmaxf(keep.mx[1], m1); keep.mx[2] = fmaxf(keep.mx[2], m2);
+    unsigned long long tot = 0;
+    for (int j = 0; j < min(T, kST); ++j) tot += shn[j];
+    refer_tail(a, hp, c, nx, step, nullptr, -1, keep.sum[0], keep.sum[1], keep.sum[2], keep.sum[3], keep.sum[4], farD,
+               keep.mx[0], keep.mx[1], keep.mx[2], tot);
+  }
+}
+
+// keep / xsAll (persistent kernel only): launch-resident statistics state; xsAll holds a.nEpisodes floats of shared memory.
 __device__ void p3_stats(const StepArgs& a, const Hyper& hp, const StepCtrl& c, StepCtrl& nx, int step, float* stage,
-                         const int2* epCache = nullptr) {
+                         const int2* epCache = nullptr, StatKeep* keep = nullptr, float* xsAll = nullptr) {
+  if (keep && xsAll && keep->valid) {
+    StatInc inc; inc.xsAll = xsAll; inc.epPos = a.rp.epPos;
+    inc.d[0] = inc.d[1] = inc.d[2] = inc.d[3] = 0.0; inc.mx[0] = inc.mx[1] = inc.mx[2] = -1e9f;
+    const int fd = apply_sample_records(a, stage, &inc);
+    stats_incremental(a, hp, c, nx, step, fd, inc, *keep, xsAll);
+    return;
+  }
   const int fd = apply_sample_records(a, stage);
   __threadfence_block();
   __syncthreads();
-  stats_and_refer(a, hp, c, nx, step, nullptr, -1, fd, stage, epCache);
+  stats_and_refer(a, hp, c, nx, step, nullptr, -1, fd, stage, epCache, keep, xsAll);
+}
+// The statistics CTA of the persistent kernel calls it as a real function: the statistics code keeps its own registers instead
+// of competing with the worker path of the same kernel.  `a` must NOT be the kernel parameter itself (see the caller).
+__device__ __noinline__ void p3_stats_call(const StepArgs& a, const Hyper& hp, const StepCtrl& c, StepCtrl& nx, int step, float* stage,
+                                          StatKeep* keep, float* xsAll) {
+  p3_stats(a, hp, c, nx, step, stage, nullptr, keep, xsAll);
 }
 
 
@@ -2480,6 +2591,15 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
   __shared__ uint32_t tcTmem;
   unsigned tcPhase = 0;
   if ((int)blockIdx.x == nw) {                  // ---- statistics CTA ----
+    // launch-resident statistics (StatKeep): the far-policy terms of all episodes live in the shared memory the workers use for
+    // the weight image; larger episode tables (or no image in shared memory) keep the full scan of every step
+    __shared__ StatKeep keep;
+    // p3_stats is not inlined: it gets a shared-memory copy of the launch arguments (taking the address of the kernel parameter
+    // would move every access of the WORKER path from the constant bank to a per-thread stack copy)
+    __shared__ StepArgs aS;
+    float* xsAll = SM && a.nEpisodes <= net->imgFloats && a.statsIncremental ? reinterpret_cast<float*>(smraw + sp.img) : nullptr;
+    if (threadIdx.x == 0) { aS = a; keep.valid = 0; }
+    __syncthreads();
     for (int s = 0; s < nSteps; ++s) {
       if (skipStatsLast && s == nSteps - 1) break;
       const int step = step0 + s;
@@ -2491,7 +2611,7 @@ __global__ void __launch_bounds__(kST, 1) k_steps_persistent(StepArgs a, int ste
       }
       __syncthreads();
       DBG_T(a, step, 6);
-      p3_stats(a, *hp, c, a.ctrl[(step + 1) & 1], step, tiles);
+      p3_stats_call(aS, *hp, c, aS.ctrl[(step + 1) & 1], step, tiles, xsAll ? &keep : nullptr, xsAll);
       __syncthreads();
       if (threadIdx.x == 0) {
         __threadfence();

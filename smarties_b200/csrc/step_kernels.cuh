@@ -161,6 +161,7 @@ struct StepArgs {
   unsigned* barrier;
   long long* dbgT;                         // optional phase timestamps [step][cta][8] (clock64)
   int useTma;                              // weight image to shared memory by cp.async.bulk (1) or ld.global.cg (0)
+  int statsIncremental;                    // persistent kernel: launch-resident statistics (StatKeep) instead of a full scan per step
   // recurrent nets: weight gradient of the LSTM layers on the tensor cores (tcgen05, see tc_wgrad_item)
   int useTc; float* tcPartial;             // [item][128][128] f32 partial tiles of the K-slices
 };

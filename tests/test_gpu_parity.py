@@ -261,6 +261,31 @@ def test_forward_matches_oracle():
     L.close()
 
 
+@pytest.mark.parametrize("case", ["vracer_cfg2mini", "vracer_prune", "racer_small_t8", "racer_lstm", "vracer_cfg2mini_t16"])
+def test_launch_resident_statistics_equal_the_full_scan(monkeypatch, case):
+    """Persistent kernel: from the second step of a launch on the statistics CTA updates its sums by what the step's samples
+    changed, takes the maxima as monotone and walks the far-policy terms kept in shared memory (stats_incremental) instead of
+    scanning every episode's aggregates (SMB200_STATS_FULL=1).  Far-policy count, beta and the maxima must be identical, the
+    f64 sums equal to round-off; weights and replay values identical."""
+    g = Golden(case)
+    monkeypatch.setenv("SMB200_STATS_FULL", "1")
+    A = make_learner(g)
+    monkeypatch.delenv("SMB200_STATS_FULL")
+    Bm = make_learner(g)
+    for k in (1, 7, 50, 300, 2, 990 - 360 + 25):       # the last call crosses the every-1000-steps sweep
+        sa, sb = A.train_steps(k), Bm.train_steps(k)
+        for i, (x, y) in enumerate(zip(sa, sb)):
+            assert x["n_far_policy"] == y["n_far_policy"] and x["n_far_exact"] == y["n_far_exact"], (k, i)
+            assert x["beta"] == y["beta"] and x["grad_step"] == y["grad_step"], (k, i)
+            assert x["max_q"] == y["max_q"] and x["min_q"] == y["min_q"] and x["max_abs_err"] == pytest.approx(y["max_abs_err"], rel=1e-12), (k, i)
+            for key in ("avg_kl", "avg_sq_err", "avg_q", "stdev_q", "avg_return"):
+                assert x[key] == pytest.approx(y[key], rel=1e-9, abs=1e-12), (k, i, key)
+    assert np.array_equal(A.get_weights(), Bm.get_weights())
+    assert np.array_equal(A.read_field("RHO"), Bm.read_field("RHO"))
+    assert np.array_equal(A.read_episodes()[2], Bm.read_episodes()[2])
+    A.close(); Bm.close()
+
+
 @pytest.mark.parametrize("case", ["vracer_cfg2mini", "vracer_prune", "racer_lstm"])
 def test_sample_ahead_queue_is_invisible(monkeypatch, case):
     """smb200_train_steps draws the next call's mini-batches while it waits for the device (sample-ahead queue).  The sampled
