@@ -2111,6 +2111,7 @@ __device__ int apply_sample_records(const StepArgs& a, float* stage /* >= 256*12
       float sQ2 = rp.epAgg[AGG_Q2 * ME + slot], sQ = rp.epAgg[AGG_Q1 * ME + slot];
       float maxQ = rp.epAgg[AGG_MAXQ * ME + slot], minQ = rp.epAgg[AGG_MINQ * ME + slot];
       const float Nf = (float)rp.epLen[slot];
+      const int pos = inc ? inc->epPos[slot] : 0;     // issued with the aggregate loads, used after the run
       const float invN = 1.0f / Nf;
       const float oKL = avgKL, oE2 = avgE2, oQ2 = sQ2, oQ1 = sQ;
       for (int j = b; j < a.B; ++j) {
@@ -2139,7 +2140,7 @@ __device__ int apply_sample_records(const StepArgs& a, float* stage /* >= 256*12
         inc->d[0] += (double)(Nf * avgKL) - (double)(Nf * oKL); inc->d[1] += (double)(Nf * avgE2) - (double)(Nf * oE2);
         inc->d[2] += (double)sQ2 - (double)oQ2; inc->d[3] += (double)sQ - (double)oQ1;
         inc->mx[0] = fmaxf(inc->mx[0], maxE); inc->mx[1] = fmaxf(inc->mx[1], maxQ); inc->mx[2] = fmaxf(inc->mx[2], -minQ);
-        inc->xsAll[inc->epPos[slot]] = Nf * frac;
+        inc->xsAll[pos] = Nf * frac;
       }
     }
     __syncthreads();
