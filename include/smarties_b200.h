@@ -275,6 +275,10 @@ int smb200_profile_phases(smb200_learner* h, int32_t n, int64_t* out, int64_t ca
  * `Uint nOffPol += float` (ReplayMemory/MemoryProcessing.cpp:202-227) with x86-64 conversion semantics —
  * the same inline function the device code calls, compiled for the host.  Returns the new count. */
 uint64_t smb200_uint_plus_float(uint64_t n, float x);
+/* The chain `n += xs[first], xs[first + stride], ...` (positions < n_pos) of ONE virtual OpenMP thread of that count as the statistics
+ * phase evaluates it: while the count is below 2^24 and the terms are non-negative as a float truncation per term (equal to the
+ * integer round trip there), otherwise term by term with smb200_uint_plus_float's emulation.  Host build of the device function. */
+uint64_t smb200_host_far_chain(uint64_t n0, const float* xs, int32_t first, int32_t n_pos, int32_t stride);
 /* Diagnostics, host only (no GPU needed): the padded parameter blob smb200_create starts from — the layout of
  * Network/Layers/Parameters.h:159-176 initialised like Builder::build does from generators[0] of a run with randSeed =
  * cfg->seed (Network/Builder.cpp:133-137, Layer_Base.h:115-141, Layer_LSTM.h:168-188, ExecutionInfo.cpp:391).

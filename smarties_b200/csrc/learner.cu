@@ -1296,6 +1296,7 @@ int smb200_set_grad_step(smb200_learner* h, int64_t n) {
 }
 int smb200_seed_sampler(smb200_learner* h, uint64_t seed) {
   if (!h) return SMB200_ERR_INVALID;
+  std::lock_guard<std::recursive_mutex> lock(h->apiMutex);
   h->gen.seed((unsigned long)seed); h->presampled = 0; h->ahead_clear();
   return 0;
 }

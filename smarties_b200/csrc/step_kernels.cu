@@ -2154,10 +2154,16 @@ constexpr int kStatChunk = 4096;   // episode positions staged per pass (floats 
 
 // `Uint += float` for the common case of a small count and a small non-negative addend: 32-bit conversions (one instruction
 // each) give what uint_plus_float_x86 gives — (float)n is exact below 2^24 and truncation agrees on [0, 2^31)
-__device__ __forceinline__ unsigned long long uint_plus_float_fast(unsigned long long n, float x) {
+__host__ __device__ __forceinline__ unsigned long long uint_plus_float_fast(unsigned long long n, float x) {
   if (n < (1ull << 24)) {
+#ifdef __CUDA_ARCH__
     const float f = (float)(unsigned)n + x;
     if (f >= 0.0f && f < 2147483648.0f) return (unsigned long long)__float2uint_rz(f);
+#else
+    const volatile float fv = (float)(unsigned)n + x;      // volatile: a plain f32 sum on the host as well
+    const float f = fv;
+    if (f >= 0.0f && f < 2147483648.0f) return (unsigned long long)(unsigned)f;
+#endif
   }
   return uint_plus_float_x86(n, x);
 }
@@ -2168,13 +2174,17 @@ __device__ __forceinline__ unsigned long long uint_plus_float_fast(unsigned long
 // fadd + trunc on a float (a dozen cycles per term instead of two int<->float conversions); the count only grows, so checking
 // the FINAL value proves every intermediate one was in range.  Anything else (a negative or NaN term, 2^24 reached) is redone
 // with the exact x86 emulation from where it started.
-__device__ __forceinline__ unsigned long long far_chain(unsigned long long n, const float* xs, int p, int n_pos, int T) {
+__host__ __device__ __forceinline__ unsigned long long far_chain(unsigned long long n, const float* xs, int p, int n_pos, int T) {
   if (n < (1ull << 24)) {
     float f = (float)(unsigned)n;
     bool bad = false;
     int q = p;
+#ifdef __CUDA_ARCH__
 #pragma unroll 8
     for (; q < n_pos; q += T) { const float x = xs[q]; bad |= !(x >= 0.0f); f = truncf(f + x); }
+#else
+    for (; q < n_pos; q += T) { const float x = xs[q]; bad |= !(x >= 0.0f); const volatile float sv = f + x; f = truncf(sv); }
+#endif
     if (!bad && f < 16777216.0f) return (unsigned long long)f;
   }
   for (; p < n_pos; p += T) n = uint_plus_float_fast(n, xs[p]);
@@ -2979,6 +2989,13 @@ extern "C" {
 
 // n elements of AdamOptimizer::apply_update (struct Adam, Network/Optimizer.cpp:61-108) exactly as the P2 epilogue applies it:
 // eta from adam_eta_for after `adam_step` completed updates with the running beta powers bt1 / bt2, then adam_step per element.
+// The far-policy chain of one virtual OpenMP thread as the statistics CTA runs it (far_chain: float truncation while the count
+// is below 2^24 and the terms are non-negative, the exact x86 emulation otherwise), compiled for the host.
+uint64_t smb200_host_far_chain(uint64_t n0, const float* xs, int32_t first, int32_t n_pos, int32_t stride) {
+  if (!xs || first < 0 || stride < 1) return ~0ull;
+  return (uint64_t)smb200::far_chain((unsigned long long)n0, xs, first, n_pos, stride);
+}
+
 int smb200_host_adam(int64_t n, const float* G, float* W, float* M1, float* M2, double learnrate, double eps_anneal, int64_t adam_step_done,
                      double bt1, double bt2, double nn_lambda, int32_t batch_global) {
   if (n < 0 || !G || !W || !M1 || !M2 || batch_global < 1) return -1;

@@ -34,7 +34,7 @@ EXPORTS = [
     "smb200_reward_state_moments", "smb200_read_field", "smb200_read_episodes", "smb200_n_rows", "smb200_get_stats",
     "smb200_forward", "smb200_forward_seq", "smb200_last_timing", "smb200_step_kernel", "smb200_presample", "smb200_train_presampled", "smb200_sync", "smb200_profile_phases",
     "smb200_comm_init", "smb200_comm_attach", "smb200_comm_error", "smb200_write_field", "smb200_save", "smb200_restart",
-    "smb200_push_episode_restored", "smb200_set_refer", "smb200_set_grad_stats", "smb200_uint_plus_float", "smb200_host_replay_trace", "smb200_host_init_weights",
+    "smb200_push_episode_restored", "smb200_set_refer", "smb200_set_grad_stats", "smb200_uint_plus_float", "smb200_host_far_chain", "smb200_host_replay_trace", "smb200_host_init_weights",
     "smb200_host_strip_weights", "smb200_host_write_grad_stats", "smb200_host_repack_episodes",
     "smb200_host_adam", "smb200_host_value_scaling", "smb200_host_return_estimator",
     "smb200_host_discrete_loss", "smb200_host_wide_plan",

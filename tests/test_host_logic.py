@@ -133,6 +133,53 @@ def test_uint_plus_float_x86_matches_oracle(built_library):
     assert n == (1 << 64) - 40 and lib.smb200_uint_plus_float(n, 3.0) == 0
 
 
+def test_far_policy_chain_fast_path_is_exact(built_library):
+    """The statistics CTA walks each virtual OpenMP thread's `Uint += float` chain (MemoryProcessing.cpp:202-227) as fadd + trunc
+    on a float while the count stays below 2^24 and the terms are non-negative, and falls back to the term-by-term x86 emulation
+    otherwise (far_chain).  Host build of that function against the oracle's integer round trip per term: terms a hair below
+    and above integers (Ns * (k / Ns) in f32), strides like the T virtual threads, counts that cross 2^24, negative and NaN terms."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import vracer_oracle as vo
+    from smarties_b200 import load_library
+    lib = load_library()
+    lib.smb200_host_far_chain.restype = C.c_uint64
+    lib.smb200_host_far_chain.argtypes = [C.c_uint64, C.POINTER(C.c_float), C.c_int32, C.c_int32, C.c_int32]
+    rng = np.random.default_rng(11)
+
+    lib.smb200_uint_plus_float.restype = C.c_uint64
+    lib.smb200_uint_plus_float.argtypes = [C.c_uint64, C.c_float]
+
+    def want(n0, xs, first, stride):
+        n = n0
+        for x in xs[first::stride]:
+            # a NaN term (never produced by the learner) is outside the oracle's restatement: there the reference is the
+            # library's own term-by-term x86 emulation (cvttss2si of NaN = the 2^63 "integer indefinite")
+            n = lib.smb200_uint_plus_float(n, float(x)) if np.isnan(x) else vo.uint_plus_float(n, np.float32(x))
+        return n
+
+    def got(n0, xs, first, stride):
+        a = np.ascontiguousarray(xs, np.float32)
+        return lib.smb200_host_far_chain(n0, a.ctypes.data_as(C.POINTER(C.c_float)), first, len(a), stride)
+
+    cases = []
+    for _ in range(40):                      # what the learner produces: Ns * fracFar with fracFar = f32(k / Ns)
+        Ns = rng.integers(2, 1200, 600).astype(np.float32)
+        k = (rng.random(600) * Ns).astype(np.int64).astype(np.float32)
+        cases.append((Ns * (k / Ns).astype(np.float32)).astype(np.float32))
+    cases.append(np.nextafter(np.arange(1, 400, dtype=np.float32), np.float32(0)))          # a hair below every integer
+    cases.append(np.nextafter(np.arange(1, 400, dtype=np.float32), np.float32(1e9)))
+    cases.append((rng.random(3000) * 9000).astype(np.float32))                              # crosses 2^24 on the way
+    cases.append(np.concatenate([np.full(50, 3.5, np.float32), [-2.0], np.full(50, 1.25, np.float32)]).astype(np.float32))
+    cases.append(np.concatenate([np.full(10, 2.0, np.float32), [np.nan], np.full(10, 2.0, np.float32)]).astype(np.float32))
+    cases.append(np.zeros(0, np.float32) + 0)
+    for xs in cases:
+        for n0 in (0, 5, (1 << 24) - 3, (1 << 24) + 7, (1 << 40) + 1):
+            for first, stride in ((0, 1), (3, 8), (31, 32), (0, 16)):
+                assert got(n0, xs, first, stride) == want(n0, xs, first, stride), (n0, first, stride, xs[:5])
+
+
 def test_every_settings_file_of_the_reference_is_parsed_or_rejected_with_a_reason():
     """The settings/*.json surface (Settings/HyperParameters.h:37-73, HyperParameters::initializeOpts): every file the reference
     ships (tests/golden/reference_settings.json, generator make_settings_fixture.py) either configures the device path or is
