@@ -374,3 +374,28 @@ def test_tensor_core_weight_gradient_matches_simt_tiles(monkeypatch, case):
     ga, gb = A.get_grad(), Bm.get_grad()
     assert np.abs(ga).max() > 0 and relerr(ga, gb) < 2e-6
     A.close(); Bm.close()
+
+
+def test_reference_settings_files_train_on_the_device():
+    """Every V-RACER / RACER settings file of the reference (tests/reference_settings.py) constructs a device learner for a
+    HalfCheetah-shaped MDP (17 states, 6 actions) and trains: finite statistics, beta in (0, 1], weights that move, and the
+    step counter of the reference.  Buffer sizes are cut to a small synthetic replay; everything else is the file's."""
+    from reference_settings import DEVICE
+    from smarties_b200 import Learner, synth
+    d = synth.make_replay(77, 60, (40, 80), 17, 6)
+    n_data = int((d["N"] - 1).sum())
+    for name, js in DEVICE.items():
+        S = dict(js, maxTotObsNum=8192, minTotObsNum=min(n_data, 2048))
+        S["batchSize"] = min(int(S.get("batchSize", 256)), 64)
+        L = Learner(17, 6, S, bounded=True)
+        L.load_replay(d)
+        L.initialize_learner()
+        w0 = L.get_weights().copy()
+        st = L.train_steps(12)
+        assert st[-1]["grad_step"] == 12, name
+        assert 0.0 < st[-1]["beta"] <= 1.0 and all(np.isfinite([st[-1][k] for k in ("avg_kl", "avg_sq_err", "avg_q", "stdev_q")])), name
+        w1 = L.get_weights()
+        assert np.isfinite(w1).all() and np.abs(w1 - w0).max() > 0, name
+        out = L.forward_seq(d["S"][:3][None].repeat(2, axis=0), [1, 3])
+        assert out.shape == (2, L.n_out) and np.isfinite(out).all(), name
+        L.close()

@@ -41,6 +41,22 @@ def test_settings_file_of_reference_parses():
         HyperParameters(4, 1, {"notAKey": 1})
 
 
+def test_racer_family_settings_files_of_the_reference_are_covered():
+    """Every V-RACER / RACER settings file the reference ships (settings/*.json, restated in tests/reference_settings.py) passes the
+    host-side coverage check and yields a device configuration; the CMA variant is refused (it stays with the reference learner)."""
+    from reference_settings import DEVICE, REFERENCE_ONLY
+    from smarties_b200 import HyperParameters
+    from smarties_b200.learner import make_config
+    for name, js in DEVICE.items():
+        hp = HyperParameters(17, 6, dict(js))
+        cfg, _ = make_config(17, 6, dict(js))
+        assert cfg.n_hidden == len([h for h in hp.nnLayerSizes if h > 0]), name
+        assert cfg.batch_size == hp.batchSize_local and cfg.algo == (1 if hp.learner == "RACER" else 0), name
+    for name, js in REFERENCE_ONLY.items():
+        with pytest.raises(NotImplementedError):
+            HyperParameters(17, 6, dict(js))
+
+
 def test_settings_outside_the_device_path_are_rejected_loudly():
     """What the device library covers of createReturnEstimator / prepareSampler / getERfilterAlgo / Builder::addLayer
     (the oracle covers more: tests/parity_utils.ORACLE_ONLY_CASES); everything else raises instead of running something else."""
