@@ -562,7 +562,6 @@ static void host_sample(smb200_learner* h, int* slotOut, int* tOut, int64_t* pos
 
 // ---- sample-ahead queue (see smb200_learner::aheadSlot) ----
 constexpr int kAheadMax = 128;     // steps
-constexpr int kAheadReserve = 32, kAheadCatchUp = 8;
 // the episode table is in its steady state: the next host_post_step neither re-sorts nor evicts
 static bool table_steady(const smb200_learner* h) {
   if (h->cfg.er_filter != SMB200_FILTER_OLDEST || h->episodes.empty()) return false;
@@ -1500,18 +1499,8 @@ static int train_steps_impl(smb200_learner* h, int32_t n, smb200_step_stats* sta
   SMB200_CUDA_CHECK(cudaEventRecord(h->ev1, h->stream));
   // the device is still working on the last segment(s): draw the next call's mini-batches meanwhile (never longer than the
   // device takes: the event is polled between steps)
-  // Reserve: until the queue holds kAheadReserve steps a call also pays for up to kAheadCatchUp steps after the device has
-  // finished (8 us each) — a few early calls build the reserve, after that every call refills what it consumed inside its own
-  // device time, and a call of up to kAheadReserve steps is ONE launch
-  if (n > 0 && !getenv("SMB200_NO_SAMPLE_AHEAD")) {
-    int paid = 0;
-    while (h->aheadCnt - h->aheadHead < kAheadMax / 2) {
-      const bool busy = cudaEventQuery(h->ev1) == cudaErrorNotReady;
-      if (!busy && (h->aheadCnt - h->aheadHead >= kAheadReserve || paid >= kAheadCatchUp)) break;
-      if (!ahead_push_one(h)) break;
-      if (!busy) ++paid;
-    }
-  }
+  if (n > 0 && !getenv("SMB200_NO_SAMPLE_AHEAD"))
+    while (cudaEventQuery(h->ev1) == cudaErrorNotReady && h->aheadCnt - h->aheadHead < kAheadMax / 2 && ahead_push_one(h)) { }
   if (reclaim(0) || reclaim(1)) return SMB200_ERR_CUDA;
   SMB200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
